@@ -1,0 +1,117 @@
+"""ctypes binding of libat3d_b200.so (include/at3d_b200.h).  No fallback: a missing library or a
+missing CUDA device raises."""
+import ctypes as C
+import os
+import numpy as np
+from .state import StateDesc, GradDesc, i32, f32, f64, P
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'lib', 'libat3d_b200.so')
+ERRLEN = 600
+
+
+class At3dError(RuntimeError):
+    """Non-zero IERR from the library (at3d.exceptions.SHDOMError equivalent)."""
+
+    def __init__(self, code, msg):
+        super().__init__('at3d_b200 error %d: %s' % (code, msg))
+        self.code, self.msg = code, msg
+
+
+class RaysC(C.Structure):
+    _fields_ = [('nrays', i32), ('memspace', i32), ('camx', C.c_void_p), ('camy', C.c_void_p),
+                ('camz', C.c_void_p), ('cammu', C.c_void_p), ('camphi', C.c_void_p)]
+
+
+class TraceC(C.Structure):
+    _fields_ = [('max_per_ray', i32), ('cells', C.c_void_p), ('ncells', C.c_void_p), ('nsub', C.c_void_p)]
+
+
+_lib = None
+
+# every symbol include/at3d_b200.h declares (tests/test_capi_symbols.py checks the export list)
+SYMBOLS = ['at3d_b200_version', 'at3d_device_count', 'at3d_set_device', 'at3d_state_create',
+           'at3d_state_attach_gradient', 'at3d_state_destroy', 'at3d_state_bytes', 'at3d_state_get_bcrad',
+           'at3d_ylmall', 'at3d_precompute_phase_check', 'at3d_compute_source', 'at3d_render',
+           'at3d_levisapprox_gradient', 'at3d_prepare_deriv_interps', 'at3d_make_direct_derivative',
+           'at3d_average_subpixel_rays', 'at3d_update_costfunction']
+
+
+class _Missing:
+    def __init__(self, name):
+        self.name = name
+
+    def __call__(self, *a, **k):
+        raise ImportError('libat3d_b200.so does not export %s (stale build?)' % self.name)
+
+
+class _Binder:
+    """Attribute access to the CDLL that tolerates a symbol missing at bind time and fails loudly
+    when such a symbol is actually called."""
+
+    def __init__(self, dll):
+        object.__setattr__(self, '_dll', dll)
+
+    def __getattr__(self, name):
+        try:
+            return getattr(self._dll, name)
+        except AttributeError:
+            m = _Missing(name)
+            object.__setattr__(self, name, m)
+            return m
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError('%s not found: build it with `python -c "import __graft_entry__ as g; g.build()"` '
+                          '(at3d_b200 has no CPU fallback)' % LIB_PATH)
+    L = _Binder(C.CDLL(LIB_PATH))
+    L.at3d_b200_version.restype = C.c_char_p
+    L.at3d_state_bytes.restype = C.c_int64
+    L.at3d_state_bytes.argtypes = [C.c_void_p]
+    L.at3d_state_create.argtypes = [P(StateDesc), P(C.c_void_p), C.c_char_p]
+    L.at3d_state_attach_gradient.argtypes = [C.c_void_p, P(GradDesc), C.c_char_p]
+    L.at3d_state_destroy.argtypes = [C.c_void_p]
+    L.at3d_state_get_bcrad.argtypes = [C.c_void_p, C.c_void_p, C.c_char_p]
+    L.at3d_render.argtypes = [C.c_void_p, P(RaysC), C.c_void_p, i32, i32, i32, P(TraceC), C.c_void_p,
+                              P(f64), C.c_char_p]
+    L.at3d_levisapprox_gradient.argtypes = [C.c_void_p, P(RaysC), P(GradDesc), C.c_void_p, C.c_void_p,
+                                            C.c_void_p, P(TraceC), C.c_void_p, P(f64), C.c_char_p]
+    L.at3d_compute_source.argtypes = [P(StateDesc), i32, f32, i32, i32, i32, i32, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_void_p, P(f32), P(f32), P(f32), P(f32), P(f64),
+                                      C.c_char_p]
+    L.at3d_ylmall.argtypes = [i32, f32, f32, i32, i32, i32, C.c_void_p, C.c_char_p]
+    L.at3d_precompute_phase_check.argtypes = [i32, i32, i32, i32, i32, i32, i32, i32, C.c_void_p,
+                                              C.c_void_p, i32, i32, i32, C.c_char_p]
+    L.at3d_prepare_deriv_interps.argtypes = [P(StateDesc), i32, i32, i32, i32, f32, f32, f32, f32,
+                                             C.c_void_p, P(GradDesc), C.c_void_p, C.c_void_p, C.c_void_p,
+                                             C.c_void_p, C.c_void_p, C.c_char_p]
+    L.at3d_make_direct_derivative.argtypes = [i32, i32, i32, i32, i32, f32, f32, f32, f32, C.c_void_p,
+                                              C.c_void_p, i32, i32, i32, i32] + [f64] * 13 + \
+                                             [C.c_void_p, C.c_void_p, i32, C.c_char_p]
+    L.at3d_average_subpixel_rays.argtypes = [i32, i32, i32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_char_p]
+    L.at3d_update_costfunction.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                           i32, i32, i32, i32, C.c_void_p, i32, C.c_char_p]
+    _lib = L
+    return L
+
+
+def check(code, buf):
+    if code != 0:
+        raise At3dError(code, buf.value.decode(errors='replace').strip())
+
+
+def errbuf():
+    return C.create_string_buffer(ERRLEN)
+
+
+def vp(a):
+    """void* of a numpy array, a torch tensor (data_ptr) or None."""
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data
+    return a.data_ptr()

@@ -1,0 +1,327 @@
+// at3d_capi.cu -- C-ABI of libat3d_b200.so (include/at3d_b200.h): state residency and RENDER.
+#include <cstdio>
+#include <cstring>
+#include <cstdarg>
+#include <cmath>
+#include "at3d_host.h"
+#include "at3d_ray.cuh"
+
+static void set_msg(char *errmsg, const char *fmt, ...)
+{
+    if (!errmsg) return;
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(errmsg, AT3D_ERRMSG_LEN, fmt, ap);
+    va_end(ap);
+}
+
+#define CUDA_TRY(expr)                                                                         \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess) {                                                               \
+            set_msg(errmsg, "CUDA error %s at %s:%d (%s)", cudaGetErrorString(_e), __FILE__,   \
+                    __LINE__, #expr);                                                          \
+            return 4;                                                                          \
+        }                                                                                      \
+    } while (0)
+
+extern "C" const char *at3d_b200_version(void) { return "at3d_b200 0.1 (sm_100a)"; }
+
+extern "C" int at3d_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+extern "C" int at3d_set_device(int device)
+{
+    return cudaSetDevice(device) == cudaSuccess ? 0 : 4;
+}
+
+template <typename T>
+static int upload(at3d_state *st, const T *host, size_t n, const T **dev, char *errmsg)
+{
+    *dev = nullptr;
+    if (!host || n == 0) return 0;
+    void *p = nullptr;
+    CUDA_TRY(cudaMalloc(&p, n * sizeof(T)));
+    st->owned.push_back(p);
+    st->bytes += n * sizeof(T);
+    CUDA_TRY(cudaMemcpy(p, host, n * sizeof(T), cudaMemcpyHostToDevice));
+    *dev = (const T *)p;
+    return 0;
+}
+
+template <typename T>
+static int dalloc(at3d_state *st, size_t n, T **dev, char *errmsg)
+{
+    void *p = nullptr;
+    if (n == 0) n = 1;
+    CUDA_TRY(cudaMalloc(&p, n * sizeof(T)));
+    st->owned.push_back(p);
+    st->bytes += n * sizeof(T);
+    *dev = (T *)p;
+    return 0;
+}
+
+// planar padded SH block offsets: point block = nstokes planes of roundup4(ns) floats
+static size_t make_sh_records(const int32_t *shptr, int npts, int nstokes, std::vector<int2> &rec)
+{
+    rec.resize(npts);
+    size_t off = 0;
+    for (int i = 0; i < npts; i++) {
+        int ns = shptr[i + 1] - shptr[i];
+        int nsp = (ns + 3) & ~3;
+        rec[i] = make_int2((int)off, ns);
+        off += (size_t)nstokes * nsp;
+    }
+    return off;
+}
+
+static int prep_sh_array(at3d_state *st, int tms, const int32_t *shptr_h, const float *sh_h,
+                         const int2 **rec_out, const float **sh_out, int *sscount, int2 *ssent, char *errmsg)
+{
+    const DevState &S = st->S;
+    std::vector<int2> rec;
+    size_t total = make_sh_records(shptr_h, S.npts, S.nstokes, rec);
+    if (total >= (size_t)1 << 31) { set_msg(errmsg, "SH array too large for 32-bit offsets"); return 2; }
+    const int2 *rec_d; float *out_d;
+    int rc = upload(st, rec.data(), rec.size(), &rec_d, errmsg); if (rc) return rc;
+    rc = dalloc(st, total + 4, &out_d, errmsg); if (rc) return rc;
+    // staging copies of the reference-layout arrays (freed after the re-layout)
+    int *shptr_d = nullptr; float *in_d = nullptr;
+    size_t nin = (size_t)S.nstokes * (size_t)shptr_h[S.npts];
+    CUDA_TRY(cudaMalloc((void **)&shptr_d, (S.npts + 1) * sizeof(int)));
+    CUDA_TRY(cudaMalloc((void **)&in_d, (nin + 1) * sizeof(float)));
+    CUDA_TRY(cudaMemcpy(shptr_d, shptr_h, (S.npts + 1) * sizeof(int), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(in_d, sh_h, nin * sizeof(float), cudaMemcpyHostToDevice));
+    CUDA_TRY(launch_prep_sh(S, tms, shptr_d, in_d, rec_d, out_d, sscount, ssent, 0));
+    CUDA_TRY(cudaDeviceSynchronize());
+    cudaFree(shptr_d); cudaFree(in_d);
+    *rec_out = rec_d; *sh_out = out_d;
+    return 0;
+}
+
+extern "C" int at3d_state_destroy(at3d_state *st)
+{
+    if (!st) return 0;
+    for (void *p : st->owned) cudaFree(p);
+    st->rays.release(); st->out.release(); st->trace.release(); st->misc.release();
+    st->slabs.release(); st->err.release();
+    delete st;
+    return 0;
+}
+
+extern "C" int64_t at3d_state_bytes(const at3d_state *st) { return st ? (int64_t)st->bytes : 0; }
+
+extern "C" int at3d_state_create(const at3d_state_desc *d, at3d_state **out, char *errmsg)
+{
+    if (errmsg) errmsg[0] = 0;
+    if (!d || !out) { set_msg(errmsg, "null argument"); return 1; }
+    *out = nullptr;
+    if (at3d_device_count() < 1) { set_msg(errmsg, "no CUDA device: at3d_b200 has no CPU fallback"); return 4; }
+    if (d->srctype != 'S') { set_msg(errmsg, "only SRCTYPE='S' (solar) is implemented on the GPU path"); return 3; }
+    if (!(d->nstokes == 1 || d->nstokes == 3)) { set_msg(errmsg, "NSTOKES must be 1 or 3"); return 3; }
+    if ((d->nstokes == 1) != (d->nstleg == 1)) { set_msg(errmsg, "NSTLEG must be 1 for NSTOKES=1 and 6 otherwise"); return 3; }
+    if (d->sfctype1 != 'L') { set_msg(errmsg, "only Lambertian surfaces (SFCTYPE 'FL','VL') are implemented"); return 3; }
+    if (d->numphase < 1) { set_msg(errmsg, "NUMPHASE=0 is not supported."); return 1; }
+    at3d_state *st = new at3d_state();
+    cudaGetDevice(&st->device);
+    DevState &S = st->S;
+    memset(&S, 0, sizeof(S));
+    S.nstokes = d->nstokes; S.nstleg = d->nstleg; S.nx = d->nx; S.ny = d->ny; S.nz = d->nz;
+    S.npts = d->npts; S.ncells = d->ncells; S.ml = d->ml; S.mm = d->mm; S.nlm = d->nlm;
+    S.nlmp = (d->nlm + 3) & ~3; S.nleg = d->nleg; S.numphase = d->numphase; S.npart = d->npart;
+    S.maxnmicro = d->maxnmicro; S.nq = 8 * d->maxnmicro; S.bcflag = d->bcflag; S.ipflag = d->ipflag;
+    S.nmu = d->nmu; S.nphi0max = d->nphi0max; S.maxnbc = d->maxnbc; S.ntoppts = d->ntoppts;
+    S.nbotpts = d->nbotpts; S.nsfcpar = d->nsfcpar; S.nscatangle = d->nscatangle; S.nstphase = d->nstphase;
+    S.deltam = d->deltam; S.srctype = d->srctype; S.sfctype0 = d->sfctype0; S.sfctype1 = d->sfctype1;
+    S.interp_new = d->interp_new; S.kmax = d->npart * 8 * d->maxnmicro;
+    S.ny_comp = d->nstokes == 1 ? 1 : 5;
+    S.solarmu = d->solarmu; S.solaraz = d->solaraz; S.gndalbedo = d->gndalbedo; S.phasemax = d->phasemax;
+    S.tautol = d->tautol; S.transcut = d->transcut;
+    int rc = 0;
+#define UP(field, count) if (!rc) rc = upload(st, d->field, (size_t)(count), &S.field, errmsg)
+    const int nxg = (d->bcflag & 5) ? d->nx : d->nx + 1;
+    const int nyg = (d->bcflag & 10) ? d->ny : d->ny + 1;
+    UP(xgrid, nxg); UP(ygrid, nyg); UP(zgrid, d->nz);
+    UP(bcptr, (size_t)d->maxnbc * 2);
+    UP(nphi0, d->nmu); UP(mu, d->nmu); UP(phi, (size_t)d->nmu * d->nphi0max);
+    UP(skyrad, (size_t)d->nstokes * (d->nmu / 2) * d->nphi0max);
+    UP(phasetab, (size_t)d->nstphase * d->numphase * d->nscatangle);
+    UP(extinct, (size_t)d->npts * d->npart); UP(albedo, (size_t)d->npts * d->npart);
+    UP(dirflux, d->npts);
+    UP(legen, (size_t)d->nstleg * (d->nleg + 1) * d->numphase);
+    UP(iphase, (size_t)S.nq * d->npts * d->npart); UP(phaseinterpwt, (size_t)S.nq * d->npts * d->npart);
+    UP(ylmsun, (size_t)d->nstleg * d->nlm);
+    UP(sfcgridparms, (size_t)d->nsfcpar * d->nbotpts);
+#undef UP
+    if (rc) { at3d_state_destroy(st); return rc; }
+    // LOFJ (shdomsub1.f:1057-1065)
+    {
+        std::vector<int> lofj(d->nlm);
+        int j = 0;
+        for (int l = 0; l <= d->ml; l++) {
+            int me = l < d->mm ? l : d->mm;
+            for (int m = -me; m <= me; m++) { if (j < d->nlm) lofj[j] = l; j++; }
+        }
+        if (j != d->nlm) { set_msg(errmsg, "NLM=%d inconsistent with ML=%d MM=%d", d->nlm, d->ml, d->mm); at3d_state_destroy(st); return 1; }
+        rc = upload(st, lofj.data(), lofj.size(), &S.lofj, errmsg);
+        if (rc) { at3d_state_destroy(st); return rc; }
+    }
+    // cell and point records
+    {
+        const int *gp, *np, *tp; const short *cf; const float *gpos, *text;
+        at3d_state tmp;   // staging allocations, freed right after
+        rc = upload(&tmp, d->gridptr, (size_t)8 * d->ncells, &gp, errmsg);
+        if (!rc) rc = upload(&tmp, d->neighptr, (size_t)6 * d->ncells, &np, errmsg);
+        if (!rc) rc = upload(&tmp, d->treeptr, (size_t)2 * d->ncells, &tp, errmsg);
+        if (!rc) rc = upload(&tmp, (const short *)d->cellflags, (size_t)d->ncells, &cf, errmsg);
+        if (!rc) rc = upload(&tmp, d->gridpos, (size_t)3 * d->npts, &gpos, errmsg);
+        if (!rc) rc = upload(&tmp, d->total_ext, (size_t)d->npts, &text, errmsg);
+        int4 *cellrec = nullptr; float4 *ptrec = nullptr;
+        if (!rc) rc = dalloc(st, (size_t)4 * d->ncells, &cellrec, errmsg);
+        if (!rc) rc = dalloc(st, (size_t)d->npts, &ptrec, errmsg);
+        if (!rc && launch_build_cellrec(d->ncells, gp, np, tp, cf, cellrec, 0) != cudaSuccess) { set_msg(errmsg, "cellrec launch failed"); rc = 4; }
+        if (!rc && launch_build_ptrec(d->npts, gpos, text, ptrec, 0) != cudaSuccess) { set_msg(errmsg, "ptrec launch failed"); rc = 4; }
+        cudaDeviceSynchronize();
+        for (void *p : tmp.owned) cudaFree(p);
+        tmp.owned.clear();
+        if (rc) { at3d_state_destroy(st); return rc; }
+        S.cellrec = cellrec; S.ptrec = ptrec;
+    }
+    // boundary radiances: copy BCRAD, then the Lambertian bottom boundary (RENDER, shdomsub4.f:201-209)
+    {
+        st->nbcrad = d->nstokes * (d->ntoppts + d->nbotpts);
+        float *bc = nullptr;
+        rc = dalloc(st, (size_t)st->nbcrad, &bc, errmsg);
+        if (!rc && d->bcrad) { if (cudaMemcpy(bc, d->bcrad, st->nbcrad * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) rc = 4; }
+        const float *fl = nullptr;
+        at3d_state tmp;
+        if (!rc) rc = upload(&tmp, d->fluxes, (size_t)2 * d->npts, &fl, errmsg);
+        S.bcrad = bc; st->bcrad_dev = bc;
+        if (!rc && launch_lambertian_boundary(S, fl, bc, 0) != cudaSuccess) { set_msg(errmsg, "boundary launch failed"); rc = 4; }
+        cudaDeviceSynchronize();
+        for (void *p : tmp.owned) cudaFree(p);
+        tmp.owned.clear();
+        if (!rc && d->bcrad) cudaMemcpy(d->bcrad, bc, st->nbcrad * sizeof(float), cudaMemcpyDeviceToHost);
+        if (rc) { at3d_state_destroy(st); return rc; }
+    }
+    // spherical-harmonic source: TMS-corrected planar blocks + single-scatter lists
+    {
+        int *sscount = nullptr; int2 *ssent = nullptr;
+        rc = dalloc(st, (size_t)d->npts, &sscount, errmsg);
+        if (!rc) rc = dalloc(st, (size_t)d->npts * S.kmax, &ssent, errmsg);
+        if (!rc) { cudaMemset(sscount, 0, (size_t)d->npts * sizeof(int)); }
+        S.sscount = sscount; S.ssent = ssent;
+        const int tms = (d->srctype != 'T' && d->deltam) ? 1 : 0;
+        if (!rc) rc = prep_sh_array(st, tms, d->shptr, d->source, &S.srcrec, &S.shsrc, sscount, ssent, errmsg);
+        if (!rc && d->rshptr && d->radiance)
+            rc = prep_sh_array(st, 0, d->rshptr, d->radiance, &S.radrec, &S.shrad, nullptr, nullptr, errmsg);
+        if (rc) { at3d_state_destroy(st); return rc; }
+    }
+    *out = st;
+    return 0;
+}
+
+extern "C" int at3d_state_get_bcrad(at3d_state *st, float *bcrad_host, char *errmsg)
+{
+    if (!st || !bcrad_host) { set_msg(errmsg, "null argument"); return 1; }
+    CUDA_TRY(cudaMemcpy(bcrad_host, st->bcrad_dev, st->nbcrad * sizeof(float), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+static const char *ray_err_text(int code)
+{
+    switch (code) {
+    case 1: return "INTEGRATE_1RAY: SO<0";
+    case 2: return "RENDER: Level below domain";
+    case 3: return "FIND_BOUNDARY_RADIANCE: Not at boundary";
+    case 4: return "ADJOINT_INTEGRATE_1RAY: The maximum number of subgrid intervals for calculation of the radiance along the ray path has been exceeded.";
+    default: return "unknown ray error";
+    }
+}
+
+int check_ray_err(at3d_state *st, cudaStream_t stream, char *errmsg)
+{
+    RayErr h;
+    CUDA_TRY(cudaMemcpyAsync(&h, st->err.p, sizeof(RayErr), cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    if (h.code) { set_msg(errmsg, "%s (ray %d)", ray_err_text(h.code), h.ray); return 1; }
+    return 0;
+}
+
+// stage the ray arrays on the device when they are host arrays
+int stage_rays(at3d_state *st, const at3d_rays *rays, cudaStream_t stream, const float **camx,
+               const float **camy, const float **camz, const double **cammu, const double **camphi,
+               char *errmsg)
+{
+    const size_t n = rays->nrays;
+    if (rays->memspace == AT3D_MEM_DEVICE) {
+        *camx = rays->camx; *camy = rays->camy; *camz = rays->camz; *cammu = rays->cammu; *camphi = rays->camphi;
+        return 0;
+    }
+    const size_t nb = n * (3 * sizeof(float) + 2 * sizeof(double)) + 64;
+    CUDA_TRY(st->rays.reserve(nb));
+    double *dmu = (double *)st->rays.p, *dphi = dmu + n;
+    float *dx = (float *)(dphi + n), *dy = dx + n, *dz = dy + n;
+    CUDA_TRY(cudaMemcpyAsync(dmu, rays->cammu, n * sizeof(double), cudaMemcpyHostToDevice, stream));
+    CUDA_TRY(cudaMemcpyAsync(dphi, rays->camphi, n * sizeof(double), cudaMemcpyHostToDevice, stream));
+    CUDA_TRY(cudaMemcpyAsync(dx, rays->camx, n * sizeof(float), cudaMemcpyHostToDevice, stream));
+    CUDA_TRY(cudaMemcpyAsync(dy, rays->camy, n * sizeof(float), cudaMemcpyHostToDevice, stream));
+    CUDA_TRY(cudaMemcpyAsync(dz, rays->camz, n * sizeof(float), cudaMemcpyHostToDevice, stream));
+    *camx = dx; *camy = dy; *camz = dz; *cammu = dmu; *camphi = dphi;
+    return 0;
+}
+
+extern "C" int at3d_render(at3d_state *st, const at3d_rays *rays, float *stokes,
+                           int correctinterpolate, int singlescatter, int nosurface,
+                           const at3d_trace *trace, void *cuda_stream, double *kernel_ms, char *errmsg)
+{
+    if (errmsg) errmsg[0] = 0;
+    if (!st || !rays || !stokes) { set_msg(errmsg, "null argument"); return 1; }
+    cudaStream_t stream = (cudaStream_t)cuda_stream;
+    const size_t n = rays->nrays;
+    const int nst = st->S.nstokes;
+    if (n == 0) return 0;
+    const float *camx, *camy, *camz; const double *cammu, *camphi;
+    int rc = stage_rays(st, rays, stream, &camx, &camy, &camz, &cammu, &camphi, errmsg);
+    if (rc) return rc;
+    const bool host = rays->memspace == AT3D_MEM_HOST;
+    float *out_d = stokes;
+    if (host) { CUDA_TRY(st->out.reserve(n * nst * sizeof(float))); out_d = (float *)st->out.p; }
+    int *tc = nullptr, *tn = nullptr, *ts = nullptr; int tcap = 0;
+    if (trace && trace->cells) {
+        tcap = trace->max_per_ray;
+        if (host) {
+            CUDA_TRY(st->trace.reserve(((size_t)tcap * n + 2 * n) * sizeof(int)));
+            tc = (int *)st->trace.p; tn = tc + (size_t)tcap * n; ts = tn + n;
+        } else { tc = trace->cells; tn = trace->ncells; ts = trace->nsub; }
+    }
+    CUDA_TRY(st->err.reserve(sizeof(RayErr)));
+    CUDA_TRY(cudaMemsetAsync(st->err.p, 0, sizeof(RayErr), stream));
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (kernel_ms) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, stream); }
+    CUDA_TRY(launch_render(st->S, (int)n, camx, camy, camz, cammu, camphi, out_d, nullptr, 0,
+                           correctinterpolate, singlescatter, nosurface, 0, tc, tcap, tn, ts,
+                           (RayErr *)st->err.p, stream));
+    if (kernel_ms) cudaEventRecord(e1, stream);
+    if (host) {
+        CUDA_TRY(cudaMemcpyAsync(stokes, out_d, n * nst * sizeof(float), cudaMemcpyDeviceToHost, stream));
+        if (tc) {
+            CUDA_TRY(cudaMemcpyAsync(trace->cells, tc, (size_t)tcap * n * sizeof(int), cudaMemcpyDeviceToHost, stream));
+            CUDA_TRY(cudaMemcpyAsync(trace->ncells, tn, n * sizeof(int), cudaMemcpyDeviceToHost, stream));
+            CUDA_TRY(cudaMemcpyAsync(trace->nsub, ts, n * sizeof(int), cudaMemcpyDeviceToHost, stream));
+        }
+    }
+    rc = check_ray_err(st, stream, errmsg);
+    if (kernel_ms) {
+        float ms = 0.0f;
+        cudaEventSynchronize(e1);
+        cudaEventElapsedTime(&ms, e0, e1);
+        *kernel_ms = ms;
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+    }
+    return rc;
+}

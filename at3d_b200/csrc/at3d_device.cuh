@@ -1,0 +1,469 @@
+// at3d_device.cuh -- device-side state layout and shared device functions (sm_100a).
+//
+// Data layout in HBM (DESIGN.md "Data layout"): the reference's pointer-chasing arrays are
+// re-packed once per solved state into records sized for single 32/64-byte sector reads:
+//   cellrec : 64 B per cell  = GRIDPTR(8) | NEIGHPTR(6) | TREEPTR(2,.) | CELLFLAGS
+//   ptrec   : 16 B per point = GRIDPOS(3) | TOTAL_EXT
+//   srcrec  :  8 B per point = offset/ns into shsrc (16-byte aligned planar SH blocks)
+//   ssent   :  8 B per entry = (phase-table index, DA*w/(1-F)) single-scatter list per point
+// Index CONTENTS stay 1-based as in the reference so cell/point ids compare bit-exactly.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define AT3D_WARPS_PER_BLOCK 4
+#define AT3D_MAX_NSTOKES 3
+
+struct DevState {
+    int nstokes, nstleg, nx, ny, nz, npts, ncells;
+    int ml, mm, nlm, nlmp, nleg, numphase, npart, maxnmicro, nq;
+    int bcflag, ipflag, nmu, nphi0max, maxnbc, ntoppts, nbotpts, nsfcpar;
+    int nscatangle, nstphase, deltam, srctype, sfctype0, sfctype1, interp_new;
+    int kmax;                 // single-scatter entries stride per point
+    int ny_comp;              // number of YLMDIR components staged per ray (1 or 5)
+    float solarmu, solaraz, gndalbedo, phasemax;
+    double tautol, transcut;
+    const int4 *cellrec;      // [ncells*4]
+    const float4 *ptrec;      // [npts]
+    const int2 *srcrec;       // [npts] (offset in floats, ns)
+    const float *shsrc;       // TMS-corrected source, planar per point, padded to 4
+    const int2 *radrec;       // [npts] radiance SH (gradient)
+    const float *shrad;
+    const int *sscount;       // [npts]
+    const int2 *ssent;        // [npts*kmax] (iph, __float_as_int(coef))
+    const float *phasetab;    // [nstphase,numphase,nscatangle]
+    const float *xgrid, *ygrid, *zgrid;
+    const int *bcptr;         // [maxnbc,2]
+    const float *bcrad;       // [nstokes, ntoppts+nbotpts]  (bottom = Lambertian boundary)
+    const int *nphi0;
+    const float *mu, *phi, *skyrad;
+    const int *lofj;          // [nlm]
+    // raw optics kept for the gradient kernels
+    const float *extinct, *albedo, *dirflux, *legen, *phaseinterpwt, *ylmsun, *sfcgridparms;
+    const int *iphase;
+};
+
+#define FULLMASK 0xffffffffu
+
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+
+// ---- arithmetic helpers with the reference's rounding (no FMA contraction; file built with
+// ---- --fmad=false, explicit fmaf() only where op order is free) ----
+__device__ __forceinline__ double ipow_d(double x, int n)
+{
+    double r = 1.0, b = x;
+    int e = n;
+    while (e > 0) {
+        if (e & 1) r *= b;
+        e >>= 1;
+        if (e) b *= b;
+    }
+    return r;
+}
+
+// DM_M10_N0  (shdomsub2.f:4580-4600)
+__device__ __forceinline__ double dev_dm_m10_n0(double x, int m)
+{
+    if (m == 0) return 1.0;
+    double cm = (m & 1) ? -1.0 : 1.0;
+    double prod = 1.0;
+    for (int p = 1; p <= m; p++) prod = prod * sqrt((double)(m + p) / (double)p);
+    return cm * prod * ipow_d(0.5 * sqrt((1.0 - x) * (1.0 + x)), m);
+}
+
+// DMM1_N0 (shdomsub2.f:4452-4486)
+__device__ __forceinline__ double dev_dmm1_n0(double x, int m, int m1)
+{
+    if (m == m1) return ipow_d((1.0 + x) / 2.0, m);
+    double cmm1 = (m1 > m) ? 1.0 : (((m - m1) & 1) ? -1.0 : 1.0);
+    int maxm = m > m1 ? m : m1, minm = m < m1 ? m : m1;
+    double prod = 1.0;
+    for (int p = 1; p <= maxm - minm; p++) prod = prod * sqrt((double)(m + m1 + p) / (double)p);
+    double fact = sqrt((1.0 - x) / 2.0);
+    double r = cmm1 * prod * ipow_d(fact, maxm - minm);
+    fact = sqrt((1.0 + x) / 2.0);
+    return r * ipow_d(fact, maxm + minm);
+}
+
+__device__ __forceinline__ int sh_index(int l, int m, int mm)
+{   // J = l(l+1)+m+1 (l<=MM) else (2MM+1)l - MM^2 + m + 1   (shdomsub2.f:4290-4294); returns 0-based
+    return (l <= mm) ? (l * (l + 1) + m) : ((2 * mm + 1) * l - mm * mm + m);
+}
+
+// YLMALL for one direction, warp-cooperative (lanes over m).  Ysh layout [ncomp][nlmp]:
+// comp 0 = YR(1,:), and for polarized 1 = YR(2,:), 2 = YR(5,:), 3 = YR(6,:), 4 = YR(3,:).
+// Follows YLMALL_UNPOL (shdomsub2.f:4490-4539) / YLMALL (shdomsub2.f:4244-4360), TRANSPOSE=.FALSE.
+static __device__ void warp_ylmall(const DevState &S, float mu, float phi, float *Ysh)
+{
+    const int ml = S.ml, mm = S.mm, nlmp = S.nlmp;
+    const int lane = lane_id();
+    const double x = (double)mu;
+    const double pi = 3.14159265358979323846;   // DACOS(-1.D0)
+    const double fct = 1.0 / sqrt(2.0 * pi);
+    // zero padding entries
+    for (int j = S.nlm + lane; j < nlmp; j += 32)
+        for (int c = 0; c < S.ny_comp; c++) Ysh[c * nlmp + j] = 0.0f;
+    if (S.nstleg == 1) {
+        for (int m = lane; m <= mm; m += 32) {
+            double cosm, sinm;
+            if (m > 0) { cosm = (double)cosf((float)m * phi); sinm = (double)sinf((float)m * phi); }
+            else { cosm = 1.0; sinm = 0.0; }
+            double dprev = 0.0, dcur;
+            if (m == 0) dcur = 1.0; else dcur = dev_dm_m10_n0(x, m);
+            for (int n = m; n <= ml; n++) {
+                // emit l = n
+                double t = sqrt(n + 0.5) * dcur;
+                t = fct * t;
+                Ysh[sh_index(n, m, mm)] = (float)((cosm - sinm) * t);
+                Ysh[sh_index(n, -m, mm)] = (float)((cosm + sinm) * t);
+                // advance recurrence
+                double dnext;
+                if (m == 0) {
+                    if (n == 0) dnext = x;
+                    else dnext = ((2 * n + 1) * x * dcur - n * dprev) / (n + 1);
+                } else {
+                    dnext = ((2 * n + 1) * x * dcur - sqrt((double)(n * n - m * m)) * dprev)
+                            / sqrt((double)((n + 1) * (n + 1) - m * m));
+                }
+                dprev = dcur;
+                dcur = dnext;
+            }
+        }
+    } else {
+        for (int m = lane; m <= mm; m += 32) {
+            double cosm = 1.0, sinm = 0.0;
+            if (m > 0) { cosm = (double)cosf((float)m * phi); sinm = (double)sinf((float)m * phi); }
+            const double xp = x, xm = -x;
+            const int n0 = m > 2 ? m : 2;
+            // WIGNERFCT02P2M_NORMALIZED recurrences (shdomsub2.f:4363-4448), streamed over n
+            double d0p = 0.0, d0c = 0.0;      // DM0(n-1), DM0(n)
+            double pp = 0.0, pc = 0.0;        // DM2P(n-1), DM2P(n)
+            double qp = 0.0, qc = 0.0;        // DM2M(n-1), DM2M(n)
+            for (int n = 0; n <= ml; n++) {
+                // --- value of DM0(n) ---
+                if (n < m) d0c = 0.0;
+                else if (n == m) d0c = (m == 0) ? 1.0 : dev_dmm1_n0(xp, m, 0);
+                // (for n > m d0c was advanced at the end of the previous iteration)
+                if (n < n0) { pc = 0.0; qc = 0.0; }
+                else if (n == n0 && ml >= 2) { pc = dev_dmm1_n0(xp, m, 2); qc = dev_dmm1_n0(xm, m, 2); }
+                if (n >= m) {
+                    double dm0 = sqrt(n + 0.5) * d0c;
+                    double dm2m = (((n + m) & 1) ? -1.0 : 1.0) * qc;
+                    double dm2p = sqrt(n + 0.5) * pc;
+                    dm2m = sqrt(n + 0.5) * dm2m;
+                    double p1 = fct * dm0;
+                    double p2 = -0.5 * fct * (dm2p + dm2m);
+                    double p3 = -0.5 * fct * (dm2p - dm2m);
+                    int jp = sh_index(n, m, mm);
+                    if (m == 0) {
+                        Ysh[0 * nlmp + jp] = (float)p1;
+                        Ysh[1 * nlmp + jp] = (float)p2;   // YR(2)
+                        Ysh[2 * nlmp + jp] = (float)p3;   // YR(5)
+                        Ysh[3 * nlmp + jp] = (float)p3;   // YR(6)
+                        Ysh[4 * nlmp + jp] = (float)p2;   // YR(3)
+                    } else {
+                        int jn = sh_index(n, -m, mm);
+                        Ysh[0 * nlmp + jp] = (float)(p1 * cosm - p1 * sinm);
+                        Ysh[1 * nlmp + jp] = (float)(p2 * cosm - p2 * sinm);
+                        Ysh[4 * nlmp + jp] = (float)(p2 * cosm + p2 * sinm);
+                        Ysh[2 * nlmp + jp] = (float)(p3 * cosm - p3 * sinm);
+                        Ysh[3 * nlmp + jp] = (float)(p3 * cosm + p3 * sinm);
+                        Ysh[0 * nlmp + jn] = (float)(p1 * sinm + p1 * cosm);
+                        Ysh[1 * nlmp + jn] = (float)(p2 * sinm + p2 * cosm);
+                        Ysh[4 * nlmp + jn] = (float)(p2 * sinm - p2 * cosm);
+                        Ysh[2 * nlmp + jn] = (float)(p3 * sinm + p3 * cosm);
+                        Ysh[3 * nlmp + jn] = (float)(p3 * sinm - p3 * cosm);
+                    }
+                }
+                // --- advance DM0 to n+1 ---
+                if (n >= m && n < ml) {
+                    double dnext;
+                    if (m == 0) {
+                        if (n == 0) dnext = xp;
+                        else {
+                            double fact1 = (double)(2 * n + 1) * xp / (double)(n + 1);
+                            double fact2 = (double)n / (double)(n + 1);
+                            dnext = fact1 * d0c - fact2 * d0p;
+                        }
+                    } else {
+                        double fact1 = (double)(n * (n + 1)) * xp;
+                        fact1 = fact1 / sqrt((double)((n + 1) * (n + 1) - m * m));
+                        fact1 = fact1 / (double)(n + 1);
+                        fact1 = fact1 * (double)(2 * n + 1) / (double)n;
+                        double fact2 = sqrt((double)(n * n - m * m)) * (double)n;
+                        fact2 = fact2 / sqrt((double)((n + 1) * (n + 1) - m * m));
+                        fact2 = fact2 / (double)(n + 1);
+                        fact2 = fact2 * (double)(n + 1) / (double)n;
+                        dnext = fact1 * d0c - fact2 * d0p;
+                    }
+                    d0p = d0c;
+                    d0c = dnext;
+                }
+                // --- advance DM2P/DM2M to n+1 ---
+                if (n >= n0 && n < ml) {
+                    double factp = (double)(n * (n + 1)) * xp - (double)(2 * m);
+                    double factm = (double)(n * (n + 1)) * xm - (double)(2 * m);
+                    double fact1 = 1.0 / sqrt((double)((n + 1) * (n + 1) - m * m));
+                    fact1 = fact1 / sqrt((double)((n + 1) * (n + 1) - 4));
+                    fact1 = fact1 * (double)(2 * n + 1) / (double)n;
+                    double fact2 = sqrt((double)(n * n - m * m)) * sqrt((double)(n * n - 4));
+                    fact2 = fact2 / sqrt((double)((n + 1) * (n + 1) - m * m));
+                    fact2 = fact2 / sqrt((double)((n + 1) * (n + 1) - 4));
+                    fact2 = fact2 * (double)(n + 1) / (double)n;
+                    double pn = factp * fact1 * pc - fact2 * pp;
+                    double qn = factm * fact1 * qc - fact2 * qp;
+                    pp = pc; pc = pn;
+                    qp = qc; qc = qn;
+                }
+            }
+        }
+    }
+    __syncwarp();
+}
+
+// ---------------- grid traversal helpers (uniform per warp; every lane runs them) ----------------
+struct CellRec {
+    int gp[8];     // GRIDPTR(1:8)
+    int nb[6];     // NEIGHPTR(1:6)
+    int child;     // TREEPTR(2)
+    int flags;     // CELLFLAGS
+};
+
+__device__ __forceinline__ CellRec load_cell(const DevState &S, int icell)
+{
+    const int4 *p = S.cellrec + 4 * (size_t)(icell - 1);
+    int4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2), d = __ldg(p + 3);
+    CellRec r;
+    r.gp[0] = a.x; r.gp[1] = a.y; r.gp[2] = a.z; r.gp[3] = a.w;
+    r.gp[4] = b.x; r.gp[5] = b.y; r.gp[6] = b.z; r.gp[7] = b.w;
+    r.nb[0] = c.x; r.nb[1] = c.y; r.nb[2] = c.z; r.nb[3] = c.w;
+    r.nb[4] = d.x; r.nb[5] = d.y; r.child = d.z; r.flags = d.w;
+    return r;
+}
+
+__device__ __forceinline__ int cell_child(const DevState &S, int icell)
+{ return __ldg(&S.cellrec[4 * (size_t)(icell - 1) + 3]).z; }
+__device__ __forceinline__ int cell_flags(const DevState &S, int icell)
+{ return __ldg(&S.cellrec[4 * (size_t)(icell - 1) + 3]).w; }
+__device__ __forceinline__ int cell_gp(const DevState &S, int icell, int n /*1..8*/)
+{
+    const int *p = (const int *)(S.cellrec + 4 * (size_t)(icell - 1));
+    return __ldg(p + (n - 1));
+}
+__device__ __forceinline__ float pt_coord(const DevState &S, int ip, int axis /*1..3*/)
+{
+    const float *p = (const float *)(S.ptrec + (size_t)(ip - 1));
+    return __ldg(p + (axis - 1));
+}
+
+#define DBTEST(x, b) ((((int)(x)) >> (b)) & 1)
+
+// LOCATE_GRID_CELL (shdomsub2.f:4043-4206); may wrap x0,y0 for periodic boundaries
+static __device__ int dev_locate_grid_cell(const DevState &S, double &x0, double &y0, double &z0)
+{
+    const int nx = S.nx, ny = S.ny, nz = S.nz, bcflag = S.bcflag, ipflag = S.ipflag;
+#define XG(i) __ldg(&S.xgrid[(i) - 1])
+#define YG(i) __ldg(&S.ygrid[(i) - 1])
+#define ZG(i) __ldg(&S.zgrid[(i) - 1])
+    if (!(DBTEST(bcflag, 0) || DBTEST(bcflag, 2))) {
+        double xdomain = (double)(XG(nx + 1) - XG(1));
+        if (x0 < XG(1)) x0 = x0 - xdomain * ((int)((x0 - XG(1)) / xdomain) - 1);
+        else if (x0 > XG(nx + 1)) x0 = x0 - xdomain * (int)((x0 - XG(1)) / xdomain);
+    }
+    if (!(DBTEST(bcflag, 1) || DBTEST(bcflag, 3))) {
+        double ydomain = (double)(YG(ny + 1) - YG(1));
+        if (y0 < YG(1)) y0 = y0 - ydomain * ((int)((y0 - YG(1)) / ydomain) - 1);
+        else if (y0 > YG(ny + 1)) y0 = y0 - ydomain * (int)((y0 - YG(1)) / ydomain);
+    }
+    int il = 0, iu, im, ix, iy, iz;
+    if (DBTEST(ipflag, 0)) {
+        iu = nx;
+        while (iu - il > 1) { im = (iu + il) / 2; if (x0 >= 0.5f * (XG(im) + XG(im + 1))) il = im; else iu = im; }
+        il = il + 1;
+    } else {
+        iu = nx + 1;
+        while (iu - il > 1) { im = (iu + il) / 2; if (x0 >= XG(im)) il = im; else iu = im; }
+    }
+    ix = il > 1 ? il : 1;
+    il = 0;
+    if (DBTEST(ipflag, 1)) {
+        iu = ny;
+        while (iu - il > 1) { im = (iu + il) / 2; if (y0 >= 0.5f * (YG(im) + YG(im + 1))) il = im; else iu = im; }
+        il = il + 1;
+    } else {
+        iu = ny + 1;
+        while (iu - il > 1) { im = (iu + il) / 2; if (y0 >= YG(im)) il = im; else iu = im; }
+    }
+    iy = il > 1 ? il : 1;
+    il = 0; iu = nz;
+    while (iu - il > 1) { im = (iu + il) / 2; if (z0 >= ZG(im)) il = im; else iu = im; }
+    iz = il > 1 ? il : 1;
+    int nyc = ny;
+    if (DBTEST(bcflag, 0)) {
+        if (x0 < XG(1)) ix = 1;
+        else if (x0 > XG(nx)) ix = nx + 1;
+        else ix = ix + 1;
+    }
+    if (DBTEST(bcflag, 2) && !DBTEST(ipflag, 0)) { int nxc = nx - 1; ix = ix < nxc ? ix : nxc; }
+    if (DBTEST(bcflag, 1)) {
+        nyc = ny + 1;
+        if (y0 < YG(1)) iy = 1;
+        else if (y0 > YG(ny)) iy = ny + 1;
+        else iy = iy + 1;
+    }
+    if (DBTEST(bcflag, 3) && !DBTEST(ipflag, 1)) { nyc = ny - 1; iy = iy < nyc ? iy : nyc; }
+#undef XG
+#undef YG
+#undef ZG
+    int icell = iz + (nz - 1) * (iy - 1) + (nz - 1) * nyc * (ix - 1);
+    int child;
+    while ((child = cell_child(S, icell)) > 0) {
+        int dir = (cell_flags(S, icell) >> 2) & 3;
+        int ic = child + 1;
+        int iptr = cell_gp(S, ic, 1);
+        if (dir == 1) { if (x0 < pt_coord(S, iptr, 1)) ic = ic - 1; }
+        else if (dir == 2) { if (y0 < pt_coord(S, iptr, 2)) ic = ic - 1; }
+        else if (dir == 3) { if (z0 < pt_coord(S, iptr, 3)) ic = ic - 1; }
+        icell = ic;
+    }
+    return icell;
+}
+
+// NEXT_CELL (shdomsub1.f:4470-4522) for a negative neighbour pointer
+static __device__ int dev_next_cell(const DevState &S, double xe, double ye, double ze,
+                             int iface, int jface, int inext_neg)
+{
+    int ic = -inext_neg, child;
+    while ((child = cell_child(S, ic)) > 0) {
+        int dir = (cell_flags(S, ic) >> 2) & 3;
+        int ic1 = child;
+        if (dir == jface) {
+            ic = ic1 + 1 - ((iface - 1) % 2);
+        } else {
+            ic = ic1;
+            int p8 = cell_gp(S, ic1, 8);
+            if (dir == 1) { if (xe > pt_coord(S, p8, 1)) ic = ic + 1; }
+            else if (dir == 2) { if (ye > pt_coord(S, p8, 2)) ic = ic + 1; }
+            else { if (ze > pt_coord(S, p8, 3)) ic = ic + 1; }
+        }
+    }
+    return ic;
+}
+
+// binary search of FIND_BOUNDARY_RADIANCE (shdomsub2.f:2791-2804); 1-based index or 0
+__device__ __forceinline__ int dev_bc_search(const int *col, int n, int ip)
+{
+    int il = 1, iu = n, im;
+    while (iu - il > 1) { im = (iu + il) / 2; if (ip >= __ldg(&col[im - 1])) il = im; else iu = im; }
+    int ibc = il;
+    if (__ldg(&col[ibc - 1]) != ip) ibc = iu;
+    if (__ldg(&col[ibc - 1]) != ip) return 0;
+    return ibc;
+}
+
+// per-ray direction quantities (shdomsub2.f:2413-2481)
+struct RayDir {
+    double cx, cy, cz, cxinv, cyinv, czinv;
+    double cos22, sin22;    // polarization-plane rotation (ROTATE_POL_PLANE)
+    float f;                // scattering-angle interpolation weight
+    int j;                  // scattering-angle table index (1-based)
+    int bitx, bity, bitz, ioct;
+    float xm, ym;
+};
+
+__device__ __forceinline__ void dev_ray_dir(const DevState &S, double mu2, double phi2, RayDir &rd)
+{
+    const double pi = acos(-1.0);
+    rd.f = 0.0f; rd.j = 1; rd.cos22 = 1.0; rd.sin22 = 0.0;
+    if (S.srctype != 'T' && S.deltam) {
+        double cosscat = S.solarmu * mu2
+            + sqrt((1.0f - S.solarmu * S.solarmu) * (1.0 - mu2 * mu2)) * cos(S.solaraz - phi2);
+        cosscat = fmax(fmin(1.0, cosscat), -1.0);
+        float f = (float)((S.nscatangle - 1) * (acos(cosscat) / pi) + 1);
+        int j = (int)f;
+        if (j > S.nscatangle - 1) j = S.nscatangle - 1;
+        rd.f = f - (float)j;
+        rd.j = j;
+        if (S.nstokes > 1) {
+            // ROTATE_POL_PLANE (shdomsub2.f:3277-3314), MU=SNGL(MU2), DELPHI=SOLARAZ-SNGL(PHI2)
+            float mu = (float)mu2;
+            float delphi = S.solaraz - (float)phi2;
+            double sin_scat = sqrt(fmax(0.0, 1.0 - cosscat * cosscat));
+            double sin_theta1 = sqrt(1.0 - (double)(S.solarmu * S.solarmu));
+            double sin_theta2 = sqrt(1.0 - (double)(mu * mu));
+            double sinphi = sin((double)delphi), cosphi = cos((double)delphi);
+            double sin2, cos2;
+            if (sin_scat == 0.0) { sin2 = 0.0; cos2 = -1.0; }
+            else {
+                sin2 = sin_theta1 * sinphi / sin_scat;
+                cos2 = (sin_theta2 * S.solarmu - sin_theta1 * mu * cosphi) / sin_scat;
+            }
+            rd.sin22 = 2.0 * sin2 * cos2;
+            rd.cos22 = 1.0 - 2.0 * (sin2 * sin2);
+        }
+    }
+    rd.cx = sqrt(1.0 - mu2 * mu2) * cos(phi2 - pi);
+    rd.cy = sqrt(1.0 - mu2 * mu2) * sin(phi2 - pi);
+    rd.cz = -mu2;
+    if (fabs(rd.cx) > 1.0e-6f) rd.cxinv = 1.0 / rd.cx; else { rd.cx = 0.0; rd.cxinv = 1.0e6f; }
+    if (fabs(rd.cy) > 1.0e-6f) rd.cyinv = 1.0 / rd.cy; else { rd.cy = 0.0; rd.cyinv = 1.0e6f; }
+    if (fabs(rd.cz) > 1.0e-6f) rd.czinv = 1.0 / rd.cz; else { rd.cz = 0.0; rd.czinv = 1.0e6f; }
+    rd.bitx = rd.cx < 0.0 ? 1 : 0;
+    rd.bity = rd.cy < 0.0 ? 1 : 0;
+    rd.bitz = rd.cz < 0.0 ? 1 : 0;
+    rd.ioct = 1 + rd.bitx + 2 * rd.bity + 4 * rd.bitz;
+    rd.xm = 0.5f * (__ldg(&S.xgrid[0]) + __ldg(&S.xgrid[S.nx - 1]));
+    rd.ym = 0.5f * (__ldg(&S.ygrid[0]) + __ldg(&S.ygrid[S.ny - 1]));
+}
+
+// start-point handling of RENDER (shdomsub4.f:214-236); returns 1 if the ray sees nothing,
+// 2 if the start is below the domain (error)
+__device__ __forceinline__ int dev_ray_start(const DevState &S, double mu2, double phi2,
+                                             double &x0, double &y0, double &z0)
+{
+    const double pi = acos(-1.0);
+    double muray = -mu2, phiray = phi2 - pi;
+    float ztop = __ldg(&S.zgrid[S.nz - 1]);
+    if (z0 > ztop) {
+        if (muray >= 0.0) return 1;
+        double r = (ztop - z0) / muray;
+        x0 = x0 + r * sqrt(1 - muray * muray) * cos(phiray);
+        y0 = y0 + r * sqrt(1 - muray * muray) * sin(phiray);
+        z0 = ztop;
+    } else if (z0 < __ldg(&S.zgrid[0])) {
+        return 2;
+    }
+    return 0;
+}
+
+// COMPUTE_TOP_RADIANCES, INTERPOLATE_FLAG=1, SRCTYPE != 'T' (shdomsub1.f:2375-2395)
+static __device__ float dev_sky_radiance(const DevState &S, float mu, float phi)
+{
+    double weightedsum = 0.0, weightsum = 0.0, weight, distance;
+    for (int i = 1; i <= S.nmu / 2; i++) {
+        int n = __ldg(&S.nphi0[i - 1]);
+        float mus = __ldg(&S.mu[i - 1]);
+        for (int j = 1; j <= n; j++) {
+            float phis = __ldg(&S.phi[(i - 1) + S.nmu * (j - 1)]);
+            distance = (double)acosf(mu * mus + sqrtf((1.0f - mu * mu) * (1.0f - mus * mus)) * cosf(phi - phis));
+            if (fabs(distance) < 1e-6f) weight = 1.0e8;
+            else weight = 1.0 / pow(distance, 3.0);
+            weightedsum = weightedsum + __ldg(&S.skyrad[0 + S.nstokes * ((i - 1) + (S.nmu / 2) * (j - 1))]) * weight;
+            weightsum = weightsum + weight;
+        }
+    }
+    return (float)(weightedsum / weightsum);
+}
+
+__device__ __forceinline__ float warp_sum(float v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULLMASK, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULLMASK, v, o);
+    return v;
+}

@@ -1,0 +1,262 @@
+// at3d_render.cu -- state preparation kernels and the RENDER kernel (sm_100a).
+// Replaces RENDER / INTEGRATE_1RAY / COMPUTE_SOURCE_1CELL[_UNPOL] / FIND_BOUNDARY_RADIANCE
+// (src/polarized/shdomsub4.f:93-286, shdomsub2.f:2311-3192 of the AT3D reference).
+#include "at3d_ray.cuh"
+#include "at3d_host.h"
+
+// ------------------------------------------------------------------------------------------
+// State preparation
+// ------------------------------------------------------------------------------------------
+__global__ void build_cellrec_kernel(int ncells, const int *gridptr, const int *neighptr,
+                                     const int *treeptr, const short *cellflags, int4 *cellrec)
+{
+    int ic = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ic >= ncells) return;
+    const int *g = gridptr + 8 * (size_t)ic;
+    const int *n = neighptr + 6 * (size_t)ic;
+    cellrec[4 * (size_t)ic + 0] = make_int4(g[0], g[1], g[2], g[3]);
+    cellrec[4 * (size_t)ic + 1] = make_int4(g[4], g[5], g[6], g[7]);
+    cellrec[4 * (size_t)ic + 2] = make_int4(n[0], n[1], n[2], n[3]);
+    cellrec[4 * (size_t)ic + 3] = make_int4(n[4], n[5], treeptr[2 * (size_t)ic + 1], (int)cellflags[ic]);
+}
+
+__global__ void build_ptrec_kernel(int npts, const float *gridpos, const float *total_ext, float4 *ptrec)
+{
+    int ip = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ip >= npts) return;
+    ptrec[ip] = make_float4(gridpos[3 * (size_t)ip], gridpos[3 * (size_t)ip + 1],
+                            gridpos[3 * (size_t)ip + 2], total_ext[ip]);
+}
+
+// FIXED / VARIABLE_LAMBERTIAN_BOUNDARY for SRCTYPE='S' (shdomsub1.f:2438-2529): bottom BCRAD
+__global__ void lambertian_boundary_kernel(DevState S, const float *fluxes, float *bcrad)
+{
+    int ibc = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ibc >= S.nbotpts) return;
+    const int i = S.bcptr[S.maxnbc + ibc];
+    float v;
+    if (S.sfctype0 == 'F') {
+        const float alb = S.gndalbedo / acosf(-1.0f);
+        v = alb * (S.dirflux[i - 1] + fluxes[2 * (size_t)(i - 1)]);
+    } else {
+        const float opi = 1.0f / acosf(-1.0f);
+        const float alb = S.sfcgridparms[1 + S.nsfcpar * ibc];
+        v = opi * alb * (S.dirflux[i - 1] + fluxes[2 * (size_t)(i - 1)]);
+    }
+    bcrad[S.nstokes * (size_t)(S.ntoppts + ibc)] = v;
+    for (int k = 1; k < S.nstokes; k++) bcrad[k + S.nstokes * (size_t)(S.ntoppts + ibc)] = 0.0f;
+}
+
+// Re-layout of one CSR spherical-harmonic array (SOURCE or RADIANCE, [nstokes,*] interleaved) into
+// planar, 16-byte aligned per-point blocks.  For SOURCE with a solar source and delta-M the
+// truncated single scattering that COMPUTE_SOURCE_1CELL subtracts per ray
+// (shdomsub2.f:2979-3003: DA*LEGENT(.,l)*YLMSUN(1,j) for j<=NS) is ray independent, so it is
+// folded in here once per state, and the per-point exact single-scatter list
+// (shdomsub2.f:3008-3019: iphase, DA*w/(1-F)) is built.  One warp per grid point.
+__global__ void prep_sh_kernel(DevState S, int tms, const int *shptr, const float *sh_in,
+                               const int2 *rec, float *sh_out, int *sscount, int2 *ssent)
+{
+    extern __shared__ float smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ip = blockIdx.x * (blockDim.x >> 5) + warp;        // 0-based
+    float *corr1 = smem + warp * 2 * (S.ml + 2);
+    float *corr5 = corr1 + (S.ml + 2);
+    if (ip >= S.npts) return;
+    const int is = shptr[ip], ns = shptr[ip + 1] - is;
+    const int2 r = rec[ip];
+    const int nsp = (ns + 3) & ~3;
+    const int nst = S.nstokes;
+    for (int l = lane; l <= S.ml + 1; l += 32) { corr1[l] = 0.0f; corr5[l] = 0.0f; }
+    __syncwarp();
+    if (tms) {
+        const float ext = S.ptrec[ip].w;
+        const float secmu0 = (float)(1.0 / fabs((double)S.solarmu));
+        const int nlt = S.nstleg * (S.nleg + 1);
+        int cnt = 0;
+        for (int ipa = 0; ipa < S.npart; ipa++) {
+            float w;
+            if (ext == 0.0f) w = 1.0f; else w = S.extinct[ip + (size_t)S.npts * ipa] / ext;
+            if (w == 0.0f) continue;
+            const int *iph = S.iphase + (size_t)S.nq * (ip + (size_t)S.npts * ipa);
+            const float *pw = S.phaseinterpwt + (size_t)S.nq * (ip + (size_t)S.npts * ipa);
+            const bool single = (!S.interp_new) || (pw[0] >= S.phasemax);
+            // F = LEGENT(1,ML+1) of the mixed table
+            float f;
+            if (single) f = S.legen[(size_t)nlt * (iph[0] - 1) + S.nstleg * (S.ml + 1)];
+            else {
+                f = 0.0f;
+                for (int q = 0; q < S.nq; q++) {
+                    if (pw[q] <= 1e-5f) continue;
+                    f = f + S.legen[(size_t)nlt * (iph[q] - 1) + S.nstleg * (S.ml + 1)] * pw[q];
+                }
+            }
+            const float da = S.albedo[ip + (size_t)S.npts * ipa] * S.dirflux[ip] * secmu0 * w;
+            for (int l = lane; l <= S.ml; l += 32) {
+                float l1, l5 = 0.0f;
+                if (single) {
+                    l1 = S.legen[(size_t)nlt * (iph[0] - 1) + S.nstleg * l];
+                    if (S.nstleg > 1) l5 = S.legen[(size_t)nlt * (iph[0] - 1) + S.nstleg * l + 4];
+                } else {
+                    l1 = 0.0f;
+                    for (int q = 0; q < S.nq; q++) {
+                        if (pw[q] <= 1e-5f) continue;
+                        l1 = l1 + S.legen[(size_t)nlt * (iph[q] - 1) + S.nstleg * l] * pw[q];
+                        if (S.nstleg > 1)
+                            l5 = l5 + S.legen[(size_t)nlt * (iph[q] - 1) + S.nstleg * l + 4] * pw[q];
+                    }
+                }
+                if (S.interp_new) { l1 = l1 / (1 - f); l5 = l5 / (1 - f); }
+                corr1[l] += da * l1;
+                corr5[l] += da * l5;
+            }
+            if (lane == 0) {
+                int2 *dst = ssent + (size_t)ip * S.kmax;
+                if (pw[0] >= S.phasemax) {
+                    dst[cnt++] = make_int2(iph[0], __float_as_int(da / (1 - f)));
+                } else {
+                    for (int q = 0; q < S.nq; q++) {
+                        if (pw[q] <= 1e-5f) continue;
+                        dst[cnt++] = make_int2(iph[q], __float_as_int(da * pw[q] / (1 - f)));
+                    }
+                }
+            }
+        }
+        if (lane == 0) sscount[ip] = cnt;
+        __syncwarp();
+    }
+    for (int j = lane; j < nsp; j += 32) {
+        float v1 = 0.0f, v2 = 0.0f, v3 = 0.0f;
+        if (j < ns) {
+            const int l = S.lofj[j];
+            const float ys = tms ? S.ylmsun[(size_t)S.nstleg * j] : 0.0f;
+            v1 = sh_in[(size_t)nst * (is + j)] - corr1[l] * ys;
+            if (nst > 1) {
+                v2 = sh_in[(size_t)nst * (is + j) + 1] - corr5[l] * ys;
+                v3 = sh_in[(size_t)nst * (is + j) + 2];
+            }
+        }
+        sh_out[r.x + j] = v1;
+        if (nst > 1) { sh_out[r.x + nsp + j] = v2; sh_out[r.x + 2 * nsp + j] = v3; }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// RENDER
+// ------------------------------------------------------------------------------------------
+template <int NST, int MODE, typename OUT>
+__global__ void __launch_bounds__(AT3D_WARPS_PER_BLOCK * 32)
+render_kernel(DevState S, int nrays, const float *camx, const float *camy, const float *camz,
+              const double *cammu, const double *camphi, OUT *stokes,
+              int correctinterpolate, int singlescatter, int nosurface, int maxsub,
+              int *trace_cells, int trace_cap, int *trace_n, int *trace_nsub, RayErr *err)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const size_t ybytes = (size_t)S.ny_comp * S.nlmp * sizeof(float);
+    float *Ysh = (float *)(smem_raw + warp * (ybytes + sizeof(CornerCache<NST>)));
+    CornerCache<NST> *cc = (CornerCache<NST> *)((unsigned char *)Ysh + ybytes);
+    const int nwarps = gridDim.x * AT3D_WARPS_PER_BLOCK;
+    for (int iray = blockIdx.x * AT3D_WARPS_PER_BLOCK + warp; iray < nrays; iray += nwarps) {
+        double x0 = (double)__ldg(&camx[iray]), y0 = (double)__ldg(&camy[iray]), z0 = (double)__ldg(&camz[iray]);
+        const double mu2 = __ldg(&cammu[iray]), phi2 = __ldg(&camphi[iray]);
+        double rad[NST];
+#pragma unroll
+        for (int k = 0; k < NST; k++) rad[k] = 0.0;
+        int ntrace = 0, nsub = 0;
+        const int st = dev_ray_start(S, mu2, phi2, x0, y0, z0);
+        if (st == 2) { if (lane == 0) set_err(err, 2, iray); }
+        else if (st == 0) {
+            RayDir rd;
+            dev_ray_dir(S, mu2, phi2, rd);
+            __syncwarp();
+            warp_ylmall(S, (float)mu2, (float)phi2, Ysh);
+            const float sky = (-mu2 > 0.0) ? dev_sky_radiance(S, (float)mu2, (float)phi2) : 0.0f;
+            const int e = march_ray<NST, MODE>(S, cc, Ysh, rd, mu2, x0, y0, z0, sky,
+                                               correctinterpolate != 0, singlescatter != 0, nosurface != 0,
+                                               maxsub, rad,
+                                               trace_cells ? trace_cells + (size_t)trace_cap * iray : nullptr,
+                                               trace_cap, ntrace, nsub);
+            if (e && lane == 0) set_err(err, e, iray);
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int k = 0; k < NST; k++) stokes[k + NST * (size_t)iray] = (OUT)rad[k];
+            if (trace_n) { trace_n[iray] = ntrace; trace_nsub[iray] = nsub; }
+        }
+        __syncwarp();
+    }
+}
+
+size_t render_smem_bytes(const DevState &S)
+{
+    size_t ccsz = S.nstokes == 1 ? sizeof(CornerCache<1>) : sizeof(CornerCache<3>);
+    return AT3D_WARPS_PER_BLOCK * ((size_t)S.ny_comp * S.nlmp * sizeof(float) + ccsz);
+}
+
+int render_grid_blocks(int nrays, size_t smem, int nst, int mode)
+{
+    int dev = 0, nsm = 148, per_sm = 1;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    const void *fn = nst == 1 ? (mode ? (const void *)render_kernel<1, 1, double> : (const void *)render_kernel<1, 0, float>)
+                              : (mode ? (const void *)render_kernel<3, 1, double> : (const void *)render_kernel<3, 0, float>);
+    cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, AT3D_WARPS_PER_BLOCK * 32, smem);
+    if (per_sm < 1) per_sm = 1;
+    long want = ((long)nrays + AT3D_WARPS_PER_BLOCK - 1) / AT3D_WARPS_PER_BLOCK;
+    long cap = (long)nsm * per_sm;       // persistent: one wave, grid = multiple of the SM count
+    return (int)(want < cap ? want : cap);
+}
+
+// Launch helpers (host).  out_f32: RENDER's STOKES; out_f64: VISRAD for the gradient driver.
+cudaError_t launch_render(const DevState &S, int nrays, const float *camx, const float *camy,
+                          const float *camz, const double *cammu, const double *camphi,
+                          float *out_f32, double *out_f64, int mode,
+                          int correctinterpolate, int singlescatter, int nosurface, int maxsub,
+                          int *trace_cells, int trace_cap, int *trace_n, int *trace_nsub,
+                          RayErr *err, cudaStream_t stream)
+{
+    if (nrays <= 0) return cudaSuccess;
+    const size_t smem = render_smem_bytes(S);
+    const int nb = render_grid_blocks(nrays, smem, S.nstokes, out_f64 ? 1 : 0);
+    const int nt = AT3D_WARPS_PER_BLOCK * 32;
+#define LAUNCH(NST, MODE, OUT, outp)                                                              \
+    cudaFuncSetAttribute(render_kernel<NST, MODE, OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    render_kernel<NST, MODE, OUT><<<nb, nt, smem, stream>>>(S, nrays, camx, camy, camz, cammu, camphi, outp, \
+        correctinterpolate, singlescatter, nosurface, maxsub, trace_cells, trace_cap, trace_n, trace_nsub, err)
+    if (S.nstokes == 1) {
+        if (out_f64) { if (mode) { LAUNCH(1, 1, double, out_f64); } else { LAUNCH(1, 0, double, out_f64); } }
+        else { LAUNCH(1, 0, float, out_f32); }
+    } else {
+        if (out_f64) { if (mode) { LAUNCH(3, 1, double, out_f64); } else { LAUNCH(3, 0, double, out_f64); } }
+        else { LAUNCH(3, 0, float, out_f32); }
+    }
+#undef LAUNCH
+    return cudaGetLastError();
+}
+
+cudaError_t launch_build_cellrec(int ncells, const int *gridptr, const int *neighptr, const int *treeptr,
+                                 const short *cellflags, int4 *cellrec, cudaStream_t s)
+{
+    build_cellrec_kernel<<<(ncells + 255) / 256, 256, 0, s>>>(ncells, gridptr, neighptr, treeptr, cellflags, cellrec);
+    return cudaGetLastError();
+}
+cudaError_t launch_build_ptrec(int npts, const float *gridpos, const float *total_ext, float4 *ptrec, cudaStream_t s)
+{
+    build_ptrec_kernel<<<(npts + 255) / 256, 256, 0, s>>>(npts, gridpos, total_ext, ptrec);
+    return cudaGetLastError();
+}
+cudaError_t launch_lambertian_boundary(const DevState &S, const float *fluxes, float *bcrad, cudaStream_t s)
+{
+    if (S.nbotpts <= 0) return cudaSuccess;
+    lambertian_boundary_kernel<<<(S.nbotpts + 255) / 256, 256, 0, s>>>(S, fluxes, bcrad);
+    return cudaGetLastError();
+}
+cudaError_t launch_prep_sh(const DevState &S, int tms, const int *shptr, const float *sh_in,
+                           const int2 *rec, float *sh_out, int *sscount, int2 *ssent, cudaStream_t s)
+{
+    const int wpb = 8;
+    const size_t smem = (size_t)wpb * 2 * (S.ml + 2) * sizeof(float);
+    prep_sh_kernel<<<(S.npts + wpb - 1) / wpb, wpb * 32, smem, s>>>(S, tms, shptr, sh_in, rec, sh_out, sscount, ssent);
+    return cudaGetLastError();
+}

@@ -1,0 +1,206 @@
+/*
+ * at3d_b200.h -- C-ABI of the B200-native SHDOM hot path (libat3d_b200.so).
+ *
+ * Drop-in boundary for the f2py extension `at3d.core` of CloudTomography/AT3D, for the hot path
+ * only.  Each entry point names the reference routine it replaces (paths relative to the AT3D
+ * checkout).  Plain pointers and sizes, no torch types, `int` return code (0 ok, 1 generic error,
+ * 2 out of spherical-harmonic memory, 3 unsupported configuration, 4 CUDA error) plus a
+ * caller-supplied `char errmsg[600]` -- the reference's IERR/ERRMSG convention
+ * (at3d/checks.py:300-311).  The library never aborts and never frees caller memory.
+ *
+ * Array layout is the reference's own: Fortran (column-major) order, 1-based index CONTENTS,
+ * REAL=float, DOUBLE PRECISION=double, INTEGER=int32, INTEGER*2=int16.
+ *
+ * There is NO CPU fallback: every compute entry point launches sm_100a kernels and returns
+ * code 4 if no CUDA device is usable.
+ */
+#ifndef AT3D_B200_H
+#define AT3D_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AT3D_ERRMSG_LEN 600
+
+/* Where the pointers of a call live. */
+#define AT3D_MEM_HOST   0
+#define AT3D_MEM_DEVICE 1
+
+/*
+ * The solved SHDOM state that RENDER / LEVISAPPROX_GRADIENT read (all read-only except bcrad).
+ * Field names are the Fortran dummy-argument names of RENDER (src/polarized/shdomsub4.f:93-109)
+ * and LEVISAPPROX_GRADIENT (shdomsub4.f:288-317), i.e. the keyword names at3d passes at
+ * at3d/solver.py:681-759 and at3d/gradient.py:262-398.  Pointers are HOST pointers.
+ */
+typedef struct at3d_state_desc {
+    int32_t nstokes, nstleg, nx, ny, nz, npts, ncells;
+    int32_t ml, mm, nlm, nleg, numphase, npart, maxnmicro;
+    int32_t bcflag, ipflag;
+    int32_t nmu, nphi0max, nang;
+    int32_t maxnbc, ntoppts, nbotpts, nsfcpar;
+    int32_t nscatangle, nstphase;
+    int32_t deltam;             /* LOGICAL */
+    int32_t srctype;            /* 'S' | 'T' | 'B'  (only 'S' is implemented; others -> code 3) */
+    int32_t units;              /* 'R' | 'T' | 'B' */
+    int32_t sfctype0, sfctype1; /* SFCTYPE(1:1), SFCTYPE(2:2); 'FL','VL' implemented */
+    int32_t interp_new;         /* INTERPMETHOD(2:2) == 'N' */
+    float solarmu, solaraz, solarflux, wavelen, gndtemp, gndalbedo, phasemax;
+    float waveno0, waveno1;
+    double tautol, transcut;
+    const int32_t *gridptr;     /* [8,ncells]  */
+    const int32_t *neighptr;    /* [6,ncells]  */
+    const int32_t *treeptr;     /* [2,ncells]  */
+    const int16_t *cellflags;   /* [ncells]    */
+    const float *xgrid, *ygrid, *zgrid;   /* [nx+1] (periodic) or [nx] (open), [ny+1]|[ny], [nz] */
+    const float *gridpos;       /* [3,npts]    */
+    const float *extinct;       /* [npts,npart] */
+    const float *albedo;        /* [npts,npart] */
+    const float *total_ext;     /* [npts] */
+    const float *legen;         /* [nstleg,0:nleg,numphase] */
+    const int32_t *iphase;      /* [8*maxnmicro,npts,npart] */
+    const float *phaseinterpwt; /* [8*maxnmicro,npts,npart] */
+    const float *dirflux;       /* [npts] */
+    const float *fluxes;        /* [2,npts] */
+    const int32_t *shptr;       /* [npts+1] */
+    const float *source;        /* [nstokes, shptr[npts]] */
+    const int32_t *rshptr;      /* [npts+2]  (gradient only; may be NULL for render) */
+    const float *radiance;      /* [nstokes, rshptr[npts]] (gradient only) */
+    const float *ylmsun;        /* [nstleg,nlm] */
+    const float *phasetab;      /* [nstphase,numphase,nscatangle] */
+    const float *planck;        /* [npts,npart] (compute_source only; may be NULL) */
+    const float *temp;          /* unused (thermal) */
+    const int32_t *nphi0;       /* [nmu] */
+    const float *mu;            /* [nmu] */
+    const float *phi;           /* [nmu,nphi0max] */
+    const float *wtdo;          /* [nmu,nphi0max] */
+    const float *skyrad;        /* [nstokes,nmu/2,nphi0max] */
+    const int32_t *bcptr;       /* [maxnbc,2] */
+    float *bcrad;               /* [nstokes, ntoppts+nbotpts(...)]; bottom part rewritten like RENDER does */
+    const float *sfcgridparms;  /* [nsfcpar,nbotpts] */
+    const float *sfcgridrad;    /* unused for solar sources */
+} at3d_state_desc;
+
+/* Sensor rays: CAMX..CAMPHI of RENDER (shdomsub4.f:164-166).  memspace says where they live. */
+typedef struct at3d_rays {
+    int32_t nrays;
+    int32_t memspace;           /* AT3D_MEM_HOST | AT3D_MEM_DEVICE */
+    const float *camx, *camy, *camz;
+    const double *cammu, *camphi;
+} at3d_rays;
+
+/* The extra inputs of LEVISAPPROX_GRADIENT (shdomsub4.f:299-317); HOST pointers except the
+ * per-ray / per-pixel arrays, which follow rays->memspace. */
+typedef struct at3d_grad_desc {
+    int32_t npix, maxpg, numder, dnumphase, deriv_maxnmicro, longest_path_pts;
+    int32_t nuncertainty, maxsubgridints, exact_single_scatter, singlescatter;
+    int32_t costfunc_ll;        /* COSTFUNC: 0 'L2', 1 'LL' */
+    double extmin, scatmin;
+    const int32_t *partder;     /* [numder] */
+    const int32_t *doexact;     /* [numder] */
+    const float *measurements;      /* [nstokes,npix]      (rays->memspace) */
+    const double *uncertainties;    /* [nunc,nunc,npix]    (rays->memspace) */
+    const int32_t *rays_per_pixel;  /* [npix]              (rays->memspace) */
+    const double *ray_weights;      /* [nrays]             (rays->memspace) */
+    const double *stokes_weights;   /* [nstokes,npix]      (rays->memspace) */
+    const float *dext, *dalb;       /* [maxpg,numder] */
+    const float *dextm;             /* [maxpg,numder] */
+    const float *dalbm, *dfj;       /* [8,npts,numder] */
+    const float *optinterpwt;       /* [8,npts] */
+    const int32_t *interpptr;       /* [8,npts] */
+    const float *dleg;              /* [nstleg,0:nleg,dnumphase] */
+    const float *dphasetab;         /* [nstphase,dnumphase,nscatangle] */
+    const int32_t *diphasep;        /* [deriv_maxnmicro,maxpg,numder] */
+    const float *dphasewtp;         /* [deriv_maxnmicro,maxpg,numder] */
+    const int32_t *iphasep;         /* [maxnmicro,maxpg,npart] */
+    const float *phasewtp;          /* [maxnmicro,maxpg,npart] */
+    const float *extinctp, *albedop;/* [maxpg,npart] */
+    const float *dtemp;             /* unused (thermal) */
+    const float *dpath;             /* [longest_path_pts,npts] */
+    const int32_t *dptr;            /* [longest_path_pts,npts] */
+} at3d_grad_desc;
+
+/* Optional per-ray trace of the visited cells (parity tests of the bit-exact indexing). */
+typedef struct at3d_trace {
+    int32_t max_per_ray;
+    int32_t *cells;             /* [max_per_ray,nrays] (rays->memspace) */
+    int32_t *ncells;            /* [nrays] */
+    int32_t *nsub;              /* [nrays] number of sub-intervals integrated */
+} at3d_trace;
+
+typedef struct at3d_state at3d_state;   /* opaque: the state resident in HBM */
+
+/* ---- library / device ---- */
+const char *at3d_b200_version(void);
+int at3d_device_count(void);
+int at3d_set_device(int device);
+
+/* ---- state residency (replaces the per-call array marshalling of f2py) ---- */
+int at3d_state_create(const at3d_state_desc *desc, at3d_state **out, char *errmsg);
+int at3d_state_attach_gradient(at3d_state *st, const at3d_grad_desc *g, char *errmsg);
+int at3d_state_destroy(at3d_state *st);
+int64_t at3d_state_bytes(const at3d_state *st);   /* HBM bytes held */
+
+/* ---- a7: YLMALL (shdomsub2.f:4244) and PRECOMPUTE_PHASE_CHECK[_GRAD] (shdomsub4.f:2388,2493) ---- */
+int at3d_ylmall(int transpose, float mu, float phi, int ml, int mm, int nstleg, float *yr /*host*/,
+                char *errmsg);
+int at3d_precompute_phase_check(int nscatangle, int numphase, int nstphase, int nstokes, int ml,
+                                int nlm, int nstleg, int nleg, const float *legen, float *phasetab,
+                                int deltam, int negcheck, int grad /*0: LEGEN/(2l+1), 1: DLEG*/,
+                                char *errmsg);
+
+/* ---- a1: COMPUTE_SOURCE (shdomsub1.f:967).  All pointers HOST; in/out arrays as the reference:
+ *      shptr, source, oshptr, delsource are updated in place. ---- */
+int at3d_compute_source(const at3d_state_desc *desc, int fixsh, float shacc, int maxiv,
+                        int first, int accelflag, int newmethod,
+                        int32_t *shptr, float *source, int32_t *oshptr, float *delsource,
+                        float *deljdot, float *deljold, float *deljnew, float *jnorm,
+                        double *kernel_ms /*optional: device time of the kernels*/, char *errmsg);
+
+/* ---- a2/a3/a4/a5/a6: RENDER (shdomsub4.f:93) ---- */
+int at3d_render(at3d_state *st, const at3d_rays *rays, float *stokes /*[nstokes,nrays], rays->memspace*/,
+                int correctinterpolate, int singlescatter, int nosurface,
+                const at3d_trace *trace /*optional*/, void *cuda_stream /*optional*/,
+                double *kernel_ms /*optional*/, char *errmsg);
+
+/* ---- a8..a14: LEVISAPPROX_GRADIENT, MAKEJACOBIAN=.FALSE. (shdomsub4.f:288) ----
+ * gradout [maxpg,numder] f64, cost [1] f64, stokesout [nstokes,npix] f32 follow rays->memspace. */
+int at3d_levisapprox_gradient(at3d_state *st, const at3d_rays *rays, const at3d_grad_desc *g,
+                              double *gradout, double *cost, float *stokesout,
+                              const at3d_trace *trace /*optional*/, void *cuda_stream /*optional*/,
+                              double *kernel_ms /*optional [4]: forward, adjoint, beam, total*/,
+                              char *errmsg);
+
+/* ---- a15: PREPARE_DERIV_INTERPS (shdomsub4.f:2917); HOST pointers ---- */
+int at3d_prepare_deriv_interps(const at3d_state_desc *desc, int npx, int npy, int npz, int maxpg,
+                               float delx, float dely, float xstart, float ystart,
+                               const float *zlevels, const at3d_grad_desc *g,
+                               float *optinterpwt, int32_t *interpptr,
+                               float *dalbm, float *dextm, float *dfj, char *errmsg);
+
+/* ---- a14 precompute: MAKE_DIRECT_DERIVATIVE (src/shdomsub5.f:1553); HOST pointers ---- */
+int at3d_make_direct_derivative(int npts, int bcflag, int npx, int npy, int npz,
+                                float delx, float dely, float xstart, float ystart,
+                                const float *gridpos, const float *zlevels,
+                                int ipdirect, int di, int dj, int dk,
+                                double cx, double cy, double cz,
+                                double cxinv, double cyinv, double czinv,
+                                double epss, double epsz, double xdomain, double ydomain,
+                                double uniformzlev, double delxd, double delyd,
+                                float *dpath, int32_t *dptr, int longest_path_pts, char *errmsg);
+
+/* ---- a16: average_subpixel_rays (src/util.f90:484); HOST pointers ---- */
+int at3d_average_subpixel_rays(int npixels, int nrays, int nstokes, const float *weighted_stokes,
+                               const int32_t *pixel_index, float *observables, char *errmsg);
+
+/* ---- a9: UPDATE_COSTFUNCTION (shdomsub4.f:13); HOST pointers ---- */
+int at3d_update_costfunction(const double *stokesout, const double *raygrad_pixel,
+                             double *gradout, double *cost, const double *uncertainties,
+                             int costfunc_ll, int nstokes, int maxpg, int numder,
+                             const double *measurement, int nuncertainty, char *errmsg);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,249 @@
+"""ctypes binding of the CPU parity oracle (oracle/libshdom_oracle.so).  TEST INFRASTRUCTURE:
+imported only by tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs."""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+from at3d_b200.state import STATE_FIELDS, GRAD_FIELDS, make_struct, i32, f32, f64, P
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, 'oracle')
+LIB = os.path.join(ORACLE_DIR, 'libshdom_oracle.so')
+
+OracleState = make_struct('OracleState', STATE_FIELDS)      # identical field order to oracle_state
+OracleGrad = make_struct('OracleGrad', GRAD_FIELDS)         # identical field order to oracle_grad_in
+
+
+class OracleRays(C.Structure):
+    _fields_ = [('nrays', i32), ('camx', C.c_void_p), ('camy', C.c_void_p), ('camz', C.c_void_p),
+                ('cammu', C.c_void_p), ('camphi', C.c_void_p)]
+
+
+class OracleTrace(C.Structure):
+    _fields_ = [('max_per_ray', i32), ('cells', C.c_void_p), ('ncells', C.c_void_p), ('nsub', C.c_void_p)]
+
+
+_lib = None
+
+
+def build():
+    subprocess.check_call(['make', '-s', '-C', ORACLE_DIR])
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB):
+            build()
+        _lib = C.CDLL(LIB)
+        _lib.oracle_ylmall.argtypes = [i32, f32, f32, i32, i32, i32, C.c_void_p]
+        _lib.oracle_ylmall.restype = None
+        _lib.oracle_make_direct_derivative.argtypes = [i32, i32, i32, i32, i32, f32, f32, f32, f32,
+                                                       C.c_void_p, C.c_void_p, i32, i32, i32, i32] + \
+            [f64] * 13 + [C.c_void_p, C.c_void_p, i32, C.c_char_p]
+        _lib.oracle_make_direct.argtypes = [i32, i32, i32, i32, i32, i32, i32, f32, f32, f32, C.c_void_p,
+                                            i32, i32, i32, f32, f32, f32, f32, C.c_void_p, C.c_void_p,
+                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, i32, i32, i32,
+                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                            C.c_void_p, C.c_char_p]
+        _lib.oracle_prepare_deriv_interps.argtypes = [P(OracleState), i32, i32, i32, i32, f32, f32, f32, f32,
+                                                      C.c_void_p, P(OracleGrad), C.c_void_p, C.c_void_p,
+                                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_char_p]
+        _lib.oracle_compute_source.argtypes = [P(OracleState), i32, f32, i32, i32, i32, i32, C.c_void_p,
+                                               C.c_void_p, C.c_void_p, C.c_void_p, P(f32), P(f32), P(f32),
+                                               P(f32), C.c_char_p]
+        _lib.oracle_render.argtypes = [P(OracleState), P(OracleRays), C.c_void_p, i32, i32, i32,
+                                       P(OracleTrace), i32, C.c_char_p]
+        _lib.oracle_levisapprox_gradient.argtypes = [P(OracleState), P(OracleRays), P(OracleGrad), C.c_void_p,
+                                                     C.c_void_p, C.c_void_p, P(OracleTrace), i32, C.c_char_p]
+        _lib.oracle_precompute_phase_check.argtypes = [i32, i32, i32, i32, i32, i32, i32, C.c_void_p,
+                                                       C.c_void_p, i32, i32, C.c_char_p]
+        _lib.oracle_precompute_phase_check_grad.argtypes = _lib.oracle_precompute_phase_check.argtypes
+        _lib.oracle_update_costfunction.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                    i32, i32, i32, i32, C.c_void_p, i32]
+        _lib.oracle_average_subpixel_rays.argtypes = [i32, i32, i32, C.c_void_p, C.c_void_p, C.c_void_p]
+        _lib.oracle_average_subpixel_rays.restype = None
+    return _lib
+
+
+class OracleError(RuntimeError):
+    pass
+
+
+def _check(code, buf):
+    if code:
+        raise OracleError('oracle ierr=%d: %s' % (code, buf.value.decode(errors='replace')))
+
+
+def _vp(a):
+    return None if a is None else a.ctypes.data
+
+
+def ylmall(transpose, mu, phi, ml, mm, nstleg, nlm):
+    yr = np.zeros((nstleg, nlm), np.float32, order='F')
+    lib().oracle_ylmall(int(transpose), mu, phi, ml, mm, nstleg, _vp(yr))
+    return yr
+
+
+def precompute_phase_check(legen, nscatangle, nstokes, ml, deltam=True, negcheck=True, grad=False):
+    legen = np.asfortranarray(legen, np.float32)
+    nstleg, nlegp1, numphase = legen.shape
+    nstphase = 1 if nstokes == 1 else 2
+    tab = np.zeros((nstphase, numphase, nscatangle), np.float32, order='F')
+    buf = C.create_string_buffer(600)
+    fn = lib().oracle_precompute_phase_check_grad if grad else lib().oracle_precompute_phase_check
+    _check(fn(nscatangle, numphase, nstphase, nstokes, ml, nstleg, nlegp1 - 1, _vp(legen), _vp(tab),
+              int(deltam), int(negcheck), buf), buf)
+    return tab
+
+
+def finalize_scene(scene):
+    """Fill YLMSUN and PHASETAB of a synthetic scene with the oracle's special functions."""
+    st = scene.state
+    st.ylmsun = ylmall(True, np.float32(st.solarmu), np.float32(st.solaraz), st.ml, st.mm, st.nstleg, st.nlm)
+    st.phasetab = precompute_phase_check(scene.pg.legenp, st.nscatangle, st.nstokes, st.ml, bool(st.deltam))
+    return scene
+
+
+def _rays(rays):
+    r = OracleRays(rays.nrays, _vp(rays.camx), _vp(rays.camy), _vp(rays.camz), _vp(rays.cammu), _vp(rays.camphi))
+    return r
+
+
+def render(state, rays, correctinterpolate=True, singlescatter=False, nosurface=False, trace_cap=0,
+           nthreads=1):
+    st = state.copy().normalize()        # BCRAD is mutated
+    d = st.fill(OracleState())
+    out = np.zeros((st.nstokes, rays.nrays), np.float32, order='F')
+    tr = None
+    trace = None
+    if trace_cap:
+        trace = dict(cells=np.zeros((trace_cap, rays.nrays), np.int32, order='F'),
+                     ncells=np.zeros(rays.nrays, np.int32), nsub=np.zeros(rays.nrays, np.int32))
+        tr = OracleTrace(trace_cap, _vp(trace['cells']), _vp(trace['ncells']), _vp(trace['nsub']))
+    buf = C.create_string_buffer(600)
+    r = _rays(rays)
+    _check(lib().oracle_render(C.byref(d), C.byref(r), _vp(out), int(correctinterpolate), int(singlescatter),
+                               int(nosurface), C.byref(tr) if tr is not None else None, nthreads, buf), buf)
+    if trace is not None:
+        return out, trace, st.bcrad
+    return out
+
+
+def compute_source(state, shptr, source, oshptr, delsource, fixsh=False, shacc=0.0, maxiv=None, first=False,
+                   accelflag=True, newmethod=True):
+    st = state.copy().normalize()
+    d = st.fill(OracleState())
+    shptr = np.array(shptr, np.int32); oshptr = np.array(oshptr, np.int32)
+    source = np.array(source, np.float32, order='F'); delsource = np.array(delsource, np.float32, order='F')
+    if maxiv is None:
+        maxiv = source.shape[1]
+    o = [f32(0), f32(0), f32(0), f32(0)]
+    buf = C.create_string_buffer(600)
+    code = lib().oracle_compute_source(C.byref(d), int(fixsh), shacc, maxiv, int(first), int(accelflag),
+                                       int(newmethod), _vp(shptr), _vp(source), _vp(oshptr), _vp(delsource),
+                                       C.byref(o[0]), C.byref(o[1]), C.byref(o[2]), C.byref(o[3]), buf)
+    return code, shptr, source, oshptr, delsource, [x.value for x in o]
+
+
+def prepare_deriv_interps(state, pg, grad):
+    st = state.copy().normalize()
+    d = st.fill(OracleState())
+    gd = grad.fill(OracleGrad())
+    npts = st.npts
+    optw = np.zeros((8, npts), np.float32, order='F')
+    iptr = np.zeros((8, npts), np.int32, order='F')
+    dalbm = np.zeros((8, npts, grad.numder), np.float32, order='F')
+    dextm = np.zeros((pg.maxpg, grad.numder), np.float32, order='F')
+    dfj = np.zeros((8, npts, grad.numder), np.float32, order='F')
+    buf = C.create_string_buffer(600)
+    zl = np.ascontiguousarray(pg.zlevels, np.float32)
+    _check(lib().oracle_prepare_deriv_interps(C.byref(d), pg.npx, pg.npy, pg.npz, pg.maxpg, pg.delx, pg.dely,
+                                              pg.xstart, pg.ystart, _vp(zl), C.byref(gd), _vp(optw), _vp(iptr),
+                                              _vp(dalbm), _vp(dextm), _vp(dfj), buf), buf)
+    return optw, iptr, dalbm, dextm, dfj
+
+
+def make_direct(state, pg, nzckd=0, zckd=None, gasabs=None):
+    """MAKE_DIRECT: returns dirflux, extdirp, dict of beam constants."""
+    st = state
+    npts = st.npts
+    extdirp = np.zeros(pg.maxpg, np.float32)
+    dirflux = np.zeros(npts, np.float32)
+    od = (f64 * 13)()
+    oi = (i32 * 5)()
+    buf = C.create_string_buffer(600)
+    gp = np.asfortranarray(st.gridpos, np.float32)
+    zl = np.ascontiguousarray(pg.zlevels, np.float32)
+    _check(lib().oracle_make_direct(npts, st.bcflag, st.ipflag, int(st.deltam), st.ml, st.nstleg, pg.nlegp,
+                                    st.solarflux, st.solarmu, st.solaraz, _vp(gp), pg.npx, pg.npy, pg.npz,
+                                    pg.delx, pg.dely, pg.xstart, pg.ystart, _vp(zl), _vp(pg.extinctp),
+                                    _vp(pg.albedop), _vp(pg.legenp), _vp(pg.iphasep), _vp(pg.phasewtp),
+                                    pg.maxnmicro, pg.npart, nzckd, _vp(zckd), _vp(gasabs), _vp(extdirp),
+                                    _vp(dirflux), od, oi, buf), buf)
+    names = ['cx', 'cy', 'cz', 'cxinv', 'cyinv', 'czinv', 'epss', 'epsz', 'xdomain', 'ydomain',
+             'uniformzlev', 'delxd', 'delyd']
+    c = dict(zip(names, list(od)))
+    c.update(ipdirect=oi[0], di=oi[1], dj=oi[2], dk=oi[3], longest_path_pts=max(oi[4], 1))
+    return dirflux, extdirp, c
+
+
+def make_direct_derivative(state, pg, c):
+    npts = state.npts
+    lpp = c['longest_path_pts']
+    dpath = np.zeros((lpp, npts), np.float32, order='F')
+    dptr = np.zeros((lpp, npts), np.int32, order='F')
+    gp = np.asfortranarray(state.gridpos, np.float32)
+    zl = np.ascontiguousarray(pg.zlevels, np.float32)
+    buf = C.create_string_buffer(600)
+    _check(lib().oracle_make_direct_derivative(
+        npts, state.bcflag, pg.npx, pg.npy, pg.npz, pg.delx, pg.dely, pg.xstart, pg.ystart, _vp(gp), _vp(zl),
+        c['ipdirect'], c['di'], c['dj'], c['dk'], c['cx'], c['cy'], c['cz'], c['cxinv'], c['cyinv'],
+        c['czinv'], c['epss'], c['epsz'], c['xdomain'], c['ydomain'], c['uniformzlev'], c['delxd'],
+        c['delyd'], _vp(dpath), _vp(dptr), lpp, buf), buf)
+    return dpath, dptr
+
+
+def levisapprox_gradient(state, rays, grad, trace_cap=0, nthreads=1):
+    st = state.copy().normalize()
+    d = st.fill(OracleState())
+    gd = grad.fill(OracleGrad())
+    gradout = np.zeros((grad.maxpg, grad.numder), np.float64, order='F')
+    cost = np.zeros(1, np.float64)
+    stokesout = np.zeros((st.nstokes, grad.npix), np.float32, order='F')
+    tr = None
+    trace = None
+    if trace_cap:
+        trace = dict(cells=np.zeros((trace_cap, rays.nrays), np.int32, order='F'),
+                     ncells=np.zeros(rays.nrays, np.int32), nsub=np.zeros(rays.nrays, np.int32))
+        tr = OracleTrace(trace_cap, _vp(trace['cells']), _vp(trace['ncells']), _vp(trace['nsub']))
+    buf = C.create_string_buffer(600)
+    r = _rays(rays)
+    _check(lib().oracle_levisapprox_gradient(C.byref(d), C.byref(r), C.byref(gd), _vp(gradout), _vp(cost),
+                                             _vp(stokesout), C.byref(tr) if tr is not None else None,
+                                             nthreads, buf), buf)
+    if trace is not None:
+        return gradout, cost[0], stokesout, trace
+    return gradout, cost[0], stokesout
+
+
+def update_costfunction(stokesout, raygrad_pixel, gradout, cost, uncertainties, costfunc, measurement):
+    nstokes = len(stokesout)
+    raygrad_pixel = np.asfortranarray(raygrad_pixel, np.float64)
+    _, maxpg, numder = raygrad_pixel.shape
+    gradout = np.array(gradout, np.float64, order='F')
+    cost = np.array(cost, np.float64)
+    unc = np.asfortranarray(uncertainties, np.float64)
+    so = np.ascontiguousarray(stokesout, np.float64); me = np.ascontiguousarray(measurement, np.float64)
+    lib().oracle_update_costfunction(_vp(so), _vp(raygrad_pixel), _vp(gradout), _vp(cost), _vp(unc),
+                                     1 if costfunc == 'LL' else 0, nstokes, maxpg, numder, _vp(me), unc.shape[0])
+    return gradout, cost
+
+
+def average_subpixel_rays(weighted_stokes, pixel_index, npixels):
+    ws = np.asfortranarray(weighted_stokes, np.float32)
+    nstokes, nrays = ws.shape
+    pi = np.ascontiguousarray(pixel_index, np.int32)
+    out = np.zeros((nstokes, npixels), np.float32, order='F')
+    lib().oracle_average_subpixel_rays(npixels, nrays, nstokes, _vp(ws), _vp(pi), _vp(out))
+    return out

@@ -1,0 +1,92 @@
+"""GPU parity of RENDER (C-ABI at3d_render) against the CPU oracle.
+
+Bars (BASELINE.json north_star): visited-cell sequence and sub-interval counts bit-exact;
+radiance / Stokes within relative 1e-4 (absolute 1e-6 on near-zero Q/U)."""
+import numpy as np
+import pytest
+import scenes
+
+pytestmark = pytest.mark.gpu
+
+RTOL, ATOL_QU = 1e-4, 1e-6
+
+
+def assert_stokes_close(out, ref):
+    scale = np.max(np.abs(ref[0]))
+    # I: relative 1e-4 (tiny radiances compared relative to the image scale)
+    np.testing.assert_allclose(out[0], ref[0], rtol=RTOL, atol=RTOL * 1e-2 * scale)
+    for k in range(1, out.shape[0]):
+        np.testing.assert_allclose(out[k], ref[k], rtol=RTOL, atol=ATOL_QU)
+
+
+@pytest.mark.parametrize('case', list(scenes.SCENE_CASES))
+def test_render_matches_oracle(case, oracle):
+    from at3d_b200.device import DeviceState
+    sc = scenes.make(case, oracle)
+    rays = scenes.ray_set(sc)
+    ref, tref, bcrad_ref = oracle.render(sc.state, rays, trace_cap=256)
+    dev = DeviceState(sc.state)
+    out, tr = dev.render(rays, trace_cap=256)
+    # bit-exact indexing
+    np.testing.assert_array_equal(tr['ncells'], tref['ncells'])
+    np.testing.assert_array_equal(tr['cells'], tref['cells'])
+    np.testing.assert_array_equal(tr['nsub'], tref['nsub'])
+    assert_stokes_close(out, ref)
+    # RENDER's in/out BCRAD: bottom boundary radiances
+    nt = sc.state.ntoppts
+    np.testing.assert_allclose(dev.bcrad()[:, nt:], bcrad_ref[:, nt:], rtol=1e-6, atol=0)
+    dev.close()
+
+
+@pytest.mark.parametrize('flags', [dict(correctinterpolate=False), dict(singlescatter=True),
+                                   dict(nosurface=True)])
+def test_render_flags(flags, oracle):
+    from at3d_b200.device import DeviceState
+    sc = scenes.make('scalar_periodic_split', oracle)
+    rays = scenes.ray_set(sc)
+    ref = oracle.render(sc.state, rays, **flags)
+    dev = DeviceState(sc.state)
+    out = dev.render(rays, **flags)
+    assert_stokes_close(out, ref)
+    dev.close()
+
+
+def test_render_device_pointers_match_host_path(oracle):
+    import torch
+    from at3d_b200.device import DeviceState
+    from at3d_b200.state import Rays
+    sc = scenes.make('polarized_periodic_split', oracle)
+    rays = scenes.ray_set(sc)
+    dev = DeviceState(sc.state)
+    host = dev.render(rays)
+
+    class R:
+        pass
+    r = R()
+    for k in ('camx', 'camy', 'camz', 'cammu', 'camphi'):
+        setattr(r, k, torch.from_numpy(getattr(rays, k)).cuda())
+    out = dev.render(r)
+    np.testing.assert_array_equal(out.cpu().numpy().T, host)
+    dev.close()
+
+
+def test_empty_ray_list(oracle):
+    from at3d_b200.device import DeviceState
+    from at3d_b200.state import Rays
+    sc = scenes.make('scalar_periodic', oracle)
+    dev = DeviceState(sc.state)
+    z = np.zeros(0)
+    out = dev.render(Rays(z, z, z, z, z))
+    assert out.shape == (1, 0)
+    dev.close()
+
+
+def test_ray_below_domain_is_an_error(oracle):
+    from at3d_b200.device import DeviceState
+    from at3d_b200._lib import At3dError
+    from at3d_b200.state import Rays
+    sc = scenes.make('scalar_periodic', oracle)
+    dev = DeviceState(sc.state)
+    with pytest.raises(At3dError):
+        dev.render(Rays([0.1], [0.1], [-1.0], [0.5], [0.0]))
+    dev.close()
