@@ -297,6 +297,7 @@ extern "C" int at3d_render(at3d_state *st, const at3d_rays *rays, float *stokes,
         if (host) {
             CUDA_TRY(st->trace.reserve(((size_t)tcap * n + 2 * n) * sizeof(int)));
             tc = (int *)st->trace.p; tn = tc + (size_t)tcap * n; ts = tn + n;
+            CUDA_TRY(cudaMemsetAsync(tc, 0, ((size_t)tcap * n + 2 * n) * sizeof(int), stream));
         } else { tc = trace->cells; tn = trace->ncells; ts = trace->nsub; }
     }
     CUDA_TRY(st->err.reserve(sizeof(RayErr)));
