@@ -34,7 +34,7 @@ SYMBOLS = ['at3d_b200_version', 'at3d_device_count', 'at3d_set_device', 'at3d_st
            'at3d_state_attach_gradient', 'at3d_state_destroy', 'at3d_state_bytes', 'at3d_state_get_bcrad',
            'at3d_ylmall', 'at3d_precompute_phase_check', 'at3d_compute_source', 'at3d_render',
            'at3d_levisapprox_gradient', 'at3d_prepare_deriv_interps', 'at3d_make_direct_derivative',
-           'at3d_average_subpixel_rays', 'at3d_update_costfunction']
+           'at3d_average_subpixel_rays', 'at3d_update_costfunction', 'at3d_make_direct', 'at3d_state_get_counts']
 
 
 class _Missing:
@@ -75,6 +75,7 @@ def lib():
     L.at3d_state_create.argtypes = [P(StateDesc), P(C.c_void_p), C.c_char_p]
     L.at3d_state_attach_gradient.argtypes = [C.c_void_p, P(GradDesc), C.c_char_p]
     L.at3d_state_destroy.argtypes = [C.c_void_p]
+    L.at3d_state_get_counts.argtypes = [C.c_void_p, C.c_void_p, C.c_char_p]
     L.at3d_state_get_bcrad.argtypes = [C.c_void_p, C.c_void_p, C.c_char_p]
     L.at3d_render.argtypes = [C.c_void_p, P(RaysC), C.c_void_p, i32, i32, i32, P(TraceC), C.c_void_p,
                               P(f64), C.c_char_p]
@@ -92,6 +93,11 @@ def lib():
     L.at3d_make_direct_derivative.argtypes = [i32, i32, i32, i32, i32, f32, f32, f32, f32, C.c_void_p,
                                               C.c_void_p, i32, i32, i32, i32] + [f64] * 13 + \
                                              [C.c_void_p, C.c_void_p, i32, C.c_char_p]
+    L.at3d_make_direct.argtypes = [i32, i32, i32, i32, i32, i32, i32, f32, f32, f32, C.c_void_p,
+                                   i32, i32, i32, f32, f32, f32, f32, C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_void_p, i32, C.c_void_p, C.c_void_p, i32, i32, i32,
+                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_char_p]
     L.at3d_average_subpixel_rays.argtypes = [i32, i32, i32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_char_p]
     L.at3d_update_costfunction.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                            i32, i32, i32, i32, C.c_void_p, i32, C.c_char_p]

@@ -1,0 +1,97 @@
+"""Array-level Python entry points of libat3d_b200.so for the helper routines of the path
+(special-function tables and the per-evaluation gradient input preparation).
+
+Same call shapes as the CPU oracle binding used by the parity tests (tests/oracle_lib.py), so that
+``gradsetup.make_gradient_inputs`` can be driven by either; every function here runs CUDA kernels
+behind the C-ABI of include/at3d_b200.h and raises ``At3dError`` on a non-zero IERR.
+"""
+import ctypes as C
+import numpy as np
+from . import _lib
+from ._lib import vp
+from .state import i32, f64
+
+
+def _call(fn, *args):
+    buf = _lib.errbuf()
+    _lib.check(fn(*args, buf), buf)
+
+
+def ylmall(transpose, mu, phi, ml, mm, nstleg, nlm):
+    """YLMALL (shdomsub2.f:4244): YR[nstleg,nlm]."""
+    yr = np.zeros((nstleg, nlm), np.float32, order='F')
+    _call(_lib.lib().at3d_ylmall, int(transpose), float(mu), float(phi), ml, mm, nstleg, vp(yr))
+    return yr
+
+
+def precompute_phase_check(legen, nscatangle, nstokes, ml, deltam=True, negcheck=True, grad=False):
+    """PRECOMPUTE_PHASE_CHECK[_GRAD] (shdomsub4.f:2388,2493): PHASETAB[nstphase,numphase,nscatangle]."""
+    legen = np.asfortranarray(legen, np.float32)
+    nstleg, nlegp1, numphase = legen.shape
+    nstphase = 1 if nstokes == 1 else 2
+    tab = np.zeros((nstphase, numphase, nscatangle), np.float32, order='F')
+    _call(_lib.lib().at3d_precompute_phase_check, nscatangle, numphase, nstphase, nstokes, ml, 0, nstleg,
+          nlegp1 - 1, vp(legen), vp(tab), int(deltam), int(negcheck), int(grad))
+    return tab
+
+
+def finalize_scene(scene):
+    """Fill YLMSUN and PHASETAB of a synthetic scene (INIT_SOLUTION / _precompute_phase equivalents)."""
+    st = scene.state
+    st.ylmsun = ylmall(True, np.float32(st.solarmu), np.float32(st.solaraz), st.ml, st.mm, st.nstleg, st.nlm)
+    st.phasetab = precompute_phase_check(scene.pg.legenp, st.nscatangle, st.nstokes, st.ml, bool(st.deltam))
+    return scene
+
+
+def prepare_deriv_interps(state, pg, grad):
+    """PREPARE_DERIV_INTERPS (shdomsub4.f:2917): (optinterpwt, interpptr, dalbm, dextm, dfj)."""
+    st = state.copy().normalize()
+    d = st.desc()
+    gd = grad.desc()
+    npts = st.npts
+    optw = np.zeros((8, npts), np.float32, order='F')
+    iptr = np.zeros((8, npts), np.int32, order='F')
+    dalbm = np.zeros((8, npts, grad.numder), np.float32, order='F')
+    dextm = np.zeros((pg.maxpg, grad.numder), np.float32, order='F')
+    dfj = np.zeros((8, npts, grad.numder), np.float32, order='F')
+    zl = np.ascontiguousarray(pg.zlevels, np.float32)
+    _call(_lib.lib().at3d_prepare_deriv_interps, C.byref(d), pg.npx, pg.npy, pg.npz, pg.maxpg, pg.delx, pg.dely,
+          pg.xstart, pg.ystart, vp(zl), C.byref(gd), vp(optw), vp(iptr), vp(dalbm), vp(dextm), vp(dfj))
+    return optw, iptr, dalbm, dextm, dfj
+
+
+_BEAM_NAMES = ['cx', 'cy', 'cz', 'cxinv', 'cyinv', 'czinv', 'epss', 'epsz', 'xdomain', 'ydomain',
+               'uniformzlev', 'delxd', 'delyd']
+
+
+def make_direct(state, pg, nzckd=0, zckd=None, gasabs=None):
+    """MAKE_DIRECT (shdomsub2.f:393): (dirflux[npts], extdirp[maxpg], dict of beam constants)."""
+    st = state
+    extdirp = np.zeros(pg.maxpg, np.float32)
+    dirflux = np.zeros(st.npts, np.float32)
+    od = (f64 * 13)()
+    oi = (i32 * 5)()
+    gp = np.asfortranarray(st.gridpos, np.float32)
+    zl = np.ascontiguousarray(pg.zlevels, np.float32)
+    _call(_lib.lib().at3d_make_direct, st.npts, st.bcflag, st.ipflag, int(st.deltam), st.ml, st.nstleg, pg.nlegp,
+          st.solarflux, st.solarmu, st.solaraz, vp(gp), pg.npx, pg.npy, pg.npz, pg.delx, pg.dely, pg.xstart,
+          pg.ystart, vp(zl), vp(pg.extinctp), vp(pg.albedop), vp(pg.legenp), pg.numphase, vp(pg.iphasep),
+          vp(pg.phasewtp), pg.maxnmicro, pg.npart, nzckd, vp(zckd), vp(gasabs), vp(extdirp), vp(dirflux), od, oi)
+    c = dict(zip(_BEAM_NAMES, list(od)))
+    c.update(ipdirect=oi[0], di=oi[1], dj=oi[2], dk=oi[3], longest_path_pts=max(oi[4], 1))
+    return dirflux, extdirp, c
+
+
+def make_direct_derivative(state, pg, c):
+    """MAKE_DIRECT_DERIVATIVE (shdomsub5.f:1553): (dpath, dptr)[longest_path_pts,npts]."""
+    npts = state.npts
+    lpp = c['longest_path_pts']
+    dpath = np.zeros((lpp, npts), np.float32, order='F')
+    dptr = np.zeros((lpp, npts), np.int32, order='F')
+    gp = np.asfortranarray(state.gridpos, np.float32)
+    zl = np.ascontiguousarray(pg.zlevels, np.float32)
+    _call(_lib.lib().at3d_make_direct_derivative, npts, state.bcflag, pg.npx, pg.npy, pg.npz, pg.delx, pg.dely,
+          pg.xstart, pg.ystart, vp(gp), vp(zl), c['ipdirect'], c['di'], c['dj'], c['dk'], c['cx'], c['cy'],
+          c['cz'], c['cxinv'], c['cyinv'], c['czinv'], c['epss'], c['epsz'], c['xdomain'], c['ydomain'],
+          c['uniformzlev'], c['delxd'], c['delyd'], vp(dpath), vp(dptr), lpp)
+    return dpath, dptr

@@ -107,6 +107,8 @@ extern "C" int at3d_state_destroy(at3d_state *st)
 {
     if (!st) return 0;
     for (void *p : st->owned) cudaFree(p);
+    for (void *p : st->grad_owned) cudaFree(p);
+    st->pix.release(); st->work.release();
     st->rays.release(); st->out.release(); st->trace.release(); st->misc.release();
     st->slabs.release(); st->err.release();
     delete st;
@@ -141,6 +143,9 @@ extern "C" int at3d_state_create(const at3d_state_desc *d, at3d_state **out, cha
     S.ny_comp = d->nstokes == 1 ? 1 : 5;
     S.solarmu = d->solarmu; S.solaraz = d->solaraz; S.gndalbedo = d->gndalbedo; S.phasemax = d->phasemax;
     S.tautol = d->tautol; S.transcut = d->transcut;
+    st->geom.solarmu = d->solarmu; st->geom.solaraz = d->solaraz; st->geom.ztop = d->zgrid[d->nz - 1];
+    st->geom.zbot = d->zgrid[0]; st->geom.nscatangle = d->nscatangle; st->geom.srctype = d->srctype;
+    st->geom.deltam = d->deltam; st->geom.nstokes = d->nstokes;
     int rc = 0;
 #define UP(field, count) if (!rc) rc = upload(st, d->field, (size_t)(count), &S.field, errmsg)
     const int nxg = (d->bcflag & 5) ? d->nx : d->nx + 1;
@@ -221,7 +226,21 @@ extern "C" int at3d_state_create(const at3d_state_desc *d, at3d_state **out, cha
             rc = prep_sh_array(st, 0, d->rshptr, d->radiance, &S.radrec, &S.shrad, nullptr, nullptr, errmsg);
         if (rc) { at3d_state_destroy(st); return rc; }
     }
+    {
+        unsigned long long *c = nullptr;
+        rc = dalloc(st, 8, &c, errmsg);
+        if (rc) { at3d_state_destroy(st); return rc; }
+        cudaMemset(c, 0, 8 * sizeof(unsigned long long));
+        st->counts_dev = c; S.counts = c;
+    }
     *out = st;
+    return 0;
+}
+
+extern "C" int at3d_state_get_counts(at3d_state *st, int64_t *counts, char *errmsg)
+{
+    if (!st || !counts) { set_msg(errmsg, "null argument"); return 1; }
+    CUDA_TRY(cudaMemcpy(counts, st->counts_dev, 8 * sizeof(int64_t), cudaMemcpyDeviceToHost));
     return 0;
 }
 
@@ -232,7 +251,7 @@ extern "C" int at3d_state_get_bcrad(at3d_state *st, float *bcrad_host, char *err
     return 0;
 }
 
-static const char *ray_err_text(int code)
+const char *ray_err_text(int code)
 {
     switch (code) {
     case 1: return "INTEGRATE_1RAY: SO<0";
@@ -252,26 +271,37 @@ int check_ray_err(at3d_state *st, cudaStream_t stream, char *errmsg)
     return 0;
 }
 
-// stage the ray arrays on the device when they are host arrays
+// Stage the ray arrays on the device when they are host arrays.  For host rays the per-ray setup
+// (make_ray_pack) is evaluated here with the host libm -- the reference's own -- so that the walk is
+// bit-exact; device-resident rays get it evaluated in the kernel (packs = nullptr).
 int stage_rays(at3d_state *st, const at3d_rays *rays, cudaStream_t stream, const float **camx,
                const float **camy, const float **camz, const double **cammu, const double **camphi,
-               char *errmsg)
+               const RayPack **packs, char *errmsg)
 {
     const size_t n = rays->nrays;
+    *packs = nullptr;
     if (rays->memspace == AT3D_MEM_DEVICE) {
         *camx = rays->camx; *camy = rays->camy; *camz = rays->camz; *cammu = rays->cammu; *camphi = rays->camphi;
         return 0;
     }
-    const size_t nb = n * (3 * sizeof(float) + 2 * sizeof(double)) + 64;
+    const size_t nb = n * (sizeof(RayPack) + 2 * sizeof(double)) + 64;
     CUDA_TRY(st->rays.reserve(nb));
-    double *dmu = (double *)st->rays.p, *dphi = dmu + n;
-    float *dx = (float *)(dphi + n), *dy = dx + n, *dz = dy + n;
+    RayPack *dpk = (RayPack *)st->rays.p;
+    double *dmu = (double *)(dpk + n), *dphi = dmu + n;
+    st->packs_h.resize(n);
+    RayPack *hp = st->packs_h.data();
+    const RayGeom g = st->geom;
+    const float *hx = rays->camx, *hy = rays->camy, *hz = rays->camz;
+    const double *hmu = rays->cammu, *hphi = rays->camphi;
+#pragma omp parallel for schedule(static) if (n > 4096)
+    for (long long i = 0; i < (long long)n; i++)
+        make_ray_pack(g, (double)hx[i], (double)hy[i], (double)hz[i], hmu[i], hphi[i], hp[i]);
+    CUDA_TRY(cudaMemcpyAsync(dpk, hp, n * sizeof(RayPack), cudaMemcpyHostToDevice, stream));
     CUDA_TRY(cudaMemcpyAsync(dmu, rays->cammu, n * sizeof(double), cudaMemcpyHostToDevice, stream));
     CUDA_TRY(cudaMemcpyAsync(dphi, rays->camphi, n * sizeof(double), cudaMemcpyHostToDevice, stream));
-    CUDA_TRY(cudaMemcpyAsync(dx, rays->camx, n * sizeof(float), cudaMemcpyHostToDevice, stream));
-    CUDA_TRY(cudaMemcpyAsync(dy, rays->camy, n * sizeof(float), cudaMemcpyHostToDevice, stream));
-    CUDA_TRY(cudaMemcpyAsync(dz, rays->camz, n * sizeof(float), cudaMemcpyHostToDevice, stream));
-    *camx = dx; *camy = dy; *camz = dz; *cammu = dmu; *camphi = dphi;
+    // the copies read pageable host memory: they are complete (staged) when the calls return,
+    // and packs_h is only rewritten by the next call on this state
+    *camx = nullptr; *camy = nullptr; *camz = nullptr; *cammu = dmu; *camphi = dphi; *packs = dpk;
     return 0;
 }
 
@@ -285,8 +315,8 @@ extern "C" int at3d_render(at3d_state *st, const at3d_rays *rays, float *stokes,
     const size_t n = rays->nrays;
     const int nst = st->S.nstokes;
     if (n == 0) return 0;
-    const float *camx, *camy, *camz; const double *cammu, *camphi;
-    int rc = stage_rays(st, rays, stream, &camx, &camy, &camz, &cammu, &camphi, errmsg);
+    const float *camx, *camy, *camz; const double *cammu, *camphi; const RayPack *packs;
+    int rc = stage_rays(st, rays, stream, &camx, &camy, &camz, &cammu, &camphi, &packs, errmsg);
     if (rc) return rc;
     const bool host = rays->memspace == AT3D_MEM_HOST;
     float *out_d = stokes;
@@ -302,9 +332,10 @@ extern "C" int at3d_render(at3d_state *st, const at3d_rays *rays, float *stokes,
     }
     CUDA_TRY(st->err.reserve(sizeof(RayErr)));
     CUDA_TRY(cudaMemsetAsync(st->err.p, 0, sizeof(RayErr), stream));
+    CUDA_TRY(cudaMemsetAsync(st->counts_dev, 0, 8 * sizeof(unsigned long long), stream));
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (kernel_ms) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, stream); }
-    CUDA_TRY(launch_render(st->S, (int)n, camx, camy, camz, cammu, camphi, out_d, nullptr, 0,
+    CUDA_TRY(launch_render(st->S, (int)n, camx, camy, camz, cammu, camphi, packs, out_d, nullptr, 0,
                            correctinterpolate, singlescatter, nosurface, 0, tc, tcap, tn, ts,
                            (RayErr *)st->err.p, stream));
     if (kernel_ms) cudaEventRecord(e1, stream);

@@ -41,6 +41,30 @@ struct DevState {
     // raw optics kept for the gradient kernels
     const float *extinct, *albedo, *dirflux, *legen, *phaseinterpwt, *ylmsun, *sfcgridparms;
     const int *iphase;
+    // optional work counters of the last call: [0] cells visited, [1] grid points evaluated,
+    // [2] sum of NS over evaluated points, [3] sum of NR (gradient), [4] sub-intervals, [5] rays marched
+    unsigned long long *counts;
+};
+
+// Derivative tables of LEVISAPPROX_GRADIENT resident in HBM (reference layouts, see at3d_grad_desc).
+struct DevGrad {
+    int maxpg, numder, dnumphase, deriv_maxnmicro, pmaxnmicro, longest_path_pts;
+    int exact_single_scatter, singlescatter, maxsub;
+    double scatmin;
+    const int *partder, *doexact;
+    const float *dext, *dalb, *dextm;       // [maxpg,numder]
+    const float *dalbm, *dfj;               // [8,npts,numder]
+    const float *optinterpwt;               // [8,npts]
+    const int *interpptr;                   // [8,npts]
+    const float *dleg;                      // [nstleg,0:nleg,dnumphase]
+    const float *dphasetab;                 // [nstphase,dnumphase,nscatangle]
+    const int *diphasep;                    // [deriv_maxnmicro,maxpg,numder]
+    const float *dphasewtp;
+    const int *iphasep;                     // [pmaxnmicro,maxpg,npart]
+    const float *phasewtp;
+    const float *extinctp, *albedop;        // [maxpg,npart]
+    const float *dpath;                     // [longest_path_pts,npts]
+    const int *dptr;
 };
 
 #define FULLMASK 0xffffffffu
@@ -361,7 +385,84 @@ __device__ __forceinline__ int dev_bc_search(const int *col, int n, int ip)
     return ibc;
 }
 
-// per-ray direction quantities (shdomsub2.f:2413-2481)
+// ---- per-ray setup: start point (RENDER, shdomsub4.f:214-236) and direction quantities
+// ---- (INTEGRATE_1RAY, shdomsub2.f:2413-2481; ROTATE_POL_PLANE, :3277-3314).
+// The cell walk is bit-exact only if CX,CY,CZ and the scattering-angle index agree to the last
+// bit with the reference, whose libm is glibc.  CUDA's double sin/cos/acos are not bit-identical to
+// glibc's, so for HOST ray arrays the library evaluates this function on the host (same libm as
+// the reference's gfortran build) and ships one 80-byte RayPack per ray; for DEVICE-resident rays
+// the same function runs on the device (ulp-level differences possible, documented in DESIGN.md).
+struct RayGeom {
+    float solarmu, solaraz, ztop, zbot;
+    int nscatangle, srctype, deltam, nstokes;
+};
+
+struct __align__(16) RayPack {
+    double x0, y0, z0;      // start point after the top-of-domain slide
+    double cx, cy, cz;      // direction cosines of the backward march (small ones zeroed)
+    double cos22, sin22;    // polarization-plane rotation
+    float f;                // scattering-angle interpolation weight
+    int j;                  // scattering-angle table index (1-based)
+    int status;             // 0 ok, 1 looks away from the domain (radiance 0), 2 below the domain (error)
+    int pad;
+};
+
+__host__ __device__ inline void make_ray_pack(const RayGeom &g, double x0, double y0, double z0,
+                                              double mu2, double phi2, RayPack &p)
+{
+    const double pi = acos(-1.0);
+    p.status = 0; p.pad = 0;
+    {
+        const double muray = -mu2, phiray = phi2 - pi;
+        if (z0 > g.ztop) {
+            if (muray >= 0.0) p.status = 1;
+            else {
+                const double r = (g.ztop - z0) / muray;
+                x0 = x0 + r * sqrt(1 - muray * muray) * cos(phiray);
+                y0 = y0 + r * sqrt(1 - muray * muray) * sin(phiray);
+                z0 = g.ztop;
+            }
+        } else if (z0 < g.zbot) {
+            p.status = 2;
+        }
+    }
+    p.x0 = x0; p.y0 = y0; p.z0 = z0;
+    p.f = 0.0f; p.j = 1; p.cos22 = 1.0; p.sin22 = 0.0;
+    if (g.srctype != 'T' && g.deltam) {
+        double cosscat = g.solarmu * mu2
+            + sqrt((1.0f - g.solarmu * g.solarmu) * (1.0 - mu2 * mu2)) * cos(g.solaraz - phi2);
+        cosscat = fmax(fmin(1.0, cosscat), -1.0);
+        float f = (float)((g.nscatangle - 1) * (acos(cosscat) / pi) + 1);
+        int j = (int)f;
+        if (j > g.nscatangle - 1) j = g.nscatangle - 1;
+        p.f = f - (float)j;
+        p.j = j;
+        if (g.nstokes > 1) {
+            // ROTATE_POL_PLANE with MU=SNGL(MU2), DELPHI=SOLARAZ-SNGL(PHI2)
+            const float mu = (float)mu2;
+            const float delphi = g.solaraz - (float)phi2;
+            const double sin_scat = sqrt(fmax(0.0, 1.0 - cosscat * cosscat));
+            const double sin_theta1 = sqrt(1.0 - (double)(g.solarmu * g.solarmu));
+            const double sin_theta2 = sqrt(1.0 - (double)(mu * mu));
+            const double sinphi = sin((double)delphi), cosphi = cos((double)delphi);
+            double sin2, cos2;
+            if (sin_scat == 0.0) { sin2 = 0.0; cos2 = -1.0; }
+            else {
+                sin2 = sin_theta1 * sinphi / sin_scat;
+                cos2 = (sin_theta2 * g.solarmu - sin_theta1 * mu * cosphi) / sin_scat;
+            }
+            p.sin22 = 2.0 * sin2 * cos2;
+            p.cos22 = 1.0 - 2.0 * (sin2 * sin2);
+        }
+    }
+    p.cx = sqrt(1.0 - mu2 * mu2) * cos(phi2 - pi);
+    p.cy = sqrt(1.0 - mu2 * mu2) * sin(phi2 - pi);
+    p.cz = -mu2;
+    if (!(fabs(p.cx) > 1.0e-6f)) p.cx = 0.0;
+    if (!(fabs(p.cy) > 1.0e-6f)) p.cy = 0.0;
+    if (!(fabs(p.cz) > 1.0e-6f)) p.cz = 0.0;
+}
+
 struct RayDir {
     double cx, cy, cz, cxinv, cyinv, czinv;
     double cos22, sin22;    // polarization-plane rotation (ROTATE_POL_PLANE)
@@ -371,43 +472,22 @@ struct RayDir {
     float xm, ym;
 };
 
-__device__ __forceinline__ void dev_ray_dir(const DevState &S, double mu2, double phi2, RayDir &rd)
+__device__ __forceinline__ RayGeom dev_ray_geom(const DevState &S)
 {
-    const double pi = acos(-1.0);
-    rd.f = 0.0f; rd.j = 1; rd.cos22 = 1.0; rd.sin22 = 0.0;
-    if (S.srctype != 'T' && S.deltam) {
-        double cosscat = S.solarmu * mu2
-            + sqrt((1.0f - S.solarmu * S.solarmu) * (1.0 - mu2 * mu2)) * cos(S.solaraz - phi2);
-        cosscat = fmax(fmin(1.0, cosscat), -1.0);
-        float f = (float)((S.nscatangle - 1) * (acos(cosscat) / pi) + 1);
-        int j = (int)f;
-        if (j > S.nscatangle - 1) j = S.nscatangle - 1;
-        rd.f = f - (float)j;
-        rd.j = j;
-        if (S.nstokes > 1) {
-            // ROTATE_POL_PLANE (shdomsub2.f:3277-3314), MU=SNGL(MU2), DELPHI=SOLARAZ-SNGL(PHI2)
-            float mu = (float)mu2;
-            float delphi = S.solaraz - (float)phi2;
-            double sin_scat = sqrt(fmax(0.0, 1.0 - cosscat * cosscat));
-            double sin_theta1 = sqrt(1.0 - (double)(S.solarmu * S.solarmu));
-            double sin_theta2 = sqrt(1.0 - (double)(mu * mu));
-            double sinphi = sin((double)delphi), cosphi = cos((double)delphi);
-            double sin2, cos2;
-            if (sin_scat == 0.0) { sin2 = 0.0; cos2 = -1.0; }
-            else {
-                sin2 = sin_theta1 * sinphi / sin_scat;
-                cos2 = (sin_theta2 * S.solarmu - sin_theta1 * mu * cosphi) / sin_scat;
-            }
-            rd.sin22 = 2.0 * sin2 * cos2;
-            rd.cos22 = 1.0 - 2.0 * (sin2 * sin2);
-        }
-    }
-    rd.cx = sqrt(1.0 - mu2 * mu2) * cos(phi2 - pi);
-    rd.cy = sqrt(1.0 - mu2 * mu2) * sin(phi2 - pi);
-    rd.cz = -mu2;
-    if (fabs(rd.cx) > 1.0e-6f) rd.cxinv = 1.0 / rd.cx; else { rd.cx = 0.0; rd.cxinv = 1.0e6f; }
-    if (fabs(rd.cy) > 1.0e-6f) rd.cyinv = 1.0 / rd.cy; else { rd.cy = 0.0; rd.cyinv = 1.0e6f; }
-    if (fabs(rd.cz) > 1.0e-6f) rd.czinv = 1.0 / rd.cz; else { rd.cz = 0.0; rd.czinv = 1.0e6f; }
+    RayGeom g;
+    g.solarmu = S.solarmu; g.solaraz = S.solaraz;
+    g.ztop = __ldg(&S.zgrid[S.nz - 1]); g.zbot = __ldg(&S.zgrid[0]);
+    g.nscatangle = S.nscatangle; g.srctype = S.srctype; g.deltam = S.deltam; g.nstokes = S.nstokes;
+    return g;
+}
+
+__device__ __forceinline__ void dev_ray_dir(const DevState &S, const RayPack &p, RayDir &rd)
+{
+    rd.f = p.f; rd.j = p.j; rd.cos22 = p.cos22; rd.sin22 = p.sin22;
+    rd.cx = p.cx; rd.cy = p.cy; rd.cz = p.cz;
+    rd.cxinv = (rd.cx != 0.0) ? 1.0 / rd.cx : (double)1.0e6f;
+    rd.cyinv = (rd.cy != 0.0) ? 1.0 / rd.cy : (double)1.0e6f;
+    rd.czinv = (rd.cz != 0.0) ? 1.0 / rd.cz : (double)1.0e6f;
     rd.bitx = rd.cx < 0.0 ? 1 : 0;
     rd.bity = rd.cy < 0.0 ? 1 : 0;
     rd.bitz = rd.cz < 0.0 ? 1 : 0;
@@ -416,24 +496,24 @@ __device__ __forceinline__ void dev_ray_dir(const DevState &S, double mu2, doubl
     rd.ym = 0.5f * (__ldg(&S.ygrid[0]) + __ldg(&S.ygrid[S.ny - 1]));
 }
 
-// start-point handling of RENDER (shdomsub4.f:214-236); returns 1 if the ray sees nothing,
-// 2 if the start is below the domain (error)
-__device__ __forceinline__ int dev_ray_start(const DevState &S, double mu2, double phi2,
-                                             double &x0, double &y0, double &z0)
+// the RayPack of ray iray: shipped from the host, or evaluated here for device-resident rays
+__device__ __forceinline__ RayPack dev_get_pack(const DevState &S, const RayPack *packs, int iray,
+                                                const float *camx, const float *camy, const float *camz,
+                                                double mu2, double phi2)
 {
-    const double pi = acos(-1.0);
-    double muray = -mu2, phiray = phi2 - pi;
-    float ztop = __ldg(&S.zgrid[S.nz - 1]);
-    if (z0 > ztop) {
-        if (muray >= 0.0) return 1;
-        double r = (ztop - z0) / muray;
-        x0 = x0 + r * sqrt(1 - muray * muray) * cos(phiray);
-        y0 = y0 + r * sqrt(1 - muray * muray) * sin(phiray);
-        z0 = ztop;
-    } else if (z0 < __ldg(&S.zgrid[0])) {
-        return 2;
+    if (packs) {
+        const double2 *q = (const double2 *)(packs + iray);
+        RayPack p;
+        double2 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2), d = __ldg(q + 3);
+        const int4 e = __ldg((const int4 *)(q + 4));
+        p.x0 = a.x; p.y0 = a.y; p.z0 = b.x; p.cx = b.y; p.cy = c.x; p.cz = c.y; p.cos22 = d.x; p.sin22 = d.y;
+        p.f = __int_as_float(e.x); p.j = e.y; p.status = e.z; p.pad = 0;
+        return p;
     }
-    return 0;
+    RayPack p;
+    make_ray_pack(dev_ray_geom(S), (double)__ldg(&camx[iray]), (double)__ldg(&camy[iray]),
+                  (double)__ldg(&camz[iray]), mu2, phi2, p);
+    return p;
 }
 
 // COMPUTE_TOP_RADIANCES, INTERPOLATE_FLAG=1, SRCTYPE != 'T' (shdomsub1.f:2375-2395)

@@ -24,41 +24,27 @@ struct DevBuf {
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
-// gradient-side device arrays (at3d_state_attach_gradient)
-struct GradDev {
-    int attached = 0;
-    int maxpg = 0, numder = 0, dnumphase = 0, deriv_maxnmicro = 0, longest_path_pts = 0;
-    int maxnmicro = 0;
-    const int *partder = nullptr, *doexact = nullptr;
-    const float *dext = nullptr, *dalb = nullptr, *dextm = nullptr, *dalbm = nullptr, *dfj = nullptr;
-    const float *optinterpwt = nullptr;
-    const int *interpptr = nullptr;
-    const float *dleg = nullptr, *dphasetab = nullptr, *dphasewtp = nullptr, *phasewtp = nullptr;
-    const int *diphasep = nullptr, *iphasep = nullptr;
-    const float *extinctp = nullptr, *albedop = nullptr;
-    // transposed direct-beam path lists (CSR by property point): GRADOUT(ib) -= DEXTM*sum(DPATH*BW)
-    const int *dbt_rowptr = nullptr;   // [maxpg+1]
-    const int *dbt_col = nullptr;      // RTE grid point (1-based)
-    const float *dbt_val = nullptr;    // DPATH
-    long long dbt_nnz = 0;
-};
-
 struct at3d_state {
     DevState S;
-    GradDev G;
+    DevGrad G;
+    int grad_attached = 0;
     std::vector<void *> owned;      // device allocations freed at destroy
+    std::vector<void *> grad_owned; // derivative tables (replaced by every attach_gradient)
     size_t bytes = 0;
     int device = 0;
     // reusable per-call buffers
-    DevBuf rays, out, trace, misc, slabs, err;
+    DevBuf rays, out, trace, misc, slabs, err, pix, work;
+    RayGeom geom;                   // host copy of the per-ray setup constants
+    std::vector<RayPack> packs_h;   // host staging of the per-ray packs
     float *bcrad_dev = nullptr;
+    unsigned long long *counts_dev = nullptr;
     int nbcrad = 0;
 };
 
 size_t render_smem_bytes(const DevState &S);
 cudaError_t launch_render(const DevState &S, int nrays, const float *camx, const float *camy,
                           const float *camz, const double *cammu, const double *camphi,
-                          float *out_f32, double *out_f64, int mode,
+                          const RayPack *packs, float *out_f32, double *out_f64, int mode,
                           int correctinterpolate, int singlescatter, int nosurface, int maxsub,
                           int *trace_cells, int trace_cap, int *trace_n, int *trace_nsub,
                           RayErr *err, cudaStream_t stream);

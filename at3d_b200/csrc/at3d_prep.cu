@@ -1,0 +1,586 @@
+// at3d_prep.cu -- per-evaluation input preparation of the gradient on the device (sm_100a):
+//   at3d_prepare_deriv_interps   PREPARE_DERIV_INTERPS / COMPUTE_INTERP_WEIGHTS (src/polarized/shdomsub4.f:2917-3169)
+//   at3d_make_direct             MAKE_DIRECT / DIRECT_BEAM_PROP (shdomsub2.f:393-478, shdom90.f90:352-867)
+//   at3d_make_direct_derivative  MAKE_DIRECT_DERIVATIVE / DIRECT_BEAM_AND_PATHS_PROP (src/shdomsub5.f:1553-2004)
+// These run once per cost-function evaluation (StateGenerator rebuilds the solvers, medium.py:1813-1831).
+// All three are embarrassingly parallel over grid points / property points: one thread each.
+#include <cstdio>
+#include <cstring>
+#include <cstdarg>
+#include <cmath>
+#include <vector>
+#include "at3d_host.h"
+
+static void set_msg(char *errmsg, const char *fmt, ...)
+{
+    if (!errmsg) return;
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(errmsg, AT3D_ERRMSG_LEN, fmt, ap);
+    va_end(ap);
+}
+
+namespace {
+struct Arena {      // device allocations of one call
+    std::vector<void *> p;
+    ~Arena() { for (void *q : p) cudaFree(q); }
+    template <typename T> T *alloc(size_t n)
+    {
+        void *q = nullptr;
+        if (cudaMalloc(&q, (n ? n : 1) * sizeof(T)) != cudaSuccess) return nullptr;
+        p.push_back(q);
+        return (T *)q;
+    }
+    template <typename T> const T *up(const T *h, size_t n)
+    {
+        if (!h) return nullptr;
+        T *d = alloc<T>(n);
+        if (!d) return nullptr;
+        if (cudaMemcpy(d, h, n * sizeof(T), cudaMemcpyHostToDevice) != cudaSuccess) return nullptr;
+        return d;
+    }
+};
+}
+
+// ------------------------------------------------------------------------------------------
+// PREPARE_DERIV_INTERPS
+// ------------------------------------------------------------------------------------------
+struct InterpGeom { int npx, npy, npz; float delx, dely, xstart, ystart; };
+
+// COMPUTE_INTERP_WEIGHTS (shdomsub4.f:3082-3169), one thread per RTE grid point
+__global__ void interp_weights_kernel(int npts, InterpGeom g, const float *gridpos, const float *zlevels,
+                                      int *interpptr, float *optinterpwt, int *bad)
+{
+    const int ip = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ip >= npts) return;
+    const float x = gridpos[3 * (size_t)ip], y = gridpos[3 * (size_t)ip + 1], z = gridpos[3 * (size_t)ip + 2];
+    int il = 0, iu = g.npz, im;
+    while (iu - il > 1) { im = (iu + il) / 2; if (z >= zlevels[im - 1]) il = im; else iu = im; }
+    const int iz = il > 1 ? il : 1;
+    double w = (double)(z - zlevels[iz - 1]) / (zlevels[iz] - zlevels[iz - 1]);
+    w = fmax(fmin(w, 1.0), 0.0);
+    int ix = (int)((x - g.xstart) / g.delx) + 1;
+    if (fabsf(x - g.xstart - g.npx * g.delx) < 0.01f * g.delx) ix = g.npx;
+    if (ix < 1 || ix > g.npx) { atomicCAS(bad, 0, 2 * (ip + 1)); return; }
+    const int ixp = (ix % g.npx) + 1;
+    double u = (double)(x - g.xstart - g.delx * (ix - 1)) / g.delx;
+    u = fmax(fmin(u, 1.0), 0.0);
+    if (u < 1.0e-5) u = 0.0;
+    if (u > 1.0 - 1.0e-5) u = 1.0;
+    int iy = (int)((y - g.ystart) / g.dely) + 1;
+    if (fabsf(y - g.ystart - g.npy * g.dely) < 0.01f * g.dely) iy = g.npy;
+    if (iy < 1 || iy > g.npy) { atomicCAS(bad, 0, 2 * (ip + 1) + 1); return; }
+    const int iyp = (iy % g.npy) + 1;
+    double v = (double)(y - g.ystart - g.dely * (iy - 1)) / g.dely;
+    v = fmax(fmin(v, 1.0), 0.0);
+    if (v < 1.0e-5) v = 0.0;
+    if (v > 1.0 - 1.0e-5) v = 1.0;
+    float *wt = optinterpwt + 8 * (size_t)ip;
+    int *pt = interpptr + 8 * (size_t)ip;
+    wt[0] = (float)((1 - u) * (1 - v) * (1 - w));
+    wt[1] = (float)(u * (1 - v) * (1 - w));
+    wt[2] = (float)((1 - u) * v * (1 - w));
+    wt[3] = (float)(u * v * (1 - w));
+    wt[4] = (float)((1 - u) * (1 - v) * w);
+    wt[5] = (float)(u * (1 - v) * w);
+    wt[6] = (float)((1 - u) * v * w);
+    wt[7] = (float)(u * v * w);
+    const int i1 = iz + g.npz * (iy - 1) + g.npz * g.npy * (ix - 1);
+    const int i2 = iz + g.npz * (iy - 1) + g.npz * g.npy * (ixp - 1);
+    const int i3 = iz + g.npz * (iyp - 1) + g.npz * g.npy * (ix - 1);
+    const int i4 = iz + g.npz * (iyp - 1) + g.npz * g.npy * (ixp - 1);
+    pt[0] = i1; pt[1] = i2; pt[2] = i3; pt[3] = i4;
+    pt[4] = i1 + 1; pt[5] = i2 + 1; pt[6] = i3 + 1; pt[7] = i4 + 1;
+}
+
+struct PdiArgs {
+    int npts, maxpg, numder, ml, nstleg, nleg, pmaxnmicro, dmaxnmicro, nq, deltam, interp_new;
+    float phasemax;
+    const int *partder, *doexact, *iphasep, *diphasep, *iphase, *interpptr;
+    const float *legen, *dleg, *phasewtp, *dphasewtp, *albedop, *extinctp, *dext, *dalb, *albedo, *phaseinterpwt;
+    float *fp, *dfp, *dextm, *dalbm, *dfj;
+};
+
+// delta-M scaled extinction derivative on the property grid (shdomsub4.f:2994-3025)
+__global__ void pdi_property_kernel(PdiArgs a)
+{
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (size_t)a.maxpg * a.numder) return;
+    const int ib = (int)(t % a.maxpg), idr = (int)(t / a.maxpg);
+    const int ipa = a.partder[idr] - 1;
+    const int nlt = a.nstleg * (a.nleg + 1);
+    float fp = 0.0f, dfp = 0.0f;
+    const float albp = a.albedop[ib + (size_t)a.maxpg * ipa], extp = a.extinctp[ib + (size_t)a.maxpg * ipa];
+    const float dext = a.dext[t], dalb = a.dalb[t];
+    if (a.deltam) {
+        for (int q = 0; q < a.dmaxnmicro; q++) {
+            const float pwp = a.phasewtp[q + (size_t)a.pmaxnmicro * (ib + (size_t)a.maxpg * ipa)];
+            const int iphp = a.iphasep[q + (size_t)a.pmaxnmicro * (ib + (size_t)a.maxpg * ipa)];
+            fp = fp + pwp * a.legen[(size_t)nlt * (iphp - 1) + a.nstleg * (a.ml + 1)];
+            if (a.doexact[idr] == 1) {
+                const int dip = a.diphasep[q + (size_t)a.dmaxnmicro * (ib + (size_t)a.maxpg * idr)];
+                dfp = dfp + pwp * a.dleg[(size_t)nlt * (dip - 1) + a.nstleg * (a.ml + 1)];
+            } else if (a.doexact[idr] == 0) {
+                const float dpw = a.dphasewtp[q + (size_t)a.dmaxnmicro * (ib + (size_t)a.maxpg * idr)];
+                dfp = dfp + dpw * a.legen[(size_t)nlt * (iphp - 1) + a.nstleg * (a.ml + 1)];
+            }
+        }
+    }
+    a.fp[t] = fp; a.dfp[t] = dfp;
+    a.dextm[t] = dext * (1 - fp * albp) - dalb * fp * extp - extp * albp * dfp;
+}
+
+// delta-M scaled albedo / truncation-fraction derivatives per RTE point and property corner (:3027-3076)
+__global__ void pdi_point_kernel(PdiArgs a)
+{
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (size_t)a.npts * a.numder) return;
+    const int ip = (int)(t % a.npts), idr = (int)(t / a.npts);
+    const int ipa = a.partder[idr] - 1;
+    const int nlt = a.nstleg * (a.nleg + 1);
+    const int *iph = a.iphase + (size_t)a.nq * (ip + (size_t)a.npts * ipa);
+    const float *pw = a.phaseinterpwt + (size_t)a.nq * (ip + (size_t)a.npts * ipa);
+    const float alb = a.albedo[ip + (size_t)a.npts * ipa];
+    float f = 0.0f, albedoj;
+    if (a.deltam) {
+        if (!a.interp_new || pw[0] >= a.phasemax) f = a.legen[(size_t)nlt * (iph[0] - 1) + a.nstleg * (a.ml + 1)];
+        else
+            for (int q = 0; q < a.nq; q++) {
+                if (pw[q] < 1e-7f) continue;
+                f = f + pw[q] * a.legen[(size_t)nlt * (iph[q] - 1) + a.nstleg * (a.ml + 1)];
+            }
+        albedoj = alb / (f * (alb - 1) + 1);
+    } else albedoj = alb;
+    const float divide = 1.0f / (1.0f - albedoj * f);
+    for (int nb = 0; nb < 8; nb++) {
+        const int ib = a.interpptr[nb + 8 * (size_t)ip] - 1;
+        const float albp = a.albedop[ib + (size_t)a.maxpg * ipa], extp = a.extinctp[ib + (size_t)a.maxpg * ipa];
+        const float dext = a.dext[ib + (size_t)a.maxpg * idr], dalb = a.dalb[ib + (size_t)a.maxpg * idr];
+        const float fp = a.fp[ib + (size_t)a.maxpg * idr], dfp = a.dfp[ib + (size_t)a.maxpg * idr];
+        a.dalbm[nb + 8 * ((size_t)ip + (size_t)a.npts * idr)] = divide * (
+            dext * ((1 - f) * (albp - albedoj) + (albedoj - 1) * albp * (fp - f))
+            + dalb * ((1 - f) * extp + (albedoj - 1) * extp * (fp - f))
+            + dfp * (albedoj - 1) * extp * albp);
+        a.dfj[nb + 8 * ((size_t)ip + (size_t)a.npts * idr)] =
+            (dext * (fp - f) * albp + dalb * (fp - f) * extp + dfp * extp * albp) / (1 - f);
+    }
+}
+
+extern "C" int at3d_prepare_deriv_interps(const at3d_state_desc *d, int npx, int npy, int npz, int maxpg,
+                                          float delx, float dely, float xstart, float ystart,
+                                          const float *zlevels, const at3d_grad_desc *g,
+                                          float *optinterpwt, int32_t *interpptr,
+                                          float *dalbm, float *dextm, float *dfj, char *errmsg)
+{
+    if (errmsg) errmsg[0] = 0;
+    if (!d || !g || !zlevels || !optinterpwt || !interpptr || !dalbm || !dextm || !dfj) { set_msg(errmsg, "null argument"); return 1; }
+    if (at3d_device_count() < 1) { set_msg(errmsg, "no CUDA device: at3d_b200 has no CPU fallback"); return 4; }
+    Arena A;
+    const size_t npts = d->npts, nd = g->numder, mp = maxpg;
+    const size_t nlt = (size_t)d->nstleg * (d->nleg + 1);
+    const int nq = 8 * d->maxnmicro;
+    PdiArgs a;
+    memset(&a, 0, sizeof(a));
+    a.npts = d->npts; a.maxpg = maxpg; a.numder = g->numder; a.ml = d->ml; a.nstleg = d->nstleg; a.nleg = d->nleg;
+    a.pmaxnmicro = d->maxnmicro; a.dmaxnmicro = g->deriv_maxnmicro; a.nq = nq; a.deltam = d->deltam;
+    a.interp_new = d->interp_new; a.phasemax = d->phasemax;
+    const float *gridpos = A.up(d->gridpos, 3 * npts);
+    const float *zl = A.up(zlevels, (size_t)npz);
+    a.partder = A.up(g->partder, nd); a.doexact = A.up(g->doexact, nd);
+    a.iphasep = A.up(g->iphasep, (size_t)d->maxnmicro * mp * d->npart);
+    a.phasewtp = A.up(g->phasewtp, (size_t)d->maxnmicro * mp * d->npart);
+    a.diphasep = A.up(g->diphasep, (size_t)g->deriv_maxnmicro * mp * nd);
+    a.dphasewtp = A.up(g->dphasewtp, (size_t)g->deriv_maxnmicro * mp * nd);
+    a.iphase = A.up(d->iphase, (size_t)nq * npts * d->npart);
+    a.phaseinterpwt = A.up(d->phaseinterpwt, (size_t)nq * npts * d->npart);
+    a.legen = A.up(d->legen, nlt * d->numphase);
+    a.dleg = A.up(g->dleg, nlt * g->dnumphase);
+    a.albedop = A.up(g->albedop, mp * d->npart); a.extinctp = A.up(g->extinctp, mp * d->npart);
+    a.dext = A.up(g->dext, mp * nd); a.dalb = A.up(g->dalb, mp * nd);
+    a.albedo = A.up(d->albedo, npts * d->npart);
+    int *iptr_d = A.alloc<int>(8 * npts); float *wt_d = A.alloc<float>(8 * npts);
+    a.fp = A.alloc<float>(mp * nd); a.dfp = A.alloc<float>(mp * nd); a.dextm = A.alloc<float>(mp * nd);
+    a.dalbm = A.alloc<float>(8 * npts * nd); a.dfj = A.alloc<float>(8 * npts * nd);
+    int *bad = A.alloc<int>(1);
+    if (!gridpos || !zl || !a.partder || !a.doexact || !a.iphasep || !a.phasewtp || !a.diphasep || !a.dphasewtp ||
+        !a.iphase || !a.phaseinterpwt || !a.legen || !a.dleg || !a.albedop || !a.extinctp || !a.dext || !a.dalb ||
+        !a.albedo || !iptr_d || !wt_d || !a.fp || !a.dfp || !a.dextm || !a.dalbm || !a.dfj || !bad) {
+        set_msg(errmsg, "at3d_prepare_deriv_interps: NULL input array or device allocation failure");
+        return 4;
+    }
+    a.interpptr = iptr_d;
+    if (g->deriv_maxnmicro > d->maxnmicro) { set_msg(errmsg, "DERIV_MAXNMICRO > MAXNMICRO is not supported"); return 3; }
+    cudaMemset(bad, 0, sizeof(int));
+    InterpGeom ig = {npx, npy, npz, delx, dely, xstart, ystart};
+    interp_weights_kernel<<<(unsigned)((npts + 127) / 128), 128>>>((int)npts, ig, gridpos, zl, iptr_d, wt_d, bad);
+    int hbad = 0;
+    if (cudaMemcpy(&hbad, bad, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) { set_msg(errmsg, "CUDA error in interp_weights_kernel"); return 4; }
+    if (hbad) { set_msg(errmsg, "TRILIN: Beyond %s domain (grid point %d)", (hbad & 1) ? "Y" : "X", hbad / 2); return 1; }
+    pdi_property_kernel<<<(unsigned)((mp * nd + 127) / 128), 128>>>(a);
+    pdi_point_kernel<<<(unsigned)((npts * nd + 127) / 128), 128>>>(a);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpy(optinterpwt, wt_d, 8 * npts * sizeof(float), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(interpptr, iptr_d, 8 * npts * sizeof(int), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(dextm, a.dextm, mp * nd * sizeof(float), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(dalbm, a.dalbm, 8 * npts * nd * sizeof(float), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(dfj, a.dfj, 8 * npts * nd * sizeof(float), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) { set_msg(errmsg, "CUDA error %s in at3d_prepare_deriv_interps", cudaGetErrorString(e)); return 4; }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Direct beam on the property grid
+// ------------------------------------------------------------------------------------------
+struct BeamGeom {
+    int bcflag, npx, npy, npz, ipdirect, di, dj, dk;
+    double cx, cy, cz, cxinv, cyinv, czinv, epss, epsz, xdomain, ydomain, delxd, delyd;
+    float xstart, ystart;
+};
+
+#define BT(x, b) ((((int)(x)) >> (b)) & 1)
+
+// One walk from a grid point toward the sun through the property grid (shdom90.f90:563-867 with the
+// closed-form trilinear path integrals; shdomsub5.f:1646-2003 for the recorded DPATH/DPTR variant).
+// Returns 0 or an error code (1 beyond X, 2 beyond Y, 3 beyond grid, 4 SO<0, 5 list overflow).
+template <bool PATHS>
+__device__ int beam_walk(const BeamGeom &g, const float *zl, float xi, float yi, float zi,
+                         const float *extdirp, double &path, int &npp,
+                         float *dpath, int *dptr, int longest_path_pts)
+{
+    const int npx = g.npx, npy = g.npy, npz = g.npz, bcflag = g.bcflag;
+    const double cx = g.cx, cy = g.cy, cz = g.cz, delxd = g.delxd, delyd = g.delyd;
+    double x, y, z, xe, ye, ze, xp, yp, zp, x0, x1, y0, y1, z0, z1, so, sox, soy, soz;
+    int il, iu, im, i, j, k, ip, jp, idp = 0;
+    path = 0.0; npp = 0;
+    z = zi; x = xi - g.xstart; y = yi - g.ystart;
+    il = 0; iu = npz;
+    while (iu - il > 1) { im = (iu + il) / 2; if (z >= zl[im - 1]) il = im; else iu = im; }
+    k = il > 1 ? il : 1;
+    i = (int)(x / delxd) + 1;
+    if (i > npx && fabs(x - g.xdomain) < 0.001f * delxd) i = npx;
+    if (i < 1 || i > npx) return 1;
+    j = (int)(y / delyd) + 1;
+    if (j > npy && fabs(y - g.ydomain) < 0.001f * delyd) j = npy;
+    if (j < 1 || j > npy) return 2;
+    xe = x; ye = y; ze = z;
+    xp = xe; yp = ye; zp = ze;
+    bool constx = BT(g.ipdirect, 0), consty = BT(g.ipdirect, 1);
+    if (cx == 0.0) constx = true;
+    if (cy == 0.0) consty = true;
+    if (BT(bcflag, 0) && (fabs(x) < 0.01f * delxd || fabs(x - (npx - 1) * delxd) < 0.01f * delxd)) constx = true;
+    if (BT(bcflag, 1) && (fabs(y) < 0.01f * delyd || fabs(y - (npy - 1) * delyd) < 0.01f * delyd)) consty = true;
+    bool hitboundary = false;
+    if (BT(bcflag, 2)) {
+        if (cx > 0.0 && fabs(x - g.xdomain) < 0.001f * delxd) hitboundary = true;
+        else if (cx < 0.0 && fabs(x) < 0.001f * delxd) hitboundary = true;
+    }
+    if (BT(bcflag, 3)) {
+        if (cy > 0.0 && fabs(y - g.ydomain) < 0.001f * delyd) hitboundary = true;
+        if (cy < 0.0 && fabs(y) < 0.001f * delyd) hitboundary = true;
+    }
+    while (!hitboundary && fabs(ze - zl[npz - 1]) > g.epsz) {
+        ip = i + 1;
+        if (i == npx) ip = (BT(bcflag, 0) || BT(bcflag, 2)) ? npx : 1;
+        jp = j + 1;
+        if (j == npy) jp = (BT(bcflag, 1) || BT(bcflag, 3)) ? npy : 1;
+        x0 = delxd * (i - 1); x1 = x0 + delxd;
+        y0 = delyd * (j - 1); y1 = y0 + delyd;
+        if (i < 1 || i > npx || j < 1 || j > npy || k < 1 || k >= npz) return 3;
+        z0 = zl[k - 1]; z1 = zl[k];
+        const int i1 = k + npz * (j - 1) + npz * npy * (i - 1);
+        const int i2 = k + npz * (j - 1) + npz * npy * (ip - 1);
+        const int i3 = k + npz * (jp - 1) + npz * npy * (i - 1);
+        const int i4 = k + npz * (jp - 1) + npz * npy * (ip - 1);
+        if (constx) sox = 1.0e30f;
+        else if (cx > 0.0) { sox = (x1 - xe) * g.cxinv; xp = x1; }
+        else { sox = (x0 - xe) * g.cxinv; xp = x0; }
+        if (consty) soy = 1.0e30f;
+        else if (cy > 0.0) { soy = (y1 - ye) * g.cyinv; yp = y1; }
+        else { soy = (y0 - ye) * g.cyinv; yp = y0; }
+        if (cz > 0.0) { soz = (z1 - ze) * g.czinv; zp = z1; }
+        else if (cz < 0.0) { soz = (z0 - ze) * g.czinv; zp = z0; }
+        else soz = 1.0e30f;
+        double xoffs = 0.0, yoffs = 0.0;
+        if (soz <= sox && soz <= soy) {
+            so = soz;
+            if (!constx) xp = xe + so * cx;
+            if (!consty) yp = ye + so * cy;
+            k = k + g.dk;
+        } else if (sox <= soy) {
+            so = sox;
+            if (!consty) yp = ye + so * cy;
+            zp = ze + so * cz;
+            i = i + g.di;
+            if (i == 0) {
+                if (BT(bcflag, 0)) { i = 1; constx = true; }
+                else if (BT(bcflag, 2)) hitboundary = true;
+                else { i = npx; xoffs = g.xdomain; }
+            } else if (i >= npx && BT(bcflag, 2)) {
+                hitboundary = true;
+            } else if (i == npx + 1) {
+                if (BT(bcflag, 0)) { i = npx; constx = true; }
+                else { i = 1; xoffs = -g.xdomain; }
+            }
+        } else {
+            so = soy;
+            if (!constx) xp = xe + so * cx;
+            zp = ze + so * cz;
+            j = j + g.dj;
+            if (j == 0) {
+                if (BT(bcflag, 1)) { j = 1; consty = true; }
+                else if (BT(bcflag, 3)) hitboundary = true;
+                else { j = npy; yoffs = g.ydomain; }
+            } else if (j >= npy && BT(bcflag, 3)) {
+                hitboundary = true;
+            } else if (j == npy + 1) {
+                if (BT(bcflag, 1)) { j = npy; consty = true; }
+                else { j = 1; yoffs = -g.ydomain; }
+            }
+        }
+        if (so < -g.epss) return 4;
+        so = fmax(so, 0.0);
+        const double ax = 1.0 / (x1 - x0), ay = 1.0 / (y1 - y0), az = 1.0 / (z1 - z0);
+        const double u0 = (xe - x0) * ax, v0 = (ye - y0) * ay, w0 = (ze - z0) * az;
+        const double u1 = (xp - x0) * ax, v1 = (yp - y0) * ay, w1 = (zp - z0) * az;
+        const double u0m = 1.0f - u0, v0m = 1.0f - v0, w0m = 1.0f - w0;
+        const double du = u1 - u0, dv = v1 - v0, dw = w1 - w0;
+        const double uv = u0 * v0, umv = u0m * v0, uvm = u0 * v0m, umvm = u0m * v0m;
+        const double uw = u0 * w0, umw = u0m * w0, uwm = u0 * w0m, umwm = u0m * w0m;
+        const double vw = v0 * w0, vmw = v0m * w0, vwm = v0 * w0m, vmwm = v0m * w0m;
+        const double b1 = -du * vmwm - dv * umwm - dw * umvm;
+        const double b2 = du * vmwm - dv * uwm - dw * uvm;
+        const double b3 = -du * vwm + dv * umwm - dw * umv;
+        const double b4 = du * vwm + dv * uwm - dw * uv;
+        const double b5 = -du * vmw - dv * umw + dw * umvm;
+        const double b6 = du * vmw - dv * uw + dw * uvm;
+        const double b7 = -du * vw + dv * umw + dw * umv;
+        const double b8 = du * vw + dv * uw + dw * uv;
+        const double vw2 = dv * dw, vwu = vw2 * u0, vwum = vw2 * u0m;
+        const double uw2 = du * dw, uwv = uw2 * v0, uwvm = uw2 * v0m;
+        const double uv2 = du * dv, uvw = uv2 * w0, uvwm = uv2 * w0m;
+        const double c1 = +vwum + uwvm + uvwm, c2 = +vwu - uwvm - uvwm;
+        const double c3 = -vwum + uwv - uvwm, c4 = -vwu - uwv + uvwm;
+        const double c5 = -vwum - uwvm + uvw, c6 = -vwu + uwvm - uvw;
+        const double c7 = +vwum - uwv - uvw, c8 = +vwu + uwv + uvw;
+        if (!PATHS) {
+            const double e1 = extdirp[i1 - 1], e2 = extdirp[i2 - 1], e3 = extdirp[i3 - 1], e4 = extdirp[i4 - 1];
+            const double e5 = extdirp[i1], e6 = extdirp[i2], e7 = extdirp[i3], e8 = extdirp[i4];
+            const double a = (e1 * u0m + e2 * u0) * vmwm + (e3 * u0m + e4 * u0) * vwm
+                           + (e5 * u0m + e6 * u0) * vmw + (e7 * u0m + e8 * u0) * vw;
+            const double b = b1 * e1 + b2 * e2 + b3 * e3 + b4 * e4 + b5 * e5 + b6 * e6 + b7 * e7 + b8 * e8;
+            const double c = c1 * e1 + c2 * e2 + c3 * e3 + c4 * e4 + c5 * e5 + c6 * e6 + c7 * e7 + c8 * e8;
+            const double dd = du * dv * dw * (e2 + e3 + e5 + e8 - e1 - e4 - e6 - e7);
+            path = path + so * (a + 0.5 * b + 0.3333333333333333 * c + 0.25 * dd);
+            npp += 8;
+        } else {
+            const double a1 = u0m * vmwm, a2 = u0 * vmwm, a3 = u0m * vwm, a4 = u0 * vwm;
+            const double a5 = u0m * vmw, a6 = u0 * vmw, a7 = u0m * vw, a8 = u0 * vw;
+            if (idp + 8 > longest_path_pts) return 5;
+            const double q = 0.25 * du * dv * dw;
+            dpath[idp + 0] = (float)(so * (a1 + 0.5 * b1 + 0.3333333333333333 * c1 - q));
+            dpath[idp + 1] = (float)(so * (a2 + 0.5 * b2 + 0.3333333333333333 * c2 + q));
+            dpath[idp + 2] = (float)(so * (a3 + 0.5 * b3 + 0.3333333333333333 * c3 + q));
+            dpath[idp + 3] = (float)(so * (a4 + 0.5 * b4 + 0.3333333333333333 * c4 - q));
+            dpath[idp + 4] = (float)(so * (a5 + 0.5 * b5 + 0.3333333333333333 * c5 + q));
+            dpath[idp + 5] = (float)(so * (a6 + 0.5 * b6 + 0.3333333333333333 * c6 - q));
+            dpath[idp + 6] = (float)(so * (a7 + 0.5 * b7 + 0.3333333333333333 * c7 - q));
+            dpath[idp + 7] = (float)(so * (a8 + 0.5 * b8 + 0.3333333333333333 * c8 + q));
+            dptr[idp + 0] = i1; dptr[idp + 1] = i2; dptr[idp + 2] = i3; dptr[idp + 3] = i4;
+            dptr[idp + 4] = i1 + 1; dptr[idp + 5] = i2 + 1; dptr[idp + 6] = i3 + 1; dptr[idp + 7] = i4 + 1;
+            idp += 8;
+        }
+        xe = xp + xoffs; ye = yp + yoffs; ze = zp;
+    }
+    return 0;
+}
+
+// delta-M scaled property-grid extinction EXTDIRP (DIRECT_BEAM_PROP INIT=1, shdom90.f90:453-483)
+__global__ void extdirp_kernel(int maxpg, int npz, int npart, int pmaxnmicro, int deltam, int ml, int nstleg,
+                               int nlegp, const float *extinctp, const float *albedop, const float *legenp,
+                               const int *iphasep, const float *phasewtp, const float *gasext, float *extdirp)
+{
+    const int ib = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ib >= maxpg) return;
+    const int iz = ib % npz;
+    float acc = 0.0f;
+    for (int ipa = 0; ipa < npart; ipa++) {
+        double extinct = extinctp[ib + (size_t)maxpg * ipa];
+        double albedo = albedop[ib + (size_t)maxpg * ipa];
+        if (gasext[iz] > 0.0f) {
+            albedo = albedo * extinct / (extinct + gasext[iz]);
+            extinct = extinct + gasext[iz];
+        }
+        if (deltam) {
+            const int l = ml + 1;
+            double f = 0.0;
+            for (int q = 0; q < pmaxnmicro; q++) {
+                const int iph = iphasep[q + (size_t)pmaxnmicro * (ib + (size_t)maxpg * ipa)];
+                const float pw = phasewtp[q + (size_t)pmaxnmicro * (ib + (size_t)maxpg * ipa)];
+                f = f + pw * legenp[nstleg * (l + (size_t)(nlegp + 1) * (iph - 1))] / (2 * l + 1);
+            }
+            extinct = (1.0f - albedo * f) * extinct;
+        }
+        acc = (float)(acc + extinct);
+    }
+    extdirp[ib] = acc;
+}
+
+__global__ void make_direct_kernel(int npts, BeamGeom g, const float *zl, const float *gridpos,
+                                   const float *extdirp, float solarflux, float *dirflux, int *longest, int *bad)
+{
+    const int ip = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ip >= npts) return;
+    double path; int npp;
+    const int e = beam_walk<false>(g, zl, gridpos[3 * (size_t)ip], gridpos[3 * (size_t)ip + 1],
+                                   gridpos[3 * (size_t)ip + 2], extdirp, path, npp, nullptr, nullptr, 0);
+    if (e) { atomicCAS(bad, 0, 8 * (ip + 1) + e); return; }
+    dirflux[ip] = (float)(solarflux * exp(-path));
+    atomicMax(longest, npp);
+}
+
+__global__ void make_direct_derivative_kernel(int npts, BeamGeom g, const float *zl, const float *gridpos,
+                                              float *dpath, int *dptr, int longest_path_pts, int *bad)
+{
+    const int ip = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ip >= npts) return;
+    double path; int npp;
+    const int e = beam_walk<true>(g, zl, gridpos[3 * (size_t)ip], gridpos[3 * (size_t)ip + 1],
+                                  gridpos[3 * (size_t)ip + 2], nullptr, path, npp,
+                                  dpath + (size_t)longest_path_pts * ip, dptr + (size_t)longest_path_pts * ip,
+                                  longest_path_pts);
+    if (e) atomicCAS(bad, 0, 8 * (ip + 1) + e);
+}
+
+static int beam_error(int code, const char *who, char *errmsg)
+{
+    static const char *txt[] = {"", "Beyond X domain", "Beyond Y domain", "beyond grid!", "SO<0",
+                                "Max number of property points to pass exceeded"};
+    const int e = code & 7;
+    set_msg(errmsg, "%s: %s (grid point %d)", who, txt[e < 6 ? e : 0], code / 8);
+    return 1;
+}
+
+extern "C" int at3d_make_direct(int npts, int bcflag, int ipflag, int deltam, int ml, int nstleg, int nlegp,
+                                float solarflux, float solarmu, float solaraz, const float *gridpos,
+                                int npx, int npy, int npz, float delx, float dely, float xstart, float ystart,
+                                const float *zlevels, const float *extinctp, const float *albedop,
+                                const float *legenp, int numphase, const int32_t *iphasep, const float *phasewtp,
+                                int maxnmicro, int npart, int nzckd, const float *zckd, const float *gasabs,
+                                float *extdirp, float *dirflux, double *out_d, int32_t *out_i, char *errmsg)
+{
+    if (errmsg) errmsg[0] = 0;
+    if (!gridpos || !zlevels || !extinctp || !albedop || !legenp || !iphasep || !phasewtp || !extdirp || !dirflux ||
+        !out_d || !out_i) { set_msg(errmsg, "null argument"); return 1; }
+    if (at3d_device_count() < 1) { set_msg(errmsg, "no CUDA device: at3d_b200 has no CPU fallback"); return 4; }
+    const int maxpg = npx * npy * npz;
+    // gas extinction per property level (shdom90.f90:425-451), host side: NPZ values
+    std::vector<float> gasext(npz, 0.0f);
+    for (int iz = 1; iz <= npz && nzckd > 0; iz++) {
+        int il = 1, iu = nzckd, im;
+        while (iu - il > 1) { im = (iu + il) / 2; if (zlevels[iz - 1] <= zckd[im - 1]) il = im; else iu = im; }
+        int i = il > 1 ? il : 1;
+        if (i > nzckd - 1) i = nzckd - 1;
+        double w0 = (zlevels[iz - 1] - zckd[i - 1]) / (zckd[i] - zckd[i - 1]);
+        w0 = fmin(fmax(w0, 0.0), 1.0);
+        gasext[iz - 1] = (float)((1.0f - w0) * gasabs[i - 1] + w0 * gasabs[i]);
+    }
+    // beam geometry constants (shdom90.f90:485-560): a handful of scalars, host libm like the reference
+    BeamGeom g;
+    g.bcflag = bcflag; g.npx = npx; g.npy = npy; g.npz = npz; g.xstart = xstart; g.ystart = ystart;
+    g.ipdirect = ipflag;
+    if (BT(ipflag, 2)) g.ipdirect = 0;
+    const double sunmu = -solarmu, sunaz = solaraz + acosf(-1.0f);
+    g.cx = sqrt(1.0f - sunmu * sunmu) * cos(sunaz);
+    g.cy = sqrt(1.0f - sunmu * sunmu) * sin(sunaz);
+    g.cz = fabs(sunmu);
+    if (fabs(g.cx) > 1.0e-6f) g.cxinv = 1.0 / g.cx; else { g.cx = 0.0; g.cxinv = 1.0e20f; }
+    if (fabs(g.cy) > 1.0e-6f) g.cyinv = 1.0 / g.cy; else { g.cy = 0.0; g.cyinv = 1.0e20f; }
+    if (fabs(g.cz) > 1.0e-6f) g.czinv = 1.0 / g.cz; else { g.cz = 0.0; g.czinv = 1.0e20f; }
+    g.di = std::signbit(g.cx) ? -1 : 1;
+    g.dj = std::signbit(g.cy) ? -1 : 1;
+    g.dk = std::signbit(g.cz) ? -1 : 1;
+    const double epsz = 1.0e-6f * (zlevels[npz - 1] - zlevels[0]);
+    double epss = 1.0e-3f * (zlevels[npz - 1] - zlevels[0]) / npz;
+    if (!BT(g.ipdirect, 0)) epss = fmax(epss, 1.0e-4 * delx);
+    if (!BT(g.ipdirect, 1)) epss = fmax(epss, 1.0e-4 * dely);
+    g.delxd = (double)delx; g.delyd = (double)dely;
+    epss = fmax(fmax(0.001f * g.delxd, 0.001f * g.delyd), epss);
+    g.epss = epss; g.epsz = epsz;
+    g.xdomain = g.delxd * npx;
+    if (BT(bcflag, 2)) g.xdomain = g.delxd * (npx - 1);
+    g.ydomain = g.delyd * npy;
+    if (BT(bcflag, 3)) g.ydomain = g.delyd * (npy - 1);
+    // UNIFORMZLEV (shdom90.f90:520-548): level above which the medium is horizontally uniform
+    double uniformzlev;
+    {
+        std::vector<float> emin(npz, 1.0e20f), emax(npz, 0.0f);
+        for (int ib = 0; ib < maxpg; ib++) {
+            float s = 0.0f;
+            for (int ipa = 0; ipa < npart; ipa++) s = s + extinctp[ib + (size_t)maxpg * ipa];
+            const int iz = ib % npz;
+            emin[iz] = fminf(s, emin[iz]); emax[iz] = fmaxf(s, emax[iz]);
+        }
+        int jz = 0;
+        for (int iz = 1; iz <= npz; iz++) if (emax[iz - 1] - emin[iz - 1] > 1.0e-4f) jz = iz;
+        jz = jz + 1 < npz ? jz + 1 : npz;
+        uniformzlev = zlevels[jz - 1];
+    }
+    Arena A;
+    const float *gp = A.up(gridpos, 3 * (size_t)npts), *zl = A.up(zlevels, (size_t)npz);
+    const float *ex = A.up(extinctp, (size_t)maxpg * npart), *al = A.up(albedop, (size_t)maxpg * npart);
+    const float *lg = A.up(legenp, (size_t)nstleg * (nlegp + 1) * numphase);
+    const int *iq = A.up(iphasep, (size_t)maxnmicro * maxpg * npart);
+    const float *pw = A.up(phasewtp, (size_t)maxnmicro * maxpg * npart);
+    const float *ge = A.up(gasext.data(), (size_t)npz);
+    float *ed = A.alloc<float>(maxpg), *df = A.alloc<float>(npts);
+    int *flags = A.alloc<int>(2);
+    if (!gp || !zl || !ex || !al || !lg || !iq || !pw || !ge || !ed || !df || !flags) { set_msg(errmsg, "at3d_make_direct: device allocation failure"); return 4; }
+    cudaMemset(flags, 0, 2 * sizeof(int));
+    extdirp_kernel<<<(maxpg + 127) / 128, 128>>>(maxpg, npz, npart, maxnmicro, deltam, ml, nstleg, nlegp, ex, al, lg, iq, pw, ge, ed);
+    make_direct_kernel<<<(npts + 127) / 128, 128>>>(npts, g, zl, gp, ed, solarflux, df, flags, flags + 1);
+    int hf[2] = {0, 0};
+    cudaError_t e = cudaMemcpy(hf, flags, 2 * sizeof(int), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(extdirp, ed, (size_t)maxpg * sizeof(float), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(dirflux, df, (size_t)npts * sizeof(float), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) { set_msg(errmsg, "CUDA error %s in at3d_make_direct", cudaGetErrorString(e)); return 4; }
+    if (hf[1]) return beam_error(hf[1], "DIRECT_BEAM_PROP", errmsg);
+    out_d[0] = g.cx; out_d[1] = g.cy; out_d[2] = g.cz; out_d[3] = g.cxinv; out_d[4] = g.cyinv; out_d[5] = g.czinv;
+    out_d[6] = g.epss; out_d[7] = g.epsz; out_d[8] = g.xdomain; out_d[9] = g.ydomain; out_d[10] = uniformzlev;
+    out_d[11] = g.delxd; out_d[12] = g.delyd;
+    out_i[0] = g.ipdirect; out_i[1] = g.di; out_i[2] = g.dj; out_i[3] = g.dk; out_i[4] = hf[0];
+    return 0;
+}
+
+extern "C" int at3d_make_direct_derivative(int npts, int bcflag, int npx, int npy, int npz,
+                                           float delx, float dely, float xstart, float ystart,
+                                           const float *gridpos, const float *zlevels,
+                                           int ipdirect, int di, int dj, int dk,
+                                           double cx, double cy, double cz,
+                                           double cxinv, double cyinv, double czinv,
+                                           double epss, double epsz, double xdomain, double ydomain,
+                                           double uniformzlev, double delxd, double delyd,
+                                           float *dpath, int32_t *dptr, int longest_path_pts, char *errmsg)
+{
+    (void)delx; (void)dely; (void)uniformzlev;
+    if (errmsg) errmsg[0] = 0;
+    if (!gridpos || !zlevels || !dpath || !dptr || longest_path_pts < 1) { set_msg(errmsg, "bad argument"); return 1; }
+    if (at3d_device_count() < 1) { set_msg(errmsg, "no CUDA device: at3d_b200 has no CPU fallback"); return 4; }
+    BeamGeom g;
+    g.bcflag = bcflag; g.npx = npx; g.npy = npy; g.npz = npz; g.ipdirect = ipdirect; g.di = di; g.dj = dj; g.dk = dk;
+    g.cx = cx; g.cy = cy; g.cz = cz; g.cxinv = cxinv; g.cyinv = cyinv; g.czinv = czinv; g.epss = epss; g.epsz = epsz;
+    g.xdomain = xdomain; g.ydomain = ydomain; g.delxd = delxd; g.delyd = delyd; g.xstart = xstart; g.ystart = ystart;
+    Arena A;
+    const size_t n = (size_t)longest_path_pts * npts;
+    const float *gp = A.up(gridpos, 3 * (size_t)npts), *zl = A.up(zlevels, (size_t)npz);
+    float *dp = A.alloc<float>(n); int *dq = A.alloc<int>(n); int *bad = A.alloc<int>(1);
+    if (!gp || !zl || !dp || !dq || !bad) { set_msg(errmsg, "at3d_make_direct_derivative: device allocation failure"); return 4; }
+    cudaMemset(dp, 0, n * sizeof(float)); cudaMemset(dq, 0, n * sizeof(int)); cudaMemset(bad, 0, sizeof(int));
+    make_direct_derivative_kernel<<<(npts + 127) / 128, 128>>>(npts, g, zl, gp, dp, dq, longest_path_pts, bad);
+    int hbad = 0;
+    cudaError_t e = cudaMemcpy(&hbad, bad, sizeof(int), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(dpath, dp, n * sizeof(float), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(dptr, dq, n * sizeof(int), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) { set_msg(errmsg, "CUDA error %s in at3d_make_direct_derivative", cudaGetErrorString(e)); return 4; }
+    if (hbad) return beam_error(hbad, "DIRECT_BEAM_AND_PATHS_PROP", errmsg);
+    return 0;
+}

@@ -185,7 +185,7 @@ __device__ int boundary_radiance(const DevState &S, double xb, double yb, float 
 template <int NST>
 __device__ __forceinline__ void refresh_corners(const DevState &S, const CellRec &c, CornerCache<NST> *cc,
                                                 const float *Ysh, const RayDir &rd, bool singlescatter,
-                                                bool first)
+                                                bool first, int &npt_eval, int &nsh_eval)
 {
     const int lane = lane_id();
     int myp = 0, hit = -1;
@@ -221,6 +221,7 @@ __device__ __forceinline__ void refresh_corners(const DevState &S, const CellRec
         const int ip = __shfl_sync(FULLMASK, myp, n);
         float ext, src[NST], ss[NST];
         eval_point<NST>(S, ip, Ysh, rd, singlescatter, ext, src, ss);
+        npt_eval++; nsh_eval += __ldg(&S.srcrec[ip - 1]).y;
         const unsigned same = __ballot_sync(FULLMASK, lane < 8 && myp == ip);
         if (lane < 8 && myp == ip) {
             cc->ext[lane] = ext;
@@ -250,7 +251,7 @@ __device__ int march_ray(const DevState &S, CornerCache<NST> *cc, const float *Y
     const double eps = (double)(1.0e-5f * (pt_coord(S, p8c, 3) - pt_coord(S, p1c, 3)));
     const int maxcellscross = 500 * max(S.nx, max(S.ny, S.nz));
     int icell = dev_locate_grid_cell(S, xe, ye, ze);
-    int iface = 0, ngrid = 0;
+    int iface = 0, ngrid = 0, npt_eval = 0, nsh_eval = 0;
     bool done = false, first = true;
     ntrace = 0; nsub = 0;
     while (!done && icell > 0) {
@@ -258,7 +259,7 @@ __device__ int march_ray(const DevState &S, CornerCache<NST> *cc, const float *Y
         if (trace_cells && lane == 0 && ntrace < trace_cap) trace_cells[ntrace] = icell;
         ntrace++;
         const CellRec c = load_cell(S, icell);
-        refresh_corners<NST>(S, c, cc, Ysh, rd, singlescatter, first);
+        refresh_corners<NST>(S, c, cc, Ysh, rd, singlescatter, first, npt_eval, nsh_eval);
         first = false;
         float e8[8], s8[NST][8];
 #pragma unroll
@@ -380,6 +381,13 @@ __device__ int march_ray(const DevState &S, CornerCache<NST> *cc, const float *Y
             icell = inextcell;
         }
         xe = xn; ye = yn; ze = zn;
+    }
+    if (S.counts && lane == 0) {
+        atomicAdd(&S.counts[0], (unsigned long long)ntrace);
+        atomicAdd(&S.counts[1], (unsigned long long)npt_eval);
+        atomicAdd(&S.counts[2], (unsigned long long)nsh_eval);
+        atomicAdd(&S.counts[4], (unsigned long long)nsub);
+        atomicAdd(&S.counts[5], 1ull);
     }
     return 0;
 }

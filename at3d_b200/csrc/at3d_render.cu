@@ -146,7 +146,7 @@ __global__ void prep_sh_kernel(DevState S, int tms, const int *shptr, const floa
 template <int NST, int MODE, typename OUT>
 __global__ void __launch_bounds__(AT3D_WARPS_PER_BLOCK * 32)
 render_kernel(DevState S, int nrays, const float *camx, const float *camy, const float *camz,
-              const double *cammu, const double *camphi, OUT *stokes,
+              const double *cammu, const double *camphi, const RayPack *packs, OUT *stokes,
               int correctinterpolate, int singlescatter, int nosurface, int maxsub,
               int *trace_cells, int trace_cap, int *trace_n, int *trace_nsub, RayErr *err)
 {
@@ -157,21 +157,20 @@ render_kernel(DevState S, int nrays, const float *camx, const float *camy, const
     CornerCache<NST> *cc = (CornerCache<NST> *)((unsigned char *)Ysh + ybytes);
     const int nwarps = gridDim.x * AT3D_WARPS_PER_BLOCK;
     for (int iray = blockIdx.x * AT3D_WARPS_PER_BLOCK + warp; iray < nrays; iray += nwarps) {
-        double x0 = (double)__ldg(&camx[iray]), y0 = (double)__ldg(&camy[iray]), z0 = (double)__ldg(&camz[iray]);
         const double mu2 = __ldg(&cammu[iray]), phi2 = __ldg(&camphi[iray]);
+        const RayPack pk = dev_get_pack(S, packs, iray, camx, camy, camz, mu2, phi2);
         double rad[NST];
 #pragma unroll
         for (int k = 0; k < NST; k++) rad[k] = 0.0;
         int ntrace = 0, nsub = 0;
-        const int st = dev_ray_start(S, mu2, phi2, x0, y0, z0);
-        if (st == 2) { if (lane == 0) set_err(err, 2, iray); }
-        else if (st == 0) {
+        if (pk.status == 2) { if (lane == 0) set_err(err, 2, iray); }
+        else if (pk.status == 0) {
             RayDir rd;
-            dev_ray_dir(S, mu2, phi2, rd);
+            dev_ray_dir(S, pk, rd);
             __syncwarp();
             warp_ylmall(S, (float)mu2, (float)phi2, Ysh);
             const float sky = (-mu2 > 0.0) ? dev_sky_radiance(S, (float)mu2, (float)phi2) : 0.0f;
-            const int e = march_ray<NST, MODE>(S, cc, Ysh, rd, mu2, x0, y0, z0, sky,
+            const int e = march_ray<NST, MODE>(S, cc, Ysh, rd, mu2, pk.x0, pk.y0, pk.z0, sky,
                                                correctinterpolate != 0, singlescatter != 0, nosurface != 0,
                                                maxsub, rad,
                                                trace_cells ? trace_cells + (size_t)trace_cap * iray : nullptr,
@@ -211,7 +210,7 @@ int render_grid_blocks(int nrays, size_t smem, int nst, int mode)
 // Launch helpers (host).  out_f32: RENDER's STOKES; out_f64: VISRAD for the gradient driver.
 cudaError_t launch_render(const DevState &S, int nrays, const float *camx, const float *camy,
                           const float *camz, const double *cammu, const double *camphi,
-                          float *out_f32, double *out_f64, int mode,
+                          const RayPack *packs, float *out_f32, double *out_f64, int mode,
                           int correctinterpolate, int singlescatter, int nosurface, int maxsub,
                           int *trace_cells, int trace_cap, int *trace_n, int *trace_nsub,
                           RayErr *err, cudaStream_t stream)
@@ -222,7 +221,7 @@ cudaError_t launch_render(const DevState &S, int nrays, const float *camx, const
     const int nt = AT3D_WARPS_PER_BLOCK * 32;
 #define LAUNCH(NST, MODE, OUT, outp)                                                              \
     cudaFuncSetAttribute(render_kernel<NST, MODE, OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-    render_kernel<NST, MODE, OUT><<<nb, nt, smem, stream>>>(S, nrays, camx, camy, camz, cammu, camphi, outp, \
+    render_kernel<NST, MODE, OUT><<<nb, nt, smem, stream>>>(S, nrays, camx, camy, camz, cammu, camphi, packs, outp, \
         correctinterpolate, singlescatter, nosurface, maxsub, trace_cells, trace_cap, trace_n, trace_nsub, err)
     if (S.nstokes == 1) {
         if (out_f64) { if (mode) { LAUNCH(1, 1, double, out_f64); } else { LAUNCH(1, 0, double, out_f64); } }

@@ -44,6 +44,14 @@ class DeviceState:
     def hbm_bytes(self):
         return int(self._L.at3d_state_bytes(self._h))
 
+    def counts(self):
+        """Work counters of the last render / gradient call (include/at3d_b200.h)."""
+        out = np.zeros(8, np.int64)
+        buf = _lib.errbuf()
+        _lib.check(self._L.at3d_state_get_counts(self._h, vp(out), buf), buf)
+        return dict(cells=int(out[0]), points=int(out[1]), sum_ns=int(out[2]), sum_nr=int(out[3]),
+                    subintervals=int(out[4]), rays=int(out[5]))
+
     def bcrad(self):
         s = self.state
         out = np.zeros((s.nstokes, s.ntoppts + s.nbotpts), np.float32, order='F')
@@ -117,6 +125,8 @@ class DeviceState:
         gd = g.desc()
         npix = int(pix.rays_per_pixel.shape[0])
         gd.npix = npix
+        # torch tensors hold the Fortran-ordered bytes, i.e. carry the reversed shape
+        gd.nuncertainty = int(pix.uncertainties.shape[-1] if dev else pix.uncertainties.shape[0])
         gd.measurements = C.cast(vp(pix.measurements), type(gd.measurements))
         gd.uncertainties = C.cast(vp(pix.uncertainties), type(gd.uncertainties))
         gd.rays_per_pixel = C.cast(vp(pix.rays_per_pixel), type(gd.rays_per_pixel))

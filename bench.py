@@ -1,0 +1,355 @@
+#!/usr/bin/env python
+"""bench.py -- radiance+gradient rays/s of the SHDOM hot path on N B200s (one process per GPU).
+
+A step is one full LEVISAPPROX_GRADIENT evaluation (forward radiances, adjoint weights, adjoint ray
+pass, direct-beam pass) over all rays of the workload: BASELINE.json configs[1] -- LES-like cloud
+field 32x37x27, NMU=16/NPHI=32 (NLM=256), 9 AirMSPI-like perspective views of 200x200 pixels, scalar
+radiance + Levis gradient w.r.t. extinction.  Synthetic state (at3d_b200/synthetic.py), no solver.
+
+  python bench.py [--gpus N --steps K --warmup W]          our CUDA path
+  python bench.py --impl reference [...]                    the reference algorithm on the host CPU cores
+
+Multi-GPU (torchrun, one rank per GPU): weak scaling.  Every rank holds its own replica of the
+workload (BASELINE.json config 5: one wavelength / state per GPU, rays never cross GPUs) and the only
+collective is the NCCL all-reduce of the per-voxel gradient and the cost; value = N x rays / max-rank time.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+VIEW_ZENITHS = [70.5, 60.0, 45.6, 26.1, 0.0, -26.1, -45.6, -60.0, -70.5]   # AirMSPI-like along-track
+
+
+def build_scene(args):
+    from at3d_b200 import synthetic as S
+    if args.workload == 'cfg2':
+        kw = dict(nx=32, ny=37, nz=27, nmu=16, nphi=32, nstokes=1, bc='open', dx=0.02, dy=0.02, dz=0.04,
+                  cloud='les', ext_max=90.0, numphase=18, nsplits=1700, seed=0, truncate=True)
+        npix_side = 200
+    elif args.workload == 'cfg3':
+        kw = dict(nx=32, ny=37, nz=27, nmu=16, nphi=32, nstokes=3, bc='open', dx=0.02, dy=0.02, dz=0.04,
+                  cloud='les', ext_max=90.0, numphase=18, nsplits=1700, seed=0, truncate=True)
+        npix_side = 200
+    else:   # 'small': CI-sized
+        kw = dict(nx=16, ny=16, nz=14, nmu=8, nphi=16, nstokes=1, bc='open', dx=0.03, dy=0.03, dz=0.04,
+                  cloud='les', ext_max=60.0, numphase=6, nsplits=60, seed=0)
+        npix_side = 48
+    if args.pixels:
+        npix_side = args.pixels
+    sc = S.make_scene(**kw)
+    m = sc.meta
+    cx, cy, cz = 0.5 * m['xmax'], 0.5 * m['ymax'], 0.5 * m['zmax']
+    alt = 20.0
+    views = []
+    for zen in VIEW_ZENITHS:
+        t = np.tan(np.deg2rad(zen))
+        pos = (cx + (alt - cz) * t, cy, alt)
+        dist = (alt - cz) / np.cos(np.deg2rad(zen))
+        fov = 2.0 * np.rad2deg(np.arctan(0.45 * max(m['xmax'], m['ymax']) / dist))
+        views.append(S.perspective_rays(pos, (cx, cy, cz), fov, npix_side, npix_side)[0])
+    rays = S.concat_rays(views)
+    return sc, rays, dict(kw, views=len(views), pixels_per_view=npix_side * npix_side)
+
+
+def algorithmic_bytes(st, gi, cnt, gradient=True):
+    """bytes the reference algorithm must touch for the work actually done
+    (cells / evaluated grid points / SH lengths / sub-intervals counted by the kernel)."""
+    nst = st.nstokes
+    P = 28 + st.npart * (8 + 64 * st.maxnmicro)          # per-point scalar payload
+    Ccell = 66                                           # GRIDPTR 32 + NEIGHPTR 24 + TREEPTR 8 + CELLFLAGS 2
+    b = 4 * nst * cnt['sum_ns'] + P * cnt['points'] + Ccell * cnt['cells']
+    if gradient:
+        nd = gi.numder
+        b += 4 * nst * cnt['sum_nr']                     # radiance expansion, read once per new point
+        b += cnt['points'] * (8 * nd * 28 + 8 * 8)       # derivative tables + INTERPPTR/OPTINTERPWT
+        b += 2 * cnt['subintervals'] * 8 * 8 * nd * 8    # gradient scatter: source term and radiance term
+    return int(b)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.samples, self._stop, self._t = index, [], threading.Event(), None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                      '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(',')]
+                if len(f) >= 6:
+                    self.samples.append(f)
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        if not self.samples:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['unsampled'])
+        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith('active') for s in self.samples)]
+        mx = [int(s[1]) for s in self.samples if s[1].isdigit()]
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons)
+
+
+def measured_peak():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            for k in ('hbm_gbs', 'hbm_gb_s', 'hbm_GBps'):
+                if k in d:
+                    return float(d[k]), 'measured (MEASURED_PEAKS.json)'
+        except Exception:
+            pass
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+def cpu_reference_rate(sc, rays, gi, pix, target_s, nthreads, steps=1, warmup=0):
+    """Times the CPU restatement of the reference algorithm (oracle/, test infrastructure) on a bounded
+    sample of the workload's pixels with `nthreads` OpenMP threads.  Returns (rays/s, sample text, ms list)."""
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    import oracle_lib as O
+    from at3d_b200 import gradsetup
+    from at3d_b200.state import Rays
+    O.build()
+    rng = np.random.default_rng(0)
+    npix = pix.npix
+    # calibration on a small random sample of pixels spread over all views
+
+    def run(nsample):
+        idx = np.sort(rng.choice(npix, size=min(nsample, npix), replace=False))
+        starts = np.concatenate([[0], np.cumsum(pix.rays_per_pixel)])
+        ridx = np.concatenate([np.arange(starts[p], starts[p + 1]) for p in idx])
+        r = Rays(rays.camx[ridx], rays.camy[ridx], rays.camz[ridx], rays.cammu[ridx], rays.camphi[ridx])
+        p = gradsetup.PixelData(pix.measurements[:, idx], pix.uncertainties[:, :, idx], pix.rays_per_pixel[idx],
+                                pix.ray_weights[ridx], pix.stokes_weights[:, idx])
+        g = gradsetup.with_pixels(gi, p)
+        t = time.perf_counter()
+        O.levisapprox_gradient(sc.state, r, g, nthreads=nthreads)
+        return r.nrays, time.perf_counter() - t
+    n0, t0 = run(64 * nthreads)
+    rate0 = n0 / max(t0, 1e-6)
+    nsample = int(min(max(rate0 * target_s, 64 * nthreads), npix))
+    times = []
+    nr = 0
+    for i in range(warmup + steps):
+        nr, t = run(nsample)
+        if i >= warmup:
+            times.append(t)
+    tm = float(np.mean(times))
+    return nr / tm, '%d of %d rays (random pixels over all views), %d OpenMP threads, %.1f s/step' % (
+        nr, rays.nrays, nthreads, tm), [1e3 * t for t in times]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--workload', default='cfg2', choices=['cfg2', 'cfg3', 'small'])
+    ap.add_argument('--pixels', type=int, default=0, help='pixels per view side (default: per workload)')
+    ap.add_argument('--cpu-seconds', type=float, default=12.0)
+    ap.add_argument('--no-cpu', action='store_true')
+    args = ap.parse_args()
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local = int(os.environ.get('LOCAL_RANK', 0))
+    ncores = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
+
+    if args.impl == 'reference':
+        # the reference's own algorithm on the host cores; rank 0 only
+        if rank != 0:
+            return
+        from at3d_b200 import gradsetup
+        sys.path.insert(0, os.path.join(ROOT, 'tests'))
+        import oracle_lib as O
+        sc, rays, cfg = build_scene(args)
+        O.finalize_scene(sc)
+        gi = gradsetup.make_gradient_inputs(sc, O, seed=0, numder=1)
+        rad = O.render(sc.state, rays, nthreads=ncores)
+        pix = gradsetup.make_pixels(sc.state.nstokes, rays.nrays, rad, seed=1)
+        rate, sample, ms = cpu_reference_rate(sc, rays, gi, pix, args.cpu_seconds, ncores, args.steps, args.warmup)
+        line = dict(metric='radiance+gradient rays/s', value=rate, unit='rays/s', n_gpus=args.gpus, steps=args.steps,
+                    warmup=args.warmup, ms_per_step=float(np.mean(ms)), higher_is_better=True, scaling='weak',
+                    vs_baseline=None, dtype='f32 optics / f64 geometry+accumulators', data='synthetic',
+                    impl='reference',
+                    config=dict(workload=args.workload + ': LES-like 32x37x27 open BC, NLM=256, 9 perspective views, '
+                                'scalar radiance + Levis gradient (NUMDER=1)', rays=int(rays.nrays), npts=int(sc.state.npts)),
+                    cpu_baseline=dict(value=rate, unit='rays/s', cores=ncores, kind='port', sample=sample),
+                    e2e=dict(value=rate, unit='rays/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    assert torch.cuda.is_available(), 'bench.py needs a CUDA device (no CPU fallback)'
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    from at3d_b200 import backend as B, gradsetup
+    from at3d_b200.device import DeviceState
+    from at3d_b200 import _lib
+    _lib.lib().at3d_set_device(local)
+
+    sc, rays, cfg = build_scene(args)
+    B.finalize_scene(sc)
+    st = sc.state
+    gi = gradsetup.make_gradient_inputs(sc, B, seed=0, numder=1)
+    dev = DeviceState(st)
+    dev.attach_gradient(gi)
+    rad = dev.render(rays)
+    pix = gradsetup.make_pixels(st.nstokes, rays.nrays, rad, seed=1)
+    nrays, npix = rays.nrays, pix.npix
+    stream = torch.cuda.current_stream().cuda_stream
+
+    # ---- device-resident inputs (value) ----
+    class Bag:
+        pass
+    dr, dp = Bag(), Bag()
+    for k in ('camx', 'camy', 'camz', 'cammu', 'camphi'):
+        setattr(dr, k, torch.from_numpy(getattr(rays, k)).cuda())
+    dp.measurements = torch.from_numpy(np.ascontiguousarray(pix.measurements.T)).cuda()
+    dp.uncertainties = torch.from_numpy(np.ascontiguousarray(pix.uncertainties.transpose(2, 1, 0))).cuda()
+    dp.rays_per_pixel = torch.from_numpy(pix.rays_per_pixel).cuda()
+    dp.ray_weights = torch.from_numpy(pix.ray_weights).cuda()
+    dp.stokes_weights = torch.from_numpy(np.ascontiguousarray(pix.stokes_weights.T)).cuda()
+    gout = torch.zeros((gi.numder, gi.maxpg), dtype=torch.float64, device='cuda')
+    sout = torch.zeros((npix, st.nstokes), dtype=torch.float32, device='cuda')
+    cout = torch.zeros(1, dtype=torch.float64, device='cuda')
+    l2flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device='cuda')   # > 126 MB L2
+
+    def step_device(timing=False):
+        l2flush.zero_()
+        out = dev.gradient(dr, dp, gradout=gout, stokesout=sout, cost=cout, stream=stream, timing=timing)
+        if world > 1:
+            dist.all_reduce(gout)          # the only collective of the path: per-voxel gradient (+cost)
+            dist.all_reduce(cout)
+        return out
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    kms = []
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    with ClockSampler(local) as cs:
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            l2flush.zero_()
+            ev[i][0].record()
+            out = dev.gradient(dr, dp, gradout=gout, stokesout=sout, cost=cout, stream=stream, timing=True)
+            if world > 1:
+                dist.all_reduce(gout)
+                dist.all_reduce(cout)
+            ev[i][1].record()
+            kms.append(out[-1])
+        barrier()
+        wall = time.perf_counter() - t0
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    t_total = sum(step_ms) * 1e-3
+    if world > 1:
+        tt = torch.tensor([t_total], dtype=torch.float64, device='cuda')
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_total = float(tt.item())
+    counts = dev.counts()
+    kms = np.array(kms)            # [steps, 4] forward, adjoint(+pixel), beam, total
+    value = world * nrays * args.steps / t_total
+
+    # ---- e2e: host buffers through the C-ABI call, copies inside the timed region ----
+    for _ in range(max(1, args.warmup // 2)):
+        dev.gradient(rays, pix)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        g_h, c_h, s_h = dev.gradient(rays, pix)
+        if world > 1:
+            gt = torch.from_numpy(g_h).cuda()
+            dist.all_reduce(gt)
+            g_h = gt.cpu().numpy()
+    barrier()
+    t_e2e = time.perf_counter() - t0
+    if world > 1:
+        tt = torch.tensor([t_e2e], dtype=torch.float64, device='cuda')
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_e2e = float(tt.item())
+    h2d = nrays * (80 + 16) + pix.measurements.nbytes + pix.uncertainties.nbytes + pix.rays_per_pixel.nbytes + \
+        pix.ray_weights.nbytes + pix.stokes_weights.nbytes
+    d2h = gi.maxpg * gi.numder * 8 + npix * st.nstokes * 4 + 8
+
+    # ---- RENDER alone and roofline of the dominant kernel ----
+    rsout = torch.zeros((nrays, st.nstokes), dtype=torch.float32, device='cuda')
+    rms = []
+    for i in range(args.warmup + args.steps):
+        l2flush.zero_()
+        o = dev.render(dr, out=rsout, stream=stream, timing=True)
+        if i >= args.warmup:
+            rms.append(o[-1])
+    rcounts = dev.counts()
+    peak, peak_src = measured_peak()
+    adj_ms = float(np.mean(kms[:, 1]))
+    abytes = algorithmic_bytes(st, gi, counts, gradient=True)
+    achieved = abytes / (adj_ms * 1e-3) / 1e9
+    rbytes = algorithmic_bytes(st, gi, rcounts, gradient=False)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        rate, sample, _ = cpu_reference_rate(sc, rays, gi, pix, args.cpu_seconds, ncores)
+        cpu = dict(value=rate, unit='rays/s', cores=ncores, kind='port', sample=sample)
+    if rank == 0:
+        line = dict(
+            metric='radiance+gradient rays/s', value=value, unit='rays/s', n_gpus=world, steps=args.steps,
+            warmup=args.warmup, ms_per_step=1e3 * t_total / args.steps, higher_is_better=True, scaling='weak',
+            vs_baseline=None, dtype='f32 optics / f64 geometry+accumulators', data='synthetic',
+            config=dict(workload=args.workload + ': LES-like 32x37x27 open BC, NLM=256, 9 perspective views, '
+                        'scalar radiance + Levis gradient (NUMDER=1); one replica of the workload per GPU, '
+                        'gradient all-reduced', rays=int(nrays), npts=int(st.npts), ncells=int(st.ncells),
+                        nlm=int(st.nlm), l2='flushed between steps (256 MiB memset)', hbm_state_bytes=dev.hbm_bytes),
+            e2e=dict(value=world * nrays * args.steps / t_e2e, unit='rays/s', h2d_bytes_per_step=int(h2d),
+                     d2h_bytes_per_step=int(d2h)),
+            gpu_launches=int(args.steps * (5 + (1 if gi.exact_single_scatter else 0))),
+            roofline=dict(kernel='adjoint_kernel<1>', bound='hbm', achieved=achieved, peak=peak, unit='GB/s',
+                          frac=achieved / peak, traffic=None, peak_source=peak_src,
+                          algorithmic_bytes_per_launch=abytes, kernel_ms=adj_ms, counts=counts),
+            phases_ms=dict(forward=float(np.mean(kms[:, 0])), adjoint=adj_ms, beam=float(np.mean(kms[:, 2])),
+                           total=float(np.mean(kms[:, 3]))),
+            render=dict(rays_per_s=nrays / (np.mean(rms) * 1e-3), kernel_ms=float(np.mean(rms)),
+                        achieved_gbs=rbytes / (np.mean(rms) * 1e-3) / 1e9, frac=rbytes / (np.mean(rms) * 1e-3) / 1e9 / peak,
+                        algorithmic_bytes=rbytes, counts=rcounts),
+            clocks=cs.summary(), cpu_baseline=cpu, wall_s=wall)
+        print(json.dumps(line))
+    dev.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -141,6 +141,12 @@ int at3d_state_create(const at3d_state_desc *desc, at3d_state **out, char *errms
 int at3d_state_attach_gradient(at3d_state *st, const at3d_grad_desc *g, char *errmsg);
 int at3d_state_destroy(at3d_state *st);
 int64_t at3d_state_bytes(const at3d_state *st);   /* HBM bytes held */
+/* RENDER returns BCRAD as an in/out argument (at3d/solver.py:747): copy it back, [nstokes,ntoppts+nbotpts] */
+int at3d_state_get_bcrad(at3d_state *st, float *bcrad_host, char *errmsg);
+/* Work counters of the last at3d_render / at3d_levisapprox_gradient (adjoint pass) on this state, for
+ * roofline accounting: [0] cells visited, [1] grid points evaluated, [2] sum of NS over them,
+ * [3] sum of NR (gradient), [4] sub-intervals integrated, [5] rays marched, [6..7] reserved. */
+int at3d_state_get_counts(at3d_state *st, int64_t *counts /*[8]*/, char *errmsg);
 
 /* ---- a7: YLMALL (shdomsub2.f:4244) and PRECOMPUTE_PHASE_CHECK[_GRAD] (shdomsub4.f:2388,2493) ---- */
 int at3d_ylmall(int transpose, float mu, float phi, int ml, int mm, int nstleg, float *yr /*host*/,
@@ -178,6 +184,19 @@ int at3d_prepare_deriv_interps(const at3d_state_desc *desc, int npx, int npy, in
                                const float *zlevels, const at3d_grad_desc *g,
                                float *optinterpwt, int32_t *interpptr,
                                float *dalbm, float *dextm, float *dfj, char *errmsg);
+
+/* ---- a14 precompute: MAKE_DIRECT (src/polarized/shdomsub2.f:393, at3d/solver.py:2827-2871); HOST pointers.
+ *      out_d[13] = CX,CY,CZ,CXINV,CYINV,CZINV,EPSS,EPSZ,XDOMAIN,YDOMAIN,UNIFORMZLEV,DELXD,DELYD
+ *      out_i[5]  = IPDIRECT,DI,DJ,DK,LONGEST_PATH_PTS ---- */
+int at3d_make_direct(int npts, int bcflag, int ipflag, int deltam, int ml, int nstleg, int nlegp,
+                     float solarflux, float solarmu, float solaraz, const float *gridpos,
+                     int npx, int npy, int npz, float delx, float dely, float xstart, float ystart,
+                     const float *zlevels, const float *extinctp, const float *albedop,
+                     const float *legenp /*[nstleg,0:nlegp,numphase]*/, int numphase,
+                     const int32_t *iphasep, const float *phasewtp, int maxnmicro, int npart,
+                     int nzckd, const float *zckd, const float *gasabs,
+                     float *extdirp /*[maxpg]*/, float *dirflux /*[npts]*/, double *out_d, int32_t *out_i,
+                     char *errmsg);
 
 /* ---- a14 precompute: MAKE_DIRECT_DERIVATIVE (src/shdomsub5.f:1553); HOST pointers ---- */
 int at3d_make_direct_derivative(int npts, int bcflag, int npx, int npy, int npz,

@@ -27,6 +27,9 @@ SCENE_CASES = {
     'rayleigh_two_species': dict(nx=7, ny=6, nz=9, nstokes=1, bc='periodic', rayleigh=True, nsplits=5, seed=7),
     'polarized_rayleigh_varsfc': dict(nx=6, ny=6, nz=8, nstokes=3, bc='open', rayleigh=True, nsplits=4,
                                       variable_sfc=True, seed=8),
+    'scalar_no_deltam': dict(nx=7, ny=7, nz=8, nstokes=1, bc='periodic', deltam=False, nsplits=4, seed=10),
+    'polarized_rayleigh_no_deltam': dict(nx=6, ny=6, nz=7, nstokes=3, bc='open', deltam=False, rayleigh=True,
+                                         nsplits=3, seed=12),
     'thick_transcut': dict(nx=8, ny=8, nz=10, nstokes=1, bc='periodic', ext_max=120.0, cloud='slab',
                            nsplits=3, seed=9),
 }

@@ -1,0 +1,133 @@
+"""GPU parity of LEVISAPPROX_GRADIENT (C-ABI at3d_levisapprox_gradient) against the CPU oracle.
+
+Bars (BASELINE.json north_star): visited-cell sequence / sub-interval counts bit-exact; cost, pixel
+Stokes vectors and the gradient within relative 1e-4.  The gradient is compared element-wise with
+rtol 1e-4 and an absolute floor of 1e-4 x the largest |gradient| of the same unknown (elements that
+are sums of cancelling ray contributions carry the rounding of their largest terms)."""
+import numpy as np
+import pytest
+import scenes
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-4
+
+
+def run_case(oracle, case, gkw, rays_per_pixel=1, trace=True, bright_only=False):
+    from at3d_b200.device import DeviceState
+    from at3d_b200 import gradsetup
+    from at3d_b200.state import Rays
+    sc = scenes.make(case, oracle)
+    rays = scenes.ray_set(sc, n_persp=7, res=0.035)
+    gi = gradsetup.make_gradient_inputs(sc, oracle, seed=11, **gkw)
+    rad = oracle.render(sc.state, rays)
+    if bright_only:
+        # the log cost function (COSTFUNC='LL') needs I > 0 and a non-zero polarized signal
+        keep = rad[0] > 0.02 * rad[0].max()
+        if rad.shape[0] > 1:
+            keep &= np.hypot(rad[1], rad[2]) > 3e-3 * rad[0]
+        idx = np.nonzero(keep)[0]
+        rays = Rays(rays.camx[idx], rays.camy[idx], rays.camz[idx], rays.cammu[idx], rays.camphi[idx])
+        rad = np.asfortranarray(rad[:, idx])
+    pix = gradsetup.make_pixels(sc.state.nstokes, rays.nrays, rad, seed=5, rays_per_pixel=rays_per_pixel)
+    gfull = gradsetup.with_pixels(gi, pix)
+    ref = oracle.levisapprox_gradient(sc.state, rays, gfull, trace_cap=256 if trace else 0)
+    dev = DeviceState(sc.state)
+    dev.attach_gradient(gi)
+    out = dev.gradient(rays, pix, trace_cap=256 if trace else 0)
+    dev.close()
+    return sc, ref, out
+
+
+def check(ref, out, trace=True):
+    gref, cref, soref = ref[:3]
+    g, cost, so = out[:3]
+    if trace:
+        np.testing.assert_array_equal(out[3]['ncells'], ref[3]['ncells'])
+        np.testing.assert_array_equal(out[3]['cells'], ref[3]['cells'])
+        np.testing.assert_array_equal(out[3]['nsub'], ref[3]['nsub'])
+    np.testing.assert_allclose(so, soref, rtol=RTOL, atol=1e-6)
+    assert abs(float(cost[0]) - cref) <= RTOL * abs(cref)
+    assert np.all(np.isfinite(g))
+    for idr in range(gref.shape[1]):
+        scale = np.max(np.abs(gref[:, idr]))
+        assert scale > 0
+        np.testing.assert_allclose(g[:, idr], gref[:, idr], rtol=RTOL, atol=RTOL * scale)
+
+
+CASES = [
+    ('scalar_periodic', dict(numder=1)),
+    ('scalar_periodic_split', dict(numder=2)),
+    ('scalar_open_split', dict(numder=3, exact_phase_derivative=True)),
+    ('scalar_nmu16', dict(numder=2)),
+    ('polarized_periodic_split', dict(numder=2)),
+    ('polarized_open', dict(numder=3, exact_phase_derivative=True)),
+    ('rayleigh_two_species', dict(numder=3, exact_phase_derivative=True)),
+    ('polarized_rayleigh_varsfc', dict(numder=2)),
+    ('thick_transcut', dict(numder=2)),
+]
+
+
+@pytest.mark.parametrize('case,gkw', CASES, ids=[c[0] for c in CASES])
+def test_gradient_matches_oracle(case, gkw, oracle):
+    sc, ref, out = run_case(oracle, case, gkw)
+    check(ref, out)
+
+
+@pytest.mark.parametrize('gkw', [dict(numder=2, exact_single_scatter=False),
+                                 dict(numder=2, singlescatter=True),
+                                 dict(numder=1, costfunc='LL')],
+                         ids=['no_exact_ss', 'singlescatter', 'costfunc_LL'])
+def test_gradient_flags(gkw, oracle):
+    sc, ref, out = run_case(oracle, 'scalar_periodic_split', gkw, bright_only=gkw.get('costfunc') == 'LL')
+    check(ref, out)
+
+
+def test_gradient_polarized_LL(oracle):
+    sc, ref, out = run_case(oracle, 'polarized_periodic_split', dict(numder=1, costfunc='LL'), bright_only=True)
+    check(ref, out)
+
+
+def test_gradient_subpixel_rays(oracle):
+    sc, ref, out = run_case(oracle, 'scalar_periodic_split', dict(numder=2), rays_per_pixel=3)
+    check(ref, out)
+
+
+def test_gradient_no_deltam(oracle):
+    sc, ref, out = run_case(oracle, 'scalar_no_deltam', dict(numder=2))
+    check(ref, out)
+    sc, ref, out = run_case(oracle, 'polarized_rayleigh_no_deltam', dict(numder=3, exact_phase_derivative=True))
+    check(ref, out)
+
+
+def test_gradient_device_pointers(oracle):
+    import torch
+    from at3d_b200.device import DeviceState
+    from at3d_b200 import gradsetup
+    sc = scenes.make('scalar_periodic_split', oracle)
+    rays = scenes.ray_set(sc, n_persp=7, res=0.035)
+    gi = gradsetup.make_gradient_inputs(sc, oracle, seed=11, numder=2)
+    rad = oracle.render(sc.state, rays)
+    pix = gradsetup.make_pixels(1, rays.nrays, rad, seed=5)
+    dev = DeviceState(sc.state)
+    dev.attach_gradient(gi)
+    g, cost, so = dev.gradient(rays, pix)
+
+    class B:
+        pass
+    r, p = B(), B()
+    for k in ('camx', 'camy', 'camz', 'cammu', 'camphi'):
+        setattr(r, k, torch.from_numpy(getattr(rays, k)).cuda())
+    for k in ('measurements', 'uncertainties', 'rays_per_pixel', 'ray_weights', 'stokes_weights'):
+        a = getattr(pix, k)
+        # device tensors hold the Fortran-ordered bytes
+        setattr(p, k, torch.from_numpy(np.ascontiguousarray(a.T)).cuda())
+    p.rays_per_pixel = torch.from_numpy(pix.rays_per_pixel).cuda()
+    p.uncertainties = torch.from_numpy(np.ascontiguousarray(pix.uncertainties.transpose(2, 1, 0))).cuda()
+    g2, cost2, so2 = dev.gradient(r, p)
+    torch.cuda.synchronize()
+    scale = np.abs(g).max()
+    np.testing.assert_allclose(g2.cpu().numpy().T, g, rtol=1e-9, atol=1e-12 * scale)
+    np.testing.assert_allclose(float(cost2.cpu()[0]), float(cost[0]), rtol=1e-12)
+    np.testing.assert_array_equal(so2.cpu().numpy().T, so)
+    dev.close()
