@@ -95,3 +95,50 @@ def make_direct_derivative(state, pg, c):
           c['cz'], c['cxinv'], c['cyinv'], c['czinv'], c['epss'], c['epsz'], c['xdomain'], c['ydomain'],
           c['uniformzlev'], c['delxd'], c['delyd'], vp(dpath), vp(dptr), lpp)
     return dpath, dptr
+
+
+def compute_source(state, shptr, source, oshptr, delsource, fixsh=False, shacc=0.0, maxiv=None, first=False,
+                   accelflag=True, newmethod=True, timing=False):
+    """COMPUTE_SOURCE (shdomsub1.f:967).  Returns (ierr, shptr, source, oshptr, delsource,
+    [deljdot, deljold, deljnew, jnorm]) (+ kernel ms when ``timing``); ierr=2 is "out of SH memory"."""
+    st = state.copy().normalize()
+    d = st.desc()
+    shptr = np.array(shptr, np.int32); oshptr = np.array(oshptr, np.int32)
+    source = np.array(source, np.float32, order='F'); delsource = np.array(delsource, np.float32, order='F')
+    if maxiv is None:
+        maxiv = source.shape[1]
+    o = [C.c_float(0), C.c_float(0), C.c_float(0), C.c_float(0)]
+    ms = C.c_double(0.0)
+    buf = _lib.errbuf()
+    code = _lib.lib().at3d_compute_source(C.byref(d), int(fixsh), shacc, int(maxiv), int(first), int(accelflag),
+                                          int(newmethod), vp(shptr), vp(source), vp(oshptr), vp(delsource),
+                                          C.byref(o[0]), C.byref(o[1]), C.byref(o[2]), C.byref(o[3]),
+                                          C.byref(ms), buf)
+    if code not in (0, 2):
+        _lib.check(code, buf)
+    res = (code, shptr, source, oshptr, delsource, [x.value for x in o])
+    return res + (ms.value,) if timing else res
+
+
+def average_subpixel_rays(weighted_stokes, pixel_index, npixels):
+    """average_subpixel_rays (src/util.f90:484)."""
+    ws = np.asfortranarray(weighted_stokes, np.float32)
+    nstokes, nrays = ws.shape
+    pi = np.ascontiguousarray(pixel_index, np.int32)
+    out = np.zeros((nstokes, npixels), np.float32, order='F')
+    _call(_lib.lib().at3d_average_subpixel_rays, npixels, nrays, nstokes, vp(ws), vp(pi), vp(out))
+    return out
+
+
+def update_costfunction(stokesout, raygrad_pixel, gradout, cost, uncertainties, costfunc, measurement):
+    """UPDATE_COSTFUNCTION (shdomsub4.f:13): returns (gradout, cost)."""
+    nstokes = len(stokesout)
+    rg = np.asfortranarray(raygrad_pixel, np.float64)
+    _, maxpg, numder = rg.shape
+    gradout = np.array(gradout, np.float64, order='F')
+    cost = np.atleast_1d(np.array(cost, np.float64))
+    unc = np.asfortranarray(uncertainties, np.float64)
+    so = np.ascontiguousarray(stokesout, np.float64); me = np.ascontiguousarray(measurement, np.float64)
+    _call(_lib.lib().at3d_update_costfunction, vp(so), vp(rg), vp(gradout), vp(cost), vp(unc),
+          1 if costfunc == 'LL' else 0, nstokes, maxpg, numder, vp(me), unc.shape[0])
+    return gradout, cost

@@ -1,0 +1,429 @@
+// at3d_source.cu -- COMPUTE_SOURCE on sm_100a.
+// Replaces COMPUTE_SOURCE and CALC_SOURCE_PNT[_UNPOL] (src/polarized/shdomsub1.f:823-1611 of the AT3D
+// reference): the per-grid-point source-function update in spherical-harmonic space, the series
+// acceleration dot products, the adaptive SH truncation and the SHPTR rebuild.
+//
+// The reference makes three passes over the grid, each recomputing the temporary source of a point.
+// Here: one streaming kernel computes the temporary source once for the four norms AND the new
+// truncation length, a device-wide exclusive scan rebuilds SHPTR, and a second streaming kernel
+// writes DELSOURCE and the re-packed SOURCE.  One warp per grid point, lanes over the SH index j
+// (coalesced on the CSR arrays); the mixed Legendre table of the point lives in shared memory.
+// HBM-bound: 4*NSTOKES*(2*NR + NS_old [+2*NS accel] + NS_new) bytes per point.
+#include <cstdio>
+#include <cstring>
+#include <cstdarg>
+#include <vector>
+#include <cub/cub.cuh>
+#include "at3d_host.h"
+
+static void set_msg(char *errmsg, const char *fmt, ...)
+{
+    if (!errmsg) return;
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(errmsg, AT3D_ERRMSG_LEN, fmt, ap);
+    va_end(ap);
+}
+
+struct CsArgs {
+    int npts, nstokes, nstleg, nlm, ml, mm, nleg, npart, nq, srctype, deltam, interp_new, newmethod;
+    int first, accelflag, fixsh;
+    float phasemax, secmu0, srcmin;
+    const float *extinct, *albedo, *total_ext, *legen, *phaseinterpwt, *dirflux, *radiance, *ylmsun, *planck;
+    const int *iphase, *rshptr, *lofj;
+    const int *shptr_old, *oshptr_old;
+    const float *source_old, *delsource_old;
+    int *ns_new;              // [npts]
+    double *partials;         // [nblocks,4]
+    int *bad;                 // NR>NLM flag
+    // second kernel
+    const int *shptr_new;
+    float *source_new, *delsource_new;
+};
+
+#define CS_WARPS 8
+
+// Mixed Legendre table of the point (NEWMETHOD=.TRUE.) into shared memory;
+// returns (albedo, planck) to use in CALC_SOURCE_PNT.  shdomsub1.f:1089-1141.
+__device__ __forceinline__ void cs_mix_newmethod(const CsArgs &a, int i, float *legent, float *legent1,
+                                                 float &albedo_out, float &planck_out)
+{
+    const int lane = threadIdx.x & 31;
+    const int nlt = a.nstleg * (a.nleg + 1);
+    const float ext = a.total_ext[i];
+    double alb = 0.0;
+    float total_planck = 0.0f;
+    for (int t = lane; t < nlt; t += 32) legent[t] = 0.0f;
+    __syncwarp();
+    for (int ipa = 0; ipa < a.npart; ipa++) {
+        const int *iph = a.iphase + (size_t)a.nq * (i + (size_t)a.npts * ipa);
+        const float *pw = a.phaseinterpwt + (size_t)a.nq * (i + (size_t)a.npts * ipa);
+        const float e = a.extinct[i + (size_t)a.npts * ipa], al = a.albedo[i + (size_t)a.npts * ipa];
+        const double scat = (double)(e * al);
+        alb = alb + scat;
+        if (a.planck) total_planck = total_planck + e * a.planck[i + (size_t)a.npts * ipa];
+        if (!a.interp_new) {
+            const float *lg = a.legen + (size_t)nlt * (iph[0] - 1);
+            for (int t = lane; t < nlt; t += 32) legent[t] = (float)(legent[t] + scat * lg[t]);
+        } else {
+            const bool single = pw[0] >= a.phasemax;
+            for (int t = lane; t < nlt; t += 32) {
+                float v;
+                if (single) v = a.legen[(size_t)nlt * (iph[0] - 1) + t];
+                else {
+                    v = 0.0f;
+                    for (int q = 0; q < a.nq; q++) {
+                        if (pw[q] <= 1e-5f) continue;
+                        v = v + a.legen[(size_t)nlt * (iph[q] - 1) + t] * pw[q];
+                    }
+                }
+                legent1[t] = v;
+            }
+            __syncwarp();
+            if (a.deltam) {
+                const float f = legent1[a.nstleg * (a.ml + 1)];
+                __syncwarp();
+                for (int t = lane; t < a.nstleg * (a.ml + 1); t += 32) legent1[t] = legent1[t] / (1 - f);
+                __syncwarp();
+            }
+            for (int t = lane; t < nlt; t += 32) legent[t] = (float)(legent[t] + scat * legent1[t]);
+        }
+        __syncwarp();
+    }
+    if (alb > 1e-10f) { for (int t = lane; t < nlt; t += 32) legent[t] = (float)(legent[t] / alb); }
+    else { for (int t = lane; t < nlt; t += 32) legent[t] = legent[t] / a.npart; }
+    if (ext > 1e-10f) { alb = alb / ext; total_planck = total_planck / ext; }
+    else { alb = 0.0; total_planck = 0.0f; }
+    __syncwarp();
+    if (lane == 0) legent[0] = 1.0f;
+    __syncwarp();
+    albedo_out = (float)alb;
+    planck_out = total_planck;
+}
+
+// CALC_SOURCE_PNT[_UNPOL] for one SH index j (0-based) (shdomsub1.f:858-898, 940-958)
+template <int NST>
+__device__ __forceinline__ void cs_calc_j(const CsArgs &a, const float *legen, int j, int nr, const float *rad,
+                                          float flux0, float planck, float albedo, float (&s)[NST])
+{
+    const int l = a.lofj[j];
+    const bool solar = a.srctype == 'S' || a.srctype == 'B';
+    const bool thermal = a.srctype == 'T' || a.srctype == 'B';
+    if (NST == 1) {
+        float v = 0.0f;
+        if (solar) v = flux0 * albedo * legen[l] * a.ylmsun[j];
+        if (thermal && j == 0) v = v + 3.544907703f * planck;
+        if (j < nr) v = v + albedo * legen[l] * rad[j];
+        s[0] = v;
+    } else {
+        const int ns = a.nstleg;
+        float v1 = 0.0f, v2 = 0.0f, v3 = 0.0f;
+        if (j < nr) {
+            const float r1 = rad[(size_t)NST * j], r2 = rad[(size_t)NST * j + 1], r3 = rad[(size_t)NST * j + 2];
+            v1 = v1 + legen[ns * l] * r1;
+            v1 = v1 + legen[4 + ns * l] * r2;
+            if (j >= 4) {
+                v2 = v2 + legen[4 + ns * l] * r1 + legen[1 + ns * l] * r2;
+                v3 = v3 + legen[2 + ns * l] * r3;
+            }
+        }
+        v1 = albedo * v1; v2 = albedo * v2; v3 = albedo * v3;
+        if (solar) {
+            v1 = v1 + flux0 * albedo * legen[ns * l] * a.ylmsun[(size_t)ns * j];
+            if (j >= 4) v2 = v2 + flux0 * albedo * legen[4 + ns * l] * a.ylmsun[(size_t)ns * j];
+        }
+        if (thermal && j == 0) v1 = v1 + 3.544907703f * planck;
+        s[0] = v1; s[1] = v2; s[NST - 1] = v3;
+    }
+}
+
+// the temporary source of point i at SH index j, both mixing methods
+template <int NST>
+struct PointSource {
+    float albedo, planck, flux0;
+    int nr;
+    const float *rad;
+    __device__ void setup(const CsArgs &a, int i, float *legent, float *legent1)
+    {
+        const int ir = a.rshptr[i];
+        nr = a.rshptr[i + 1] - ir;
+        rad = a.radiance + (size_t)NST * ir;
+        flux0 = a.dirflux[i] * a.secmu0;
+        cs_mix_newmethod(a, i, legent, legent1, albedo, planck);
+    }
+    __device__ void eval(const CsArgs &a, int i, const float *legent, int j, float (&s)[NST]) const
+    {
+        cs_calc_j<NST>(a, legent, j, nr, rad, flux0, planck, albedo, s);
+    }
+};
+
+// Kernel A: norms (passes 1 of the reference) and the new truncation length (first half of pass 3)
+template <int NST>
+__global__ void __launch_bounds__(CS_WARPS * 32) cs_norms_kernel(CsArgs a)
+{
+    extern __shared__ float smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nlt = a.nstleg * (a.nleg + 1);
+    float *legent = smem + (size_t)warp * 2 * nlt, *legent1 = legent + nlt;
+    __shared__ double red[CS_WARPS][4];
+    double sdot = 0.0, sold = 0.0, snew = 0.0, snorm = 0.0;
+    for (int i = blockIdx.x * CS_WARPS + warp; i < a.npts; i += gridDim.x * CS_WARPS) {
+        PointSource<NST> ps;
+        ps.setup(a, i, legent, legent1);
+        if (ps.nr > a.nlm) { if (lane == 0) atomicCAS(a.bad, 0, i + 1); continue; }
+        const int is = a.shptr_old[i];
+        int ns = a.shptr_old[i + 1] - is;
+        int iso = 0;
+        if (a.accelflag && !a.first) {
+            iso = a.oshptr_old[i];
+            const int nso = a.oshptr_old[i + 1] - iso;
+            if (nso < ns) ns = nso;
+        }
+        int jlast = -1;                       // last j with |SOURCET| > SRCMIN
+        for (int j = lane; j < a.nlm; j += 32) {
+            float s[NST];
+#pragma unroll
+            for (int k = 0; k < NST; k++) s[k] = 0.0f;
+            ps.eval(a, i, legent, j, s);
+#pragma unroll
+            for (int k = 0; k < NST; k++) if (fabsf(s[k]) > a.srcmin) jlast = j;
+            if (!a.first && j < ns) {
+#pragma unroll
+                for (int k = 0; k < NST; k++) {
+                    const float so = a.source_old[(size_t)NST * (is + j) + k];
+                    const float d = s[k] - so;
+                    if (a.accelflag) {
+                        const float ds = a.delsource_old[(size_t)NST * (iso + j) + k];
+                        sdot += (double)(d * ds);
+                        sold += (double)(ds * ds);
+                    }
+                    snew += (double)(d * d);
+                    snorm += (double)(so * so);
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) jlast = max(jlast, __shfl_xor_sync(FULLMASK, jlast, o));
+        if (lane == 0) {
+            int nsn;
+            if (a.fixsh) nsn = a.shptr_old[i + 1] - a.shptr_old[i];
+            else {
+                int js = jlast + 1;                            // 1-based; 0 = none
+                if (js == 0 && a.srctype != 'S') js = 1;
+                if (js == 0) nsn = 0;
+                else {
+                    const int ls = a.lofj[js - 1], mm = a.mm;
+                    if (ls <= mm) nsn = ls * (ls + 1) + ls + 1;
+                    else nsn = (2 * mm + 1) * ls - (mm * (1 + (mm - 1))) + mm + 1;
+                }
+            }
+            a.ns_new[i] = nsn;
+        }
+        __syncwarp();
+    }
+    sdot = warp_sum_d(sdot); sold = warp_sum_d(sold); snew = warp_sum_d(snew); snorm = warp_sum_d(snorm);
+    if (lane == 0) { red[warp][0] = sdot; red[warp][1] = sold; red[warp][2] = snew; red[warp][3] = snorm; }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        double t = 0.0;
+        for (int w = 0; w < CS_WARPS; w++) t += red[w][threadIdx.x];
+        a.partials[(size_t)blockIdx.x * 4 + threadIdx.x] = t;
+    }
+}
+
+// Kernel B: DELSOURCE at the old offsets (pass 2) and the re-packed SOURCE at the new offsets (pass 3)
+template <int NST>
+__global__ void __launch_bounds__(CS_WARPS * 32) cs_write_kernel(CsArgs a)
+{
+    extern __shared__ float smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nlt = a.nstleg * (a.nleg + 1);
+    float *legent = smem + (size_t)warp * 2 * nlt, *legent1 = legent + nlt;
+    for (int i = blockIdx.x * CS_WARPS + warp; i < a.npts; i += gridDim.x * CS_WARPS) {
+        PointSource<NST> ps;
+        ps.setup(a, i, legent, legent1);
+        const int is_old = a.shptr_old[i], ns_old = a.shptr_old[i + 1] - is_old;
+        const int is_new = a.shptr_new[i], ns_new = a.shptr_new[i + 1] - is_new;
+        const int nmax = ns_old > ns_new ? ns_old : ns_new;
+        const bool dodel = !a.first && a.accelflag;
+        for (int j = lane; j < nmax; j += 32) {
+            float s[NST];
+            ps.eval(a, i, legent, j, s);
+#pragma unroll
+            for (int k = 0; k < NST; k++) {
+                if (dodel && j < ns_old)
+                    a.delsource_new[(size_t)NST * (is_old + j) + k] = s[k] - a.source_old[(size_t)NST * (is_old + j) + k];
+                if (j < ns_new) a.source_new[(size_t)NST * (is_new + j) + k] = s[k];
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// deterministic final reduction of the per-block partial sums
+__global__ void cs_reduce_kernel(int nblocks, const double *partials, double *out)
+{
+    __shared__ double sh[4][256];
+    const int q = threadIdx.x >> 8 & 3, t = threadIdx.x & 255;
+    double acc = 0.0;
+    for (int b = t; b < nblocks; b += 256) acc += partials[(size_t)b * 4 + q];
+    sh[q][t] = acc;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (t < o) sh[q][t] += sh[q][t + o];
+        __syncthreads();
+    }
+    if (t == 0) out[q] = sh[q][0];
+}
+
+namespace {
+struct Arena {
+    std::vector<void *> p;
+    ~Arena() { for (void *q : p) cudaFree(q); }
+    template <typename T> T *alloc(size_t n)
+    {
+        void *q = nullptr;
+        if (cudaMalloc(&q, (n ? n : 1) * sizeof(T)) != cudaSuccess) return nullptr;
+        p.push_back(q);
+        return (T *)q;
+    }
+    template <typename T> const T *up(const T *h, size_t n)
+    {
+        if (!h) return nullptr;
+        T *d = alloc<T>(n);
+        if (!d) return nullptr;
+        if (cudaMemcpy(d, h, n * sizeof(T), cudaMemcpyHostToDevice) != cudaSuccess) return nullptr;
+        return d;
+    }
+};
+}
+
+extern "C" int at3d_compute_source(const at3d_state_desc *d, int fixsh, float shacc, int maxiv,
+                                   int first, int accelflag, int newmethod,
+                                   int32_t *shptr, float *source, int32_t *oshptr, float *delsource,
+                                   float *deljdot, float *deljold, float *deljnew, float *jnorm,
+                                   double *kernel_ms, char *errmsg)
+{
+    if (errmsg) errmsg[0] = 0;
+    if (!d || !shptr || !source || !oshptr || !delsource || !deljdot || !deljold || !deljnew || !jnorm) { set_msg(errmsg, "null argument"); return 1; }
+    if (at3d_device_count() < 1) { set_msg(errmsg, "no CUDA device: at3d_b200 has no CPU fallback"); return 4; }
+    if (!(d->nstokes == 1 || d->nstokes == 3)) { set_msg(errmsg, "NSTOKES must be 1 or 3"); return 3; }
+    if (!newmethod) { set_msg(errmsg, "COMPUTE_SOURCE: only NEWMETHOD=.TRUE. (the at3d default, solver.py:178) is implemented"); return 3; }
+    if (!d->rshptr || !d->radiance) { set_msg(errmsg, "COMPUTE_SOURCE needs RSHPTR/RADIANCE"); return 1; }
+    const size_t npts = d->npts;
+    const int nst = d->nstokes;
+    const size_t nlt = (size_t)d->nstleg * (d->nleg + 1);
+    const int nq = 8 * d->maxnmicro;
+    Arena A;
+    CsArgs a;
+    memset(&a, 0, sizeof(a));
+    a.npts = d->npts; a.nstokes = nst; a.nstleg = d->nstleg; a.nlm = d->nlm; a.ml = d->ml; a.mm = d->mm; a.nleg = d->nleg;
+    a.npart = d->npart; a.nq = nq; a.srctype = d->srctype; a.deltam = d->deltam; a.interp_new = d->interp_new;
+    a.newmethod = newmethod; a.first = first; a.accelflag = accelflag; a.fixsh = fixsh;
+    a.phasemax = d->phasemax; a.secmu0 = 1.0f / fabsf(d->solarmu); a.srcmin = shacc;
+    std::vector<int> lofj(d->nlm);
+    {
+        int j = 0;
+        for (int l = 0; l <= d->ml; l++) {
+            const int me = l < d->mm ? l : d->mm;
+            for (int m = -me; m <= me; m++) { if (j < d->nlm) lofj[j] = l; j++; }
+        }
+        if (j != d->nlm) { set_msg(errmsg, "NLM inconsistent with ML, MM"); return 1; }
+    }
+    const size_t nrad = (size_t)nst * d->rshptr[npts];
+    const size_t nsrc_old = (size_t)nst * shptr[npts];
+    const size_t ndel_old = (size_t)nst * (accelflag && !first ? (size_t)oshptr[npts] : 0);
+    a.extinct = A.up(d->extinct, npts * d->npart); a.albedo = A.up(d->albedo, npts * d->npart);
+    a.total_ext = A.up(d->total_ext, npts);
+    a.legen = A.up(d->legen, nlt * d->numphase);
+    a.iphase = A.up(d->iphase, (size_t)nq * npts * d->npart);
+    a.phaseinterpwt = A.up(d->phaseinterpwt, (size_t)nq * npts * d->npart);
+    a.dirflux = A.up(d->dirflux, npts);
+    a.rshptr = A.up(d->rshptr, npts + 1);
+    a.radiance = A.up(d->radiance, nrad ? nrad : 1);
+    a.ylmsun = A.up(d->ylmsun, (size_t)d->nstleg * d->nlm);
+    a.planck = d->planck ? A.up(d->planck, npts * d->npart) : nullptr;
+    a.lofj = A.up(lofj.data(), lofj.size());
+    a.shptr_old = A.up(shptr, npts + 1);
+    a.oshptr_old = A.up(oshptr, npts + 1);
+    a.source_old = A.up(source, nsrc_old ? nsrc_old : 1);
+    a.delsource_old = A.up(delsource, ndel_old ? ndel_old : 1);
+    int dev = 0, nsm = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    const size_t smem = (size_t)CS_WARPS * 2 * nlt * sizeof(float);
+    const int want = (int)((npts + CS_WARPS - 1) / CS_WARPS);
+    const int nblk = want < nsm * 8 ? want : nsm * 8;          // persistent: a multiple of the SM count
+    a.ns_new = A.alloc<int>(npts + 1);
+    a.partials = A.alloc<double>((size_t)nblk * 4);
+    a.bad = A.alloc<int>(1);
+    int *shptr_new = A.alloc<int>(npts + 1);
+    double *sums = A.alloc<double>(4);
+    if (!a.extinct || !a.albedo || !a.total_ext || !a.legen || !a.iphase || !a.phaseinterpwt || !a.dirflux ||
+        !a.rshptr || !a.radiance || !a.ylmsun || !a.lofj || !a.shptr_old || !a.oshptr_old || !a.source_old ||
+        !a.delsource_old || !a.ns_new || !a.partials || !a.bad || !shptr_new || !sums) {
+        set_msg(errmsg, "at3d_compute_source: NULL input array or device allocation failure");
+        return 4;
+    }
+    cudaMemset(a.bad, 0, sizeof(int));
+    cudaMemset(a.ns_new + npts, 0, sizeof(int));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0, 0);
+    if (nst == 1) cs_norms_kernel<1><<<nblk, CS_WARPS * 32, smem>>>(a);
+    else cs_norms_kernel<3><<<nblk, CS_WARPS * 32, smem>>>(a);
+    cs_reduce_kernel<<<1, 1024>>>(nblk, a.partials, sums);
+    size_t tmpb = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmpb, a.ns_new, shptr_new, (int)npts + 1);
+    void *tmp = A.alloc<unsigned char>(tmpb);
+    if (!tmp) { set_msg(errmsg, "device allocation failure"); cudaEventDestroy(e0); cudaEventDestroy(e1); return 4; }
+    cub::DeviceScan::ExclusiveSum(tmp, tmpb, a.ns_new, shptr_new, (int)npts + 1);
+    int total_new = 0, hbad = 0;
+    cudaMemcpy(&total_new, shptr_new + npts, sizeof(int), cudaMemcpyDeviceToHost);
+    cudaMemcpy(&hbad, a.bad, sizeof(int), cudaMemcpyDeviceToHost);
+    int rc = 0;
+    if (hbad) { set_msg(errmsg, "COMPUTE_SOURCE: NR>NLM 3 %d", hbad); rc = 1; }
+    else if (total_new > maxiv) {
+        set_msg(errmsg, "COMPUTE_SOURCE: MAXIV exceeded %d Out of memory for more spherical harmonic terms.", maxiv);
+        rc = 2;
+    }
+    float ms = 0.0f;
+    if (!rc) {
+        a.shptr_new = shptr_new;
+        a.source_new = A.alloc<float>((size_t)nst * (total_new ? total_new : 1));
+        a.delsource_new = (float *)a.delsource_old;
+        if (!a.source_new) { set_msg(errmsg, "device allocation failure"); rc = 4; }
+    }
+    if (!rc) {
+        // DELSOURCE is rewritten at the OLD SHPTR offsets (pass 2); make sure the buffer covers them
+        if (accelflag && !first && (size_t)nst * shptr[npts] > ndel_old) {
+            float *dn = A.alloc<float>((size_t)nst * shptr[npts]);
+            if (!dn) { set_msg(errmsg, "device allocation failure"); rc = 4; }
+            else a.delsource_new = dn;
+        }
+    }
+    if (!rc) {
+        if (nst == 1) cs_write_kernel<1><<<nblk, CS_WARPS * 32, smem>>>(a);
+        else cs_write_kernel<3><<<nblk, CS_WARPS * 32, smem>>>(a);
+        cudaEventRecord(e1, 0);
+        cudaError_t e = cudaEventSynchronize(e1);
+        if (e != cudaSuccess) { set_msg(errmsg, "CUDA error %s in at3d_compute_source", cudaGetErrorString(e)); rc = 4; }
+        else cudaEventElapsedTime(&ms, e0, e1);
+    }
+    if (!rc) {
+        double hs[4];
+        cudaMemcpy(hs, sums, sizeof(hs), cudaMemcpyDeviceToHost);
+        *deljdot = (float)hs[0]; *deljold = (float)hs[1]; *deljnew = (float)hs[2]; *jnorm = (float)hs[3];
+        cudaMemcpy(source, a.source_new, (size_t)nst * total_new * sizeof(float), cudaMemcpyDeviceToHost);
+        if (accelflag && !first) {
+            cudaMemcpy(delsource, a.delsource_new, (size_t)nst * shptr[npts] * sizeof(float), cudaMemcpyDeviceToHost);
+            memcpy(oshptr, shptr, (npts + 1) * sizeof(int32_t));          // OSHPTR(I)=SHPTR(I) (old)
+        }
+        if (cudaMemcpy(shptr, shptr_new, (npts + 1) * sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) {
+            set_msg(errmsg, "CUDA error copying SHPTR back"); rc = 4;
+        }
+    }
+    if (kernel_ms) *kernel_ms = ms;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return rc;
+}

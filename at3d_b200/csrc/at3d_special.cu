@@ -228,3 +228,122 @@ extern "C" int at3d_precompute_phase_check(int nscatangle, int numphase, int nst
     cudaFree(dl); cudaFree(dt); cudaFree(bad);
     return rc;
 }
+
+// ------------------------------------------------------------------------------------------
+// average_subpixel_rays (src/util.f90:484-518): ray -> pixel segmented sum over the sorted
+// pixel_index (0-based pixel numbers).  One thread per pixel sums its contiguous run in order in
+// double; like the reference the last ray is left out of the runs and added to the last pixel, and
+// the first ray is taken to belong to pixel 0.
+// ------------------------------------------------------------------------------------------
+__global__ void average_subpixel_kernel(int npixels, int nrays, int nstokes, const float *ws,
+                                        const int *pixel_index, float *obs)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npixels) return;
+    // first ray index whose pixel number is >= p  (ray 0 counts as pixel 0)
+    auto lower = [&](int v) {
+        int lo = 0, hi = nrays;
+        while (lo < hi) {
+            const int mid = (lo + hi) / 2;
+            const int pv = mid == 0 ? 0 : pixel_index[mid];
+            if (pv < v) lo = mid + 1; else hi = mid;
+        }
+        return lo;
+    };
+    const int r0 = lower(p);
+    int r1 = lower(p + 1);
+    if (r1 > nrays - 1) r1 = nrays - 1;          // the loop of the reference never consumes the last ray
+    for (int k = 0; k < nstokes; k++) {
+        double t = 0.0;
+        for (int r = r0; r < r1; r++) t = t + ws[k + nstokes * (size_t)r];
+        float o = (float)t;
+        if (p == npixels - 1) o = o + ws[k + nstokes * (size_t)(nrays - 1)];
+        obs[k + nstokes * (size_t)p] = o;
+    }
+}
+
+extern "C" int at3d_average_subpixel_rays(int npixels, int nrays, int nstokes, const float *weighted_stokes,
+                                          const int32_t *pixel_index, float *observables, char *errmsg)
+{
+    if (errmsg) errmsg[0] = 0;
+    if (!weighted_stokes || !pixel_index || !observables || npixels < 1 || nrays < 1 || nstokes < 1) { set_msg2(errmsg, "at3d_average_subpixel_rays: bad argument"); return 1; }
+    if (at3d_device_count() < 1) { set_msg2(errmsg, "no CUDA device: at3d_b200 has no CPU fallback"); return 4; }
+    float *w = nullptr, *o = nullptr; int *pi = nullptr;
+    int rc = 0;
+    if (cudaMalloc((void **)&w, (size_t)nstokes * nrays * sizeof(float)) != cudaSuccess ||
+        cudaMalloc((void **)&o, (size_t)nstokes * npixels * sizeof(float)) != cudaSuccess ||
+        cudaMalloc((void **)&pi, (size_t)nrays * sizeof(int)) != cudaSuccess) { set_msg2(errmsg, "cudaMalloc failed"); rc = 4; }
+    if (!rc) {
+        cudaMemcpy(w, weighted_stokes, (size_t)nstokes * nrays * sizeof(float), cudaMemcpyHostToDevice);
+        cudaMemcpy(pi, pixel_index, (size_t)nrays * sizeof(int), cudaMemcpyHostToDevice);
+        average_subpixel_kernel<<<(npixels + 127) / 128, 128>>>(npixels, nrays, nstokes, w, pi, o);
+        if (cudaMemcpy(observables, o, (size_t)nstokes * npixels * sizeof(float), cudaMemcpyDeviceToHost) != cudaSuccess) { set_msg2(errmsg, "CUDA error in average_subpixel_kernel"); rc = 4; }
+    }
+    cudaFree(w); cudaFree(o); cudaFree(pi);
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------------
+// UPDATE_COSTFUNCTION (src/polarized/shdomsub4.f:13-91): cost and gradient update of one pixel from
+// its ray gradient RAYGRAD_PIXEL[nstokes,maxpg,numder] (Jacobian path).  The per-Stokes weights are
+// scalars computed on the host; the kernel is the axpy over maxpg*numder.
+// ------------------------------------------------------------------------------------------
+__global__ void update_cost_kernel(size_t n, int nstokes, const double *rg, double *gradout, double w0, double w1, double w2, double w3)
+{
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    double g = gradout[t] + w0 * rg[(size_t)nstokes * t];
+    if (nstokes > 1) g = g + w1 * rg[(size_t)nstokes * t + 1];
+    if (nstokes > 2) g = g + w2 * rg[(size_t)nstokes * t + 2];
+    if (nstokes > 3) g = g + w3 * rg[(size_t)nstokes * t + 3];
+    gradout[t] = g;
+}
+
+extern "C" int at3d_update_costfunction(const double *stokesout, const double *raygrad_pixel,
+                                        double *gradout, double *cost, const double *uncertainties,
+                                        int costfunc_ll, int nstokes, int maxpg, int numder,
+                                        const double *measurement, int nuncertainty, char *errmsg)
+{
+    if (errmsg) errmsg[0] = 0;
+    if (!stokesout || !raygrad_pixel || !gradout || !cost || !uncertainties || !measurement) { set_msg2(errmsg, "at3d_update_costfunction: null argument"); return 1; }
+    if (at3d_device_count() < 1) { set_msg2(errmsg, "no CUDA device: at3d_b200 has no CPU fallback"); return 4; }
+    const int nu = nuncertainty;
+#define UNC(a, b) uncertainties[((a) - 1) + nu * ((b) - 1)]
+    double w[4] = {0.0, 0.0, 0.0, 0.0};
+    if (!costfunc_ll) {
+        if (nstokes > 4 || nu < nstokes) { set_msg2(errmsg, "at3d_update_costfunction: NSTOKES<=4 and NUNCERTAINTY>=NSTOKES required"); return 3; }
+        for (int i = 1; i <= nstokes; i++) {
+            const double pe = stokesout[i - 1] - measurement[i - 1];
+            for (int j = 1; j <= nstokes; j++) {
+                cost[0] = cost[0] + 0.5 * UNC(i, j) * (pe * pe);
+                w[i - 1] = w[i - 1] + UNC(i, j) * pe;      // gradient weight of RAYGRAD_PIXEL(i,:,:)
+            }
+        }
+    } else {
+        const double raderror = log(stokesout[0]) - log(measurement[0]);
+        cost[0] = cost[0] + 0.5 * (raderror * raderror * UNC(1, 1));
+        w[0] = raderror * UNC(1, 1) / stokesout[0];
+        if (nstokes > 1) {
+            const double q = stokesout[1], u = stokesout[2];
+            const double dolp1 = sqrt(q * q + u * u) / stokesout[0];
+            const double dolp2 = sqrt(measurement[1] * measurement[1] + measurement[2] * measurement[2]) / measurement[0];
+            const double dolperr = log(dolp1) - log(dolp2);
+            cost[0] = cost[0] + 0.5 * (dolperr * dolperr * UNC(2, 2));
+            w[1] = dolperr * UNC(2, 2) * q / (q * q + u * u);
+            w[2] = dolperr * UNC(2, 2) * u / (q * q + u * u);
+        }
+    }
+#undef UNC
+    const size_t n = (size_t)maxpg * numder;
+    double *rg = nullptr, *go = nullptr;
+    int rc = 0;
+    if (cudaMalloc((void **)&rg, n * nstokes * sizeof(double)) != cudaSuccess || cudaMalloc((void **)&go, n * sizeof(double)) != cudaSuccess) { set_msg2(errmsg, "cudaMalloc failed"); rc = 4; }
+    if (!rc) {
+        cudaMemcpy(rg, raygrad_pixel, n * nstokes * sizeof(double), cudaMemcpyHostToDevice);
+        cudaMemcpy(go, gradout, n * sizeof(double), cudaMemcpyHostToDevice);
+        update_cost_kernel<<<(unsigned)((n + 255) / 256), 256>>>(n, nstokes, rg, go, w[0], w[1], w[2], w[3]);
+        if (cudaMemcpy(gradout, go, n * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess) { set_msg2(errmsg, "CUDA error in update_cost_kernel"); rc = 4; }
+    }
+    cudaFree(rg); cudaFree(go);
+    return rc;
+}

@@ -1,0 +1,209 @@
+"""Pins the CPU oracle (oracle/, the checker of every GPU parity test) against what the reference
+itself asserts for the hot path and is readable in this environment:
+
+* tests/golden/dirflux_gradient_{True,False}_{open,periodic}.npy -- the reference's finite-difference
+  Jacobians of the direct beam (reference tests/test_direct_beam.py:149-497, atol=1e-5): pins
+  MAKE_DIRECT / MAKE_DIRECT_DERIVATIVE (DPATH, DPTR) and COMPUTE_DIRECT_BEAM_DERIV;
+* the known answers of UPDATE_COSTFUNCTION (reference tests/test_derivatives.py:75-135);
+* closed forms: orthonormality of the real spherical harmonics (YLMALL), the Henyey-Greenstein phase
+  function (PRECOMPUTE_PHASE_CHECK), the radiance of an absorbing slab over a Lambertian surface
+  (INTEGRATE_1RAY + FIND_BOUNDARY_RADIANCE; cf. reference tests/test_shdom.py:855-908), and
+  finite differences of the oracle's own forward model for the gradient terms that are exact
+  derivatives (extinction of a non-scattering medium), cf. reference tests/test_derivatives.py:765-780.
+"""
+import os
+import numpy as np
+import pytest
+from at3d_b200 import grid as G
+from at3d_b200 import medium as M
+from at3d_b200 import synthetic as S
+from at3d_b200.state import ShdomState, Rays
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+
+
+# --------------------------------------------------------------------------------------------
+def _direct_beam_case(bc):
+    """The scene of reference tests/test_direct_beam.py:19-118: 8x3x7 grid, dx=dy=dz=0.05,
+    extinction ~ U(1e-6,100) (np.random.seed(1)), ssalb=0, sun mu0=0.3, azimuth 10 deg."""
+    npx, npy = 8, 3
+    z = np.arange(0.1, 0.4, 0.05)
+    npz = z.size
+    assert npz == 7
+    np.random.seed(1)
+    ext = np.random.uniform(1e-6, 100, size=(npx, npy, npz))
+    maxpg = npx * npy * npz
+    extp = ext.reshape(-1, 1).astype(np.float32)
+    albp = np.zeros((maxpg, 1), np.float32)
+    legenp = S.hg_legendre_table([0.85], 40, 1)
+    pg = M.PropertyGrid(npx, npy, npz, 0.05, 0.05, z.astype(np.float32), extp, albp,
+                        np.ones((1, maxpg, 1), np.int32), np.ones((1, maxpg, 1), np.float32), legenp, 40, 1)
+    bcflag = 3 if bc == 'open' else 0
+    nx, ny, nz = npx, npy, npz
+    nx1, ny1, nbpts, nbcells = G.grid_sizes(nx, ny, nz, bcflag, 0)
+    xg, yg, zg = G.new_grids(bcflag, 'P', npx, npy, npz, nx, ny, nz, 0.0, 0.0, 0.05, 0.05, pg.zlevels)
+    npts, ncells, gridpos, *_ = G.init_cell_structure(bcflag, 0, nx, ny, nz, nx1, ny1, xg[:nx1], yg[:ny1], zg,
+                                                      maxic=nbcells + 2, maxig=nbpts + 2)
+    st = ShdomState(npts=npts, bcflag=bcflag, ipflag=0, deltam=1, ml=1, nstleg=1, solarflux=1.0, solarmu=-0.3,
+                    solaraz=float(np.deg2rad(10.0)), gridpos=np.asfortranarray(gridpos[:, :npts]))
+    return st, pg
+
+
+@pytest.mark.parametrize('bc', ['open', 'periodic'])
+@pytest.mark.parametrize('deltam', [True, False])
+def test_direct_beam_derivative_matches_reference_golden(bc, deltam, oracle):
+    st, pg = _direct_beam_case(bc)
+    st.deltam = int(deltam)
+    dirflux, extdirp, c = oracle.make_direct(st, pg)
+    dpath, dptr = oracle.make_direct_derivative(st, pg, c)
+    golden = np.load(os.path.join(GOLDEN, 'dirflux_gradient_%s_%s.npy' % (deltam, bc)))
+    assert golden.shape == (pg.maxpg, st.npts)
+    # COMPUTE_DIRECT_BEAM_DERIV with DEXTM=1, TRANSMIT=ABSCELL=1, INPUTWEIGHT=DIRFLUX(ip)
+    jac = np.zeros((pg.maxpg, st.npts))
+    for ip in range(st.npts):
+        n = np.count_nonzero(dptr[:, ip] > 0)
+        assert np.all(dptr[:n, ip] > 0) and np.all(dptr[n:, ip] == 0)
+        np.subtract.at(jac[:, ip], dptr[:n, ip] - 1, dpath[:n, ip].astype(np.float64) * dirflux[ip])
+    assert np.all(np.isfinite(jac))
+    np.testing.assert_allclose(jac, golden, rtol=1e-5, atol=1e-5)    # np.allclose(atol=1e-5), the reference's own assertion
+    assert np.abs(golden).max() > 10 * 1e-5                      # the comparison is not vacuous
+
+
+def test_update_costfunction_known_answers(oracle):
+    so = np.ones(4) * 10.0; so[3] = 0.0
+    g, c = oracle.update_costfunction(so, np.ones((4, 10, 1)), np.zeros((10, 1)), [0.0], np.ones((4, 4)) * 5,
+                                      'L2', np.ones(4) * 13.0)
+    assert abs(c[0] - 1960.0) < 1e-5 and abs(g[0, 0] + 440.0) < 1e-5
+    unc = np.zeros((2, 2)); unc[0, 0] = (1.0 / 0.03) ** 2; unc[1, 1] = (1.0 / 0.005) ** 2
+    so = np.ones(3); so[1] = 0.5; so[2] = 0.0
+    me = np.ones(3) * 1.25; me[1] = 0.25; me[2] = 0.25
+    g, c = oracle.update_costfunction(so, np.ones((3, 10, 1)), np.zeros((10, 1)), [0.0], unc, 'LL', me)
+    assert abs(c[0] - 6519.21) < 1e-2 and abs(g[0, 0] - 45329.43) < 1e-2
+
+
+# --------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('ml,mm', [(7, 7), (15, 15), (9, 5)])
+def test_ylmall_is_orthonormal(ml, mm, oracle):
+    """The unpolarized real spherical harmonics are orthonormal on the sphere."""
+    nlm = sum(2 * min(l, mm) + 1 for l in range(ml + 1))
+    nmu, nphi = ml + 2, 2 * mm + 4
+    x, w = np.polynomial.legendre.leggauss(nmu)
+    gram = np.zeros((nlm, nlm))
+    for mu, wt in zip(x, w):
+        for k in range(nphi):
+            y = oracle.ylmall(False, np.float32(mu), np.float32(2 * np.pi * k / nphi), ml, mm, 1, nlm)[0].astype(np.float64)
+            gram += wt * (2 * np.pi / nphi) * np.outer(y, y)
+    np.testing.assert_allclose(gram, np.eye(nlm), atol=2e-6)
+
+
+def test_ylmall_polarized_first_row_is_the_scalar_basis(oracle):
+    ml = mm = 7
+    nlm = 64
+    for mu, phi in [(0.3, 1.0), (-0.8, 4.0)]:
+        y1 = oracle.ylmall(False, np.float32(mu), np.float32(phi), ml, mm, 1, nlm)
+        y6 = oracle.ylmall(False, np.float32(mu), np.float32(phi), ml, mm, 6, nlm)
+        np.testing.assert_allclose(y6[0], y1[0], rtol=2e-6, atol=1e-7)
+        assert np.all(y6[[1, 2, 4, 5], :4] == 0.0)   # the spin-2 functions vanish for l < 2 (j <= 4)
+
+
+def test_phase_table_reproduces_henyey_greenstein(oracle):
+    g = 0.6
+    nleg = 300
+    legenp = S.hg_legendre_table([g], nleg, 1)
+    tab = oracle.precompute_phase_check(legenp, 181, 1, 15)[0, 0]
+    cs = np.cos(np.pi * np.arange(181) / 180)
+    hg = (1 - g * g) / (1 + g * g - 2 * g * cs) ** 1.5 / (4 * np.pi)
+    np.testing.assert_allclose(tab, hg, rtol=2e-5)
+
+
+# --------------------------------------------------------------------------------------------
+def _absorbing_scene(oracle, ext=4.0, seed=0, bc='periodic', nx=6, ny=5, nz=7, cloud='slab'):
+    """Non-scattering medium (ssalb=0), zero SH source, Lambertian surface lit by the direct beam only."""
+    sc = S.make_scene(nx=nx, ny=ny, nz=nz, nstokes=1, bc=bc, cloud=cloud, ext_max=ext, ssalb=0.0, numphase=2,
+                      mix_fraction=0.0, nsplits=0, truncate=False, seed=seed, gndalbedo=0.3, dz=0.05)
+    oracle.finalize_scene(sc)
+    return sc
+
+
+def _set_absorbing_fields(sc, oracle):
+    st = sc.state
+    t = M.transfer_pa_to_grid(sc.pg, st.gridpos, st.npts, st.ml, bool(st.deltam))
+    st.extinct, st.albedo, st.total_ext = t['extinct'], t['albedo'], t['total_ext']
+    st.dirflux = oracle.make_direct(st, sc.pg)[0]
+    st.source = np.zeros_like(st.source)
+    st.radiance = np.zeros_like(st.radiance)
+    st.fluxes = np.zeros_like(st.fluxes)
+    st.skyrad = np.zeros_like(st.skyrad)
+    return st
+
+
+def test_absorbing_slab_radiance_closed_form(oracle):
+    sc = _absorbing_scene(oracle, ext=4.0)
+    st = _set_absorbing_fields(sc, oracle)
+    m = sc.meta
+    tau = 4.0 * m['zmax']
+    rays = S.orthographic_rays(sc, 0.0, 0.0, 0.04)[0]
+    rad = oracle.render(st, rays)[0]
+    mu0 = abs(float(st.solarmu))
+    expect = 0.3 / np.pi * np.exp(-tau / mu0) * np.exp(-tau)
+    np.testing.assert_allclose(rad, expect, rtol=2e-3)
+    # oblique view: slant path
+    rays = S.orthographic_rays(sc, 40.0, 70.0, 0.04)[0]
+    rad = oracle.render(st, rays)[0]
+    expect = 0.3 / np.pi * np.exp(-tau / mu0) * np.exp(-tau / np.cos(np.deg2rad(40.0)))
+    np.testing.assert_allclose(rad, expect, rtol=2e-3)
+
+
+def test_gradient_is_the_exact_derivative_for_an_absorbing_medium(oracle):
+    """For ssalb=0 the Levis approximation neglects nothing: d(cost)/d(extinction) from the adjoint path
+    (radiance term a13 + direct-beam term a14 + surface term) must equal finite differences of the
+    oracle's own forward model (MAKE_DIRECT + RENDER + cost).  The extinction is positive everywhere:
+    like the reference, the adjoint skips sub-intervals whose extinction is exactly zero
+    (shdomsub4.f:3699,4072), so clear-air points carry no radiance-term derivative by construction."""
+    from at3d_b200 import gradsetup
+    for bc in ('open', 'periodic'):
+        sc = _absorbing_scene(oracle, ext=5.0, seed=4, cloud='slab', bc=bc)
+        rng = np.random.default_rng(7)
+        sc.pg.extinctp[:, 0] *= rng.uniform(0.4, 1.6, sc.pg.maxpg).astype(np.float32)
+        st = _set_absorbing_fields(sc, oracle)
+        m = sc.meta
+        cx, cy = 0.5 * m['xmax'], 0.5 * m['ymax']
+        rays = S.concat_rays([S.orthographic_rays(sc, 0.0, 0.0, 0.03)[0],
+                              S.perspective_rays((cx + 0.5, cy - 0.3, 2.0), (cx, cy, 0.1), 9.0, 9, 9)[0]])
+        gi = gradsetup.make_gradient_inputs(sc, oracle, seed=0, numder=1)
+        gi.dext[:] = 1.0                                            # unknown = extinction everywhere
+        gi.optinterpwt, gi.interpptr, gi.dalbm, gi.dextm, gi.dfj = oracle.prepare_deriv_interps(st, sc.pg, gi)
+        rad0 = oracle.render(st, rays)
+        pix = gradsetup.make_pixels(1, rays.nrays, rad0, seed=2, noise=0.2)
+
+        def cost_of(state):
+            r = oracle.render(state, rays)[0].astype(np.float64)
+            return 0.5 * np.sum(pix.uncertainties[0, 0] * (r - pix.measurements[0].astype(np.float64)) ** 2)
+        g, c, _ = oracle.levisapprox_gradient(st, rays, gradsetup.with_pixels(gi, pix))
+        assert abs(c - cost_of(st)) <= 1e-5 * abs(c)
+        gi.exact_single_scatter = 0
+        g_rad = oracle.levisapprox_gradient(st, rays, gradsetup.with_pixels(gi, pix))[0]   # radiance term only
+        base = sc.pg.extinctp.copy()
+        idx = np.concatenate([np.argsort(-np.abs(g[:, 0]))[:4], np.argsort(-np.abs(g_rad[:, 0]))[:4]])
+        h = 0.02
+        for ib in idx:
+            fd = {}
+            for which in ('all', 'ext'):
+                cs = []
+                for sgn in (+1, -1):
+                    sc.pg.extinctp = base.copy()
+                    _set_absorbing_fields(sc, oracle)
+                    sc.pg.extinctp[ib, 0] += sgn * h
+                    if which == 'all':
+                        stp = _set_absorbing_fields(sc, oracle)
+                    else:               # extinction along the rays only; the direct beam stays frozen
+                        t = M.transfer_pa_to_grid(sc.pg, sc.state.gridpos, sc.state.npts, sc.state.ml, True)
+                        stp = sc.state
+                        stp.extinct, stp.albedo, stp.total_ext = t['extinct'], t['albedo'], t['total_ext']
+                    cs.append(cost_of(stp))
+                fd[which] = (cs[0] - cs[1]) / (2 * h)
+            sc.pg.extinctp = base.copy()
+            _set_absorbing_fields(sc, oracle)
+            scale = np.abs(g).max()
+            assert abs(g[ib, 0] - fd['all']) <= 0.01 * abs(fd['all']) + 2e-3 * scale, (bc, ib, g[ib, 0], fd)
+            assert abs(g_rad[ib, 0] - fd['ext']) <= 0.02 * abs(fd['ext']) + 2e-3 * scale, (bc, ib, g_rad[ib, 0], fd)
