@@ -65,14 +65,14 @@ static int dalloc(at3d_state *st, size_t n, T **dev, char *errmsg)
     return 0;
 }
 
-// planar padded SH block offsets: point block = nstokes planes of roundup4(ns) floats
+// planar padded SH block offsets: point block = nstokes planes of AT3D_SHPAD(ns) floats
 static size_t make_sh_records(const int32_t *shptr, int npts, int nstokes, std::vector<int2> &rec)
 {
     rec.resize(npts);
     size_t off = 0;
     for (int i = 0; i < npts; i++) {
         int ns = shptr[i + 1] - shptr[i];
-        int nsp = (ns + 3) & ~3;
+        int nsp = AT3D_SHPAD(ns);
         rec[i] = make_int2((int)off, ns);
         off += (size_t)nstokes * nsp;
     }
@@ -134,7 +134,7 @@ extern "C" int at3d_state_create(const at3d_state_desc *d, at3d_state **out, cha
     memset(&S, 0, sizeof(S));
     S.nstokes = d->nstokes; S.nstleg = d->nstleg; S.nx = d->nx; S.ny = d->ny; S.nz = d->nz;
     S.npts = d->npts; S.ncells = d->ncells; S.ml = d->ml; S.mm = d->mm; S.nlm = d->nlm;
-    S.nlmp = (d->nlm + 3) & ~3; S.nleg = d->nleg; S.numphase = d->numphase; S.npart = d->npart;
+    S.nlmp = AT3D_SHPAD(d->nlm); S.nleg = d->nleg; S.numphase = d->numphase; S.npart = d->npart;
     S.maxnmicro = d->maxnmicro; S.nq = 8 * d->maxnmicro; S.bcflag = d->bcflag; S.ipflag = d->ipflag;
     S.nmu = d->nmu; S.nphi0max = d->nphi0max; S.maxnbc = d->maxnbc; S.ntoppts = d->ntoppts;
     S.nbotpts = d->nbotpts; S.nsfcpar = d->nsfcpar; S.nscatangle = d->nscatangle; S.nstphase = d->nstphase;
@@ -232,6 +232,10 @@ extern "C" int at3d_state_create(const at3d_state_desc *d, at3d_state **out, cha
         if (rc) { at3d_state_destroy(st); return rc; }
         cudaMemset(c, 0, 8 * sizeof(unsigned long long));
         st->counts_dev = c; S.counts = c;
+        int *rcnt = nullptr;
+        rc = dalloc(st, 4, &rcnt, errmsg);
+        if (rc) { at3d_state_destroy(st); return rc; }
+        st->ray_counter = rcnt;
     }
     *out = st;
     return 0;
@@ -335,9 +339,9 @@ extern "C" int at3d_render(at3d_state *st, const at3d_rays *rays, float *stokes,
     CUDA_TRY(cudaMemsetAsync(st->counts_dev, 0, 8 * sizeof(unsigned long long), stream));
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (kernel_ms) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, stream); }
-    CUDA_TRY(launch_render(st->S, (int)n, camx, camy, camz, cammu, camphi, packs, out_d, nullptr, 0,
-                           correctinterpolate, singlescatter, nosurface, 0, tc, tcap, tn, ts,
-                           (RayErr *)st->err.p, stream));
+    CUDA_TRY(launch_forward(st->S, (int)n, camx, camy, camz, cammu, camphi, packs, out_d, nullptr, nullptr, 1,
+                            correctinterpolate, singlescatter, nosurface, 0, tc, tcap, tn, ts,
+                            (RayErr *)st->err.p, st->ray_counter, stream));
     if (kernel_ms) cudaEventRecord(e1, stream);
     if (host) {
         CUDA_TRY(cudaMemcpyAsync(stokes, out_d, n * nst * sizeof(float), cudaMemcpyDeviceToHost, stream));

@@ -11,8 +11,14 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-#define AT3D_WARPS_PER_BLOCK 4
 #define AT3D_MAX_NSTOKES 3
+// Ray kernels: 8 lanes ("octet") integrate one ray, 4 rays per warp.
+#define AT3D_OCT 8
+#define AT3D_RAY_THREADS 128
+#define AT3D_RAYS_PER_BLOCK (AT3D_RAY_THREADS / AT3D_OCT)
+// planar SH blocks are padded to full 128-byte lines (32 floats): an octet reads them with
+// 4 float4 per lane and iteration, no tail handling
+#define AT3D_SHPAD(ns) (((ns) + 31) & ~31)
 
 struct DevState {
     int nstokes, nstleg, nx, ny, nz, npts, ncells;
@@ -65,6 +71,12 @@ struct DevGrad {
     const float *extinctp, *albedop;        // [maxpg,npart]
     const float *dpath;                     // [longest_path_pts,npts]
     const int *dptr;
+    // ray-independent tables built once per attach by grad_prep_kernel (at3d_grad.cu)
+    int ncomp, ntup;                        // Legendre components that reach I,Q,U (1|4); padded row length
+    const float *grec;                      // [npts,numder,8 nb][8]: dext,dalb,dextm,dalbm,dfj,albp,extp,alb
+    const float *dlegt;                     // [npts,numder,8 nb][ntup]: DLEGT(comp + ncomp*l)
+    const float2 *gpnt;                     // [npts,numder]: SCATTERJ, F
+    const float *legs;                      // [npts,numder][ntup]: table for SOURCET (NPART>1) or null
 };
 
 #define FULLMASK 0xffffffffu
@@ -114,21 +126,22 @@ __device__ __forceinline__ int sh_index(int l, int m, int mm)
     return (l <= mm) ? (l * (l + 1) + m) : ((2 * mm + 1) * l - mm * mm + m);
 }
 
-// YLMALL for one direction, warp-cooperative (lanes over m).  Ysh layout [ncomp][nlmp]:
+// YLMALL for one direction, cooperative over a lane group (member gl of gsize lanes, lanes over m).
+// Ysh layout [ncomp][nlmp]:
 // comp 0 = YR(1,:), and for polarized 1 = YR(2,:), 2 = YR(5,:), 3 = YR(6,:), 4 = YR(3,:).
 // Follows YLMALL_UNPOL (shdomsub2.f:4490-4539) / YLMALL (shdomsub2.f:4244-4360), TRANSPOSE=.FALSE.
-static __device__ void warp_ylmall(const DevState &S, float mu, float phi, float *Ysh)
+static __device__ void group_ylmall(const DevState &S, float mu, float phi, float *Ysh,
+                                    const int lane, const int gsize, const unsigned gmask)
 {
     const int ml = S.ml, mm = S.mm, nlmp = S.nlmp;
-    const int lane = lane_id();
     const double x = (double)mu;
     const double pi = 3.14159265358979323846;   // DACOS(-1.D0)
     const double fct = 1.0 / sqrt(2.0 * pi);
     // zero padding entries
-    for (int j = S.nlm + lane; j < nlmp; j += 32)
+    for (int j = S.nlm + lane; j < nlmp; j += gsize)
         for (int c = 0; c < S.ny_comp; c++) Ysh[c * nlmp + j] = 0.0f;
     if (S.nstleg == 1) {
-        for (int m = lane; m <= mm; m += 32) {
+        for (int m = lane; m <= mm; m += gsize) {
             double cosm, sinm;
             if (m > 0) { cosm = (double)cosf((float)m * phi); sinm = (double)sinf((float)m * phi); }
             else { cosm = 1.0; sinm = 0.0; }
@@ -154,7 +167,7 @@ static __device__ void warp_ylmall(const DevState &S, float mu, float phi, float
             }
         }
     } else {
-        for (int m = lane; m <= mm; m += 32) {
+        for (int m = lane; m <= mm; m += gsize) {
             double cosm = 1.0, sinm = 0.0;
             if (m > 0) { cosm = (double)cosf((float)m * phi); sinm = (double)sinf((float)m * phi); }
             const double xp = x, xm = -x;
@@ -242,7 +255,7 @@ static __device__ void warp_ylmall(const DevState &S, float mu, float phi, float
             }
         }
     }
-    __syncwarp();
+    __syncwarp(gmask);
 }
 
 // ---------------- grid traversal helpers (uniform per warp; every lane runs them) ----------------
@@ -535,6 +548,17 @@ static __device__ float dev_sky_radiance(const DevState &S, float mu, float phi)
     return (float)(weightedsum / weightsum);
 }
 
+// sums over the 8 lanes of an octet (m = the octet's lane mask)
+__device__ __forceinline__ float oct_sum(unsigned m, float v)
+{
+    v += __shfl_xor_sync(m, v, 4); v += __shfl_xor_sync(m, v, 2); v += __shfl_xor_sync(m, v, 1);
+    return v;
+}
+__device__ __forceinline__ double oct_sum_d(unsigned m, double v)
+{
+    v += __shfl_xor_sync(m, v, 4); v += __shfl_xor_sync(m, v, 2); v += __shfl_xor_sync(m, v, 1);
+    return v;
+}
 __device__ __forceinline__ float warp_sum(float v)
 {
 #pragma unroll

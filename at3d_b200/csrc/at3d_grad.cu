@@ -5,17 +5,19 @@
 //   COMPUTE_ADJOINT_WEIGHTS :3969-4034, COMPUTE_RADIANCE_DERIVATIVE_ADJOINT :4037-4114,
 //   COMPUTE_DIRECT_BEAM_DERIV_ADJOINT :4117-4143.
 //
-// Design (DESIGN.md "Gradient kernels"): one warp per ray, same bit-exact FP64 walk as RENDER.
-//  * The reference evaluates the radiance SH contraction 8*NUMDER times per new grid point
-//    (COMPUTE_SOURCE_DIRECTION per property corner and unknown).  That contraction is linear in the
-//    Legendre table, so the warp forms the per-degree shell sums sum_m RADIANCE(.,j)*YLMDIR(.,j) once
-//    (radiance SH read once per (ray, point)) and every (corner, unknown) then costs one
-//    (NLEG+1)*NSTLEG dot product.
-//  * GRAD8 is contracted with the per-ray adjoint weight at once, so a corner keeps 8*NUMDER scalars
-//    instead of the reference's five NSTOKES*8*8*NUMDER arrays.
-//  * The backward cumulative sum over saved sub-intervals (PASSEDRAD) becomes "total - running",
-//    the total coming from a forward march with identical arithmetic; nothing is saved per
-//    sub-interval.
+// Design (DESIGN.md "Gradient kernels"): one octet (8 lanes) per ray, same bit-exact FP64 walk as RENDER.
+//  * Everything in COMPUTE_SOURCE_GRAD_1CELL that does not depend on the ray -- the mixed Legendre
+//    tables LEGENT/LEGENP/DLEGP and DLEGT(l) per (grid point, property corner, unknown) -- is
+//    evaluated once per cost-function evaluation by grad_prep_kernel (at attach time) and kept in HBM.
+//  * The reference evaluates the radiance SH contraction COMPUTE_SOURCE_DIRECTION 8*NUMDER times per
+//    new grid point.  It is linear in the Legendre table, so the octet forms the per-degree shell sums
+//    sum_m RADIANCE(.,j)*YLMDIR(.,j) once (radiance SH read once per (ray, point)) and every
+//    (corner, unknown) then costs one dot product of length (ML+1)*{1|4}; lane = property corner.
+//  * GRAD8 is contracted with the per-ray adjoint weight at once, so a cell corner keeps 8*NUMDER
+//    scalars (a shared-memory row) instead of the reference's five NSTOKES*8*8*NUMDER arrays; rows
+//    follow their grid point from cell to cell.
+//  * The backward cumulative sum over saved sub-intervals (PASSEDRAD) becomes "total - running", the
+//    total coming from the forward pass (same arithmetic); nothing is saved per sub-interval.
 //  * Sub-interval weights accumulate in registers (lane n owns corner n); global memory is touched
 //    once per cell and corner with red.global.add.f64, never inside the sub-interval loop.
 #include <cstdio>
@@ -26,46 +28,31 @@
 #include "at3d_host.h"
 #include "at3d_ray.cuh"
 
+#define AT3D_GRAD_ROWS 16       // shared-memory rows of contracted GRAD8 per octet (8 live + 8 spare)
+
 // ------------------------------------------------------------------------------------------
-// per-warp shared scratch of the adjoint kernel
+// per-octet shared scratch of the adjoint kernel (byte offsets)
 // ------------------------------------------------------------------------------------------
 struct GradLayout {
-    int y, rad, cc, dslot, ib, xg, legent, tc, vsh, wacc, total;   // byte offsets
+    int y, stage, shell, tc, vsh, rowd, rowx, rowib, wacc, total;
 };
 
-__host__ __device__ inline GradLayout grad_layout(int nstokes, int ny_comp, int nlmp, int nstleg, int nleg,
-                                                  int ml, int numder)
+__host__ __device__ inline GradLayout grad_layout(int nstokes, int ny_comp, int nlmp, int ml, int ncomp,
+                                                  int ntup, int numder)
 {
     GradLayout L;
     int o = 0;
     L.y = o;      o += ny_comp * nlmp * 4;
-    L.rad = o;    o += nstokes * nlmp * 4;
-    L.dslot = o;  o += 8 * 8 * numder * 8;                 // double D[8 corners][8 nb][numder]
-    L.wacc = o;   o += 3 * 8 * 8;                          // double W[8], G[8], BW[8]
-    L.tc = o;     o += nstleg * (nleg + 1) * 8;            // double Tc[nlt]
-    o = (o + 15) & ~15;
-    L.cc = o;     o += (nstokes == 1 ? (int)sizeof(CornerCache<1>) : (int)sizeof(CornerCache<3>));
-    L.ib = o;     o += 8 * 8 * 4;                          // int IB[8][8]
-    L.xg = o;     o += 8 * 8 * numder * 4;                 // float XG[8][8][numder]
-    L.legent = o; o += nstleg * (nleg + 1) * 4;            // float legent[nlt]
-    L.vsh = o;    o += 3 * (ml + 1) * 4;                   // float V1[ml+1], V2[ml+1], V6[ml+1]
+    L.stage = o;  o += nstokes * nlmp * 4;                        // RADIANCE*YLMDIR products (scalar) / RADIANCE planes
+    L.tc = o;     o += ntup * 8;                                  // double Tc[ntup]
+    L.rowd = o;   o += AT3D_GRAD_ROWS * 8 * numder * 8;           // double D[row][nb][numder]
+    L.wacc = o;   o += 2 * 8 * 8;                                 // double W[8], G[8]
+    L.rowx = o;   o += AT3D_GRAD_ROWS * 8 * numder * 4;           // float  XG[row][nb][numder]
+    L.rowib = o;  o += AT3D_GRAD_ROWS * 8 * 4 + 8 * 4;            // int    IB[row][nb], ROWOF[8]
+    L.shell = o;  o += (nstokes == 1 ? 1 : 8) * (ml + 1) * 4;     // float shell sums (NPART>1 only)
+    L.vsh = o;    o += 3 * (ml + 1) * 4;                          // float V1, V5, V6 (no delta-M only)
     L.total = (o + 15) & ~15;
     return L;
-}
-
-// SINGSCAT(:,iph) of the ray (shdomsub2.f:2425-2441), evaluated on demand
-template <int NST>
-__device__ __forceinline__ void ray_singscat(const float *tab, int nstphase, int numphase, int iph,
-                                             const RayDir &rd, float (&s)[NST])
-{
-    const float *p0 = tab + (size_t)nstphase * ((iph - 1) + (size_t)numphase * (rd.j - 1));
-    const float *p1 = p0 + (size_t)nstphase * numphase;
-    s[0] = (1 - rd.f) * __ldg(p0) + rd.f * __ldg(p1);
-    if (NST > 1) {
-        const float b1 = (1 - rd.f) * __ldg(p0 + 1) + rd.f * __ldg(p1 + 1);
-        s[1] = (float)(b1 * rd.cos22);
-        s[NST - 1] = (float)(b1 * rd.sin22);
-    }
 }
 
 // "unscaling" of a delta-M scaled tabulated Legendre entry (shdomsub4.f:1905-1925)
@@ -78,211 +65,50 @@ __device__ __forceinline__ float unscale_leg(float x, int k /*0-based component*
     return x;
 }
 
-// COMPUTE_SOURCE_GRAD_1CELL for one new grid point (all lanes cooperate).
-template <int NST>
-__device__ void eval_point_grad(const DevState &S, const DevGrad &G, int ip, unsigned char *sm,
-                                const GradLayout &L, const RayDir &rd, const double (&adj)[NST],
-                                float &ext_out, float (&src_out)[NST], float (&ss_out)[NST],
-                                double *Dslot, int *IBslot, float *XGslot, float &fpersist)
+// compact index of Legendre component k (0-based) among those that reach I,Q,U: 0,1,2,4 -> 0,1,2,3
+__device__ __forceinline__ int comp_slot(int k) { return k == 4 ? 3 : k; }
+
+// ------------------------------------------------------------------------------------------
+// Ray-independent part of COMPUTE_SOURCE_GRAD_1CELL (shdomsub4.f:1801-1981), once per attach:
+// per (grid point, unknown): SCATTERJ, F and -- for NPART>1 -- the mixed table used for SOURCET;
+// per (grid point, unknown, property corner): the packed scalars and DLEGT(l).  One warp per point,
+// lane = nb + 8*g4 (g4 splits the table entries).
+// ------------------------------------------------------------------------------------------
+__global__ void grad_prep_kernel(DevState S, DevGrad G, float *grec, float *dlegt, float2 *gpnt, float *legs)
 {
-    const int lane = lane_id();
-    const float *Ysh = (const float *)(sm + L.y);
-    float *radsh = (float *)(sm + L.rad);
-    float *legent = (float *)(sm + L.legent);
-    double *Tc = (double *)(sm + L.tc);
-    const float *Vsh = (const float *)(sm + L.vsh);
-    const int nlmp = S.nlmp, nstleg = S.nstleg, ml = S.ml, mm = S.mm;
+    extern __shared__ float prep_smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ipz = blockIdx.x * (blockDim.x >> 5) + warp;
+    const int nstleg = S.nstleg, ml = S.ml;
     const int nlt = nstleg * (S.nleg + 1);
+    if (ipz >= S.npts) return;
+    const int ip = ipz + 1;
+    float *legent = prep_smem + (size_t)warp * nlt;
     const bool deltam = S.deltam != 0, interp_new = S.interp_new != 0;
-    const float secmu0 = (float)(1.0 / fabs((double)S.solarmu));
-    // ---------------- forward part (shdomsub4.f:1660-1785) ----------------
-    const float4 pr = __ldg(&S.ptrec[ip - 1]);
-    const float ext = pr.w;
-    float a[NST], b[NST];
-    {
-        const int2 sr = __ldg(&S.srcrec[ip - 1]);
-        const int nsp = (sr.y + 3) & ~3;
-        const float *base = S.shsrc + sr.x;
-#pragma unroll
-        for (int k = 0; k < NST; k++) { a[k] = 0.0f; b[k] = 0.0f; }
-        for (int j4 = lane * 4; j4 < nsp; j4 += 128) {
-            const float4 s = __ldg((const float4 *)(base + j4));
-            const float4 y = *(const float4 *)(Ysh + j4);
-            a[0] = fmaf(s.x, y.x, a[0]); a[0] = fmaf(s.y, y.y, a[0]);
-            a[0] = fmaf(s.z, y.z, a[0]); a[0] = fmaf(s.w, y.w, a[0]);
-            if (NST > 1) {
-                const float4 q = __ldg((const float4 *)(base + nsp + j4));
-                const float4 u = __ldg((const float4 *)(base + 2 * nsp + j4));
-                const float4 y2 = *(const float4 *)(Ysh + 1 * nlmp + j4);
-                const float4 y5 = *(const float4 *)(Ysh + 2 * nlmp + j4);
-                const float4 y6 = *(const float4 *)(Ysh + 3 * nlmp + j4);
-                const float4 y3 = *(const float4 *)(Ysh + 4 * nlmp + j4);
-                a[1] = fmaf(q.x, y2.x, a[1]); a[1] = fmaf(u.x, y5.x, a[1]);
-                a[1] = fmaf(q.y, y2.y, a[1]); a[1] = fmaf(u.y, y5.y, a[1]);
-                a[1] = fmaf(q.z, y2.z, a[1]); a[1] = fmaf(u.z, y5.z, a[1]);
-                a[1] = fmaf(q.w, y2.w, a[1]); a[1] = fmaf(u.w, y5.w, a[1]);
-                a[NST - 1] = fmaf(q.x, y6.x, a[NST - 1]); a[NST - 1] = fmaf(u.x, y3.x, a[NST - 1]);
-                a[NST - 1] = fmaf(q.y, y6.y, a[NST - 1]); a[NST - 1] = fmaf(u.y, y3.y, a[NST - 1]);
-                a[NST - 1] = fmaf(q.z, y6.z, a[NST - 1]); a[NST - 1] = fmaf(u.z, y3.z, a[NST - 1]);
-                a[NST - 1] = fmaf(q.w, y6.w, a[NST - 1]); a[NST - 1] = fmaf(u.w, y3.w, a[NST - 1]);
-            }
-        }
-        const int cnt = __ldg(&S.sscount[ip - 1]);
-        for (int k = lane; k < cnt; k += 32) {
-            const int2 e = __ldg(&S.ssent[(size_t)(ip - 1) * S.kmax + k]);
-            const float coef = __int_as_float(e.y);
-            float sv[NST];
-            ray_singscat<NST>(S.phasetab, S.nstphase, S.numphase, e.x, rd, sv);
-#pragma unroll
-            for (int kk = 0; kk < NST; kk++) b[kk] = fmaf(coef, sv[kk], b[kk]);
-        }
-#pragma unroll
-        for (int k = 0; k < NST; k++) { a[k] = warp_sum(a[k]); b[k] = warp_sum(b[k]); }
-    }
-    if (!deltam) {
-        // without delta-M SINGSCAT8 is the truncated single scattering (shdomsub4.f:1723-1760,1781):
-        // sum over species of DA*LEGENT(.,l)*sum_m YLMDIR*YLMSUN for the shells present in SOURCE
-        const int ns = __ldg(&S.srcrec[ip - 1]).y;
-        const float dirflux0 = __ldg(&S.dirflux[ip - 1]);
-        float t[NST];
-#pragma unroll
-        for (int k = 0; k < NST; k++) t[k] = 0.0f;
-        for (int ipa = 0; ipa < S.npart; ipa++) {
-            float w;
-            if (ext == 0.0f) w = 1.0f; else w = __ldg(&S.extinct[(ip - 1) + (size_t)S.npts * ipa]) / ext;
-            if (w == 0.0f) continue;
-            const int *iph = S.iphase + (size_t)S.nq * ((ip - 1) + (size_t)S.npts * ipa);
-            const float *pw = S.phaseinterpwt + (size_t)S.nq * ((ip - 1) + (size_t)S.npts * ipa);
-            const bool single = (!interp_new) || (__ldg(&pw[0]) >= S.phasemax);
-            const float da = __ldg(&S.albedo[(ip - 1) + (size_t)S.npts * ipa]) * dirflux0 * secmu0 * w;
-            for (int l = lane; l <= ml; l += 32) {
-                const int me = l < mm ? l : mm;
-                if (sh_index(l, -me, mm) >= ns) continue;
-                float l1, l5 = 0.0f;
-                if (single) {
-                    l1 = __ldg(&S.legen[(size_t)nlt * (__ldg(&iph[0]) - 1) + nstleg * l]);
-                    if (nstleg > 1) l5 = __ldg(&S.legen[(size_t)nlt * (__ldg(&iph[0]) - 1) + nstleg * l + 4]);
-                } else {
-                    l1 = 0.0f;
-                    for (int q = 0; q < S.nq; q++) {
-                        const float wq = __ldg(&pw[q]);
-                        if (wq <= 1e-5f) continue;
-                        l1 = l1 + __ldg(&S.legen[(size_t)nlt * (__ldg(&iph[q]) - 1) + nstleg * l]) * wq;
-                        if (nstleg > 1) l5 = l5 + __ldg(&S.legen[(size_t)nlt * (__ldg(&iph[q]) - 1) + nstleg * l + 4]) * wq;
-                    }
-                }
-                t[0] = t[0] + da * l1 * Vsh[l];
-                if (NST > 1) {
-                    t[1] = t[1] + da * l5 * Vsh[(ml + 1) + l];
-                    t[NST - 1] = t[NST - 1] + da * l5 * Vsh[2 * (ml + 1) + l];
-                }
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < NST; k++) b[k] = warp_sum(t[k]);
-    }
-    float srcfull[NST];      // SRCEXT8 before the multiplication by the extinction
-#pragma unroll
-    for (int k = 0; k < NST; k++) {
-        srcfull[k] = deltam ? a[k] + b[k] : a[k];
-        ss_out[k] = b[k] * ext;
-        src_out[k] = G.singlescatter ? ss_out[k] : srcfull[k] * ext;
-    }
-    ext_out = ext;
-    // ---------------- radiance SH block -> shared memory ----------------
-    const int2 rr = __ldg(&S.radrec[ip - 1]);
-    const int rns = rr.y, nrp = (rr.y + 3) & ~3;
-    {
-        const float *rb = S.shrad + rr.x;
-        for (int j4 = lane * 4; j4 < nrp; j4 += 128) {
-#pragma unroll
-            for (int k = 0; k < NST; k++)
-                *(float4 *)(radsh + k * nlmp + j4) = __ldg((const float4 *)(rb + k * nrp + j4));
-        }
-    }
-    for (int t = lane; t < nlt; t += 32) Tc[t] = 0.0;
-    __syncwarp();
-    // shell sums  T_k(l) = sum_m adj . RADIANCE(.,j) YLMDIR(.,j)   (lane <-> degree l)
-    const float dirflux = __ldg(&S.dirflux[ip - 1]);
-    for (int l = lane; l <= ml; l += 32) {
-        const int me = l < mm ? l : mm;
-        const int jlo = sh_index(l, -me, mm), cnt = 2 * me + 1;
-        float A = 0, B = 0, C = 0, D = 0, E = 0, F = 0, Gq = 0, H = 0;
-        for (int i = 0; i < cnt; i++) {
-            const int j = jlo + i;
-            if (j >= rns) break;
-            const float r1 = radsh[j], y1 = Ysh[j];
-            A = A + r1 * y1;
-            if (NST > 1) {
-                const float r2 = radsh[nlmp + j], r3 = radsh[2 * nlmp + j];
-                const float y2 = Ysh[nlmp + j], y5 = Ysh[2 * nlmp + j], y6 = Ysh[3 * nlmp + j], y3 = Ysh[4 * nlmp + j];
-                B = B + r2 * y1; C = C + r1 * y2; D = D + r2 * y2; E = E + r3 * y5;
-                F = F + r1 * y6; Gq = Gq + r2 * y6; H = H + r3 * y3;
-            }
-        }
-        double t1 = adj[0] * A;
-        if (!deltam) t1 += adj[0] * (double)(dirflux * secmu0 * Vsh[l]);
-        Tc[0 + nstleg * l] = t1;
-        if (NST > 1) {
-            double t5 = adj[0] * B + adj[1] * C + adj[NST - 1] * F;
-            if (!deltam) t5 += adj[1] * (double)(dirflux * secmu0 * Vsh[(ml + 1) + l]);
-            Tc[4 + nstleg * l] = t5;
-            Tc[1 + nstleg * l] = adj[1] * D + adj[NST - 1] * Gq;
-            Tc[2 + nstleg * l] = adj[1] * E + adj[NST - 1] * H;
-        }
-    }
-    __syncwarp();
-    // ---------------- gradient part (shdomsub4.f:1786-2019) ----------------
     const int nb = lane & 7, g4 = lane >> 3;
-    const int ib = __ldg(&G.interpptr[nb + 8 * (size_t)(ip - 1)]);
-    const float xi = __ldg(&G.optinterpwt[nb + 8 * (size_t)(ip - 1)]);
-    if (lane < 8) IBslot[lane] = ib;
+    const int ib = __ldg(&G.interpptr[nb + 8 * (size_t)ipz]);
+    const float xi = __ldg(&G.optinterpwt[nb + 8 * (size_t)ipz]);
+    const int pm = G.pmaxnmicro, nd = G.numder, ncomp = G.ncomp, ntup = G.ntup;
     int last_ipa = -1;
-    float scatterj = 0.0f, singscatj[NST], sourcet[NST], f = fpersist;
-#pragma unroll
-    for (int k = 0; k < NST; k++) { singscatj[k] = 0.0f; sourcet[k] = 0.0f; }
-    const int pm = G.pmaxnmicro;
-    for (int idr = 0; idr < G.numder; idr++) {
+    float scatterj = 0.0f, f = 0.0f;
+    for (int idr = 0; idr < nd; idr++) {
         const int ipa = __ldg(&G.partder[idr]);       // 1-based species
         const float albp = __ldg(&G.albedop[(ib - 1) + (size_t)G.maxpg * (ipa - 1)]);
         const float extp = __ldg(&G.extinctp[(ib - 1) + (size_t)G.maxpg * (ipa - 1)]);
         const int *iphp = G.iphasep + (size_t)pm * ((ib - 1) + (size_t)G.maxpg * (ipa - 1));
         const float *pwp = G.phasewtp + (size_t)pm * ((ib - 1) + (size_t)G.maxpg * (ipa - 1));
-        const float alb_ip = __ldg(&S.albedo[(ip - 1) + (size_t)S.npts * (ipa - 1)]);
+        const float alb_ip = __ldg(&S.albedo[ipz + (size_t)S.npts * (ipa - 1)]);
+        float *legs_row = legs ? legs + ((size_t)ipz * nd + idr) * ntup : nullptr;
         if (ipa != last_ipa) {
             last_ipa = ipa;
             __syncwarp();
             const float sw = xi * albp * extp;       // SPATIAL_WEIGHT of property corner nb
             scatterj = 0.0f;
-#pragma unroll
-            for (int k = 0; k < NST; k++) singscatj[k] = 0.0f;
-            if (deltam) {
-                for (int n = 0; n < 8; n++) scatterj = scatterj + __shfl_sync(FULLMASK, sw, n);
-                float part[NST];
-#pragma unroll
-                for (int k = 0; k < NST; k++) part[k] = 0.0f;
-                if (g4 == 0 && sw > 1e-6f) {
-                    for (int q = 0; q < pm; q++) {
-                        const float w = __ldg(&pwp[q]);
-                        if (w <= 1e-6f) continue;
-                        float sv[NST];
-                        ray_singscat<NST>(S.phasetab, S.nstphase, S.numphase, __ldg(&iphp[q]), rd, sv);
-#pragma unroll
-                        for (int k = 0; k < NST; k++) part[k] = part[k] + sw * w * sv[k];
-                    }
-                }
-#pragma unroll
-                for (int k = 0; k < NST; k++) {
-                    float tot = 0.0f;
-                    for (int n = 0; n < 8; n++) tot = tot + __shfl_sync(FULLMASK, part[k], n);
-                    if (scatterj > G.scatmin) singscatj[k] = tot / scatterj;
-                    else singscatj[k] = (float)(tot / G.scatmin);
-                }
-            }
+            if (deltam) for (int n = 0; n < 8; n++) scatterj = scatterj + __shfl_sync(FULLMASK, sw, n);
             if (S.npart == 1) {
                 // LEGENT left by the forward part: the PHASEINTERPWT mix at this grid point
-                const int *iph = S.iphase + (size_t)S.nq * ((ip - 1) + (size_t)S.npts * (ipa - 1));
-                const float *pw = S.phaseinterpwt + (size_t)S.nq * ((ip - 1) + (size_t)S.npts * (ipa - 1));
+                const int *iph = S.iphase + (size_t)S.nq * (ipz + (size_t)S.npts * (ipa - 1));
+                const float *pw = S.phaseinterpwt + (size_t)S.nq * (ipz + (size_t)S.npts * (ipa - 1));
                 const bool single = (!interp_new) || (__ldg(&pw[0]) >= S.phasemax);
                 for (int t = lane; t < nlt; t += 32) {
                     float v;
@@ -309,8 +135,6 @@ __device__ void eval_point_grad(const DevState &S, const DevGrad &G, int ip, uns
                         legent[t] = v;
                     }
                 }
-#pragma unroll
-                for (int k = 0; k < NST; k++) sourcet[k] = (alb_ip > 1e-8f) ? srcfull[k] / alb_ip : 0.0f;
             } else {
                 // property-grid mix of the Legendre table for this species (shdomsub4.f:1835-1880)
                 float swn[8]; int ibn[8];
@@ -339,38 +163,11 @@ __device__ void eval_point_grad(const DevState &S, const DevGrad &G, int ip, uns
                 if (deltam && interp_new)
                     for (int t = lane; t < nstleg * (ml + 1); t += 32) legent[t] = legent[t] / (1 - f);
                 __syncwarp();
-#pragma unroll
-                for (int k = 0; k < NST; k++) sourcet[k] = 0.0f;
-                if (scatterj > G.scatmin) {
-                    // COMPUTE_SOURCE_DIRECTION with the mixed table
-                    float acc[NST];
-#pragma unroll
-                    for (int k = 0; k < NST; k++) acc[k] = 0.0f;
-                    for (int j = lane; j < rns; j += 32) {
-                        const int l = __ldg(&S.lofj[j]);
-                        const float r1 = radsh[j], y1 = Ysh[j];
-                        acc[0] = acc[0] + legent[nstleg * l] * r1 * y1;
-                        if (NST > 1) {
-                            const float r2 = radsh[nlmp + j], r3 = radsh[2 * nlmp + j];
-                            const float l5 = legent[4 + nstleg * l], l2 = legent[1 + nstleg * l], l3 = legent[2 + nstleg * l];
-                            acc[0] = acc[0] + l5 * r2 * y1;
-                            acc[1] = acc[1] + l5 * r1 * Ysh[nlmp + j] + l2 * r2 * Ysh[nlmp + j] + l3 * r3 * Ysh[2 * nlmp + j];
-                            acc[NST - 1] = acc[NST - 1] + l5 * r1 * Ysh[3 * nlmp + j] + l2 * r2 * Ysh[3 * nlmp + j]
-                                           + l3 * r3 * Ysh[4 * nlmp + j];
-                        }
-                    }
-                    if (!deltam) {
-                        for (int l = lane; l <= ml; l += 32) {
-                            acc[0] = acc[0] + dirflux * secmu0 * legent[nstleg * l] * Vsh[l];
-                            if (NST > 1) acc[1] = acc[1] + dirflux * secmu0 * legent[4 + nstleg * l] * Vsh[(ml + 1) + l];
-                        }
-                    }
-#pragma unroll
-                    for (int k = 0; k < NST; k++) sourcet[k] = warp_sum(acc[k]);
-                    if (deltam) {
-#pragma unroll
-                        for (int k = 0; k < NST; k++) sourcet[k] = sourcet[k] + dirflux * singscatj[k] * secmu0 / (1 - f);
-                    }
+                // the table COMPUTE_SOURCE_DIRECTION contracts with the radiance for SOURCET
+                for (int t = lane; t < nstleg * (ml + 1); t += 32) {
+                    const int k = t % nstleg, l = t / nstleg;
+                    if (k == 3 || k == 5) continue;
+                    legs_row[comp_slot(k) + ncomp * l] = legent[t];
                 }
                 __syncwarp();
                 if (deltam) {
@@ -382,20 +179,30 @@ __device__ void eval_point_grad(const DevState &S, const DevGrad &G, int ip, uns
                     }
                 }
             }
-            sourcet[0] = fmaxf(0.0f, sourcet[0]);
             __syncwarp();
+        } else if (legs_row && idr > 0) {
+            // same species as the previous unknown: same table
+            const float *prev = legs + ((size_t)ipz * nd + idr - 1) * ntup;
+            for (int t = lane; t < ntup; t += 32) legs_row[t] = prev[t];
         }
-        // ---- per property corner nb (lane = nb + 8*g4, g4 splits the table entries) ----
+        if (lane == 0) gpnt[(size_t)ipz * nd + idr] = make_float2(scatterj, f);
+        // ---- per property corner nb ----
         const float dext_v = __ldg(&G.dext[(ib - 1) + (size_t)G.maxpg * idr]);
         const float dalb_v = __ldg(&G.dalb[(ib - 1) + (size_t)G.maxpg * idr]);
         const float dextm_v = __ldg(&G.dextm[(ib - 1) + (size_t)G.maxpg * idr]);
-        const float dalbm_v = __ldg(&G.dalbm[nb + 8 * ((size_t)(ip - 1) + (size_t)S.npts * idr)]);
-        const float dfj_v = __ldg(&G.dfj[nb + 8 * ((size_t)(ip - 1) + (size_t)S.npts * idr)]);
+        const float dalbm_v = __ldg(&G.dalbm[nb + 8 * ((size_t)ipz + (size_t)S.npts * idr)]);
+        const float dfj_v = __ldg(&G.dfj[nb + 8 * ((size_t)ipz + (size_t)S.npts * idr)]);
         const int doex = __ldg(&G.doexact[idr]);
         const int *dip = G.diphasep + (size_t)G.deriv_maxnmicro * ((ib - 1) + (size_t)G.maxpg * idr);
         const float *dpw = G.dphasewtp + (size_t)G.deriv_maxnmicro * ((ib - 1) + (size_t)G.maxpg * idr);
-        double dot = 0.0;
+        const size_t row = ((size_t)ipz * nd + idr) * 8 + nb;
+        if (g4 == 0) {
+            float4 *gr = (float4 *)(grec + row * 8);
+            gr[0] = make_float4(dext_v, dalb_v, dextm_v, dalbm_v);
+            gr[1] = make_float4(dfj_v, albp, extp, alb_ip);
+        }
         if (xi >= 1e-7f) {
+            float *drow = dlegt + row * ntup;
             for (int t = g4; t < nlt; t += 4) {
                 const int k = t % nstleg, l = t / nstleg;
                 if (k == 3 || k == 5 || l > ml) continue;       // components that never reach I,Q,U
@@ -412,171 +219,360 @@ __device__ void eval_point_grad(const DevState &S, const DevGrad &G, int ip, uns
                         dlegp = dlegp + __ldg(&pwp[q]) * __ldg(&G.dleg[(size_t)nlt * (__ldg(&dip[q]) - 1) + t]);
                 const float lt = legent[t];
                 const float leg_diff = legenp - lt;
-                const float dlegt = dext_v * leg_diff * albp + dalb_v * leg_diff * extp + dlegp * extp * albp
-                                    + (lt - 1) * dfj_v;
-                dot += (double)dlegt * Tc[t];
+                drow[comp_slot(k) + ncomp * l] = dext_v * leg_diff * albp + dalb_v * leg_diff * extp
+                                                 + dlegp * extp * albp + (lt - 1) * dfj_v;
             }
-        }
-        dot += __shfl_xor_sync(FULLMASK, dot, 8);
-        dot += __shfl_xor_sync(FULLMASK, dot, 16);
-        if (lane < 8) {
-            double d = 0.0;
-            if (xi >= 1e-7f) {
-                float singscatp[NST], dsingscatp[NST];
-#pragma unroll
-                for (int k = 0; k < NST; k++) { singscatp[k] = 0.0f; dsingscatp[k] = 0.0f; }
-                if (deltam) {
-                    for (int q = 0; q < pm; q++) {
-                        float sv[NST];
-                        ray_singscat<NST>(S.phasetab, S.nstphase, S.numphase, __ldg(&iphp[q]), rd, sv);
-                        const float w = __ldg(&pwp[q]);
-#pragma unroll
-                        for (int k = 0; k < NST; k++) singscatp[k] = singscatp[k] + w * sv[k];
-                        if (doex == 0 && q < G.deriv_maxnmicro) {
-                            const float dw = __ldg(&dpw[q]);
-#pragma unroll
-                            for (int k = 0; k < NST; k++) dsingscatp[k] = dsingscatp[k] + dw * sv[k];
-                        }
-                    }
-                    if (doex == 1) {
-                        for (int q = 0; q < G.deriv_maxnmicro; q++) {
-                            float sv[NST];
-                            ray_singscat<NST>(G.dphasetab, S.nstphase, G.dnumphase, __ldg(&dip[q]), rd, sv);
-                            const float w = __ldg(&pwp[q]);
-#pragma unroll
-                            for (int k = 0; k < NST; k++) dsingscatp[k] = dsingscatp[k] + w * sv[k];
-                        }
-                    }
-                }
-                double sum = 0.0;
-#pragma unroll
-                for (int k = 0; k < NST; k++) {
-                    float g8 = xi * (sourcet[k] * (alb_ip * dextm_v + dalbm_v));
-                    if (deltam)
-                        g8 = g8 + dirflux * secmu0 * xi * (singscatj[k] * dfj_v + dsingscatp[k] * extp * albp
-                                  + dalb_v * (singscatp[k] - singscatj[k]) * extp
-                                  + dext_v * (singscatp[k] - singscatj[k]) * albp);
-                    sum += adj[k] * (double)g8;
-                }
-                d = sum + (double)xi * dot;
-            }
-            Dslot[lane * G.numder + idr] = d;
-            XGslot[lane * G.numder + idr] = dextm_v * xi;
         }
     }
-    fpersist = f;
-    __syncwarp();
 }
 
-// Corner refresh for the adjoint walk: values (and the contracted GRAD8 rows) of points shared with
-// the previous cell are carried over (OLDIPTS/DONEFACE logic of shdomsub4.f:1645-1659).
+// ------------------------------------------------------------------------------------------
+// COMPUTE_SOURCE_GRAD_1CELL for one new grid point (the 8 lanes of the octet cooperate): forward
+// values of the point and its contracted GRAD8 row (written to shared-memory row `row`).
+// ------------------------------------------------------------------------------------------
+template <int NST>
+__device__ void eval_point_grad(const DevState &S, const DevGrad &G, int ip, unsigned char *sm,
+                                const GradLayout &L, const RayDir &rd, const double (&adj)[NST], const Oct &o,
+                                int row, float &ext_out, float (&src_out)[NST], float (&ss_out)[NST],
+                                int &ns_out, int &nr_out)
+{
+    const float *Ysh = (const float *)(sm + L.y);
+    float *stage = (float *)(sm + L.stage);
+    float *shell = (float *)(sm + L.shell);
+    double *Tc = (double *)(sm + L.tc);
+    const float *Vsh = (const float *)(sm + L.vsh);
+    const int nlmp = S.nlmp, nstleg = S.nstleg, ml = S.ml, mm = S.mm;
+    const int nlt = nstleg * (S.nleg + 1);
+    const int ncomp = G.ncomp, ntup = G.ntup, nd = G.numder;
+    const bool deltam = S.deltam != 0, interp_new = S.interp_new != 0;
+    const float secmu0 = (float)(1.0 / fabs((double)S.solarmu));
+    const int ipz = ip - 1;
+    // ---------------- forward part (shdomsub4.f:1660-1785) ----------------
+    float ext, a[NST], b[NST];
+    eval_point<NST>(S, ip, Ysh, rd, false, o, ext, ns_out, a, b);
+    const float dirflux = __ldg(&S.dirflux[ipz]);
+    if (!deltam) {
+        // without delta-M SINGSCAT8 is the truncated single scattering (shdomsub4.f:1723-1760,1781):
+        // sum over species of DA*LEGENT(.,l)*sum_m YLMDIR*YLMSUN for the shells present in SOURCE
+        float t[NST];
+#pragma unroll
+        for (int k = 0; k < NST; k++) t[k] = 0.0f;
+        for (int ipa = 0; ipa < S.npart; ipa++) {
+            float w;
+            if (ext == 0.0f) w = 1.0f; else w = __ldg(&S.extinct[ipz + (size_t)S.npts * ipa]) / ext;
+            if (w == 0.0f) continue;
+            const int *iph = S.iphase + (size_t)S.nq * (ipz + (size_t)S.npts * ipa);
+            const float *pw = S.phaseinterpwt + (size_t)S.nq * (ipz + (size_t)S.npts * ipa);
+            const bool single = (!interp_new) || (__ldg(&pw[0]) >= S.phasemax);
+            const float da = __ldg(&S.albedo[ipz + (size_t)S.npts * ipa]) * dirflux * secmu0 * w;
+            for (int l = o.ol; l <= ml; l += 8) {
+                const int me = l < mm ? l : mm;
+                if (sh_index(l, -me, mm) >= ns_out) continue;
+                float l1, l5 = 0.0f;
+                if (single) {
+                    l1 = __ldg(&S.legen[(size_t)nlt * (__ldg(&iph[0]) - 1) + nstleg * l]);
+                    if (nstleg > 1) l5 = __ldg(&S.legen[(size_t)nlt * (__ldg(&iph[0]) - 1) + nstleg * l + 4]);
+                } else {
+                    l1 = 0.0f;
+                    for (int q = 0; q < S.nq; q++) {
+                        const float wq = __ldg(&pw[q]);
+                        if (wq <= 1e-5f) continue;
+                        l1 = l1 + __ldg(&S.legen[(size_t)nlt * (__ldg(&iph[q]) - 1) + nstleg * l]) * wq;
+                        if (nstleg > 1) l5 = l5 + __ldg(&S.legen[(size_t)nlt * (__ldg(&iph[q]) - 1) + nstleg * l + 4]) * wq;
+                    }
+                }
+                t[0] = t[0] + da * l1 * Vsh[l];
+                if (NST > 1) {
+                    t[1] = t[1] + da * l5 * Vsh[(ml + 1) + l];
+                    t[NST - 1] = t[NST - 1] + da * l5 * Vsh[2 * (ml + 1) + l];
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < NST; k++) b[k] = oct_sum(o.m, t[k]);
+    }
+    float srcfull[NST];      // SRCEXT8 before the multiplication by the extinction
+#pragma unroll
+    for (int k = 0; k < NST; k++) {
+        srcfull[k] = deltam ? a[k] + b[k] : a[k];
+        ss_out[k] = b[k] * ext;
+        src_out[k] = G.singlescatter ? ss_out[k] : srcfull[k] * ext;
+    }
+    ext_out = ext;
+    // ---------------- radiance SH block: shell sums over m ----------------
+    const int2 rr = __ldg(&S.radrec[ipz]);
+    const int rns = rr.y, nrp = AT3D_SHPAD(rr.y);
+    nr_out = rns;
+    {
+        const float *rb = S.shrad + rr.x + o.ol * 4;
+        if (NST == 1) {
+#pragma unroll 4
+            for (int j = 0; j < nrp; j += 32) {
+                const float4 r = __ldg((const float4 *)(rb + j));
+                const float4 y = *(const float4 *)(Ysh + o.ol * 4 + j);
+                *(float4 *)(stage + o.ol * 4 + j) = make_float4(r.x * y.x, r.y * y.y, r.z * y.z, r.w * y.w);
+            }
+        } else {
+#pragma unroll 2
+            for (int j = 0; j < nrp; j += 32) {
+#pragma unroll
+                for (int k = 0; k < NST; k++)
+                    *(float4 *)(stage + k * nlmp + o.ol * 4 + j) = __ldg((const float4 *)(rb + k * nrp + j));
+            }
+        }
+    }
+    for (int t = o.ol; t < ntup; t += 8) Tc[t] = 0.0;
+    __syncwarp(o.m);
+    // T(l) = adj . sum_m RADIANCE(.,j) YLMDIR(.,j); degrees are paired (l, ML-l) to balance the lanes
+    const bool keep_shell = S.npart > 1;
+    for (int q = o.ol; 2 * q <= ml; q += 8) {
+        for (int half = 0; half < 2; half++) {
+            const int l = half ? ml - q : q;
+            if (half && l == q) break;
+            const int me = l < mm ? l : mm;
+            const int jlo = sh_index(l, -me, mm);
+            int cnt = 2 * me + 1;
+            if (jlo + cnt > rns) cnt = rns - jlo;
+            if (NST == 1) {
+                float A = 0.0f;
+                for (int i = 0; i < cnt; i++) A = A + stage[jlo + i];
+                double t1 = adj[0] * A;
+                if (!deltam) t1 += adj[0] * (double)(dirflux * secmu0 * Vsh[l]);
+                Tc[l] = t1;
+                if (keep_shell) shell[l] = A;
+            } else {
+                float A = 0, B = 0, C = 0, D = 0, E = 0, F = 0, Gq = 0, H = 0;
+                for (int i = 0; i < cnt; i++) {
+                    const int j = jlo + i;
+                    const float r1 = stage[j], y1 = Ysh[j];
+                    const float r2 = stage[nlmp + j], r3 = stage[2 * nlmp + j];
+                    const float y2 = Ysh[nlmp + j], y5 = Ysh[2 * nlmp + j], y6 = Ysh[3 * nlmp + j], y3 = Ysh[4 * nlmp + j];
+                    A = A + r1 * y1;
+                    B = B + r2 * y1; C = C + r1 * y2; D = D + r2 * y2; E = E + r3 * y5;
+                    F = F + r1 * y6; Gq = Gq + r2 * y6; H = H + r3 * y3;
+                }
+                double t1 = adj[0] * A;
+                if (!deltam) t1 += adj[0] * (double)(dirflux * secmu0 * Vsh[l]);
+                double t5 = adj[0] * B + adj[1] * C + adj[NST - 1] * F;
+                if (!deltam) t5 += adj[1] * (double)(dirflux * secmu0 * Vsh[(ml + 1) + l]);
+                Tc[0 + ncomp * l] = t1;
+                Tc[1 + ncomp * l] = adj[1] * D + adj[NST - 1] * Gq;
+                Tc[2 + ncomp * l] = adj[1] * E + adj[NST - 1] * H;
+                Tc[3 + ncomp * l] = t5;
+                if (keep_shell) {
+                    const int s = ml + 1;
+                    shell[l] = A; shell[s + l] = B; shell[2 * s + l] = C; shell[3 * s + l] = D;
+                    shell[4 * s + l] = E; shell[5 * s + l] = F; shell[6 * s + l] = Gq; shell[7 * s + l] = H;
+                }
+            }
+        }
+    }
+    __syncwarp(o.m);
+    // ---------------- gradient part (shdomsub4.f:1786-2019): lane = property corner nb ----------------
+    const int nb = o.ol;
+    const int ib = __ldg(&G.interpptr[nb + 8 * (size_t)ipz]);
+    const float xi = __ldg(&G.optinterpwt[nb + 8 * (size_t)ipz]);
+    double *Drow = (double *)(sm + L.rowd) + (size_t)row * 8 * nd;
+    float *XGrow = (float *)(sm + L.rowx) + (size_t)row * 8 * nd;
+    int *IBrow = (int *)(sm + L.rowib) + row * 8;
+    IBrow[nb] = ib;
+    int last_ipa = -1;
+    float scatterj = 0.0f, f = 0.0f, singscatj[NST], sourcet[NST];
+#pragma unroll
+    for (int k = 0; k < NST; k++) { singscatj[k] = 0.0f; sourcet[k] = 0.0f; }
+    const int pm = G.pmaxnmicro;
+    for (int idr = 0; idr < nd; idr++) {
+        const int ipa = __ldg(&G.partder[idr]);       // 1-based species
+        const size_t prow = ((size_t)ipz * nd + idr) * 8 + nb;
+        const float4 g0 = __ldg((const float4 *)(G.grec + prow * 8));
+        const float4 g1 = __ldg((const float4 *)(G.grec + prow * 8) + 1);
+        const float dext_v = g0.x, dalb_v = g0.y, dextm_v = g0.z, dalbm_v = g0.w;
+        const float dfj_v = g1.x, albp = g1.y, extp = g1.z, alb_ip = g1.w;
+        const int *iphp = G.iphasep + (size_t)pm * ((ib - 1) + (size_t)G.maxpg * (ipa - 1));
+        const float *pwp = G.phasewtp + (size_t)pm * ((ib - 1) + (size_t)G.maxpg * (ipa - 1));
+        if (ipa != last_ipa) {
+            last_ipa = ipa;
+            const float2 pn = __ldg(&G.gpnt[(size_t)ipz * nd + idr]);
+            scatterj = pn.x; f = pn.y;
+            const float sw = xi * albp * extp;       // SPATIAL_WEIGHT of property corner nb
+#pragma unroll
+            for (int k = 0; k < NST; k++) singscatj[k] = 0.0f;
+            if (deltam) {
+                float part[NST];
+#pragma unroll
+                for (int k = 0; k < NST; k++) part[k] = 0.0f;
+                if (sw > 1e-6f) {
+                    for (int q = 0; q < pm; q++) {
+                        const float w = __ldg(&pwp[q]);
+                        if (w <= 1e-6f) continue;
+                        float sv[NST];
+                        ray_singscat<NST>(S.phasetab, S.nstphase, S.numphase, __ldg(&iphp[q]), rd, sv);
+#pragma unroll
+                        for (int k = 0; k < NST; k++) part[k] = part[k] + sw * w * sv[k];
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < NST; k++) {
+                    float tot = 0.0f;
+#pragma unroll
+                    for (int n = 0; n < 8; n++) tot = tot + __shfl_sync(o.m, part[k], n, 8);
+                    if (scatterj > G.scatmin) singscatj[k] = tot / scatterj;
+                    else singscatj[k] = (float)(tot / G.scatmin);
+                }
+            }
+            if (S.npart == 1) {
+#pragma unroll
+                for (int k = 0; k < NST; k++) sourcet[k] = (alb_ip > 1e-8f) ? srcfull[k] / alb_ip : 0.0f;
+            } else {
+#pragma unroll
+                for (int k = 0; k < NST; k++) sourcet[k] = 0.0f;
+                if (scatterj > G.scatmin) {
+                    // COMPUTE_SOURCE_DIRECTION with the mixed table, from the shell sums
+                    const float *lg = G.legs + ((size_t)ipz * nd + idr) * ntup;
+                    float acc[NST];
+#pragma unroll
+                    for (int k = 0; k < NST; k++) acc[k] = 0.0f;
+                    const int s = ml + 1;
+                    for (int l = o.ol; l <= ml; l += 8) {
+                        const float l1 = __ldg(&lg[ncomp * l]);
+                        acc[0] = acc[0] + l1 * shell[l];
+                        if (!deltam) acc[0] = acc[0] + dirflux * secmu0 * l1 * Vsh[l];
+                        if (NST > 1) {
+                            const float l2 = __ldg(&lg[1 + ncomp * l]), l3 = __ldg(&lg[2 + ncomp * l]);
+                            const float l5 = __ldg(&lg[3 + ncomp * l]);
+                            acc[0] = acc[0] + l5 * shell[s + l];
+                            acc[1] = acc[1] + l5 * shell[2 * s + l] + l2 * shell[3 * s + l] + l3 * shell[4 * s + l];
+                            acc[NST - 1] = acc[NST - 1] + l5 * shell[5 * s + l] + l2 * shell[6 * s + l]
+                                           + l3 * shell[7 * s + l];
+                            if (!deltam) acc[1] = acc[1] + dirflux * secmu0 * l5 * Vsh[s + l];
+                        }
+                    }
+#pragma unroll
+                    for (int k = 0; k < NST; k++) sourcet[k] = oct_sum(o.m, acc[k]);
+                    if (deltam) {
+#pragma unroll
+                        for (int k = 0; k < NST; k++) sourcet[k] = sourcet[k] + dirflux * singscatj[k] * secmu0 / (1 - f);
+                    }
+                }
+            }
+            sourcet[0] = fmaxf(0.0f, sourcet[0]);
+        }
+        double d = 0.0;
+        if (xi >= 1e-7f) {
+            // DSOURCE contracted with the adjoint weight: DLEGT(l) . T(l)
+            const float4 *dl = (const float4 *)(G.dlegt + prow * ntup);
+            double dot = 0.0;
+            for (int t4 = 0; t4 < ntup / 4; t4++) {
+                const float4 v = __ldg(&dl[t4]);
+                dot += (double)v.x * Tc[4 * t4];
+                dot += (double)v.y * Tc[4 * t4 + 1];
+                dot += (double)v.z * Tc[4 * t4 + 2];
+                dot += (double)v.w * Tc[4 * t4 + 3];
+            }
+            const int doex = __ldg(&G.doexact[idr]);
+            const int *dip = G.diphasep + (size_t)G.deriv_maxnmicro * ((ib - 1) + (size_t)G.maxpg * idr);
+            const float *dpw = G.dphasewtp + (size_t)G.deriv_maxnmicro * ((ib - 1) + (size_t)G.maxpg * idr);
+            float singscatp[NST], dsingscatp[NST];
+#pragma unroll
+            for (int k = 0; k < NST; k++) { singscatp[k] = 0.0f; dsingscatp[k] = 0.0f; }
+            if (deltam) {
+                for (int q = 0; q < pm; q++) {
+                    float sv[NST];
+                    ray_singscat<NST>(S.phasetab, S.nstphase, S.numphase, __ldg(&iphp[q]), rd, sv);
+                    const float w = __ldg(&pwp[q]);
+#pragma unroll
+                    for (int k = 0; k < NST; k++) singscatp[k] = singscatp[k] + w * sv[k];
+                    if (doex == 0 && q < G.deriv_maxnmicro) {
+                        const float dw = __ldg(&dpw[q]);
+#pragma unroll
+                        for (int k = 0; k < NST; k++) dsingscatp[k] = dsingscatp[k] + dw * sv[k];
+                    }
+                }
+                if (doex == 1) {
+                    for (int q = 0; q < G.deriv_maxnmicro; q++) {
+                        float sv[NST];
+                        ray_singscat<NST>(G.dphasetab, S.nstphase, G.dnumphase, __ldg(&dip[q]), rd, sv);
+                        const float w = __ldg(&pwp[q]);
+#pragma unroll
+                        for (int k = 0; k < NST; k++) dsingscatp[k] = dsingscatp[k] + w * sv[k];
+                    }
+                }
+            }
+            double sum = 0.0;
+#pragma unroll
+            for (int k = 0; k < NST; k++) {
+                float g8 = xi * (sourcet[k] * (alb_ip * dextm_v + dalbm_v));
+                if (deltam)
+                    g8 = g8 + dirflux * secmu0 * xi * (singscatj[k] * dfj_v + dsingscatp[k] * extp * albp
+                              + dalb_v * (singscatp[k] - singscatj[k]) * extp
+                              + dext_v * (singscatp[k] - singscatj[k]) * albp);
+                sum += adj[k] * (double)g8;
+            }
+            d = sum + (double)xi * dot;
+        }
+        Drow[nb * nd + idr] = d;
+        XGrow[nb * nd + idr] = dextm_v * xi;
+    }
+    __syncwarp(o.m);
+}
+
+// Corner refresh for the adjoint walk: values and the shared-memory row (contracted GRAD8) of points
+// shared with the previous cell are carried over (OLDIPTS/DONEFACE logic of shdomsub4.f:1645-1659).
 template <int NST>
 __device__ __forceinline__ void refresh_corners_grad(const DevState &S, const DevGrad &G, const CellRec &c,
                                                      unsigned char *sm, const GradLayout &L, const RayDir &rd,
-                                                     const double (&adj)[NST], bool first, float &fpersist,
-                                                     int &npt_eval, int &nsh_eval, int &nrh_eval)
+                                                     const double (&adj)[NST], bool first, const Oct &o,
+                                                     int &cpt, int &crow, float &cext, float (&csrc)[NST],
+                                                     float (&css)[NST], int &npt_eval, int &nsh_eval, int &nrh_eval)
 {
-    const int lane = lane_id();
-    CornerCache<NST> *cc = (CornerCache<NST> *)(sm + L.cc);
-    double *Dall = (double *)(sm + L.dslot);
-    int *IBall = (int *)(sm + L.ib);
-    float *XGall = (float *)(sm + L.xg);
-    const int nd = G.numder;
-    // lane n<8 decides; then every lane helps copying the 8*nd rows of reused corners
-    int myp = 0, hit = -1;
-    if (lane < 8) {
-        myp = c.gp[0];
+    const int myp = own_corner(c, o.ol);
+    int hit = -1;
+    if (!first) {
 #pragma unroll
-        for (int n = 1; n < 8; n++) if (lane == n) myp = c.gp[n];
-        if (!first) {
+        for (int k = 0; k < 8; k++) { const int pk = __shfl_sync(o.m, cpt, k, 8); if (pk == myp) hit = k; }
+    }
+    const int from = hit < 0 ? o.ol : hit;
+    cext = __shfl_sync(o.m, cext, from, 8);
+    crow = __shfl_sync(o.m, crow, from, 8);
 #pragma unroll
-            for (int k = 0; k < 8; k++) if (cc->pt[k] == myp) hit = k;
-        }
+    for (int k = 0; k < NST; k++) {
+        csrc[k] = __shfl_sync(o.m, csrc[k], from, 8);
+        css[k] = __shfl_sync(o.m, css[k], from, 8);
     }
-    float oext = 0.0f, osrc[NST], oss[NST];
-    if (lane < 8 && hit >= 0) {
-        oext = cc->ext[hit];
-#pragma unroll
-        for (int k = 0; k < NST; k++) { osrc[k] = cc->src[k][hit]; oss[k] = cc->ss[k][hit]; }
-    }
-    // row copies: each lane handles (slot = lane&7, part = lane>>3) of the 8*nd doubles/floats + ints
-    const int slot = lane & 7, part = lane >> 3;
-    const int shit = __shfl_sync(FULLMASK, hit, slot);
-    double dtmp[16]; float xtmp[16]; int itmp[2];
-    const int per = (8 * nd + 3) / 4;      // entries per part
-    int cntd = 0;
-    if (shit >= 0 && shit != slot) {
-        for (int e = part * per; e < (part + 1) * per && e < 8 * nd && cntd < 16; e++, cntd++) {
-            dtmp[cntd] = Dall[shit * 8 * nd + e];
-            xtmp[cntd] = XGall[shit * 8 * nd + e];
-        }
-        itmp[0] = IBall[shit * 8 + 2 * part];
-        itmp[1] = IBall[shit * 8 + 2 * part + 1];
-    }
-    __syncwarp();
-    if (lane < 8) {
-        cc->pt[lane] = myp;
-        if (hit >= 0) {
-            cc->ext[lane] = oext;
-#pragma unroll
-            for (int k = 0; k < NST; k++) { cc->src[k][lane] = osrc[k]; cc->ss[k][lane] = oss[k]; }
-        }
-    }
-    if (shit >= 0 && shit != slot) {
-        int i = 0;
-        for (int e = part * per; e < (part + 1) * per && e < 8 * nd && i < 16; e++, i++) {
-            Dall[slot * 8 * nd + e] = dtmp[i];
-            XGall[slot * 8 * nd + e] = xtmp[i];
-        }
-        IBall[slot * 8 + 2 * part] = itmp[0];
-        IBall[slot * 8 + 2 * part + 1] = itmp[1];
-    }
-    __syncwarp();
-    unsigned need = __ballot_sync(FULLMASK, lane < 8 && hit < 0);
+    cpt = myp;
+    unsigned used = oct_or(o, hit >= 0 ? (1u << crow) : 0u);
+    unsigned need = oct_ballot(o, hit < 0);
     while (need) {
         const int n = __ffs(need) - 1;
-        need &= need - 1;
-        const int ip = __shfl_sync(FULLMASK, myp, n);
+        const int ip = __shfl_sync(o.m, myp, n, 8);
+        const int row = __ffs(~used) - 1;
+        used |= 1u << row;
         float ext, src[NST], ss[NST];
-        eval_point_grad<NST>(S, G, ip, sm, L, rd, adj, ext, src, ss, Dall + n * 8 * nd, IBall + n * 8,
-                             XGall + n * 8 * nd, fpersist);
-        npt_eval++; nsh_eval += __ldg(&S.srcrec[ip - 1]).y; nrh_eval += __ldg(&S.radrec[ip - 1]).y;
-        // duplicate corners inside one cell share the evaluation
-        const unsigned same = __ballot_sync(FULLMASK, lane < 8 && myp == ip);
-        if (lane < 8 && myp == ip) {
-            cc->ext[lane] = ext;
+        int ns, nr;
+        eval_point_grad<NST>(S, G, ip, sm, L, rd, adj, o, row, ext, src, ss, ns, nr);
+        npt_eval++; nsh_eval += ns; nrh_eval += nr;
+        const bool mine = (myp == ip);
+        if (mine) {
+            cext = ext; crow = row;
 #pragma unroll
-            for (int k = 0; k < NST; k++) { cc->src[k][lane] = src[k]; cc->ss[k][lane] = ss[k]; }
+            for (int k = 0; k < NST; k++) { csrc[k] = src[k]; css[k] = ss[k]; }
         }
-        unsigned dup = same & ~(1u << n);
-        while (dup) {
-            const int m = __ffs(dup) - 1;
-            dup &= dup - 1;
-            for (int e = lane; e < 8 * nd; e += 32) {
-                Dall[m * 8 * nd + e] = Dall[n * 8 * nd + e];
-                XGall[m * 8 * nd + e] = XGall[n * 8 * nd + e];
-            }
-            if (lane < 8) IBall[m * 8 + lane] = IBall[n * 8 + lane];
-        }
-        need &= ~same;
-        __syncwarp();
+        need &= ~oct_ballot(o, mine);
     }
-    __syncwarp();
 }
 
-// ADJOINT_INTEGRATE_1RAY for one ray (one warp).
+// ADJOINT_INTEGRATE_1RAY for one ray (one octet).
 template <int NST>
 __device__ int march_ray_adjoint(const DevState &S, const DevGrad &G, unsigned char *sm, const GradLayout &L,
                                  const RayDir &rd, double mu2, double x0, double y0, double z0, float sky,
-                                 const double (&adj)[NST], const double (&total)[NST],
+                                 const double (&adj)[NST], const double (&total)[NST], const Oct &o,
                                  double *gradout, double *beam_weight,
                                  int *trace_cells, int trace_cap, int &ntrace, int &nsub)
 {
-    const int lane = lane_id();
-    CornerCache<NST> *cc = (CornerCache<NST> *)(sm + L.cc);
-    const double *Dall = (const double *)(sm + L.dslot);
-    const int *IBall = (const int *)(sm + L.ib);
-    const float *XGall = (const float *)(sm + L.xg);
+    const double *Dall = (const double *)(sm + L.rowd);
+    const float *XGall = (const float *)(sm + L.rowx);
+    const int *IBall = (const int *)(sm + L.rowib);
+    int *rowof = (int *)(sm + L.rowib) + AT3D_GRAD_ROWS * 8;
     double *Wacc = (double *)(sm + L.wacc);
     const int nd = G.numder;
     double xe = x0, ye = y0, ze = z0, transmit = 1.0;
@@ -590,25 +586,25 @@ __device__ int march_ray_adjoint(const DevState &S, const DevGrad &G, unsigned c
     int icell = dev_locate_grid_cell(S, xe, ye, ze);
     int iface = 0, npassed = 1;
     bool done = false, first = true;
-    float fpersist = 0.0f;
     int npt_eval = 0, nsh_eval = 0, nrh_eval = 0;
+    int cpt = 0, crow = 0; float cext = 0.0f, csrc[NST], css[NST];
+#pragma unroll
+    for (int k = 0; k < NST; k++) { csrc[k] = 0.0f; css[k] = 0.0f; }
     ntrace = 0; nsub = 0;
     while (!done && icell > 0) {
-        if (trace_cells && lane == 0 && ntrace < trace_cap) trace_cells[ntrace] = icell;
+        if (trace_cells && o.ol == 0 && ntrace < trace_cap) trace_cells[ntrace] = icell;
         ntrace++;
         const CellRec c = load_cell(S, icell);
-        refresh_corners_grad<NST>(S, G, c, sm, L, rd, adj, first, fpersist, npt_eval, nsh_eval, nrh_eval);
+        refresh_corners_grad<NST>(S, G, c, sm, L, rd, adj, first, o, cpt, crow, cext, csrc, css,
+                                  npt_eval, nsh_eval, nrh_eval);
         first = false;
         float e8[8], s8[NST][8];
 #pragma unroll
         for (int n = 0; n < 8; n++) {
-            e8[n] = cc->ext[n];
+            e8[n] = __shfl_sync(o.m, cext, n, 8);
 #pragma unroll
-            for (int k = 0; k < NST; k++) s8[k][n] = cc->src[k][n];
+            for (int k = 0; k < NST; k++) s8[k][n] = __shfl_sync(o.m, csrc[k], n, 8);
         }
-        float myss[NST];           // SINGSCAT8(:,n) of the corner this lane owns
-#pragma unroll
-        for (int k = 0; k < NST; k++) myss[k] = cc->ss[k][lane & 7];
         const float4 q1 = __ldg(&S.ptrec[c.gp[0] - 1]);
         const float4 q8 = __ldg(&S.ptrec[c.gp[7] - 1]);
         const double delx = (double)(q8.x - q1.x), dely = (double)(q8.y - q1.y), delz = (double)(q8.z - q1.z);
@@ -616,8 +612,9 @@ __device__ int march_ray_adjoint(const DevState &S, const DevGrad &G, unsigned c
         const double invdely = (dely <= 0.0) ? 1.0 : 1.0 / dely;
         const double invdelz = 1.0 / delz;
         double u = (xe - q1.x) * invdelx, v = (ye - q1.y) * invdely, w = (ze - q1.z) * invdelz;
-        double fc[8], fcprev[8];
+        double fc[8];
         interp_kernel(u, v, w, fc);
+        double fown = interp_kernel_own(u, v, w, o.ol);
 #pragma unroll
         for (int k = 0; k < NST; k++) srcext1[k] = (float)fcsum(fc, s8[k]);
         srcext1[0] = fmaxf(0.0f, srcext1[0]);
@@ -644,18 +641,19 @@ __device__ int march_ray_adjoint(const DevState &S, const DevGrad &G, unsigned c
         int ntau = 1 + (int)(taugrid / S.tautol);
         if (ntau < 1) ntau = 1;
         const double dels = so / ntau;
-        // per-corner accumulators of this cell (lane n < 8 owns corner n)
+        // per-corner accumulators of this cell (lane n owns corner n)
         double Wn = 0.0, Gn = 0.0;
         float bw[NST];
 #pragma unroll
         for (int k = 0; k < NST; k++) bw[k] = 0.0f;
         for (int it = 1; it <= ntau; it++) {
-#pragma unroll
-            for (int n = 0; n < 8; n++) fcprev[n] = fc[n];
+            const double f1 = fown;                  // previous interpolation weight of the own corner
             const double s = it * dels;
             const double xi = xe + s * rd.cx, yi = ye + s * rd.cy, zi = ze + s * rd.cz;
             u = (xi - q1.x) * invdelx; v = (yi - q1.y) * invdely; w = (zi - q1.z) * invdelz;
             interp_kernel(u, v, w, fc);
+            fown = interp_kernel_own(u, v, w, o.ol);
+            const double f0 = fown;
             float ext0, srcext0[NST];
 #pragma unroll
             for (int k = 0; k < NST; k++) srcext0[k] = (float)fcsum(fc, s8[k]);
@@ -684,14 +682,11 @@ __device__ int march_ray_adjoint(const DevState &S, const DevGrad &G, unsigned c
                 for (int k = 0; k < NST; k++) rnext += adj[k] * (total[k] - radout[k]);
                 rnext = rnext / tnext;
                 // lane-private corner weights
-                double f0 = fc[0], f1 = fcprev[0];
-#pragma unroll
-                for (int n = 1; n < 8; n++) if ((lane & 7) == n) { f0 = fc[n]; f1 = fcprev[n]; }
                 Wn += transmit * abscell * ((0.5f * (f0 + f1) + 0.08333333333f * (ext0 * f1 - ext1 * f0) * corr) / ext);
                 if (exact_ss) {
 #pragma unroll
                     for (int k = 0; k < NST; k++) {
-                        float ss0 = (float)(f0 * myss[k]), ss1 = (float)(f1 * myss[k]);
+                        float ss0 = (float)(f0 * css[k]), ss1 = (float)(f1 * css[k]);
                         if (k == 0) { ss0 = fmaxf(0.0f, ss0); ss1 = fmaxf(0.0f, ss1); }
                         bw[k] = (float)(bw[k] + transmit * abscell *
                                 (0.5f * (ss0 + ss1) + 0.08333333333f * (ext0 * ss1 - ext1 * ss0) * corr) / ext);
@@ -718,25 +713,28 @@ __device__ int march_ray_adjoint(const DevState &S, const DevGrad &G, unsigned c
             for (int k = 0; k < NST; k++) srcext1[k] = srcext0[k];
         }
         // ---- flush this cell's contributions (once per cell and corner, no atomics above) ----
-        if (lane < 8) {
-            Wacc[lane] = Wn; Wacc[8 + lane] = Gn;
-            if (exact_ss) {
-                double bsum = 0.0;
+        Wacc[o.ol] = Wn; Wacc[8 + o.ol] = Gn; rowof[o.ol] = crow;
+        if (exact_ss) {
+            double bsum = 0.0;
 #pragma unroll
-                for (int k = 0; k < NST; k++) bsum += adj[k] * (double)bw[k];
-                int ipn = c.gp[0];
-#pragma unroll
-                for (int n = 1; n < 8; n++) if (lane == n) ipn = c.gp[n];
-                if (bsum != 0.0) atomicAdd(&beam_weight[ipn - 1], bsum);
+            for (int k = 0; k < NST; k++) bsum += adj[k] * (double)bw[k];
+            if (bsum != 0.0) atomicAdd(&beam_weight[cpt - 1], bsum);
+        }
+        __syncwarp(o.m);
+        {
+            const int nb = o.ol;
+            for (int slot = 0; slot < 8; slot++) {
+                const int r = rowof[slot];
+                const double Ws = Wacc[slot], Gs = Wacc[8 + slot];
+                const int ibp = IBall[r * 8 + nb];
+                for (int idr = 0; idr < nd; idr++) {
+                    const int e = (r * 8 + nb) * nd + idr;
+                    const double val = Ws * Dall[e] + (double)XGall[e] * Gs;
+                    if (val != 0.0) atomicAdd(&gradout[(size_t)(ibp - 1) + (size_t)G.maxpg * idr], val);
+                }
             }
         }
-        __syncwarp();
-        for (int e = lane; e < 64 * nd; e += 32) {
-            const int slot = e / (8 * nd), r = e - slot * 8 * nd, nb = r / nd, idr = r - nb * nd;
-            const double val = Wacc[slot] * Dall[e] + (double)XGall[e] * Wacc[8 + slot];
-            if (val != 0.0) atomicAdd(&gradout[(size_t)(IBall[slot * 8 + nb] - 1) + (size_t)G.maxpg * idr], val);
-        }
-        __syncwarp();
+        __syncwarp(o.m);
         int jface;
         bool openbcface;
         if (sox <= soz && sox <= soy) { iface = 2 - rd.bitx; jface = 1; openbcface = DBTEST(c.flags, 0) && DBTEST(S.bcflag, 0); }
@@ -765,10 +763,10 @@ __device__ int march_ray_adjoint(const DevState &S, const DevGrad &G, unsigned c
             const int e = boundary_radiance<NST, true>(S, xn, yn, (float)mu2, sky, ic, kface, radbnd,
                                                        boundpts, boundinterp, dirrad1);
             if (e) return e;
-            if (exact_ss && lane < 4) {
+            if (exact_ss && o.ol < 4) {
                 int bp = boundpts[0]; double bi = boundinterp[0], dr = dirrad1[0];
 #pragma unroll
-                for (int n = 1; n < 4; n++) if (lane == n) { bp = boundpts[n]; bi = boundinterp[n]; dr = dirrad1[n]; }
+                for (int n = 1; n < 4; n++) if (o.ol == n) { bp = boundpts[n]; bi = boundinterp[n]; dr = dirrad1[n]; }
                 const double val = adj[0] * transmit * bi * dr;
                 if (val != 0.0) atomicAdd(&beam_weight[bp - 1], val);
             }
@@ -777,7 +775,7 @@ __device__ int march_ray_adjoint(const DevState &S, const DevGrad &G, unsigned c
         }
         xe = xn; ye = yn; ze = zn;
     }
-    if (S.counts && lane == 0) {
+    if (S.counts && o.ol == 0) {
         atomicAdd(&S.counts[0], (unsigned long long)ntrace);
         atomicAdd(&S.counts[1], (unsigned long long)npt_eval);
         atomicAdd(&S.counts[2], (unsigned long long)nsh_eval);
@@ -789,61 +787,68 @@ __device__ int march_ray_adjoint(const DevState &S, const DevGrad &G, unsigned c
 }
 
 template <int NST>
-__global__ void __launch_bounds__(AT3D_WARPS_PER_BLOCK * 32)
+__global__ void __launch_bounds__(AT3D_RAY_THREADS)
 adjoint_kernel(DevState S, DevGrad G, GradLayout L, int nrays, const float *camx, const float *camy,
                const float *camz, const double *cammu, const double *camphi, const RayPack *packs,
                const int *raypix, const double *adjw /*[NST,npix]*/, const double *ray_weights,
                const double *stokes_weights, const double *total /*[NST,nrays]*/,
                double *gradout, double *beam_weight,
-               int *trace_cells, int trace_cap, int *trace_n, int *trace_nsub, RayErr *err)
+               int *trace_cells, int trace_cap, int *trace_n, int *trace_nsub, RayErr *err, int *ray_counter)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    unsigned char *sm = smem_raw + (size_t)warp * L.total;
+    const Oct o = oct_id();
+    const int lane = threadIdx.x & 31;
+    unsigned char *sm = smem_raw + (size_t)(threadIdx.x >> 3) * L.total;
     float *Ysh = (float *)(sm + L.y);
     float *Vsh = (float *)(sm + L.vsh);
-    const int nwarps = gridDim.x * AT3D_WARPS_PER_BLOCK;
-    for (int iray = blockIdx.x * AT3D_WARPS_PER_BLOCK + warp; iray < nrays; iray += nwarps) {
-        const double mu2 = __ldg(&cammu[iray]), phi2 = __ldg(&camphi[iray]);
-        const RayPack pk = dev_get_pack(S, packs, iray, camx, camy, camz, mu2, phi2);
-        int ntrace = 0, nsub = 0;
-        if (pk.status == 2) { if (lane == 0) set_err(err, 2, iray); }
-        else if (pk.status == 0) {
-            const int pix = __ldg(&raypix[iray]);
-            double adj[NST], tot[NST];
-            const double rw = __ldg(&ray_weights[iray]);
+    for (;;) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(ray_counter, 32 / AT3D_OCT);
+        base = __shfl_sync(FULLMASK, base, 0);
+        if (base >= nrays) break;
+        const int iray = base + (lane >> 3);
+        if (iray < nrays) {
+            const double mu2 = __ldg(&cammu[iray]), phi2 = __ldg(&camphi[iray]);
+            const RayPack pk = dev_get_pack(S, packs, iray, camx, camy, camz, mu2, phi2);
+            int ntrace = 0, nsub = 0;
+            if (pk.status == 2) { if (o.ol == 0) set_err(err, 2, iray); }
+            else if (pk.status == 0) {
+                const int pix = __ldg(&raypix[iray]);
+                double adj[NST], tot[NST];
+                const double rw = __ldg(&ray_weights[iray]);
 #pragma unroll
-            for (int k = 0; k < NST; k++) {
-                adj[k] = __ldg(&adjw[k + NST * (size_t)pix]) * rw * __ldg(&stokes_weights[k + NST * (size_t)pix]);
-                tot[k] = __ldg(&total[k + NST * (size_t)iray]);
-            }
-            RayDir rd;
-            dev_ray_dir(S, pk, rd);
-            __syncwarp();
-            warp_ylmall(S, (float)mu2, (float)phi2, Ysh);
-            if (!S.deltam) {
-                // shell sums of YLMSUN*YLMDIR for the untruncated solar term of COMPUTE_SOURCE_DIRECTION
-                for (int l = lane; l <= S.ml; l += 32) {
-                    const int me = l < S.mm ? l : S.mm;
-                    const int jlo = sh_index(l, -me, S.mm);
-                    float v1 = 0.0f, v5 = 0.0f, v6 = 0.0f;
-                    for (int i = 0; i < 2 * me + 1; i++) {
-                        const float ys = __ldg(&S.ylmsun[(size_t)S.nstleg * (jlo + i)]);
-                        v1 = v1 + ys * Ysh[jlo + i];
-                        if (NST > 1) { v5 = v5 + ys * Ysh[S.nlmp + jlo + i]; v6 = v6 + ys * Ysh[3 * S.nlmp + jlo + i]; }
-                    }
-                    Vsh[l] = v1; Vsh[(S.ml + 1) + l] = v5; Vsh[2 * (S.ml + 1) + l] = v6;
+                for (int k = 0; k < NST; k++) {
+                    adj[k] = __ldg(&adjw[k + NST * (size_t)pix]) * rw * __ldg(&stokes_weights[k + NST * (size_t)pix]);
+                    tot[k] = __ldg(&total[k + NST * (size_t)iray]);
                 }
-                __syncwarp();
+                RayDir rd;
+                dev_ray_dir(S, pk, rd);
+                __syncwarp(o.m);
+                group_ylmall(S, (float)mu2, (float)phi2, Ysh, o.ol, AT3D_OCT, o.m);
+                if (!S.deltam) {
+                    // shell sums of YLMSUN*YLMDIR for the untruncated solar term of COMPUTE_SOURCE_DIRECTION
+                    for (int l = o.ol; l <= S.ml; l += 8) {
+                        const int me = l < S.mm ? l : S.mm;
+                        const int jlo = sh_index(l, -me, S.mm);
+                        float v1 = 0.0f, v5 = 0.0f, v6 = 0.0f;
+                        for (int i = 0; i < 2 * me + 1; i++) {
+                            const float ys = __ldg(&S.ylmsun[(size_t)S.nstleg * (jlo + i)]);
+                            v1 = v1 + ys * Ysh[jlo + i];
+                            if (NST > 1) { v5 = v5 + ys * Ysh[S.nlmp + jlo + i]; v6 = v6 + ys * Ysh[3 * S.nlmp + jlo + i]; }
+                        }
+                        Vsh[l] = v1; Vsh[(S.ml + 1) + l] = v5; Vsh[2 * (S.ml + 1) + l] = v6;
+                    }
+                    __syncwarp(o.m);
+                }
+                const float sky = (-mu2 > 0.0) ? dev_sky_radiance(S, (float)mu2, (float)phi2) : 0.0f;
+                const int e = march_ray_adjoint<NST>(S, G, sm, L, rd, mu2, pk.x0, pk.y0, pk.z0, sky, adj, tot, o,
+                                                     gradout, beam_weight,
+                                                     trace_cells ? trace_cells + (size_t)trace_cap * iray : nullptr,
+                                                     trace_cap, ntrace, nsub);
+                if (e && o.ol == 0) set_err(err, e, iray);
             }
-            const float sky = (-mu2 > 0.0) ? dev_sky_radiance(S, (float)mu2, (float)phi2) : 0.0f;
-            const int e = march_ray_adjoint<NST>(S, G, sm, L, rd, mu2, pk.x0, pk.y0, pk.z0, sky, adj, tot, gradout,
-                                                 beam_weight,
-                                                 trace_cells ? trace_cells + (size_t)trace_cap * iray : nullptr,
-                                                 trace_cap, ntrace, nsub);
-            if (e && lane == 0) set_err(err, e, iray);
+            if (o.ol == 0 && trace_n) { trace_n[iray] = ntrace; trace_nsub[iray] = nsub; }
         }
-        if (lane == 0 && trace_n) { trace_n[iray] = ntrace; trace_nsub[iray] = nsub; }
         __syncwarp();
     }
 }
@@ -1035,6 +1040,30 @@ extern "C" int at3d_state_attach_gradient(at3d_state *st, const at3d_grad_desc *
         return 1;
     }
     if (g->exact_single_scatter && (!G.dpath || !G.dptr)) { set_msg(errmsg, "EXACT_SINGLE_SCATTER needs DPATH/DPTR"); return 1; }
+    // ray-independent tables of COMPUTE_SOURCE_GRAD_1CELL (grad_prep_kernel)
+    {
+        G.ncomp = S.nstleg == 1 ? 1 : 4;
+        G.ntup = (G.ncomp * (S.ml + 1) + 3) & ~3;
+        const size_t nrow = np * nd * 8;
+        float *grec = nullptr, *dlegt = nullptr, *legs = nullptr; float2 *gpnt = nullptr;
+        void *p = nullptr;
+        CUDA_TRY(cudaMalloc(&p, nrow * 8 * sizeof(float))); own.push_back(p); grec = (float *)p; st->bytes += nrow * 8 * sizeof(float);
+        CUDA_TRY(cudaMalloc(&p, nrow * G.ntup * sizeof(float))); own.push_back(p); dlegt = (float *)p; st->bytes += nrow * G.ntup * sizeof(float);
+        CUDA_TRY(cudaMalloc(&p, np * nd * sizeof(float2))); own.push_back(p); gpnt = (float2 *)p; st->bytes += np * nd * sizeof(float2);
+        CUDA_TRY(cudaMemset(dlegt, 0, nrow * G.ntup * sizeof(float)));
+        if (S.npart > 1) {
+            CUDA_TRY(cudaMalloc(&p, np * nd * G.ntup * sizeof(float))); own.push_back(p); legs = (float *)p;
+            st->bytes += np * nd * G.ntup * sizeof(float);
+            CUDA_TRY(cudaMemset(legs, 0, np * nd * G.ntup * sizeof(float)));
+        }
+        const int wpb = 4;
+        const size_t smem = (size_t)wpb * nlt * sizeof(float);
+        if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(grad_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        grad_prep_kernel<<<(S.npts + wpb - 1) / wpb, wpb * 32, smem>>>(S, G, grec, dlegt, gpnt, legs);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaDeviceSynchronize());
+        G.grec = grec; G.dlegt = dlegt; G.gpnt = gpnt; G.legs = legs;
+    }
     st->grad_attached = 1;
     return 0;
 }
@@ -1131,10 +1160,9 @@ extern "C" int at3d_levisapprox_gradient(at3d_state *st, const at3d_rays *rays, 
         DevState Sf = S;          // the work counters describe the adjoint pass only
         Sf.counts = nullptr;
         CUDA_TRY(cudaMemsetAsync(st->counts_dev, 0, 8 * sizeof(unsigned long long), stream));
-        CUDA_TRY(launch_render(Sf, (int)n, camx, camy, camz, cammu, camphi, packs, nullptr, visrad, 0, 1, G.singlescatter, 0, 0,
-                               nullptr, 0, nullptr, nullptr, (RayErr *)st->err.p, stream));
-        CUDA_TRY(launch_render(Sf, (int)n, camx, camy, camz, cammu, camphi, packs, nullptr, total, 1, 1, G.singlescatter, 0,
-                               G.maxsub, nullptr, 0, nullptr, nullptr, (RayErr *)st->err.p, stream));
+        CUDA_TRY(launch_forward(Sf, (int)n, camx, camy, camz, cammu, camphi, packs, nullptr, visrad, total, 3, 1,
+                                G.singlescatter, 0, G.maxsub, nullptr, 0, nullptr, nullptr, (RayErr *)st->err.p,
+                                st->ray_counter, stream));
         if (kernel_ms) cudaEventRecord(ev[1], stream);
         // ---- Phase 2 ----
         CUDA_TRY(cub::DeviceScan::ExclusiveSum(wb + w_cub, cubtmp, rpp, pixstart, (int)npix, stream));
@@ -1149,26 +1177,28 @@ extern "C" int at3d_levisapprox_gradient(at3d_state *st, const at3d_rays *rays, 
         cost_reduce_kernel<<<1, 1024, 0, stream>>>((int)npix, costp, cost_d);
         CUDA_TRY(cudaGetLastError());
         // ---- Phase 3 ----
-        const GradLayout L = grad_layout(nst, S.ny_comp, S.nlmp, S.nstleg, S.nleg, S.ml, G.numder);
-        const size_t smem = (size_t)AT3D_WARPS_PER_BLOCK * L.total;
+        const GradLayout L = grad_layout(nst, S.ny_comp, S.nlmp, S.ml, G.ncomp, G.ntup, G.numder);
+        const size_t smem = (size_t)AT3D_RAYS_PER_BLOCK * L.total;
         if (smem > 227 * 1024) { set_msg(errmsg, "gradient kernel needs %zu bytes of shared memory (NUMDER too large)", smem); return 3; }
-        if (8 * G.numder > 64) { set_msg(errmsg, "NUMDER > 8 is not supported by the adjoint kernel"); return 3; }
         const void *fn = nst == 1 ? (const void *)adjoint_kernel<1> : (const void *)adjoint_kernel<3>;
         CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int dev = 0, nsm = 148, per_sm = 1;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, AT3D_WARPS_PER_BLOCK * 32, smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, AT3D_RAY_THREADS, smem);
         if (per_sm < 1) per_sm = 1;
-        long want = ((long)n + AT3D_WARPS_PER_BLOCK - 1) / AT3D_WARPS_PER_BLOCK;
+        long want = ((long)n + AT3D_RAYS_PER_BLOCK - 1) / AT3D_RAYS_PER_BLOCK;
         long cap = (long)nsm * per_sm;
         const int nblk = (int)(want < cap ? want : cap);
+        CUDA_TRY(cudaMemsetAsync(st->ray_counter, 0, sizeof(int), stream));
         if (nst == 1)
-            adjoint_kernel<1><<<nblk, AT3D_WARPS_PER_BLOCK * 32, smem, stream>>>(S, G, L, (int)n, camx, camy, camz, cammu,
-                camphi, packs, raypix, adjw, rw, sw, total, grad_d, beam, tc, tcap, tn, ts, (RayErr *)st->err.p);
+            adjoint_kernel<1><<<nblk, AT3D_RAY_THREADS, smem, stream>>>(S, G, L, (int)n, camx, camy, camz, cammu,
+                camphi, packs, raypix, adjw, rw, sw, total, grad_d, beam, tc, tcap, tn, ts, (RayErr *)st->err.p,
+                st->ray_counter);
         else
-            adjoint_kernel<3><<<nblk, AT3D_WARPS_PER_BLOCK * 32, smem, stream>>>(S, G, L, (int)n, camx, camy, camz, cammu,
-                camphi, packs, raypix, adjw, rw, sw, total, grad_d, beam, tc, tcap, tn, ts, (RayErr *)st->err.p);
+            adjoint_kernel<3><<<nblk, AT3D_RAY_THREADS, smem, stream>>>(S, G, L, (int)n, camx, camy, camz, cammu,
+                camphi, packs, raypix, adjw, rw, sw, total, grad_d, beam, tc, tcap, tn, ts, (RayErr *)st->err.p,
+                st->ray_counter);
         CUDA_TRY(cudaGetLastError());
         if (kernel_ms) cudaEventRecord(ev[2], stream);
         // ---- Phase 4 ----

@@ -38,16 +38,17 @@ struct at3d_state {
     std::vector<RayPack> packs_h;   // host staging of the per-ray packs
     float *bcrad_dev = nullptr;
     unsigned long long *counts_dev = nullptr;
+    int *ray_counter = nullptr;     // work counter of the persistent ray kernels
     int nbcrad = 0;
 };
 
 size_t render_smem_bytes(const DevState &S);
-cudaError_t launch_render(const DevState &S, int nrays, const float *camx, const float *camy,
-                          const float *camz, const double *cammu, const double *camphi,
-                          const RayPack *packs, float *out_f32, double *out_f64, int mode,
-                          int correctinterpolate, int singlescatter, int nosurface, int maxsub,
-                          int *trace_cells, int trace_cap, int *trace_n, int *trace_nsub,
-                          RayErr *err, cudaStream_t stream);
+cudaError_t launch_forward(const DevState &S, int nrays, const float *camx, const float *camy,
+                           const float *camz, const double *cammu, const double *camphi,
+                           const RayPack *packs, float *out_f32, double *out_f64, double *out_tot, int modes,
+                           int correctinterpolate, int singlescatter, int nosurface, int maxsub,
+                           int *trace_cells, int trace_cap, int *trace_n, int *trace_nsub,
+                           RayErr *err, int *ray_counter, cudaStream_t stream);
 cudaError_t launch_build_cellrec(int ncells, const int *gridptr, const int *neighptr, const int *treeptr,
                                  const short *cellflags, int4 *cellrec, cudaStream_t s);
 cudaError_t launch_build_ptrec(int npts, const float *gridpos, const float *total_ext, float4 *ptrec, cudaStream_t s);

@@ -1,21 +1,15 @@
-// at3d_ray.cuh -- warp-per-ray march shared by the RENDER and gradient kernels.
+// at3d_ray.cuh -- octet-per-ray march shared by the RENDER and gradient kernels (sm_100a).
 //
-// One warp integrates one ray.  The per-ray direction tables (YLMDIR) live in shared memory,
-// lanes split the spherical-harmonic sums (float4 coalesced loads of the planar, 16-byte aligned
-// source blocks), and the cell-walk geometry is evaluated redundantly (warp-uniform) in FP64
-// with the exact operation order of INTEGRATE_1RAY (shdomsub2.f:2311-2743) /
-// ADJOINT_INTEGRATE_1RAY (shdomsub4.f:3223-3967) so that the visited-cell sequence is bit-exact.
+// Eight lanes (an "octet") integrate one ray; a warp carries four neighbouring rays.  The cell walk
+// (geometry, extinction interpolation, NTAU, transmission) is evaluated by every lane of the octet in
+// FP64 with the exact operation order of INTEGRATE_1RAY (shdomsub2.f:2311-2743) /
+// ADJOINT_INTEGRATE_1RAY (shdomsub4.f:3223-3967), so the visited-cell sequence and the
+// sub-interval counts are bit-exact.  The spherical-harmonic sums of COMPUTE_SOURCE_1CELL are
+// split over the 8 lanes (float4 loads of 128-byte aligned planar blocks, 3-step shuffle
+// reduction); lane n owns corner n of the current cell (values in registers, exchanged by
+// shuffles).  The per-ray direction table YLMDIR lives in shared memory.
 #pragma once
 #include "at3d_device.cuh"
-
-// Per-warp shared scratch for the 8 corner values of the current and previous cell.
-template <int NST>
-struct CornerCache {
-    int pt[8];
-    float ext[8];
-    float src[NST][8];
-    float ss[NST][8];
-};
 
 struct RayErr {
     int code;       // 0 ok, 1 SO<0, 2 below domain, 3 not at boundary, 4 too many sub-intervals
@@ -27,69 +21,97 @@ __device__ __forceinline__ void set_err(RayErr *err, int code, int ray)
     if (atomicCAS(&err->code, 0, code) == 0) err->ray = ray;
 }
 
-// Evaluate source*extinction (and the exact single-scatter part separately) of one grid point in
-// the ray direction: COMPUTE_SOURCE_1CELL (shdomsub2.f:2911-3038) for one corner, with the
-// TMS-corrected SH source prepared by prep_source_kernel.  Returns reduced values on every lane.
+// lanes of the calling thread's octet
+struct Oct {
+    unsigned m;     // lane mask of the octet inside its warp
+    int ol;         // lane index inside the octet (0..7) = the cell corner this lane owns
+    int ob;         // first lane of the octet in the warp
+};
+__device__ __forceinline__ Oct oct_id()
+{
+    Oct o;
+    const int lane = threadIdx.x & 31;
+    o.ol = lane & 7; o.ob = lane & ~7; o.m = 0xFFu << o.ob;
+    return o;
+}
+__device__ __forceinline__ unsigned oct_ballot(const Oct &o, bool p)
+{ return (__ballot_sync(o.m, p) >> o.ob) & 0xFFu; }
+__device__ __forceinline__ unsigned oct_or(const Oct &o, unsigned v)
+{
+    v |= __shfl_xor_sync(o.m, v, 4); v |= __shfl_xor_sync(o.m, v, 2); v |= __shfl_xor_sync(o.m, v, 1);
+    return v;
+}
+
+// SINGSCAT(:,iph) of the ray (shdomsub2.f:2425-2441), evaluated on demand
+template <int NST>
+__device__ __forceinline__ void ray_singscat(const float *tab, int nstphase, int numphase, int iph,
+                                             const RayDir &rd, float (&s)[NST])
+{
+    const float *p0 = tab + (size_t)nstphase * ((iph - 1) + (size_t)numphase * (rd.j - 1));
+    const float *p1 = p0 + (size_t)nstphase * numphase;
+    s[0] = (1 - rd.f) * __ldg(p0) + rd.f * __ldg(p1);
+    if (NST > 1) {
+        const float b1 = (1 - rd.f) * __ldg(p0 + 1) + rd.f * __ldg(p1 + 1);
+        s[1] = (float)(b1 * rd.cos22);
+        s[NST - 1] = (float)(b1 * rd.sin22);
+    }
+}
+
+// One grid point in the ray direction: COMPUTE_SOURCE_1CELL (shdomsub2.f:2911-3038) for one corner,
+// with the TMS-corrected SH source prepared by prep_sh_kernel.  Returns on every lane of the octet
+// the extinction, the SH part a[] and the exact single-scatter part b[] (both before the
+// multiplication by the extinction).
 template <int NST>
 __device__ __forceinline__ void eval_point(const DevState &S, int ip, const float *Ysh, const RayDir &rd,
-                                           bool singlescatter, float &ext, float (&src)[NST], float (&ss)[NST])
+                                           bool singlescatter, const Oct &o, float &ext, int &ns,
+                                           float (&a)[NST], float (&b)[NST])
 {
-    const int lane = lane_id();
     const float4 pr = __ldg(&S.ptrec[ip - 1]);
     const int2 sr = __ldg(&S.srcrec[ip - 1]);
     ext = pr.w;
-    const int nsp = (sr.y + 3) & ~3;
-    float acc[NST], sacc[NST];
+    ns = sr.y;
+    const int nsp = AT3D_SHPAD(sr.y);
 #pragma unroll
-    for (int k = 0; k < NST; k++) { acc[k] = 0.0f; sacc[k] = 0.0f; }
+    for (int k = 0; k < NST; k++) { a[k] = 0.0f; b[k] = 0.0f; }
     if (!singlescatter) {
-        const float *base = S.shsrc + sr.x;
-        for (int j4 = lane * 4; j4 < nsp; j4 += 128) {
-            const float4 s = __ldg((const float4 *)(base + j4));
-            const float4 y = *(const float4 *)(Ysh + j4);
-            acc[0] = fmaf(s.x, y.x, acc[0]); acc[0] = fmaf(s.y, y.y, acc[0]);
-            acc[0] = fmaf(s.z, y.z, acc[0]); acc[0] = fmaf(s.w, y.w, acc[0]);
+        const float *base = S.shsrc + sr.x + o.ol * 4;
+        const float *yb = Ysh + o.ol * 4;
+        const int nlmp = S.nlmp;
+#pragma unroll 4
+        for (int j = 0; j < nsp; j += 32) {
+            const float4 s = __ldg((const float4 *)(base + j));
+            const float4 y = *(const float4 *)(yb + j);
+            a[0] = fmaf(s.x, y.x, a[0]); a[0] = fmaf(s.y, y.y, a[0]);
+            a[0] = fmaf(s.z, y.z, a[0]); a[0] = fmaf(s.w, y.w, a[0]);
             if (NST > 1) {
-                const float4 q = __ldg((const float4 *)(base + nsp + j4));
-                const float4 u = __ldg((const float4 *)(base + 2 * nsp + j4));
-                const float4 y2 = *(const float4 *)(Ysh + 1 * S.nlmp + j4);
-                const float4 y5 = *(const float4 *)(Ysh + 2 * S.nlmp + j4);
-                const float4 y6 = *(const float4 *)(Ysh + 3 * S.nlmp + j4);
-                const float4 y3 = *(const float4 *)(Ysh + 4 * S.nlmp + j4);
-                acc[1] = fmaf(q.x, y2.x, acc[1]); acc[1] = fmaf(u.x, y5.x, acc[1]);
-                acc[1] = fmaf(q.y, y2.y, acc[1]); acc[1] = fmaf(u.y, y5.y, acc[1]);
-                acc[1] = fmaf(q.z, y2.z, acc[1]); acc[1] = fmaf(u.z, y5.z, acc[1]);
-                acc[1] = fmaf(q.w, y2.w, acc[1]); acc[1] = fmaf(u.w, y5.w, acc[1]);
-                acc[NST - 1] = fmaf(q.x, y6.x, acc[NST - 1]); acc[NST - 1] = fmaf(u.x, y3.x, acc[NST - 1]);
-                acc[NST - 1] = fmaf(q.y, y6.y, acc[NST - 1]); acc[NST - 1] = fmaf(u.y, y3.y, acc[NST - 1]);
-                acc[NST - 1] = fmaf(q.z, y6.z, acc[NST - 1]); acc[NST - 1] = fmaf(u.z, y3.z, acc[NST - 1]);
-                acc[NST - 1] = fmaf(q.w, y6.w, acc[NST - 1]); acc[NST - 1] = fmaf(u.w, y3.w, acc[NST - 1]);
+                const float4 q = __ldg((const float4 *)(base + nsp + j));
+                const float4 u = __ldg((const float4 *)(base + 2 * nsp + j));
+                const float4 y2 = *(const float4 *)(yb + 1 * nlmp + j);
+                const float4 y5 = *(const float4 *)(yb + 2 * nlmp + j);
+                const float4 y6 = *(const float4 *)(yb + 3 * nlmp + j);
+                const float4 y3 = *(const float4 *)(yb + 4 * nlmp + j);
+                a[1] = fmaf(q.x, y2.x, a[1]); a[1] = fmaf(u.x, y5.x, a[1]);
+                a[1] = fmaf(q.y, y2.y, a[1]); a[1] = fmaf(u.y, y5.y, a[1]);
+                a[1] = fmaf(q.z, y2.z, a[1]); a[1] = fmaf(u.z, y5.z, a[1]);
+                a[1] = fmaf(q.w, y2.w, a[1]); a[1] = fmaf(u.w, y5.w, a[1]);
+                a[NST - 1] = fmaf(q.x, y6.x, a[NST - 1]); a[NST - 1] = fmaf(u.x, y3.x, a[NST - 1]);
+                a[NST - 1] = fmaf(q.y, y6.y, a[NST - 1]); a[NST - 1] = fmaf(u.y, y3.y, a[NST - 1]);
+                a[NST - 1] = fmaf(q.z, y6.z, a[NST - 1]); a[NST - 1] = fmaf(u.z, y3.z, a[NST - 1]);
+                a[NST - 1] = fmaf(q.w, y6.w, a[NST - 1]); a[NST - 1] = fmaf(u.w, y3.w, a[NST - 1]);
             }
         }
     }
     const int cnt = __ldg(&S.sscount[ip - 1]);
-    for (int k = lane; k < cnt; k += 32) {
+    for (int k = o.ol; k < cnt; k += 8) {
         const int2 e = __ldg(&S.ssent[(size_t)(ip - 1) * S.kmax + k]);
         const float coef = __int_as_float(e.y);
-        const float *p0 = S.phasetab + (size_t)S.nstphase * ((e.x - 1) + (size_t)S.numphase * (rd.j - 1));
-        const float *p1 = p0 + (size_t)S.nstphase * S.numphase;
-        const float a = (1 - rd.f) * __ldg(p0) + rd.f * __ldg(p1);
-        sacc[0] = fmaf(coef, a, sacc[0]);
-        if (NST > 1) {
-            const float b1 = (1 - rd.f) * __ldg(p0 + 1) + rd.f * __ldg(p1 + 1);
-            const float q = (float)(b1 * rd.cos22);
-            const float u = (float)(b1 * rd.sin22);
-            sacc[1] = fmaf(coef, q, sacc[1]);
-            sacc[NST - 1] = fmaf(coef, u, sacc[NST - 1]);
-        }
+        float sv[NST];
+        ray_singscat<NST>(S.phasetab, S.nstphase, S.numphase, e.x, rd, sv);
+#pragma unroll
+        for (int kk = 0; kk < NST; kk++) b[kk] = fmaf(coef, sv[kk], b[kk]);
     }
 #pragma unroll
-    for (int k = 0; k < NST; k++) {
-        const float a = warp_sum(acc[k]);
-        const float b = warp_sum(sacc[k]);
-        ss[k] = b * ext;
-        src[k] = (a + b) * ext;
-    }
+    for (int k = 0; k < NST; k++) { a[k] = oct_sum(o.m, a[k]); b[k] = oct_sum(o.m, b[k]); }
 }
 
 // nested-lerp trilinear interpolation of INTEGRATE_1RAY (shdomsub2.f:2563-2571), double weights
@@ -109,6 +131,14 @@ __device__ __forceinline__ void interp_kernel(double u, double v, double w, doub
     f[5] = w * (1 - v) * u;
     f[6] = w * v * (1 - u);
     f[7] = w * v * u;
+}
+// element `corner` of GET_INTERP_KERNEL (same products in the same order)
+__device__ __forceinline__ double interp_kernel_own(double u, double v, double w, int corner)
+{
+    const double fw = (corner & 4) ? w : (1 - w);
+    const double fv = (corner & 2) ? v : (1 - v);
+    const double fu = (corner & 1) ? u : (1 - u);
+    return fw * fv * fu;
 }
 __device__ __forceinline__ double fcsum(const double *f, const float *a)
 {
@@ -179,114 +209,120 @@ __device__ int boundary_radiance(const DevState &S, double xb, double yb, float 
     return 0;
 }
 
-// Refresh the 8 corner values of cell `c` in the per-warp cache: values of points shared with the
-// previous cell are reused (they are bit-identical to a recomputation, so this is the reference's
-// OLDIPTS/DONEFACE shortcut, shdomsub2.f:2509-2515,2914-2919, without its slot restriction).
-template <int NST>
-__device__ __forceinline__ void refresh_corners(const DevState &S, const CellRec &c, CornerCache<NST> *cc,
-                                                const float *Ysh, const RayDir &rd, bool singlescatter,
-                                                bool first, int &npt_eval, int &nsh_eval)
+// GRIDPTR entry of the corner this lane owns
+__device__ __forceinline__ int own_corner(const CellRec &c, int ol)
 {
-    const int lane = lane_id();
-    int myp = 0, hit = -1;
-    float oext = 0.0f, osrc[NST], oss[NST];
-    if (lane < 8) {
-        myp = c.gp[0];
+    int p = c.gp[0];
 #pragma unroll
-        for (int n = 1; n < 8; n++) if (lane == n) myp = c.gp[n];
-        if (!first) {
-#pragma unroll
-            for (int k = 0; k < 8; k++) if (cc->pt[k] == myp) hit = k;
-        }
-        if (hit >= 0) {
-            oext = cc->ext[hit];
-#pragma unroll
-            for (int k = 0; k < NST; k++) { osrc[k] = cc->src[k][hit]; oss[k] = cc->ss[k][hit]; }
-        }
-    }
-    __syncwarp();
-    if (lane < 8) {
-        cc->pt[lane] = myp;
-        if (hit >= 0) {
-            cc->ext[lane] = oext;
-#pragma unroll
-            for (int k = 0; k < NST; k++) { cc->src[k][lane] = osrc[k]; cc->ss[k][lane] = oss[k]; }
-        }
-    }
-    unsigned need = __ballot_sync(FULLMASK, lane < 8 && hit < 0);
-    // duplicate corners inside one cell (IP-mode / open-boundary end cells): evaluate once
-    while (need) {
-        const int n = __ffs(need) - 1;
-        need &= need - 1;
-        const int ip = __shfl_sync(FULLMASK, myp, n);
-        float ext, src[NST], ss[NST];
-        eval_point<NST>(S, ip, Ysh, rd, singlescatter, ext, src, ss);
-        npt_eval++; nsh_eval += __ldg(&S.srcrec[ip - 1]).y;
-        const unsigned same = __ballot_sync(FULLMASK, lane < 8 && myp == ip);
-        if (lane < 8 && myp == ip) {
-            cc->ext[lane] = ext;
-#pragma unroll
-            for (int k = 0; k < NST; k++) { cc->src[k][lane] = src[k]; cc->ss[k][lane] = ss[k]; }
-        }
-        need &= ~same;
-    }
-    __syncwarp();
+    for (int n = 1; n < 8; n++) if (ol == n) p = c.gp[n];
+    return p;
 }
 
-// Integrate one ray.  MODE 0: INTEGRATE_1RAY arithmetic; MODE 1: the forward part of
-// ADJOINT_INTEGRATE_1RAY (GET_INTERP_KERNEL weights, EXT0=EXTN on the last sub-interval,
-// no MAXCELLSCROSS stop).  Returns the radiance in rad[] (all lanes) and an error code.
-template <int NST, int MODE>
-__device__ int march_ray(const DevState &S, CornerCache<NST> *cc, const float *Ysh, const RayDir &rd,
-                         double mu2, double x0, double y0, double z0, float sky,
-                         bool correctinterpolate, bool singlescatter, bool nosurface, int maxsub,
-                         double (&rad)[NST], int *trace_cells, int trace_cap, int &ntrace, int &nsub)
+// Exit geometry of one cell, identical for every march (shdomsub2.f:2575-2606, 2668-2716).
+struct CellExit {
+    double so, sox, soy, soz, xn, yn, zn;
+    int iface, jface, inextcell, kface, ic;
+};
+
+// Refresh the corner values of the lanes for cell `c`: values of points shared with the previous
+// cell are taken over from the lane that owned them (they are bit-identical to a recomputation, so
+// this is the reference's OLDIPTS/DONEFACE shortcut, shdomsub2.f:2509-2515,2914-2919, without its
+// slot restriction); duplicate corners inside one cell are evaluated once.
+template <int NST>
+__device__ __forceinline__ void refresh_corners(const DevState &S, const CellRec &c, const float *Ysh,
+                                                const RayDir &rd, bool singlescatter, bool first, const Oct &o,
+                                                int &cpt, float &cext, float (&csrc)[NST],
+                                                int &npt_eval, int &nsh_eval)
 {
-    const int lane = lane_id();
-    double xe = x0, ye = y0, ze = z0, transmit = 1.0;
-    float ext1 = 0.0f, srcext1[NST];
+    const int myp = own_corner(c, o.ol);
+    int hit = -1;
+    if (!first) {
 #pragma unroll
-    for (int k = 0; k < NST; k++) { rad[k] = 0.0; srcext1[k] = 0.0f; }
+        for (int k = 0; k < 8; k++) { const int pk = __shfl_sync(o.m, cpt, k, 8); if (pk == myp) hit = k; }
+    }
+    const int from = hit < 0 ? o.ol : hit;
+    cext = __shfl_sync(o.m, cext, from, 8);
+#pragma unroll
+    for (int k = 0; k < NST; k++) csrc[k] = __shfl_sync(o.m, csrc[k], from, 8);
+    cpt = myp;
+    unsigned need = oct_ballot(o, hit < 0);
+    while (need) {
+        const int n = __ffs(need) - 1;
+        const int ip = __shfl_sync(o.m, myp, n, 8);
+        float ext, a[NST], b[NST];
+        int ns;
+        eval_point<NST>(S, ip, Ysh, rd, singlescatter, o, ext, ns, a, b);
+        npt_eval++; nsh_eval += ns;
+        const bool mine = (myp == ip);
+        if (mine) {
+            cext = ext;
+#pragma unroll
+            for (int k = 0; k < NST; k++) csrc[k] = (a[k] + b[k]) * ext;
+        }
+        need &= ~oct_ballot(o, mine);
+    }
+}
+
+// Forward integration of one ray by one octet.
+// MODES bit 0: INTEGRATE_1RAY arithmetic (result radA, nsubA counts every sub-interval);
+// MODES bit 1: the forward part of ADJOINT_INTEGRATE_1RAY (GET_INTERP_KERNEL weights, EXT0=EXTN on
+//              the last sub-interval, no MAXCELLSCROSS stop; result radB, nsubB counts EXT!=0).
+// Both share the walk (it depends on the geometry only) and the corner evaluations.
+template <int NST, int MODES>
+__device__ int march_forward(const DevState &S, const float *Ysh, const RayDir &rd, double mu2,
+                             double x0, double y0, double z0, float sky, bool correctinterpolate,
+                             bool singlescatter, bool nosurface, int maxsub, const Oct &o,
+                             double (&radA)[NST], double (&radB)[NST],
+                             int *trace_cells, int trace_cap, int &ntrace, int &nsubA, int &nsubB)
+{
+    double xe = x0, ye = y0, ze = z0, trA = 1.0, trB = 1.0;
+    float ext1A = 0.0f, srcext1A[NST], ext1B = 0.0f, srcext1B[NST];
+#pragma unroll
+    for (int k = 0; k < NST; k++) { radA[k] = 0.0; radB[k] = 0.0; srcext1A[k] = 0.0f; srcext1B[k] = 0.0f; }
     const int p1c = cell_gp(S, 1, 1), p8c = cell_gp(S, 1, 8);
     const double eps = (double)(1.0e-5f * (pt_coord(S, p8c, 3) - pt_coord(S, p1c, 3)));
     const int maxcellscross = 500 * max(S.nx, max(S.ny, S.nz));
     int icell = dev_locate_grid_cell(S, xe, ye, ze);
     int iface = 0, ngrid = 0, npt_eval = 0, nsh_eval = 0;
-    bool done = false, first = true;
-    ntrace = 0; nsub = 0;
-    while (!done && icell > 0) {
+    bool doneA = !(MODES & 1), doneB = !(MODES & 2), first = true;
+    int cpt = 0; float cext = 0.0f, csrc[NST];
+#pragma unroll
+    for (int k = 0; k < NST; k++) csrc[k] = 0.0f;
+    ntrace = 0; nsubA = 0; nsubB = 0;
+    while (!(doneA && doneB) && icell > 0) {
         ngrid++;
-        if (trace_cells && lane == 0 && ntrace < trace_cap) trace_cells[ntrace] = icell;
+        if (trace_cells && o.ol == 0 && ntrace < trace_cap) trace_cells[ntrace] = icell;
         ntrace++;
         const CellRec c = load_cell(S, icell);
-        refresh_corners<NST>(S, c, cc, Ysh, rd, singlescatter, first, npt_eval, nsh_eval);
+        refresh_corners<NST>(S, c, Ysh, rd, singlescatter, first, o, cpt, cext, csrc, npt_eval, nsh_eval);
         first = false;
         float e8[8], s8[NST][8];
 #pragma unroll
         for (int n = 0; n < 8; n++) {
-            e8[n] = cc->ext[n];
+            e8[n] = __shfl_sync(o.m, cext, n, 8);
 #pragma unroll
-            for (int k = 0; k < NST; k++) s8[k][n] = cc->src[k][n];
+            for (int k = 0; k < NST; k++) s8[k][n] = __shfl_sync(o.m, csrc[k], n, 8);
         }
         const float4 q1 = __ldg(&S.ptrec[c.gp[0] - 1]);
         const float4 q8 = __ldg(&S.ptrec[c.gp[7] - 1]);
-        double delx = (double)(q8.x - q1.x), dely = (double)(q8.y - q1.y), delz = (double)(q8.z - q1.z);
-        double invdelx = (delx <= 0.0) ? 1.0 : 1.0 / delx;
-        double invdely = (dely <= 0.0) ? 1.0 : 1.0 / dely;
-        double invdelz = 1.0 / delz;
+        const double delx = (double)(q8.x - q1.x), dely = (double)(q8.y - q1.y), delz = (double)(q8.z - q1.z);
+        const double invdelx = (delx <= 0.0) ? 1.0 : 1.0 / delx;
+        const double invdely = (dely <= 0.0) ? 1.0 : 1.0 / dely;
+        const double invdelz = 1.0 / delz;
         double u = (xe - q1.x) * invdelx, v = (ye - q1.y) * invdely, w = (ze - q1.z) * invdelz;
         double fc[8];
-        if (MODE == 1) {
+        if ((MODES & 2) && !doneB) {
             interp_kernel(u, v, w, fc);
 #pragma unroll
-            for (int k = 0; k < NST; k++) srcext1[k] = (float)fcsum(fc, s8[k]);
-            srcext1[0] = fmaxf(0.0f, srcext1[0]);
-            ext1 = (float)fcsum(fc, e8);
-        } else if (correctinterpolate || ngrid == 1) {
+            for (int k = 0; k < NST; k++) srcext1B[k] = (float)fcsum(fc, s8[k]);
+            srcext1B[0] = fmaxf(0.0f, srcext1B[0]);
+            ext1B = (float)fcsum(fc, e8);
+        }
+        if ((MODES & 1) && !doneA && (correctinterpolate || ngrid == 1)) {
 #pragma unroll
-            for (int k = 0; k < NST; k++) srcext1[k] = (float)trilerp(s8[k], u, v, w);
-            srcext1[0] = fmaxf(0.0f, srcext1[0]);
-            ext1 = (float)trilerp(e8, u, v, w);
+            for (int k = 0; k < NST; k++) srcext1A[k] = (float)trilerp(s8[k], u, v, w);
+            srcext1A[0] = fmaxf(0.0f, srcext1A[0]);
+            ext1A = (float)trilerp(e8, u, v, w);
         }
         const bool ipinx = DBTEST(c.flags, 0) &&
             !(DBTEST(S.bcflag, 0) && ((rd.cx > 0 && xe < rd.xm) || (rd.cx < 0 && xe > rd.xm)));
@@ -296,55 +332,85 @@ __device__ int march_ray(const DevState &S, CornerCache<NST> *cc, const float *Y
 #pragma unroll
         for (int n = 1; n < 8; n++) if (8 - rd.ioct == n) iopp = c.gp[n];
         const float4 qo = __ldg(&S.ptrec[iopp - 1]);
-        double sox = ipinx ? (double)1.0e20f : (qo.x - xe) * rd.cxinv;
-        double soy = ipiny ? (double)1.0e20f : (qo.y - ye) * rd.cyinv;
-        double soz = (qo.z - ze) * rd.czinv;
-        double so = fmin(fmin(sox, soy), soz);
+        const double sox = ipinx ? (double)1.0e20f : (qo.x - xe) * rd.cxinv;
+        const double soy = ipiny ? (double)1.0e20f : (qo.y - ye) * rd.cyinv;
+        const double soz = (qo.z - ze) * rd.czinv;
+        const double so = fmin(fmin(sox, soy), soz);
         if (so < -eps) return 1;
         double xn = xe + so * rd.cx, yn = ye + so * rd.cy, zn = ze + so * rd.cz;
         u = (xn - q1.x) * invdelx; v = (yn - q1.y) * invdely; w = (zn - q1.z) * invdelz;
-        float extn;
-        if (MODE == 1) { double fcn[8]; interp_kernel(u, v, w, fcn); extn = (float)fcsum(fcn, e8); }
-        else extn = (float)trilerp(e8, u, v, w);
-        const double taugrid = so * 0.5f * (ext1 + extn);
-        int ntau = 1 + (int)(taugrid / S.tautol);
-        if (ntau < 1) ntau = 1;
-        const double dels = so / ntau;
-        for (int it = 1; it <= ntau; it++) {
-            const double s = it * dels;
-            const double xi = xe + s * rd.cx, yi = ye + s * rd.cy, zi = ze + s * rd.cz;
-            u = (xi - q1.x) * invdelx; v = (yi - q1.y) * invdely; w = (zi - q1.z) * invdelz;
-            float ext0, srcext0[NST];
-            if (MODE == 1) {
-                interp_kernel(u, v, w, fc);
+        if ((MODES & 1) && !doneA) {
+            const float extn = (float)trilerp(e8, u, v, w);
+            const double taugrid = so * 0.5f * (ext1A + extn);
+            int ntau = 1 + (int)(taugrid / S.tautol);
+            if (ntau < 1) ntau = 1;
+            const double dels = so / ntau;
+            for (int it = 1; it <= ntau; it++) {
+                const double s = it * dels;
+                const double xi = xe + s * rd.cx, yi = ye + s * rd.cy, zi = ze + s * rd.cz;
+                const double ui = (xi - q1.x) * invdelx, vi = (yi - q1.y) * invdely, wi = (zi - q1.z) * invdelz;
+                const float ext0 = (float)trilerp(e8, ui, vi, wi);
+                float srcext0[NST];
+#pragma unroll
+                for (int k = 0; k < NST; k++) srcext0[k] = (float)trilerp(s8[k], ui, vi, wi);
+                srcext0[0] = fmaxf(0.0f, srcext0[0]);
+                const double ext = (double)(0.5f * (ext0 + ext1A));
+                if (ext != 0.0) {
+                    const double tau = ext * dels;
+                    const double abscell = tau * (1.0f - 0.5f * tau * (1.0f - 0.33333333333f * tau));
+                    const double transcell = 1.0f - abscell;
+#pragma unroll
+                    for (int k = 0; k < NST; k++) {
+                        const double src = (0.5f * (srcext0[k] + srcext1A[k])
+                            + 0.08333333333f * (ext0 * srcext1A[k] - ext1A * srcext0[k]) * dels
+                              * (1.0f - 0.05f * (ext1A - ext0) * dels)) / ext;
+                        radA[k] = radA[k] + trA * src * abscell;
+                    }
+                    trA = trA * transcell;
+                }
+                nsubA++;
+                ext1A = ext0;
+#pragma unroll
+                for (int k = 0; k < NST; k++) srcext1A[k] = srcext0[k];
+            }
+        }
+        if ((MODES & 2) && !doneB) {
+            float extn;
+            { double fcn[8]; interp_kernel(u, v, w, fcn); extn = (float)fcsum(fcn, e8); }
+            const double taugrid = so * 0.5f * (ext1B + extn);
+            int ntau = 1 + (int)(taugrid / S.tautol);
+            if (ntau < 1) ntau = 1;
+            const double dels = so / ntau;
+            for (int it = 1; it <= ntau; it++) {
+                const double s = it * dels;
+                const double xi = xe + s * rd.cx, yi = ye + s * rd.cy, zi = ze + s * rd.cz;
+                const double ui = (xi - q1.x) * invdelx, vi = (yi - q1.y) * invdely, wi = (zi - q1.z) * invdelz;
+                interp_kernel(ui, vi, wi, fc);
+                float srcext0[NST];
 #pragma unroll
                 for (int k = 0; k < NST; k++) srcext0[k] = (float)fcsum(fc, s8[k]);
-                ext0 = (it != ntau) ? (float)fcsum(fc, e8) : extn;
-            } else {
-                ext0 = (float)trilerp(e8, u, v, w);
+                const float ext0 = (it != ntau) ? (float)fcsum(fc, e8) : extn;
+                srcext0[0] = fmaxf(0.0f, srcext0[0]);
+                const double ext = (double)(0.5f * (ext0 + ext1B));
+                if (ext != 0.0) {
+                    const double tau = ext * dels;
+                    const double abscell = tau * (1.0f - 0.5f * tau * (1.0f - 0.33333333333f * tau));
+                    const double transcell = 1.0f - abscell;
 #pragma unroll
-                for (int k = 0; k < NST; k++) srcext0[k] = (float)trilerp(s8[k], u, v, w);
-            }
-            srcext0[0] = fmaxf(0.0f, srcext0[0]);
-            const double ext = (double)(0.5f * (ext0 + ext1));
-            if (ext != 0.0) {
-                const double tau = ext * dels;
-                const double abscell = tau * (1.0f - 0.5f * tau * (1.0f - 0.33333333333f * tau));
-                const double transcell = 1.0f - abscell;
-#pragma unroll
-                for (int k = 0; k < NST; k++) {
-                    const double src = (0.5f * (srcext0[k] + srcext1[k])
-                        + 0.08333333333f * (ext0 * srcext1[k] - ext1 * srcext0[k]) * dels
-                          * (1.0f - 0.05f * (ext1 - ext0) * dels)) / ext;
-                    rad[k] = rad[k] + transmit * src * abscell;
+                    for (int k = 0; k < NST; k++) {
+                        const double src = (0.5f * (srcext0[k] + srcext1B[k])
+                            + 0.08333333333f * (ext0 * srcext1B[k] - ext1B * srcext0[k]) * dels
+                              * (1.0f - 0.05f * (ext1B - ext0) * dels)) / ext;
+                        radB[k] = radB[k] + trB * src * abscell;
+                    }
+                    trB = trB * transcell;
+                    nsubB++;
+                    if (nsubB + 1 > maxsub) return 4;
                 }
-                transmit = transmit * transcell;
-                if (MODE == 1) { nsub++; if (nsub + 1 > maxsub) return 4; }
-            }
-            if (MODE == 0) nsub++;
-            ext1 = ext0;
+                ext1B = ext0;
 #pragma unroll
-            for (int k = 0; k < NST; k++) srcext1[k] = srcext0[k];
+                for (int k = 0; k < NST; k++) srcext1B[k] = srcext0[k];
+            }
         }
         int jface;
         bool openbcface;
@@ -365,28 +431,43 @@ __device__ int march_ray(const DevState &S, CornerCache<NST> *cc, const float *Y
             else if (jface == 2) yn = (double)pt_coord(S, pn, 2);
             else zn = (double)pt_coord(S, pn, 3);
         }
-        if (transmit < S.transcut || (MODE == 0 && ngrid > maxcellscross)) {
-            done = true;
-        } else if (inextcell == 0 && iface >= 5) {
-            done = true;
-            float radbnd[NST];
-            const int e = boundary_radiance<NST, MODE == 1>(S, xn, yn, (float)mu2, sky, ic, kface, radbnd,
+        const bool atbnd = (inextcell == 0 && iface >= 5);
+        if ((MODES & 1) && !doneA) {
+            if (trA < S.transcut || ngrid > maxcellscross) doneA = true;
+            else if (atbnd) {
+                doneA = true;
+                float radbnd[NST];
+                const int e = boundary_radiance<NST, false>(S, xn, yn, (float)mu2, sky, ic, kface, radbnd,
                                                             nullptr, nullptr, nullptr);
-            if (e) return e;
-            if (!nosurface) {
+                if (e) return e;
+                if (!nosurface) {
 #pragma unroll
-                for (int k = 0; k < NST; k++) rad[k] = rad[k] + transmit * radbnd[k];
+                    for (int k = 0; k < NST; k++) radA[k] = radA[k] + trA * radbnd[k];
+                }
             }
-        } else {
-            icell = inextcell;
         }
+        if ((MODES & 2) && !doneB) {
+            if (trB < S.transcut) doneB = true;
+            else if (atbnd) {
+                doneB = true;
+                float radbnd[NST];
+                const int e = boundary_radiance<NST, true>(S, xn, yn, (float)mu2, sky, ic, kface, radbnd,
+                                                           nullptr, nullptr, nullptr);
+                if (e) return e;
+                if (!nosurface) {
+#pragma unroll
+                    for (int k = 0; k < NST; k++) radB[k] = radB[k] + trB * radbnd[k];
+                }
+            }
+        }
+        if (!atbnd) icell = inextcell;
         xe = xn; ye = yn; ze = zn;
     }
-    if (S.counts && lane == 0) {
+    if (S.counts && o.ol == 0) {
         atomicAdd(&S.counts[0], (unsigned long long)ntrace);
         atomicAdd(&S.counts[1], (unsigned long long)npt_eval);
         atomicAdd(&S.counts[2], (unsigned long long)nsh_eval);
-        atomicAdd(&S.counts[4], (unsigned long long)nsub);
+        atomicAdd(&S.counts[4], (unsigned long long)((MODES & 1) ? nsubA : nsubB));
         atomicAdd(&S.counts[5], 1ull);
     }
     return 0;

@@ -64,7 +64,7 @@ __global__ void prep_sh_kernel(DevState S, int tms, const int *shptr, const floa
     if (ip >= S.npts) return;
     const int is = shptr[ip], ns = shptr[ip + 1] - is;
     const int2 r = rec[ip];
-    const int nsp = (ns + 3) & ~3;
+    const int nsp = AT3D_SHPAD(ns);
     const int nst = S.nstokes;
     for (int l = lane; l <= S.ml + 1; l += 32) { corr1[l] = 0.0f; corr5[l] = 0.0f; }
     __syncwarp();
@@ -141,46 +141,56 @@ __global__ void prep_sh_kernel(DevState S, int tms, const int *shptr, const floa
 }
 
 // ------------------------------------------------------------------------------------------
-// RENDER
+// RENDER / forward pass of the gradient
 // ------------------------------------------------------------------------------------------
-template <int NST, int MODE, typename OUT>
-__global__ void __launch_bounds__(AT3D_WARPS_PER_BLOCK * 32)
-render_kernel(DevState S, int nrays, const float *camx, const float *camy, const float *camz,
-              const double *cammu, const double *camphi, const RayPack *packs, OUT *stokes,
-              int correctinterpolate, int singlescatter, int nosurface, int maxsub,
-              int *trace_cells, int trace_cap, int *trace_n, int *trace_nsub, RayErr *err)
+// Persistent grid; a warp draws four consecutive rays at a time from a global counter (rays differ
+// a lot in length: clear sky vs. cloud), one ray per octet.
+template <int NST, int MODES, typename OUTA>
+__global__ void __launch_bounds__(AT3D_RAY_THREADS)
+forward_kernel(DevState S, int nrays, const float *camx, const float *camy, const float *camz,
+               const double *cammu, const double *camphi, const RayPack *packs, OUTA *outA, double *outB,
+               int correctinterpolate, int singlescatter, int nosurface, int maxsub,
+               int *trace_cells, int trace_cap, int *trace_n, int *trace_nsub, RayErr *err, int *ray_counter)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const size_t ybytes = (size_t)S.ny_comp * S.nlmp * sizeof(float);
-    float *Ysh = (float *)(smem_raw + warp * (ybytes + sizeof(CornerCache<NST>)));
-    CornerCache<NST> *cc = (CornerCache<NST> *)((unsigned char *)Ysh + ybytes);
-    const int nwarps = gridDim.x * AT3D_WARPS_PER_BLOCK;
-    for (int iray = blockIdx.x * AT3D_WARPS_PER_BLOCK + warp; iray < nrays; iray += nwarps) {
-        const double mu2 = __ldg(&cammu[iray]), phi2 = __ldg(&camphi[iray]);
-        const RayPack pk = dev_get_pack(S, packs, iray, camx, camy, camz, mu2, phi2);
-        double rad[NST];
+    const Oct o = oct_id();
+    const int lane = threadIdx.x & 31;
+    float *Ysh = (float *)smem_raw + (size_t)(threadIdx.x >> 3) * S.ny_comp * S.nlmp;
+    for (;;) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(ray_counter, 32 / AT3D_OCT);
+        base = __shfl_sync(FULLMASK, base, 0);
+        if (base >= nrays) break;
+        const int iray = base + (lane >> 3);
+        if (iray < nrays) {
+            const double mu2 = __ldg(&cammu[iray]), phi2 = __ldg(&camphi[iray]);
+            const RayPack pk = dev_get_pack(S, packs, iray, camx, camy, camz, mu2, phi2);
+            double radA[NST], radB[NST];
 #pragma unroll
-        for (int k = 0; k < NST; k++) rad[k] = 0.0;
-        int ntrace = 0, nsub = 0;
-        if (pk.status == 2) { if (lane == 0) set_err(err, 2, iray); }
-        else if (pk.status == 0) {
-            RayDir rd;
-            dev_ray_dir(S, pk, rd);
-            __syncwarp();
-            warp_ylmall(S, (float)mu2, (float)phi2, Ysh);
-            const float sky = (-mu2 > 0.0) ? dev_sky_radiance(S, (float)mu2, (float)phi2) : 0.0f;
-            const int e = march_ray<NST, MODE>(S, cc, Ysh, rd, mu2, pk.x0, pk.y0, pk.z0, sky,
-                                               correctinterpolate != 0, singlescatter != 0, nosurface != 0,
-                                               maxsub, rad,
-                                               trace_cells ? trace_cells + (size_t)trace_cap * iray : nullptr,
-                                               trace_cap, ntrace, nsub);
-            if (e && lane == 0) set_err(err, e, iray);
-        }
-        if (lane == 0) {
+            for (int k = 0; k < NST; k++) { radA[k] = 0.0; radB[k] = 0.0; }
+            int ntrace = 0, nsubA = 0, nsubB = 0;
+            if (pk.status == 2) { if (o.ol == 0) set_err(err, 2, iray); }
+            else if (pk.status == 0) {
+                RayDir rd;
+                dev_ray_dir(S, pk, rd);
+                __syncwarp(o.m);
+                group_ylmall(S, (float)mu2, (float)phi2, Ysh, o.ol, AT3D_OCT, o.m);
+                const float sky = (-mu2 > 0.0) ? dev_sky_radiance(S, (float)mu2, (float)phi2) : 0.0f;
+                const int e = march_forward<NST, MODES>(S, Ysh, rd, mu2, pk.x0, pk.y0, pk.z0, sky,
+                                                        correctinterpolate != 0, singlescatter != 0, nosurface != 0,
+                                                        maxsub, o, radA, radB,
+                                                        trace_cells ? trace_cells + (size_t)trace_cap * iray : nullptr,
+                                                        trace_cap, ntrace, nsubA, nsubB);
+                if (e && o.ol == 0) set_err(err, e, iray);
+            }
+            if (o.ol == 0) {
 #pragma unroll
-            for (int k = 0; k < NST; k++) stokes[k + NST * (size_t)iray] = (OUT)rad[k];
-            if (trace_n) { trace_n[iray] = ntrace; trace_nsub[iray] = nsub; }
+                for (int k = 0; k < NST; k++) {
+                    if (MODES & 1) outA[k + NST * (size_t)iray] = (OUTA)radA[k];
+                    if (MODES & 2) outB[k + NST * (size_t)iray] = radB[k];
+                }
+                if (trace_n) { trace_n[iray] = ntrace; trace_nsub[iray] = (MODES & 1) ? nsubA : nsubB; }
+            }
         }
         __syncwarp();
     }
@@ -188,47 +198,52 @@ render_kernel(DevState S, int nrays, const float *camx, const float *camy, const
 
 size_t render_smem_bytes(const DevState &S)
 {
-    size_t ccsz = S.nstokes == 1 ? sizeof(CornerCache<1>) : sizeof(CornerCache<3>);
-    return AT3D_WARPS_PER_BLOCK * ((size_t)S.ny_comp * S.nlmp * sizeof(float) + ccsz);
+    return (size_t)AT3D_RAYS_PER_BLOCK * S.ny_comp * S.nlmp * sizeof(float);
 }
 
-int render_grid_blocks(int nrays, size_t smem, int nst, int mode)
+// persistent launch: one wave, grid = #SMs x resident blocks
+template <typename K>
+static int persistent_blocks(K kernel, int nrays, size_t smem)
 {
     int dev = 0, nsm = 148, per_sm = 1;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
-    const void *fn = nst == 1 ? (mode ? (const void *)render_kernel<1, 1, double> : (const void *)render_kernel<1, 0, float>)
-                              : (mode ? (const void *)render_kernel<3, 1, double> : (const void *)render_kernel<3, 0, float>);
-    cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, AT3D_WARPS_PER_BLOCK * 32, smem);
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, AT3D_RAY_THREADS, smem);
     if (per_sm < 1) per_sm = 1;
-    long want = ((long)nrays + AT3D_WARPS_PER_BLOCK - 1) / AT3D_WARPS_PER_BLOCK;
-    long cap = (long)nsm * per_sm;       // persistent: one wave, grid = multiple of the SM count
+    const long want = ((long)nrays + AT3D_RAYS_PER_BLOCK - 1) / AT3D_RAYS_PER_BLOCK;
+    const long cap = (long)nsm * per_sm;
     return (int)(want < cap ? want : cap);
 }
 
-// Launch helpers (host).  out_f32: RENDER's STOKES; out_f64: VISRAD for the gradient driver.
-cudaError_t launch_render(const DevState &S, int nrays, const float *camx, const float *camy,
-                          const float *camz, const double *cammu, const double *camphi,
-                          const RayPack *packs, float *out_f32, double *out_f64, int mode,
-                          int correctinterpolate, int singlescatter, int nosurface, int maxsub,
-                          int *trace_cells, int trace_cap, int *trace_n, int *trace_nsub,
-                          RayErr *err, cudaStream_t stream)
+// Launch helper (host).  modes 1: RENDER (out_f32 = STOKES, or out_f64); modes 3: forward pass of the
+// gradient (out_f64 = VISRAD in INTEGRATE_1RAY arithmetic, out_tot = totals in the adjoint arithmetic).
+cudaError_t launch_forward(const DevState &S, int nrays, const float *camx, const float *camy,
+                           const float *camz, const double *cammu, const double *camphi,
+                           const RayPack *packs, float *out_f32, double *out_f64, double *out_tot, int modes,
+                           int correctinterpolate, int singlescatter, int nosurface, int maxsub,
+                           int *trace_cells, int trace_cap, int *trace_n, int *trace_nsub,
+                           RayErr *err, int *ray_counter, cudaStream_t stream)
 {
     if (nrays <= 0) return cudaSuccess;
     const size_t smem = render_smem_bytes(S);
-    const int nb = render_grid_blocks(nrays, smem, S.nstokes, out_f64 ? 1 : 0);
-    const int nt = AT3D_WARPS_PER_BLOCK * 32;
-#define LAUNCH(NST, MODE, OUT, outp)                                                              \
-    cudaFuncSetAttribute(render_kernel<NST, MODE, OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-    render_kernel<NST, MODE, OUT><<<nb, nt, smem, stream>>>(S, nrays, camx, camy, camz, cammu, camphi, packs, outp, \
-        correctinterpolate, singlescatter, nosurface, maxsub, trace_cells, trace_cap, trace_n, trace_nsub, err)
+    cudaError_t ce = cudaMemsetAsync(ray_counter, 0, sizeof(int), stream);
+    if (ce != cudaSuccess) return ce;
+#define LAUNCH(NST, MODES, OUTA, outa)                                                            \
+    {                                                                                             \
+        const int nb = persistent_blocks(forward_kernel<NST, MODES, OUTA>, nrays, smem);          \
+        forward_kernel<NST, MODES, OUTA><<<nb, AT3D_RAY_THREADS, smem, stream>>>(S, nrays, camx, camy, camz, \
+            cammu, camphi, packs, outa, out_tot, correctinterpolate, singlescatter, nosurface, maxsub,        \
+            trace_cells, trace_cap, trace_n, trace_nsub, err, ray_counter);                                   \
+    }
     if (S.nstokes == 1) {
-        if (out_f64) { if (mode) { LAUNCH(1, 1, double, out_f64); } else { LAUNCH(1, 0, double, out_f64); } }
-        else { LAUNCH(1, 0, float, out_f32); }
+        if (modes == 3) LAUNCH(1, 3, double, out_f64)
+        else if (out_f64) LAUNCH(1, 1, double, out_f64)
+        else LAUNCH(1, 1, float, out_f32)
     } else {
-        if (out_f64) { if (mode) { LAUNCH(3, 1, double, out_f64); } else { LAUNCH(3, 0, double, out_f64); } }
-        else { LAUNCH(3, 0, float, out_f32); }
+        if (modes == 3) LAUNCH(3, 3, double, out_f64)
+        else if (out_f64) LAUNCH(3, 1, double, out_f64)
+        else LAUNCH(3, 1, float, out_f32)
     }
 #undef LAUNCH
     return cudaGetLastError();
