@@ -222,8 +222,18 @@ extern "C" int at3d_state_create(const at3d_state_desc *d, at3d_state **out, cha
         S.sscount = sscount; S.ssent = ssent;
         const int tms = (d->srctype != 'T' && d->deltam) ? 1 : 0;
         if (!rc) rc = prep_sh_array(st, tms, d->shptr, d->source, &S.srcrec, &S.shsrc, sscount, ssent, errmsg);
-        if (!rc && d->rshptr && d->radiance)
+        if (!rc && d->rshptr && d->radiance) {
             rc = prep_sh_array(st, 0, d->rshptr, d->radiance, &S.radrec, &S.shrad, nullptr, nullptr, errmsg);
+            st->nr_h.resize(d->npts);
+            for (int i = 0; i < d->npts; i++) st->nr_h[i] = d->rshptr[i + 1] - d->rshptr[i];
+        }
+        if (!rc) {
+            int4 *ptsrc = nullptr;
+            rc = dalloc(st, (size_t)d->npts, &ptsrc, errmsg);
+            if (!rc && launch_build_ptsrc(d->npts, S.kmax, S.srcrec, sscount, ssent, ptsrc, 0) != cudaSuccess) { set_msg(errmsg, "ptsrc launch failed"); rc = 4; }
+            cudaDeviceSynchronize();
+            S.ptsrc = ptsrc;
+        }
         if (rc) { at3d_state_destroy(st); return rc; }
     }
     {

@@ -32,6 +32,7 @@ struct DevState {
     const int4 *cellrec;      // [ncells*4]
     const float4 *ptrec;      // [npts]
     const int2 *srcrec;       // [npts] (offset in floats, ns)
+    const int4 *ptsrc;        // [npts] (offset, ns | count<<16, first single-scatter entry): one load per new corner
     const float *shsrc;       // TMS-corrected source, planar per point, padded to 4
     const int2 *radrec;       // [npts] radiance SH (gradient)
     const float *shrad;
@@ -71,12 +72,17 @@ struct DevGrad {
     const float *extinctp, *albedop;        // [maxpg,npart]
     const float *dpath;                     // [longest_path_pts,npts]
     const int *dptr;
-    // ray-independent tables built once per attach by grad_prep_kernel (at3d_grad.cu)
-    int ncomp, ntup;                        // Legendre components that reach I,Q,U (1|4); padded row length
-    const float *grec;                      // [npts,numder,8 nb][8]: dext,dalb,dextm,dalbm,dfj,albp,extp,alb
-    const float *dlegt;                     // [npts,numder,8 nb][ntup]: DLEGT(comp + ncomp*l)
-    const float2 *gpnt;                     // [npts,numder]: SCATTERJ, F
-    const float *legs;                      // [npts,numder][ntup]: table for SOURCET (NPART>1) or null
+    // ray-independent tables built once per attach by the grad_prep kernels (at3d_grad.cu).  A grid point
+    // owns NNZ*NUMDER "rows" (unknown-major, then its property corners with a non-zero weight).
+    int ncomp, ntup;                        // Legendre components that reach I,Q,U (1|4); padded table length
+    int prow_stride;                        // int4 per row record
+    int sp_stride;                          // int4 per species record
+    const int4 *gptrec;                     // [npts]: first row, nrows | nnz<<16, DSH block (units of 32 floats), SHPAD(NR)/32
+    const int4 *rowrec;                     // [rows][prow_stride]: c_src, Cj, DEXTM*XI, IB | nb, npl, 0, 0 | (iph, coef) list
+    const int4 *sprec;                      // [npts,numder][sp_stride]: alb, F, SCATTERJ, count | (iph, coef) list of SINGSCATJ
+    const float *dsh;                       // rows of XI*DLEGT(l_j)*RADIANCE(.,j), planar like the source blocks
+    const float *dlegt;                     // [rows][ntup]: DLEGT(comp + ncomp*l)          (no delta-M only, else null)
+    const float *legs;                      // [npts,numder][ntup]: table for SOURCET (NPART>1 and no delta-M only)
 };
 
 #define FULLMASK 0xffffffffu

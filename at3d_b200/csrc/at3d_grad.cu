@@ -29,27 +29,24 @@
 #include "at3d_ray.cuh"
 
 #define AT3D_GRAD_ROWS 16       // shared-memory rows of contracted GRAD8 per octet (8 live + 8 spare)
+#define AT3D_DTAB_FLAG 0x40000000   // list entry refers to DPHASETAB instead of PHASETAB
 
 // ------------------------------------------------------------------------------------------
 // per-octet shared scratch of the adjoint kernel (byte offsets)
 // ------------------------------------------------------------------------------------------
 struct GradLayout {
-    int y, stage, shell, tc, vsh, rowd, rowx, rowib, wacc, total;
+    int y, vsh, rowd, rowx, rowib, wacc, total;
 };
 
-__host__ __device__ inline GradLayout grad_layout(int nstokes, int ny_comp, int nlmp, int ml, int ncomp,
-                                                  int ntup, int numder)
+__host__ __device__ inline GradLayout grad_layout(int ny_comp, int nlmp, int ml, int numder)
 {
     GradLayout L;
     int o = 0;
     L.y = o;      o += ny_comp * nlmp * 4;
-    L.stage = o;  o += nstokes * nlmp * 4;                        // RADIANCE*YLMDIR products (scalar) / RADIANCE planes
-    L.tc = o;     o += ntup * 8;                                  // double Tc[ntup]
     L.rowd = o;   o += AT3D_GRAD_ROWS * 8 * numder * 8;           // double D[row][nb][numder]
     L.wacc = o;   o += 2 * 8 * 8;                                 // double W[8], G[8]
     L.rowx = o;   o += AT3D_GRAD_ROWS * 8 * numder * 4;           // float  XG[row][nb][numder]
     L.rowib = o;  o += AT3D_GRAD_ROWS * 8 * 4 + 8 * 4;            // int    IB[row][nb], ROWOF[8]
-    L.shell = o;  o += (nstokes == 1 ? 1 : 8) * (ml + 1) * 4;     // float shell sums (NPART>1 only)
     L.vsh = o;    o += 3 * (ml + 1) * 4;                          // float V1, V5, V6 (no delta-M only)
     L.total = (o + 15) & ~15;
     return L;
@@ -69,42 +66,52 @@ __device__ __forceinline__ float unscale_leg(float x, int k /*0-based component*
 __device__ __forceinline__ int comp_slot(int k) { return k == 4 ? 3 : k; }
 
 // ------------------------------------------------------------------------------------------
-// Ray-independent part of COMPUTE_SOURCE_GRAD_1CELL (shdomsub4.f:1801-1981), once per attach:
-// per (grid point, unknown): SCATTERJ, F and -- for NPART>1 -- the mixed table used for SOURCET;
-// per (grid point, unknown, property corner): the packed scalars and DLEGT(l).  One warp per point,
-// lane = nb + 8*g4 (g4 splits the table entries).
+// Ray-independent part of COMPUTE_SOURCE_GRAD_1CELL (shdomsub4.f:1801-2007), once per attach.
+// One warp per grid point.  Per (point, unknown): SCATTERJ, F and the (phase index, weight) list of
+// SINGSCATJ.  Per row = (point, unknown, property corner with XI>=1e-7): DLEGT(l) (shdomsub4.f:1978),
+// folded with the radiance into SH rows  XI*DLEGT(l_j)*RADIANCE(.,j)  so that the ray only contracts
+// them with YLMDIR like a source block; the scalar factors of the GRAD8 terms; the (phase index,
+// coefficient) list of the single-scatter terms (shdomsub4.f:1996-2007).
 // ------------------------------------------------------------------------------------------
-__global__ void grad_prep_kernel(DevState S, DevGrad G, float *grec, float *dlegt, float2 *gpnt, float *legs)
+__global__ void grad_prep_kernel(DevState S, DevGrad G, int4 *rowrec, int4 *sprec, float *dsh, float *dlegt_out,
+                                 float *legs_out)
 {
     extern __shared__ float prep_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ipz = blockIdx.x * (blockDim.x >> 5) + warp;
-    const int nstleg = S.nstleg, ml = S.ml;
+    const int nstleg = S.nstleg, ml = S.ml, nst = S.nstokes;
     const int nlt = nstleg * (S.nleg + 1);
     if (ipz >= S.npts) return;
-    const int ip = ipz + 1;
-    float *legent = prep_smem + (size_t)warp * nlt;
+    const int pm = G.pmaxnmicro, dm = G.deriv_maxnmicro, nd = G.numder, ncomp = G.ncomp, ntup = G.ntup;
+    float *legent = prep_smem + (size_t)warp * (nlt + ntup);
+    float *dl = legent + nlt;                     // compact DLEGT (or SOURCET table) of the current row
     const bool deltam = S.deltam != 0, interp_new = S.interp_new != 0;
-    const int nb = lane & 7, g4 = lane >> 3;
-    const int ib = __ldg(&G.interpptr[nb + 8 * (size_t)ipz]);
-    const float xi = __ldg(&G.optinterpwt[nb + 8 * (size_t)ipz]);
-    const int pm = G.pmaxnmicro, nd = G.numder, ncomp = G.ncomp, ntup = G.ntup;
+    const float secmu0 = (float)(1.0 / fabs((double)S.solarmu));
+    const float dirflux = __ldg(&S.dirflux[ipz]);
+    const int nb_l = lane & 7;
+    const int ib_l = __ldg(&G.interpptr[nb_l + 8 * (size_t)ipz]);
+    const float xi_l = __ldg(&G.optinterpwt[nb_l + 8 * (size_t)ipz]);
+    const unsigned active = __ballot_sync(FULLMASK, lane < 8 && xi_l >= 1e-7f) & 0xFFu;
+    const int4 gp = __ldg(&G.gptrec[ipz]);
+    const int nnz = gp.y >> 16, nrp = (gp.w & 0xFF) * 32;
+    const size_t rowbase = (size_t)gp.x;
+    float *dshp = dsh + (size_t)(unsigned)gp.z * 32;
+    const int2 rr = __ldg(&S.radrec[ipz]);
+    const float *rad = S.shrad + rr.x;
+    const int rns = rr.y;
     int last_ipa = -1;
     float scatterj = 0.0f, f = 0.0f;
     for (int idr = 0; idr < nd; idr++) {
         const int ipa = __ldg(&G.partder[idr]);       // 1-based species
-        const float albp = __ldg(&G.albedop[(ib - 1) + (size_t)G.maxpg * (ipa - 1)]);
-        const float extp = __ldg(&G.extinctp[(ib - 1) + (size_t)G.maxpg * (ipa - 1)]);
-        const int *iphp = G.iphasep + (size_t)pm * ((ib - 1) + (size_t)G.maxpg * (ipa - 1));
-        const float *pwp = G.phasewtp + (size_t)pm * ((ib - 1) + (size_t)G.maxpg * (ipa - 1));
+        const float albp_l = __ldg(&G.albedop[(ib_l - 1) + (size_t)G.maxpg * (ipa - 1)]);
+        const float extp_l = __ldg(&G.extinctp[(ib_l - 1) + (size_t)G.maxpg * (ipa - 1)]);
         const float alb_ip = __ldg(&S.albedo[ipz + (size_t)S.npts * (ipa - 1)]);
-        float *legs_row = legs ? legs + ((size_t)ipz * nd + idr) * ntup : nullptr;
+        const float sw_l = xi_l * albp_l * extp_l;       // SPATIAL_WEIGHT of property corner nb
         if (ipa != last_ipa) {
             last_ipa = ipa;
             __syncwarp();
-            const float sw = xi * albp * extp;       // SPATIAL_WEIGHT of property corner nb
             scatterj = 0.0f;
-            if (deltam) for (int n = 0; n < 8; n++) scatterj = scatterj + __shfl_sync(FULLMASK, sw, n);
+            if (deltam) for (int n = 0; n < 8; n++) scatterj = scatterj + __shfl_sync(FULLMASK, sw_l, n);
             if (S.npart == 1) {
                 // LEGENT left by the forward part: the PHASEINTERPWT mix at this grid point
                 const int *iph = S.iphase + (size_t)S.nq * (ipz + (size_t)S.npts * (ipa - 1));
@@ -139,7 +146,7 @@ __global__ void grad_prep_kernel(DevState S, DevGrad G, float *grec, float *dleg
                 // property-grid mix of the Legendre table for this species (shdomsub4.f:1835-1880)
                 float swn[8]; int ibn[8];
 #pragma unroll
-                for (int n = 0; n < 8; n++) { swn[n] = __shfl_sync(FULLMASK, sw, n); ibn[n] = __shfl_sync(FULLMASK, ib, n); }
+                for (int n = 0; n < 8; n++) { swn[n] = __shfl_sync(FULLMASK, sw_l, n); ibn[n] = __shfl_sync(FULLMASK, ib_l, n); }
                 for (int t = lane; t < nlt; t += 32) {
                     float v = 0.0f;
 #pragma unroll
@@ -163,11 +170,13 @@ __global__ void grad_prep_kernel(DevState S, DevGrad G, float *grec, float *dleg
                 if (deltam && interp_new)
                     for (int t = lane; t < nstleg * (ml + 1); t += 32) legent[t] = legent[t] / (1 - f);
                 __syncwarp();
-                // the table COMPUTE_SOURCE_DIRECTION contracts with the radiance for SOURCET
+                // the table COMPUTE_SOURCE_DIRECTION contracts with the radiance for SOURCET -> dl
+                for (int t = lane; t < ntup; t += 32) dl[t] = 0.0f;
+                __syncwarp();
                 for (int t = lane; t < nstleg * (ml + 1); t += 32) {
                     const int k = t % nstleg, l = t / nstleg;
                     if (k == 3 || k == 5) continue;
-                    legs_row[comp_slot(k) + ncomp * l] = legent[t];
+                    dl[comp_slot(k) + ncomp * l] = legent[t];
                 }
                 __syncwarp();
                 if (deltam) {
@@ -180,30 +189,87 @@ __global__ void grad_prep_kernel(DevState S, DevGrad G, float *grec, float *dleg
                 }
             }
             __syncwarp();
-        } else if (legs_row && idr > 0) {
-            // same species as the previous unknown: same table
-            const float *prev = legs + ((size_t)ipz * nd + idr - 1) * ntup;
-            for (int t = lane; t < ntup; t += 32) legs_row[t] = prev[t];
         }
-        if (lane == 0) gpnt[(size_t)ipz * nd + idr] = make_float2(scatterj, f);
-        // ---- per property corner nb ----
-        const float dext_v = __ldg(&G.dext[(ib - 1) + (size_t)G.maxpg * idr]);
-        const float dalb_v = __ldg(&G.dalb[(ib - 1) + (size_t)G.maxpg * idr]);
-        const float dextm_v = __ldg(&G.dextm[(ib - 1) + (size_t)G.maxpg * idr]);
-        const float dalbm_v = __ldg(&G.dalbm[nb + 8 * ((size_t)ipz + (size_t)S.npts * idr)]);
-        const float dfj_v = __ldg(&G.dfj[nb + 8 * ((size_t)ipz + (size_t)S.npts * idr)]);
+        if (S.npart > 1) {
+            // SOURCET row of this unknown: table(l_j)*RADIANCE(.,j) (same species as the previous unknown
+            // leaves dl untouched: rebuilt identically)
+            if (ipa == last_ipa && idr > 0 && __ldg(&G.partder[idr - 1]) == ipa) {
+                // dl was overwritten by the rows of the previous unknown: copy its SOURCET row instead
+                const float *prev = dshp + (size_t)(nnz * nd + idr - 1) * nst * nrp;
+                float *cur = dshp + (size_t)(nnz * nd + idr) * nst * nrp;
+                for (int j = lane; j < nst * nrp; j += 32) cur[j] = prev[j];
+                if (legs_out) for (int t = lane; t < ntup; t += 32)
+                    legs_out[((size_t)ipz * nd + idr) * ntup + t] = legs_out[((size_t)ipz * nd + idr - 1) * ntup + t];
+            } else {
+                float *cur = dshp + (size_t)(nnz * nd + idr) * nst * nrp;
+                for (int j = lane; j < nrp; j += 32) {
+                    float p1 = 0.0f, p2 = 0.0f, p3 = 0.0f;
+                    if (j < rns) {
+                        const int l = __ldg(&S.lofj[j]);
+                        const float r1 = rad[j];
+                        p1 = dl[ncomp * l] * r1;
+                        if (nst > 1) {
+                            const float r2 = rad[nrp + j], r3 = rad[2 * nrp + j];
+                            p1 = p1 + dl[3 + ncomp * l] * r2;
+                            p2 = dl[3 + ncomp * l] * r1 + dl[1 + ncomp * l] * r2;
+                            p3 = dl[2 + ncomp * l] * r3;
+                        }
+                    }
+                    cur[j] = p1;
+                    if (nst > 1) { cur[nrp + j] = p2; cur[2 * nrp + j] = p3; }
+                }
+                if (legs_out) for (int t = lane; t < ntup; t += 32) legs_out[((size_t)ipz * nd + idr) * ntup + t] = dl[t];
+            }
+            __syncwarp();
+        }
+        // ---- species record: alb, F, SCATTERJ and the SINGSCATJ list (shdomsub4.f:1809-1832) ----
+        if (lane == 0) {
+            int4 *sp = sprec + ((size_t)ipz * nd + idr) * G.sp_stride;
+            int2 *list = (int2 *)(sp + 1);
+            int cnt = 0;
+            if (deltam) {
+                const float sdiv = (scatterj > G.scatmin) ? scatterj : (float)G.scatmin;
+                for (int n = 0; n < 8; n++) {
+                    const int ibn = __ldg(&G.interpptr[n + 8 * (size_t)ipz]);
+                    const float swn = __ldg(&G.optinterpwt[n + 8 * (size_t)ipz]) *
+                                      __ldg(&G.albedop[(ibn - 1) + (size_t)G.maxpg * (ipa - 1)]) *
+                                      __ldg(&G.extinctp[(ibn - 1) + (size_t)G.maxpg * (ipa - 1)]);
+                    if (swn <= 1e-6f) continue;
+                    const int *iq = G.iphasep + (size_t)pm * ((ibn - 1) + (size_t)G.maxpg * (ipa - 1));
+                    const float *wq = G.phasewtp + (size_t)pm * ((ibn - 1) + (size_t)G.maxpg * (ipa - 1));
+                    for (int q = 0; q < pm; q++) {
+                        const float w = __ldg(&wq[q]);
+                        if (w <= 1e-6f) continue;
+                        list[cnt++] = make_int2(__ldg(&iq[q]), __float_as_int(swn * w / sdiv));
+                    }
+                }
+            }
+            sp[0] = make_int4(__float_as_int(alb_ip), __float_as_int(f), __float_as_int(scatterj), cnt);
+        }
+        // ---- rows: one per property corner with a non-zero interpolation weight ----
+        unsigned todo = active;
+        int rank = 0;
         const int doex = __ldg(&G.doexact[idr]);
-        const int *dip = G.diphasep + (size_t)G.deriv_maxnmicro * ((ib - 1) + (size_t)G.maxpg * idr);
-        const float *dpw = G.dphasewtp + (size_t)G.deriv_maxnmicro * ((ib - 1) + (size_t)G.maxpg * idr);
-        const size_t row = ((size_t)ipz * nd + idr) * 8 + nb;
-        if (g4 == 0) {
-            float4 *gr = (float4 *)(grec + row * 8);
-            gr[0] = make_float4(dext_v, dalb_v, dextm_v, dalbm_v);
-            gr[1] = make_float4(dfj_v, albp, extp, alb_ip);
-        }
-        if (xi >= 1e-7f) {
-            float *drow = dlegt + row * ntup;
-            for (int t = g4; t < nlt; t += 4) {
+        while (todo) {
+            const int nb = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int ib = __shfl_sync(FULLMASK, ib_l, nb);
+            const float xi = __shfl_sync(FULLMASK, xi_l, nb);
+            const float albp = __shfl_sync(FULLMASK, albp_l, nb), extp = __shfl_sync(FULLMASK, extp_l, nb);
+            const int *iphp = G.iphasep + (size_t)pm * ((ib - 1) + (size_t)G.maxpg * (ipa - 1));
+            const float *pwp = G.phasewtp + (size_t)pm * ((ib - 1) + (size_t)G.maxpg * (ipa - 1));
+            const float dext_v = __ldg(&G.dext[(ib - 1) + (size_t)G.maxpg * idr]);
+            const float dalb_v = __ldg(&G.dalb[(ib - 1) + (size_t)G.maxpg * idr]);
+            const float dextm_v = __ldg(&G.dextm[(ib - 1) + (size_t)G.maxpg * idr]);
+            const float dalbm_v = __ldg(&G.dalbm[nb + 8 * ((size_t)ipz + (size_t)S.npts * idr)]);
+            const float dfj_v = __ldg(&G.dfj[nb + 8 * ((size_t)ipz + (size_t)S.npts * idr)]);
+            const int *dip = G.diphasep + (size_t)dm * ((ib - 1) + (size_t)G.maxpg * idr);
+            const float *dpw = G.dphasewtp + (size_t)dm * ((ib - 1) + (size_t)G.maxpg * idr);
+            const size_t R = rowbase + (size_t)idr * nnz + rank;
+            __syncwarp();
+            for (int t = lane; t < ntup; t += 32) dl[t] = 0.0f;
+            __syncwarp();
+            for (int t = lane; t < nlt; t += 32) {
                 const int k = t % nstleg, l = t / nstleg;
                 if (k == 3 || k == 5 || l > ml) continue;       // components that never reach I,Q,U
                 float legenp = 0.0f, dlegp = 0.0f;
@@ -212,48 +278,114 @@ __global__ void grad_prep_kernel(DevState S, DevGrad G, float *grec, float *dleg
                     const float ftemp = deltam ? __ldg(&lg[nstleg * (ml + 1)]) : 0.0f;
                     const float un = unscale_leg(__ldg(&lg[t]), k, l, ml, deltam, interp_new, ftemp, nstleg);
                     legenp = legenp + __ldg(&pwp[q]) * un;
-                    if (doex == 0 && q < G.deriv_maxnmicro) dlegp = dlegp + __ldg(&dpw[q]) * un;
+                    if (doex == 0 && q < dm) dlegp = dlegp + __ldg(&dpw[q]) * un;
                 }
                 if (doex == 1)
-                    for (int q = 0; q < G.deriv_maxnmicro; q++)
+                    for (int q = 0; q < dm; q++)
                         dlegp = dlegp + __ldg(&pwp[q]) * __ldg(&G.dleg[(size_t)nlt * (__ldg(&dip[q]) - 1) + t]);
                 const float lt = legent[t];
                 const float leg_diff = legenp - lt;
-                drow[comp_slot(k) + ncomp * l] = dext_v * leg_diff * albp + dalb_v * leg_diff * extp
-                                                 + dlegp * extp * albp + (lt - 1) * dfj_v;
+                dl[comp_slot(k) + ncomp * l] = dext_v * leg_diff * albp + dalb_v * leg_diff * extp
+                                               + dlegp * extp * albp + (lt - 1) * dfj_v;
             }
+            __syncwarp();
+            if (dlegt_out) for (int t = lane; t < ntup; t += 32) dlegt_out[R * ntup + t] = dl[t];
+            // SH row: XI * DLEGT(l_j) (x) RADIANCE(.,j), Stokes coupling of COMPUTE_SOURCE_DIRECTION
+            {
+                float *cur = dshp + (size_t)(idr * nnz + rank) * nst * nrp;
+                for (int j = lane; j < nrp; j += 32) {
+                    float p1 = 0.0f, p2 = 0.0f, p3 = 0.0f;
+                    if (j < rns) {
+                        const int l = __ldg(&S.lofj[j]);
+                        const float r1 = rad[j];
+                        p1 = dl[ncomp * l] * r1;
+                        if (nst > 1) {
+                            const float r2 = rad[nrp + j], r3 = rad[2 * nrp + j];
+                            p1 = p1 + dl[3 + ncomp * l] * r2;
+                            p2 = dl[3 + ncomp * l] * r1 + dl[1 + ncomp * l] * r2;
+                            p3 = dl[2 + ncomp * l] * r3;
+                        }
+                    }
+                    cur[j] = xi * p1;
+                    if (nst > 1) { cur[nrp + j] = xi * p2; cur[2 * nrp + j] = xi * p3; }
+                }
+            }
+            if (lane == 0) {
+                int4 *rw = rowrec + R * G.prow_stride;
+                int2 *list = (int2 *)(rw + 2);
+                int cnt = 0;
+                float cj = 0.0f;
+                if (deltam) {
+                    const float K = dirflux * secmu0 * xi;
+                    cj = K * (dfj_v - dalb_v * extp - dext_v * albp);
+                    const float cp = K * (dalb_v * extp + dext_v * albp);
+                    const float cd = K * extp * albp;
+                    for (int q = 0; q < pm; q++) {
+                        const float c = cp * __ldg(&pwp[q]);
+                        if (c != 0.0f) list[cnt++] = make_int2(__ldg(&iphp[q]), __float_as_int(c));
+                    }
+                    for (int q = 0; q < dm; q++) {
+                        if (doex == 0) {
+                            const float c = cd * __ldg(&dpw[q]);
+                            if (c != 0.0f) list[cnt++] = make_int2(__ldg(&iphp[q]), __float_as_int(c));
+                        } else if (doex == 1) {
+                            const float c = cd * __ldg(&pwp[q]);
+                            if (c != 0.0f) list[cnt++] = make_int2(__ldg(&dip[q]) | AT3D_DTAB_FLAG, __float_as_int(c));
+                        }
+                    }
+                }
+                rw[0] = make_int4(__float_as_int(xi * (alb_ip * dextm_v + dalbm_v)), __float_as_int(cj),
+                                  __float_as_int(dextm_v * xi), ib);
+                rw[1] = make_int4(nb | (cnt << 8), 0, 0, 0);
+            }
+            rank++;
         }
     }
 }
 
+// The values lane n keeps for corner n of the current cell in the adjoint walk.
+template <int NST>
+struct GCorner {
+    int pt, row;            // grid point; shared-memory row of its contracted GRAD8
+    float x, y, z, ext;
+    float src[NST], ss[NST];
+};
+
 // ------------------------------------------------------------------------------------------
 // COMPUTE_SOURCE_GRAD_1CELL for one new grid point (the 8 lanes of the octet cooperate): forward
 // values of the point and its contracted GRAD8 row (written to shared-memory row `row`).
+// ip, soff/sns (SH block), b (exact single scatter), ext, gp (gradient record) come from the lane
+// that owns the corner.
 // ------------------------------------------------------------------------------------------
 template <int NST>
-__device__ void eval_point_grad(const DevState &S, const DevGrad &G, int ip, unsigned char *sm,
+__device__ __forceinline__ void eval_point_grad(const DevState &S, const DevGrad &G, int ip, int soff, int sns,
+                                const float (&bin)[NST], float ext, const int4 gp, unsigned char *sm,
                                 const GradLayout &L, const RayDir &rd, const double (&adj)[NST], const Oct &o,
-                                int row, float &ext_out, float (&src_out)[NST], float (&ss_out)[NST],
-                                int &ns_out, int &nr_out)
+                                int row, float (&src_out)[NST], float (&ss_out)[NST])
 {
     const float *Ysh = (const float *)(sm + L.y);
-    float *stage = (float *)(sm + L.stage);
-    float *shell = (float *)(sm + L.shell);
-    double *Tc = (double *)(sm + L.tc);
     const float *Vsh = (const float *)(sm + L.vsh);
     const int nlmp = S.nlmp, nstleg = S.nstleg, ml = S.ml, mm = S.mm;
-    const int nlt = nstleg * (S.nleg + 1);
-    const int ncomp = G.ncomp, ntup = G.ntup, nd = G.numder;
-    const bool deltam = S.deltam != 0, interp_new = S.interp_new != 0;
-    const float secmu0 = (float)(1.0 / fabs((double)S.solarmu));
+    const int nd = G.numder;
+    const bool deltam = S.deltam != 0;
     const int ipz = ip - 1;
     // ---------------- forward part (shdomsub4.f:1660-1785) ----------------
-    float ext, a[NST], b[NST];
-    eval_point<NST>(S, ip, Ysh, rd, false, o, ext, ns_out, a, b);
-    const float dirflux = __ldg(&S.dirflux[ipz]);
+    float a[NST], b[NST];
+#pragma unroll
+    for (int k = 0; k < NST; k++) { a[k] = 0.0f; b[k] = bin[k]; }
+    sh_dot_partial<NST>(S.shsrc + soff, AT3D_SHPAD(sns), Ysh, nlmp, o, a);
+#pragma unroll
+    for (int k = 0; k < NST; k++) a[k] = oct_sum(o.m, a[k]);
+    float dirflux = 0.0f, secmu0 = 0.0f;
+    if (!deltam || S.npart > 1) {
+        dirflux = __ldg(&S.dirflux[ipz]);
+        secmu0 = (float)(1.0 / fabs((double)S.solarmu));
+    }
     if (!deltam) {
         // without delta-M SINGSCAT8 is the truncated single scattering (shdomsub4.f:1723-1760,1781):
         // sum over species of DA*LEGENT(.,l)*sum_m YLMDIR*YLMSUN for the shells present in SOURCE
+        const int nlt = nstleg * (S.nleg + 1);
+        const bool interp_new = S.interp_new != 0;
         float t[NST];
 #pragma unroll
         for (int k = 0; k < NST; k++) t[k] = 0.0f;
@@ -267,7 +399,7 @@ __device__ void eval_point_grad(const DevState &S, const DevGrad &G, int ip, uns
             const float da = __ldg(&S.albedo[ipz + (size_t)S.npts * ipa]) * dirflux * secmu0 * w;
             for (int l = o.ol; l <= ml; l += 8) {
                 const int me = l < mm ? l : mm;
-                if (sh_index(l, -me, mm) >= ns_out) continue;
+                if (sh_index(l, -me, mm) >= sns) continue;
                 float l1, l5 = 0.0f;
                 if (single) {
                     l1 = __ldg(&S.legen[(size_t)nlt * (__ldg(&iph[0]) - 1) + nstleg * l]);
@@ -298,220 +430,110 @@ __device__ void eval_point_grad(const DevState &S, const DevGrad &G, int ip, uns
         ss_out[k] = b[k] * ext;
         src_out[k] = G.singlescatter ? ss_out[k] : srcfull[k] * ext;
     }
-    ext_out = ext;
-    // ---------------- radiance SH block: shell sums over m ----------------
-    const int2 rr = __ldg(&S.radrec[ipz]);
-    const int rns = rr.y, nrp = AT3D_SHPAD(rr.y);
-    nr_out = rns;
-    {
-        const float *rb = S.shrad + rr.x + o.ol * 4;
-        if (NST == 1) {
-#pragma unroll 4
-            for (int j = 0; j < nrp; j += 32) {
-                const float4 r = __ldg((const float4 *)(rb + j));
-                const float4 y = *(const float4 *)(Ysh + o.ol * 4 + j);
-                *(float4 *)(stage + o.ol * 4 + j) = make_float4(r.x * y.x, r.y * y.y, r.z * y.z, r.w * y.w);
-            }
-        } else {
-#pragma unroll 2
-            for (int j = 0; j < nrp; j += 32) {
-#pragma unroll
-                for (int k = 0; k < NST; k++)
-                    *(float4 *)(stage + k * nlmp + o.ol * 4 + j) = __ldg((const float4 *)(rb + k * nrp + j));
-            }
-        }
-    }
-    for (int t = o.ol; t < ntup; t += 8) Tc[t] = 0.0;
-    __syncwarp(o.m);
-    // T(l) = adj . sum_m RADIANCE(.,j) YLMDIR(.,j); degrees are paired (l, ML-l) to balance the lanes
-    const bool keep_shell = S.npart > 1;
-    for (int q = o.ol; 2 * q <= ml; q += 8) {
-        for (int half = 0; half < 2; half++) {
-            const int l = half ? ml - q : q;
-            if (half && l == q) break;
-            const int me = l < mm ? l : mm;
-            const int jlo = sh_index(l, -me, mm);
-            int cnt = 2 * me + 1;
-            if (jlo + cnt > rns) cnt = rns - jlo;
-            if (NST == 1) {
-                float A = 0.0f;
-                for (int i = 0; i < cnt; i++) A = A + stage[jlo + i];
-                double t1 = adj[0] * A;
-                if (!deltam) t1 += adj[0] * (double)(dirflux * secmu0 * Vsh[l]);
-                Tc[l] = t1;
-                if (keep_shell) shell[l] = A;
-            } else {
-                float A = 0, B = 0, C = 0, D = 0, E = 0, F = 0, Gq = 0, H = 0;
-                for (int i = 0; i < cnt; i++) {
-                    const int j = jlo + i;
-                    const float r1 = stage[j], y1 = Ysh[j];
-                    const float r2 = stage[nlmp + j], r3 = stage[2 * nlmp + j];
-                    const float y2 = Ysh[nlmp + j], y5 = Ysh[2 * nlmp + j], y6 = Ysh[3 * nlmp + j], y3 = Ysh[4 * nlmp + j];
-                    A = A + r1 * y1;
-                    B = B + r2 * y1; C = C + r1 * y2; D = D + r2 * y2; E = E + r3 * y5;
-                    F = F + r1 * y6; Gq = Gq + r2 * y6; H = H + r3 * y3;
-                }
-                double t1 = adj[0] * A;
-                if (!deltam) t1 += adj[0] * (double)(dirflux * secmu0 * Vsh[l]);
-                double t5 = adj[0] * B + adj[1] * C + adj[NST - 1] * F;
-                if (!deltam) t5 += adj[1] * (double)(dirflux * secmu0 * Vsh[(ml + 1) + l]);
-                Tc[0 + ncomp * l] = t1;
-                Tc[1 + ncomp * l] = adj[1] * D + adj[NST - 1] * Gq;
-                Tc[2 + ncomp * l] = adj[1] * E + adj[NST - 1] * H;
-                Tc[3 + ncomp * l] = t5;
-                if (keep_shell) {
-                    const int s = ml + 1;
-                    shell[l] = A; shell[s + l] = B; shell[2 * s + l] = C; shell[3 * s + l] = D;
-                    shell[4 * s + l] = E; shell[5 * s + l] = F; shell[6 * s + l] = Gq; shell[7 * s + l] = H;
-                }
-            }
-        }
-    }
-    __syncwarp(o.m);
-    // ---------------- gradient part (shdomsub4.f:1786-2019): lane = property corner nb ----------------
-    const int nb = o.ol;
-    const int ib = __ldg(&G.interpptr[nb + 8 * (size_t)ipz]);
-    const float xi = __ldg(&G.optinterpwt[nb + 8 * (size_t)ipz]);
+    // ---------------- gradient part (shdomsub4.f:1786-2019), row by row ----------------
     double *Drow = (double *)(sm + L.rowd) + (size_t)row * 8 * nd;
     float *XGrow = (float *)(sm + L.rowx) + (size_t)row * 8 * nd;
     int *IBrow = (int *)(sm + L.rowib) + row * 8;
-    IBrow[nb] = ib;
-    int last_ipa = -1;
-    float scatterj = 0.0f, f = 0.0f, singscatj[NST], sourcet[NST];
+    for (int idr = 0; idr < nd; idr++) { Drow[o.ol * nd + idr] = 0.0; XGrow[o.ol * nd + idr] = 0.0f; }
+    const int nnz = gp.y >> 16, nrows = gp.y & 0xFFFF, nrp = (gp.w & 0xFF) * 32;
+    const float *dshp = G.dsh + (size_t)(unsigned)gp.z * 32;
+    int last_idr = -1, last_ipa = -1;
+    float sourcet[NST], ssj[NST];        // SOURCET; lane-partial SINGSCATJ
 #pragma unroll
-    for (int k = 0; k < NST; k++) { singscatj[k] = 0.0f; sourcet[k] = 0.0f; }
-    const int pm = G.pmaxnmicro;
-    for (int idr = 0; idr < nd; idr++) {
-        const int ipa = __ldg(&G.partder[idr]);       // 1-based species
-        const size_t prow = ((size_t)ipz * nd + idr) * 8 + nb;
-        const float4 g0 = __ldg((const float4 *)(G.grec + prow * 8));
-        const float4 g1 = __ldg((const float4 *)(G.grec + prow * 8) + 1);
-        const float dext_v = g0.x, dalb_v = g0.y, dextm_v = g0.z, dalbm_v = g0.w;
-        const float dfj_v = g1.x, albp = g1.y, extp = g1.z, alb_ip = g1.w;
-        const int *iphp = G.iphasep + (size_t)pm * ((ib - 1) + (size_t)G.maxpg * (ipa - 1));
-        const float *pwp = G.phasewtp + (size_t)pm * ((ib - 1) + (size_t)G.maxpg * (ipa - 1));
-        if (ipa != last_ipa) {
-            last_ipa = ipa;
-            const float2 pn = __ldg(&G.gpnt[(size_t)ipz * nd + idr]);
-            scatterj = pn.x; f = pn.y;
-            const float sw = xi * albp * extp;       // SPATIAL_WEIGHT of property corner nb
+    for (int k = 0; k < NST; k++) { sourcet[k] = 0.0f; ssj[k] = 0.0f; }
+    for (int r = 0; r < nrows; r++) {
+        const int idr = r / nnz;
+        const int4 *rw = G.rowrec + ((size_t)gp.x + r) * G.prow_stride;
+        const int4 h0 = __ldg(rw), h1 = __ldg(rw + 1);
+        if (idr != last_idr) {
+            last_idr = idr;
+            const int ipa = __ldg(&G.partder[idr]);
+            if (ipa != last_ipa) {
+                last_ipa = ipa;
+                const int4 *sp = G.sprec + ((size_t)ipz * nd + idr) * G.sp_stride;
+                const int4 s0 = __ldg(sp);
+                const float alb_ip = __int_as_float(s0.x), f = __int_as_float(s0.y), scatterj = __int_as_float(s0.z);
 #pragma unroll
-            for (int k = 0; k < NST; k++) singscatj[k] = 0.0f;
-            if (deltam) {
-                float part[NST];
+                for (int k = 0; k < NST; k++) ssj[k] = 0.0f;
+                for (int e = o.ol; e < s0.w; e += 8) {
+                    const int2 en = __ldg((const int2 *)(sp + 1) + e);
+                    float sv[NST];
+                    ray_singscat<NST>(S.phasetab, S.nstphase, S.numphase, en.x, rd, sv);
+                    const float c = __int_as_float(en.y);
 #pragma unroll
-                for (int k = 0; k < NST; k++) part[k] = 0.0f;
-                if (sw > 1e-6f) {
-                    for (int q = 0; q < pm; q++) {
-                        const float w = __ldg(&pwp[q]);
-                        if (w <= 1e-6f) continue;
-                        float sv[NST];
-                        ray_singscat<NST>(S.phasetab, S.nstphase, S.numphase, __ldg(&iphp[q]), rd, sv);
-#pragma unroll
-                        for (int k = 0; k < NST; k++) part[k] = part[k] + sw * w * sv[k];
-                    }
+                    for (int k = 0; k < NST; k++) ssj[k] = ssj[k] + c * sv[k];
                 }
+                if (S.npart == 1) {
 #pragma unroll
-                for (int k = 0; k < NST; k++) {
-                    float tot = 0.0f;
+                    for (int k = 0; k < NST; k++) sourcet[k] = (alb_ip > 1e-8f) ? srcfull[k] / alb_ip : 0.0f;
+                } else {
+                    // SINGSCATJ is needed on its own; afterwards only lane 0 carries it into the row sums
+                    float sj[NST];
 #pragma unroll
-                    for (int n = 0; n < 8; n++) tot = tot + __shfl_sync(o.m, part[k], n, 8);
-                    if (scatterj > G.scatmin) singscatj[k] = tot / scatterj;
-                    else singscatj[k] = (float)(tot / G.scatmin);
-                }
-            }
-            if (S.npart == 1) {
+                    for (int k = 0; k < NST; k++) { sj[k] = oct_sum(o.m, ssj[k]); ssj[k] = (o.ol == 0) ? sj[k] : 0.0f; sourcet[k] = 0.0f; }
+                    if (scatterj > G.scatmin) {
+                        // COMPUTE_SOURCE_DIRECTION with the mixed table: the SOURCET row of this unknown
+                        float acc[NST];
 #pragma unroll
-                for (int k = 0; k < NST; k++) sourcet[k] = (alb_ip > 1e-8f) ? srcfull[k] / alb_ip : 0.0f;
-            } else {
+                        for (int k = 0; k < NST; k++) acc[k] = 0.0f;
+                        sh_dot_partial<NST>(dshp + (size_t)(nnz * nd + idr) * NST * nrp, nrp, Ysh, nlmp, o, acc);
+                        if (!deltam) {
+                            const float *lg = G.legs + ((size_t)ipz * nd + idr) * G.ntup;
+                            for (int l = o.ol; l <= ml; l += 8) {
+                                acc[0] = acc[0] + dirflux * secmu0 * __ldg(&lg[G.ncomp * l]) * Vsh[l];
+                                if (NST > 1) acc[1] = acc[1] + dirflux * secmu0 * __ldg(&lg[3 + G.ncomp * l]) * Vsh[(ml + 1) + l];
+                            }
+                        }
 #pragma unroll
-                for (int k = 0; k < NST; k++) sourcet[k] = 0.0f;
-                if (scatterj > G.scatmin) {
-                    // COMPUTE_SOURCE_DIRECTION with the mixed table, from the shell sums
-                    const float *lg = G.legs + ((size_t)ipz * nd + idr) * ntup;
-                    float acc[NST];
+                        for (int k = 0; k < NST; k++) sourcet[k] = oct_sum(o.m, acc[k]);
+                        if (deltam) {
 #pragma unroll
-                    for (int k = 0; k < NST; k++) acc[k] = 0.0f;
-                    const int s = ml + 1;
-                    for (int l = o.ol; l <= ml; l += 8) {
-                        const float l1 = __ldg(&lg[ncomp * l]);
-                        acc[0] = acc[0] + l1 * shell[l];
-                        if (!deltam) acc[0] = acc[0] + dirflux * secmu0 * l1 * Vsh[l];
-                        if (NST > 1) {
-                            const float l2 = __ldg(&lg[1 + ncomp * l]), l3 = __ldg(&lg[2 + ncomp * l]);
-                            const float l5 = __ldg(&lg[3 + ncomp * l]);
-                            acc[0] = acc[0] + l5 * shell[s + l];
-                            acc[1] = acc[1] + l5 * shell[2 * s + l] + l2 * shell[3 * s + l] + l3 * shell[4 * s + l];
-                            acc[NST - 1] = acc[NST - 1] + l5 * shell[5 * s + l] + l2 * shell[6 * s + l]
-                                           + l3 * shell[7 * s + l];
-                            if (!deltam) acc[1] = acc[1] + dirflux * secmu0 * l5 * Vsh[s + l];
+                            for (int k = 0; k < NST; k++) sourcet[k] = sourcet[k] + dirflux * sj[k] * secmu0 / (1 - f);
                         }
                     }
-#pragma unroll
-                    for (int k = 0; k < NST; k++) sourcet[k] = oct_sum(o.m, acc[k]);
-                    if (deltam) {
-#pragma unroll
-                        for (int k = 0; k < NST; k++) sourcet[k] = sourcet[k] + dirflux * singscatj[k] * secmu0 / (1 - f);
-                    }
                 }
+                sourcet[0] = fmaxf(0.0f, sourcet[0]);
             }
-            sourcet[0] = fmaxf(0.0f, sourcet[0]);
         }
-        double d = 0.0;
-        if (xi >= 1e-7f) {
-            // DSOURCE contracted with the adjoint weight: DLEGT(l) . T(l)
-            const float4 *dl = (const float4 *)(G.dlegt + prow * ntup);
-            double dot = 0.0;
-            for (int t4 = 0; t4 < ntup / 4; t4++) {
-                const float4 v = __ldg(&dl[t4]);
-                dot += (double)v.x * Tc[4 * t4];
-                dot += (double)v.y * Tc[4 * t4 + 1];
-                dot += (double)v.z * Tc[4 * t4 + 2];
-                dot += (double)v.w * Tc[4 * t4 + 3];
-            }
-            const int doex = __ldg(&G.doexact[idr]);
-            const int *dip = G.diphasep + (size_t)G.deriv_maxnmicro * ((ib - 1) + (size_t)G.maxpg * idr);
-            const float *dpw = G.dphasewtp + (size_t)G.deriv_maxnmicro * ((ib - 1) + (size_t)G.maxpg * idr);
-            float singscatp[NST], dsingscatp[NST];
+        const float c_src = __int_as_float(h0.x), cj = __int_as_float(h0.y);
+        const int nb = h1.x & 0xFF, npl = h1.x >> 8;
+        // DSOURCE: the row's SH block in the ray direction (lane partial)
+        float dp[NST];
 #pragma unroll
-            for (int k = 0; k < NST; k++) { singscatp[k] = 0.0f; dsingscatp[k] = 0.0f; }
-            if (deltam) {
-                for (int q = 0; q < pm; q++) {
-                    float sv[NST];
-                    ray_singscat<NST>(S.phasetab, S.nstphase, S.numphase, __ldg(&iphp[q]), rd, sv);
-                    const float w = __ldg(&pwp[q]);
+        for (int k = 0; k < NST; k++) dp[k] = cj * ssj[k];
+        sh_dot_partial<NST>(dshp + (size_t)r * NST * nrp, nrp, Ysh, nlmp, o, dp);
+        // single-scatter terms of the row (SINGSCATP, DSINGSCATP with their factors)
+        for (int e = o.ol; e < npl; e += 8) {
+            const int2 en = __ldg((const int2 *)(rw + 2) + e);
+            float sv[NST];
+            if (en.x & AT3D_DTAB_FLAG)
+                ray_singscat<NST>(G.dphasetab, S.nstphase, G.dnumphase, en.x & ~AT3D_DTAB_FLAG, rd, sv);
+            else
+                ray_singscat<NST>(S.phasetab, S.nstphase, S.numphase, en.x, rd, sv);
+            const float c = __int_as_float(en.y);
 #pragma unroll
-                    for (int k = 0; k < NST; k++) singscatp[k] = singscatp[k] + w * sv[k];
-                    if (doex == 0 && q < G.deriv_maxnmicro) {
-                        const float dw = __ldg(&dpw[q]);
-#pragma unroll
-                        for (int k = 0; k < NST; k++) dsingscatp[k] = dsingscatp[k] + dw * sv[k];
-                    }
-                }
-                if (doex == 1) {
-                    for (int q = 0; q < G.deriv_maxnmicro; q++) {
-                        float sv[NST];
-                        ray_singscat<NST>(G.dphasetab, S.nstphase, G.dnumphase, __ldg(&dip[q]), rd, sv);
-                        const float w = __ldg(&pwp[q]);
-#pragma unroll
-                        for (int k = 0; k < NST; k++) dsingscatp[k] = dsingscatp[k] + w * sv[k];
-                    }
-                }
-            }
-            double sum = 0.0;
-#pragma unroll
-            for (int k = 0; k < NST; k++) {
-                float g8 = xi * (sourcet[k] * (alb_ip * dextm_v + dalbm_v));
-                if (deltam)
-                    g8 = g8 + dirflux * secmu0 * xi * (singscatj[k] * dfj_v + dsingscatp[k] * extp * albp
-                              + dalb_v * (singscatp[k] - singscatj[k]) * extp
-                              + dext_v * (singscatp[k] - singscatj[k]) * albp);
-                sum += adj[k] * (double)g8;
-            }
-            d = sum + (double)xi * dot;
+            for (int k = 0; k < NST; k++) dp[k] = dp[k] + c * sv[k];
         }
-        Drow[nb * nd + idr] = d;
-        XGrow[nb * nd + idr] = dextm_v * xi;
+        double v = 0.0;
+#pragma unroll
+        for (int k = 0; k < NST; k++) v += adj[k] * (double)dp[k];
+        if (!deltam) {
+            // untruncated solar term of COMPUTE_SOURCE_DIRECTION applied to DLEGT (SOURCET(1), SOURCET(2) only)
+            const float xi = __ldg(&G.optinterpwt[nb + 8 * (size_t)ipz]);
+            const float *dlg = G.dlegt + ((size_t)gp.x + r) * G.ntup;
+            for (int l = o.ol; l <= ml; l += 8) {
+                v += adj[0] * (double)(xi * (dirflux * secmu0 * __ldg(&dlg[G.ncomp * l]) * Vsh[l]));
+                if (NST > 1) v += adj[1] * (double)(xi * (dirflux * secmu0 * __ldg(&dlg[3 + G.ncomp * l]) * Vsh[(ml + 1) + l]));
+            }
+        }
+        v = oct_sum_d(o.m, v);
+#pragma unroll
+        for (int k = 0; k < NST; k++) v += adj[k] * (double)(c_src * sourcet[k]);
+        if (o.ol == nb) {
+            Drow[nb * nd + idr] = v;
+            XGrow[nb * nd + idr] = __int_as_float(h0.z);
+            IBrow[nb] = h0.w;
+        }
     }
     __syncwarp(o.m);
 }
@@ -522,40 +544,56 @@ template <int NST>
 __device__ __forceinline__ void refresh_corners_grad(const DevState &S, const DevGrad &G, const CellRec &c,
                                                      unsigned char *sm, const GradLayout &L, const RayDir &rd,
                                                      const double (&adj)[NST], bool first, const Oct &o,
-                                                     int &cpt, int &crow, float &cext, float (&csrc)[NST],
-                                                     float (&css)[NST], int &npt_eval, int &nsh_eval, int &nrh_eval)
+                                                     GCorner<NST> &K, int &npt_eval, int &nsh_eval, int &nrh_eval)
 {
     const int myp = own_corner(c, o.ol);
     int hit = -1;
     if (!first) {
 #pragma unroll
-        for (int k = 0; k < 8; k++) { const int pk = __shfl_sync(o.m, cpt, k, 8); if (pk == myp) hit = k; }
+        for (int k = 0; k < 8; k++) { const int pk = __shfl_sync(o.m, K.pt, k, 8); if (pk == myp) hit = k; }
     }
     const int from = hit < 0 ? o.ol : hit;
-    cext = __shfl_sync(o.m, cext, from, 8);
-    crow = __shfl_sync(o.m, crow, from, 8);
+    K.x = __shfl_sync(o.m, K.x, from, 8); K.y = __shfl_sync(o.m, K.y, from, 8);
+    K.z = __shfl_sync(o.m, K.z, from, 8); K.ext = __shfl_sync(o.m, K.ext, from, 8);
+    K.row = __shfl_sync(o.m, K.row, from, 8);
 #pragma unroll
     for (int k = 0; k < NST; k++) {
-        csrc[k] = __shfl_sync(o.m, csrc[k], from, 8);
-        css[k] = __shfl_sync(o.m, css[k], from, 8);
+        K.src[k] = __shfl_sync(o.m, K.src[k], from, 8);
+        K.ss[k] = __shfl_sync(o.m, K.ss[k], from, 8);
     }
-    cpt = myp;
-    unsigned used = oct_or(o, hit >= 0 ? (1u << crow) : 0u);
+    K.pt = myp;
+    int soff = 0, sns = 0;
+    float b[NST];
+    int4 gp = make_int4(0, 0, 0, 0);
+#pragma unroll
+    for (int k = 0; k < NST; k++) b[k] = 0.0f;
+    if (hit < 0) {
+        gp = __ldg(&G.gptrec[myp - 1]);
+        load_corner<NST>(S, myp, rd, K.x, K.y, K.z, K.ext, soff, sns, b);
+    }
+    unsigned used = oct_or(o, hit >= 0 ? (1u << K.row) : 0u);
     unsigned need = oct_ballot(o, hit < 0);
     while (need) {
         const int n = __ffs(need) - 1;
         const int ip = __shfl_sync(o.m, myp, n, 8);
+        const int off = __shfl_sync(o.m, soff, n, 8), ns = __shfl_sync(o.m, sns, n, 8);
+        const float ext = __shfl_sync(o.m, K.ext, n, 8);
+        float bn[NST];
+#pragma unroll
+        for (int k = 0; k < NST; k++) bn[k] = __shfl_sync(o.m, b[k], n, 8);
+        int4 gn;
+        gn.x = __shfl_sync(o.m, gp.x, n, 8); gn.y = __shfl_sync(o.m, gp.y, n, 8);
+        gn.z = __shfl_sync(o.m, gp.z, n, 8); gn.w = __shfl_sync(o.m, gp.w, n, 8);
         const int row = __ffs(~used) - 1;
         used |= 1u << row;
-        float ext, src[NST], ss[NST];
-        int ns, nr;
-        eval_point_grad<NST>(S, G, ip, sm, L, rd, adj, o, row, ext, src, ss, ns, nr);
-        npt_eval++; nsh_eval += ns; nrh_eval += nr;
+        float src[NST], ss[NST];
+        eval_point_grad<NST>(S, G, ip, off, ns, bn, ext, gn, sm, L, rd, adj, o, row, src, ss);
+        npt_eval++; nsh_eval += ns; nrh_eval += gn.w >> 8;
         const bool mine = (myp == ip);
         if (mine) {
-            cext = ext; crow = row;
+            K.row = row;
 #pragma unroll
-            for (int k = 0; k < NST; k++) { csrc[k] = src[k]; css[k] = ss[k]; }
+            for (int k = 0; k < NST; k++) { K.src[k] = src[k]; K.ss[k] = ss[k]; }
         }
         need &= ~oct_ballot(o, mine);
     }
@@ -587,31 +625,34 @@ __device__ int march_ray_adjoint(const DevState &S, const DevGrad &G, unsigned c
     int iface = 0, npassed = 1;
     bool done = false, first = true;
     int npt_eval = 0, nsh_eval = 0, nrh_eval = 0;
-    int cpt = 0, crow = 0; float cext = 0.0f, csrc[NST], css[NST];
+    GCorner<NST> K;
+    K.pt = 0; K.row = 0; K.x = K.y = K.z = K.ext = 0.0f;
 #pragma unroll
-    for (int k = 0; k < NST; k++) { csrc[k] = 0.0f; css[k] = 0.0f; }
+    for (int k = 0; k < NST; k++) { K.src[k] = 0.0f; K.ss[k] = 0.0f; }
     ntrace = 0; nsub = 0;
+    CellRec c;
+    if (icell > 0) c = load_cell(S, icell);
     while (!done && icell > 0) {
         if (trace_cells && o.ol == 0 && ntrace < trace_cap) trace_cells[ntrace] = icell;
         ntrace++;
-        const CellRec c = load_cell(S, icell);
-        refresh_corners_grad<NST>(S, G, c, sm, L, rd, adj, first, o, cpt, crow, cext, csrc, css,
-                                  npt_eval, nsh_eval, nrh_eval);
+        refresh_corners_grad<NST>(S, G, c, sm, L, rd, adj, first, o, K, npt_eval, nsh_eval, nrh_eval);
         first = false;
         float e8[8], s8[NST][8];
 #pragma unroll
         for (int n = 0; n < 8; n++) {
-            e8[n] = __shfl_sync(o.m, cext, n, 8);
+            e8[n] = __shfl_sync(o.m, K.ext, n, 8);
 #pragma unroll
-            for (int k = 0; k < NST; k++) s8[k][n] = __shfl_sync(o.m, csrc[k], n, 8);
+            for (int k = 0; k < NST; k++) s8[k][n] = __shfl_sync(o.m, K.src[k], n, 8);
         }
-        const float4 q1 = __ldg(&S.ptrec[c.gp[0] - 1]);
-        const float4 q8 = __ldg(&S.ptrec[c.gp[7] - 1]);
-        const double delx = (double)(q8.x - q1.x), dely = (double)(q8.y - q1.y), delz = (double)(q8.z - q1.z);
+        const float q1x = __shfl_sync(o.m, K.x, 0, 8), q1y = __shfl_sync(o.m, K.y, 0, 8), q1z = __shfl_sync(o.m, K.z, 0, 8);
+        const float q8x = __shfl_sync(o.m, K.x, 7, 8), q8y = __shfl_sync(o.m, K.y, 7, 8), q8z = __shfl_sync(o.m, K.z, 7, 8);
+        const float qox = __shfl_sync(o.m, K.x, 8 - rd.ioct, 8), qoy = __shfl_sync(o.m, K.y, 8 - rd.ioct, 8),
+                    qoz = __shfl_sync(o.m, K.z, 8 - rd.ioct, 8);
+        const double delx = (double)(q8x - q1x), dely = (double)(q8y - q1y), delz = (double)(q8z - q1z);
         const double invdelx = (delx <= 0.0) ? 1.0 : 1.0 / delx;
         const double invdely = (dely <= 0.0) ? 1.0 : 1.0 / dely;
         const double invdelz = 1.0 / delz;
-        double u = (xe - q1.x) * invdelx, v = (ye - q1.y) * invdely, w = (ze - q1.z) * invdelz;
+        double u = (xe - q1x) * invdelx, v = (ye - q1y) * invdely, w = (ze - q1z) * invdelz;
         double fc[8];
         interp_kernel(u, v, w, fc);
         double fown = interp_kernel_own(u, v, w, o.ol);
@@ -624,17 +665,36 @@ __device__ int march_ray_adjoint(const DevState &S, const DevGrad &G, unsigned c
             !(DBTEST(S.bcflag, 0) && ((rd.cx > 0 && xe < rd.xm) || (rd.cx < 0 && xe > rd.xm)));
         const bool ipiny = DBTEST(c.flags, 1) &&
             !(DBTEST(S.bcflag, 1) && ((rd.cy > 0 && ye < rd.ym) || (rd.cy < 0 && ye > rd.ym)));
-        int iopp = c.gp[0];
-#pragma unroll
-        for (int n = 1; n < 8; n++) if (8 - rd.ioct == n) iopp = c.gp[n];
-        const float4 qo = __ldg(&S.ptrec[iopp - 1]);
-        const double sox = ipinx ? (double)1.0e20f : (qo.x - xe) * rd.cxinv;
-        const double soy = ipiny ? (double)1.0e20f : (qo.y - ye) * rd.cyinv;
-        const double soz = (qo.z - ze) * rd.czinv;
+        const double sox = ipinx ? (double)1.0e20f : (qox - xe) * rd.cxinv;
+        const double soy = ipiny ? (double)1.0e20f : (qoy - ye) * rd.cyinv;
+        const double soz = (qoz - ze) * rd.czinv;
         const double so = fmin(fmin(sox, soy), soz);
         if (so < -eps) return 1;
         double xn = xe + so * rd.cx, yn = ye + so * rd.cy, zn = ze + so * rd.cz;
-        u = (xn - q1.x) * invdelx; v = (yn - q1.y) * invdely; w = (zn - q1.z) * invdelz;
+        // ---- exit face and next cell; its record is requested before the sub-interval loop ----
+        int jface;
+        bool openbcface;
+        if (sox <= soz && sox <= soy) { iface = 2 - rd.bitx; jface = 1; openbcface = DBTEST(c.flags, 0) && DBTEST(S.bcflag, 0); }
+        else if (soy <= soz) { iface = 4 - rd.bity; jface = 2; openbcface = DBTEST(c.flags, 1) && DBTEST(S.bcflag, 1); }
+        else { iface = 6 - rd.bitz; jface = 3; openbcface = false; }
+        int nbr = c.nb[0];
+#pragma unroll
+        for (int n = 1; n < 6; n++) if (iface - 1 == n) nbr = c.nb[n];
+        int inextcell = nbr;
+        if (inextcell < 0) inextcell = dev_next_cell(S, xn, yn, zn, iface, jface, inextcell);
+        int kface, ic;
+        if (nbr >= 0 && !openbcface) { kface = iface; ic = icell; }
+        else { kface = ((iface - 1) ^ 1) + 1; ic = inextcell; iface = 0; }
+        CellRec cn = c;
+        float snap = 0.0f;
+        if (inextcell > 0) {
+            cn = load_cell(S, inextcell);
+            int pn = cn.gp[0];
+#pragma unroll
+            for (int n = 1; n < 8; n++) if (rd.ioct - 1 == n) pn = cn.gp[n];
+            snap = pt_coord(S, pn, jface);
+        }
+        u = (xn - q1x) * invdelx; v = (yn - q1y) * invdely; w = (zn - q1z) * invdelz;
         float extn;
         { double fcn[8]; interp_kernel(u, v, w, fcn); extn = (float)fcsum(fcn, e8); }
         const double taugrid = so * 0.5f * (ext1 + extn);
@@ -650,7 +710,7 @@ __device__ int march_ray_adjoint(const DevState &S, const DevGrad &G, unsigned c
             const double f1 = fown;                  // previous interpolation weight of the own corner
             const double s = it * dels;
             const double xi = xe + s * rd.cx, yi = ye + s * rd.cy, zi = ze + s * rd.cz;
-            u = (xi - q1.x) * invdelx; v = (yi - q1.y) * invdely; w = (zi - q1.z) * invdelz;
+            u = (xi - q1x) * invdelx; v = (yi - q1y) * invdely; w = (zi - q1z) * invdelz;
             interp_kernel(u, v, w, fc);
             fown = interp_kernel_own(u, v, w, o.ol);
             const double f0 = fown;
@@ -686,7 +746,7 @@ __device__ int march_ray_adjoint(const DevState &S, const DevGrad &G, unsigned c
                 if (exact_ss) {
 #pragma unroll
                     for (int k = 0; k < NST; k++) {
-                        float ss0 = (float)(f0 * css[k]), ss1 = (float)(f1 * css[k]);
+                        float ss0 = (float)(f0 * K.ss[k]), ss1 = (float)(f1 * K.ss[k]);
                         if (k == 0) { ss0 = fmaxf(0.0f, ss0); ss1 = fmaxf(0.0f, ss1); }
                         bw[k] = (float)(bw[k] + transmit * abscell *
                                 (0.5f * (ss0 + ss1) + 0.08333333333f * (ext0 * ss1 - ext1 * ss0) * corr) / ext);
@@ -713,12 +773,12 @@ __device__ int march_ray_adjoint(const DevState &S, const DevGrad &G, unsigned c
             for (int k = 0; k < NST; k++) srcext1[k] = srcext0[k];
         }
         // ---- flush this cell's contributions (once per cell and corner, no atomics above) ----
-        Wacc[o.ol] = Wn; Wacc[8 + o.ol] = Gn; rowof[o.ol] = crow;
+        Wacc[o.ol] = Wn; Wacc[8 + o.ol] = Gn; rowof[o.ol] = K.row;
         if (exact_ss) {
             double bsum = 0.0;
 #pragma unroll
             for (int k = 0; k < NST; k++) bsum += adj[k] * (double)bw[k];
-            if (bsum != 0.0) atomicAdd(&beam_weight[cpt - 1], bsum);
+            if (bsum != 0.0) atomicAdd(&beam_weight[K.pt - 1], bsum);
         }
         __syncwarp(o.m);
         {
@@ -726,33 +786,18 @@ __device__ int march_ray_adjoint(const DevState &S, const DevGrad &G, unsigned c
             for (int slot = 0; slot < 8; slot++) {
                 const int r = rowof[slot];
                 const double Ws = Wacc[slot], Gs = Wacc[8 + slot];
-                const int ibp = IBall[r * 8 + nb];
                 for (int idr = 0; idr < nd; idr++) {
                     const int e = (r * 8 + nb) * nd + idr;
                     const double val = Ws * Dall[e] + (double)XGall[e] * Gs;
-                    if (val != 0.0) atomicAdd(&gradout[(size_t)(ibp - 1) + (size_t)G.maxpg * idr], val);
+                    if (val != 0.0) atomicAdd(&gradout[(size_t)(IBall[r * 8 + nb] - 1) + (size_t)G.maxpg * idr], val);
                 }
             }
         }
         __syncwarp(o.m);
-        int jface;
-        bool openbcface;
-        if (sox <= soz && sox <= soy) { iface = 2 - rd.bitx; jface = 1; openbcface = DBTEST(c.flags, 0) && DBTEST(S.bcflag, 0); }
-        else if (soy <= soz) { iface = 4 - rd.bity; jface = 2; openbcface = DBTEST(c.flags, 1) && DBTEST(S.bcflag, 1); }
-        else { iface = 6 - rd.bitz; jface = 3; openbcface = false; }
-        int nbr = c.nb[0];
-#pragma unroll
-        for (int n = 1; n < 6; n++) if (iface - 1 == n) nbr = c.nb[n];
-        int inextcell = nbr;
-        if (inextcell < 0) inextcell = dev_next_cell(S, xn, yn, zn, iface, jface, inextcell);
-        int kface, ic;
-        if (nbr >= 0 && !openbcface) { kface = iface; ic = icell; }
-        else { kface = ((iface - 1) ^ 1) + 1; ic = inextcell; iface = 0; }
         if (inextcell > 0) {
-            const int pn = cell_gp(S, inextcell, rd.ioct);
-            if (jface == 1) xn = (double)pt_coord(S, pn, 1);
-            else if (jface == 2) yn = (double)pt_coord(S, pn, 2);
-            else zn = (double)pt_coord(S, pn, 3);
+            if (jface == 1) xn = (double)snap;
+            else if (jface == 2) yn = (double)snap;
+            else zn = (double)snap;
         }
         if (transmit < S.transcut) {
             done = true;
@@ -771,7 +816,7 @@ __device__ int march_ray_adjoint(const DevState &S, const DevGrad &G, unsigned c
                 if (val != 0.0) atomicAdd(&beam_weight[bp - 1], val);
             }
         } else {
-            icell = inextcell;
+            icell = inextcell; c = cn;
         }
         xe = xn; ye = yn; ze = zn;
     }
@@ -995,6 +1040,8 @@ static int gupload(at3d_state *st, std::vector<void *> &owned, const T *host, si
     return 0;
 }
 
+static inline int nst_of(const DevState &S) { return S.nstokes; }
+
 extern "C" int at3d_state_attach_gradient(at3d_state *st, const at3d_grad_desc *g, char *errmsg)
 {
     if (errmsg) errmsg[0] = 0;
@@ -1042,27 +1089,55 @@ extern "C" int at3d_state_attach_gradient(at3d_state *st, const at3d_grad_desc *
     if (g->exact_single_scatter && (!G.dpath || !G.dptr)) { set_msg(errmsg, "EXACT_SINGLE_SCATTER needs DPATH/DPTR"); return 1; }
     // ray-independent tables of COMPUTE_SOURCE_GRAD_1CELL (grad_prep_kernel)
     {
+        const bool deltam = S.deltam != 0;
         G.ncomp = S.nstleg == 1 ? 1 : 4;
         G.ntup = (G.ncomp * (S.ml + 1) + 3) & ~3;
-        const size_t nrow = np * nd * 8;
-        float *grec = nullptr, *dlegt = nullptr, *legs = nullptr; float2 *gpnt = nullptr;
+        const int pmaxp = S.maxnmicro + g->deriv_maxnmicro;            // row list: SINGSCATP + DSINGSCATP entries
+        G.prow_stride = 2 + (pmaxp + 1) / 2;
+        G.sp_stride = 1 + (8 * S.maxnmicro + 1) / 2;                   // species list: SINGSCATJ entries
+        if ((int)st->nr_h.size() != S.npts) { set_msg(errmsg, "the state has no RADIANCE/RSHPTR"); return 1; }
+        // row / SH-block offsets per grid point (host prefix sums)
+        std::vector<int4> gp(np);
+        size_t nrows_tot = 0, units = 0;
+        const int extra = S.npart > 1 ? (int)nd : 0;                    // SOURCET rows
+        for (size_t i = 0; i < np; i++) {
+            int nnz = 0;
+            for (int nb = 0; nb < 8; nb++) if (g->optinterpwt[nb + 8 * i] >= 1e-7f) nnz++;
+            const int nr = st->nr_h[i], nrp32 = AT3D_SHPAD(nr) / 32;
+            const size_t nrows = (size_t)nnz * nd;
+            if (nnz == 0) nnz = 1;
+            if (nrows > 0xFFFF || nrp32 > 0xFF) { set_msg(errmsg, "too many gradient rows per grid point"); return 3; }
+            gp[i] = make_int4((int)nrows_tot, (int)nrows | (nnz << 16), (int)(unsigned)units, nrp32 | (nr << 8));
+            nrows_tot += nrows;
+            units += (nrows + extra) * (size_t)nst_of(S) * nrp32;
+            if (nrows_tot >= ((size_t)1 << 31) || units >= ((size_t)1 << 32)) { set_msg(errmsg, "gradient tables too large"); return 2; }
+        }
+        const int4 *gp_d = nullptr;
+        rc = gupload(st, own, gp.data(), np, &gp_d, errmsg); if (rc) return rc;
+        G.gptrec = gp_d;
+        int4 *rowrec = nullptr, *sprec = nullptr; float *dsh = nullptr, *dlegt = nullptr, *legs = nullptr;
         void *p = nullptr;
-        CUDA_TRY(cudaMalloc(&p, nrow * 8 * sizeof(float))); own.push_back(p); grec = (float *)p; st->bytes += nrow * 8 * sizeof(float);
-        CUDA_TRY(cudaMalloc(&p, nrow * G.ntup * sizeof(float))); own.push_back(p); dlegt = (float *)p; st->bytes += nrow * G.ntup * sizeof(float);
-        CUDA_TRY(cudaMalloc(&p, np * nd * sizeof(float2))); own.push_back(p); gpnt = (float2 *)p; st->bytes += np * nd * sizeof(float2);
-        CUDA_TRY(cudaMemset(dlegt, 0, nrow * G.ntup * sizeof(float)));
-        if (S.npart > 1) {
-            CUDA_TRY(cudaMalloc(&p, np * nd * G.ntup * sizeof(float))); own.push_back(p); legs = (float *)p;
-            st->bytes += np * nd * G.ntup * sizeof(float);
-            CUDA_TRY(cudaMemset(legs, 0, np * nd * G.ntup * sizeof(float)));
+        size_t nb_ = (nrows_tot + 1) * G.prow_stride * sizeof(int4);
+        CUDA_TRY(cudaMalloc(&p, nb_)); own.push_back(p); rowrec = (int4 *)p; st->bytes += nb_;
+        nb_ = np * nd * G.sp_stride * sizeof(int4);
+        CUDA_TRY(cudaMalloc(&p, nb_)); own.push_back(p); sprec = (int4 *)p; st->bytes += nb_;
+        nb_ = (units + 1) * 32 * sizeof(float);
+        CUDA_TRY(cudaMalloc(&p, nb_)); own.push_back(p); dsh = (float *)p; st->bytes += nb_;
+        if (!deltam) {
+            nb_ = (nrows_tot + 1) * G.ntup * sizeof(float);
+            CUDA_TRY(cudaMalloc(&p, nb_)); own.push_back(p); dlegt = (float *)p; st->bytes += nb_;
+            if (S.npart > 1) {
+                nb_ = np * nd * G.ntup * sizeof(float);
+                CUDA_TRY(cudaMalloc(&p, nb_)); own.push_back(p); legs = (float *)p; st->bytes += nb_;
+            }
         }
         const int wpb = 4;
-        const size_t smem = (size_t)wpb * nlt * sizeof(float);
+        const size_t smem = (size_t)wpb * (nlt + G.ntup) * sizeof(float);
         if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(grad_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        grad_prep_kernel<<<(S.npts + wpb - 1) / wpb, wpb * 32, smem>>>(S, G, grec, dlegt, gpnt, legs);
+        grad_prep_kernel<<<(S.npts + wpb - 1) / wpb, wpb * 32, smem>>>(S, G, rowrec, sprec, dsh, dlegt, legs);
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaDeviceSynchronize());
-        G.grec = grec; G.dlegt = dlegt; G.gpnt = gpnt; G.legs = legs;
+        G.rowrec = rowrec; G.sprec = sprec; G.dsh = dsh; G.dlegt = dlegt; G.legs = legs;
     }
     st->grad_attached = 1;
     return 0;
@@ -1177,7 +1252,7 @@ extern "C" int at3d_levisapprox_gradient(at3d_state *st, const at3d_rays *rays, 
         cost_reduce_kernel<<<1, 1024, 0, stream>>>((int)npix, costp, cost_d);
         CUDA_TRY(cudaGetLastError());
         // ---- Phase 3 ----
-        const GradLayout L = grad_layout(nst, S.ny_comp, S.nlmp, S.ml, G.ncomp, G.ntup, G.numder);
+        const GradLayout L = grad_layout(S.ny_comp, S.nlmp, S.ml, G.numder);
         const size_t smem = (size_t)AT3D_RAYS_PER_BLOCK * L.total;
         if (smem > 227 * 1024) { set_msg(errmsg, "gradient kernel needs %zu bytes of shared memory (NUMDER too large)", smem); return 3; }
         const void *fn = nst == 1 ? (const void *)adjoint_kernel<1> : (const void *)adjoint_kernel<3>;

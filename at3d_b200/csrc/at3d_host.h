@@ -38,6 +38,7 @@ struct at3d_state {
     std::vector<RayPack> packs_h;   // host staging of the per-ray packs
     float *bcrad_dev = nullptr;
     unsigned long long *counts_dev = nullptr;
+    std::vector<int> nr_h;          // radiance SH length per point (host copy, for the gradient tables)
     int *ray_counter = nullptr;     // work counter of the persistent ray kernels
     int nbcrad = 0;
 };
@@ -52,6 +53,8 @@ cudaError_t launch_forward(const DevState &S, int nrays, const float *camx, cons
 cudaError_t launch_build_cellrec(int ncells, const int *gridptr, const int *neighptr, const int *treeptr,
                                  const short *cellflags, int4 *cellrec, cudaStream_t s);
 cudaError_t launch_build_ptrec(int npts, const float *gridpos, const float *total_ext, float4 *ptrec, cudaStream_t s);
+cudaError_t launch_build_ptsrc(int npts, int kmax, const int2 *srcrec, const int *sscount, const int2 *ssent,
+                               int4 *ptsrc, cudaStream_t s);
 cudaError_t launch_lambertian_boundary(const DevState &S, const float *fluxes, float *bcrad, cudaStream_t s);
 cudaError_t launch_prep_sh(const DevState &S, int tms, const int *shptr, const float *sh_in,
                            const int2 *rec, float *sh_out, int *sscount, int2 *ssent, cudaStream_t s);

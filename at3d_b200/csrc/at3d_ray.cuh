@@ -57,61 +57,76 @@ __device__ __forceinline__ void ray_singscat(const float *tab, int nstphase, int
     }
 }
 
-// One grid point in the ray direction: COMPUTE_SOURCE_1CELL (shdomsub2.f:2911-3038) for one corner,
-// with the TMS-corrected SH source prepared by prep_sh_kernel.  Returns on every lane of the octet
-// the extinction, the SH part a[] and the exact single-scatter part b[] (both before the
-// multiplication by the extinction).
+// Spherical-harmonic part of COMPUTE_SOURCE_1CELL (shdomsub2.f:2930-2947) for one planar block of
+// `nsp` (multiple of 32) coefficients per Stokes component at `base`: the 8 lanes of the octet split
+// j (float4 per lane and 128-byte line); returns the lane-partial sums (reduce with oct_sum).
 template <int NST>
-__device__ __forceinline__ void eval_point(const DevState &S, int ip, const float *Ysh, const RayDir &rd,
-                                           bool singlescatter, const Oct &o, float &ext, int &ns,
-                                           float (&a)[NST], float (&b)[NST])
+__device__ __forceinline__ void sh_dot_partial(const float *base, int nsp, const float *Ysh, int nlmp, const Oct &o,
+                                               float (&a)[NST])
 {
-    const float4 pr = __ldg(&S.ptrec[ip - 1]);
-    const int2 sr = __ldg(&S.srcrec[ip - 1]);
-    ext = pr.w;
-    ns = sr.y;
-    const int nsp = AT3D_SHPAD(sr.y);
-#pragma unroll
-    for (int k = 0; k < NST; k++) { a[k] = 0.0f; b[k] = 0.0f; }
-    if (!singlescatter) {
-        const float *base = S.shsrc + sr.x + o.ol * 4;
-        const float *yb = Ysh + o.ol * 4;
-        const int nlmp = S.nlmp;
+    base += o.ol * 4;
+    const float *yb = Ysh + o.ol * 4;
 #pragma unroll 4
-        for (int j = 0; j < nsp; j += 32) {
-            const float4 s = __ldg((const float4 *)(base + j));
-            const float4 y = *(const float4 *)(yb + j);
-            a[0] = fmaf(s.x, y.x, a[0]); a[0] = fmaf(s.y, y.y, a[0]);
-            a[0] = fmaf(s.z, y.z, a[0]); a[0] = fmaf(s.w, y.w, a[0]);
-            if (NST > 1) {
-                const float4 q = __ldg((const float4 *)(base + nsp + j));
-                const float4 u = __ldg((const float4 *)(base + 2 * nsp + j));
-                const float4 y2 = *(const float4 *)(yb + 1 * nlmp + j);
-                const float4 y5 = *(const float4 *)(yb + 2 * nlmp + j);
-                const float4 y6 = *(const float4 *)(yb + 3 * nlmp + j);
-                const float4 y3 = *(const float4 *)(yb + 4 * nlmp + j);
-                a[1] = fmaf(q.x, y2.x, a[1]); a[1] = fmaf(u.x, y5.x, a[1]);
-                a[1] = fmaf(q.y, y2.y, a[1]); a[1] = fmaf(u.y, y5.y, a[1]);
-                a[1] = fmaf(q.z, y2.z, a[1]); a[1] = fmaf(u.z, y5.z, a[1]);
-                a[1] = fmaf(q.w, y2.w, a[1]); a[1] = fmaf(u.w, y5.w, a[1]);
-                a[NST - 1] = fmaf(q.x, y6.x, a[NST - 1]); a[NST - 1] = fmaf(u.x, y3.x, a[NST - 1]);
-                a[NST - 1] = fmaf(q.y, y6.y, a[NST - 1]); a[NST - 1] = fmaf(u.y, y3.y, a[NST - 1]);
-                a[NST - 1] = fmaf(q.z, y6.z, a[NST - 1]); a[NST - 1] = fmaf(u.z, y3.z, a[NST - 1]);
-                a[NST - 1] = fmaf(q.w, y6.w, a[NST - 1]); a[NST - 1] = fmaf(u.w, y3.w, a[NST - 1]);
-            }
+    for (int j = 0; j < nsp; j += 32) {
+        const float4 s = __ldg((const float4 *)(base + j));
+        const float4 y = *(const float4 *)(yb + j);
+        a[0] = fmaf(s.x, y.x, a[0]); a[0] = fmaf(s.y, y.y, a[0]);
+        a[0] = fmaf(s.z, y.z, a[0]); a[0] = fmaf(s.w, y.w, a[0]);
+        if (NST > 1) {
+            const float4 q = __ldg((const float4 *)(base + nsp + j));
+            const float4 u = __ldg((const float4 *)(base + 2 * nsp + j));
+            const float4 y2 = *(const float4 *)(yb + 1 * nlmp + j);
+            const float4 y5 = *(const float4 *)(yb + 2 * nlmp + j);
+            const float4 y6 = *(const float4 *)(yb + 3 * nlmp + j);
+            const float4 y3 = *(const float4 *)(yb + 4 * nlmp + j);
+            a[1] = fmaf(q.x, y2.x, a[1]); a[1] = fmaf(u.x, y5.x, a[1]);
+            a[1] = fmaf(q.y, y2.y, a[1]); a[1] = fmaf(u.y, y5.y, a[1]);
+            a[1] = fmaf(q.z, y2.z, a[1]); a[1] = fmaf(u.z, y5.z, a[1]);
+            a[1] = fmaf(q.w, y2.w, a[1]); a[1] = fmaf(u.w, y5.w, a[1]);
+            a[NST - 1] = fmaf(q.x, y6.x, a[NST - 1]); a[NST - 1] = fmaf(u.x, y3.x, a[NST - 1]);
+            a[NST - 1] = fmaf(q.y, y6.y, a[NST - 1]); a[NST - 1] = fmaf(u.y, y3.y, a[NST - 1]);
+            a[NST - 1] = fmaf(q.z, y6.z, a[NST - 1]); a[NST - 1] = fmaf(u.z, y3.z, a[NST - 1]);
+            a[NST - 1] = fmaf(q.w, y6.w, a[NST - 1]); a[NST - 1] = fmaf(u.w, y3.w, a[NST - 1]);
         }
     }
-    const int cnt = __ldg(&S.sscount[ip - 1]);
-    for (int k = o.ol; k < cnt; k += 8) {
-        const int2 e = __ldg(&S.ssent[(size_t)(ip - 1) * S.kmax + k]);
-        const float coef = __int_as_float(e.y);
+}
+
+// The values lane n keeps for corner n of the current cell.
+template <int NST>
+struct Corner {
+    int pt;                 // grid point (1-based), 0 = none yet
+    float x, y, z, ext;     // GRIDPOS, TOTAL_EXT
+    float src[NST];         // SRCEXT8(:,n)
+};
+
+// Records of a corner's grid point that is new in this cell, loaded by the lane that owns the corner
+// (all new corners of a cell in parallel): coordinates/extinction, SH block and the exact
+// single-scatter sum (shdomsub2.f:3008-3019) from the per-point list.
+template <int NST>
+__device__ __forceinline__ void load_corner(const DevState &S, int ip, const RayDir &rd, float &x, float &y, float &z,
+                                            float &ext, int &soff, int &sns, float (&b)[NST])
+{
+    const float4 pr = __ldg(&S.ptrec[ip - 1]);
+    const int4 ps = __ldg(&S.ptsrc[ip - 1]);
+    x = pr.x; y = pr.y; z = pr.z; ext = pr.w;
+    soff = ps.x; sns = ps.y & 0xFFFF;
+    const int cnt = ps.y >> 16;
+#pragma unroll
+    for (int k = 0; k < NST; k++) b[k] = 0.0f;
+    if (cnt > 0) {
         float sv[NST];
-        ray_singscat<NST>(S.phasetab, S.nstphase, S.numphase, e.x, rd, sv);
+        ray_singscat<NST>(S.phasetab, S.nstphase, S.numphase, ps.z, rd, sv);
+        const float coef = __int_as_float(ps.w);
 #pragma unroll
-        for (int kk = 0; kk < NST; kk++) b[kk] = fmaf(coef, sv[kk], b[kk]);
+        for (int k = 0; k < NST; k++) b[k] = fmaf(coef, sv[k], b[k]);
+        for (int e = 1; e < cnt; e++) {
+            const int2 en = __ldg(&S.ssent[(size_t)(ip - 1) * S.kmax + e]);
+            ray_singscat<NST>(S.phasetab, S.nstphase, S.numphase, en.x, rd, sv);
+            const float c2 = __int_as_float(en.y);
+#pragma unroll
+            for (int k = 0; k < NST; k++) b[k] = fmaf(c2, sv[k], b[k]);
+        }
     }
-#pragma unroll
-    for (int k = 0; k < NST; k++) { a[k] = oct_sum(o.m, a[k]); b[k] = oct_sum(o.m, b[k]); }
 }
 
 // nested-lerp trilinear interpolation of INTEGRATE_1RAY (shdomsub2.f:2563-2571), double weights
@@ -218,46 +233,51 @@ __device__ __forceinline__ int own_corner(const CellRec &c, int ol)
     return p;
 }
 
-// Exit geometry of one cell, identical for every march (shdomsub2.f:2575-2606, 2668-2716).
-struct CellExit {
-    double so, sox, soy, soz, xn, yn, zn;
-    int iface, jface, inextcell, kface, ic;
-};
-
 // Refresh the corner values of the lanes for cell `c`: values of points shared with the previous
 // cell are taken over from the lane that owned them (they are bit-identical to a recomputation, so
 // this is the reference's OLDIPTS/DONEFACE shortcut, shdomsub2.f:2509-2515,2914-2919, without its
-// slot restriction); duplicate corners inside one cell are evaluated once.
+// slot restriction).  New corners: every owner lane loads its point's records at once, then the
+// octet evaluates the SH sums point by point.
 template <int NST>
 __device__ __forceinline__ void refresh_corners(const DevState &S, const CellRec &c, const float *Ysh,
                                                 const RayDir &rd, bool singlescatter, bool first, const Oct &o,
-                                                int &cpt, float &cext, float (&csrc)[NST],
-                                                int &npt_eval, int &nsh_eval)
+                                                Corner<NST> &K, int &npt_eval, int &nsh_eval)
 {
     const int myp = own_corner(c, o.ol);
     int hit = -1;
     if (!first) {
 #pragma unroll
-        for (int k = 0; k < 8; k++) { const int pk = __shfl_sync(o.m, cpt, k, 8); if (pk == myp) hit = k; }
+        for (int k = 0; k < 8; k++) { const int pk = __shfl_sync(o.m, K.pt, k, 8); if (pk == myp) hit = k; }
     }
     const int from = hit < 0 ? o.ol : hit;
-    cext = __shfl_sync(o.m, cext, from, 8);
+    K.x = __shfl_sync(o.m, K.x, from, 8); K.y = __shfl_sync(o.m, K.y, from, 8);
+    K.z = __shfl_sync(o.m, K.z, from, 8); K.ext = __shfl_sync(o.m, K.ext, from, 8);
 #pragma unroll
-    for (int k = 0; k < NST; k++) csrc[k] = __shfl_sync(o.m, csrc[k], from, 8);
-    cpt = myp;
+    for (int k = 0; k < NST; k++) K.src[k] = __shfl_sync(o.m, K.src[k], from, 8);
+    K.pt = myp;
+    int soff = 0, sns = 0;
+    float b[NST];
+#pragma unroll
+    for (int k = 0; k < NST; k++) b[k] = 0.0f;
+    if (hit < 0) load_corner<NST>(S, myp, rd, K.x, K.y, K.z, K.ext, soff, sns, b);
     unsigned need = oct_ballot(o, hit < 0);
     while (need) {
         const int n = __ffs(need) - 1;
         const int ip = __shfl_sync(o.m, myp, n, 8);
-        float ext, a[NST], b[NST];
-        int ns;
-        eval_point<NST>(S, ip, Ysh, rd, singlescatter, o, ext, ns, a, b);
+        const int off = __shfl_sync(o.m, soff, n, 8), ns = __shfl_sync(o.m, sns, n, 8);
+        float a[NST];
+#pragma unroll
+        for (int k = 0; k < NST; k++) a[k] = 0.0f;
+        if (!singlescatter) {
+            sh_dot_partial<NST>(S.shsrc + off, AT3D_SHPAD(ns), Ysh, S.nlmp, o, a);
+#pragma unroll
+            for (int k = 0; k < NST; k++) a[k] = oct_sum(o.m, a[k]);
+        }
         npt_eval++; nsh_eval += ns;
         const bool mine = (myp == ip);
         if (mine) {
-            cext = ext;
 #pragma unroll
-            for (int k = 0; k < NST; k++) csrc[k] = (a[k] + b[k]) * ext;
+            for (int k = 0; k < NST; k++) K.src[k] = (a[k] + b[k]) * K.ext;
         }
         need &= ~oct_ballot(o, mine);
     }
@@ -267,7 +287,8 @@ __device__ __forceinline__ void refresh_corners(const DevState &S, const CellRec
 // MODES bit 0: INTEGRATE_1RAY arithmetic (result radA, nsubA counts every sub-interval);
 // MODES bit 1: the forward part of ADJOINT_INTEGRATE_1RAY (GET_INTERP_KERNEL weights, EXT0=EXTN on
 //              the last sub-interval, no MAXCELLSCROSS stop; result radB, nsubB counts EXT!=0).
-// Both share the walk (it depends on the geometry only) and the corner evaluations.
+// Both share the walk (it depends on the geometry only) and the corner evaluations.  The record of
+// the next cell is requested as soon as the exit face is known, before the sub-interval loop.
 template <int NST, int MODES>
 __device__ int march_forward(const DevState &S, const float *Ysh, const RayDir &rd, double mu2,
                              double x0, double y0, double z0, float sky, bool correctinterpolate,
@@ -285,31 +306,35 @@ __device__ int march_forward(const DevState &S, const float *Ysh, const RayDir &
     int icell = dev_locate_grid_cell(S, xe, ye, ze);
     int iface = 0, ngrid = 0, npt_eval = 0, nsh_eval = 0;
     bool doneA = !(MODES & 1), doneB = !(MODES & 2), first = true;
-    int cpt = 0; float cext = 0.0f, csrc[NST];
+    Corner<NST> K;
+    K.pt = 0; K.x = K.y = K.z = K.ext = 0.0f;
 #pragma unroll
-    for (int k = 0; k < NST; k++) csrc[k] = 0.0f;
+    for (int k = 0; k < NST; k++) K.src[k] = 0.0f;
     ntrace = 0; nsubA = 0; nsubB = 0;
+    CellRec c;
+    if (icell > 0) c = load_cell(S, icell);
     while (!(doneA && doneB) && icell > 0) {
         ngrid++;
         if (trace_cells && o.ol == 0 && ntrace < trace_cap) trace_cells[ntrace] = icell;
         ntrace++;
-        const CellRec c = load_cell(S, icell);
-        refresh_corners<NST>(S, c, Ysh, rd, singlescatter, first, o, cpt, cext, csrc, npt_eval, nsh_eval);
+        refresh_corners<NST>(S, c, Ysh, rd, singlescatter, first, o, K, npt_eval, nsh_eval);
         first = false;
         float e8[8], s8[NST][8];
 #pragma unroll
         for (int n = 0; n < 8; n++) {
-            e8[n] = __shfl_sync(o.m, cext, n, 8);
+            e8[n] = __shfl_sync(o.m, K.ext, n, 8);
 #pragma unroll
-            for (int k = 0; k < NST; k++) s8[k][n] = __shfl_sync(o.m, csrc[k], n, 8);
+            for (int k = 0; k < NST; k++) s8[k][n] = __shfl_sync(o.m, K.src[k], n, 8);
         }
-        const float4 q1 = __ldg(&S.ptrec[c.gp[0] - 1]);
-        const float4 q8 = __ldg(&S.ptrec[c.gp[7] - 1]);
-        const double delx = (double)(q8.x - q1.x), dely = (double)(q8.y - q1.y), delz = (double)(q8.z - q1.z);
+        const float q1x = __shfl_sync(o.m, K.x, 0, 8), q1y = __shfl_sync(o.m, K.y, 0, 8), q1z = __shfl_sync(o.m, K.z, 0, 8);
+        const float q8x = __shfl_sync(o.m, K.x, 7, 8), q8y = __shfl_sync(o.m, K.y, 7, 8), q8z = __shfl_sync(o.m, K.z, 7, 8);
+        const float qox = __shfl_sync(o.m, K.x, 8 - rd.ioct, 8), qoy = __shfl_sync(o.m, K.y, 8 - rd.ioct, 8),
+                    qoz = __shfl_sync(o.m, K.z, 8 - rd.ioct, 8);
+        const double delx = (double)(q8x - q1x), dely = (double)(q8y - q1y), delz = (double)(q8z - q1z);
         const double invdelx = (delx <= 0.0) ? 1.0 : 1.0 / delx;
         const double invdely = (dely <= 0.0) ? 1.0 : 1.0 / dely;
         const double invdelz = 1.0 / delz;
-        double u = (xe - q1.x) * invdelx, v = (ye - q1.y) * invdely, w = (ze - q1.z) * invdelz;
+        double u = (xe - q1x) * invdelx, v = (ye - q1y) * invdely, w = (ze - q1z) * invdelz;
         double fc[8];
         if ((MODES & 2) && !doneB) {
             interp_kernel(u, v, w, fc);
@@ -328,17 +353,36 @@ __device__ int march_forward(const DevState &S, const float *Ysh, const RayDir &
             !(DBTEST(S.bcflag, 0) && ((rd.cx > 0 && xe < rd.xm) || (rd.cx < 0 && xe > rd.xm)));
         const bool ipiny = DBTEST(c.flags, 1) &&
             !(DBTEST(S.bcflag, 1) && ((rd.cy > 0 && ye < rd.ym) || (rd.cy < 0 && ye > rd.ym)));
-        int iopp = c.gp[0];
-#pragma unroll
-        for (int n = 1; n < 8; n++) if (8 - rd.ioct == n) iopp = c.gp[n];
-        const float4 qo = __ldg(&S.ptrec[iopp - 1]);
-        const double sox = ipinx ? (double)1.0e20f : (qo.x - xe) * rd.cxinv;
-        const double soy = ipiny ? (double)1.0e20f : (qo.y - ye) * rd.cyinv;
-        const double soz = (qo.z - ze) * rd.czinv;
+        const double sox = ipinx ? (double)1.0e20f : (qox - xe) * rd.cxinv;
+        const double soy = ipiny ? (double)1.0e20f : (qoy - ye) * rd.cyinv;
+        const double soz = (qoz - ze) * rd.czinv;
         const double so = fmin(fmin(sox, soy), soz);
         if (so < -eps) return 1;
         double xn = xe + so * rd.cx, yn = ye + so * rd.cy, zn = ze + so * rd.cz;
-        u = (xn - q1.x) * invdelx; v = (yn - q1.y) * invdely; w = (zn - q1.z) * invdelz;
+        // ---- exit face and next cell (shdomsub2.f:2668-2716); its record is requested now ----
+        int jface;
+        bool openbcface;
+        if (sox <= soz && sox <= soy) { iface = 2 - rd.bitx; jface = 1; openbcface = DBTEST(c.flags, 0) && DBTEST(S.bcflag, 0); }
+        else if (soy <= soz) { iface = 4 - rd.bity; jface = 2; openbcface = DBTEST(c.flags, 1) && DBTEST(S.bcflag, 1); }
+        else { iface = 6 - rd.bitz; jface = 3; openbcface = false; }
+        int nbr = c.nb[0];
+#pragma unroll
+        for (int n = 1; n < 6; n++) if (iface - 1 == n) nbr = c.nb[n];
+        int inextcell = nbr;
+        if (inextcell < 0) inextcell = dev_next_cell(S, xn, yn, zn, iface, jface, inextcell);
+        int kface, ic;
+        if (nbr >= 0 && !openbcface) { kface = iface; ic = icell; }
+        else { kface = ((iface - 1) ^ 1) + 1; ic = inextcell; iface = 0; }
+        CellRec cn = c;
+        float snap = 0.0f;
+        if (inextcell > 0) {
+            cn = load_cell(S, inextcell);
+            int pn = cn.gp[0];
+#pragma unroll
+            for (int n = 1; n < 8; n++) if (rd.ioct - 1 == n) pn = cn.gp[n];
+            snap = pt_coord(S, pn, jface);
+        }
+        u = (xn - q1x) * invdelx; v = (yn - q1y) * invdely; w = (zn - q1z) * invdelz;
         if ((MODES & 1) && !doneA) {
             const float extn = (float)trilerp(e8, u, v, w);
             const double taugrid = so * 0.5f * (ext1A + extn);
@@ -348,7 +392,7 @@ __device__ int march_forward(const DevState &S, const float *Ysh, const RayDir &
             for (int it = 1; it <= ntau; it++) {
                 const double s = it * dels;
                 const double xi = xe + s * rd.cx, yi = ye + s * rd.cy, zi = ze + s * rd.cz;
-                const double ui = (xi - q1.x) * invdelx, vi = (yi - q1.y) * invdely, wi = (zi - q1.z) * invdelz;
+                const double ui = (xi - q1x) * invdelx, vi = (yi - q1y) * invdely, wi = (zi - q1z) * invdelz;
                 const float ext0 = (float)trilerp(e8, ui, vi, wi);
                 float srcext0[NST];
 #pragma unroll
@@ -384,7 +428,7 @@ __device__ int march_forward(const DevState &S, const float *Ysh, const RayDir &
             for (int it = 1; it <= ntau; it++) {
                 const double s = it * dels;
                 const double xi = xe + s * rd.cx, yi = ye + s * rd.cy, zi = ze + s * rd.cz;
-                const double ui = (xi - q1.x) * invdelx, vi = (yi - q1.y) * invdely, wi = (zi - q1.z) * invdelz;
+                const double ui = (xi - q1x) * invdelx, vi = (yi - q1y) * invdely, wi = (zi - q1z) * invdelz;
                 interp_kernel(ui, vi, wi, fc);
                 float srcext0[NST];
 #pragma unroll
@@ -412,24 +456,10 @@ __device__ int march_forward(const DevState &S, const float *Ysh, const RayDir &
                 for (int k = 0; k < NST; k++) srcext1B[k] = srcext0[k];
             }
         }
-        int jface;
-        bool openbcface;
-        if (sox <= soz && sox <= soy) { iface = 2 - rd.bitx; jface = 1; openbcface = DBTEST(c.flags, 0) && DBTEST(S.bcflag, 0); }
-        else if (soy <= soz) { iface = 4 - rd.bity; jface = 2; openbcface = DBTEST(c.flags, 1) && DBTEST(S.bcflag, 1); }
-        else { iface = 6 - rd.bitz; jface = 3; openbcface = false; }
-        int nbr = c.nb[0];
-#pragma unroll
-        for (int n = 1; n < 6; n++) if (iface - 1 == n) nbr = c.nb[n];
-        int inextcell = nbr;
-        if (inextcell < 0) inextcell = dev_next_cell(S, xn, yn, zn, iface, jface, inextcell);
-        int kface, ic;
-        if (nbr >= 0 && !openbcface) { kface = iface; ic = icell; }
-        else { kface = ((iface - 1) ^ 1) + 1; ic = inextcell; iface = 0; }
         if (inextcell > 0) {
-            const int pn = cell_gp(S, inextcell, rd.ioct);
-            if (jface == 1) xn = (double)pt_coord(S, pn, 1);
-            else if (jface == 2) yn = (double)pt_coord(S, pn, 2);
-            else zn = (double)pt_coord(S, pn, 3);
+            if (jface == 1) xn = (double)snap;
+            else if (jface == 2) yn = (double)snap;
+            else zn = (double)snap;
         }
         const bool atbnd = (inextcell == 0 && iface >= 5);
         if ((MODES & 1) && !doneA) {
@@ -460,7 +490,7 @@ __device__ int march_forward(const DevState &S, const float *Ysh, const RayDir &
                 }
             }
         }
-        if (!atbnd) icell = inextcell;
+        if (!atbnd) { icell = inextcell; c = cn; }
         xe = xn; ye = yn; ze = zn;
     }
     if (S.counts && o.ol == 0) {

@@ -28,6 +28,20 @@ __global__ void build_ptrec_kernel(int npts, const float *gridpos, const float *
                             gridpos[3 * (size_t)ip + 2], total_ext[ip]);
 }
 
+// one 16-byte record per point with everything a new corner needs besides its coordinates:
+// SH block offset, NS, single-scatter count and the first single-scatter entry
+__global__ void build_ptsrc_kernel(int npts, int kmax, const int2 *srcrec, const int *sscount, const int2 *ssent,
+                                   int4 *ptsrc)
+{
+    int ip = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ip >= npts) return;
+    const int2 r = srcrec[ip];
+    const int cnt = sscount[ip];
+    int2 e = make_int2(1, 0);
+    if (cnt > 0) e = ssent[(size_t)ip * kmax];
+    ptsrc[ip] = make_int4(r.x, r.y | (cnt << 16), e.x, e.y);
+}
+
 // FIXED / VARIABLE_LAMBERTIAN_BOUNDARY for SRCTYPE='S' (shdomsub1.f:2438-2529): bottom BCRAD
 __global__ void lambertian_boundary_kernel(DevState S, const float *fluxes, float *bcrad)
 {
@@ -258,6 +272,12 @@ cudaError_t launch_build_cellrec(int ncells, const int *gridptr, const int *neig
 cudaError_t launch_build_ptrec(int npts, const float *gridpos, const float *total_ext, float4 *ptrec, cudaStream_t s)
 {
     build_ptrec_kernel<<<(npts + 255) / 256, 256, 0, s>>>(npts, gridpos, total_ext, ptrec);
+    return cudaGetLastError();
+}
+cudaError_t launch_build_ptsrc(int npts, int kmax, const int2 *srcrec, const int *sscount, const int2 *ssent,
+                               int4 *ptsrc, cudaStream_t s)
+{
+    build_ptsrc_kernel<<<(npts + 255) / 256, 256, 0, s>>>(npts, kmax, srcrec, sscount, ssent, ptsrc);
     return cudaGetLastError();
 }
 cudaError_t launch_lambertian_boundary(const DevState &S, const float *fluxes, float *bcrad, cudaStream_t s)
