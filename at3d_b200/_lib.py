@@ -6,7 +6,8 @@ import numpy as np
 from .state import StateDesc, GradDesc, i32, f32, f64, P
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'lib', 'libat3d_b200.so')
+# AT3D_B200_LIB: developer override used to compare kernel build variants on the GPU box
+LIB_PATH = os.environ.get('AT3D_B200_LIB') or os.path.join(_HERE, 'lib', 'libat3d_b200.so')
 ERRLEN = 600
 
 

@@ -16,6 +16,19 @@
 #define AT3D_OCT 8
 #define AT3D_RAY_THREADS 128
 #define AT3D_RAYS_PER_BLOCK (AT3D_RAY_THREADS / AT3D_OCT)
+// resident blocks per SM the ray kernels are compiled for (register budget): scalar / polarized
+#ifndef AT3D_MINB_FWD1
+#define AT3D_MINB_FWD1 3
+#endif
+#ifndef AT3D_MINB_FWD3
+#define AT3D_MINB_FWD3 2
+#endif
+#ifndef AT3D_MINB_ADJ1
+#define AT3D_MINB_ADJ1 3
+#endif
+#ifndef AT3D_MINB_ADJ3
+#define AT3D_MINB_ADJ3 2
+#endif
 // planar SH blocks are padded to full 128-byte lines (32 floats): an octet reads them with
 // 4 float4 per lane and iteration, no tail handling
 #define AT3D_SHPAD(ns) (((ns) + 31) & ~31)

@@ -832,7 +832,7 @@ __device__ int march_ray_adjoint(const DevState &S, const DevGrad &G, unsigned c
 }
 
 template <int NST>
-__global__ void __launch_bounds__(AT3D_RAY_THREADS)
+__global__ void __launch_bounds__(AT3D_RAY_THREADS, NST == 1 ? AT3D_MINB_ADJ1 : AT3D_MINB_ADJ3)
 adjoint_kernel(DevState S, DevGrad G, GradLayout L, int nrays, const float *camx, const float *camy,
                const float *camz, const double *cammu, const double *camphi, const RayPack *packs,
                const int *raypix, const double *adjw /*[NST,npix]*/, const double *ray_weights,

@@ -160,7 +160,7 @@ __global__ void prep_sh_kernel(DevState S, int tms, const int *shptr, const floa
 // Persistent grid; a warp draws four consecutive rays at a time from a global counter (rays differ
 // a lot in length: clear sky vs. cloud), one ray per octet.
 template <int NST, int MODES, typename OUTA>
-__global__ void __launch_bounds__(AT3D_RAY_THREADS)
+__global__ void __launch_bounds__(AT3D_RAY_THREADS, NST == 1 ? AT3D_MINB_FWD1 : AT3D_MINB_FWD3)
 forward_kernel(DevState S, int nrays, const float *camx, const float *camy, const float *camz,
                const double *cammu, const double *camphi, const RayPack *packs, OUTA *outA, double *outB,
                int correctinterpolate, int singlescatter, int nosurface, int maxsub,
