@@ -1,7 +1,7 @@
 // at3d_render.cu -- state preparation kernels and the RENDER kernel (sm_100a).
 // Replaces RENDER / INTEGRATE_1RAY / COMPUTE_SOURCE_1CELL[_UNPOL] / FIND_BOUNDARY_RADIANCE
 // (src/polarized/shdomsub4.f:93-286, shdomsub2.f:2311-3192 of the AT3D reference).
-#include "at3d_ray.cuh"
+#include "at3d_tray.cuh"
 #include "at3d_host.h"
 
 // ------------------------------------------------------------------------------------------
@@ -210,6 +210,71 @@ forward_kernel(DevState S, int nrays, const float *camx, const float *camy, cons
     }
 }
 
+// Thread-per-ray variant for NSTOKES=1 (at3d_tray.cuh): a warp draws 32 consecutive rays at a time.
+template <int MODES, typename OUTA>
+__global__ void __launch_bounds__(256)
+forward_kernel_t(DevState S, int nrays, const float *camx, const float *camy, const float *camz,
+                 const double *cammu, const double *camphi, const RayPack *packs, OUTA *outA, double *outB,
+                 int correctinterpolate, int singlescatter, int nosurface, int maxsub,
+                 int *trace_cells, int trace_cap, int *trace_n, int *trace_nsub, RayErr *err, int *ray_counter)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int bt = blockDim.x, lane = threadIdx.x & 31;
+    float4 *Y4 = (float4 *)smem_raw + threadIdx.x;
+    for (;;) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(ray_counter, 32);
+        base = __shfl_sync(FULLMASK, base, 0);
+        if (base >= nrays) break;
+        const int iray = base + lane;
+        int ntrace = 0, nsubA = 0, nsubB = 0, npt = 0, nsh = 0, marched = 0;
+        if (iray < nrays) {
+            const double mu2 = __ldg(&cammu[iray]), phi2 = __ldg(&camphi[iray]);
+            const RayPack pk = dev_get_pack(S, packs, iray, camx, camy, camz, mu2, phi2);
+            double radA = 0.0, radB = 0.0;
+            if (pk.status == 2) set_err(err, 2, iray);
+            else if (pk.status == 0) {
+                RayDir rd;
+                dev_ray_dir(S, pk, rd);
+                thread_ylmall_unpol(S, (float)mu2, (float)phi2, (float *)Y4, bt);
+                const float sky = (-mu2 > 0.0) ? dev_sky_radiance(S, (float)mu2, (float)phi2) : 0.0f;
+                const int e = thread_march_forward<MODES>(S, Y4, bt, rd, mu2, pk.x0, pk.y0, pk.z0, sky,
+                                                          correctinterpolate != 0, singlescatter != 0, nosurface != 0,
+                                                          maxsub, radA, radB,
+                                                          trace_cells ? trace_cells + (size_t)trace_cap * iray : nullptr,
+                                                          trace_cap, ntrace, nsubA, nsubB, npt, nsh);
+                if (e) set_err(err, e, iray);
+                else marched = 1;
+            }
+            if (MODES & 1) outA[iray] = (OUTA)radA;
+            if (MODES & 2) outB[iray] = radB;
+            if (trace_n) { trace_n[iray] = ntrace; trace_nsub[iray] = (MODES & 1) ? nsubA : nsubB; }
+        }
+        __syncwarp();
+        if (S.counts) {
+            const int c0 = __reduce_add_sync(FULLMASK, marched ? ntrace : 0), c1 = __reduce_add_sync(FULLMASK, marched ? npt : 0);
+            const int c2 = __reduce_add_sync(FULLMASK, marched ? nsh : 0);
+            const int c4 = __reduce_add_sync(FULLMASK, marched ? ((MODES & 1) ? nsubA : nsubB) : 0);
+            const int c5 = __reduce_add_sync(FULLMASK, marched);
+            if (lane == 0) {
+                atomicAdd(&S.counts[0], (unsigned long long)c0); atomicAdd(&S.counts[1], (unsigned long long)c1);
+                atomicAdd(&S.counts[2], (unsigned long long)c2); atomicAdd(&S.counts[4], (unsigned long long)c4);
+                atomicAdd(&S.counts[5], (unsigned long long)c5);
+            }
+        }
+    }
+}
+
+// threads per block of the thread-per-ray kernels: as many YLMDIR columns (4*NLMP bytes) as fit
+int tray_block_threads(const DevState &S)
+{
+    if (S.nstokes != 1) return 0;
+    const size_t per = (size_t)S.nlmp * sizeof(float);
+    int bt = (int)((220 * 1024) / per) & ~31;
+    if (bt > 256) bt = 256;
+    return bt >= 64 ? bt : 0;
+}
+
 size_t render_smem_bytes(const DevState &S)
 {
     return (size_t)AT3D_RAYS_PER_BLOCK * S.ny_comp * S.nlmp * sizeof(float);
@@ -240,9 +305,31 @@ cudaError_t launch_forward(const DevState &S, int nrays, const float *camx, cons
                            RayErr *err, int *ray_counter, cudaStream_t stream)
 {
     if (nrays <= 0) return cudaSuccess;
-    const size_t smem = render_smem_bytes(S);
     cudaError_t ce = cudaMemsetAsync(ray_counter, 0, sizeof(int), stream);
     if (ce != cudaSuccess) return ce;
+    const int bt = tray_block_threads(S);
+    if (bt > 0) {
+        const size_t smem_t = (size_t)bt * S.nlmp * sizeof(float);
+        int dev = 0, nsm = 148, per_sm = 1;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+#define LAUNCHT(MODES, OUTA, outa)                                                                 \
+        {                                                                                          \
+            cudaFuncSetAttribute(forward_kernel_t<MODES, OUTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t); \
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, forward_kernel_t<MODES, OUTA>, bt, smem_t);    \
+            if (per_sm < 1) per_sm = 1;                                                            \
+            const long want = ((long)nrays + bt - 1) / bt, cap = (long)nsm * per_sm;               \
+            forward_kernel_t<MODES, OUTA><<<(int)(want < cap ? want : cap), bt, smem_t, stream>>>(S, nrays, camx, camy, \
+                camz, cammu, camphi, packs, outa, out_tot, correctinterpolate, singlescatter, nosurface, maxsub,  \
+                trace_cells, trace_cap, trace_n, trace_nsub, err, ray_counter);                    \
+        }
+        if (modes == 3) LAUNCHT(3, double, out_f64)
+        else if (out_f64) LAUNCHT(1, double, out_f64)
+        else LAUNCHT(1, float, out_f32)
+#undef LAUNCHT
+        return cudaGetLastError();
+    }
+    const size_t smem = render_smem_bytes(S);
 #define LAUNCH(NST, MODES, OUTA, outa)                                                            \
     {                                                                                             \
         const int nb = persistent_blocks(forward_kernel<NST, MODES, OUTA>, nrays, smem);          \
