@@ -110,7 +110,7 @@ extern "C" int at3d_state_destroy(at3d_state *st)
     for (void *p : st->grad_owned) cudaFree(p);
     st->pix.release(); st->work.release();
     st->rays.release(); st->out.release(); st->trace.release(); st->misc.release();
-    st->slabs.release(); st->err.release();
+    st->slabs.release(); st->err.release(); st->recs.release();
     delete st;
     return 0;
 }
@@ -351,7 +351,7 @@ extern "C" int at3d_render(at3d_state *st, const at3d_rays *rays, float *stokes,
     if (kernel_ms) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, stream); }
     CUDA_TRY(launch_forward(st->S, (int)n, camx, camy, camz, cammu, camphi, packs, out_d, nullptr, nullptr, 1,
                             correctinterpolate, singlescatter, nosurface, 0, tc, tcap, tn, ts,
-                            (RayErr *)st->err.p, st->ray_counter, stream));
+                            (RayErr *)st->err.p, st->ray_counter, nullptr, stream));
     if (kernel_ms) cudaEventRecord(e1, stream);
     if (host) {
         CUDA_TRY(cudaMemcpyAsync(stokes, out_d, n * nst * sizeof(float), cudaMemcpyDeviceToHost, stream));

@@ -5,21 +5,22 @@
 //   COMPUTE_ADJOINT_WEIGHTS :3969-4034, COMPUTE_RADIANCE_DERIVATIVE_ADJOINT :4037-4114,
 //   COMPUTE_DIRECT_BEAM_DERIV_ADJOINT :4117-4143.
 //
-// Design (DESIGN.md "Gradient kernels"): one octet (8 lanes) per ray, same bit-exact FP64 walk as RENDER.
-//  * Everything in COMPUTE_SOURCE_GRAD_1CELL that does not depend on the ray -- the mixed Legendre
-//    tables LEGENT/LEGENP/DLEGP and DLEGT(l) per (grid point, property corner, unknown) -- is
-//    evaluated once per cost-function evaluation by grad_prep_kernel (at attach time) and kept in HBM.
-//  * The reference evaluates the radiance SH contraction COMPUTE_SOURCE_DIRECTION 8*NUMDER times per
-//    new grid point.  It is linear in the Legendre table, so the octet forms the per-degree shell sums
-//    sum_m RADIANCE(.,j)*YLMDIR(.,j) once (radiance SH read once per (ray, point)) and every
-//    (corner, unknown) then costs one dot product of length (ML+1)*{1|4}; lane = property corner.
-//  * GRAD8 is contracted with the per-ray adjoint weight at once, so a cell corner keeps 8*NUMDER
-//    scalars (a shared-memory row) instead of the reference's five NSTOKES*8*8*NUMDER arrays; rows
-//    follow their grid point from cell to cell.
-//  * The backward cumulative sum over saved sub-intervals (PASSEDRAD) becomes "total - running", the
-//    total coming from the forward pass (same arithmetic); nothing is saved per sub-interval.
-//  * Sub-interval weights accumulate in registers (lane n owns corner n); global memory is touched
-//    once per cell and corner with red.global.add.f64, never inside the sub-interval loop.
+// Design (DESIGN.md "Gradient kernels"): the derivative pass is split into two small kernels.
+//  * weights_kernel (phase A): the bit-exact ADJOINT_INTEGRATE_1RAY walk, one octet per ray.  Per visit
+//    of a grid point (from the cell where it becomes a corner to the cell where it stops being one) it
+//    accumulates in registers the two scalars the gradient is linear in -- W (source term,
+//    shdomsub4.f:3692-3764) and G (radiance term, COMPUTE_RADIANCE_DERIVATIVE_ADJOINT, with the
+//    backward cumulative sum PASSEDRAD rewritten as "total - running") -- and writes one 32-byte
+//    record (point, SRCEXT8/EXT, W, G) per visit.  The forward pass counted the visits per ray, so the
+//    records of a ray are contiguous.  BEAM_WEIGHT is accumulated here as well.
+//  * apply_kernel (phase B): one octet per ray contracts, for every record, the point's precomputed
+//    gradient SH rows with YLMDIR, adds the scalar single-scatter terms and issues one
+//    red.global.add.f64 per (property corner, unknown).  No geometry, no FP64 chains, small code.
+//  * Everything in COMPUTE_SOURCE_GRAD_1CELL that does not depend on the ray (LEGENT/LEGENP/DLEGP,
+//    DLEGT(l), the factors of the single-scatter terms) is evaluated once per cost-function evaluation
+//    by grad_prep_kernel; DLEGT is folded with the radiance into SH rows XI*DLEGT(l_j)*RADIANCE(.,j),
+//    so the reference's 8*NUMDER COMPUTE_SOURCE_DIRECTION calls per new point become one SH dot
+//    product per non-zero property corner.
 #include <cstdio>
 #include <cstring>
 #include <cstdarg>
@@ -28,29 +29,14 @@
 #include "at3d_host.h"
 #include "at3d_ray.cuh"
 
-#define AT3D_GRAD_ROWS 16       // shared-memory rows of contracted GRAD8 per octet (8 live + 8 spare)
 #define AT3D_DTAB_FLAG 0x40000000   // list entry refers to DPHASETAB instead of PHASETAB
 
-// ------------------------------------------------------------------------------------------
-// per-octet shared scratch of the adjoint kernel (byte offsets)
-// ------------------------------------------------------------------------------------------
-struct GradLayout {
-    int y, vsh, rowd, rowx, rowib, wacc, total;
+// one record per visit of a grid point by a ray (phase A -> phase B)
+struct __align__(16) VisitRec {
+    int ip;                 // grid point (1-based)
+    float srcfull[3];       // SRCEXT8 before the multiplication by the extinction
+    double W, G;            // accumulated source-term / radiance-term weights
 };
-
-__host__ __device__ inline GradLayout grad_layout(int ny_comp, int nlmp, int ml, int numder)
-{
-    GradLayout L;
-    int o = 0;
-    L.y = o;      o += ny_comp * nlmp * 4;
-    L.rowd = o;   o += AT3D_GRAD_ROWS * 8 * numder * 8;           // double D[row][nb][numder]
-    L.wacc = o;   o += 2 * 8 * 8;                                 // double W[8], G[8]
-    L.rowx = o;   o += AT3D_GRAD_ROWS * 8 * numder * 4;           // float  XG[row][nb][numder]
-    L.rowib = o;  o += AT3D_GRAD_ROWS * 8 * 4 + 8 * 4;            // int    IB[row][nb], ROWOF[8]
-    L.vsh = o;    o += 3 * (ml + 1) * 4;                          // float V1, V5, V6 (no delta-M only)
-    L.total = (o + 15) & ~15;
-    return L;
-}
 
 // "unscaling" of a delta-M scaled tabulated Legendre entry (shdomsub4.f:1905-1925)
 __device__ __forceinline__ float unscale_leg(float x, int k /*0-based component*/, int l, int ml, bool deltam,
@@ -343,100 +329,474 @@ __global__ void grad_prep_kernel(DevState S, DevGrad G, int4 *rowrec, int4 *spre
     }
 }
 
+// Truncated single scattering of one grid point without delta-M (shdomsub4.f:1723-1760,1781): sum over
+// species of DA*LEGENT(.,l)*sum_m YLMDIR*YLMSUN for the shells present in SOURCE (octet-cooperative).
+template <int NST>
+__device__ __forceinline__ void nodeltam_singscat(const DevState &S, int ip, int sns, float ext, const float *Vsh,
+                                                  const Oct &o, float (&b)[NST])
+{
+    const int nstleg = S.nstleg, ml = S.ml, mm = S.mm, ipz = ip - 1;
+    const int nlt = nstleg * (S.nleg + 1);
+    const bool interp_new = S.interp_new != 0;
+    const float dirflux = __ldg(&S.dirflux[ipz]);
+    const float secmu0 = (float)(1.0 / fabs((double)S.solarmu));
+    float t[NST];
+#pragma unroll
+    for (int k = 0; k < NST; k++) t[k] = 0.0f;
+    for (int ipa = 0; ipa < S.npart; ipa++) {
+        float w;
+        if (ext == 0.0f) w = 1.0f; else w = __ldg(&S.extinct[ipz + (size_t)S.npts * ipa]) / ext;
+        if (w == 0.0f) continue;
+        const int *iph = S.iphase + (size_t)S.nq * (ipz + (size_t)S.npts * ipa);
+        const float *pw = S.phaseinterpwt + (size_t)S.nq * (ipz + (size_t)S.npts * ipa);
+        const bool single = (!interp_new) || (__ldg(&pw[0]) >= S.phasemax);
+        const float da = __ldg(&S.albedo[ipz + (size_t)S.npts * ipa]) * dirflux * secmu0 * w;
+        for (int l = o.ol; l <= ml; l += 8) {
+            const int me = l < mm ? l : mm;
+            if (sh_index(l, -me, mm) >= sns) continue;
+            float l1, l5 = 0.0f;
+            if (single) {
+                l1 = __ldg(&S.legen[(size_t)nlt * (__ldg(&iph[0]) - 1) + nstleg * l]);
+                if (nstleg > 1) l5 = __ldg(&S.legen[(size_t)nlt * (__ldg(&iph[0]) - 1) + nstleg * l + 4]);
+            } else {
+                l1 = 0.0f;
+                for (int q = 0; q < S.nq; q++) {
+                    const float wq = __ldg(&pw[q]);
+                    if (wq <= 1e-5f) continue;
+                    l1 = l1 + __ldg(&S.legen[(size_t)nlt * (__ldg(&iph[q]) - 1) + nstleg * l]) * wq;
+                    if (nstleg > 1) l5 = l5 + __ldg(&S.legen[(size_t)nlt * (__ldg(&iph[q]) - 1) + nstleg * l + 4]) * wq;
+                }
+            }
+            t[0] = t[0] + da * l1 * Vsh[l];
+            if (NST > 1) {
+                t[1] = t[1] + da * l5 * Vsh[(ml + 1) + l];
+                t[NST - 1] = t[NST - 1] + da * l5 * Vsh[2 * (ml + 1) + l];
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < NST; k++) b[k] = oct_sum(o.m, t[k]);
+}
+
 // The values lane n keeps for corner n of the current cell in the adjoint walk.
 template <int NST>
 struct GCorner {
-    int pt, row;            // grid point; shared-memory row of its contracted GRAD8
+    int pt;
     float x, y, z, ext;
-    float src[NST], ss[NST];
+    float src[NST], ss[NST], srcfull[NST];
+    double W, G;            // weights accumulated since the point became a corner
 };
 
+template <int NST>
+__device__ __forceinline__ void write_visit(VisitRec *dst, const GCorner<NST> &K)
+{
+    int4 a;
+    a.x = K.pt;
+    a.y = __float_as_int(K.srcfull[0]);
+    a.z = NST > 1 ? __float_as_int(K.srcfull[NST > 1 ? 1 : 0]) : 0;
+    a.w = NST > 2 ? __float_as_int(K.srcfull[NST > 2 ? 2 : 0]) : 0;
+    *(int4 *)dst = a;
+    *((double2 *)dst + 1) = make_double2(K.W, K.G);
+}
+
 // ------------------------------------------------------------------------------------------
-// COMPUTE_SOURCE_GRAD_1CELL for one new grid point (the 8 lanes of the octet cooperate): forward
-// values of the point and its contracted GRAD8 row (written to shared-memory row `row`).
-// ip, soff/sns (SH block), b (exact single scatter), ext, gp (gradient record) come from the lane
-// that owns the corner.
+// Phase A: ADJOINT_INTEGRATE_1RAY walk of one ray (one octet), forward values only; emits VisitRecs.
 // ------------------------------------------------------------------------------------------
 template <int NST>
-__device__ __forceinline__ void eval_point_grad(const DevState &S, const DevGrad &G, int ip, int soff, int sns,
-                                const float (&bin)[NST], float ext, const int4 gp, unsigned char *sm,
-                                const GradLayout &L, const RayDir &rd, const double (&adj)[NST], const Oct &o,
-                                int row, float (&src_out)[NST], float (&ss_out)[NST])
+__device__ int march_weights(const DevState &S, const DevGrad &G, const float *Ysh, const float *Vsh,
+                             const RayDir &rd, double mu2, double x0, double y0, double z0, float sky,
+                             const double (&adj)[NST], const double (&total)[NST], const Oct &o,
+                             VisitRec *rec, int cap, double *beam_weight,
+                             int *trace_cells, int trace_cap, int &ntrace, int &nsub, int &nrec)
 {
-    const float *Ysh = (const float *)(sm + L.y);
-    const float *Vsh = (const float *)(sm + L.vsh);
-    const int nlmp = S.nlmp, nstleg = S.nstleg, ml = S.ml, mm = S.mm;
-    const int nd = G.numder;
+    double xe = x0, ye = y0, ze = z0, transmit = 1.0;
+    double radout[NST];
+    float ext1 = 0.0f, srcext1[NST];
+#pragma unroll
+    for (int k = 0; k < NST; k++) { radout[k] = 0.0; srcext1[k] = 0.0f; }
+    const int p1c = cell_gp(S, 1, 1), p8c = cell_gp(S, 1, 8);
+    const double eps = (double)(1.0e-5f * (pt_coord(S, p8c, 3) - pt_coord(S, p1c, 3)));
+    const bool exact_ss = G.exact_single_scatter != 0;
     const bool deltam = S.deltam != 0;
-    const int ipz = ip - 1;
-    // ---------------- forward part (shdomsub4.f:1660-1785) ----------------
-    float a[NST], b[NST];
+    int icell = dev_locate_grid_cell(S, xe, ye, ze);
+    int iface = 0, npassed = 1, jf = 0;
+    bool done = false;
+    int npt_eval = 0, nsh_eval = 0;
+    GCorner<NST> K;
+    K.pt = 0; K.x = K.y = K.z = K.ext = 0.0f; K.W = 0.0; K.G = 0.0;
 #pragma unroll
-    for (int k = 0; k < NST; k++) { a[k] = 0.0f; b[k] = bin[k]; }
-    sh_dot_partial<NST>(S.shsrc + soff, AT3D_SHPAD(sns), Ysh, nlmp, o, a);
+    for (int k = 0; k < NST; k++) { K.src[k] = 0.0f; K.ss[k] = 0.0f; K.srcfull[k] = 0.0f; }
+    ntrace = 0; nsub = 0; nrec = 0;
+    int err = 0;
+    bool any_cell = false;
+    CellRec c;
+    if (icell > 0) c = load_cell(S, icell);
+    while (!done && icell > 0) {
+        if (trace_cells && o.ol == 0 && ntrace < trace_cap) trace_cells[ntrace] = icell;
+        ntrace++;
+        // ---- corners: DONEFACE carry-over (values and accumulated weights), records of the points that left ----
+        {
+            const int myp = own_corner(c, o.ol);
+            const int from = o.ol ^ (jf == 1 ? 1 : jf == 2 ? 2 : 4);
+            const int cand = __shfl_sync(o.m, K.pt, from, 8);
+            const bool hit = (jf != 0) && (cand == myp);
+            // the old corner of this lane survives iff lane `from` (its only possible heir) hit it
+            const bool heir_hit = __shfl_sync(o.m, (int)hit, from, 8) != 0;
+            const bool evict = any_cell && !heir_hit;
+            const unsigned ev = oct_ballot(o, evict);
+            if (evict) {
+                const int k = nrec + __popc(ev & ((1u << o.ol) - 1));
+                if (k < cap) write_visit<NST>(rec + k, K); else err = 5;
+            }
+            nrec += __popc(ev);
+            const int src_lane = hit ? from : o.ol;
+            K.x = __shfl_sync(o.m, K.x, src_lane, 8); K.y = __shfl_sync(o.m, K.y, src_lane, 8);
+            K.z = __shfl_sync(o.m, K.z, src_lane, 8); K.ext = __shfl_sync(o.m, K.ext, src_lane, 8);
+            K.W = __shfl_sync(o.m, K.W, src_lane, 8); K.G = __shfl_sync(o.m, K.G, src_lane, 8);
 #pragma unroll
-    for (int k = 0; k < NST; k++) a[k] = oct_sum(o.m, a[k]);
+            for (int k = 0; k < NST; k++) {
+                K.src[k] = __shfl_sync(o.m, K.src[k], src_lane, 8);
+                K.ss[k] = __shfl_sync(o.m, K.ss[k], src_lane, 8);
+                K.srcfull[k] = __shfl_sync(o.m, K.srcfull[k], src_lane, 8);
+            }
+            K.pt = myp;
+            any_cell = true;
+            int soff = 0, sns = 0;
+            float b[NST];
+#pragma unroll
+            for (int k = 0; k < NST; k++) b[k] = 0.0f;
+            if (!hit) {
+                load_corner<NST>(S, myp, rd, K.x, K.y, K.z, K.ext, soff, sns, b);
+                K.W = 0.0; K.G = 0.0;
+            }
+            unsigned need = oct_ballot(o, !hit);
+            while (need) {
+                const int n = __ffs(need) - 1;
+                need &= need - 1;
+                const int off = __shfl_sync(o.m, soff, n, 8), ns = __shfl_sync(o.m, sns, n, 8);
+                float a[NST];
+#pragma unroll
+                for (int k = 0; k < NST; k++) a[k] = 0.0f;
+                sh_dot_partial<NST>(S.shsrc + off, AT3D_SHPAD(ns), Ysh, S.nlmp, o, a);
+#pragma unroll
+                for (int k = 0; k < NST; k++) a[k] = oct_sum(o.m, a[k]);
+                float bt[NST];
+#pragma unroll
+                for (int k = 0; k < NST; k++) bt[k] = 0.0f;
+                if (!deltam) {
+                    const int ipn = __shfl_sync(o.m, myp, n, 8);
+                    const float extn_ = __shfl_sync(o.m, K.ext, n, 8);
+                    nodeltam_singscat<NST>(S, ipn, ns, extn_, Vsh, o, bt);
+                }
+                npt_eval++; nsh_eval += ns;
+                if (o.ol == n) {
+#pragma unroll
+                    for (int k = 0; k < NST; k++) {
+                        const float bb = deltam ? b[k] : bt[k];
+                        K.srcfull[k] = deltam ? a[k] + bb : a[k];
+                        K.ss[k] = bb * K.ext;
+                        K.src[k] = G.singlescatter ? K.ss[k] : K.srcfull[k] * K.ext;
+                    }
+                }
+            }
+        }
+        float e8[8], s8[NST][8];
+#pragma unroll
+        for (int n = 0; n < 8; n++) {
+            e8[n] = __shfl_sync(o.m, K.ext, n, 8);
+#pragma unroll
+            for (int k = 0; k < NST; k++) s8[k][n] = __shfl_sync(o.m, K.src[k], n, 8);
+        }
+        const float q1x = __shfl_sync(o.m, K.x, 0, 8), q1y = __shfl_sync(o.m, K.y, 0, 8), q1z = __shfl_sync(o.m, K.z, 0, 8);
+        const float q8x = __shfl_sync(o.m, K.x, 7, 8), q8y = __shfl_sync(o.m, K.y, 7, 8), q8z = __shfl_sync(o.m, K.z, 7, 8);
+        const float qox = __shfl_sync(o.m, K.x, 8 - rd.ioct, 8), qoy = __shfl_sync(o.m, K.y, 8 - rd.ioct, 8),
+                    qoz = __shfl_sync(o.m, K.z, 8 - rd.ioct, 8);
+        const double delx = (double)(q8x - q1x), dely = (double)(q8y - q1y), delz = (double)(q8z - q1z);
+        const double invdelx = (delx <= 0.0) ? 1.0 : 1.0 / delx;
+        const double invdely = (dely <= 0.0) ? 1.0 : 1.0 / dely;
+        const double invdelz = 1.0 / delz;
+        double u = (xe - q1x) * invdelx, v = (ye - q1y) * invdely, w = (ze - q1z) * invdelz;
+        double fc[8];
+        interp_kernel(u, v, w, fc);
+        double fown = interp_kernel_own(u, v, w, o.ol);
+#pragma unroll
+        for (int k = 0; k < NST; k++) srcext1[k] = (float)fcsum(fc, s8[k]);
+        srcext1[0] = fmaxf(0.0f, srcext1[0]);
+        double ext1d = fcsum(fc, e8);
+        ext1 = (float)ext1d;
+        const bool ipinx = DBTEST(c.flags, 0) &&
+            !(DBTEST(S.bcflag, 0) && ((rd.cx > 0 && xe < rd.xm) || (rd.cx < 0 && xe > rd.xm)));
+        const bool ipiny = DBTEST(c.flags, 1) &&
+            !(DBTEST(S.bcflag, 1) && ((rd.cy > 0 && ye < rd.ym) || (rd.cy < 0 && ye > rd.ym)));
+        const double sox = ipinx ? (double)1.0e20f : (qox - xe) * rd.cxinv;
+        const double soy = ipiny ? (double)1.0e20f : (qoy - ye) * rd.cyinv;
+        const double soz = (qoz - ze) * rd.czinv;
+        const double so = fmin(fmin(sox, soy), soz);
+        if (so < -eps) { err = 1; break; }
+        double xn = xe + so * rd.cx, yn = ye + so * rd.cy, zn = ze + so * rd.cz;
+        // ---- exit face and next cell; its record is requested before the sub-interval loop ----
+        int jface;
+        bool openbcface;
+        if (sox <= soz && sox <= soy) { iface = 2 - rd.bitx; jface = 1; openbcface = DBTEST(c.flags, 0) && DBTEST(S.bcflag, 0); }
+        else if (soy <= soz) { iface = 4 - rd.bity; jface = 2; openbcface = DBTEST(c.flags, 1) && DBTEST(S.bcflag, 1); }
+        else { iface = 6 - rd.bitz; jface = 3; openbcface = false; }
+        int nbr = c.nb[0];
+#pragma unroll
+        for (int n = 1; n < 6; n++) if (iface - 1 == n) nbr = c.nb[n];
+        int inextcell = nbr;
+        if (inextcell < 0) inextcell = dev_next_cell(S, xn, yn, zn, iface, jface, inextcell);
+        int kface, ic;
+        if (nbr >= 0 && !openbcface) { kface = iface; ic = icell; }
+        else { kface = ((iface - 1) ^ 1) + 1; ic = inextcell; iface = 0; }
+        CellRec cn = c;
+        float snap = 0.0f;
+        if (inextcell > 0) {
+            cn = load_cell(S, inextcell);
+            int pn = cn.gp[0];
+#pragma unroll
+            for (int n = 1; n < 8; n++) if (rd.ioct - 1 == n) pn = cn.gp[n];
+            snap = pt_coord(S, pn, jface);
+        }
+        u = (xn - q1x) * invdelx; v = (yn - q1y) * invdely; w = (zn - q1z) * invdelz;
+        float extn;
+        { double fcn[8]; interp_kernel(u, v, w, fcn); extn = (float)fcsum(fcn, e8); }
+        const double taugrid = so * 0.5f * (ext1 + extn);
+        int ntau = 1 + (int)(taugrid / S.tautol);
+        if (ntau < 1) ntau = 1;
+        const double dels = so / ntau;
+        float bw[NST];                               // SRCSINGSCAT of the own corner in this cell
+#pragma unroll
+        for (int k = 0; k < NST; k++) bw[k] = 0.0f;
+        for (int it = 1; it <= ntau; it++) {
+            const double f1 = fown;                  // previous interpolation weight of the own corner
+            const double s = it * dels;
+            const double xi = xe + s * rd.cx, yi = ye + s * rd.cy, zi = ze + s * rd.cz;
+            u = (xi - q1x) * invdelx; v = (yi - q1y) * invdely; w = (zi - q1z) * invdelz;
+            interp_kernel(u, v, w, fc);
+            fown = interp_kernel_own(u, v, w, o.ol);
+            const double f0 = fown;
+            float ext0, srcext0[NST];
+#pragma unroll
+            for (int k = 0; k < NST; k++) srcext0[k] = (float)fcsum(fc, s8[k]);
+            const double ext0d = fcsum(fc, e8);
+            ext0 = (it != ntau) ? (float)ext0d : extn;
+            srcext0[0] = fmaxf(0.0f, srcext0[0]);
+            const double ext = (double)(0.5f * (ext0 + ext1));
+            if (ext != 0.0) {
+                const double tau = ext * dels;
+                const double abscell = tau * (1.0f - 0.5f * tau * (1.0f - 0.33333333333f * tau));
+                const double transcell = 1.0f - abscell;
+                const double corr = dels * (1.0f - 0.05f * (ext1 - ext0) * dels);
+                double rcur = 0.0, rnext = 0.0;      // adj . PASSEDRAD(kk), adj . PASSEDRAD(kk+1)
+#pragma unroll
+                for (int k = 0; k < NST; k++) rcur += adj[k] * (total[k] - radout[k]);
+                rcur = rcur / transmit;
+#pragma unroll
+                for (int k = 0; k < NST; k++) {
+                    const double src = (0.5f * (srcext0[k] + srcext1[k])
+                        + 0.08333333333f * (ext0 * srcext1[k] - ext1 * srcext0[k]) * dels
+                          * (1.0f - 0.05f * (ext1 - ext0) * dels)) / ext;
+                    radout[k] = radout[k] + transmit * src * abscell;
+                }
+                const double tnext = transmit * transcell;
+#pragma unroll
+                for (int k = 0; k < NST; k++) rnext += adj[k] * (total[k] - radout[k]);
+                rnext = rnext / tnext;
+                // lane-private corner weights
+                K.W += transmit * abscell * ((0.5f * (f0 + f1) + 0.08333333333f * (ext0 * f1 - ext1 * f0) * corr) / ext);
+                if (exact_ss) {
+#pragma unroll
+                    for (int k = 0; k < NST; k++) {
+                        float ss0 = (float)(f0 * K.ss[k]), ss1 = (float)(f1 * K.ss[k]);
+                        if (k == 0) { ss0 = fmaxf(0.0f, ss0); ss1 = fmaxf(0.0f, ss1); }
+                        bw[k] = (float)(bw[k] + transmit * abscell *
+                                (0.5f * (ss0 + ss1) + 0.08333333333f * (ext0 * ss1 - ext1 * ss0) * corr) / ext);
+                    }
+                }
+                // radiance term (COMPUTE_RADIANCE_DERIVATIVE_ADJOINT): extinctions re-interpolated in double
+                const double aext = 0.5f * (ext0d + ext1d);
+                if (aext != 0.0) {
+                    const double g0 = -rnext * f0, g1 = -rcur * f1;
+                    const double ag = (0.5f * (g0 + g1) + 0.08333333333f * (ext0d * g1 - ext1d * g0) * dels
+                                       * (1.0f - 0.05f * (ext1d - ext0d) * dels)) / aext;
+                    K.G += ag * transmit * abscell;
+                }
+                transmit = tnext;
+                npassed++;
+                nsub++;
+                if (npassed > G.maxsub) { err = 4; break; }
+            } else {
+#pragma unroll
+                for (int k = 0; k < NST; k++) bw[k] = 0.0f;
+            }
+            ext1 = ext0; ext1d = ext0d;
+#pragma unroll
+            for (int k = 0; k < NST; k++) srcext1[k] = srcext0[k];
+        }
+        if (err) break;
+        if (exact_ss) {
+            double bsum = 0.0;
+#pragma unroll
+            for (int k = 0; k < NST; k++) bsum += adj[k] * (double)bw[k];
+            if (bsum != 0.0) atomicAdd(&beam_weight[K.pt - 1], bsum);
+        }
+        if (inextcell > 0) {
+            if (jface == 1) xn = (double)snap;
+            else if (jface == 2) yn = (double)snap;
+            else zn = (double)snap;
+        }
+        if (transmit < S.transcut) {
+            done = true;
+        } else if (inextcell == 0 && iface >= 5) {
+            done = true;
+            float radbnd[NST];
+            int boundpts[4]; double boundinterp[4], dirrad1[4];
+            const int e = boundary_radiance<NST, true>(S, xn, yn, (float)mu2, sky, ic, kface, radbnd,
+                                                       boundpts, boundinterp, dirrad1);
+            if (e) { err = e; break; }
+            if (exact_ss && o.ol < 4) {
+                int bp = boundpts[0]; double bi = boundinterp[0], dr = dirrad1[0];
+#pragma unroll
+                for (int n = 1; n < 4; n++) if (o.ol == n) { bp = boundpts[n]; bi = boundinterp[n]; dr = dirrad1[n]; }
+                const double val = adj[0] * transmit * bi * dr;
+                if (val != 0.0) atomicAdd(&beam_weight[bp - 1], val);
+            }
+        } else {
+            icell = inextcell; c = cn;
+        }
+        jf = jface;
+        xe = xn; ye = yn; ze = zn;
+    }
+    // the corners of the last cell
+    if (any_cell && !err) {
+        const int k = nrec + o.ol;
+        if (k < cap) write_visit<NST>(rec + k, K); else err = 5;
+        nrec += 8;
+    }
+    err = __reduce_max_sync(o.m, err);
+    if (S.counts && o.ol == 0) {
+        atomicAdd(&S.counts[0], (unsigned long long)ntrace);
+        atomicAdd(&S.counts[1], (unsigned long long)npt_eval);
+        atomicAdd(&S.counts[2], (unsigned long long)nsh_eval);
+        atomicAdd(&S.counts[4], (unsigned long long)nsub);
+        atomicAdd(&S.counts[5], 1ull);
+    }
+    return err;
+}
+
+// shell sums of YLMSUN*YLMDIR for the untruncated solar terms (no delta-M only)
+template <int NST>
+__device__ __forceinline__ void ray_vsh(const DevState &S, const float *Ysh, float *Vsh, const Oct &o)
+{
+    for (int l = o.ol; l <= S.ml; l += 8) {
+        const int me = l < S.mm ? l : S.mm;
+        const int jlo = sh_index(l, -me, S.mm);
+        float v1 = 0.0f, v5 = 0.0f, v6 = 0.0f;
+        for (int i = 0; i < 2 * me + 1; i++) {
+            const float ys = __ldg(&S.ylmsun[(size_t)S.nstleg * (jlo + i)]);
+            v1 = v1 + ys * Ysh[jlo + i];
+            if (NST > 1) { v5 = v5 + ys * Ysh[S.nlmp + jlo + i]; v6 = v6 + ys * Ysh[3 * S.nlmp + jlo + i]; }
+        }
+        Vsh[l] = v1; Vsh[(S.ml + 1) + l] = v5; Vsh[2 * (S.ml + 1) + l] = v6;
+    }
+    __syncwarp(o.m);
+}
+
+// per-ray setup shared by the two phases; returns false when the ray contributes nothing
+template <int NST>
+__device__ __forceinline__ bool ray_setup(const DevState &S, int iray, const float *camx, const float *camy,
+                                          const float *camz, const double *cammu, const double *camphi,
+                                          const RayPack *packs, const int *raypix, const double *adjw,
+                                          const double *ray_weights, const double *stokes_weights, float *Ysh,
+                                          float *Vsh, const Oct &o, RayErr *err, RayPack &pk, RayDir &rd,
+                                          double &mu2, double &phi2, double (&adj)[NST])
+{
+    mu2 = __ldg(&cammu[iray]); phi2 = __ldg(&camphi[iray]);
+    pk = dev_get_pack(S, packs, iray, camx, camy, camz, mu2, phi2);
+    if (pk.status == 2) { if (o.ol == 0) set_err(err, 2, iray); return false; }
+    if (pk.status != 0) return false;
+    const int pix = __ldg(&raypix[iray]);
+    const double rw = __ldg(&ray_weights[iray]);
+#pragma unroll
+    for (int k = 0; k < NST; k++)
+        adj[k] = __ldg(&adjw[k + NST * (size_t)pix]) * rw * __ldg(&stokes_weights[k + NST * (size_t)pix]);
+    dev_ray_dir(S, pk, rd);
+    __syncwarp(o.m);
+    group_ylmall(S, (float)mu2, (float)phi2, Ysh, o.ol, AT3D_OCT, o.m);
+    if (!S.deltam) ray_vsh<NST>(S, Ysh, Vsh, o);
+    return true;
+}
+
+template <int NST>
+__global__ void __launch_bounds__(AT3D_RAY_THREADS, NST == 1 ? AT3D_MINB_ADJ1 : AT3D_MINB_ADJ3)
+weights_kernel(DevState S, DevGrad G, int nrays, const float *camx, const float *camy,
+               const float *camz, const double *cammu, const double *camphi, const RayPack *packs,
+               const int *raypix, const double *adjw /*[NST,npix]*/, const double *ray_weights,
+               const double *stokes_weights, const double *total /*[NST,nrays]*/,
+               const int *recoff /*[nrays+1]*/, VisitRec *recs, int *nrec_out, double *beam_weight,
+               int *trace_cells, int trace_cap, int *trace_n, int *trace_nsub, RayErr *err, int *ray_counter)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const Oct o = oct_id();
+    const int lane = threadIdx.x & 31;
+    const int ysz = S.ny_comp * S.nlmp, vsz = (3 * (S.ml + 1) + 3) & ~3;
+    float *Ysh = (float *)smem_raw + (size_t)(threadIdx.x >> 3) * (ysz + vsz);
+    float *Vsh = Ysh + ysz;
+    for (;;) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(ray_counter, 32 / AT3D_OCT);
+        base = __shfl_sync(FULLMASK, base, 0);
+        if (base >= nrays) break;
+        const int iray = base + (lane >> 3);
+        if (iray < nrays) {
+            RayPack pk; RayDir rd; double mu2, phi2, adj[NST];
+            int ntrace = 0, nsub = 0, nrec = 0;
+            if (ray_setup<NST>(S, iray, camx, camy, camz, cammu, camphi, packs, raypix, adjw, ray_weights,
+                               stokes_weights, Ysh, Vsh, o, err, pk, rd, mu2, phi2, adj)) {
+                double tot[NST];
+#pragma unroll
+                for (int k = 0; k < NST; k++) tot[k] = __ldg(&total[k + NST * (size_t)iray]);
+                const float sky = (-mu2 > 0.0) ? dev_sky_radiance(S, (float)mu2, (float)phi2) : 0.0f;
+                const int r0 = __ldg(&recoff[iray]), r1 = __ldg(&recoff[iray + 1]);
+                const int e = march_weights<NST>(S, G, Ysh, Vsh, rd, mu2, pk.x0, pk.y0, pk.z0, sky, adj, tot, o,
+                                                 recs + r0, r1 - r0, beam_weight,
+                                                 trace_cells ? trace_cells + (size_t)trace_cap * iray : nullptr,
+                                                 trace_cap, ntrace, nsub, nrec);
+                if (e && o.ol == 0) set_err(err, e, iray);
+                if (e) nrec = 0;
+            }
+            if (o.ol == 0) {
+                nrec_out[iray] = nrec;
+                if (trace_n) { trace_n[iray] = ntrace; trace_nsub[iray] = nsub; }
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Phase B: COMPUTE_SOURCE_GRAD_1CELL's ray-dependent remainder for every visit record of a ray
+// (shdomsub4.f:1786-2019 with the tables of grad_prep_kernel) and the scatter into GRADOUT
+// (shdomsub4.f:3751-3764, 4101-4109).  One octet per ray.
+// ------------------------------------------------------------------------------------------
+template <int NST>
+__device__ __forceinline__ void apply_record(const DevState &S, const DevGrad &G, const VisitRec &rc,
+                                             const float *Ysh, const float *Vsh, const RayDir &rd,
+                                             const double (&adj)[NST], const Oct &o, double *gradout,
+                                             int &nrh_eval)
+{
+    const int nlmp = S.nlmp, ml = S.ml, nd = G.numder;
+    const bool deltam = S.deltam != 0;
+    const int ipz = rc.ip - 1;
+    const int4 gp = __ldg(&G.gptrec[ipz]);
+    const int nnz = gp.y >> 16, nrows = gp.y & 0xFFFF, nrp = (gp.w & 0xFF) * 32;
+    const float *dshp = G.dsh + (size_t)(unsigned)gp.z * 32;
+    nrh_eval += gp.w >> 8;
     float dirflux = 0.0f, secmu0 = 0.0f;
     if (!deltam || S.npart > 1) {
         dirflux = __ldg(&S.dirflux[ipz]);
         secmu0 = (float)(1.0 / fabs((double)S.solarmu));
     }
-    if (!deltam) {
-        // without delta-M SINGSCAT8 is the truncated single scattering (shdomsub4.f:1723-1760,1781):
-        // sum over species of DA*LEGENT(.,l)*sum_m YLMDIR*YLMSUN for the shells present in SOURCE
-        const int nlt = nstleg * (S.nleg + 1);
-        const bool interp_new = S.interp_new != 0;
-        float t[NST];
-#pragma unroll
-        for (int k = 0; k < NST; k++) t[k] = 0.0f;
-        for (int ipa = 0; ipa < S.npart; ipa++) {
-            float w;
-            if (ext == 0.0f) w = 1.0f; else w = __ldg(&S.extinct[ipz + (size_t)S.npts * ipa]) / ext;
-            if (w == 0.0f) continue;
-            const int *iph = S.iphase + (size_t)S.nq * (ipz + (size_t)S.npts * ipa);
-            const float *pw = S.phaseinterpwt + (size_t)S.nq * (ipz + (size_t)S.npts * ipa);
-            const bool single = (!interp_new) || (__ldg(&pw[0]) >= S.phasemax);
-            const float da = __ldg(&S.albedo[ipz + (size_t)S.npts * ipa]) * dirflux * secmu0 * w;
-            for (int l = o.ol; l <= ml; l += 8) {
-                const int me = l < mm ? l : mm;
-                if (sh_index(l, -me, mm) >= sns) continue;
-                float l1, l5 = 0.0f;
-                if (single) {
-                    l1 = __ldg(&S.legen[(size_t)nlt * (__ldg(&iph[0]) - 1) + nstleg * l]);
-                    if (nstleg > 1) l5 = __ldg(&S.legen[(size_t)nlt * (__ldg(&iph[0]) - 1) + nstleg * l + 4]);
-                } else {
-                    l1 = 0.0f;
-                    for (int q = 0; q < S.nq; q++) {
-                        const float wq = __ldg(&pw[q]);
-                        if (wq <= 1e-5f) continue;
-                        l1 = l1 + __ldg(&S.legen[(size_t)nlt * (__ldg(&iph[q]) - 1) + nstleg * l]) * wq;
-                        if (nstleg > 1) l5 = l5 + __ldg(&S.legen[(size_t)nlt * (__ldg(&iph[q]) - 1) + nstleg * l + 4]) * wq;
-                    }
-                }
-                t[0] = t[0] + da * l1 * Vsh[l];
-                if (NST > 1) {
-                    t[1] = t[1] + da * l5 * Vsh[(ml + 1) + l];
-                    t[NST - 1] = t[NST - 1] + da * l5 * Vsh[2 * (ml + 1) + l];
-                }
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < NST; k++) b[k] = oct_sum(o.m, t[k]);
-    }
-    float srcfull[NST];      // SRCEXT8 before the multiplication by the extinction
-#pragma unroll
-    for (int k = 0; k < NST; k++) {
-        srcfull[k] = deltam ? a[k] + b[k] : a[k];
-        ss_out[k] = b[k] * ext;
-        src_out[k] = G.singlescatter ? ss_out[k] : srcfull[k] * ext;
-    }
-    // ---------------- gradient part (shdomsub4.f:1786-2019), row by row ----------------
-    double *Drow = (double *)(sm + L.rowd) + (size_t)row * 8 * nd;
-    float *XGrow = (float *)(sm + L.rowx) + (size_t)row * 8 * nd;
-    int *IBrow = (int *)(sm + L.rowib) + row * 8;
-    for (int idr = 0; idr < nd; idr++) { Drow[o.ol * nd + idr] = 0.0; XGrow[o.ol * nd + idr] = 0.0f; }
-    const int nnz = gp.y >> 16, nrows = gp.y & 0xFFFF, nrp = (gp.w & 0xFF) * 32;
-    const float *dshp = G.dsh + (size_t)(unsigned)gp.z * 32;
     int last_idr = -1, last_ipa = -1;
     float sourcet[NST], ssj[NST];        // SOURCET; lane-partial SINGSCATJ
 #pragma unroll
@@ -459,13 +819,13 @@ __device__ __forceinline__ void eval_point_grad(const DevState &S, const DevGrad
                     const int2 en = __ldg((const int2 *)(sp + 1) + e);
                     float sv[NST];
                     ray_singscat<NST>(S.phasetab, S.nstphase, S.numphase, en.x, rd, sv);
-                    const float c = __int_as_float(en.y);
+                    const float cc = __int_as_float(en.y);
 #pragma unroll
-                    for (int k = 0; k < NST; k++) ssj[k] = ssj[k] + c * sv[k];
+                    for (int k = 0; k < NST; k++) ssj[k] = ssj[k] + cc * sv[k];
                 }
                 if (S.npart == 1) {
 #pragma unroll
-                    for (int k = 0; k < NST; k++) sourcet[k] = (alb_ip > 1e-8f) ? srcfull[k] / alb_ip : 0.0f;
+                    for (int k = 0; k < NST; k++) sourcet[k] = (alb_ip > 1e-8f) ? rc.srcfull[k] / alb_ip : 0.0f;
                 } else {
                     // SINGSCATJ is needed on its own; afterwards only lane 0 carries it into the row sums
                     float sj[NST];
@@ -510,9 +870,9 @@ __device__ __forceinline__ void eval_point_grad(const DevState &S, const DevGrad
                 ray_singscat<NST>(G.dphasetab, S.nstphase, G.dnumphase, en.x & ~AT3D_DTAB_FLAG, rd, sv);
             else
                 ray_singscat<NST>(S.phasetab, S.nstphase, S.numphase, en.x, rd, sv);
-            const float c = __int_as_float(en.y);
+            const float cc = __int_as_float(en.y);
 #pragma unroll
-            for (int k = 0; k < NST; k++) dp[k] = dp[k] + c * sv[k];
+            for (int k = 0; k < NST; k++) dp[k] = dp[k] + cc * sv[k];
         }
         double v = 0.0;
 #pragma unroll
@@ -529,323 +889,27 @@ __device__ __forceinline__ void eval_point_grad(const DevState &S, const DevGrad
         v = oct_sum_d(o.m, v);
 #pragma unroll
         for (int k = 0; k < NST; k++) v += adj[k] * (double)(c_src * sourcet[k]);
-        if (o.ol == nb) {
-            Drow[nb * nd + idr] = v;
-            XGrow[nb * nd + idr] = __int_as_float(h0.z);
-            IBrow[nb] = h0.w;
+        if (o.ol == 0) {
+            const double val = rc.W * v + (double)__int_as_float(h0.z) * rc.G;
+            if (val != 0.0) atomicAdd(&gradout[(size_t)(h0.w - 1) + (size_t)G.maxpg * idr], val);
         }
-    }
-    __syncwarp(o.m);
-}
-
-// Corner refresh for the adjoint walk: values and the shared-memory row (contracted GRAD8) of points
-// shared with the previous cell are carried over (OLDIPTS/DONEFACE logic of shdomsub4.f:1645-1659).
-template <int NST>
-__device__ __forceinline__ void refresh_corners_grad(const DevState &S, const DevGrad &G, const CellRec &c,
-                                                     unsigned char *sm, const GradLayout &L, const RayDir &rd,
-                                                     const double (&adj)[NST], bool first, const Oct &o,
-                                                     GCorner<NST> &K, int &npt_eval, int &nsh_eval, int &nrh_eval)
-{
-    const int myp = own_corner(c, o.ol);
-    int hit = -1;
-    if (!first) {
-#pragma unroll
-        for (int k = 0; k < 8; k++) { const int pk = __shfl_sync(o.m, K.pt, k, 8); if (pk == myp) hit = k; }
-    }
-    const int from = hit < 0 ? o.ol : hit;
-    K.x = __shfl_sync(o.m, K.x, from, 8); K.y = __shfl_sync(o.m, K.y, from, 8);
-    K.z = __shfl_sync(o.m, K.z, from, 8); K.ext = __shfl_sync(o.m, K.ext, from, 8);
-    K.row = __shfl_sync(o.m, K.row, from, 8);
-#pragma unroll
-    for (int k = 0; k < NST; k++) {
-        K.src[k] = __shfl_sync(o.m, K.src[k], from, 8);
-        K.ss[k] = __shfl_sync(o.m, K.ss[k], from, 8);
-    }
-    K.pt = myp;
-    int soff = 0, sns = 0;
-    float b[NST];
-    int4 gp = make_int4(0, 0, 0, 0);
-#pragma unroll
-    for (int k = 0; k < NST; k++) b[k] = 0.0f;
-    if (hit < 0) {
-        gp = __ldg(&G.gptrec[myp - 1]);
-        load_corner<NST>(S, myp, rd, K.x, K.y, K.z, K.ext, soff, sns, b);
-    }
-    unsigned used = oct_or(o, hit >= 0 ? (1u << K.row) : 0u);
-    unsigned need = oct_ballot(o, hit < 0);
-    while (need) {
-        const int n = __ffs(need) - 1;
-        const int ip = __shfl_sync(o.m, myp, n, 8);
-        const int off = __shfl_sync(o.m, soff, n, 8), ns = __shfl_sync(o.m, sns, n, 8);
-        const float ext = __shfl_sync(o.m, K.ext, n, 8);
-        float bn[NST];
-#pragma unroll
-        for (int k = 0; k < NST; k++) bn[k] = __shfl_sync(o.m, b[k], n, 8);
-        int4 gn;
-        gn.x = __shfl_sync(o.m, gp.x, n, 8); gn.y = __shfl_sync(o.m, gp.y, n, 8);
-        gn.z = __shfl_sync(o.m, gp.z, n, 8); gn.w = __shfl_sync(o.m, gp.w, n, 8);
-        const int row = __ffs(~used) - 1;
-        used |= 1u << row;
-        float src[NST], ss[NST];
-        eval_point_grad<NST>(S, G, ip, off, ns, bn, ext, gn, sm, L, rd, adj, o, row, src, ss);
-        npt_eval++; nsh_eval += ns; nrh_eval += gn.w >> 8;
-        const bool mine = (myp == ip);
-        if (mine) {
-            K.row = row;
-#pragma unroll
-            for (int k = 0; k < NST; k++) { K.src[k] = src[k]; K.ss[k] = ss[k]; }
-        }
-        need &= ~oct_ballot(o, mine);
     }
 }
 
-// ADJOINT_INTEGRATE_1RAY for one ray (one octet).
 template <int NST>
-__device__ int march_ray_adjoint(const DevState &S, const DevGrad &G, unsigned char *sm, const GradLayout &L,
-                                 const RayDir &rd, double mu2, double x0, double y0, double z0, float sky,
-                                 const double (&adj)[NST], const double (&total)[NST], const Oct &o,
-                                 double *gradout, double *beam_weight,
-                                 int *trace_cells, int trace_cap, int &ntrace, int &nsub)
-{
-    const double *Dall = (const double *)(sm + L.rowd);
-    const float *XGall = (const float *)(sm + L.rowx);
-    const int *IBall = (const int *)(sm + L.rowib);
-    int *rowof = (int *)(sm + L.rowib) + AT3D_GRAD_ROWS * 8;
-    double *Wacc = (double *)(sm + L.wacc);
-    const int nd = G.numder;
-    double xe = x0, ye = y0, ze = z0, transmit = 1.0;
-    double radout[NST];
-    float ext1 = 0.0f, srcext1[NST];
-#pragma unroll
-    for (int k = 0; k < NST; k++) { radout[k] = 0.0; srcext1[k] = 0.0f; }
-    const int p1c = cell_gp(S, 1, 1), p8c = cell_gp(S, 1, 8);
-    const double eps = (double)(1.0e-5f * (pt_coord(S, p8c, 3) - pt_coord(S, p1c, 3)));
-    const bool exact_ss = G.exact_single_scatter != 0;
-    int icell = dev_locate_grid_cell(S, xe, ye, ze);
-    int iface = 0, npassed = 1;
-    bool done = false, first = true;
-    int npt_eval = 0, nsh_eval = 0, nrh_eval = 0;
-    GCorner<NST> K;
-    K.pt = 0; K.row = 0; K.x = K.y = K.z = K.ext = 0.0f;
-#pragma unroll
-    for (int k = 0; k < NST; k++) { K.src[k] = 0.0f; K.ss[k] = 0.0f; }
-    ntrace = 0; nsub = 0;
-    CellRec c;
-    if (icell > 0) c = load_cell(S, icell);
-    while (!done && icell > 0) {
-        if (trace_cells && o.ol == 0 && ntrace < trace_cap) trace_cells[ntrace] = icell;
-        ntrace++;
-        refresh_corners_grad<NST>(S, G, c, sm, L, rd, adj, first, o, K, npt_eval, nsh_eval, nrh_eval);
-        first = false;
-        float e8[8], s8[NST][8];
-#pragma unroll
-        for (int n = 0; n < 8; n++) {
-            e8[n] = __shfl_sync(o.m, K.ext, n, 8);
-#pragma unroll
-            for (int k = 0; k < NST; k++) s8[k][n] = __shfl_sync(o.m, K.src[k], n, 8);
-        }
-        const float q1x = __shfl_sync(o.m, K.x, 0, 8), q1y = __shfl_sync(o.m, K.y, 0, 8), q1z = __shfl_sync(o.m, K.z, 0, 8);
-        const float q8x = __shfl_sync(o.m, K.x, 7, 8), q8y = __shfl_sync(o.m, K.y, 7, 8), q8z = __shfl_sync(o.m, K.z, 7, 8);
-        const float qox = __shfl_sync(o.m, K.x, 8 - rd.ioct, 8), qoy = __shfl_sync(o.m, K.y, 8 - rd.ioct, 8),
-                    qoz = __shfl_sync(o.m, K.z, 8 - rd.ioct, 8);
-        const double delx = (double)(q8x - q1x), dely = (double)(q8y - q1y), delz = (double)(q8z - q1z);
-        const double invdelx = (delx <= 0.0) ? 1.0 : 1.0 / delx;
-        const double invdely = (dely <= 0.0) ? 1.0 : 1.0 / dely;
-        const double invdelz = 1.0 / delz;
-        double u = (xe - q1x) * invdelx, v = (ye - q1y) * invdely, w = (ze - q1z) * invdelz;
-        double fc[8];
-        interp_kernel(u, v, w, fc);
-        double fown = interp_kernel_own(u, v, w, o.ol);
-#pragma unroll
-        for (int k = 0; k < NST; k++) srcext1[k] = (float)fcsum(fc, s8[k]);
-        srcext1[0] = fmaxf(0.0f, srcext1[0]);
-        double ext1d = fcsum(fc, e8);
-        ext1 = (float)ext1d;
-        const bool ipinx = DBTEST(c.flags, 0) &&
-            !(DBTEST(S.bcflag, 0) && ((rd.cx > 0 && xe < rd.xm) || (rd.cx < 0 && xe > rd.xm)));
-        const bool ipiny = DBTEST(c.flags, 1) &&
-            !(DBTEST(S.bcflag, 1) && ((rd.cy > 0 && ye < rd.ym) || (rd.cy < 0 && ye > rd.ym)));
-        const double sox = ipinx ? (double)1.0e20f : (qox - xe) * rd.cxinv;
-        const double soy = ipiny ? (double)1.0e20f : (qoy - ye) * rd.cyinv;
-        const double soz = (qoz - ze) * rd.czinv;
-        const double so = fmin(fmin(sox, soy), soz);
-        if (so < -eps) return 1;
-        double xn = xe + so * rd.cx, yn = ye + so * rd.cy, zn = ze + so * rd.cz;
-        // ---- exit face and next cell; its record is requested before the sub-interval loop ----
-        int jface;
-        bool openbcface;
-        if (sox <= soz && sox <= soy) { iface = 2 - rd.bitx; jface = 1; openbcface = DBTEST(c.flags, 0) && DBTEST(S.bcflag, 0); }
-        else if (soy <= soz) { iface = 4 - rd.bity; jface = 2; openbcface = DBTEST(c.flags, 1) && DBTEST(S.bcflag, 1); }
-        else { iface = 6 - rd.bitz; jface = 3; openbcface = false; }
-        int nbr = c.nb[0];
-#pragma unroll
-        for (int n = 1; n < 6; n++) if (iface - 1 == n) nbr = c.nb[n];
-        int inextcell = nbr;
-        if (inextcell < 0) inextcell = dev_next_cell(S, xn, yn, zn, iface, jface, inextcell);
-        int kface, ic;
-        if (nbr >= 0 && !openbcface) { kface = iface; ic = icell; }
-        else { kface = ((iface - 1) ^ 1) + 1; ic = inextcell; iface = 0; }
-        CellRec cn = c;
-        float snap = 0.0f;
-        if (inextcell > 0) {
-            cn = load_cell(S, inextcell);
-            int pn = cn.gp[0];
-#pragma unroll
-            for (int n = 1; n < 8; n++) if (rd.ioct - 1 == n) pn = cn.gp[n];
-            snap = pt_coord(S, pn, jface);
-        }
-        u = (xn - q1x) * invdelx; v = (yn - q1y) * invdely; w = (zn - q1z) * invdelz;
-        float extn;
-        { double fcn[8]; interp_kernel(u, v, w, fcn); extn = (float)fcsum(fcn, e8); }
-        const double taugrid = so * 0.5f * (ext1 + extn);
-        int ntau = 1 + (int)(taugrid / S.tautol);
-        if (ntau < 1) ntau = 1;
-        const double dels = so / ntau;
-        // per-corner accumulators of this cell (lane n owns corner n)
-        double Wn = 0.0, Gn = 0.0;
-        float bw[NST];
-#pragma unroll
-        for (int k = 0; k < NST; k++) bw[k] = 0.0f;
-        for (int it = 1; it <= ntau; it++) {
-            const double f1 = fown;                  // previous interpolation weight of the own corner
-            const double s = it * dels;
-            const double xi = xe + s * rd.cx, yi = ye + s * rd.cy, zi = ze + s * rd.cz;
-            u = (xi - q1x) * invdelx; v = (yi - q1y) * invdely; w = (zi - q1z) * invdelz;
-            interp_kernel(u, v, w, fc);
-            fown = interp_kernel_own(u, v, w, o.ol);
-            const double f0 = fown;
-            float ext0, srcext0[NST];
-#pragma unroll
-            for (int k = 0; k < NST; k++) srcext0[k] = (float)fcsum(fc, s8[k]);
-            const double ext0d = fcsum(fc, e8);
-            ext0 = (it != ntau) ? (float)ext0d : extn;
-            srcext0[0] = fmaxf(0.0f, srcext0[0]);
-            const double ext = (double)(0.5f * (ext0 + ext1));
-            if (ext != 0.0) {
-                const double tau = ext * dels;
-                const double abscell = tau * (1.0f - 0.5f * tau * (1.0f - 0.33333333333f * tau));
-                const double transcell = 1.0f - abscell;
-                const double corr = dels * (1.0f - 0.05f * (ext1 - ext0) * dels);
-                double rcur = 0.0, rnext = 0.0;      // adj . PASSEDRAD(kk), adj . PASSEDRAD(kk+1)
-#pragma unroll
-                for (int k = 0; k < NST; k++) rcur += adj[k] * (total[k] - radout[k]);
-                rcur = rcur / transmit;
-#pragma unroll
-                for (int k = 0; k < NST; k++) {
-                    const double src = (0.5f * (srcext0[k] + srcext1[k])
-                        + 0.08333333333f * (ext0 * srcext1[k] - ext1 * srcext0[k]) * dels
-                          * (1.0f - 0.05f * (ext1 - ext0) * dels)) / ext;
-                    radout[k] = radout[k] + transmit * src * abscell;
-                }
-                const double tnext = transmit * transcell;
-#pragma unroll
-                for (int k = 0; k < NST; k++) rnext += adj[k] * (total[k] - radout[k]);
-                rnext = rnext / tnext;
-                // lane-private corner weights
-                Wn += transmit * abscell * ((0.5f * (f0 + f1) + 0.08333333333f * (ext0 * f1 - ext1 * f0) * corr) / ext);
-                if (exact_ss) {
-#pragma unroll
-                    for (int k = 0; k < NST; k++) {
-                        float ss0 = (float)(f0 * K.ss[k]), ss1 = (float)(f1 * K.ss[k]);
-                        if (k == 0) { ss0 = fmaxf(0.0f, ss0); ss1 = fmaxf(0.0f, ss1); }
-                        bw[k] = (float)(bw[k] + transmit * abscell *
-                                (0.5f * (ss0 + ss1) + 0.08333333333f * (ext0 * ss1 - ext1 * ss0) * corr) / ext);
-                    }
-                }
-                // radiance term (COMPUTE_RADIANCE_DERIVATIVE_ADJOINT): extinctions re-interpolated in double
-                const double aext = 0.5f * (ext0d + ext1d);
-                if (aext != 0.0) {
-                    const double g0 = -rnext * f0, g1 = -rcur * f1;
-                    const double ag = (0.5f * (g0 + g1) + 0.08333333333f * (ext0d * g1 - ext1d * g0) * dels
-                                       * (1.0f - 0.05f * (ext1d - ext0d) * dels)) / aext;
-                    Gn += ag * transmit * abscell;
-                }
-                transmit = tnext;
-                npassed++;
-                nsub++;
-                if (npassed > G.maxsub) return 4;
-            } else {
-#pragma unroll
-                for (int k = 0; k < NST; k++) bw[k] = 0.0f;
-            }
-            ext1 = ext0; ext1d = ext0d;
-#pragma unroll
-            for (int k = 0; k < NST; k++) srcext1[k] = srcext0[k];
-        }
-        // ---- flush this cell's contributions (once per cell and corner, no atomics above) ----
-        Wacc[o.ol] = Wn; Wacc[8 + o.ol] = Gn; rowof[o.ol] = K.row;
-        if (exact_ss) {
-            double bsum = 0.0;
-#pragma unroll
-            for (int k = 0; k < NST; k++) bsum += adj[k] * (double)bw[k];
-            if (bsum != 0.0) atomicAdd(&beam_weight[K.pt - 1], bsum);
-        }
-        __syncwarp(o.m);
-        {
-            const int nb = o.ol;
-            for (int slot = 0; slot < 8; slot++) {
-                const int r = rowof[slot];
-                const double Ws = Wacc[slot], Gs = Wacc[8 + slot];
-                for (int idr = 0; idr < nd; idr++) {
-                    const int e = (r * 8 + nb) * nd + idr;
-                    const double val = Ws * Dall[e] + (double)XGall[e] * Gs;
-                    if (val != 0.0) atomicAdd(&gradout[(size_t)(IBall[r * 8 + nb] - 1) + (size_t)G.maxpg * idr], val);
-                }
-            }
-        }
-        __syncwarp(o.m);
-        if (inextcell > 0) {
-            if (jface == 1) xn = (double)snap;
-            else if (jface == 2) yn = (double)snap;
-            else zn = (double)snap;
-        }
-        if (transmit < S.transcut) {
-            done = true;
-        } else if (inextcell == 0 && iface >= 5) {
-            done = true;
-            float radbnd[NST];
-            int boundpts[4]; double boundinterp[4], dirrad1[4];
-            const int e = boundary_radiance<NST, true>(S, xn, yn, (float)mu2, sky, ic, kface, radbnd,
-                                                       boundpts, boundinterp, dirrad1);
-            if (e) return e;
-            if (exact_ss && o.ol < 4) {
-                int bp = boundpts[0]; double bi = boundinterp[0], dr = dirrad1[0];
-#pragma unroll
-                for (int n = 1; n < 4; n++) if (o.ol == n) { bp = boundpts[n]; bi = boundinterp[n]; dr = dirrad1[n]; }
-                const double val = adj[0] * transmit * bi * dr;
-                if (val != 0.0) atomicAdd(&beam_weight[bp - 1], val);
-            }
-        } else {
-            icell = inextcell; c = cn;
-        }
-        xe = xn; ye = yn; ze = zn;
-    }
-    if (S.counts && o.ol == 0) {
-        atomicAdd(&S.counts[0], (unsigned long long)ntrace);
-        atomicAdd(&S.counts[1], (unsigned long long)npt_eval);
-        atomicAdd(&S.counts[2], (unsigned long long)nsh_eval);
-        atomicAdd(&S.counts[3], (unsigned long long)nrh_eval);
-        atomicAdd(&S.counts[4], (unsigned long long)nsub);
-        atomicAdd(&S.counts[5], 1ull);
-    }
-    return 0;
-}
-
-template <int NST>
-__global__ void __launch_bounds__(AT3D_RAY_THREADS, NST == 1 ? AT3D_MINB_ADJ1 : AT3D_MINB_ADJ3)
-adjoint_kernel(DevState S, DevGrad G, GradLayout L, int nrays, const float *camx, const float *camy,
-               const float *camz, const double *cammu, const double *camphi, const RayPack *packs,
-               const int *raypix, const double *adjw /*[NST,npix]*/, const double *ray_weights,
-               const double *stokes_weights, const double *total /*[NST,nrays]*/,
-               double *gradout, double *beam_weight,
-               int *trace_cells, int trace_cap, int *trace_n, int *trace_nsub, RayErr *err, int *ray_counter)
+__global__ void __launch_bounds__(AT3D_RAY_THREADS)
+apply_kernel(DevState S, DevGrad G, int nrays, const float *camx, const float *camy,
+             const float *camz, const double *cammu, const double *camphi, const RayPack *packs,
+             const int *raypix, const double *adjw, const double *ray_weights, const double *stokes_weights,
+             const int *recoff, const VisitRec *recs, const int *nrec_in, double *gradout,
+             RayErr *err, int *ray_counter)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const Oct o = oct_id();
     const int lane = threadIdx.x & 31;
-    unsigned char *sm = smem_raw + (size_t)(threadIdx.x >> 3) * L.total;
-    float *Ysh = (float *)(sm + L.y);
-    float *Vsh = (float *)(sm + L.vsh);
+    const int ysz = S.ny_comp * S.nlmp, vsz = (3 * (S.ml + 1) + 3) & ~3;
+    float *Ysh = (float *)smem_raw + (size_t)(threadIdx.x >> 3) * (ysz + vsz);
+    float *Vsh = Ysh + ysz;
     for (;;) {
         int base = 0;
         if (lane == 0) base = atomicAdd(ray_counter, 32 / AT3D_OCT);
@@ -853,46 +917,22 @@ adjoint_kernel(DevState S, DevGrad G, GradLayout L, int nrays, const float *camx
         if (base >= nrays) break;
         const int iray = base + (lane >> 3);
         if (iray < nrays) {
-            const double mu2 = __ldg(&cammu[iray]), phi2 = __ldg(&camphi[iray]);
-            const RayPack pk = dev_get_pack(S, packs, iray, camx, camy, camz, mu2, phi2);
-            int ntrace = 0, nsub = 0;
-            if (pk.status == 2) { if (o.ol == 0) set_err(err, 2, iray); }
-            else if (pk.status == 0) {
-                const int pix = __ldg(&raypix[iray]);
-                double adj[NST], tot[NST];
-                const double rw = __ldg(&ray_weights[iray]);
-#pragma unroll
-                for (int k = 0; k < NST; k++) {
-                    adj[k] = __ldg(&adjw[k + NST * (size_t)pix]) * rw * __ldg(&stokes_weights[k + NST * (size_t)pix]);
-                    tot[k] = __ldg(&total[k + NST * (size_t)iray]);
+            const int nrec = __ldg(&nrec_in[iray]);
+            RayPack pk; RayDir rd; double mu2, phi2, adj[NST];
+            if (nrec > 0 && ray_setup<NST>(S, iray, camx, camy, camz, cammu, camphi, packs, raypix, adjw, ray_weights,
+                                           stokes_weights, Ysh, Vsh, o, err, pk, rd, mu2, phi2, adj)) {
+                const VisitRec *rp = recs + __ldg(&recoff[iray]);
+                int nrh = 0;
+                for (int i = 0; i < nrec; i++) {
+                    VisitRec rc;
+                    const int4 a = __ldg((const int4 *)(rp + i));
+                    const double2 b = __ldg((const double2 *)(rp + i) + 1);
+                    rc.ip = a.x; rc.srcfull[0] = __int_as_float(a.y); rc.srcfull[1] = __int_as_float(a.z);
+                    rc.srcfull[2] = __int_as_float(a.w); rc.W = b.x; rc.G = b.y;
+                    apply_record<NST>(S, G, rc, Ysh, Vsh, rd, adj, o, gradout, nrh);
                 }
-                RayDir rd;
-                dev_ray_dir(S, pk, rd);
-                __syncwarp(o.m);
-                group_ylmall(S, (float)mu2, (float)phi2, Ysh, o.ol, AT3D_OCT, o.m);
-                if (!S.deltam) {
-                    // shell sums of YLMSUN*YLMDIR for the untruncated solar term of COMPUTE_SOURCE_DIRECTION
-                    for (int l = o.ol; l <= S.ml; l += 8) {
-                        const int me = l < S.mm ? l : S.mm;
-                        const int jlo = sh_index(l, -me, S.mm);
-                        float v1 = 0.0f, v5 = 0.0f, v6 = 0.0f;
-                        for (int i = 0; i < 2 * me + 1; i++) {
-                            const float ys = __ldg(&S.ylmsun[(size_t)S.nstleg * (jlo + i)]);
-                            v1 = v1 + ys * Ysh[jlo + i];
-                            if (NST > 1) { v5 = v5 + ys * Ysh[S.nlmp + jlo + i]; v6 = v6 + ys * Ysh[3 * S.nlmp + jlo + i]; }
-                        }
-                        Vsh[l] = v1; Vsh[(S.ml + 1) + l] = v5; Vsh[2 * (S.ml + 1) + l] = v6;
-                    }
-                    __syncwarp(o.m);
-                }
-                const float sky = (-mu2 > 0.0) ? dev_sky_radiance(S, (float)mu2, (float)phi2) : 0.0f;
-                const int e = march_ray_adjoint<NST>(S, G, sm, L, rd, mu2, pk.x0, pk.y0, pk.z0, sky, adj, tot, o,
-                                                     gradout, beam_weight,
-                                                     trace_cells ? trace_cells + (size_t)trace_cap * iray : nullptr,
-                                                     trace_cap, ntrace, nsub);
-                if (e && o.ol == 0) set_err(err, e, iray);
+                if (S.counts && o.ol == 0) atomicAdd(&S.counts[3], (unsigned long long)nrh);
             }
-            if (o.ol == 0 && trace_n) { trace_n[iray] = ntrace; trace_nsub[iray] = nsub; }
         }
         __syncwarp();
     }
@@ -1191,7 +1231,7 @@ extern "C" int at3d_levisapprox_gradient(at3d_state *st, const at3d_rays *rays, 
     if ((rc = stage_in(g->stokes_weights, (size_t)nst * npix, host, pb + o_sw, &sw, stream, errmsg))) return rc;
     // ---- work buffers ----
     size_t cubtmp = 0;
-    cub::DeviceScan::ExclusiveSum(nullptr, cubtmp, (const int *)nullptr, (int *)nullptr, (int)npix, stream);
+    cub::DeviceScan::ExclusiveSum(nullptr, cubtmp, (const int *)nullptr, (int *)nullptr, (int)(npix > n + 1 ? npix : n + 1), stream);
     o = 0;
     const size_t w_vis = o; o += al256(sizeof(double) * nst * n);
     const size_t w_tot = o; o += al256(sizeof(double) * nst * n);
@@ -1201,6 +1241,9 @@ extern "C" int at3d_levisapprox_gradient(at3d_state *st, const at3d_rays *rays, 
     const size_t w_raypix = o; o += al256(sizeof(int) * n);
     const size_t w_beam = o; o += al256(sizeof(double) * S.npts);
     const size_t w_cub = o; o += al256(cubtmp);
+    const size_t w_npt = o; o += al256(sizeof(int) * (n + 1));
+    const size_t w_recoff = o; o += al256(sizeof(int) * (n + 1));
+    const size_t w_nrec = o; o += al256(sizeof(int) * n);
     const size_t w_grad = o; o += al256(sizeof(double) * ngrad);
     const size_t w_so = o; o += al256(sizeof(float) * nst * npix);
     const size_t w_cost = o; o += 256;
@@ -1209,6 +1252,7 @@ extern "C" int at3d_levisapprox_gradient(at3d_state *st, const at3d_rays *rays, 
     double *visrad = (double *)(wb + w_vis), *total = (double *)(wb + w_tot), *adjw = (double *)(wb + w_adj);
     double *costp = (double *)(wb + w_costp), *beam = (double *)(wb + w_beam);
     int *pixstart = (int *)(wb + w_pixstart), *raypix = (int *)(wb + w_raypix);
+    int *npt = (int *)(wb + w_npt), *recoff = (int *)(wb + w_recoff), *nrec = (int *)(wb + w_nrec);
     double *grad_d = host ? (double *)(wb + w_grad) : gradout;
     float *so_d = host ? (float *)(wb + w_so) : stokesout;
     double *cost_d = host ? (double *)(wb + w_cost) : cost;
@@ -1227,17 +1271,20 @@ extern "C" int at3d_levisapprox_gradient(at3d_state *st, const at3d_rays *rays, 
     CUDA_TRY(cudaMemsetAsync(beam, 0, sizeof(double) * S.npts, stream));
     CUDA_TRY(cudaMemsetAsync(so_d, 0, sizeof(float) * nst * npix, stream));
     CUDA_TRY(cudaMemsetAsync(cost_d, 0, sizeof(double), stream));
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-    if (kernel_ms) { for (int i = 0; i < 4; i++) cudaEventCreate(&ev[i]); cudaEventRecord(ev[0], stream); }
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    if (kernel_ms) { for (int i = 0; i < 5; i++) cudaEventCreate(&ev[i]); cudaEventRecord(ev[0], stream); cudaEventRecord(ev[4], stream); }
     if (n > 0 && npix > 0) {
         // ---- Phase 1: forward radiances (INTEGRATE_1RAY arithmetic for the pixel values; the
         //      ADJOINT_INTEGRATE_1RAY arithmetic for the totals the derivative pass needs) ----
         DevState Sf = S;          // the work counters describe the adjoint pass only
         Sf.counts = nullptr;
         CUDA_TRY(cudaMemsetAsync(st->counts_dev, 0, 8 * sizeof(unsigned long long), stream));
+        CUDA_TRY(cudaMemsetAsync(npt, 0, sizeof(int) * (n + 1), stream));
         CUDA_TRY(launch_forward(Sf, (int)n, camx, camy, camz, cammu, camphi, packs, nullptr, visrad, total, 3, 1,
                                 G.singlescatter, 0, G.maxsub, nullptr, 0, nullptr, nullptr, (RayErr *)st->err.p,
-                                st->ray_counter, stream));
+                                st->ray_counter, npt, stream));
+        // visit records of a ray are contiguous: offsets = exclusive scan of the per-ray visit counts
+        CUDA_TRY(cub::DeviceScan::ExclusiveSum(wb + w_cub, cubtmp, npt, recoff, (int)(n + 1), stream));
         if (kernel_ms) cudaEventRecord(ev[1], stream);
         // ---- Phase 2 ----
         CUDA_TRY(cub::DeviceScan::ExclusiveSum(wb + w_cub, cubtmp, rpp, pixstart, (int)npix, stream));
@@ -1252,28 +1299,51 @@ extern "C" int at3d_levisapprox_gradient(at3d_state *st, const at3d_rays *rays, 
         cost_reduce_kernel<<<1, 1024, 0, stream>>>((int)npix, costp, cost_d);
         CUDA_TRY(cudaGetLastError());
         // ---- Phase 3 ----
-        const GradLayout L = grad_layout(S.ny_comp, S.nlmp, S.ml, G.numder);
-        const size_t smem = (size_t)AT3D_RAYS_PER_BLOCK * L.total;
-        if (smem > 227 * 1024) { set_msg(errmsg, "gradient kernel needs %zu bytes of shared memory (NUMDER too large)", smem); return 3; }
-        const void *fn = nst == 1 ? (const void *)adjoint_kernel<1> : (const void *)adjoint_kernel<3>;
-        CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int nrec_total = 0;
+        CUDA_TRY(cudaMemcpyAsync(&nrec_total, recoff + n, sizeof(int), cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(cudaStreamSynchronize(stream));
+        if (nrec_total < 0) { set_msg(errmsg, "more than 2^31 visit records: split the ray list"); return 2; }
+        CUDA_TRY(st->recs.reserve(((size_t)nrec_total + 8) * sizeof(VisitRec)));
+        VisitRec *recs = (VisitRec *)st->recs.p;
+        const size_t smem = (size_t)AT3D_RAYS_PER_BLOCK * (S.ny_comp * S.nlmp + ((3 * (S.ml + 1) + 3) & ~3)) * sizeof(float);
         int dev = 0, nsm = 148, per_sm = 1;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, AT3D_RAY_THREADS, smem);
-        if (per_sm < 1) per_sm = 1;
-        long want = ((long)n + AT3D_RAYS_PER_BLOCK - 1) / AT3D_RAYS_PER_BLOCK;
-        long cap = (long)nsm * per_sm;
-        const int nblk = (int)(want < cap ? want : cap);
-        CUDA_TRY(cudaMemsetAsync(st->ray_counter, 0, sizeof(int), stream));
-        if (nst == 1)
-            adjoint_kernel<1><<<nblk, AT3D_RAY_THREADS, smem, stream>>>(S, G, L, (int)n, camx, camy, camz, cammu,
-                camphi, packs, raypix, adjw, rw, sw, total, grad_d, beam, tc, tcap, tn, ts, (RayErr *)st->err.p,
-                st->ray_counter);
-        else
-            adjoint_kernel<3><<<nblk, AT3D_RAY_THREADS, smem, stream>>>(S, G, L, (int)n, camx, camy, camz, cammu,
-                camphi, packs, raypix, adjw, rw, sw, total, grad_d, beam, tc, tcap, tn, ts, (RayErr *)st->err.p,
-                st->ray_counter);
+        const long want = ((long)n + AT3D_RAYS_PER_BLOCK - 1) / AT3D_RAYS_PER_BLOCK;
+        {
+            const void *fn = nst == 1 ? (const void *)weights_kernel<1> : (const void *)weights_kernel<3>;
+            CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, AT3D_RAY_THREADS, smem);
+            if (per_sm < 1) per_sm = 1;
+            const long cap = (long)nsm * per_sm;
+            const int nblk = (int)(want < cap ? want : cap);
+            CUDA_TRY(cudaMemsetAsync(st->ray_counter, 0, sizeof(int), stream));
+            if (nst == 1)
+                weights_kernel<1><<<nblk, AT3D_RAY_THREADS, smem, stream>>>(S, G, (int)n, camx, camy, camz, cammu, camphi,
+                    packs, raypix, adjw, rw, sw, total, recoff, recs, nrec, beam, tc, tcap, tn, ts, (RayErr *)st->err.p,
+                    st->ray_counter);
+            else
+                weights_kernel<3><<<nblk, AT3D_RAY_THREADS, smem, stream>>>(S, G, (int)n, camx, camy, camz, cammu, camphi,
+                    packs, raypix, adjw, rw, sw, total, recoff, recs, nrec, beam, tc, tcap, tn, ts, (RayErr *)st->err.p,
+                    st->ray_counter);
+            CUDA_TRY(cudaGetLastError());
+        }
+        if (kernel_ms) cudaEventRecord(ev[4], stream);
+        {
+            const void *fn = nst == 1 ? (const void *)apply_kernel<1> : (const void *)apply_kernel<3>;
+            CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, AT3D_RAY_THREADS, smem);
+            if (per_sm < 1) per_sm = 1;
+            const long cap = (long)nsm * per_sm;
+            const int nblk = (int)(want < cap ? want : cap);
+            CUDA_TRY(cudaMemsetAsync(st->ray_counter, 0, sizeof(int), stream));
+            if (nst == 1)
+                apply_kernel<1><<<nblk, AT3D_RAY_THREADS, smem, stream>>>(S, G, (int)n, camx, camy, camz, cammu, camphi,
+                    packs, raypix, adjw, rw, sw, recoff, recs, nrec, grad_d, (RayErr *)st->err.p, st->ray_counter);
+            else
+                apply_kernel<3><<<nblk, AT3D_RAY_THREADS, smem, stream>>>(S, G, (int)n, camx, camy, camz, cammu, camphi,
+                    packs, raypix, adjw, rw, sw, recoff, recs, nrec, grad_d, (RayErr *)st->err.p, st->ray_counter);
+        }
         CUDA_TRY(cudaGetLastError());
         if (kernel_ms) cudaEventRecord(ev[2], stream);
         // ---- Phase 4 ----
@@ -1302,7 +1372,8 @@ extern "C" int at3d_levisapprox_gradient(at3d_state *st, const at3d_rays *rays, 
         cudaEventElapsedTime(&ms, ev[1], ev[2]); kernel_ms[1] = ms;
         cudaEventElapsedTime(&ms, ev[2], ev[3]); kernel_ms[2] = ms;
         cudaEventElapsedTime(&ms, ev[0], ev[3]); kernel_ms[3] = ms;
-        for (int i = 0; i < 4; i++) cudaEventDestroy(ev[i]);
+        cudaEventElapsedTime(&ms, ev[1], ev[4]); kernel_ms[4] = ms;      // phase A (weights) incl. pixel kernels
+        for (int i = 0; i < 5; i++) cudaEventDestroy(ev[i]);
     }
     return rc;
 }

@@ -33,7 +33,7 @@ struct at3d_state {
     size_t bytes = 0;
     int device = 0;
     // reusable per-call buffers
-    DevBuf rays, out, trace, misc, slabs, err, pix, work;
+    DevBuf rays, out, trace, misc, slabs, err, pix, work, recs;
     RayGeom geom;                   // host copy of the per-ray setup constants
     std::vector<RayPack> packs_h;   // host staging of the per-ray packs
     float *bcrad_dev = nullptr;
@@ -49,7 +49,7 @@ cudaError_t launch_forward(const DevState &S, int nrays, const float *camx, cons
                            const RayPack *packs, float *out_f32, double *out_f64, double *out_tot, int modes,
                            int correctinterpolate, int singlescatter, int nosurface, int maxsub,
                            int *trace_cells, int trace_cap, int *trace_n, int *trace_nsub,
-                           RayErr *err, int *ray_counter, cudaStream_t stream);
+                           RayErr *err, int *ray_counter, int *npt_out, cudaStream_t stream);
 cudaError_t launch_build_cellrec(int ncells, const int *gridptr, const int *neighptr, const int *treeptr,
                                  const short *cellflags, int4 *cellrec, cudaStream_t s);
 cudaError_t launch_build_ptrec(int npts, const float *gridpos, const float *total_ext, float4 *ptrec, cudaStream_t s);

@@ -233,37 +233,36 @@ __device__ __forceinline__ int own_corner(const CellRec &c, int ol)
     return p;
 }
 
-// Refresh the corner values of the lanes for cell `c`: values of points shared with the previous
-// cell are taken over from the lane that owned them (they are bit-identical to a recomputation, so
-// this is the reference's OLDIPTS/DONEFACE shortcut, shdomsub2.f:2509-2515,2914-2919, without its
-// slot restriction).  New corners: every owner lane loads its point's records at once, then the
-// octet evaluates the SH sums point by point.
+// Refresh the corner values of the lanes for cell `c`.  Points shared with the previous cell are found
+// with the reference's DONEFACE rule (shdomsub2.f:2395-2397, 2509-2515): after crossing a face normal to
+// axis `jf`, corner n of the new cell can only coincide with corner n^bit of the old one; the ids decide.
+// Reused values are bit-identical to a recomputation.  New corners: every owner lane loads its point's
+// records at once, then the octet evaluates the SH sums point by point.  The thread-per-ray kernels
+// (at3d_tray.cuh) use the same rule, so all marches evaluate the same (ray, point) pairs.
 template <int NST>
 __device__ __forceinline__ void refresh_corners(const DevState &S, const CellRec &c, const float *Ysh,
-                                                const RayDir &rd, bool singlescatter, bool first, const Oct &o,
-                                                Corner<NST> &K, int &npt_eval, int &nsh_eval)
+                                                const RayDir &rd, bool singlescatter, int jf /*0: first cell*/,
+                                                const Oct &o, Corner<NST> &K, int &npt_eval, int &nsh_eval)
 {
     const int myp = own_corner(c, o.ol);
-    int hit = -1;
-    if (!first) {
+    const int from = o.ol ^ (jf == 1 ? 1 : jf == 2 ? 2 : 4);
+    const int cand = __shfl_sync(o.m, K.pt, from, 8);
+    const bool hit = (jf != 0) && (cand == myp);
+    const int src_lane = hit ? from : o.ol;
+    K.x = __shfl_sync(o.m, K.x, src_lane, 8); K.y = __shfl_sync(o.m, K.y, src_lane, 8);
+    K.z = __shfl_sync(o.m, K.z, src_lane, 8); K.ext = __shfl_sync(o.m, K.ext, src_lane, 8);
 #pragma unroll
-        for (int k = 0; k < 8; k++) { const int pk = __shfl_sync(o.m, K.pt, k, 8); if (pk == myp) hit = k; }
-    }
-    const int from = hit < 0 ? o.ol : hit;
-    K.x = __shfl_sync(o.m, K.x, from, 8); K.y = __shfl_sync(o.m, K.y, from, 8);
-    K.z = __shfl_sync(o.m, K.z, from, 8); K.ext = __shfl_sync(o.m, K.ext, from, 8);
-#pragma unroll
-    for (int k = 0; k < NST; k++) K.src[k] = __shfl_sync(o.m, K.src[k], from, 8);
+    for (int k = 0; k < NST; k++) K.src[k] = __shfl_sync(o.m, K.src[k], src_lane, 8);
     K.pt = myp;
     int soff = 0, sns = 0;
     float b[NST];
 #pragma unroll
     for (int k = 0; k < NST; k++) b[k] = 0.0f;
-    if (hit < 0) load_corner<NST>(S, myp, rd, K.x, K.y, K.z, K.ext, soff, sns, b);
-    unsigned need = oct_ballot(o, hit < 0);
+    if (!hit) load_corner<NST>(S, myp, rd, K.x, K.y, K.z, K.ext, soff, sns, b);
+    unsigned need = oct_ballot(o, !hit);
     while (need) {
         const int n = __ffs(need) - 1;
-        const int ip = __shfl_sync(o.m, myp, n, 8);
+        need &= need - 1;
         const int off = __shfl_sync(o.m, soff, n, 8), ns = __shfl_sync(o.m, sns, n, 8);
         float a[NST];
 #pragma unroll
@@ -274,12 +273,10 @@ __device__ __forceinline__ void refresh_corners(const DevState &S, const CellRec
             for (int k = 0; k < NST; k++) a[k] = oct_sum(o.m, a[k]);
         }
         npt_eval++; nsh_eval += ns;
-        const bool mine = (myp == ip);
-        if (mine) {
+        if (o.ol == n) {
 #pragma unroll
             for (int k = 0; k < NST; k++) K.src[k] = (a[k] + b[k]) * K.ext;
         }
-        need &= ~oct_ballot(o, mine);
     }
 }
 
@@ -294,7 +291,7 @@ __device__ int march_forward(const DevState &S, const float *Ysh, const RayDir &
                              double x0, double y0, double z0, float sky, bool correctinterpolate,
                              bool singlescatter, bool nosurface, int maxsub, const Oct &o,
                              double (&radA)[NST], double (&radB)[NST],
-                             int *trace_cells, int trace_cap, int &ntrace, int &nsubA, int &nsubB)
+                             int *trace_cells, int trace_cap, int &ntrace, int &nsubA, int &nsubB, int &nptB)
 {
     double xe = x0, ye = y0, ze = z0, trA = 1.0, trB = 1.0;
     float ext1A = 0.0f, srcext1A[NST], ext1B = 0.0f, srcext1B[NST];
@@ -304,8 +301,9 @@ __device__ int march_forward(const DevState &S, const float *Ysh, const RayDir &
     const double eps = (double)(1.0e-5f * (pt_coord(S, p8c, 3) - pt_coord(S, p1c, 3)));
     const int maxcellscross = 500 * max(S.nx, max(S.ny, S.nz));
     int icell = dev_locate_grid_cell(S, xe, ye, ze);
-    int iface = 0, ngrid = 0, npt_eval = 0, nsh_eval = 0;
-    bool doneA = !(MODES & 1), doneB = !(MODES & 2), first = true;
+    int iface = 0, ngrid = 0, npt_eval = 0, nsh_eval = 0, jf = 0;
+    bool doneA = !(MODES & 1), doneB = !(MODES & 2);
+    nptB = 0;
     Corner<NST> K;
     K.pt = 0; K.x = K.y = K.z = K.ext = 0.0f;
 #pragma unroll
@@ -317,8 +315,9 @@ __device__ int march_forward(const DevState &S, const float *Ysh, const RayDir &
         ngrid++;
         if (trace_cells && o.ol == 0 && ntrace < trace_cap) trace_cells[ntrace] = icell;
         ntrace++;
-        refresh_corners<NST>(S, c, Ysh, rd, singlescatter, first, o, K, npt_eval, nsh_eval);
-        first = false;
+        const int ne0 = npt_eval;
+        refresh_corners<NST>(S, c, Ysh, rd, singlescatter, jf, o, K, npt_eval, nsh_eval);
+        if ((MODES & 2) && !doneB) nptB += npt_eval - ne0;
         float e8[8], s8[NST][8];
 #pragma unroll
         for (int n = 0; n < 8; n++) {
@@ -490,7 +489,7 @@ __device__ int march_forward(const DevState &S, const float *Ysh, const RayDir &
                 }
             }
         }
-        if (!atbnd) { icell = inextcell; c = cn; }
+        if (!atbnd) { icell = inextcell; c = cn; jf = jface; }
         xe = xn; ye = yn; ze = zn;
     }
     if (S.counts && o.ol == 0) {

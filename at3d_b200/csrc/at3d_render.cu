@@ -164,7 +164,8 @@ __global__ void __launch_bounds__(AT3D_RAY_THREADS, NST == 1 ? AT3D_MINB_FWD1 : 
 forward_kernel(DevState S, int nrays, const float *camx, const float *camy, const float *camz,
                const double *cammu, const double *camphi, const RayPack *packs, OUTA *outA, double *outB,
                int correctinterpolate, int singlescatter, int nosurface, int maxsub,
-               int *trace_cells, int trace_cap, int *trace_n, int *trace_nsub, RayErr *err, int *ray_counter)
+               int *trace_cells, int trace_cap, int *trace_n, int *trace_nsub, RayErr *err, int *ray_counter,
+               int *npt_out)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const Oct o = oct_id();
@@ -182,7 +183,7 @@ forward_kernel(DevState S, int nrays, const float *camx, const float *camy, cons
             double radA[NST], radB[NST];
 #pragma unroll
             for (int k = 0; k < NST; k++) { radA[k] = 0.0; radB[k] = 0.0; }
-            int ntrace = 0, nsubA = 0, nsubB = 0;
+            int ntrace = 0, nsubA = 0, nsubB = 0, nptB = 0;
             if (pk.status == 2) { if (o.ol == 0) set_err(err, 2, iray); }
             else if (pk.status == 0) {
                 RayDir rd;
@@ -194,7 +195,7 @@ forward_kernel(DevState S, int nrays, const float *camx, const float *camy, cons
                                                         correctinterpolate != 0, singlescatter != 0, nosurface != 0,
                                                         maxsub, o, radA, radB,
                                                         trace_cells ? trace_cells + (size_t)trace_cap * iray : nullptr,
-                                                        trace_cap, ntrace, nsubA, nsubB);
+                                                        trace_cap, ntrace, nsubA, nsubB, nptB);
                 if (e && o.ol == 0) set_err(err, e, iray);
             }
             if (o.ol == 0) {
@@ -204,6 +205,7 @@ forward_kernel(DevState S, int nrays, const float *camx, const float *camy, cons
                     if (MODES & 2) outB[k + NST * (size_t)iray] = radB[k];
                 }
                 if (trace_n) { trace_n[iray] = ntrace; trace_nsub[iray] = (MODES & 1) ? nsubA : nsubB; }
+                if (npt_out) npt_out[iray] = nptB;
             }
         }
         __syncwarp();
@@ -216,7 +218,8 @@ __global__ void __launch_bounds__(256)
 forward_kernel_t(DevState S, int nrays, const float *camx, const float *camy, const float *camz,
                  const double *cammu, const double *camphi, const RayPack *packs, OUTA *outA, double *outB,
                  int correctinterpolate, int singlescatter, int nosurface, int maxsub,
-                 int *trace_cells, int trace_cap, int *trace_n, int *trace_nsub, RayErr *err, int *ray_counter)
+                 int *trace_cells, int trace_cap, int *trace_n, int *trace_nsub, RayErr *err, int *ray_counter,
+                 int *npt_out)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int bt = blockDim.x, lane = threadIdx.x & 31;
@@ -227,7 +230,7 @@ forward_kernel_t(DevState S, int nrays, const float *camx, const float *camy, co
         base = __shfl_sync(FULLMASK, base, 0);
         if (base >= nrays) break;
         const int iray = base + lane;
-        int ntrace = 0, nsubA = 0, nsubB = 0, npt = 0, nsh = 0, marched = 0;
+        int ntrace = 0, nsubA = 0, nsubB = 0, npt = 0, nsh = 0, marched = 0, nptB = 0;
         if (iray < nrays) {
             const double mu2 = __ldg(&cammu[iray]), phi2 = __ldg(&camphi[iray]);
             const RayPack pk = dev_get_pack(S, packs, iray, camx, camy, camz, mu2, phi2);
@@ -242,13 +245,14 @@ forward_kernel_t(DevState S, int nrays, const float *camx, const float *camy, co
                                                           correctinterpolate != 0, singlescatter != 0, nosurface != 0,
                                                           maxsub, radA, radB,
                                                           trace_cells ? trace_cells + (size_t)trace_cap * iray : nullptr,
-                                                          trace_cap, ntrace, nsubA, nsubB, npt, nsh);
+                                                          trace_cap, ntrace, nsubA, nsubB, npt, nsh, nptB);
                 if (e) set_err(err, e, iray);
                 else marched = 1;
             }
             if (MODES & 1) outA[iray] = (OUTA)radA;
             if (MODES & 2) outB[iray] = radB;
             if (trace_n) { trace_n[iray] = ntrace; trace_nsub[iray] = (MODES & 1) ? nsubA : nsubB; }
+            if (npt_out) npt_out[iray] = nptB;
         }
         __syncwarp();
         if (S.counts) {
@@ -302,7 +306,7 @@ cudaError_t launch_forward(const DevState &S, int nrays, const float *camx, cons
                            const RayPack *packs, float *out_f32, double *out_f64, double *out_tot, int modes,
                            int correctinterpolate, int singlescatter, int nosurface, int maxsub,
                            int *trace_cells, int trace_cap, int *trace_n, int *trace_nsub,
-                           RayErr *err, int *ray_counter, cudaStream_t stream)
+                           RayErr *err, int *ray_counter, int *npt_out, cudaStream_t stream)
 {
     if (nrays <= 0) return cudaSuccess;
     cudaError_t ce = cudaMemsetAsync(ray_counter, 0, sizeof(int), stream);
@@ -321,7 +325,7 @@ cudaError_t launch_forward(const DevState &S, int nrays, const float *camx, cons
             const long want = ((long)nrays + bt - 1) / bt, cap = (long)nsm * per_sm;               \
             forward_kernel_t<MODES, OUTA><<<(int)(want < cap ? want : cap), bt, smem_t, stream>>>(S, nrays, camx, camy, \
                 camz, cammu, camphi, packs, outa, out_tot, correctinterpolate, singlescatter, nosurface, maxsub,  \
-                trace_cells, trace_cap, trace_n, trace_nsub, err, ray_counter);                    \
+                trace_cells, trace_cap, trace_n, trace_nsub, err, ray_counter, npt_out);           \
         }
         if (modes == 3) LAUNCHT(3, double, out_f64)
         else if (out_f64) LAUNCHT(1, double, out_f64)
@@ -335,7 +339,7 @@ cudaError_t launch_forward(const DevState &S, int nrays, const float *camx, cons
         const int nb = persistent_blocks(forward_kernel<NST, MODES, OUTA>, nrays, smem);          \
         forward_kernel<NST, MODES, OUTA><<<nb, AT3D_RAY_THREADS, smem, stream>>>(S, nrays, camx, camy, camz, \
             cammu, camphi, packs, outa, out_tot, correctinterpolate, singlescatter, nosurface, maxsub,        \
-            trace_cells, trace_cap, trace_n, trace_nsub, err, ray_counter);                                   \
+            trace_cells, trace_cap, trace_n, trace_nsub, err, ray_counter, npt_out);                          \
     }
     if (S.nstokes == 1) {
         if (modes == 3) LAUNCH(1, 3, double, out_f64)

@@ -55,32 +55,10 @@ struct TCorners {
 #define SEL8(arr, n) ((n) == 0 ? arr[0] : (n) == 1 ? arr[1] : (n) == 2 ? arr[2] : (n) == 3 ? arr[3] : \
                       (n) == 4 ? arr[4] : (n) == 5 ? arr[5] : (n) == 6 ? arr[6] : arr[7])
 
-// Source*extinction of one grid point in the thread's ray direction: COMPUTE_SOURCE_1CELL_UNPOL
-// (shdomsub2.f:3046-3192) with the TMS-corrected SH block and the per-point single-scatter list.
-__device__ __forceinline__ void thread_eval_point(const DevState &S, int ip, const float4 *Y4, int bt,
-                                                  const RayDir &rd, bool singlescatter,
-                                                  float &x, float &y, float &z, float &ext, float &src, int &ns)
+// exact single-scatter sum of one point from its record / list (shdomsub2.f:3172-3183)
+__device__ __forceinline__ float thread_singscat_sum(const DevState &S, int ip, const int4 ps, const RayDir &rd)
 {
-    const float4 pr = __ldg(&S.ptrec[ip - 1]);
-    const int4 ps = __ldg(&S.ptsrc[ip - 1]);
-    x = pr.x; y = pr.y; z = pr.z; ext = pr.w;
-    ns = ps.y & 0xFFFF;
     const int cnt = ps.y >> 16;
-    float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
-    if (!singlescatter) {
-        const float4 *base = (const float4 *)(S.shsrc + ps.x);
-        const int n4 = AT3D_SHPAD(ns) >> 2;                 // multiple of 8
-#pragma unroll 1
-        for (int j = 0; j < n4; j += 4) {
-            const float4 s0 = __ldg(base + j), s1 = __ldg(base + j + 1), s2 = __ldg(base + j + 2), s3 = __ldg(base + j + 3);
-            const float4 y0 = Y4[(size_t)j * bt], y1 = Y4[(size_t)(j + 1) * bt];
-            const float4 y2 = Y4[(size_t)(j + 2) * bt], y3 = Y4[(size_t)(j + 3) * bt];
-            a0 = fmaf(s0.x, y0.x, a0); a1 = fmaf(s0.y, y0.y, a1); a2 = fmaf(s0.z, y0.z, a2); a3 = fmaf(s0.w, y0.w, a3);
-            a0 = fmaf(s1.x, y1.x, a0); a1 = fmaf(s1.y, y1.y, a1); a2 = fmaf(s1.z, y1.z, a2); a3 = fmaf(s1.w, y1.w, a3);
-            a0 = fmaf(s2.x, y2.x, a0); a1 = fmaf(s2.y, y2.y, a1); a2 = fmaf(s2.z, y2.z, a2); a3 = fmaf(s2.w, y2.w, a3);
-            a0 = fmaf(s3.x, y3.x, a0); a1 = fmaf(s3.y, y3.y, a1); a2 = fmaf(s3.z, y3.z, a2); a3 = fmaf(s3.w, y3.w, a3);
-        }
-    }
     float b = 0.0f;
     if (cnt > 0) {
         float sv[1];
@@ -92,13 +70,16 @@ __device__ __forceinline__ void thread_eval_point(const DevState &S, int ip, con
             b = fmaf(__int_as_float(en.y), sv[0], b);
         }
     }
-    src = (((a0 + a1) + (a2 + a3)) + b) * ext;
+    return b;
 }
 
 // Corner refresh of one thread.  Points shared with the previous cell are found with the reference's
 // DONEFACE rule (shdomsub2.f:2395-2397, 2509-2515): after crossing a face normal to axis `jf`, corner n
 // of the new cell can only coincide with corner n^bit of the old one; the ids decide.  Reused values
-// are bit-identical to a recomputation.
+// are bit-identical to a recomputation.  New corners -- COMPUTE_SOURCE_1CELL_UNPOL
+// (shdomsub2.f:3046-3192) with the TMS-corrected SH blocks -- are evaluated four at a time: their
+// records are requested together, the SH blocks stream through 16 independent 16-byte loads per
+// iteration and share the reads of the thread's YLMDIR column.
 __device__ __forceinline__ void thread_refresh(const DevState &S, const CellRec &c, const float4 *Y4, int bt,
                                                const RayDir &rd, bool singlescatter, int jf /*0: first cell*/,
                                                TCorners &K, int &npt_eval, int &nsh_eval)
@@ -121,16 +102,58 @@ __device__ __forceinline__ void thread_refresh(const DevState &S, const CellRec 
     }
     K = N;
     while (need) {
-        const int n = __ffs(need) - 1;
-        need &= need - 1;
-        const int ip = SEL8(K.pt, n);
-        float x, y, z, ext, src;
-        int ns;
-        thread_eval_point(S, ip, Y4, bt, rd, singlescatter, x, y, z, ext, src, ns);
-        npt_eval++; nsh_eval += ns;
+        int nn[4], ipp[4];
+        bool valid[4];
 #pragma unroll
-        for (int k = 0; k < 8; k++)
-            if (k == n) { K.x[k] = x; K.y[k] = y; K.z[k] = z; K.ext[k] = ext; K.src[k] = src; }
+        for (int i = 0; i < 4; i++) {
+            valid[i] = need != 0;
+            nn[i] = valid[i] ? __ffs(need) - 1 : nn[0];
+            need &= need - 1;
+            ipp[i] = SEL8(K.pt, nn[i]);
+        }
+        float4 pr[4]; int4 ps[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) { pr[i] = __ldg(&S.ptrec[ipp[i] - 1]); ps[i] = __ldg(&S.ptsrc[ipp[i] - 1]); }
+        int n4[4], nmax = 0;
+        const float4 *base[4];
+        float acc[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int ns = ps[i].y & 0xFFFF;
+            n4[i] = (valid[i] && !singlescatter) ? (AT3D_SHPAD(ns) >> 2) : 0;     // multiple of 8
+            nmax = max(nmax, n4[i]);
+            base[i] = (const float4 *)(S.shsrc + ps[i].x);
+            acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.0f;
+            if (valid[i]) { npt_eval++; nsh_eval += ns; }
+        }
+#pragma unroll 1
+        for (int j = 0; j < nmax; j += 4) {
+            float4 s[4][4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const bool on = j < n4[i];
+#pragma unroll
+                for (int q = 0; q < 4; q++) s[i][q] = on ? __ldg(base[i] + j + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const float4 y = Y4[(size_t)(j + q) * bt];
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    acc[i][0] = fmaf(s[i][q].x, y.x, acc[i][0]); acc[i][1] = fmaf(s[i][q].y, y.y, acc[i][1]);
+                    acc[i][2] = fmaf(s[i][q].z, y.z, acc[i][2]); acc[i][3] = fmaf(s[i][q].w, y.w, acc[i][3]);
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            if (!valid[i]) continue;
+            const float b = thread_singscat_sum(S, ipp[i], ps[i], rd);
+            const float src = (((acc[i][0] + acc[i][1]) + (acc[i][2] + acc[i][3])) + b) * pr[i].w;
+#pragma unroll
+            for (int k = 0; k < 8; k++)
+                if (k == nn[i]) { K.x[k] = pr[i].x; K.y[k] = pr[i].y; K.z[k] = pr[i].z; K.ext[k] = pr[i].w; K.src[k] = src; }
+        }
     }
 }
 
@@ -141,7 +164,7 @@ __device__ int thread_march_forward(const DevState &S, const float4 *Y4, int bt,
                                     bool singlescatter, bool nosurface, int maxsub,
                                     double &radA, double &radB,
                                     int *trace_cells, int trace_cap, int &ntrace, int &nsubA, int &nsubB,
-                                    int &npt_eval, int &nsh_eval)
+                                    int &npt_eval, int &nsh_eval, int &nptB)
 {
     double xe = x0, ye = y0, ze = z0, trA = 1.0, trB = 1.0;
     float ext1A = 0.0f, srcext1A = 0.0f, ext1B = 0.0f, srcext1B = 0.0f;
@@ -153,7 +176,7 @@ __device__ int thread_march_forward(const DevState &S, const float4 *Y4, int bt,
     int iface = 0, ngrid = 0, jf = 0;
     bool doneA = !(MODES & 1), doneB = !(MODES & 2);
     TCorners K;
-    npt_eval = 0; nsh_eval = 0;
+    npt_eval = 0; nsh_eval = 0; nptB = 0;
 #pragma unroll
     for (int n = 0; n < 8; n++) { K.pt[n] = 0; K.x[n] = K.y[n] = K.z[n] = K.ext[n] = K.src[n] = 0.0f; }
     ntrace = 0; nsubA = 0; nsubB = 0;
@@ -163,7 +186,9 @@ __device__ int thread_march_forward(const DevState &S, const float4 *Y4, int bt,
         ngrid++;
         if (trace_cells && ntrace < trace_cap) trace_cells[ntrace] = icell;
         ntrace++;
+        const int ne0 = npt_eval;
         thread_refresh(S, c, Y4, bt, rd, singlescatter, jf, K, npt_eval, nsh_eval);
+        if ((MODES & 2) && !doneB) nptB += npt_eval - ne0;
         const float q1x = K.x[0], q1y = K.y[0], q1z = K.z[0];
         const float q8x = K.x[7], q8y = K.y[7], q8z = K.z[7];
         const int io = 8 - rd.ioct;

@@ -336,10 +336,11 @@ def main():
             e2e=dict(value=world * nrays * args.steps / t_e2e, unit='rays/s', h2d_bytes_per_step=int(h2d),
                      d2h_bytes_per_step=int(d2h)),
             gpu_launches=int(args.steps * (5 + (1 if gi.exact_single_scatter else 0))),
-            roofline=dict(kernel='adjoint_kernel<1>', bound='hbm', achieved=achieved, peak=peak, unit='GB/s',
+            roofline=dict(kernel='weights_kernel+apply_kernel (derivative pass)', bound='hbm', achieved=achieved, peak=peak, unit='GB/s',
                           frac=achieved / peak, traffic=None, peak_source=peak_src,
                           algorithmic_bytes_per_launch=abytes, kernel_ms=adj_ms, counts=counts),
-            phases_ms=dict(forward=float(np.mean(kms[:, 0])), adjoint=adj_ms, beam=float(np.mean(kms[:, 2])),
+            phases_ms=dict(forward=float(np.mean(kms[:, 0])), adjoint=adj_ms, weights=float(np.mean(kms[:, 4])),
+                           apply=adj_ms - float(np.mean(kms[:, 4])), beam=float(np.mean(kms[:, 2])),
                            total=float(np.mean(kms[:, 3]))),
             render=dict(rays_per_s=nrays / (np.mean(rms) * 1e-3), kernel_ms=float(np.mean(rms)),
                         achieved_gbs=rbytes / (np.mean(rms) * 1e-3) / 1e9, frac=rbytes / (np.mean(rms) * 1e-3) / 1e9 / peak,

@@ -175,7 +175,7 @@ int at3d_render(at3d_state *st, const at3d_rays *rays, float *stokes /*[nstokes,
 int at3d_levisapprox_gradient(at3d_state *st, const at3d_rays *rays, const at3d_grad_desc *g,
                               double *gradout, double *cost, float *stokesout,
                               const at3d_trace *trace /*optional*/, void *cuda_stream /*optional*/,
-                              double *kernel_ms /*optional [4]: forward, adjoint, beam, total*/,
+                              double *kernel_ms /*optional [5]: forward, adjoint (weights+apply), beam, total, weights*/,
                               char *errmsg);
 
 /* ---- a15: PREPARE_DERIV_INTERPS (shdomsub4.f:2917); HOST pointers ---- */
