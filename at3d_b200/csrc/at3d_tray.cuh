@@ -76,10 +76,8 @@ __device__ __forceinline__ float thread_singscat_sum(const DevState &S, int ip, 
 // Corner refresh of one thread.  Points shared with the previous cell are found with the reference's
 // DONEFACE rule (shdomsub2.f:2395-2397, 2509-2515): after crossing a face normal to axis `jf`, corner n
 // of the new cell can only coincide with corner n^bit of the old one; the ids decide.  Reused values
-// are bit-identical to a recomputation.  New corners -- COMPUTE_SOURCE_1CELL_UNPOL
-// (shdomsub2.f:3046-3192) with the TMS-corrected SH blocks -- are evaluated four at a time: their
-// records are requested together, the SH blocks stream through 16 independent 16-byte loads per
-// iteration and share the reads of the thread's YLMDIR column.
+// are bit-identical to a recomputation.  New corners: COMPUTE_SOURCE_1CELL_UNPOL
+// (shdomsub2.f:3046-3192) with the TMS-corrected SH block of the point.
 __device__ __forceinline__ void thread_refresh(const DevState &S, const CellRec &c, const float4 *Y4, int bt,
                                                const RayDir &rd, bool singlescatter, int jf /*0: first cell*/,
                                                TCorners &K, int &npt_eval, int &nsh_eval)
@@ -102,58 +100,33 @@ __device__ __forceinline__ void thread_refresh(const DevState &S, const CellRec 
     }
     K = N;
     while (need) {
-        int nn[4], ipp[4];
-        bool valid[4];
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            valid[i] = need != 0;
-            nn[i] = valid[i] ? __ffs(need) - 1 : nn[0];
-            need &= need - 1;
-            ipp[i] = SEL8(K.pt, nn[i]);
-        }
-        float4 pr[4]; int4 ps[4];
-#pragma unroll
-        for (int i = 0; i < 4; i++) { pr[i] = __ldg(&S.ptrec[ipp[i] - 1]); ps[i] = __ldg(&S.ptsrc[ipp[i] - 1]); }
-        int n4[4], nmax = 0;
-        const float4 *base[4];
-        float acc[4][4];
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            const int ns = ps[i].y & 0xFFFF;
-            n4[i] = (valid[i] && !singlescatter) ? (AT3D_SHPAD(ns) >> 2) : 0;     // multiple of 8
-            nmax = max(nmax, n4[i]);
-            base[i] = (const float4 *)(S.shsrc + ps[i].x);
-            acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.0f;
-            if (valid[i]) { npt_eval++; nsh_eval += ns; }
-        }
+        const int n = __ffs(need) - 1;
+        need &= need - 1;
+        const int ip = SEL8(K.pt, n);
+        const float4 pr = __ldg(&S.ptrec[ip - 1]);
+        const int4 ps = __ldg(&S.ptsrc[ip - 1]);
+        const int ns = ps.y & 0xFFFF;
+        float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+        if (!singlescatter) {
+            const float4 *base = (const float4 *)(S.shsrc + ps.x);
+            const int n4 = AT3D_SHPAD(ns) >> 2;                 // multiple of 8
 #pragma unroll 1
-        for (int j = 0; j < nmax; j += 4) {
-            float4 s[4][4];
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-                const bool on = j < n4[i];
-#pragma unroll
-                for (int q = 0; q < 4; q++) s[i][q] = on ? __ldg(base[i] + j + q) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-#pragma unroll
-            for (int q = 0; q < 4; q++) {
-                const float4 y = Y4[(size_t)(j + q) * bt];
-#pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    acc[i][0] = fmaf(s[i][q].x, y.x, acc[i][0]); acc[i][1] = fmaf(s[i][q].y, y.y, acc[i][1]);
-                    acc[i][2] = fmaf(s[i][q].z, y.z, acc[i][2]); acc[i][3] = fmaf(s[i][q].w, y.w, acc[i][3]);
-                }
+            for (int j = 0; j < n4; j += 4) {
+                const float4 s0 = __ldg(base + j), s1 = __ldg(base + j + 1), s2 = __ldg(base + j + 2), s3 = __ldg(base + j + 3);
+                const float4 y0 = Y4[(size_t)j * bt], y1 = Y4[(size_t)(j + 1) * bt];
+                const float4 y2 = Y4[(size_t)(j + 2) * bt], y3 = Y4[(size_t)(j + 3) * bt];
+                a0 = fmaf(s0.x, y0.x, a0); a1 = fmaf(s0.y, y0.y, a1); a2 = fmaf(s0.z, y0.z, a2); a3 = fmaf(s0.w, y0.w, a3);
+                a0 = fmaf(s1.x, y1.x, a0); a1 = fmaf(s1.y, y1.y, a1); a2 = fmaf(s1.z, y1.z, a2); a3 = fmaf(s1.w, y1.w, a3);
+                a0 = fmaf(s2.x, y2.x, a0); a1 = fmaf(s2.y, y2.y, a1); a2 = fmaf(s2.z, y2.z, a2); a3 = fmaf(s2.w, y2.w, a3);
+                a0 = fmaf(s3.x, y3.x, a0); a1 = fmaf(s3.y, y3.y, a1); a2 = fmaf(s3.z, y3.z, a2); a3 = fmaf(s3.w, y3.w, a3);
             }
         }
+        const float b = thread_singscat_sum(S, ip, ps, rd);
+        const float src = (((a0 + a1) + (a2 + a3)) + b) * pr.w;
+        npt_eval++; nsh_eval += ns;
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-            if (!valid[i]) continue;
-            const float b = thread_singscat_sum(S, ipp[i], ps[i], rd);
-            const float src = (((acc[i][0] + acc[i][1]) + (acc[i][2] + acc[i][3])) + b) * pr[i].w;
-#pragma unroll
-            for (int k = 0; k < 8; k++)
-                if (k == nn[i]) { K.x[k] = pr[i].x; K.y[k] = pr[i].y; K.z[k] = pr[i].z; K.ext[k] = pr[i].w; K.src[k] = src; }
-        }
+        for (int k = 0; k < 8; k++)
+            if (k == n) { K.x[k] = pr.x; K.y[k] = pr.y; K.z[k] = pr.z; K.ext[k] = pr.w; K.src[k] = src; }
     }
 }
 
