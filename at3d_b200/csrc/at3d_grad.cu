@@ -733,8 +733,9 @@ weights_kernel(DevState S, DevGrad G, int nrays, const float *camx, const float 
                const float *camz, const double *cammu, const double *camphi, const RayPack *packs,
                const int *raypix, const double *adjw /*[NST,npix]*/, const double *ray_weights,
                const double *stokes_weights, const double *total /*[NST,nrays]*/,
-               const int *recoff /*[nrays+1]*/, VisitRec *recs, int *nrec_out, double *beam_weight,
-               int *trace_cells, int trace_cap, int *trace_n, int *trace_nsub, RayErr *err, int *ray_counter)
+               const long long *recoff /*[nrays+1]*/, long long rec_base, VisitRec *recs, int *nrec_out,
+               double *beam_weight, int *trace_cells, int trace_cap, int *trace_n, int *trace_nsub, RayErr *err,
+               int *ray_counter, int ray0)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const Oct o = oct_id();
@@ -746,8 +747,8 @@ weights_kernel(DevState S, DevGrad G, int nrays, const float *camx, const float 
         int base = 0;
         if (lane == 0) base = atomicAdd(ray_counter, 32 / AT3D_OCT);
         base = __shfl_sync(FULLMASK, base, 0);
-        if (base >= nrays) break;
-        const int iray = base + (lane >> 3);
+        if (ray0 + base >= nrays) break;
+        const int iray = ray0 + base + (lane >> 3);
         if (iray < nrays) {
             RayPack pk; RayDir rd; double mu2, phi2, adj[NST];
             int ntrace = 0, nsub = 0, nrec = 0;
@@ -757,9 +758,9 @@ weights_kernel(DevState S, DevGrad G, int nrays, const float *camx, const float 
 #pragma unroll
                 for (int k = 0; k < NST; k++) tot[k] = __ldg(&total[k + NST * (size_t)iray]);
                 const float sky = (-mu2 > 0.0) ? dev_sky_radiance(S, (float)mu2, (float)phi2) : 0.0f;
-                const int r0 = __ldg(&recoff[iray]), r1 = __ldg(&recoff[iray + 1]);
+                const long long r0 = __ldg(&recoff[iray]), r1 = __ldg(&recoff[iray + 1]);
                 const int e = march_weights<NST>(S, G, Ysh, Vsh, rd, mu2, pk.x0, pk.y0, pk.z0, sky, adj, tot, o,
-                                                 recs + r0, r1 - r0, beam_weight,
+                                                 recs + (r0 - rec_base), (int)(r1 - r0), beam_weight,
                                                  trace_cells ? trace_cells + (size_t)trace_cap * iray : nullptr,
                                                  trace_cap, ntrace, nsub, nrec);
                 if (e && o.ol == 0) set_err(err, e, iray);
@@ -901,8 +902,8 @@ __global__ void __launch_bounds__(AT3D_RAY_THREADS)
 apply_kernel(DevState S, DevGrad G, int nrays, const float *camx, const float *camy,
              const float *camz, const double *cammu, const double *camphi, const RayPack *packs,
              const int *raypix, const double *adjw, const double *ray_weights, const double *stokes_weights,
-             const int *recoff, const VisitRec *recs, const int *nrec_in, double *gradout,
-             RayErr *err, int *ray_counter)
+             const long long *recoff, long long rec_base, const VisitRec *recs, const int *nrec_in, double *gradout,
+             RayErr *err, int *ray_counter, int ray0)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const Oct o = oct_id();
@@ -914,14 +915,14 @@ apply_kernel(DevState S, DevGrad G, int nrays, const float *camx, const float *c
         int base = 0;
         if (lane == 0) base = atomicAdd(ray_counter, 32 / AT3D_OCT);
         base = __shfl_sync(FULLMASK, base, 0);
-        if (base >= nrays) break;
-        const int iray = base + (lane >> 3);
+        if (ray0 + base >= nrays) break;
+        const int iray = ray0 + base + (lane >> 3);
         if (iray < nrays) {
             const int nrec = __ldg(&nrec_in[iray]);
             RayPack pk; RayDir rd; double mu2, phi2, adj[NST];
             if (nrec > 0 && ray_setup<NST>(S, iray, camx, camy, camz, cammu, camphi, packs, raypix, adjw, ray_weights,
                                            stokes_weights, Ysh, Vsh, o, err, pk, rd, mu2, phi2, adj)) {
-                const VisitRec *rp = recs + __ldg(&recoff[iray]);
+                const VisitRec *rp = recs + (__ldg(&recoff[iray]) - rec_base);
                 int nrh = 0;
                 for (int i = 0; i < nrec; i++) {
                     VisitRec rc;
@@ -1192,6 +1193,8 @@ static int stage_in(const T *src, size_t n, int host, void *dst, const T **out, 
     return 0;
 }
 
+struct IntToLL { __host__ __device__ long long operator()(int v) const { return (long long)v; } };
+
 static size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 extern "C" int at3d_levisapprox_gradient(at3d_state *st, const at3d_rays *rays, const at3d_grad_desc *g,
@@ -1232,6 +1235,12 @@ extern "C" int at3d_levisapprox_gradient(at3d_state *st, const at3d_rays *rays, 
     // ---- work buffers ----
     size_t cubtmp = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, cubtmp, (const int *)nullptr, (int *)nullptr, (int)(npix > n + 1 ? npix : n + 1), stream);
+    {
+        size_t t2 = 0;
+        cub::TransformInputIterator<long long, IntToLL, const int *> it((const int *)nullptr, IntToLL());
+        cub::DeviceScan::ExclusiveSum(nullptr, t2, it, (long long *)nullptr, (int)(n + 1), stream);
+        if (t2 > cubtmp) cubtmp = t2;
+    }
     o = 0;
     const size_t w_vis = o; o += al256(sizeof(double) * nst * n);
     const size_t w_tot = o; o += al256(sizeof(double) * nst * n);
@@ -1242,7 +1251,7 @@ extern "C" int at3d_levisapprox_gradient(at3d_state *st, const at3d_rays *rays, 
     const size_t w_beam = o; o += al256(sizeof(double) * S.npts);
     const size_t w_cub = o; o += al256(cubtmp);
     const size_t w_npt = o; o += al256(sizeof(int) * (n + 1));
-    const size_t w_recoff = o; o += al256(sizeof(int) * (n + 1));
+    const size_t w_recoff = o; o += al256(sizeof(long long) * (n + 1));
     const size_t w_nrec = o; o += al256(sizeof(int) * n);
     const size_t w_grad = o; o += al256(sizeof(double) * ngrad);
     const size_t w_so = o; o += al256(sizeof(float) * nst * npix);
@@ -1252,7 +1261,8 @@ extern "C" int at3d_levisapprox_gradient(at3d_state *st, const at3d_rays *rays, 
     double *visrad = (double *)(wb + w_vis), *total = (double *)(wb + w_tot), *adjw = (double *)(wb + w_adj);
     double *costp = (double *)(wb + w_costp), *beam = (double *)(wb + w_beam);
     int *pixstart = (int *)(wb + w_pixstart), *raypix = (int *)(wb + w_raypix);
-    int *npt = (int *)(wb + w_npt), *recoff = (int *)(wb + w_recoff), *nrec = (int *)(wb + w_nrec);
+    int *npt = (int *)(wb + w_npt), *nrec = (int *)(wb + w_nrec);
+    long long *recoff = (long long *)(wb + w_recoff);
     double *grad_d = host ? (double *)(wb + w_grad) : gradout;
     float *so_d = host ? (float *)(wb + w_so) : stokesout;
     double *cost_d = host ? (double *)(wb + w_cost) : cost;
@@ -1271,8 +1281,8 @@ extern "C" int at3d_levisapprox_gradient(at3d_state *st, const at3d_rays *rays, 
     CUDA_TRY(cudaMemsetAsync(beam, 0, sizeof(double) * S.npts, stream));
     CUDA_TRY(cudaMemsetAsync(so_d, 0, sizeof(float) * nst * npix, stream));
     CUDA_TRY(cudaMemsetAsync(cost_d, 0, sizeof(double), stream));
-    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-    if (kernel_ms) { for (int i = 0; i < 5; i++) cudaEventCreate(&ev[i]); cudaEventRecord(ev[0], stream); cudaEventRecord(ev[4], stream); }
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    if (kernel_ms) { for (int i = 0; i < 4; i++) cudaEventCreate(&ev[i]); cudaEventRecord(ev[0], stream); kernel_ms[4] = 0.0; }
     if (n > 0 && npix > 0) {
         // ---- Phase 1: forward radiances (INTEGRATE_1RAY arithmetic for the pixel values; the
         //      ADJOINT_INTEGRATE_1RAY arithmetic for the totals the derivative pass needs) ----
@@ -1283,8 +1293,11 @@ extern "C" int at3d_levisapprox_gradient(at3d_state *st, const at3d_rays *rays, 
         CUDA_TRY(launch_forward(Sf, (int)n, camx, camy, camz, cammu, camphi, packs, nullptr, visrad, total, 3, 1,
                                 G.singlescatter, 0, G.maxsub, nullptr, 0, nullptr, nullptr, (RayErr *)st->err.p,
                                 st->ray_counter, npt, stream));
-        // visit records of a ray are contiguous: offsets = exclusive scan of the per-ray visit counts
-        CUDA_TRY(cub::DeviceScan::ExclusiveSum(wb + w_cub, cubtmp, npt, recoff, (int)(n + 1), stream));
+        // visit records of a ray are contiguous: offsets = exclusive scan (64-bit) of the per-ray visit counts
+        {
+            cub::TransformInputIterator<long long, IntToLL, const int *> it(npt, IntToLL());
+            CUDA_TRY(cub::DeviceScan::ExclusiveSum(wb + w_cub, cubtmp, it, recoff, (int)(n + 1), stream));
+        }
         if (kernel_ms) cudaEventRecord(ev[1], stream);
         // ---- Phase 2 ----
         CUDA_TRY(cub::DeviceScan::ExclusiveSum(wb + w_cub, cubtmp, rpp, pixstart, (int)npix, stream));
@@ -1299,51 +1312,71 @@ extern "C" int at3d_levisapprox_gradient(at3d_state *st, const at3d_rays *rays, 
         cost_reduce_kernel<<<1, 1024, 0, stream>>>((int)npix, costp, cost_d);
         CUDA_TRY(cudaGetLastError());
         // ---- Phase 3 ----
-        int nrec_total = 0;
-        CUDA_TRY(cudaMemcpyAsync(&nrec_total, recoff + n, sizeof(int), cudaMemcpyDeviceToHost, stream));
+        // The records of all rays may not fit (cfg4: ~80 GB): the derivative pass runs over chunks of rays whose
+        // records fit the budget (AT3D_B200_REC_GB, default 8 GB); chunk boundaries from the offsets on the host.
+        st->recoff_h.resize(n + 1);
+        CUDA_TRY(cudaMemcpyAsync(st->recoff_h.data(), recoff, sizeof(long long) * (n + 1), cudaMemcpyDeviceToHost, stream));
         CUDA_TRY(cudaStreamSynchronize(stream));
-        if (nrec_total < 0) { set_msg(errmsg, "more than 2^31 visit records: split the ray list"); return 2; }
-        CUDA_TRY(st->recs.reserve(((size_t)nrec_total + 8) * sizeof(VisitRec)));
-        VisitRec *recs = (VisitRec *)st->recs.p;
+        const long long *roff = st->recoff_h.data();
+        double budget_gb = 8.0;
+        if (const char *e = getenv("AT3D_B200_REC_GB")) { const double v = atof(e); if (v > 0.0) budget_gb = v; }
+        const long long budget = (long long)(budget_gb * 1073741824.0 / sizeof(VisitRec));
         const size_t smem = (size_t)AT3D_RAYS_PER_BLOCK * (S.ny_comp * S.nlmp + ((3 * (S.ml + 1) + 3) & ~3)) * sizeof(float);
-        int dev = 0, nsm = 148, per_sm = 1;
+        int dev = 0, nsm = 148, per_sm_w = 1, per_sm_a = 1;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
-        const long want = ((long)n + AT3D_RAYS_PER_BLOCK - 1) / AT3D_RAYS_PER_BLOCK;
-        {
-            const void *fn = nst == 1 ? (const void *)weights_kernel<1> : (const void *)weights_kernel<3>;
-            CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, AT3D_RAY_THREADS, smem);
-            if (per_sm < 1) per_sm = 1;
-            const long cap = (long)nsm * per_sm;
-            const int nblk = (int)(want < cap ? want : cap);
+        const void *fnw = nst == 1 ? (const void *)weights_kernel<1> : (const void *)weights_kernel<3>;
+        const void *fna = nst == 1 ? (const void *)apply_kernel<1> : (const void *)apply_kernel<3>;
+        CUDA_TRY(cudaFuncSetAttribute(fnw, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaFuncSetAttribute(fna, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_w, fnw, AT3D_RAY_THREADS, smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_a, fna, AT3D_RAY_THREADS, smem);
+        if (per_sm_w < 1) per_sm_w = 1;
+        if (per_sm_a < 1) per_sm_a = 1;
+        float ms_weights = 0.0f;
+        size_t r0 = 0;
+        while (r0 < n) {
+            size_t r1 = r0 + 1;
+            while (r1 < n && roff[r1 + 1] - roff[r0] <= budget) r1++;
+            const long long nrec_chunk = roff[r1] - roff[r0];
+            CUDA_TRY(st->recs.reserve(((size_t)nrec_chunk + 8) * sizeof(VisitRec)));
+            VisitRec *recs = (VisitRec *)st->recs.p;
+            const long want = ((long)(r1 - r0) + AT3D_RAYS_PER_BLOCK - 1) / AT3D_RAYS_PER_BLOCK;
+            const long capw = (long)nsm * per_sm_w, capa = (long)nsm * per_sm_a;
+            const int nblkw = (int)(want < capw ? want : capw), nblka = (int)(want < capa ? want : capa);
+            cudaEvent_t c0 = nullptr, c1 = nullptr;
+            if (kernel_ms) { cudaEventCreate(&c0); cudaEventCreate(&c1); cudaEventRecord(c0, stream); }
             CUDA_TRY(cudaMemsetAsync(st->ray_counter, 0, sizeof(int), stream));
             if (nst == 1)
-                weights_kernel<1><<<nblk, AT3D_RAY_THREADS, smem, stream>>>(S, G, (int)n, camx, camy, camz, cammu, camphi,
-                    packs, raypix, adjw, rw, sw, total, recoff, recs, nrec, beam, tc, tcap, tn, ts, (RayErr *)st->err.p,
-                    st->ray_counter);
+                weights_kernel<1><<<nblkw, AT3D_RAY_THREADS, smem, stream>>>(S, G, (int)r1, camx, camy, camz, cammu, camphi,
+                    packs, raypix, adjw, rw, sw, total, recoff, roff[r0], recs, nrec, beam, tc, tcap, tn, ts,
+                    (RayErr *)st->err.p, st->ray_counter, (int)r0);
             else
-                weights_kernel<3><<<nblk, AT3D_RAY_THREADS, smem, stream>>>(S, G, (int)n, camx, camy, camz, cammu, camphi,
-                    packs, raypix, adjw, rw, sw, total, recoff, recs, nrec, beam, tc, tcap, tn, ts, (RayErr *)st->err.p,
-                    st->ray_counter);
+                weights_kernel<3><<<nblkw, AT3D_RAY_THREADS, smem, stream>>>(S, G, (int)r1, camx, camy, camz, cammu, camphi,
+                    packs, raypix, adjw, rw, sw, total, recoff, roff[r0], recs, nrec, beam, tc, tcap, tn, ts,
+                    (RayErr *)st->err.p, st->ray_counter, (int)r0);
             CUDA_TRY(cudaGetLastError());
-        }
-        if (kernel_ms) cudaEventRecord(ev[4], stream);
-        {
-            const void *fn = nst == 1 ? (const void *)apply_kernel<1> : (const void *)apply_kernel<3>;
-            CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, AT3D_RAY_THREADS, smem);
-            if (per_sm < 1) per_sm = 1;
-            const long cap = (long)nsm * per_sm;
-            const int nblk = (int)(want < cap ? want : cap);
+            if (kernel_ms) cudaEventRecord(c1, stream);
             CUDA_TRY(cudaMemsetAsync(st->ray_counter, 0, sizeof(int), stream));
             if (nst == 1)
-                apply_kernel<1><<<nblk, AT3D_RAY_THREADS, smem, stream>>>(S, G, (int)n, camx, camy, camz, cammu, camphi,
-                    packs, raypix, adjw, rw, sw, recoff, recs, nrec, grad_d, (RayErr *)st->err.p, st->ray_counter);
+                apply_kernel<1><<<nblka, AT3D_RAY_THREADS, smem, stream>>>(S, G, (int)r1, camx, camy, camz, cammu, camphi,
+                    packs, raypix, adjw, rw, sw, recoff, roff[r0], recs, nrec, grad_d, (RayErr *)st->err.p,
+                    st->ray_counter, (int)r0);
             else
-                apply_kernel<3><<<nblk, AT3D_RAY_THREADS, smem, stream>>>(S, G, (int)n, camx, camy, camz, cammu, camphi,
-                    packs, raypix, adjw, rw, sw, recoff, recs, nrec, grad_d, (RayErr *)st->err.p, st->ray_counter);
+                apply_kernel<3><<<nblka, AT3D_RAY_THREADS, smem, stream>>>(S, G, (int)r1, camx, camy, camz, cammu, camphi,
+                    packs, raypix, adjw, rw, sw, recoff, roff[r0], recs, nrec, grad_d, (RayErr *)st->err.p,
+                    st->ray_counter, (int)r0);
+            CUDA_TRY(cudaGetLastError());
+            if (kernel_ms) {
+                float t = 0.0f;
+                cudaEventSynchronize(c1); cudaEventElapsedTime(&t, c0, c1); ms_weights += t;
+                cudaEventDestroy(c0); cudaEventDestroy(c1);
+            } else if (r1 < n) {
+                CUDA_TRY(cudaStreamSynchronize(stream));      // the record buffer is reused by the next chunk
+            }
+            r0 = r1;
         }
+        if (kernel_ms) kernel_ms[4] = ms_weights;
         CUDA_TRY(cudaGetLastError());
         if (kernel_ms) cudaEventRecord(ev[2], stream);
         // ---- Phase 4 ----
@@ -1372,8 +1405,7 @@ extern "C" int at3d_levisapprox_gradient(at3d_state *st, const at3d_rays *rays, 
         cudaEventElapsedTime(&ms, ev[1], ev[2]); kernel_ms[1] = ms;
         cudaEventElapsedTime(&ms, ev[2], ev[3]); kernel_ms[2] = ms;
         cudaEventElapsedTime(&ms, ev[0], ev[3]); kernel_ms[3] = ms;
-        cudaEventElapsedTime(&ms, ev[1], ev[4]); kernel_ms[4] = ms;      // phase A (weights) incl. pixel kernels
-        for (int i = 0; i < 5; i++) cudaEventDestroy(ev[i]);
+        for (int i = 0; i < 4; i++) cudaEventDestroy(ev[i]);
     }
     return rc;
 }

@@ -38,6 +38,7 @@ struct at3d_state {
     std::vector<RayPack> packs_h;   // host staging of the per-ray packs
     float *bcrad_dev = nullptr;
     unsigned long long *counts_dev = nullptr;
+    std::vector<long long> recoff_h; // per-ray visit-record offsets of the last gradient call (host copy)
     std::vector<int> nr_h;          // radiance SH length per point (host copy, for the gradient tables)
     int *ray_counter = nullptr;     // work counter of the persistent ray kernels
     int nbcrad = 0;

@@ -131,3 +131,24 @@ def test_gradient_device_pointers(oracle):
     np.testing.assert_allclose(float(cost2.cpu()[0]), float(cost[0]), rtol=1e-12)
     np.testing.assert_array_equal(so2.cpu().numpy().T, so)
     dev.close()
+
+
+def test_chunked_derivative_pass_matches_single_chunk(oracle, monkeypatch):
+    """The derivative pass runs over chunks of rays when the visit records exceed the budget
+    (AT3D_B200_REC_GB); a tiny budget (one ray per chunk) must give the same gradient."""
+    from at3d_b200.device import DeviceState
+    from at3d_b200 import gradsetup
+    sc = scenes.make('polarized_periodic_split', oracle)
+    rays = scenes.ray_set(sc, n_persp=5, res=0.05)
+    gi = gradsetup.make_gradient_inputs(sc, oracle, seed=3, numder=2)
+    rad = oracle.render(sc.state, rays)
+    pix = gradsetup.make_pixels(sc.state.nstokes, rays.nrays, rad, seed=4)
+    dev = DeviceState(sc.state)
+    dev.attach_gradient(gi)
+    g1, c1, s1 = dev.gradient(rays, pix)
+    monkeypatch.setenv('AT3D_B200_REC_GB', '0.000001')
+    g2, c2, s2 = dev.gradient(rays, pix)
+    dev.close()
+    assert float(c1[0]) == float(c2[0])
+    np.testing.assert_array_equal(s1, s2)
+    np.testing.assert_allclose(g2, g1, rtol=1e-10, atol=1e-12 * np.max(np.abs(g1)))
