@@ -39,6 +39,14 @@ def build_scene(args):
         kw = dict(nx=32, ny=37, nz=27, nmu=16, nphi=32, nstokes=3, bc='open', dx=0.02, dy=0.02, dz=0.04,
                   cloud='les', ext_max=90.0, numphase=18, nsplits=1700, seed=0, truncate=True)
         npix_side = 200
+    elif args.workload in ('cfg4', 'cfg4s'):
+        # BASELINE.json configs[3]: 256x256x100 cloud + Rayleigh (NPART=2), 9 views x 512x512 (cfg4s: 128x128x64,
+        # 9 x 256x256); Lambertian surface instead of the ocean BRDF (not on the GPU path yet)
+        big = args.workload == 'cfg4'
+        kw = dict(nx=256 if big else 128, ny=256 if big else 128, nz=100 if big else 64, nmu=16, nphi=32, nstokes=1,
+                  bc='open', dx=0.02, dy=0.02, dz=0.04, cloud='les', ext_max=60.0, numphase=18, nsplits=0, seed=1,
+                  truncate=True, rayleigh=True, mix_fraction=0.0)
+        npix_side = 512 if big else 256
     else:   # 'small': CI-sized
         kw = dict(nx=16, ny=16, nz=14, nmu=8, nphi=16, nstokes=1, bc='open', dx=0.03, dy=0.03, dz=0.04,
                   cloud='les', ext_max=60.0, numphase=6, nsplits=60, seed=0)
@@ -170,7 +178,7 @@ def main():
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--workload', default='cfg2', choices=['cfg2', 'cfg3', 'small'])
+    ap.add_argument('--workload', default='cfg2', choices=['cfg2', 'cfg3', 'cfg4', 'cfg4s', 'small'])
     ap.add_argument('--pixels', type=int, default=0, help='pixels per view side (default: per workload)')
     ap.add_argument('--cpu-seconds', type=float, default=12.0)
     ap.add_argument('--no-cpu', action='store_true')
@@ -329,9 +337,9 @@ def main():
             metric='radiance+gradient rays/s', value=value, unit='rays/s', n_gpus=world, steps=args.steps,
             warmup=args.warmup, ms_per_step=1e3 * t_total / args.steps, higher_is_better=True, scaling='weak',
             vs_baseline=None, dtype='f32 optics / f64 geometry+accumulators', data='synthetic',
-            config=dict(workload=args.workload + ': LES-like 32x37x27 open BC, NLM=256, 9 perspective views, '
-                        'scalar radiance + Levis gradient (NUMDER=1); one replica of the workload per GPU, '
-                        'gradient all-reduced', rays=int(nrays), npts=int(st.npts), ncells=int(st.ncells),
+            config=dict(workload=args.workload + ': LES-like %dx%dx%d open BC, NLM=%d, NSTOKES=%d, NPART=%d, 9 perspective '
+                        'views, radiance + Levis gradient (NUMDER=1); one replica of the workload per GPU, gradient '
+                        'all-reduced' % (st.nx, st.ny, st.nz, st.nlm, st.nstokes, st.npart), rays=int(nrays), npts=int(st.npts), ncells=int(st.ncells),
                         nlm=int(st.nlm), l2='flushed between steps (256 MiB memset)', hbm_state_bytes=dev.hbm_bytes),
             e2e=dict(value=world * nrays * args.steps / t_e2e, unit='rays/s', h2d_bytes_per_step=int(h2d),
                      d2h_bytes_per_step=int(d2h)),
