@@ -470,9 +470,10 @@ __device__ int march_weights(const DevState &S, const DevGrad &G, const float *Y
                 K.W = 0.0; K.G = 0.0;
             }
             unsigned need = oct_ballot(o, !hit);
+            npt_eval += __popc(need);
             while (need) {
                 const int n = __ffs(need) - 1;
-                need &= need - 1;
+                const int ipn = __shfl_sync(o.m, myp, n, 8);
                 const int off = __shfl_sync(o.m, soff, n, 8), ns = __shfl_sync(o.m, sns, n, 8);
                 float a[NST];
 #pragma unroll
@@ -484,12 +485,15 @@ __device__ int march_weights(const DevState &S, const DevGrad &G, const float *Y
 #pragma unroll
                 for (int k = 0; k < NST; k++) bt[k] = 0.0f;
                 if (!deltam) {
-                    const int ipn = __shfl_sync(o.m, myp, n, 8);
                     const float extn_ = __shfl_sync(o.m, K.ext, n, 8);
                     nodeltam_singscat<NST>(S, ipn, ns, extn_, Vsh, o, bt);
                 }
-                npt_eval++; nsh_eval += ns;
-                if (o.ol == n) {
+                // new corners that are the same grid point (zero-width open-boundary cells) share the evaluation
+                const bool mine = !hit && (myp == ipn);
+                const unsigned same = oct_ballot(o, mine);
+                nsh_eval += ns * __popc(same);
+                need &= ~same;
+                if (mine) {
 #pragma unroll
                     for (int k = 0; k < NST; k++) {
                         const float bb = deltam ? b[k] : bt[k];

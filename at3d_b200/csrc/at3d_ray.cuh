@@ -260,9 +260,10 @@ __device__ __forceinline__ void refresh_corners(const DevState &S, const CellRec
     for (int k = 0; k < NST; k++) b[k] = 0.0f;
     if (!hit) load_corner<NST>(S, myp, rd, K.x, K.y, K.z, K.ext, soff, sns, b);
     unsigned need = oct_ballot(o, !hit);
+    npt_eval += __popc(need);
     while (need) {
         const int n = __ffs(need) - 1;
-        need &= need - 1;
+        const int ipn = __shfl_sync(o.m, myp, n, 8);
         const int off = __shfl_sync(o.m, soff, n, 8), ns = __shfl_sync(o.m, sns, n, 8);
         float a[NST];
 #pragma unroll
@@ -272,11 +273,15 @@ __device__ __forceinline__ void refresh_corners(const DevState &S, const CellRec
 #pragma unroll
             for (int k = 0; k < NST; k++) a[k] = oct_sum(o.m, a[k]);
         }
-        npt_eval++; nsh_eval += ns;
-        if (o.ol == n) {
+        // new corners that are the same grid point (zero-width open-boundary cells) share the evaluation
+        const bool mine = !hit && (myp == ipn);
+        const unsigned same = oct_ballot(o, mine);
+        nsh_eval += ns * __popc(same);
+        if (mine) {
 #pragma unroll
             for (int k = 0; k < NST; k++) K.src[k] = (a[k] + b[k]) * K.ext;
         }
+        need &= ~same;
     }
 }
 

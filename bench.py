@@ -188,6 +188,11 @@ def main():
     local = int(os.environ.get('LOCAL_RANK', 0))
     ncores = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
 
+    if world > 1 and args.impl != 'reference':
+        # torchrun pins OMP_NUM_THREADS=1; the host side of the C-ABI call (per-ray setup with the host libm)
+        # is OpenMP-parallel: give every rank its share of the cores
+        lw = int(os.environ.get('LOCAL_WORLD_SIZE', world))
+        os.environ['OMP_NUM_THREADS'] = str(max(1, ncores // max(lw, 1)))
     if args.impl == 'reference':
         # the reference's own algorithm on the host cores; rank 0 only
         if rank != 0:
