@@ -554,11 +554,74 @@ static void compute_radiance_derivative_adjoint(const oracle_state *st, const or
     }
 }
 
-/* ADJOINT_INTEGRATE_1RAY  shdomsub4.f:3223-3967 */
+/* COMPUTE_RADIANCE_DERIVATIVE  shdomsub4.f:2588-2662 (single-sweep / Jacobian path; REAL temporaries) */
+static void compute_radiance_derivative(const oracle_state *st, const oracle_grad_in *g,
+                                        const grad_work *gw, double *raygrad, int npassed)
+{
+    const int nstokes = st->nstokes, maxpg = g->maxpg;
+    int kk, k, nb, idr, ns;
+    for (kk = 1; kk <= npassed - 1; kk++) {
+        double ext0 = 0.0, ext1 = 0.0, dels = gw->passeddels[kk - 1], ext;
+        const int *pp = &gw->passedpoints[8 * (size_t)(kk - 1)];
+        const double *i0 = &gw->passedinterp0[8 * (size_t)(kk - 1)];
+        const double *i1 = &gw->passedinterp1[8 * (size_t)(kk - 1)];
+        for (k = 0; k < 8; k++) {
+            ext0 = ext0 + st->total_ext[pp[k] - 1] * i0[k];
+            ext1 = ext1 + st->total_ext[pp[k] - 1] * i1[k];
+        }
+        ext = 0.5f * (ext0 + ext1);
+        if (ext != 0.0) {
+            for (k = 0; k < 8; k++) {
+                int ip = pp[k];
+                for (idr = 1; idr <= g->numder; idr++) {
+                    for (nb = 1; nb <= 8; nb++) {
+                        int ib = g->interpptr[(nb - 1) + 8 * (size_t)(ip - 1)];
+                        float xi = g->optinterpwt[(nb - 1) + 8 * (size_t)(ip - 1)];
+                        float extgrad = g->dextm[(ib - 1) + (size_t)maxpg * (idr - 1)] * xi;
+                        for (ns = 0; ns < nstokes; ns++) {
+                            float radgrad0 = (float)(-1 * gw->passedrad[ns + nstokes * (size_t)kk] * extgrad * i0[k]);
+                            float radgrad1 = (float)(-1 * gw->passedrad[ns + nstokes * (size_t)(kk - 1)] * extgrad * i1[k]);
+                            float radgrad = (float)((0.5f * (radgrad0 + radgrad1)
+                                + 0.08333333333f * (ext0 * radgrad1 - ext1 * radgrad0) * dels
+                                  * (1.0f - 0.05f * (ext1 - ext0) * dels)) / ext);
+                            raygrad[ns + nstokes * ((size_t)(ib - 1) + (size_t)maxpg * (idr - 1))] +=
+                                radgrad * gw->passedtransmit[kk - 1] * gw->passedabscell[kk - 1];
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
+/* COMPUTE_DIRECT_BEAM_DERIV  shdomsub4.f:2778-2834 */
+static void compute_direct_beam_deriv(const oracle_grad_in *g, int nstokes, int ip, double transmit,
+                                      double abscell, const float *inputweight, double *raygrad)
+{
+    const float *dpath = &g->dpath[(size_t)g->longest_path_pts * (ip - 1)];
+    const int *dptr = &g->dptr[(size_t)g->longest_path_pts * (ip - 1)];
+    int ii = 1, idr, ns;
+    while (ii <= g->longest_path_pts && dptr[ii - 1] > 0) {
+        int ib = dptr[ii - 1];
+        for (idr = 1; idr <= g->numder; idr++)
+            for (ns = 0; ns < nstokes; ns++)
+                raygrad[ns + nstokes * ((size_t)(ib - 1) + (size_t)g->maxpg * (idr - 1))] -=
+                    g->dextm[(ib - 1) + (size_t)g->maxpg * (idr - 1)] * dpath[ii - 1] * abscell * transmit
+                    * inputweight[ns];
+        ii = ii + 1;
+    }
+}
+
+/* ADJOINT_INTEGRATE_1RAY  shdomsub4.f:3223-3967; with RAYGRAD != NULL the same walk is GRAD_INTEGRATE_1RAY
+ * (shdomsub4.f:811-1544, the single-sweep / Jacobian path): the two routines share everything up to
+ * where the per-sub-interval source gradient goes (RAYGRAD(NSTOKES,MAXPG,NUMDER) un-contracted vs.
+ * GRADOUT contracted with the adjoint weight), how the direct-beam derivative is applied (per cell,
+ * COMPUTE_DIRECT_BEAM_DERIV, vs. BEAM_WEIGHT batching) and the radiance-derivative routine. */
+
 static int adjoint_integrate_1ray(const oracle_state *st, const oracle_grad_in *g, grad_work *gw,
                                   const float *bcrad, double mu2, double phi2,
                                   double x0, double y0, double z0, const double *adj_weight,
-                                  double *gradout, double *beam_weight,
+                                  double *gradout, double *beam_weight, double *raygrad, double *radout_ret,
                                   int *trace_cells, int trace_cap, int *trace_n, int *nsub_out,
                                   char *errmsg)
 {
@@ -718,10 +781,16 @@ static int adjoint_integrate_1ray(const oracle_state *st, const oracle_grad_in *
                     for (k = 1; k <= 8; k++) {
                         int ib = g->interpptr[(k - 1) + 8 * (size_t)(ip - 1)];
                         for (idr = 1; idr <= numder; idr++) {
-                            double contrib = 0.0;
-                            for (ns = 1; ns <= nstokes; ns++)
-                                contrib = contrib + adj_weight[ns - 1] * G8(gw->srcgrad, ns, k, kk, idr);
-                            gradout[(ib - 1) + (size_t)maxpg * (idr - 1)] += transmit * contrib * abscell;
+                            if (raygrad) {       /* shdomsub4.f:1335-1341 */
+                                for (ns = 1; ns <= nstokes; ns++)
+                                    raygrad[(ns - 1) + nstokes * ((size_t)(ib - 1) + (size_t)maxpg * (idr - 1))] +=
+                                        transmit * G8(gw->srcgrad, ns, k, kk, idr) * abscell;
+                            } else {
+                                double contrib = 0.0;
+                                for (ns = 1; ns <= nstokes; ns++)
+                                    contrib = contrib + adj_weight[ns - 1] * G8(gw->srcgrad, ns, k, kk, idr);
+                                gradout[(ib - 1) + (size_t)maxpg * (idr - 1)] += transmit * contrib * abscell;
+                            }
                         }
                     }
                 }
@@ -750,9 +819,13 @@ static int adjoint_integrate_1ray(const oracle_state *st, const oracle_grad_in *
         if (exact_ss) {
             for (kk = 1; kk <= 8; kk++) {
                 int ip = GRIDPTR(st, kk, icell);
-                for (ns = 0; ns < nstokes; ns++)
-                    beam_weight[ip - 1] = beam_weight[ip - 1]
-                        + adj_weight[ns] * srcsingscat[ns + nstokes * (kk - 1)];
+                if (raygrad) {           /* shdomsub4.f:1386-1398 */
+                    compute_direct_beam_deriv(g, nstokes, ip, 1.0, 1.0, &srcsingscat[nstokes * (kk - 1)], raygrad);
+                } else {
+                    for (ns = 0; ns < nstokes; ns++)
+                        beam_weight[ip - 1] = beam_weight[ip - 1]
+                            + adj_weight[ns] * srcsingscat[ns + nstokes * (kk - 1)];
+                }
             }
         }
         if (sox <= soz && sox <= soy) {
@@ -799,9 +872,15 @@ static int adjoint_integrate_1ray(const oracle_state *st, const oracle_grad_in *
             if (exact_ss) {
                 for (kk = 0; kk < 4; kk++) {
                     int ip = boundpts[kk];
-                    for (ns = 0; ns < nstokes; ns++)
-                        beam_weight[ip - 1] = beam_weight[ip - 1]
-                            + adj_weight[ns] * transmit * boundinterp[kk] * dirrad[ns + nstokes * kk];
+                    if (raygrad) {       /* shdomsub4.f:1495-1505 */
+                        float wgt[4];
+                        for (ns = 0; ns < nstokes; ns++) wgt[ns] = (float)(boundinterp[kk] * dirrad[ns + nstokes * kk]);
+                        compute_direct_beam_deriv(g, nstokes, ip, transmit, 1.0, wgt, raygrad);
+                    } else {
+                        for (ns = 0; ns < nstokes; ns++)
+                            beam_weight[ip - 1] = beam_weight[ip - 1]
+                                + adj_weight[ns] * transmit * boundinterp[kk] * dirrad[ns + nstokes * kk];
+                    }
                 }
             }
         } else {
@@ -821,7 +900,9 @@ static int adjoint_integrate_1ray(const oracle_state *st, const oracle_grad_in *
     for (kk = 1; kk <= npassed; kk++)
         for (k = 0; k < nstokes; k++)
             gw->passedrad[k + nstokes * (size_t)(kk - 1)] /= gw->passedtransmit[kk - 1];
-    compute_radiance_derivative_adjoint(st, g, gw, adj_weight, gradout, npassed);
+    if (raygrad) compute_radiance_derivative(st, g, gw, raygrad, npassed);
+    else compute_radiance_derivative_adjoint(st, g, gw, adj_weight, gradout, npassed);
+    if (radout_ret) for (k = 0; k < nstokes; k++) radout_ret[k] = radout[k];
     if (trace_n) *trace_n = ntrace;
     if (nsub_out) *nsub_out = nsub;
     return 0;
@@ -1094,7 +1175,7 @@ int oracle_levisapprox_gradient(const oracle_state *st, const oracle_rays *rays,
                             weight_vec[k] = adj_weights[k + nstokes * jp] * g->ray_weights[iray]
                                             * g->stokes_weights[k + nstokes * jp];
                         ierr = adjoint_integrate_1ray(st, g, gw, bcrad, mu2, phi2, x0, y0, z0, weight_vec,
-                                    pgrad[me], pbeam[me],
+                                    pgrad[me], pbeam[me], NULL, NULL,
                                     trace ? trace->cells + (size_t)trace->max_per_ray * iray : NULL,
                                     trace ? trace->max_per_ray : 0, &ntr, &nsub, lmsg);
                     }
@@ -1141,6 +1222,75 @@ int oracle_levisapprox_gradient(const oracle_state *st, const oracle_rays *rays,
 done:
     free(raystart); free(adj_weights); free(beam_weight);
     return ierr_all;
+}
+
+/* LEVISAPPROX_GRADIENT with MAKEJACOBIAN=.TRUE. (single sweep)  shdomsub4.f:536-631: per ray
+ * GRAD_INTEGRATE_1RAY -> RAYGRAD, per pixel RAYGRAD_PIXEL -> UPDATE_COSTFUNCTION and
+ * JACOBIAN(:,:,JI,IPIX) = RAYGRAD_PIXEL(:,JACOBIANPTR(JI),:).  Serial (test sizes only). */
+int oracle_levisapprox_jacobian(const oracle_state *st, const oracle_rays *rays,
+                                const oracle_grad_in *g, int num_jacobian_pts, const int *jacobianptr,
+                                double *gradout, double *cost, float *stokesout, float *jacobian,
+                                char *errmsg)
+{
+    const int nstokes = st->nstokes, npix = g->npix, numder = g->numder, maxpg = g->maxpg;
+    const size_t ngrad = (size_t)maxpg * numder, nrg = (size_t)nstokes * ngrad;
+    size_t nbc = (size_t)nstokes * (st->ntoppts + st->nbotpts), t;
+    double *raygrad, *raygrad_pixel;
+    float *bcrad;
+    grad_work *gw;
+    int ipix, iray = 0, i2, k, ji, idr, ierr = 0;
+    if (st->srctype != 'S') {
+        if (errmsg) snprintf(errmsg, 600, "oracle: only SRCTYPE='S' is restated");
+        return 3;
+    }
+    oracle_lambertian_boundary(st, st->bcrad);
+    raygrad = (double *)calloc(nrg, sizeof(double));
+    raygrad_pixel = (double *)calloc(nrg, sizeof(double));
+    bcrad = (float *)malloc(sizeof(float) * (nbc + 1));
+    memcpy(bcrad, st->bcrad, sizeof(float) * nbc);
+    gw = grad_work_new(st, g);
+    for (t = 0; t < ngrad; t++) gradout[t] = 0.0;
+    for (t = 0; t < (size_t)nstokes * npix; t++) stokesout[t] = 0.0f;
+    cost[0] = 0.0;
+    for (ipix = 0; ipix < npix && !ierr; ipix++) {
+        double so[4], me[4];
+        for (t = 0; t < nrg; t++) raygrad_pixel[t] = 0.0;
+        for (i2 = 0; i2 < g->rays_per_pixel[ipix] && !ierr; i2++, iray++) {
+            double x0 = rays->camx[iray], y0 = rays->camy[iray], z0 = rays->camz[iray];
+            double mu2 = rays->cammu[iray], phi2 = rays->camphi[iray];
+            double visrad[4] = {0, 0, 0, 0};
+            int dark = oracle_ray_start(st, mu2, phi2, &x0, &y0, &z0, &ierr);
+            if (ierr) { if (errmsg) snprintf(errmsg, 600, "LEVISAPPROX_GRADIENT: Level below domain"); break; }
+            for (t = 0; t < nrg; t++) raygrad[t] = 0.0;
+            if (!dark) {
+                set_top_bcrad(st, bcrad, mu2, phi2);
+                ierr = adjoint_integrate_1ray(st, g, gw, bcrad, mu2, phi2, x0, y0, z0, NULL, NULL, NULL,
+                                              raygrad, visrad, NULL, 0, NULL, NULL, errmsg);
+                if (ierr) break;
+            }
+            for (k = 0; k < nstokes; k++) {
+                const double wgt = g->ray_weights[iray] * g->stokes_weights[k + nstokes * ipix];
+                stokesout[k + nstokes * ipix] = (float)(stokesout[k + nstokes * ipix] + visrad[k] * wgt);
+                for (t = 0; t < ngrad; t++) raygrad_pixel[k + nstokes * t] += raygrad[k + nstokes * t] * wgt;
+            }
+        }
+        if (ierr) break;
+        for (k = 0; k < nstokes; k++) {
+            so[k] = (double)stokesout[k + nstokes * ipix];
+            me[k] = (double)g->measurements[k + nstokes * ipix];
+        }
+        oracle_update_costfunction(so, raygrad_pixel, gradout, cost,
+                                   &g->uncertainties[(size_t)g->nuncertainty * g->nuncertainty * ipix],
+                                   g->costfunc_ll, nstokes, maxpg, numder, me, g->nuncertainty);
+        for (ji = 0; ji < num_jacobian_pts; ji++)
+            for (idr = 0; idr < numder; idr++)
+                for (k = 0; k < nstokes; k++)
+                    jacobian[k + nstokes * (idr + numder * (ji + (size_t)num_jacobian_pts * ipix))] =
+                        (float)raygrad_pixel[k + nstokes * ((size_t)(jacobianptr[ji] - 1) + (size_t)maxpg * idr)];
+    }
+    free(raygrad); free(raygrad_pixel); free(bcrad);
+    grad_work_free(gw);
+    return ierr;
 }
 
 /* COMPUTE_INTERP_WEIGHTS  shdomsub4.f:3082-3169 */

@@ -165,6 +165,12 @@ int  oracle_levisapprox_gradient(const oracle_state *st, const oracle_rays *rays
                                  const oracle_grad_in *g, double *gradout /*[maxpg,numder]*/,
                                  double *cost, float *stokesout /*[nstokes,npix]*/,
                                  oracle_trace *trace, int nthreads, char *errmsg);
+/* LEVISAPPROX_GRADIENT, MAKEJACOBIAN=.TRUE. (GRAD_INTEGRATE_1RAY shdomsub4.f:811-1544, COMPUTE_RADIANCE_DERIVATIVE
+ * :2588-2662, COMPUTE_DIRECT_BEAM_DERIV :2778-2834).  jacobian: float[nstokes, numder, num_jacobian_pts, npix]. */
+int  oracle_levisapprox_jacobian(const oracle_state *st, const oracle_rays *rays,
+                                 const oracle_grad_in *g, int num_jacobian_pts, const int *jacobianptr,
+                                 double *gradout, double *cost, float *stokesout, float *jacobian,
+                                 char *errmsg);
 
 /* ---- helpers on the path ---- */
 int  oracle_update_costfunction(const double *stokesout, const double *raygrad_pixel,

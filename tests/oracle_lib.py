@@ -56,6 +56,8 @@ def lib():
                                        P(OracleTrace), i32, C.c_char_p]
         _lib.oracle_levisapprox_gradient.argtypes = [P(OracleState), P(OracleRays), P(OracleGrad), C.c_void_p,
                                                      C.c_void_p, C.c_void_p, P(OracleTrace), i32, C.c_char_p]
+        _lib.oracle_levisapprox_jacobian.argtypes = [P(OracleState), P(OracleRays), P(OracleGrad), i32, C.c_void_p,
+                                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_char_p]
         _lib.oracle_precompute_phase_check.argtypes = [i32, i32, i32, i32, i32, i32, i32, C.c_void_p,
                                                        C.c_void_p, i32, i32, C.c_char_p]
         _lib.oracle_precompute_phase_check_grad.argtypes = _lib.oracle_precompute_phase_check.argtypes
@@ -225,6 +227,23 @@ def levisapprox_gradient(state, rays, grad, trace_cap=0, nthreads=1):
     if trace is not None:
         return gradout, cost[0], stokesout, trace
     return gradout, cost[0], stokesout
+
+
+def levisapprox_jacobian(state, rays, grad, jacobianptr):
+    """Single-sweep (MAKEJACOBIAN=.TRUE.) path: returns gradout, cost, stokesout, jacobian[nstokes,numder,njac,npix]."""
+    st = state.copy().normalize()
+    d = st.fill(OracleState())
+    gd = grad.fill(OracleGrad())
+    jp = np.ascontiguousarray(jacobianptr, np.int32)
+    gradout = np.zeros((grad.maxpg, grad.numder), np.float64, order='F')
+    cost = np.zeros(1, np.float64)
+    stokesout = np.zeros((st.nstokes, grad.npix), np.float32, order='F')
+    jac = np.zeros((st.nstokes, grad.numder, jp.size, grad.npix), np.float32, order='F')
+    buf = C.create_string_buffer(600)
+    r = _rays(rays)
+    _check(lib().oracle_levisapprox_jacobian(C.byref(d), C.byref(r), C.byref(gd), int(jp.size), _vp(jp),
+                                             _vp(gradout), _vp(cost), _vp(stokesout), _vp(jac), buf), buf)
+    return gradout, cost[0], stokesout, jac
 
 
 def update_costfunction(stokesout, raygrad_pixel, gradout, cost, uncertainties, costfunc, measurement):
