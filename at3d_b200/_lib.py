@@ -34,7 +34,7 @@ _lib = None
 SYMBOLS = ['at3d_b200_version', 'at3d_device_count', 'at3d_set_device', 'at3d_state_create',
            'at3d_state_attach_gradient', 'at3d_state_destroy', 'at3d_state_bytes', 'at3d_state_get_bcrad',
            'at3d_ylmall', 'at3d_precompute_phase_check', 'at3d_compute_source', 'at3d_render',
-           'at3d_levisapprox_gradient', 'at3d_prepare_deriv_interps', 'at3d_make_direct_derivative',
+           'at3d_levisapprox_gradient', 'at3d_levisapprox_gradient_jacobian', 'at3d_prepare_deriv_interps', 'at3d_make_direct_derivative',
            'at3d_average_subpixel_rays', 'at3d_update_costfunction', 'at3d_make_direct', 'at3d_state_get_counts']
 
 
@@ -82,6 +82,8 @@ def lib():
                               P(f64), C.c_char_p]
     L.at3d_levisapprox_gradient.argtypes = [C.c_void_p, P(RaysC), P(GradDesc), C.c_void_p, C.c_void_p,
                                             C.c_void_p, P(TraceC), C.c_void_p, P(f64), C.c_char_p]
+    L.at3d_levisapprox_gradient_jacobian.argtypes = [C.c_void_p, P(RaysC), P(GradDesc), C.c_void_p, C.c_void_p,
+                                                     C.c_void_p, i32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_char_p]
     L.at3d_compute_source.argtypes = [P(StateDesc), i32, f32, i32, i32, i32, i32, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_void_p, P(f32), P(f32), P(f32), P(f32), P(f64),
                                       C.c_char_p]

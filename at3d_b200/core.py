@@ -21,7 +21,7 @@ Everything runs on the GPU through libat3d_b200.so (include/at3d_b200.h); there 
 Unlike f2py, the solved state is not re-marshalled on every call: ``render`` / ``levisapprox_gradient``
 keep the state resident in HBM (``DeviceState``) and re-use it while the caller passes the same arrays
 (the reference calls these once per sensor chunk / per L-BFGS evaluation with unchanged solver arrays).
-Unsupported configurations (thermal sources, non-Lambertian surfaces, MAKEJACOBIAN) return ``ierr=3``.
+Unsupported configurations (thermal sources, non-Lambertian surfaces) return ``ierr=3``.
 """
 import numpy as np
 from . import backend as B
@@ -169,8 +169,7 @@ def levisapprox_gradient(**kw):
     loss = np.zeros(1, np.float64)
     images = np.zeros((nstokes, npixels), np.float32, order='F')
     jacobian = kw.get('jacobian')
-    if bool(kw.get('makejacobian', False)):
-        return gradient, loss, images, jacobian, 3, _errmsg('at3d_b200: MAKEJACOBIAN=.TRUE. (GRAD_INTEGRATE_1RAY) is not implemented')
+    makejac = bool(kw.get('makejacobian', False))
     try:
         dev = _device_state(kw, True)
         dev.attach_gradient(_grad_from_kwargs(kw, dev.state))
@@ -179,7 +178,12 @@ def levisapprox_gradient(**kw):
                     np.asarray(kw['cammu'])[:npix], np.asarray(kw['camphi'])[:npix])
         pix = PixelData(np.asarray(kw['measurements'])[:nstokes], kw['uncertainties'], rpp, kw['ray_weights'],
                         np.asarray(kw['stokes_weights'])[:nstokes])
-        g, c, so = dev.gradient(rays, pix)
+        if makejac:
+            # single-sweep semantics (shdomsub4.f:536-631): gradient, cost, images and the per-pixel Jacobian
+            g, c, so, jacobian = dev.gradient_jacobian(rays, pix, np.asarray(kw['jacobianptr']).ravel()
+                                                       [:int(kw.get('num_jacobian_pts', np.size(kw['jacobianptr'])))])
+        else:
+            g, c, so = dev.gradient(rays, pix)
         gradient[:, :, 0] = g
         loss[0] = c[0]
         images = so

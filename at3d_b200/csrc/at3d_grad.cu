@@ -1201,10 +1201,27 @@ struct IntToLL { __host__ __device__ long long operator()(int v) const { return 
 
 static size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
 
-extern "C" int at3d_levisapprox_gradient(at3d_state *st, const at3d_rays *rays, const at3d_grad_desc *g,
-                                         double *gradout, double *cost, float *stokesout,
-                                         const at3d_trace *trace, void *cuda_stream, double *kernel_ms,
-                                         char *errmsg)
+// unit adjoint weights of Stokes component k for every pixel (Jacobian path)
+__global__ void unit_adj_kernel(int nst, int npix, int k, double *adjw)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nst * npix) adjw[i] = (i % nst == k) ? 1.0 : 0.0;
+}
+
+// JACOBIAN(k,:,JI,IPIX) = RAYGRAD_PIXEL(k,JACOBIANPTR(JI),:)  (shdomsub4.f:627-630)
+__global__ void jac_gather_kernel(int nst, int nd, int njac, int maxpg, int k, int ipix, const int *jacptr,
+                                  const double *gtmp, float *jac)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nd * njac) return;
+    const int idr = i % nd, ji = i / nd;
+    jac[k + nst * (idr + nd * ((size_t)ji + (size_t)njac * ipix))] = (float)gtmp[(size_t)(jacptr[ji] - 1) + (size_t)maxpg * idr];
+}
+
+static int gradient_impl(at3d_state *st, const at3d_rays *rays, const at3d_grad_desc *g,
+                         double *gradout, double *cost, float *stokesout,
+                         const at3d_trace *trace, void *cuda_stream, double *kernel_ms,
+                         int njac, const int32_t *jacobianptr, float *jacobian, char *errmsg)
 {
     if (errmsg) errmsg[0] = 0;
     if (!st || !rays || !g || !gradout || !cost || !stokesout) { set_msg(errmsg, "null argument"); return 1; }
@@ -1389,6 +1406,78 @@ extern "C" int at3d_levisapprox_gradient(at3d_state *st, const at3d_rays *rays, 
             beam_kernel<<<(S.npts + wpb - 1) / wpb, wpb * 32, 0, stream>>>(G, S.npts, beam, grad_d);
             CUDA_TRY(cudaGetLastError());
         }
+        // ---- Jacobian (MAKEJACOBIAN=.TRUE., shdomsub4.f:536-631): RAYGRAD_PIXEL(k,:,:) of a pixel is the
+        //      derivative pass over that pixel's rays with the unit adjoint weight e_k (the pass is linear in
+        //      the weight).  One pass per pixel and Stokes component, like the reference's slow path. ----
+        if (njac > 0 && jacobian) {
+            std::vector<int> rpp_h(npix);
+            if (host) memcpy(rpp_h.data(), g->rays_per_pixel, sizeof(int) * npix);
+            else CUDA_TRY(cudaMemcpy(rpp_h.data(), g->rays_per_pixel, sizeof(int) * npix, cudaMemcpyDeviceToHost));
+            const size_t njv = (size_t)nst * G.numder * njac * npix;
+            size_t oj = 0;
+            const size_t j_adj = oj; oj += al256(sizeof(double) * nst * npix);
+            const size_t j_gtmp = oj; oj += al256(sizeof(double) * ngrad);
+            const size_t j_beam = oj; oj += al256(sizeof(double) * S.npts);
+            const size_t j_ptr = oj; oj += al256(sizeof(int) * njac);
+            const size_t j_jac = oj; oj += al256(sizeof(float) * njv);
+            CUDA_TRY(st->misc.reserve(oj + 256));
+            unsigned char *jb = (unsigned char *)st->misc.p;
+            double *adj1 = (double *)(jb + j_adj), *gtmp = (double *)(jb + j_gtmp), *beam1 = (double *)(jb + j_beam);
+            int *jptr_d = (int *)(jb + j_ptr);
+            float *jac_d = host ? (float *)(jb + j_jac) : jacobian;
+            CUDA_TRY(cudaMemcpyAsync(jptr_d, jacobianptr, sizeof(int) * njac,
+                                     host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, stream));
+            CUDA_TRY(cudaMemsetAsync(jac_d, 0, sizeof(float) * njv, stream));
+            DevState Sq = S;
+            Sq.counts = nullptr;
+            const size_t smem = (size_t)AT3D_RAYS_PER_BLOCK * (S.ny_comp * S.nlmp + ((3 * (S.ml + 1) + 3) & ~3)) * sizeof(float);
+            const long long *roff = st->recoff_h.data();
+            {   // one record buffer large enough for the rays of any single pixel
+                long long mx = 0; size_t q0 = 0;
+                for (size_t p = 0; p < npix; p++) { const size_t q1 = q0 + rpp_h[p]; if (roff[q1] - roff[q0] > mx) mx = roff[q1] - roff[q0]; q0 = q1; }
+                CUDA_TRY(st->recs.reserve(((size_t)mx + 8) * sizeof(VisitRec)));
+            }
+            for (int k = 0; k < nst; k++) {
+                unit_adj_kernel<<<(int)((nst * npix + 255) / 256), 256, 0, stream>>>(nst, (int)npix, k, adj1);
+                size_t r0 = 0;
+                for (size_t p = 0; p < npix; p++) {
+                    const size_t r1 = r0 + rpp_h[p];
+                    if (r1 > r0) {
+                        VisitRec *recs = (VisitRec *)st->recs.p;
+                        const int nblk = (int)((r1 - r0 + AT3D_RAYS_PER_BLOCK - 1) / AT3D_RAYS_PER_BLOCK);
+                        CUDA_TRY(cudaMemsetAsync(gtmp, 0, sizeof(double) * ngrad, stream));
+                        CUDA_TRY(cudaMemsetAsync(beam1, 0, sizeof(double) * S.npts, stream));
+                        CUDA_TRY(cudaMemsetAsync(st->ray_counter, 0, sizeof(int), stream));
+                        if (nst == 1)
+                            weights_kernel<1><<<nblk, AT3D_RAY_THREADS, smem, stream>>>(Sq, G, (int)r1, camx, camy, camz, cammu,
+                                camphi, packs, raypix, adj1, rw, sw, total, recoff, roff[r0], recs, nrec, beam1, nullptr, 0,
+                                nullptr, nullptr, (RayErr *)st->err.p, st->ray_counter, (int)r0);
+                        else
+                            weights_kernel<3><<<nblk, AT3D_RAY_THREADS, smem, stream>>>(Sq, G, (int)r1, camx, camy, camz, cammu,
+                                camphi, packs, raypix, adj1, rw, sw, total, recoff, roff[r0], recs, nrec, beam1, nullptr, 0,
+                                nullptr, nullptr, (RayErr *)st->err.p, st->ray_counter, (int)r0);
+                        CUDA_TRY(cudaMemsetAsync(st->ray_counter, 0, sizeof(int), stream));
+                        if (nst == 1)
+                            apply_kernel<1><<<nblk, AT3D_RAY_THREADS, smem, stream>>>(Sq, G, (int)r1, camx, camy, camz, cammu,
+                                camphi, packs, raypix, adj1, rw, sw, recoff, roff[r0], recs, nrec, gtmp, (RayErr *)st->err.p,
+                                st->ray_counter, (int)r0);
+                        else
+                            apply_kernel<3><<<nblk, AT3D_RAY_THREADS, smem, stream>>>(Sq, G, (int)r1, camx, camy, camz, cammu,
+                                camphi, packs, raypix, adj1, rw, sw, recoff, roff[r0], recs, nrec, gtmp, (RayErr *)st->err.p,
+                                st->ray_counter, (int)r0);
+                        if (G.exact_single_scatter) {
+                            const int wpb = 8;
+                            beam_kernel<<<(S.npts + wpb - 1) / wpb, wpb * 32, 0, stream>>>(G, S.npts, beam1, gtmp);
+                        }
+                        jac_gather_kernel<<<(G.numder * njac + 127) / 128, 128, 0, stream>>>(nst, G.numder, njac, G.maxpg, k,
+                                                                                           (int)p, jptr_d, gtmp, jac_d);
+                        CUDA_TRY(cudaGetLastError());
+                    }
+                    r0 = r1;
+                }
+            }
+            if (host) CUDA_TRY(cudaMemcpyAsync(jacobian, jac_d, sizeof(float) * njv, cudaMemcpyDeviceToHost, stream));
+        }
     } else if (kernel_ms) { cudaEventRecord(ev[1], stream); cudaEventRecord(ev[2], stream); }
     if (kernel_ms) cudaEventRecord(ev[3], stream);
     if (host) {
@@ -1412,4 +1501,25 @@ extern "C" int at3d_levisapprox_gradient(at3d_state *st, const at3d_rays *rays, 
         for (int i = 0; i < 4; i++) cudaEventDestroy(ev[i]);
     }
     return rc;
+}
+
+extern "C" int at3d_levisapprox_gradient(at3d_state *st, const at3d_rays *rays, const at3d_grad_desc *g,
+                                         double *gradout, double *cost, float *stokesout,
+                                         const at3d_trace *trace, void *cuda_stream, double *kernel_ms,
+                                         char *errmsg)
+{
+    return gradient_impl(st, rays, g, gradout, cost, stokesout, trace, cuda_stream, kernel_ms, 0, nullptr, nullptr, errmsg);
+}
+
+extern "C" int at3d_levisapprox_gradient_jacobian(at3d_state *st, const at3d_rays *rays, const at3d_grad_desc *g,
+                                                  double *gradout, double *cost, float *stokesout,
+                                                  int num_jacobian_pts, const int32_t *jacobianptr, float *jacobian,
+                                                  void *cuda_stream, char *errmsg)
+{
+    if (num_jacobian_pts < 1 || !jacobianptr || !jacobian) {
+        if (errmsg) snprintf(errmsg, AT3D_ERRMSG_LEN, "at3d_levisapprox_gradient_jacobian: NUM_JACOBIAN_PTS >= 1 and non-null arrays required");
+        return 1;
+    }
+    return gradient_impl(st, rays, g, gradout, cost, stokesout, nullptr, cuda_stream, nullptr, num_jacobian_pts,
+                         jacobianptr, jacobian, errmsg);
 }

@@ -112,6 +112,36 @@ class DeviceState:
         buf = _lib.errbuf()
         _lib.check(self._L.at3d_state_attach_gradient(self._h, C.byref(self._gdesc), buf), buf)
 
+    def gradient_jacobian(self, rays, pix, jacobianptr):
+        """LEVISAPPROX_GRADIENT with MAKEJACOBIAN=.TRUE. (shdomsub4.f:536-631), host arrays.
+        ``jacobianptr``: 1-based property-grid indices.  Returns (gradout, cost, stokesout,
+        jacobian [nstokes,numder,njac,npix] f32)."""
+        if self._grad is None:
+            raise RuntimeError('attach_gradient() first')
+        g = self._grad
+        r, dev = self._rays_struct(rays.camx, rays.camy, rays.camz, rays.cammu, rays.camphi)
+        if dev:
+            raise NotImplementedError('gradient_jacobian takes host (numpy) arrays')
+        gd = g.desc()
+        npix = int(pix.rays_per_pixel.shape[0])
+        gd.npix = npix
+        gd.nuncertainty = int(pix.uncertainties.shape[0])
+        gd.measurements = C.cast(vp(pix.measurements), type(gd.measurements))
+        gd.uncertainties = C.cast(vp(pix.uncertainties), type(gd.uncertainties))
+        gd.rays_per_pixel = C.cast(vp(pix.rays_per_pixel), type(gd.rays_per_pixel))
+        gd.ray_weights = C.cast(vp(pix.ray_weights), type(gd.ray_weights))
+        gd.stokes_weights = C.cast(vp(pix.stokes_weights), type(gd.stokes_weights))
+        jp = np.ascontiguousarray(jacobianptr, np.int32).ravel()
+        gradout = np.zeros((g.maxpg, g.numder), np.float64, order='F')
+        stokesout = np.zeros((self.nstokes, npix), np.float32, order='F')
+        cost = np.zeros(1, np.float64)
+        jac = np.zeros((self.nstokes, g.numder, jp.size, npix), np.float32, order='F')
+        buf = _lib.errbuf()
+        code = self._L.at3d_levisapprox_gradient_jacobian(self._h, C.byref(r), C.byref(gd), vp(gradout), vp(cost),
+                                                          vp(stokesout), int(jp.size), vp(jp), vp(jac), None, buf)
+        _lib.check(code, buf)
+        return gradout, cost, stokesout, jac
+
     def gradient(self, rays, pix, gradout=None, stokesout=None, cost=None, trace_cap=0, stream=None,
                  timing=False):
         """LEVISAPPROX_GRADIENT, MAKEJACOBIAN=.FALSE. (shdomsub4.f:288).  ``pix``: object with

@@ -178,6 +178,15 @@ int at3d_levisapprox_gradient(at3d_state *st, const at3d_rays *rays, const at3d_
                               double *kernel_ms /*optional [5]: forward, adjoint (weights+apply), beam, total, weights*/,
                               char *errmsg);
 
+/* ---- a10: LEVISAPPROX_GRADIENT with MAKEJACOBIAN=.TRUE. (shdomsub4.f:536-631, GRAD_INTEGRATE_1RAY :811) ----
+ * As at3d_levisapprox_gradient, plus JACOBIAN(NSTOKES,NUMDER,NUM_JACOBIAN_PTS,NPIX) f32 at the property points
+ * JACOBIANPTR(NUM_JACOBIAN_PTS) (1-based); both follow rays->memspace.  One derivative pass per pixel and
+ * Stokes component (the reference's slow path as well). */
+int at3d_levisapprox_gradient_jacobian(at3d_state *st, const at3d_rays *rays, const at3d_grad_desc *g,
+                                       double *gradout, double *cost, float *stokesout,
+                                       int num_jacobian_pts, const int32_t *jacobianptr, float *jacobian,
+                                       void *cuda_stream /*optional*/, char *errmsg);
+
 /* ---- a15: PREPARE_DERIV_INTERPS (shdomsub4.f:2917); HOST pointers ---- */
 int at3d_prepare_deriv_interps(const at3d_state_desc *desc, int npx, int npy, int npz, int maxpg,
                                float delx, float dely, float xstart, float ystart,

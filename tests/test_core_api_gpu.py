@@ -82,8 +82,15 @@ def test_core_gradient_keyword_api(oracle):
     np.testing.assert_allclose(images, soref, rtol=1e-4, atol=1e-6)
     for idr in range(gi.numder):
         np.testing.assert_allclose(gradient[:, idr, 0], gref[:, idr], rtol=1e-4, atol=1e-4 * np.abs(gref[:, idr]).max())
-    kw['makejacobian'] = True
-    assert core.levisapprox_gradient(**kw)[4] == 3
+    # MAKEJACOBIAN=.TRUE.: gradient / cost as above plus the per-pixel Jacobian at the selected property points
+    jp = (np.argsort(-np.abs(gref[:, 0]))[:3] + 1).astype(np.int32)
+    g1, c1, s1, jref = oracle.levisapprox_jacobian(st, rays, gradsetup.with_pixels(gi, pix), jp)
+    kw.update(makejacobian=True, jacobianptr=jp, num_jacobian_pts=jp.size,
+              jacobian=np.zeros((1, gi.numder, jp.size, pix.npix), np.float32, order='F'))
+    gradient, loss, images, jac, ierr, errmsg = core.levisapprox_gradient(**kw)
+    assert ierr == 0 and jac.shape == (1, gi.numder, jp.size, pix.npix)
+    assert abs(loss[0] - c1) <= 1e-4 * abs(c1)
+    np.testing.assert_allclose(jac, jref, rtol=1e-4, atol=1e-4 * np.abs(jref).max())
     core.clear_cache()
 
 

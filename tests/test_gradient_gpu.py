@@ -152,3 +152,33 @@ def test_chunked_derivative_pass_matches_single_chunk(oracle, monkeypatch):
     assert float(c1[0]) == float(c2[0])
     np.testing.assert_array_equal(s1, s2)
     np.testing.assert_allclose(g2, g1, rtol=1e-10, atol=1e-12 * np.max(np.abs(g1)))
+
+
+@pytest.mark.parametrize('case,gkw', [('scalar_open_split', dict(numder=2)), ('polarized_periodic_split', dict(numder=2)),
+                                      ('rayleigh_two_species', dict(numder=2))])
+def test_jacobian_path_matches_oracle_single_sweep(case, gkw, oracle):
+    """at3d_levisapprox_gradient_jacobian (MAKEJACOBIAN=.TRUE.) against the oracle's GRAD_INTEGRATE_1RAY path."""
+    from at3d_b200.device import DeviceState
+    from at3d_b200 import gradsetup
+    sc = scenes.make(case, oracle)
+    rays = scenes.ray_set(sc, n_persp=4, res=0.07)
+    gi = gradsetup.make_gradient_inputs(sc, oracle, seed=11, **gkw)
+    rad = oracle.render(sc.state, rays)
+    pix = gradsetup.make_pixels(sc.state.nstokes, rays.nrays, rad, seed=5, rays_per_pixel=2)
+    g = gradsetup.with_pixels(gi, pix)
+    g2, c2, s2 = oracle.levisapprox_gradient(sc.state, rays, g)
+    jp = (np.argsort(-np.abs(g2[:, 0]))[:6] + 1).astype(np.int32)
+    gref, cref, sref, jref = oracle.levisapprox_jacobian(sc.state, rays, g, jp)
+    dev = DeviceState(sc.state)
+    dev.attach_gradient(gi)
+    gout, cost, so, jac = dev.gradient_jacobian(rays, pix, jp)
+    dev.close()
+    assert abs(float(cost[0]) - cref) <= RTOL * abs(cref)
+    np.testing.assert_allclose(so, sref, rtol=RTOL, atol=1e-6)
+    for idr in range(gref.shape[1]):
+        scale = np.max(np.abs(gref[:, idr]))
+        np.testing.assert_allclose(gout[:, idr], gref[:, idr], rtol=RTOL, atol=RTOL * scale)
+    for k in range(jref.shape[0]):
+        for idr in range(jref.shape[1]):
+            scale = np.max(np.abs(jref[k, idr]))
+            np.testing.assert_allclose(jac[k, idr], jref[k, idr], rtol=RTOL, atol=RTOL * scale)
