@@ -1057,6 +1057,11 @@ int oracle_levisapprox_gradient(const oracle_state *st, const oracle_rays *rays,
     int *raystart;
     int ierr_all = 0, ipix, ip, idr, ii;
     size_t t;
+    if (st->sfctype1 != 'L') {
+        /* the reference itself STOPs here: SURFACE_BRDF_GRAD has no linearisation for W/D/O/R (surface.f:395-399) */
+        if (errmsg) snprintf(errmsg, 600, "oracle: gradient with a non-Lambertian surface is not restated");
+        return 3;
+    }
     if (st->srctype != 'S') {
         if (errmsg) snprintf(errmsg, 600, "oracle: only SRCTYPE='S' is restated");
         return 3;
@@ -1239,6 +1244,11 @@ int oracle_levisapprox_jacobian(const oracle_state *st, const oracle_rays *rays,
     float *bcrad;
     grad_work *gw;
     int ipix, iray = 0, i2, k, ji, idr, ierr = 0;
+    if (st->sfctype1 != 'L') {
+        /* the reference itself STOPs here: SURFACE_BRDF_GRAD has no linearisation for W/D/O/R (surface.f:395-399) */
+        if (errmsg) snprintf(errmsg, 600, "oracle: gradient with a non-Lambertian surface is not restated");
+        return 3;
+    }
     if (st->srctype != 'S') {
         if (errmsg) snprintf(errmsg, 600, "oracle: only SRCTYPE='S' is restated");
         return 3;

@@ -39,8 +39,15 @@ void oracle_ray_setup(const oracle_state *st, double mu2, double phi2, ray_dir *
 int  oracle_bc_search(const int *bcptr_col, int n, int ip);
 float oracle_sky_radiance(const oracle_state *st, float mu, float phi);
 void oracle_lambertian_boundary(const oracle_state *st, float *bcrad);
+void oracle_compute_top_radiances(const oracle_state *st, const float *skyrad, int imu, int iphi,
+                                  float mu, float phi, int flag, float *out);
+float oracle_planck_function(float temp, int units, const float *waveno, float wavelen);
+int  oracle_surface_brdf(int sfctype, const float *refparms, float wavelen, float mu2, float phi2,
+                         float mu1, float phi1, int nstokes, float *reflect);
+int  oracle_variable_brdf_surface(const oracle_state *st, int ibeg, int iend, float mu2, float phi2,
+                                  float *bcrad_bot);
 void oracle_donethis(const oracle_state *st, int iface, int *donethis);
-int  oracle_integrate_1ray(const oracle_state *st, const float *bcrad, float skyrad_top,
+int  oracle_integrate_1ray(const oracle_state *st, float *bcrad, float skyrad_top,
                            double mu2, double phi2, double x0, double y0, double z0,
                            double *transmit_io, double *radiance,
                            int correctinterpolate, int singlescatter, int nosurface,

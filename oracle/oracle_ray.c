@@ -390,18 +390,54 @@ int oracle_bc_search(const int *bcptr_col, int n, int ip)
 
 static const int GRIDFACE[6][4] = {{1,3,5,7},{2,4,6,8},{1,2,5,6},{3,4,7,8},{1,2,3,4},{5,6,7,8}};
 
-static int find_boundary_radiance(const oracle_state *st, const float *bcrad, double xb, double yb,
+/* COMPUTE_TOP_RADIANCES (shdomsub1.f:2336-2433) for one boundary point.  flag 1: inverse-distance-cubed
+ * interpolation over the downward ordinates, flag 2: over the upward ordinates (the "surface emission hack"
+ * of FIND_BOUNDARY_RADIANCE), else the ordinate (imu,iphi).  skyrad is SKYRAD(NSTOKES,NMU/2,NPHI0MAX).
+ * Only the first Stokes component is interpolated (SKYRAD3(1:1) = WEIGHTEDSUM/WEIGHTSUM). */
+void oracle_compute_top_radiances(const oracle_state *st, const float *skyrad, int imu, int iphi,
+                                  float mu, float phi, int flag, float *out)
+{
+    const int ns = st->nstokes, nh = st->nmu / 2;
+    float skyrad3[4] = {0, 0, 0, 0};
+    int i, j, k;
+    if (flag == 1 || flag == 2) {
+        const double power = 3.0;
+        double weightedsum = 0.0, weightsum = 0.0, weight, distance;
+        const int i0 = (flag == 1) ? 1 : nh + 1, i1 = (flag == 1) ? nh : st->nmu;
+        for (i = i0; i <= i1; i++) {
+            for (j = 1; j <= st->nphi0[i - 1]; j++) {
+                const float mus = st->mu[i - 1];
+                const float phis = st->phi[(i - 1) + st->nmu * (j - 1)];
+                const int is = (flag == 1) ? i : i - nh;
+                distance = (double)acosf(mu * mus + sqrtf((1.0f - mu * mu) * (1.0f - mus * mus)) * cosf(phi - phis));
+                if (fabs(distance) < 1e-6f) weight = 1.0e8;
+                else weight = 1.0 / pow(distance, power);
+                weightedsum = weightedsum + skyrad[0 + ns * ((is - 1) + nh * (j - 1))] * weight;
+                weightsum = weightsum + weight;
+            }
+        }
+        skyrad3[0] = (float)(weightedsum / weightsum);
+    } else {
+        for (k = 0; k < ns; k++) skyrad3[k] = skyrad[k + ns * ((imu - 1) + nh * (iphi - 1))];
+    }
+    if (st->srctype == 'T') {
+        const float wn[2] = {st->waveno0, st->waveno1};
+        for (k = 0; k < ns; k++) out[k] = 0.0f;
+        out[0] = oracle_planck_function(skyrad3[0], st->units, wn, st->wavelen);
+    } else {
+        for (k = 0; k < ns; k++) out[k] = skyrad3[k];
+    }
+}
+
+/* FIND_BOUNDARY_RADIANCE  shdomsub2.f:2748-2863.  bcrad is the caller's private, mutable BCRAD. */
+static int find_boundary_radiance(const oracle_state *st, float *bcrad, double xb, double yb,
                                   float mu2, float phi2, int icell, int kface, float *radbnd,
                                   char *errmsg)
 {
     const int nstokes = st->nstokes;
+    const int lambertian = st->sfctype1 == 'L';
     float x[4], y[4], rad[4][4], u, v;
     int j, k;
-    (void)phi2;
-    if (st->sfctype1 != 'L') {
-        if (errmsg) snprintf(errmsg, 600, "oracle: only Lambertian surfaces are restated");
-        return 3;
-    }
     for (j = 0; j < 4; j++) {
         int ip = GRIDPTR(st, GRIDFACE[kface - 1][j], icell);
         int ibc;
@@ -414,10 +450,37 @@ static int find_boundary_radiance(const oracle_state *st, const float *bcrad, do
         } else {
             ibc = oracle_bc_search(st->bcptr + st->maxnbc, st->nbotpts, ip);
             if (!ibc) { if (errmsg) snprintf(errmsg, 600, "FIND_BOUNDARY_RADIANCE: Not at boundary"); return 1; }
-            /* surface emission hack (COMPUTE_TOP_RADIANCES flag 2, shdomsub2.f:2832-2846):
-             * for SRCTYPE='S' SFCGRIDRAD is identically zero and the term is 0. */
+            if (!lambertian) {
+                if (oracle_variable_brdf_surface(st, ibc, ibc, mu2, phi2, bcrad + (size_t)nstokes * st->ntoppts)) {
+                    if (errmsg) snprintf(errmsg, 600, "SURFACE_BRDF: Unknown BRDF type / polarized call of a scalar BRDF");
+                    return 1;
+                }
+            }
+            /* surface emission "hack" (shdomsub2.f:2832-2846): COMPUTE_TOP_RADIANCES, flag 2, on
+             * SFCGRIDRAD(2:,IBC); identically zero while SFCGRIDRAD is (solar problems). */
+            for (k = 0; k < nstokes; k++) rad[j][k] = 0.0f;
+            if (st->sfcgridrad) {
+                float tmp[4 * 64 * 128];
+                const int nh = st->nmu / 2;
+                int i, ja, iang = 1;
+                if ((size_t)nstokes * nh * st->nphi0max > sizeof(tmp) / sizeof(float)) {
+                    if (errmsg) snprintf(errmsg, 600, "oracle: ordinate set too large for the emission scratch");
+                    return 3;
+                }
+                memset(tmp, 0, sizeof(float) * (size_t)nstokes * nh * st->nphi0max);
+                for (i = 1; i <= nh; i++)
+                    for (ja = 1; ja <= st->nphi0[i - 1]; ja++) {
+                        tmp[0 + nstokes * ((i - 1) + nh * (ja - 1))] =
+                            st->sfcgridrad[iang + (size_t)(st->nang / 2 + 1) * (ibc - 1)];
+                        iang = iang + 1;
+                    }
+                oracle_compute_top_radiances(st, tmp, -1, -1, mu2, phi2, 2, rad[j]);
+            } else if (st->srctype == 'T') {
+                const float wn[2] = {st->waveno0, st->waveno1};
+                rad[j][0] = oracle_planck_function(0.0f, st->units, wn, st->wavelen);
+            }
             for (k = 0; k < nstokes; k++)
-                rad[j][k] = 0.0f + bcrad[k + nstokes * (st->ntoppts + ibc - 1)];
+                rad[j][k] = rad[j][k] + bcrad[k + nstokes * (st->ntoppts + ibc - 1)];
         }
     }
     if (x[1] - x[0] > 0.0f) u = (float)((xb - x[0]) / (x[1] - x[0])); else u = 0.0f;
@@ -428,48 +491,50 @@ static int find_boundary_radiance(const oracle_state *st, const float *bcrad, do
     return 0;
 }
 
-/* COMPUTE_TOP_RADIANCES with INTERPOLATE_FLAG=1 (shdomsub1.f:2375-2395) for SRCTYPE != 'T':
- * inverse-distance-cubed interpolation of SKYRAD to (mu,phi); returns the (I only) value */
+/* COMPUTE_TOP_RADIANCES with INTERPOLATE_FLAG=1 (shdomsub1.f:2375-2395): the (I only) sky radiance RENDER
+ * writes into BCRAD(:,1:NTOPPTS) for an upward-looking ray */
 float oracle_sky_radiance(const oracle_state *st, float mu, float phi)
 {
-    double power = 3.0, weightedsum = 0.0, weightsum = 0.0, weight, distance;
-    int i, j;
-    for (i = 1; i <= st->nmu / 2; i++) {
-        for (j = 1; j <= st->nphi0[i - 1]; j++) {
-            float mus = st->mu[i - 1];
-            float phis = st->phi[(i - 1) + st->nmu * (j - 1)];
-            distance = (double)acosf(mu * mus + sqrtf((1.0f - mu * mu) * (1.0f - mus * mus)) * cosf(phi - phis));
-            if (fabs(distance) < 1e-6f) weight = 1.0e8;
-            else weight = 1.0 / pow(distance, power);
-            weightedsum = weightedsum
-                + st->skyrad[0 + st->nstokes * ((i - 1) + (st->nmu / 2) * (j - 1))] * weight;
-            weightsum = weightsum + weight;
-        }
-    }
-    return (float)(weightedsum / weightsum);
+    float out[4];
+    oracle_compute_top_radiances(st, st->skyrad, 1, 1, mu, phi, 1, out);
+    return out[0];
 }
 
-/* FIXED / VARIABLE_LAMBERTIAN_BOUNDARY for SRCTYPE='S'  shdomsub1.f:2438-2529 */
+/* FIXED / VARIABLE_LAMBERTIAN_BOUNDARY  shdomsub1.f:2438-2529 */
 void oracle_lambertian_boundary(const oracle_state *st, float *bcrad)
 {
     const int nstokes = st->nstokes;
+    const float wn[2] = {st->waveno0, st->waveno1};
     int ibc, k;
     if (st->sfctype0 == 'F' && st->sfctype1 == 'L') {
-        float alb = st->gndalbedo / acosf(-1.0f);
+        float alb = st->gndalbedo / acosf(-1.0f), gndrad = 0.0f;
+        if (st->srctype == 'T' || st->srctype == 'B') {
+            gndrad = oracle_planck_function(st->gndtemp, st->units, wn, st->wavelen);
+            gndrad = gndrad * (1.0f - st->gndalbedo);
+        }
         for (ibc = 1; ibc <= st->nbotpts; ibc++) {
             int i = st->bcptr[st->maxnbc + ibc - 1];
-            bcrad[nstokes * (st->ntoppts + ibc - 1)] =
-                alb * (st->dirflux[i - 1] + st->fluxes[0 + 2 * (i - 1)]);
-            for (k = 1; k < nstokes; k++) bcrad[k + nstokes * (st->ntoppts + ibc - 1)] = 0.0f;
+            float *b = &bcrad[nstokes * (st->ntoppts + ibc - 1)];
+            if (st->srctype == 'S') b[0] = alb * (st->dirflux[i - 1] + st->fluxes[0 + 2 * (i - 1)]);
+            else if (st->srctype == 'T') b[0] = gndrad + alb * st->fluxes[0 + 2 * (i - 1)];
+            else if (st->srctype == 'B') b[0] = alb * (st->dirflux[i - 1] + st->fluxes[0 + 2 * (i - 1)]) + gndrad;
+            for (k = 1; k < nstokes; k++) b[k] = 0.0f;
         }
     } else if (st->sfctype0 == 'V' && st->sfctype1 == 'L') {
         float opi = 1.0f / acosf(-1.0f);
         for (ibc = 1; ibc <= st->nbotpts; ibc++) {
             int i = st->bcptr[st->maxnbc + ibc - 1];
             float alb = st->sfcgridparms[1 + st->nsfcpar * (ibc - 1)];
-            bcrad[nstokes * (st->ntoppts + ibc - 1)] =
-                opi * alb * (st->dirflux[i - 1] + st->fluxes[0 + 2 * (i - 1)]);
-            for (k = 1; k < nstokes; k++) bcrad[k + nstokes * (st->ntoppts + ibc - 1)] = 0.0f;
+            float *b = &bcrad[nstokes * (st->ntoppts + ibc - 1)];
+            if (st->srctype == 'S') {
+                b[0] = opi * alb * (st->dirflux[i - 1] + st->fluxes[0 + 2 * (i - 1)]);
+            } else {
+                float gndrad = st->sfcgridparms[0 + st->nsfcpar * (ibc - 1)] * (1 - alb);
+                if (st->srctype == 'T') b[0] = gndrad + opi * alb * st->fluxes[0 + 2 * (i - 1)];
+                else if (st->srctype == 'B')
+                    b[0] = opi * alb * (st->dirflux[i - 1] + st->fluxes[0 + 2 * (i - 1)]) + gndrad;
+            }
+            for (k = 1; k < nstokes; k++) b[k] = 0.0f;
         }
     }
 }
@@ -500,7 +565,7 @@ void oracle_donethis(const oracle_state *st, int iface, int *donethis)
     ((1 - (w)) * ((1 - (v)) * ((1 - (u)) * A(1) + (u) * A(2)) + (v) * ((1 - (u)) * A(3) + (u) * A(4))) \
      + (w) * ((1 - (v)) * ((1 - (u)) * A(5) + (u) * A(6)) + (v) * ((1 - (u)) * A(7) + (u) * A(8))))
 
-int oracle_integrate_1ray(const oracle_state *st, const float *bcrad, float skyrad_top,
+int oracle_integrate_1ray(const oracle_state *st, float *bcrad, float skyrad_top,
                           double mu2, double phi2, double x0, double y0, double z0,
                           double *transmit_io, double *radiance,
                           int correctinterpolate, int singlescatter, int nosurface,
@@ -720,10 +785,6 @@ int oracle_render(const oracle_state *st, const oracle_rays *rays, float *stokes
 {
     const int nstokes = st->nstokes;
     int ierr_all = 0;
-    if (st->srctype != 'S') {
-        if (errmsg) snprintf(errmsg, 600, "oracle: only SRCTYPE='S' is restated");
-        return 3;
-    }
     /* bottom boundary radiances (shdomsub4.f:201-209); BCRAD is mutated like the reference */
     oracle_lambertian_boundary(st, st->bcrad);
     if (nthreads < 1) nthreads = 1;
@@ -734,7 +795,8 @@ int oracle_render(const oracle_state *st, const oracle_rays *rays, float *stokes
         ray_scratch *sc = oracle_scratch_new(st, 0);
         /* private BCRAD: the reference rewrites BCRAD(:,1:NTOPPTS) per ray (shdomsub4.f:238-248),
          * which is why at3d deep-copies it per thread (solver.py:747) */
-        size_t nbc = (size_t)nstokes * (st->ntoppts + st->nbotpts);
+        size_t nbc = (size_t)nstokes * (st->ntoppts + (size_t)st->nbotpts *
+                                        (st->sfctype1 == 'L' ? 1 : 1 + st->nang / 2));
         float *bcrad = (float *)malloc(sizeof(float) * (nbc + 1));
         char lmsg[600];
         int ivis, k, itop;

@@ -352,3 +352,46 @@ int oracle_precompute_phase_check_grad(int nscatangle, int dnumphase, int nstpha
     return phase_check_impl(nscatangle, dnumphase, nstphase, nstokes, nstleg, nleg, dleg,
                             dphasetab, negcheck, 0, "PRECOMPUTE_PHASE_CHECK_GRAD", errmsg);
 }
+
+/* PLMALL  shdomsub2.f:4650-4752: the mu-dependent part of the generalised spherical harmonics used by the
+ * SH <-> discrete-ordinate transforms.  prc is PRC(6,NLM) in Fortran order. */
+void oracle_plmall(int transpose, float mu, int ml, int mm, float *prc)
+{
+    const double x = (double)mu;
+    const double pi = acos(-1.0);
+    const double fct = 1.0 / sqrt(2.0 * pi);
+    const double sign = transpose ? -1.0 : 1.0;
+    double *dm0 = (double *)malloc(sizeof(double) * 3 * (ml + 2));
+    double *dm2p = dm0 + (ml + 2), *dm2m = dm2p + (ml + 2);
+    int l, m, mabs, j;
+    double p1, p2, p3;
+#define PRC(q, j) prc[((q) - 1) + 6 * ((j) - 1)]
+    m = 0;
+    wignerfct02p2m_normalized(x, ml, m, dm0, dm2p, dm2m);
+    for (l = 0; l <= ml; l++) {
+        if (l <= mm) j = l * (l + 1) + m + 1; else j = (2 * mm + 1) * l - mm * mm + m + 1;
+        p1 = fct * dm0[l];
+        p2 = -0.5 * fct * (dm2p[l] + dm2m[l]);
+        p3 = -0.5 * fct * (dm2p[l] - dm2m[l]);
+        PRC(1, j) = (float)p1; PRC(2, j) = (float)p2; PRC(3, j) = (float)p2;
+        PRC(4, j) = (float)p1; PRC(5, j) = (float)p3; PRC(6, j) = (float)p3;
+    }
+    for (mabs = 1; mabs <= mm; mabs++) {
+        wignerfct02p2m_normalized(x, ml, mabs, dm0, dm2p, dm2m);
+        for (l = mabs; l <= ml; l++) {
+            m = mabs;
+            if (l <= mm) j = l * (l + 1) + m + 1; else j = (2 * mm + 1) * l - mm * mm + m + 1;
+            p1 = fct * dm0[l];
+            p2 = -0.5 * fct * (dm2p[l] + dm2m[l]);
+            p3 = -0.5 * fct * (dm2p[l] - dm2m[l]);
+            PRC(1, j) = (float)p1; PRC(2, j) = (float)p2; PRC(3, j) = (float)p2;
+            PRC(4, j) = (float)p1; PRC(5, j) = (float)p3; PRC(6, j) = (float)p3;
+            m = -mabs;
+            if (l <= mm) j = l * (l + 1) + m + 1; else j = (2 * mm + 1) * l - mm * mm + m + 1;
+            PRC(1, j) = (float)p1; PRC(2, j) = (float)p2; PRC(3, j) = (float)(-p2);
+            PRC(4, j) = (float)(-p1); PRC(5, j) = (float)(sign * p3); PRC(6, j) = (float)(-sign * p3);
+        }
+    }
+#undef PRC
+    free(dm0);
+}

@@ -266,3 +266,47 @@ def average_subpixel_rays(weighted_stokes, pixel_index, npixels):
     out = np.zeros((nstokes, npixels), np.float32, order='F')
     lib().oracle_average_subpixel_rays(npixels, nrays, nstokes, _vp(ws), _vp(pi), _vp(out))
     return out
+
+
+def solve_fixed_grid(state, wtmu, maxiter=100, solacc=1e-5, shacc=0.0, accelflag=True, highorderrad=False,
+                     iterfixsh=30, maxiv=None):
+    """Fixed-grid SHDOM solution iterations (oracle/oracle_solver.c).  Fills and returns a copy of `state`
+    with shptr/source/rshptr/radiance/fluxes/bcrad of the converged solution, plus (iters, solcrit)."""
+    st = state.copy().normalize()
+    npts, ns = st.npts, st.nstokes
+    if maxiv is None:
+        maxiv = npts * st.nlm
+    lamb = st.sfctype1 == 'L' or st.sfctype1 == ord('L')
+    nbc = st.ntoppts + st.nbotpts * (1 if lamb else 1 + st.nang // 2)
+    st.shptr = np.zeros(npts + 1, np.int32)
+    st.source = np.zeros((ns, maxiv), np.float32, order='F')
+    st.rshptr = np.zeros(npts + 2, np.int32)
+    st.radiance = np.zeros((ns, maxiv + npts), np.float32, order='F')
+    st.fluxes = np.zeros((2, npts), np.float32, order='F')
+    st.bcrad = np.zeros((ns, nbc), np.float32, order='F')
+    d = st.fill(OracleState())
+    wtmu = np.ascontiguousarray(wtmu, np.float32)
+    iters, solcrit = i32(0), f32(0)
+    buf = C.create_string_buffer(600)
+    fn = lib().oracle_solve_fixed_grid
+    fn.argtypes = [P(OracleState), C.c_void_p, i32, f32, f32, i32, i32, i32, i32, C.c_void_p, C.c_void_p,
+                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, P(i32), P(f32), C.c_char_p]
+    _check(fn(C.byref(d), _vp(wtmu), maxiter, solacc, shacc, int(accelflag), int(highorderrad), iterfixsh, maxiv,
+              _vp(st.shptr), _vp(st.source), _vp(st.rshptr), _vp(st.radiance), _vp(st.fluxes), _vp(st.bcrad),
+              C.byref(iters), C.byref(solcrit), buf), buf)
+    tot = int(st.shptr[npts])
+    st.source = np.asfortranarray(st.source[:, :max(tot, 1)])
+    st.radiance = np.asfortranarray(st.radiance[:, :max(int(st.rshptr[npts]), 1)])
+    return st, iters.value, solcrit.value
+
+
+def surface_brdf(sfctype, refparms, wavelen, mu2, phi2, mu1, phi1, nstokes):
+    """SURFACE_BRDF: REFLECT(1:nstokes,1:nstokes)."""
+    refl = np.zeros((4, 4), np.float32, order='F')
+    parms = np.ascontiguousarray(refparms, np.float32)
+    fn = lib().oracle_surface_brdf
+    fn.argtypes = [i32, C.c_void_p, f32, f32, f32, f32, f32, i32, C.c_void_p]
+    code = fn(ord(sfctype), _vp(parms), wavelen, mu2, phi2, mu1, phi1, nstokes, _vp(refl))
+    if code:
+        raise OracleError('SURFACE_BRDF: unsupported call')
+    return refl[:nstokes, :nstokes].copy()
