@@ -109,6 +109,7 @@ extern "C" int at3d_state_destroy(at3d_state *st)
     for (void *p : st->owned) cudaFree(p);
     for (void *p : st->grad_owned) cudaFree(p);
     st->pix.release(); st->work.release();
+    st->hits.release();
     st->rays.release(); st->out.release(); st->trace.release(); st->misc.release();
     st->slabs.release(); st->err.release(); st->recs.release();
     delete st;
@@ -123,10 +124,17 @@ extern "C" int at3d_state_create(const at3d_state_desc *d, at3d_state **out, cha
     if (!d || !out) { set_msg(errmsg, "null argument"); return 1; }
     *out = nullptr;
     if (at3d_device_count() < 1) { set_msg(errmsg, "no CUDA device: at3d_b200 has no CPU fallback"); return 4; }
-    if (d->srctype != 'S') { set_msg(errmsg, "only SRCTYPE='S' (solar) is implemented on the GPU path"); return 3; }
+    if (!(d->srctype == 'S' || d->srctype == 'T' || d->srctype == 'B')) { set_msg(errmsg, "SRCTYPE must be S, T or B"); return 1; }
+    if (d->srctype != 'S' && d->units == 'B') { set_msg(errmsg, "band-integrated Planck units (UNITS='B') are not implemented"); return 3; }
     if (!(d->nstokes == 1 || d->nstokes == 3)) { set_msg(errmsg, "NSTOKES must be 1 or 3"); return 3; }
     if ((d->nstokes == 1) != (d->nstleg == 1)) { set_msg(errmsg, "NSTLEG must be 1 for NSTOKES=1 and 6 otherwise"); return 3; }
-    if (d->sfctype1 != 'L') { set_msg(errmsg, "only Lambertian surfaces (SFCTYPE 'FL','VL') are implemented"); return 3; }
+    {
+        const int t = d->sfctype1;
+        if (!(t == 'L' || t == 'W' || t == 'D' || t == 'O' || t == 'R' || t == 'M')) { set_msg(errmsg, "SURFACE_BRDF: Unknown BRDF type"); return 1; }
+        if (t != 'L' && d->sfctype0 != 'V') { set_msg(errmsg, "general BRDF surfaces are variable surfaces (SFCTYPE 'V?')"); return 1; }
+        if ((t == 'O' || t == 'R' || t == 'M') && d->nstokes > 1) { set_msg(errmsg, "Ocean, RPV and RossLi BRDFs are only for the unpolarized case"); return 1; }
+        if (t != 'L' && (!d->wtdo || !d->bcrad || !d->sfcgridparms)) { set_msg(errmsg, "general BRDF surfaces need WTDO, SFCGRIDPARMS and the stored downwelling BCRAD"); return 1; }
+    }
     if (d->numphase < 1) { set_msg(errmsg, "NUMPHASE=0 is not supported."); return 1; }
     at3d_state *st = new at3d_state();
     cudaGetDevice(&st->device);
@@ -143,6 +151,7 @@ extern "C" int at3d_state_create(const at3d_state_desc *d, at3d_state **out, cha
     S.ny_comp = d->nstokes == 1 ? 1 : 5;
     S.solarmu = d->solarmu; S.solaraz = d->solaraz; S.gndalbedo = d->gndalbedo; S.phasemax = d->phasemax;
     S.tautol = d->tautol; S.transcut = d->transcut;
+    S.nang = d->nang; S.units = d->units; S.wavelen = d->wavelen; S.gndtemp = d->gndtemp;
     st->geom.solarmu = d->solarmu; st->geom.solaraz = d->solaraz; st->geom.ztop = d->zgrid[d->nz - 1];
     st->geom.zbot = d->zgrid[0]; st->geom.nscatangle = d->nscatangle; st->geom.srctype = d->srctype;
     st->geom.deltam = d->deltam; st->geom.nstokes = d->nstokes;
@@ -175,6 +184,47 @@ extern "C" int at3d_state_create(const at3d_state_desc *d, at3d_state **out, cha
         rc = upload(st, lofj.data(), lofj.size(), &S.lofj, errmsg);
         if (rc) { at3d_state_destroy(st); return rc; }
     }
+    // ordinate tables of the surface kernels: downward ordinates in VARIABLE_BRDF_SURFACE order with
+    // W = OPI*ABS(MU)*WTDO (shdomsub1.f:2652), upward ordinates with the row of SFCGRIDRAD that the
+    // "surface emission hack" of FIND_BOUNDARY_RADIANCE reads for them (shdomsub2.f:2832-2846)
+    if (d->sfctype1 != 'L' || d->sfcgridrad || d->srctype != 'S') {
+        const int nh = d->nang / 2, nmu = d->nmu;
+        std::vector<float> omu(nh), ophi(nh), ow(nh), umu(nh), uphi(nh);
+        std::vector<int> usrc(nh, -1);
+        const float opi = 1.0f / acosf(-1.0f);
+        int q = 0;
+        for (int jmu = 1; jmu <= nmu / 2; jmu++)
+            for (int jphi = 1; jphi <= d->nphi0[jmu - 1]; jphi++) {
+                if (q >= nh) break;
+                omu[q] = d->mu[jmu - 1]; ophi[q] = d->phi[(jmu - 1) + nmu * (jphi - 1)];
+                ow[q] = d->wtdo ? opi * fabsf(d->mu[jmu - 1]) * d->wtdo[(jmu - 1) + nmu * (jphi - 1)] : 0.0f;
+                q++;
+            }
+        std::vector<int> first(nmu / 2 + 1, 0);      // IANG before row I of SFCRAD_TEMP
+        for (int i = 1; i <= nmu / 2; i++) first[i] = first[i - 1] + d->nphi0[i - 1];
+        q = 0;
+        for (int i = nmu / 2 + 1; i <= nmu; i++)
+            for (int j = 1; j <= d->nphi0[i - 1]; j++) {
+                if (q >= nh) break;
+                umu[q] = d->mu[i - 1]; uphi[q] = d->phi[(i - 1) + nmu * (j - 1)];
+                const int is = i - nmu / 2;           // SKYRAD(:,I-NMU/2,J): filled only for J <= NPHI0(I-NMU/2)
+                usrc[q] = (j <= d->nphi0[is - 1]) ? first[is - 1] + j : -1;
+                q++;
+            }
+        rc = upload(st, omu.data(), omu.size(), &S.ord_mu, errmsg);
+        if (!rc) rc = upload(st, ophi.data(), ophi.size(), &S.ord_phi, errmsg);
+        if (!rc) rc = upload(st, ow.data(), ow.size(), &S.ord_w, errmsg);
+        if (!rc) rc = upload(st, umu.data(), umu.size(), &S.up_mu, errmsg);
+        if (!rc) rc = upload(st, uphi.data(), uphi.size(), &S.up_phi, errmsg);
+        if (!rc) rc = upload(st, usrc.data(), usrc.size(), &S.up_src, errmsg);
+        if (!rc && d->sfcgridrad) {
+            const size_t n = (size_t)(nh + 1) * d->nbotpts;
+            bool nonzero = false;
+            for (size_t i = 0; i < n && !nonzero; i++) nonzero = d->sfcgridrad[i] != 0.0f;
+            if (nonzero) rc = upload(st, d->sfcgridrad, n, &S.sfcgridrad, errmsg);
+        }
+        if (rc) { at3d_state_destroy(st); return rc; }
+    }
     // cell and point records
     {
         const int *gp, *np, *tp; const short *cf; const float *gpos, *text;
@@ -198,7 +248,7 @@ extern "C" int at3d_state_create(const at3d_state_desc *d, at3d_state **out, cha
     }
     // boundary radiances: copy BCRAD, then the Lambertian bottom boundary (RENDER, shdomsub4.f:201-209)
     {
-        st->nbcrad = d->nstokes * (d->ntoppts + d->nbotpts);
+        st->nbcrad = d->nstokes * (d->ntoppts + d->nbotpts * (d->sfctype1 == 'L' ? 1 : 1 + d->nang / 2));
         float *bc = nullptr;
         rc = dalloc(st, (size_t)st->nbcrad, &bc, errmsg);
         if (!rc && d->bcrad) { if (cudaMemcpy(bc, d->bcrad, st->nbcrad * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) rc = 4; }
@@ -347,11 +397,21 @@ extern "C" int at3d_render(at3d_state *st, const at3d_rays *rays, float *stokes,
     CUDA_TRY(st->err.reserve(sizeof(RayErr)));
     CUDA_TRY(cudaMemsetAsync(st->err.p, 0, sizeof(RayErr), stream));
     CUDA_TRY(cudaMemsetAsync(st->counts_dev, 0, 8 * sizeof(unsigned long long), stream));
+    DevState S = st->S;
+    const bool general_brdf = S.sfctype1 != 'L' && !nosurface;
+    if (general_brdf) {
+        CUDA_TRY(st->hits.reserve(n * sizeof(SurfHit)));
+        CUDA_TRY(cudaMemsetAsync(st->hits.p, 0, n * sizeof(SurfHit), stream));
+        S.surfhits = st->hits.p;
+    }
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (kernel_ms) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, stream); }
-    CUDA_TRY(launch_forward(st->S, (int)n, camx, camy, camz, cammu, camphi, packs, out_d, nullptr, nullptr, 1,
+    CUDA_TRY(launch_forward(S, (int)n, camx, camy, camz, cammu, camphi, packs, out_d, nullptr, nullptr, 1,
                             correctinterpolate, singlescatter, nosurface, 0, tc, tcap, tn, ts,
                             (RayErr *)st->err.p, st->ray_counter, nullptr, stream));
+    if (general_brdf)
+        CUDA_TRY(launch_surface(S, (int)n, (const SurfHit *)st->hits.p, cammu, camphi, out_d,
+                                (RayErr *)st->err.p, stream));
     if (kernel_ms) cudaEventRecord(e1, stream);
     if (host) {
         CUDA_TRY(cudaMemcpyAsync(stokes, out_d, n * nst * sizeof(float), cudaMemcpyDeviceToHost, stream));

@@ -61,6 +61,14 @@ struct DevState {
     // raw optics kept for the gradient kernels
     const float *extinct, *albedo, *dirflux, *legen, *phaseinterpwt, *ylmsun, *sfcgridparms;
     const int *iphase;
+    // surfaces other than Lambertian and thermal sources (at3d_surface.cu)
+    int nang, units;
+    float wavelen, gndtemp;
+    const float *ord_mu, *ord_phi, *ord_w;   // [nang/2] downward ordinates: MU, PHI, OPI*|MU|*WTDO
+    const float *up_mu, *up_phi;             // [nang/2] upward ordinates (surface-emission interpolation)
+    const int *up_src;                       // [nang/2] row of SFCGRIDRAD each upward ordinate reads, or -1
+    const float *sfcgridrad;                 // [nang/2+1, nbotpts] or null when identically zero
+    void *surfhits;                          // SurfHit[nrays] of the current RENDER call (non-Lambertian only)
     // optional work counters of the last call: [0] cells visited, [1] grid points evaluated,
     // [2] sum of NS over evaluated points, [3] sum of NR (gradient), [4] sub-intervals, [5] rays marched
     unsigned long long *counts;
@@ -495,6 +503,14 @@ __host__ __device__ inline void make_ray_pack(const RayGeom &g, double x0, doubl
     if (!(fabs(p.cz) > 1.0e-6f)) p.cz = 0.0;
 }
 
+// A ray that ended on a non-Lambertian bottom boundary: the reflected radiance needs NANG/2 BRDF evaluations for
+// each of the 4 face points, which a warp per ray does afterwards (surface_kernel) instead of one lane here.
+struct __align__(16) SurfHit {
+    double xb, yb, transmit;
+    double rad[3];          // radiance accumulated along the ray (INTEGRATE_1RAY arithmetic)
+    int icell, kface;       // kface = 0: no surface hit
+};
+
 struct RayDir {
     double cx, cy, cz, cxinv, cyinv, czinv;
     double cos22, sin22;    // polarization-plane rotation (ROTATE_POL_PLANE)
@@ -502,6 +518,8 @@ struct RayDir {
     int j;                  // scattering-angle table index (1-based)
     int bitx, bity, bitz, ioct;
     float xm, ym;
+    float phi2;             // SNGL(PHI2) (surface emission interpolation)
+    SurfHit *hit;           // where to leave a non-Lambertian surface hit (null: Lambertian surface)
 };
 
 __device__ __forceinline__ RayGeom dev_ray_geom(const DevState &S)
@@ -515,6 +533,7 @@ __device__ __forceinline__ RayGeom dev_ray_geom(const DevState &S)
 
 __device__ __forceinline__ void dev_ray_dir(const DevState &S, const RayPack &p, RayDir &rd)
 {
+    rd.phi2 = 0.0f; rd.hit = nullptr;
     rd.f = p.f; rd.j = p.j; rd.cos22 = p.cos22; rd.sin22 = p.sin22;
     rd.cx = p.cx; rd.cy = p.cy; rd.cz = p.cz;
     rd.cxinv = (rd.cx != 0.0) ? 1.0 / rd.cx : (double)1.0e6f;
@@ -548,7 +567,16 @@ __device__ __forceinline__ RayPack dev_get_pack(const DevState &S, const RayPack
     return p;
 }
 
-// COMPUTE_TOP_RADIANCES, INTERPOLATE_FLAG=1, SRCTYPE != 'T' (shdomsub1.f:2375-2395)
+// PLANCK_FUNCTION (shdomsub2.f:4756-4790), UNITS 'T' or radiance units
+__device__ __forceinline__ float dev_planck(float temp, int units, float wavelen)
+{
+    if (units == 'T') return temp;
+    if (temp > 0.0f)
+        return 1.1911e8f / (wavelen * wavelen * wavelen * wavelen * wavelen) / (expf(1.4388e4f / (wavelen * temp)) - 1);
+    return 0.0f;
+}
+
+// COMPUTE_TOP_RADIANCES, INTERPOLATE_FLAG=1 (shdomsub1.f:2375-2395, :2421-2427)
 static __device__ float dev_sky_radiance(const DevState &S, float mu, float phi)
 {
     double weightedsum = 0.0, weightsum = 0.0, weight, distance;
@@ -564,7 +592,31 @@ static __device__ float dev_sky_radiance(const DevState &S, float mu, float phi)
             weightsum = weightsum + weight;
         }
     }
-    return (float)(weightedsum / weightsum);
+    const float sky3 = (float)(weightedsum / weightsum);
+    if (S.srctype == 'T') return dev_planck(sky3, S.units, S.wavelen);
+    return sky3;
+}
+
+// surface emission term of FIND_BOUNDARY_RADIANCE (shdomsub2.f:2832-2846): COMPUTE_TOP_RADIANCES with
+// INTERPOLATE_FLAG=2 on SFCGRIDRAD(2:,IBC), i.e. inverse-distance-cubed weights over the upward ordinates
+static __device__ float dev_surface_emission(const DevState &S, int ibc, float mu, float phi)
+{
+    if (!S.sfcgridrad) return (S.srctype == 'T') ? dev_planck(0.0f, S.units, S.wavelen) : 0.0f;
+    double weightedsum = 0.0, weightsum = 0.0, weight, distance;
+    const int nh = S.nang / 2;
+    for (int q = 0; q < nh; q++) {
+        const float mus = __ldg(&S.up_mu[q]), phis = __ldg(&S.up_phi[q]);
+        distance = (double)acosf(mu * mus + sqrtf((1.0f - mu * mu) * (1.0f - mus * mus)) * cosf(phi - phis));
+        if (fabs(distance) < 1e-6f) weight = 1.0e8;
+        else weight = 1.0 / pow(distance, 3.0);
+        const int src = __ldg(&S.up_src[q]);
+        const float v = src >= 0 ? __ldg(&S.sfcgridrad[src + (size_t)(nh + 1) * (ibc - 1)]) : 0.0f;
+        weightedsum = weightedsum + v * weight;
+        weightsum = weightsum + weight;
+    }
+    const float e = (float)(weightedsum / weightsum);
+    if (S.srctype == 'T') return dev_planck(e, S.units, S.wavelen);
+    return e;
 }
 
 // sums over the 8 lanes of an octet (m = the octet's lane mask)

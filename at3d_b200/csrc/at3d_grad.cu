@@ -655,7 +655,7 @@ __device__ int march_weights(const DevState &S, const DevGrad &G, const float *Y
             done = true;
             float radbnd[NST];
             int boundpts[4]; double boundinterp[4], dirrad1[4];
-            const int e = boundary_radiance<NST, true>(S, xn, yn, (float)mu2, sky, ic, kface, radbnd,
+            const int e = boundary_radiance<NST, true>(S, xn, yn, (float)mu2, rd.phi2, sky, ic, kface, radbnd,
                                                        boundpts, boundinterp, dirrad1);
             if (e) { err = e; break; }
             if (exact_ss && o.ol < 4) {
@@ -724,7 +724,7 @@ __device__ __forceinline__ bool ray_setup(const DevState &S, int iray, const flo
 #pragma unroll
     for (int k = 0; k < NST; k++)
         adj[k] = __ldg(&adjw[k + NST * (size_t)pix]) * rw * __ldg(&stokes_weights[k + NST * (size_t)pix]);
-    dev_ray_dir(S, pk, rd);
+    dev_ray_dir(S, pk, rd); rd.phi2 = (float)phi2;
     __syncwarp(o.m);
     group_ylmall(S, (float)mu2, (float)phi2, Ysh, o.ol, AT3D_OCT, o.m);
     if (!S.deltam) ray_vsh<NST>(S, Ysh, Vsh, o);
@@ -1093,6 +1093,9 @@ extern "C" int at3d_state_attach_gradient(at3d_state *st, const at3d_grad_desc *
     if (!st || !g) { set_msg(errmsg, "null argument"); return 1; }
     if (!st->S.radrec) { set_msg(errmsg, "the state was created without RADIANCE/RSHPTR: the gradient needs them"); return 1; }
     if (g->numder < 1) { set_msg(errmsg, "NUMDER must be >= 1"); return 1; }
+    if (st->S.srctype != 'S') { set_msg(errmsg, "the gradient is implemented for SRCTYPE='S' (solar) only"); return 3; }
+    // the reference itself stops here: SURFACE_BRDF_GRAD has no linearisation for W/D/O/R surfaces (surface.f:395-399)
+    if (st->S.sfctype1 != 'L') { set_msg(errmsg, "the gradient needs a Lambertian surface (SFCTYPE 'FL','VL')"); return 3; }
     if (g->deriv_maxnmicro > st->S.maxnmicro) { set_msg(errmsg, "DERIV_MAXNMICRO > MAXNMICRO is not supported"); return 3; }
     // drop a previous attachment
     for (void *p : st->grad_owned) cudaFree(p);

@@ -33,7 +33,7 @@ struct at3d_state {
     size_t bytes = 0;
     int device = 0;
     // reusable per-call buffers
-    DevBuf rays, out, trace, misc, slabs, err, pix, work, recs;
+    DevBuf rays, out, trace, misc, slabs, err, pix, work, recs, hits;
     RayGeom geom;                   // host copy of the per-ray setup constants
     std::vector<RayPack> packs_h;   // host staging of the per-ray packs
     float *bcrad_dev = nullptr;
@@ -57,5 +57,7 @@ cudaError_t launch_build_ptrec(int npts, const float *gridpos, const float *tota
 cudaError_t launch_build_ptsrc(int npts, int kmax, const int2 *srcrec, const int *sscount, const int2 *ssent,
                                int4 *ptsrc, cudaStream_t s);
 cudaError_t launch_lambertian_boundary(const DevState &S, const float *fluxes, float *bcrad, cudaStream_t s);
+cudaError_t launch_surface(const DevState &S, int nrays, const SurfHit *hits, const double *cammu,
+                           const double *camphi, float *out, RayErr *err, cudaStream_t stream);
 cudaError_t launch_prep_sh(const DevState &S, int tms, const int *shptr, const float *sh_in,
                            const int2 *rec, float *sh_out, int *sscount, int2 *ssent, cudaStream_t s);

@@ -163,9 +163,9 @@ __device__ __forceinline__ double fcsum(const double *f, const float *a)
 
 // Boundary radiance at the ray exit: FIND_BOUNDARY_RADIANCE (shdomsub2.f:2748-2863, REAL u,v) when
 // GRADMODE is false, FIND_BOUNDARY_RADIANCE_GRAD (shdomsub4.f:2151-2347, DOUBLE u,v) otherwise.
-// Lambertian surfaces; solar source (the surface-emission term is identically zero).
+// Lambertian surfaces (other BRDFs: surface_kernel, at3d_surface.cu).
 template <int NST, bool GRADMODE>
-__device__ int boundary_radiance(const DevState &S, double xb, double yb, float mu2, float sky,
+__device__ int boundary_radiance(const DevState &S, double xb, double yb, float mu2, float phi2, float sky,
                                  int icell, int kface, float (&radbnd)[NST],
                                  int *boundpts, double *boundinterp, double *dirrad1)
 {
@@ -190,6 +190,8 @@ __device__ int boundary_radiance(const DevState &S, double xb, double yb, float 
 #pragma unroll
             for (int k = 0; k < NST; k++)
                 rad[j][k] = 0.0f + __ldg(&S.bcrad[k + NST * (S.ntoppts + ibc - 1)]);
+            if (S.sfcgridrad || S.srctype == 'T')
+                rad[j][0] = dev_surface_emission(S, ibc, mu2, phi2) + __ldg(&S.bcrad[NST * (S.ntoppts + ibc - 1)]);
             if (GRADMODE && boundpts) {
                 if (S.sfctype0 == 'V')
                     dirrad1[j] = (double)(opi * __ldg(&S.sfcgridparms[1 + S.nsfcpar * (ibc - 1)]) * __ldg(&S.dirflux[ip - 1]));
@@ -470,13 +472,24 @@ __device__ int march_forward(const DevState &S, const float *Ysh, const RayDir &
             if (trA < S.transcut || ngrid > maxcellscross) doneA = true;
             else if (atbnd) {
                 doneA = true;
+                if (rd.hit && !((float)mu2 < 0.0f)) {
+                    // general BRDF: the reflected radiance is added by surface_kernel (at3d_surface.cu)
+                    if (!nosurface && o.ol == 0) {
+                        SurfHit h;
+                        h.xb = xn; h.yb = yn; h.transmit = trA; h.icell = ic; h.kface = kface;
+#pragma unroll
+                        for (int k = 0; k < 3; k++) h.rad[k] = k < NST ? radA[k < NST ? k : 0] : 0.0;
+                        *rd.hit = h;
+                    }
+                } else {
                 float radbnd[NST];
-                const int e = boundary_radiance<NST, false>(S, xn, yn, (float)mu2, sky, ic, kface, radbnd,
+                const int e = boundary_radiance<NST, false>(S, xn, yn, (float)mu2, rd.phi2, sky, ic, kface, radbnd,
                                                             nullptr, nullptr, nullptr);
                 if (e) return e;
                 if (!nosurface) {
 #pragma unroll
                     for (int k = 0; k < NST; k++) radA[k] = radA[k] + trA * radbnd[k];
+                }
                 }
             }
         }
@@ -485,7 +498,7 @@ __device__ int march_forward(const DevState &S, const float *Ysh, const RayDir &
             else if (atbnd) {
                 doneB = true;
                 float radbnd[NST];
-                const int e = boundary_radiance<NST, true>(S, xn, yn, (float)mu2, sky, ic, kface, radbnd,
+                const int e = boundary_radiance<NST, true>(S, xn, yn, (float)mu2, rd.phi2, sky, ic, kface, radbnd,
                                                            nullptr, nullptr, nullptr);
                 if (e) return e;
                 if (!nosurface) {

@@ -42,20 +42,33 @@ __global__ void build_ptsrc_kernel(int npts, int kmax, const int2 *srcrec, const
     ptsrc[ip] = make_int4(r.x, r.y | (cnt << 16), e.x, e.y);
 }
 
-// FIXED / VARIABLE_LAMBERTIAN_BOUNDARY for SRCTYPE='S' (shdomsub1.f:2438-2529): bottom BCRAD
+// FIXED / VARIABLE_LAMBERTIAN_BOUNDARY (shdomsub1.f:2438-2529): bottom BCRAD
 __global__ void lambertian_boundary_kernel(DevState S, const float *fluxes, float *bcrad)
 {
     int ibc = blockIdx.x * blockDim.x + threadIdx.x;
     if (ibc >= S.nbotpts) return;
     const int i = S.bcptr[S.maxnbc + ibc];
-    float v;
+    const float down = fluxes[2 * (size_t)(i - 1)];
+    float v = 0.0f;
     if (S.sfctype0 == 'F') {
         const float alb = S.gndalbedo / acosf(-1.0f);
-        v = alb * (S.dirflux[i - 1] + fluxes[2 * (size_t)(i - 1)]);
+        float gndrad = 0.0f;
+        if (S.srctype == 'T' || S.srctype == 'B') {
+            gndrad = dev_planck(S.gndtemp, S.units, S.wavelen);
+            gndrad = gndrad * (1.0f - S.gndalbedo);
+        }
+        if (S.srctype == 'S') v = alb * (S.dirflux[i - 1] + down);
+        else if (S.srctype == 'T') v = gndrad + alb * down;
+        else if (S.srctype == 'B') v = alb * (S.dirflux[i - 1] + down) + gndrad;
     } else {
         const float opi = 1.0f / acosf(-1.0f);
         const float alb = S.sfcgridparms[1 + S.nsfcpar * ibc];
-        v = opi * alb * (S.dirflux[i - 1] + fluxes[2 * (size_t)(i - 1)]);
+        if (S.srctype == 'S') v = opi * alb * (S.dirflux[i - 1] + down);
+        else {
+            const float gndrad = S.sfcgridparms[0 + S.nsfcpar * ibc] * (1 - alb);
+            if (S.srctype == 'T') v = gndrad + opi * alb * down;
+            else if (S.srctype == 'B') v = opi * alb * (S.dirflux[i - 1] + down) + gndrad;
+        }
     }
     bcrad[S.nstokes * (size_t)(S.ntoppts + ibc)] = v;
     for (int k = 1; k < S.nstokes; k++) bcrad[k + S.nstokes * (size_t)(S.ntoppts + ibc)] = 0.0f;
@@ -187,7 +200,8 @@ forward_kernel(DevState S, int nrays, const float *camx, const float *camy, cons
             if (pk.status == 2) { if (o.ol == 0) set_err(err, 2, iray); }
             else if (pk.status == 0) {
                 RayDir rd;
-                dev_ray_dir(S, pk, rd);
+                dev_ray_dir(S, pk, rd); rd.phi2 = (float)phi2;
+                rd.hit = S.surfhits ? (SurfHit *)S.surfhits + iray : nullptr;
                 __syncwarp(o.m);
                 group_ylmall(S, (float)mu2, (float)phi2, Ysh, o.ol, AT3D_OCT, o.m);
                 const float sky = (-mu2 > 0.0) ? dev_sky_radiance(S, (float)mu2, (float)phi2) : 0.0f;
@@ -238,7 +252,8 @@ forward_kernel_t(DevState S, int nrays, const float *camx, const float *camy, co
             if (pk.status == 2) set_err(err, 2, iray);
             else if (pk.status == 0) {
                 RayDir rd;
-                dev_ray_dir(S, pk, rd);
+                dev_ray_dir(S, pk, rd); rd.phi2 = (float)phi2;
+                rd.hit = S.surfhits ? (SurfHit *)S.surfhits + iray : nullptr;
                 thread_ylmall_unpol(S, (float)mu2, (float)phi2, (float *)Y4, bt);
                 const float sky = (-mu2 > 0.0) ? dev_sky_radiance(S, (float)mu2, (float)phi2) : 0.0f;
                 const int e = thread_march_forward<MODES>(S, Y4, bt, rd, mu2, pk.x0, pk.y0, pk.z0, sky,
@@ -373,7 +388,7 @@ cudaError_t launch_build_ptsrc(int npts, int kmax, const int2 *srcrec, const int
 }
 cudaError_t launch_lambertian_boundary(const DevState &S, const float *fluxes, float *bcrad, cudaStream_t s)
 {
-    if (S.nbotpts <= 0) return cudaSuccess;
+    if (S.nbotpts <= 0 || S.sfctype1 != 'L') return cudaSuccess;
     lambertian_boundary_kernel<<<(S.nbotpts + 255) / 256, 256, 0, s>>>(S, fluxes, bcrad);
     return cudaGetLastError();
 }

@@ -284,11 +284,21 @@ __device__ int thread_march_forward(const DevState &S, const float4 *Y4, int bt,
             if (trA < S.transcut || ngrid > maxcellscross) doneA = true;
             else if (atbnd) {
                 doneA = true;
-                float radbnd[1];
-                const int e = boundary_radiance<1, false>(S, xn, yn, (float)mu2, sky, ic, kface, radbnd,
-                                                          nullptr, nullptr, nullptr);
-                if (e) return e;
-                if (!nosurface) radA = radA + trA * radbnd[0];
+                if (rd.hit && !((float)mu2 < 0.0f)) {
+                    // general BRDF: the reflected radiance is added by surface_kernel (at3d_surface.cu)
+                    if (!nosurface) {
+                        SurfHit h;
+                        h.xb = xn; h.yb = yn; h.transmit = trA; h.icell = ic; h.kface = kface;
+                        h.rad[0] = radA; h.rad[1] = 0.0; h.rad[2] = 0.0;
+                        *rd.hit = h;
+                    }
+                } else {
+                    float radbnd[1];
+                    const int e = boundary_radiance<1, false>(S, xn, yn, (float)mu2, rd.phi2, sky, ic, kface, radbnd,
+                                                              nullptr, nullptr, nullptr);
+                    if (e) return e;
+                    if (!nosurface) radA = radA + trA * radbnd[0];
+                }
             }
         }
         if ((MODES & 2) && !doneB) {
@@ -296,7 +306,7 @@ __device__ int thread_march_forward(const DevState &S, const float4 *Y4, int bt,
             else if (atbnd) {
                 doneB = true;
                 float radbnd[1];
-                const int e = boundary_radiance<1, true>(S, xn, yn, (float)mu2, sky, ic, kface, radbnd,
+                const int e = boundary_radiance<1, true>(S, xn, yn, (float)mu2, rd.phi2, sky, ic, kface, radbnd,
                                                          nullptr, nullptr, nullptr);
                 if (e) return e;
                 if (!nosurface) radB = radB + trB * radbnd[0];

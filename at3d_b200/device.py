@@ -54,7 +54,8 @@ class DeviceState:
 
     def bcrad(self):
         s = self.state
-        out = np.zeros((s.nstokes, s.ntoppts + s.nbotpts), np.float32, order='F')
+        lamb = s.sfctype1 in ('L', ord('L'))
+        out = np.zeros((s.nstokes, s.ntoppts + s.nbotpts * (1 if lamb else 1 + s.nang // 2)), np.float32, order='F')
         buf = _lib.errbuf()
         _lib.check(self._L.at3d_state_get_bcrad(self._h, vp(out), buf), buf)
         return out
