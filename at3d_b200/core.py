@@ -73,13 +73,31 @@ def _state_from_kwargs(kw, with_radiance):
         source=np.asarray(kw['source'])[:, :max(int(shptr[npts]), 1)], ylmsun=kw['ylmsun'], phasetab=kw['phasetab'],
         nphi0=kw['nphi0'], mu=kw['mu'], phi=np.asarray(kw['phi']).reshape(int(kw['nmu']), -1),
         wtdo=np.asarray(kw['wtdo']).reshape(int(kw['nmu']), -1), skyrad=_skyrad(kw), bcptr=kw['bcptr'],
-        bcrad=np.asarray(kw['bcrad'])[:, :int(kw['ntoppts']) + int(kw['nbotpts'])].copy(order='F'),
-        sfcgridparms=kw['sfcgridparms'])
+        bcrad=np.asarray(kw['bcrad'])[:, :_nbcrad(kw)].copy(order='F'),
+        sfcgridparms=kw['sfcgridparms'], sfcgridrad=_sfcgridrad(kw))
     if with_radiance:
         rshptr = np.asarray(kw['rshptr'], np.int32)[:npts + 2]
         st.rshptr = rshptr
         st.radiance = np.asarray(kw['radiance'])[:, :max(int(rshptr[npts]), 1)]
     return st.normalize()
+
+
+def _nbcrad(kw):
+    """Columns of BCRAD in use: top + bottom points, plus the stored downwelling radiance of the NANG/2 downward
+    ordinates at every bottom point for general BRDF surfaces (shdomsub1.f:2139-2145)."""
+    lamb = _ch(kw['sfctype'])[1] == 'L'
+    return int(kw['ntoppts']) + int(kw['nbotpts']) * (1 if lamb else 1 + int(kw['nang']) // 2)
+
+
+def _sfcgridrad(kw):
+    s = kw.get('sfcgridrad')
+    if s is None or 'nang' not in kw:
+        return None
+    s = np.asarray(s, np.float32)
+    nrow, nbot = int(kw['nang']) // 2 + 1, int(kw['nbotpts'])
+    if s.size < nrow * nbot or not s.any():
+        return None
+    return s.reshape((nrow, -1), order='F')[:, :nbot]
 
 
 def _skyrad(kw):
@@ -98,6 +116,8 @@ def _cache_key(kw, with_radiance):
              'iphase', 'phaseinterpwt', 'fluxes', 'ylmsun']
     if with_radiance:
         names += ['radiance', 'rshptr']
+    if _ch(kw['sfctype'])[1] != 'L':
+        names += ['bcrad', 'sfcgridparms']
     key = []
     for n in names:
         a = np.asarray(kw[n])
@@ -140,7 +160,7 @@ def render(**kw):
                             singlescatter=bool(kw.get('singlescatter', False)),
                             nosurface=bool(kw.get('nosurface', False)))
         nb = int(kw['ntoppts']) + int(kw['nbotpts'])
-        bcrad[:, :nb] = dev.bcrad()
+        bcrad[:, :nb] = dev.bcrad()[:, :nb]
     except At3dError as e:
         return bcrad, stokes, e.code, _errmsg(e.msg)
     return bcrad, stokes, 0, _errmsg('')

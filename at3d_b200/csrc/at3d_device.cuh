@@ -70,7 +70,8 @@ struct DevState {
     const float *sfcgridrad;                 // [nang/2+1, nbotpts] or null when identically zero
     void *surfhits;                          // SurfHit[nrays] of the current RENDER call (non-Lambertian only)
     // optional work counters of the last call: [0] cells visited, [1] grid points evaluated,
-    // [2] sum of NS over evaluated points, [3] sum of NR (gradient), [4] sub-intervals, [5] rays marched
+    // [2] sum of NS over evaluated points, [3] sum of NR (gradient), [4] sub-intervals, [5] rays marched,
+    // [6] rays that ended on a general-BRDF surface
     unsigned long long *counts;
 };
 

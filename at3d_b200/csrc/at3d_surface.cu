@@ -81,6 +81,7 @@ surface_kernel(DevState S, int nrays, const SurfHit *hits, const double *cammu, 
                                      + (1 - u) * v * rad[2][k] + u * v * rad[3][k];
                 out[k + NST * (size_t)iray] = (OUTA)(hits[iray].rad[k] + tr * radbnd);
             }
+            if (S.counts) atomicAdd(&S.counts[6], 1ull);
         }
     }
 }

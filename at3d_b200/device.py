@@ -50,7 +50,7 @@ class DeviceState:
         buf = _lib.errbuf()
         _lib.check(self._L.at3d_state_get_counts(self._h, vp(out), buf), buf)
         return dict(cells=int(out[0]), points=int(out[1]), sum_ns=int(out[2]), sum_nr=int(out[3]),
-                    subintervals=int(out[4]), rays=int(out[5]))
+                    subintervals=int(out[4]), rays=int(out[5]), surface_hits=int(out[6]))
 
     def bcrad(self):
         s = self.state

@@ -257,3 +257,42 @@ def perspective_rays(position, lookat, fov_deg, nx, ny, up=(0.0, 1.0, 0.0)):
 def concat_rays(rays_list):
     return Rays(*[np.concatenate([getattr(r, k) for r in rays_list])
                   for k in ('camx', 'camy', 'camz', 'cammu', 'camphi')])
+
+
+# ------------------------------------------------------------------------------------------
+# general BRDF surfaces (SURFACE_BRDF types, src/polarized/shdomsub2.f:1222-1301)
+# ------------------------------------------------------------------------------------------
+BRDF_PARAMETERS = {
+    # type: rows of SFCGRIDPARMS after the Planck term: (low, high) ranges sampled per bottom point
+    'L': [(0.02, 0.4)],
+    'W': [(1.33, 1.33), (0.0, 0.0), (2.0, 12.0)],
+    'D': [(0.1, 0.3), (0.7, 0.9), (0.1, 0.4), (0.0, 1.0), (-1.0, -1.0)],
+    'O': [(2.0, 12.0), (0.0, 0.3)],
+    'R': [(0.05, 0.3), (0.5, 1.0), (-0.3, -0.1)],
+    'M': [(0.05, 0.3), (0.0, 0.05), (0.0, 0.1)],
+}
+
+
+def with_brdf_surface(state, kind, seed=0, wavelen=None):
+    """Copy of a synthetic ``ShdomState`` over a variable surface of SURFACE_BRDF type `kind`: per-point BRDF
+    parameters and a stored downwelling radiance BCRAD(:, ibc, 2:) for the NANG/2 downward ordinates."""
+    rng = np.random.default_rng(seed)
+    st = state.copy()
+    nst, nbot, ntop, nh = st.nstokes, st.nbotpts, st.ntoppts, st.nang // 2
+    rows = BRDF_PARAMETERS[kind]
+    parms = np.zeros((1 + len(rows), nbot), np.float32, order='F')
+    for i, (lo, hi) in enumerate(rows):
+        parms[1 + i] = rng.uniform(lo, hi, nbot)
+    bcrad = np.zeros((nst, ntop + nbot * (1 + nh)), np.float32, order='F')
+    down = 0.02 + 0.06 * rng.random((nbot * nh))
+    bcrad[0, ntop + nbot:] = down
+    if nst > 1:
+        bcrad[1, ntop + nbot:] = 0.1 * down * rng.standard_normal(nbot * nh)
+        bcrad[2, ntop + nbot:] = 0.1 * down * rng.standard_normal(nbot * nh)
+    st.sfctype0, st.sfctype1 = 'V', kind
+    st.nsfcpar = parms.shape[0]
+    st.sfcgridparms = parms
+    st.bcrad = bcrad
+    if wavelen is not None:
+        st.wavelen = wavelen
+    return st.normalize()

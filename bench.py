@@ -327,6 +327,18 @@ def main():
         if i >= args.warmup:
             rms.append(o[-1])
     rcounts = dev.counts()
+    # ---- RENDER over an ocean surface (BASELINE.json configs[3]: ocean BRDF): every ray that reaches the surface
+    # costs 4 x (NANG/2 + 1) evaluations of ocean_brdf_sw in surface_kernel ----
+    from at3d_b200 import synthetic as S
+    devo = DeviceState(S.with_brdf_surface(st, 'O', seed=2, wavelen=0.66))
+    oms = []
+    for i in range(args.warmup + args.steps):
+        l2flush.zero_()
+        o = devo.render(dr, out=rsout, stream=stream, timing=True)
+        if i >= args.warmup:
+            oms.append(o[-1])
+    ocounts = devo.counts()
+    devo.close()
     peak, peak_src = measured_peak()
     adj_ms = float(np.mean(kms[:, 1]))
     abytes = algorithmic_bytes(st, gi, counts, gradient=True)
@@ -358,6 +370,9 @@ def main():
             render=dict(rays_per_s=nrays / (np.mean(rms) * 1e-3), kernel_ms=float(np.mean(rms)),
                         achieved_gbs=rbytes / (np.mean(rms) * 1e-3) / 1e9, frac=rbytes / (np.mean(rms) * 1e-3) / 1e9 / peak,
                         algorithmic_bytes=rbytes, counts=rcounts),
+            render_ocean=dict(rays_per_s=nrays / (np.mean(oms) * 1e-3), kernel_ms=float(np.mean(oms)),
+                              surface_ms=float(np.mean(oms) - np.mean(rms)), surface_hits=ocounts['surface_hits'],
+                              brdf_evals=ocounts['surface_hits'] * 4 * (st.nang // 2 + 1)),
             clocks=cs.summary(), cpu_baseline=cpu, wall_s=wall)
         print(json.dumps(line))
     dev.close()

@@ -96,3 +96,38 @@ def test_render_thermal_sources(srctype, variable):
     dev.close()
     assert np.abs(ref).max() > 1e-3
     close(out, ref)
+
+
+def test_core_render_keyword_api_with_ocean_surface():
+    # at3d.core.render(**kwargs) as solver.RTE.integrate_to_sensor calls it (at3d/solver.py:681-759), SFCTYPE='VO'
+    from at3d_b200 import core
+    from test_core_api_gpu import solver_kwargs
+    sol = solved('O')
+    rays = V.sensor_rays()
+    kw = solver_kwargs(sol)
+    kw.update(camx=rays.camx, camy=rays.camy, camz=rays.camz, cammu=rays.cammu, camphi=rays.camphi, npix=rays.nrays,
+              nosurface=False, correctinterpolate=True, singlescatter=False, sfcgridrad=sol.sfcgridrad)
+    assert kw['sfctype'] == 'VO'
+    bcrad, stokes, ierr, errmsg = core.render(**kw)
+    assert ierr == 0, errmsg
+    gold = V.parse_shdom_output(os.path.join(GOLD, 'brdf_O1r.out'))
+    np.testing.assert_allclose(stokes[0], gold[:, 2], rtol=0, atol=9e-6)
+    core.clear_cache()
+
+
+@pytest.mark.parametrize('kind,nstokes,bc', [('O', 1, 'periodic'), ('R', 1, 'open'), ('M', 1, 'periodic'), ('L', 3, 'open'),
+                                             ('W', 3, 'periodic'), ('D', 3, 'open')])
+def test_render_brdf_surface_3d_adaptive_grid(kind, nstokes, bc):
+    # 3-D scene with split cells: rays reach the surface obliquely and through open-boundary cells
+    sc = S.make_scene(nx=7, ny=6, nz=8, nstokes=nstokes, bc=bc, nsplits=6, seed=21, variable_sfc=True)
+    O.finalize_scene(sc)
+    st = S.with_brdf_surface(sc.state, kind, seed=4, wavelen=0.55)
+    rays = scenes.ray_set(sc)
+    ref, tr_ref, _ = O.render(st, rays, trace_cap=64)
+    dev = DeviceState(st)
+    out, tr = dev.render(rays, trace_cap=64)
+    dev.close()
+    assert np.array_equal(tr['ncells'], tr_ref['ncells']) and np.array_equal(tr['cells'], tr_ref['cells'])
+    close(out, ref)
+    lamb = O.render(sc.state, rays)
+    assert np.abs(ref - lamb).max() > 1e-3          # the surface does matter for these rays
