@@ -42,9 +42,9 @@ typedef struct at3d_state_desc {
     int32_t maxnbc, ntoppts, nbotpts, nsfcpar;
     int32_t nscatangle, nstphase;
     int32_t deltam;             /* LOGICAL */
-    int32_t srctype;            /* 'S' | 'T' | 'B'  (only 'S' is implemented; others -> code 3) */
+    int32_t srctype;            /* 'S' | 'T' | 'B'  (gradient entry points: 'S' only, others -> code 3) */
     int32_t units;              /* 'R' | 'T' | 'B' */
-    int32_t sfctype0, sfctype1; /* SFCTYPE(1:1), SFCTYPE(2:2); 'FL','VL' implemented */
+    int32_t sfctype0, sfctype1; /* SFCTYPE(1:1), SFCTYPE(2:2): FL, VL, VW, VD, VO, VR, VM (gradient: FL, VL) */
     int32_t interp_new;         /* INTERPMETHOD(2:2) == 'N' */
     float solarmu, solaraz, solarflux, wavelen, gndtemp, gndalbedo, phasemax;
     float waveno0, waveno1;
@@ -79,7 +79,7 @@ typedef struct at3d_state_desc {
     const int32_t *bcptr;       /* [maxnbc,2] */
     float *bcrad;               /* [nstokes, ntoppts+nbotpts(...)]; bottom part rewritten like RENDER does */
     const float *sfcgridparms;  /* [nsfcpar,nbotpts] */
-    const float *sfcgridrad;    /* unused for solar sources */
+    const float *sfcgridrad;    /* [nang/2+1, nbotpts] surface emission (may be null / zero) */
 } at3d_state_desc;
 
 /* Sensor rays: CAMX..CAMPHI of RENDER (shdomsub4.f:164-166).  memspace says where they live. */
@@ -141,11 +141,13 @@ int at3d_state_create(const at3d_state_desc *desc, at3d_state **out, char *errms
 int at3d_state_attach_gradient(at3d_state *st, const at3d_grad_desc *g, char *errmsg);
 int at3d_state_destroy(at3d_state *st);
 int64_t at3d_state_bytes(const at3d_state *st);   /* HBM bytes held */
-/* RENDER returns BCRAD as an in/out argument (at3d/solver.py:747): copy it back, [nstokes,ntoppts+nbotpts] */
+/* RENDER returns BCRAD as an in/out argument (at3d/solver.py:747): copy it back, [nstokes,ntoppts+nbotpts]
+ * (general BRDF surfaces: [nstokes, ntoppts + nbotpts*(1+nang/2)], the stored downwelling radiances included) */
 int at3d_state_get_bcrad(at3d_state *st, float *bcrad_host, char *errmsg);
 /* Work counters of the last at3d_render / at3d_levisapprox_gradient (adjoint pass) on this state, for
  * roofline accounting: [0] cells visited, [1] grid points evaluated, [2] sum of NS over them,
- * [3] sum of NR (gradient), [4] sub-intervals integrated, [5] rays marched, [6..7] reserved. */
+ * [3] sum of NR (gradient), [4] sub-intervals integrated, [5] rays marched,
+ * [6] rays that ended on a general-BRDF surface (at3d_render), [7] reserved. */
 int at3d_state_get_counts(at3d_state *st, int64_t *counts /*[8]*/, char *errmsg);
 
 /* ---- a7: YLMALL (shdomsub2.f:4244) and PRECOMPUTE_PHASE_CHECK[_GRAD] (shdomsub4.f:2388,2493) ---- */

@@ -13,7 +13,7 @@
  *   src/polarized/shdomsub2.f:4043-4206  LOCATE_GRID_CELL
  *   src/polarized/shdomsub1.f:4470-4522  NEXT_CELL
  *   src/polarized/shdomsub2.f:2311-2743  INTEGRATE_1RAY
- *   src/polarized/shdomsub2.f:2748-2863  FIND_BOUNDARY_RADIANCE (Lambertian surfaces)
+ *   src/polarized/shdomsub2.f:2748-2863  FIND_BOUNDARY_RADIANCE
  *   src/polarized/shdomsub2.f:2868-3192  COMPUTE_SOURCE_1CELL[_UNPOL]
  *   src/polarized/shdomsub2.f:3277-3314  ROTATE_POL_PLANE
  *   src/polarized/shdomsub1.f:823-1611   CALC_SOURCE_PNT[_UNPOL], COMPUTE_SOURCE
@@ -25,6 +25,10 @@
  *   src/polarized/shdomsub4.f:3223-4143  ADJOINT_INTEGRATE_1RAY and adjoint helpers
  *   src/shdomsub5.f:1497-2004            GET_INTERP_KERNEL, MAKE_DIRECT_DERIVATIVE
  *   src/util.f90:484-518                 average_subpixel_rays
+ *   src/polarized/shdomsub1.f:2597-2669, shdomsub2.f:1222-1699, src/ocean_brdf.f
+ *                                        VARIABLE_BRDF_SURFACE, SURFACE_BRDF and its models (oracle_surface.c)
+ *   src/polarized/shdomsub1.f:445-4700 (parts), src/shdom_nompi.f:317-349
+ *                                        fixed-grid SOLUTION_ITERATIONS / PATH_INTEGRATION (oracle_solver.c)
  *
  * All arrays are in the reference's own layout: Fortran (column-major) order,
  * 1-based index CONTENTS (GRIDPTR, NEIGHPTR, IPHASE, BCPTR, INTERPPTR ... hold
@@ -171,6 +175,16 @@ int  oracle_levisapprox_jacobian(const oracle_state *st, const oracle_rays *rays
                                  const oracle_grad_in *g, int num_jacobian_pts, const int *jacobianptr,
                                  double *gradout, double *cost, float *stokesout, float *jacobian,
                                  char *errmsg);
+
+/* ---- fixed-grid solution iterations (oracle_solver.c; IPFLAG=3 sweeps), used to reproduce the reference's
+ * SHDOM verification outputs.  shptr[npts+1], source[nstokes,maxiv], rshptr[npts+2], radiance[nstokes,maxiv+npts],
+ * fluxes[2,npts], bcrad[nstokes, ntop + nbot*(1 or 1+nang/2)] are outputs. ---- */
+int  oracle_solve_fixed_grid(const oracle_state *st, const float *wtmu, int maxiter, float solacc, float shacc,
+                             int accelflag, int highorderrad, int iterfixsh, int maxiv,
+                             int *shptr, float *source, int *rshptr, float *radiance, float *fluxes, float *bcrad,
+                             int *iters_out, float *solcrit_out, char *errmsg);
+int  oracle_surface_brdf(int sfctype, const float *refparms, float wavelen, float mu2, float phi2,
+                         float mu1, float phi1, int nstokes, float *reflect /*REFLECT(4,4)*/);
 
 /* ---- helpers on the path ---- */
 int  oracle_update_costfunction(const double *stokesout, const double *raygrad_pixel,
