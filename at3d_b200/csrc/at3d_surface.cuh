@@ -335,41 +335,35 @@ __device__ __forceinline__ float dev_ocean_fresnel(float nr, float ni, float cos
     return (rr2 + rl2) / 2.f;
 }
 
-// sunglint (ocean_brdf.f:322-377)
-static __device__ float dev_sunglint(float wspd, float nr, float ni, float azw, float ts, float tv, float fi)
+// ocean_brdf_sw + sunglint (ocean_brdf.f:1-129, 322-377), split by what each sub-expression depends on so that
+// the surface kernel evaluates every part once: OceanPoint = everything that depends on the surface parameters and the
+// wavelength only (index of refraction, whitecaps, water-leaving reflectance, slope variances), OceanGeom = everything
+// that depends on the incident/outgoing directions only (angles, facet slope, tilt, Fresnel angle).  dev_ocean_eval
+// combines them; each arithmetic expression is the reference's.
+struct OceanPoint { float nr, ni, n12, w, rwc, rw, sigmac, sigmau, c21, c03; int iws1; };
+struct OceanGeom { float cs, cv, zx, zy, cphw, sphw, coschi, sinchi, ct4; int isz1, ivz1; };
+
+static __device__ void dev_ocean_point(float pws, float xsal, float pcl, float pwl, OceanPoint &p)
 {
-    const float pi = atanf(1.f) * 4.f, fac = pi / 180.f;
-    const float phw = azw * fac;
-    const float cs = cosf(ts * fac), cv = cosf(tv * fac), ss = sinf(ts * fac), sv = sinf(tv * fac);
-    const float phi = fi * fac;
-    const float zx = -sv * sinf(phi) / (cs + cv);
-    const float zy = (ss + sv * cosf(phi)) / (cs + cv);
-    const float tantilt = sqrtf(zx * zx + zy * zy);
-    const float tilt = atanf(tantilt);
-    const float sigmac = 0.003f + 0.00192f * wspd, sigmau = 0.00316f * wspd;
-    const float c21 = 0.01f - 0.0086f * wspd, c03 = 0.04f - 0.033f * wspd;
-    const float c40 = 0.40f, c22 = 0.12f, c04 = 0.23f;
-    const float xe = (cosf(phw) * zx + sinf(phw) * zy) / sqrtf(sigmac);
-    const float xn = (-sinf(phw) * zx + cosf(phw) * zy) / sqrtf(sigmau);
-    const float xe2 = xe * xe, xn2 = xn * xn;
-    float coef = 1 - c21 / 2.f * (xe2 - 1) * xn - c03 / 6.f * (xn2 - 3) * xn;
-    coef = coef + c40 / 24.f * (xe2 * xe2 - 6 * xe2 + 3);
-    coef = coef + c04 / 24.f * (xn2 * xn2 - 6 * xn2 + 3);
-    coef = coef + c22 / 4.f * (xe2 - 1) * (xn2 - 1);
-    const float proba = coef / 2.f / pi / sqrtf(sigmau) / sqrtf(sigmac) * expf(-(xe2 + xn2) / 2.f);
-    float cos2chi = cv * cs + sv * ss * cosf(phi);
-    if (cos2chi > 1.0f) cos2chi = 0.99999999999f;
-    if (cos2chi < -1.0f) cos2chi = -0.99999999999f;
-    const float coschi = sqrtf(0.5f * (1 + cos2chi)), sinchi = sqrtf(0.5f * (1 - cos2chi));
-    const float r1 = dev_ocean_fresnel(nr, ni, coschi, sinchi);
-    float ct = cosf(tilt);
-    ct = (ct * ct) * (ct * ct);
-    return pi * r1 * proba / 4.f / cs / cv / ct;
+    float wl;
+    if (pwl < 0.4f) wl = 0.4f; else if (pwl > 4.0f) wl = 4.0f; else wl = pwl;
+    const float wspd = fmaxf(0.25f, pws);
+    dev_indwat(wl, xsal, p.nr, p.ni);
+    p.n12 = sqrtf(p.nr * p.nr + p.ni * p.ni);
+    p.w = 2.95E-06f * powf(wspd, 3.52f);
+    const int iwl = 1 + (int)((wl - 0.2f) / 0.1f);
+    const float wlp = 0.5f + (iwl - 1) * 0.1f;
+    const float ref_i = c_oc_ref[iwl] + (wl - wlp) / 0.1f * (c_oc_ref[iwl - 1] - c_oc_ref[iwl]);
+    p.rwc = p.w * ref_i;
+    p.rw = dev_morcasiwat(wl, pcl);
+    p.iws1 = dev_getbound(c_oc_wsbnd, 6, wspd);
+    p.sigmac = 0.003f + 0.00192f * wspd;
+    p.sigmau = 0.00316f * wspd;
+    p.c21 = 0.01f - 0.0086f * wspd;
+    p.c03 = 0.04f - 0.033f * wspd;
 }
 
-// ocean_brdf_sw (ocean_brdf.f:1-129)
-static __device__ float dev_ocean_brdf_sw(float pws, float xsal, float pcl, float pwl, float xmuo, float xmu,
-                                          float xphi, float xpaw)
+static __device__ void dev_ocean_geom(float xmuo, float xmu, float xphi, float xpaw, OceanGeom &g)
 {
     const float pi = atanf(1.f) * 4.f, fac = pi / 180.f;
     const float paw = xpaw / fac;
@@ -377,29 +371,58 @@ static __device__ float dev_ocean_brdf_sw(float pws, float xsal, float pcl, floa
     if (xphi < 0.0f) phi = -xphi;
     else if (xphi >= 2.0f * pi) phi = xphi - 2.0f * pi;
     else phi = xphi;
-    float tetas, tetav, wl;
+    float tetas, tetav;
     if (xmuo <= 0.028f) tetas = acosf(0.028f) / fac; else tetas = acosf(xmuo) / fac;
     if (xmu <= 0.028f) tetav = acosf(0.028f) / fac; else tetav = acosf(xmu) / fac;
-    if (pwl < 0.4f) wl = 0.4f; else if (pwl > 4.0f) wl = 4.0f; else wl = pwl;
     const float fi = 180.0f - phi / fac;
-    const float wspd = fmaxf(0.25f, pws);
-    float nr, ni;
-    dev_indwat(wl, xsal, nr, ni);
-    const float n12 = sqrtf(nr * nr + ni * ni);
-    const float w = 2.95E-06f * powf(wspd, 3.52f);
-    const int iwl = 1 + (int)((wl - 0.2f) / 0.1f);
-    const float wlp = 0.5f + (iwl - 1) * 0.1f;
-    const float ref_i = c_oc_ref[iwl] + (wl - wlp) / 0.1f * (c_oc_ref[iwl - 1] - c_oc_ref[iwl]);
-    const float rwc = w * ref_i;
-    const float rw = dev_morcasiwat(wl, pcl);
-    const int iws1 = dev_getbound(c_oc_wsbnd, 6, wspd);
-    const int isz1 = dev_getbound(c_oc_angbnd, 5, tetas);
-    const int ivz1 = dev_getbound(c_oc_angbnd, 5, tetav);
-    const float tds = c_oc_tds[isz1 - 1][iws1 - 1], tdv = c_oc_tdv[ivz1 - 1][iws1 - 1];
-    const float rog = dev_sunglint(wspd, nr, ni, paw, tetas, tetav, fi);
+    g.isz1 = dev_getbound(c_oc_angbnd, 5, tetas);
+    g.ivz1 = dev_getbound(c_oc_angbnd, 5, tetav);
+    // sunglint(wspd, nr, ni, azw=paw, ts=tetas, tv=tetav, fi)
+    const float phw = paw * fac;
+    const float cs = cosf(tetas * fac), cv = cosf(tetav * fac), ss = sinf(tetas * fac), sv = sinf(tetav * fac);
+    const float phir = fi * fac;
+    g.cs = cs; g.cv = cv;
+    g.zx = -sv * sinf(phir) / (cs + cv);
+    g.zy = (ss + sv * cosf(phir)) / (cs + cv);
+    const float tantilt = sqrtf(g.zx * g.zx + g.zy * g.zy);
+    const float tilt = atanf(tantilt);
+    g.cphw = cosf(phw); g.sphw = sinf(phw);
+    float cos2chi = cv * cs + sv * ss * cosf(phir);
+    if (cos2chi > 1.0f) cos2chi = 0.99999999999f;
+    if (cos2chi < -1.0f) cos2chi = -0.99999999999f;
+    g.coschi = sqrtf(0.5f * (1 + cos2chi));
+    g.sinchi = sqrtf(0.5f * (1 - cos2chi));
+    float ct = cosf(tilt);
+    g.ct4 = (ct * ct) * (ct * ct);
+}
+
+__device__ __forceinline__ float dev_ocean_eval(const OceanPoint &p, const OceanGeom &g)
+{
+    const float pi = atanf(1.f) * 4.f;
+    const float tds = c_oc_tds[g.isz1 - 1][p.iws1 - 1], tdv = c_oc_tdv[g.ivz1 - 1][p.iws1 - 1];
+    const float c40 = 0.40f, c22 = 0.12f, c04 = 0.23f;
+    const float xe = (g.cphw * g.zx + g.sphw * g.zy) / sqrtf(p.sigmac);
+    const float xn = (-g.sphw * g.zx + g.cphw * g.zy) / sqrtf(p.sigmau);
+    const float xe2 = xe * xe, xn2 = xn * xn;
+    float coef = 1 - p.c21 / 2.f * (xe2 - 1) * xn - p.c03 / 6.f * (xn2 - 3) * xn;
+    coef = coef + c40 / 24.f * (xe2 * xe2 - 6 * xe2 + 3);
+    coef = coef + c04 / 24.f * (xn2 * xn2 - 6 * xn2 + 3);
+    coef = coef + c22 / 4.f * (xe2 - 1) * (xn2 - 1);
+    const float proba = coef / 2.f / pi / sqrtf(p.sigmau) / sqrtf(p.sigmac) * expf(-(xe2 + xn2) / 2.f);
+    const float r1 = dev_ocean_fresnel(p.nr, p.ni, g.coschi, g.sinchi);
+    const float rog = pi * r1 * proba / 4.f / g.cs / g.cv / g.ct4;
     const float a = 0.485f;
-    const float rwb = (1 / (n12 * n12)) * tds * tdv * rw / (1 - a * rw);
-    return rwc + (1 - w) * rog + (1 - rwc) * rwb;
+    const float rwb = (1 / (p.n12 * p.n12)) * tds * tdv * p.rw / (1 - a * p.rw);
+    return p.rwc + (1 - p.w) * rog + (1 - p.rwc) * rwb;
+}
+
+static __device__ float dev_ocean_brdf_sw(float pws, float xsal, float pcl, float pwl, float xmuo, float xmu,
+                                          float xphi, float xpaw)
+{
+    OceanPoint p; OceanGeom g;
+    dev_ocean_point(pws, xsal, pcl, pwl, p);
+    dev_ocean_geom(xmuo, xmu, xphi, xpaw, g);
+    return dev_ocean_eval(p, g);
 }
 
 // SURFACE_BRDF (shdomsub2.f:1222-1301)

@@ -68,6 +68,12 @@ def build_scene(args):
     return sc, rays, dict(kw, views=len(views), pixels_per_view=npix_side * npix_side)
 
 
+def workload_text(name, st):
+    return name + (': LES-like %dx%dx%d open BC, NLM=%d, NSTOKES=%d, NPART=%d, 9 perspective views, radiance + Levis '
+                   'gradient (NUMDER=1); one replica of the workload per GPU, gradient all-reduced'
+                   % (st.nx, st.ny, st.nz, st.nlm, st.nstokes, st.npart))
+
+
 def algorithmic_bytes(st, gi, cnt, gradient=True):
     """bytes the reference algorithm must touch for the work actually done
     (cells / evaluated grid points / SH lengths / sub-intervals counted by the kernel)."""
@@ -210,8 +216,8 @@ def main():
                     warmup=args.warmup, ms_per_step=float(np.mean(ms)), higher_is_better=True, scaling='weak',
                     vs_baseline=None, dtype='f32 optics / f64 geometry+accumulators', data='synthetic',
                     impl='reference',
-                    config=dict(workload=args.workload + ': LES-like 32x37x27 open BC, NLM=256, 9 perspective views, '
-                                'scalar radiance + Levis gradient (NUMDER=1)', rays=int(rays.nrays), npts=int(sc.state.npts)),
+                    config=dict(workload=workload_text(args.workload, sc.state), rays=int(rays.nrays),
+                                npts=int(sc.state.npts), ncells=int(sc.state.ncells), nlm=int(sc.state.nlm)),
                     cpu_baseline=dict(value=rate, unit='rays/s', cores=ncores, kind='port', sample=sample),
                     e2e=dict(value=rate, unit='rays/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0))
         print(json.dumps(line))
@@ -354,9 +360,7 @@ def main():
             metric='radiance+gradient rays/s', value=value, unit='rays/s', n_gpus=world, steps=args.steps,
             warmup=args.warmup, ms_per_step=1e3 * t_total / args.steps, higher_is_better=True, scaling='weak',
             vs_baseline=None, dtype='f32 optics / f64 geometry+accumulators', data='synthetic',
-            config=dict(workload=args.workload + ': LES-like %dx%dx%d open BC, NLM=%d, NSTOKES=%d, NPART=%d, 9 perspective '
-                        'views, radiance + Levis gradient (NUMDER=1); one replica of the workload per GPU, gradient '
-                        'all-reduced' % (st.nx, st.ny, st.nz, st.nlm, st.nstokes, st.npart), rays=int(nrays), npts=int(st.npts), ncells=int(st.ncells),
+            config=dict(workload=workload_text(args.workload, st), rays=int(nrays), npts=int(st.npts), ncells=int(st.ncells),
                         nlm=int(st.nlm), l2='flushed between steps (256 MiB memset)', hbm_state_bytes=dev.hbm_bytes),
             e2e=dict(value=world * nrays * args.steps / t_e2e, unit='rays/s', h2d_bytes_per_step=int(h2d),
                      d2h_bytes_per_step=int(d2h)),
