@@ -74,6 +74,41 @@ def workload_text(name, st):
                    % (st.nx, st.ny, st.nz, st.nlm, st.nstokes, st.npart))
 
 
+def compute_source_leg(B, st, steps, warmup, oracle=None):
+    """COMPUTE_SOURCE (a1) on the workload's state: ms per call (CUDA events around the three kernels inside the C-ABI
+    call, and wall time of the whole host-buffer call), algorithmic bytes per SURVEY 8(d) and the HBM fraction."""
+    npts, nst = st.npts, st.nstokes
+    tot = int(st.shptr[npts])
+    if tot * nst * 4 > 6 * (1 << 30):
+        return dict(skipped='host staging of SOURCE/DELSOURCE would need %.1f GB per array' % (tot * nst * 4 / 2**30))
+    big = st.nlm * npts * nst * 4 > (1 << 31)
+    fixsh = big                                    # adaptive truncation may grow NS up to NLM: needs MAXIV = NLM*NPTS
+    maxiv = tot if big else st.nlm * npts
+    source = np.zeros((nst, maxiv), np.float32, order='F')
+    source[:, :tot] = st.source[:, :tot]
+    delsource = np.zeros((nst, maxiv), np.float32, order='F')
+    shptr = st.shptr[:npts + 1].copy()
+    kms, wms, res = [], [], None
+    for i in range(warmup + steps):
+        t = time.perf_counter()
+        res = B.compute_source(st, shptr, source, shptr.copy(), delsource, fixsh=fixsh, maxiv=maxiv, timing=True)
+        if res[0] != 0:
+            return dict(error='COMPUTE_SOURCE returned %d' % res[0])
+        if i >= warmup:
+            kms.append(res[-1]); wms.append(1e3 * (time.perf_counter() - t))
+    ns_new = int(res[1][npts])
+    nr = int(st.rshptr[npts])
+    P = 28 + st.npart * (8 + 64 * st.maxnmicro)
+    # 4*NSTOKES*(NR + NS_old + NS_new + 2*NS [acceleration: DELSOURCE read and written]) + P + 4*NPART + 8 per point
+    b = 4 * nst * (nr + tot + ns_new + 2 * tot) + npts * (P + 4 * st.npart + 8)
+    out = dict(kernel_ms=float(np.mean(kms)), call_ms_host_buffers=float(np.mean(wms)), algorithmic_bytes=int(b),
+               achieved_gbs=b / (np.mean(kms) * 1e-3) / 1e9, npts=int(npts), sum_ns=tot, sum_nr=nr, fixsh=bool(fixsh))
+    if oracle is not None:
+        out['cpu_ms'] = oracle.compute_source(st, shptr, source, shptr.copy(), delsource, fixsh=fixsh, maxiv=maxiv,
+                                              timing=True)[-1]
+    return out
+
+
 def algorithmic_bytes(st, gi, cnt, gradient=True):
     """bytes the reference algorithm must touch for the work actually done
     (cells / evaluated grid points / SH lengths / sub-intervals counted by the kernel)."""
@@ -178,6 +213,84 @@ def cpu_reference_rate(sc, rays, gi, pix, target_s, nthreads, steps=1, warmup=0)
         nr, rays.nrays, nthreads, tm), [1e3 * t for t in times]
 
 
+def render_only(args, dev, st, sc, rays, dr, l2flush, stream, barrier, world, rank, local, ncores, B, DeviceState):
+    """BASELINE.json configs[3]: RENDER of all rays (Lambertian and ocean surface), COMPUTE_SOURCE; no gradient."""
+    import torch
+    import torch.distributed as dist
+    from at3d_b200 import synthetic as S
+    nrays = rays.nrays
+    rsout = torch.zeros((nrays, st.nstokes), dtype=torch.float32, device='cuda')
+    devo = DeviceState(S.with_brdf_surface(st, 'O', seed=2, wavelen=0.66))
+
+    def timed(d):
+        for _ in range(args.warmup):
+            l2flush.zero_()
+            d.render(dr, out=rsout, stream=stream)
+        barrier()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        kms = []
+        for i in range(args.steps):
+            l2flush.zero_()
+            ev[i][0].record()
+            o = d.render(dr, out=rsout, stream=stream, timing=True)
+            ev[i][1].record()
+            kms.append(o[-1])
+        barrier()
+        t = sum(a.elapsed_time(b) for a, b in ev) * 1e-3
+        if world > 1:
+            tt = torch.tensor([t], dtype=torch.float64, device='cuda')
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            t = float(tt.item())
+        return t, float(np.mean(kms)), d.counts()
+    with ClockSampler(local) as cs:
+        t0 = time.perf_counter()
+        t_ocean, ms_ocean, c_ocean = timed(devo)
+        t_lamb, ms_lamb, c_lamb = timed(dev)
+        wall = time.perf_counter() - t0
+    # e2e: host ray arrays in, host Stokes out, through the C-ABI call (ocean surface)
+    devo.render(rays)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        out_h = devo.render(rays)
+    barrier()
+    t_e2e = time.perf_counter() - t0
+    if world > 1:
+        tt = torch.tensor([t_e2e], dtype=torch.float64, device='cuda')
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_e2e = float(tt.item())
+    peak, peak_src = measured_peak()
+    rbytes = algorithmic_bytes(st, None, c_lamb, gradient=False)
+    csrc = compute_source_leg(B, st, args.steps, args.warmup, None)
+    if 'kernel_ms' in csrc:
+        csrc['frac'] = csrc['achieved_gbs'] / peak
+    hbm = dev.hbm_bytes
+    devo.close()
+    if rank == 0:
+        line = dict(
+            metric='radiance rays/s', value=world * nrays * args.steps / t_ocean, unit='rays/s', n_gpus=world,
+            steps=args.steps, warmup=args.warmup, ms_per_step=1e3 * t_ocean / args.steps, higher_is_better=True,
+            scaling='weak', vs_baseline=None, dtype='f32 optics / f64 geometry+accumulators', data='synthetic',
+            config=dict(workload=args.workload + ': LES-like %dx%dx%d open BC + Rayleigh (NPART=%d), NLM=%d, ocean BRDF surface, '
+                        '9 perspective views, RENDER only; one replica of the ray set per GPU'
+                        % (st.nx, st.ny, st.nz, st.npart, st.nlm), rays=int(nrays), npts=int(st.npts),
+                        ncells=int(st.ncells), nlm=int(st.nlm), l2='flushed between steps (256 MiB memset)',
+                        hbm_state_bytes=hbm),
+            e2e=dict(value=world * nrays * args.steps / t_e2e, unit='rays/s', h2d_bytes_per_step=int(nrays * 96),
+                     d2h_bytes_per_step=int(nrays * st.nstokes * 4)),
+            gpu_launches=int(args.steps * 2),
+            roofline=dict(kernel='forward_kernel_t (RENDER march, Lambertian run)', bound='hbm',
+                          achieved=rbytes / (ms_lamb * 1e-3) / 1e9, peak=peak, unit='GB/s',
+                          frac=rbytes / (ms_lamb * 1e-3) / 1e9 / peak, traffic=None, peak_source=peak_src,
+                          algorithmic_bytes_per_launch=rbytes, kernel_ms=ms_lamb, counts=c_lamb),
+            render=dict(rays_per_s=world * nrays * args.steps / t_lamb, kernel_ms=ms_lamb),
+            render_ocean=dict(rays_per_s=world * nrays * args.steps / t_ocean, kernel_ms=ms_ocean,
+                              surface_ms=ms_ocean - ms_lamb, surface_hits=c_ocean['surface_hits'],
+                              brdf_evals=c_ocean['surface_hits'] * 4 * (st.nang // 2 + 1)),
+            compute_source=csrc, clocks=cs.summary(), cpu_baseline=None, wall_s=wall)
+        print(json.dumps(line))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -188,7 +301,12 @@ def main():
     ap.add_argument('--pixels', type=int, default=0, help='pixels per view side (default: per workload)')
     ap.add_argument('--cpu-seconds', type=float, default=12.0)
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--render-only', action='store_true',
+                    help='RENDER only (forced for cfg4: DPATH/DPTR of the direct-beam derivative need '
+                         'LONGEST_PATH_PTS x NPTS x 8 B = ~125 GB at 256x256x100, in the reference as well)')
     args = ap.parse_args()
+    if args.workload == 'cfg4':
+        args.render_only = True
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
     local = int(os.environ.get('LOCAL_RANK', 0))
@@ -218,7 +336,9 @@ def main():
                     impl='reference',
                     config=dict(workload=workload_text(args.workload, sc.state), rays=int(rays.nrays),
                                 npts=int(sc.state.npts), ncells=int(sc.state.ncells), nlm=int(sc.state.nlm)),
-                    cpu_baseline=dict(value=rate, unit='rays/s', cores=ncores, kind='port', sample=sample),
+                    cpu_baseline=dict(value=rate, unit='rays/s', cores=ncores, kind='port', sample=sample,
+                                      compute_source_ms=compute_source_leg(O, sc.state, 1, 0)['kernel_ms'],
+                                      compute_source_cores=1),
                     e2e=dict(value=rate, unit='rays/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0))
         print(json.dumps(line))
         return
@@ -237,20 +357,37 @@ def main():
     sc, rays, cfg = build_scene(args)
     B.finalize_scene(sc)
     st = sc.state
-    gi = gradsetup.make_gradient_inputs(sc, B, seed=0, numder=1)
     dev = DeviceState(st)
-    dev.attach_gradient(gi)
-    rad = dev.render(rays)
-    pix = gradsetup.make_pixels(st.nstokes, rays.nrays, rad, seed=1)
-    nrays, npix = rays.nrays, pix.npix
+    nrays = rays.nrays
     stream = torch.cuda.current_stream().cuda_stream
 
-    # ---- device-resident inputs (value) ----
     class Bag:
         pass
     dr, dp = Bag(), Bag()
     for k in ('camx', 'camy', 'camz', 'cammu', 'camphi'):
         setattr(dr, k, torch.from_numpy(getattr(rays, k)).cuda())
+    l2flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device='cuda')   # > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    if args.render_only:
+        render_only(args, dev, st, sc, rays, dr, l2flush, stream, barrier, world, rank, local, ncores, B, DeviceState)
+        dev.close()
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    gi = gradsetup.make_gradient_inputs(sc, B, seed=0, numder=1)
+    dev.attach_gradient(gi)
+    rad = dev.render(rays)
+    pix = gradsetup.make_pixels(st.nstokes, rays.nrays, rad, seed=1)
+    npix = pix.npix
+
+    # ---- device-resident inputs (value) ----
     dp.measurements = torch.from_numpy(np.ascontiguousarray(pix.measurements.T)).cuda()
     dp.uncertainties = torch.from_numpy(np.ascontiguousarray(pix.uncertainties.transpose(2, 1, 0))).cuda()
     dp.rays_per_pixel = torch.from_numpy(pix.rays_per_pixel).cuda()
@@ -259,7 +396,6 @@ def main():
     gout = torch.zeros((gi.numder, gi.maxpg), dtype=torch.float64, device='cuda')
     sout = torch.zeros((npix, st.nstokes), dtype=torch.float32, device='cuda')
     cout = torch.zeros(1, dtype=torch.float64, device='cuda')
-    l2flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device='cuda')   # > 126 MB L2
 
     def step_device(timing=False):
         l2flush.zero_()
@@ -268,12 +404,6 @@ def main():
             dist.all_reduce(gout)          # the only collective of the path: per-voxel gradient (+cost)
             dist.all_reduce(cout)
         return out
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
 
     for _ in range(args.warmup):
         step_device()
@@ -352,9 +482,21 @@ def main():
     rbytes = algorithmic_bytes(st, gi, rcounts, gradient=False)
 
     cpu = None
+    orc = None
     if rank == 0 and world == 1 and not args.no_cpu:
         rate, sample, _ = cpu_reference_rate(sc, rays, gi, pix, args.cpu_seconds, ncores)
         cpu = dict(value=rate, unit='rays/s', cores=ncores, kind='port', sample=sample)
+        import oracle_lib as orc
+    csrc = compute_source_leg(B, st, args.steps, args.warmup, orc)
+    if 'kernel_ms' in csrc:
+        csrc['frac'] = csrc['achieved_gbs'] / peak
+        if cpu is not None and 'cpu_ms' in csrc:
+            cpu['compute_source_ms'] = csrc.pop('cpu_ms')
+            cpu['compute_source_cores'] = 1
+    if world > 1 and 'kernel_ms' in csrc:
+        tt = torch.tensor([csrc['kernel_ms']], dtype=torch.float64, device='cuda')
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        csrc['kernel_ms'] = float(tt.item())
     if rank == 0:
         line = dict(
             metric='radiance+gradient rays/s', value=value, unit='rays/s', n_gpus=world, steps=args.steps,
@@ -374,6 +516,7 @@ def main():
             render=dict(rays_per_s=nrays / (np.mean(rms) * 1e-3), kernel_ms=float(np.mean(rms)),
                         achieved_gbs=rbytes / (np.mean(rms) * 1e-3) / 1e9, frac=rbytes / (np.mean(rms) * 1e-3) / 1e9 / peak,
                         algorithmic_bytes=rbytes, counts=rcounts),
+            compute_source=csrc,
             render_ocean=dict(rays_per_s=nrays / (np.mean(oms) * 1e-3), kernel_ms=float(np.mean(oms)),
                               surface_ms=float(np.mean(oms) - np.mean(rms)), surface_hits=ocounts['surface_hits'],
                               brdf_evals=ocounts['surface_hits'] * 4 * (st.nang // 2 + 1)),

@@ -133,7 +133,8 @@ def render(state, rays, correctinterpolate=True, singlescatter=False, nosurface=
 
 
 def compute_source(state, shptr, source, oshptr, delsource, fixsh=False, shacc=0.0, maxiv=None, first=False,
-                   accelflag=True, newmethod=True):
+                   accelflag=True, newmethod=True, timing=False):
+    import time
     st = state.copy().normalize()
     d = st.fill(OracleState())
     shptr = np.array(shptr, np.int32); oshptr = np.array(oshptr, np.int32)
@@ -142,10 +143,13 @@ def compute_source(state, shptr, source, oshptr, delsource, fixsh=False, shacc=0
         maxiv = source.shape[1]
     o = [f32(0), f32(0), f32(0), f32(0)]
     buf = C.create_string_buffer(600)
+    t = time.perf_counter()
     code = lib().oracle_compute_source(C.byref(d), int(fixsh), shacc, maxiv, int(first), int(accelflag),
                                        int(newmethod), _vp(shptr), _vp(source), _vp(oshptr), _vp(delsource),
                                        C.byref(o[0]), C.byref(o[1]), C.byref(o[2]), C.byref(o[3]), buf)
-    return code, shptr, source, oshptr, delsource, [x.value for x in o]
+    ms = 1e3 * (time.perf_counter() - t)
+    res = (code, shptr, source, oshptr, delsource, [x.value for x in o])
+    return res + (ms,) if timing else res
 
 
 def prepare_deriv_interps(state, pg, grad):
