@@ -120,6 +120,39 @@ def compute_source(state, shptr, source, oshptr, delsource, fixsh=False, shacc=0
     return res + (ms.value,) if timing else res
 
 
+def _angles(state, wtmu):
+    return (np.ascontiguousarray(state.nphi0, np.int32), np.ascontiguousarray(state.mu, np.float32),
+            np.asfortranarray(state.phi, np.float32), np.ascontiguousarray(wtmu, np.float32))
+
+
+def sh_to_do(state, wtmu, shptr, indata, timing=False):
+    """SH_TO_DO (shdomsub1.f:2789) for all ordinates: DOFIELD[npts, nstokes, nang] (Fortran order)."""
+    nphi0, mu, phi, wt = _angles(state, wtmu)
+    shptr = np.ascontiguousarray(shptr, np.int32)
+    indata = np.asfortranarray(indata, np.float32)
+    out = np.zeros((state.npts, state.nstokes, int(nphi0.sum())), np.float32, order='F')
+    ms = C.c_double(0.0)
+    buf = _lib.errbuf()
+    _lib.check(_lib.lib().at3d_sh_to_do(state.npts, state.nstokes, state.nstleg, state.ml, state.mm, state.nlm,
+                                        state.nmu, state.nphi0max, vp(nphi0), vp(mu), vp(phi), vp(wt), vp(shptr),
+                                        vp(indata), vp(out), C.byref(ms), buf), buf)
+    return (out, ms.value) if timing else out
+
+
+def do_to_sh(state, wtmu, rshptr, dofield, timing=False):
+    """DO_TO_SH (shdomsub1.f:3041) summed over all zenith angles: OUTDATA[nstokes, rshptr[npts]]."""
+    nphi0, mu, phi, wt = _angles(state, wtmu)
+    rshptr = np.ascontiguousarray(rshptr, np.int32)
+    dofield = np.asfortranarray(dofield, np.float32)
+    out = np.zeros((state.nstokes, max(int(rshptr[state.npts]), 1)), np.float32, order='F')
+    ms = C.c_double(0.0)
+    buf = _lib.errbuf()
+    _lib.check(_lib.lib().at3d_do_to_sh(state.npts, state.nstokes, state.nstleg, state.ml, state.mm, state.nlm,
+                                        state.nmu, state.nphi0max, vp(nphi0), vp(mu), vp(phi), vp(wt), vp(rshptr),
+                                        vp(dofield), vp(out), C.byref(ms), buf), buf)
+    return (out, ms.value) if timing else out
+
+
 def average_subpixel_rays(weighted_stokes, pixel_index, npixels):
     """average_subpixel_rays (src/util.f90:484)."""
     ws = np.asfortranarray(weighted_stokes, np.float32)

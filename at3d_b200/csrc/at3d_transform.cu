@@ -1,0 +1,439 @@
+// at3d_transform.cu -- spherical-harmonic <-> discrete-ordinate transforms on the device (sm_100a).
+// Replaces SH_TO_DO[_UNPOL] / DO_TO_SH[_UNPOL] (src/polarized/shdomsub1.f:2789-3260 of the AT3D reference) with the
+// coefficient tables of MAKE_SH_DO_COEF / PLMALL (src/polarized/shdomsub2.f:1146-1220, 4650-4752), for ALL zenith
+// angles in one launch (the reference transforms one zenith angle at a time inside PATH_INTEGRATION to save memory).
+//
+// The transform is kept in the reference's factorised form -- Legendre/Wigner sum per azimuthal mode m
+// (NLM x NMU multiply-adds per point) followed by the azimuthal Fourier sum ((2MM+1) x NANG) -- which needs 6.5x
+// fewer flops than the dense [NPTS x NLM].[NLM x NANG] product (15 k instead of 90 k multiply-adds per point at
+// NMU=16, NPHI=32).  Its inner dimensions (<= 16 degrees l per mode, <= 31 modes per ordinate) are too short and too
+// ragged for tcgen05 tiles, and TF32 inputs would not meet the 1e-4 parity bar without the 3x split; the kernels use
+// FP32 FMA with both stages fused through shared memory, so HBM sees each SH block and each ordinate value once.
+// A block owns a tile of 32 grid points; lane = point, so every shared-memory access is conflict free (points are
+// the fastest index) and the discrete-ordinate field DOFIELD(NPTS, NSTOKES, NANG) is written/read in 128-byte rows.
+#include <cstdio>
+#include <cstring>
+#include <cstdarg>
+#include <cmath>
+#include <vector>
+#include "at3d_host.h"
+
+#define TR_TP 32          // points per tile (= warp width)
+#define TR_THREADS 256
+#define TR_WARPS (TR_THREADS / 32)
+
+static void set_msg(char *errmsg, const char *fmt, ...)
+{
+    if (!errmsg) return;
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(errmsg, AT3D_ERRMSG_LEN, fmt, ap);
+    va_end(ap);
+}
+
+struct TrArgs {
+    int npts, nst, nstleg, ml, mm, nlm, nmu, nang;
+    const int *shptr;         // [npts+1] offsets into the SH array
+    const float *sh;          // SH array (NSTOKES, *) interleaved  (input of sh_to_do / output of do_to_sh)
+    float *sh_out;
+    float *dofield;           // DOFIELD(NPTS, NSTOKES, NANG)
+    const float *cmu;         // [ncomp][nmu][nlm]: CMU1 (sh_to_do) or CMU2 (do_to_sh)
+    const float *az;          // [nang][2mm+1]: cos(m phi) for m>=0, sin(|m| phi) for m<0 (x DELPHI for do_to_sh)
+    const int *imu_of;        // [nang]
+    const int *me_of;         // [nmu]: min(NPHI0/2-1, MM) >= 0
+    const int *ang0;          // [nmu+1] first ordinate of each zenith angle
+    const int *mofj;          // [nlm]
+};
+
+// PLMALL (shdomsub2.f:4650-4752) for every zenith angle: prc[(q-1) + 6*((j-1) + nlm*imu)].  Thread = (imu, m>=0).
+__global__ void plmall_kernel(int nmu, const float *mu, int ml, int mm, int nlm, int transpose, float *prc)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nmu * (mm + 1)) return;
+    const int imu = t / (mm + 1), m = t % (mm + 1);
+    const double xp = (double)mu[imu], xm = -xp;
+    const double pi = 3.14159265358979323846;
+    const double fct = 1.0 / sqrt(2.0 * pi);
+    const double sign = transpose ? -1.0 : 1.0;
+    float *P = prc + (size_t)6 * nlm * imu;
+    const int n0 = m > 2 ? m : 2;
+    // WIGNERFCT02P2M_NORMALIZED recurrences (shdomsub2.f:4363-4448), streamed over n
+    double d0p = 0.0, d0c = 0.0, pp = 0.0, pc = 0.0, qp = 0.0, qc = 0.0;
+    for (int n = 0; n <= ml; n++) {
+        if (n < m) d0c = 0.0;
+        else if (n == m) d0c = (m == 0) ? 1.0 : dev_dmm1_n0(xp, m, 0);
+        if (n < n0) { pc = 0.0; qc = 0.0; }
+        else if (n == n0 && ml >= 2) { pc = dev_dmm1_n0(xp, m, 2); qc = dev_dmm1_n0(xm, m, 2); }
+        if (n >= m) {
+            const double dm0 = sqrt(n + 0.5) * d0c;
+            double dm2m = (((n + m) & 1) ? -1.0 : 1.0) * qc;
+            const double dm2p = sqrt(n + 0.5) * pc;
+            dm2m = sqrt(n + 0.5) * dm2m;
+            const double p1 = fct * dm0;
+            const double p2 = -0.5 * fct * (dm2p + dm2m);
+            const double p3 = -0.5 * fct * (dm2p - dm2m);
+            const int jp = sh_index(n, m, mm);
+            P[0 + 6 * jp] = (float)p1; P[1 + 6 * jp] = (float)p2; P[2 + 6 * jp] = (float)p2;
+            P[3 + 6 * jp] = (float)p1; P[4 + 6 * jp] = (float)p3; P[5 + 6 * jp] = (float)p3;
+            if (m > 0) {
+                const int jn = sh_index(n, -m, mm);
+                P[0 + 6 * jn] = (float)p1; P[1 + 6 * jn] = (float)p2; P[2 + 6 * jn] = (float)(-p2);
+                P[3 + 6 * jn] = (float)(-p1); P[4 + 6 * jn] = (float)(sign * p3); P[5 + 6 * jn] = (float)(-sign * p3);
+            }
+        }
+        if (n >= m && n < ml) {
+            double dnext;
+            if (m == 0) {
+                if (n == 0) dnext = xp;
+                else {
+                    const double fact1 = (double)(2 * n + 1) * xp / (double)(n + 1);
+                    const double fact2 = (double)n / (double)(n + 1);
+                    dnext = fact1 * d0c - fact2 * d0p;
+                }
+            } else {
+                double fact1 = (double)(n * (n + 1)) * xp;
+                fact1 = fact1 / sqrt((double)((n + 1) * (n + 1) - m * m));
+                fact1 = fact1 / (double)(n + 1);
+                fact1 = fact1 * (double)(2 * n + 1) / (double)n;
+                double fact2 = sqrt((double)(n * n - m * m)) * (double)n;
+                fact2 = fact2 / sqrt((double)((n + 1) * (n + 1) - m * m));
+                fact2 = fact2 / (double)(n + 1);
+                fact2 = fact2 * (double)(n + 1) / (double)n;
+                dnext = fact1 * d0c - fact2 * d0p;
+            }
+            d0p = d0c; d0c = dnext;
+        }
+        if (n >= n0 && n < ml) {
+            const double factp = (double)(n * (n + 1)) * xp - (double)(2 * m);
+            const double factm = (double)(n * (n + 1)) * xm - (double)(2 * m);
+            double fact1 = 1.0 / sqrt((double)((n + 1) * (n + 1) - m * m));
+            fact1 = fact1 / sqrt((double)((n + 1) * (n + 1) - 4));
+            fact1 = fact1 * (double)(2 * n + 1) / (double)n;
+            double fact2 = sqrt((double)(n * n - m * m)) * sqrt((double)(n * n - 4));
+            fact2 = fact2 / sqrt((double)((n + 1) * (n + 1) - m * m));
+            fact2 = fact2 / sqrt((double)((n + 1) * (n + 1) - 4));
+            fact2 = fact2 * (double)(n + 1) / (double)n;
+            const double pn = factp * fact1 * pc - fact2 * pp;
+            const double qn = factm * fact1 * qc - fact2 * qp;
+            pp = pc; pc = pn; qp = qc; qc = qn;
+        }
+    }
+}
+
+// re-pack PRC(6,NLM) per angle into component planes cmu[c][imu][j] (x WTMU for CMU2)
+__global__ void pack_cmu_kernel(int nmu, int nlm, int ncomp, const float *prc, const float *wtmu, float *cmu)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nmu * nlm * ncomp) return;
+    const int j = t % nlm, imu = (t / nlm) % nmu, c = t / (nlm * nmu);
+    float v = prc[c + 6 * (j + (size_t)nlm * imu)];
+    if (wtmu) v = v * wtmu[imu];
+    cmu[j + (size_t)nlm * (imu + (size_t)nmu * c)] = v;
+}
+
+// terms of the Stokes coupling (SH_TO_DO: shdomsub1.f:2853-2866, DO_TO_SH: :3144-3153): (table component, SH plane)
+// that build discrete-ordinate plane n, both 0-based
+__device__ __forceinline__ int tr_nterms(int n) { return n == 0 ? 1 : 2; }
+__device__ __forceinline__ void tr_term(int n, int t, int &comp, int &plane)
+{
+    if (n == 0) { comp = 0; plane = 0; }
+    else if (n == 1) { comp = t == 0 ? 1 : 4; plane = t == 0 ? 1 : 2; }     // CMU(2)*Q + CMU(5)*U
+    else { comp = t == 0 ? 5 : 2; plane = t == 0 ? 1 : 2; }                 // CMU(6)*Q + CMU(3)*U
+}
+
+// shared-memory carve-up common to both kernels
+struct TrSmem { float *sh_s, *cmu_s, *uv_s, *az_s; };
+__device__ __forceinline__ TrSmem tr_smem(float *base, int nlm, int nmu, int nm, int nang, int nplanes)
+{
+    TrSmem s;
+    s.sh_s = base;                                     // [nplanes][nlm][33]
+    s.cmu_s = s.sh_s + (size_t)nplanes * nlm * 33;     // [nmu][nlm]
+    s.uv_s = s.cmu_s + (size_t)nmu * nlm;              // [nmu][nm][32]
+    s.az_s = s.uv_s + (size_t)nmu * nm * TR_TP;        // [nang][nm]
+    return s;
+}
+
+// SH_TO_DO for all ordinates
+__global__ void __launch_bounds__(TR_THREADS)
+sh_to_do_kernel(TrArgs a, int ntiles)
+{
+    extern __shared__ __align__(16) float tr_sm[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int mm = a.mm, nm = 2 * mm + 1, nlm = a.nlm, nmu = a.nmu;
+    const TrSmem s = tr_smem(tr_sm, nlm, nmu, nm, a.nang, 1);
+    for (int i = threadIdx.x; i < a.nang * nm; i += TR_THREADS) s.az_s[i] = a.az[i];
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int p0 = tile * TR_TP;
+        for (int n = 0; n < a.nst; n++) {
+            __syncthreads();
+            for (int i = threadIdx.x; i < nmu * nm * TR_TP; i += TR_THREADS) s.uv_s[i] = 0.0f;
+            for (int t = 0; t < tr_nterms(n); t++) {
+                int comp, plane;
+                tr_term(n, t, comp, plane);
+                __syncthreads();
+                // stage the SH plane of the tile, transposed to [j][point]; and the coefficient table
+                for (int q = warp; q < TR_TP; q += TR_WARPS) {
+                    const int p = p0 + q;
+                    int is = 0, ns = 0;
+                    if (p < a.npts) { is = a.shptr[p]; ns = a.shptr[p + 1] - is; }
+                    for (int j = lane; j < nlm; j += 32)
+                        s.sh_s[j * 33 + q] = j < ns ? __ldg(&a.sh[plane + (size_t)a.nst * (is + j)]) : 0.0f;
+                }
+                for (int i = threadIdx.x; i < nmu * nlm; i += TR_THREADS)
+                    s.cmu_s[i] = __ldg(&a.cmu[i + (size_t)nmu * nlm * comp]);
+                __syncthreads();
+                // stage A: SUMUV(m) += CMU1(comp, j, imu) * SH(plane, j) over the degrees l of mode m
+                for (int mi = warp; mi < nm; mi += TR_WARPS) {
+                    const int m = mi - mm, am = m < 0 ? -m : m;
+                    float acc[16];
+                    for (int i0 = 0; i0 < nmu; i0 += 16) {
+#pragma unroll
+                        for (int i = 0; i < 16; i++) acc[i] = 0.0f;
+                        for (int l = am; l <= a.ml; l++) {
+                            const int j = sh_index(l, m, mm);
+                            const float v = s.sh_s[j * 33 + lane];
+#pragma unroll
+                            for (int i = 0; i < 16; i++)
+                                if (i0 + i < nmu) acc[i] = fmaf(s.cmu_s[(i0 + i) * nlm + j], v, acc[i]);
+                        }
+#pragma unroll
+                        for (int i = 0; i < 16; i++)
+                            if (i0 + i < nmu) s.uv_s[((i0 + i) * nm + mi) * TR_TP + lane] += acc[i];
+                    }
+                }
+            }
+            __syncthreads();
+            // SUMCS from SUMUV (shdomsub1.f:2871-2890), in place
+            for (int task = warp; task < nmu * mm; task += TR_WARPS) {
+                const int imu = task / mm, m = task % mm + 1;
+                float *pu = &s.uv_s[(imu * nm + (mm + m)) * TR_TP + lane], *nu = &s.uv_s[(imu * nm + (mm - m)) * TR_TP + lane];
+                const float up = *pu, un = *nu;
+                if (n == 2) { *nu = up - un; *pu = up + un; }
+                else { *pu = up + un; *nu = un - up; }
+            }
+            __syncthreads();
+            // stage B: azimuthal sums, one ordinate per warp and iteration; 128-byte rows of DOFIELD
+            for (int iang = warp; iang < a.nang; iang += TR_WARPS) {
+                const int imu = a.imu_of[iang], me = a.me_of[imu];
+                const float *azr = s.az_s + (size_t)iang * nm;
+                const float *cs = s.uv_s + (size_t)imu * nm * TR_TP + lane;
+                float sum = 0.0f;
+                for (int mi = mm - me; mi <= mm + me; mi++) sum = fmaf(azr[mi], cs[mi * TR_TP], sum);
+                if (p0 + lane < a.npts) a.dofield[(p0 + lane) + (size_t)a.npts * (n + (size_t)a.nst * iang)] = sum;
+            }
+        }
+    }
+}
+
+// DO_TO_SH summed over all zenith angles (OUTDATA is set, not accumulated)
+__global__ void __launch_bounds__(TR_THREADS)
+do_to_sh_kernel(TrArgs a, int ntiles)
+{
+    extern __shared__ __align__(16) float tr_sm[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int mm = a.mm, nm = 2 * mm + 1, nlm = a.nlm, nmu = a.nmu;
+    const int nplanes = a.nst == 1 ? 1 : 2;
+    const TrSmem s = tr_smem(tr_sm, nlm, nmu, nm, a.nang, nplanes);
+    float *in_s = s.az_s;        // [nang][32] one Stokes plane of the tile's DO field (the azimuthal table stays in L1/L2)
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int p0 = tile * TR_TP;
+        // output groups: {I} and {Q,U} (Q and U both need SUMUV(2,.) and SUMUV(3,.))
+        for (int grp = 0; grp < (a.nst == 1 ? 1 : 2); grp++) {
+            const int nout = grp == 0 ? 1 : 2;
+            __syncthreads();
+            for (int i = threadIdx.x; i < nout * nlm * 33; i += TR_THREADS) s.sh_s[i] = 0.0f;
+            for (int n = (grp == 0 ? 0 : 1); n < (grp == 0 ? 1 : 3); n++) {
+                __syncthreads();
+                for (int i = threadIdx.x; i < a.nang * TR_TP; i += TR_THREADS) {
+                    const int iang = i / TR_TP, q = i % TR_TP;
+                    in_s[i] = (p0 + q < a.npts) ? __ldg(&a.dofield[(p0 + q) + (size_t)a.npts * (n + (size_t)a.nst * iang)]) : 0.0f;
+                }
+                __syncthreads();
+                // stage B': SUMCS(n, m) = sum over the azimuths of CPHI2 * INDATA  (az already carries DELPHI)
+                for (int task = warp; task < nmu * nm; task += TR_WARPS) {
+                    const int imu = task / nm, mi = task % nm, m = mi - mm, me = a.me_of[imu];
+                    float sum = 0.0f;
+                    if (m >= -me && m <= me)
+                        for (int iang = a.ang0[imu]; iang < a.ang0[imu + 1]; iang++)
+                            sum = fmaf(__ldg(&a.az[(size_t)iang * nm + mi]), in_s[iang * TR_TP + lane], sum);
+                    s.uv_s[(imu * nm + mi) * TR_TP + lane] = sum;
+                }
+                __syncthreads();
+                // SUMUV from SUMCS (shdomsub1.f:3121-3136), in place
+                for (int task = warp; task < nmu * mm; task += TR_WARPS) {
+                    const int imu = task / mm, m = task % mm + 1;
+                    float *pu = &s.uv_s[(imu * nm + (mm + m)) * TR_TP + lane], *nu = &s.uv_s[(imu * nm + (mm - m)) * TR_TP + lane];
+                    const float cp = *pu, cn = *nu;
+                    if (n == 2) { *pu = cp + cn; *nu = cp - cn; }
+                    else { *pu = cp - cn; *nu = cp + cn; }
+                }
+                // stage A': OUTDATA(out, j) += CMU2(comp, imu, j) * SUMUV(n, m(j)) summed over the zenith angles
+                for (int o = 0; o < nout; o++) {
+                    // I <- (1, n=0); Q <- (2, n=1) + (5, n=2); U <- (6, n=1) + (3, n=2)
+                    int comp;
+                    if (grp == 0) comp = 0;
+                    else if (o == 0) comp = n == 1 ? 1 : 4;
+                    else comp = n == 1 ? 5 : 2;
+                    __syncthreads();
+                    for (int i = threadIdx.x; i < nmu * nlm; i += TR_THREADS)
+                        s.cmu_s[i] = __ldg(&a.cmu[i + (size_t)nmu * nlm * comp]);
+                    __syncthreads();
+                    for (int j = warp; j < nlm; j += TR_WARPS) {
+                        const int mi = a.mofj[j] + mm;
+                        float sum = 0.0f;
+                        for (int imu = 0; imu < nmu; imu++)
+                            sum = fmaf(s.cmu_s[imu * nlm + j], s.uv_s[(imu * nm + mi) * TR_TP + lane], sum);
+                        s.sh_s[(o * nlm + j) * 33 + lane] += sum;
+                    }
+                }
+            }
+            __syncthreads();
+            // write the truncated SH blocks (RSHPTR), lanes over j
+            for (int q = warp; q < TR_TP; q += TR_WARPS) {
+                const int p = p0 + q;
+                if (p >= a.npts) continue;
+                const int is = a.shptr[p], ns = a.shptr[p + 1] - is;
+                for (int o = 0; o < nout; o++) {
+                    const int plane = grp == 0 ? 0 : 1 + o;
+                    for (int j = lane; j < ns; j += 32)
+                        a.sh_out[plane + (size_t)a.nst * (is + j)] = s.sh_s[(o * nlm + j) * 33 + q];
+                }
+            }
+        }
+    }
+}
+
+namespace {
+struct Arena {
+    std::vector<void *> ptrs;
+    ~Arena() { for (void *p : ptrs) cudaFree(p); }
+    template <typename T> T *alloc(size_t n)
+    {
+        void *p = nullptr;
+        if (cudaMalloc(&p, (n ? n : 1) * sizeof(T)) != cudaSuccess) return nullptr;
+        ptrs.push_back(p);
+        return (T *)p;
+    }
+    template <typename T> T *up(const T *h, size_t n)
+    {
+        T *d = alloc<T>(n);
+        if (d && n && cudaMemcpy(d, h, n * sizeof(T), cudaMemcpyHostToDevice) != cudaSuccess) return nullptr;
+        return d;
+    }
+};
+}
+
+// direction: 0 = SH_TO_DO, 1 = DO_TO_SH
+static int transform(int direction, int npts, int nstokes, int nstleg, int ml, int mm, int nlm, int nmu, int nphi0max,
+                     const int32_t *nphi0, const float *mu, const float *phi, const float *wtmu,
+                     const int32_t *ptr, float *sh, float *dofield, double *kernel_ms, char *errmsg)
+{
+    if (errmsg) errmsg[0] = 0;
+    if (!nphi0 || !mu || !phi || !wtmu || !ptr || !sh || !dofield) { set_msg(errmsg, "null argument"); return 1; }
+    if (at3d_device_count() < 1) { set_msg(errmsg, "no CUDA device: at3d_b200 has no CPU fallback"); return 4; }
+    if (!(nstokes == 1 || nstokes == 3) || (nstokes == 1) != (nstleg == 1)) { set_msg(errmsg, "NSTOKES must be 1 (NSTLEG=1) or 3 (NSTLEG=6)"); return 3; }
+    if (nmu > 64 || nlm != (2 * mm + 1) * (ml + 1) - mm * (mm + 1)) { set_msg(errmsg, "inconsistent NLM/ML/MM or NMU > 64"); return 1; }
+    const int nm = 2 * mm + 1;
+    int nang = 0;
+    std::vector<int> imu_of, me_of(nmu), ang0(nmu + 1), mofj(nlm);
+    for (int i = 0; i < nmu; i++) {
+        ang0[i] = nang;
+        for (int k = 0; k < nphi0[i]; k++) imu_of.push_back(i);
+        nang += nphi0[i];
+        int me = nphi0[i] / 2 - 1; if (me > mm) me = mm; if (me < 0) me = 0;
+        me_of[i] = me;
+    }
+    ang0[nmu] = nang;
+    {
+        int j = 0;
+        for (int l = 0; l <= ml; l++) { const int me = l < mm ? l : mm; for (int m = -me; m <= me; m++) mofj[j++] = m; }
+    }
+    // azimuthal basis.  FFTFLAG (MAKE_ANGLE_SET, shdomsub2.f:1131): the reference uses FFTPACK on the exact angles
+    // 2 pi k/N there, and REAL COS(M*PHI(I,K)) tables otherwise; DO_TO_SH carries DELPHI = WTDO/WTMU
+    std::vector<float> az((size_t)nang * nm);
+    const int mmax = nphi0max / 2 - 1 > 0 ? nphi0max / 2 - 1 : 0;
+    for (int i = 0, ia = 0; i < nmu; i++) {
+        const bool fft = nphi0[i] > 14 || mmax > 15;
+        const float delphi = 2.0f * acosf(-1.0f) / nphi0[i];
+        for (int k = 0; k < nphi0[i]; k++, ia++)
+            for (int m = -mm; m <= mm; m++) {
+                double v;
+                if (m == 0) v = 1.0;
+                else if (fft) {
+                    const double ang = 2.0 * acos(-1.0) * (double)((abs(m) * k) % nphi0[i]) / (double)nphi0[i];
+                    v = m > 0 ? cos(ang) : sin(ang);
+                } else {
+                    const float ph = phi[i + (size_t)nmu * k];
+                    v = m > 0 ? (double)cosf(m * ph) : (double)sinf(-m * ph);
+                }
+                az[(size_t)ia * nm + (m + mm)] = direction == 0 ? (float)v : (float)v * delphi;
+            }
+    }
+    Arena A;
+    const int ncomp = nstleg;
+    float *mu_d = A.up(mu, nmu), *wt_d = A.up(wtmu, nmu);
+    float *prc = A.alloc<float>((size_t)6 * nlm * nmu), *cmu = A.alloc<float>((size_t)ncomp * nmu * nlm);
+    const size_t nsh = (size_t)nstokes * ptr[npts], ndo = (size_t)npts * nstokes * nang;
+    TrArgs a;
+    memset(&a, 0, sizeof(a));
+    a.npts = npts; a.nst = nstokes; a.nstleg = nstleg; a.ml = ml; a.mm = mm; a.nlm = nlm; a.nmu = nmu; a.nang = nang;
+    a.shptr = A.up(ptr, (size_t)npts + 1);
+    float *sh_d = direction == 0 ? A.up(sh, nsh) : A.alloc<float>(nsh);
+    float *do_d = direction == 1 ? A.up(dofield, ndo) : A.alloc<float>(ndo);
+    a.sh = sh_d; a.sh_out = sh_d; a.dofield = do_d; a.cmu = cmu;
+    a.az = A.up(az.data(), az.size()); a.imu_of = A.up(imu_of.data(), imu_of.size());
+    a.me_of = A.up(me_of.data(), me_of.size()); a.ang0 = A.up(ang0.data(), ang0.size()); a.mofj = A.up(mofj.data(), mofj.size());
+    if (!mu_d || !wt_d || !prc || !cmu || !a.shptr || !sh_d || !do_d || !a.az || !a.imu_of || !a.me_of || !a.ang0 || !a.mofj) {
+        set_msg(errmsg, "device allocation failure"); return 4;
+    }
+    cudaMemset(prc, 0, (size_t)6 * nlm * nmu * sizeof(float));
+    plmall_kernel<<<(nmu * (mm + 1) + 127) / 128, 128>>>(nmu, mu_d, ml, mm, nlm, direction, prc);
+    pack_cmu_kernel<<<(nmu * nlm * ncomp + 255) / 256, 256>>>(nmu, nlm, ncomp, prc, direction ? wt_d : nullptr, cmu);
+    const int nplanes = (direction == 1 && nstokes > 1) ? 2 : 1;
+    size_t smem = ((size_t)nplanes * nlm * 33 + (size_t)nmu * nlm + (size_t)nmu * nm * TR_TP) * sizeof(float);
+    smem += (direction == 0 ? (size_t)nang * nm : (size_t)nang * TR_TP) * sizeof(float);
+    if (smem > 227 * 1024) { set_msg(errmsg, "angular resolution too high for the shared-memory tiles (%zu bytes)", smem); return 3; }
+    int dev = 0, nsm = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    const int ntiles = (npts + TR_TP - 1) / TR_TP;
+    const int nb = ntiles < nsm ? ntiles : nsm;        // persistent: one block per SM (shared memory bound)
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0, 0);
+    if (direction == 0) {
+        cudaFuncSetAttribute(sh_to_do_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        sh_to_do_kernel<<<nb, TR_THREADS, smem>>>(a, ntiles);
+    } else {
+        cudaFuncSetAttribute(do_to_sh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        do_to_sh_kernel<<<nb, TR_THREADS, smem>>>(a, ntiles);
+    }
+    cudaEventRecord(e1, 0);
+    cudaError_t e = cudaEventSynchronize(e1);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    float ms = 0.0f;
+    if (e == cudaSuccess) cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (e != cudaSuccess) { set_msg(errmsg, "CUDA error %s in the SH/DO transform", cudaGetErrorString(e)); return 4; }
+    if (kernel_ms) *kernel_ms = ms;
+    if (direction == 0) e = cudaMemcpy(dofield, do_d, ndo * sizeof(float), cudaMemcpyDeviceToHost);
+    else e = cudaMemcpy(sh, sh_d, nsh * sizeof(float), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) { set_msg(errmsg, "CUDA error %s copying the result", cudaGetErrorString(e)); return 4; }
+    return 0;
+}
+
+extern "C" int at3d_sh_to_do(int npts, int nstokes, int nstleg, int ml, int mm, int nlm, int nmu, int nphi0max,
+                             const int32_t *nphi0, const float *mu, const float *phi, const float *wtmu,
+                             const int32_t *shptr, const float *indata, float *dofield, double *kernel_ms, char *errmsg)
+{
+    return transform(0, npts, nstokes, nstleg, ml, mm, nlm, nmu, nphi0max, nphi0, mu, phi, wtmu, shptr,
+                     (float *)indata, dofield, kernel_ms, errmsg);
+}
+
+extern "C" int at3d_do_to_sh(int npts, int nstokes, int nstleg, int ml, int mm, int nlm, int nmu, int nphi0max,
+                             const int32_t *nphi0, const float *mu, const float *phi, const float *wtmu,
+                             const int32_t *rshptr, const float *dofield, float *outdata, double *kernel_ms, char *errmsg)
+{
+    return transform(1, npts, nstokes, nstleg, ml, mm, nlm, nmu, nphi0max, nphi0, mu, phi, wtmu, rshptr,
+                     outdata, (float *)dofield, kernel_ms, errmsg);
+}

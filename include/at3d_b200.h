@@ -230,6 +230,19 @@ int at3d_update_costfunction(const double *stokesout, const double *raygrad_pixe
                              int costfunc_ll, int nstokes, int maxpg, int numder,
                              const double *measurement, int nuncertainty, char *errmsg);
 
+/* ---- next: the SH <-> discrete-ordinate transforms of PATH_INTEGRATION ----
+ * SH_TO_DO / DO_TO_SH (src/polarized/shdomsub1.f:2789-3260) with MAKE_SH_DO_COEF's tables (shdomsub2.f:1146-1220), for
+ * ALL zenith angles at once.  dofield is DOFIELD(NPTS, NSTOKES, NANG) (Fortran order), ordinate IANG = (IMU, IPHI) in
+ * PATH_INTEGRATION order; indata/outdata are (NSTOKES, *) SH arrays addressed by SHPTR / RSHPTR.  mu[nmu], phi[nmu,
+ * nphi0max], wtmu[nmu], nphi0[nmu] come from MAKE_ANGLE_SET.  at3d_do_to_sh returns the sum over all zenith angles
+ * (the reference accumulates one angle per call into a zeroed RADIANCE, shdomsub1.f:2043-2046). Host pointers. */
+int at3d_sh_to_do(int npts, int nstokes, int nstleg, int ml, int mm, int nlm, int nmu, int nphi0max,
+                  const int32_t *nphi0, const float *mu, const float *phi, const float *wtmu,
+                  const int32_t *shptr, const float *indata, float *dofield, double *kernel_ms, char *errmsg);
+int at3d_do_to_sh(int npts, int nstokes, int nstleg, int ml, int mm, int nlm, int nmu, int nphi0max,
+                  const int32_t *nphi0, const float *mu, const float *phi, const float *wtmu,
+                  const int32_t *rshptr, const float *dofield, float *outdata, double *kernel_ms, char *errmsg);
+
 #ifdef __cplusplus
 }
 #endif

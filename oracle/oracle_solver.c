@@ -710,3 +710,50 @@ done:
     free_sh_do_coef(c); free(sweepord); free(oshptr); free(lofj); free(delsource); free(work); free(gridrad);
     return ierr;
 }
+
+/* ---- the two transforms alone, for all zenith angles (parity checks of the GPU transforms) ----
+ * dofield is DOFIELD(NPTS, NSTOKES, NANG): ordinate IANG = (IMU, IPHI) in PATH_INTEGRATION order. */
+int oracle_sh_to_do_all(const oracle_state *st, const float *wtmu, const int *shptr, const float *indata,
+                        float *dofield)
+{
+    shdo_coef *c = make_sh_do_coef(st, wtmu);
+    const int ns = st->nstokes, npts = st->npts, na = st->nphi0max, mm = st->mm;
+    float *work = (float *)calloc((size_t)ns * na * npts, sizeof(float));
+    double *aztab = (double *)malloc(sizeof(double) * (2 * mm + 1) * na);
+    int imu, k, m, i, n, iang = 0;
+    for (imu = 1; imu <= st->nmu; imu++) {
+        const int nphi0 = st->nphi0[imu - 1];
+        for (k = 1; k <= nphi0; k++)
+            for (m = -mm; m <= mm; m++) aztab[(m + mm) + (2 * mm + 1) * (k - 1)] = az_basis(st, c, imu, k, m);
+        sh_to_do(st, c, imu, shptr, indata, work, aztab);
+        for (k = 1; k <= nphi0; k++, iang++)
+            for (i = 0; i < npts; i++)
+                for (n = 0; n < ns; n++)
+                    dofield[i + (size_t)npts * (n + (size_t)ns * iang)] = work[n + (size_t)ns * ((k - 1) + (size_t)na * i)];
+    }
+    free(work); free(aztab); free_sh_do_coef(c);
+    return 0;
+}
+
+int oracle_do_to_sh_all(const oracle_state *st, const float *wtmu, const int *rshptr, const float *dofield,
+                        float *outdata)
+{
+    shdo_coef *c = make_sh_do_coef(st, wtmu);
+    const int ns = st->nstokes, npts = st->npts, na = st->nphi0max, mm = st->mm;
+    float *work = (float *)calloc((size_t)ns * na * npts, sizeof(float));
+    double *aztab = (double *)malloc(sizeof(double) * (2 * mm + 1) * na);
+    int imu, k, m, i, n, iang = 0;
+    memset(outdata, 0, sizeof(float) * (size_t)ns * rshptr[npts]);
+    for (imu = 1; imu <= st->nmu; imu++) {
+        const int nphi0 = st->nphi0[imu - 1];
+        for (k = 1; k <= nphi0; k++)
+            for (m = -mm; m <= mm; m++) aztab[(m + mm) + (2 * mm + 1) * (k - 1)] = az_basis(st, c, imu, k, m);
+        for (k = 1; k <= nphi0; k++, iang++)
+            for (i = 0; i < npts; i++)
+                for (n = 0; n < ns; n++)
+                    work[n + (size_t)ns * ((k - 1) + (size_t)na * i)] = dofield[i + (size_t)npts * (n + (size_t)ns * iang)];
+        do_to_sh(st, c, imu, rshptr, work, outdata, aztab);
+    }
+    free(work); free(aztab); free_sh_do_coef(c);
+    return 0;
+}

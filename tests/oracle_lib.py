@@ -314,3 +314,29 @@ def surface_brdf(sfctype, refparms, wavelen, mu2, phi2, mu1, phi1, nstokes):
     if code:
         raise OracleError('SURFACE_BRDF: unsupported call')
     return refl[:nstokes, :nstokes].copy()
+
+
+def sh_to_do(state, wtmu, shptr, indata):
+    st = state.copy().normalize()
+    d = st.fill(OracleState())
+    wtmu = np.ascontiguousarray(wtmu, np.float32)
+    shptr = np.ascontiguousarray(shptr, np.int32)
+    indata = np.asfortranarray(indata, np.float32)
+    out = np.zeros((st.npts, st.nstokes, int(np.sum(st.nphi0))), np.float32, order='F')
+    fn = lib().oracle_sh_to_do_all
+    fn.argtypes = [P(OracleState), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    fn(C.byref(d), _vp(wtmu), _vp(shptr), _vp(indata), _vp(out))
+    return out
+
+
+def do_to_sh(state, wtmu, rshptr, dofield):
+    st = state.copy().normalize()
+    d = st.fill(OracleState())
+    wtmu = np.ascontiguousarray(wtmu, np.float32)
+    rshptr = np.ascontiguousarray(rshptr, np.int32)
+    dofield = np.asfortranarray(dofield, np.float32)
+    out = np.zeros((st.nstokes, max(int(rshptr[st.npts]), 1)), np.float32, order='F')
+    fn = lib().oracle_do_to_sh_all
+    fn.argtypes = [P(OracleState), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    fn(C.byref(d), _vp(wtmu), _vp(rshptr), _vp(dofield), _vp(out))
+    return out
