@@ -43,18 +43,22 @@ struct CsArgs {
 
 #define CS_WARPS 8
 
-// Mixed Legendre table of the point (NEWMETHOD=.TRUE.) into shared memory;
-// returns (albedo, planck) to use in CALC_SOURCE_PNT.  shdomsub1.f:1089-1141.
+// Mixed Legendre table of the point (NEWMETHOD=.TRUE.) into shared memory; returns (albedo, planck) to use in
+// CALC_SOURCE_PNT.  shdomsub1.f:1089-1141.  Lane t owns table entries t, t+32, ... in registers through the whole
+// mixing (the delta-M fraction F of a species travels by shuffle), so a point costs one pass and one warp sync.
+// CS_SLOTS = table entries per lane (1, 2, 4 or 8: NSTLEG*(NLEG+1) <= 256), a template parameter of the kernels.
+template <int CS_SLOTS>
 __device__ __forceinline__ void cs_mix_newmethod(const CsArgs &a, int i, float *legent, float *legent1,
                                                  float &albedo_out, float &planck_out)
 {
     const int lane = threadIdx.x & 31;
-    const int nlt = a.nstleg * (a.nleg + 1);
+    const int nlt = a.nstleg * (a.nleg + 1), ndm = a.nstleg * (a.ml + 1), nslots = (nlt + 31) >> 5;
     const float ext = a.total_ext[i];
     double alb = 0.0;
     float total_planck = 0.0f;
-    for (int t = lane; t < nlt; t += 32) legent[t] = 0.0f;
-    __syncwarp();
+    float acc[CS_SLOTS];
+#pragma unroll
+    for (int u = 0; u < CS_SLOTS; u++) acc[u] = 0.0f;
     for (int ipa = 0; ipa < a.npart; ipa++) {
         const int *iph = a.iphase + (size_t)a.nq * (i + (size_t)a.npts * ipa);
         const float *pw = a.phaseinterpwt + (size_t)a.nq * (i + (size_t)a.npts * ipa);
@@ -62,48 +66,63 @@ __device__ __forceinline__ void cs_mix_newmethod(const CsArgs &a, int i, float *
         const double scat = (double)(e * al);
         alb = alb + scat;
         if (a.planck) total_planck = total_planck + e * a.planck[i + (size_t)a.npts * ipa];
+        float l1[CS_SLOTS];
         if (!a.interp_new) {
             const float *lg = a.legen + (size_t)nlt * (iph[0] - 1);
-            for (int t = lane; t < nlt; t += 32) legent[t] = (float)(legent[t] + scat * lg[t]);
+#pragma unroll
+            for (int u = 0; u < CS_SLOTS; u++) {
+                if (u >= nslots) break; const int t = lane + 32 * u; l1[u] = t < nlt ? __ldg(&lg[t]) : 0.0f; }
         } else {
             const bool single = pw[0] >= a.phasemax;
-            for (int t = lane; t < nlt; t += 32) {
-                float v;
-                if (single) v = a.legen[(size_t)nlt * (iph[0] - 1) + t];
-                else {
-                    v = 0.0f;
-                    for (int q = 0; q < a.nq; q++) {
-                        if (pw[q] <= 1e-5f) continue;
-                        v = v + a.legen[(size_t)nlt * (iph[q] - 1) + t] * pw[q];
+#pragma unroll
+            for (int u = 0; u < CS_SLOTS; u++) {
+                if (u >= nslots) break;
+                const int t = lane + 32 * u;
+                float v = 0.0f;
+                if (t < nlt) {
+                    if (single) v = __ldg(&a.legen[(size_t)nlt * (iph[0] - 1) + t]);
+                    else {
+                        for (int q = 0; q < a.nq; q++) {
+                            if (pw[q] <= 1e-5f) continue;
+                            v = v + __ldg(&a.legen[(size_t)nlt * (iph[q] - 1) + t]) * pw[q];
+                        }
                     }
                 }
-                legent1[t] = v;
+                l1[u] = v;
             }
-            __syncwarp();
             if (a.deltam) {
-                const float f = legent1[a.nstleg * (a.ml + 1)];
-                __syncwarp();
-                for (int t = lane; t < a.nstleg * (a.ml + 1); t += 32) legent1[t] = legent1[t] / (1 - f);
-                __syncwarp();
+                // F = LEGENT1(1, ML+1): entry ndm of the table
+                float f = 0.0f;
+#pragma unroll
+                for (int u = 0; u < CS_SLOTS; u++)
+                    if (ndm / 32 == u) f = __shfl_sync(FULLMASK, l1[u], ndm % 32);
+#pragma unroll
+                for (int u = 0; u < CS_SLOTS; u++) if (u < nslots && lane + 32 * u < ndm) l1[u] = l1[u] / (1 - f);
             }
-            for (int t = lane; t < nlt; t += 32) legent[t] = (float)(legent[t] + scat * legent1[t]);
         }
-        __syncwarp();
+#pragma unroll
+        for (int u = 0; u < CS_SLOTS; u++) if (u < nslots) acc[u] = (float)(acc[u] + scat * l1[u]);
     }
-    if (alb > 1e-10f) { for (int t = lane; t < nlt; t += 32) legent[t] = (float)(legent[t] / alb); }
-    else { for (int t = lane; t < nlt; t += 32) legent[t] = legent[t] / a.npart; }
+#pragma unroll
+    for (int u = 0; u < CS_SLOTS; u++) {
+                if (u >= nslots) break;
+        if (alb > 1e-10f) acc[u] = (float)(acc[u] / alb);
+        else acc[u] = acc[u] / a.npart;
+    }
     if (ext > 1e-10f) { alb = alb / ext; total_planck = total_planck / ext; }
     else { alb = 0.0; total_planck = 0.0f; }
-    __syncwarp();
-    if (lane == 0) legent[0] = 1.0f;
+    if (lane == 0) acc[0] = 1.0f;
+    __syncwarp();                 // the previous point's reads of legent are complete
+#pragma unroll
+    for (int u = 0; u < CS_SLOTS; u++) if (lane + 32 * u < nlt) legent[lane + 32 * u] = acc[u];
     __syncwarp();
     albedo_out = (float)alb;
     planck_out = total_planck;
 }
 
-// CALC_SOURCE_PNT[_UNPOL] for one SH index j (0-based) (shdomsub1.f:858-898, 940-958)
+// CALC_SOURCE_PNT[_UNPOL] for one SH index j (0-based) (shdomsub1.f:858-898, 940-958); r = RADIANCE(:,j) (0 beyond NR)
 template <int NST>
-__device__ __forceinline__ void cs_calc_j(const CsArgs &a, const float *legen, int j, int nr, const float *rad,
+__device__ __forceinline__ void cs_calc_j(const CsArgs &a, const float *legen, int j, bool inr, const float (&r)[NST],
                                           float flux0, float planck, float albedo, float (&s)[NST])
 {
     const int l = a.lofj[j];
@@ -113,13 +132,13 @@ __device__ __forceinline__ void cs_calc_j(const CsArgs &a, const float *legen, i
         float v = 0.0f;
         if (solar) v = flux0 * albedo * legen[l] * a.ylmsun[j];
         if (thermal && j == 0) v = v + 3.544907703f * planck;
-        if (j < nr) v = v + albedo * legen[l] * rad[j];
+        if (inr) v = v + albedo * legen[l] * r[0];
         s[0] = v;
     } else {
         const int ns = a.nstleg;
         float v1 = 0.0f, v2 = 0.0f, v3 = 0.0f;
-        if (j < nr) {
-            const float r1 = rad[(size_t)NST * j], r2 = rad[(size_t)NST * j + 1], r3 = rad[(size_t)NST * j + 2];
+        if (inr) {
+            const float r1 = r[0], r2 = r[1], r3 = r[NST - 1];
             v1 = v1 + legen[ns * l] * r1;
             v1 = v1 + legen[4 + ns * l] * r2;
             if (j >= 4) {
@@ -137,68 +156,90 @@ __device__ __forceinline__ void cs_calc_j(const CsArgs &a, const float *legen, i
     }
 }
 
-// the temporary source of point i at SH index j, both mixing methods
-template <int NST>
-struct PointSource {
-    float albedo, planck, flux0;
-    int nr;
-    const float *rad;
-    __device__ void setup(const CsArgs &a, int i, float *legent, float *legent1)
-    {
-        const int ir = a.rshptr[i];
-        nr = a.rshptr[i + 1] - ir;
-        rad = a.radiance + (size_t)NST * ir;
-        flux0 = a.dirflux[i] * a.secmu0;
-        cs_mix_newmethod(a, i, legent, legent1, albedo, planck);
-    }
-    __device__ void eval(const CsArgs &a, int i, const float *legent, int j, float (&s)[NST]) const
-    {
-        cs_calc_j<NST>(a, legent, j, nr, rad, flux0, planck, albedo, s);
-    }
-};
+// A point is one warp; its SH index j runs over the lanes in batches of CS_BATCH x 32.  The loads of a batch
+// (RADIANCE, old SOURCE, old DELSOURCE: the HBM streams of the routine) are all issued before anything is computed, and
+// those of the first batch even before the Legendre table of the point is mixed, so that a warp keeps
+// 3 x CS_BATCH x 128 B x NSTOKES in flight instead of one line per array.
+template <int NST> struct CsBatch { static const int N = NST == 1 ? 4 : 2; };
 
 // Kernel A: norms (passes 1 of the reference) and the new truncation length (first half of pass 3)
-template <int NST>
+template <int NST, int SLOTS>
 __global__ void __launch_bounds__(CS_WARPS * 32) cs_norms_kernel(CsArgs a)
 {
     extern __shared__ float smem[];
+    constexpr int NB = CsBatch<NST>::N;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nlt = a.nstleg * (a.nleg + 1);
     float *legent = smem + (size_t)warp * 2 * nlt, *legent1 = legent + nlt;
     __shared__ double red[CS_WARPS][4];
     double sdot = 0.0, sold = 0.0, snew = 0.0, snorm = 0.0;
-    for (int i = blockIdx.x * CS_WARPS + warp; i < a.npts; i += gridDim.x * CS_WARPS) {
-        PointSource<NST> ps;
-        ps.setup(a, i, legent, legent1);
-        if (ps.nr > a.nlm) { if (lane == 0) atomicCAS(a.bad, 0, i + 1); continue; }
-        const int is = a.shptr_old[i];
-        int ns = a.shptr_old[i + 1] - is;
-        int iso = 0;
-        if (a.accelflag && !a.first) {
-            iso = a.oshptr_old[i];
-            const int nso = a.oshptr_old[i + 1] - iso;
-            if (nso < ns) ns = nso;
+    const bool donorm = !a.first, doacc = a.accelflag && !a.first;
+    // software pipeline over the warp's points: the block pointers of the next point are requested at the top of an
+    // iteration and its first batch of SH values at the bottom, so their HBM latency overlaps this point's arithmetic
+    const int stride = gridDim.x * CS_WARPS;
+    int i = blockIdx.x * CS_WARPS + warp;
+    int ir = 0, nr = 0, is = 0, ns = 0, iso = 0;
+    float r[NB][NST], so[NB][NST], ds[NB][NST];
+    auto load_ptrs = [&](int ip, int &ir_, int &nr_, int &is_, int &ns_, int &iso_) {
+        ir_ = a.rshptr[ip]; nr_ = a.rshptr[ip + 1] - ir_;
+        is_ = a.shptr_old[ip]; ns_ = a.shptr_old[ip + 1] - is_;
+        iso_ = 0;
+        if (doacc) {
+            iso_ = a.oshptr_old[ip];
+            const int nso = a.oshptr_old[ip + 1] - iso_;
+            if (nso < ns_) ns_ = nso;
         }
+    };
+    auto load_batch = [&](int j0, int ir_, int nr_, int is_, int ns_, int iso_) {
+        const float *rad = a.radiance + (size_t)NST * ir_;
+        const float *sop = a.source_old + (size_t)NST * is_, *dsp = a.delsource_old + (size_t)NST * iso_;
+#pragma unroll
+        for (int u = 0; u < NB; u++) {
+            const int j = j0 + 32 * u + lane;
+#pragma unroll
+            for (int k = 0; k < NST; k++) {
+                r[u][k] = (j < nr_) ? __ldg(&rad[(size_t)NST * j + k]) : 0.0f;
+                so[u][k] = (donorm && j < ns_) ? __ldg(&sop[(size_t)NST * j + k]) : 0.0f;
+                ds[u][k] = (doacc && j < ns_) ? __ldg(&dsp[(size_t)NST * j + k]) : 0.0f;
+            }
+        }
+    };
+    if (i < a.npts) { load_ptrs(i, ir, nr, is, ns, iso); load_batch(0, ir, nr, is, ns, iso); }
+    for (; i < a.npts; i += stride) {
+        const int inext = i + stride;
+        int ir2 = 0, nr2 = 0, is2 = 0, ns2 = 0, iso2 = 0;
+        if (inext < a.npts) load_ptrs(inext, ir2, nr2, is2, ns2, iso2);
+        if (nr > a.nlm) {
+            if (lane == 0) atomicCAS(a.bad, 0, i + 1);
+            ir = ir2; nr = nr2; is = is2; ns = ns2; iso = iso2;
+            if (inext < a.npts) load_batch(0, ir, nr, is, ns, iso);
+            continue;
+        }
+        float albedo, planck;
+        const float flux0 = a.dirflux[i] * a.secmu0;
+        cs_mix_newmethod<SLOTS>(a, i, legent, legent1, albedo, planck);
         int jlast = -1;                       // last j with |SOURCET| > SRCMIN
-        for (int j = lane; j < a.nlm; j += 32) {
-            float s[NST];
+        for (int j0 = 0; j0 < a.nlm; j0 += 32 * NB) {
+            if (j0 > 0) load_batch(j0, ir, nr, is, ns, iso);
 #pragma unroll
-            for (int k = 0; k < NST; k++) s[k] = 0.0f;
-            ps.eval(a, i, legent, j, s);
+            for (int u = 0; u < NB; u++) {
+                const int j = j0 + 32 * u + lane;
+                if (j >= a.nlm) continue;
+                float s[NST];
+                cs_calc_j<NST>(a, legent, j, j < nr, r[u], flux0, planck, albedo, s);
 #pragma unroll
-            for (int k = 0; k < NST; k++) if (fabsf(s[k]) > a.srcmin) jlast = j;
-            if (!a.first && j < ns) {
+                for (int k = 0; k < NST; k++) if (fabsf(s[k]) > a.srcmin) jlast = j;
+                if (donorm && j < ns) {
 #pragma unroll
-                for (int k = 0; k < NST; k++) {
-                    const float so = a.source_old[(size_t)NST * (is + j) + k];
-                    const float d = s[k] - so;
-                    if (a.accelflag) {
-                        const float ds = a.delsource_old[(size_t)NST * (iso + j) + k];
-                        sdot += (double)(d * ds);
-                        sold += (double)(ds * ds);
+                    for (int k = 0; k < NST; k++) {
+                        const float d = s[k] - so[u][k];
+                        if (a.accelflag) {
+                            sdot += (double)(d * ds[u][k]);
+                            sold += (double)(ds[u][k] * ds[u][k]);
+                        }
+                        snew += (double)(d * d);
+                        snorm += (double)(so[u][k] * so[u][k]);
                     }
-                    snew += (double)(d * d);
-                    snorm += (double)(so * so);
                 }
             }
         }
@@ -220,6 +261,8 @@ __global__ void __launch_bounds__(CS_WARPS * 32) cs_norms_kernel(CsArgs a)
             a.ns_new[i] = nsn;
         }
         __syncwarp();
+        ir = ir2; nr = nr2; is = is2; ns = ns2; iso = iso2;
+        if (inext < a.npts) load_batch(0, ir, nr, is, ns, iso);
     }
     sdot = warp_sum_d(sdot); sold = warp_sum_d(sold); snew = warp_sum_d(snew); snorm = warp_sum_d(snorm);
     if (lane == 0) { red[warp][0] = sdot; red[warp][1] = sold; red[warp][2] = snew; red[warp][3] = snorm; }
@@ -232,31 +275,65 @@ __global__ void __launch_bounds__(CS_WARPS * 32) cs_norms_kernel(CsArgs a)
 }
 
 // Kernel B: DELSOURCE at the old offsets (pass 2) and the re-packed SOURCE at the new offsets (pass 3)
-template <int NST>
+template <int NST, int SLOTS>
 __global__ void __launch_bounds__(CS_WARPS * 32) cs_write_kernel(CsArgs a)
 {
     extern __shared__ float smem[];
+    constexpr int NB = CsBatch<NST>::N;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nlt = a.nstleg * (a.nleg + 1);
     float *legent = smem + (size_t)warp * 2 * nlt, *legent1 = legent + nlt;
-    for (int i = blockIdx.x * CS_WARPS + warp; i < a.npts; i += gridDim.x * CS_WARPS) {
-        PointSource<NST> ps;
-        ps.setup(a, i, legent, legent1);
-        const int is_old = a.shptr_old[i], ns_old = a.shptr_old[i + 1] - is_old;
-        const int is_new = a.shptr_new[i], ns_new = a.shptr_new[i + 1] - is_new;
-        const int nmax = ns_old > ns_new ? ns_old : ns_new;
-        const bool dodel = !a.first && a.accelflag;
-        for (int j = lane; j < nmax; j += 32) {
-            float s[NST];
-            ps.eval(a, i, legent, j, s);
+    const bool dodel = !a.first && a.accelflag;
+    // same software pipeline over the warp's points as in cs_norms_kernel
+    const int stride = gridDim.x * CS_WARPS;
+    int i = blockIdx.x * CS_WARPS + warp;
+    int ir = 0, nr = 0, is_old = 0, ns_old = 0;
+    float r[NB][NST], so[NB][NST];
+    auto load_ptrs = [&](int ip, int &ir_, int &nr_, int &is_, int &ns_) {
+        ir_ = a.rshptr[ip]; nr_ = a.rshptr[ip + 1] - ir_;
+        is_ = a.shptr_old[ip]; ns_ = a.shptr_old[ip + 1] - is_;
+    };
+    auto load_batch = [&](int j0, int ir_, int nr_, int is_, int ns_) {
+        const float *rad = a.radiance + (size_t)NST * ir_;
+        const float *sop = a.source_old + (size_t)NST * is_;
+#pragma unroll
+        for (int u = 0; u < NB; u++) {
+            const int j = j0 + 32 * u + lane;
 #pragma unroll
             for (int k = 0; k < NST; k++) {
-                if (dodel && j < ns_old)
-                    a.delsource_new[(size_t)NST * (is_old + j) + k] = s[k] - a.source_old[(size_t)NST * (is_old + j) + k];
-                if (j < ns_new) a.source_new[(size_t)NST * (is_new + j) + k] = s[k];
+                r[u][k] = (j < nr_) ? __ldg(&rad[(size_t)NST * j + k]) : 0.0f;
+                so[u][k] = (dodel && j < ns_) ? __ldg(&sop[(size_t)NST * j + k]) : 0.0f;
+            }
+        }
+    };
+    if (i < a.npts) { load_ptrs(i, ir, nr, is_old, ns_old); load_batch(0, ir, nr, is_old, ns_old); }
+    for (; i < a.npts; i += stride) {
+        const int inext = i + stride;
+        int ir2 = 0, nr2 = 0, is2 = 0, ns2 = 0;
+        if (inext < a.npts) load_ptrs(inext, ir2, nr2, is2, ns2);
+        const int is_new = a.shptr_new[i], ns_new = a.shptr_new[i + 1] - is_new;
+        const int nmax = ns_old > ns_new ? ns_old : ns_new;
+        float albedo, planck;
+        const float flux0 = a.dirflux[i] * a.secmu0;
+        cs_mix_newmethod<SLOTS>(a, i, legent, legent1, albedo, planck);
+        for (int j0 = 0; j0 < nmax; j0 += 32 * NB) {
+            if (j0 > 0) load_batch(j0, ir, nr, is_old, ns_old);
+#pragma unroll
+            for (int u = 0; u < NB; u++) {
+                const int j = j0 + 32 * u + lane;
+                if (j >= nmax) continue;
+                float s[NST];
+                cs_calc_j<NST>(a, legent, j, j < nr, r[u], flux0, planck, albedo, s);
+#pragma unroll
+                for (int k = 0; k < NST; k++) {
+                    if (dodel && j < ns_old) a.delsource_new[(size_t)NST * (is_old + j) + k] = s[k] - so[u][k];
+                    if (j < ns_new) a.source_new[(size_t)NST * (is_new + j) + k] = s[k];
+                }
             }
         }
         __syncwarp();
+        ir = ir2; nr = nr2; is_old = is2; ns_old = ns2;
+        if (inext < a.npts) load_batch(0, ir, nr, is_old, ns_old);
     }
 }
 
@@ -351,6 +428,8 @@ extern "C" int at3d_compute_source(const at3d_state_desc *d, int fixsh, float sh
     int dev = 0, nsm = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    if (nlt > 256) { set_msg(errmsg, "COMPUTE_SOURCE: Legendre table longer than 256 entries"); return 3; }
+    const int slots = nlt <= 32 ? 1 : nlt <= 64 ? 2 : nlt <= 128 ? 4 : 8;
     const size_t smem = (size_t)CS_WARPS * 2 * nlt * sizeof(float);
     const int want = (int)((npts + CS_WARPS - 1) / CS_WARPS);
     const int nblk = want < nsm * 8 ? want : nsm * 8;          // persistent: a multiple of the SM count
@@ -367,44 +446,54 @@ extern "C" int at3d_compute_source(const at3d_state_desc *d, int fixsh, float sh
     }
     cudaMemset(a.bad, 0, sizeof(int));
     cudaMemset(a.ns_new + npts, 0, sizeof(int));
-    cudaEvent_t e0, e1;
-    cudaEventCreate(&e0); cudaEventCreate(&e1);
-    cudaEventRecord(e0, 0);
-    if (nst == 1) cs_norms_kernel<1><<<nblk, CS_WARPS * 32, smem>>>(a);
-    else cs_norms_kernel<3><<<nblk, CS_WARPS * 32, smem>>>(a);
-    cs_reduce_kernel<<<1, 1024>>>(nblk, a.partials, sums);
+    // every allocation happens before the timed region: the new SOURCE at its largest possible size
+    // (FIXSH keeps the old truncation; otherwise at most NLM terms per point, capped by MAXIV), the scan scratch,
+    // and a DELSOURCE that covers the OLD SHPTR offsets it is rewritten at (pass 2)
+    const size_t cap_new = fixsh ? (size_t)shptr[npts]
+                                 : ((size_t)maxiv < npts * (size_t)d->nlm ? (size_t)maxiv : npts * (size_t)d->nlm);
+    float *source_new = A.alloc<float>((size_t)nst * (cap_new ? cap_new : 1));
     size_t tmpb = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, tmpb, a.ns_new, shptr_new, (int)npts + 1);
     void *tmp = A.alloc<unsigned char>(tmpb);
-    if (!tmp) { set_msg(errmsg, "device allocation failure"); cudaEventDestroy(e0); cudaEventDestroy(e1); return 4; }
+    a.delsource_new = (float *)a.delsource_old;
+    if (accelflag && !first && (size_t)nst * shptr[npts] > ndel_old) a.delsource_new = A.alloc<float>((size_t)nst * shptr[npts]);
+    if (!source_new || !tmp || !a.delsource_new) { set_msg(errmsg, "device allocation failure"); return 4; }
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0, 0);
+#define CS_LAUNCH(K)                                                                              \
+    {                                                                                             \
+        if (nst == 1) {                                                                           \
+            if (slots == 1) K<1, 1><<<nblk, CS_WARPS * 32, smem>>>(a);                            \
+            else if (slots == 2) K<1, 2><<<nblk, CS_WARPS * 32, smem>>>(a);                       \
+            else if (slots == 4) K<1, 4><<<nblk, CS_WARPS * 32, smem>>>(a);                       \
+            else K<1, 8><<<nblk, CS_WARPS * 32, smem>>>(a);                                       \
+        } else {                                                                                  \
+            if (slots == 1) K<3, 1><<<nblk, CS_WARPS * 32, smem>>>(a);                            \
+            else if (slots == 2) K<3, 2><<<nblk, CS_WARPS * 32, smem>>>(a);                       \
+            else if (slots == 4) K<3, 4><<<nblk, CS_WARPS * 32, smem>>>(a);                       \
+            else K<3, 8><<<nblk, CS_WARPS * 32, smem>>>(a);                                       \
+        }                                                                                         \
+    }
+    CS_LAUNCH(cs_norms_kernel)
+    cs_reduce_kernel<<<1, 1024>>>(nblk, a.partials, sums);
     cub::DeviceScan::ExclusiveSum(tmp, tmpb, a.ns_new, shptr_new, (int)npts + 1);
     int total_new = 0, hbad = 0;
     cudaMemcpy(&total_new, shptr_new + npts, sizeof(int), cudaMemcpyDeviceToHost);
     cudaMemcpy(&hbad, a.bad, sizeof(int), cudaMemcpyDeviceToHost);
     int rc = 0;
     if (hbad) { set_msg(errmsg, "COMPUTE_SOURCE: NR>NLM 3 %d", hbad); rc = 1; }
-    else if (total_new > maxiv) {
+    else if (total_new > maxiv || (size_t)total_new > cap_new) {
         set_msg(errmsg, "COMPUTE_SOURCE: MAXIV exceeded %d Out of memory for more spherical harmonic terms.", maxiv);
         rc = 2;
     }
     float ms = 0.0f;
     if (!rc) {
         a.shptr_new = shptr_new;
-        a.source_new = A.alloc<float>((size_t)nst * (total_new ? total_new : 1));
-        a.delsource_new = (float *)a.delsource_old;
-        if (!a.source_new) { set_msg(errmsg, "device allocation failure"); rc = 4; }
+        a.source_new = source_new;
     }
     if (!rc) {
-        // DELSOURCE is rewritten at the OLD SHPTR offsets (pass 2); make sure the buffer covers them
-        if (accelflag && !first && (size_t)nst * shptr[npts] > ndel_old) {
-            float *dn = A.alloc<float>((size_t)nst * shptr[npts]);
-            if (!dn) { set_msg(errmsg, "device allocation failure"); rc = 4; }
-            else a.delsource_new = dn;
-        }
-    }
-    if (!rc) {
-        if (nst == 1) cs_write_kernel<1><<<nblk, CS_WARPS * 32, smem>>>(a);
-        else cs_write_kernel<3><<<nblk, CS_WARPS * 32, smem>>>(a);
+        CS_LAUNCH(cs_write_kernel)
         cudaEventRecord(e1, 0);
         cudaError_t e = cudaEventSynchronize(e1);
         if (e != cudaSuccess) { set_msg(errmsg, "CUDA error %s in at3d_compute_source", cudaGetErrorString(e)); rc = 4; }

@@ -19,7 +19,9 @@
 #include "at3d_host.h"
 
 #define TR_TP 32          // points per tile (= warp width)
-#define TR_THREADS 256
+#ifndef TR_THREADS
+#define TR_THREADS 1024
+#endif
 #define TR_WARPS (TR_THREADS / 32)
 
 static void set_msg(char *errmsg, const char *fmt, ...)
@@ -32,17 +34,18 @@ static void set_msg(char *errmsg, const char *fmt, ...)
 }
 
 struct TrArgs {
-    int npts, nst, nstleg, ml, mm, nlm, nmu, nang;
+    int npts, nst, nstleg, ml, mm, nlm, nmu, nang, ntask;
     const int *shptr;         // [npts+1] offsets into the SH array
     const float *sh;          // SH array (NSTOKES, *) interleaved  (input of sh_to_do / output of do_to_sh)
     float *sh_out;
     float *dofield;           // DOFIELD(NPTS, NSTOKES, NANG)
-    const float *cmu;         // [ncomp][nmu][nlm]: CMU1 (sh_to_do) or CMU2 (do_to_sh)
-    const float *az;          // [nang][2mm+1]: cos(m phi) for m>=0, sin(|m| phi) for m<0 (x DELPHI for do_to_sh)
-    const int *imu_of;        // [nang]
+    const float *cmu;         // sh_to_do: CMU1 as [comp][j][16] (zenith angle fastest); do_to_sh: CMU2 as [comp][m][imu][16] (degree fastest)
+    const float *az;          // sh_to_do: per zenith angle [m][NPHI0 rounded up to 8]; do_to_sh: [iang][32] (m fastest, x DELPHI)
+    const int *azoff;         // [nmu] offset of each zenith angle's block in az (sh_to_do)
+    const int2 *tasks;        // sh_to_do stage B: (imu, first azimuth of a group of 8)
     const int *me_of;         // [nmu]: min(NPHI0/2-1, MM) >= 0
     const int *ang0;          // [nmu+1] first ordinate of each zenith angle
-    const int *mofj;          // [nlm]
+    int azsize;
 };
 
 // PLMALL (shdomsub2.f:4650-4752) for every zenith angle: prc[(q-1) + 6*((j-1) + nlm*imu)].  Thread = (imu, m>=0).
@@ -120,171 +123,216 @@ __global__ void plmall_kernel(int nmu, const float *mu, int ml, int mm, int nlm,
     }
 }
 
-// re-pack PRC(6,NLM) per angle into component planes cmu[c][imu][j] (x WTMU for CMU2)
-__global__ void pack_cmu_kernel(int nmu, int nlm, int ncomp, const float *prc, const float *wtmu, float *cmu)
+// re-pack PRC(6,NLM) per angle: layout 0 = [comp][j][16] for SH_TO_DO, layout 1 = [comp][m][imu][16] (x WTMU) for
+// DO_TO_SH; unused slots are zero
+__global__ void pack_cmu_kernel(int nmu, int nlm, int ncomp, int ml, int mm, int layout, const float *prc,
+                                const float *wtmu, float *cmu)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nmu * nlm * ncomp) return;
     const int j = t % nlm, imu = (t / nlm) % nmu, c = t / (nlm * nmu);
     float v = prc[c + 6 * (j + (size_t)nlm * imu)];
-    if (wtmu) v = v * wtmu[imu];
-    cmu[j + (size_t)nlm * (imu + (size_t)nmu * c)] = v;
+    if (layout == 0) {
+        cmu[imu + 16 * (j + (size_t)nlm * c)] = v;
+    } else {
+        // l and m of j (inverse of sh_index)
+        int l = 0, m = 0, jj = 0;
+        for (l = 0; l <= ml; l++) {
+            const int me = l < mm ? l : mm;
+            if (j < jj + 2 * me + 1) { m = j - jj - me; break; }
+            jj += 2 * me + 1;
+        }
+        const int am = m < 0 ? -m : m, nm = 2 * mm + 1;
+        cmu[(l - am) + 16 * (imu + (size_t)nmu * ((m + mm) + (size_t)nm * c))] = v * wtmu[imu];
+    }
 }
 
-// terms of the Stokes coupling (SH_TO_DO: shdomsub1.f:2853-2866, DO_TO_SH: :3144-3153): (table component, SH plane)
-// that build discrete-ordinate plane n, both 0-based
+// terms of the Stokes coupling (SH_TO_DO: shdomsub1.f:2853-2866, DO_TO_SH: :3144-3153), 0-based:
+// sh_to_do: discrete-ordinate plane n is built from (table component, SH plane) terms;
+// do_to_sh: SH plane o is built from (table component, discrete-ordinate plane) terms
 __device__ __forceinline__ int tr_nterms(int n) { return n == 0 ? 1 : 2; }
 __device__ __forceinline__ void tr_term(int n, int t, int &comp, int &plane)
 {
     if (n == 0) { comp = 0; plane = 0; }
-    else if (n == 1) { comp = t == 0 ? 1 : 4; plane = t == 0 ? 1 : 2; }     // CMU(2)*Q + CMU(5)*U
-    else { comp = t == 0 ? 5 : 2; plane = t == 0 ? 1 : 2; }                 // CMU(6)*Q + CMU(3)*U
+    else if (n == 1) { comp = t == 0 ? 1 : 4; plane = t == 0 ? 1 : 2; }     // CMU(2), CMU(5)
+    else { comp = t == 0 ? 5 : 2; plane = t == 0 ? 1 : 2; }                 // CMU(6), CMU(3)
 }
 
-// shared-memory carve-up common to both kernels
-struct TrSmem { float *sh_s, *cmu_s, *uv_s, *az_s; };
-__device__ __forceinline__ TrSmem tr_smem(float *base, int nlm, int nmu, int nm, int nang, int nplanes)
+// SUMCS <-> SUMUV (shdomsub1.f:2871-2890 and :3121-3136), in place on uv_s[imu][m][point]; stokes3 = third Stokes plane
+__device__ __forceinline__ void tr_combine(float *uv_s, int nmu, int mm, bool to_cs, bool stokes3, int warp, int lane)
 {
-    TrSmem s;
-    s.sh_s = base;                                     // [nplanes][nlm][33]
-    s.cmu_s = s.sh_s + (size_t)nplanes * nlm * 33;     // [nmu][nlm]
-    s.uv_s = s.cmu_s + (size_t)nmu * nlm;              // [nmu][nm][32]
-    s.az_s = s.uv_s + (size_t)nmu * nm * TR_TP;        // [nang][nm]
-    return s;
+    const int nm = 2 * mm + 1;
+    for (int task = warp; task < nmu * mm; task += TR_WARPS) {
+        const int imu = task / mm, m = task % mm + 1;
+        float *pu = &uv_s[(imu * nm + (mm + m)) * TR_TP + lane], *nu = &uv_s[(imu * nm + (mm - m)) * TR_TP + lane];
+        const float vp = *pu, vn = *nu;
+        if (to_cs) {
+            if (stokes3) { *nu = vp - vn; *pu = vp + vn; }
+            else { *pu = vp + vn; *nu = vn - vp; }
+        } else {
+            if (stokes3) { *pu = vp + vn; *nu = vp - vn; }
+            else { *pu = vp - vn; *nu = vp + vn; }
+        }
+    }
 }
 
-// SH_TO_DO for all ordinates
+// SH_TO_DO for all ordinates.  Shared memory: sh_s[nlm][33] | cmu_s[nlm][16] | uv_s[nmu][nm][32] | az_s[azsize]
 __global__ void __launch_bounds__(TR_THREADS)
 sh_to_do_kernel(TrArgs a, int ntiles)
 {
     extern __shared__ __align__(16) float tr_sm[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int mm = a.mm, nm = 2 * mm + 1, nlm = a.nlm, nmu = a.nmu;
-    const TrSmem s = tr_smem(tr_sm, nlm, nmu, nm, a.nang, 1);
-    for (int i = threadIdx.x; i < a.nang * nm; i += TR_THREADS) s.az_s[i] = a.az[i];
+    float *sh_s = tr_sm, *cmu_s = sh_s + (size_t)nlm * 33, *uv_s = cmu_s + (size_t)nlm * 16;
+    float *az_s = uv_s + (size_t)nmu * nm * TR_TP;
+    for (int i = threadIdx.x; i < a.azsize; i += TR_THREADS) az_s[i] = a.az[i];
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int p0 = tile * TR_TP;
         for (int n = 0; n < a.nst; n++) {
             __syncthreads();
-            for (int i = threadIdx.x; i < nmu * nm * TR_TP; i += TR_THREADS) s.uv_s[i] = 0.0f;
+            for (int i = threadIdx.x; i < nmu * nm * TR_TP; i += TR_THREADS) uv_s[i] = 0.0f;
             for (int t = 0; t < tr_nterms(n); t++) {
                 int comp, plane;
                 tr_term(n, t, comp, plane);
                 __syncthreads();
-                // stage the SH plane of the tile, transposed to [j][point]; and the coefficient table
+                // stage the SH plane of the tile, transposed to [j][point], and the coefficient table
                 for (int q = warp; q < TR_TP; q += TR_WARPS) {
                     const int p = p0 + q;
                     int is = 0, ns = 0;
                     if (p < a.npts) { is = a.shptr[p]; ns = a.shptr[p + 1] - is; }
                     for (int j = lane; j < nlm; j += 32)
-                        s.sh_s[j * 33 + q] = j < ns ? __ldg(&a.sh[plane + (size_t)a.nst * (is + j)]) : 0.0f;
+                        sh_s[j * 33 + q] = j < ns ? __ldg(&a.sh[plane + (size_t)a.nst * (is + j)]) : 0.0f;
                 }
-                for (int i = threadIdx.x; i < nmu * nlm; i += TR_THREADS)
-                    s.cmu_s[i] = __ldg(&a.cmu[i + (size_t)nmu * nlm * comp]);
+                for (int i = threadIdx.x; i < nlm * 16; i += TR_THREADS) cmu_s[i] = __ldg(&a.cmu[i + (size_t)nlm * 16 * comp]);
                 __syncthreads();
-                // stage A: SUMUV(m) += CMU1(comp, j, imu) * SH(plane, j) over the degrees l of mode m
+                // stage A: SUMUV(imu, m) += CMU1(comp, j, imu) * SH(plane, j) over the degrees l of mode m;
+                // 16 zenith angles per SH value: 1 + 4 shared-memory loads for 16 FMAs
                 for (int mi = warp; mi < nm; mi += TR_WARPS) {
                     const int m = mi - mm, am = m < 0 ? -m : m;
                     float acc[16];
-                    for (int i0 = 0; i0 < nmu; i0 += 16) {
 #pragma unroll
-                        for (int i = 0; i < 16; i++) acc[i] = 0.0f;
-                        for (int l = am; l <= a.ml; l++) {
-                            const int j = sh_index(l, m, mm);
-                            const float v = s.sh_s[j * 33 + lane];
+                    for (int i = 0; i < 16; i++) acc[i] = 0.0f;
+                    for (int l = am; l <= a.ml; l++) {
+                        const int j = sh_index(l, m, mm);
+                        const float v = sh_s[j * 33 + lane];
+                        const float4 *c4 = (const float4 *)(cmu_s + j * 16);
 #pragma unroll
-                            for (int i = 0; i < 16; i++)
-                                if (i0 + i < nmu) acc[i] = fmaf(s.cmu_s[(i0 + i) * nlm + j], v, acc[i]);
+                        for (int q = 0; q < 4; q++) {
+                            const float4 c = c4[q];
+                            acc[4 * q] = fmaf(c.x, v, acc[4 * q]); acc[4 * q + 1] = fmaf(c.y, v, acc[4 * q + 1]);
+                            acc[4 * q + 2] = fmaf(c.z, v, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(c.w, v, acc[4 * q + 3]);
                         }
-#pragma unroll
-                        for (int i = 0; i < 16; i++)
-                            if (i0 + i < nmu) s.uv_s[((i0 + i) * nm + mi) * TR_TP + lane] += acc[i];
                     }
+#pragma unroll
+                    for (int i = 0; i < 16; i++)
+                        if (i < nmu) uv_s[(i * nm + mi) * TR_TP + lane] += acc[i];
                 }
             }
             __syncthreads();
-            // SUMCS from SUMUV (shdomsub1.f:2871-2890), in place
-            for (int task = warp; task < nmu * mm; task += TR_WARPS) {
-                const int imu = task / mm, m = task % mm + 1;
-                float *pu = &s.uv_s[(imu * nm + (mm + m)) * TR_TP + lane], *nu = &s.uv_s[(imu * nm + (mm - m)) * TR_TP + lane];
-                const float up = *pu, un = *nu;
-                if (n == 2) { *nu = up - un; *pu = up + un; }
-                else { *pu = up + un; *nu = un - up; }
-            }
+            tr_combine(uv_s, nmu, mm, true, n == 2, warp, lane);
             __syncthreads();
-            // stage B: azimuthal sums, one ordinate per warp and iteration; 128-byte rows of DOFIELD
-            for (int iang = warp; iang < a.nang; iang += TR_WARPS) {
-                const int imu = a.imu_of[iang], me = a.me_of[imu];
-                const float *azr = s.az_s + (size_t)iang * nm;
-                const float *cs = s.uv_s + (size_t)imu * nm * TR_TP + lane;
-                float sum = 0.0f;
-                for (int mi = mm - me; mi <= mm + me; mi++) sum = fmaf(azr[mi], cs[mi * TR_TP], sum);
-                if (p0 + lane < a.npts) a.dofield[(p0 + lane) + (size_t)a.npts * (n + (size_t)a.nst * iang)] = sum;
+            // stage B: azimuthal sums for 8 ordinates of one zenith angle at a time: 1 + 2 loads for 8 FMAs;
+            // every ordinate is a 128-byte row of DOFIELD
+            for (int task = warp; task < a.ntask; task += TR_WARPS) {
+                const int2 tk = a.tasks[task];
+                const int imu = tk.x, k0 = tk.y, me = a.me_of[imu];
+                const int nphi0 = a.ang0[imu + 1] - a.ang0[imu], np8 = (nphi0 + 7) & ~7;
+                const float *azb = az_s + a.azoff[imu] + k0;
+                const float *cs = uv_s + (size_t)imu * nm * TR_TP + lane;
+                float acc[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) acc[k] = 0.0f;
+                for (int mi = mm - me; mi <= mm + me; mi++) {
+                    const float c = cs[mi * TR_TP];
+                    const float4 a0 = *(const float4 *)(azb + mi * np8), a1 = *(const float4 *)(azb + mi * np8 + 4);
+                    acc[0] = fmaf(a0.x, c, acc[0]); acc[1] = fmaf(a0.y, c, acc[1]);
+                    acc[2] = fmaf(a0.z, c, acc[2]); acc[3] = fmaf(a0.w, c, acc[3]);
+                    acc[4] = fmaf(a1.x, c, acc[4]); acc[5] = fmaf(a1.y, c, acc[5]);
+                    acc[6] = fmaf(a1.z, c, acc[6]); acc[7] = fmaf(a1.w, c, acc[7]);
+                }
+                if (p0 + lane < a.npts) {
+#pragma unroll
+                    for (int k = 0; k < 8; k++)
+                        if (k0 + k < nphi0)
+                            a.dofield[(p0 + lane) + (size_t)a.npts * (n + (size_t)a.nst * (a.ang0[imu] + k0 + k))] = acc[k];
+                }
             }
         }
     }
 }
 
-// DO_TO_SH summed over all zenith angles (OUTDATA is set, not accumulated)
+// DO_TO_SH summed over all zenith angles (OUTDATA is set, not accumulated).
+// Shared memory: sh_s[nlm][33] | cmu_s[nm][nmu][16] | uv_s[nmu][nm][32] | in_s[nang][32] | az_s[nang][32]
 __global__ void __launch_bounds__(TR_THREADS)
 do_to_sh_kernel(TrArgs a, int ntiles)
 {
     extern __shared__ __align__(16) float tr_sm[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int mm = a.mm, nm = 2 * mm + 1, nlm = a.nlm, nmu = a.nmu;
-    const int nplanes = a.nst == 1 ? 1 : 2;
-    const TrSmem s = tr_smem(tr_sm, nlm, nmu, nm, a.nang, nplanes);
-    float *in_s = s.az_s;        // [nang][32] one Stokes plane of the tile's DO field (the azimuthal table stays in L1/L2)
+    float *sh_s = tr_sm, *cmu_s = sh_s + (size_t)nlm * 33, *uv_s = cmu_s + (size_t)nm * nmu * 16;
+    float *in_s = uv_s + (size_t)nmu * nm * TR_TP, *az_s = in_s + (size_t)a.nang * TR_TP;
+    for (int i = threadIdx.x; i < a.nang * 32; i += TR_THREADS) az_s[i] = a.az[i];
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int p0 = tile * TR_TP;
-        // output groups: {I} and {Q,U} (Q and U both need SUMUV(2,.) and SUMUV(3,.))
-        for (int grp = 0; grp < (a.nst == 1 ? 1 : 2); grp++) {
-            const int nout = grp == 0 ? 1 : 2;
+        for (int o = 0; o < a.nst; o++) {
             __syncthreads();
-            for (int i = threadIdx.x; i < nout * nlm * 33; i += TR_THREADS) s.sh_s[i] = 0.0f;
-            for (int n = (grp == 0 ? 0 : 1); n < (grp == 0 ? 1 : 3); n++) {
+            for (int i = threadIdx.x; i < nlm * 33; i += TR_THREADS) sh_s[i] = 0.0f;
+            for (int t = 0; t < tr_nterms(o); t++) {
+                int comp, n;
+                tr_term(o, t, comp, n);
+                if (o == 2) comp = t == 0 ? 5 : 2;       // U <- CMU2(6)*SUMUV(2) + CMU2(3)*SUMUV(3)
+                if (o == 1) comp = t == 0 ? 1 : 4;       // Q <- CMU2(2)*SUMUV(2) + CMU2(5)*SUMUV(3)
                 __syncthreads();
                 for (int i = threadIdx.x; i < a.nang * TR_TP; i += TR_THREADS) {
                     const int iang = i / TR_TP, q = i % TR_TP;
                     in_s[i] = (p0 + q < a.npts) ? __ldg(&a.dofield[(p0 + q) + (size_t)a.npts * (n + (size_t)a.nst * iang)]) : 0.0f;
                 }
+                for (int i = threadIdx.x; i < nm * nmu * 16; i += TR_THREADS)
+                    cmu_s[i] = __ldg(&a.cmu[i + (size_t)nm * nmu * 16 * comp]);
                 __syncthreads();
-                // stage B': SUMCS(n, m) = sum over the azimuths of CPHI2 * INDATA  (az already carries DELPHI)
-                for (int task = warp; task < nmu * nm; task += TR_WARPS) {
-                    const int imu = task / nm, mi = task % nm, m = mi - mm, me = a.me_of[imu];
-                    float sum = 0.0f;
-                    if (m >= -me && m <= me)
-                        for (int iang = a.ang0[imu]; iang < a.ang0[imu + 1]; iang++)
-                            sum = fmaf(__ldg(&a.az[(size_t)iang * nm + mi]), in_s[iang * TR_TP + lane], sum);
-                    s.uv_s[(imu * nm + mi) * TR_TP + lane] = sum;
-                }
-                __syncthreads();
-                // SUMUV from SUMCS (shdomsub1.f:3121-3136), in place
-                for (int task = warp; task < nmu * mm; task += TR_WARPS) {
-                    const int imu = task / mm, m = task % mm + 1;
-                    float *pu = &s.uv_s[(imu * nm + (mm + m)) * TR_TP + lane], *nu = &s.uv_s[(imu * nm + (mm - m)) * TR_TP + lane];
-                    const float cp = *pu, cn = *nu;
-                    if (n == 2) { *pu = cp + cn; *nu = cp - cn; }
-                    else { *pu = cp - cn; *nu = cp + cn; }
-                }
-                // stage A': OUTDATA(out, j) += CMU2(comp, imu, j) * SUMUV(n, m(j)) summed over the zenith angles
-                for (int o = 0; o < nout; o++) {
-                    // I <- (1, n=0); Q <- (2, n=1) + (5, n=2); U <- (6, n=1) + (3, n=2)
-                    int comp;
-                    if (grp == 0) comp = 0;
-                    else if (o == 0) comp = n == 1 ? 1 : 4;
-                    else comp = n == 1 ? 5 : 2;
-                    __syncthreads();
-                    for (int i = threadIdx.x; i < nmu * nlm; i += TR_THREADS)
-                        s.cmu_s[i] = __ldg(&a.cmu[i + (size_t)nmu * nlm * comp]);
-                    __syncthreads();
-                    for (int j = warp; j < nlm; j += TR_WARPS) {
-                        const int mi = a.mofj[j] + mm;
-                        float sum = 0.0f;
-                        for (int imu = 0; imu < nmu; imu++)
-                            sum = fmaf(s.cmu_s[imu * nlm + j], s.uv_s[(imu * nm + mi) * TR_TP + lane], sum);
-                        s.sh_s[(o * nlm + j) * 33 + lane] += sum;
+                // stage B': SUMCS(m) = sum over the azimuths of CPHI2 * INDATA for 8 modes at a time (az carries DELPHI)
+                for (int task = warp; task < nmu * 4; task += TR_WARPS) {
+                    const int imu = task >> 2, mi0 = (task & 3) * 8, me = a.me_of[imu];
+                    float acc[8];
+#pragma unroll
+                    for (int k = 0; k < 8; k++) acc[k] = 0.0f;
+                    for (int iang = a.ang0[imu]; iang < a.ang0[imu + 1]; iang++) {
+                        const float x = in_s[iang * TR_TP + lane];
+                        const float4 a0 = *(const float4 *)(az_s + iang * 32 + mi0), a1 = *(const float4 *)(az_s + iang * 32 + mi0 + 4);
+                        acc[0] = fmaf(a0.x, x, acc[0]); acc[1] = fmaf(a0.y, x, acc[1]);
+                        acc[2] = fmaf(a0.z, x, acc[2]); acc[3] = fmaf(a0.w, x, acc[3]);
+                        acc[4] = fmaf(a1.x, x, acc[4]); acc[5] = fmaf(a1.y, x, acc[5]);
+                        acc[6] = fmaf(a1.z, x, acc[6]); acc[7] = fmaf(a1.w, x, acc[7]);
                     }
+#pragma unroll
+                    for (int k = 0; k < 8; k++) {
+                        const int mi = mi0 + k, m = mi - mm;
+                        if (mi < nm) uv_s[(imu * nm + mi) * TR_TP + lane] = (m >= -me && m <= me) ? acc[k] : 0.0f;
+                    }
+                }
+                __syncthreads();
+                tr_combine(uv_s, nmu, mm, false, n == 2, warp, lane);
+                __syncthreads();
+                // stage A': OUTDATA(j) += CMU2(comp, imu, j) * SUMUV(m(j)) summed over the zenith angles, all degrees l of
+                // one mode m per task: 1 + 4 loads for 16 FMAs
+                for (int mi = warp; mi < nm; mi += TR_WARPS) {
+                    const int m = mi - mm, am = m < 0 ? -m : m;
+                    float acc[16];
+#pragma unroll
+                    for (int i = 0; i < 16; i++) acc[i] = 0.0f;
+                    for (int imu = 0; imu < nmu; imu++) {
+                        const float u = uv_s[(imu * nm + mi) * TR_TP + lane];
+                        const float4 *c4 = (const float4 *)(cmu_s + (mi * nmu + imu) * 16);
+#pragma unroll
+                        for (int q = 0; q < 4; q++) {
+                            const float4 c = c4[q];
+                            acc[4 * q] = fmaf(c.x, u, acc[4 * q]); acc[4 * q + 1] = fmaf(c.y, u, acc[4 * q + 1]);
+                            acc[4 * q + 2] = fmaf(c.z, u, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(c.w, u, acc[4 * q + 3]);
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < 16; i++)
+                        if (am + i <= a.ml) sh_s[sh_index(am + i, m, mm) * 33 + lane] += acc[i];
                 }
             }
             __syncthreads();
@@ -293,11 +341,7 @@ do_to_sh_kernel(TrArgs a, int ntiles)
                 const int p = p0 + q;
                 if (p >= a.npts) continue;
                 const int is = a.shptr[p], ns = a.shptr[p + 1] - is;
-                for (int o = 0; o < nout; o++) {
-                    const int plane = grp == 0 ? 0 : 1 + o;
-                    for (int j = lane; j < ns; j += 32)
-                        a.sh_out[plane + (size_t)a.nst * (is + j)] = s.sh_s[(o * nlm + j) * 33 + q];
-                }
+                for (int j = lane; j < ns; j += 32) a.sh_out[o + (size_t)a.nst * (is + j)] = sh_s[j * 33 + q];
             }
         }
     }
@@ -333,28 +377,31 @@ static int transform(int direction, int npts, int nstokes, int nstleg, int ml, i
     if (at3d_device_count() < 1) { set_msg(errmsg, "no CUDA device: at3d_b200 has no CPU fallback"); return 4; }
     if (!(nstokes == 1 || nstokes == 3) || (nstokes == 1) != (nstleg == 1)) { set_msg(errmsg, "NSTOKES must be 1 (NSTLEG=1) or 3 (NSTLEG=6)"); return 3; }
     if (nmu > 64 || nlm != (2 * mm + 1) * (ml + 1) - mm * (mm + 1)) { set_msg(errmsg, "inconsistent NLM/ML/MM or NMU > 64"); return 1; }
+    if (nmu > 16 || ml > 15) { set_msg(errmsg, "the tiled SH/DO transforms support NMU <= 16 (ML <= 15)"); return 3; }
     const int nm = 2 * mm + 1;
     int nang = 0;
-    std::vector<int> imu_of, me_of(nmu), ang0(nmu + 1), mofj(nlm);
+    std::vector<int> me_of(nmu), ang0(nmu + 1), azoff(nmu);
+    std::vector<int2> tasks;
+    int azsize = 0;
     for (int i = 0; i < nmu; i++) {
         ang0[i] = nang;
-        for (int k = 0; k < nphi0[i]; k++) imu_of.push_back(i);
         nang += nphi0[i];
         int me = nphi0[i] / 2 - 1; if (me > mm) me = mm; if (me < 0) me = 0;
         me_of[i] = me;
+        azoff[i] = azsize;
+        azsize += nm * ((nphi0[i] + 7) & ~7);
+        for (int k0 = 0; k0 < nphi0[i]; k0 += 8) tasks.push_back(make_int2(i, k0));
     }
     ang0[nmu] = nang;
-    {
-        int j = 0;
-        for (int l = 0; l <= ml; l++) { const int me = l < mm ? l : mm; for (int m = -me; m <= me; m++) mofj[j++] = m; }
-    }
     // azimuthal basis.  FFTFLAG (MAKE_ANGLE_SET, shdomsub2.f:1131): the reference uses FFTPACK on the exact angles
     // 2 pi k/N there, and REAL COS(M*PHI(I,K)) tables otherwise; DO_TO_SH carries DELPHI = WTDO/WTMU
-    std::vector<float> az((size_t)nang * nm);
+    if (direction == 1) azsize = nang * 32;
+    std::vector<float> az((size_t)azsize, 0.0f);
     const int mmax = nphi0max / 2 - 1 > 0 ? nphi0max / 2 - 1 : 0;
     for (int i = 0, ia = 0; i < nmu; i++) {
         const bool fft = nphi0[i] > 14 || mmax > 15;
         const float delphi = 2.0f * acosf(-1.0f) / nphi0[i];
+        const int np8 = (nphi0[i] + 7) & ~7;
         for (int k = 0; k < nphi0[i]; k++, ia++)
             for (int m = -mm; m <= mm; m++) {
                 double v;
@@ -366,32 +413,37 @@ static int transform(int direction, int npts, int nstokes, int nstleg, int ml, i
                     const float ph = phi[i + (size_t)nmu * k];
                     v = m > 0 ? (double)cosf(m * ph) : (double)sinf(-m * ph);
                 }
-                az[(size_t)ia * nm + (m + mm)] = direction == 0 ? (float)v : (float)v * delphi;
+                if (direction == 0) az[(size_t)azoff[i] + (size_t)(m + mm) * np8 + k] = (float)v;
+                else az[(size_t)ia * 32 + (m + mm)] = (float)v * delphi;
             }
     }
     Arena A;
     const int ncomp = nstleg;
     float *mu_d = A.up(mu, nmu), *wt_d = A.up(wtmu, nmu);
-    float *prc = A.alloc<float>((size_t)6 * nlm * nmu), *cmu = A.alloc<float>((size_t)ncomp * nmu * nlm);
+    const size_t ncmu = direction == 0 ? (size_t)ncomp * nlm * 16 : (size_t)ncomp * nm * nmu * 16;
+    float *prc = A.alloc<float>((size_t)6 * nlm * nmu), *cmu = A.alloc<float>(ncmu);
     const size_t nsh = (size_t)nstokes * ptr[npts], ndo = (size_t)npts * nstokes * nang;
     TrArgs a;
     memset(&a, 0, sizeof(a));
     a.npts = npts; a.nst = nstokes; a.nstleg = nstleg; a.ml = ml; a.mm = mm; a.nlm = nlm; a.nmu = nmu; a.nang = nang;
+    a.ntask = (int)tasks.size(); a.azsize = azsize;
     a.shptr = A.up(ptr, (size_t)npts + 1);
     float *sh_d = direction == 0 ? A.up(sh, nsh) : A.alloc<float>(nsh);
     float *do_d = direction == 1 ? A.up(dofield, ndo) : A.alloc<float>(ndo);
     a.sh = sh_d; a.sh_out = sh_d; a.dofield = do_d; a.cmu = cmu;
-    a.az = A.up(az.data(), az.size()); a.imu_of = A.up(imu_of.data(), imu_of.size());
-    a.me_of = A.up(me_of.data(), me_of.size()); a.ang0 = A.up(ang0.data(), ang0.size()); a.mofj = A.up(mofj.data(), mofj.size());
-    if (!mu_d || !wt_d || !prc || !cmu || !a.shptr || !sh_d || !do_d || !a.az || !a.imu_of || !a.me_of || !a.ang0 || !a.mofj) {
+    a.az = A.up(az.data(), az.size()); a.azoff = A.up(azoff.data(), azoff.size());
+    a.tasks = A.up(tasks.data(), tasks.size());
+    a.me_of = A.up(me_of.data(), me_of.size()); a.ang0 = A.up(ang0.data(), ang0.size());
+    if (!mu_d || !wt_d || !prc || !cmu || !a.shptr || !sh_d || !do_d || !a.az || !a.azoff || !a.tasks || !a.me_of || !a.ang0) {
         set_msg(errmsg, "device allocation failure"); return 4;
     }
     cudaMemset(prc, 0, (size_t)6 * nlm * nmu * sizeof(float));
+    cudaMemset(cmu, 0, ncmu * sizeof(float));
     plmall_kernel<<<(nmu * (mm + 1) + 127) / 128, 128>>>(nmu, mu_d, ml, mm, nlm, direction, prc);
-    pack_cmu_kernel<<<(nmu * nlm * ncomp + 255) / 256, 256>>>(nmu, nlm, ncomp, prc, direction ? wt_d : nullptr, cmu);
-    const int nplanes = (direction == 1 && nstokes > 1) ? 2 : 1;
-    size_t smem = ((size_t)nplanes * nlm * 33 + (size_t)nmu * nlm + (size_t)nmu * nm * TR_TP) * sizeof(float);
-    smem += (direction == 0 ? (size_t)nang * nm : (size_t)nang * TR_TP) * sizeof(float);
+    pack_cmu_kernel<<<(nmu * nlm * ncomp + 255) / 256, 256>>>(nmu, nlm, ncomp, ml, mm, direction, prc, wt_d, cmu);
+    size_t smem;
+    if (direction == 0) smem = ((size_t)nlm * 33 + (size_t)nlm * 16 + (size_t)nmu * nm * TR_TP + (size_t)azsize) * sizeof(float);
+    else smem = ((size_t)nlm * 33 + (size_t)nm * nmu * 16 + (size_t)nmu * nm * TR_TP + (size_t)2 * nang * TR_TP) * sizeof(float);
     if (smem > 227 * 1024) { set_msg(errmsg, "angular resolution too high for the shared-memory tiles (%zu bytes)", smem); return 3; }
     int dev = 0, nsm = 148;
     cudaGetDevice(&dev);

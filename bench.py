@@ -109,6 +109,40 @@ def compute_source_leg(B, st, steps, warmup, oracle=None):
     return out
 
 
+def transform_leg(B, st, steps, warmup):
+    """SH_TO_DO / DO_TO_SH on the workload's SOURCE / RADIANCE: kernel ms (CUDA events inside the
+    C-ABI call), FP32 FMA rate against the CUDA-core peak and bytes against HBM."""
+    npts, nst = st.npts, st.nstokes
+    nang = int(st.nphi0.sum())
+    if npts * nst * nang * 4 > 6 * (1 << 30):
+        return dict(skipped='host staging of DOFIELD would need %.1f GB' % (npts * nst * nang * 4 / 2**30))
+    delphi = np.float32(2.0 * np.pi) / st.nphi0.astype(np.float32)
+    wtmu = (st.wtdo[:, 0] / delphi).astype(np.float32)
+    ms1, ms2, do = [], [], None
+    for i in range(warmup + steps):
+        do, t = B.sh_to_do(st, wtmu, st.shptr, st.source, timing=True)
+        if i >= warmup:
+            ms1.append(t)
+    for i in range(warmup + steps):
+        _, t = B.do_to_sh(st, wtmu, st.rshptr, do, timing=True)
+        if i >= warmup:
+            ms2.append(t)
+    me = np.clip(st.nphi0 // 2 - 1, 0, st.mm)
+    azmacs = int(np.sum(st.nphi0 * (2 * me + 1)))                      # azimuthal stage, per point and Stokes plane
+    planes = 1 if nst == 1 else 5                                      # I; Q,U each from two coupled terms
+    tot_s, tot_r = int(st.shptr[npts]), int(st.rshptr[npts])
+    fl1 = 2.0 * (planes * tot_s * st.nmu + nst * npts * azmacs)
+    fl2 = 2.0 * (planes * tot_r * st.nmu + nst * npts * azmacs)
+    by1 = 4.0 * nst * (tot_s + npts * nang)
+    by2 = 4.0 * nst * (tot_r + npts * nang)
+    fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12                         # TFLOP/s, CUDA-core FMA at the boost clock
+    t1, t2 = float(np.mean(ms1)) * 1e-3, float(np.mean(ms2)) * 1e-3
+    return dict(sh_to_do_ms=1e3 * t1, do_to_sh_ms=1e3 * t2, nang=nang,
+                sh_to_do=dict(tflops=fl1 / t1 / 1e12, fma_pipe_frac=fl1 / t1 / 1e12 / fp32_peak, gbs=by1 / t1 / 1e9),
+                do_to_sh=dict(tflops=fl2 / t2 / 1e12, fma_pipe_frac=fl2 / t2 / 1e12 / fp32_peak, gbs=by2 / t2 / 1e9),
+                fp32_peak_tflops=fp32_peak)
+
+
 def algorithmic_bytes(st, gi, cnt, gradient=True):
     """bytes the reference algorithm must touch for the work actually done
     (cells / evaluated grid points / SH lengths / sub-intervals counted by the kernel)."""
@@ -220,7 +254,7 @@ def render_only(args, dev, st, sc, rays, dr, l2flush, stream, barrier, world, ra
     from at3d_b200 import synthetic as S
     nrays = rays.nrays
     rsout = torch.zeros((nrays, st.nstokes), dtype=torch.float32, device='cuda')
-    devo = DeviceState(S.with_brdf_surface(st, 'O', seed=2, wavelen=0.66))
+    devo = DeviceState(S.with_brdf_surface(st, 'O' if st.nstokes == 1 else 'W', seed=2, wavelen=0.66))
 
     def timed(d):
         for _ in range(args.warmup):
@@ -287,7 +321,8 @@ def render_only(args, dev, st, sc, rays, dr, l2flush, stream, barrier, world, ra
             render_ocean=dict(rays_per_s=world * nrays * args.steps / t_ocean, kernel_ms=ms_ocean,
                               surface_ms=ms_ocean - ms_lamb, surface_hits=c_ocean['surface_hits'],
                               brdf_evals=c_ocean['surface_hits'] * 4 * (st.nang // 2 + 1)),
-            compute_source=csrc, clocks=cs.summary(), cpu_baseline=None, wall_s=wall)
+            compute_source=csrc, transforms=transform_leg(B, st, args.steps, args.warmup),
+            clocks=cs.summary(), cpu_baseline=None, wall_s=wall)
         print(json.dumps(line))
 
 
@@ -466,7 +501,7 @@ def main():
     # ---- RENDER over an ocean surface (BASELINE.json configs[3]: ocean BRDF): every ray that reaches the surface
     # costs 4 x (NANG/2 + 1) evaluations of ocean_brdf_sw in surface_kernel ----
     from at3d_b200 import synthetic as S
-    devo = DeviceState(S.with_brdf_surface(st, 'O', seed=2, wavelen=0.66))
+    devo = DeviceState(S.with_brdf_surface(st, 'O' if st.nstokes == 1 else 'W', seed=2, wavelen=0.66))
     oms = []
     for i in range(args.warmup + args.steps):
         l2flush.zero_()
@@ -516,7 +551,7 @@ def main():
             render=dict(rays_per_s=nrays / (np.mean(rms) * 1e-3), kernel_ms=float(np.mean(rms)),
                         achieved_gbs=rbytes / (np.mean(rms) * 1e-3) / 1e9, frac=rbytes / (np.mean(rms) * 1e-3) / 1e9 / peak,
                         algorithmic_bytes=rbytes, counts=rcounts),
-            compute_source=csrc,
+            compute_source=csrc, transforms=transform_leg(B, st, args.steps, args.warmup),
             render_ocean=dict(rays_per_s=nrays / (np.mean(oms) * 1e-3), kernel_ms=float(np.mean(oms)),
                               surface_ms=float(np.mean(oms) - np.mean(rms)), surface_hits=ocounts['surface_hits'],
                               brdf_evals=ocounts['surface_hits'] * 4 * (st.nang // 2 + 1)),
