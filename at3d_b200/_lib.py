@@ -101,6 +101,7 @@ def lib():
                                    C.c_void_p, C.c_void_p, i32, C.c_void_p, C.c_void_p, i32, i32, i32,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_char_p]
+    L.at3d_path_integration_ip.argtypes = [P(StateDesc)] + [C.c_void_p] * 7 + [P(C.c_double), C.c_char_p]
     L.at3d_sh_to_do.argtypes = [i32] * 8 + [C.c_void_p] * 7 + [P(C.c_double), C.c_char_p]
     L.at3d_do_to_sh.argtypes = [i32] * 8 + [C.c_void_p] * 7 + [P(C.c_double), C.c_char_p]
     L.at3d_average_subpixel_rays.argtypes = [i32, i32, i32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_char_p]

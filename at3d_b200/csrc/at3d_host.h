@@ -61,3 +61,12 @@ cudaError_t launch_surface(const DevState &S, int nrays, const SurfHit *hits, co
                            const double *camphi, float *out, RayErr *err, cudaStream_t stream);
 cudaError_t launch_prep_sh(const DevState &S, int tms, const int *shptr, const float *sh_in,
                            const int2 *rec, float *sh_out, int *sscount, int2 *ssent, cudaStream_t s);
+
+// SH <-> discrete-ordinate transforms on device-resident arrays (at3d_transform.cu)
+struct TrPlan;
+int tr_plan_create(int nstokes, int nstleg, int ml, int mm, int nlm, int nmu, int nphi0max, const int32_t *nphi0,
+                   const float *mu, const float *phi, const float *wtmu, TrPlan **out, char *errmsg);
+void tr_plan_destroy(TrPlan *p);
+int tr_plan_nang(const TrPlan *p);
+cudaError_t tr_sh_to_do(const TrPlan *P, int npts, const int *shptr_d, const float *sh_d, float *do_d, cudaStream_t st);
+cudaError_t tr_do_to_sh(const TrPlan *P, int npts, const int *rshptr_d, const float *do_d, float *sh_d, cudaStream_t st);

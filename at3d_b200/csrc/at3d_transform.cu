@@ -347,10 +347,13 @@ do_to_sh_kernel(TrArgs a, int ntiles)
     }
 }
 
-namespace {
-struct Arena {
+// ---- host side: a plan holds the coefficient tables of one angular resolution on the device ----
+struct TrPlan {
     std::vector<void *> ptrs;
-    ~Arena() { for (void *p : ptrs) cudaFree(p); }
+    TrArgs fwd, bwd;            // table pointers of the two directions (point arrays are filled per launch)
+    size_t smem_fwd = 0, smem_bwd = 0;
+    int nang = 0, nsm = 148;
+    ~TrPlan() { for (void *p : ptrs) cudaFree(p); }
     template <typename T> T *alloc(size_t n)
     {
         void *p = nullptr;
@@ -365,24 +368,22 @@ struct Arena {
         return d;
     }
 };
-}
 
-// direction: 0 = SH_TO_DO, 1 = DO_TO_SH
-static int transform(int direction, int npts, int nstokes, int nstleg, int ml, int mm, int nlm, int nmu, int nphi0max,
-                     const int32_t *nphi0, const float *mu, const float *phi, const float *wtmu,
-                     const int32_t *ptr, float *sh, float *dofield, double *kernel_ms, char *errmsg)
+void tr_plan_destroy(TrPlan *p) { delete p; }
+int tr_plan_nang(const TrPlan *p) { return p->nang; }
+
+// builds CMU1/CMU2 (PLMALL on the device), the azimuthal tables of both directions and the stage-B task list
+int tr_plan_create(int nstokes, int nstleg, int ml, int mm, int nlm, int nmu, int nphi0max, const int32_t *nphi0,
+                   const float *mu, const float *phi, const float *wtmu, TrPlan **out, char *errmsg)
 {
-    if (errmsg) errmsg[0] = 0;
-    if (!nphi0 || !mu || !phi || !wtmu || !ptr || !sh || !dofield) { set_msg(errmsg, "null argument"); return 1; }
-    if (at3d_device_count() < 1) { set_msg(errmsg, "no CUDA device: at3d_b200 has no CPU fallback"); return 4; }
+    *out = nullptr;
     if (!(nstokes == 1 || nstokes == 3) || (nstokes == 1) != (nstleg == 1)) { set_msg(errmsg, "NSTOKES must be 1 (NSTLEG=1) or 3 (NSTLEG=6)"); return 3; }
-    if (nmu > 64 || nlm != (2 * mm + 1) * (ml + 1) - mm * (mm + 1)) { set_msg(errmsg, "inconsistent NLM/ML/MM or NMU > 64"); return 1; }
+    if (nlm != (2 * mm + 1) * (ml + 1) - mm * (mm + 1)) { set_msg(errmsg, "inconsistent NLM/ML/MM"); return 1; }
     if (nmu > 16 || ml > 15) { set_msg(errmsg, "the tiled SH/DO transforms support NMU <= 16 (ML <= 15)"); return 3; }
     const int nm = 2 * mm + 1;
-    int nang = 0;
+    int nang = 0, azsize = 0;
     std::vector<int> me_of(nmu), ang0(nmu + 1), azoff(nmu);
     std::vector<int2> tasks;
-    int azsize = 0;
     for (int i = 0; i < nmu; i++) {
         ang0[i] = nang;
         nang += nphi0[i];
@@ -395,8 +396,7 @@ static int transform(int direction, int npts, int nstokes, int nstleg, int ml, i
     ang0[nmu] = nang;
     // azimuthal basis.  FFTFLAG (MAKE_ANGLE_SET, shdomsub2.f:1131): the reference uses FFTPACK on the exact angles
     // 2 pi k/N there, and REAL COS(M*PHI(I,K)) tables otherwise; DO_TO_SH carries DELPHI = WTDO/WTMU
-    if (direction == 1) azsize = nang * 32;
-    std::vector<float> az((size_t)azsize, 0.0f);
+    std::vector<float> azf((size_t)azsize, 0.0f), azb((size_t)nang * 32, 0.0f);
     const int mmax = nphi0max / 2 - 1 > 0 ? nphi0max / 2 - 1 : 0;
     for (int i = 0, ia = 0; i < nmu; i++) {
         const bool fft = nphi0[i] > 14 || mmax > 15;
@@ -413,63 +413,100 @@ static int transform(int direction, int npts, int nstokes, int nstleg, int ml, i
                     const float ph = phi[i + (size_t)nmu * k];
                     v = m > 0 ? (double)cosf(m * ph) : (double)sinf(-m * ph);
                 }
-                if (direction == 0) az[(size_t)azoff[i] + (size_t)(m + mm) * np8 + k] = (float)v;
-                else az[(size_t)ia * 32 + (m + mm)] = (float)v * delphi;
+                azf[(size_t)azoff[i] + (size_t)(m + mm) * np8 + k] = (float)v;
+                azb[(size_t)ia * 32 + (m + mm)] = (float)v * delphi;
             }
     }
-    Arena A;
+    TrPlan *P = new TrPlan();
     const int ncomp = nstleg;
-    float *mu_d = A.up(mu, nmu), *wt_d = A.up(wtmu, nmu);
-    const size_t ncmu = direction == 0 ? (size_t)ncomp * nlm * 16 : (size_t)ncomp * nm * nmu * 16;
-    float *prc = A.alloc<float>((size_t)6 * nlm * nmu), *cmu = A.alloc<float>(ncmu);
-    const size_t nsh = (size_t)nstokes * ptr[npts], ndo = (size_t)npts * nstokes * nang;
+    float *mu_d = P->up(mu, nmu), *wt_d = P->up(wtmu, nmu);
+    const size_t n1 = (size_t)ncomp * nlm * 16, n2 = (size_t)ncomp * nm * nmu * 16;
+    float *prc = P->alloc<float>((size_t)6 * nlm * nmu), *cmu1 = P->alloc<float>(n1), *cmu2 = P->alloc<float>(n2);
     TrArgs a;
     memset(&a, 0, sizeof(a));
-    a.npts = npts; a.nst = nstokes; a.nstleg = nstleg; a.ml = ml; a.mm = mm; a.nlm = nlm; a.nmu = nmu; a.nang = nang;
-    a.ntask = (int)tasks.size(); a.azsize = azsize;
-    a.shptr = A.up(ptr, (size_t)npts + 1);
-    float *sh_d = direction == 0 ? A.up(sh, nsh) : A.alloc<float>(nsh);
-    float *do_d = direction == 1 ? A.up(dofield, ndo) : A.alloc<float>(ndo);
-    a.sh = sh_d; a.sh_out = sh_d; a.dofield = do_d; a.cmu = cmu;
-    a.az = A.up(az.data(), az.size()); a.azoff = A.up(azoff.data(), azoff.size());
-    a.tasks = A.up(tasks.data(), tasks.size());
-    a.me_of = A.up(me_of.data(), me_of.size()); a.ang0 = A.up(ang0.data(), ang0.size());
-    if (!mu_d || !wt_d || !prc || !cmu || !a.shptr || !sh_d || !do_d || !a.az || !a.azoff || !a.tasks || !a.me_of || !a.ang0) {
-        set_msg(errmsg, "device allocation failure"); return 4;
+    a.nst = nstokes; a.nstleg = nstleg; a.ml = ml; a.mm = mm; a.nlm = nlm; a.nmu = nmu; a.nang = nang;
+    a.ntask = (int)tasks.size();
+    a.azoff = P->up(azoff.data(), azoff.size());
+    a.tasks = P->up(tasks.data(), tasks.size());
+    a.me_of = P->up(me_of.data(), me_of.size()); a.ang0 = P->up(ang0.data(), ang0.size());
+    const float *azf_d = P->up(azf.data(), azf.size()), *azb_d = P->up(azb.data(), azb.size());
+    if (!mu_d || !wt_d || !prc || !cmu1 || !cmu2 || !a.azoff || !a.tasks || !a.me_of || !a.ang0 || !azf_d || !azb_d) {
+        delete P; set_msg(errmsg, "device allocation failure"); return 4;
     }
-    cudaMemset(prc, 0, (size_t)6 * nlm * nmu * sizeof(float));
-    cudaMemset(cmu, 0, ncmu * sizeof(float));
-    plmall_kernel<<<(nmu * (mm + 1) + 127) / 128, 128>>>(nmu, mu_d, ml, mm, nlm, direction, prc);
-    pack_cmu_kernel<<<(nmu * nlm * ncomp + 255) / 256, 256>>>(nmu, nlm, ncomp, ml, mm, direction, prc, wt_d, cmu);
-    size_t smem;
-    if (direction == 0) smem = ((size_t)nlm * 33 + (size_t)nlm * 16 + (size_t)nmu * nm * TR_TP + (size_t)azsize) * sizeof(float);
-    else smem = ((size_t)nlm * 33 + (size_t)nm * nmu * 16 + (size_t)nmu * nm * TR_TP + (size_t)2 * nang * TR_TP) * sizeof(float);
-    if (smem > 227 * 1024) { set_msg(errmsg, "angular resolution too high for the shared-memory tiles (%zu bytes)", smem); return 3; }
-    int dev = 0, nsm = 148;
+    cudaMemset(cmu1, 0, n1 * sizeof(float)); cudaMemset(cmu2, 0, n2 * sizeof(float));
+    for (int dir = 0; dir < 2; dir++) {
+        cudaMemset(prc, 0, (size_t)6 * nlm * nmu * sizeof(float));
+        plmall_kernel<<<(nmu * (mm + 1) + 127) / 128, 128>>>(nmu, mu_d, ml, mm, nlm, dir, prc);
+        pack_cmu_kernel<<<(nmu * nlm * ncomp + 255) / 256, 256>>>(nmu, nlm, ncomp, ml, mm, dir, prc, wt_d, dir ? cmu2 : cmu1);
+    }
+    P->fwd = a; P->fwd.cmu = cmu1; P->fwd.az = azf_d; P->fwd.azsize = azsize;
+    P->bwd = a; P->bwd.cmu = cmu2; P->bwd.az = azb_d; P->bwd.azsize = nang * 32;
+    P->smem_fwd = ((size_t)nlm * 33 + (size_t)nlm * 16 + (size_t)nmu * nm * TR_TP + (size_t)azsize) * sizeof(float);
+    P->smem_bwd = ((size_t)nlm * 33 + (size_t)nm * nmu * 16 + (size_t)nmu * nm * TR_TP + (size_t)2 * nang * TR_TP) * sizeof(float);
+    if (P->smem_fwd > 227 * 1024 || P->smem_bwd > 227 * 1024) {
+        delete P; set_msg(errmsg, "angular resolution too high for the shared-memory tiles"); return 3;
+    }
+    int dev = 0;
     cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&P->nsm, cudaDevAttrMultiProcessorCount, dev);
+    cudaFuncSetAttribute(sh_to_do_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->smem_fwd);
+    cudaFuncSetAttribute(do_to_sh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->smem_bwd);
+    P->nang = nang;
+    if (cudaDeviceSynchronize() != cudaSuccess) { delete P; set_msg(errmsg, "CUDA error building the SH/DO tables"); return 4; }
+    *out = P;
+    return 0;
+}
+
+// device-resident launches: SH array (NSTOKES,*) at shptr offsets <-> DOFIELD(NPTS,NSTOKES,NANG)
+cudaError_t tr_sh_to_do(const TrPlan *P, int npts, const int *shptr_d, const float *sh_d, float *do_d, cudaStream_t st)
+{
+    TrArgs a = P->fwd;
+    a.npts = npts; a.shptr = shptr_d; a.sh = sh_d; a.dofield = do_d;
     const int ntiles = (npts + TR_TP - 1) / TR_TP;
-    const int nb = ntiles < nsm ? ntiles : nsm;        // persistent: one block per SM (shared memory bound)
+    sh_to_do_kernel<<<ntiles < P->nsm ? ntiles : P->nsm, TR_THREADS, P->smem_fwd, st>>>(a, ntiles);
+    return cudaGetLastError();
+}
+
+cudaError_t tr_do_to_sh(const TrPlan *P, int npts, const int *rshptr_d, const float *do_d, float *sh_d, cudaStream_t st)
+{
+    TrArgs a = P->bwd;
+    a.npts = npts; a.shptr = rshptr_d; a.sh_out = sh_d; a.dofield = (float *)do_d;
+    const int ntiles = (npts + TR_TP - 1) / TR_TP;
+    do_to_sh_kernel<<<ntiles < P->nsm ? ntiles : P->nsm, TR_THREADS, P->smem_bwd, st>>>(a, ntiles);
+    return cudaGetLastError();
+}
+
+// direction: 0 = SH_TO_DO, 1 = DO_TO_SH; host buffers
+static int transform(int direction, int npts, int nstokes, int nstleg, int ml, int mm, int nlm, int nmu, int nphi0max,
+                     const int32_t *nphi0, const float *mu, const float *phi, const float *wtmu,
+                     const int32_t *ptr, float *sh, float *dofield, double *kernel_ms, char *errmsg)
+{
+    if (errmsg) errmsg[0] = 0;
+    if (!nphi0 || !mu || !phi || !wtmu || !ptr || !sh || !dofield) { set_msg(errmsg, "null argument"); return 1; }
+    if (at3d_device_count() < 1) { set_msg(errmsg, "no CUDA device: at3d_b200 has no CPU fallback"); return 4; }
+    TrPlan *P = nullptr;
+    int rc = tr_plan_create(nstokes, nstleg, ml, mm, nlm, nmu, nphi0max, nphi0, mu, phi, wtmu, &P, errmsg);
+    if (rc) return rc;
+    const size_t nsh = (size_t)nstokes * ptr[npts], ndo = (size_t)npts * nstokes * P->nang;
+    const int *ptr_d = P->up(ptr, (size_t)npts + 1);
+    float *sh_d = direction == 0 ? P->up(sh, nsh) : P->alloc<float>(nsh);
+    float *do_d = direction == 1 ? P->up(dofield, ndo) : P->alloc<float>(ndo);
+    if (!ptr_d || !sh_d || !do_d) { delete P; set_msg(errmsg, "device allocation failure"); return 4; }
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     cudaEventRecord(e0, 0);
-    if (direction == 0) {
-        cudaFuncSetAttribute(sh_to_do_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        sh_to_do_kernel<<<nb, TR_THREADS, smem>>>(a, ntiles);
-    } else {
-        cudaFuncSetAttribute(do_to_sh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        do_to_sh_kernel<<<nb, TR_THREADS, smem>>>(a, ntiles);
-    }
+    cudaError_t e = direction == 0 ? tr_sh_to_do(P, npts, ptr_d, sh_d, do_d, 0) : tr_do_to_sh(P, npts, ptr_d, do_d, sh_d, 0);
     cudaEventRecord(e1, 0);
-    cudaError_t e = cudaEventSynchronize(e1);
+    if (e == cudaSuccess) e = cudaEventSynchronize(e1);
     if (e == cudaSuccess) e = cudaGetLastError();
     float ms = 0.0f;
     if (e == cudaSuccess) cudaEventElapsedTime(&ms, e0, e1);
     cudaEventDestroy(e0); cudaEventDestroy(e1);
-    if (e != cudaSuccess) { set_msg(errmsg, "CUDA error %s in the SH/DO transform", cudaGetErrorString(e)); return 4; }
+    if (e != cudaSuccess) { delete P; set_msg(errmsg, "CUDA error %s in the SH/DO transform", cudaGetErrorString(e)); return 4; }
     if (kernel_ms) *kernel_ms = ms;
     if (direction == 0) e = cudaMemcpy(dofield, do_d, ndo * sizeof(float), cudaMemcpyDeviceToHost);
     else e = cudaMemcpy(sh, sh_d, nsh * sizeof(float), cudaMemcpyDeviceToHost);
+    delete P;
     if (e != cudaSuccess) { set_msg(errmsg, "CUDA error %s copying the result", cudaGetErrorString(e)); return 4; }
     return 0;
 }

@@ -1,0 +1,187 @@
+"""Fixed-grid SHDOM solution iterations for independent-pixel grids, on the GPU.
+
+Mirrors ``at3d.solver.RTE.solve`` -> ``core.solution_iterations`` (``SOLUTION_ITERATIONS``,
+src/polarized/shdomsub1.f:445-822) for ``ip_flag=3`` and ``split_accuracy=0``: every iteration runs
+``RADIANCE_TRUNCATION`` (host, integer bookkeeping), ``PATH_INTEGRATION`` (C-ABI ``at3d_path_integration_ip``:
+SH->DO transform, 1-D sweeps, boundaries, DO->SH transform on the GPU) and ``COMPUTE_SOURCE`` (C-ABI
+``at3d_compute_source``), then the sequence acceleration of ``CALC_ACCEL_SOLCRIT`` / ``ACCELERATE_SOLUTION``
+(src/shdom_nompi.f:317-349, shdomsub1.f:1807-1832).  The first guess is a zero radiance field (``INIT_RADIANCE``'s
+Eddington field is not restated; the fixed point does not depend on it).  The 3-D sweep is SURVEY.md 8f "next".
+"""
+import ctypes as C
+import numpy as np
+from . import _lib
+from . import backend as B
+from . import grid as G
+from ._lib import vp
+
+
+def radiance_truncation(st, shptr, radiance, rshptr, fixsh, shacc, highorderrad, maxir):
+    """RADIANCE_TRUNCATION (shdomsub1.f:1615-1805): the new RSHPTR[npts+2] (host; integer results)."""
+    npts, ml, mm, nq = st.npts, st.ml, st.mm, 8 * st.maxnmicro
+    f32 = np.float32
+    full = (ml * (ml + 1)) + ml + 1 if ml <= mm else (2 * mm + 1) * ml - (mm * (1 + (mm - 1))) + mm + 1
+    ns = np.diff(shptr[:npts + 1]).astype(np.int64)
+    if not fixsh:
+        lofj = G.lofj(ml, mm)
+        nro = np.diff(rshptr[:npts + 1]).astype(np.int64)
+        # NOTEND turns false at the first point without radiance terms and stays false
+        zero = np.nonzero(nro == 0)[0]
+        notend = np.ones(npts, bool)
+        if zero.size:
+            notend[zero[0]:] = False
+        rad0 = radiance[0, np.minimum(rshptr[:npts], max(radiance.shape[1] - 1, 0))].astype(f32)
+        ext = st.total_ext[:npts].astype(f32)
+        nlt = st.nstleg * (st.nleg + 1)
+        legen_flat = np.asfortranarray(st.legen, f32).ravel(order='F')
+        iph = st.iphase.reshape(nq, npts, st.npart, order='F')
+        pwt = st.phaseinterpwt.reshape(nq, npts, st.npart, order='F')
+        single = pwt[0] >= f32(st.phasemax)                               # [npts, npart]
+        fs = np.ones((npts, st.npart), f32)
+        if st.interp_new and st.deltam:
+            for ipa in range(st.npart):
+                fsum = np.zeros(npts, f32)
+                for q in range(nq):
+                    # the reference indexes LEGEN(Q,ML+1,IPHASE(Q,.)) with the mixture index Q (shdomsub1.f:1672)
+                    off = np.minimum(nlt * (iph[q, :, ipa].astype(np.int64) - 1) + st.nstleg * (ml + 1) + q,
+                                     legen_flat.size - 1)
+                    use = pwt[q, :, ipa] > f32(1e-5)
+                    fsum = np.where(use, fsum + legen_flat[off] * pwt[q, :, ipa], fsum).astype(f32)
+                f1 = legen_flat[nlt * (iph[0, :, ipa].astype(np.int64) - 1) + st.nstleg * (ml + 1)]
+                f = np.where(single[:, ipa], f1, fsum).astype(f32)
+                fs[:, ipa] = (f32(1.0) / (f32(1.0) - f)).astype(f32)
+        lr = np.ones(npts, np.int64)
+        for l in range(1, ml + 1):
+            rad = np.zeros(npts, f32)
+            for ipa in range(st.npart):
+                e = st.extinct.reshape(npts, st.npart, order='F')[:, ipa].astype(f32)
+                with np.errstate(divide='ignore', invalid='ignore'):
+                    w = np.where(ext == 0, f32(1.0), e / ext).astype(f32)
+                alb = st.albedo.reshape(npts, st.npart, order='F')[:, ipa].astype(f32)
+                leg1 = legen_flat[nlt * (iph[0, :, ipa].astype(np.int64) - 1) + st.nstleg * l]
+                if st.interp_new:
+                    mix = np.zeros(npts, f32)
+                    for q in range(nq):
+                        lq = legen_flat[nlt * (iph[q, :, ipa].astype(np.int64) - 1) + st.nstleg * l]
+                        mix = np.where(pwt[q, :, ipa] > f32(1e-5), mix + lq * pwt[q, :, ipa], mix).astype(f32)
+                    legent = np.where(single[:, ipa], leg1, mix).astype(f32)
+                    if st.deltam:
+                        legent = (legent * fs[:, ipa]).astype(f32)
+                else:
+                    legent = leg1
+                term = (w * alb * legent * rad0).astype(f32)
+                rad = np.where(w == 0, rad, rad + term).astype(f32)
+            lr = np.where(rad > f32(shacc), l, lr)
+        lr = np.where(notend, lr, ml)
+        ls = lofj[np.maximum(ns, 1) - 1]
+        lr = np.minimum(lr, ls + ml // 8 + 2)
+        if highorderrad:
+            lr = np.full(npts, ml)
+        nr = np.where(lr <= mm, lr * (lr + 1) + lr + 1, (2 * mm + 1) * lr - (mm * (1 + (mm - 1))) + mm + 1)
+        out = np.zeros(npts + 2, np.int32)
+        csum = np.cumsum(nr)
+        if csum[-1] <= maxir:
+            out[1:npts + 1] = csum
+            out[npts + 1] = csum[-1]
+            return out
+    nr = np.maximum(4, ns)
+    if highorderrad:
+        nr = np.full(npts, full)
+    csum = np.cumsum(nr)
+    if csum[-1] > maxir:
+        raise MemoryError('RADIANCE_TRUNCATION: Really out of memory for more radiance terms. Increase MAXIV.')
+    out = np.zeros(npts + 2, np.int32)
+    out[1:npts + 1] = csum
+    out[npts + 1] = csum[-1]
+    return out
+
+
+def path_integration_ip(st, wtmu, shptr, source, rshptr, timing=False):
+    """PATH_INTEGRATION on the GPU: returns (radiance[nstokes, rshptr[npts]], fluxes[2,npts], bcrad)."""
+    lamb = st.sfctype1 in ('L', ord('L'))
+    nbc = st.ntoppts + st.nbotpts * (1 if lamb else 1 + st.nang // 2)
+    rad = np.zeros((st.nstokes, max(int(rshptr[st.npts]), 1)), np.float32, order='F')
+    fluxes = np.zeros((2, st.npts), np.float32, order='F')
+    bcrad = np.zeros((st.nstokes, nbc), np.float32, order='F')
+    d = st.desc()
+    wt = np.ascontiguousarray(wtmu, np.float32)
+    shptr = np.ascontiguousarray(shptr, np.int32); rshptr = np.ascontiguousarray(rshptr, np.int32)
+    source = np.asfortranarray(source, np.float32)
+    ms = C.c_double(0.0)
+    buf = _lib.errbuf()
+    _lib.check(_lib.lib().at3d_path_integration_ip(C.byref(d), vp(wt), vp(shptr), vp(source), vp(rshptr), vp(rad),
+                                                   vp(fluxes), vp(bcrad), C.byref(ms), buf), buf)
+    return (rad, fluxes, bcrad, ms.value) if timing else (rad, fluxes, bcrad)
+
+
+def solve_ip(state, wtmu, maxiter=100, solacc=1e-4, shacc=0.0, accelflag=True, highorderrad=False, iterfixsh=30,
+             maxiv=None, verbose=False):
+    """Returns (solved copy of `state` with shptr/source/rshptr/radiance/fluxes/bcrad, iters, solcrit, timings)."""
+    st = state.copy().normalize()
+    npts, ns = st.npts, st.nstokes
+    f32 = np.float32
+    if maxiv is None:
+        maxiv = npts * st.nlm
+    maxir = maxiv + npts
+    rshptr = np.zeros(npts + 2, np.int32)
+    rshptr[:npts + 1] = 4 * np.arange(npts + 1)
+    rshptr[npts + 1] = rshptr[npts]
+    st.rshptr = rshptr
+    st.radiance = np.zeros((ns, int(rshptr[npts])), np.float32, order='F')
+    shptr = np.zeros(npts + 1, np.int32)
+    source = np.zeros((ns, maxiv), np.float32, order='F')
+    delsource = np.zeros((ns, maxiv), np.float32, order='F')
+    rc, shptr, source, oshptr, delsource, sums = B.compute_source(st, shptr, source, shptr.copy(), delsource, fixsh=False,
+                                                                 shacc=shacc, maxiv=maxiv, first=True, accelflag=accelflag)
+    if rc:
+        raise MemoryError('COMPUTE_SOURCE: out of spherical-harmonic memory')
+    if accelflag:
+        oshptr = shptr.copy()
+        delsource[:, :int(oshptr[npts])] = 0.0
+    albmax = float(np.max(st.albedo))
+    solcrit, a, it, fixsh = f32(1.0), f32(0.0), 0, False
+    t_path = t_src = 0.0
+    while it < maxiter and solcrit > solacc:
+        it += 1
+        st.rshptr = radiance_truncation(st, shptr, st.radiance, st.rshptr, fixsh, shacc, highorderrad, maxir)
+        st.shptr, st.source = shptr, source
+        rad, fluxes, bcrad, ms = path_integration_ip(st, wtmu, shptr, source, st.rshptr, timing=True)
+        t_path += ms
+        st.radiance, st.fluxes, st.bcrad = rad, fluxes, bcrad
+        if solcrit < 0.001 or it > iterfixsh:
+            fixsh = True
+        res = B.compute_source(st, shptr, source, oshptr, delsource, fixsh=fixsh, shacc=shacc, maxiv=maxiv,
+                               first=False, accelflag=accelflag, timing=True)
+        rc, shptr, source, oshptr, delsource, sums = res[:6]
+        t_src += res[6]
+        if rc:
+            raise MemoryError('COMPUTE_SOURCE: out of spherical-harmonic memory')
+        deljdot, deljold, deljnew, jnorm = (f32(x) for x in sums)
+        # CALC_ACCEL_SOLCRIT
+        if accelflag and a == 0 and deljnew < deljold:
+            r = f32(np.sqrt(deljnew / deljold))
+            theta = f32(np.arccos(deljdot / f32(np.sqrt(deljold * deljnew))))
+            a = f32((1 - r * f32(np.cos(theta)) + r ** f32(1 + 0.5 * 3.14159 / theta)) /
+                    (1 + r * r - 2 * r * f32(np.cos(theta))) - 1.0)
+            a = f32(min(10.0, max(0.0, float(a))))
+        else:
+            a = f32(0.0)
+        if jnorm > 0:
+            solcrit = f32(np.sqrt(deljnew / jnorm))
+        elif deljnew == 0:
+            solcrit = f32(0.0)
+        # ACCELERATE_SOLUTION
+        if a > 0:
+            nsn, nsd = np.diff(shptr[:npts + 1]), np.diff(oshptr[:npts + 1])
+            nsc = np.minimum(nsn, nsd)
+            idx_s = np.concatenate([np.arange(s0, s0 + n) for s0, n in zip(shptr[:npts], nsc)]) if nsc.sum() else np.zeros(0, int)
+            idx_d = np.concatenate([np.arange(s0, s0 + n) for s0, n in zip(oshptr[:npts], nsc)]) if nsc.sum() else np.zeros(0, int)
+            source[:, idx_s] = (source[:, idx_s] + a * delsource[:, idx_d]).astype(f32)
+        if albmax < solacc:
+            solcrit = f32(solacc)
+        if verbose:
+            print('  %4d %8.3f %8d' % (it, np.log10(max(float(solcrit), 1e-20)), npts))
+    tot = int(shptr[npts])
+    st.shptr = shptr
+    st.source = np.asfortranarray(source[:, :max(tot, 1)])
+    return st, it, float(solcrit), dict(path_integration_ms=t_path, compute_source_ms=t_src)

@@ -243,6 +243,15 @@ int at3d_do_to_sh(int npts, int nstokes, int nstleg, int ml, int mm, int nlm, in
                   const int32_t *nphi0, const float *mu, const float *phi, const float *wtmu,
                   const int32_t *rshptr, const float *dofield, float *outdata, double *kernel_ms, char *errmsg);
 
+/* PATH_INTEGRATION (src/polarized/shdomsub1.f:1836-2167) for independent-pixel grids (IPFLAG=3, unsplit base grid):
+ * SH_TO_DO of SOURCE, the BACK_INT_GRID1D sweeps of all ordinates with the top / Lambertian / general-BRDF boundary
+ * conditions, hemispheric fluxes, DO_TO_SH into RADIANCE (addressed by RSHPTR).  bcrad is BCRAD (in: unused; out: top
+ * radiances, upwelling bottom radiances and, for general BRDF surfaces, the stored downwelling radiances); fluxes is
+ * FLUXES(2,NPTS).  Host pointers; desc supplies the grid, TOTAL_EXT, DIRFLUX, the ordinate set and the surface. */
+int at3d_path_integration_ip(const at3d_state_desc *desc, const float *wtmu, const int32_t *shptr, const float *source,
+                             const int32_t *rshptr, float *radiance, float *fluxes, float *bcrad,
+                             double *kernel_ms, char *errmsg);
+
 #ifdef __cplusplus
 }
 #endif

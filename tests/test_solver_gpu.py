@@ -1,0 +1,60 @@
+"""The fixed-grid, independent-pixel SHDOM solve on the GPU (at3d_b200/solver.py: PATH_INTEGRATION and COMPUTE_SOURCE
+through the C ABI) followed by the GPU RENDER, checked end to end against SHDOM's own verification outputs
+(tests/golden/brdf_*1{f,r}.out, reference tests/test_shdom.py:597-805) and against the oracle's solve."""
+import os
+import numpy as np
+import pytest
+import oracle_lib as O
+import shdom_verification as V
+from at3d_b200 import solver
+from at3d_b200.device import DeviceState
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+
+
+def unsolved(kind):
+    st, pg, wtmu = V.make_state(O, kind)
+    st.nscatangle = 721
+    st.phasetab = O.precompute_phase_check(pg.legenp, 721, st.nstokes, st.ml, True)
+    return st, wtmu
+
+
+@pytest.mark.parametrize('kind', ['L', 'O', 'R', 'W', 'D'])
+def test_gpu_solve_and_render_reproduce_shdom(kind):
+    st, wtmu = unsolved(kind)
+    sol, iters, solcrit, _ = solver.solve_ip(st, wtmu, solacc=1e-5)
+    assert solcrit <= 1e-5 and iters <= 6
+    # the same iteration on the CPU oracle: same truncation, same iteration count, radiance expansion within 1e-4
+    ref, iters_r, _ = O.solve_fixed_grid(st, wtmu, solacc=1e-5)
+    assert iters == iters_r
+    np.testing.assert_array_equal(sol.shptr, ref.shptr)
+    np.testing.assert_array_equal(sol.rshptr, ref.rshptr)
+    scale = np.abs(ref.radiance).max()
+    np.testing.assert_allclose(sol.radiance, ref.radiance, rtol=1e-4, atol=2e-6 * scale)
+    np.testing.assert_allclose(sol.fluxes, ref.fluxes, rtol=1e-4, atol=1e-7)
+    # SHDOM's printed fluxes and radiances
+    gold = V.parse_shdom_output(os.path.join(GOLD, 'brdf_%s1f.out' % kind))
+    bot = sol.bcptr[:sol.nbotpts, 1] - 1
+    np.testing.assert_allclose(sol.fluxes[0, bot], gold[:, 3], rtol=0, atol=4e-6)
+    np.testing.assert_allclose(sol.fluxes[1, bot], gold[:, 2], rtol=0, atol=6e-6)
+    dev = DeviceState(sol)
+    out = dev.render(V.sensor_rays())
+    dev.close()
+    gold = V.parse_shdom_output(os.path.join(GOLD, 'brdf_%s1r.out' % kind))
+    np.testing.assert_allclose(out[0], gold[:, 2], rtol=0, atol=9e-6)
+    if sol.nstokes == 3:
+        np.testing.assert_allclose(out[1], gold[:, 3], rtol=0, atol=9e-6)
+        np.testing.assert_allclose(out[2], gold[:, 4], rtol=0, atol=1e-8)
+
+
+def test_path_integration_refuses_3d_grids():
+    import scenes
+    from at3d_b200._lib import At3dError
+    sc = scenes.make('scalar_periodic', O)
+    st = sc.state
+    delphi = np.float32(2.0 * np.pi) / st.nphi0.astype(np.float32)
+    w = (st.wtdo[:, 0] / delphi).astype(np.float32)
+    with pytest.raises(At3dError) as e:
+        solver.path_integration_ip(st, w, st.shptr, st.source, st.rshptr)
+    assert e.value.code == 3
