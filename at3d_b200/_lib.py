@@ -35,7 +35,8 @@ SYMBOLS = ['at3d_b200_version', 'at3d_device_count', 'at3d_set_device', 'at3d_st
            'at3d_state_attach_gradient', 'at3d_state_destroy', 'at3d_state_bytes', 'at3d_state_get_bcrad',
            'at3d_ylmall', 'at3d_precompute_phase_check', 'at3d_compute_source', 'at3d_render',
            'at3d_levisapprox_gradient', 'at3d_levisapprox_gradient_jacobian', 'at3d_prepare_deriv_interps', 'at3d_make_direct_derivative',
-           'at3d_average_subpixel_rays', 'at3d_update_costfunction', 'at3d_make_direct', 'at3d_state_get_counts']
+           'at3d_average_subpixel_rays', 'at3d_update_costfunction', 'at3d_make_direct', 'at3d_state_get_counts',
+           'at3d_sh_to_do', 'at3d_do_to_sh', 'at3d_path_integration_ip']
 
 
 class _Missing:
