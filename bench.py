@@ -197,6 +197,15 @@ class ClockSampler:
         return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons)
 
 
+def measured_traffic(workload, kernel):
+    """DRAM bytes per launch of `kernel` from the committed ncu capture (profiles/traffic.json), or None."""
+    try:
+        d = json.load(open(os.path.join(ROOT, 'profiles', 'traffic.json')))
+        return int(d[workload][kernel]['bytes'])
+    except Exception:
+        return None
+
+
 def measured_peak():
     p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(p):
@@ -543,7 +552,9 @@ def main():
                      d2h_bytes_per_step=int(d2h)),
             gpu_launches=int(args.steps * (5 + (1 if gi.exact_single_scatter else 0))),
             roofline=dict(kernel='weights_kernel+apply_kernel (derivative pass)', bound='hbm', achieved=achieved, peak=peak, unit='GB/s',
-                          frac=achieved / peak, traffic=None, peak_source=peak_src,
+                          frac=achieved / peak,
+                          traffic=measured_traffic(args.workload, 'weights_kernel+apply_kernel (derivative pass)'),
+                          peak_source=peak_src,
                           algorithmic_bytes_per_launch=abytes, kernel_ms=adj_ms, counts=counts),
             phases_ms=dict(forward=float(np.mean(kms[:, 0])), adjoint=adj_ms, weights=float(np.mean(kms[:, 4])),
                            apply=adj_ms - float(np.mean(kms[:, 4])), beam=float(np.mean(kms[:, 2])),
