@@ -21,7 +21,8 @@ Everything runs on the GPU through libat3d_b200.so (include/at3d_b200.h); there 
 Unlike f2py, the solved state is not re-marshalled on every call: ``render`` / ``levisapprox_gradient``
 keep the state resident in HBM (``DeviceState``) and re-use it while the caller passes the same arrays
 (the reference calls these once per sensor chunk / per L-BFGS evaluation with unchanged solver arrays).
-Unsupported configurations (thermal sources, non-Lambertian surfaces) return ``ierr=3``.
+Configurations the GPU path does not implement (gradients with a thermal source or a non-Lambertian surface, band-integrated
+Planck units) return ``ierr=3``.
 """
 import numpy as np
 from . import backend as B

@@ -175,3 +175,100 @@ def parse_shdom_output(filename, comment='!'):
             if comment not in line and line.strip():
                 rows.append(np.array(line.split(), dtype=np.float64))
     return np.array(rows)
+
+
+def planck_radiance(temperature, wavelength):
+    """at3d.util.planck_function (at3d/util.py:336-347): W / m^2 / micron / sr."""
+    c, h, k = 2.99792458e8, 6.62606876e-34, 1.3806503e-23
+    w = wavelength * 1e-6
+    return 2 * h * c ** 2 / w ** 5 / (np.exp(h * c / (w * k * temperature)) - 1.0) * 1e-6
+
+
+def make_thermal_state(oracle, nmu=16, nphi=32, wavelen=11.0, tair=288.0, tsfc=300.0, albedo=0.5):
+    """The isothermal absorbing slab of the reference's Verify_Thermal (tests/test_shdom.py:910-982): 50 columns
+    with extinction 0.001 ... 0.5 /km (no scattering) at 288 K over a Lambertian surface (albedo 0.5) at 300 K,
+    thermal source at 11 um.  The reference runs it with ip_flag=1 (y is a single periodic column); ip_flag=3 is
+    the same medium for the 1-D sweep."""
+    nstokes, nstleg = 1, 1
+    ml, mm, nlm = G.sh_sizes(nmu, nphi)
+    dx = 0.02
+    nx, ny, nz = NX, 1, ZLEV.size
+    bcflag, ipflag = 0, 3
+    nlegp = ml
+    legenp = rayleigh_phase_function(wavelen, max(nlegp, 2), nstleg)
+    maxpg = nx * ny * nz
+    extp = np.repeat(np.linspace(0.001, 0.5, nx), nz).reshape(maxpg, 1).astype(np.float32)
+    albp = np.zeros((maxpg, 1), np.float32)
+    pg = M.PropertyGrid(nx, ny, nz, dx, dx, ZLEV, extp, albp, np.ones((1, maxpg, 1), np.int32),
+                        np.ones((1, maxpg, 1), np.float32), legenp, max(nlegp, 2), nstleg)
+    nx1, ny1, nbpts, nbcells = G.grid_sizes(nx, ny, nz, bcflag, ipflag)
+    xg, yg, zg = G.new_grids(bcflag, 'P', nx, ny, nz, nx, ny, nz, 0.0, 0.0, dx, dx, ZLEV)
+    npts, ncells, gridpos, gridptr, neighptr, treeptr, cellflags = G.init_cell_structure(
+        bcflag, ipflag, nx, ny, nz, nx1, ny1, xg[:nx1], yg[:ny1], zg)
+    t = M.transfer_pa_to_grid(pg, gridpos, npts, ml, False)
+    mu, phi, wtdo, nphi0, nang = M.make_angle_set(nmu, nphi)
+    wtmu = (wtdo[:, 0] / (np.float32(2.0 * np.pi) / nphi0.astype(np.float32))).astype(np.float32)
+    ntop, nbot, bcptr = G.boundary_pnts(npts, gridpos, zg[0], zg[-1])
+    # PREPARE_PROP (shdomsub2.f:575-578): PLANCK = (1-ALBEDO)*B(TEMP), B from PLANCK_FUNCTION in REAL
+    f = np.float32
+    bb = f(f(1.1911e8) / f(wavelen) ** 5 / (np.exp(f(1.4388e4) / (f(wavelen) * f(tair))) - f(1)))
+    planck = ((f(1.0) - t['albedo']) * bb).astype(np.float32)
+    st = ShdomState(
+        nstokes=nstokes, nstleg=nstleg, nx=nx, ny=ny, nz=nz, npts=npts, ncells=ncells,
+        ml=ml, mm=mm, nlm=nlm, nleg=t['nleg'], numphase=1, npart=1, maxnmicro=1,
+        bcflag=bcflag, ipflag=ipflag, nmu=nmu, nphi0max=nphi, nang=nang,
+        maxnbc=bcptr.shape[0], ntoppts=ntop, nbotpts=nbot, nsfcpar=2,
+        nscatangle=36, nstphase=1, deltam=0, srctype='T', units='R', sfctype0='F', sfctype1='L', interp_new=1,
+        solarmu=-1.0, solaraz=0.0, solarflux=0.0, wavelen=wavelen, gndtemp=tsfc, gndalbedo=albedo,
+        phasemax=0.999, waveno0=0.0, waveno1=0.0, tautol=0.1, transcut=1e-5,
+        gridptr=np.asfortranarray(gridptr[:, :ncells]), neighptr=np.asfortranarray(neighptr[:, :ncells]),
+        treeptr=np.asfortranarray(treeptr[:, :ncells]), cellflags=cellflags[:ncells].copy(),
+        xgrid=xg, ygrid=yg, zgrid=zg, gridpos=np.asfortranarray(gridpos[:, :npts]),
+        extinct=t['extinct'], albedo=t['albedo'], total_ext=t['total_ext'], legen=t['legen'],
+        iphase=t['iphase'], phaseinterpwt=t['phaseinterpwt'],
+        dirflux=np.zeros(npts, np.float32), fluxes=np.zeros((2, npts), np.float32, order='F'),
+        shptr=np.zeros(npts + 1, np.int32), source=np.zeros((nstokes, 1), np.float32, order='F'),
+        rshptr=np.zeros(npts + 2, np.int32), radiance=np.zeros((nstokes, 1), np.float32, order='F'),
+        ylmsun=np.zeros((nstleg, nlm), np.float32, order='F'), phasetab=np.zeros((1, 1, 36), np.float32, order='F'),
+        planck=planck, temp=np.full(npts, tair, np.float32),
+        nphi0=nphi0, mu=mu, phi=phi, wtdo=wtdo,
+        skyrad=np.zeros((nstokes, nmu // 2, nphi), np.float32, order='F'),
+        bcptr=bcptr, bcrad=np.zeros((nstokes, ntop + nbot), np.float32, order='F'),
+        sfcgridparms=np.zeros((2, nbot), np.float32, order='F'), sfcgridrad=None)
+    st.normalize()
+    return st, pg, wtmu
+
+
+def thermal_slab_radiance(wavelen=11.0, tair=288.0, tsfc=300.0, albedo=0.5):
+    """Closed form of tests/test_shdom.py:965-975 for the nadir radiance at the top of the slab."""
+    from scipy.special import exp1
+    tau = 30.0 * np.linspace(0.001, 0.5, NX)
+    tr = np.exp(-tau)
+    ba, bs = planck_radiance(tair, wavelen), planck_radiance(tsfc, wavelen)
+    return (1.0 - albedo) * bs * tr + ba * (1.0 - tr) + tr * (albedo * ba * (-tr * (1.0 - tau) - tau ** 2 * exp1(tau) + 1))
+
+
+def nadir_rays():
+    x = np.linspace(0, 1.0 - 1.0 / 50, 50)
+    return Rays(x, np.zeros(50), np.full(50, 30.0), np.ones(50), np.zeros(50))
+
+
+def make_absorbing_state(oracle, nmu=16, nphi=32):
+    """Verify_NonuniformGasAbsorption of the reference (tests/test_shdom.py:855-908): purely absorbing columns with
+    absorption 0 ... 1 /km, overhead sun, Lambertian albedo 0.04, TRANSCUT=0; I = e^-tau * 0.04/pi * e^-tau.
+    The absorber is entered as a non-scattering species (the reference enters it as gas absorption)."""
+    st, pg, wtmu = make_thermal_state(oracle, nmu, nphi, wavelen=0.85)
+    npts, nz = st.npts, ZLEV.size
+    ext = np.repeat(np.linspace(0.0, 1.0, NX), nz).astype(np.float32)
+    pg.extinctp[:, 0] = ext
+    st.extinct = np.asfortranarray(ext.reshape(npts, 1))
+    st.total_ext = ext.copy()
+    st.planck = np.zeros((npts, 1), np.float32, order='F')
+    st.srctype, st.solarmu, st.solaraz, st.solarflux = 'S', -1.0, 0.0, 1.0
+    st.gndalbedo, st.gndtemp, st.transcut = 0.04, 288.0, 0.0      # delta-M is moot without scattering: left off
+    st.ylmsun = oracle.ylmall(True, np.float32(-1.0), np.float32(0.0), st.ml, st.mm, 1, st.nlm)
+    st.nscatangle = 36
+    st.phasetab = oracle.precompute_phase_check(pg.legenp, 36, 1, st.ml, False)
+    st.normalize()
+    st.dirflux, _, _ = oracle.make_direct(st, pg)
+    return st, pg, wtmu

@@ -84,3 +84,33 @@ def test_brdf_closed_forms():
     w1 = O.surface_brdf('W', [1.33, 0.0, 5.0], 0.85, mu2, dphi, -mu1, 0.0, 3)
     w2 = O.surface_brdf('W', [1.33, 0.0, 5.0], 0.85, mu1, 0.0, -mu2, dphi, 3)
     assert abs(w1[0, 0] - w2[0, 0]) < 1e-5 * abs(w1[0, 0])
+
+
+def test_thermal_slab_closed_form():
+    """Verify_Thermal of the reference (tests/test_shdom.py:910-982): isothermal absorbing columns over a warm
+    Lambertian surface, thermal source, NMU=128/NPHI=256, nadir radiances against the closed form with E1, atol 3e-4.
+    The reference's closed form uses CODATA constants (at3d/util.py:336) while the solver uses PLANCK_FUNCTION's
+    (1.1911e8, 1.4388e4), 3e-5 apart -- most of that tolerance; both variants are checked."""
+    st, pg, wtmu = V.make_thermal_state(O, 128, 256)
+    sol, iters, solcrit = O.solve_fixed_grid(st, wtmu, solacc=1e-5)
+    assert iters == 1                                   # no scattering: ALBMAX < SOLACC ends the iteration
+    rad = O.render(sol, V.nadir_rays())[0]
+    assert rad.min() > 5.0 and rad.max() < 8.1
+    np.testing.assert_allclose(rad, V.thermal_slab_radiance(), rtol=0, atol=3.5e-4)
+    codata = V.planck_radiance
+    try:
+        V.planck_radiance = lambda t, w: 1.1911e8 / w ** 5 / (np.exp(1.4388e4 / (w * t)) - 1)
+        np.testing.assert_allclose(rad, V.thermal_slab_radiance(), rtol=0, atol=3e-4)
+    finally:
+        V.planck_radiance = codata
+
+
+def test_absorbing_columns_closed_form():
+    """Verify_NonuniformGasAbsorption (reference tests/test_shdom.py:855-908), the reference's own atol=2e-7."""
+    st, pg, wtmu = V.make_absorbing_state(O)
+    sol, iters, _ = O.solve_fixed_grid(st, wtmu, solacc=1e-5)
+    assert iters == 1
+    rad = O.render(sol, V.nadir_rays())[0]
+    tau = np.linspace(0.0, 1.0, 50) * 30.0
+    np.testing.assert_allclose(rad, np.exp(-tau) * 0.04 / np.pi * np.exp(-tau), rtol=0, atol=2e-7)
+    assert rad[0] > 0.0127

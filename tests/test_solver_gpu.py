@@ -58,3 +58,34 @@ def test_path_integration_refuses_3d_grids():
     with pytest.raises(At3dError) as e:
         solver.path_integration_ip(st, w, st.shptr, st.source, st.rshptr)
     assert e.value.code == 3
+
+
+def test_gpu_thermal_slab():
+    # Verify_Thermal (reference tests/test_shdom.py:910-982) at the angular resolution the GPU transforms support:
+    # GPU solve + GPU RENDER against the oracle at the same resolution, and against the closed form within the
+    # quadrature error of NMU=16 (the oracle meets the reference's 3e-4 at its NMU=128, test_shdom_verification.py)
+    st, pg, wtmu = V.make_thermal_state(O, 16, 32)
+    sol, iters, solcrit, _ = solver.solve_ip(st, wtmu, solacc=1e-5)
+    ref, iters_r, _ = O.solve_fixed_grid(st, wtmu, solacc=1e-5)
+    assert iters == iters_r == 1
+    np.testing.assert_array_equal(sol.shptr, ref.shptr)
+    np.testing.assert_allclose(sol.fluxes, ref.fluxes, rtol=1e-5)
+    np.testing.assert_allclose(sol.source, ref.source, rtol=1e-5)
+    rays = V.nadir_rays()
+    dev = DeviceState(sol)
+    out = dev.render(rays)
+    dev.close()
+    np.testing.assert_allclose(out, O.render(ref, rays), rtol=1e-5)
+    np.testing.assert_allclose(out[0], V.thermal_slab_radiance(), rtol=0, atol=1.2e-2)
+
+
+def test_gpu_absorbing_columns_closed_form():
+    # Verify_NonuniformGasAbsorption (reference tests/test_shdom.py:855-908) on the GPU, the reference's own atol=2e-7
+    st, pg, wtmu = V.make_absorbing_state(O)
+    sol, iters, solcrit, _ = solver.solve_ip(st, wtmu, solacc=1e-5)
+    assert iters == 1
+    dev = DeviceState(sol)
+    out = dev.render(V.nadir_rays())
+    dev.close()
+    tau = np.linspace(0.0, 1.0, 50) * 30.0
+    np.testing.assert_allclose(out[0], np.exp(-tau) * 0.04 / np.pi * np.exp(-tau), rtol=0, atol=2e-7)
