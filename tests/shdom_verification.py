@@ -272,3 +272,14 @@ def make_absorbing_state(oracle, nmu=16, nphi=32):
     st.normalize()
     st.dirflux, _, _ = oracle.make_direct(st, pg)
     return st, pg, wtmu
+
+
+def make_combined_state(oracle, nmu=16, nphi=32):
+    """VerifyCombined of the reference (tests/test_shdom.py:984-1056): the thermal slab lit by an overhead sun of unit
+    flux (SRCTYPE='B'); the closed form gains 0.5 * T^2 / pi."""
+    st, pg, wtmu = make_thermal_state(oracle, nmu, nphi)
+    st.srctype, st.solarmu, st.solaraz, st.solarflux = 'B', -1.0, 0.0, 1.0
+    st.ylmsun = oracle.ylmall(True, np.float32(-1.0), np.float32(0.0), st.ml, st.mm, 1, st.nlm)
+    st.normalize()
+    st.dirflux, _, _ = oracle.make_direct(st, pg)
+    return st, pg, wtmu

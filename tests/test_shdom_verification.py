@@ -114,3 +114,14 @@ def test_absorbing_columns_closed_form():
     tau = np.linspace(0.0, 1.0, 50) * 30.0
     np.testing.assert_allclose(rad, np.exp(-tau) * 0.04 / np.pi * np.exp(-tau), rtol=0, atol=2e-7)
     assert rad[0] > 0.0127
+
+
+def test_combined_source_closed_form():
+    """VerifyCombined (reference tests/test_shdom.py:984-1056): thermal slab + overhead sun, SRCTYPE='B', atol 3e-4
+    (3.5e-4 with the reference's mixed Planck constants, see test_thermal_slab_closed_form)."""
+    st, pg, wtmu = V.make_combined_state(O, 128, 256)
+    sol, iters, _ = O.solve_fixed_grid(st, wtmu, solacc=1e-5)
+    rad = O.render(sol, V.nadir_rays())[0]
+    tr = np.exp(-30.0 * np.linspace(0.001, 0.5, 50))
+    np.testing.assert_allclose(rad, 0.5 * tr * tr / np.pi + V.thermal_slab_radiance(), rtol=0, atol=3.5e-4)
+    assert (0.5 * tr * tr / np.pi).max() > 0.14           # the solar part is far above the tolerance

@@ -89,3 +89,19 @@ def test_gpu_absorbing_columns_closed_form():
     dev.close()
     tau = np.linspace(0.0, 1.0, 50) * 30.0
     np.testing.assert_allclose(out[0], np.exp(-tau) * 0.04 / np.pi * np.exp(-tau), rtol=0, atol=2e-7)
+
+
+def test_gpu_combined_source():
+    # VerifyCombined (reference tests/test_shdom.py:984-1056), SRCTYPE='B', GPU solve + RENDER vs the oracle
+    st, pg, wtmu = V.make_combined_state(O, 16, 32)
+    sol, iters, solcrit, _ = solver.solve_ip(st, wtmu, solacc=1e-5)
+    ref, iters_r, _ = O.solve_fixed_grid(st, wtmu, solacc=1e-5)
+    assert iters == iters_r
+    np.testing.assert_allclose(sol.fluxes, ref.fluxes, rtol=1e-5)
+    rays = V.nadir_rays()
+    dev = DeviceState(sol)
+    out = dev.render(rays)
+    dev.close()
+    np.testing.assert_allclose(out, O.render(ref, rays), rtol=1e-5)
+    tr = np.exp(-30.0 * np.linspace(0.001, 0.5, 50))
+    np.testing.assert_allclose(out[0], 0.5 * tr * tr / np.pi + V.thermal_slab_radiance(), rtol=0, atol=1.2e-2)
