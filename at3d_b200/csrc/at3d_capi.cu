@@ -110,6 +110,7 @@ extern "C" int at3d_state_destroy(at3d_state *st)
     for (void *p : st->grad_owned) cudaFree(p);
     st->pix.release(); st->work.release();
     st->hits.release();
+    if (st->packs_h) cudaFreeHost(st->packs_h);
     st->rays.release(); st->out.release(); st->trace.release(); st->misc.release();
     st->slabs.release(); st->err.release(); st->recs.release();
     delete st;
@@ -352,19 +353,31 @@ int stage_rays(at3d_state *st, const at3d_rays *rays, cudaStream_t stream, const
     CUDA_TRY(st->rays.reserve(nb));
     RayPack *dpk = (RayPack *)st->rays.p;
     double *dmu = (double *)(dpk + n), *dphi = dmu + n;
-    st->packs_h.resize(n);
-    RayPack *hp = st->packs_h.data();
+    if (n > st->packs_cap) {
+        // pinned, so that the copy below is a true asynchronous DMA
+        if (st->packs_h) cudaFreeHost(st->packs_h);
+        st->packs_h = nullptr; st->packs_cap = 0;
+        CUDA_TRY(cudaMallocHost((void **)&st->packs_h, n * sizeof(RayPack)));
+        st->packs_cap = n;
+    }
+    RayPack *hp = st->packs_h;
     const RayGeom g = st->geom;
     const float *hx = rays->camx, *hy = rays->camy, *hz = rays->camz;
     const double *hmu = rays->cammu, *hphi = rays->camphi;
-#pragma omp parallel for schedule(static) if (n > 4096)
-    for (long long i = 0; i < (long long)n; i++)
-        make_ray_pack(g, (double)hx[i], (double)hy[i], (double)hz[i], hmu[i], hphi[i], hp[i]);
-    CUDA_TRY(cudaMemcpyAsync(dpk, hp, n * sizeof(RayPack), cudaMemcpyHostToDevice, stream));
     CUDA_TRY(cudaMemcpyAsync(dmu, rays->cammu, n * sizeof(double), cudaMemcpyHostToDevice, stream));
     CUDA_TRY(cudaMemcpyAsync(dphi, rays->camphi, n * sizeof(double), cudaMemcpyHostToDevice, stream));
-    // the copies read pageable host memory: they are complete (staged) when the calls return,
-    // and packs_h is only rewritten by the next call on this state
+    // in chunks, so that the DMA of one chunk overlaps the host libm work on the next
+    const size_t chunk = 65536;
+    for (size_t c0 = 0; c0 < n; c0 += chunk) {
+        const long long c1 = (long long)(c0 + chunk < n ? c0 + chunk : n);
+#pragma omp parallel for schedule(static) if (n > 4096)
+        for (long long i = (long long)c0; i < c1; i++)
+            make_ray_pack(g, (double)hx[i], (double)hy[i], (double)hz[i], hmu[i], hphi[i], hp[i]);
+        CUDA_TRY(cudaMemcpyAsync(dpk + c0, hp + c0, (size_t)(c1 - (long long)c0) * sizeof(RayPack), cudaMemcpyHostToDevice, stream));
+    }
+    // cammu/camphi are pageable caller memory: staged when the calls return.  packs_h is pinned: its DMA completes
+    // before this call returns (every entry point synchronises the stream before returning results), and it is only
+    // rewritten by the next call on this state
     *camx = nullptr; *camy = nullptr; *camz = nullptr; *cammu = dmu; *camphi = dphi; *packs = dpk;
     return 0;
 }

@@ -35,7 +35,8 @@ struct at3d_state {
     // reusable per-call buffers
     DevBuf rays, out, trace, misc, slabs, err, pix, work, recs, hits;
     RayGeom geom;                   // host copy of the per-ray setup constants
-    std::vector<RayPack> packs_h;   // host staging of the per-ray packs
+    RayPack *packs_h = nullptr;     // pinned host staging of the per-ray packs (grows on demand)
+    size_t packs_cap = 0;
     float *bcrad_dev = nullptr;
     unsigned long long *counts_dev = nullptr;
     std::vector<long long> recoff_h; // per-ray visit-record offsets of the last gradient call (host copy)

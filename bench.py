@@ -477,7 +477,12 @@ def main():
     kms = np.array(kms)            # [steps, 4] forward, adjoint(+pixel), beam, total
     value = world * nrays * args.steps / t_total
 
-    # ---- e2e: host buffers through the C-ABI call, copies inside the timed region ----
+    # ---- e2e: host buffers (pinned) through the C-ABI call, copies inside the timed region ----
+    def pinned(a):
+        t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        return t.numpy()
+    for k in ('camx', 'camy', 'camz', 'cammu', 'camphi'):
+        setattr(rays, k, pinned(getattr(rays, k)))
     for _ in range(max(1, args.warmup // 2)):
         dev.gradient(rays, pix)
     barrier()
