@@ -122,15 +122,14 @@ __device__ __forceinline__ void cs_mix_newmethod(const CsArgs &a, int i, float *
 
 // CALC_SOURCE_PNT[_UNPOL] for one SH index j (0-based) (shdomsub1.f:858-898, 940-958); r = RADIANCE(:,j) (0 beyond NR)
 template <int NST>
-__device__ __forceinline__ void cs_calc_j(const CsArgs &a, const float *legen, int j, bool inr, const float (&r)[NST],
-                                          float flux0, float planck, float albedo, float (&s)[NST])
+__device__ __forceinline__ void cs_calc_j(const CsArgs &a, const float *legen, int j, int l, float ysun, bool inr,
+                                          const float (&r)[NST], float flux0, float planck, float albedo, float (&s)[NST])
 {
-    const int l = a.lofj[j];
     const bool solar = a.srctype == 'S' || a.srctype == 'B';
     const bool thermal = a.srctype == 'T' || a.srctype == 'B';
     if (NST == 1) {
         float v = 0.0f;
-        if (solar) v = flux0 * albedo * legen[l] * a.ylmsun[j];
+        if (solar) v = flux0 * albedo * legen[l] * ysun;
         if (thermal && j == 0) v = v + 3.544907703f * planck;
         if (inr) v = v + albedo * legen[l] * r[0];
         s[0] = v;
@@ -148,8 +147,8 @@ __device__ __forceinline__ void cs_calc_j(const CsArgs &a, const float *legen, i
         }
         v1 = albedo * v1; v2 = albedo * v2; v3 = albedo * v3;
         if (solar) {
-            v1 = v1 + flux0 * albedo * legen[ns * l] * a.ylmsun[(size_t)ns * j];
-            if (j >= 4) v2 = v2 + flux0 * albedo * legen[4 + ns * l] * a.ylmsun[(size_t)ns * j];
+            v1 = v1 + flux0 * albedo * legen[ns * l] * ysun;
+            if (j >= 4) v2 = v2 + flux0 * albedo * legen[4 + ns * l] * ysun;
         }
         if (thermal && j == 0) v1 = v1 + 3.544907703f * planck;
         s[0] = v1; s[1] = v2; s[NST - 1] = v3;
@@ -161,6 +160,23 @@ __device__ __forceinline__ void cs_calc_j(const CsArgs &a, const float *legen, i
 // those of the first batch even before the Legendre table of the point is mixed, so that a warp keeps
 // 3 x CS_BATCH x 128 B x NSTOKES in flight instead of one line per array.
 template <int NST> struct CsBatch { static const int N = NST == 1 ? 4 : 2; };
+
+// The SH indices a lane meets are the same for every point: j = lane + 32*slot.  Their degree l(j) and YLMSUN(1,j)
+// are kept in registers for the first CS_JSLOTS slots (NLM <= 256), instead of two table loads per element.
+#define CS_JSLOTS 8
+struct CsLaneTab {
+    int l[CS_JSLOTS];
+    float ys[CS_JSLOTS];
+    __device__ __forceinline__ void init(const CsArgs &a, int lane)
+    {
+#pragma unroll
+        for (int q = 0; q < CS_JSLOTS; q++) {
+            const int j = lane + 32 * q;
+            l[q] = j < a.nlm ? a.lofj[j] : 0;
+            ys[q] = j < a.nlm ? a.ylmsun[(size_t)a.nstleg * j] : 0.0f;
+        }
+    }
+};
 
 // Kernel A: norms (passes 1 of the reference) and the new truncation length (first half of pass 3)
 template <int NST, int SLOTS>
@@ -174,6 +190,8 @@ __global__ void __launch_bounds__(CS_WARPS * 32) cs_norms_kernel(CsArgs a)
     __shared__ double red[CS_WARPS][4];
     double sdot = 0.0, sold = 0.0, snew = 0.0, snorm = 0.0;
     const bool donorm = !a.first, doacc = a.accelflag && !a.first;
+    CsLaneTab tab;
+    tab.init(a, lane);
     // software pipeline over the warp's points: the block pointers of the next point are requested at the top of an
     // iteration and its first batch of SH values at the bottom, so their HBM latency overlaps this point's arithmetic
     const int stride = gridDim.x * CS_WARPS;
@@ -219,14 +237,20 @@ __global__ void __launch_bounds__(CS_WARPS * 32) cs_norms_kernel(CsArgs a)
         const float flux0 = a.dirflux[i] * a.secmu0;
         cs_mix_newmethod<SLOTS>(a, i, legent, legent1, albedo, planck);
         int jlast = -1;                       // last j with |SOURCET| > SRCMIN
-        for (int j0 = 0; j0 < a.nlm; j0 += 32 * NB) {
-            if (j0 > 0) load_batch(j0, ir, nr, is, ns, iso);
+        // the four norms of this point are summed in REAL per lane (at most NLM/32 terms) and added to the DOUBLE
+        // accumulators once per point
+        float pdot = 0.0f, pold = 0.0f, pnew = 0.0f, pnorm = 0.0f;
+#pragma unroll
+        for (int b = 0; b < CS_JSLOTS / NB; b++) {
+            const int j0 = 32 * NB * b;
+            if (j0 >= a.nlm) break;
+            if (b > 0) load_batch(j0, ir, nr, is, ns, iso);
 #pragma unroll
             for (int u = 0; u < NB; u++) {
                 const int j = j0 + 32 * u + lane;
                 if (j >= a.nlm) continue;
                 float s[NST];
-                cs_calc_j<NST>(a, legent, j, j < nr, r[u], flux0, planck, albedo, s);
+                cs_calc_j<NST>(a, legent, j, tab.l[b * NB + u], tab.ys[b * NB + u], j < nr, r[u], flux0, planck, albedo, s);
 #pragma unroll
                 for (int k = 0; k < NST; k++) if (fabsf(s[k]) > a.srcmin) jlast = j;
                 if (donorm && j < ns) {
@@ -234,15 +258,40 @@ __global__ void __launch_bounds__(CS_WARPS * 32) cs_norms_kernel(CsArgs a)
                     for (int k = 0; k < NST; k++) {
                         const float d = s[k] - so[u][k];
                         if (a.accelflag) {
-                            sdot += (double)(d * ds[u][k]);
-                            sold += (double)(ds[u][k] * ds[u][k]);
+                            pdot = pdot + d * ds[u][k];
+                            pold = pold + ds[u][k] * ds[u][k];
                         }
-                        snew += (double)(d * d);
-                        snorm += (double)(so[u][k] * so[u][k]);
+                        pnew = pnew + d * d;
+                        pnorm = pnorm + so[u][k] * so[u][k];
                     }
                 }
             }
         }
+        for (int j0 = 32 * CS_JSLOTS; j0 < a.nlm; j0 += 32 * NB) {        // NLM > 256: table loads
+            load_batch(j0, ir, nr, is, ns, iso);
+#pragma unroll
+            for (int u = 0; u < NB; u++) {
+                const int j = j0 + 32 * u + lane;
+                if (j >= a.nlm) continue;
+                float s[NST];
+                cs_calc_j<NST>(a, legent, j, a.lofj[j], a.ylmsun[(size_t)a.nstleg * j], j < nr, r[u], flux0, planck, albedo, s);
+#pragma unroll
+                for (int k = 0; k < NST; k++) if (fabsf(s[k]) > a.srcmin) jlast = j;
+                if (donorm && j < ns) {
+#pragma unroll
+                    for (int k = 0; k < NST; k++) {
+                        const float d = s[k] - so[u][k];
+                        if (a.accelflag) {
+                            pdot = pdot + d * ds[u][k];
+                            pold = pold + ds[u][k] * ds[u][k];
+                        }
+                        pnew = pnew + d * d;
+                        pnorm = pnorm + so[u][k] * so[u][k];
+                    }
+                }
+            }
+        }
+        sdot += (double)pdot; sold += (double)pold; snew += (double)pnew; snorm += (double)pnorm;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) jlast = max(jlast, __shfl_xor_sync(FULLMASK, jlast, o));
         if (lane == 0) {
@@ -284,6 +333,8 @@ __global__ void __launch_bounds__(CS_WARPS * 32) cs_write_kernel(CsArgs a)
     const int nlt = a.nstleg * (a.nleg + 1);
     float *legent = smem + (size_t)warp * 2 * nlt, *legent1 = legent + nlt;
     const bool dodel = !a.first && a.accelflag;
+    CsLaneTab tab;
+    tab.init(a, lane);
     // same software pipeline over the warp's points as in cs_norms_kernel
     const int stride = gridDim.x * CS_WARPS;
     int i = blockIdx.x * CS_WARPS + warp;
@@ -316,14 +367,32 @@ __global__ void __launch_bounds__(CS_WARPS * 32) cs_write_kernel(CsArgs a)
         float albedo, planck;
         const float flux0 = a.dirflux[i] * a.secmu0;
         cs_mix_newmethod<SLOTS>(a, i, legent, legent1, albedo, planck);
-        for (int j0 = 0; j0 < nmax; j0 += 32 * NB) {
-            if (j0 > 0) load_batch(j0, ir, nr, is_old, ns_old);
+#pragma unroll
+        for (int b = 0; b < CS_JSLOTS / NB; b++) {
+            const int j0 = 32 * NB * b;
+            if (j0 >= nmax) break;
+            if (b > 0) load_batch(j0, ir, nr, is_old, ns_old);
 #pragma unroll
             for (int u = 0; u < NB; u++) {
                 const int j = j0 + 32 * u + lane;
                 if (j >= nmax) continue;
                 float s[NST];
-                cs_calc_j<NST>(a, legent, j, j < nr, r[u], flux0, planck, albedo, s);
+                cs_calc_j<NST>(a, legent, j, tab.l[b * NB + u], tab.ys[b * NB + u], j < nr, r[u], flux0, planck, albedo, s);
+#pragma unroll
+                for (int k = 0; k < NST; k++) {
+                    if (dodel && j < ns_old) a.delsource_new[(size_t)NST * (is_old + j) + k] = s[k] - so[u][k];
+                    if (j < ns_new) a.source_new[(size_t)NST * (is_new + j) + k] = s[k];
+                }
+            }
+        }
+        for (int j0 = 32 * CS_JSLOTS; j0 < nmax; j0 += 32 * NB) {          // NLM > 256: table loads
+            load_batch(j0, ir, nr, is_old, ns_old);
+#pragma unroll
+            for (int u = 0; u < NB; u++) {
+                const int j = j0 + 32 * u + lane;
+                if (j >= nmax) continue;
+                float s[NST];
+                cs_calc_j<NST>(a, legent, j, a.lofj[j], a.ylmsun[(size_t)a.nstleg * j], j < nr, r[u], flux0, planck, albedo, s);
 #pragma unroll
                 for (int k = 0; k < NST; k++) {
                     if (dodel && j < ns_old) a.delsource_new[(size_t)NST * (is_old + j) + k] = s[k] - so[u][k];
