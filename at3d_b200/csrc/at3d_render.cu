@@ -287,6 +287,9 @@ forward_kernel_t(DevState S, int nrays, const float *camx, const float *camy, co
 // threads per block of the thread-per-ray kernels: as many YLMDIR columns (4*NLMP bytes) as fit
 int tray_block_threads(const DevState &S)
 {
+#ifdef AT3D_FORCE_OCTET
+    return 0;
+#endif
     if (S.nstokes != 1) return 0;
     const size_t per = (size_t)S.nlmp * sizeof(float);
     int bt = (int)((220 * 1024) / per) & ~31;

@@ -105,11 +105,21 @@ surface_ocean_kernel(DevState S, int nrays, const SurfHit *hits, const double *c
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
     const int nh = S.nang / 2;
     const float opi = 1.0f / acosf(-1.0f);
+    // incident-direction part of the BRDF geometry: once per block for the stored ordinates and the sun
+    extern __shared__ __align__(16) unsigned char surf_sm[];
+    OceanInc *inc_s = (OceanInc *)surf_sm;           // [nh + 1]
+    for (int jang = threadIdx.x; jang <= nh; jang += blockDim.x) {
+        if (jang < nh) dev_ocean_inc(-__ldg(&S.ord_mu[jang]), __ldg(&S.ord_phi[jang]), inc_s[jang]);
+        else dev_ocean_inc(-S.solarmu, S.solaraz, inc_s[nh]);
+    }
+    __syncthreads();
     for (int iray = warp; iray < nrays; iray += nwarps) {
         const int kface = hits[iray].kface;
         if (kface == 0) continue;
         const int icell = hits[iray].icell;
         const float mu2 = (float)__ldg(&cammu[iray]), phi2 = (float)__ldg(&camphi[iray]);
+        OceanView view;
+        dev_ocean_view(mu2, view);
         float x[4], y[4], rad[4][1], planck[4], acc[4];
         int ibcs[4], ips[4];
         OceanPoint pt[4];
@@ -131,9 +141,9 @@ surface_ocean_kernel(DevState S, int nrays, const SurfHit *hits, const double *c
         }
         if (bad) { if (lane == 0) set_err(err, 3, iray); continue; }
         for (int jang = lane; jang < nh; jang += 32) {
-            const float mu1 = __ldg(&S.ord_mu[jang]), phi1 = __ldg(&S.ord_phi[jang]);
+            const float phi1 = __ldg(&S.ord_phi[jang]);
             OceanGeom g;
-            dev_ocean_geom(-mu1, mu2, phi1 - phi2, phi1, g);
+            dev_ocean_pair(inc_s[jang], view, phi1 - phi2, g);
             const float w = __ldg(&S.ord_w[jang]);
 #pragma unroll
             for (int j = 0; j < 4; j++) {
@@ -147,7 +157,7 @@ surface_ocean_kernel(DevState S, int nrays, const SurfHit *hits, const double *c
         for (int j = 0; j < 4; j++) acc[j] = warp_sum(acc[j]);
         if (S.srctype != 'T') {
             OceanGeom g;
-            dev_ocean_geom(-S.solarmu, mu2, S.solaraz - phi2, S.solaraz, g);
+            dev_ocean_pair(inc_s[nh], view, S.solaraz - phi2, g);
 #pragma unroll
             for (int j = 0; j < 4; j++)
                 acc[j] = acc[j] + opi * dev_ocean_eval(pt[j], g) * __ldg(&S.dirflux[ips[j] - 1]);
@@ -172,7 +182,7 @@ cudaError_t launch_surface(const DevState &S, int nrays, const SurfHit *hits, co
     const long cap = (long)nsm * 8;
     const int nb = (int)(want < cap ? want : cap);
     if (S.nstokes == 1 && S.sfctype1 == 'O')
-        surface_ocean_kernel<float><<<nb, 256, 0, stream>>>(S, nrays, hits, cammu, camphi, out, err);
+        surface_ocean_kernel<float><<<nb, 256, (size_t)(S.nang / 2 + 1) * sizeof(OceanInc), stream>>>(S, nrays, hits, cammu, camphi, out, err);
     else if (S.nstokes == 1) surface_kernel<1, float><<<nb, 256, 0, stream>>>(S, nrays, hits, cammu, camphi, out, err);
     else surface_kernel<3, float><<<nb, 256, 0, stream>>>(S, nrays, hits, cammu, camphi, out, err);
     return cudaGetLastError();

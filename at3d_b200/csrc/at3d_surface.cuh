@@ -363,30 +363,50 @@ static __device__ void dev_ocean_point(float pws, float xsal, float pcl, float p
     p.c03 = 0.04f - 0.033f * wspd;
 }
 
-static __device__ void dev_ocean_geom(float xmuo, float xmu, float xphi, float xpaw, OceanGeom &g)
+// The direction-only part splits once more: OceanInc depends on the incident direction alone (one per stored ordinate
+// and state), OceanView on the outgoing direction alone (one per ray), and only the relative azimuth couples them.
+struct OceanInc { float cs, ss, cphw, sphw; int isz1; };
+struct OceanView { float cv, sv; int ivz1; };
+
+__device__ __forceinline__ void dev_ocean_inc(float xmuo, float xpaw, OceanInc &q)
 {
     const float pi = atanf(1.f) * 4.f, fac = pi / 180.f;
     const float paw = xpaw / fac;
+    float tetas;
+    if (xmuo <= 0.028f) tetas = acosf(0.028f) / fac; else tetas = acosf(xmuo) / fac;
+    q.isz1 = dev_getbound(c_oc_angbnd, 5, tetas);
+    const float phw = paw * fac;
+    q.cs = cosf(tetas * fac); q.ss = sinf(tetas * fac);
+    q.cphw = cosf(phw); q.sphw = sinf(phw);
+}
+
+__device__ __forceinline__ void dev_ocean_view(float xmu, OceanView &v)
+{
+    const float pi = atanf(1.f) * 4.f, fac = pi / 180.f;
+    float tetav;
+    if (xmu <= 0.028f) tetav = acosf(0.028f) / fac; else tetav = acosf(xmu) / fac;
+    v.ivz1 = dev_getbound(c_oc_angbnd, 5, tetav);
+    v.cv = cosf(tetav * fac); v.sv = sinf(tetav * fac);
+}
+
+__device__ __forceinline__ void dev_ocean_pair(const OceanInc &q, const OceanView &v, float xphi, OceanGeom &g)
+{
+    const float pi = atanf(1.f) * 4.f, fac = pi / 180.f;
     float phi;
     if (xphi < 0.0f) phi = -xphi;
     else if (xphi >= 2.0f * pi) phi = xphi - 2.0f * pi;
     else phi = xphi;
-    float tetas, tetav;
-    if (xmuo <= 0.028f) tetas = acosf(0.028f) / fac; else tetas = acosf(xmuo) / fac;
-    if (xmu <= 0.028f) tetav = acosf(0.028f) / fac; else tetav = acosf(xmu) / fac;
     const float fi = 180.0f - phi / fac;
-    g.isz1 = dev_getbound(c_oc_angbnd, 5, tetas);
-    g.ivz1 = dev_getbound(c_oc_angbnd, 5, tetav);
-    // sunglint(wspd, nr, ni, azw=paw, ts=tetas, tv=tetav, fi)
-    const float phw = paw * fac;
-    const float cs = cosf(tetas * fac), cv = cosf(tetav * fac), ss = sinf(tetas * fac), sv = sinf(tetav * fac);
+    g.isz1 = q.isz1; g.ivz1 = v.ivz1;
+    // sunglint(wspd, nr, ni, azw, ts, tv, fi)
+    const float cs = q.cs, cv = v.cv, ss = q.ss, sv = v.sv;
     const float phir = fi * fac;
     g.cs = cs; g.cv = cv;
     g.zx = -sv * sinf(phir) / (cs + cv);
     g.zy = (ss + sv * cosf(phir)) / (cs + cv);
     const float tantilt = sqrtf(g.zx * g.zx + g.zy * g.zy);
     const float tilt = atanf(tantilt);
-    g.cphw = cosf(phw); g.sphw = sinf(phw);
+    g.cphw = q.cphw; g.sphw = q.sphw;
     float cos2chi = cv * cs + sv * ss * cosf(phir);
     if (cos2chi > 1.0f) cos2chi = 0.99999999999f;
     if (cos2chi < -1.0f) cos2chi = -0.99999999999f;
@@ -394,6 +414,14 @@ static __device__ void dev_ocean_geom(float xmuo, float xmu, float xphi, float x
     g.sinchi = sqrtf(0.5f * (1 - cos2chi));
     float ct = cosf(tilt);
     g.ct4 = (ct * ct) * (ct * ct);
+}
+
+static __device__ void dev_ocean_geom(float xmuo, float xmu, float xphi, float xpaw, OceanGeom &g)
+{
+    OceanInc q; OceanView v;
+    dev_ocean_inc(xmuo, xpaw, q);
+    dev_ocean_view(xmu, v);
+    dev_ocean_pair(q, v, xphi, g);
 }
 
 __device__ __forceinline__ float dev_ocean_eval(const OceanPoint &p, const OceanGeom &g)
