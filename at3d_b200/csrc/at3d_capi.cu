@@ -1,5 +1,6 @@
 // at3d_capi.cu -- C-ABI of libat3d_b200.so (include/at3d_b200.h): state residency and RENDER.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <cstdarg>
 #include <cmath>
@@ -109,7 +110,7 @@ extern "C" int at3d_state_destroy(at3d_state *st)
     for (void *p : st->owned) cudaFree(p);
     for (void *p : st->grad_owned) cudaFree(p);
     st->pix.release(); st->work.release();
-    st->hits.release();
+    st->hits.release(); st->viewsrc.release();
     if (st->packs_h) cudaFreeHost(st->packs_h);
     st->rays.release(); st->out.release(); st->trace.release(); st->misc.release();
     st->slabs.release(); st->err.release(); st->recs.release();
@@ -138,6 +139,7 @@ extern "C" int at3d_state_create(const at3d_state_desc *d, at3d_state **out, cha
     }
     if (d->numphase < 1) { set_msg(errmsg, "NUMPHASE=0 is not supported."); return 1; }
     at3d_state *st = new at3d_state();
+    if (const char *e = getenv("AT3D_VIEW_MIN_RAYS")) st->view_min_rays = atoi(e);   // developer knob (0 disables view sources)
     cudaGetDevice(&st->device);
     DevState &S = st->S;
     memset(&S, 0, sizeof(S));
@@ -419,9 +421,42 @@ extern "C" int at3d_render(at3d_state *st, const at3d_rays *rays, float *stokes,
     }
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (kernel_ms) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, stream); }
-    CUDA_TRY(launch_forward(S, (int)n, camx, camy, camz, cammu, camphi, packs, out_d, nullptr, nullptr, 1,
-                            correctinterpolate, singlescatter, nosurface, 0, tc, tcap, tn, ts,
-                            (RayErr *)st->err.p, st->ray_counter, nullptr, stream));
+    // Orthographic views: runs of rays with one common direction (host ray arrays, NSTOKES=1).  Their SRCEXT is
+    // evaluated once per grid point (view_source_kernel) instead of once per (ray, corner); same arithmetic per point.
+    std::vector<size_t> seg_start, seg_len;
+    std::vector<char> seg_view;
+    if (host && tray_block_threads(S) > 0 && st->view_min_rays > 0) {
+        const double *hmu = rays->cammu, *hphi = rays->camphi;
+        size_t i = 0;
+        while (i < n) {
+            size_t j = i + 1;
+            while (j < n && hmu[j] == hmu[i] && hphi[j] == hphi[i]) j++;
+            const bool view = (j - i) >= (size_t)st->view_min_rays;
+            if (!seg_view.empty() && !view && !seg_view.back()) seg_len.back() += j - i;
+            else { seg_start.push_back(i); seg_len.push_back(j - i); seg_view.push_back(view ? 1 : 0); }
+            i = j;
+        }
+    } else {
+        seg_start.push_back(0); seg_len.push_back(n); seg_view.push_back(0);
+    }
+    for (size_t sgi = 0; sgi < seg_start.size(); sgi++) {
+        const size_t s0 = seg_start[sgi], sn = seg_len[sgi];
+        DevState Sg = S;
+        if (seg_view[sgi]) {
+            CUDA_TRY(st->viewsrc.reserve((size_t)S.npts * sizeof(float)));
+            CUDA_TRY(launch_view_source(S, st->packs_h[s0], rays->cammu[s0], rays->camphi[s0], singlescatter,
+                                        (float *)st->viewsrc.p, stream));
+            Sg.viewsrc = (const float *)st->viewsrc.p;
+        }
+        if (Sg.surfhits) Sg.surfhits = (SurfHit *)Sg.surfhits + s0;
+        Sg.ray_base = (int)s0;
+        CUDA_TRY(launch_forward(Sg, (int)sn, camx ? camx + s0 : nullptr, camy ? camy + s0 : nullptr,
+                                camz ? camz + s0 : nullptr, cammu + s0, camphi + s0, packs ? packs + s0 : nullptr,
+                                out_d + (size_t)nst * s0, nullptr, nullptr, 1,
+                                correctinterpolate, singlescatter, nosurface, 0, tc ? tc + (size_t)tcap * s0 : nullptr, tcap,
+                                tn ? tn + s0 : nullptr, ts ? ts + s0 : nullptr,
+                                (RayErr *)st->err.p, st->ray_counter, nullptr, stream));
+    }
     if (general_brdf)
         CUDA_TRY(launch_surface(S, (int)n, (const SurfHit *)st->hits.p, cammu, camphi, out_d,
                                 (RayErr *)st->err.p, stream));

@@ -69,6 +69,9 @@ struct DevState {
     const int *up_src;                       // [nang/2] row of SFCGRIDRAD each upward ordinate reads, or -1
     const float *sfcgridrad;                 // [nang/2+1, nbotpts] or null when identically zero
     void *surfhits;                          // SurfHit[nrays] of the current RENDER call (non-Lambertian only)
+    int ray_base;                            // index of the launch's first ray in the caller's ray arrays (error reports)
+    const float *viewsrc;                    // [npts] SRCEXT of every grid point for the direction shared by all rays of the
+                                             // current launch (orthographic views, NSTOKES=1), or null
     // optional work counters of the last call: [0] cells visited, [1] grid points evaluated,
     // [2] sum of NS over evaluated points, [3] sum of NR (gradient), [4] sub-intervals, [5] rays marched,
     // [6] rays that ended on a general-BRDF surface

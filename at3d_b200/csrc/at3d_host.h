@@ -33,7 +33,7 @@ struct at3d_state {
     size_t bytes = 0;
     int device = 0;
     // reusable per-call buffers
-    DevBuf rays, out, trace, misc, slabs, err, pix, work, recs, hits;
+    DevBuf rays, out, trace, misc, slabs, err, pix, work, recs, hits, viewsrc;
     RayGeom geom;                   // host copy of the per-ray setup constants
     RayPack *packs_h = nullptr;     // pinned host staging of the per-ray packs (grows on demand)
     size_t packs_cap = 0;
@@ -43,6 +43,7 @@ struct at3d_state {
     std::vector<int> nr_h;          // radiance SH length per point (host copy, for the gradient tables)
     int *ray_counter = nullptr;     // work counter of the persistent ray kernels
     int nbcrad = 0;
+    int view_min_rays = 256;        // shortest run of equal-direction rays that gets a pre-evaluated view source (0: off)
 };
 
 size_t render_smem_bytes(const DevState &S);
@@ -58,6 +59,9 @@ cudaError_t launch_build_ptrec(int npts, const float *gridpos, const float *tota
 cudaError_t launch_build_ptsrc(int npts, int kmax, const int2 *srcrec, const int *sscount, const int2 *ssent,
                                int4 *ptsrc, cudaStream_t s);
 cudaError_t launch_lambertian_boundary(const DevState &S, const float *fluxes, float *bcrad, cudaStream_t s);
+cudaError_t launch_view_source(const DevState &S, const RayPack &pk, double mu2, double phi2, int singlescatter,
+                               float *viewsrc, cudaStream_t stream);
+int tray_block_threads(const DevState &S);
 cudaError_t launch_surface(const DevState &S, int nrays, const SurfHit *hits, const double *cammu,
                            const double *camphi, float *out, RayErr *err, cudaStream_t stream);
 cudaError_t launch_prep_sh(const DevState &S, int tms, const int *shptr, const float *sh_in,

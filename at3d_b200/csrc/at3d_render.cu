@@ -1,6 +1,7 @@
 // at3d_render.cu -- state preparation kernels and the RENDER kernel (sm_100a).
 // Replaces RENDER / INTEGRATE_1RAY / COMPUTE_SOURCE_1CELL[_UNPOL] / FIND_BOUNDARY_RADIANCE
 // (src/polarized/shdomsub4.f:93-286, shdomsub2.f:2311-3192 of the AT3D reference).
+#include <cstring>
 #include "at3d_tray.cuh"
 #include "at3d_host.h"
 
@@ -197,7 +198,7 @@ forward_kernel(DevState S, int nrays, const float *camx, const float *camy, cons
 #pragma unroll
             for (int k = 0; k < NST; k++) { radA[k] = 0.0; radB[k] = 0.0; }
             int ntrace = 0, nsubA = 0, nsubB = 0, nptB = 0;
-            if (pk.status == 2) { if (o.ol == 0) set_err(err, 2, iray); }
+            if (pk.status == 2) { if (o.ol == 0) set_err(err, 2, iray + S.ray_base); }
             else if (pk.status == 0) {
                 RayDir rd;
                 dev_ray_dir(S, pk, rd); rd.phi2 = (float)phi2;
@@ -210,7 +211,7 @@ forward_kernel(DevState S, int nrays, const float *camx, const float *camy, cons
                                                         maxsub, o, radA, radB,
                                                         trace_cells ? trace_cells + (size_t)trace_cap * iray : nullptr,
                                                         trace_cap, ntrace, nsubA, nsubB, nptB);
-                if (e && o.ol == 0) set_err(err, e, iray);
+                if (e && o.ol == 0) set_err(err, e, iray + S.ray_base);
             }
             if (o.ol == 0) {
 #pragma unroll
@@ -249,19 +250,19 @@ forward_kernel_t(DevState S, int nrays, const float *camx, const float *camy, co
             const double mu2 = __ldg(&cammu[iray]), phi2 = __ldg(&camphi[iray]);
             const RayPack pk = dev_get_pack(S, packs, iray, camx, camy, camz, mu2, phi2);
             double radA = 0.0, radB = 0.0;
-            if (pk.status == 2) set_err(err, 2, iray);
+            if (pk.status == 2) set_err(err, 2, iray + S.ray_base);
             else if (pk.status == 0) {
                 RayDir rd;
                 dev_ray_dir(S, pk, rd); rd.phi2 = (float)phi2;
                 rd.hit = S.surfhits ? (SurfHit *)S.surfhits + iray : nullptr;
-                thread_ylmall_unpol(S, (float)mu2, (float)phi2, (float *)Y4, bt);
+                if (!S.viewsrc) thread_ylmall_unpol(S, (float)mu2, (float)phi2, (float *)Y4, bt);
                 const float sky = (-mu2 > 0.0) ? dev_sky_radiance(S, (float)mu2, (float)phi2) : 0.0f;
                 const int e = thread_march_forward<MODES>(S, Y4, bt, rd, mu2, pk.x0, pk.y0, pk.z0, sky,
                                                           correctinterpolate != 0, singlescatter != 0, nosurface != 0,
                                                           maxsub, radA, radB,
                                                           trace_cells ? trace_cells + (size_t)trace_cap * iray : nullptr,
                                                           trace_cap, ntrace, nsubA, nsubB, npt, nsh, nptB);
-                if (e) set_err(err, e, iray);
+                if (e) set_err(err, e, iray + S.ray_base);
                 else marched = 1;
             }
             if (MODES & 1) outA[iray] = (OUTA)radA;
@@ -282,6 +283,37 @@ forward_kernel_t(DevState S, int nrays, const float *camx, const float *camy, co
             }
         }
     }
+}
+
+// SRCEXT of every grid point for one direction (orthographic views): thread = grid point, the same arithmetic as a
+// ray's corner evaluation (thread_point_source), YLMDIR once per block in shared memory.  The march of the view's rays
+// then gathers 4 bytes per corner instead of contracting an SH block per (ray, corner).
+__global__ void __launch_bounds__(256)
+view_source_kernel(DevState S, float mu2, float phi2, RayDir rd, int singlescatter, float *viewsrc)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float4 *Y4 = (float4 *)smem_raw;
+    if (threadIdx.x == 0) thread_ylmall_unpol(S, mu2, phi2, (float *)Y4, 1);
+    __syncthreads();
+    for (int ip = 1 + blockIdx.x * blockDim.x + threadIdx.x; ip <= S.npts; ip += gridDim.x * blockDim.x) {
+        int ns;
+        viewsrc[ip - 1] = thread_point_source(S, Y4, 1, rd, singlescatter != 0, ip, __ldg(&S.ptrec[ip - 1]).w, ns);
+    }
+}
+
+cudaError_t launch_view_source(const DevState &S, const RayPack &pk, double mu2, double phi2, int singlescatter,
+                               float *viewsrc, cudaStream_t stream)
+{
+    RayDir rd;
+    memset(&rd, 0, sizeof(rd));
+    rd.f = pk.f; rd.j = pk.j; rd.cos22 = pk.cos22; rd.sin22 = pk.sin22;
+    int dev = 0, nsm = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    const int want = (S.npts + 255) / 256, cap = nsm * 8;
+    view_source_kernel<<<want < cap ? want : cap, 256, (size_t)S.nlmp * sizeof(float), stream>>>(
+        S, (float)mu2, (float)phi2, rd, singlescatter, viewsrc);
+    return cudaGetLastError();
 }
 
 // threads per block of the thread-per-ray kernels: as many YLMDIR columns (4*NLMP bytes) as fit

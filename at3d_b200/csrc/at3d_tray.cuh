@@ -73,6 +73,32 @@ __device__ __forceinline__ float thread_singscat_sum(const DevState &S, int ip, 
     return b;
 }
 
+// SRCEXT of one grid point for the direction whose YLMDIR is in Y4 (column stride bt): COMPUTE_SOURCE_1CELL_UNPOL
+// (shdomsub2.f:3046-3192) with the TMS-corrected SH block of the point, times the extinction
+__device__ __forceinline__ float thread_point_source(const DevState &S, const float4 *Y4, int bt, const RayDir &rd,
+                                                     bool singlescatter, int ip, float ext, int &ns)
+{
+    const int4 ps = __ldg(&S.ptsrc[ip - 1]);
+    ns = ps.y & 0xFFFF;
+    float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+    if (!singlescatter) {
+        const float4 *base = (const float4 *)(S.shsrc + ps.x);
+        const int n4 = AT3D_SHPAD(ns) >> 2;                 // multiple of 8
+#pragma unroll 1
+        for (int j = 0; j < n4; j += 4) {
+            const float4 s0 = __ldg(base + j), s1 = __ldg(base + j + 1), s2 = __ldg(base + j + 2), s3 = __ldg(base + j + 3);
+            const float4 y0 = Y4[(size_t)j * bt], y1 = Y4[(size_t)(j + 1) * bt];
+            const float4 y2 = Y4[(size_t)(j + 2) * bt], y3 = Y4[(size_t)(j + 3) * bt];
+            a0 = fmaf(s0.x, y0.x, a0); a1 = fmaf(s0.y, y0.y, a1); a2 = fmaf(s0.z, y0.z, a2); a3 = fmaf(s0.w, y0.w, a3);
+            a0 = fmaf(s1.x, y1.x, a0); a1 = fmaf(s1.y, y1.y, a1); a2 = fmaf(s1.z, y1.z, a2); a3 = fmaf(s1.w, y1.w, a3);
+            a0 = fmaf(s2.x, y2.x, a0); a1 = fmaf(s2.y, y2.y, a1); a2 = fmaf(s2.z, y2.z, a2); a3 = fmaf(s2.w, y2.w, a3);
+            a0 = fmaf(s3.x, y3.x, a0); a1 = fmaf(s3.y, y3.y, a1); a2 = fmaf(s3.z, y3.z, a2); a3 = fmaf(s3.w, y3.w, a3);
+        }
+    }
+    const float b = thread_singscat_sum(S, ip, ps, rd);
+    return (((a0 + a1) + (a2 + a3)) + b) * ext;
+}
+
 // Corner refresh of one thread.  Points shared with the previous cell are found with the reference's
 // DONEFACE rule (shdomsub2.f:2395-2397, 2509-2515): after crossing a face normal to axis `jf`, corner n
 // of the new cell can only coincide with corner n^bit of the old one; the ids decide.  Reused values
@@ -104,26 +130,16 @@ __device__ __forceinline__ void thread_refresh(const DevState &S, const CellRec 
         need &= need - 1;
         const int ip = SEL8(K.pt, n);
         const float4 pr = __ldg(&S.ptrec[ip - 1]);
-        const int4 ps = __ldg(&S.ptsrc[ip - 1]);
-        const int ns = ps.y & 0xFFFF;
-        float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
-        if (!singlescatter) {
-            const float4 *base = (const float4 *)(S.shsrc + ps.x);
-            const int n4 = AT3D_SHPAD(ns) >> 2;                 // multiple of 8
-#pragma unroll 1
-            for (int j = 0; j < n4; j += 4) {
-                const float4 s0 = __ldg(base + j), s1 = __ldg(base + j + 1), s2 = __ldg(base + j + 2), s3 = __ldg(base + j + 3);
-                const float4 y0 = Y4[(size_t)j * bt], y1 = Y4[(size_t)(j + 1) * bt];
-                const float4 y2 = Y4[(size_t)(j + 2) * bt], y3 = Y4[(size_t)(j + 3) * bt];
-                a0 = fmaf(s0.x, y0.x, a0); a1 = fmaf(s0.y, y0.y, a1); a2 = fmaf(s0.z, y0.z, a2); a3 = fmaf(s0.w, y0.w, a3);
-                a0 = fmaf(s1.x, y1.x, a0); a1 = fmaf(s1.y, y1.y, a1); a2 = fmaf(s1.z, y1.z, a2); a3 = fmaf(s1.w, y1.w, a3);
-                a0 = fmaf(s2.x, y2.x, a0); a1 = fmaf(s2.y, y2.y, a1); a2 = fmaf(s2.z, y2.z, a2); a3 = fmaf(s2.w, y2.w, a3);
-                a0 = fmaf(s3.x, y3.x, a0); a1 = fmaf(s3.y, y3.y, a1); a2 = fmaf(s3.z, y3.z, a2); a3 = fmaf(s3.w, y3.w, a3);
-            }
+        float src;
+        if (S.viewsrc) {
+            // all rays of this launch share their direction: the point's SRCEXT was evaluated once (view_source_kernel)
+            src = __ldg(&S.viewsrc[ip - 1]);
+            npt_eval++; nsh_eval += __ldg(&S.ptsrc[ip - 1]).y & 0xFFFF;
+        } else {
+            int ns;
+            src = thread_point_source(S, Y4, bt, rd, singlescatter, ip, pr.w, ns);
+            npt_eval++; nsh_eval += ns;
         }
-        const float b = thread_singscat_sum(S, ip, ps, rd);
-        const float src = (((a0 + a1) + (a2 + a3)) + b) * pr.w;
-        npt_eval++; nsh_eval += ns;
 #pragma unroll
         for (int k = 0; k < 8; k++)
             if (k == n) { K.x[k] = pr.x; K.y[k] = pr.y; K.z[k] = pr.z; K.ext[k] = pr.w; K.src[k] = src; }

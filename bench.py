@@ -109,6 +109,25 @@ def compute_source_leg(B, st, steps, warmup, oracle=None):
     return out
 
 
+def orthographic_leg(dev, sc, npix_side, steps, warmup):
+    """RENDER of 9 orthographic views (all rays of a view share their direction): the library evaluates the source of
+    every grid point once per view (view_source_kernel) instead of once per (ray, corner).  Host ray arrays through the
+    C ABI; kernel ms = CUDA events around the launches inside the call."""
+    from at3d_b200 import synthetic as S
+    m = sc.meta
+    res = max(m['xmax'], m['ymax']) / npix_side
+    views = [S.orthographic_rays(sc, abs(z), 0.0 if z >= 0 else 180.0, res)[0] for z in VIEW_ZENITHS]
+    rays = S.concat_rays(views)
+    ms, wall = [], []
+    for i in range(warmup + steps):
+        t = time.perf_counter()
+        o = dev.render(rays, timing=True)
+        if i >= warmup:
+            ms.append(o[-1]); wall.append(time.perf_counter() - t)
+    return dict(rays=int(rays.nrays), kernel_ms=float(np.mean(ms)), rays_per_s=rays.nrays / (np.mean(ms) * 1e-3),
+                e2e_rays_per_s=rays.nrays / float(np.mean(wall)))
+
+
 def transform_leg(B, st, steps, warmup):
     """SH_TO_DO / DO_TO_SH on the workload's SOURCE / RADIANCE: kernel ms (CUDA events inside the
     C-ABI call), FP32 FMA rate against the CUDA-core peak and bytes against HBM."""
@@ -331,6 +350,7 @@ def render_only(args, dev, st, sc, rays, dr, l2flush, stream, barrier, world, ra
                               surface_ms=ms_ocean - ms_lamb, surface_hits=c_ocean['surface_hits'],
                               brdf_evals=c_ocean['surface_hits'] * 4 * (st.nang // 2 + 1)),
             compute_source=csrc, transforms=transform_leg(B, st, args.steps, args.warmup),
+            render_orthographic=orthographic_leg(dev, sc, int(round((nrays / 9) ** 0.5)), args.steps, args.warmup),
             clocks=cs.summary(), cpu_baseline=None, wall_s=wall)
         print(json.dumps(line))
 
@@ -568,6 +588,7 @@ def main():
                         achieved_gbs=rbytes / (np.mean(rms) * 1e-3) / 1e9, frac=rbytes / (np.mean(rms) * 1e-3) / 1e9 / peak,
                         algorithmic_bytes=rbytes, counts=rcounts),
             compute_source=csrc, transforms=transform_leg(B, st, args.steps, args.warmup),
+            render_orthographic=orthographic_leg(dev, sc, cfg['pixels_per_view'] ** 0.5, args.steps, args.warmup),
             render_ocean=dict(rays_per_s=nrays / (np.mean(oms) * 1e-3), kernel_ms=float(np.mean(oms)),
                               surface_ms=float(np.mean(oms) - np.mean(rms)), surface_hits=ocounts['surface_hits'],
                               brdf_evals=ocounts['surface_hits'] * 4 * (st.nang // 2 + 1)),
