@@ -425,7 +425,7 @@ extern "C" int at3d_render(at3d_state *st, const at3d_rays *rays, float *stokes,
     // evaluated once per grid point (view_source_kernel) instead of once per (ray, corner); same arithmetic per point.
     std::vector<size_t> seg_start, seg_len;
     std::vector<char> seg_view;
-    if (host && tray_block_threads(S) > 0 && st->view_min_rays > 0) {
+    if (host && st->view_min_rays > 0) {
         const double *hmu = rays->cammu, *hphi = rays->camphi;
         size_t i = 0;
         while (i < n) {
@@ -443,7 +443,7 @@ extern "C" int at3d_render(at3d_state *st, const at3d_rays *rays, float *stokes,
         const size_t s0 = seg_start[sgi], sn = seg_len[sgi];
         DevState Sg = S;
         if (seg_view[sgi]) {
-            CUDA_TRY(st->viewsrc.reserve((size_t)S.npts * sizeof(float)));
+            CUDA_TRY(st->viewsrc.reserve((size_t)S.npts * nst * sizeof(float)));
             CUDA_TRY(launch_view_source(S, st->packs_h[s0], rays->cammu[s0], rays->camphi[s0], singlescatter,
                                         (float *)st->viewsrc.p, stream));
             Sg.viewsrc = (const float *)st->viewsrc.p;

@@ -260,6 +260,21 @@ __device__ __forceinline__ void refresh_corners(const DevState &S, const CellRec
     float b[NST];
 #pragma unroll
     for (int k = 0; k < NST; k++) b[k] = 0.0f;
+    if (S.viewsrc) {
+        // all rays of this launch share their direction: SRCEXT of the point was evaluated once (view_source_kernel_oct)
+        if (!hit) {
+            const float4 pr = __ldg(&S.ptrec[myp - 1]);
+            K.x = pr.x; K.y = pr.y; K.z = pr.z; K.ext = pr.w;
+#pragma unroll
+            for (int k = 0; k < NST; k++) K.src[k] = __ldg(&S.viewsrc[k + NST * (size_t)(myp - 1)]);
+        }
+        const unsigned nw = oct_ballot(o, !hit);
+        npt_eval += __popc(nw);
+        int nsm = hit ? 0 : (__ldg(&S.ptsrc[myp - 1]).y & 0xFFFF);         // work counters as in the generic path
+        nsm += __shfl_xor_sync(o.m, nsm, 4, 8); nsm += __shfl_xor_sync(o.m, nsm, 2, 8); nsm += __shfl_xor_sync(o.m, nsm, 1, 8);
+        nsh_eval += nsm;
+        return;
+    }
     if (!hit) load_corner<NST>(S, myp, rd, K.x, K.y, K.z, K.ext, soff, sns, b);
     unsigned need = oct_ballot(o, !hit);
     npt_eval += __popc(need);

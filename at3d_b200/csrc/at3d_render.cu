@@ -204,7 +204,7 @@ forward_kernel(DevState S, int nrays, const float *camx, const float *camy, cons
                 dev_ray_dir(S, pk, rd); rd.phi2 = (float)phi2;
                 rd.hit = S.surfhits ? (SurfHit *)S.surfhits + iray : nullptr;
                 __syncwarp(o.m);
-                group_ylmall(S, (float)mu2, (float)phi2, Ysh, o.ol, AT3D_OCT, o.m);
+                if (!S.viewsrc) group_ylmall(S, (float)mu2, (float)phi2, Ysh, o.ol, AT3D_OCT, o.m);
                 const float sky = (-mu2 > 0.0) ? dev_sky_radiance(S, (float)mu2, (float)phi2) : 0.0f;
                 const int e = march_forward<NST, MODES>(S, Ysh, rd, mu2, pk.x0, pk.y0, pk.z0, sky,
                                                         correctinterpolate != 0, singlescatter != 0, nosurface != 0,
@@ -301,6 +301,42 @@ view_source_kernel(DevState S, float mu2, float phi2, RayDir rd, int singlescatt
     }
 }
 
+// The same for the octet kernels (NSTOKES=3, or NSTOKES=1 when NLM is too large for the thread-per-ray layout): an
+// octet evaluates one grid point exactly as refresh_corners does (load_corner, sh_dot_partial, oct_sum), YLMDIR once
+// per block.
+template <int NST>
+__global__ void __launch_bounds__(AT3D_RAY_THREADS)
+view_source_kernel_oct(DevState S, float mu2, float phi2, RayDir rd, int singlescatter, float *viewsrc)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float *Ysh = (float *)smem_raw;
+    const Oct o = oct_id();
+    if (threadIdx.x < 32) group_ylmall(S, mu2, phi2, Ysh, threadIdx.x, 32, FULLMASK);
+    __syncthreads();
+    const int octs = (gridDim.x * blockDim.x) >> 3;
+    const int first = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    // whole warps iterate together (4 points per warp and iteration) so that the octet shuffles stay converged
+    for (int base = first - ((threadIdx.x & 31) >> 3); base < S.npts; base += octs) {
+        const int ip0 = base + ((threadIdx.x & 31) >> 3);          // 0-based
+        const bool valid = ip0 < S.npts;
+        const int ip = valid ? ip0 + 1 : 1;
+        float x, y, z, ext, b[NST], a[NST];
+        int soff, sns;
+        load_corner<NST>(S, ip, rd, x, y, z, ext, soff, sns, b);
+#pragma unroll
+        for (int k = 0; k < NST; k++) a[k] = 0.0f;
+        if (!singlescatter) {
+            sh_dot_partial<NST>(S.shsrc + soff, AT3D_SHPAD(sns), Ysh, S.nlmp, o, a);
+#pragma unroll
+            for (int k = 0; k < NST; k++) a[k] = oct_sum(o.m, a[k]);
+        }
+        if (valid && o.ol == 0) {
+#pragma unroll
+            for (int k = 0; k < NST; k++) viewsrc[k + NST * (size_t)ip0] = (a[k] + b[k]) * ext;
+        }
+    }
+}
+
 cudaError_t launch_view_source(const DevState &S, const RayPack &pk, double mu2, double phi2, int singlescatter,
                                float *viewsrc, cudaStream_t stream)
 {
@@ -310,9 +346,21 @@ cudaError_t launch_view_source(const DevState &S, const RayPack &pk, double mu2,
     int dev = 0, nsm = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
-    const int want = (S.npts + 255) / 256, cap = nsm * 8;
-    view_source_kernel<<<want < cap ? want : cap, 256, (size_t)S.nlmp * sizeof(float), stream>>>(
-        S, (float)mu2, (float)phi2, rd, singlescatter, viewsrc);
+    if (tray_block_threads(S) > 0) {
+        const int want = (S.npts + 255) / 256, cap = nsm * 8;
+        view_source_kernel<<<want < cap ? want : cap, 256, (size_t)S.nlmp * sizeof(float), stream>>>(
+            S, (float)mu2, (float)phi2, rd, singlescatter, viewsrc);
+    } else {
+        const int per = AT3D_RAY_THREADS / 8;
+        const int want = (S.npts + per - 1) / per, cap = nsm * 8;
+        const size_t smem = (size_t)S.ny_comp * S.nlmp * sizeof(float);
+        if (S.nstokes == 1)
+            view_source_kernel_oct<1><<<want < cap ? want : cap, AT3D_RAY_THREADS, smem, stream>>>(
+                S, (float)mu2, (float)phi2, rd, singlescatter, viewsrc);
+        else
+            view_source_kernel_oct<3><<<want < cap ? want : cap, AT3D_RAY_THREADS, smem, stream>>>(
+                S, (float)mu2, (float)phi2, rd, singlescatter, viewsrc);
+    }
     return cudaGetLastError();
 }
 
