@@ -384,6 +384,29 @@ int stage_rays(at3d_state *st, const at3d_rays *rays, cudaStream_t stream, const
     return 0;
 }
 
+// Runs of rays with one common direction (orthographic views; host ray arrays only) of at least view_min_rays rays
+// get a pre-evaluated view source; everything in between is merged into generic segments.
+void view_segments(const at3d_state *st, const at3d_rays *rays, std::vector<size_t> &seg_start,
+                   std::vector<size_t> &seg_len, std::vector<char> &seg_view)
+{
+    const size_t n = rays->nrays;
+    seg_start.clear(); seg_len.clear(); seg_view.clear();
+    if (rays->memspace == AT3D_MEM_HOST && st->view_min_rays > 0) {
+        const double *hmu = rays->cammu, *hphi = rays->camphi;
+        size_t i = 0;
+        while (i < n) {
+            size_t j = i + 1;
+            while (j < n && hmu[j] == hmu[i] && hphi[j] == hphi[i]) j++;
+            const bool view = (j - i) >= (size_t)st->view_min_rays;
+            if (!seg_view.empty() && !view && !seg_view.back()) seg_len.back() += j - i;
+            else { seg_start.push_back(i); seg_len.push_back(j - i); seg_view.push_back(view ? 1 : 0); }
+            i = j;
+        }
+    } else if (n > 0) {
+        seg_start.push_back(0); seg_len.push_back(n); seg_view.push_back(0);
+    }
+}
+
 extern "C" int at3d_render(at3d_state *st, const at3d_rays *rays, float *stokes,
                            int correctinterpolate, int singlescatter, int nosurface,
                            const at3d_trace *trace, void *cuda_stream, double *kernel_ms, char *errmsg)
@@ -425,20 +448,7 @@ extern "C" int at3d_render(at3d_state *st, const at3d_rays *rays, float *stokes,
     // evaluated once per grid point (view_source_kernel) instead of once per (ray, corner); same arithmetic per point.
     std::vector<size_t> seg_start, seg_len;
     std::vector<char> seg_view;
-    if (host && st->view_min_rays > 0) {
-        const double *hmu = rays->cammu, *hphi = rays->camphi;
-        size_t i = 0;
-        while (i < n) {
-            size_t j = i + 1;
-            while (j < n && hmu[j] == hmu[i] && hphi[j] == hphi[i]) j++;
-            const bool view = (j - i) >= (size_t)st->view_min_rays;
-            if (!seg_view.empty() && !view && !seg_view.back()) seg_len.back() += j - i;
-            else { seg_start.push_back(i); seg_len.push_back(j - i); seg_view.push_back(view ? 1 : 0); }
-            i = j;
-        }
-    } else {
-        seg_start.push_back(0); seg_len.push_back(n); seg_view.push_back(0);
-    }
+    view_segments(st, rays, seg_start, seg_len, seg_view);
     for (size_t sgi = 0; sgi < seg_start.size(); sgi++) {
         const size_t s0 = seg_start[sgi], sn = seg_len[sgi];
         DevState Sg = S;

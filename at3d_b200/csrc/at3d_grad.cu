@@ -1314,9 +1314,26 @@ static int gradient_impl(at3d_state *st, const at3d_rays *rays, const at3d_grad_
         Sf.counts = nullptr;
         CUDA_TRY(cudaMemsetAsync(st->counts_dev, 0, 8 * sizeof(unsigned long long), stream));
         CUDA_TRY(cudaMemsetAsync(npt, 0, sizeof(int) * (n + 1), stream));
-        CUDA_TRY(launch_forward(Sf, (int)n, camx, camy, camz, cammu, camphi, packs, nullptr, visrad, total, 3, 1,
-                                G.singlescatter, 0, G.maxsub, nullptr, 0, nullptr, nullptr, (RayErr *)st->err.p,
-                                st->ray_counter, npt, stream));
+        // orthographic views (runs of rays with one direction) read a per-view source evaluated once per grid point
+        std::vector<size_t> seg_start, seg_len;
+        std::vector<char> seg_view;
+        view_segments(st, rays, seg_start, seg_len, seg_view);
+        for (size_t sgi = 0; sgi < seg_start.size(); sgi++) {
+            const size_t s0 = seg_start[sgi], sn = seg_len[sgi];
+            DevState Sg = Sf;
+            Sg.ray_base = (int)s0;
+            if (seg_view[sgi]) {
+                CUDA_TRY(st->viewsrc.reserve((size_t)S.npts * nst * sizeof(float)));
+                CUDA_TRY(launch_view_source(Sf, st->packs_h[s0], rays->cammu[s0], rays->camphi[s0], G.singlescatter,
+                                            (float *)st->viewsrc.p, stream));
+                Sg.viewsrc = (const float *)st->viewsrc.p;
+            }
+            CUDA_TRY(launch_forward(Sg, (int)sn, camx ? camx + s0 : nullptr, camy ? camy + s0 : nullptr,
+                                    camz ? camz + s0 : nullptr, cammu + s0, camphi + s0, packs ? packs + s0 : nullptr,
+                                    nullptr, visrad + (size_t)nst * s0, total + (size_t)nst * s0, 3, 1,
+                                    G.singlescatter, 0, G.maxsub, nullptr, 0, nullptr, nullptr, (RayErr *)st->err.p,
+                                    st->ray_counter, npt + s0, stream));
+        }
         // visit records of a ray are contiguous: offsets = exclusive scan (64-bit) of the per-ray visit counts
         {
             cub::TransformInputIterator<long long, IntToLL, const int *> it(npt, IntToLL());

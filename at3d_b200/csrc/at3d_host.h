@@ -59,6 +59,8 @@ cudaError_t launch_build_ptrec(int npts, const float *gridpos, const float *tota
 cudaError_t launch_build_ptsrc(int npts, int kmax, const int2 *srcrec, const int *sscount, const int2 *ssent,
                                int4 *ptsrc, cudaStream_t s);
 cudaError_t launch_lambertian_boundary(const DevState &S, const float *fluxes, float *bcrad, cudaStream_t s);
+void view_segments(const at3d_state *st, const at3d_rays *rays, std::vector<size_t> &seg_start,
+                   std::vector<size_t> &seg_len, std::vector<char> &seg_view);
 cudaError_t launch_view_source(const DevState &S, const RayPack &pk, double mu2, double phi2, int singlescatter,
                                float *viewsrc, cudaStream_t stream);
 int tray_block_threads(const DevState &S);

@@ -182,3 +182,24 @@ def test_jacobian_path_matches_oracle_single_sweep(case, gkw, oracle):
         for idr in range(jref.shape[1]):
             scale = np.max(np.abs(jref[k, idr]))
             np.testing.assert_allclose(jac[k, idr], jref[k, idr], rtol=RTOL, atol=RTOL * scale)
+
+
+@pytest.mark.parametrize('case', ['scalar_periodic_split', 'polarized_periodic_split'])
+def test_gradient_with_orthographic_views(case, oracle):
+    """Runs of >= 256 rays with one direction: the forward pass of the gradient reads the per-view source
+    (view_source_kernel[_oct]); cost, pixel values and gradient against the oracle at the usual bars."""
+    from at3d_b200.device import DeviceState
+    from at3d_b200 import gradsetup, synthetic as S
+    sc = scenes.make(case, oracle)
+    views = [S.orthographic_rays(sc, z, a, 0.016)[0] for z, a in ((0.0, 0.0), (50.0, 200.0))]
+    rays = S.concat_rays(views)
+    assert min(v.nrays for v in views) >= 256
+    gi = gradsetup.make_gradient_inputs(sc, oracle, seed=11, numder=2)
+    rad = oracle.render(sc.state, rays)
+    pix = gradsetup.make_pixels(sc.state.nstokes, rays.nrays, rad, seed=5)
+    ref = oracle.levisapprox_gradient(sc.state, rays, gradsetup.with_pixels(gi, pix), trace_cap=128)
+    dev = DeviceState(sc.state)
+    dev.attach_gradient(gi)
+    out = dev.gradient(rays, pix, trace_cap=128)
+    dev.close()
+    check(ref, out)
