@@ -64,12 +64,11 @@ def make_scene(nx=8, ny=8, nz=9, nmu=8, nphi=16, nstokes=1, bc='periodic', dx=0.
                cloud='blob', ext_max=20.0, ssalb=1.0, rayleigh=False, numphase=5, mix_fraction=0.3,
                deltam=True, solarmu=-0.5, solaraz=0.3, solarflux=1.0, gndalbedo=0.05,
                nsplits=0, truncate=True, seed=0, tautol=0.1, transcut=1e-5, with_radiance=True,
-               variable_sfc=False):
+               variable_sfc=False, ipflag=0):
     """Build a complete synthetic ``ShdomState`` (+ its ``PropertyGrid``)."""
     rng = np.random.default_rng(seed)
     nstleg = 1 if nstokes == 1 else 6
     ml, mm, nlm = G.sh_sizes(nmu, nphi)
-    ipflag = 0
     bcflag = 0
     if bc == 'open':
         bcflag = 3

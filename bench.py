@@ -128,6 +128,44 @@ def orthographic_leg(dev, sc, npix_side, steps, warmup):
                 e2e_rays_per_s=rays.nrays / float(np.mean(wall)))
 
 
+def solver_leg(steps, warmup, oracle=None, n=96, nz=48):
+    """One SHDOM solution iteration (PATH_INTEGRATION + COMPUTE_SOURCE) on an independent-pixel grid
+    of n x n columns x nz levels, NLM=256: kernel ms on the GPU (CUDA events inside the two C-ABI calls) and, when the
+    oracle is given, the same iteration of the reference algorithm on one host core."""
+    from at3d_b200 import synthetic as S, backend as B, solver
+    sc = S.make_scene(nx=n, ny=n, nz=nz, nmu=16, nphi=32, nstokes=1, bc='periodic', dx=0.02, dy=0.02, dz=0.04,
+                      cloud='les', ext_max=40.0, numphase=8, nsplits=0, seed=3, truncate=False, ipflag=3, mix_fraction=0.0)
+    B.finalize_scene(sc)
+    st = sc.state
+    delphi = np.float32(2.0 * np.pi) / st.nphi0.astype(np.float32)
+    wtmu = (st.wtdo[:, 0] / delphi).astype(np.float32)
+    npts = st.npts
+    maxiv = st.nlm * npts
+    source = np.zeros((1, maxiv), np.float32, order='F')
+    tot = int(st.shptr[npts])
+    source[:, :tot] = st.source[:, :tot]
+    delsource = np.zeros((1, maxiv), np.float32, order='F')
+    rshptr = solver.radiance_truncation(st, st.shptr, st.radiance, st.rshptr, False, 0.0, False, maxiv + npts)
+    pms, cms = [], []
+    for i in range(warmup + steps):
+        rad, fluxes, bcrad, ms = solver.path_integration_ip(st, wtmu, st.shptr, source, rshptr, timing=True)
+        st2 = st.copy(); st2.rshptr, st2.radiance = rshptr, rad
+        res = B.compute_source(st2, st.shptr, source, st.shptr.copy(), delsource, maxiv=maxiv, timing=True)
+        if i >= warmup:
+            pms.append(ms); cms.append(res[-1])
+    out = dict(grid='%dx%dx%d independent-pixel columns' % (n, n, nz), npts=int(npts), nang=int(st.nphi0.sum()),
+               path_integration_ms=float(np.mean(pms)), compute_source_ms=float(np.mean(cms)),
+               iteration_ms=float(np.mean(pms) + np.mean(cms)))
+    if oracle is not None:
+        # the oracle's solve runs the same two routines per iteration; time one iteration
+        t = time.perf_counter()
+        oracle.solve_fixed_grid(st, wtmu, maxiter=1, solacc=1e-9)
+        out['cpu_iteration_ms'] = 1e3 * (time.perf_counter() - t)
+        out['cpu_cores'] = 1
+        out['cpu_note'] = 'oracle solve with maxiter=1: first-guess COMPUTE_SOURCE + one full iteration'
+    return out
+
+
 def transform_leg(B, st, steps, warmup):
     """SH_TO_DO / DO_TO_SH on the workload's SOURCE / RADIANCE: kernel ms (CUDA events inside the
     C-ABI call), FP32 FMA rate against the CUDA-core peak and bytes against HBM."""
@@ -589,6 +627,7 @@ def main():
                         algorithmic_bytes=rbytes, counts=rcounts),
             compute_source=csrc, transforms=transform_leg(B, st, args.steps, args.warmup),
             render_orthographic=orthographic_leg(dev, sc, cfg['pixels_per_view'] ** 0.5, args.steps, args.warmup),
+            solver_iteration=solver_leg(max(1, args.steps // 2), 1, orc if args.workload == 'cfg2' else None),
             render_ocean=dict(rays_per_s=nrays / (np.mean(oms) * 1e-3), kernel_ms=float(np.mean(oms)),
                               surface_ms=float(np.mean(oms) - np.mean(rms)), surface_hits=ocounts['surface_hits'],
                               brdf_evals=ocounts['surface_hits'] * 4 * (st.nang // 2 + 1)),
