@@ -757,3 +757,18 @@ int oracle_do_to_sh_all(const oracle_state *st, const float *wtmu, const int *rs
     free(work); free(aztab); free_sh_do_coef(c);
     return 0;
 }
+
+/* RADIANCE_TRUNCATION alone (parity check of the host-side restatement in at3d_b200/solver.py) */
+int oracle_radiance_truncation(const oracle_state *st, int highorderrad, const int *shptr, const float *radiance,
+                               int maxir, int fixsh, float shacc, int *rshptr)
+{
+    int *lofj = (int *)malloc(sizeof(int) * st->nlm);
+    int j = 0, l, m, rc;
+    for (l = 0; l <= st->ml; l++) {
+        const int me = l < st->mm ? l : st->mm;
+        for (m = -me; m <= me; m++) lofj[j++] = l;
+    }
+    rc = radiance_truncation(st, highorderrad, shptr, radiance, maxir, fixsh, shacc, rshptr, lofj);
+    free(lofj);
+    return rc;
+}

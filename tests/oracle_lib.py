@@ -340,3 +340,17 @@ def do_to_sh(state, wtmu, rshptr, dofield):
     fn.argtypes = [P(OracleState), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     fn(C.byref(d), _vp(wtmu), _vp(rshptr), _vp(dofield), _vp(out))
     return out
+
+
+def radiance_truncation(state, shptr, radiance, rshptr, fixsh, shacc, highorderrad, maxir):
+    st = state.copy().normalize()
+    d = st.fill(OracleState())
+    shptr = np.ascontiguousarray(shptr, np.int32)
+    radiance = np.asfortranarray(radiance, np.float32)
+    out = np.array(rshptr, np.int32)
+    fn = lib().oracle_radiance_truncation
+    fn.argtypes = [P(OracleState), i32, C.c_void_p, C.c_void_p, i32, i32, f32, C.c_void_p]
+    rc = fn(C.byref(d), int(highorderrad), _vp(shptr), _vp(radiance), int(maxir), int(fixsh), shacc, _vp(out))
+    if rc:
+        raise OracleError('RADIANCE_TRUNCATION: out of memory')
+    return out

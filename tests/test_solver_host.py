@@ -1,0 +1,29 @@
+"""Host-side logic of the fixed-grid solve (at3d_b200/solver.py) against the oracle, no GPU needed."""
+import numpy as np
+import pytest
+import oracle_lib as O
+import scenes
+from at3d_b200 import solver
+
+
+@pytest.mark.parametrize('case', ['scalar_periodic_split', 'rayleigh_two_species', 'polarized_rayleigh_varsfc',
+                                  'scalar_no_deltam'])
+@pytest.mark.parametrize('mode', ['adaptive', 'shacc', 'fixsh', 'highorder'])
+def test_radiance_truncation_matches_oracle(case, mode):
+    st = scenes.make(case, O).state
+    kw = dict(fixsh=mode == 'fixsh', shacc=2e-3 if mode == 'shacc' else 0.0, highorderrad=mode == 'highorder',
+              maxir=st.nlm * st.npts + st.npts)
+    ref = O.radiance_truncation(st, st.shptr, st.radiance, st.rshptr, **kw)
+    out = solver.radiance_truncation(st, st.shptr, st.radiance, st.rshptr, **kw)
+    np.testing.assert_array_equal(out, ref)
+    assert out[st.npts] > 0 and out[st.npts + 1] == out[st.npts]
+
+
+def test_radiance_truncation_out_of_memory_falls_back():
+    st = scenes.make('scalar_periodic_split', O).state
+    tight = int(np.sum(np.maximum(4, np.diff(st.shptr[:st.npts + 1])))) + 1     # room for the FIXSH layout only
+    ref = O.radiance_truncation(st, st.shptr, st.radiance, st.rshptr, False, 0.0, False, tight)
+    out = solver.radiance_truncation(st, st.shptr, st.radiance, st.rshptr, False, 0.0, False, tight)
+    np.testing.assert_array_equal(out, ref)
+    with pytest.raises(MemoryError):
+        solver.radiance_truncation(st, st.shptr, st.radiance, st.rshptr, True, 0.0, False, 10)
