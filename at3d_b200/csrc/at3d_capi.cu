@@ -413,6 +413,7 @@ extern "C" int at3d_render(at3d_state *st, const at3d_rays *rays, float *stokes,
 {
     if (errmsg) errmsg[0] = 0;
     if (!st || !rays || !stokes) { set_msg(errmsg, "null argument"); return 1; }
+    std::lock_guard<std::mutex> lock(st->mu);
     cudaStream_t stream = (cudaStream_t)cuda_stream;
     const size_t n = rays->nrays;
     const int nst = st->S.nstokes;

@@ -1091,6 +1091,7 @@ extern "C" int at3d_state_attach_gradient(at3d_state *st, const at3d_grad_desc *
 {
     if (errmsg) errmsg[0] = 0;
     if (!st || !g) { set_msg(errmsg, "null argument"); return 1; }
+    std::lock_guard<std::mutex> lock(st->mu);
     if (!st->S.radrec) { set_msg(errmsg, "the state was created without RADIANCE/RSHPTR: the gradient needs them"); return 1; }
     if (g->numder < 1) { set_msg(errmsg, "NUMDER must be >= 1"); return 1; }
     if (st->S.srctype != 'S') { set_msg(errmsg, "the gradient is implemented for SRCTYPE='S' (solar) only"); return 3; }
@@ -1226,6 +1227,8 @@ static int gradient_impl(at3d_state *st, const at3d_rays *rays, const at3d_grad_
                          const at3d_trace *trace, void *cuda_stream, double *kernel_ms,
                          int njac, const int32_t *jacobianptr, float *jacobian, char *errmsg)
 {
+    std::unique_lock<std::mutex> lock;
+    if (st) lock = std::unique_lock<std::mutex>(st->mu);
     if (errmsg) errmsg[0] = 0;
     if (!st || !rays || !g || !gradout || !cost || !stokesout) { set_msg(errmsg, "null argument"); return 1; }
     if (!st->grad_attached) { set_msg(errmsg, "at3d_state_attach_gradient must be called first"); return 1; }

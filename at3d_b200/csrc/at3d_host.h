@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <vector>
+#include <mutex>
 #include <string>
 #include "at3d_device.cuh"
 #include "../../include/at3d_b200.h"
@@ -43,6 +44,8 @@ struct at3d_state {
     std::vector<int> nr_h;          // radiance SH length per point (host copy, for the gradient tables)
     int *ray_counter = nullptr;     // work counter of the persistent ray kernels
     int nbcrad = 0;
+    std::mutex mu;                  // the per-call buffers above are shared: calls on one state are serialised (the
+                                    // reference calls RENDER from several joblib threads on slices of the rays)
     int view_min_rays = 256;        // shortest run of equal-direction rays that gets a pre-evaluated view source (0: off)
 };
 

@@ -116,3 +116,36 @@ def test_orthographic_views_use_one_source_per_grid_point(case, oracle):
     np.testing.assert_allclose(out[0], ref[0], rtol=1e-4, atol=1e-6 * ref[0].max())
     if sc.state.nstokes > 1:
         np.testing.assert_allclose(out[1:], ref[1:], rtol=1e-4, atol=1e-6)
+
+
+def test_concurrent_render_calls_on_slices(oracle):
+    """The reference calls RENDER from several joblib threads on slices of the ray arrays with one shared state
+    (at3d/solver.py:681-759, at3d/parallel.py:114-174).  Calls on one state are serialised inside the library; the
+    concatenated slices equal one call over all rays bit for bit."""
+    import threading
+    from at3d_b200.device import DeviceState
+    from at3d_b200.state import Rays
+    sc = scenes.make('scalar_periodic_split', oracle)
+    rays = scenes.ray_set(sc)
+    dev = DeviceState(sc.state)
+    whole = dev.render(rays)
+    nthreads = 4
+    bounds = np.linspace(0, rays.nrays, nthreads + 1).astype(int)
+    parts = [None] * nthreads
+    errors = []
+
+    def work(k):
+        try:
+            s = slice(bounds[k], bounds[k + 1])
+            for _ in range(3):
+                parts[k] = dev.render(Rays(rays.camx[s], rays.camy[s], rays.camz[s], rays.cammu[s], rays.camphi[s]))
+        except Exception as e:  # noqa: BLE001
+            errors.append(e)
+    ts = [threading.Thread(target=work, args=(k,)) for k in range(nthreads)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errors, errors
+    np.testing.assert_array_equal(np.concatenate(parts, axis=1), whole)
+    dev.close()
