@@ -41,6 +41,8 @@ struct PiArgs {
     float *bcrad;              // [nst, ntop + nbot*(1 or 1+nang/2)]
     float *botrad;             // [nst, nbot, nang/2] upwelling boundary radiance per upward ordinate (general BRDF)
     float *fluxes;             // [2, npts]
+    const int *botpt;          // [nbot] 0-based grid point of bottom boundary point ibc (null: column layout nz*ibc)
+    const float *fluxsrc;      // field the hemispheric fluxes are summed from (null: dofield)
 };
 
 // one backward step of BACK_INT_GRID1D (shdomsub1.f:4404-4447): radiance at a point from the known radiance rad0 at the
@@ -173,9 +175,10 @@ __global__ void pi_flux_kernel(PiArgs a, int up)
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= a.npts) return;
     const int nh = a.nang / 2;
+    const float *f = a.fluxsrc ? a.fluxsrc : a.dofield;
     float s = 0.0f;
     for (int ia = up ? nh : 0; ia < (up ? a.nang : nh); ia++)
-        s = s + a.ang_w[ia] * a.dofield[p + (size_t)a.npts * NST * ia];
+        s = s + a.ang_w[ia] * f[p + (size_t)a.npts * NST * ia];
     a.fluxes[up + 2 * (size_t)p] = s;
 }
 
@@ -184,7 +187,7 @@ __global__ void pi_lambertian_kernel(PiArgs a)
 {
     const int ibc = blockIdx.x * blockDim.x + threadIdx.x;
     if (ibc >= a.nbot) return;
-    const int i = a.nz * ibc;                         // bottom point of column ibc (0-based)
+    const int i = a.botpt ? a.botpt[ibc] : a.nz * ibc;   // bottom boundary point ibc (0-based)
     const float down = a.fluxes[2 * (size_t)i];
     float v = 0.0f;
     if (a.sfctype0 == 'F') {
@@ -225,7 +228,7 @@ __global__ void pi_brdf_kernel(PiArgs a)
     for (int k = 0; k < NST; k++) out[k] = 0.0f;
     if (a.srctype != 'T') {
         dev_surface_brdf(a.sfctype1, parms + 1, a.wavelen, mu2, phi2, a.solarmu, a.solaraz, NST, reflect);
-        const float df = a.dirflux[a.nz * ibc];
+        const float df = a.dirflux[a.botpt ? a.botpt[ibc] : a.nz * ibc];
 #pragma unroll
         for (int k = 0; k < NST; k++) out[k] = out[k] + opi * reflect[k] * df;
     }
@@ -363,6 +366,573 @@ extern "C" int at3d_path_integration_ip(const at3d_state_desc *d, const float *w
     if (e == cudaSuccess) e = cudaMemcpy(bcrad, a.bcrad, nbc * sizeof(float), cudaMemcpyDeviceToHost);
     tr_plan_destroy(P);
     if (e != cudaSuccess) { set_msg(errmsg, "CUDA error %s in at3d_path_integration_ip", cudaGetErrorString(e)); return 4; }
+    if (kernel_ms) *kernel_ms = ms;
+    return 0;
+}
+
+// =====================================================================================================================
+// 3-D grids: PATH_INTEGRATION with BACK_INT_GRID3D[_UNPOL] (src/polarized/shdomsub1.f:3354-4036) on a fixed grid.
+//
+// The reference visits the grid points of an ordinate serially in the order SWEEPING_ORDER built for the ordinate's
+// octant (:3261-3352); a point traces a ray backwards until it reaches a cell face whose four points already have a
+// radiance, i.e. were visited EARLIER in that order (or are boundary points of the hemisphere), and interpolates there.
+// Which face that is depends on the geometry and on the order only, never on the values, so the serial loop becomes a
+// data-flow kernel with the same results: thread = (ordinate, position r in the sweep order); a face point is "valid"
+// iff it is a preset boundary point or its position is < r (static test), and the thread then waits for the four
+// radiances it needs (GRIDRAD(1,.) = -1 marks "not yet", as in the reference).  Blocks take their (ordinate, chunk of
+// positions) from a ticket counter in chunk-major order, so everything a thread waits for belongs to a block that is
+// already running or done: the waits terminate (and are bounded anyway: a timeout raises an error instead of hanging).
+// All ordinates of a hemisphere run in ONE launch; the reference's loop over ordinates carries a dependence only
+// through the surface.
+// =====================================================================================================================
+struct OrdDir {
+    double cx, cy, cz, cxinv, cyinv, czinv;
+    int bitx, bity, bitz, ioct, joct, pad;
+};
+
+struct SwArgs {
+    DevState S;                 // cellrec / ptrec only
+    int npts, nang, nchunks, group;
+    const OrdDir *dir;          // [nang]
+    const int *sweepord;        // [noct][npts]  cell<<3 | corner-1 (SWEEPORD)
+    const int *rank;            // [noct][npts]  position of a point in the octant's order
+    const unsigned char *bflag; // [npts] bit 0: top boundary point, bit 1: bottom boundary point
+    const float *srcdo;         // [npts, nst, nang] discrete-ordinate source function
+    float *radf;                // [npts, nst, nang] radiance (GRIDRAD of every ordinate)
+    double eps, transmin;
+    int *ticket, *err;
+};
+
+__device__ __forceinline__ float ld_vol(const float *p) { return *(const volatile float *)p; }
+// GRIDFACE(n+1,kface) of BACK_INT_GRID3D: the four corners (1..8) of cell face kface (1..6: -x,+x,-y,+y,-z,+z)
+__device__ __forceinline__ int face_corner(int kface, int n)
+{
+    const int axis = (kface - 1) >> 1, s = (kface - 1) & 1;
+    if (axis == 0) return 1 + (s | ((n & 1) << 1) | ((n >> 1) << 2));
+    if (axis == 1) return 1 + ((n & 1) | (s << 1) | ((n >> 1) << 2));
+    return 1 + (n | (s << 2));
+}
+
+template <int NST>
+__global__ void __launch_bounds__(256) sweep3d_kernel(SwArgs a, int up)
+{
+    __shared__ int s_ticket;
+    if (threadIdx.x == 0) s_ticket = atomicAdd(a.ticket, 1);
+    __syncthreads();
+    const int nh = a.nang / 2, G = a.group, per = a.nchunks * G;
+    int t = s_ticket, grp = t / per, io, chunk;
+    const int ngrp = (nh + G - 1) / G;
+    if (grp >= ngrp - 1) {
+        grp = ngrp - 1;
+        const int gl = nh - grp * G;
+        t -= grp * per;
+        chunk = t / gl; io = grp * G + t % gl;
+    } else {
+        t -= grp * per;
+        chunk = t / G; io = grp * G + t % G;
+    }
+    const int r = chunk * 256 + threadIdx.x;
+    if (r >= a.npts) return;
+    const int ia = (up ? nh : 0) + io;
+    const OrdDir D = a.dir[ia];
+    const int *so_oct = a.sweepord + (size_t)a.npts * (D.joct - 1);
+    const int *rank = a.rank + (size_t)a.npts * (D.joct - 1);
+    const unsigned char bmask = up ? 2 : 1;
+    const int entry = so_oct[r];
+    const int ipcell = entry >> 3;
+    const DevState &S = a.S;
+    const int ipt = cell_gp(S, ipcell, (entry & 7) + 1);
+    if (a.bflag[ipt - 1] & bmask) return;                     // GRIDRAD(1,IPT) >= 0: preset boundary point
+    const size_t fo = (size_t)a.npts * NST * ia;
+    const float *src = a.srcdo + fo;
+    float *R = a.radf + fo;
+    const int ioct = D.ioct;
+    int icell = ipcell, fail = 0;
+    double transmit = 1.0, rad[NST], srcext1[NST], srcext0[NST];
+    float4 pp = __ldg(&S.ptrec[ipt - 1]);
+    double ext1 = (double)pp.w, ext0 = 0.0, f1 = 0, f2 = 0, f3 = 0, f4 = 0;
+    double xe = (double)pp.x, ye = (double)pp.y, ze = (double)pp.z;
+    int i1 = 0, i2 = 0, i3 = 0, i4 = 0;
+#pragma unroll
+    for (int k = 0; k < NST; k++) {
+        float s = __ldg(&src[(ipt - 1) + (size_t)a.npts * k]);
+        if (k == 0) s = fmaxf(0.0f, s);                       // PATH_INTEGRATION clamps the I source (shdomsub1.f:2001-2005)
+        rad[k] = 0.0; srcext1[k] = ext1 * (double)s;
+    }
+    for (;;) {
+        if (icell <= 0) { fail = 1; break; }
+        const CellRec c = load_cell(S, icell);
+        const bool ipinx = c.flags & 1, ipiny = c.flags & 2;
+        const float4 po = __ldg(&S.ptrec[c.gp[8 - ioct] - 1]);     // GRIDPTR(9-IOCT,ICELL)
+        const double sox = ipinx ? (double)1.0E20f : ((double)po.x - xe) * D.cxinv;
+        const double soy = ipiny ? (double)1.0E20f : ((double)po.y - ye) * D.cyinv;
+        const double soz = ((double)po.z - ze) * D.czinv;
+        const double so = fmin(fmin(sox, soy), soz);
+        if (so < -a.eps) { fail = 2; break; }
+        xe = xe + so * D.cx;
+        ye = ye + so * D.cy;
+        ze = ze + so * D.cz;
+        int iface, jface;
+        if (sox <= soz && sox <= soy) { iface = 2 - D.bitx; jface = 1; }
+        else if (soy <= soz) { iface = 4 - D.bity; jface = 2; }
+        else { iface = 6 - D.bitz; jface = 3; }
+        const int nb = c.nb[iface - 1];
+        int inextcell = nb;
+        if (nb < 0) inextcell = dev_next_cell(S, xe, ye, ze, iface, jface, nb);
+        int kface;
+        if (nb >= 0) {
+            kface = iface;
+            i1 = c.gp[face_corner(kface, 0) - 1]; i2 = c.gp[face_corner(kface, 1) - 1];
+            i3 = c.gp[face_corner(kface, 2) - 1]; i4 = c.gp[face_corner(kface, 3) - 1];
+        } else {
+            kface = ((iface - 1) ^ 1) + 1;                     // OPPFACE
+            i1 = cell_gp(S, inextcell, face_corner(kface, 0)); i2 = cell_gp(S, inextcell, face_corner(kface, 1));
+            i3 = cell_gp(S, inextcell, face_corner(kface, 2)); i4 = cell_gp(S, inextcell, face_corner(kface, 3));
+        }
+        const float4 p1 = __ldg(&S.ptrec[i1 - 1]), p2 = __ldg(&S.ptrec[i2 - 1]);
+        const float4 p3 = __ldg(&S.ptrec[i3 - 1]), p4 = __ldg(&S.ptrec[i4 - 1]);
+        double u, v;
+        if (jface == 1) {
+            u = (ze - (double)p1.z) / (double)(p3.z - p1.z);
+            v = ipiny ? 0.5 : (ye - (double)p1.y) / (double)(p2.y - p1.y);
+        } else if (jface == 2) {
+            u = (ze - (double)p1.z) / (double)(p3.z - p1.z);
+            v = ipinx ? 0.5 : (xe - (double)p1.x) / (double)(p2.x - p1.x);
+        } else {
+            u = ipiny ? 0.5 : (ye - (double)p1.y) / (double)(p3.y - p1.y);
+            v = ipinx ? 0.5 : (xe - (double)p1.x) / (double)(p2.x - p1.x);
+        }
+        if (inextcell > 0) {
+            const int pn = cell_gp(S, inextcell, ioct);
+            if (jface == 1) xe = (double)pt_coord(S, pn, 1);
+            else if (jface == 2) ye = (double)pt_coord(S, pn, 2);
+            else ze = (double)pt_coord(S, pn, 3);
+        }
+        f1 = (1 - u) * (1 - v);
+        f2 = (1 - u) * v;
+        f3 = u * (1 - v);
+        f4 = u * v;
+        ext0 = f1 * (double)p1.w + f2 * (double)p2.w + f3 * (double)p3.w + f4 * (double)p4.w;
+#pragma unroll
+        for (int k = 0; k < NST; k++) {
+            const size_t ko = (size_t)a.npts * k;
+            float s1 = __ldg(&src[(i1 - 1) + ko]), s2 = __ldg(&src[(i2 - 1) + ko]);
+            float s3 = __ldg(&src[(i3 - 1) + ko]), s4 = __ldg(&src[(i4 - 1) + ko]);
+            if (k == 0) { s1 = fmaxf(0.0f, s1); s2 = fmaxf(0.0f, s2); s3 = fmaxf(0.0f, s3); s4 = fmaxf(0.0f, s4); }
+            srcext0[k] = f1 * (double)s1 * (double)p1.w + f2 * (double)s2 * (double)p2.w
+                       + f3 * (double)s3 * (double)p3.w + f4 * (double)s4 * (double)p4.w;
+        }
+        const double ext = 0.5 * (ext0 + ext1);
+        const double tau = ext * so;
+        double transcell, abscell, sc[NST];
+        if (tau >= 0.5) { transcell = exp(-tau); abscell = 1.0 - transcell; }
+        else { abscell = tau * (1.0 - 0.5 * tau * (1.0 - 0.33333333333 * tau * (1 - 0.25 * tau))); transcell = 1.0 - abscell; }
+        if (tau <= 2.0) {
+            if (ext == 0.0) {
+#pragma unroll
+                for (int k = 0; k < NST; k++) sc[k] = 0.0;
+            } else {
+#pragma unroll
+                for (int k = 0; k < NST; k++)
+                    sc[k] = (0.5 * (srcext0[k] + srcext1[k]) + 0.08333333333 * (ext0 * srcext1[k] - ext1 * srcext0[k]) * so) / ext;
+            }
+        } else {
+            double ext0p = ext0, srcext0p[NST];
+#pragma unroll
+            for (int k = 0; k < NST; k++) srcext0p[k] = srcext0[k];
+            if (tau > 4.0) {
+                ext0p = ext1 + (ext0 - ext1) * 4.0 / tau;
+                if (ext0 > 0.0) {
+#pragma unroll
+                    for (int k = 0; k < NST; k++) srcext0p[k] = srcext0[k] * ext0p / ext0;
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < NST; k++)
+                sc[k] = 1.0 / (ext0p + ext1) * (srcext0p[k] + srcext1[k]
+                        + (ext0p * srcext1[k] - ext1 * srcext0p[k]) * 2.0 / (ext0p + ext1) * (1 - 2 / tau + 2 * transcell / abscell));
+        }
+        sc[0] = fmax(sc[0], 0.0);
+#pragma unroll
+        for (int k = 0; k < NST; k++) rad[k] = rad[k] + transmit * sc[k] * abscell;
+        transmit = transmit * transcell;
+        // VALIDFACE, statically: all four face points are preset or earlier in the sweep order
+        const bool validface = ((a.bflag[i1 - 1] & bmask) || rank[i1 - 1] < r) && ((a.bflag[i2 - 1] & bmask) || rank[i2 - 1] < r)
+                            && ((a.bflag[i3 - 1] & bmask) || rank[i3 - 1] < r) && ((a.bflag[i4 - 1] & bmask) || rank[i4 - 1] < r);
+        if (inextcell <= 0 || (transmit <= a.transmin && validface)) {
+            if (!validface) fail = 3;
+            break;
+        }
+        ext1 = ext0;
+#pragma unroll
+        for (int k = 0; k < NST; k++) srcext1[k] = srcext0[k];
+        icell = inextcell;
+    }
+    float out[NST];
+    if (!fail) {
+        // wait for the four face radiances (bounded; polls go to L2)
+        float g1, g2, g3, g4;
+        int spins = 0;
+        for (;;) {
+            g1 = ld_vol(&R[i1 - 1]); g2 = ld_vol(&R[i2 - 1]); g3 = ld_vol(&R[i3 - 1]); g4 = ld_vol(&R[i4 - 1]);
+            if (g1 >= -0.1f && g2 >= -0.1f && g3 >= -0.1f && g4 >= -0.1f) break;
+            if (++spins > (1 << 22) || ((spins & 255) == 0 && *(volatile int *)a.err)) { fail = 4; break; }
+            __nanosleep(64);
+        }
+        if (!fail) {
+            __threadfence();
+            rad[0] = rad[0] + transmit * (f1 * (double)g1 + f2 * (double)g2 + f3 * (double)g3 + f4 * (double)g4);
+#pragma unroll
+            for (int k = 1; k < NST; k++) {
+                const size_t ko = (size_t)a.npts * k;
+                const double rad0 = f1 * (double)__ldcg(&R[(i1 - 1) + ko]) + f2 * (double)__ldcg(&R[(i2 - 1) + ko])
+                                  + f3 * (double)__ldcg(&R[(i3 - 1) + ko]) + f4 * (double)__ldcg(&R[(i4 - 1) + ko]);
+                rad[k] = rad[k] + transmit * rad0;
+            }
+        }
+    }
+    if (fail) {
+        atomicCAS(a.err, 0, fail);
+#pragma unroll
+        for (int k = 0; k < NST; k++) out[k] = 0.0f;
+    } else {
+#pragma unroll
+        for (int k = 0; k < NST; k++) out[k] = (float)rad[k];
+        if (!(out[0] >= 0.0f)) { atomicCAS(a.err, 0, 5); out[0] = 0.0f; }     // RAD<0 / NaN: the reference aborts
+    }
+#pragma unroll
+    for (int k = 1; k < NST; k++) __stcg(&R[(ipt - 1) + (size_t)a.npts * k], out[k]);
+    if (NST > 1) __threadfence();
+    *(volatile float *)&R[ipt - 1] = out[0];
+}
+
+// GRIDRAD(1,.) = -1 everywhere, then the boundary values of every ordinate (shdomsub1.f:1968-1972, 2024-2071):
+// thread = (point, ordinate)
+template <int NST>
+__global__ void sweep3d_init_kernel(PiArgs a, float *radf, const int *toppt, int up)
+{
+    const int nh = a.nang / 2;
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (size_t)a.npts * nh) return;
+    const int p = (int)(t % a.npts), ia = (up ? nh : 0) + (int)(t / a.npts);
+    radf[p + (size_t)a.npts * NST * ia] = -1.0f;
+}
+
+template <int NST>
+__global__ void sweep3d_boundary_kernel(PiArgs a, float *radf, const int *toppt, int up)
+{
+    const int nh = a.nang / 2, nb = up ? a.nbot : a.ntop;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nb * nh) return;
+    const int ibc = t % nb, io = t / nb, ia = (up ? nh : 0) + io;
+    float v[NST];
+    int p;
+    if (!up) {
+        const int imu = a.ang_imu[ia], iphi = a.ang_iphi[ia];
+#pragma unroll
+        for (int k = 0; k < NST; k++) v[k] = a.skyrad[k + NST * (imu + (a.nmu / 2) * iphi)];
+        if (a.srctype == 'T') {
+            v[0] = dev_planck(v[0], a.units, a.wavelen);
+#pragma unroll
+            for (int k = 1; k < NST; k++) v[k] = 0.0f;
+        }
+        p = toppt[ibc];
+        if (io == nh - 1) {
+#pragma unroll
+            for (int k = 0; k < NST; k++) a.bcrad[k + NST * (size_t)ibc] = v[k];
+        }
+    } else {
+        const float sg = a.sfcgridrad ? a.sfcgridrad[(io + 1) + (size_t)(nh + 1) * ibc] : 0.0f;
+#pragma unroll
+        for (int k = 0; k < NST; k++) {
+            const float b = (a.sfctype1 == 'L') ? a.bcrad[k + NST * (size_t)(a.ntop + ibc)]
+                                                : a.botrad[k + NST * (ibc + (size_t)a.nbot * io)];
+            v[k] = b + sg;
+        }
+        p = a.botpt[ibc];
+    }
+#pragma unroll
+    for (int k = 0; k < NST; k++) radf[p + (size_t)a.npts * (k + (size_t)NST * ia)] = v[k];
+}
+
+// BCRAD(:,IBC+NTOPPTS+NBOTPTS*IANG) = downwelling radiance at the bottom points, per downward ordinate (:2139-2145)
+template <int NST>
+__global__ void sweep3d_store_down_kernel(PiArgs a, const float *radf)
+{
+    const int nh = a.nang / 2;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= a.nbot * nh) return;
+    const int ibc = t % a.nbot, ia = t / a.nbot, p = a.botpt[ibc];
+#pragma unroll
+    for (int k = 0; k < NST; k++)
+        a.bcrad[k + NST * (a.ntop + ibc + (size_t)a.nbot * (ia + 1))] = radf[p + (size_t)a.npts * (k + (size_t)NST * ia)];
+}
+
+namespace {
+// SWEEPING_ORDER (shdomsub1.f:3261-3352) with SWEEP_BASE_CELL / SWEEP_NEXT_CELL (:4529-4700): base cells in the
+// octant's x-fastest order (open boundaries: the boundary column first), leaves of a base cell depth-first with the
+// upstream child first, the 8 corners of a leaf upstream first; a point is listed at its first visit.
+bool host_sweeping_order(const at3d_state_desc *d, int noct, std::vector<int> &sweepord, std::vector<int> &rank)
+{
+    static const int ioctorder[8] = {1, 5, 2, 6, 3, 7, 4, 8};
+    const int npts = d->npts, nz = d->nz;
+    int nxc = d->nx, nyc = d->ny;
+    if (d->bcflag & 1) nxc = d->nx + 1;
+    if (d->bcflag & 2) nyc = d->ny + 1;
+    sweepord.assign((size_t)noct * npts, 0);
+    rank.assign((size_t)noct * npts, 0);
+    std::vector<char> seen(npts);
+    std::vector<int> stack;
+    auto axis_seq = [](int n, bool positive, bool open) {
+        int s, e, dstep;
+        if (positive) { dstep = +1; if (open) { s = n; e = n - 1 > 1 ? n - 1 : 1; } else { s = 1; e = n; } }
+        else { dstep = -1; if (open) { s = 1; e = 2 < n ? 2 : n; } else { s = n; e = 1; } }
+        std::vector<int> v;
+        for (int i = s;; i = (i + dstep + n - 1) % n + 1) { v.push_back(i); if (i == e) break; }
+        return v;
+    };
+    for (int joct = 1; joct <= noct; joct++) {
+        const int ioct = ioctorder[joct - 1], ob = ioct - 1;
+        std::fill(seen.begin(), seen.end(), 0);
+        const std::vector<int> xs = axis_seq(nxc, ob & 1, d->bcflag & 1), ys = axis_seq(nyc, ob & 2, d->bcflag & 2);
+        int iorder = 0;
+        int *so = sweepord.data() + (size_t)npts * (joct - 1), *rk = rank.data() + (size_t)npts * (joct - 1);
+        const int z0 = (ob & 4) ? 1 : nz - 1, z1 = (ob & 4) ? nz - 1 : 1, dz = (ob & 4) ? 1 : -1;
+        for (int iz = z0;; iz += dz) {
+            for (int iy : ys)
+                for (int ix : xs) {
+                    stack.clear();
+                    stack.push_back(iz + (nz - 1) * (iy - 1) + (nz - 1) * nyc * (ix - 1));
+                    while (!stack.empty()) {
+                        const int ic = stack.back();
+                        stack.pop_back();
+                        const int child = d->treeptr[1 + 2 * (size_t)(ic - 1)];
+                        if (child > 0) {
+                            const int idir = ((d->cellflags[ic - 1] >> 2) & 3) - 1;
+                            if ((ob >> idir) & 1) { stack.push_back(child + 1); stack.push_back(child); }
+                            else { stack.push_back(child); stack.push_back(child + 1); }
+                            continue;
+                        }
+                        for (int index = 0; index < 8; index++) {
+                            const int icorner = ((~(index ^ ob)) & 7) + 1;
+                            const int ipt = d->gridptr[(icorner - 1) + 8 * (size_t)(ic - 1)];
+                            if (seen[ipt - 1]) continue;
+                            seen[ipt - 1] = 1;
+                            if (iorder >= npts) return false;
+                            so[iorder] = (ic << 3) | (icorner - 1);
+                            rk[ipt - 1] = iorder;
+                            iorder++;
+                        }
+                    }
+                }
+            if (iz == z1) break;
+        }
+        if (iorder != npts) return false;
+    }
+    return true;
+}
+}
+
+struct at3d_solver {
+    Arena A;
+    TrPlan *P = nullptr;
+    PiArgs a;
+    SwArgs w;
+    int nst = 0, npts = 0, nang = 0, ntop = 0, nbot = 0;
+    size_t nbc = 0;
+    bool lamb = true;
+    int *toppt = nullptr;
+    int *shptr_d = nullptr, *rshptr_d = nullptr;
+    int blocks_resident = 0;
+};
+
+extern "C" int at3d_solver_destroy(at3d_solver *sv)
+{
+    if (!sv) return 0;
+    if (sv->P) tr_plan_destroy(sv->P);
+    delete sv;
+    return 0;
+}
+
+extern "C" int at3d_solver_create(const at3d_state_desc *d, const float *wtmu, float transmin, at3d_solver **out, char *errmsg)
+{
+    if (errmsg) errmsg[0] = 0;
+    if (!d || !wtmu || !out) { set_msg(errmsg, "null argument"); return 1; }
+    *out = nullptr;
+    if (at3d_device_count() < 1) { set_msg(errmsg, "no CUDA device: at3d_b200 has no CPU fallback"); return 4; }
+    if (d->ipflag & 2) { set_msg(errmsg, "at3d_solver_create: grids with independent-pixel Y (BACK_INT_GRID2D / 1D) are not handled here; IPFLAG=3 has at3d_path_integration_ip"); return 3; }
+    if (d->bcflag & 12) { set_msg(errmsg, "at3d_solver_create: multi-processor boundary flags are not supported"); return 3; }
+    if (d->srctype != 'S' && d->units == 'B') { set_msg(errmsg, "UNITS='B' is not implemented"); return 3; }
+    if (!(transmin >= 0.0f && transmin <= 1.0f)) { set_msg(errmsg, "TRANSMIN must be in [0,1]"); return 1; }
+    const int npts = d->npts, nst = d->nstokes, noct = 8;
+    std::vector<int> sweepord, rank;
+    if (!host_sweeping_order(d, noct, sweepord, rank)) { set_msg(errmsg, "SWEEPING_ORDER: not every grid point was reached"); return 1; }
+    at3d_solver *sv = new at3d_solver();
+    int rc = tr_plan_create(nst, d->nstleg, d->ml, d->mm, d->nlm, d->nmu, d->nphi0max, d->nphi0, d->mu, d->phi, wtmu, &sv->P, errmsg);
+    if (rc) { delete sv; return rc; }
+    const int nang = tr_plan_nang(sv->P), nh = nang / 2;
+    sv->nst = nst; sv->npts = npts; sv->nang = nang; sv->ntop = d->ntoppts; sv->nbot = d->nbotpts;
+    sv->lamb = d->sfctype1 == 'L';
+    std::vector<float> amu(nang), aphi(nang), aw(nang);
+    std::vector<int> aimu(nang), aiphi(nang);
+    std::vector<OrdDir> dirs(nang);
+    static const int joctorder3[8] = {1, 3, 5, 7, 2, 4, 6, 8};
+    for (int i = 0, ia = 0; i < d->nmu; i++)
+        for (int k = 0; k < d->nphi0[i]; k++, ia++) {
+            const float mu = d->mu[i], phi = d->phi[i + (size_t)d->nmu * k];
+            amu[ia] = mu; aphi[ia] = phi;
+            aw[ia] = fabsf(mu) * d->wtdo[i + (size_t)d->nmu * k];
+            aimu[ia] = i; aiphi[ia] = k;
+            // the ray direction of BACK_INT_GRID3D (shdomsub1.f:3401-3441), host libm like the reference
+            OrdDir &D = dirs[ia];
+            const double pi = (double)acosf(-1.0f);
+            D.cx = (double)sqrtf(1.0f - mu * mu) * cos((double)phi + pi);
+            D.cy = (double)sqrtf(1.0f - mu * mu) * sin((double)phi + pi);
+            D.cz = -(double)mu;
+            if (fabs(D.cx) > (double)1.0E-5f) D.cxinv = 1.0 / D.cx; else { D.cx = 0.0; D.cxinv = (double)1.0E6f; }
+            if (fabs(D.cy) > (double)1.0E-5f) D.cyinv = 1.0 / D.cy; else { D.cy = 0.0; D.cyinv = (double)1.0E6f; }
+            D.czinv = 1.0 / D.cz;
+            D.bitx = D.cx < 0.0 ? 1 : 0;
+            D.bity = D.cy < 0.0 ? 1 : 0;
+            if (D.cz < -(double)1.0E-3f) D.bitz = 1;
+            else if (D.cz > (double)1.0E-3f) D.bitz = 0;
+            else { at3d_solver_destroy(sv); set_msg(errmsg, "BACK_INT_GRID: Bad MU"); return 1; }
+            if ((D.bitz == 1) != (ia >= nh)) { at3d_solver_destroy(sv); set_msg(errmsg, "unexpected ordinate order"); return 1; }
+            D.ioct = 1 + D.bitx + 2 * D.bity + 4 * D.bitz;
+            D.joct = joctorder3[D.ioct - 1];
+            D.pad = 0;
+        }
+    std::vector<unsigned char> bflag(npts, 0);
+    std::vector<int> toppt(d->ntoppts), botpt(d->nbotpts);
+    for (int i = 0; i < d->ntoppts; i++) { toppt[i] = d->bcptr[i] - 1; bflag[toppt[i]] |= 1; }
+    for (int i = 0; i < d->nbotpts; i++) { botpt[i] = d->bcptr[d->maxnbc + i] - 1; bflag[botpt[i]] |= 2; }
+    Arena &A = sv->A;
+    PiArgs &a = sv->a;
+    memset(&a, 0, sizeof(a));
+    a.npts = npts; a.nst = nst; a.nz = d->nz; a.ncol = 0; a.nang = nang; a.nmu = d->nmu; a.nphi0max = d->nphi0max;
+    a.ntop = d->ntoppts; a.nbot = d->nbotpts; a.nsfcpar = d->nsfcpar; a.srctype = d->srctype; a.units = d->units;
+    a.sfctype0 = d->sfctype0; a.sfctype1 = d->sfctype1; a.wavelen = d->wavelen; a.solarmu = d->solarmu;
+    a.solaraz = d->solaraz; a.gndalbedo = d->gndalbedo; a.gndtemp = d->gndtemp;
+    sv->nbc = (size_t)nst * (a.ntop + (size_t)a.nbot * (sv->lamb ? 1 : 1 + nh));
+    a.dofield = A.alloc<float>((size_t)npts * nst * nang);
+    float *radf = A.alloc<float>((size_t)npts * nst * nang);
+    a.fluxsrc = radf;
+    a.total_ext = A.up(d->total_ext, npts); a.zlev = A.up(d->zgrid, d->nz); a.dirflux = A.up(d->dirflux, npts);
+    a.ang_mu = A.up(amu.data(), nang); a.ang_phi = A.up(aphi.data(), nang); a.ang_w = A.up(aw.data(), nang);
+    a.ang_imu = A.up(aimu.data(), nang); a.ang_iphi = A.up(aiphi.data(), nang);
+    a.skyrad = A.up(d->skyrad, (size_t)nst * (d->nmu / 2) * d->nphi0max);
+    a.sfcgridparms = A.up(d->sfcgridparms, (size_t)d->nsfcpar * a.nbot);
+    if (d->sfcgridrad) {
+        bool nonzero = false;
+        for (size_t i = 0; i < (size_t)(nh + 1) * a.nbot && !nonzero; i++) nonzero = d->sfcgridrad[i] != 0.0f;
+        if (nonzero) a.sfcgridrad = A.up(d->sfcgridrad, (size_t)(nh + 1) * a.nbot);
+    }
+    a.bcrad = A.alloc<float>(sv->nbc);
+    a.botrad = A.alloc<float>((size_t)nst * a.nbot * nh);
+    a.fluxes = A.alloc<float>((size_t)2 * npts);
+    a.botpt = A.up(botpt.data(), botpt.size());
+    sv->toppt = A.up(toppt.data(), toppt.size());
+    sv->shptr_d = A.alloc<int>((size_t)npts + 1);
+    sv->rshptr_d = A.alloc<int>((size_t)npts + 1);
+    // topology records of the ray kernels
+    const int *gp = A.up(d->gridptr, (size_t)8 * d->ncells), *np = A.up(d->neighptr, (size_t)6 * d->ncells);
+    const int *tp = A.up(d->treeptr, (size_t)2 * d->ncells);
+    const short *cf = A.up((const short *)d->cellflags, (size_t)d->ncells);
+    const float *gpos = A.up(d->gridpos, (size_t)3 * npts);
+    int4 *cellrec = A.alloc<int4>((size_t)4 * d->ncells);
+    float4 *ptrec = A.alloc<float4>((size_t)npts);
+    SwArgs &w = sv->w;
+    memset(&w, 0, sizeof(w));
+    w.npts = npts; w.nang = nang; w.nchunks = (npts + 255) / 256;
+    w.dir = A.up(dirs.data(), dirs.size());
+    w.sweepord = A.up(sweepord.data(), sweepord.size());
+    w.rank = A.up(rank.data(), rank.size());
+    w.bflag = A.up(bflag.data(), bflag.size());
+    w.srcdo = a.dofield; w.radf = radf;
+    w.eps = (double)(1.0E-3f * (d->gridpos[2 + 3 * (size_t)(d->gridptr[7] - 1)] - d->gridpos[2 + 3 * (size_t)(d->gridptr[0] - 1)]));
+    w.transmin = (double)transmin;
+    w.ticket = A.alloc<int>(2); w.err = w.ticket ? w.ticket + 1 : nullptr;
+    bool ok = a.dofield && radf && a.total_ext && a.zlev && a.dirflux && a.ang_mu && a.ang_phi && a.ang_w && a.ang_imu && a.ang_iphi &&
+              a.skyrad && a.sfcgridparms && a.bcrad && a.botrad && a.fluxes && a.botpt && sv->toppt && sv->shptr_d && sv->rshptr_d &&
+              gp && np && tp && cf && gpos && cellrec && ptrec && w.dir && w.sweepord && w.rank && w.bflag && w.ticket;
+    if (ok) ok = launch_build_cellrec(d->ncells, gp, np, tp, cf, cellrec, 0) == cudaSuccess &&
+                 launch_build_ptrec(npts, gpos, a.total_ext, ptrec, 0) == cudaSuccess && cudaDeviceSynchronize() == cudaSuccess;
+    if (!ok) { at3d_solver_destroy(sv); set_msg(errmsg, "device allocation failure"); return 4; }
+    memset(&w.S, 0, sizeof(w.S));
+    w.S.npts = npts; w.S.ncells = d->ncells; w.S.cellrec = cellrec; w.S.ptrec = ptrec;
+    // ordinates in flight together: enough of the sweep order per ordinate for a few z-slabs of the wavefront
+    int dev = 0, nsm = 148, per_sm = 1;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    if (nst == 1) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sweep3d_kernel<1>, 256, 0);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sweep3d_kernel<3>, 256, 0);
+    sv->blocks_resident = nsm * (per_sm > 0 ? per_sm : 1);
+    const long slab = (long)(d->nx + 1) * (d->ny + 1);
+    long g = (long)sv->blocks_resident * 256 / (4 * slab > 0 ? 4 * slab : 1);
+    const char *genv = getenv("AT3D_SWEEP_GROUP");
+    if (genv) g = atol(genv);
+    w.group = (int)(g < 1 ? 1 : (g > nh ? nh : g));
+    *out = sv;
+    return 0;
+}
+
+extern "C" int at3d_solver_path_integration(at3d_solver *sv, const int32_t *shptr, const float *source, const int32_t *rshptr,
+                                            float *radiance, float *fluxes, float *bcrad, double *kernel_ms, char *errmsg)
+{
+    if (errmsg) errmsg[0] = 0;
+    if (!sv || !shptr || !source || !rshptr || !radiance || !fluxes || !bcrad) { set_msg(errmsg, "null argument"); return 1; }
+    const int npts = sv->npts, nst = sv->nst, nang = sv->nang, nh = nang / 2;
+    PiArgs &a = sv->a;
+    SwArgs &w = sv->w;
+    const size_t nsh = (size_t)nst * shptr[npts], nrad = (size_t)nst * rshptr[npts];
+    Arena T;                                   // per-call: the SH arrays change length every iteration
+    float *src_d = T.up(source, nsh), *rad_d = T.alloc<float>(nrad);
+    if (!src_d || !rad_d) { set_msg(errmsg, "device allocation failure"); return 4; }
+    cudaError_t e = cudaMemcpy(sv->shptr_d, shptr, ((size_t)npts + 1) * sizeof(int), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(sv->rshptr_d, rshptr, ((size_t)npts + 1) * sizeof(int), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemset(a.bcrad, 0, sv->nbc * sizeof(float));
+    if (e != cudaSuccess) { set_msg(errmsg, "CUDA error %s in at3d_solver_path_integration", cudaGetErrorString(e)); return 4; }
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0, 0);
+    e = tr_sh_to_do(sv->P, npts, sv->shptr_d, src_d, a.dofield, 0);
+    const int nsweep = w.nchunks * nh, npb = (npts + 255) / 256;
+    const int ninit = (int)(((size_t)npts * nh + 255) / 256);
+    const int ntb = (a.ntop * nh + 127) / 128, nbb = (a.nbot * nh + 127) / 128;
+#define AT3D_SWEEP3D(NST)                                                                              \
+    for (int up = 0; up < 2; up++) {                                                                   \
+        cudaMemsetAsync(w.ticket, 0, up == 0 ? 2 * sizeof(int) : sizeof(int), 0);                      \
+        sweep3d_init_kernel<NST><<<ninit, 256>>>(a, w.radf, sv->toppt, up);                            \
+        if (up) {                                                                                      \
+            if (sv->lamb) pi_lambertian_kernel<<<(a.nbot + 127) / 128, 128>>>(a);                      \
+            else pi_brdf_kernel<NST><<<nbb, 128>>>(a);                                                 \
+        }                                                                                              \
+        sweep3d_boundary_kernel<NST><<<up ? nbb : ntb, 128>>>(a, w.radf, sv->toppt, up);               \
+        sweep3d_kernel<NST><<<nsweep, 256>>>(w, up);                                                   \
+        pi_flux_kernel<NST><<<npb, 256>>>(a, up);                                                      \
+        if (!up && !sv->lamb) sweep3d_store_down_kernel<NST><<<nbb, 128>>>(a, w.radf);                 \
+    }
+    if (nst == 1) { AT3D_SWEEP3D(1) } else { AT3D_SWEEP3D(3) }
+#undef AT3D_SWEEP3D
+    if (e == cudaSuccess) e = tr_do_to_sh(sv->P, npts, sv->rshptr_d, w.radf, rad_d, 0);
+    cudaEventRecord(e1, 0);
+    if (e == cudaSuccess) e = cudaEventSynchronize(e1);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    float ms = 0.0f;
+    if (e == cudaSuccess) cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    int err = 0;
+    if (e == cudaSuccess) e = cudaMemcpy(&err, w.err, sizeof(int), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(radiance, rad_d, nrad * sizeof(float), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(fluxes, a.fluxes, (size_t)2 * npts * sizeof(float), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(bcrad, a.bcrad, sv->nbc * sizeof(float), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) { set_msg(errmsg, "CUDA error %s in at3d_solver_path_integration", cudaGetErrorString(e)); return 4; }
+    if (err) {
+        static const char *what[] = {"", "BACK_INT_GRID: ICELL=0", "BACK_INT_GRID: SO<0", "BACK_INT_GRID3D: INEXTCELL=0 without a valid face",
+                                     "sweep wait timed out", "BACK_INT_GRID3D: RAD<0"};
+        set_msg(errmsg, "%s", what[err < 6 ? err : 0]);
+        return 1;
+    }
     if (kernel_ms) *kernel_ms = ms;
     return 0;
 }

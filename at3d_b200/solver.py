@@ -114,10 +114,57 @@ def path_integration_ip(st, wtmu, shptr, source, rshptr, timing=False):
     return (rad, fluxes, bcrad, ms.value) if timing else (rad, fluxes, bcrad)
 
 
-def solve_ip(state, wtmu, maxiter=100, solacc=1e-4, shacc=0.0, accelflag=True, highorderrad=False, iterfixsh=30,
-             maxiv=None, verbose=False):
-    """Returns (solved copy of `state` with shptr/source/rshptr/radiance/fluxes/bcrad, iters, solcrit, timings)."""
+class SweepSolver:
+    """PATH_INTEGRATION on a fixed 3-D grid (IPFLAG 0 or 1): the device-resident solver object of
+    at3d_solver_create (topology, SWEEPING_ORDER, ordinate geometry, transform tables, discrete-ordinate fields)."""
+
+    def __init__(self, st, wtmu, transmin=1.0):
+        self.st = st
+        self._keep = st.desc()
+        self.h = C.c_void_p()
+        wt = np.ascontiguousarray(wtmu, np.float32)
+        buf = _lib.errbuf()
+        _lib.check(_lib.lib().at3d_solver_create(C.byref(self._keep), vp(wt), float(transmin), C.byref(self.h), buf), buf)
+
+    def path_integration(self, shptr, source, rshptr, timing=False):
+        st = self.st
+        lamb = st.sfctype1 in ('L', ord('L'))
+        nbc = st.ntoppts + st.nbotpts * (1 if lamb else 1 + st.nang // 2)
+        rad = np.zeros((st.nstokes, max(int(rshptr[st.npts]), 1)), np.float32, order='F')
+        fluxes = np.zeros((2, st.npts), np.float32, order='F')
+        bcrad = np.zeros((st.nstokes, nbc), np.float32, order='F')
+        shptr = np.ascontiguousarray(shptr, np.int32); rshptr = np.ascontiguousarray(rshptr, np.int32)
+        source = np.asfortranarray(source, np.float32)
+        ms = C.c_double(0.0)
+        buf = _lib.errbuf()
+        _lib.check(_lib.lib().at3d_solver_path_integration(self.h, vp(shptr), vp(source), vp(rshptr), vp(rad), vp(fluxes),
+                                                           vp(bcrad), C.byref(ms), buf), buf)
+        return (rad, fluxes, bcrad, ms.value) if timing else (rad, fluxes, bcrad)
+
+    def close(self):
+        if self.h:
+            _lib.lib().at3d_solver_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+
+def solve_ip(state, wtmu, **kw):
+    """The fixed-grid solve for independent-pixel grids (IPFLAG=3); see solve_fixed_grid."""
+    return solve_fixed_grid(state, wtmu, **kw)
+
+
+def solve_fixed_grid(state, wtmu, maxiter=100, solacc=1e-4, shacc=0.0, accelflag=True, highorderrad=False, iterfixsh=30,
+                     maxiv=None, verbose=False, transmin=1.0):
+    """SOLUTION_ITERATIONS on a fixed grid (shdomsub1.f:445-822): RADIANCE_TRUNCATION, PATH_INTEGRATION (GPU: independent
+    columns for IPFLAG=3, the BACK_INT_GRID3D sweep otherwise), COMPUTE_SOURCE (GPU), sequence acceleration.
+    Returns (solved copy of `state` with shptr/source/rshptr/radiance/fluxes/bcrad, iters, solcrit, timings)."""
     st = state.copy().normalize()
+    sweep = None if (st.ipflag & 3) == 3 else SweepSolver(st, wtmu, transmin)
     npts, ns = st.npts, st.nstokes
     f32 = np.float32
     if maxiv is None:
@@ -145,7 +192,10 @@ def solve_ip(state, wtmu, maxiter=100, solacc=1e-4, shacc=0.0, accelflag=True, h
         it += 1
         st.rshptr = radiance_truncation(st, shptr, st.radiance, st.rshptr, fixsh, shacc, highorderrad, maxir)
         st.shptr, st.source = shptr, source
-        rad, fluxes, bcrad, ms = path_integration_ip(st, wtmu, shptr, source, st.rshptr, timing=True)
+        if sweep is None:
+            rad, fluxes, bcrad, ms = path_integration_ip(st, wtmu, shptr, source, st.rshptr, timing=True)
+        else:
+            rad, fluxes, bcrad, ms = sweep.path_integration(shptr, source, st.rshptr, timing=True)
         t_path += ms
         st.radiance, st.fluxes, st.bcrad = rad, fluxes, bcrad
         if solcrit < 0.001 or it > iterfixsh:
@@ -181,6 +231,8 @@ def solve_ip(state, wtmu, maxiter=100, solacc=1e-4, shacc=0.0, accelflag=True, h
             solcrit = f32(solacc)
         if verbose:
             print('  %4d %8.3f %8d' % (it, np.log10(max(float(solcrit), 1e-20)), npts))
+    if sweep is not None:
+        sweep.close()
     tot = int(shptr[npts])
     st.shptr = shptr
     st.source = np.asfortranarray(source[:, :max(tot, 1)])

@@ -166,6 +166,37 @@ def solver_leg(steps, warmup, oracle=None, n=96, nz=48):
     return out
 
 
+def sweep3d_leg(st, steps, warmup, oracle=None):
+    """PATH_INTEGRATION on the workload's own 3-D grid (BACK_INT_GRID3D data-flow sweep, all ordinates of a hemisphere per
+    launch): kernel ms per call (CUDA events inside the C-ABI call, SH_TO_DO and DO_TO_SH included) and
+    (ordinate, grid point) updates per second; with the oracle, the reference's serial sweep on one host core."""
+    from at3d_b200 import solver
+    if st.ipflag & 2:
+        return dict(skipped='independent-pixel grid')
+    nang = int(st.nphi0.sum())
+    if st.npts * st.nstokes * nang * 8 > 60 * (1 << 30):
+        return dict(skipped='two discrete-ordinate fields would need %.0f GB' % (st.npts * st.nstokes * nang * 8 / 2**30))
+    delphi = np.float32(2.0 * np.pi) / st.nphi0.astype(np.float32)
+    wtmu = (st.wtdo[:, 0] / delphi).astype(np.float32)
+    t0 = time.perf_counter()
+    sv = solver.SweepSolver(st, wtmu)
+    setup_ms = 1e3 * (time.perf_counter() - t0)
+    ms = []
+    for i in range(warmup + steps):
+        out = sv.path_integration(st.shptr, st.source, st.rshptr, timing=True)
+        if i >= warmup:
+            ms.append(out[3])
+    sv.close()
+    res = dict(npts=int(st.npts), nang=nang, path_integration_ms=float(np.mean(ms)), setup_ms=setup_ms,
+               point_updates_per_s=st.npts * nang / (np.mean(ms) * 1e-3))
+    if oracle is not None:
+        t = time.perf_counter()
+        oracle.path_integration(st, wtmu, st.shptr, st.source, st.rshptr)
+        res['cpu_path_integration_ms'] = 1e3 * (time.perf_counter() - t)
+        res['cpu_cores'] = 1
+    return res
+
+
 def transform_leg(B, st, steps, warmup):
     """SH_TO_DO / DO_TO_SH on the workload's SOURCE / RADIANCE: kernel ms (CUDA events inside the
     C-ABI call), FP32 FMA rate against the CUDA-core peak and bytes against HBM."""
@@ -628,6 +659,7 @@ def main():
             compute_source=csrc, transforms=transform_leg(B, st, args.steps, args.warmup),
             render_orthographic=orthographic_leg(dev, sc, cfg['pixels_per_view'] ** 0.5, args.steps, args.warmup),
             solver_iteration=solver_leg(max(1, args.steps // 2), 1, orc if args.workload == 'cfg2' else None),
+            path_integration_3d=sweep3d_leg(st, args.steps, 1, orc if args.workload == 'cfg2' else None),
             render_ocean=dict(rays_per_s=nrays / (np.mean(oms) * 1e-3), kernel_ms=float(np.mean(oms)),
                               surface_ms=float(np.mean(oms) - np.mean(rms)), surface_hits=ocounts['surface_hits'],
                               brdf_evals=ocounts['surface_hits'] * 4 * (st.nang // 2 + 1)),

@@ -252,6 +252,18 @@ int at3d_path_integration_ip(const at3d_state_desc *desc, const float *wtmu, con
                              const int32_t *rshptr, float *radiance, float *fluxes, float *bcrad,
                              double *kernel_ms, char *errmsg);
 
+/* ---- f1: PATH_INTEGRATION on 3-D grids (fixed grid, base or already split) ----
+ * Replaces PATH_INTEGRATION (src/polarized/shdomsub1.f:1836-2167) with BACK_INT_GRID3D[_UNPOL] (:3354-4036) in the
+ * order of SWEEPING_ORDER (:3261-3352), for IPFLAG 0 or 1 and periodic or open boundaries.  The solver object holds
+ * what does not change over the solution iterations on a fixed grid (topology, sweep order, ordinate geometry, the
+ * SH <-> ordinate transform tables, the two discrete-ordinate fields); transmin is TRANSMIN (at3d default 1.0).
+ * at3d_solver_path_integration has the argument meaning of at3d_path_integration_ip. */
+typedef struct at3d_solver at3d_solver;
+int at3d_solver_create(const at3d_state_desc *desc, const float *wtmu, float transmin, at3d_solver **out, char *errmsg);
+int at3d_solver_path_integration(at3d_solver *sv, const int32_t *shptr, const float *source, const int32_t *rshptr,
+                                 float *radiance, float *fluxes, float *bcrad, double *kernel_ms, char *errmsg);
+int at3d_solver_destroy(at3d_solver *sv);
+
 #ifdef __cplusplus
 }
 #endif

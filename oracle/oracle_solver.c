@@ -440,6 +440,151 @@ static int back_int_grid1d(const oracle_state *st, const int *sweepord, float mu
     return 0;
 }
 
+/* BACK_INT_GRID3D / BACK_INT_GRID3D_UNPOL  shdomsub1.f:3354-3690 / 3696-4036 (identical apart from NSTOKES).
+   source is SOURCE(NSTOKES,NA,NPTS) (the discrete-ordinate source of one zenith angle), gridrad GRIDRAD(NSTOKES,NPTS)
+   with GRIDRAD(1,.) < 0 for points without a value yet.  The multi-processor branch (BCFLAG bits 2,3) is not restated. */
+static int back_int_grid3d(const oracle_state *st, const int *sweepord, float mu, float phi, float transmin, int kang,
+                           const float *extinct, const float *source, float *gridrad, char *errmsg)
+{
+    static const int gridface[6][4] = {{1, 3, 5, 7}, {2, 4, 6, 8}, {1, 2, 5, 6}, {3, 4, 7, 8}, {1, 2, 3, 4}, {5, 6, 7, 8}};
+    static const int oppface[6] = {2, 1, 4, 3, 6, 5};
+    static const int joctorder3[8] = {1, 3, 5, 7, 2, 4, 6, 8}, joctorder2[8] = {1, 3, 1, 3, 2, 4, 2, 4};
+    const int ns = st->nstokes, na = st->nphi0max, npts = st->npts;
+    double eps, pi, cx, cy, cz, cxinv, cyinv, czinv, xe, ye, ze, so, sox, soy, soz, u, v, f1, f2, f3, f4;
+    double ext, ext0, ext1, ext0p, tau, transcell, abscell, transmit;
+    double src[4], srcext0[4], srcext1[4], srcext0p[4], rad[4], rad0[4];
+    int bitx, bity, bitz, ioct, joct, iorder, k;
+    eps = 1.0E-3f * (GRIDPOS(st, 3, GRIDPTR(st, 8, 1)) - GRIDPOS(st, 3, GRIDPTR(st, 1, 1)));
+    pi = acosf(-1.0f);
+    cx = sqrtf(1.0f - mu * mu) * cos(phi + pi);
+    cy = sqrtf(1.0f - mu * mu) * sin(phi + pi);
+    cz = -mu;
+    if (fabs(cx) > 1.0E-5f) cxinv = 1.0 / cx; else { cx = 0.0; cxinv = 1.0E6f; }
+    if (fabs(cy) > 1.0E-5f) cyinv = 1.0 / cy; else { cy = 0.0; cyinv = 1.0E6f; }
+    czinv = 1.0 / cz;
+    bitx = cx < 0.0 ? 1 : 0;
+    bity = cy < 0.0 ? 1 : 0;
+    if (cz < -1.0E-3f) bitz = 1;
+    else if (cz > 1.0E-3f) bitz = 0;
+    else { if (errmsg) snprintf(errmsg, 600, "BACK_INT_GRID: Bad MU"); return 1; }
+    ioct = 1 + bitx + 2 * bity + 4 * bitz;
+    joct = BTEST(st->ipflag, 1) ? joctorder2[ioct - 1] : joctorder3[ioct - 1];
+    for (iorder = 1; iorder <= npts; iorder++) {
+        const int so_entry = sweepord[(iorder - 1) + (size_t)npts * (joct - 1)];
+        const int ipcell = so_entry >> 3, icorner = (so_entry & 7) + 1;
+        const int ipt = GRIDPTR(st, icorner, ipcell);
+        int icell, validrad, inextcell = 0;
+        if (GR(1, ipt) >= 0.0f) continue;
+        icell = ipcell;
+        transmit = 1.0;
+        ext1 = extinct[ipt - 1];
+        for (k = 0; k < ns; k++) { rad[k] = 0.0; srcext1[k] = ext1 * SRC(k + 1, kang, ipt); }
+        xe = GRIDPOS(st, 1, ipt);
+        ye = GRIDPOS(st, 2, ipt);
+        ze = GRIDPOS(st, 3, ipt);
+        validrad = 0;
+        while (!validrad) {
+            int ipinx, ipiny, iopp, iface, jface, kface, ic, i1, i2, i3, i4, validface;
+            if (icell <= 0) { if (errmsg) snprintf(errmsg, 600, "BACK_INT_GRID: ICELL=0"); return 1; }
+            ipinx = BTEST(CELLFLAGS(st, icell), 0);
+            ipiny = BTEST(CELLFLAGS(st, icell), 1);
+            iopp = GRIDPTR(st, 9 - ioct, icell);
+            sox = ipinx ? 1.0E20f : (GRIDPOS(st, 1, iopp) - xe) * cxinv;
+            soy = ipiny ? 1.0E20f : (GRIDPOS(st, 2, iopp) - ye) * cyinv;
+            soz = (GRIDPOS(st, 3, iopp) - ze) * czinv;
+            so = fmin(fmin(sox, soy), soz);
+            if (so < -eps) { if (errmsg) snprintf(errmsg, 600, "BACK_INT_GRID: SO<0"); return 1; }
+            xe = xe + so * cx;
+            ye = ye + so * cy;
+            ze = ze + so * cz;
+            if (sox <= soz && sox <= soy) { iface = 2 - bitx; jface = 1; }
+            else if (soy <= soz) { iface = 4 - bity; jface = 2; }
+            else { iface = 6 - bitz; jface = 3; }
+            inextcell = oracle_next_cell(st, xe, ye, ze, iface, jface, icell);
+            if (NEIGHPTR(st, iface, icell) >= 0) { kface = iface; ic = icell; }
+            else { kface = oppface[iface - 1]; ic = inextcell; }
+            i1 = GRIDPTR(st, gridface[kface - 1][0], ic);
+            i2 = GRIDPTR(st, gridface[kface - 1][1], ic);
+            i3 = GRIDPTR(st, gridface[kface - 1][2], ic);
+            i4 = GRIDPTR(st, gridface[kface - 1][3], ic);
+            if (jface == 1) {
+                u = (ze - GRIDPOS(st, 3, i1)) / (GRIDPOS(st, 3, i3) - GRIDPOS(st, 3, i1));
+                v = ipiny ? 0.5 : (ye - GRIDPOS(st, 2, i1)) / (GRIDPOS(st, 2, i2) - GRIDPOS(st, 2, i1));
+            } else if (jface == 2) {
+                u = (ze - GRIDPOS(st, 3, i1)) / (GRIDPOS(st, 3, i3) - GRIDPOS(st, 3, i1));
+                v = ipinx ? 0.5 : (xe - GRIDPOS(st, 1, i1)) / (GRIDPOS(st, 1, i2) - GRIDPOS(st, 1, i1));
+            } else {
+                u = ipiny ? 0.5 : (ye - GRIDPOS(st, 2, i1)) / (GRIDPOS(st, 2, i3) - GRIDPOS(st, 2, i1));
+                v = ipinx ? 0.5 : (xe - GRIDPOS(st, 1, i1)) / (GRIDPOS(st, 1, i2) - GRIDPOS(st, 1, i1));
+            }
+            if (inextcell > 0) {
+                if (jface == 1) xe = GRIDPOS(st, 1, GRIDPTR(st, ioct, inextcell));
+                else if (jface == 2) ye = GRIDPOS(st, 2, GRIDPTR(st, ioct, inextcell));
+                else ze = GRIDPOS(st, 3, GRIDPTR(st, ioct, inextcell));
+            }
+            f1 = (1 - u) * (1 - v);
+            f2 = (1 - u) * v;
+            f3 = u * (1 - v);
+            f4 = u * v;
+            ext0 = f1 * extinct[i1 - 1] + f2 * extinct[i2 - 1] + f3 * extinct[i3 - 1] + f4 * extinct[i4 - 1];
+            for (k = 0; k < ns; k++)
+                srcext0[k] = f1 * SRC(k + 1, kang, i1) * extinct[i1 - 1] + f2 * SRC(k + 1, kang, i2) * extinct[i2 - 1]
+                           + f3 * SRC(k + 1, kang, i3) * extinct[i3 - 1] + f4 * SRC(k + 1, kang, i4) * extinct[i4 - 1];
+            ext = 0.5 * (ext0 + ext1);
+            tau = ext * so;
+            if (tau >= 0.5) {
+                transcell = exp(-tau);
+                abscell = 1.0 - transcell;
+            } else {
+                abscell = tau * (1.0 - 0.5 * tau * (1.0 - 0.33333333333 * tau * (1 - 0.25 * tau)));
+                transcell = 1.0 - abscell;
+            }
+            if (tau <= 2.0) {
+                if (ext == 0.0) { for (k = 0; k < ns; k++) src[k] = 0.0; }
+                else {
+                    for (k = 0; k < ns; k++)
+                        src[k] = (0.5 * (srcext0[k] + srcext1[k])
+                                  + 0.08333333333 * (ext0 * srcext1[k] - ext1 * srcext0[k]) * so) / ext;
+                }
+            } else {
+                ext0p = ext0;
+                for (k = 0; k < ns; k++) srcext0p[k] = srcext0[k];
+                if (tau > 4.0) {
+                    ext0p = ext1 + (ext0 - ext1) * 4.0 / tau;
+                    if (ext0 > 0.0) for (k = 0; k < ns; k++) srcext0p[k] = srcext0[k] * ext0p / ext0;
+                }
+                for (k = 0; k < ns; k++)
+                    src[k] = 1.0 / (ext0p + ext1) * (srcext0p[k] + srcext1[k]
+                             + (ext0p * srcext1[k] - ext1 * srcext0p[k]) * 2.0 / (ext0p + ext1)
+                               * (1 - 2 / tau + 2 * transcell / abscell));
+            }
+            src[0] = fmax(src[0], 0.0);
+            for (k = 0; k < ns; k++) rad[k] = rad[k] + transmit * src[k] * abscell;
+            transmit = transmit * transcell;
+            if (rad[0] < -1.0E-5f) { if (errmsg) snprintf(errmsg, 600, "BACK_INT_GRID3D: RAD<0"); return 1; }
+            validface = GR(1, i1) >= -0.1f && GR(1, i2) >= -0.1f && GR(1, i3) >= -0.1f && GR(1, i4) >= -0.1f;
+            if (inextcell <= 0 || (transmit <= transmin && validface)) {
+                if (validface) {
+                    validrad = 1;
+                    for (k = 0; k < ns; k++) {
+                        rad0[k] = f1 * GR(k + 1, i1) + f2 * GR(k + 1, i2) + f3 * GR(k + 1, i3) + f4 * GR(k + 1, i4);
+                        rad[k] = rad[k] + transmit * rad0[k];
+                    }
+                } else {
+                    if (errmsg) snprintf(errmsg, 600, "BACK_INT_GRID3D: INEXTCELL=0 without a valid face");
+                    return 1;
+                }
+            } else {
+                ext1 = ext0;
+                for (k = 0; k < ns; k++) srcext1[k] = srcext0[k];
+                icell = inextcell;
+            }
+        }
+        for (k = 0; k < ns; k++) GR(k + 1, ipt) = (float)rad[k];
+    }
+    return 0;
+}
+
 /* RADIANCE_TRUNCATION  shdomsub1.f:1615-1805 */
 static int radiance_truncation(const oracle_state *st, int highorderrad, const int *shptr, const float *radiance,
                                int maxir, int fixsh, float shacc, int *rshptr, const int *lofj)
@@ -596,8 +741,12 @@ static int path_integration(oracle_state *st, const shdo_coef *c, const int *swe
             }
             if (BTEST(st->ipflag, 1) && BTEST(st->ipflag, 0)) {
                 ierr = back_int_grid1d(st, sweepord, st->mu[imu - 1], iphi, st->total_ext, work, gridrad, errmsg);
+            } else if (!BTEST(st->ipflag, 1) && !BTEST(st->bcflag, 2) && !BTEST(st->bcflag, 3)) {
+                /* TRANSMIN = 1.00 (SOLUTION_ITERATIONS, shdomsub1.f:575) */
+                ierr = back_int_grid3d(st, sweepord, st->mu[imu - 1], st->phi[(imu - 1) + st->nmu * (iphi - 1)], 1.00f,
+                                       iphi, st->total_ext, work, gridrad, errmsg);
             } else {
-                if (errmsg) snprintf(errmsg, 600, "oracle solver: only IPFLAG=3 (BACK_INT_GRID1D) is restated");
+                if (errmsg) snprintf(errmsg, 600, "oracle solver: BACK_INT_GRID2D and the multi-processor sweeps are not restated");
                 ierr = 3;
             }
             if (ierr) break;
@@ -771,4 +920,25 @@ int oracle_radiance_truncation(const oracle_state *st, int highorderrad, const i
     rc = radiance_truncation(st, highorderrad, shptr, radiance, maxir, fixsh, shacc, rshptr, lofj);
     free(lofj);
     return rc;
+}
+
+/* One PATH_INTEGRATION alone (parity check of the GPU sweeps): radiance[nstokes, rshptr[npts]], fluxes[2,npts],
+   bcrad as in oracle_solve_fixed_grid. */
+int oracle_path_integration_once(const oracle_state *st_in, const float *wtmu, const int *shptr, const float *source,
+                                 const int *rshptr, float *radiance, float *fluxes, float *bcrad, char *errmsg)
+{
+    oracle_state st = *st_in;
+    const int npts = st.npts, ns = st.nstokes;
+    shdo_coef *c = make_sh_do_coef(&st, wtmu);
+    int *sweepord = (int *)malloc(sizeof(int) * (size_t)npts * 8);
+    float *work = (float *)calloc((size_t)ns * st.nphi0max * npts, sizeof(float));
+    float *gridrad = (float *)calloc((size_t)ns * npts, sizeof(float));
+    int ierr = sweeping_order(&st, sweepord);
+    if (ierr) { if (errmsg) snprintf(errmsg, 600, "SWEEPING_ORDER: not every grid point was reached"); }
+    else {
+        st.fluxes = fluxes; st.bcrad = bcrad;
+        ierr = path_integration(&st, c, sweepord, shptr, source, rshptr, radiance, fluxes, bcrad, work, gridrad, errmsg);
+    }
+    free_sh_do_coef(c); free(sweepord); free(work); free(gridrad);
+    return ierr;
 }

@@ -304,6 +304,27 @@ def solve_fixed_grid(state, wtmu, maxiter=100, solacc=1e-5, shacc=0.0, accelflag
     return st, iters.value, solcrit.value
 
 
+def path_integration(state, wtmu, shptr, source, rshptr):
+    """One PATH_INTEGRATION (oracle/oracle_solver.c): returns (radiance, fluxes, bcrad)."""
+    st = state.copy().normalize()
+    npts, ns = st.npts, st.nstokes
+    lamb = st.sfctype1 == 'L' or st.sfctype1 == ord('L')
+    nbc = st.ntoppts + st.nbotpts * (1 if lamb else 1 + st.nang // 2)
+    rad = np.zeros((ns, max(int(rshptr[npts]), 1)), np.float32, order='F')
+    fluxes = np.zeros((2, npts), np.float32, order='F')
+    bcrad = np.zeros((ns, nbc), np.float32, order='F')
+    st.bcrad = bcrad
+    d = st.fill(OracleState())
+    wtmu = np.ascontiguousarray(wtmu, np.float32)
+    shptr = np.ascontiguousarray(shptr, np.int32); rshptr = np.ascontiguousarray(rshptr, np.int32)
+    source = np.asfortranarray(source, np.float32)
+    buf = C.create_string_buffer(600)
+    fn = lib().oracle_path_integration_once
+    fn.argtypes = [P(OracleState)] + [C.c_void_p] * 7 + [C.c_char_p]
+    _check(fn(C.byref(d), _vp(wtmu), _vp(shptr), _vp(source), _vp(rshptr), _vp(rad), _vp(fluxes), _vp(bcrad), buf), buf)
+    return rad, fluxes, bcrad
+
+
 def surface_brdf(sfctype, refparms, wavelen, mu2, phi2, mu1, phi1, nstokes):
     """SURFACE_BRDF: REFLECT(1:nstokes,1:nstokes)."""
     refl = np.zeros((4, 4), np.float32, order='F')

@@ -125,3 +125,28 @@ def test_combined_source_closed_form():
     tr = np.exp(-30.0 * np.linspace(0.001, 0.5, 50))
     np.testing.assert_allclose(rad, 0.5 * tr * tr / np.pi + V.thermal_slab_radiance(), rtol=0, atol=3.5e-4)
     assert (0.5 * tr * tr / np.pi).max() > 0.14           # the solar part is far above the tolerance
+
+
+def test_oracle_3d_sweep_converges_to_the_pinned_column_solve():
+    """BACK_INT_GRID3D has no SHDOM output of its own in the reference checkout (rico32x36x26w672ar.out needs the
+    adaptive grid).  Pin by consistency: the 3-D periodic solve of a horizontally uniform slab is horizontally uniform
+    and converges, at second order in the layer thickness, to the independent-column solve (BACK_INT_GRID1D, which
+    reproduces SHDOM's brdf_*.out)."""
+    from at3d_b200 import synthetic as S
+    err, spread = [], []
+    for nz in (11, 21, 41):
+        flux = {}
+        for ipflag in (0, 3):
+            sc = S.make_scene(nx=4, ny=3, nz=nz, cloud='slab', numphase=1, mix_fraction=0.0, ext_max=8.0, ipflag=ipflag,
+                              dz=0.4 / (nz - 1), seed=1, gndalbedo=0.3)
+            O.finalize_scene(sc)
+            st = sc.state
+            delphi = np.float32(2.0 * np.pi) / st.nphi0.astype(np.float32)
+            w = (st.wtdo[:, 0] / delphi).astype(np.float32)
+            ref, iters, solcrit = O.solve_fixed_grid(st, w, solacc=1e-5, maxiter=100)
+            assert solcrit <= 1e-5
+            flux[ipflag] = ref.fluxes.reshape(2, -1, nz)
+        spread.append(np.abs(flux[0] - flux[0][:, :1]).max() / flux[3].max())
+        err.append(np.abs(flux[0][:, 0] - flux[3][:, 0]).max() / flux[3].max())
+    assert err[1] < 0.35 * err[0] and err[2] < 0.35 * err[1] and err[2] < 3e-3
+    assert spread[2] < 0.35 * spread[1] and spread[2] < 3e-3

@@ -48,18 +48,6 @@ def test_gpu_solve_and_render_reproduce_shdom(kind):
         np.testing.assert_allclose(out[2], gold[:, 4], rtol=0, atol=1e-8)
 
 
-def test_path_integration_refuses_3d_grids():
-    import scenes
-    from at3d_b200._lib import At3dError
-    sc = scenes.make('scalar_periodic', O)
-    st = sc.state
-    delphi = np.float32(2.0 * np.pi) / st.nphi0.astype(np.float32)
-    w = (st.wtdo[:, 0] / delphi).astype(np.float32)
-    with pytest.raises(At3dError) as e:
-        solver.path_integration_ip(st, w, st.shptr, st.source, st.rshptr)
-    assert e.value.code == 3
-
-
 def test_gpu_thermal_slab():
     # Verify_Thermal (reference tests/test_shdom.py:910-982) at the angular resolution the GPU transforms support:
     # GPU solve + GPU RENDER against the oracle at the same resolution, and against the closed form within the

@@ -1,0 +1,106 @@
+"""PATH_INTEGRATION on 3-D grids on the GPU (at3d_solver_*: SWEEPING_ORDER + the BACK_INT_GRID3D data-flow sweep,
+src/polarized/shdomsub1.f:3261-4036) against the oracle's serial sweep: periodic and open boundaries, split (adaptive)
+cells, NSTOKES 1 and 3, two species, Lambertian and general BRDF surfaces; then whole fixed-grid solves."""
+import numpy as np
+import pytest
+import oracle_lib as O
+import scenes
+from at3d_b200 import solver
+from at3d_b200 import synthetic as S
+
+pytestmark = pytest.mark.gpu
+
+CASES = ['scalar_periodic', 'scalar_periodic_split', 'scalar_open_split', 'scalar_nmu16', 'polarized_periodic_split',
+         'polarized_open', 'rayleigh_two_species', 'polarized_rayleigh_varsfc', 'thick_transcut']
+
+
+def wtmu_of(st):
+    delphi = np.float32(2.0 * np.pi) / st.nphi0.astype(np.float32)
+    return (st.wtdo[:, 0] / delphi).astype(np.float32)
+
+
+def compare_path_integration(st, rtol=2e-5):
+    w = wtmu_of(st)
+    ref_rad, ref_flux, ref_bc = O.path_integration(st, w, st.shptr, st.source, st.rshptr)
+    sv = solver.SweepSolver(st, w)
+    for _ in range(2):                       # the solver object is reusable
+        rad, flux, bc = sv.path_integration(st.shptr, st.source, st.rshptr)
+    sv.close()
+    scale = np.abs(ref_rad).max()
+    np.testing.assert_allclose(flux, ref_flux, rtol=rtol, atol=1e-7)
+    np.testing.assert_allclose(bc, ref_bc, rtol=rtol, atol=1e-7 * scale)
+    np.testing.assert_allclose(rad, ref_rad, rtol=1e-4, atol=2e-6 * scale)
+    return rad, ref_rad
+
+
+@pytest.mark.parametrize('case', CASES)
+def test_sweep3d_matches_serial_sweep(case):
+    sc = scenes.make(case, O)
+    compare_path_integration(sc.state)
+
+
+@pytest.mark.parametrize('kind', ['O', 'R', 'W'])
+def test_sweep3d_brdf_surfaces(kind):
+    sc = scenes.make('polarized_open' if kind == 'W' else 'scalar_periodic_split', O)
+    st = S.with_brdf_surface(sc.state, kind, seed=3, wavelen=0.85)
+    compare_path_integration(st)
+
+
+def test_sweep3d_thermal_source():
+    sc = scenes.make('scalar_periodic', O)
+    st = sc.state.copy()
+    st.srctype, st.units, st.wavelen, st.gndtemp = 'T', 'R', 11.0, 295.0
+    st.skyrad = np.full_like(st.skyrad, 3.0)        # sky brightness temperature [K] for thermal sources
+    compare_path_integration(st.normalize())
+
+
+@pytest.mark.parametrize('group', ['1', '7'])
+def test_sweep3d_result_does_not_depend_on_the_schedule(group, monkeypatch):
+    """Ordinates in flight together (ticket order) only change the schedule: bit-identical radiances."""
+    sc = scenes.make('scalar_open_split', O)
+    st = sc.state
+    w = wtmu_of(st)
+    sv = solver.SweepSolver(st, w)
+    base = sv.path_integration(st.shptr, st.source, st.rshptr)
+    sv.close()
+    monkeypatch.setenv('AT3D_SWEEP_GROUP', group)
+    sv = solver.SweepSolver(st, w)
+    out = sv.path_integration(st.shptr, st.source, st.rshptr)
+    sv.close()
+    for x, y in zip(out, base):
+        np.testing.assert_array_equal(x, y)
+
+
+@pytest.mark.parametrize('case', ['scalar_periodic_split', 'polarized_open', 'rayleigh_two_species'])
+def test_fixed_grid_solve_3d(case):
+    """SOLUTION_ITERATIONS on a fixed 3-D grid: GPU PATH_INTEGRATION + COMPUTE_SOURCE vs the oracle's solve, then the
+    GPU RENDER of the GPU solution vs the oracle's RENDER of the oracle's solution."""
+    from at3d_b200.device import DeviceState
+    sc = scenes.make(case, O)
+    st = sc.state
+    w = wtmu_of(st)
+    sol, iters, solcrit, _ = solver.solve_fixed_grid(st, w, solacc=1e-4, maxiter=50)
+    ref, iters_r, solcrit_r = O.solve_fixed_grid(st, w, solacc=1e-4, maxiter=50)
+    assert iters == iters_r and solcrit <= 1e-4
+    np.testing.assert_array_equal(sol.shptr, ref.shptr)
+    np.testing.assert_array_equal(sol.rshptr, ref.rshptr)
+    scale = np.abs(ref.radiance).max()
+    np.testing.assert_allclose(sol.radiance, ref.radiance, rtol=1e-4, atol=5e-6 * scale)
+    np.testing.assert_allclose(sol.fluxes, ref.fluxes, rtol=1e-4, atol=1e-7)
+    rays = scenes.ray_set(sc)
+    dev = DeviceState(sol)
+    out = dev.render(rays)
+    dev.close()
+    refout = O.render(ref, rays)
+    np.testing.assert_allclose(out[0], refout[0], rtol=1e-4, atol=1e-6 * np.abs(refout[0]).max())
+    for k in range(1, out.shape[0]):
+        np.testing.assert_allclose(out[k], refout[k], rtol=1e-4, atol=1e-6)
+
+
+def test_solver_refuses_what_it_does_not_cover():
+    from at3d_b200._lib import At3dError
+    sc = S.make_scene(nx=5, ny=5, nz=6, ipflag=3, seed=1)
+    O.finalize_scene(sc)
+    with pytest.raises(At3dError) as e:
+        solver.SweepSolver(sc.state, wtmu_of(sc.state))
+    assert e.value.code == 3
