@@ -15,6 +15,7 @@
 #include <cstdarg>
 #include <cmath>
 #include <vector>
+#include <cub/cub.cuh>
 #include "at3d_host.h"
 #include "at3d_surface.cuh"
 
@@ -401,6 +402,9 @@ struct SwArgs {
     float *radf;                // [npts, nst, nang] radiance (GRIDRAD of every ordinate)
     double eps, transmin;
     int *ticket, *err;
+    const int *perm;            // [nang][npts] processing order of an ordinate: positions r sorted by dependency level
+                                // (null: the reference order itself)
+    int *level;                 // [nang][npts] dependency level of (ordinate, point); -1 = not yet (level pass only)
 };
 
 __device__ __forceinline__ float ld_vol(const float *p) { return *(const volatile float *)p; }
@@ -413,7 +417,10 @@ __device__ __forceinline__ int face_corner(int kface, int n)
     return 1 + (n | (s << 2));
 }
 
-template <int NST>
+// LEVEL = true: the same walk and waits, but what travels is the dependency level 1 + max(level of the four face
+// points) instead of the radiance (run once per solver object; the levels order the threads of the real sweep so that
+// a thread's face points were finished a whole wavefront earlier and neighbouring lanes never wait for each other)
+template <int NST, bool LEVEL>
 __global__ void __launch_bounds__(256) sweep3d_kernel(SwArgs a, int up)
 {
     __shared__ int s_ticket;
@@ -431,9 +438,10 @@ __global__ void __launch_bounds__(256) sweep3d_kernel(SwArgs a, int up)
         t -= grp * per;
         chunk = t / G; io = grp * G + t % G;
     }
-    const int r = chunk * 256 + threadIdx.x;
-    if (r >= a.npts) return;
+    const int kpos = chunk * 256 + threadIdx.x;
+    if (kpos >= a.npts) return;
     const int ia = (up ? nh : 0) + io;
+    const int r = (!LEVEL && a.perm) ? a.perm[(size_t)a.npts * ia + kpos] : kpos;
     const OrdDir D = a.dir[ia];
     const int *so_oct = a.sweepord + (size_t)a.npts * (D.joct - 1);
     const int *rank = a.rank + (size_t)a.npts * (D.joct - 1);
@@ -568,6 +576,23 @@ __global__ void __launch_bounds__(256) sweep3d_kernel(SwArgs a, int up)
         for (int k = 0; k < NST; k++) srcext1[k] = srcext0[k];
         icell = inextcell;
     }
+    if (LEVEL) {
+        int *L = a.level + (size_t)a.npts * ia;
+        int lv = 0;
+        if (!fail) {
+            int spins = 0;
+            for (;;) {
+                const int l1 = *(volatile int *)&L[i1 - 1], l2 = *(volatile int *)&L[i2 - 1];
+                const int l3 = *(volatile int *)&L[i3 - 1], l4 = *(volatile int *)&L[i4 - 1];
+                if (l1 >= 0 && l2 >= 0 && l3 >= 0 && l4 >= 0) { lv = 1 + max(max(l1, l2), max(l3, l4)); break; }
+                if (++spins > (1 << 22) || ((spins & 255) == 0 && *(volatile int *)a.err)) { fail = 4; break; }
+                __nanosleep(64);
+            }
+        }
+        if (fail) atomicCAS(a.err, 0, fail);
+        *(volatile int *)&L[ipt - 1] = lv;
+        return;
+    }
     float out[NST];
     if (!fail) {
         // wait for the four face radiances (bounded; polls go to L2)
@@ -608,6 +633,32 @@ __global__ void __launch_bounds__(256) sweep3d_kernel(SwArgs a, int up)
 
 // GRIDRAD(1,.) = -1 everywhere, then the boundary values of every ordinate (shdomsub1.f:1968-1972, 2024-2071):
 // thread = (point, ordinate)
+__global__ void sweep3d_level_init_kernel(int npts, int nang, const unsigned char *bflag, int *level)
+{
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (size_t)npts * nang) return;
+    const int p = (int)(t % npts), ia = (int)(t / npts);
+    level[t] = (bflag[p] & (ia >= nang / 2 ? 2 : 1)) ? 0 : -1;
+}
+
+// sort key of (ordinate, position r): ordinate | level | r
+__global__ void sweep3d_key_kernel(SwArgs a, unsigned long long *keys)
+{
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (size_t)a.npts * a.nang) return;
+    const int r = (int)(t % a.npts), ia = (int)(t / a.npts);
+    const int entry = a.sweepord[(size_t)a.npts * (a.dir[ia].joct - 1) + r];
+    const int ipt = cell_gp(a.S, entry >> 3, (entry & 7) + 1);
+    const int lv = a.level[(size_t)a.npts * ia + (ipt - 1)];
+    keys[t] = ((unsigned long long)ia << 48) | ((unsigned long long)(lv < 0 ? 0 : lv) << 24) | (unsigned long long)r;
+}
+
+__global__ void sweep3d_perm_kernel(size_t n, const unsigned long long *keys, int *perm)
+{
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) perm[t] = (int)(keys[t] & 0xFFFFFFull);
+}
+
 template <int NST>
 __global__ void sweep3d_init_kernel(PiArgs a, float *radf, const int *toppt, int up)
 {
@@ -864,14 +915,52 @@ extern "C" int at3d_solver_create(const at3d_state_desc *d, const float *wtmu, f
     int dev = 0, nsm = 148, per_sm = 1;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
-    if (nst == 1) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sweep3d_kernel<1>, 256, 0);
-    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sweep3d_kernel<3>, 256, 0);
+    if (nst == 1) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sweep3d_kernel<1, false>, 256, 0);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sweep3d_kernel<3, false>, 256, 0);
     sv->blocks_resident = nsm * (per_sm > 0 ? per_sm : 1);
     const long slab = (long)(d->nx + 1) * (d->ny + 1);
     long g = (long)sv->blocks_resident * 256 / (4 * slab > 0 ? 4 * slab : 1);
     const char *genv = getenv("AT3D_SWEEP_GROUP");
     if (genv) g = atol(genv);
     w.group = (int)(g < 1 ? 1 : (g > nh ? nh : g));
+    // dependency levels -> processing order (skipped for very large grids: the reference order is used as it is)
+    const size_t nkeys = (size_t)npts * nang;
+    const char *lenv = getenv("AT3D_SWEEP_LEVELS");
+    const bool want_levels = lenv ? atoi(lenv) != 0 : true;
+    if (want_levels && npts < (1 << 24) && nkeys * 24 < ((size_t)8 << 30)) {
+        Arena T;
+        int *level = T.alloc<int>(nkeys);
+        unsigned long long *k0 = T.alloc<unsigned long long>(nkeys), *k1 = T.alloc<unsigned long long>(nkeys);
+        int *perm = A.alloc<int>(nkeys);
+        size_t tmpb = 0;
+        cub::DeviceRadixSort::SortKeys(nullptr, tmpb, k0, k1, nkeys, 0, 57, 0);
+        char *tmp = T.alloc<char>(tmpb);
+        cudaError_t e = cudaSuccess;
+        if (!level || !k0 || !k1 || !perm || !tmp) { at3d_solver_destroy(sv); set_msg(errmsg, "device allocation failure"); return 4; }
+        const int nb = (int)((nkeys + 255) / 256);
+        cudaMemset(a.dofield, 0, (size_t)npts * nst * nang * sizeof(float));
+        sweep3d_level_init_kernel<<<nb, 256>>>(npts, nang, w.bflag, level);
+        w.level = level; w.perm = nullptr;
+        for (int up = 0; up < 2; up++) {
+            cudaMemsetAsync(w.ticket, 0, up == 0 ? 2 * sizeof(int) : sizeof(int), 0);
+            sweep3d_kernel<1, true><<<w.nchunks * nh, 256>>>(w, up);
+        }
+        sweep3d_key_kernel<<<nb, 256>>>(w, k0);
+        cub::DeviceRadixSort::SortKeys(tmp, tmpb, k0, k1, nkeys, 0, 57, 0);
+        sweep3d_perm_kernel<<<nb, 256>>>(nkeys, k1, perm);
+        int err = 0;
+        e = cudaDeviceSynchronize();
+        if (e == cudaSuccess) e = cudaMemcpy(&err, w.err, sizeof(int), cudaMemcpyDeviceToHost);
+        w.level = nullptr;
+        if (e != cudaSuccess || err) {
+            at3d_solver_destroy(sv);
+            set_msg(errmsg, e != cudaSuccess ? "CUDA error in the level pass of at3d_solver_create: %s" : "BACK_INT_GRID3D walk failed in the level pass (code %s)",
+                    e != cudaSuccess ? cudaGetErrorString(e) : (err == 3 ? "3: boundary without a valid face" : err == 4 ? "4: wait timed out" : "1/2: bad cell or SO<0"));
+            return e != cudaSuccess ? 4 : 1;
+        }
+        w.perm = perm;
+        if (!genv) w.group = nh;             // all ordinates advance through the levels together
+    }
     *out = sv;
     return 0;
 }
@@ -908,7 +997,7 @@ extern "C" int at3d_solver_path_integration(at3d_solver *sv, const int32_t *shpt
             else pi_brdf_kernel<NST><<<nbb, 128>>>(a);                                                 \
         }                                                                                              \
         sweep3d_boundary_kernel<NST><<<up ? nbb : ntb, 128>>>(a, w.radf, sv->toppt, up);               \
-        sweep3d_kernel<NST><<<nsweep, 256>>>(w, up);                                                   \
+        sweep3d_kernel<NST, false><<<nsweep, 256>>>(w, up);                                                   \
         pi_flux_kernel<NST><<<npb, 256>>>(a, up);                                                      \
         if (!up && !sv->lamb) sweep3d_store_down_kernel<NST><<<nbb, 128>>>(a, w.radf);                 \
     }

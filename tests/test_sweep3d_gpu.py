@@ -54,16 +54,20 @@ def test_sweep3d_thermal_source():
     compare_path_integration(st.normalize())
 
 
-@pytest.mark.parametrize('group', ['1', '7'])
-def test_sweep3d_result_does_not_depend_on_the_schedule(group, monkeypatch):
-    """Ordinates in flight together (ticket order) only change the schedule: bit-identical radiances."""
-    sc = scenes.make('scalar_open_split', O)
+@pytest.mark.parametrize('group,levels', [('1', '1'), ('7', '1'), ('1', '0'), ('5', '0')])
+def test_sweep3d_result_does_not_depend_on_the_schedule(group, levels, monkeypatch):
+    """Ordinates in flight together (ticket order) and the processing order within an ordinate (dependency levels or
+    the reference's sweep order) only change the schedule: bit-identical radiances."""
+    monkeypatch.delenv('AT3D_SWEEP_GROUP', raising=False)
+    monkeypatch.delenv('AT3D_SWEEP_LEVELS', raising=False)
+    sc = scenes.make('polarized_periodic_split', O)
     st = sc.state
     w = wtmu_of(st)
     sv = solver.SweepSolver(st, w)
     base = sv.path_integration(st.shptr, st.source, st.rshptr)
     sv.close()
     monkeypatch.setenv('AT3D_SWEEP_GROUP', group)
+    monkeypatch.setenv('AT3D_SWEEP_LEVELS', levels)
     sv = solver.SweepSolver(st, w)
     out = sv.path_integration(st.shptr, st.source, st.rshptr)
     sv.close()
