@@ -80,3 +80,25 @@ void tr_plan_destroy(TrPlan *p);
 int tr_plan_nang(const TrPlan *p);
 cudaError_t tr_sh_to_do(const TrPlan *P, int npts, const int *shptr_d, const float *sh_d, float *do_d, cudaStream_t st);
 cudaError_t tr_do_to_sh(const TrPlan *P, int npts, const int *rshptr_d, const float *do_d, float *sh_d, cudaStream_t st);
+
+// ---- COMPUTE_SOURCE on device-resident arrays (at3d_source.cu), shared with the solution iterations (at3d_solver.cu) ----
+struct CsArgs {
+    int npts, nstokes, nstleg, nlm, ml, mm, nleg, npart, nq, srctype, deltam, interp_new, newmethod;
+    int first, accelflag, fixsh;
+    float phasemax, secmu0, srcmin;
+    const float *extinct, *albedo, *total_ext, *legen, *phaseinterpwt, *dirflux, *radiance, *ylmsun, *planck;
+    const int *iphase, *rshptr, *lofj;
+    const int *shptr_old, *oshptr_old;
+    const float *source_old, *delsource_old;
+    int *ns_new;              // [npts]
+    double *partials;         // [nblocks,4]
+    int *bad;                 // NR>NLM flag
+    // second kernel
+    const int *shptr_new;
+    float *source_new, *delsource_new;
+};
+
+size_t cs_scan_bytes(int npts);
+int cs_grid_blocks(int npts);
+int cs_device_step(CsArgs &a, int nblk, void *scan_tmp, size_t tmpb, int *shptr_new, double *sums, int maxiv, size_t cap_new,
+                   float *source_new, int *total_new_out, char *errmsg);

@@ -965,26 +965,15 @@ extern "C" int at3d_solver_create(const at3d_state_desc *d, const float *wtmu, f
     return 0;
 }
 
-extern "C" int at3d_solver_path_integration(at3d_solver *sv, const int32_t *shptr, const float *source, const int32_t *rshptr,
-                                            float *radiance, float *fluxes, float *bcrad, double *kernel_ms, char *errmsg)
+// PATH_INTEGRATION on device-resident SH arrays: shptr_d/src_d -> rad_d (addressed by rshptr_d), fluxes and BCRAD stay in
+// the solver object.  Launches only (stream 0); *err_out is read back by the caller after a synchronisation.
+static cudaError_t sv_path_integration_device(at3d_solver *sv, const int *shptr_d, const float *src_d, const int *rshptr_d, float *rad_d)
 {
-    if (errmsg) errmsg[0] = 0;
-    if (!sv || !shptr || !source || !rshptr || !radiance || !fluxes || !bcrad) { set_msg(errmsg, "null argument"); return 1; }
-    const int npts = sv->npts, nst = sv->nst, nang = sv->nang, nh = nang / 2;
+    const int npts = sv->npts, nst = sv->nst, nh = sv->nang / 2;
     PiArgs &a = sv->a;
     SwArgs &w = sv->w;
-    const size_t nsh = (size_t)nst * shptr[npts], nrad = (size_t)nst * rshptr[npts];
-    Arena T;                                   // per-call: the SH arrays change length every iteration
-    float *src_d = T.up(source, nsh), *rad_d = T.alloc<float>(nrad);
-    if (!src_d || !rad_d) { set_msg(errmsg, "device allocation failure"); return 4; }
-    cudaError_t e = cudaMemcpy(sv->shptr_d, shptr, ((size_t)npts + 1) * sizeof(int), cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMemcpy(sv->rshptr_d, rshptr, ((size_t)npts + 1) * sizeof(int), cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMemset(a.bcrad, 0, sv->nbc * sizeof(float));
-    if (e != cudaSuccess) { set_msg(errmsg, "CUDA error %s in at3d_solver_path_integration", cudaGetErrorString(e)); return 4; }
-    cudaEvent_t e0, e1;
-    cudaEventCreate(&e0); cudaEventCreate(&e1);
-    cudaEventRecord(e0, 0);
-    e = tr_sh_to_do(sv->P, npts, sv->shptr_d, src_d, a.dofield, 0);
+    cudaError_t e = cudaMemsetAsync(a.bcrad, 0, sv->nbc * sizeof(float), 0);
+    if (e == cudaSuccess) e = tr_sh_to_do(sv->P, npts, shptr_d, src_d, a.dofield, 0);
     const int nsweep = w.nchunks * nh, npb = (npts + 255) / 256;
     const int ninit = (int)(((size_t)npts * nh + 255) / 256);
     const int ntb = (a.ntop * nh + 127) / 128, nbb = (a.nbot * nh + 127) / 128;
@@ -997,31 +986,343 @@ extern "C" int at3d_solver_path_integration(at3d_solver *sv, const int32_t *shpt
             else pi_brdf_kernel<NST><<<nbb, 128>>>(a);                                                 \
         }                                                                                              \
         sweep3d_boundary_kernel<NST><<<up ? nbb : ntb, 128>>>(a, w.radf, sv->toppt, up);               \
-        sweep3d_kernel<NST, false><<<nsweep, 256>>>(w, up);                                                   \
+        sweep3d_kernel<NST, false><<<nsweep, 256>>>(w, up);                                            \
         pi_flux_kernel<NST><<<npb, 256>>>(a, up);                                                      \
         if (!up && !sv->lamb) sweep3d_store_down_kernel<NST><<<nbb, 128>>>(a, w.radf);                 \
     }
     if (nst == 1) { AT3D_SWEEP3D(1) } else { AT3D_SWEEP3D(3) }
 #undef AT3D_SWEEP3D
-    if (e == cudaSuccess) e = tr_do_to_sh(sv->P, npts, sv->rshptr_d, w.radf, rad_d, 0);
-    cudaEventRecord(e1, 0);
-    if (e == cudaSuccess) e = cudaEventSynchronize(e1);
-    if (e == cudaSuccess) e = cudaGetLastError();
-    float ms = 0.0f;
-    if (e == cudaSuccess) cudaEventElapsedTime(&ms, e0, e1);
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (e == cudaSuccess) e = tr_do_to_sh(sv->P, npts, rshptr_d, w.radf, rad_d, 0);
+    return e;
+}
+
+static int sv_sweep_error(at3d_solver *sv, char *errmsg)
+{
     int err = 0;
-    if (e == cudaSuccess) e = cudaMemcpy(&err, w.err, sizeof(int), cudaMemcpyDeviceToHost);
-    if (e == cudaSuccess) e = cudaMemcpy(radiance, rad_d, nrad * sizeof(float), cudaMemcpyDeviceToHost);
-    if (e == cudaSuccess) e = cudaMemcpy(fluxes, a.fluxes, (size_t)2 * npts * sizeof(float), cudaMemcpyDeviceToHost);
-    if (e == cudaSuccess) e = cudaMemcpy(bcrad, a.bcrad, sv->nbc * sizeof(float), cudaMemcpyDeviceToHost);
-    if (e != cudaSuccess) { set_msg(errmsg, "CUDA error %s in at3d_solver_path_integration", cudaGetErrorString(e)); return 4; }
+    cudaError_t e = cudaMemcpy(&err, sv->w.err, sizeof(int), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) { set_msg(errmsg, "CUDA error %s in the 3-D sweep", cudaGetErrorString(e)); return 4; }
     if (err) {
         static const char *what[] = {"", "BACK_INT_GRID: ICELL=0", "BACK_INT_GRID: SO<0", "BACK_INT_GRID3D: INEXTCELL=0 without a valid face",
                                      "sweep wait timed out", "BACK_INT_GRID3D: RAD<0"};
         set_msg(errmsg, "%s", what[err < 6 ? err : 0]);
         return 1;
     }
+    return 0;
+}
+
+extern "C" int at3d_solver_path_integration(at3d_solver *sv, const int32_t *shptr, const float *source, const int32_t *rshptr,
+                                            float *radiance, float *fluxes, float *bcrad, double *kernel_ms, char *errmsg)
+{
+    if (errmsg) errmsg[0] = 0;
+    if (!sv || !shptr || !source || !rshptr || !radiance || !fluxes || !bcrad) { set_msg(errmsg, "null argument"); return 1; }
+    const int npts = sv->npts, nst = sv->nst;
+    PiArgs &a = sv->a;
+    const size_t nsh = (size_t)nst * shptr[npts], nrad = (size_t)nst * rshptr[npts];
+    Arena T;                                   // per-call: the SH arrays change length every iteration
+    float *src_d = T.up(source, nsh), *rad_d = T.alloc<float>(nrad);
+    if (!src_d || !rad_d) { set_msg(errmsg, "device allocation failure"); return 4; }
+    cudaError_t e = cudaMemcpy(sv->shptr_d, shptr, ((size_t)npts + 1) * sizeof(int), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(sv->rshptr_d, rshptr, ((size_t)npts + 1) * sizeof(int), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { set_msg(errmsg, "CUDA error %s in at3d_solver_path_integration", cudaGetErrorString(e)); return 4; }
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0, 0);
+    e = sv_path_integration_device(sv, sv->shptr_d, src_d, sv->rshptr_d, rad_d);
+    cudaEventRecord(e1, 0);
+    if (e == cudaSuccess) e = cudaEventSynchronize(e1);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    float ms = 0.0f;
+    if (e == cudaSuccess) cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (e == cudaSuccess) e = cudaMemcpy(radiance, rad_d, nrad * sizeof(float), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(fluxes, a.fluxes, (size_t)2 * npts * sizeof(float), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(bcrad, a.bcrad, sv->nbc * sizeof(float), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) { set_msg(errmsg, "CUDA error %s in at3d_solver_path_integration", cudaGetErrorString(e)); return 4; }
+    const int rc = sv_sweep_error(sv, errmsg);
+    if (rc) return rc;
     if (kernel_ms) *kernel_ms = ms;
     return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// SOLUTION_ITERATIONS on a fixed grid, device-resident (src/polarized/shdomsub1.f:445-822 without SPLIT_GRID):
+// SOURCE, DELSOURCE, RADIANCE and their pointer arrays stay in HBM for the whole solve; per iteration only the four
+// norms of COMPUTE_SOURCE, the two SH totals and the sweep's error flag come back to the host.
+// ---------------------------------------------------------------------------------------------------------------------
+struct RtArgs {
+    int npts, ml, mm, nstleg, nleg, npart, nq, nstokes, interp_new, deltam, highorderrad;
+    float phasemax, shacc;
+    const float *total_ext, *extinct, *albedo, *legen, *phaseinterpwt, *radiance;
+    const int *iphase, *shptr, *rshptr_old, *lofj;
+    int *first_zero;        // first point (0-based) whose old NR is 0 (NOTEND turns false there), npts if none
+    int *nr;                // [npts+1] out
+};
+
+__global__ void rt_first_zero_kernel(RtArgs a)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.npts) return;
+    if (a.rshptr_old[i + 1] - a.rshptr_old[i] == 0) atomicMin(a.first_zero, i);
+}
+
+// RADIANCE_TRUNCATION (shdomsub1.f:1615-1805), the adaptive branch: thread = grid point
+__global__ void rt_adaptive_kernel(RtArgs a)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.npts) return;
+    const int ml = a.ml, mm = a.mm, nq = a.nq;
+    const size_t nlt = (size_t)a.nstleg * (a.nleg + 1);
+    int lr;
+    if (i < *a.first_zero) {
+        const float ext = a.total_ext[i];
+        const float rad0 = a.radiance[(size_t)a.nstokes * a.rshptr_old[i]];
+        lr = 1;
+        for (int l = 1; l <= ml; l++) {
+            float rad = 0.0f;
+            for (int ipa = 0; ipa < a.npart; ipa++) {
+                const size_t po = (size_t)i + (size_t)a.npts * ipa;
+                const float w = ext == 0.0f ? 1.0f : a.extinct[po] / ext;
+                if (w == 0.0f) continue;
+                const int *iph = a.iphase + (size_t)nq * po;
+                const float *pw = a.phaseinterpwt + (size_t)nq * po;
+                float legent;
+                if (!a.interp_new) {
+                    legent = a.legen[nlt * (size_t)(iph[0] - 1) + (size_t)a.nstleg * l];
+                } else {
+                    if (pw[0] >= a.phasemax) legent = a.legen[nlt * (size_t)(iph[0] - 1) + (size_t)a.nstleg * l];
+                    else {
+                        legent = 0.0f;
+                        for (int q = 0; q < nq; q++) {
+                            if (pw[q] <= 1e-5f) continue;
+                            legent = legent + a.legen[nlt * (size_t)(iph[q] - 1) + (size_t)a.nstleg * l] * pw[q];
+                        }
+                    }
+                    if (a.deltam) {
+                        // F(IPA) of the point; the reference indexes LEGEN(Q,ML+1,IPHASE(Q,.)) with the mixture index Q (:1672)
+                        float f;
+                        if (pw[0] >= a.phasemax) f = a.legen[nlt * (size_t)(iph[0] - 1) + (size_t)a.nstleg * (ml + 1)];
+                        else {
+                            f = 0.0f;
+                            for (int q = 0; q < nq; q++) {
+                                if (pw[q] <= 1e-5f) continue;
+                                f = f + a.legen[nlt * (size_t)(iph[q] - 1) + (size_t)a.nstleg * (ml + 1) + q] * pw[q];
+                            }
+                        }
+                        legent = legent * (1.0f / (1 - f));
+                    }
+                }
+                rad = rad + w * a.albedo[po] * legent * rad0;
+            }
+            if (rad > a.shacc) lr = l;
+        }
+    } else {
+        lr = ml;
+    }
+    int ns = a.shptr[i + 1] - a.shptr[i];
+    if (ns < 1) ns = 1;
+    const int ls = a.lofj[ns - 1];
+    lr = min(lr, ls + ml / 8 + 2);
+    if (a.highorderrad) lr = ml;
+    a.nr[i] = lr <= mm ? lr * (lr + 1) + lr + 1 : (2 * mm + 1) * lr - (mm * (1 + (mm - 1))) + mm + 1;
+}
+
+// the FIXSH / out-of-memory branch (:1774-1802)
+__global__ void rt_fixed_kernel(RtArgs a)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.npts) return;
+    int nr = max(4, a.shptr[i + 1] - a.shptr[i]);
+    if (a.highorderrad) nr = a.ml <= a.mm ? a.ml * (a.ml + 1) + a.ml + 1 : (2 * a.mm + 1) * a.ml - (a.mm * (1 + (a.mm - 1))) + a.mm + 1;
+    a.nr[i] = nr;
+}
+
+__global__ void sv_iota_kernel(int n, int step, int *out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = step * i;
+}
+
+// ACCELERATE_SOLUTION (shdomsub1.f:1807-1832): warp = grid point
+__global__ void sv_accelerate_kernel(int npts, int nst, float accelpar, const int *shptr, const int *oshptr, float *source, const float *delsource)
+{
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (i >= npts) return;
+    const int is = shptr[i], isd = oshptr[i];
+    const int nsc = min(shptr[i + 1] - is, oshptr[i + 1] - isd) * nst;
+    float *s = source + (size_t)nst * is;
+    const float *d = delsource + (size_t)nst * isd;
+    for (int j = lane; j < nsc; j += 32) s[j] = s[j] + accelpar * d[j];
+}
+
+extern "C" int at3d_solver_solve(at3d_solver *sv, const at3d_state_desc *d, int maxiter, float solacc, float shacc, int accelflag,
+                                 int highorderrad, int iterfixsh, int maxiv, int32_t *shptr, float *source, int32_t *rshptr,
+                                 float *radiance, float *fluxes, float *bcrad, int32_t *iters_out, float *solcrit_out,
+                                 double *ms_out /*[3]: PATH_INTEGRATION, COMPUTE_SOURCE, whole loop*/, char *errmsg)
+{
+    if (errmsg) errmsg[0] = 0;
+    if (!sv || !d || !shptr || !source || !rshptr || !radiance || !fluxes || !bcrad) { set_msg(errmsg, "null argument"); return 1; }
+    if (d->npts != sv->npts || d->nstokes != sv->nst) { set_msg(errmsg, "at3d_solver_solve: desc does not match the solver object"); return 1; }
+    const int npts = sv->npts, nst = sv->nst;
+    const size_t nlt = (size_t)d->nstleg * (d->nleg + 1);
+    if (nlt > 256) { set_msg(errmsg, "COMPUTE_SOURCE: Legendre table longer than 256 entries"); return 3; }
+    const size_t maxir = (size_t)maxiv + npts;
+    if ((size_t)4 * npts > maxir || maxiv < 1) { set_msg(errmsg, "MAXIV too small"); return 2; }
+    const int nq = 8 * d->maxnmicro;
+    Arena A;
+    CsArgs a;
+    memset(&a, 0, sizeof(a));
+    a.npts = npts; a.nstokes = nst; a.nstleg = d->nstleg; a.nlm = d->nlm; a.ml = d->ml; a.mm = d->mm; a.nleg = d->nleg;
+    a.npart = d->npart; a.nq = nq; a.srctype = d->srctype; a.deltam = d->deltam; a.interp_new = d->interp_new;
+    a.newmethod = 1; a.accelflag = accelflag;
+    a.phasemax = d->phasemax; a.secmu0 = 1.0f / fabsf(d->solarmu); a.srcmin = shacc;
+    std::vector<int> lofj(d->nlm);
+    {
+        int j = 0;
+        for (int l = 0; l <= d->ml; l++) {
+            const int me = l < d->mm ? l : d->mm;
+            for (int m = -me; m <= me; m++) { if (j < d->nlm) lofj[j] = l; j++; }
+        }
+        if (j != d->nlm) { set_msg(errmsg, "NLM inconsistent with ML, MM"); return 1; }
+    }
+    float albmax = 0.0f;
+    for (size_t i = 0; i < (size_t)npts * d->npart; i++) albmax = d->albedo[i] > albmax ? d->albedo[i] : albmax;
+    a.extinct = A.up(d->extinct, (size_t)npts * d->npart); a.albedo = A.up(d->albedo, (size_t)npts * d->npart);
+    a.total_ext = sv->a.total_ext;
+    a.legen = A.up(d->legen, nlt * d->numphase);
+    a.iphase = A.up(d->iphase, (size_t)nq * npts * d->npart);
+    a.phaseinterpwt = A.up(d->phaseinterpwt, (size_t)nq * npts * d->npart);
+    a.dirflux = sv->a.dirflux;
+    a.ylmsun = A.up(d->ylmsun, (size_t)d->nstleg * d->nlm);
+    a.planck = d->planck ? A.up(d->planck, (size_t)npts * d->npart) : nullptr;
+    a.lofj = A.up(lofj.data(), lofj.size());
+    const int nblk = cs_grid_blocks(npts);
+    size_t tmpb = cs_scan_bytes(npts);
+    void *tmp = A.alloc<unsigned char>(tmpb);
+    a.ns_new = A.alloc<int>((size_t)npts + 1);
+    a.partials = A.alloc<double>((size_t)nblk * 4);
+    a.bad = A.alloc<int>(2);
+    double *sums = A.alloc<double>(4);
+    float *src[2] = {A.alloc<float>((size_t)nst * maxiv), A.alloc<float>((size_t)nst * maxiv)};
+    float *dels = A.alloc<float>((size_t)nst * maxiv);
+    float *rad = A.alloc<float>((size_t)nst * maxir);
+    int *sh[2] = {A.alloc<int>((size_t)npts + 1), A.alloc<int>((size_t)npts + 1)};
+    int *osh = A.alloc<int>((size_t)npts + 1);
+    int *rsh[2] = {A.alloc<int>((size_t)npts + 2), A.alloc<int>((size_t)npts + 2)};
+    int *nr = A.alloc<int>((size_t)npts + 1);
+    if (!a.extinct || !a.albedo || !a.legen || !a.iphase || !a.phaseinterpwt || !a.ylmsun || !a.lofj || !tmp || !a.ns_new || !a.partials ||
+        !a.bad || !sums || !src[0] || !src[1] || !dels || !rad || !sh[0] || !sh[1] || !osh || !rsh[0] || !rsh[1] || !nr || (d->planck && !a.planck)) {
+        set_msg(errmsg, "at3d_solver_solve: NULL input array or device allocation failure"); return 4;
+    }
+    RtArgs rt;
+    memset(&rt, 0, sizeof(rt));
+    rt.npts = npts; rt.ml = d->ml; rt.mm = d->mm; rt.nstleg = d->nstleg; rt.nleg = d->nleg; rt.npart = d->npart; rt.nq = nq;
+    rt.nstokes = nst; rt.interp_new = d->interp_new; rt.deltam = d->deltam; rt.highorderrad = highorderrad;
+    rt.phasemax = d->phasemax; rt.shacc = shacc;
+    rt.total_ext = a.total_ext; rt.extinct = a.extinct; rt.albedo = a.albedo; rt.legen = a.legen; rt.phaseinterpwt = a.phaseinterpwt;
+    rt.iphase = a.iphase; rt.lofj = a.lofj; rt.first_zero = a.bad + 1; rt.nr = nr; rt.radiance = rad;
+    const int pb = (npts + 255) / 256;
+    cudaEvent_t ev[4];
+    for (auto &x : ev) cudaEventCreate(&x);
+    cudaEventRecord(ev[0], 0);
+    // first guess: zero radiance with 4 terms per point, SOURCE from COMPUTE_SOURCE(FIRST=.TRUE.)
+    int cur = 0, rcur = 0, rc = 0, total_s = 0, iter = 0, fixsh = 0;
+    sv_iota_kernel<<<(npts + 2 + 255) / 256, 256>>>(npts + 1, 4, rsh[rcur]);
+    cudaMemcpyAsync(rsh[rcur] + npts + 1, rsh[rcur] + npts, sizeof(int), cudaMemcpyDeviceToDevice, 0);
+    cudaMemsetAsync(rad, 0, (size_t)nst * 4 * npts * sizeof(float), 0);
+    cudaMemsetAsync(sh[cur], 0, ((size_t)npts + 1) * sizeof(int), 0);
+    cudaMemsetAsync(osh, 0, ((size_t)npts + 1) * sizeof(int), 0);
+    int total_r = 4 * npts;
+    a.first = 1; a.fixsh = 0;
+    a.rshptr = rsh[rcur]; a.radiance = rad; a.shptr_old = sh[cur]; a.oshptr_old = osh; a.source_old = src[cur];
+    a.delsource_old = dels; a.delsource_new = dels;
+    size_t cap_new = (size_t)maxiv < (size_t)npts * d->nlm ? (size_t)maxiv : (size_t)npts * d->nlm;
+    rc = cs_device_step(a, nblk, tmp, tmpb, sh[1 - cur], sums, maxiv, cap_new, src[1 - cur], &total_s, errmsg);
+    cur = 1 - cur;
+    if (!rc && accelflag) {
+        cudaMemcpyAsync(osh, sh[cur], ((size_t)npts + 1) * sizeof(int), cudaMemcpyDeviceToDevice, 0);
+        cudaMemsetAsync(dels, 0, (size_t)nst * total_s * sizeof(float), 0);
+    }
+    float solcrit = 1.0f, acc = 0.0f, deljdot = 0, deljold = 0, deljnew = 0, jnorm = 0;
+    double ms_path = 0.0, ms_src = 0.0;
+    while (!rc && iter < maxiter && solcrit > solacc) {
+        iter++;
+        // RADIANCE_TRUNCATION -> new RSHPTR (the old RADIANCE / RSHPTR are still in place)
+        rt.shptr = sh[cur]; rt.rshptr_old = rsh[rcur];
+        bool fixed = fixsh != 0;
+        for (int attempt = 0; attempt < 2; attempt++) {
+            if (!fixed) {
+                cudaMemcpyAsync(rt.first_zero, &npts, sizeof(int), cudaMemcpyHostToDevice, 0);
+                rt_first_zero_kernel<<<pb, 256>>>(rt);
+                rt_adaptive_kernel<<<pb, 256>>>(rt);
+            } else {
+                rt_fixed_kernel<<<pb, 256>>>(rt);
+            }
+            cudaMemsetAsync(nr + npts, 0, sizeof(int), 0);
+            cub::DeviceScan::ExclusiveSum(tmp, tmpb, nr, rsh[1 - rcur], npts + 1);
+            cudaMemcpy(&total_r, rsh[1 - rcur] + npts, sizeof(int), cudaMemcpyDeviceToHost);
+            if ((size_t)total_r <= maxir) break;
+            if (fixed) { set_msg(errmsg, "RADIANCE_TRUNCATION: Really out of memory for more radiance terms. Increase MAXIV."); rc = 2; break; }
+            fixed = true;
+        }
+        if (rc) break;
+        rcur = 1 - rcur;
+        cudaMemcpyAsync(rsh[rcur] + npts + 1, rsh[rcur] + npts, sizeof(int), cudaMemcpyDeviceToDevice, 0);
+        // PATH_INTEGRATION
+        cudaEventRecord(ev[1], 0);
+        cudaError_t e = sv_path_integration_device(sv, sh[cur], src[cur], rsh[rcur], rad);
+        cudaEventRecord(ev[2], 0);
+        if (e != cudaSuccess) { set_msg(errmsg, "CUDA error %s in PATH_INTEGRATION", cudaGetErrorString(e)); rc = 4; break; }
+        if (solcrit < 0.001f || iter > iterfixsh) fixsh = 1;
+        // COMPUTE_SOURCE
+        a.first = 0; a.fixsh = fixsh;
+        a.rshptr = rsh[rcur]; a.radiance = rad; a.shptr_old = sh[cur]; a.oshptr_old = osh; a.source_old = src[cur];
+        int old_total = total_s;
+        cap_new = fixsh ? (size_t)old_total : ((size_t)maxiv < (size_t)npts * d->nlm ? (size_t)maxiv : (size_t)npts * d->nlm);
+        rc = cs_device_step(a, nblk, tmp, tmpb, sh[1 - cur], sums, maxiv, cap_new, src[1 - cur], &total_s, errmsg);
+        cudaEventRecord(ev[3], 0);
+        if (rc) break;
+        if (accelflag) cudaMemcpyAsync(osh, sh[cur], ((size_t)npts + 1) * sizeof(int), cudaMemcpyDeviceToDevice, 0);   // OSHPTR = old SHPTR
+        cur = 1 - cur;
+        double hs[4];
+        e = cudaMemcpy(hs, sums, sizeof(hs), cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) { set_msg(errmsg, "CUDA error %s in the solution iterations", cudaGetErrorString(e)); rc = 4; break; }
+        rc = sv_sweep_error(sv, errmsg);
+        if (rc) break;
+        float t1 = 0, t2 = 0;
+        cudaEventElapsedTime(&t1, ev[1], ev[2]); cudaEventElapsedTime(&t2, ev[2], ev[3]);
+        ms_path += t1; ms_src += t2;
+        deljdot = (float)hs[0]; deljold = (float)hs[1]; deljnew = (float)hs[2]; jnorm = (float)hs[3];
+        // CALC_ACCEL_SOLCRIT (src/shdom_nompi.f:317-349)
+        if (accelflag && acc == 0.0f && deljnew < deljold) {
+            const float r = sqrtf(deljnew / deljold);
+            const float theta = acosf(deljdot / sqrtf(deljold * deljnew));
+            acc = (1 - r * cosf(theta) + powf(r, 1 + 0.5f * 3.14159f / theta)) / (1 + r * r - 2 * r * cosf(theta)) - 1.0f;
+            acc = fminf(10.0f, fmaxf(0.0f, acc));
+        } else {
+            acc = 0.0f;
+        }
+        if (jnorm > 0.0f) solcrit = sqrtf(deljnew / jnorm);
+        else if (deljnew == 0.0f) solcrit = 0.0f;
+        if (acc > 0.0f) sv_accelerate_kernel<<<(int)(((size_t)npts * 32 + 255) / 256), 256>>>(npts, nst, acc, sh[cur], osh, src[cur], dels);
+        if (albmax < solacc) solcrit = solacc;
+    }
+    float ms_all = 0.0f;
+    cudaEventRecord(ev[3], 0);
+    cudaError_t e = cudaEventSynchronize(ev[3]);
+    if (e == cudaSuccess) cudaEventElapsedTime(&ms_all, ev[0], ev[3]);
+    for (auto &x : ev) cudaEventDestroy(x);
+    if (!rc && e != cudaSuccess) { set_msg(errmsg, "CUDA error %s in the solution iterations", cudaGetErrorString(e)); rc = 4; }
+    if (!rc) {
+        e = cudaMemcpy(shptr, sh[cur], ((size_t)npts + 1) * sizeof(int), cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess) e = cudaMemcpy(rshptr, rsh[rcur], ((size_t)npts + 2) * sizeof(int), cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess) e = cudaMemcpy(source, src[cur], (size_t)nst * total_s * sizeof(float), cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess) e = cudaMemcpy(radiance, rad, (size_t)nst * total_r * sizeof(float), cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess) e = cudaMemcpy(fluxes, sv->a.fluxes, (size_t)2 * npts * sizeof(float), cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess) e = cudaMemcpy(bcrad, sv->a.bcrad, sv->nbc * sizeof(float), cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) { set_msg(errmsg, "CUDA error %s copying the solution back", cudaGetErrorString(e)); rc = 4; }
+    }
+    if (iters_out) *iters_out = iter;
+    if (solcrit_out) *solcrit_out = solcrit;
+    if (ms_out) { ms_out[0] = ms_path; ms_out[1] = ms_src; ms_out[2] = ms_all; }
+    return rc;
 }

@@ -25,21 +25,6 @@ static void set_msg(char *errmsg, const char *fmt, ...)
     va_end(ap);
 }
 
-struct CsArgs {
-    int npts, nstokes, nstleg, nlm, ml, mm, nleg, npart, nq, srctype, deltam, interp_new, newmethod;
-    int first, accelflag, fixsh;
-    float phasemax, secmu0, srcmin;
-    const float *extinct, *albedo, *total_ext, *legen, *phaseinterpwt, *dirflux, *radiance, *ylmsun, *planck;
-    const int *iphase, *rshptr, *lofj;
-    const int *shptr_old, *oshptr_old;
-    const float *source_old, *delsource_old;
-    int *ns_new;              // [npts]
-    double *partials;         // [nblocks,4]
-    int *bad;                 // NR>NLM flag
-    // second kernel
-    const int *shptr_new;
-    float *source_new, *delsource_new;
-};
 
 #define CS_WARPS 8
 
@@ -444,6 +429,68 @@ struct Arena {
 };
 }
 
+// The three launches of one COMPUTE_SOURCE on device-resident arrays (every pointer of `a` except shptr_new /
+// source_new set by the caller; scan_tmp sized by cs_scan_bytes): norms + new truncation lengths, SHPTR scan, write.
+// Returns 0, 1 (NR>NLM) or 2 (MAXIV exceeded); *total_new = SHPTR(NPTS+1) of the new source.
+size_t cs_scan_bytes(int npts)
+{
+    size_t tmpb = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmpb, (int *)nullptr, (int *)nullptr, npts + 1);
+    return tmpb;
+}
+
+int cs_grid_blocks(int npts)
+{
+    int dev = 0, nsm = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    const int want = (npts + CS_WARPS - 1) / CS_WARPS;
+    return want < nsm * 8 ? want : nsm * 8;          // persistent: a multiple of the SM count
+}
+
+int cs_device_step(CsArgs &a, int nblk, void *scan_tmp, size_t tmpb, int *shptr_new, double *sums, int maxiv, size_t cap_new,
+                   float *source_new, int *total_new_out, char *errmsg)
+{
+    const int nst = a.nstokes, npts = a.npts;
+    const size_t nlt = (size_t)a.nstleg * (a.nleg + 1);
+    const int slots = nlt <= 32 ? 1 : nlt <= 64 ? 2 : nlt <= 128 ? 4 : 8;
+    const size_t smem = (size_t)CS_WARPS * 2 * nlt * sizeof(float);
+#define CS_LAUNCH(K)                                                                              \
+    {                                                                                             \
+        if (nst == 1) {                                                                           \
+            if (slots == 1) K<1, 1><<<nblk, CS_WARPS * 32, smem>>>(a);                            \
+            else if (slots == 2) K<1, 2><<<nblk, CS_WARPS * 32, smem>>>(a);                       \
+            else if (slots == 4) K<1, 4><<<nblk, CS_WARPS * 32, smem>>>(a);                       \
+            else K<1, 8><<<nblk, CS_WARPS * 32, smem>>>(a);                                       \
+        } else {                                                                                  \
+            if (slots == 1) K<3, 1><<<nblk, CS_WARPS * 32, smem>>>(a);                            \
+            else if (slots == 2) K<3, 2><<<nblk, CS_WARPS * 32, smem>>>(a);                       \
+            else if (slots == 4) K<3, 4><<<nblk, CS_WARPS * 32, smem>>>(a);                       \
+            else K<3, 8><<<nblk, CS_WARPS * 32, smem>>>(a);                                       \
+        }                                                                                         \
+    }
+    cudaMemsetAsync(a.bad, 0, sizeof(int), 0);
+    cudaMemsetAsync(a.ns_new + npts, 0, sizeof(int), 0);
+    a.shptr_new = nullptr; a.source_new = nullptr;
+    CS_LAUNCH(cs_norms_kernel)
+    cs_reduce_kernel<<<1, 1024>>>(nblk, a.partials, sums);
+    cub::DeviceScan::ExclusiveSum(scan_tmp, tmpb, a.ns_new, shptr_new, npts + 1);
+    int total_new = 0, hbad = 0;
+    cudaMemcpy(&total_new, shptr_new + npts, sizeof(int), cudaMemcpyDeviceToHost);
+    cudaMemcpy(&hbad, a.bad, sizeof(int), cudaMemcpyDeviceToHost);
+    if (total_new_out) *total_new_out = total_new;
+    if (hbad) { set_msg(errmsg, "COMPUTE_SOURCE: NR>NLM 3 %d", hbad); return 1; }
+    if (total_new > maxiv || (size_t)total_new > cap_new) {
+        set_msg(errmsg, "COMPUTE_SOURCE: MAXIV exceeded %d Out of memory for more spherical harmonic terms.", maxiv);
+        return 2;
+    }
+    a.shptr_new = shptr_new;
+    a.source_new = source_new;
+    CS_LAUNCH(cs_write_kernel)
+#undef CS_LAUNCH
+    return 0;
+}
+
 extern "C" int at3d_compute_source(const at3d_state_desc *d, int fixsh, float shacc, int maxiv,
                                    int first, int accelflag, int newmethod,
                                    int32_t *shptr, float *source, int32_t *oshptr, float *delsource,
@@ -530,39 +577,10 @@ extern "C" int at3d_compute_source(const at3d_state_desc *d, int fixsh, float sh
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     cudaEventRecord(e0, 0);
-#define CS_LAUNCH(K)                                                                              \
-    {                                                                                             \
-        if (nst == 1) {                                                                           \
-            if (slots == 1) K<1, 1><<<nblk, CS_WARPS * 32, smem>>>(a);                            \
-            else if (slots == 2) K<1, 2><<<nblk, CS_WARPS * 32, smem>>>(a);                       \
-            else if (slots == 4) K<1, 4><<<nblk, CS_WARPS * 32, smem>>>(a);                       \
-            else K<1, 8><<<nblk, CS_WARPS * 32, smem>>>(a);                                       \
-        } else {                                                                                  \
-            if (slots == 1) K<3, 1><<<nblk, CS_WARPS * 32, smem>>>(a);                            \
-            else if (slots == 2) K<3, 2><<<nblk, CS_WARPS * 32, smem>>>(a);                       \
-            else if (slots == 4) K<3, 4><<<nblk, CS_WARPS * 32, smem>>>(a);                       \
-            else K<3, 8><<<nblk, CS_WARPS * 32, smem>>>(a);                                       \
-        }                                                                                         \
-    }
-    CS_LAUNCH(cs_norms_kernel)
-    cs_reduce_kernel<<<1, 1024>>>(nblk, a.partials, sums);
-    cub::DeviceScan::ExclusiveSum(tmp, tmpb, a.ns_new, shptr_new, (int)npts + 1);
-    int total_new = 0, hbad = 0;
-    cudaMemcpy(&total_new, shptr_new + npts, sizeof(int), cudaMemcpyDeviceToHost);
-    cudaMemcpy(&hbad, a.bad, sizeof(int), cudaMemcpyDeviceToHost);
-    int rc = 0;
-    if (hbad) { set_msg(errmsg, "COMPUTE_SOURCE: NR>NLM 3 %d", hbad); rc = 1; }
-    else if (total_new > maxiv || (size_t)total_new > cap_new) {
-        set_msg(errmsg, "COMPUTE_SOURCE: MAXIV exceeded %d Out of memory for more spherical harmonic terms.", maxiv);
-        rc = 2;
-    }
+    int total_new = 0;
+    int rc = cs_device_step(a, nblk, tmp, tmpb, shptr_new, sums, maxiv, cap_new, source_new, &total_new, errmsg);
     float ms = 0.0f;
     if (!rc) {
-        a.shptr_new = shptr_new;
-        a.source_new = source_new;
-    }
-    if (!rc) {
-        CS_LAUNCH(cs_write_kernel)
         cudaEventRecord(e1, 0);
         cudaError_t e = cudaEventSynchronize(e1);
         if (e != cudaSuccess) { set_msg(errmsg, "CUDA error %s in at3d_compute_source", cudaGetErrorString(e)); rc = 4; }

@@ -141,6 +141,37 @@ class SweepSolver:
                                                            vp(bcrad), C.byref(ms), buf), buf)
         return (rad, fluxes, bcrad, ms.value) if timing else (rad, fluxes, bcrad)
 
+    def solve(self, maxiter=100, solacc=1e-4, shacc=0.0, accelflag=True, highorderrad=False, iterfixsh=30, maxiv=None):
+        """The whole fixed-grid solve on the device (at3d_solver_solve).  Returns (solved copy of the state, iterations,
+        solcrit, timings)."""
+        st = self.st.copy().normalize()
+        npts, ns = st.npts, st.nstokes
+        if maxiv is None:
+            maxiv = npts * st.nlm
+        lamb = st.sfctype1 in ('L', ord('L'))
+        nbc = st.ntoppts + st.nbotpts * (1 if lamb else 1 + st.nang // 2)
+        shptr = np.zeros(npts + 1, np.int32)
+        source = np.zeros((ns, maxiv), np.float32, order='F')
+        rshptr = np.zeros(npts + 2, np.int32)
+        radiance = np.zeros((ns, maxiv + npts), np.float32, order='F')
+        fluxes = np.zeros((2, npts), np.float32, order='F')
+        bcrad = np.zeros((ns, nbc), np.float32, order='F')
+        iters, solcrit = C.c_int32(0), C.c_float(0.0)
+        ms = np.zeros(3, np.float64)
+        buf = _lib.errbuf()
+        rc = _lib.lib().at3d_solver_solve(self.h, C.byref(self._keep), int(maxiter), float(solacc), float(shacc), int(accelflag),
+                                          int(highorderrad), int(iterfixsh), int(maxiv), vp(shptr), vp(source), vp(rshptr),
+                                          vp(radiance), vp(fluxes), vp(bcrad), C.byref(iters), C.byref(solcrit), vp(ms), buf)
+        if rc == 2:
+            raise MemoryError(buf.value.decode(errors='replace'))
+        _lib.check(rc, buf)
+        st.shptr, st.rshptr = shptr, rshptr
+        st.source = np.asfortranarray(source[:, :max(int(shptr[npts]), 1)])
+        st.radiance = np.asfortranarray(radiance[:, :max(int(rshptr[npts]), 1)])
+        st.fluxes, st.bcrad = fluxes, bcrad
+        return st, int(iters.value), float(solcrit.value), dict(path_integration_ms=float(ms[0]), compute_source_ms=float(ms[1]),
+                                                                   loop_ms=float(ms[2]))
+
     def close(self):
         if self.h:
             _lib.lib().at3d_solver_destroy(self.h)
@@ -159,12 +190,19 @@ def solve_ip(state, wtmu, **kw):
 
 
 def solve_fixed_grid(state, wtmu, maxiter=100, solacc=1e-4, shacc=0.0, accelflag=True, highorderrad=False, iterfixsh=30,
-                     maxiv=None, verbose=False, transmin=1.0):
+                     maxiv=None, verbose=False, transmin=1.0, device_loop=True):
     """SOLUTION_ITERATIONS on a fixed grid (shdomsub1.f:445-822): RADIANCE_TRUNCATION, PATH_INTEGRATION (GPU: independent
     columns for IPFLAG=3, the BACK_INT_GRID3D sweep otherwise), COMPUTE_SOURCE (GPU), sequence acceleration.
     Returns (solved copy of `state` with shptr/source/rshptr/radiance/fluxes/bcrad, iters, solcrit, timings)."""
     st = state.copy().normalize()
     sweep = None if (st.ipflag & 3) == 3 else SweepSolver(st, wtmu, transmin)
+    if sweep is not None and device_loop and not verbose:
+        # 3-D grids: the whole iteration loop stays on the device
+        try:
+            return sweep.solve(maxiter=maxiter, solacc=solacc, shacc=shacc, accelflag=accelflag, highorderrad=highorderrad,
+                               iterfixsh=iterfixsh, maxiv=maxiv)
+        finally:
+            sweep.close()
     npts, ns = st.npts, st.nstokes
     f32 = np.float32
     if maxiv is None:

@@ -262,6 +262,16 @@ typedef struct at3d_solver at3d_solver;
 int at3d_solver_create(const at3d_state_desc *desc, const float *wtmu, float transmin, at3d_solver **out, char *errmsg);
 int at3d_solver_path_integration(at3d_solver *sv, const int32_t *shptr, const float *source, const int32_t *rshptr,
                                  float *radiance, float *fluxes, float *bcrad, double *kernel_ms, char *errmsg);
+/* SOLUTION_ITERATIONS on a fixed grid (src/polarized/shdomsub1.f:445-822 without SPLIT_GRID; at3d/solver.py:279
+ * RTE.solve with split_accuracy=0), device-resident: RADIANCE_TRUNCATION (:1615), PATH_INTEGRATION, COMPUTE_SOURCE
+ * (:967), CALC_ACCEL_SOLCRIT (src/shdom_nompi.f:317), ACCELERATE_SOLUTION (:1807) loop in HBM; the first guess is a zero
+ * radiance field.  desc supplies the optical properties of the grid the solver object was created for.  Outputs (host):
+ * shptr[npts+1], source[nstokes,maxiv], rshptr[npts+2], radiance[nstokes,maxiv+npts], fluxes[2,npts], bcrad; iterations
+ * done, final SOLCRIT, ms[3] = CUDA-event time in PATH_INTEGRATION, in COMPUTE_SOURCE, of the whole loop.
+ * Returns 2 (the reference's IERR=2) when MAXIV is too small. */
+int at3d_solver_solve(at3d_solver *sv, const at3d_state_desc *desc, int maxiter, float solacc, float shacc, int accelflag,
+                      int highorderrad, int iterfixsh, int maxiv, int32_t *shptr, float *source, int32_t *rshptr,
+                      float *radiance, float *fluxes, float *bcrad, int32_t *iters, float *solcrit, double *ms, char *errmsg);
 int at3d_solver_destroy(at3d_solver *sv);
 
 #ifdef __cplusplus

@@ -101,6 +101,36 @@ def test_fixed_grid_solve_3d(case):
         np.testing.assert_allclose(out[k], refout[k], rtol=1e-4, atol=1e-6)
 
 
+@pytest.mark.parametrize('case,kw', [('scalar_open_split', dict()), ('polarized_periodic_split', dict(shacc=0.003)),
+                                     ('rayleigh_two_species', dict(accelflag=False)),
+                                     ('scalar_nmu16', dict(highorderrad=True, iterfixsh=3))])
+def test_device_resident_loop_equals_host_driven_loop(case, kw):
+    """at3d_solver_solve (SOURCE/RADIANCE/DELSOURCE resident in HBM, RADIANCE_TRUNCATION and the acceleration on the
+    device) against the per-iteration C-ABI calls driven from Python: same iteration count, same truncations, and the
+    same solution (the norms are summed in a different order only)."""
+    sc = scenes.make(case, O)
+    st = sc.state
+    w = wtmu_of(st)
+    a, ia, ca, ta = solver.solve_fixed_grid(st, w, solacc=1e-4, maxiter=40, device_loop=True, **kw)
+    b, ib, cb, _ = solver.solve_fixed_grid(st, w, solacc=1e-4, maxiter=40, device_loop=False, **kw)
+    assert ia == ib and ta['loop_ms'] > 0
+    np.testing.assert_array_equal(a.shptr, b.shptr)
+    np.testing.assert_array_equal(a.rshptr, b.rshptr)
+    np.testing.assert_allclose(ca, cb, rtol=1e-3)
+    scale = np.abs(b.source).max()
+    np.testing.assert_allclose(a.source, b.source, rtol=1e-4, atol=1e-6 * scale)
+    np.testing.assert_allclose(a.radiance, b.radiance, rtol=1e-4, atol=1e-6 * np.abs(b.radiance).max())
+    np.testing.assert_allclose(a.fluxes, b.fluxes, rtol=1e-5)
+    np.testing.assert_allclose(a.bcrad, b.bcrad, rtol=1e-5, atol=1e-8)
+
+
+def test_device_loop_out_of_sh_memory_is_ierr_2():
+    sc = scenes.make('scalar_periodic', O)
+    st = sc.state
+    with pytest.raises(MemoryError):
+        solver.solve_fixed_grid(st, wtmu_of(st), maxiv=5 * st.npts)
+
+
 def test_solver_refuses_what_it_does_not_cover():
     from at3d_b200._lib import At3dError
     sc = S.make_scene(nx=5, ny=5, nz=6, ipflag=3, seed=1)
