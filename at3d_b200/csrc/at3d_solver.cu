@@ -396,7 +396,8 @@ struct SwArgs {
     int npts, nang, nchunks, group;
     const OrdDir *dir;          // [nang]
     const int *sweepord;        // [noct][npts]  cell<<3 | corner-1 (SWEEPORD)
-    const int *rank;            // [noct][npts]  position of a point in the octant's order
+    const int *rank;            // [noct][npts]  position of a point in the octant's order; -1 for the boundary points that
+                                // are preset in the octant's hemisphere (top for downward, bottom for upward ordinates)
     const unsigned char *bflag; // [npts] bit 0: top boundary point, bit 1: bottom boundary point
     const float *srcdo;         // [npts, nst, nang] discrete-ordinate source function
     float *radf;                // [npts, nst, nang] radiance (GRIDRAD of every ordinate)
@@ -420,8 +421,11 @@ __device__ __forceinline__ int face_corner(int kface, int n)
 // LEVEL = true: the same walk and waits, but what travels is the dependency level 1 + max(level of the four face
 // points) instead of the radiance (run once per solver object; the levels order the threads of the real sweep so that
 // a thread's face points were finished a whole wavefront earlier and neighbouring lanes never wait for each other)
+#ifndef AT3D_SWEEP_MINB
+#define AT3D_SWEEP_MINB 3
+#endif
 template <int NST, bool LEVEL>
-__global__ void __launch_bounds__(256) sweep3d_kernel(SwArgs a, int up)
+__global__ void __launch_bounds__(256, (NST == 1 ? AT3D_SWEEP_MINB : 2)) sweep3d_kernel(SwArgs a, int up)
 {
     __shared__ int s_ticket;
     if (threadIdx.x == 0) s_ticket = atomicAdd(a.ticket, 1);
@@ -565,8 +569,8 @@ __global__ void __launch_bounds__(256) sweep3d_kernel(SwArgs a, int up)
         for (int k = 0; k < NST; k++) rad[k] = rad[k] + transmit * sc[k] * abscell;
         transmit = transmit * transcell;
         // VALIDFACE, statically: all four face points are preset or earlier in the sweep order
-        const bool validface = ((a.bflag[i1 - 1] & bmask) || rank[i1 - 1] < r) && ((a.bflag[i2 - 1] & bmask) || rank[i2 - 1] < r)
-                            && ((a.bflag[i3 - 1] & bmask) || rank[i3 - 1] < r) && ((a.bflag[i4 - 1] & bmask) || rank[i4 - 1] < r);
+        // (preset boundary points of the hemisphere carry rank -1)
+        const bool validface = __ldg(&rank[i1 - 1]) < r && __ldg(&rank[i2 - 1]) < r && __ldg(&rank[i3 - 1]) < r && __ldg(&rank[i4 - 1]) < r;
         if (inextcell <= 0 || (transmit <= a.transmin && validface)) {
             if (!validface) fail = 3;
             break;
@@ -897,6 +901,12 @@ extern "C" int at3d_solver_create(const at3d_state_desc *d, const float *wtmu, f
     w.npts = npts; w.nang = nang; w.nchunks = (npts + 255) / 256;
     w.dir = A.up(dirs.data(), dirs.size());
     w.sweepord = A.up(sweepord.data(), sweepord.size());
+    for (int joct = 1; joct <= noct; joct++) {
+        static const int ioctorder[8] = {1, 5, 2, 6, 3, 7, 4, 8};
+        const bool upward = ((ioctorder[joct - 1] - 1) >> 2) & 1;          // BITZ = 1: CZ < 0, an upward ordinate
+        int *rk = rank.data() + (size_t)npts * (joct - 1);
+        for (int p : (upward ? botpt : toppt)) rk[p] = -1;
+    }
     w.rank = A.up(rank.data(), rank.size());
     w.bflag = A.up(bflag.data(), bflag.size());
     w.srcdo = a.dofield; w.radf = radf;
@@ -927,7 +937,9 @@ extern "C" int at3d_solver_create(const at3d_state_desc *d, const float *wtmu, f
     const size_t nkeys = (size_t)npts * nang;
     const char *lenv = getenv("AT3D_SWEEP_LEVELS");
     const bool want_levels = lenv ? atoi(lenv) != 0 : true;
-    if (want_levels && npts < (1 << 24) && nkeys * 24 < ((size_t)8 << 30)) {
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    if (want_levels && npts < (1 << 24) && nkeys * 32 < free_b / 2) {
         Arena T;
         int *level = T.alloc<int>(nkeys);
         unsigned long long *k0 = T.alloc<unsigned long long>(nkeys), *k1 = T.alloc<unsigned long long>(nkeys);

@@ -189,10 +189,20 @@ def sweep3d_leg(st, steps, warmup, oracle=None):
     sv.close()
     res = dict(npts=int(st.npts), nang=nang, path_integration_ms=float(np.mean(ms)), setup_ms=setup_ms,
                point_updates_per_s=st.npts * nang / (np.mean(ms) * 1e-3))
+    # the whole fixed-grid solve (RTE.solve with split_accuracy=0), device-resident loop, host buffers in and out
+    maxit = 8
+    t0 = time.perf_counter()
+    sol, iters, solcrit, tm = solver.solve_fixed_grid(st, wtmu, solacc=1e-4, maxiter=maxit)
+    res['solve'] = dict(iterations=iters, solcrit=solcrit, loop_ms=tm['loop_ms'], path_integration_ms=tm['path_integration_ms'],
+                        compute_source_ms=tm['compute_source_ms'], e2e_ms=1e3 * (time.perf_counter() - t0), maxiter=maxit)
     if oracle is not None:
         t = time.perf_counter()
         oracle.path_integration(st, wtmu, st.shptr, st.source, st.rshptr)
         res['cpu_path_integration_ms'] = 1e3 * (time.perf_counter() - t)
+        t = time.perf_counter()
+        _, it_cpu, _ = oracle.solve_fixed_grid(st, wtmu, solacc=1e-4, maxiter=maxit)
+        res['solve']['cpu_ms'] = 1e3 * (time.perf_counter() - t)
+        res['solve']['cpu_iterations'] = it_cpu
         res['cpu_cores'] = 1
     return res
 

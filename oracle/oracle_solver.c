@@ -440,6 +440,9 @@ static int back_int_grid1d(const oracle_state *st, const int *sweepord, float mu
     return 0;
 }
 
+static float oracle_transmin = 1.00f;
+void oracle_set_transmin(float t) { oracle_transmin = t; }
+
 /* BACK_INT_GRID3D / BACK_INT_GRID3D_UNPOL  shdomsub1.f:3354-3690 / 3696-4036 (identical apart from NSTOKES).
    source is SOURCE(NSTOKES,NA,NPTS) (the discrete-ordinate source of one zenith angle), gridrad GRIDRAD(NSTOKES,NPTS)
    with GRIDRAD(1,.) < 0 for points without a value yet.  The multi-processor branch (BCFLAG bits 2,3) is not restated. */
@@ -742,8 +745,8 @@ static int path_integration(oracle_state *st, const shdo_coef *c, const int *swe
             if (BTEST(st->ipflag, 1) && BTEST(st->ipflag, 0)) {
                 ierr = back_int_grid1d(st, sweepord, st->mu[imu - 1], iphi, st->total_ext, work, gridrad, errmsg);
             } else if (!BTEST(st->ipflag, 1) && !BTEST(st->bcflag, 2) && !BTEST(st->bcflag, 3)) {
-                /* TRANSMIN = 1.00 (SOLUTION_ITERATIONS, shdomsub1.f:575) */
-                ierr = back_int_grid3d(st, sweepord, st->mu[imu - 1], st->phi[(imu - 1) + st->nmu * (iphi - 1)], 1.00f,
+                /* TRANSMIN: numerical parameter `transmin` of at3d (configuration.py:28, default 1.0) */
+                ierr = back_int_grid3d(st, sweepord, st->mu[imu - 1], st->phi[(imu - 1) + st->nmu * (iphi - 1)], oracle_transmin,
                                        iphi, st->total_ext, work, gridrad, errmsg);
             } else {
                 if (errmsg) snprintf(errmsg, 600, "oracle solver: BACK_INT_GRID2D and the multi-processor sweeps are not restated");

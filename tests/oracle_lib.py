@@ -304,8 +304,11 @@ def solve_fixed_grid(state, wtmu, maxiter=100, solacc=1e-5, shacc=0.0, accelflag
     return st, iters.value, solcrit.value
 
 
-def path_integration(state, wtmu, shptr, source, rshptr):
+def path_integration(state, wtmu, shptr, source, rshptr, transmin=1.0):
     """One PATH_INTEGRATION (oracle/oracle_solver.c): returns (radiance, fluxes, bcrad)."""
+    lib().oracle_set_transmin.argtypes = [f32]
+    lib().oracle_set_transmin.restype = None
+    lib().oracle_set_transmin(transmin)
     st = state.copy().normalize()
     npts, ns = st.npts, st.nstokes
     lamb = st.sfctype1 == 'L' or st.sfctype1 == ord('L')
@@ -321,7 +324,10 @@ def path_integration(state, wtmu, shptr, source, rshptr):
     buf = C.create_string_buffer(600)
     fn = lib().oracle_path_integration_once
     fn.argtypes = [P(OracleState)] + [C.c_void_p] * 7 + [C.c_char_p]
-    _check(fn(C.byref(d), _vp(wtmu), _vp(shptr), _vp(source), _vp(rshptr), _vp(rad), _vp(fluxes), _vp(bcrad), buf), buf)
+    try:
+        _check(fn(C.byref(d), _vp(wtmu), _vp(shptr), _vp(source), _vp(rshptr), _vp(rad), _vp(fluxes), _vp(bcrad), buf), buf)
+    finally:
+        lib().oracle_set_transmin(1.0)
     return rad, fluxes, bcrad
 
 

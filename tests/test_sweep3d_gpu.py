@@ -19,10 +19,10 @@ def wtmu_of(st):
     return (st.wtdo[:, 0] / delphi).astype(np.float32)
 
 
-def compare_path_integration(st, rtol=2e-5):
+def compare_path_integration(st, rtol=2e-5, transmin=1.0):
     w = wtmu_of(st)
-    ref_rad, ref_flux, ref_bc = O.path_integration(st, w, st.shptr, st.source, st.rshptr)
-    sv = solver.SweepSolver(st, w)
+    ref_rad, ref_flux, ref_bc = O.path_integration(st, w, st.shptr, st.source, st.rshptr, transmin=transmin)
+    sv = solver.SweepSolver(st, w, transmin)
     for _ in range(2):                       # the solver object is reusable
         rad, flux, bc = sv.path_integration(st.shptr, st.source, st.rshptr)
     sv.close()
@@ -36,6 +36,23 @@ def compare_path_integration(st, rtol=2e-5):
 @pytest.mark.parametrize('case', CASES)
 def test_sweep3d_matches_serial_sweep(case):
     sc = scenes.make(case, O)
+    compare_path_integration(sc.state)
+
+
+@pytest.mark.parametrize('transmin', [0.9, 0.3])
+def test_sweep3d_transmin_below_one(transmin):
+    """TRANSMIN < 1: a ray goes on through valid faces until its transmission falls below TRANSMIN."""
+    for case in ('scalar_periodic_split', 'polarized_open'):
+        sc = scenes.make(case, O)
+        rad, _ = compare_path_integration(sc.state, transmin=transmin)
+        base = solver.SweepSolver(sc.state, wtmu_of(sc.state)).path_integration(sc.state.shptr, sc.state.source, sc.state.rshptr)[0]
+        assert np.abs(rad - base).max() > 0            # the parameter does change the result
+
+
+def test_sweep3d_independent_pixel_in_x():
+    """IPFLAG=1: the 3-D routine with the cells' IPINX flags (rays never leave through x faces)."""
+    sc = S.make_scene(nx=6, ny=7, nz=8, nstokes=1, bc='periodic', nsplits=0, seed=21, ipflag=1)
+    O.finalize_scene(sc)
     compare_path_integration(sc.state)
 
 
