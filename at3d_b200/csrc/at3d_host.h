@@ -93,6 +93,10 @@ struct CsArgs {
     int *ns_new;              // [npts]
     double *partials;         // [nblocks,4]
     int *bad;                 // NR>NLM flag
+    // mixed Legendre table of every point (cs_mix_kernel; the optical properties only): [npts][NSTLEG*(NLEG+1)], and
+    // (albedo, planck) per point
+    float *mix_legent;
+    float2 *mix_ap;
     // second kernel
     const int *shptr_new;
     float *source_new, *delsource_new;
@@ -101,4 +105,4 @@ struct CsArgs {
 size_t cs_scan_bytes(int npts);
 int cs_grid_blocks(int npts);
 int cs_device_step(CsArgs &a, int nblk, void *scan_tmp, size_t tmpb, int *shptr_new, double *sums, int maxiv, size_t cap_new,
-                   float *source_new, int *total_new_out, char *errmsg);
+                   float *source_new, int *total_new_out, bool mix_ready, char *errmsg);

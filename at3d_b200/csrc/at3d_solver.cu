@@ -1214,6 +1214,9 @@ extern "C" int at3d_solver_solve(at3d_solver *sv, const at3d_state_desc *d, int 
     a.partials = A.alloc<double>((size_t)nblk * 4);
     a.bad = A.alloc<int>(2);
     double *sums = A.alloc<double>(4);
+    a.mix_legent = A.alloc<float>((size_t)npts * nlt);       // mixed once: the optical properties do not change over the solve
+    a.mix_ap = A.alloc<float2>((size_t)npts);
+    if (!a.mix_legent || !a.mix_ap) { set_msg(errmsg, "device allocation failure"); return 4; }
     float *src[2] = {A.alloc<float>((size_t)nst * maxiv), A.alloc<float>((size_t)nst * maxiv)};
     float *dels = A.alloc<float>((size_t)nst * maxiv);
     float *rad = A.alloc<float>((size_t)nst * maxir);
@@ -1248,7 +1251,7 @@ extern "C" int at3d_solver_solve(at3d_solver *sv, const at3d_state_desc *d, int 
     a.rshptr = rsh[rcur]; a.radiance = rad; a.shptr_old = sh[cur]; a.oshptr_old = osh; a.source_old = src[cur];
     a.delsource_old = dels; a.delsource_new = dels;
     size_t cap_new = (size_t)maxiv < (size_t)npts * d->nlm ? (size_t)maxiv : (size_t)npts * d->nlm;
-    rc = cs_device_step(a, nblk, tmp, tmpb, sh[1 - cur], sums, maxiv, cap_new, src[1 - cur], &total_s, errmsg);
+    rc = cs_device_step(a, nblk, tmp, tmpb, sh[1 - cur], sums, maxiv, cap_new, src[1 - cur], &total_s, false, errmsg);
     cur = 1 - cur;
     if (!rc && accelflag) {
         cudaMemcpyAsync(osh, sh[cur], ((size_t)npts + 1) * sizeof(int), cudaMemcpyDeviceToDevice, 0);
@@ -1290,7 +1293,7 @@ extern "C" int at3d_solver_solve(at3d_solver *sv, const at3d_state_desc *d, int 
         a.rshptr = rsh[rcur]; a.radiance = rad; a.shptr_old = sh[cur]; a.oshptr_old = osh; a.source_old = src[cur];
         int old_total = total_s;
         cap_new = fixsh ? (size_t)old_total : ((size_t)maxiv < (size_t)npts * d->nlm ? (size_t)maxiv : (size_t)npts * d->nlm);
-        rc = cs_device_step(a, nblk, tmp, tmpb, sh[1 - cur], sums, maxiv, cap_new, src[1 - cur], &total_s, errmsg);
+        rc = cs_device_step(a, nblk, tmp, tmpb, sh[1 - cur], sums, maxiv, cap_new, src[1 - cur], &total_s, true, errmsg);
         cudaEventRecord(ev[3], 0);
         if (rc) break;
         if (accelflag) cudaMemcpyAsync(osh, sh[cur], ((size_t)npts + 1) * sizeof(int), cudaMemcpyDeviceToDevice, 0);   // OSHPTR = old SHPTR

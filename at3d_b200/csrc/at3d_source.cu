@@ -105,6 +105,44 @@ __device__ __forceinline__ void cs_mix_newmethod(const CsArgs &a, int i, float *
     planck_out = total_planck;
 }
 
+// The mixing depends on the optical properties only: it runs once per call (once per solve in at3d_solver_solve), one
+// warp per point, and leaves the table and (albedo, planck) of every point in HBM; the two source kernels stream the
+// rows (68 B per point for NSTOKES=1, NLEG=16) one point ahead instead of chasing IPHASE -> LEGEN per point.
+template <int SLOTS>
+__global__ void __launch_bounds__(CS_WARPS * 32) cs_mix_kernel(CsArgs a)
+{
+    extern __shared__ float smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nlt = a.nstleg * (a.nleg + 1);
+    float *legent = smem + (size_t)warp * 2 * nlt, *legent1 = legent + nlt;
+    for (int i = blockIdx.x * CS_WARPS + warp; i < a.npts; i += gridDim.x * CS_WARPS) {
+        float albedo, planck;
+        cs_mix_newmethod<SLOTS>(a, i, legent, legent1, albedo, planck);
+        for (int t = lane; t < nlt; t += 32) a.mix_legent[(size_t)nlt * i + t] = legent[t];
+        if (lane == 0) a.mix_ap[i] = make_float2(albedo, planck);
+    }
+}
+
+// a point's row of the mixed table, lane t holding entries t, t+32, ...
+template <int SLOTS>
+struct CsMixRow {
+    float v[SLOTS];
+    float2 ap;
+    __device__ __forceinline__ void load(const CsArgs &a, int ip, int lane, int nlt)
+    {
+#pragma unroll
+        for (int u = 0; u < SLOTS; u++) { const int t = lane + 32 * u; v[u] = t < nlt ? __ldg(&a.mix_legent[(size_t)nlt * ip + t]) : 0.0f; }
+        ap = __ldg(&a.mix_ap[ip]);
+    }
+    __device__ __forceinline__ void to_shared(float *legent, int lane, int nlt) const
+    {
+        __syncwarp();                 // the previous point's reads of legent are complete
+#pragma unroll
+        for (int u = 0; u < SLOTS; u++) if (lane + 32 * u < nlt) legent[lane + 32 * u] = v[u];
+        __syncwarp();
+    }
+};
+
 // CALC_SOURCE_PNT[_UNPOL] for one SH index j (0-based) (shdomsub1.f:858-898, 940-958); r = RADIANCE(:,j) (0 beyond NR)
 template <int NST>
 __device__ __forceinline__ void cs_calc_j(const CsArgs &a, const float *legen, int j, int l, float ysun, bool inr,
@@ -207,7 +245,9 @@ __global__ void __launch_bounds__(CS_WARPS * 32) cs_norms_kernel(CsArgs a)
             }
         }
     };
-    if (i < a.npts) { load_ptrs(i, ir, nr, is, ns, iso); load_batch(0, ir, nr, is, ns, iso); }
+    CsMixRow<SLOTS> mix;
+    (void)legent1;
+    if (i < a.npts) { load_ptrs(i, ir, nr, is, ns, iso); mix.load(a, i, lane, nlt); load_batch(0, ir, nr, is, ns, iso); }
     for (; i < a.npts; i += stride) {
         const int inext = i + stride;
         int ir2 = 0, nr2 = 0, is2 = 0, ns2 = 0, iso2 = 0;
@@ -215,12 +255,13 @@ __global__ void __launch_bounds__(CS_WARPS * 32) cs_norms_kernel(CsArgs a)
         if (nr > a.nlm) {
             if (lane == 0) atomicCAS(a.bad, 0, i + 1);
             ir = ir2; nr = nr2; is = is2; ns = ns2; iso = iso2;
-            if (inext < a.npts) load_batch(0, ir, nr, is, ns, iso);
+            if (inext < a.npts) { mix.load(a, inext, lane, nlt); load_batch(0, ir, nr, is, ns, iso); }
             continue;
         }
-        float albedo, planck;
         const float flux0 = a.dirflux[i] * a.secmu0;
-        cs_mix_newmethod<SLOTS>(a, i, legent, legent1, albedo, planck);
+        mix.to_shared(legent, lane, nlt);
+        const float albedo = mix.ap.x, planck = mix.ap.y;
+        if (inext < a.npts) mix.load(a, inext, lane, nlt);
         int jlast = -1;                       // last j with |SOURCET| > SRCMIN
         // the four norms of this point are summed in REAL per lane (at most NLM/32 terms) and added to the DOUBLE
         // accumulators once per point
@@ -342,16 +383,19 @@ __global__ void __launch_bounds__(CS_WARPS * 32) cs_write_kernel(CsArgs a)
             }
         }
     };
-    if (i < a.npts) { load_ptrs(i, ir, nr, is_old, ns_old); load_batch(0, ir, nr, is_old, ns_old); }
+    CsMixRow<SLOTS> mix;
+    (void)legent1;
+    if (i < a.npts) { load_ptrs(i, ir, nr, is_old, ns_old); mix.load(a, i, lane, nlt); load_batch(0, ir, nr, is_old, ns_old); }
     for (; i < a.npts; i += stride) {
         const int inext = i + stride;
         int ir2 = 0, nr2 = 0, is2 = 0, ns2 = 0;
         if (inext < a.npts) load_ptrs(inext, ir2, nr2, is2, ns2);
         const int is_new = a.shptr_new[i], ns_new = a.shptr_new[i + 1] - is_new;
         const int nmax = ns_old > ns_new ? ns_old : ns_new;
-        float albedo, planck;
         const float flux0 = a.dirflux[i] * a.secmu0;
-        cs_mix_newmethod<SLOTS>(a, i, legent, legent1, albedo, planck);
+        mix.to_shared(legent, lane, nlt);
+        const float albedo = mix.ap.x, planck = mix.ap.y;
+        if (inext < a.npts) mix.load(a, inext, lane, nlt);
 #pragma unroll
         for (int b = 0; b < CS_JSLOTS / NB; b++) {
             const int j0 = 32 * NB * b;
@@ -449,7 +493,7 @@ int cs_grid_blocks(int npts)
 }
 
 int cs_device_step(CsArgs &a, int nblk, void *scan_tmp, size_t tmpb, int *shptr_new, double *sums, int maxiv, size_t cap_new,
-                   float *source_new, int *total_new_out, char *errmsg)
+                   float *source_new, int *total_new_out, bool mix_ready, char *errmsg)
 {
     const int nst = a.nstokes, npts = a.npts;
     const size_t nlt = (size_t)a.nstleg * (a.nleg + 1);
@@ -472,6 +516,13 @@ int cs_device_step(CsArgs &a, int nblk, void *scan_tmp, size_t tmpb, int *shptr_
     cudaMemsetAsync(a.bad, 0, sizeof(int), 0);
     cudaMemsetAsync(a.ns_new + npts, 0, sizeof(int), 0);
     a.shptr_new = nullptr; a.source_new = nullptr;
+    if (!mix_ready) {
+        const int nmix = (npts + CS_WARPS - 1) / CS_WARPS;
+        if (slots == 1) cs_mix_kernel<1><<<nmix, CS_WARPS * 32, smem>>>(a);
+        else if (slots == 2) cs_mix_kernel<2><<<nmix, CS_WARPS * 32, smem>>>(a);
+        else if (slots == 4) cs_mix_kernel<4><<<nmix, CS_WARPS * 32, smem>>>(a);
+        else cs_mix_kernel<8><<<nmix, CS_WARPS * 32, smem>>>(a);
+    }
     CS_LAUNCH(cs_norms_kernel)
     cs_reduce_kernel<<<1, 1024>>>(nblk, a.partials, sums);
     cub::DeviceScan::ExclusiveSum(scan_tmp, tmpb, a.ns_new, shptr_new, npts + 1);
@@ -554,6 +605,9 @@ extern "C" int at3d_compute_source(const at3d_state_desc *d, int fixsh, float sh
     a.bad = A.alloc<int>(1);
     int *shptr_new = A.alloc<int>(npts + 1);
     double *sums = A.alloc<double>(4);
+    a.mix_legent = A.alloc<float>(npts * nlt);
+    a.mix_ap = A.alloc<float2>(npts);
+    if (!a.mix_legent || !a.mix_ap) { set_msg(errmsg, "device allocation failure"); return 4; }
     if (!a.extinct || !a.albedo || !a.total_ext || !a.legen || !a.iphase || !a.phaseinterpwt || !a.dirflux ||
         !a.rshptr || !a.radiance || !a.ylmsun || !a.lofj || !a.shptr_old || !a.oshptr_old || !a.source_old ||
         !a.delsource_old || !a.ns_new || !a.partials || !a.bad || !shptr_new || !sums) {
@@ -578,7 +632,7 @@ extern "C" int at3d_compute_source(const at3d_state_desc *d, int fixsh, float sh
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     cudaEventRecord(e0, 0);
     int total_new = 0;
-    int rc = cs_device_step(a, nblk, tmp, tmpb, shptr_new, sums, maxiv, cap_new, source_new, &total_new, errmsg);
+    int rc = cs_device_step(a, nblk, tmp, tmpb, shptr_new, sums, maxiv, cap_new, source_new, &total_new, false, errmsg);
     float ms = 0.0f;
     if (!rc) {
         cudaEventRecord(e1, 0);
