@@ -202,8 +202,11 @@ struct CsLaneTab {
 };
 
 // Kernel A: norms (passes 1 of the reference) and the new truncation length (first half of pass 3)
+#ifndef AT3D_CS_MINB
+#define AT3D_CS_MINB 3
+#endif
 template <int NST, int SLOTS>
-__global__ void __launch_bounds__(CS_WARPS * 32) cs_norms_kernel(CsArgs a)
+__global__ void __launch_bounds__(CS_WARPS * 32, (NST == 1 ? AT3D_CS_MINB : 1)) cs_norms_kernel(CsArgs a)
 {
     extern __shared__ float smem[];
     constexpr int NB = CsBatch<NST>::N;
@@ -220,8 +223,10 @@ __global__ void __launch_bounds__(CS_WARPS * 32) cs_norms_kernel(CsArgs a)
     const int stride = gridDim.x * CS_WARPS;
     int i = blockIdx.x * CS_WARPS + warp;
     int ir = 0, nr = 0, is = 0, ns = 0, iso = 0;
+    float dfl = 0.0f;
     float r[NB][NST], so[NB][NST], ds[NB][NST];
-    auto load_ptrs = [&](int ip, int &ir_, int &nr_, int &is_, int &ns_, int &iso_) {
+    auto load_ptrs = [&](int ip, int &ir_, int &nr_, int &is_, int &ns_, int &iso_, float &dfl_) {
+        dfl_ = __ldg(&a.dirflux[ip]);
         ir_ = a.rshptr[ip]; nr_ = a.rshptr[ip + 1] - ir_;
         is_ = a.shptr_old[ip]; ns_ = a.shptr_old[ip + 1] - is_;
         iso_ = 0;
@@ -247,18 +252,19 @@ __global__ void __launch_bounds__(CS_WARPS * 32) cs_norms_kernel(CsArgs a)
     };
     CsMixRow<SLOTS> mix;
     (void)legent1;
-    if (i < a.npts) { load_ptrs(i, ir, nr, is, ns, iso); mix.load(a, i, lane, nlt); load_batch(0, ir, nr, is, ns, iso); }
+    if (i < a.npts) { load_ptrs(i, ir, nr, is, ns, iso, dfl); mix.load(a, i, lane, nlt); load_batch(0, ir, nr, is, ns, iso); }
     for (; i < a.npts; i += stride) {
         const int inext = i + stride;
         int ir2 = 0, nr2 = 0, is2 = 0, ns2 = 0, iso2 = 0;
-        if (inext < a.npts) load_ptrs(inext, ir2, nr2, is2, ns2, iso2);
+        float dfl2 = 0.0f;
+        if (inext < a.npts) load_ptrs(inext, ir2, nr2, is2, ns2, iso2, dfl2);
         if (nr > a.nlm) {
             if (lane == 0) atomicCAS(a.bad, 0, i + 1);
-            ir = ir2; nr = nr2; is = is2; ns = ns2; iso = iso2;
+            ir = ir2; nr = nr2; is = is2; ns = ns2; iso = iso2; dfl = dfl2;
             if (inext < a.npts) { mix.load(a, inext, lane, nlt); load_batch(0, ir, nr, is, ns, iso); }
             continue;
         }
-        const float flux0 = a.dirflux[i] * a.secmu0;
+        const float flux0 = dfl * a.secmu0;
         mix.to_shared(legent, lane, nlt);
         const float albedo = mix.ap.x, planck = mix.ap.y;
         if (inext < a.npts) mix.load(a, inext, lane, nlt);
@@ -336,7 +342,7 @@ __global__ void __launch_bounds__(CS_WARPS * 32) cs_norms_kernel(CsArgs a)
             a.ns_new[i] = nsn;
         }
         __syncwarp();
-        ir = ir2; nr = nr2; is = is2; ns = ns2; iso = iso2;
+        ir = ir2; nr = nr2; is = is2; ns = ns2; iso = iso2; dfl = dfl2;
         if (inext < a.npts) load_batch(0, ir, nr, is, ns, iso);
     }
     sdot = warp_sum_d(sdot); sold = warp_sum_d(sold); snew = warp_sum_d(snew); snorm = warp_sum_d(snorm);
@@ -364,11 +370,14 @@ __global__ void __launch_bounds__(CS_WARPS * 32) cs_write_kernel(CsArgs a)
     // same software pipeline over the warp's points as in cs_norms_kernel
     const int stride = gridDim.x * CS_WARPS;
     int i = blockIdx.x * CS_WARPS + warp;
-    int ir = 0, nr = 0, is_old = 0, ns_old = 0;
+    int ir = 0, nr = 0, is_old = 0, ns_old = 0, is_new = 0, ns_new = 0;
+    float dfl = 0.0f;
     float r[NB][NST], so[NB][NST];
-    auto load_ptrs = [&](int ip, int &ir_, int &nr_, int &is_, int &ns_) {
+    auto load_ptrs = [&](int ip, int &ir_, int &nr_, int &is_, int &ns_, int &isn_, int &nsn_, float &dfl_) {
+        dfl_ = __ldg(&a.dirflux[ip]);
         ir_ = a.rshptr[ip]; nr_ = a.rshptr[ip + 1] - ir_;
         is_ = a.shptr_old[ip]; ns_ = a.shptr_old[ip + 1] - is_;
+        isn_ = a.shptr_new[ip]; nsn_ = a.shptr_new[ip + 1] - isn_;
     };
     auto load_batch = [&](int j0, int ir_, int nr_, int is_, int ns_) {
         const float *rad = a.radiance + (size_t)NST * ir_;
@@ -385,14 +394,14 @@ __global__ void __launch_bounds__(CS_WARPS * 32) cs_write_kernel(CsArgs a)
     };
     CsMixRow<SLOTS> mix;
     (void)legent1;
-    if (i < a.npts) { load_ptrs(i, ir, nr, is_old, ns_old); mix.load(a, i, lane, nlt); load_batch(0, ir, nr, is_old, ns_old); }
+    if (i < a.npts) { load_ptrs(i, ir, nr, is_old, ns_old, is_new, ns_new, dfl); mix.load(a, i, lane, nlt); load_batch(0, ir, nr, is_old, ns_old); }
     for (; i < a.npts; i += stride) {
         const int inext = i + stride;
-        int ir2 = 0, nr2 = 0, is2 = 0, ns2 = 0;
-        if (inext < a.npts) load_ptrs(inext, ir2, nr2, is2, ns2);
-        const int is_new = a.shptr_new[i], ns_new = a.shptr_new[i + 1] - is_new;
+        int ir2 = 0, nr2 = 0, is2 = 0, ns2 = 0, isn2 = 0, nsn2 = 0;
+        float dfl2 = 0.0f;
+        if (inext < a.npts) load_ptrs(inext, ir2, nr2, is2, ns2, isn2, nsn2, dfl2);
         const int nmax = ns_old > ns_new ? ns_old : ns_new;
-        const float flux0 = a.dirflux[i] * a.secmu0;
+        const float flux0 = dfl * a.secmu0;
         mix.to_shared(legent, lane, nlt);
         const float albedo = mix.ap.x, planck = mix.ap.y;
         if (inext < a.npts) mix.load(a, inext, lane, nlt);
@@ -430,7 +439,7 @@ __global__ void __launch_bounds__(CS_WARPS * 32) cs_write_kernel(CsArgs a)
             }
         }
         __syncwarp();
-        ir = ir2; nr = nr2; is_old = is2; ns_old = ns2;
+        ir = ir2; nr = nr2; is_old = is2; ns_old = ns2; is_new = isn2; ns_new = nsn2; dfl = dfl2;
         if (inext < a.npts) load_batch(0, ir, nr, is_old, ns_old);
     }
 }
