@@ -1066,6 +1066,7 @@ struct RtArgs {
     float phasemax, shacc;
     const float *total_ext, *extinct, *albedo, *legen, *phaseinterpwt, *radiance;
     const int *iphase, *shptr, *rshptr_old, *lofj;
+    size_t legen_size;      // elements of LEGEN
     int *first_zero;        // first point (0-based) whose old NR is 0 (NOTEND turns false there), npts if none
     int *nr;                // [npts+1] out
 };
@@ -1117,7 +1118,11 @@ __global__ void rt_adaptive_kernel(RtArgs a)
                             f = 0.0f;
                             for (int q = 0; q < nq; q++) {
                                 if (pw[q] <= 1e-5f) continue;
-                                f = f + a.legen[nlt * (size_t)(iph[q] - 1) + (size_t)a.nstleg * (ml + 1) + q] * pw[q];
+                                // (Q > NSTLEG runs into the following table entries; past the end of LEGEN the last
+                                // element is read, as the host restatement and the oracle do)
+                                size_t off = nlt * (size_t)(iph[q] - 1) + (size_t)a.nstleg * (ml + 1) + q;
+                                if (off >= a.legen_size) off = a.legen_size - 1;
+                                f = f + a.legen[off] * pw[q];
                             }
                         }
                         legent = legent * (1.0f / (1 - f));
@@ -1232,7 +1237,7 @@ extern "C" int at3d_solver_solve(at3d_solver *sv, const at3d_state_desc *d, int 
     memset(&rt, 0, sizeof(rt));
     rt.npts = npts; rt.ml = d->ml; rt.mm = d->mm; rt.nstleg = d->nstleg; rt.nleg = d->nleg; rt.npart = d->npart; rt.nq = nq;
     rt.nstokes = nst; rt.interp_new = d->interp_new; rt.deltam = d->deltam; rt.highorderrad = highorderrad;
-    rt.phasemax = d->phasemax; rt.shacc = shacc;
+    rt.phasemax = d->phasemax; rt.shacc = shacc; rt.legen_size = nlt * (size_t)d->numphase;
     rt.total_ext = a.total_ext; rt.extinct = a.extinct; rt.albedo = a.albedo; rt.legen = a.legen; rt.phaseinterpwt = a.phaseinterpwt;
     rt.iphase = a.iphase; rt.lofj = a.lofj; rt.first_zero = a.bad + 1; rt.nr = nr; rt.radiance = rad;
     const int pb = (npts + 255) / 256;
