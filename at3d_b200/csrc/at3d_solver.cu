@@ -799,6 +799,7 @@ struct at3d_solver {
     int *toppt = nullptr;
     int *shptr_d = nullptr, *rshptr_d = nullptr;
     int blocks_resident = 0;
+    bool ip = false;            // IPFLAG=3: independent columns (BACK_INT_GRID1D), no sweep order, DOFIELD in place
 };
 
 extern "C" int at3d_solver_destroy(at3d_solver *sv)
@@ -809,13 +810,75 @@ extern "C" int at3d_solver_destroy(at3d_solver *sv)
     return 0;
 }
 
+// the solver object for independent-pixel grids (IPFLAG=3): the state of at3d_path_integration_ip kept resident
+static int solver_create_ip(const at3d_state_desc *d, const float *wtmu, at3d_solver **out, char *errmsg)
+{
+    const int nz = d->nz, npts = d->npts, nst = d->nstokes;
+    if (nz < 1 || npts % nz != 0) { set_msg(errmsg, "at3d_solver_create: the independent-pixel grid must be the unsplit base grid"); return 3; }
+    const int ncol = npts / nz;
+    for (int c = 0; c < ncol; c++) {
+        for (int iz = 0; iz < nz; iz++)
+            if (d->gridpos[2 + 3 * (size_t)(iz + nz * c)] != d->zgrid[iz]) { set_msg(errmsg, "at3d_solver_create: the independent-pixel grid must be the unsplit base grid"); return 3; }
+        if (d->bcptr[c] != nz * c + nz || d->bcptr[d->maxnbc + c] != nz * c + 1) { set_msg(errmsg, "at3d_solver_create: unexpected boundary point lists"); return 3; }
+    }
+    if (d->ntoppts != ncol || d->nbotpts != ncol) { set_msg(errmsg, "at3d_solver_create: unexpected boundary point counts"); return 3; }
+    if (d->srctype != 'S' && d->units == 'B') { set_msg(errmsg, "UNITS='B' is not implemented"); return 3; }
+    at3d_solver *sv = new at3d_solver();
+    sv->ip = true;
+    int rc = tr_plan_create(nst, d->nstleg, d->ml, d->mm, d->nlm, d->nmu, d->nphi0max, d->nphi0, d->mu, d->phi, wtmu, &sv->P, errmsg);
+    if (rc) { delete sv; return rc; }
+    const int nang = tr_plan_nang(sv->P), nh = nang / 2;
+    sv->nst = nst; sv->npts = npts; sv->nang = nang; sv->ntop = ncol; sv->nbot = ncol;
+    sv->lamb = d->sfctype1 == 'L';
+    std::vector<float> amu(nang), aphi(nang), aw(nang);
+    std::vector<int> aimu(nang), aiphi(nang);
+    for (int i = 0, ia = 0; i < d->nmu; i++)
+        for (int k = 0; k < d->nphi0[i]; k++, ia++) {
+            amu[ia] = d->mu[i]; aphi[ia] = d->phi[i + (size_t)d->nmu * k];
+            aw[ia] = fabsf(d->mu[i]) * d->wtdo[i + (size_t)d->nmu * k];
+            aimu[ia] = i; aiphi[ia] = k;
+        }
+    Arena &A = sv->A;
+    PiArgs &a = sv->a;
+    memset(&a, 0, sizeof(a));
+    memset(&sv->w, 0, sizeof(sv->w));
+    a.npts = npts; a.nst = nst; a.nz = nz; a.ncol = ncol; a.nang = nang; a.nmu = d->nmu; a.nphi0max = d->nphi0max;
+    a.ntop = ncol; a.nbot = ncol; a.nsfcpar = d->nsfcpar; a.srctype = d->srctype; a.units = d->units;
+    a.sfctype0 = d->sfctype0; a.sfctype1 = d->sfctype1; a.wavelen = d->wavelen; a.solarmu = d->solarmu;
+    a.solaraz = d->solaraz; a.gndalbedo = d->gndalbedo; a.gndtemp = d->gndtemp;
+    sv->nbc = (size_t)nst * (ncol + (size_t)ncol * (sv->lamb ? 1 : 1 + nh));
+    a.dofield = A.alloc<float>((size_t)npts * nst * nang);
+    a.total_ext = A.up(d->total_ext, npts); a.zlev = A.up(d->zgrid, nz); a.dirflux = A.up(d->dirflux, npts);
+    a.ang_mu = A.up(amu.data(), nang); a.ang_phi = A.up(aphi.data(), nang); a.ang_w = A.up(aw.data(), nang);
+    a.ang_imu = A.up(aimu.data(), nang); a.ang_iphi = A.up(aiphi.data(), nang);
+    a.skyrad = A.up(d->skyrad, (size_t)nst * (d->nmu / 2) * d->nphi0max);
+    a.sfcgridparms = A.up(d->sfcgridparms, (size_t)d->nsfcpar * ncol);
+    if (d->sfcgridrad) {
+        bool nonzero = false;
+        for (size_t i = 0; i < (size_t)(nh + 1) * ncol && !nonzero; i++) nonzero = d->sfcgridrad[i] != 0.0f;
+        if (nonzero) a.sfcgridrad = A.up(d->sfcgridrad, (size_t)(nh + 1) * ncol);
+    }
+    a.bcrad = A.alloc<float>(sv->nbc);
+    a.botrad = A.alloc<float>((size_t)nst * ncol * nh);
+    a.fluxes = A.alloc<float>((size_t)2 * npts);
+    sv->shptr_d = A.alloc<int>((size_t)npts + 1);
+    sv->rshptr_d = A.alloc<int>((size_t)npts + 1);
+    if (!a.dofield || !a.total_ext || !a.zlev || !a.dirflux || !a.ang_mu || !a.ang_phi || !a.ang_w || !a.ang_imu || !a.ang_iphi ||
+        !a.skyrad || !a.sfcgridparms || !a.bcrad || !a.botrad || !a.fluxes || !sv->shptr_d || !sv->rshptr_d) {
+        at3d_solver_destroy(sv); set_msg(errmsg, "device allocation failure"); return 4;
+    }
+    *out = sv;
+    return 0;
+}
+
 extern "C" int at3d_solver_create(const at3d_state_desc *d, const float *wtmu, float transmin, at3d_solver **out, char *errmsg)
 {
     if (errmsg) errmsg[0] = 0;
     if (!d || !wtmu || !out) { set_msg(errmsg, "null argument"); return 1; }
     *out = nullptr;
     if (at3d_device_count() < 1) { set_msg(errmsg, "no CUDA device: at3d_b200 has no CPU fallback"); return 4; }
-    if (d->ipflag & 2) { set_msg(errmsg, "at3d_solver_create: grids with independent-pixel Y (BACK_INT_GRID2D / 1D) are not handled here; IPFLAG=3 has at3d_path_integration_ip"); return 3; }
+    if ((d->ipflag & 3) == 3) return solver_create_ip(d, wtmu, out, errmsg);
+    if (d->ipflag & 2) { set_msg(errmsg, "at3d_solver_create: IPFLAG=2 (BACK_INT_GRID2D) is not implemented"); return 3; }
     if (d->bcflag & 12) { set_msg(errmsg, "at3d_solver_create: multi-processor boundary flags are not supported"); return 3; }
     if (d->srctype != 'S' && d->units == 'B') { set_msg(errmsg, "UNITS='B' is not implemented"); return 3; }
     if (!(transmin >= 0.0f && transmin <= 1.0f)) { set_msg(errmsg, "TRANSMIN must be in [0,1]"); return 1; }
@@ -986,6 +1049,21 @@ static cudaError_t sv_path_integration_device(at3d_solver *sv, const int *shptr_
     SwArgs &w = sv->w;
     cudaError_t e = cudaMemsetAsync(a.bcrad, 0, sv->nbc * sizeof(float), 0);
     if (e == cudaSuccess) e = tr_sh_to_do(sv->P, npts, shptr_d, src_d, a.dofield, 0);
+    if (sv->ip) {
+        // independent columns: all downward ordinates, the surface, all upward ordinates (in place on DOFIELD)
+        const int nsw = (a.ncol * nh + 127) / 128, npbi = (npts + 255) / 256;
+#define AT3D_SWEEP1D(NST)                                                      \
+        pi_sweep_kernel<NST><<<nsw, 128>>>(a, 0);                              \
+        pi_flux_kernel<NST><<<npbi, 256>>>(a, 0);                              \
+        if (sv->lamb) pi_lambertian_kernel<<<(a.ncol + 127) / 128, 128>>>(a);  \
+        else pi_brdf_kernel<NST><<<nsw, 128>>>(a);                             \
+        pi_sweep_kernel<NST><<<nsw, 128>>>(a, 1);                              \
+        pi_flux_kernel<NST><<<npbi, 256>>>(a, 1);
+        if (nst == 1) { AT3D_SWEEP1D(1) } else { AT3D_SWEEP1D(3) }
+#undef AT3D_SWEEP1D
+        if (e == cudaSuccess) e = tr_do_to_sh(sv->P, npts, rshptr_d, a.dofield, rad_d, 0);
+        return e;
+    }
     const int nsweep = w.nchunks * nh, npb = (npts + 255) / 256;
     const int ninit = (int)(((size_t)npts * nh + 255) / 256);
     const int ntb = (a.ntop * nh + 127) / 128, nbb = (a.nbot * nh + 127) / 128;
@@ -1011,6 +1089,7 @@ static cudaError_t sv_path_integration_device(at3d_solver *sv, const int *shptr_
 static int sv_sweep_error(at3d_solver *sv, char *errmsg)
 {
     int err = 0;
+    if (sv->ip) return 0;
     cudaError_t e = cudaMemcpy(&err, sv->w.err, sizeof(int), cudaMemcpyDeviceToHost);
     if (e != cudaSuccess) { set_msg(errmsg, "CUDA error %s in the 3-D sweep", cudaGetErrorString(e)); return 4; }
     if (err) {

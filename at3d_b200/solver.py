@@ -115,8 +115,9 @@ def path_integration_ip(st, wtmu, shptr, source, rshptr, timing=False):
 
 
 class SweepSolver:
-    """PATH_INTEGRATION on a fixed 3-D grid (IPFLAG 0 or 1): the device-resident solver object of
-    at3d_solver_create (topology, SWEEPING_ORDER, ordinate geometry, transform tables, discrete-ordinate fields)."""
+    """PATH_INTEGRATION / SOLUTION_ITERATIONS on a fixed grid: the device-resident solver object of at3d_solver_create
+    (3-D grids, IPFLAG 0 or 1: topology, SWEEPING_ORDER, ordinate geometry, transform tables, discrete-ordinate fields;
+    IPFLAG=3: independent columns)."""
 
     def __init__(self, st, wtmu, transmin=1.0):
         self.st = st
@@ -185,7 +186,8 @@ class SweepSolver:
 
 
 def solve_ip(state, wtmu, **kw):
-    """The fixed-grid solve for independent-pixel grids (IPFLAG=3); see solve_fixed_grid."""
+    """The fixed-grid solve for independent-pixel grids (IPFLAG=3); see solve_fixed_grid (device_loop=False drives the
+    iterations from Python through at3d_path_integration_ip and at3d_compute_source)."""
     return solve_fixed_grid(state, wtmu, **kw)
 
 
@@ -195,9 +197,9 @@ def solve_fixed_grid(state, wtmu, maxiter=100, solacc=1e-4, shacc=0.0, accelflag
     columns for IPFLAG=3, the BACK_INT_GRID3D sweep otherwise), COMPUTE_SOURCE (GPU), sequence acceleration.
     Returns (solved copy of `state` with shptr/source/rshptr/radiance/fluxes/bcrad, iters, solcrit, timings)."""
     st = state.copy().normalize()
-    sweep = None if (st.ipflag & 3) == 3 else SweepSolver(st, wtmu, transmin)
-    if sweep is not None and device_loop and not verbose:
-        # 3-D grids: the whole iteration loop stays on the device
+    sweep = None if ((st.ipflag & 3) == 3 and not device_loop) else SweepSolver(st, wtmu, transmin)
+    if device_loop and not verbose:
+        # the whole iteration loop stays on the device (independent-pixel and 3-D grids)
         try:
             return sweep.solve(maxiter=maxiter, solacc=solacc, shacc=shacc, accelflag=accelflag, highorderrad=highorderrad,
                                iterfixsh=iterfixsh, maxiv=maxiv)

@@ -48,6 +48,22 @@ def test_gpu_solve_and_render_reproduce_shdom(kind):
         np.testing.assert_allclose(out[2], gold[:, 4], rtol=0, atol=1e-8)
 
 
+@pytest.mark.parametrize('kind', ['L', 'O'])
+def test_device_resident_loop_equals_host_driven_loop_ip(kind):
+    """The goldens above run through at3d_solver_solve (everything resident in HBM); the same solve driven from Python
+    through at3d_path_integration_ip + at3d_compute_source gives the same truncations and the same solution."""
+    st, wtmu = unsolved(kind)
+    a, ia, ca, ta = solver.solve_fixed_grid(st, wtmu, solacc=1e-5)
+    b, ib, cb, _ = solver.solve_fixed_grid(st, wtmu, solacc=1e-5, device_loop=False)
+    assert ia == ib and 'loop_ms' in ta
+    np.testing.assert_array_equal(a.shptr, b.shptr)
+    np.testing.assert_array_equal(a.rshptr, b.rshptr)
+    np.testing.assert_allclose(a.source, b.source, rtol=1e-5, atol=1e-7 * np.abs(b.source).max())
+    np.testing.assert_allclose(a.radiance, b.radiance, rtol=1e-5, atol=1e-7 * np.abs(b.radiance).max())
+    np.testing.assert_allclose(a.fluxes, b.fluxes, rtol=1e-6)
+    np.testing.assert_allclose(a.bcrad, b.bcrad, rtol=1e-6, atol=1e-9)
+
+
 def test_gpu_thermal_slab():
     # Verify_Thermal (reference tests/test_shdom.py:910-982) at the angular resolution the GPU transforms support:
     # GPU solve + GPU RENDER against the oracle at the same resolution, and against the closed form within the

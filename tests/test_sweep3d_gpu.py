@@ -150,7 +150,7 @@ def test_device_loop_out_of_sh_memory_is_ierr_2():
 
 def test_solver_refuses_what_it_does_not_cover():
     from at3d_b200._lib import At3dError
-    sc = S.make_scene(nx=5, ny=5, nz=6, ipflag=3, seed=1)
+    sc = S.make_scene(nx=5, ny=5, nz=6, ipflag=2, seed=1)           # BACK_INT_GRID2D
     O.finalize_scene(sc)
     with pytest.raises(At3dError) as e:
         solver.SweepSolver(sc.state, wtmu_of(sc.state))
