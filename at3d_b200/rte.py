@@ -1,0 +1,283 @@
+"""``RTE``: the host-side mirror of ``at3d.solver.RTE`` for the B200 hot path.
+
+Same constructor arguments, ``solve`` and ``integrate_to_sensor`` as the reference class (at3d/solver.py:143, :279,
+:633), with the same dataset variables (``medium``: at3d/medium.py:100-112; ``sensor``: at3d/sensor.py:93-107;
+``numerical_params``: at3d/configuration.py:14-75; ``source`` / ``surface``: at3d/source.py, at3d/surface.py).  The
+containers may be ``xarray.Dataset`` objects (the reference's) or plain mappings ``name -> array`` with the same
+variable names: only ``ds[name]`` and, for datasets, ``.data`` are used, so the class works where xarray is absent.
+
+What runs where: grid construction and property interpolation follow ``_setup_grid`` / ``_prepare_optical_properties``
+(:2036-2520) on the host; ``MAKE_DIRECT``, ``YLMALL``, ``PRECOMPUTE_PHASE_CHECK``, the whole ``SOLUTION_ITERATIONS``
+loop (``at3d_solver_solve``) and ``RENDER`` run on the GPU through the C ABI.  Not covered (NotImplementedError with
+the reason): ``split_accuracy > 0`` (SPLIT_GRID), thermal sources and non-Lambertian surfaces in
+this facade (the C ABI has them; they need SURFACE_PARM_INTERP / PLANCK tables built by the caller).
+"""
+import numpy as np
+from . import backend as B
+from . import grid as G
+from . import medium as M
+from . import solver as S
+from .device import DeviceState
+from .state import ShdomState, Rays
+
+
+def _v(ds, key, default=None):
+    """Variable `key` of an xarray.Dataset or of a plain mapping, as a numpy array / scalar."""
+    try:
+        x = ds[key]
+    except (KeyError, TypeError):
+        if default is not None:
+            return default
+        raise KeyError(key)
+    x = getattr(x, 'data', x)
+    return np.asarray(x)
+
+
+def _scalar(ds, key, default=None):
+    x = _v(ds, key, default)
+    return x.item() if isinstance(x, np.ndarray) and x.ndim == 0 else (x.ravel()[0].item() if isinstance(x, np.ndarray) else x)
+
+
+class RTE:
+    def __init__(self, numerical_params, medium, source, surface, num_stokes=1, name=None, atmosphere=None):
+        if num_stokes not in (1, 3):
+            raise NotImplementedError('num_stokes must be 1 or 3 (NSTOKES=4 is not on the path)')
+        if atmosphere is not None:
+            raise NotImplementedError('`atmosphere` (temperature / gas absorption) is only needed by thermal sources')
+        self._name = name
+        self._nstokes = num_stokes
+        self._nstleg = 1 if num_stokes == 1 else 6
+        self.numerical_params = numerical_params
+        self.medium = dict(medium) if isinstance(medium, dict) else {'medium': medium}
+        self.source, self.surface = source, surface
+        p = numerical_params
+        self._nmu = max(2, 2 * int((int(_scalar(p, 'num_mu_bins')) + 1) / 2))
+        self._nphi = max(1, int(_scalar(p, 'num_phi_bins')))
+        self._deltam = bool(_scalar(p, 'deltam', True))
+        self._splitacc = float(_scalar(p, 'split_accuracy', 0.0))
+        self._shacc = float(_scalar(p, 'spherical_harmonics_accuracy', 0.0))
+        self._solacc = float(_scalar(p, 'solution_accuracy', 1e-4))
+        self._accelflag = bool(_scalar(p, 'acceleration_flag', True))
+        self._highorderrad = bool(_scalar(p, 'high_order_radiance', False))
+        self._ipflag = int(_scalar(p, 'ip_flag', 0))
+        self._iterfixsh = int(_scalar(p, 'iterfixsh', 30))
+        self._tautol = float(_scalar(p, 'tautol', 0.2))
+        self._transcut = float(_scalar(p, 'transcut', 5e-5))
+        self._transmin = float(_scalar(p, 'transmin', 1.0))
+        self._xbc = str(_scalar(p, 'x_boundary_condition', 'periodic'))
+        self._ybc = str(_scalar(p, 'y_boundary_condition', 'periodic'))
+        if int(_scalar(p, 'angle_set', 2)) != 2:
+            raise NotImplementedError('angle_set must be 2 (reduced Gaussian, the at3d default)')
+        # ---- source (at3d/solver.py:1847-1888) ----
+        self.wavelength = float(_scalar(source, 'wavelength'))
+        self._srctype = str(_scalar(source, 'srctype', 'S'))
+        if self._srctype != 'S':
+            raise NotImplementedError("only solar sources (srctype 'S') in this facade")
+        self._solarflux = float(_scalar(source, 'solarflux'))
+        self._solarmu = float(_scalar(source, 'solarmu'))
+        self._solaraz = float(_scalar(source, 'solaraz'))
+        self._skyrad = float(_scalar(source, 'skyrad', 0.0))
+        if not (-1.0 <= self._solarmu < 0.0):
+            raise ValueError('solarmu must be in the range -1.0 <= solarmu < 0.0 (direction of propagation)')
+        # ---- surface (:1890-1958) ----
+        self._sfctype = str(_scalar(surface, 'sfctype', 'FL'))
+        if self._sfctype != 'FL':
+            raise NotImplementedError("only the fixed Lambertian surface ('FL') in this facade")
+        self._gndalbedo = float(_scalar(surface, 'gndalbedo'))
+        self._gndtemp = float(_scalar(surface, 'gndtemp', 298.15))
+        self._setup_grid(next(iter(self.medium.values())))
+        self._prepare_optical_properties()
+        self._solved = None
+        self._dev = None
+        self._iters, self._solcrit, self._timings = 0, 1.0, {}
+
+    # -- _setup_grid (at3d/solver.py:2036-2168) --
+    def _setup_grid(self, grid):
+        x, y, z = _v(grid, 'x'), _v(grid, 'y'), _v(grid, 'z')
+        if not (np.allclose(x[0], 0.0) and np.allclose(y[0], 0.0)):
+            raise ValueError('The property grid should start from 0.0 in x and y')
+        self._npx, self._npy, self._npz = x.size, y.size, z.size
+        self._delx, self._dely = np.float32(_scalar(grid, 'delx')), np.float32(_scalar(grid, 'dely'))
+        self._zlevels = z.astype(np.float32)
+        self._nx, self._ny, self._nz = max(1, self._npx), max(1, self._npy), max(2, self._npz)
+        if self._nx == 1:
+            self._ipflag |= 1
+        if self._ny == 1:
+            self._ipflag |= 2
+        self._bcflag = 0
+        if self._xbc == 'open' and self._ipflag in (0, 2, 4, 6):
+            self._bcflag += 1
+        if self._ybc == 'open' and self._ipflag in (0, 1, 4, 5):
+            self._bcflag += 2
+        nx1, ny1, nbpts, nbcells = G.grid_sizes(self._nx, self._ny, self._nz, self._bcflag, self._ipflag)
+        xg, yg, zg = G.new_grids(self._bcflag, 'P', self._npx, self._npy, self._npz, self._nx, self._ny, self._nz,
+                                 0.0, 0.0, self._delx, self._dely, self._zlevels)
+        self._nx1, self._ny1, self._xgrid, self._ygrid, self._zgrid = nx1, ny1, xg, yg, zg
+        (self._npts, self._ncells, gridpos, gridptr, neighptr, treeptr, cellflags) = G.init_cell_structure(
+            self._bcflag, self._ipflag, self._nx, self._ny, self._nz, nx1, ny1, xg[:nx1], yg[:ny1], zg)
+        n, c = self._npts, self._ncells
+        self._gridpos = np.asfortranarray(gridpos[:, :n])
+        self._gridptr = np.asfortranarray(gridptr[:, :c])
+        self._neighptr = np.asfortranarray(neighptr[:, :c])
+        self._treeptr = np.asfortranarray(treeptr[:, :c])
+        self._cellflags = cellflags[:c].copy()
+        self._ml = self._nmu - 1
+        self._mm = max(0, int(self._nphi / 2) - 1)
+        self._nlm = (2 * self._mm + 1) * (self._ml + 1) - self._mm * (self._mm + 1)
+        if self._nlm < 4:
+            raise ValueError('Insufficient spherical harmonics (NLM=%d)' % self._nlm)
+
+    # -- _prepare_optical_properties (:2324-2520) --
+    def _prepare_optical_properties(self):
+        species = list(self.medium.values())
+        npart = len(species)
+        maxpg = self._npx * self._npy * self._npz
+        mnm = max(_v(s, 'table_index').shape[0] for s in species)
+        extp = np.zeros((maxpg, npart), np.float32, order='F')
+        albp = np.zeros((maxpg, npart), np.float32, order='F')
+        iphp = np.zeros((mnm, maxpg, npart), np.int32, order='F')
+        pwp = np.zeros((mnm, maxpg, npart), np.float32, order='F')
+        tables = []
+        maxleg = max(_v(s, 'legcoef').shape[1] for s in species)
+        for i, s in enumerate(species):
+            e = _v(s, 'extinction')
+            if e.shape != (self._npx, self._npy, self._npz):
+                raise ValueError('every scatterer must be on the same (x, y, z) grid')
+            extp[:, i] = e.reshape(-1)
+            albp[:, i] = _v(s, 'ssalb').reshape(-1)
+            ti = _v(s, 'table_index').reshape(_v(s, 'table_index').shape[0], -1)
+            pw = _v(s, 'phase_weights').reshape(ti.shape[0], -1)
+            # the reference offsets a species' table indices by the largest index assigned so far
+            # (`+ self._pa.iphasep.max()`, at3d/solver.py:2355), not by the number of tables before it
+            offset = int(iphp.max())
+            iphp[:ti.shape[0], :, i] = ti + offset
+            iphp[ti.shape[0]:, :, i] = 1 + offset
+            pwp[:ti.shape[0], :, i] = pw
+            lc = _v(s, 'legcoef').astype(np.float32)                    # [stokes_index=6, legendre_index, table_index]
+            lc = np.pad(lc, ((0, 0), (0, maxleg - lc.shape[1]), (0, 0)))
+            tables.append(lc)
+        iphp[iphp == 0] = 1
+        leg = np.concatenate(tables, axis=2)
+        numphase = leg.shape[2]
+        if np.any(iphp < 1) or np.any(iphp > numphase):
+            raise ValueError('Phase function indices are out of bounds.')
+        self._nleg = self._ml + 1 if self._deltam else self._ml
+        nlegp = max(leg.shape[1] - 1, self._nleg)
+        if nlegp + 1 > leg.shape[1]:
+            leg = np.pad(leg, ((0, 0), (0, nlegp + 1 - leg.shape[1]), (0, 0)))
+        legenp = np.asfortranarray(leg[:1] if self._nstokes == 1 else leg, dtype=np.float32)
+        self._nscatangle = max(36, min(721, 2 * nlegp))
+        self._pg = M.PropertyGrid(self._npx, self._npy, self._npz, self._delx, self._dely, self._zlevels, extp, albp,
+                                  iphp, pwp, legenp, nlegp, self._nstleg)
+        self._t = M.transfer_pa_to_grid(self._pg, self._gridpos, self._npts, self._ml, self._deltam)
+
+    # -- _init_solution (:2539-2798): angle set, boundary points, direct beam, YLMSUN, phase table --
+    def _init_solution(self):
+        nst, npts, t = self._nstokes, self._npts, self._t
+        mu, phi, wtdo, nphi0, nang = M.make_angle_set(self._nmu, self._nphi)
+        ntop, nbot, bcptr = G.boundary_pnts(npts, self._gridpos, self._zgrid[0], self._zgrid[-1])
+        lamb_bc = np.zeros((nst, ntop + nbot), np.float32, order='F')
+        skyrad = np.zeros((nst, self._nmu // 2, self._nphi), np.float32, order='F')
+        skyrad[0] = self._skyrad
+        st = ShdomState(
+            nstokes=nst, nstleg=self._nstleg, nx=self._nx, ny=self._ny, nz=self._nz, npts=npts, ncells=self._ncells,
+            ml=self._ml, mm=self._mm, nlm=self._nlm, nleg=t['nleg'], numphase=self._pg.numphase, npart=self._pg.npart,
+            maxnmicro=self._pg.maxnmicro, bcflag=self._bcflag, ipflag=self._ipflag, nmu=self._nmu, nphi0max=self._nphi,
+            nang=nang, maxnbc=bcptr.shape[0], ntoppts=ntop, nbotpts=nbot, nsfcpar=2, nscatangle=self._nscatangle,
+            nstphase=1 if nst == 1 else 2, deltam=int(self._deltam), srctype='S', units='R', sfctype0='F', sfctype1='L',
+            interp_new=1, solarmu=self._solarmu, solaraz=self._solaraz, solarflux=self._solarflux,
+            wavelen=self.wavelength, gndtemp=self._gndtemp, gndalbedo=self._gndalbedo, phasemax=0.999, waveno0=0.0,
+            waveno1=0.0, tautol=self._tautol, transcut=self._transcut,
+            gridptr=self._gridptr, neighptr=self._neighptr, treeptr=self._treeptr, cellflags=self._cellflags,
+            xgrid=self._xgrid if not (self._bcflag & 5) else self._xgrid[:self._nx],
+            ygrid=self._ygrid if not (self._bcflag & 10) else self._ygrid[:self._ny], zgrid=self._zgrid,
+            gridpos=self._gridpos, extinct=t['extinct'], albedo=t['albedo'], total_ext=t['total_ext'], legen=t['legen'],
+            iphase=t['iphase'], phaseinterpwt=t['phaseinterpwt'], dirflux=np.zeros(npts, np.float32),
+            fluxes=np.zeros((2, npts), np.float32, order='F'), shptr=np.zeros(npts + 1, np.int32),
+            source=np.zeros((nst, 1), np.float32, order='F'), rshptr=np.zeros(npts + 2, np.int32),
+            radiance=np.zeros((nst, 1), np.float32, order='F'), ylmsun=None, phasetab=None,
+            planck=np.zeros((npts, self._pg.npart), np.float32, order='F'), temp=None, nphi0=nphi0, mu=mu, phi=phi,
+            wtdo=wtdo, skyrad=skyrad, bcptr=bcptr, bcrad=lamb_bc,
+            sfcgridparms=np.zeros((2, nbot), np.float32, order='F'), sfcgridrad=None).normalize()
+        st.dirflux, self._extdirp, self._beam = B.make_direct(st, self._pg)
+        st.ylmsun = B.ylmall(True, np.float32(st.solarmu), np.float32(st.solaraz), st.ml, st.mm, st.nstleg, st.nlm)
+        st.phasetab = B.precompute_phase_check(self._pg.legenp, st.nscatangle, st.nstokes, st.ml, bool(st.deltam))
+        delphi = np.float32(2.0 * np.pi) / nphi0.astype(np.float32)
+        self._wtmu = (wtdo[:, 0] / delphi).astype(np.float32)
+        self._unsolved = st
+        return st
+
+    def solve(self, maxiter, init_solution=True, setup_grid=True, verbose=False, solve=True):
+        """``RTE.solve`` (at3d/solver.py:279): SHDOM solution iterations on the GPU; fixed grid (``split_accuracy`` 0)."""
+        if self._splitacc > 0.0:
+            raise NotImplementedError('adaptive grid splitting (split_accuracy > 0: SPLIT_GRID) is not implemented; '
+                                      'set split_accuracy=0.0')
+        st = self._init_solution()
+        if not solve:
+            return
+        sol, self._iters, self._solcrit, self._timings = S.solve_fixed_grid(
+            st, self._wtmu, maxiter=maxiter, solacc=self._solacc, shacc=self._shacc, accelflag=self._accelflag,
+            highorderrad=self._highorderrad, iterfixsh=self._iterfixsh, transmin=self._transmin)
+        if verbose:
+            print('  %d iterations, solution criterion %.3e' % (self._iters, self._solcrit))
+        self._set_solution(sol)
+
+    def _set_solution(self, sol):
+        if self._dev is not None:
+            self._dev.close()
+        self._solved, self._dev = sol, DeviceState(sol)
+
+    def check_solved(self, verbose=True):
+        return self._solved is not None and self._solcrit <= self._solacc
+
+    @property
+    def num_iterations(self):
+        return self._iters
+
+    @property
+    def solution_accuracy(self):
+        return self._solacc
+
+    def integrate_to_sensor(self, sensor, single_scatter=False, nosurface=False):
+        """``RTE.integrate_to_sensor`` (at3d/solver.py:633): RENDER of the sensor's rays; adds per-ray ``I`` (``Q``,
+        ``U``) to the sensor and returns it."""
+        if self._solved is None:
+            raise RuntimeError('solve() first')
+        rays = Rays(_v(sensor, 'ray_x'), _v(sensor, 'ray_y'), _v(sensor, 'ray_z'), _v(sensor, 'ray_mu'), _v(sensor, 'ray_phi'))
+        want = _v(sensor, 'stokes', np.array([True] + [False] * 3))
+        if int(np.sum(np.any(np.atleast_2d(want), axis=0) if want.ndim > 1 else want)) > self._nstokes:
+            raise ValueError('the sensor requires more Stokes components than the RTE has')
+        out = self._dev.render(rays, singlescatter=single_scatter, nosurface=nosurface)
+        names = ('I', 'Q', 'U')
+        for k in range(self._nstokes):
+            try:
+                import xarray as xr
+                if isinstance(sensor, xr.Dataset):
+                    sensor[names[k]] = xr.DataArray(data=out[k], dims='nrays')
+                    continue
+            except ImportError:
+                pass
+            sensor[names[k]] = out[k]
+        return sensor
+
+    def average_subpixel_rays(self, sensor):
+        """Per-pixel observables from the per-ray ones (at3d/containers.py:642-647, src/util.f90:484): returns
+        [nstokes, npixels]."""
+        pix = _v(sensor, 'pixel_index').astype(np.int32)
+        w = _v(sensor, 'ray_weight').astype(np.float64)
+        npix = int(pix.max()) + 1 if pix.size else 0
+        ws = np.asfortranarray(np.stack([_v(sensor, n) * w for n in ('I', 'Q', 'U')[:self._nstokes]]).astype(np.float32))
+        return B.average_subpixel_rays(ws, pix, npix)            # pixel_index is 0-based, as in the reference
+
+    @property
+    def fluxes(self):
+        """Hemispheric fluxes on the base grid, [2 (down, up), nx1, ny1, nz] (at3d/solver.py:1148)."""
+        if self._solved is None:
+            raise RuntimeError('solve() first')
+        n = self._nx1 * self._ny1 * self._nz
+        return self._solved.fluxes[:, :n].reshape(2, self._nx1, self._ny1, self._nz)
+
+    def close(self):
+        if self._dev is not None:
+            self._dev.close()
+            self._dev = None

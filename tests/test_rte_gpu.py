@@ -1,0 +1,115 @@
+"""The `at3d.solver.RTE`-shaped facade (at3d_b200/rte.py): constructor from medium / source / surface / numerical
+parameter containers with the reference's variable names, `solve`, `integrate_to_sensor`, sub-pixel averaging -- end to
+end on the GPU, checked against the oracle run on the same prepared state (MAKE_DIRECT, fixed-grid solve, RENDER)."""
+import numpy as np
+import pytest
+import oracle_lib as O
+
+pytestmark = pytest.mark.gpu
+
+
+def hg_legcoef(gs, nleg, polarized):
+    l = np.arange(nleg + 1)
+    out = np.zeros((6, nleg + 1, len(gs)), np.float32)
+    for k, g in enumerate(gs):
+        out[0, :, k] = (2 * l + 1) * g ** l
+        if polarized:
+            out[1, :, k] = out[0, :, k] * (l >= 2)
+            out[2, :, k] = 0.9 * out[0, :, k] * (l >= 2)
+            out[3, :, k] = 0.9 * out[0, :, k]
+            out[4, :, k] = -0.1 * out[0, :, k] * (l >= 2)
+            out[5, :, k] = 0.03 * out[0, :, k] * (l >= 2)
+    return out
+
+
+def make_inputs(nx, ny, nz, bc, nstokes, two_species, seed=0):
+    rng = np.random.default_rng(seed)
+    dx = dy = 0.05
+    x, y, z = np.arange(nx) * dx, np.arange(ny) * dy, np.linspace(0.0, 0.5, nz)
+    X, Y, Z = np.meshgrid((np.arange(nx) + 0.5) / nx, (np.arange(ny) + 0.5) / ny, np.arange(nz) / (nz - 1), indexing='ij')
+    r2 = ((X - 0.5) / 0.3) ** 2 + ((Y - 0.5) / 0.3) ** 2 + ((Z - 0.5) / 0.3) ** 2
+    ext = (25.0 * np.exp(-r2)).astype(np.float32)
+    ext[r2 > 1.5] = 0.0
+    gs = [0.80, 0.84, 0.87]
+    cloud = dict(x=x, y=y, z=z, delx=dx, dely=dy, extinction=ext, ssalb=np.full_like(ext, 0.999),
+                 table_index=rng.integers(1, len(gs) + 1, (1, nx, ny, nz)).astype(np.int32),
+                 phase_weights=np.ones((1, nx, ny, nz), np.float32), legcoef=hg_legcoef(gs, 180, nstokes > 1))
+    medium = {'cloud': cloud}
+    if two_species:
+        ray = np.zeros((6, 3, 1), np.float32)
+        ray[0, 0, 0] = 1.0; ray[0, 2, 0] = 0.5
+        ray[1, 2, 0] = 3.0; ray[3, 1, 0] = 1.5; ray[4, 2, 0] = np.sqrt(1.5)
+        rext = (0.03 * np.exp(-Z * 0.5 / 8.0)).astype(np.float32)
+        medium['rayleigh'] = dict(x=x, y=y, z=z, delx=dx, dely=dy, extinction=rext, ssalb=np.ones_like(rext),
+                                  table_index=np.ones((1, nx, ny, nz), np.int32),
+                                  phase_weights=np.ones((1, nx, ny, nz), np.float32), legcoef=ray)
+    params = dict(num_mu_bins=8, num_phi_bins=16, split_accuracy=0.0, deltam=True, spherical_harmonics_accuracy=0.0,
+                  solution_accuracy=1e-4, acceleration_flag=True, high_order_radiance=False, ip_flag=0, iterfixsh=30,
+                  tautol=0.2, transcut=5e-5, transmin=1.0, angle_set=2, x_boundary_condition=bc, y_boundary_condition=bc)
+    source = dict(wavelength=0.672, srctype='S', solarflux=1.0, solarmu=-0.5, solaraz=0.2, skyrad=0.0, units='R')
+    surface = dict(sfctype='FL', gndalbedo=0.05, gndtemp=298.15)
+    return params, medium, source, surface
+
+
+def make_sensor(xmax, ymax, seed=0):
+    """Two orthographic views with 2x2 sub-pixel rays per pixel (variable names of at3d/sensor.py:93-107)."""
+    rng = np.random.default_rng(seed)
+    xs, ys = np.meshgrid(np.linspace(0.02, xmax - 0.02, 9), np.linspace(0.02, ymax - 0.02, 8), indexing='ij')
+    npix1 = xs.size
+    rx, ry, rmu, rphi, pix, w = [], [], [], [], [], []
+    for iv, (mu, phi) in enumerate(((1.0, 0.0), (0.6, 1.1))):
+        for sx, sy in ((-0.004, -0.004), (0.004, -0.004), (-0.004, 0.004), (0.004, 0.004)):
+            rx.append(xs.ravel() + sx); ry.append(ys.ravel() + sy)
+            rmu.append(np.full(npix1, mu)); rphi.append(np.full(npix1, phi))
+            pix.append(np.arange(npix1) + iv * npix1); w.append(np.full(npix1, 0.25))
+    order = np.argsort(np.concatenate(pix), kind='stable')
+    cat = lambda a: np.concatenate(a)[order]
+    return dict(ray_x=cat(rx), ray_y=cat(ry), ray_z=np.full(order.size, 0.5), ray_mu=cat(rmu), ray_phi=cat(rphi),
+                ray_weight=cat(w), pixel_index=cat(pix).astype(np.int64), stokes=np.array([True, True, True, False]))
+
+
+@pytest.mark.parametrize('bc,nstokes,two', [('periodic', 1, False), ('open', 3, True)])
+def test_rte_solve_and_integrate_to_sensor(bc, nstokes, two):
+    from at3d_b200.rte import RTE
+    from at3d_b200.state import Rays
+    params, medium, source, surface = make_inputs(9, 8, 11, bc, nstokes, two)
+    rte = RTE(params, medium, source, surface, num_stokes=nstokes)
+    rte.solve(maxiter=60)
+    assert rte.check_solved() and 2 < rte.num_iterations < 60
+    st0 = rte._unsolved
+    # the prepared state: direct beam against the oracle's MAKE_DIRECT
+    dirflux_ref = O.make_direct(st0, rte._pg)[0]
+    np.testing.assert_allclose(st0.dirflux, dirflux_ref, rtol=1e-5, atol=1e-7)
+    assert st0.bcflag == (3 if bc == 'open' else 0) and st0.npart == (2 if two else 1)
+    # the solve and the rendering against the oracle on the same prepared state
+    ref, iters, solcrit = O.solve_fixed_grid(st0, rte._wtmu, solacc=1e-4, maxiter=60)
+    assert iters == rte.num_iterations
+    np.testing.assert_array_equal(rte._solved.shptr, ref.shptr)
+    np.testing.assert_allclose(rte._solved.fluxes, ref.fluxes, rtol=1e-4, atol=1e-7)
+    xmax = 0.05 * (8 if bc == 'open' else 9); ymax = 0.05 * (7 if bc == 'open' else 8)
+    sensor = make_sensor(xmax, ymax)
+    if nstokes == 1:
+        sensor['stokes'] = np.array([True, False, False, False])
+    out = rte.integrate_to_sensor(sensor)
+    rays = Rays(sensor['ray_x'], sensor['ray_y'], sensor['ray_z'], sensor['ray_mu'], sensor['ray_phi'])
+    refrad = O.render(ref, rays)
+    np.testing.assert_allclose(out['I'], refrad[0], rtol=1e-4, atol=1e-6 * refrad[0].max())
+    if nstokes == 3:
+        np.testing.assert_allclose(out['Q'], refrad[1], rtol=1e-4, atol=1e-6)
+        np.testing.assert_allclose(out['U'], refrad[2], rtol=1e-4, atol=1e-6)
+    # pixel observables: 4 sub-pixel rays of weight 1/4 each
+    obs = rte.average_subpixel_rays(out)
+    npix = obs.shape[1]
+    want = (refrad[:, :4 * npix].reshape(nstokes, npix, 4) * 0.25).sum(axis=2)
+    np.testing.assert_allclose(obs, want, rtol=2e-4, atol=1e-6)
+    assert rte.fluxes.shape[0] == 2 and np.all(rte.fluxes >= 0)
+    rte.close()
+
+
+def test_rte_refuses_adaptive_splitting():
+    from at3d_b200.rte import RTE
+    params, medium, source, surface = make_inputs(5, 5, 6, 'periodic', 1, False)
+    params['split_accuracy'] = 0.03
+    rte = RTE(params, medium, source, surface)
+    with pytest.raises(NotImplementedError):
+        rte.solve(maxiter=5)
