@@ -161,6 +161,48 @@ def make_gradient_inputs(scene, backend, seed=0, numder=2, exact_single_scatter=
     return gi.normalize()
 
 
+def extinction_gradient_inputs(state, pg, backend, species, extmin, scatmin, exact_single_scatter=True,
+                               costfunc='L2', maxsubgridints=0):
+    """Derivative tables for the unknowns "extinction of species k" (k in `species`, 0-based), the unknown of
+    BASELINE.json configs[1]: d(extinction)/d(unknown) = 1 on the property grid, albedo and phase function unchanged
+    (what at3d.solver.RTE.calculate_microphysical_partial_derivatives produces for variable 'extinction',
+    at3d/solver.py:1327-1517)."""
+    st = state
+    numder = len(species)
+    maxpg, mnm = pg.maxpg, pg.maxnmicro
+    partder = np.asarray([k + 1 for k in species], np.int32)
+    doexact = np.zeros(numder, np.int32)
+    dext = np.ones((maxpg, numder), np.float32, order='F')
+    dalb = np.zeros((maxpg, numder), np.float32, order='F')
+    diphasep = np.ones((mnm, maxpg, numder), np.int32, order='F')
+    dphasewtp = np.zeros((mnm, maxpg, numder), np.float32, order='F')
+    for i, k in enumerate(species):
+        diphasep[:, :, i] = pg.iphasep[:, :, k]
+    gi = GradInputs(
+        npix=0, maxpg=maxpg, numder=numder, dnumphase=1, deriv_maxnmicro=mnm,
+        longest_path_pts=1, nuncertainty=st.nstokes, maxsubgridints=maxsubgridints,
+        exact_single_scatter=int(exact_single_scatter), singlescatter=0,
+        costfunc_ll=1 if costfunc == 'LL' else 0, extmin=extmin, scatmin=scatmin,
+        partder=partder, doexact=doexact, dext=dext, dalb=dalb,
+        dleg=np.zeros((st.nstleg, st.nleg + 1, 1), np.float32, order='F'),
+        dphasetab=np.zeros((st.nstphase, 1, st.nscatangle), np.float32, order='F'),
+        diphasep=diphasep, dphasewtp=dphasewtp,
+        iphasep=pg.iphasep, phasewtp=pg.phasewtp, extinctp=pg.extinctp, albedop=pg.albedop,
+        dtemp=np.zeros((maxpg, numder), np.float32, order='F'))
+    gi.normalize()
+    optw, iptr, dalbm, dextm, dfj = backend.prepare_deriv_interps(st, pg, gi)
+    gi.optinterpwt, gi.interpptr, gi.dalbm, gi.dextm, gi.dfj = optw, iptr, dalbm, dextm, dfj
+    if exact_single_scatter:
+        _, _, c = backend.make_direct(st, pg)
+        dpath, dptr = backend.make_direct_derivative(st, pg, c)
+        gi.longest_path_pts = int(dpath.shape[0])
+        gi.dpath, gi.dptr = dpath, dptr
+    else:
+        gi.dpath = np.zeros((1, st.npts), np.float32, order='F')
+        gi.dptr = np.zeros((1, st.npts), np.int32, order='F')
+    return gi.normalize()
+
+
 def with_pixels(gi, pix):
     """Copy of ``gi`` carrying the per-pixel arrays (for backends that take one flat structure)."""
     out = gi.copy()

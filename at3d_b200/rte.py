@@ -269,6 +269,30 @@ class RTE:
         ws = np.asfortranarray(np.stack([_v(sensor, n) * w for n in ('I', 'Q', 'U')[:self._nstokes]]).astype(np.float32))
         return B.average_subpixel_rays(ws, pix, npix)            # pixel_index is 0-based, as in the reference
 
+    def levis_approx_gradient(self, sensor, unknown_scatterers=None, exact_single_scatter=True, cost_function='L2'):
+        """The Levis-approximation gradient of the cost function with respect to the extinction of the named scatterers
+        (at3d/gradient.py:262-398 `levis_approximation_grad` -> `core.levisapprox_gradient`, MAKEJACOBIAN=.FALSE.).
+
+        `sensor`: the merged RTE sensor of at3d/containers.py:296-349 (ray_* arrays sorted by pixel, `rays_per_pixel`
+        [npixels], `ray_weight`, `stokes_weights` [nstokes, npixels], `measurement_data` [nstokes, npixels],
+        `uncertainties` [nstokes, nstokes, npixels]).  Returns (loss, gradient [x, y, z, derivative_index] -- the
+        layout of at3d/gradient.py:492-503 --, modelled pixel observables [nstokes, npixels])."""
+        from . import gradsetup
+        if self._solved is None:
+            raise RuntimeError('solve() first')
+        names = list(self.medium.keys())
+        species = [names.index(n) for n in (unknown_scatterers or names[:1])]
+        gi = gradsetup.extinction_gradient_inputs(self._solved, self._pg, B, species, self._t['extmin'], self._t['scatmin'],
+                                                  exact_single_scatter=exact_single_scatter, costfunc=cost_function)
+        self._dev.attach_gradient(gi)
+        rays = Rays(_v(sensor, 'ray_x'), _v(sensor, 'ray_y'), _v(sensor, 'ray_z'), _v(sensor, 'ray_mu'), _v(sensor, 'ray_phi'))
+        pix = gradsetup.PixelData(_v(sensor, 'measurement_data')[:self._nstokes], _v(sensor, 'uncertainties'),
+                                  _v(sensor, 'rays_per_pixel'), _v(sensor, 'ray_weight'),
+                                  _v(sensor, 'stokes_weights')[:self._nstokes])
+        g, cost, images = self._dev.gradient(rays, pix)
+        grad = g.reshape(self._npx, self._npy, self._npz, len(species))
+        return float(cost[0]), grad, images
+
     @property
     def fluxes(self):
         """Hemispheric fluxes on the base grid, [2 (down, up), nx1, ny1, nz] (at3d/solver.py:1148)."""
