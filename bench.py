@@ -207,6 +207,28 @@ def sweep3d_leg(st, steps, warmup, oracle=None):
     return res
 
 
+def inversion_step_leg(sc, rays, gi, pix, DeviceState):
+    """One cost-function + gradient evaluation of an inversion (BASELINE.json configs[4], per wavelength / GPU): the
+    fixed-grid solve of the workload's medium from scratch (device-resident iterations), the upload of the solved state,
+    the derivative tables, and the radiance + gradient pass with host buffers; wall-clock ms of each part."""
+    from at3d_b200 import solver
+    st = sc.state
+    delphi = np.float32(2.0 * np.pi) / st.nphi0.astype(np.float32)
+    wtmu = (st.wtdo[:, 0] / delphi).astype(np.float32)
+    t0 = time.perf_counter()
+    sol, iters, solcrit, tm = solver.solve_fixed_grid(st, wtmu, solacc=1e-4, maxiter=60)
+    t1 = time.perf_counter()
+    dev = DeviceState(sol)
+    dev.attach_gradient(gi)
+    t2 = time.perf_counter()
+    g, cost, so = dev.gradient(rays, pix)
+    t3 = time.perf_counter()
+    dev.close()
+    return dict(solve_iterations=iters, solcrit=solcrit, solve_ms=1e3 * (t1 - t0), solve_loop_ms=tm.get('loop_ms'),
+                state_upload_ms=1e3 * (t2 - t1), gradient_ms=1e3 * (t3 - t2), total_ms=1e3 * (t3 - t0),
+                rays=int(rays.nrays), cost=float(cost[0]))
+
+
 def transform_leg(B, st, steps, warmup):
     """SH_TO_DO / DO_TO_SH on the workload's SOURCE / RADIANCE: kernel ms (CUDA events inside the
     C-ABI call), FP32 FMA rate against the CUDA-core peak and bytes against HBM."""
@@ -670,6 +692,7 @@ def main():
             render_orthographic=orthographic_leg(dev, sc, cfg['pixels_per_view'] ** 0.5, args.steps, args.warmup),
             solver_iteration=solver_leg(max(1, args.steps // 2), 1, orc if args.workload == 'cfg2' else None),
             path_integration_3d=sweep3d_leg(st, args.steps, 1, orc if args.workload == 'cfg2' else None),
+            inversion_step=inversion_step_leg(sc, rays, gi, pix, DeviceState),
             render_ocean=dict(rays_per_s=nrays / (np.mean(oms) * 1e-3), kernel_ms=float(np.mean(oms)),
                               surface_ms=float(np.mean(oms) - np.mean(rms)), surface_hits=ocounts['surface_hits'],
                               brdf_evals=ocounts['surface_hits'] * 4 * (st.nang // 2 + 1)),
