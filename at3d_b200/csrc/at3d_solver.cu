@@ -403,9 +403,12 @@ struct SwArgs {
     float *radf;                // [npts, nst, nang] radiance (GRIDRAD of every ordinate)
     double eps, transmin;
     int *ticket, *err;
-    const int *perm;            // [nang][npts] processing order of an ordinate: positions r sorted by dependency level
-                                // (null: the reference order itself)
+    const int2 *plan;           // [nang][npts] processing order of an ordinate, sorted by dependency level (the preset boundary
+                                // points, level 0, come first and are skipped): x = SWEEPORD entry, y = point-1 | cells to walk
+                                // << 24 (255: decide with the rank test); null: the reference order itself
+    int npre[2];                // preset boundary points per hemisphere (down: top points, up: bottom points)
     int *level;                 // [nang][npts] dependency level of (ordinate, point); -1 = not yet (level pass only)
+    unsigned char *nwalk;       // [nang][npts] cells walked by (ordinate, point), capped at 255 (level pass only)
 };
 
 __device__ __forceinline__ float ld_vol(const float *p) { return *(const volatile float *)p; }
@@ -430,7 +433,9 @@ __global__ void __launch_bounds__(256, (NST == 1 ? AT3D_SWEEP_MINB : 2)) sweep3d
     __shared__ int s_ticket;
     if (threadIdx.x == 0) s_ticket = atomicAdd(a.ticket, 1);
     __syncthreads();
-    const int nh = a.nang / 2, G = a.group, per = a.nchunks * G;
+    const bool planned = !LEVEL && a.plan != nullptr;
+    const int npre = planned ? a.npre[up] : 0, nact = a.npts - npre, nchunks = (nact + 255) / 256;
+    const int nh = a.nang / 2, G = a.group, per = nchunks * G;
     int t = s_ticket, grp = t / per, io, chunk;
     const int ngrp = (nh + G - 1) / G;
     if (grp >= ngrp - 1) {
@@ -443,23 +448,28 @@ __global__ void __launch_bounds__(256, (NST == 1 ? AT3D_SWEEP_MINB : 2)) sweep3d
         chunk = t / G; io = grp * G + t % G;
     }
     const int kpos = chunk * 256 + threadIdx.x;
-    if (kpos >= a.npts) return;
+    if (kpos >= nact) return;
     const int ia = (up ? nh : 0) + io;
-    const int r = (!LEVEL && a.perm) ? a.perm[(size_t)a.npts * ia + kpos] : kpos;
     const OrdDir D = a.dir[ia];
-    const int *so_oct = a.sweepord + (size_t)a.npts * (D.joct - 1);
     const int *rank = a.rank + (size_t)a.npts * (D.joct - 1);
-    const unsigned char bmask = up ? 2 : 1;
-    const int entry = so_oct[r];
-    const int ipcell = entry >> 3;
     const DevState &S = a.S;
-    const int ipt = cell_gp(S, ipcell, (entry & 7) + 1);
-    if (a.bflag[ipt - 1] & bmask) return;                     // GRIDRAD(1,IPT) >= 0: preset boundary point
+    int r, ipcell, ipt, nwalk = 255;
+    if (planned) {
+        const int2 pl = __ldg(&a.plan[(size_t)a.npts * ia + npre + kpos]);
+        ipcell = pl.x >> 3; ipt = (pl.y & 0xFFFFFF) + 1; nwalk = (int)((unsigned)pl.y >> 24);
+        r = nwalk == 255 ? __ldg(&rank[ipt - 1]) : 0;
+    } else {
+        r = kpos;
+        const int entry = a.sweepord[(size_t)a.npts * (D.joct - 1) + r];
+        ipcell = entry >> 3;
+        ipt = cell_gp(S, ipcell, (entry & 7) + 1);
+        if (a.bflag[ipt - 1] & (up ? 2 : 1)) return;          // GRIDRAD(1,IPT) >= 0: preset boundary point
+    }
     const size_t fo = (size_t)a.npts * NST * ia;
     const float *src = a.srcdo + fo;
     float *R = a.radf + fo;
     const int ioct = D.ioct;
-    int icell = ipcell, fail = 0;
+    int icell = ipcell, fail = 0, step = 0;
     double transmit = 1.0, rad[NST], srcext1[NST], srcext0[NST];
     float4 pp = __ldg(&S.ptrec[ipt - 1]);
     double ext1 = (double)pp.w, ext0 = 0.0, f1 = 0, f2 = 0, f3 = 0, f4 = 0;
@@ -568,12 +578,18 @@ __global__ void __launch_bounds__(256, (NST == 1 ? AT3D_SWEEP_MINB : 2)) sweep3d
 #pragma unroll
         for (int k = 0; k < NST; k++) rad[k] = rad[k] + transmit * sc[k] * abscell;
         transmit = transmit * transcell;
-        // VALIDFACE, statically: all four face points are preset or earlier in the sweep order
-        // (preset boundary points of the hemisphere carry rank -1)
-        const bool validface = __ldg(&rank[i1 - 1]) < r && __ldg(&rank[i2 - 1]) < r && __ldg(&rank[i3 - 1]) < r && __ldg(&rank[i4 - 1]) < r;
-        if (inextcell <= 0 || (transmit <= a.transmin && validface)) {
-            if (!validface) fail = 3;
-            break;
+        step++;
+        if (nwalk != 255) {
+            // the level pass walked this (ordinate, point) with the test below and recorded where it stopped
+            if (step == nwalk) break;
+        } else {
+            // VALIDFACE, statically: all four face points are preset or earlier in the sweep order
+            // (preset boundary points of the hemisphere carry rank -1)
+            const bool validface = __ldg(&rank[i1 - 1]) < r && __ldg(&rank[i2 - 1]) < r && __ldg(&rank[i3 - 1]) < r && __ldg(&rank[i4 - 1]) < r;
+            if (inextcell <= 0 || (transmit <= a.transmin && validface)) {
+                if (!validface) fail = 3;
+                break;
+            }
         }
         ext1 = ext0;
 #pragma unroll
@@ -594,6 +610,7 @@ __global__ void __launch_bounds__(256, (NST == 1 ? AT3D_SWEEP_MINB : 2)) sweep3d
             }
         }
         if (fail) atomicCAS(a.err, 0, fail);
+        a.nwalk[(size_t)a.npts * ia + (ipt - 1)] = (unsigned char)(step < 255 ? step : 255);
         *(volatile int *)&L[ipt - 1] = lv;
         return;
     }
@@ -657,10 +674,15 @@ __global__ void sweep3d_key_kernel(SwArgs a, unsigned long long *keys)
     keys[t] = ((unsigned long long)ia << 48) | ((unsigned long long)(lv < 0 ? 0 : lv) << 24) | (unsigned long long)r;
 }
 
-__global__ void sweep3d_perm_kernel(size_t n, const unsigned long long *keys, int *perm)
+__global__ void sweep3d_plan_kernel(SwArgs a, const unsigned long long *keys, int2 *plan)
 {
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < n) perm[t] = (int)(keys[t] & 0xFFFFFFull);
+    if (t >= (size_t)a.npts * a.nang) return;
+    const int ia = (int)(t / a.npts), r = (int)(keys[t] & 0xFFFFFFull);
+    const int entry = a.sweepord[(size_t)a.npts * (a.dir[ia].joct - 1) + r];
+    const int ipt = cell_gp(a.S, entry >> 3, (entry & 7) + 1);
+    const int nw = a.nwalk[(size_t)a.npts * ia + (ipt - 1)];
+    plan[t] = make_int2(entry, (ipt - 1) | (nw << 24));
 }
 
 template <int NST>
@@ -962,6 +984,7 @@ extern "C" int at3d_solver_create(const at3d_state_desc *d, const float *wtmu, f
     SwArgs &w = sv->w;
     memset(&w, 0, sizeof(w));
     w.npts = npts; w.nang = nang; w.nchunks = (npts + 255) / 256;
+    w.npre[0] = d->ntoppts; w.npre[1] = d->nbotpts;
     w.dir = A.up(dirs.data(), dirs.size());
     w.sweepord = A.up(sweepord.data(), sweepord.size());
     for (int joct = 1; joct <= noct; joct++) {
@@ -1006,34 +1029,35 @@ extern "C" int at3d_solver_create(const at3d_state_desc *d, const float *wtmu, f
         Arena T;
         int *level = T.alloc<int>(nkeys);
         unsigned long long *k0 = T.alloc<unsigned long long>(nkeys), *k1 = T.alloc<unsigned long long>(nkeys);
-        int *perm = A.alloc<int>(nkeys);
+        int2 *plan = A.alloc<int2>(nkeys);
+        unsigned char *nwalk = T.alloc<unsigned char>(nkeys);
         size_t tmpb = 0;
         cub::DeviceRadixSort::SortKeys(nullptr, tmpb, k0, k1, nkeys, 0, 57, 0);
         char *tmp = T.alloc<char>(tmpb);
         cudaError_t e = cudaSuccess;
-        if (!level || !k0 || !k1 || !perm || !tmp) { at3d_solver_destroy(sv); set_msg(errmsg, "device allocation failure"); return 4; }
+        if (!level || !k0 || !k1 || !plan || !nwalk || !tmp) { at3d_solver_destroy(sv); set_msg(errmsg, "device allocation failure"); return 4; }
         const int nb = (int)((nkeys + 255) / 256);
         cudaMemset(a.dofield, 0, (size_t)npts * nst * nang * sizeof(float));
         sweep3d_level_init_kernel<<<nb, 256>>>(npts, nang, w.bflag, level);
-        w.level = level; w.perm = nullptr;
+        w.level = level; w.nwalk = nwalk; w.plan = nullptr;
         for (int up = 0; up < 2; up++) {
             cudaMemsetAsync(w.ticket, 0, up == 0 ? 2 * sizeof(int) : sizeof(int), 0);
             sweep3d_kernel<1, true><<<w.nchunks * nh, 256>>>(w, up);
         }
         sweep3d_key_kernel<<<nb, 256>>>(w, k0);
         cub::DeviceRadixSort::SortKeys(tmp, tmpb, k0, k1, nkeys, 0, 57, 0);
-        sweep3d_perm_kernel<<<nb, 256>>>(nkeys, k1, perm);
+        sweep3d_plan_kernel<<<nb, 256>>>(w, k1, plan);
         int err = 0;
         e = cudaDeviceSynchronize();
         if (e == cudaSuccess) e = cudaMemcpy(&err, w.err, sizeof(int), cudaMemcpyDeviceToHost);
-        w.level = nullptr;
+        w.level = nullptr; w.nwalk = nullptr;
         if (e != cudaSuccess || err) {
             at3d_solver_destroy(sv);
             set_msg(errmsg, e != cudaSuccess ? "CUDA error in the level pass of at3d_solver_create: %s" : "BACK_INT_GRID3D walk failed in the level pass (code %s)",
                     e != cudaSuccess ? cudaGetErrorString(e) : (err == 3 ? "3: boundary without a valid face" : err == 4 ? "4: wait timed out" : "1/2: bad cell or SO<0"));
             return e != cudaSuccess ? 4 : 1;
         }
-        w.perm = perm;
+        w.plan = plan;
         if (!genv) w.group = nh;             // all ordinates advance through the levels together
     }
     *out = sv;
@@ -1064,7 +1088,7 @@ static cudaError_t sv_path_integration_device(at3d_solver *sv, const int *shptr_
         if (e == cudaSuccess) e = tr_do_to_sh(sv->P, npts, rshptr_d, a.dofield, rad_d, 0);
         return e;
     }
-    const int nsweep = w.nchunks * nh, npb = (npts + 255) / 256;
+    const int npb = (npts + 255) / 256;
     const int ninit = (int)(((size_t)npts * nh + 255) / 256);
     const int ntb = (a.ntop * nh + 127) / 128, nbb = (a.nbot * nh + 127) / 128;
 #define AT3D_SWEEP3D(NST)                                                                              \
@@ -1076,7 +1100,7 @@ static cudaError_t sv_path_integration_device(at3d_solver *sv, const int *shptr_
             else pi_brdf_kernel<NST><<<nbb, 128>>>(a);                                                 \
         }                                                                                              \
         sweep3d_boundary_kernel<NST><<<up ? nbb : ntb, 128>>>(a, w.radf, sv->toppt, up);               \
-        sweep3d_kernel<NST, false><<<nsweep, 256>>>(w, up);                                            \
+        sweep3d_kernel<NST, false><<<((npts - (w.plan ? w.npre[up] : 0) + 255) / 256) * nh, 256>>>(w, up);  \
         pi_flux_kernel<NST><<<npb, 256>>>(a, up);                                                      \
         if (!up && !sv->lamb) sweep3d_store_down_kernel<NST><<<nbb, 128>>>(a, w.radf);                 \
     }
