@@ -114,6 +114,15 @@ def path_integration_ip(st, wtmu, shptr, source, rshptr, timing=False):
     return (rad, fluxes, bcrad, ms.value) if timing else (rad, fluxes, bcrad)
 
 
+def sweeping_order(st):
+    """SWEEPING_ORDER (shdomsub1.f:3261-3352) of a 3-D grid: SWEEPORD[npts, 8] (Fortran order), host only."""
+    out = np.zeros((st.npts, 8), np.int32, order='F')
+    d = st.desc()
+    buf = _lib.errbuf()
+    _lib.check(_lib.lib().at3d_sweeping_order(C.byref(d), vp(out), buf), buf)
+    return out
+
+
 class SweepSolver:
     """PATH_INTEGRATION / SOLUTION_ITERATIONS on a fixed grid: the device-resident solver object of at3d_solver_create
     (3-D grids, IPFLAG 0 or 1: topology, SWEEPING_ORDER, ordinate geometry, transform tables, discrete-ordinate fields;

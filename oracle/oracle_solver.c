@@ -945,3 +945,9 @@ int oracle_path_integration_once(const oracle_state *st_in, const float *wtmu, c
     free_sh_do_coef(c); free(sweepord); free(work); free(gridrad);
     return ierr;
 }
+
+/* SWEEPING_ORDER alone: sweepord is SWEEPORD(NPTS,8) (parity check of the product's host-side order) */
+int oracle_sweeping_order(const oracle_state *st, int *sweepord)
+{
+    return sweeping_order(st, sweepord);
+}

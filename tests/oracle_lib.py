@@ -304,6 +304,17 @@ def solve_fixed_grid(state, wtmu, maxiter=100, solacc=1e-5, shacc=0.0, accelflag
     return st, iters.value, solcrit.value
 
 
+def sweeping_order(state):
+    st = state.copy().normalize()
+    out = np.zeros((st.npts, 8), np.int32, order='F')
+    d = st.fill(OracleState())
+    fn = lib().oracle_sweeping_order
+    fn.argtypes = [P(OracleState), C.c_void_p]
+    if fn(C.byref(d), _vp(out)) != 0:
+        raise RuntimeError('SWEEPING_ORDER failed')
+    return out
+
+
 def path_integration(state, wtmu, shptr, source, rshptr, transmin=1.0):
     """One PATH_INTEGRATION (oracle/oracle_solver.c): returns (radiance, fluxes, bcrad)."""
     lib().oracle_set_transmin.argtypes = [f32]
