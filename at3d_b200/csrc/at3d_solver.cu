@@ -758,8 +758,6 @@ bool host_sweeping_order(const at3d_state_desc *d, int noct, std::vector<int> &s
     if (d->bcflag & 2) nyc = d->ny + 1;
     sweepord.assign((size_t)noct * npts, 0);
     rank.assign((size_t)noct * npts, 0);
-    std::vector<char> seen(npts);
-    std::vector<int> stack;
     auto axis_seq = [](int n, bool positive, bool open) {
         int s, e, dstep;
         if (positive) { dstep = +1; if (open) { s = n; e = n - 1 > 1 ? n - 1 : 1; } else { s = 1; e = n; } }
@@ -768,14 +766,19 @@ bool host_sweeping_order(const at3d_state_desc *d, int noct, std::vector<int> &s
         for (int i = s;; i = (i + dstep + n - 1) % n + 1) { v.push_back(i); if (i == e) break; }
         return v;
     };
+    int bad = 0;
+    // the octants are independent: one host thread each
+#pragma omp parallel for schedule(dynamic, 1) reduction(+ : bad)
     for (int joct = 1; joct <= noct; joct++) {
         const int ioct = ioctorder[joct - 1], ob = ioct - 1;
-        std::fill(seen.begin(), seen.end(), 0);
+        std::vector<char> seen(npts, 0);
+        std::vector<int> stack;
         const std::vector<int> xs = axis_seq(nxc, ob & 1, d->bcflag & 1), ys = axis_seq(nyc, ob & 2, d->bcflag & 2);
         int iorder = 0;
+        bool ok = true;
         int *so = sweepord.data() + (size_t)npts * (joct - 1), *rk = rank.data() + (size_t)npts * (joct - 1);
         const int z0 = (ob & 4) ? 1 : nz - 1, z1 = (ob & 4) ? nz - 1 : 1, dz = (ob & 4) ? 1 : -1;
-        for (int iz = z0;; iz += dz) {
+        for (int iz = z0; ok; iz += dz) {
             for (int iy : ys)
                 for (int ix : xs) {
                     stack.clear();
@@ -795,7 +798,7 @@ bool host_sweeping_order(const at3d_state_desc *d, int noct, std::vector<int> &s
                             const int ipt = d->gridptr[(icorner - 1) + 8 * (size_t)(ic - 1)];
                             if (seen[ipt - 1]) continue;
                             seen[ipt - 1] = 1;
-                            if (iorder >= npts) return false;
+                            if (iorder >= npts) { ok = false; break; }
                             so[iorder] = (ic << 3) | (icorner - 1);
                             rk[ipt - 1] = iorder;
                             iorder++;
@@ -804,8 +807,9 @@ bool host_sweeping_order(const at3d_state_desc *d, int noct, std::vector<int> &s
                 }
             if (iz == z1) break;
         }
-        if (iorder != npts) return false;
+        if (!ok || iorder != npts) bad += 1;
     }
+    if (bad) return false;
     return true;
 }
 }
