@@ -10,6 +10,7 @@
  *   src/polarized/shdomsub1.f:1836-2167  PATH_INTEGRATION
  *   src/polarized/shdomsub1.f:2789-3260  SH_TO_DO[_UNPOL], DO_TO_SH[_UNPOL]
  *   src/polarized/shdomsub1.f:3261-3353  SWEEPING_ORDER
+ *   src/polarized/shdomsub1.f:3354-4036  BACK_INT_GRID3D[_UNPOL] (3-D grids, IPFLAG 0 or 1)
  *   src/polarized/shdomsub1.f:4295-4468  BACK_INT_GRID1D (IPFLAG=3: independent columns)
  *   src/polarized/shdomsub1.f:4529-4700  SWEEP_BASE_CELL, SWEEP_NEXT_CELL
  *   src/polarized/shdomsub2.f:1146-1220  MAKE_SH_DO_COEF
@@ -19,7 +20,11 @@
  *     two-stream field of INIT_RADIANCE (shdomsub2.f:614-996); the fixed point of the iteration does
  *     not depend on it;
  *   - the azimuthal FFTs (FFTPACK RFFTB/RFFTF) are evaluated as the direct real DFT sums they equal.
- * Only the sweeps this restatement covers are accepted: IPFLAG=3 (BACK_INT_GRID1D); others return 3.
+ * Only the sweeps this restatement covers are accepted: IPFLAG=3 (BACK_INT_GRID1D) and IPFLAG 0/1 (BACK_INT_GRID3D);
+ * BACK_INT_GRID2D (IPFLAG=2) and the multi-processor boundary flags return 3.
+ * Pinning: BACK_INT_GRID1D and everything around it against SHDOM's brdf_*.out (tests/test_shdom_verification.py);
+ * BACK_INT_GRID3D has no SHDOM output in the checkout that does not also need SPLIT_GRID -- it is pinned by
+ * consistency with the pinned column solve (horizontally uniform slab, second-order convergence), same file.
  */
 #include <math.h>
 #include <stdio.h>
