@@ -1054,6 +1054,7 @@ extern "C" int at3d_solver_create(const at3d_state_desc *d, const float *wtmu, f
         if (!level || !k0 || !k1 || !plan || !nwalk || !tmp) { at3d_solver_destroy(sv); set_msg(errmsg, "device allocation failure"); return 4; }
         const int nb = (int)((nkeys + 255) / 256);
         cudaMemset(a.dofield, 0, (size_t)npts * nst * nang * sizeof(float));
+        cudaMemset(nwalk, 0, nkeys);                               // the preset boundary points are never walked
         sweep3d_level_init_kernel<<<nb, 256>>>(npts, nang, w.bflag, level);
         w.level = level; w.nwalk = nwalk; w.plan = nullptr;
         for (int up = 0; up < 2; up++) {
