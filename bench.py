@@ -327,13 +327,33 @@ def measured_traffic(workload, kernel):
 
 
 def measured_peak():
+    """HBM peak for the roofline: the driver-written MEASURED_PEAKS.json when present (the sustained figure is preferred:
+    the kernels are timed inside a step), else the fallback of B200_PROFILING.md.  The file's schema is not fixed here:
+    every numeric entry whose key path mentions HBM / copy bandwidth is considered; values below 50 are read as TB/s."""
     p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(p):
         try:
-            d = json.load(open(p))
-            for k in ('hbm_gbs', 'hbm_gb_s', 'hbm_GBps'):
-                if k in d:
-                    return float(d[k]), 'measured (MEASURED_PEAKS.json)'
+            found = []
+
+            def walk(x, path):
+                if isinstance(x, dict):
+                    for k, v in x.items():
+                        walk(v, path + [str(k).lower()])
+                elif isinstance(x, (list, tuple)):
+                    for i, v in enumerate(x):
+                        walk(v, path + [str(i)])
+                elif isinstance(x, (int, float)) and not isinstance(x, bool):
+                    key = '/'.join(path)
+                    if any(t in key for t in ('hbm', 'copy', 'dram', 'mem_bw', 'membw', 'bandwidth')) and \
+                            not any(t in key for t in ('flop', 'tf', 'nvlink', 'pcie', 'bytes', 'size', 'ms', 'time')):
+                        v = float(x) * (1000.0 if 0 < float(x) < 50 else 1.0)
+                        if 1000.0 <= v <= 9000.0:
+                            found.append((key, v))
+            walk(json.load(open(p)), [])
+            if found:
+                pref = [f for f in found if 'sustain' in f[0]] or found
+                key, v = pref[0]
+                return v, 'measured (MEASURED_PEAKS.json: %s)' % key
         except Exception:
             pass
     return 6650.0, 'fallback (B200_PROFILING.md)'
