@@ -97,6 +97,38 @@ def make_direct_derivative(state, pg, c):
     return dpath, dptr
 
 
+def transfer_pa_to_grid(pg, gridpos, npts, ml, deltam, phasemax=0.999):
+    """TRANSFER_PA_TO_GRID on the GPU (C `at3d_transfer_pa_to_grid`): the dict of `medium.transfer_pa_to_grid`
+    (extinct, albedo, total_ext, legen, iphase, phaseinterpwt, nleg, extmin, scatmin).  The Legendre table (a few kB)
+    is scaled on the host; everything per grid point runs in one kernel."""
+    npart, mnm = pg.npart, pg.maxnmicro
+    nq = 8 * mnm
+    extmin = 1.0e-5 / ((float(pg.zlevels[-1]) - float(pg.zlevels[0])) / pg.npz)
+    nleg = ml + 1 if deltam else ml
+    nleg = min(max(nleg, 1), pg.nlegp) if not deltam else nleg
+    if pg.nlegp < nleg:
+        raise ValueError('property Legendre table shorter than ML+1')
+    l = np.arange(nleg + 1, dtype=np.float32)
+    legen = np.asfortranarray(pg.legenp[:, :nleg + 1, :] / (2 * l + 1)[None, :, None], dtype=np.float32)
+    ftab = np.ascontiguousarray(legen[0, ml + 1, :]) if deltam else None
+    extinct = np.zeros((npts, npart), np.float32, order='F')
+    albedo = np.zeros((npts, npart), np.float32, order='F')
+    total_ext = np.zeros(npts, np.float32)
+    iphase = np.ones((nq, npts, npart), np.int32, order='F')
+    pwt = np.zeros((nq, npts, npart), np.float32, order='F')
+    gp = np.asfortranarray(np.asarray(gridpos, np.float32)[:, :npts])
+    zl = np.ascontiguousarray(pg.zlevels, np.float32)
+    _call(_lib.lib().at3d_transfer_pa_to_grid, npts, vp(gp), pg.npx, pg.npy, pg.npz, pg.delx, pg.dely, pg.xstart, pg.ystart,
+          vp(zl), npart, mnm, vp(pg.extinctp), vp(pg.albedop), vp(pg.iphasep), vp(pg.phasewtp), pg.numphase, vp(ftab), ml,
+          int(deltam), phasemax, vp(extinct), vp(albedo), vp(total_ext), vp(iphase), vp(pwt))
+    if deltam:
+        legen[0, :ml + 1, :] -= ftab[None, :]
+        if pg.nstleg > 1:
+            legen[1:4, :ml + 1, :] -= ftab[None, None, :]
+    return dict(extinct=extinct, albedo=albedo, total_ext=total_ext, legen=legen, iphase=iphase, phaseinterpwt=pwt,
+                nleg=nleg, extmin=extmin, scatmin=0.1 * extmin)
+
+
 def compute_source(state, shptr, source, oshptr, delsource, fixsh=False, shacc=0.0, maxiv=None, first=False,
                    accelflag=True, newmethod=True, timing=False):
     """COMPUTE_SOURCE (shdomsub1.f:967).  Returns (ierr, shptr, source, oshptr, delsource,

@@ -584,3 +584,150 @@ extern "C" int at3d_make_direct_derivative(int npts, int bcflag, int npx, int np
     if (hbad) return beam_error(hbad, "DIRECT_BEAM_AND_PATHS_PROP", errmsg);
     return 0;
 }
+
+// ------------------------------------------------------------------------------------------
+// TRANSFER_PA_TO_GRID: TRILIN_INTERP_PROP (src/polarized/shdom90.f90:17-346) + the delta-M scaling of PREPARE_PROP
+// (src/polarized/shdomsub2.f:479-608) in the 'N' interpolation mode, thread = grid point.
+// Same operation order as the host restatement at3d_b200/medium.py: transfer_pa_to_grid (double accumulators over the
+// 8 property corners in corner order; duplicate phase-table entries merged into their first occurrence; stable sort by
+// descending weight; REAL arithmetic in the delta-M step).
+// ------------------------------------------------------------------------------------------
+#define TPA_MAXQ 32
+struct TpaArgs {
+    int npts, npart, mnm, npx, npy, npz, ml, deltam, nlt_stride;
+    float delx, dely, xstart, ystart, phasemax;
+    double extmin, scatmin;
+    const float *gridpos, *zlevels, *extinctp, *albedop, *phasewtp, *ftab;   // ftab[numphase] = LEGEN(1,ML+1,.)
+    const int *iphasep;
+    float *extinct, *albedo, *total_ext, *phaseinterpwt;
+    int *iphase, *bad;
+};
+
+__global__ void tpa_kernel(TpaArgs a)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.npts) return;
+    const float x = a.gridpos[3 * (size_t)i], y = a.gridpos[3 * (size_t)i + 1], z = a.gridpos[3 * (size_t)i + 2];
+    const int npx = a.npx, npy = a.npy, npz = a.npz, mnm = a.mnm, nq = 8 * a.mnm;
+    // vertical: searchsorted(zlevels, z, side='right') clipped to [1, npz-1]
+    int lo = 0, hi = npz;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (a.zlevels[mid] <= z) lo = mid + 1; else hi = mid; }
+    int iz = lo < 1 ? 1 : (lo > npz - 1 ? npz - 1 : lo);
+    double w = (double)(z - a.zlevels[iz - 1]) / (double)(a.zlevels[iz] - a.zlevels[iz - 1]);
+    w = fmin(fmax(w, 0.0), 1.0);
+    long ix = (long)((x - a.xstart) / a.delx) + 1;
+    if (fabsf(x - a.xstart - (float)npx * a.delx) < 0.01f * a.delx) ix = npx;
+    long iy = (long)((y - a.ystart) / a.dely) + 1;
+    if (fabsf(y - a.ystart - (float)npy * a.dely) < 0.01f * a.dely) iy = npy;
+    if (ix < 1 || ix > npx) { atomicCAS(a.bad, 0, 1); return; }
+    if (iy < 1 || iy > npy) { atomicCAS(a.bad, 0, 2); return; }
+    const long ixp = ix % npx + 1, iyp = iy % npy + 1;
+    double u = (double)(x - a.xstart - a.delx * (float)(ix - 1)) / (double)a.delx;
+    u = fmin(fmax(u, 0.0), 1.0); if (u < 1e-5) u = 0.0; if (u > 1 - 1e-5) u = 1.0;
+    double v = (double)(y - a.ystart - a.dely * (float)(iy - 1)) / (double)a.dely;
+    v = fmin(fmax(v, 0.0), 1.0); if (v < 1e-5) v = 0.0; if (v > 1 - 1e-5) v = 1.0;
+    long ptr[8];
+    ptr[0] = iz + (long)npz * (iy - 1) + (long)npz * npy * (ix - 1);
+    ptr[1] = iz + (long)npz * (iy - 1) + (long)npz * npy * (ixp - 1);
+    ptr[2] = iz + (long)npz * (iyp - 1) + (long)npz * npy * (ix - 1);
+    ptr[3] = iz + (long)npz * (iyp - 1) + (long)npz * npy * (ixp - 1);
+    for (int c = 0; c < 4; c++) ptr[4 + c] = ptr[c] + 1;
+    const double wt[8] = {(1 - u) * (1 - v) * (1 - w), u * (1 - v) * (1 - w), (1 - u) * v * (1 - w), u * v * (1 - w),
+                          (1 - u) * (1 - v) * w, u * (1 - v) * w, (1 - u) * v * w, u * v * w};
+    const size_t maxpg = (size_t)npx * npy * npz;
+    float esum = 0.0f;
+    for (int ipa = 0; ipa < a.npart; ipa++) {
+        double ext = 0.0, scatter = 0.0, scat8[8];
+        for (int c = 0; c < 8; c++) {
+            const double e = (double)a.extinctp[(ptr[c] - 1) + maxpg * ipa], al = (double)a.albedop[(ptr[c] - 1) + maxpg * ipa];
+            ext = ext + wt[c] * e;
+            scat8[c] = wt[c] * e * al;
+            scatter = scatter + scat8[c];
+        }
+        const double alb = ext > a.extmin ? scatter / fmax(ext, 1e-300) : scatter / a.extmin;
+        const double denom = scatter >= a.scatmin ? scatter : a.scatmin;
+        int ip[TPA_MAXQ];
+        double pw[TPA_MAXQ];
+        for (int c = 0; c < 8; c++)
+            for (int m = 0; m < mnm; m++) {
+                const size_t o = m + (size_t)mnm * ((ptr[c] - 1) + maxpg * ipa);
+                ip[c * mnm + m] = a.iphasep[o];
+                pw[c * mnm + m] = (double)a.phasewtp[o] * (scat8[c] / denom);
+            }
+        for (int q = 0; q < nq; q++)
+            for (int q2 = q + 1; q2 < nq; q2++)
+                if (ip[q] == ip[q2]) { pw[q] = pw[q] + pw[q2]; pw[q2] = 0.0; }
+        // stable insertion sort by descending weight
+        for (int q = 1; q < nq; q++) {
+            const int ipq = ip[q]; const double pwq = pw[q];
+            int k = q - 1;
+            while (k >= 0 && pw[k] < pwq) { ip[k + 1] = ip[k]; pw[k + 1] = pw[k]; k--; }
+            ip[k + 1] = ipq; pw[k + 1] = pwq;
+        }
+        float extf = (float)ext, albf = (float)alb;
+        const size_t po = (size_t)i + (size_t)a.npts * ipa;
+        float pwf[TPA_MAXQ];
+        for (int q = 0; q < nq; q++) {
+            pwf[q] = (float)pw[q];
+            a.iphase[q + (size_t)nq * po] = ip[q];
+            a.phaseinterpwt[q + (size_t)nq * po] = pwf[q];
+        }
+        if (a.deltam) {
+            float f;
+            if (pwf[0] >= a.phasemax) f = a.ftab[ip[0] - 1];
+            else { f = 0.0f; for (int q = 0; q < nq; q++) f = f + a.ftab[ip[q] - 1] * pwf[q]; }
+            const float a0 = albf;
+            extf = (1.0f - a0 * f) * extf;
+            albf = (1.0f - f) * a0 / (1.0f - a0 * f);
+        }
+        a.extinct[po] = extf;
+        a.albedo[po] = albf;
+        esum = esum + extf;
+    }
+    a.total_ext[i] = esum;
+}
+
+extern "C" int at3d_transfer_pa_to_grid(int npts, const float *gridpos, int npx, int npy, int npz, float delx, float dely,
+                                        float xstart, float ystart, const float *zlevels, int npart, int maxnmicro,
+                                        const float *extinctp, const float *albedop, const int32_t *iphasep,
+                                        const float *phasewtp, int numphase, const float *ftab, int ml, int deltam,
+                                        float phasemax, float *extinct, float *albedo, float *total_ext, int32_t *iphase,
+                                        float *phaseinterpwt, char *errmsg)
+{
+    if (errmsg) errmsg[0] = 0;
+    if (!gridpos || !zlevels || !extinctp || !albedop || !iphasep || !phasewtp || !extinct || !albedo || !total_ext || !iphase ||
+        !phaseinterpwt || (deltam && !ftab)) { set_msg(errmsg, "null argument"); return 1; }
+    if (at3d_device_count() < 1) { set_msg(errmsg, "no CUDA device: at3d_b200 has no CPU fallback"); return 4; }
+    if (8 * maxnmicro > TPA_MAXQ) { set_msg(errmsg, "at3d_transfer_pa_to_grid: MAXNMICRO > %d", TPA_MAXQ / 8); return 3; }
+    if (npz < 2 || npts < 1) { set_msg(errmsg, "at3d_transfer_pa_to_grid: bad sizes"); return 1; }
+    const size_t maxpg = (size_t)npx * npy * npz, nq = 8 * (size_t)maxnmicro;
+    Arena A;
+    TpaArgs a;
+    memset(&a, 0, sizeof(a));
+    a.npts = npts; a.npart = npart; a.mnm = maxnmicro; a.npx = npx; a.npy = npy; a.npz = npz; a.ml = ml; a.deltam = deltam;
+    a.delx = delx; a.dely = dely; a.xstart = xstart; a.ystart = ystart; a.phasemax = phasemax;
+    a.extmin = 1.0e-5 / (((double)zlevels[npz - 1] - (double)zlevels[0]) / npz);
+    a.scatmin = 0.1 * a.extmin;
+    a.gridpos = A.up(gridpos, (size_t)3 * npts); a.zlevels = A.up(zlevels, npz);
+    a.extinctp = A.up(extinctp, maxpg * npart); a.albedop = A.up(albedop, maxpg * npart);
+    a.iphasep = A.up(iphasep, (size_t)maxnmicro * maxpg * npart); a.phasewtp = A.up(phasewtp, (size_t)maxnmicro * maxpg * npart);
+    a.ftab = deltam ? A.up(ftab, numphase) : nullptr;
+    a.extinct = A.alloc<float>((size_t)npts * npart); a.albedo = A.alloc<float>((size_t)npts * npart);
+    a.total_ext = A.alloc<float>(npts);
+    a.iphase = A.alloc<int>(nq * npts * npart); a.phaseinterpwt = A.alloc<float>(nq * npts * npart);
+    a.bad = A.alloc<int>(1);
+    if (!a.gridpos || !a.zlevels || !a.extinctp || !a.albedop || !a.iphasep || !a.phasewtp || (deltam && !a.ftab) || !a.extinct ||
+        !a.albedo || !a.total_ext || !a.iphase || !a.phaseinterpwt || !a.bad) { set_msg(errmsg, "device allocation failure"); return 4; }
+    cudaMemset(a.bad, 0, sizeof(int));
+    tpa_kernel<<<(npts + 127) / 128, 128>>>(a);
+    int bad = 0;
+    cudaError_t e = cudaMemcpy(&bad, a.bad, sizeof(int), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(extinct, a.extinct, (size_t)npts * npart * sizeof(float), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(albedo, a.albedo, (size_t)npts * npart * sizeof(float), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(total_ext, a.total_ext, (size_t)npts * sizeof(float), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(iphase, a.iphase, nq * npts * npart * sizeof(int), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(phaseinterpwt, a.phaseinterpwt, nq * npts * npart * sizeof(float), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) { set_msg(errmsg, "CUDA error %s in at3d_transfer_pa_to_grid", cudaGetErrorString(e)); return 4; }
+    if (bad) { set_msg(errmsg, bad == 1 ? "TRILIN: Beyond X domain" : "TRILIN: Beyond Y domain"); return 1; }
+    return 0;
+}

@@ -7,7 +7,7 @@ containers may be ``xarray.Dataset`` objects (the reference's) or plain mappings
 variable names: only ``ds[name]`` and, for datasets, ``.data`` are used, so the class works where xarray is absent.
 
 What runs where: grid construction and property interpolation follow ``_setup_grid`` / ``_prepare_optical_properties``
-(:2036-2520) on the host; ``MAKE_DIRECT``, ``YLMALL``, ``PRECOMPUTE_PHASE_CHECK``, the whole ``SOLUTION_ITERATIONS``
+(:2036-2520) on the host; ``TRANSFER_PA_TO_GRID`` (property interpolation + delta-M scaling), ``MAKE_DIRECT``, ``YLMALL``, ``PRECOMPUTE_PHASE_CHECK``, the whole ``SOLUTION_ITERATIONS``
 loop (``at3d_solver_solve``) and ``RENDER`` run on the GPU through the C ABI.  Not covered (NotImplementedError with
 the reason): ``split_accuracy > 0`` (SPLIT_GRID), thermal sources and non-Lambertian surfaces in
 this facade (the C ABI has them; they need SURFACE_PARM_INTERP / PLANCK tables built by the caller).
@@ -169,7 +169,7 @@ class RTE:
         self._nscatangle = max(36, min(721, 2 * nlegp))
         self._pg = M.PropertyGrid(self._npx, self._npy, self._npz, self._delx, self._dely, self._zlevels, extp, albp,
                                   iphp, pwp, legenp, nlegp, self._nstleg)
-        self._t = M.transfer_pa_to_grid(self._pg, self._gridpos, self._npts, self._ml, self._deltam)
+        self._t = B.transfer_pa_to_grid(self._pg, self._gridpos, self._npts, self._ml, self._deltam)
 
     # -- _init_solution (:2539-2798): angle set, boundary points, direct beam, YLMSUN, phase table --
     def _init_solution(self):

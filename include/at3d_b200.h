@@ -252,6 +252,18 @@ int at3d_path_integration_ip(const at3d_state_desc *desc, const float *wtmu, con
                              const int32_t *rshptr, float *radiance, float *fluxes, float *bcrad,
                              double *kernel_ms, char *errmsg);
 
+/* ---- f2: TRANSFER_PA_TO_GRID: TRILIN_INTERP_PROP (src/polarized/shdom90.f90:17-346) + the delta-M scaling of
+ * PREPARE_PROP (src/polarized/shdomsub2.f:479-608), INTERPMETHOD 'ON' (at3d/solver.py:2405-2447).  HOST pointers.
+ * Property grid: extinctp/albedop[maxpg,npart], iphasep/phasewtp[maxnmicro,maxpg,npart]; ftab[numphase] =
+ * LEGEN(1,ML+1,.) before the delta-M subtraction (needed when deltam).  Outputs on the RTE grid: extinct/albedo
+ * [npts,npart], total_ext[npts], iphase/phaseinterpwt[8*maxnmicro,npts,npart]. ---- */
+int at3d_transfer_pa_to_grid(int npts, const float *gridpos, int npx, int npy, int npz, float delx, float dely,
+                             float xstart, float ystart, const float *zlevels, int npart, int maxnmicro,
+                             const float *extinctp, const float *albedop, const int32_t *iphasep,
+                             const float *phasewtp, int numphase, const float *ftab, int ml, int deltam,
+                             float phasemax, float *extinct, float *albedo, float *total_ext, int32_t *iphase,
+                             float *phaseinterpwt, char *errmsg);
+
 /* ---- f1: PATH_INTEGRATION on 3-D grids (fixed grid, base or already split) ----
  * Replaces PATH_INTEGRATION (src/polarized/shdomsub1.f:1836-2167) with BACK_INT_GRID3D[_UNPOL] (:3354-4036) in the
  * order of SWEEPING_ORDER (:3261-3352), for IPFLAG 0 or 1 and periodic or open boundaries.  The solver object holds

@@ -88,3 +88,19 @@ def test_make_direct_derivative_overflow_is_an_error(oracle):
     c['longest_path_pts'] = 8
     with pytest.raises(At3dError):
         B.make_direct_derivative(sc.state, sc.pg, c)
+
+
+@pytest.mark.parametrize('kw', [dict(bc='periodic', nsplits=6), dict(bc='open', nsplits=5, rayleigh=True),
+                                dict(bc='open', nstokes=3, deltam=False), dict(bc='periodic', nstokes=3, rayleigh=True)])
+def test_transfer_pa_to_grid(kw):
+    """TRANSFER_PA_TO_GRID on the GPU (property interpolation to base and split grid points, phase-table pointer lists,
+    delta-M scaling) against the host restatement that builds every test scene and the SHDOM verification states."""
+    from at3d_b200 import backend as B, medium as M, synthetic as S
+    sc = S.make_scene(nx=7, ny=6, nz=9, seed=17, **kw)
+    st, pg = sc.state, sc.pg
+    ref = M.transfer_pa_to_grid(pg, st.gridpos, st.npts, st.ml, bool(st.deltam))
+    out = B.transfer_pa_to_grid(pg, st.gridpos, st.npts, st.ml, bool(st.deltam))
+    np.testing.assert_array_equal(out['iphase'], ref['iphase'])
+    for k in ('extinct', 'albedo', 'total_ext', 'phaseinterpwt', 'legen'):
+        np.testing.assert_allclose(out[k], ref[k], rtol=2e-6, atol=1e-9, err_msg=k)
+    assert out['nleg'] == ref['nleg'] and out['extmin'] == ref['extmin']
