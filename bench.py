@@ -533,7 +533,20 @@ def main():
     assert torch.cuda.is_available(), 'bench.py needs a CUDA device (no CPU fallback)'
     torch.cuda.set_device(local)
     if world > 1:
-        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+        # stdout carries exactly one JSON line: whatever NCCL prints while the communicator is created (its version
+        # line when NCCL_DEBUG is set on the box) goes to stderr
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+            warm = torch.zeros(1, device='cuda')
+            dist.all_reduce(warm)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     from at3d_b200 import backend as B, gradsetup
     from at3d_b200.device import DeviceState
     from at3d_b200 import _lib
