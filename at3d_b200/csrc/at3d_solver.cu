@@ -406,6 +406,7 @@ struct SwArgs {
     const int2 *plan;           // [nang][npts] processing order of an ordinate, sorted by dependency level (the preset boundary
                                 // points, level 0, come first and are skipped): x = SWEEPORD entry, y = point-1 | cells to walk
                                 // << 24 (255: decide with the rank test); null: the reference order itself
+    int two_d;                  // BACK_INT_GRID2D (IPFLAG bit 1): rays stay in the X-Z plane, faces of two points
     int npre[2];                // preset boundary points per hemisphere (down: top points, up: bottom points)
     int *level;                 // [nang][npts] dependency level of (ordinate, point); -1 = not yet (level pass only)
     unsigned char *nwalk;       // [nang][npts] cells walked by (ordinate, point), capped at 255 (level pass only)
@@ -484,7 +485,7 @@ __global__ void __launch_bounds__(256, (NST == 1 ? AT3D_SWEEP_MINB : 2)) sweep3d
     for (;;) {
         if (icell <= 0) { fail = 1; break; }
         const CellRec c = load_cell(S, icell);
-        const bool ipinx = c.flags & 1, ipiny = c.flags & 2;
+        const bool ipinx = c.flags & 1, ipiny = a.two_d || (c.flags & 2);
         const float4 po = __ldg(&S.ptrec[c.gp[8 - ioct] - 1]);     // GRIDPTR(9-IOCT,ICELL)
         const double sox = ipinx ? (double)1.0E20f : ((double)po.x - xe) * D.cxinv;
         const double soy = ipiny ? (double)1.0E20f : ((double)po.y - ye) * D.cyinv;
@@ -511,6 +512,11 @@ __global__ void __launch_bounds__(256, (NST == 1 ? AT3D_SWEEP_MINB : 2)) sweep3d
             i1 = cell_gp(S, inextcell, face_corner(kface, 0)); i2 = cell_gp(S, inextcell, face_corner(kface, 1));
             i3 = cell_gp(S, inextcell, face_corner(kface, 2)); i4 = cell_gp(S, inextcell, face_corner(kface, 3));
         }
+        if (a.two_d) {
+            // GRIDFACE(2,6) of BACK_INT_GRID2D: X faces {1,5},{2,6} = (I1,I3) here, Z faces {1,2},{5,6} = (I1,I2); the
+            // other two weights are exact zeros below, so the four-point formulas reduce to the two-point ones
+            if (jface == 1) { i2 = i1; i4 = i3; } else { i3 = i1; i4 = i2; }
+        }
         const float4 p1 = __ldg(&S.ptrec[i1 - 1]), p2 = __ldg(&S.ptrec[i2 - 1]);
         const float4 p3 = __ldg(&S.ptrec[i3 - 1]), p4 = __ldg(&S.ptrec[i4 - 1]);
         double u, v;
@@ -524,6 +530,7 @@ __global__ void __launch_bounds__(256, (NST == 1 ? AT3D_SWEEP_MINB : 2)) sweep3d
             u = ipiny ? 0.5 : (ye - (double)p1.y) / (double)(p3.y - p1.y);
             v = ipinx ? 0.5 : (xe - (double)p1.x) / (double)(p2.x - p1.x);
         }
+        if (a.two_d) { if (jface == 1) v = 0.0; else u = 0.0; }     // F = (1-U, U) on the face's two points
         if (inextcell > 0) {
             const int pn = cell_gp(S, inextcell, ioct);
             if (jface == 1) xe = (double)pt_coord(S, pn, 1);
@@ -916,11 +923,11 @@ extern "C" int at3d_solver_create(const at3d_state_desc *d, const float *wtmu, f
     *out = nullptr;
     if (at3d_device_count() < 1) { set_msg(errmsg, "no CUDA device: at3d_b200 has no CPU fallback"); return 4; }
     if ((d->ipflag & 3) == 3) return solver_create_ip(d, wtmu, out, errmsg);
-    if (d->ipflag & 2) { set_msg(errmsg, "at3d_solver_create: IPFLAG=2 (BACK_INT_GRID2D) is not implemented"); return 3; }
+    const bool two_d = (d->ipflag & 2) != 0;                   // IPFLAG=2: BACK_INT_GRID2D
     if (d->bcflag & 12) { set_msg(errmsg, "at3d_solver_create: multi-processor boundary flags are not supported"); return 3; }
     if (d->srctype != 'S' && d->units == 'B') { set_msg(errmsg, "UNITS='B' is not implemented"); return 3; }
     if (!(transmin >= 0.0f && transmin <= 1.0f)) { set_msg(errmsg, "TRANSMIN must be in [0,1]"); return 1; }
-    const int npts = d->npts, nst = d->nstokes, noct = 8;
+    const int npts = d->npts, nst = d->nstokes, noct = two_d ? 4 : 8;
     std::vector<int> sweepord, rank;
     if (!host_sweeping_order(d, noct, sweepord, rank)) { set_msg(errmsg, "SWEEPING_ORDER: not every grid point was reached"); return 1; }
     at3d_solver *sv = new at3d_solver();
@@ -932,7 +939,7 @@ extern "C" int at3d_solver_create(const at3d_state_desc *d, const float *wtmu, f
     std::vector<float> amu(nang), aphi(nang), aw(nang);
     std::vector<int> aimu(nang), aiphi(nang);
     std::vector<OrdDir> dirs(nang);
-    static const int joctorder3[8] = {1, 3, 5, 7, 2, 4, 6, 8};
+    static const int joctorder3[8] = {1, 3, 5, 7, 2, 4, 6, 8}, joctorder2[8] = {1, 3, 1, 3, 2, 4, 2, 4};
     for (int i = 0, ia = 0; i < d->nmu; i++)
         for (int k = 0; k < d->nphi0[i]; k++, ia++) {
             const float mu = d->mu[i], phi = d->phi[i + (size_t)d->nmu * k];
@@ -947,6 +954,7 @@ extern "C" int at3d_solver_create(const at3d_state_desc *d, const float *wtmu, f
             D.cz = -(double)mu;
             if (fabs(D.cx) > (double)1.0E-5f) D.cxinv = 1.0 / D.cx; else { D.cx = 0.0; D.cxinv = (double)1.0E6f; }
             if (fabs(D.cy) > (double)1.0E-5f) D.cyinv = 1.0 / D.cy; else { D.cy = 0.0; D.cyinv = (double)1.0E6f; }
+            if (two_d) { D.cy = 0.0; D.cyinv = (double)1.0E6f; }        // BACK_INT_GRID2D has no Y component (:4073-4095)
             D.czinv = 1.0 / D.cz;
             D.bitx = D.cx < 0.0 ? 1 : 0;
             D.bity = D.cy < 0.0 ? 1 : 0;
@@ -955,7 +963,7 @@ extern "C" int at3d_solver_create(const at3d_state_desc *d, const float *wtmu, f
             else { at3d_solver_destroy(sv); set_msg(errmsg, "BACK_INT_GRID: Bad MU"); return 1; }
             if ((D.bitz == 1) != (ia >= nh)) { at3d_solver_destroy(sv); set_msg(errmsg, "unexpected ordinate order"); return 1; }
             D.ioct = 1 + D.bitx + 2 * D.bity + 4 * D.bitz;
-            D.joct = joctorder3[D.ioct - 1];
+            D.joct = two_d ? joctorder2[D.ioct - 1] : joctorder3[D.ioct - 1];
             D.pad = 0;
         }
     std::vector<unsigned char> bflag(npts, 0);
@@ -1001,6 +1009,7 @@ extern "C" int at3d_solver_create(const at3d_state_desc *d, const float *wtmu, f
     memset(&w, 0, sizeof(w));
     w.npts = npts; w.nang = nang; w.nchunks = (npts + 255) / 256;
     w.npre[0] = d->ntoppts; w.npre[1] = d->nbotpts;
+    w.two_d = two_d ? 1 : 0;
     w.dir = A.up(dirs.data(), dirs.size());
     w.sweepord = A.up(sweepord.data(), sweepord.size());
     for (int joct = 1; joct <= noct; joct++) {

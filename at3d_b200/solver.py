@@ -125,8 +125,8 @@ def sweeping_order(st):
 
 class SweepSolver:
     """PATH_INTEGRATION / SOLUTION_ITERATIONS on a fixed grid: the device-resident solver object of at3d_solver_create
-    (3-D grids, IPFLAG 0 or 1: topology, SWEEPING_ORDER, ordinate geometry, transform tables, discrete-ordinate fields;
-    IPFLAG=3: independent columns)."""
+    (3-D grids, IPFLAG 0 or 1, and 2-D grids, IPFLAG=2: topology, SWEEPING_ORDER, ordinate geometry, transform tables,
+    discrete-ordinate fields; IPFLAG=3: independent columns)."""
 
     def __init__(self, st, wtmu, transmin=1.0):
         self.st = st

@@ -72,6 +72,8 @@ def make_scene(nx=8, ny=8, nz=9, nmu=8, nphi=16, nstokes=1, bc='periodic', dx=0.
     bcflag = 0
     if bc == 'open':
         bcflag = 3
+    elif bc == 'open_x':          # open in X only (what at3d sets for open boundaries with independent pixels in Y)
+        bcflag = 1
     npx, npy, npz = nx, ny, nz
     zlevels = (np.arange(nz) * dz).astype(np.float32)
     # ---- property grid ----

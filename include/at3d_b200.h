@@ -266,7 +266,8 @@ int at3d_transfer_pa_to_grid(int npts, const float *gridpos, int npx, int npy, i
 
 /* ---- f1: PATH_INTEGRATION on 3-D grids (fixed grid, base or already split) ----
  * Replaces PATH_INTEGRATION (src/polarized/shdomsub1.f:1836-2167) with BACK_INT_GRID3D[_UNPOL] (:3354-4036) in the
- * order of SWEEPING_ORDER (:3261-3352), for IPFLAG 0 or 1 and periodic or open boundaries.  The solver object holds
+ * order of SWEEPING_ORDER (:3261-3352), for IPFLAG 0 or 1 and periodic or open boundaries; IPFLAG=2 (independent pixels
+ * in Y, e.g. ny = 1) takes BACK_INT_GRID2D (:4039-4293), IPFLAG=3 the independent columns of at3d_path_integration_ip.  The solver object holds
  * what does not change over the solution iterations on a fixed grid (topology, sweep order, ordinate geometry, the
  * SH <-> ordinate transform tables, the two discrete-ordinate fields); transmin is TRANSMIN (at3d default 1.0).
  * at3d_solver_path_integration has the argument meaning of at3d_path_integration_ip. */

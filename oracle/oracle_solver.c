@@ -20,8 +20,9 @@
  *     two-stream field of INIT_RADIANCE (shdomsub2.f:614-996); the fixed point of the iteration does
  *     not depend on it;
  *   - the azimuthal FFTs (FFTPACK RFFTB/RFFTF) are evaluated as the direct real DFT sums they equal.
- * Only the sweeps this restatement covers are accepted: IPFLAG=3 (BACK_INT_GRID1D) and IPFLAG 0/1 (BACK_INT_GRID3D);
- * BACK_INT_GRID2D (IPFLAG=2) and the multi-processor boundary flags return 3.
+ *   src/polarized/shdomsub1.f:4039-4293  BACK_INT_GRID2D (IPFLAG=2: independent pixels in Y)
+ * Sweeps covered: IPFLAG=3 (BACK_INT_GRID1D), IPFLAG=2 (BACK_INT_GRID2D), IPFLAG 0/1 (BACK_INT_GRID3D); the
+ * multi-processor boundary flags return 3.
  * Pinning: BACK_INT_GRID1D and everything around it against SHDOM's brdf_*.out (tests/test_shdom_verification.py);
  * BACK_INT_GRID3D has no SHDOM output in the checkout that does not also need SPLIT_GRID -- it is pinned by
  * consistency with the pinned column solve (horizontally uniform slab, second-order convergence), same file.
@@ -593,6 +594,128 @@ static int back_int_grid3d(const oracle_state *st, const int *sweepord, float mu
     return 0;
 }
 
+/* BACK_INT_GRID2D  shdomsub1.f:4039-4293: independent pixels in Y (IPFLAG bit 1), rays in the X-Z plane, faces of two
+   grid points. */
+static int back_int_grid2d(const oracle_state *st, const int *sweepord, float mu, float phi, float transmin, int kang,
+                           const float *extinct, const float *source, float *gridrad, char *errmsg)
+{
+    static const int gridface[6][2] = {{1, 5}, {2, 6}, {0, 0}, {0, 0}, {1, 2}, {5, 6}};
+    static const int oppface[6] = {2, 1, 4, 3, 6, 5};
+    static const int joctorder[8] = {1, 3, 1, 3, 2, 4, 2, 4};
+    const int ns = st->nstokes, na = st->nphi0max, npts = st->npts;
+    double eps, pi, cx, cz, cxinv, czinv, xe, ye, ze, so, sox, soz, u, f1, f2;
+    double ext, ext0, ext1, ext0p, tau, transcell, abscell, transmit;
+    double src[4], srcext0[4], srcext1[4], srcext0p[4], rad[4], rad0[4];
+    int bitx, bitz, ioct, joct, iorder, k;
+    eps = 1.0E-3f * (GRIDPOS(st, 3, GRIDPTR(st, 8, 1)) - GRIDPOS(st, 3, GRIDPTR(st, 1, 1)));
+    pi = acosf(-1.0f);
+    cx = sqrtf(1.0f - mu * mu) * cos(phi + pi);
+    cz = -mu;
+    if (fabs(cx) > 1.0E-5f) cxinv = 1.0 / cx; else { cx = 0.0; cxinv = 1.0E6f; }
+    czinv = 1.0 / cz;
+    bitx = cx < 0.0 ? 1 : 0;
+    if (cz < -1.0E-3f) bitz = 1;
+    else if (cz > 1.0E-3f) bitz = 0;
+    else { if (errmsg) snprintf(errmsg, 600, "BACK_INT_GRID: Bad MU"); return 1; }
+    ioct = 1 + bitx + 4 * bitz;
+    joct = joctorder[ioct - 1];
+    for (iorder = 1; iorder <= npts; iorder++) {
+        const int so_entry = sweepord[(iorder - 1) + (size_t)npts * (joct - 1)];
+        const int ipcell = so_entry >> 3, icorner = (so_entry & 7) + 1;
+        const int ipt = GRIDPTR(st, icorner, ipcell);
+        int icell, validrad, inextcell = 0;
+        if (GR(1, ipt) >= 0.0f) continue;
+        icell = ipcell;
+        transmit = 1.0;
+        ext1 = extinct[ipt - 1];
+        for (k = 0; k < ns; k++) { rad[k] = 0.0; srcext1[k] = ext1 * SRC(k + 1, kang, ipt); }
+        xe = GRIDPOS(st, 1, ipt);
+        ye = GRIDPOS(st, 2, ipt);
+        ze = GRIDPOS(st, 3, ipt);
+        validrad = 0;
+        while (!validrad) {
+            int ipinx, iopp, iface, jface, kface, ic, i1, i2, validface;
+            if (icell <= 0) { if (errmsg) snprintf(errmsg, 600, "BACK_INT_GRID: ICELL=0"); return 1; }
+            ipinx = BTEST(CELLFLAGS(st, icell), 0);
+            iopp = GRIDPTR(st, 9 - ioct, icell);
+            sox = ipinx ? 1.0E20f : (GRIDPOS(st, 1, iopp) - xe) * cxinv;
+            soz = (GRIDPOS(st, 3, iopp) - ze) * czinv;
+            so = fmin(sox, soz);
+            if (so < -eps) { if (errmsg) snprintf(errmsg, 600, "BACK_INT_GRID2D: SO<0"); return 1; }
+            xe = xe + so * cx;
+            ze = ze + so * cz;
+            if (sox <= soz) { iface = 2 - bitx; jface = 1; }
+            else { iface = 6 - bitz; jface = 3; }
+            inextcell = oracle_next_cell(st, xe, ye, ze, iface, jface, icell);
+            if (NEIGHPTR(st, iface, icell) >= 0) { kface = iface; ic = icell; }
+            else { kface = oppface[iface - 1]; ic = inextcell; }
+            i1 = GRIDPTR(st, gridface[kface - 1][0], ic);
+            i2 = GRIDPTR(st, gridface[kface - 1][1], ic);
+            if (jface == 1) u = (ze - GRIDPOS(st, 3, i1)) / (GRIDPOS(st, 3, i2) - GRIDPOS(st, 3, i1));
+            else u = ipinx ? 0.5 : (xe - GRIDPOS(st, 1, i1)) / (GRIDPOS(st, 1, i2) - GRIDPOS(st, 1, i1));
+            if (inextcell > 0) {
+                if (jface == 1) xe = GRIDPOS(st, 1, GRIDPTR(st, ioct, inextcell));
+                else ze = GRIDPOS(st, 3, GRIDPTR(st, ioct, inextcell));
+            }
+            f1 = 1 - u;
+            f2 = u;
+            ext0 = f1 * extinct[i1 - 1] + f2 * extinct[i2 - 1];
+            for (k = 0; k < ns; k++)
+                srcext0[k] = f1 * SRC(k + 1, kang, i1) * extinct[i1 - 1] + f2 * SRC(k + 1, kang, i2) * extinct[i2 - 1];
+            ext = 0.5 * (ext0 + ext1);
+            tau = ext * so;
+            if (tau >= 0.5) {
+                transcell = exp(-tau);
+                abscell = 1.0 - transcell;
+            } else {
+                abscell = tau * (1.0 - 0.5 * tau * (1.0 - 0.33333333333 * tau * (1 - 0.25 * tau)));
+                transcell = 1.0 - abscell;
+            }
+            if (tau <= 2.0) {
+                if (ext == 0.0) { for (k = 0; k < ns; k++) src[k] = 0.0; }
+                else {
+                    for (k = 0; k < ns; k++)
+                        src[k] = (0.5 * (srcext0[k] + srcext1[k])
+                                  + 0.08333333333 * (ext0 * srcext1[k] - ext1 * srcext0[k]) * so) / ext;
+                }
+            } else {
+                ext0p = ext0;
+                for (k = 0; k < ns; k++) srcext0p[k] = srcext0[k];
+                if (tau > 4.0) {
+                    ext0p = ext1 + (ext0 - ext1) * 4.0 / tau;
+                    if (ext0 > 0.0) for (k = 0; k < ns; k++) srcext0p[k] = srcext0[k] * ext0p / ext0;
+                }
+                for (k = 0; k < ns; k++)
+                    src[k] = 1.0 / (ext0p + ext1) * (srcext0p[k] + srcext1[k]
+                             + (ext0p * srcext1[k] - ext1 * srcext0p[k]) * 2.0 / (ext0p + ext1)
+                               * (1 - 2 / tau + 2 * transcell / abscell));
+            }
+            src[0] = fmax(src[0], 0.0);
+            for (k = 0; k < ns; k++) rad[k] = rad[k] + transmit * src[k] * abscell;
+            transmit = transmit * transcell;
+            validface = GR(1, i1) >= -0.1f && GR(1, i2) >= -0.1f;
+            if (inextcell <= 0 || (transmit <= transmin && validface)) {
+                if (validface) {
+                    validrad = 1;
+                    for (k = 0; k < ns; k++) {
+                        rad0[k] = f1 * GR(k + 1, i1) + f2 * GR(k + 1, i2);
+                        rad[k] = rad[k] + transmit * rad0[k];
+                    }
+                } else {
+                    if (errmsg) snprintf(errmsg, 600, "BACK_INT_GRID2D: INEXTCELL=0 without a valid face");
+                    return 1;
+                }
+            } else {
+                ext1 = ext0;
+                for (k = 0; k < ns; k++) srcext1[k] = srcext0[k];
+                icell = inextcell;
+            }
+        }
+        for (k = 0; k < ns; k++) GR(k + 1, ipt) = (float)rad[k];
+    }
+    return 0;
+}
+
 /* RADIANCE_TRUNCATION  shdomsub1.f:1615-1805 */
 static int radiance_truncation(const oracle_state *st, int highorderrad, const int *shptr, const float *radiance,
                                int maxir, int fixsh, float shacc, int *rshptr, const int *lofj)
@@ -749,12 +872,15 @@ static int path_integration(oracle_state *st, const shdo_coef *c, const int *swe
             }
             if (BTEST(st->ipflag, 1) && BTEST(st->ipflag, 0)) {
                 ierr = back_int_grid1d(st, sweepord, st->mu[imu - 1], iphi, st->total_ext, work, gridrad, errmsg);
+            } else if (BTEST(st->ipflag, 1) && !BTEST(st->bcflag, 2) && !BTEST(st->bcflag, 3)) {
+                ierr = back_int_grid2d(st, sweepord, st->mu[imu - 1], st->phi[(imu - 1) + st->nmu * (iphi - 1)], oracle_transmin,
+                                       iphi, st->total_ext, work, gridrad, errmsg);
             } else if (!BTEST(st->ipflag, 1) && !BTEST(st->bcflag, 2) && !BTEST(st->bcflag, 3)) {
                 /* TRANSMIN: numerical parameter `transmin` of at3d (configuration.py:28, default 1.0) */
                 ierr = back_int_grid3d(st, sweepord, st->mu[imu - 1], st->phi[(imu - 1) + st->nmu * (iphi - 1)], oracle_transmin,
                                        iphi, st->total_ext, work, gridrad, errmsg);
             } else {
-                if (errmsg) snprintf(errmsg, 600, "oracle solver: BACK_INT_GRID2D and the multi-processor sweeps are not restated");
+                if (errmsg) snprintf(errmsg, 600, "oracle solver: the multi-processor sweeps are not restated");
                 ierr = 3;
             }
             if (ierr) break;

@@ -158,6 +158,28 @@ def test_rte_levis_gradient_wrt_extinction():
     assert np.sign(fd) == np.sign(directional) and 0.2 * abs(fd) <= abs(directional) <= 1.5 * abs(fd)
 
 
+def test_rte_two_dimensional_domain():
+    """ny = 1: the reference switches to independent pixels in Y (IPFLAG bit 1, at3d/solver.py:2111) -> BACK_INT_GRID2D."""
+    from at3d_b200.rte import RTE
+    from at3d_b200.state import Rays
+    params, medium, source, surface = make_inputs(10, 1, 9, 'periodic', 1, False)
+    rte = RTE(params, medium, source, surface)
+    rte.solve(maxiter=60)
+    st0 = rte._unsolved
+    assert st0.ipflag == 2 and rte.check_solved()
+    ref, iters, solcrit = O.solve_fixed_grid(st0, rte._wtmu, solacc=1e-4, maxiter=60)
+    assert iters == rte.num_iterations
+    np.testing.assert_allclose(rte._solved.fluxes, ref.fluxes, rtol=1e-4, atol=1e-7)
+    n = 40
+    rays = Rays(np.linspace(0.01, 0.49, n), np.zeros(n), np.full(n, 0.5), np.full(n, 0.7), np.zeros(n))
+    sensor = dict(ray_x=rays.camx, ray_y=rays.camy, ray_z=rays.camz, ray_mu=rays.cammu, ray_phi=rays.camphi,
+                  stokes=np.array([True, False, False, False]))
+    out = rte.integrate_to_sensor(sensor)
+    refrad = O.render(ref, rays)
+    np.testing.assert_allclose(out['I'], refrad[0], rtol=1e-4, atol=1e-6 * refrad[0].max())
+    rte.close()
+
+
 def test_rte_refuses_adaptive_splitting():
     from at3d_b200.rte import RTE
     params, medium, source, surface = make_inputs(5, 5, 6, 'periodic', 1, False)

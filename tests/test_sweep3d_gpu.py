@@ -148,10 +148,39 @@ def test_device_loop_out_of_sh_memory_is_ierr_2():
         solver.solve_fixed_grid(st, wtmu_of(st), maxiv=5 * st.npts)
 
 
+TWO_D = [dict(nx=7, ny=1, nz=9, bc='periodic'), dict(nx=6, ny=4, nz=8, bc='periodic', nsplits=5),
+         dict(nx=7, ny=1, nz=9, bc='open_x', rayleigh=True), dict(nx=6, ny=3, nz=8, bc='open_x', nstokes=3, nsplits=4)]
+
+
+@pytest.mark.parametrize('kw', TWO_D)
+def test_sweep2d_matches_serial_sweep(kw):
+    """IPFLAG=2 (what at3d sets for ny=1, the usual 2-D x-z domains): BACK_INT_GRID2D (shdomsub1.f:4039-4293), rays in
+    the X-Z plane and two-point faces, through the same data-flow kernel (the two extra face weights are exact zeros)."""
+    sc = S.make_scene(seed=5, ipflag=2, **kw)
+    O.finalize_scene(sc)
+    compare_path_integration(sc.state)
+    compare_path_integration(sc.state, transmin=0.5)
+
+
+def test_fixed_grid_solve_2d():
+    sc = S.make_scene(nx=9, ny=1, nz=10, bc='periodic', seed=8, ipflag=2)
+    O.finalize_scene(sc)
+    st = sc.state
+    w = wtmu_of(st)
+    sol, iters, solcrit, _ = solver.solve_fixed_grid(st, w, solacc=1e-4, maxiter=50)
+    ref, iters_r, _ = O.solve_fixed_grid(st, w, solacc=1e-4, maxiter=50)
+    assert iters == iters_r and solcrit <= 1e-4
+    np.testing.assert_array_equal(sol.shptr, ref.shptr)
+    np.testing.assert_allclose(sol.fluxes, ref.fluxes, rtol=1e-4, atol=1e-7)
+    np.testing.assert_allclose(sol.radiance, ref.radiance, rtol=1e-4, atol=5e-6 * np.abs(ref.radiance).max())
+
+
 def test_solver_refuses_what_it_does_not_cover():
     from at3d_b200._lib import At3dError
-    sc = S.make_scene(nx=5, ny=5, nz=6, ipflag=2, seed=1)           # BACK_INT_GRID2D
+    sc = S.make_scene(nx=5, ny=5, nz=6, seed=1)
     O.finalize_scene(sc)
+    st = sc.state.copy()
+    st.bcflag = 4                                                    # multi-processor boundary flags
     with pytest.raises(At3dError) as e:
-        solver.SweepSolver(sc.state, wtmu_of(sc.state))
+        solver.SweepSolver(st.normalize(), wtmu_of(st))
     assert e.value.code == 3
