@@ -1,12 +1,14 @@
-"""Fixed-grid SHDOM solution iterations for independent-pixel grids, on the GPU.
+"""Fixed-grid SHDOM solution iterations on the GPU.
 
 Mirrors ``at3d.solver.RTE.solve`` -> ``core.solution_iterations`` (``SOLUTION_ITERATIONS``,
-src/polarized/shdomsub1.f:445-822) for ``ip_flag=3`` and ``split_accuracy=0``: every iteration runs
-``RADIANCE_TRUNCATION`` (host, integer bookkeeping), ``PATH_INTEGRATION`` (C-ABI ``at3d_path_integration_ip``:
-SH->DO transform, 1-D sweeps, boundaries, DO->SH transform on the GPU) and ``COMPUTE_SOURCE`` (C-ABI
-``at3d_compute_source``), then the sequence acceleration of ``CALC_ACCEL_SOLCRIT`` / ``ACCELERATE_SOLUTION``
-(src/shdom_nompi.f:317-349, shdomsub1.f:1807-1832).  The first guess is a zero radiance field (``INIT_RADIANCE``'s
-Eddington field is not restated; the fixed point does not depend on it).  The 3-D sweep is SURVEY.md 8f "next".
+src/polarized/shdomsub1.f:445-822) for ``split_accuracy=0``.  ``solve_fixed_grid`` runs the whole loop resident in HBM
+through ``at3d_solver_create`` / ``at3d_solver_solve`` (``RADIANCE_TRUNCATION``, ``PATH_INTEGRATION`` -- independent
+columns for ``ip_flag=3``, ``BACK_INT_GRID2D`` for ``ip_flag=2``, the ``BACK_INT_GRID3D`` data-flow sweep otherwise --
+``COMPUTE_SOURCE``, ``CALC_ACCEL_SOLCRIT`` / ``ACCELERATE_SOLUTION``); with ``device_loop=False`` the same iteration is
+driven from Python through the per-routine C-ABI calls (``at3d_path_integration_ip`` / ``at3d_solver_path_integration``,
+``at3d_compute_source``) with ``RADIANCE_TRUNCATION`` on the host.  The first guess is a zero radiance field
+(``INIT_RADIANCE``'s Eddington field is not restated; the fixed point does not depend on it).  Adaptive cell splitting
+(``SPLIT_GRID``) is SURVEY.md 8f "next".
 """
 import ctypes as C
 import numpy as np
