@@ -821,14 +821,14 @@ bool host_sweeping_order(const at3d_state_desc *d, int noct, std::vector<int> &s
 }
 }
 
-// SWEEPING_ORDER alone (host only, no device needed): SWEEPORD(NPTS,8), entries cell<<3 | corner-1
+// SWEEPING_ORDER alone (host only, no device needed): SWEEPORD(NPTS,NOCT), NOCT = 8 (4 for IPFLAG=2), entries cell<<3 | corner-1
 extern "C" int at3d_sweeping_order(const at3d_state_desc *d, int32_t *sweepord, char *errmsg)
 {
     if (errmsg) errmsg[0] = 0;
     if (!d || !sweepord) { set_msg(errmsg, "null argument"); return 1; }
-    if ((d->ipflag & 2) || (d->bcflag & 12)) { set_msg(errmsg, "at3d_sweeping_order: 8-octant grids without multi-processor flags only"); return 3; }
+    if ((d->ipflag & 3) == 3 || (d->bcflag & 12)) { set_msg(errmsg, "at3d_sweeping_order: 3-D (8 octants) and 2-D (IPFLAG=2, 4 octants) grids without multi-processor flags only"); return 3; }
     std::vector<int> so, rank;
-    if (!host_sweeping_order(d, 8, so, rank)) { set_msg(errmsg, "SWEEPING_ORDER: not every grid point was reached"); return 1; }
+    if (!host_sweeping_order(d, (d->ipflag & 2) ? 4 : 8, so, rank)) { set_msg(errmsg, "SWEEPING_ORDER: not every grid point was reached"); return 1; }
     memcpy(sweepord, so.data(), so.size() * sizeof(int));
     return 0;
 }

@@ -117,8 +117,9 @@ def path_integration_ip(st, wtmu, shptr, source, rshptr, timing=False):
 
 
 def sweeping_order(st):
-    """SWEEPING_ORDER (shdomsub1.f:3261-3352) of a 3-D grid: SWEEPORD[npts, 8] (Fortran order), host only."""
-    out = np.zeros((st.npts, 8), np.int32, order='F')
+    """SWEEPING_ORDER (shdomsub1.f:3261-3352) of a 3-D (8 octants) or 2-D (IPFLAG=2, 4 octants) grid: SWEEPORD[npts,
+    noct] (Fortran order), host only."""
+    out = np.zeros((st.npts, 4 if (st.ipflag & 2) else 8), np.int32, order='F')
     d = st.desc()
     buf = _lib.errbuf()
     _lib.check(_lib.lib().at3d_sweeping_order(C.byref(d), vp(out), buf), buf)

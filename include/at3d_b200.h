@@ -272,7 +272,8 @@ int at3d_transfer_pa_to_grid(int npts, const float *gridpos, int npx, int npy, i
  * SH <-> ordinate transform tables, the two discrete-ordinate fields); transmin is TRANSMIN (at3d default 1.0).
  * at3d_solver_path_integration has the argument meaning of at3d_path_integration_ip. */
 typedef struct at3d_solver at3d_solver;
-/* SWEEPING_ORDER (:3261-3352) alone, on the host: sweepord is SWEEPORD(NPTS,8) (cell<<3 | corner-1); no device needed. */
+/* SWEEPING_ORDER (:3261-3352) alone, on the host: sweepord is SWEEPORD(NPTS,NOCT), NOCT = 8 (4 for IPFLAG=2), entries
+ * cell<<3 | corner-1; no device needed. */
 int at3d_sweeping_order(const at3d_state_desc *desc, int32_t *sweepord, char *errmsg);
 int at3d_solver_create(const at3d_state_desc *desc, const float *wtmu, float transmin, at3d_solver **out, char *errmsg);
 int at3d_solver_path_integration(at3d_solver *sv, const int32_t *shptr, const float *source, const int32_t *rshptr,
