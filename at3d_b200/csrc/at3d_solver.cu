@@ -14,6 +14,7 @@
 #include <cstring>
 #include <cstdarg>
 #include <cmath>
+#include <ctime>
 #include <vector>
 #include <cub/cub.cuh>
 #include "at3d_host.h"
@@ -916,8 +917,24 @@ static int solver_create_ip(const at3d_state_desc *d, const float *wtmu, at3d_so
     return 0;
 }
 
+static double wall_ms()
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return 1e3 * ts.tv_sec + 1e-6 * ts.tv_nsec;
+}
+
 extern "C" int at3d_solver_create(const at3d_state_desc *d, const float *wtmu, float transmin, at3d_solver **out, char *errmsg)
 {
+    const bool timing = getenv("AT3D_SOLVER_TIMING") != nullptr;     // developer aid: set-up phases on stderr
+    double t_prev = wall_ms();
+    auto lap = [&](const char *what) {
+        if (!timing) return;
+        cudaDeviceSynchronize();
+        const double t = wall_ms();
+        fprintf(stderr, "at3d_solver_create: %-28s %9.2f ms\n", what, t - t_prev);
+        t_prev = t;
+    };
     if (errmsg) errmsg[0] = 0;
     if (!d || !wtmu || !out) { set_msg(errmsg, "null argument"); return 1; }
     *out = nullptr;
@@ -930,6 +947,7 @@ extern "C" int at3d_solver_create(const at3d_state_desc *d, const float *wtmu, f
     const int npts = d->npts, nst = d->nstokes, noct = two_d ? 4 : 8;
     std::vector<int> sweepord, rank;
     if (!host_sweeping_order(d, noct, sweepord, rank)) { set_msg(errmsg, "SWEEPING_ORDER: not every grid point was reached"); return 1; }
+    lap("host SWEEPING_ORDER");
     at3d_solver *sv = new at3d_solver();
     int rc = tr_plan_create(nst, d->nstleg, d->ml, d->mm, d->nlm, d->nmu, d->nphi0max, d->nphi0, d->mu, d->phi, wtmu, &sv->P, errmsg);
     if (rc) { delete sv; return rc; }
@@ -1030,17 +1048,18 @@ extern "C" int at3d_solver_create(const at3d_state_desc *d, const float *wtmu, f
     if (ok) ok = launch_build_cellrec(d->ncells, gp, np, tp, cf, cellrec, 0) == cudaSuccess &&
                  launch_build_ptrec(npts, gpos, a.total_ext, ptrec, 0) == cudaSuccess && cudaDeviceSynchronize() == cudaSuccess;
     if (!ok) { at3d_solver_destroy(sv); set_msg(errmsg, "device allocation failure"); return 4; }
+    lap("uploads, records, tables");
     memset(&w.S, 0, sizeof(w.S));
     w.S.npts = npts; w.S.ncells = d->ncells; w.S.cellrec = cellrec; w.S.ptrec = ptrec;
-    // ordinates in flight together: enough of the sweep order per ordinate for a few z-slabs of the wavefront
     int dev = 0, nsm = 148, per_sm = 1;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
     if (nst == 1) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sweep3d_kernel<1, false>, 256, 0);
     else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sweep3d_kernel<3, false>, 256, 0);
     sv->blocks_resident = nsm * (per_sm > 0 ? per_sm : 1);
-    const long slab = (long)(d->nx + 1) * (d->ny + 1);
-    long g = (long)sv->blocks_resident * 256 / (4 * slab > 0 ? 4 * slab : 1);
+    // ordinates in flight together: all of a hemisphere (measured: the sweep in the reference order, i.e. the level pass,
+    // takes 199 ms at 1.05 M points with all 177 in flight, 251 ms with 32, 487 ms with 8, 758 ms with 1)
+    long g = nh;
     const char *genv = getenv("AT3D_SWEEP_GROUP");
     if (genv) g = atol(genv);
     w.group = (int)(g < 1 ? 1 : (g > nh ? nh : g));
@@ -1062,6 +1081,7 @@ extern "C" int at3d_solver_create(const at3d_state_desc *d, const float *wtmu, f
         cudaError_t e = cudaSuccess;
         if (!level || !k0 || !k1 || !plan || !nwalk || !tmp) { at3d_solver_destroy(sv); set_msg(errmsg, "device allocation failure"); return 4; }
         const int nb = (int)((nkeys + 255) / 256);
+        lap("level-pass allocations");
         cudaMemset(a.dofield, 0, (size_t)npts * nst * nang * sizeof(float));
         cudaMemset(nwalk, 0, nkeys);                               // the preset boundary points are never walked
         sweep3d_level_init_kernel<<<nb, 256>>>(npts, nang, w.bflag, level);
@@ -1070,6 +1090,7 @@ extern "C" int at3d_solver_create(const at3d_state_desc *d, const float *wtmu, f
             cudaMemsetAsync(w.ticket, 0, up == 0 ? 2 * sizeof(int) : sizeof(int), 0);
             sweep3d_kernel<1, true><<<w.nchunks * nh, 256>>>(w, up);
         }
+        lap("level pass");
         sweep3d_key_kernel<<<nb, 256>>>(w, k0);
         cub::DeviceRadixSort::SortKeys(tmp, tmpb, k0, k1, nkeys, 0, 57, 0);
         sweep3d_plan_kernel<<<nb, 256>>>(w, k1, plan);
@@ -1084,8 +1105,9 @@ extern "C" int at3d_solver_create(const at3d_state_desc *d, const float *wtmu, f
             return e != cudaSuccess ? 4 : 1;
         }
         w.plan = plan;
-        if (!genv) w.group = nh;             // all ordinates advance through the levels together
+        lap("sort + plan records");
     }
+    lap("release of the temporaries");
     *out = sv;
     return 0;
 }
