@@ -113,6 +113,7 @@ class RTE:
         xg, yg, zg = G.new_grids(self._bcflag, 'P', self._npx, self._npy, self._npz, self._nx, self._ny, self._nz,
                                  0.0, 0.0, self._delx, self._dely, self._zlevels)
         self._nx1, self._ny1, self._xgrid, self._ygrid, self._zgrid = nx1, ny1, xg, yg, zg
+        self._nbcells_base = nbcells
         (self._npts, self._ncells, gridpos, gridptr, neighptr, treeptr, cellflags) = G.init_cell_structure(
             self._bcflag, self._ipflag, self._nx, self._ny, self._nz, nx1, ny1, xg[:nx1], yg[:ny1], zg)
         n, c = self._npts, self._ncells
@@ -226,6 +227,55 @@ class RTE:
         if self._dev is not None:
             self._dev.close()
         self._solved, self._dev = sol, DeviceState(sol)
+
+    def save_solution(self, save_radiances=True):
+        """``RTE.save_solution`` (at3d/solver.py:1621-1686): the (adaptive) grid and the spherical-harmonic source /
+        radiance fields under the reference's variable names (1-based pointer contents preserved), as a plain dict --
+        `xarray.Dataset(dict)`-compatible shapes."""
+        if self._solved is None:
+            raise RuntimeError('solve() first')
+        st = self._solved
+        out = dict(nstokes=st.nstokes, nx=st.nx, ny=st.ny, nz=st.nz, ml=st.ml, mm=st.mm, nlm=st.nlm, npts=st.npts,
+                   ncells=st.ncells, nbcells=self._nbcells_base, xgrid=self._xgrid[:self._nx1], ygrid=self._ygrid[:self._ny1],
+                   zgrid=self._zgrid, gridpos=st.gridpos[:, :st.npts], gridptr=st.gridptr[:, :st.ncells],
+                   neighptr=st.neighptr[:, :st.ncells], treeptr=st.treeptr[:, :st.ncells], cellflags=st.cellflags[:st.ncells])
+        if save_radiances:
+            out.update(fluxes=st.fluxes[:, :st.npts], shptr=st.shptr[:st.npts + 1], rshptr=st.rshptr[:st.npts + 2],
+                       source=st.source[:, :int(st.shptr[st.npts])], radiance=st.radiance[:, :int(st.rshptr[st.npts])])
+        return out
+
+    def load_solution(self, input_dataset, load_radiance=True):
+        """``RTE.load_solution`` (at3d/solver.py:1519-1619): adopt a saved grid -- including the cells an adaptive solve of
+        the reference has split -- and its SOURCE / RADIANCE fields; the optical properties and the direct beam are
+        re-evaluated on the loaded grid points, after which `integrate_to_sensor` and `levis_approx_gradient` work without
+        a solve."""
+        d = input_dataset
+        if int(_scalar(d, 'nx')) != self._nx or int(_scalar(d, 'ny')) != self._ny or int(_scalar(d, 'nz')) != self._nz:
+            raise ValueError('Incompatible grid sizes in the saved solution')
+        if (np.any(_v(d, 'xgrid') != self._xgrid[:self._nx1]) or np.any(_v(d, 'ygrid') != self._ygrid[:self._ny1])
+                or np.any(_v(d, 'zgrid') != self._zgrid)):
+            raise ValueError('Incompatible base grid in the saved solution')
+        self._npts, self._ncells = int(_scalar(d, 'npts')), int(_scalar(d, 'ncells'))
+        self._gridpos = np.asfortranarray(_v(d, 'gridpos'), np.float32)[:, :self._npts]
+        self._gridptr = np.asfortranarray(_v(d, 'gridptr'), np.int32)[:, :self._ncells]
+        self._neighptr = np.asfortranarray(_v(d, 'neighptr'), np.int32)[:, :self._ncells]
+        self._treeptr = np.asfortranarray(_v(d, 'treeptr'), np.int32)[:, :self._ncells]
+        self._cellflags = np.ascontiguousarray(_v(d, 'cellflags'), np.int16)[:self._ncells]
+        self._t = B.transfer_pa_to_grid(self._pg, self._gridpos, self._npts, self._ml, self._deltam)
+        st = self._init_solution()
+        if not load_radiance:
+            return
+        if int(_scalar(d, 'nstokes')) != self._nstokes:
+            raise ValueError('Incompatible nstokes in the saved solution')
+        if int(_scalar(d, 'ml')) != self._ml or int(_scalar(d, 'mm')) != self._mm:
+            raise NotImplementedError('a saved solution with another angular resolution (ml, mm) is not re-truncated here')
+        st.shptr = np.ascontiguousarray(_v(d, 'shptr'), np.int32)
+        st.rshptr = np.ascontiguousarray(_v(d, 'rshptr'), np.int32)
+        st.source = np.asfortranarray(_v(d, 'source'), np.float32)
+        st.radiance = np.asfortranarray(_v(d, 'radiance'), np.float32)
+        st.fluxes = np.asfortranarray(_v(d, 'fluxes'), np.float32)
+        self._solcrit = self._solacc                       # the saved fields are taken as converged
+        self._set_solution(st.normalize())
 
     def check_solved(self, verbose=True):
         return self._solved is not None and self._solcrit <= self._solacc

@@ -180,6 +180,58 @@ def test_rte_two_dimensional_domain():
     rte.close()
 
 
+def test_rte_save_and_load_solution():
+    """save_solution / load_solution with the reference's variable names (at3d/solver.py:1519-1686): a second RTE that
+    loads the saved fields renders bit-identical radiances without solving; a saved ADAPTIVE grid (cells split, as an
+    adaptive solve of the reference leaves them) is adopted with the properties re-interpolated to its points."""
+    from at3d_b200.rte import RTE
+    from at3d_b200.state import Rays
+    from at3d_b200 import grid as G
+    params, medium, source, surface = make_inputs(8, 7, 9, 'periodic', 3, False)
+    a = RTE(params, medium, source, surface, num_stokes=3)
+    a.solve(maxiter=60)
+    ds = a.save_solution()
+    assert set(('gridptr', 'neighptr', 'treeptr', 'cellflags', 'shptr', 'rshptr', 'source', 'radiance', 'fluxes')) <= set(ds)
+    assert ds['gridptr'].min() >= 1                                    # 1-based contents, as the reference stores them
+    sensor = make_sensor(0.05 * 8, 0.05 * 7)
+    ia = a.integrate_to_sensor(dict(sensor))
+    b = RTE(params, medium, source, surface, num_stokes=3)
+    b.load_solution(ds)
+    ib = b.integrate_to_sensor(dict(sensor))
+    for k in ('I', 'Q', 'U'):
+        np.testing.assert_array_equal(ia[k], ib[k])
+    # an adaptive grid: split some cells of the saved grid the way DIVIDE_CELL does, interpolate the fields to the new points
+    st = a._solved
+    tree = G.CellTree(st.npts, st.ncells, np.pad(st.gridpos, ((0, 0), (0, 200))), np.pad(st.gridptr, ((0, 0), (0, 100))),
+                      np.pad(st.neighptr, ((0, 0), (0, 100))), np.pad(st.treeptr, ((0, 0), (0, 100))),
+                      np.pad(st.cellflags, (0, 100)))
+    rng = np.random.default_rng(3)
+    for _ in range(12):
+        ic = int(rng.integers(1, tree.ncells + 1))
+        if tree.treeptr[1, ic - 1] == 0:
+            tree.divide_cell(ic, int(rng.integers(1, 4)))
+    nnew = tree.npts - st.npts
+    assert nnew > 0
+    ds2 = dict(ds, npts=tree.npts, ncells=tree.ncells, gridpos=tree.gridpos[:, :tree.npts], gridptr=tree.gridptr[:, :tree.ncells],
+               neighptr=tree.neighptr[:, :tree.ncells], treeptr=tree.treeptr[:, :tree.ncells], cellflags=tree.cellflags[:tree.ncells])
+    # new points: 4 SH terms each (zero), fluxes zero -- enough for a consistency check of the adopted topology
+    shptr = np.concatenate([st.shptr[:st.npts + 1], st.shptr[st.npts] + 4 * np.arange(1, nnew + 1)]).astype(np.int32)
+    rshptr = np.concatenate([st.rshptr[:st.npts + 1], st.rshptr[st.npts] + 4 * np.arange(1, nnew + 1)]).astype(np.int32)
+    rshptr = np.concatenate([rshptr, rshptr[-1:]])
+    ds2.update(shptr=shptr, rshptr=rshptr, source=np.pad(ds['source'], ((0, 0), (0, 4 * nnew))),
+               radiance=np.pad(ds['radiance'], ((0, 0), (0, 4 * nnew))), fluxes=np.pad(ds['fluxes'], ((0, 0), (0, nnew))))
+    c = RTE(params, medium, source, surface, num_stokes=3)
+    c.load_solution(ds2)
+    assert c._solved.npts == tree.npts and c._solved.ncells == tree.ncells
+    rays = Rays(sensor['ray_x'], sensor['ray_y'], sensor['ray_z'], sensor['ray_mu'], sensor['ray_phi'])
+    ic_ = c.integrate_to_sensor(dict(sensor))
+    ref = O.render(c._solved, rays)
+    np.testing.assert_allclose(ic_['I'], ref[0], rtol=1e-4, atol=1e-6 * ref[0].max())
+    np.testing.assert_allclose(ic_['Q'], ref[1], rtol=1e-4, atol=1e-6)
+    for r in (a, b, c):
+        r.close()
+
+
 def test_rte_refuses_adaptive_splitting():
     from at3d_b200.rte import RTE
     params, medium, source, surface = make_inputs(5, 5, 6, 'periodic', 1, False)
