@@ -426,6 +426,9 @@ __device__ __forceinline__ int face_corner(int kface, int n)
 // LEVEL = true: the same walk and waits, but what travels is the dependency level 1 + max(level of the four face
 // points) instead of the radiance (run once per solver object; the levels order the threads of the real sweep so that
 // a thread's face points were finished a whole wavefront earlier and neighbouring lanes never wait for each other)
+#ifndef AT3D_SWEEP_SLEEP
+#define AT3D_SWEEP_SLEEP 64          // ns between two polls of a waiting thread
+#endif
 #ifndef AT3D_SWEEP_MINB
 #define AT3D_SWEEP_MINB 3
 #endif
@@ -614,7 +617,7 @@ __global__ void __launch_bounds__(256, (NST == 1 ? AT3D_SWEEP_MINB : 2)) sweep3d
                 const int l3 = *(volatile int *)&L[i3 - 1], l4 = *(volatile int *)&L[i4 - 1];
                 if (l1 >= 0 && l2 >= 0 && l3 >= 0 && l4 >= 0) { lv = 1 + max(max(l1, l2), max(l3, l4)); break; }
                 if (++spins > (1 << 22) || ((spins & 255) == 0 && *(volatile int *)a.err)) { fail = 4; break; }
-                __nanosleep(64);
+                __nanosleep(AT3D_SWEEP_SLEEP);
             }
         }
         if (fail) atomicCAS(a.err, 0, fail);
@@ -631,7 +634,7 @@ __global__ void __launch_bounds__(256, (NST == 1 ? AT3D_SWEEP_MINB : 2)) sweep3d
             g1 = ld_vol(&R[i1 - 1]); g2 = ld_vol(&R[i2 - 1]); g3 = ld_vol(&R[i3 - 1]); g4 = ld_vol(&R[i4 - 1]);
             if (g1 >= -0.1f && g2 >= -0.1f && g3 >= -0.1f && g4 >= -0.1f) break;
             if (++spins > (1 << 22) || ((spins & 255) == 0 && *(volatile int *)a.err)) { fail = 4; break; }
-            __nanosleep(64);
+            __nanosleep(AT3D_SWEEP_SLEEP);
         }
         if (!fail) {
             __threadfence();
