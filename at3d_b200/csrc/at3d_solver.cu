@@ -535,7 +535,8 @@ __global__ void __launch_bounds__(256, (NST == 1 ? AT3D_SWEEP_MINB : 2)) sweep3d
             v = ipinx ? 0.5 : (xe - (double)p1.x) / (double)(p2.x - p1.x);
         }
         if (a.two_d) { if (jface == 1) v = 0.0; else u = 0.0; }     // F = (1-U, U) on the face's two points
-        if (inextcell > 0) {
+        // (the exit point is only needed to go on into the next cell: skipped on the last cell of a recorded walk)
+        if (inextcell > 0 && !(nwalk != 255 && step + 1 == nwalk)) {
             const int pn = cell_gp(S, inextcell, ioct);
             if (jface == 1) xe = (double)pt_coord(S, pn, 1);
             else if (jface == 2) ye = (double)pt_coord(S, pn, 2);
