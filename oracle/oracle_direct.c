@@ -339,6 +339,26 @@ int oracle_make_direct(int npts, int bcflag, int ipflag, int deltam, int ml, int
     return ierr;
 }
 
+/* DIRECT_BEAM_PROP(INIT=0) for one point (the call of INTERPOLATE_POINT, shdomsub1.f:5093-5107), with the beam
+ * constants oracle_make_direct returned in out_d / out_i. */
+int oracle_direct_beam_point(const double *out_d, const int *out_i, int bcflag, int npx, int npy, int npz,
+                             float xstart, float ystart, const float *zlevels, const float *extdirp,
+                             float solarflux, float x, float y, float z, float *dirflux, char *errmsg)
+{
+    beam_geom g;
+    double path = 0.0;
+    int npp = 0, ierr;
+    g.bcflag = bcflag; g.npx = npx; g.npy = npy; g.npz = npz;
+    g.xstart = xstart; g.ystart = ystart; g.zlevels = zlevels;
+    g.cx = out_d[0]; g.cy = out_d[1]; g.cz = out_d[2]; g.cxinv = out_d[3]; g.cyinv = out_d[4]; g.czinv = out_d[5];
+    g.epss = out_d[6]; g.epsz = out_d[7]; g.xdomain = out_d[8]; g.ydomain = out_d[9];
+    g.delxd = out_d[11]; g.delyd = out_d[12];
+    g.ipdirect = out_i[0]; g.di = out_i[1]; g.dj = out_i[2]; g.dk = out_i[3];
+    ierr = beam_walk(&g, x, y, z, extdirp, &path, &npp, NULL, NULL, 0, errmsg);
+    *dirflux = (float)(solarflux * exp(-path));
+    return ierr;
+}
+
 /* MAKE_DIRECT_DERIVATIVE  shdomsub5.f:1553-1605 */
 int oracle_make_direct_derivative(int npts, int bcflag, int npx, int npy, int npz,
                                   float delx, float dely, float xstart, float ystart,

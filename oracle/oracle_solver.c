@@ -1082,3 +1082,200 @@ int oracle_sweeping_order(const oracle_state *st, int *sweepord)
 {
     return sweeping_order(st, sweepord);
 }
+
+/* ---- INIT_SOLUTION + SOLUTION_ITERATIONS with adaptive cell splitting  shdomsub1.f:113-822 ----
+ * The point arrays of `st` (extinct, albedo, planck, iphase, phaseinterpwt) have leading dimension maxig; the other
+ * routines of this oracle expect leading dimension npts, so for NPART > 1 a compact copy is refreshed whenever the
+ * number of points changes (for NPART = 1 the two layouts coincide). */
+typedef struct {
+    float *extinct, *albedo, *planck, *pwt;
+    int *iphase;
+} compact_view;
+
+static void refresh_view(oracle_state *v, const oracle_adapt *a, compact_view *cv, int npart, int nq)
+{
+    const int npts = a->npts, ld = a->maxig;
+    int ipa;
+    v->npts = npts; v->ncells = a->ncells;
+    if (npart == 1) {
+        v->extinct = a->extinct; v->albedo = a->albedo; v->planck = a->planck;
+        v->iphase = a->iphase; v->phaseinterpwt = a->phaseinterpwt;
+        return;
+    }
+    for (ipa = 0; ipa < npart; ipa++) {
+        memcpy(cv->extinct + (size_t)npts * ipa, a->extinct + (size_t)ld * ipa, sizeof(float) * npts);
+        memcpy(cv->albedo + (size_t)npts * ipa, a->albedo + (size_t)ld * ipa, sizeof(float) * npts);
+        if (a->planck) memcpy(cv->planck + (size_t)npts * ipa, a->planck + (size_t)ld * ipa, sizeof(float) * npts);
+        memcpy(cv->iphase + (size_t)nq * npts * ipa, a->iphase + (size_t)nq * ld * ipa, sizeof(int) * (size_t)nq * npts);
+        memcpy(cv->pwt + (size_t)nq * npts * ipa, a->phaseinterpwt + (size_t)nq * ld * ipa,
+               sizeof(float) * (size_t)nq * npts);
+    }
+    v->extinct = cv->extinct; v->albedo = cv->albedo; v->planck = a->planck ? cv->planck : NULL;
+    v->iphase = cv->iphase; v->phaseinterpwt = cv->pwt;
+}
+
+int oracle_solve_adaptive(oracle_state *st, oracle_prop *pg, const float *wtmu, float *temp,
+                          int maxig, int maxic, int maxiv, int maxido, int maxbcrad, int nbpts, int nbcells,
+                          int maxiter, float solacc, float splitacc, float shacc, int accelflag, int highorderrad,
+                          int iterfixsh, int inradflag, float *extdirp, int *iters_out, float *solcrit_out,
+                          float *splitcrit_out, char *errmsg)
+{
+    const int ns = st->nstokes, npart = st->npart, nq = 8 * st->maxnmicro, maxir = maxiv + maxig;
+    const int lambertian = st->sfctype1 == 'L';
+    oracle_state v = *st;
+    oracle_adapt a;
+    compact_view cv = {0};
+    shdo_coef *c = make_sh_do_coef(st, wtmu);
+    int *sweepord = (int *)malloc(sizeof(int) * (size_t)maxig * 8);
+    int *oshptr = (int *)calloc(maxig + 2, sizeof(int));
+    int *lofj = (int *)malloc(sizeof(int) * st->nlm);
+    float *delsource = (float *)calloc((size_t)ns * maxiv, sizeof(float));
+    float *work = (float *)calloc((size_t)ns * st->nphi0max * maxig, sizeof(float));
+    float *gridrad = (float *)calloc((size_t)ns * maxig, sizeof(float));
+    float deljdot = 0, deljold = 0, deljnew = 0, jnorm = 0, solcrit = 1.0f, acc = 0.0f, accelpar, albmax = 0.0f;
+    float splitcrit = 0.0f, skyradalb;
+    const float endadaptsol = 0.001f, startadaptsol = 0.1f;
+    float adaptrange, cursplitacc, startsplitacc, avgsolcrit, beta;
+    int iter = 0, ierr = 0, fixsh = 0, splittesting = 1, outofmem = 0, oldnpts = 0, i, j, l, m, k, imu, iphi;
+    if (st->sfctype0 == 'V' && splitacc > 0.0f) {
+        if (errmsg) snprintf(errmsg, 600, "oracle adaptive solve: SURFACE_PARM_INTERP for new bottom points is not restated");
+        ierr = 3; goto done;
+    }
+    if (npart > 1) {
+        cv.extinct = (float *)malloc(sizeof(float) * (size_t)maxig * npart);
+        cv.albedo = (float *)malloc(sizeof(float) * (size_t)maxig * npart);
+        cv.planck = (float *)malloc(sizeof(float) * (size_t)maxig * npart);
+        cv.iphase = (int *)malloc(sizeof(int) * (size_t)nq * maxig * npart);
+        cv.pwt = (float *)malloc(sizeof(float) * (size_t)nq * maxig * npart);
+    }
+    j = 0;
+    for (l = 0; l <= st->ml; l++) {
+        const int me = l < st->mm ? l : st->mm;
+        for (m = -me; m <= me; m++) lofj[j++] = l;
+    }
+    memset(&a, 0, sizeof(a));
+    a.maxig = maxig; a.maxic = maxic; a.maxiv = maxiv; a.maxido = maxido;
+    a.npts = st->npts; a.ncells = st->ncells; a.accelflag = accelflag;
+    a.gridptr = (int *)st->gridptr; a.neighptr = (int *)st->neighptr; a.treeptr = (int *)st->treeptr;
+    a.cellflags = (short *)st->cellflags; a.gridpos = (float *)st->gridpos;
+    a.temp = temp; a.planck = (float *)st->planck; a.extinct = (float *)st->extinct; a.albedo = (float *)st->albedo;
+    a.total_ext = (float *)st->total_ext; a.dirflux = (float *)st->dirflux;
+    a.iphase = (int *)st->iphase; a.phaseinterpwt = (float *)st->phaseinterpwt;
+    a.shptr = (int *)st->shptr; a.rshptr = (int *)st->rshptr; a.oshptr = oshptr;
+    a.source = (float *)st->source; a.radiance = (float *)st->radiance;
+    a.pg = pg; a.extdirp = extdirp;
+    oracle_prop_extmin(pg, &a.extmin, &a.scatmin);
+    /* ALBMAX of TRANSFER_PA_TO_GRID */
+    for (k = 0; k < npart; k++)
+        for (i = 0; i < a.npts; i++) if (a.albedo[i + (size_t)maxig * k] > albmax) albmax = a.albedo[i + (size_t)maxig * k];
+    /* ---- INIT_SOLUTION ---- */
+    if (st->srctype != 'T') {
+        ierr = oracle_make_direct(a.npts, st->bcflag, st->ipflag, st->deltam, st->ml, st->nstleg, pg->nlegp,
+                                  st->solarflux, st->solarmu, st->solaraz, a.gridpos, pg->npx, pg->npy, pg->npz,
+                                  pg->delx, pg->dely, pg->xstart, pg->ystart, pg->zlevels, pg->extinctp, pg->albedop,
+                                  pg->legenp, pg->iphasep, pg->phasewtp, pg->maxnmicro, npart, pg->nzckd, pg->zckd,
+                                  pg->gasabs, extdirp, a.dirflux, a.beam_d, a.beam_i, errmsg);
+        if (ierr) goto done;
+    }
+    refresh_view(&v, &a, &cv, npart, nq);
+    v.rshptr = a.rshptr; v.radiance = a.radiance; v.shptr = a.shptr; v.source = a.source;
+    if (inradflag) {
+        const int nx1ny1 = nbpts / st->nz;
+        skyradalb = 0.0f;
+        for (imu = 1; imu <= st->nmu / 2; imu++)
+            for (iphi = 1; iphi <= st->nphi0[imu - 1]; iphi++)
+                skyradalb = skyradalb + fabsf(st->mu[imu - 1]) * st->wtdo[(imu - 1) + st->nmu * (iphi - 1)]
+                            * st->skyrad[ns * ((imu - 1) + (size_t)(st->nmu / 2) * (iphi - 1))];
+        ierr = oracle_init_radiance(st, maxig, nx1ny1, st->nz, a.extinct, a.albedo, a.total_ext, temp, a.iphase,
+                                    a.phaseinterpwt, skyradalb, 0.0f, a.rshptr, a.radiance);
+        if (ierr) { if (errmsg) snprintf(errmsg, 600, "INIT_RADIANCE/EDDRTF failed (%d)", ierr); goto done; }
+        ierr = oracle_interp_radiance(ns, nbpts, nbcells, a.ncells, a.treeptr, a.gridptr, a.gridpos, a.rshptr, a.radiance);
+        if (ierr) { if (errmsg) snprintf(errmsg, 600, "INTERP_RADIANCE: point not on an edge"); goto done; }
+    } else {
+        for (i = 0; i <= a.npts; i++) a.rshptr[i] = 4 * i;
+        memset(a.radiance, 0, sizeof(float) * (size_t)ns * a.rshptr[a.npts]);
+    }
+    a.rshptr[a.npts + 1] = a.rshptr[a.npts];
+    ierr = oracle_compute_source(&v, 0, shacc, maxiv, 1, accelflag, 1, a.shptr, a.source, oshptr, delsource,
+                                 &deljdot, &deljold, &deljnew, &jnorm, errmsg);
+    if (ierr) goto done;
+    if (accelflag) {
+        memcpy(oshptr, a.shptr, sizeof(int) * (a.npts + 1));
+        memset(delsource, 0, sizeof(float) * (size_t)ns * oshptr[a.npts]);
+    }
+    /* ---- SOLUTION_ITERATIONS ---- */
+    adaptrange = startadaptsol / (3.0f * endadaptsol);
+    cursplitacc = splitacc * adaptrange;
+    startsplitacc = cursplitacc;
+    avgsolcrit = solcrit;
+    while (iter < maxiter && (solcrit > solacc || (splitcrit > splitacc && cursplitacc > splitacc && !outofmem))) {
+        iter = iter + 1;
+        if (splitacc > 0.0f) {
+            int dosplit;
+            avgsolcrit = sqrtf(avgsolcrit * solcrit);
+            dosplit = solcrit <= startadaptsol && (solcrit > endadaptsol || cursplitacc > splitacc) && !outofmem;
+            beta = logf(startsplitacc / splitacc) / logf(adaptrange);
+            cursplitacc = fminf(cursplitacc, fmaxf(splitacc, splitacc * powf(avgsolcrit / (3.0f * endadaptsol), beta)));
+            if (solcrit <= endadaptsol) cursplitacc = splitacc;
+            if (splittesting) {
+                ierr = oracle_split_grid(&a, st, dosplit, &outofmem, cursplitacc, &splitcrit, errmsg);
+                if (ierr) goto done;
+                if (solcrit > startadaptsol) startsplitacc = splitcrit;
+            }
+            if (solcrit <= endadaptsol) splittesting = 0;
+        }
+        refresh_view(&v, &a, &cv, npart, nq);
+        ierr = radiance_truncation(&v, highorderrad, a.shptr, a.radiance, maxir, fixsh, shacc, a.rshptr, lofj);
+        if (ierr) { if (errmsg) snprintf(errmsg, 600, "RADIANCE_TRUNCATION: out of memory"); goto done; }
+        if (a.npts != oldnpts) {
+            ierr = sweeping_order(&v, sweepord);
+            if (ierr) { if (errmsg) snprintf(errmsg, 600, "SWEEPING_ORDER: not every grid point was reached"); goto done; }
+            if (oracle_boundary_pnts(a.npts, st->nang, lambertian, st->maxnbc, maxbcrad, st->zgrid[0],
+                                     st->zgrid[st->nz - 1], a.gridpos, &v.ntoppts, &v.nbotpts, (int *)st->bcptr)) {
+                if (errmsg) snprintf(errmsg, 600, "BOUNDARY_PNTS: MAXNBC exceeded");
+                ierr = 1; goto done;
+            }
+        }
+        ierr = path_integration(&v, c, sweepord, a.shptr, a.source, a.rshptr, a.radiance, (float *)st->fluxes,
+                                st->bcrad, work, gridrad, errmsg);
+        if (ierr) goto done;
+        oldnpts = a.npts;
+        if (solcrit < endadaptsol || iter > iterfixsh) fixsh = 1;
+        ierr = oracle_compute_source(&v, fixsh, shacc, maxiv, 0, accelflag, 1, a.shptr, a.source, oshptr, delsource,
+                                     &deljdot, &deljold, &deljnew, &jnorm, errmsg);
+        if (ierr) goto done;
+        if (accelflag && acc == 0.0f && deljnew < deljold) {
+            const float r = sqrtf(deljnew / deljold);
+            const float theta = acosf(deljdot / sqrtf(deljold * deljnew));
+            acc = (1 - r * cosf(theta) + powf(r, 1 + 0.5f * 3.14159f / theta)) / (1 + r * r - 2 * r * cosf(theta)) - 1.0f;
+            acc = fminf(10.0f, fmaxf(0.0f, acc));
+        } else {
+            acc = 0.0f;
+        }
+        accelpar = acc;
+        if (jnorm > 0.0f) solcrit = sqrtf(deljnew / jnorm);
+        else if (deljnew == 0.0f) solcrit = 0.0f;
+        if (accelpar > 0.0f) {
+            for (i = 1; i <= a.npts; i++) {
+                const int is = a.shptr[i - 1], nsx = a.shptr[i] - is, isd = oshptr[i - 1], nsd = oshptr[i] - isd;
+                const int nsc = nsx < nsd ? nsx : nsd;
+                for (j = 1; j <= nsc; j++)
+                    for (k = 0; k < ns; k++)
+                        a.source[k + (size_t)ns * (is + j - 1)] = a.source[k + (size_t)ns * (is + j - 1)]
+                                                                  + accelpar * delsource[k + (size_t)ns * (isd + j - 1)];
+            }
+        }
+        if (albmax < solacc) solcrit = solacc;
+        if (getenv("ORACLE_VERBOSE"))
+            fprintf(stderr, "  %4d %8.3f %10.3E %8d %8.2f %6.3f\n", iter, log10f(fmaxf(solcrit, 1.0e-20f)), splitcrit,
+                    a.npts, (float)a.shptr[a.npts] / a.npts, (float)a.shptr[a.npts] / (a.npts * (float)st->nlm));
+    }
+    st->npts = a.npts; st->ncells = a.ncells; st->ntoppts = v.ntoppts; st->nbotpts = v.nbotpts;
+done:
+    if (iters_out) *iters_out = iter;
+    if (solcrit_out) *solcrit_out = solcrit;
+    if (splitcrit_out) *splitcrit_out = splitcrit;
+    free_sh_do_coef(c); free(sweepord); free(oshptr); free(lofj); free(delsource); free(work); free(gridrad);
+    free(cv.extinct); free(cv.albedo); free(cv.planck); free(cv.iphase); free(cv.pwt);
+    return ierr;
+}

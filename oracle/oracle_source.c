@@ -87,10 +87,10 @@ static void calc_source_pnt_unpol(const src_work *w, int srctype, float flux0, c
 
 /* the per-point temporary source function (three textual copies in the reference:
  * shdomsub1.f:1089-1219, :1269-1398, :1433-1561) */
-static void point_source(const oracle_state *st, const src_work *w, int i, int newmethod,
-                         float secmu0, float *sourcet)
+static void point_source_ld(const oracle_state *st, const src_work *w, int i, int newmethod,
+                            float secmu0, float *sourcet, int npts /* leading dimension of the point arrays */)
 {
-    const int npart = st->npart, npts = st->npts, nq = 8 * st->maxnmicro;
+    const int npart = st->npart, nq = 8 * st->maxnmicro;
     const int nlt = w->nstleg * (w->nleg + 1), ml = w->ml;
     const int nsl = w->nstokes * w->nlm;
     float ext = st->total_ext[i - 1];
@@ -195,6 +195,40 @@ static void point_source(const oracle_state *st, const src_work *w, int i, int n
             for (t = 0; t < nsl; t++) sourcet[t] = sourcet[t] + wgt * w->sourcet1[t];
         }
     }
+}
+
+static void point_source(const oracle_state *st, const src_work *w, int i, int newmethod,
+                         float secmu0, float *sourcet)
+{
+    point_source_ld(st, w, i, newmethod, secmu0, sourcet, st->npts);
+}
+
+static void src_work_init(src_work *w, const oracle_state *st)
+{
+    int j = 0, l, m;
+    w->nstokes = st->nstokes; w->nstleg = st->nstleg; w->nleg = st->nleg; w->nlm = st->nlm;
+    w->ml = st->ml; w->mm = st->mm;
+    w->lofj = (int *)malloc(sizeof(int) * st->nlm);
+    w->legent = (float *)malloc(sizeof(float) * st->nstleg * (st->nleg + 2));
+    w->legent1 = (float *)malloc(sizeof(float) * st->nstleg * (st->nleg + 2));
+    w->sourcet = (float *)malloc(sizeof(float) * st->nstokes * st->nlm);
+    w->sourcet1 = (float *)malloc(sizeof(float) * st->nstokes * st->nlm);
+    for (l = 0; l <= st->ml; l++) {
+        int me = l < st->mm ? l : st->mm;
+        for (m = -me; m <= me; m++) { w->lofj[j] = l; j++; }
+    }
+}
+
+/* The source function of one point with the "new method" species mixing, as INTERPOLATE_POINT evaluates it for a
+ * new grid point (shdomsub1.f:5133-5211; the same arithmetic as COMPUTE_SOURCE's per-point block).  The point arrays
+ * of st have leading dimension ld (MAXIG inside SOLUTION_ITERATIONS).  sourcet[nstokes,nlm]. */
+void oracle_point_source(const oracle_state *st, int ld, int i, float *sourcet)
+{
+    src_work wk;
+    float secmu0 = 1.0f / fabsf(st->solarmu);
+    src_work_init(&wk, st);
+    point_source_ld(st, &wk, i, 1, secmu0, sourcet, ld);
+    free(wk.lofj); free(wk.legent); free(wk.legent1); free(wk.sourcet); free(wk.sourcet1);
 }
 
 /* COMPUTE_SOURCE  shdomsub1.f:967-1611.  st->shptr/st->source are ignored; the in/out arrays

@@ -28,7 +28,11 @@
  *   src/polarized/shdomsub1.f:2597-2669, shdomsub2.f:1222-1699, src/ocean_brdf.f
  *                                        VARIABLE_BRDF_SURFACE, SURFACE_BRDF and its models (oracle_surface.c)
  *   src/polarized/shdomsub1.f:445-4700 (parts), src/shdom_nompi.f:317-349
- *                                        fixed-grid SOLUTION_ITERATIONS / PATH_INTEGRATION (oracle_solver.c)
+ *                                        SOLUTION_ITERATIONS / PATH_INTEGRATION (oracle_solver.c)
+ *   src/polarized/shdomsub1.f:4703-5902, shdomsub2.f:614-1057, :1924-1987
+ *                                        SPLIT_GRID and helpers, INIT_RADIANCE, EDDRTF, INTERP_RADIANCE (oracle_adapt.c)
+ *   src/polarized/shdom90.f90:17-346, shdomsub2.f:313-612, shdomsub1.f:19-112
+ *                                        TRILIN_INTERP_PROP, INTERP_GRID, PREPARE_PROP, TRANSFER_PA_TO_GRID (oracle_prop.c)
  *
  * All arrays are in the reference's own layout: Fortran (column-major) order,
  * 1-based index CONTENTS (GRIDPTR, NEIGHPTR, IPHASE, BCPTR, INTERPPTR ... hold
@@ -189,6 +193,80 @@ int  oracle_path_integration_once(const oracle_state *st, const float *wtmu, con
                                   const int *rshptr, float *radiance, float *fluxes, float *bcrad, char *errmsg);
 int  oracle_surface_brdf(int sfctype, const float *refparms, float wavelen, float mu2, float phi2,
                          float mu1, float phi1, int nstokes, float *reflect /*REFLECT(4,4)*/);
+
+/* ---- property grid (ShdomPropertyArrays of at3d/solver.py:25-104) and the adaptive solve ---- */
+typedef struct {
+    int npx, npy, npz, numphase, nlegp, maxnmicro, npart, nzckd, nstleg;
+    float delx, dely, xstart, ystart;
+    const float *zlevels;     /* [npz] */
+    const float *tempp;       /* [maxpg] or NULL */
+    const float *extinctp;    /* [maxpg,npart] */
+    const float *albedop;     /* [maxpg,npart] */
+    const float *legenp;      /* [nstleg,0:nlegp,numphase] */
+    int *iphasep;             /* [maxnmicro,maxpg,npart] (sorted in place by the 'O' interpolation mode) */
+    float *phasewtp;          /* [maxnmicro,maxpg,npart] */
+    const float *zckd, *gasabs; /* [nzckd] */
+} oracle_prop;
+
+/* mutable arrays of SOLUTION_ITERATIONS; point arrays have leading dimension maxig */
+typedef struct {
+    int maxig, maxic, maxiv, maxido;
+    int npts, ncells, accelflag;
+    int *gridptr, *neighptr, *treeptr;
+    short *cellflags;
+    float *gridpos;
+    float *temp, *planck, *extinct, *albedo, *total_ext, *dirflux;
+    int *iphase;
+    float *phaseinterpwt;
+    int *shptr, *rshptr, *oshptr;
+    float *source, *radiance;
+    const oracle_prop *pg;
+    double extmin, scatmin;
+    double beam_d[13];
+    int beam_i[5];
+    const float *extdirp;
+} oracle_adapt;
+
+void oracle_ssort(float *x, int *y, int n, int kflag);
+void oracle_prop_extmin(const oracle_prop *pg, double *extmin, double *scatmin);
+int  oracle_trilin_interp_prop(const oracle_prop *pg, int ipa, float x, float y, float z, int interp_new,
+                               double extmin, double scatmin, float *temp, float *extinct, float *albedo,
+                               int *iphase, float *phaseinterpwt, float *kg, char *errmsg);
+float oracle_deltam_f(const float *legen, int nstleg, int nleg, int ml, const int *iphase, const float *pwt, int nq,
+                      int interp_new, float phasemax);
+int  oracle_transfer_pa_to_grid(const oracle_prop *pg, int npts, const float *gridpos, int ml, int nleg, int deltam,
+                                int interp_new, float phasemax, int srctype, int units, const float *waveno,
+                                float wavelen, float *temp, float *planck, float *extinct, float *albedo, float *legen,
+                                int *iphase, float *phaseinterpwt, float *total_ext, double *extmin,
+                                double *scatmin, float *albmax, char *errmsg);
+void oracle_point_source(const oracle_state *st, int ld, int i, float *sourcet);
+int  oracle_direct_beam_point(const double *out_d, const int *out_i, int bcflag, int npx, int npy, int npz,
+                              float xstart, float ystart, const float *zlevels, const float *extdirp,
+                              float solarflux, float x, float y, float z, float *dirflux, char *errmsg);
+void oracle_cell_split_test(const oracle_adapt *a, int nstokes, int icell, float *adaptcrit, float *maxadapt, int *idir);
+int  oracle_divide_cell(oracle_adapt *a, int icell, int idir, int newpoints[4][3]);
+int  oracle_split_grid(oracle_adapt *a, const oracle_state *cst, int dosplit, int *outofmem, float cursplitacc,
+                       float *splitcrit, char *errmsg);
+int  oracle_boundary_pnts(int npts, int nang, int lambertian, int maxnbc, int maxbcrad, float zbot, float ztop,
+                          const float *gridpos, int *ntoppts, int *nbotpts, int *bcptr);
+int  oracle_eddrtf(int nlayer, const float *optdepths, const float *albedos, const float *asymmetries,
+                   const float *temps, int deltam, int srctype, float solarflux, float solarmu, float gndtemp,
+                   float gndemis, float skyrad, int units, const float *waveno, float wavelen, float *fluxes,
+                   float surface_flux);
+int  oracle_init_radiance(const oracle_state *st, int ld, int nxy, int nz, const float *extinct, const float *albedo,
+                          const float *total_ext, const float *temp, const int *iphase, const float *phaseinterpwt,
+                          float skyrad, float surface_flux, int *rshptr, float *radiance);
+int  oracle_interp_radiance(int nstokes, int oldnpts, int nbcells, int ncells, const int *treeptr, const int *gridptr,
+                            const float *gridpos, int *rshptr, float *radiance);
+/* INIT_SOLUTION + SOLUTION_ITERATIONS with adaptive cell splitting (shdomsub1.f:113-822).  Every array of `st` that
+ * grows (grid, optics, SH arrays, fluxes, dirflux, bcptr, bcrad) must have the capacity given by the max* arguments,
+ * point arrays with leading dimension maxig; npts / ncells / ntoppts / nbotpts of `st` are updated.
+ * sizes[0..3] out: shptr[npts], rshptr[npts] totals, iterations, oldnpts. */
+int  oracle_solve_adaptive(oracle_state *st, oracle_prop *pg, const float *wtmu, float *temp,
+                           int maxig, int maxic, int maxiv, int maxido, int maxbcrad, int nbpts, int nbcells,
+                           int maxiter, float solacc, float splitacc, float shacc, int accelflag, int highorderrad,
+                           int iterfixsh, int inradflag, float *extdirp, int *iters_out, float *solcrit_out,
+                           float *splitcrit_out, char *errmsg);
 
 /* ---- helpers on the path ---- */
 int  oracle_update_costfunction(const double *stokesout, const double *raygrad_pixel,

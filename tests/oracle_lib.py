@@ -392,3 +392,129 @@ def radiance_truncation(state, shptr, radiance, rshptr, fixsh, shacc, highorderr
     if rc:
         raise OracleError('RADIANCE_TRUNCATION: out of memory')
     return out
+
+
+class OracleProp(C.Structure):
+    _fields_ = [(n, i32) for n in ('npx', 'npy', 'npz', 'numphase', 'nlegp', 'maxnmicro', 'npart', 'nzckd', 'nstleg')] + \
+               [(n, f32) for n in ('delx', 'dely', 'xstart', 'ystart')] + \
+               [(n, C.c_void_p) for n in ('zlevels', 'tempp', 'extinctp', 'albedop', 'legenp', 'iphasep', 'phasewtp',
+                                          'zckd', 'gasabs')]
+
+
+def _prop(pg, tempp=None, zckd=None, gasabs=None):
+    """oracle_prop view of a PropertyGrid; returns (struct, keep-alive list)."""
+    keep = [np.ascontiguousarray(pg.zlevels, np.float32), None if tempp is None else np.ascontiguousarray(tempp, np.float32),
+            None if zckd is None else np.ascontiguousarray(zckd, np.float32),
+            None if gasabs is None else np.ascontiguousarray(gasabs, np.float32)]
+    p = OracleProp(pg.npx, pg.npy, pg.npz, pg.numphase, pg.nlegp, pg.maxnmicro, pg.npart,
+                   0 if zckd is None else len(zckd), pg.nstleg, pg.delx, pg.dely, pg.xstart, pg.ystart,
+                   _vp(keep[0]), _vp(keep[1]), _vp(pg.extinctp), _vp(pg.albedop), _vp(pg.legenp), _vp(pg.iphasep),
+                   _vp(pg.phasewtp), _vp(keep[2]), _vp(keep[3]))
+    return p, keep
+
+
+def transfer_pa_to_grid(pg, gridpos, npts, ml, deltam, interp_new=True, phasemax=0.999, srctype='S', units='R',
+                        wavelen=0.0, tempp=None, zckd=None, gasabs=None):
+    """TRANSFER_PA_TO_GRID (oracle/oracle_prop.c) -> dict like at3d_b200.medium.transfer_pa_to_grid, plus temp/planck."""
+    p, keep = _prop(pg, tempp, zckd, gasabs)
+    nleg = ml + 1 if deltam else ml
+    nq = 8 * pg.maxnmicro
+    gp = np.asfortranarray(gridpos[:, :npts], np.float32)
+    out = dict(temp=np.zeros(npts, np.float32), planck=np.zeros((npts, pg.npart), np.float32, order='F'),
+               extinct=np.zeros((npts, pg.npart), np.float32, order='F'),
+               albedo=np.zeros((npts, pg.npart), np.float32, order='F'),
+               legen=np.zeros((pg.nstleg, nleg + 1, pg.numphase), np.float32, order='F'),
+               iphase=np.zeros((nq, npts, pg.npart), np.int32, order='F'),
+               phaseinterpwt=np.zeros((nq, npts, pg.npart), np.float32, order='F'),
+               total_ext=np.zeros(npts, np.float32))
+    extmin, scatmin, albmax = f64(0), f64(0), f32(0)
+    waveno = np.zeros(2, np.float32)
+    buf = C.create_string_buffer(600)
+    fn = lib().oracle_transfer_pa_to_grid
+    fn.argtypes = [P(OracleProp), i32, C.c_void_p, i32, i32, i32, i32, f32, i32, i32, C.c_void_p, f32] + \
+        [C.c_void_p] * 8 + [P(f64), P(f64), P(f32), C.c_char_p]
+    _check(fn(C.byref(p), npts, _vp(gp), ml, nleg, int(deltam), int(interp_new), phasemax, ord(srctype), ord(units),
+              _vp(waveno), wavelen, _vp(out['temp']), _vp(out['planck']), _vp(out['extinct']), _vp(out['albedo']),
+              _vp(out['legen']), _vp(out['iphase']), _vp(out['phaseinterpwt']), _vp(out['total_ext']),
+              C.byref(extmin), C.byref(scatmin), C.byref(albmax), buf), buf)
+    out.update(nleg=nleg, extmin=extmin.value, scatmin=scatmin.value, albmax=albmax.value)
+    return out
+
+
+def solve_adaptive(state, pg, wtmu, tempp=None, splitacc=0.03, shacc=0.0, solacc=1e-4, maxiter=100, accelflag=True,
+                   highorderrad=False, iterfixsh=30, adapt_grid_factor=5.0, num_sh_term_factor=1.0,
+                   cell_to_point_ratio=1.5, inradflag=True, temp=None):
+    """INIT_SOLUTION + SOLUTION_ITERATIONS with adaptive cell splitting (oracle/oracle_solver.c).  `state` holds the
+    base grid and the optical properties on it; array capacities follow RTE._setup_memory (at3d/solver.py:2286-2322).
+    Returns (solved state with the split grid, iters, solcrit, splitcrit)."""
+    st = state.copy().normalize()
+    ns, nbpts, nbcells, npart, nq = st.nstokes, st.npts, st.ncells, st.npart, 8 * st.maxnmicro
+    maxig = int(adapt_grid_factor * nbpts)
+    maxic = max(int(cell_to_point_ratio * maxig), nbcells)
+    maxiv = max(int(num_sh_term_factor * st.nlm * maxig), nbpts * 4)
+    maxido = maxig * st.nphi0max
+    maxnbc = int(maxig * 3 / st.nz)
+    lamb = st.sfctype1 in ('L', ord('L'))
+    maxbcrad = 2 * maxnbc if lamb else int((2 + st.nmu * st.nphi0max / 2) * maxnbc)
+
+    def grow(a, shape, dtype):
+        out = np.zeros(shape, dtype, order='F')
+        if a is not None:
+            a = np.asarray(a)
+            out[tuple(slice(0, s) for s in a.shape)] = a
+        return out
+    st.gridpos = grow(st.gridpos, (3, maxig), np.float32)
+    st.gridptr = grow(st.gridptr, (8, maxic), np.int32)
+    st.neighptr = grow(st.neighptr, (6, maxic), np.int32)
+    st.treeptr = grow(st.treeptr, (2, maxic), np.int32)
+    st.cellflags = grow(st.cellflags, (maxic,), np.int16)
+    st.extinct = grow(st.extinct, (maxig, npart), np.float32)
+    st.albedo = grow(st.albedo, (maxig, npart), np.float32)
+    st.planck = grow(st.planck, (maxig, npart), np.float32)
+    st.total_ext = grow(st.total_ext, (maxig,), np.float32)
+    st.iphase = grow(st.iphase, (nq, maxig, npart), np.int32)
+    st.iphase[st.iphase == 0] = 1
+    st.phaseinterpwt = grow(st.phaseinterpwt, (nq, maxig, npart), np.float32)
+    st.dirflux = np.zeros(maxig, np.float32)
+    st.fluxes = np.zeros((2, maxig), np.float32, order='F')
+    st.shptr = np.zeros(maxig + 1, np.int32)
+    st.rshptr = np.zeros(maxig + 2, np.int32)
+    st.source = np.zeros((ns, maxiv), np.float32, order='F')
+    st.radiance = np.zeros((ns, maxiv + maxig), np.float32, order='F')
+    st.bcptr = np.zeros((maxnbc, 2), np.int32, order='F')
+    st.maxnbc = maxnbc
+    st.bcrad = np.zeros((ns, maxbcrad), np.float32, order='F')
+    tgrid = grow(temp, (maxig,), np.float32)
+    extdirp = np.zeros(pg.maxpg, np.float32)
+    p, keep = _prop(pg, tempp)
+    d = st.fill(OracleState())
+    wtmu = np.ascontiguousarray(wtmu, np.float32)
+    iters, solcrit, splitcrit = i32(0), f32(0), f32(0)
+    buf = C.create_string_buffer(600)
+    fn = lib().oracle_solve_adaptive
+    fn.argtypes = [P(OracleState), P(OracleProp), C.c_void_p, C.c_void_p] + [i32] * 8 + [f32, f32, f32, i32, i32, i32, i32,
+                                                                                   C.c_void_p, P(i32), P(f32), P(f32),
+                                                                                   C.c_char_p]
+    _check(fn(C.byref(d), C.byref(p), _vp(wtmu), _vp(tgrid), maxig, maxic, maxiv, maxido, maxbcrad, nbpts, nbcells,
+              maxiter, solacc, splitacc, shacc, int(accelflag), int(highorderrad), iterfixsh, int(inradflag),
+              _vp(extdirp), C.byref(iters), C.byref(solcrit), C.byref(splitcrit), buf), buf)
+    npts, ncells = d.npts, d.ncells
+    st.npts, st.ncells, st.ntoppts, st.nbotpts = npts, ncells, d.ntoppts, d.nbotpts
+    st.gridpos = np.asfortranarray(st.gridpos[:, :npts])
+    for n in ('gridptr', 'neighptr', 'treeptr'):
+        setattr(st, n, np.asfortranarray(getattr(st, n)[:, :ncells]))
+    st.cellflags = st.cellflags[:ncells].copy()
+    for n in ('extinct', 'albedo', 'planck'):
+        setattr(st, n, np.asfortranarray(getattr(st, n)[:npts, :]))
+    for n in ('iphase', 'phaseinterpwt'):
+        setattr(st, n, np.asfortranarray(getattr(st, n)[:, :npts, :]))
+    st.total_ext = st.total_ext[:npts].copy()
+    st.dirflux = st.dirflux[:npts].copy()
+    st.fluxes = np.asfortranarray(st.fluxes[:, :npts])
+    st.shptr = st.shptr[:npts + 1].copy()
+    st.rshptr = st.rshptr[:npts + 2].copy()
+    st.source = np.asfortranarray(st.source[:, :max(int(st.shptr[npts]), 1)])
+    st.radiance = np.asfortranarray(st.radiance[:, :max(int(st.rshptr[npts]), 1)])
+    st.temp = tgrid[:npts].copy()
+    st.extdirp = extdirp
+    return st, iters.value, solcrit.value, splitcrit.value
