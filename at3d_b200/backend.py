@@ -103,7 +103,8 @@ def transfer_pa_to_grid(pg, gridpos, npts, ml, deltam, phasemax=0.999):
     is scaled on the host; everything per grid point runs in one kernel."""
     npart, mnm = pg.npart, pg.maxnmicro
     nq = 8 * mnm
-    extmin = 1.0e-5 / ((float(pg.zlevels[-1]) - float(pg.zlevels[0])) / pg.npz)
+    zl32 = np.asarray(pg.zlevels, np.float32)
+    extmin = float(np.float32(1.0e-5) / ((zl32[-1] - zl32[0]) / np.float32(pg.npz)))     # REAL arithmetic (shdom90.f90:73)
     nleg = ml + 1 if deltam else ml
     nleg = min(max(nleg, 1), pg.nlegp) if not deltam else nleg
     if pg.nlegp < nleg:
@@ -126,7 +127,7 @@ def transfer_pa_to_grid(pg, gridpos, npts, ml, deltam, phasemax=0.999):
         if pg.nstleg > 1:
             legen[1:4, :ml + 1, :] -= ftab[None, None, :]
     return dict(extinct=extinct, albedo=albedo, total_ext=total_ext, legen=legen, iphase=iphase, phaseinterpwt=pwt,
-                nleg=nleg, extmin=extmin, scatmin=0.1 * extmin)
+                nleg=nleg, extmin=extmin, scatmin=float(np.float32(0.1)) * extmin)
 
 
 def compute_source(state, shptr, source, oshptr, delsource, fixsh=False, shacc=0.0, maxiv=None, first=False,

@@ -84,6 +84,7 @@ cudaError_t tr_do_to_sh(const TrPlan *P, int npts, const int *rshptr_d, const fl
 // ---- COMPUTE_SOURCE on device-resident arrays (at3d_source.cu), shared with the solution iterations (at3d_solver.cu) ----
 struct CsArgs {
     int npts, nstokes, nstleg, nlm, ml, mm, nleg, npart, nq, srctype, deltam, interp_new, newmethod;
+    int ldp;                  // leading dimension of the per-species point arrays (0: npts)
     int first, accelflag, fixsh;
     float phasemax, secmu0, srcmin;
     const float *extinct, *albedo, *total_ext, *legen, *phaseinterpwt, *dirflux, *radiance, *ylmsun, *planck;
@@ -106,3 +107,31 @@ size_t cs_scan_bytes(int npts);
 int cs_grid_blocks(int npts);
 int cs_device_step(CsArgs &a, int nblk, void *scan_tmp, size_t tmpb, int *shptr_new, double *sums, int maxiv, size_t cap_new,
                    float *source_new, int *total_new_out, bool mix_ready, char *errmsg);
+
+// ---- TRILIN_INTERP_PROP on the device (at3d_prep.cu), shared with the adaptive solve (at3d_adapt.cu) ----
+#define TPA_MAXQ 32
+struct TpaArgs {
+    int first, count, ld, npart, mnm, npx, npy, npz, ml, deltam, interp_new, nzckd, srctype, units;
+    int prepare_prop;         // 1: TOTAL_EXT in the operation order of PREPARE_PROP (base grid), 0: of INTERPOLATE_POINT
+    float delx, dely, xstart, ystart, phasemax, wavelen;
+    double extmin, scatmin;
+    const float *gridpos, *zlevels, *tempp, *extinctp, *albedop, *ftab, *zckd, *gasabs;   // ftab[numphase] = LEGEN(1,ML+1,.)
+    const int *iphasep;
+    const float *phasewtp;
+    float *extinct, *albedo, *total_ext, *phaseinterpwt, *temp, *planck;
+    int *iphase, *bad;
+};
+
+cudaError_t launch_tpa(const TpaArgs &a, cudaStream_t s);
+void tpa_extmin(const float *zlevels, int npz, double *extmin, double *scatmin);
+cudaError_t launch_direct_points(const double *out_d, const int *out_i, int bcflag, int npx, int npy, int npz,
+                                 float xstart, float ystart, const float *zlevels_d, const float *gridpos_d,
+                                 const float *extdirp_d, float solarflux, float *dirflux_d, int count, int *flags_d,
+                                 cudaStream_t s);
+
+// ---- new grid points of SPLIT_GRID (INTERPOLATE_POINT, shdomsub1.f:5109-5211): radiance = mean of the two parents,
+// source function from it.  rec[k] = {ip1, ip2, ip, ir, nr, is, ns} (0-based points, SH offsets / lengths). ----
+struct NewPointRec { int ip1, ip2, ip, ir, nr, is, ns, pad; };
+cudaError_t cs_mix_points(CsArgs a, int first, int count, cudaStream_t s);
+cudaError_t launch_interp_points(const CsArgs &a, const NewPointRec *rec_d, int count, const int *rshptr_d, float *radiance,
+                                 float *source, cudaStream_t s);

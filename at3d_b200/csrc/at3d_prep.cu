@@ -551,6 +551,24 @@ extern "C" int at3d_make_direct(int npts, int bcflag, int ipflag, int deltam, in
     return 0;
 }
 
+// DIRECT_BEAM_PROP for `count` device-resident points (the call of INTERPOLATE_POINT, shdomsub1.f:5093-5107), with the
+// beam constants at3d_make_direct returned (out_d / out_i); flags[2] as in make_direct_kernel (flags[1] != 0: error).
+cudaError_t launch_direct_points(const double *out_d, const int *out_i, int bcflag, int npx, int npy, int npz,
+                                 float xstart, float ystart, const float *zlevels_d, const float *gridpos_d,
+                                 const float *extdirp_d, float solarflux, float *dirflux_d, int count, int *flags_d,
+                                 cudaStream_t s)
+{
+    if (count < 1) return cudaSuccess;
+    BeamGeom g;
+    g.bcflag = bcflag; g.npx = npx; g.npy = npy; g.npz = npz; g.xstart = xstart; g.ystart = ystart;
+    g.cx = out_d[0]; g.cy = out_d[1]; g.cz = out_d[2]; g.cxinv = out_d[3]; g.cyinv = out_d[4]; g.czinv = out_d[5];
+    g.epss = out_d[6]; g.epsz = out_d[7]; g.xdomain = out_d[8]; g.ydomain = out_d[9]; g.delxd = out_d[11]; g.delyd = out_d[12];
+    g.ipdirect = out_i[0]; g.di = out_i[1]; g.dj = out_i[2]; g.dk = out_i[3];
+    make_direct_kernel<<<(count + 127) / 128, 128, 0, s>>>(count, g, zlevels_d, gridpos_d, extdirp_d, solarflux, dirflux_d,
+                                                           flags_d, flags_d + 1);
+    return cudaGetLastError();
+}
+
 extern "C" int at3d_make_direct_derivative(int npts, int bcflag, int npx, int npy, int npz,
                                            float delx, float dely, float xstart, float ystart,
                                            const float *gridpos, const float *zlevels,
@@ -592,99 +610,210 @@ extern "C" int at3d_make_direct_derivative(int npts, int bcflag, int npx, int np
 // 8 property corners in corner order; duplicate phase-table entries merged into their first occurrence; stable sort by
 // descending weight; REAL arithmetic in the delta-M step).
 // ------------------------------------------------------------------------------------------
-#define TPA_MAXQ 32
-struct TpaArgs {
-    int npts, npart, mnm, npx, npy, npz, ml, deltam, nlt_stride;
-    float delx, dely, xstart, ystart, phasemax;
-    double extmin, scatmin;
-    const float *gridpos, *zlevels, *extinctp, *albedop, *phasewtp, *ftab;   // ftab[numphase] = LEGEN(1,ML+1,.)
-    const int *iphasep;
-    float *extinct, *albedo, *total_ext, *phaseinterpwt;
-    int *iphase, *bad;
-};
+// SSORT (src/polarized/shdomsub2.f:4961-5244; Singleton's quicksort, KFLAG=-2: decreasing X carrying Y) for the short
+// per-point lists of TRILIN_INTERP_PROP.  The order of equal keys follows the reference's algorithm, so IPHASE comes out
+// identical to the Fortran's, entries of weight zero included.  Arrays are 1-based inside, n <= TPA_MAXQ.
+__host__ __device__ inline void tpa_ssort_desc(float *x0, int *y0, int n)
+{
+    float *x = x0 - 1;
+    int *y = y0 - 1;
+    float r = 0.375f, t, tt;
+    int ty, tty, i = 1, j = n, k, l, m = 1, ij;
+    int il[24], iu[24];
+    if (n < 1) return;
+    for (k = 1; k <= n; k++) x[k] = -x[k];
+    int state = 110;     // the labels of the Fortran as a small state machine
+    for (;;) {
+        if (state == 110) {
+            if (i == j) { state = 150; continue; }
+            if (r <= 0.5898437f) r = r + 3.90625e-2f; else r = r - 0.21875f;
+            state = 120;
+        }
+        if (state == 120) {
+            k = i;
+            ij = i + (int)((j - i) * r);
+            t = x[ij]; ty = y[ij];
+            if (x[i] > t) { x[ij] = x[i]; x[i] = t; t = x[ij]; y[ij] = y[i]; y[i] = ty; ty = y[ij]; }
+            l = j;
+            if (x[j] < t) {
+                x[ij] = x[j]; x[j] = t; t = x[ij]; y[ij] = y[j]; y[j] = ty; ty = y[ij];
+                if (x[i] > t) { x[ij] = x[i]; x[i] = t; t = x[ij]; y[ij] = y[i]; y[i] = ty; ty = y[ij]; }
+            }
+            for (;;) {
+                do { l = l - 1; } while (x[l] > t);
+                do { k = k + 1; } while (x[k] < t);
+                if (k <= l) { tt = x[l]; x[l] = x[k]; x[k] = tt; tty = y[l]; y[l] = y[k]; y[k] = tty; }
+                else break;
+            }
+            if (l - i > j - k) { il[m] = i; iu[m] = l; i = k; m = m + 1; }
+            else { il[m] = k; iu[m] = j; j = l; m = m + 1; }
+            state = 160;
+        }
+        if (state == 150) {
+            m = m - 1;
+            if (m == 0) break;
+            i = il[m]; j = iu[m];
+            state = 160;
+        }
+        if (state == 160) {
+            if (j - i >= 1) { state = 120; continue; }
+            if (i == 1) { state = 110; continue; }
+            i = i - 1;
+            for (;;) {
+                i = i + 1;
+                if (i == j) break;
+                t = x[i + 1]; ty = y[i + 1];
+                if (x[i] <= t) continue;
+                k = i;
+                do { x[k + 1] = x[k]; y[k + 1] = y[k]; k = k - 1; } while (t < x[k]);
+                x[k + 1] = t; y[k + 1] = ty;
+            }
+            state = 150;
+        }
+    }
+    for (k = 1; k <= n; k++) x[k] = -x[k];
+}
 
+// TRILIN_INTERP_PROP (src/polarized/shdom90.f90:78-346) + the per-point delta-M scaling of PREPARE_PROP
+// (shdomsub2.f:554-571) / INTERPOLATE_POINT (shdomsub1.f:5063-5095), thread = grid point of [first, first+count).
+// Every expression keeps the reference's precision (REAL products, DOUBLE PRECISION interpolation factors), so the
+// outputs are bit-identical to the Fortran's for both INTERPMETHOD(2:2) modes.  Point arrays have leading dimension ld.
 __global__ void tpa_kernel(TpaArgs a)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= a.npts) return;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= a.count) return;
+    const int i = a.first + t;
     const float x = a.gridpos[3 * (size_t)i], y = a.gridpos[3 * (size_t)i + 1], z = a.gridpos[3 * (size_t)i + 2];
     const int npx = a.npx, npy = a.npy, npz = a.npz, mnm = a.mnm, nq = 8 * a.mnm;
-    // vertical: searchsorted(zlevels, z, side='right') clipped to [1, npz-1]
-    int lo = 0, hi = npz;
-    while (lo < hi) { const int mid = (lo + hi) >> 1; if (a.zlevels[mid] <= z) lo = mid + 1; else hi = mid; }
-    int iz = lo < 1 ? 1 : (lo > npz - 1 ? npz - 1 : lo);
-    double w = (double)(z - a.zlevels[iz - 1]) / (double)(a.zlevels[iz] - a.zlevels[iz - 1]);
-    w = fmin(fmax(w, 0.0), 1.0);
-    long ix = (long)((x - a.xstart) / a.delx) + 1;
-    if (fabsf(x - a.xstart - (float)npx * a.delx) < 0.01f * a.delx) ix = npx;
-    long iy = (long)((y - a.ystart) / a.dely) + 1;
-    if (fabsf(y - a.ystart - (float)npy * a.dely) < 0.01f * a.dely) iy = npy;
+    int il = 0, iu = npz;
+    while (iu - il > 1) { const int im = (iu + il) / 2; if (z >= a.zlevels[im - 1]) il = im; else iu = im; }
+    const int iz = il > 1 ? il : 1;
+    double w = (double)(z - a.zlevels[iz - 1]) / (a.zlevels[iz] - a.zlevels[iz - 1]);
+    w = fmax(fmin(w, 1.0), 0.0);
+    int ix = (int)((x - a.xstart) / a.delx) + 1;
+    if (fabsf(x - a.xstart - npx * a.delx) < 0.01f * a.delx) ix = npx;
+    int iy = (int)((y - a.ystart) / a.dely) + 1;
+    if (fabsf(y - a.ystart - npy * a.dely) < 0.01f * a.dely) iy = npy;
     if (ix < 1 || ix > npx) { atomicCAS(a.bad, 0, 1); return; }
     if (iy < 1 || iy > npy) { atomicCAS(a.bad, 0, 2); return; }
-    const long ixp = ix % npx + 1, iyp = iy % npy + 1;
-    double u = (double)(x - a.xstart - a.delx * (float)(ix - 1)) / (double)a.delx;
-    u = fmin(fmax(u, 0.0), 1.0); if (u < 1e-5) u = 0.0; if (u > 1 - 1e-5) u = 1.0;
-    double v = (double)(y - a.ystart - a.dely * (float)(iy - 1)) / (double)a.dely;
-    v = fmin(fmax(v, 0.0), 1.0); if (v < 1e-5) v = 0.0; if (v > 1 - 1e-5) v = 1.0;
-    long ptr[8];
-    ptr[0] = iz + (long)npz * (iy - 1) + (long)npz * npy * (ix - 1);
-    ptr[1] = iz + (long)npz * (iy - 1) + (long)npz * npy * (ixp - 1);
-    ptr[2] = iz + (long)npz * (iyp - 1) + (long)npz * npy * (ix - 1);
-    ptr[3] = iz + (long)npz * (iyp - 1) + (long)npz * npy * (ixp - 1);
+    const int ixp = ix % npx + 1, iyp = iy % npy + 1;
+    double u = (double)(x - a.xstart - a.delx * (ix - 1)) / a.delx;
+    u = fmax(fmin(u, 1.0), 0.0); if (u < 1.0e-5) u = 0.0; if (u > 1.0 - 1.0e-5) u = 1.0;
+    double v = (double)(y - a.ystart - a.dely * (iy - 1)) / a.dely;
+    v = fmax(fmin(v, 1.0), 0.0); if (v < 1.0e-5) v = 0.0; if (v > 1.0 - 1.0e-5) v = 1.0;
+    int ptr[8];
+    ptr[0] = iz + npz * (iy - 1) + npz * npy * (ix - 1);
+    ptr[1] = iz + npz * (iy - 1) + npz * npy * (ixp - 1);
+    ptr[2] = iz + npz * (iyp - 1) + npz * npy * (ix - 1);
+    ptr[3] = iz + npz * (iyp - 1) + npz * npy * (ixp - 1);
     for (int c = 0; c < 4; c++) ptr[4 + c] = ptr[c] + 1;
-    const double wt[8] = {(1 - u) * (1 - v) * (1 - w), u * (1 - v) * (1 - w), (1 - u) * v * (1 - w), u * v * (1 - w),
-                          (1 - u) * (1 - v) * w, u * (1 - v) * w, (1 - u) * v * w, u * v * w};
+    const double f[8] = {(1 - u) * (1 - v) * (1 - w), u * (1 - v) * (1 - w), (1 - u) * v * (1 - w), u * v * (1 - w),
+                         (1 - u) * (1 - v) * w, u * (1 - v) * w, (1 - u) * v * w, u * v * w};
     const size_t maxpg = (size_t)npx * npy * npz;
-    float esum = 0.0f;
+    float tempv = 0.0f;
+    if (a.tempp) {
+        const float *tp = a.tempp;
+        tempv = (float)(f[0] * tp[ptr[0] - 1] + f[1] * tp[ptr[1] - 1] + f[2] * tp[ptr[2] - 1] + f[3] * tp[ptr[3] - 1]
+                        + f[4] * tp[ptr[4] - 1] + f[5] * tp[ptr[5] - 1] + f[6] * tp[ptr[6] - 1] + f[7] * tp[ptr[7] - 1]);
+    }
+    if (a.temp) a.temp[i] = tempv;
+    float kg = 0.0f;
+    if (a.nzckd > 0) {
+        int jl = 1, ju = a.nzckd;
+        while (ju - jl > 1) { const int jm = (ju + jl) / 2; if (z <= a.zckd[jm - 1]) jl = jm; else ju = jm; }
+        int k = jl > 1 ? jl : 1;
+        if (k > a.nzckd - 1) k = a.nzckd - 1;
+        double ff = (z - a.zckd[k - 1]) / (a.zckd[k] - a.zckd[k - 1]);
+        ff = fmin(fmax(ff, 0.0), 1.0);
+        kg = (float)((1.0f - ff) * a.gasabs[k - 1] + ff * a.gasabs[k]);
+    }
+    float total = 0.0f, total_unscaled = 0.0f, sum_unscaled = 0.0f;
     for (int ipa = 0; ipa < a.npart; ipa++) {
-        double ext = 0.0, scatter = 0.0, scat8[8];
-        for (int c = 0; c < 8; c++) {
-            const double e = (double)a.extinctp[(ptr[c] - 1) + maxpg * ipa], al = (double)a.albedop[(ptr[c] - 1) + maxpg * ipa];
-            ext = ext + wt[c] * e;
-            scat8[c] = wt[c] * e * al;
-            scatter = scatter + scat8[c];
-        }
-        const double alb = ext > a.extmin ? scatter / fmax(ext, 1e-300) : scatter / a.extmin;
-        const double denom = scatter >= a.scatmin ? scatter : a.scatmin;
+        const float *extp = a.extinctp + maxpg * ipa, *albp = a.albedop + maxpg * ipa;
+        const int *iphp = a.iphasep + (size_t)mnm * maxpg * ipa;
+        const float *pwp = a.phasewtp + (size_t)mnm * maxpg * ipa;
+        double scat[8], scatter;
+        float extf = (float)(f[0] * extp[ptr[0] - 1] + f[1] * extp[ptr[1] - 1] + f[2] * extp[ptr[2] - 1] + f[3] * extp[ptr[3] - 1]
+                             + f[4] * extp[ptr[4] - 1] + f[5] * extp[ptr[5] - 1] + f[6] * extp[ptr[6] - 1] + f[7] * extp[ptr[7] - 1]);
+        for (int c = 0; c < 8; c++) scat[c] = f[c] * extp[ptr[c] - 1] * albp[ptr[c] - 1];
+        scatter = scat[0] + scat[1] + scat[2] + scat[3] + scat[4] + scat[5] + scat[6] + scat[7];
+        float albf = extf > a.extmin ? (float)(scatter / extf) : (float)(scatter / a.extmin);
         int ip[TPA_MAXQ];
-        double pw[TPA_MAXQ];
+        float pw[TPA_MAXQ];
         for (int c = 0; c < 8; c++)
-            for (int m = 0; m < mnm; m++) {
-                const size_t o = m + (size_t)mnm * ((ptr[c] - 1) + maxpg * ipa);
-                ip[c * mnm + m] = a.iphasep[o];
-                pw[c * mnm + m] = (double)a.phasewtp[o] * (scat8[c] / denom);
-            }
-        for (int q = 0; q < nq; q++)
-            for (int q2 = q + 1; q2 < nq; q2++)
-                if (ip[q] == ip[q2]) { pw[q] = pw[q] + pw[q2]; pw[q2] = 0.0; }
-        // stable insertion sort by descending weight
-        for (int q = 1; q < nq; q++) {
-            const int ipq = ip[q]; const double pwq = pw[q];
-            int k = q - 1;
-            while (k >= 0 && pw[k] < pwq) { ip[k + 1] = ip[k]; pw[k + 1] = pw[k]; k--; }
-            ip[k + 1] = ipq; pw[k + 1] = pwq;
+            for (int m = 0; m < mnm; m++) ip[c * mnm + m] = iphp[m + (size_t)mnm * (ptr[c] - 1)];
+        if (a.interp_new) {
+            const double den = scatter >= a.scatmin ? scatter : a.scatmin;
+            for (int c = 0; c < 8; c++)
+                for (int m = 0; m < mnm; m++) pw[c * mnm + m] = (float)(pwp[m + (size_t)mnm * (ptr[c] - 1)] * scat[c] / den);
+            for (int q = 0; q < nq; q++)
+                for (int q2 = q + 1; q2 < nq; q2++)
+                    if (ip[q] == ip[q2]) { pw[q] = pw[q] + pw[q2]; pw[q2] = 0.0f; }
+            tpa_ssort_desc(pw, ip, nq);
+        } else {
+            double maxscat = -1.0f;
+            for (int q = 0; q < nq; q++) pw[q] = 0.0f;
+            pw[0] = 1.0f;
+            for (int c = 0; c < 8; c++)
+                if (scat[c] > maxscat || fabs(f[c] - 1) < 0.001f) {
+                    // SSORT(PHASEWTP(:,I), IPHASEP(:,I), MAXNMICRO, -2): the dominant entry of the property point
+                    int best = 0;
+                    if (mnm > 1) {
+                        float xs[TPA_MAXQ / 8]; int ys[TPA_MAXQ / 8];
+                        for (int m = 0; m < mnm; m++) { xs[m] = pwp[m + (size_t)mnm * (ptr[c] - 1)]; ys[m] = iphp[m + (size_t)mnm * (ptr[c] - 1)]; }
+                        tpa_ssort_desc(xs, ys, mnm);
+                        best = ys[0];
+                    } else best = iphp[(size_t)mnm * (ptr[c] - 1)];
+                    maxscat = scat[c];
+                    ip[0] = best;
+                }
         }
-        float extf = (float)ext, albf = (float)alb;
-        const size_t po = (size_t)i + (size_t)a.npts * ipa;
-        float pwf[TPA_MAXQ];
+        const size_t po = (size_t)i + (size_t)a.ld * ipa;
+        if (ipa == 0) total_unscaled = total_unscaled + kg;
+        total_unscaled = total_unscaled + extf;
+        sum_unscaled = sum_unscaled + extf;
         for (int q = 0; q < nq; q++) {
-            pwf[q] = (float)pw[q];
             a.iphase[q + (size_t)nq * po] = ip[q];
-            a.phaseinterpwt[q + (size_t)nq * po] = pwf[q];
+            a.phaseinterpwt[q + (size_t)nq * po] = pw[q];
         }
         if (a.deltam) {
-            float f;
-            if (pwf[0] >= a.phasemax) f = a.ftab[ip[0] - 1];
-            else { f = 0.0f; for (int q = 0; q < nq; q++) f = f + a.ftab[ip[q] - 1] * pwf[q]; }
+            float fd;
+            if (!a.interp_new || pw[0] >= a.phasemax) fd = a.ftab[ip[0] - 1];
+            else { fd = 0.0f; for (int q = 0; q < nq; q++) fd = fd + a.ftab[ip[q] - 1] * pw[q]; }
             const float a0 = albf;
-            extf = (1.0f - a0 * f) * extf;
-            albf = (1.0f - f) * a0 / (1.0f - a0 * f);
+            extf = (1.0f - a0 * fd) * extf;
+            albf = (1.0f - fd) * a0 / (1.0f - a0 * fd);
         }
         a.extinct[po] = extf;
         a.albedo[po] = albf;
-        esum = esum + extf;
+        if (ipa == 0) total = total + kg;
+        total = total + extf;
+        if (a.planck && a.srctype != 'S') a.planck[po] = (1.0f - albf) * dev_planck(tempv, a.units, a.wavelen);
     }
-    a.total_ext[i] = esum;
+    if (a.prepare_prop && a.deltam) {
+        // PREPARE_PROP (shdomsub2.f:545-571): TOTAL_EXT - SUM(EXTINCT) of the unscaled values (clipped at 0; this is the gas
+        // absorption up to rounding), then the scaled extinctions are added
+        float t = total_unscaled - sum_unscaled;
+        if (t < 0.0f) t = 0.0f;
+        for (int ipa = 0; ipa < a.npart; ipa++) t = t + a.extinct[(size_t)i + (size_t)a.ld * ipa];
+        total = t;
+    }
+    a.total_ext[i] = total;
+}
+
+cudaError_t launch_tpa(const TpaArgs &a, cudaStream_t s)
+{
+    if (a.count < 1) return cudaSuccess;
+    tpa_kernel<<<(a.count + 127) / 128, 128, 0, s>>>(a);
+    return cudaGetLastError();
+}
+
+// EXTMIN, SCATMIN of TRILIN_INTERP_PROP(INIT=.TRUE.) (shdom90.f90:73-75): REAL arithmetic, then DOUBLE PRECISION
+void tpa_extmin(const float *zlevels, int npz, double *extmin, double *scatmin)
+{
+    const float e = 1.0e-5f / ((zlevels[npz - 1] - zlevels[0]) / npz);
+    *extmin = (double)e;
+    *scatmin = 0.1f * *extmin;
 }
 
 extern "C" int at3d_transfer_pa_to_grid(int npts, const float *gridpos, int npx, int npy, int npz, float delx, float dely,
@@ -704,13 +833,14 @@ extern "C" int at3d_transfer_pa_to_grid(int npts, const float *gridpos, int npx,
     Arena A;
     TpaArgs a;
     memset(&a, 0, sizeof(a));
-    a.npts = npts; a.npart = npart; a.mnm = maxnmicro; a.npx = npx; a.npy = npy; a.npz = npz; a.ml = ml; a.deltam = deltam;
+    a.first = 0; a.count = npts; a.ld = npts; a.interp_new = 1; a.srctype = 'S'; a.prepare_prop = 1;
+    a.npart = npart; a.mnm = maxnmicro; a.npx = npx; a.npy = npy; a.npz = npz; a.ml = ml; a.deltam = deltam;
     a.delx = delx; a.dely = dely; a.xstart = xstart; a.ystart = ystart; a.phasemax = phasemax;
-    a.extmin = 1.0e-5 / (((double)zlevels[npz - 1] - (double)zlevels[0]) / npz);
-    a.scatmin = 0.1 * a.extmin;
+    tpa_extmin(zlevels, npz, &a.extmin, &a.scatmin);
     a.gridpos = A.up(gridpos, (size_t)3 * npts); a.zlevels = A.up(zlevels, npz);
     a.extinctp = A.up(extinctp, maxpg * npart); a.albedop = A.up(albedop, maxpg * npart);
-    a.iphasep = A.up(iphasep, (size_t)maxnmicro * maxpg * npart); a.phasewtp = A.up(phasewtp, (size_t)maxnmicro * maxpg * npart);
+    a.iphasep = A.up(iphasep, (size_t)maxnmicro * maxpg * npart);
+    a.phasewtp = A.up(phasewtp, (size_t)maxnmicro * maxpg * npart);
     a.ftab = deltam ? A.up(ftab, numphase) : nullptr;
     a.extinct = A.alloc<float>((size_t)npts * npart); a.albedo = A.alloc<float>((size_t)npts * npart);
     a.total_ext = A.alloc<float>(npts);
@@ -719,7 +849,7 @@ extern "C" int at3d_transfer_pa_to_grid(int npts, const float *gridpos, int npx,
     if (!a.gridpos || !a.zlevels || !a.extinctp || !a.albedop || !a.iphasep || !a.phasewtp || (deltam && !a.ftab) || !a.extinct ||
         !a.albedo || !a.total_ext || !a.iphase || !a.phaseinterpwt || !a.bad) { set_msg(errmsg, "device allocation failure"); return 4; }
     cudaMemset(a.bad, 0, sizeof(int));
-    tpa_kernel<<<(npts + 127) / 128, 128>>>(a);
+    launch_tpa(a, 0);
     int bad = 0;
     cudaError_t e = cudaMemcpy(&bad, a.bad, sizeof(int), cudaMemcpyDeviceToHost);
     if (e == cudaSuccess) e = cudaMemcpy(extinct, a.extinct, (size_t)npts * npart * sizeof(float), cudaMemcpyDeviceToHost);

@@ -1073,14 +1073,18 @@ extern "C" int at3d_solver_create(const at3d_state_desc *d, const float *wtmu, f
     const bool want_levels = lenv ? atoi(lenv) != 0 : true;
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
-    if (want_levels && npts < (1 << 24) && nkeys * 32 < free_b / 2) {
+    // key = ordinate << 48 | level << 24 | position: the sort must cover every ordinate bit (NMU=32 / NPHI=64 has ~1600
+    // ordinates), so the end bit follows NANG; NANG is limited by the 16 bits above bit 48
+    int key_end_bit = 49;
+    while (key_end_bit < 64 && (1ull << (key_end_bit - 48)) < (unsigned long long)nang) key_end_bit++;
+    if (want_levels && npts < (1 << 24) && nang < 65536 && nkeys * 32 < free_b / 2) {
         Arena T;
         int *level = T.alloc<int>(nkeys);
         unsigned long long *k0 = T.alloc<unsigned long long>(nkeys), *k1 = T.alloc<unsigned long long>(nkeys);
         int2 *plan = A.alloc<int2>(nkeys);
         unsigned char *nwalk = T.alloc<unsigned char>(nkeys);
         size_t tmpb = 0;
-        cub::DeviceRadixSort::SortKeys(nullptr, tmpb, k0, k1, nkeys, 0, 57, 0);
+        cub::DeviceRadixSort::SortKeys(nullptr, tmpb, k0, k1, nkeys, 0, key_end_bit, 0);
         char *tmp = T.alloc<char>(tmpb);
         cudaError_t e = cudaSuccess;
         if (!level || !k0 || !k1 || !plan || !nwalk || !tmp) { at3d_solver_destroy(sv); set_msg(errmsg, "device allocation failure"); return 4; }
@@ -1096,7 +1100,7 @@ extern "C" int at3d_solver_create(const at3d_state_desc *d, const float *wtmu, f
         }
         lap("level pass");
         sweep3d_key_kernel<<<nb, 256>>>(w, k0);
-        cub::DeviceRadixSort::SortKeys(tmp, tmpb, k0, k1, nkeys, 0, 57, 0);
+        cub::DeviceRadixSort::SortKeys(tmp, tmpb, k0, k1, nkeys, 0, key_end_bit, 0);
         sweep3d_plan_kernel<<<nb, 256>>>(w, k1, plan);
         int err = 0;
         e = cudaDeviceSynchronize();
@@ -1218,6 +1222,7 @@ extern "C" int at3d_solver_path_integration(at3d_solver *sv, const int32_t *shpt
 // ---------------------------------------------------------------------------------------------------------------------
 struct RtArgs {
     int npts, ml, mm, nstleg, nleg, npart, nq, nstokes, interp_new, deltam, highorderrad;
+    int ldp;                // leading dimension of the per-species point arrays (0: npts)
     float phasemax, shacc;
     const float *total_ext, *extinct, *albedo, *legen, *phaseinterpwt, *radiance;
     const int *iphase, *shptr, *rshptr_old, *lofj;
@@ -1248,7 +1253,7 @@ __global__ void rt_adaptive_kernel(RtArgs a)
         for (int l = 1; l <= ml; l++) {
             float rad = 0.0f;
             for (int ipa = 0; ipa < a.npart; ipa++) {
-                const size_t po = (size_t)i + (size_t)a.npts * ipa;
+                const size_t po = (size_t)i + (size_t)(a.ldp ? a.ldp : a.npts) * ipa;
                 const float w = ext == 0.0f ? 1.0f : a.extinct[po] / ext;
                 if (w == 0.0f) continue;
                 const int *iph = a.iphase + (size_t)nq * po;
@@ -1499,5 +1504,438 @@ extern "C" int at3d_solver_solve(at3d_solver *sv, const at3d_state_desc *d, int 
     if (iters_out) *iters_out = iter;
     if (solcrit_out) *solcrit_out = solcrit;
     if (ms_out) { ms_out[0] = ms_path; ms_out[1] = ms_src; ms_out[2] = ms_all; }
+    return rc;
+}
+
+// =====================================================================================================================
+// The adaptive solve: INIT_SOLUTION + SOLUTION_ITERATIONS with SPLIT_GRID (shdomsub1.f:113-822, :4703-5902).
+// The loop of at3d_solver_solve with every array at its RTE._setup_memory capacity, the Eddington first guess
+// (INIT_RADIANCE), and -- between iterations -- the cell splitting of at3d_adapt.cu.  When the grid has grown, the sweep
+// structures (order, levels, plan records, boundary lists) are rebuilt for the new grid by at3d_solver_create.
+// =====================================================================================================================
+#include "at3d_adapt.h"
+
+namespace {
+struct AdaptCtx {
+    const at3d_state_desc *d;
+    const at3d_prop_desc *pg;
+    at3d_adapt_io *io;
+    AdaptGrid *G;
+    CsArgs *cs;
+    TpaArgs tpa;
+    int npts_done, ncells_done, nst, nq, npart, maxig;
+    float *gridpos_d; int *gridptr_d;
+    float *extinct_d, *albedo_d, *planck_d, *temp_d, *total_ext_d, *pwt_d, *dirflux_d;
+    int *iphase_d;
+    const float *zlevels_d, *extdirp_d;
+    int *flags_d;
+    double beam_d[13]; int beam_i[5];
+    int **sh, *cur, **rsh, *rcur, *osh, osh_end;
+    float **src, *rad;
+    DevBuf recs;
+};
+
+int adapt_interpolate_cb(void *arg, const std::vector<NewPointRec> &recs, char *errmsg)
+{
+    AdaptCtx &c = *(AdaptCtx *)arg;
+    AdaptGrid &G = *c.G;
+    const int p0 = c.npts_done, p1 = G.npts, np = p1 - p0, c0 = c.ncells_done, c1 = G.ncells, nst = c.nst;
+    if (np != (int)recs.size()) { set_msg(errmsg, "SPLIT_GRID: new point bookkeeping mismatch"); return 1; }
+    cudaError_t e = cudaSuccess;
+    auto ok = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
+    ok(cudaMemcpy(c.gridptr_d + (size_t)8 * c0, G.gridptr + (size_t)8 * c0, (size_t)8 * (c1 - c0) * sizeof(int), cudaMemcpyHostToDevice));
+    c.ncells_done = c1;
+    if (np == 0) { if (e != cudaSuccess) { set_msg(errmsg, "CUDA error %s in SPLIT_GRID", cudaGetErrorString(e)); return 4; } return 0; }
+    ok(cudaMemcpy(c.gridpos_d + (size_t)3 * p0, G.gridpos + (size_t)3 * p0, (size_t)3 * np * sizeof(float), cudaMemcpyHostToDevice));
+    // medium properties of the new points from the property grid (TRILIN_INTERP_PROP + delta-M), Planck source, direct beam
+    c.tpa.first = p0; c.tpa.count = np;
+    ok(cudaMemsetAsync(c.flags_d, 0, 3 * sizeof(int), 0));
+    ok(launch_tpa(c.tpa, 0));
+    if (c.d->srctype != 'T')
+        ok(launch_direct_points(c.beam_d, c.beam_i, c.d->bcflag, c.pg->npx, c.pg->npy, c.pg->npz, c.pg->xstart, c.pg->ystart, c.zlevels_d,
+                                c.gridpos_d + (size_t)3 * p0, c.extdirp_d, c.d->solarflux, c.dirflux_d + p0, np, c.flags_d + 1, 0));
+    // SH pointers of the new points (assigned on the host in creation order), zero-length DELSOURCE ranges
+    ok(cudaMemcpyAsync(c.sh[*c.cur] + p0 + 1, G.shptr.data() + p0 + 1, (size_t)np * sizeof(int), cudaMemcpyHostToDevice, 0));
+    G.rshptr[p1 + 1] = G.rshptr[p1];
+    ok(cudaMemcpyAsync(c.rsh[*c.rcur] + p0 + 1, G.rshptr.data() + p0 + 1, (size_t)(np + 1) * sizeof(int), cudaMemcpyHostToDevice, 0));
+    {
+        std::vector<int> fill(np, c.osh_end);
+        ok(cudaMemcpy(c.osh + p0 + 1, fill.data(), (size_t)np * sizeof(int), cudaMemcpyHostToDevice));
+    }
+    if (c.recs.reserve(recs.size() * sizeof(NewPointRec)) != cudaSuccess) { set_msg(errmsg, "SPLIT_GRID: device allocation failure"); return 4; }
+    ok(cudaMemcpy(c.recs.p, recs.data(), recs.size() * sizeof(NewPointRec), cudaMemcpyHostToDevice));
+    // radiance = mean of the parents, source function from it
+    CsArgs a = *c.cs;
+    a.npts = p1;
+    ok(cs_mix_points(a, p0, np, 0));
+    ok(launch_interp_points(a, (const NewPointRec *)c.recs.p, np, c.rsh[*c.rcur], c.rad, c.src[*c.cur], 0));
+    // host copies of the new points' properties (sweep set-up, the caller's arrays)
+    int hf[3] = {0, 0, 0};
+    ok(cudaMemcpy(hf, c.flags_d, sizeof(hf), cudaMemcpyDeviceToHost));
+    ok(cudaMemcpy(c.io->total_ext + p0, c.total_ext_d + p0, (size_t)np * sizeof(float), cudaMemcpyDeviceToHost));
+    ok(cudaMemcpy(c.io->dirflux + p0, c.dirflux_d + p0, (size_t)np * sizeof(float), cudaMemcpyDeviceToHost));
+    if (c.io->temp) ok(cudaMemcpy(c.io->temp + p0, c.temp_d + p0, (size_t)np * sizeof(float), cudaMemcpyDeviceToHost));
+    for (int ipa = 0; ipa < c.npart; ipa++) {
+        const size_t o = (size_t)c.maxig * ipa + p0;
+        ok(cudaMemcpy(c.io->extinct + o, c.extinct_d + o, (size_t)np * sizeof(float), cudaMemcpyDeviceToHost));
+        ok(cudaMemcpy(c.io->albedo + o, c.albedo_d + o, (size_t)np * sizeof(float), cudaMemcpyDeviceToHost));
+        if (c.io->planck && c.planck_d) ok(cudaMemcpy(c.io->planck + o, c.planck_d + o, (size_t)np * sizeof(float), cudaMemcpyDeviceToHost));
+        ok(cudaMemcpy(c.io->iphase + (size_t)c.nq * o, c.iphase_d + (size_t)c.nq * o, (size_t)c.nq * np * sizeof(int), cudaMemcpyDeviceToHost));
+        ok(cudaMemcpy(c.io->phaseinterpwt + (size_t)c.nq * o, c.pwt_d + (size_t)c.nq * o, (size_t)c.nq * np * sizeof(float), cudaMemcpyDeviceToHost));
+    }
+    if (e != cudaSuccess) { set_msg(errmsg, "CUDA error %s in INTERPOLATE_POINT", cudaGetErrorString(e)); return 4; }
+    if (hf[0]) { set_msg(errmsg, hf[0] == 1 ? "TRILIN: Beyond X domain" : "TRILIN: Beyond Y domain"); return 1; }
+    if (hf[2]) { set_msg(errmsg, "DIRECT_BEAM_PROP failed for a new grid point (code %d)", hf[2] & 7); return 1; }
+    (void)nst;
+    c.npts_done = p1;
+    return 0;
+}
+
+float host_planck(float temp, int units, float wavelen)
+{
+    if (units == 'T') return temp;
+    if (temp > 0.0f) return 1.1911e8f / (wavelen * wavelen * wavelen * wavelen * wavelen) / (expf(1.4388e4f / (wavelen * temp)) - 1);
+    return 0.0f;
+}
+
+// SURFACE_PARM_INTERP (shdomsub1.f:2221-2275) on the host: a few parameters per bottom point
+void surface_parm_interp(int nbot, const int *bcptr_bot, const float *gridpos, int srctype, int units, float wavelen, int nxsfc, int nysfc,
+                         float delxsfc, float delysfc, int nsfcpar, const float *sfcparms, float *out)
+{
+    for (int ibc = 0; ibc < nbot; ibc++) {
+        const int i = bcptr_bot[ibc];
+        const float rx = gridpos[3 * (size_t)(i - 1)] / delxsfc, ry = gridpos[1 + 3 * (size_t)(i - 1)] / delysfc;
+        const int ix = std::max(1, std::min(nxsfc, (int)rx + 1)), iy = std::max(1, std::min(nysfc, (int)ry + 1));
+        const float u = fmaxf(0.0f, fminf(1.0f, rx - (ix - 1))), v = fmaxf(0.0f, fminf(1.0f, ry - (iy - 1)));
+        auto P = [&](int j, int x, int y) { return sfcparms[j + (size_t)nsfcpar * ((x - 1) + (size_t)(nxsfc + 1) * (y - 1))]; };
+        for (int j = 0; j < nsfcpar; j++)
+            out[j + (size_t)nsfcpar * ibc] = (1 - u) * (1 - v) * P(j, ix, iy) + (1 - u) * v * P(j, ix, iy + 1)
+                                             + u * (1 - v) * P(j, ix + 1, iy) + u * v * P(j, ix + 1, iy + 1);
+        out[(size_t)nsfcpar * ibc] = srctype == 'S' ? 0.0f : host_planck(out[(size_t)nsfcpar * ibc], units, wavelen);
+    }
+}
+}  // namespace
+
+extern "C" int at3d_solve_adaptive(const at3d_state_desc *d, const at3d_prop_desc *pg, const float *wtmu, at3d_adapt_io *io,
+                                   double *ms_out, char *errmsg)
+{
+    if (errmsg) errmsg[0] = 0;
+    if (!d || !pg || !wtmu || !io) { set_msg(errmsg, "null argument"); return 1; }
+    if (!io->gridpos || !io->gridptr || !io->neighptr || !io->treeptr || !io->cellflags || !io->extinct || !io->albedo || !io->total_ext ||
+        !io->dirflux || !io->fluxes || !io->iphase || !io->phaseinterpwt || !io->shptr || !io->rshptr || !io->source || !io->radiance ||
+        !io->bcptr || !io->bcrad || !io->extdirp) { set_msg(errmsg, "at3d_solve_adaptive: null array in at3d_adapt_io"); return 1; }
+    if (at3d_device_count() < 1) { set_msg(errmsg, "no CUDA device: at3d_b200 has no CPU fallback"); return 4; }
+    if ((d->ipflag & 3) == 3) { set_msg(errmsg, "at3d_solve_adaptive: independent-pixel grids (IPFLAG=3) take at3d_solver_solve"); return 3; }
+    if (d->npts != io->nbpts || d->ncells != io->nbcells) { set_msg(errmsg, "at3d_solve_adaptive: the solve must start from the base grid"); return 3; }
+    if (d->sfctype0 == 'V' && io->splitacc > 0.0f && (!io->sfcparms || !io->sfcgridparms)) {
+        set_msg(errmsg, "at3d_solve_adaptive: a variable surface needs SFCPARMS to place new bottom points"); return 1;
+    }
+    const int nst = d->nstokes, npart = d->npart, nq = 8 * d->maxnmicro, nlm = d->nlm;
+    const int maxig = io->maxig, maxic = io->maxic, maxiv = io->maxiv;
+    const size_t nlt = (size_t)d->nstleg * (d->nleg + 1), maxir = (size_t)maxiv + maxig;
+    if (nlt > 256) { set_msg(errmsg, "COMPUTE_SOURCE: Legendre table longer than 256 entries"); return 3; }
+    if (8 * d->maxnmicro > TPA_MAXQ) { set_msg(errmsg, "at3d_solve_adaptive: MAXNMICRO > %d", TPA_MAXQ / 8); return 3; }
+    if (maxig < d->npts || maxic < d->ncells || (size_t)4 * d->npts > (size_t)maxiv) { set_msg(errmsg, "MAXIG / MAXIC / MAXIV too small"); return 2; }
+    const bool lamb = d->sfctype1 == 'L';
+    const double t_begin = wall_ms();
+    double ms_split = 0.0;
+    int rc = 0;
+    // ---- MAKE_DIRECT on the base grid (also EXTDIRP and the beam constants for the new points) ----
+    AdaptCtx ctx;
+    memset(ctx.beam_d, 0, sizeof(ctx.beam_d)); memset(ctx.beam_i, 0, sizeof(ctx.beam_i));
+    if (d->srctype != 'T') {
+        rc = at3d_make_direct(d->npts, d->bcflag, d->ipflag, d->deltam, d->ml, d->nstleg, pg->nlegp, d->solarflux, d->solarmu, d->solaraz,
+                              io->gridpos, pg->npx, pg->npy, pg->npz, pg->delx, pg->dely, pg->xstart, pg->ystart, pg->zlevels, pg->extinctp,
+                              pg->albedop, pg->legenp, pg->numphase, pg->iphasep, pg->phasewtp, pg->maxnmicro, npart, pg->nzckd, pg->zckd,
+                              pg->gasabs, io->extdirp, io->dirflux, ctx.beam_d, ctx.beam_i, errmsg);
+        if (rc) return rc;
+    } else {
+        for (int i = 0; i < d->npts; i++) io->dirflux[i] = 0.0f;
+    }
+    AdaptGrid G;
+    G.maxig = maxig; G.maxic = maxic; G.maxiv = maxiv; G.maxido = io->maxido; G.npts = d->npts; G.ncells = d->ncells;
+    G.gridptr = io->gridptr; G.neighptr = io->neighptr; G.treeptr = io->treeptr; G.cellflags = io->cellflags; G.gridpos = io->gridpos;
+    G.shptr.assign((size_t)maxig + 2, 0); G.rshptr.assign((size_t)maxig + 3, 0);
+    // ---- device arrays at their capacities ----
+    Arena A;
+    const size_t maxpg = (size_t)pg->npx * pg->npy * pg->npz;
+    float *gridpos_d = A.alloc<float>((size_t)3 * maxig), *total_ext_d = A.alloc<float>(maxig), *dirflux_d = A.alloc<float>(maxig);
+    float *temp_d = A.alloc<float>(maxig);
+    float *extinct_d = A.alloc<float>((size_t)maxig * npart), *albedo_d = A.alloc<float>((size_t)maxig * npart);
+    float *planck_d = (io->planck && d->srctype != 'S') ? A.alloc<float>((size_t)maxig * npart) : nullptr;
+    int *iphase_d = A.alloc<int>((size_t)nq * maxig * npart);
+    float *pwt_d = A.alloc<float>((size_t)nq * maxig * npart);
+    int *gridptr_d = A.alloc<int>((size_t)8 * maxic);
+    std::vector<float> ftab(d->numphase > 0 ? d->numphase : 1, 0.0f);
+    for (int i = 0; i < d->numphase; i++) ftab[i] = d->legen[nlt * i + (size_t)d->nstleg * (d->ml + 1 <= d->nleg ? d->ml + 1 : d->nleg)];
+    std::vector<int> lofj(nlm);
+    {
+        int j = 0;
+        for (int l = 0; l <= d->ml; l++) { const int me = l < d->mm ? l : d->mm; for (int m = -me; m <= me; m++) { if (j < nlm) lofj[j] = l; j++; } }
+        if (j != nlm) { set_msg(errmsg, "NLM inconsistent with ML, MM"); return 1; }
+    }
+    CsArgs a;
+    memset(&a, 0, sizeof(a));
+    a.npts = G.npts; a.ldp = maxig; a.nstokes = nst; a.nstleg = d->nstleg; a.nlm = nlm; a.ml = d->ml; a.mm = d->mm; a.nleg = d->nleg;
+    a.npart = npart; a.nq = nq; a.srctype = d->srctype; a.deltam = d->deltam; a.interp_new = d->interp_new;
+    a.newmethod = 1; a.accelflag = io->accelflag;
+    a.phasemax = d->phasemax; a.secmu0 = 1.0f / fabsf(d->solarmu); a.srcmin = io->shacc;
+    a.extinct = extinct_d; a.albedo = albedo_d; a.total_ext = total_ext_d; a.iphase = iphase_d; a.phaseinterpwt = pwt_d; a.dirflux = dirflux_d;
+    a.planck = planck_d;
+    a.legen = A.up(d->legen, nlt * d->numphase);
+    a.ylmsun = A.up(d->ylmsun, (size_t)d->nstleg * nlm);
+    a.lofj = A.up(lofj.data(), lofj.size());
+    const int nblk_max = cs_grid_blocks(maxig);
+    size_t tmpb = cs_scan_bytes(maxig + 1);
+    void *tmp = A.alloc<unsigned char>(tmpb);
+    a.ns_new = A.alloc<int>((size_t)maxig + 1);
+    a.partials = A.alloc<double>((size_t)nblk_max * 4);
+    a.bad = A.alloc<int>(2);
+    double *sums = A.alloc<double>(4);
+    a.mix_legent = A.alloc<float>((size_t)maxig * nlt);
+    a.mix_ap = A.alloc<float2>((size_t)maxig);
+    float *src[2] = {A.alloc<float>((size_t)nst * maxiv), A.alloc<float>((size_t)nst * maxiv)};
+    float *dels = A.alloc<float>((size_t)nst * maxiv);
+    float *rad = A.alloc<float>((size_t)nst * maxir);
+    int *sh[2] = {A.alloc<int>((size_t)maxig + 2), A.alloc<int>((size_t)maxig + 2)};
+    int *osh = A.alloc<int>((size_t)maxig + 2);
+    int *rsh[2] = {A.alloc<int>((size_t)maxig + 3), A.alloc<int>((size_t)maxig + 3)};
+    int *nr = A.alloc<int>((size_t)maxig + 2);
+    int *flags_d = A.alloc<int>(3);
+    const float *zgrid_d = A.up(d->zgrid, d->nz);
+    // property grid on the device (TRILIN_INTERP_PROP / DIRECT_BEAM_PROP of the new points)
+    TpaArgs &tp = ctx.tpa;
+    memset(&tp, 0, sizeof(tp));
+    tp.ld = maxig; tp.npart = npart; tp.mnm = pg->maxnmicro; tp.npx = pg->npx; tp.npy = pg->npy; tp.npz = pg->npz; tp.ml = d->ml;
+    tp.deltam = d->deltam; tp.interp_new = d->interp_new; tp.nzckd = pg->nzckd; tp.srctype = d->srctype; tp.units = d->units;
+    tp.delx = pg->delx; tp.dely = pg->dely; tp.xstart = pg->xstart; tp.ystart = pg->ystart; tp.phasemax = d->phasemax; tp.wavelen = d->wavelen;
+    tpa_extmin(pg->zlevels, pg->npz, &tp.extmin, &tp.scatmin);
+    tp.gridpos = gridpos_d; tp.zlevels = A.up(pg->zlevels, pg->npz);
+    tp.tempp = pg->tempp ? A.up(pg->tempp, maxpg) : nullptr;
+    tp.extinctp = A.up(pg->extinctp, maxpg * npart); tp.albedop = A.up(pg->albedop, maxpg * npart);
+    tp.iphasep = A.up(pg->iphasep, (size_t)pg->maxnmicro * maxpg * npart); tp.phasewtp = A.up(pg->phasewtp, (size_t)pg->maxnmicro * maxpg * npart);
+    tp.ftab = A.up(ftab.data(), ftab.size());
+    tp.zckd = pg->nzckd > 0 ? A.up(pg->zckd, pg->nzckd) : nullptr; tp.gasabs = pg->nzckd > 0 ? A.up(pg->gasabs, pg->nzckd) : nullptr;
+    tp.extinct = extinct_d; tp.albedo = albedo_d; tp.total_ext = total_ext_d; tp.phaseinterpwt = pwt_d; tp.temp = temp_d; tp.planck = planck_d;
+    tp.iphase = iphase_d; tp.bad = flags_d;
+    const float *extdirp_d = A.up(io->extdirp, maxpg);
+    if (!gridpos_d || !total_ext_d || !dirflux_d || !temp_d || !extinct_d || !albedo_d || !iphase_d || !pwt_d || !gridptr_d || !a.legen ||
+        !a.ylmsun || !a.lofj || !tmp || !a.ns_new || !a.partials || !a.bad || !sums || !a.mix_legent || !a.mix_ap || !src[0] || !src[1] ||
+        !dels || !rad || !sh[0] || !sh[1] || !osh || !rsh[0] || !rsh[1] || !nr || !flags_d || !zgrid_d || !tp.zlevels || !tp.extinctp ||
+        !tp.albedop || !tp.iphasep || !tp.phasewtp || !tp.ftab || !extdirp_d || (io->planck && d->srctype != 'S' && !planck_d)) {
+        set_msg(errmsg, "at3d_solve_adaptive: device allocation failure"); return 4;
+    }
+    {
+        const int n0 = G.npts;
+        cudaMemcpy(gridpos_d, io->gridpos, (size_t)3 * n0 * sizeof(float), cudaMemcpyHostToDevice);
+        cudaMemcpy(gridptr_d, io->gridptr, (size_t)8 * G.ncells * sizeof(int), cudaMemcpyHostToDevice);
+        cudaMemcpy(total_ext_d, io->total_ext, (size_t)n0 * sizeof(float), cudaMemcpyHostToDevice);
+        cudaMemcpy(dirflux_d, io->dirflux, (size_t)n0 * sizeof(float), cudaMemcpyHostToDevice);
+        if (io->temp) cudaMemcpy(temp_d, io->temp, (size_t)n0 * sizeof(float), cudaMemcpyHostToDevice);
+        else cudaMemset(temp_d, 0, (size_t)maxig * sizeof(float));
+        for (int ipa = 0; ipa < npart; ipa++) {
+            const size_t o = (size_t)maxig * ipa;
+            cudaMemcpy(extinct_d + o, io->extinct + o, (size_t)n0 * sizeof(float), cudaMemcpyHostToDevice);
+            cudaMemcpy(albedo_d + o, io->albedo + o, (size_t)n0 * sizeof(float), cudaMemcpyHostToDevice);
+            if (planck_d) cudaMemcpy(planck_d + o, io->planck + o, (size_t)n0 * sizeof(float), cudaMemcpyHostToDevice);
+            cudaMemcpy(iphase_d + (size_t)nq * o, io->iphase + (size_t)nq * o, (size_t)nq * n0 * sizeof(int), cudaMemcpyHostToDevice);
+            cudaMemcpy(pwt_d + (size_t)nq * o, io->phaseinterpwt + (size_t)nq * o, (size_t)nq * n0 * sizeof(float), cudaMemcpyHostToDevice);
+        }
+    }
+    float albmax = 0.0f;
+    for (int ipa = 0; ipa < npart; ipa++)
+        for (int i = 0; i < G.npts; i++) albmax = std::max(albmax, io->albedo[i + (size_t)maxig * ipa]);
+    RtArgs rt;
+    memset(&rt, 0, sizeof(rt));
+    rt.npts = G.npts; rt.ldp = maxig; rt.ml = d->ml; rt.mm = d->mm; rt.nstleg = d->nstleg; rt.nleg = d->nleg; rt.npart = npart; rt.nq = nq;
+    rt.nstokes = nst; rt.interp_new = d->interp_new; rt.deltam = d->deltam; rt.highorderrad = io->highorderrad;
+    rt.phasemax = d->phasemax; rt.shacc = io->shacc; rt.legen_size = nlt * (size_t)d->numphase;
+    rt.total_ext = total_ext_d; rt.extinct = extinct_d; rt.albedo = albedo_d; rt.legen = a.legen; rt.phaseinterpwt = pwt_d;
+    rt.iphase = iphase_d; rt.lofj = a.lofj; rt.first_zero = a.bad + 1; rt.nr = nr; rt.radiance = rad;
+    cudaEvent_t ev[4];
+    for (auto &x : ev) cudaEventCreate(&x);
+    cudaEventRecord(ev[0], 0);
+    // ---- first guess: INIT_RADIANCE (Eddington) or zero, 4 terms per point; SOURCE from COMPUTE_SOURCE(FIRST=.TRUE.) ----
+    int cur = 0, rcur = 0, total_s = 0, iter = 0, fixsh = 0, npts = G.npts, oldnpts = 0;
+    int total_r = 4 * npts;
+    sv_iota_kernel<<<(npts + 2 + 255) / 256, 256>>>(npts + 1, 4, rsh[rcur]);
+    cudaMemcpyAsync(rsh[rcur] + npts + 1, rsh[rcur] + npts, sizeof(int), cudaMemcpyDeviceToDevice, 0);
+    cudaMemsetAsync(rad, 0, (size_t)nst * 4 * npts * sizeof(float), 0);
+    cudaMemsetAsync(sh[cur], 0, ((size_t)maxig + 2) * sizeof(int), 0);
+    cudaMemsetAsync(osh, 0, ((size_t)maxig + 2) * sizeof(int), 0);
+    if (io->inradflag) {
+        float skyradalb = 0.0f;
+        for (int imu = 1; imu <= d->nmu / 2; imu++)
+            for (int iphi = 1; iphi <= d->nphi0[imu - 1]; iphi++)
+                skyradalb = skyradalb + fabsf(d->mu[imu - 1]) * d->wtdo[(imu - 1) + (size_t)d->nmu * (iphi - 1)]
+                            * d->skyrad[(size_t)nst * ((imu - 1) + (size_t)(d->nmu / 2) * (iphi - 1))];
+        rc = adapt_init_radiance(d, maxig, npts / d->nz, zgrid_d, extinct_d, albedo_d, total_ext_d, temp_d, a.legen, iphase_d, pwt_d,
+                                 skyradalb, 0.0f, rad, errmsg);
+    }
+    a.first = 1; a.fixsh = 0;
+    a.rshptr = rsh[rcur]; a.radiance = rad; a.shptr_old = sh[cur]; a.oshptr_old = osh; a.source_old = src[cur];
+    a.delsource_old = dels; a.delsource_new = dels;
+    size_t cap_new = std::min((size_t)maxiv, (size_t)npts * nlm);
+    int nblk = cs_grid_blocks(npts);
+    if (!rc) rc = cs_device_step(a, nblk, tmp, tmpb, sh[1 - cur], sums, maxiv, cap_new, src[1 - cur], &total_s, false, errmsg);
+    cur = 1 - cur;
+    int osh_end = 0;
+    if (!rc && io->accelflag) {
+        cudaMemcpyAsync(osh, sh[cur], ((size_t)npts + 1) * sizeof(int), cudaMemcpyDeviceToDevice, 0);
+        cudaMemsetAsync(dels, 0, (size_t)nst * total_s * sizeof(float), 0);
+        osh_end = total_s;
+    }
+    // ---- the callback context of SPLIT_GRID ----
+    ctx.d = d; ctx.pg = pg; ctx.io = io; ctx.G = &G; ctx.cs = &a; ctx.npts_done = npts; ctx.ncells_done = G.ncells; ctx.nst = nst; ctx.nq = nq;
+    ctx.npart = npart; ctx.maxig = maxig; ctx.gridpos_d = gridpos_d; ctx.gridptr_d = gridptr_d; ctx.extinct_d = extinct_d;
+    ctx.albedo_d = albedo_d; ctx.planck_d = planck_d; ctx.temp_d = temp_d; ctx.total_ext_d = total_ext_d; ctx.pwt_d = pwt_d;
+    ctx.dirflux_d = dirflux_d; ctx.iphase_d = iphase_d; ctx.zlevels_d = tp.zlevels; ctx.extdirp_d = extdirp_d; ctx.flags_d = flags_d;
+    ctx.sh = sh; ctx.cur = &cur; ctx.rsh = rsh; ctx.rcur = &rcur; ctx.osh = osh; ctx.src = src; ctx.rad = rad;
+    at3d_solver *sv = nullptr;
+    at3d_state_desc dd = *d;
+    std::vector<float> sfcgp;
+    const float endadaptsol = 0.001f, startadaptsol = 0.1f, splitacc = io->splitacc, solacc = io->solacc;
+    const float adaptrange = startadaptsol / (3.0f * endadaptsol);
+    float cursplitacc = splitacc * adaptrange, startsplitacc = cursplitacc, solcrit = 1.0f, avgsolcrit = solcrit, splitcrit = 0.0f;
+    float acc = 0.0f, deljdot = 0, deljold = 0, deljnew = 0, jnorm = 0;
+    bool splittesting = true, outofmem = false, mix_ready = true;     // the first COMPUTE_SOURCE mixed the base points
+    int nsplit_calls = 0;
+    double ms_path = 0.0, ms_src = 0.0;
+    while (!rc && iter < io->maxiter && (solcrit > solacc || (splitcrit > splitacc && cursplitacc > splitacc && !outofmem))) {
+        iter++;
+        if (splitacc > 0.0f) {
+            avgsolcrit = sqrtf(avgsolcrit * solcrit);
+            const bool dosplit = solcrit <= startadaptsol && (solcrit > endadaptsol || cursplitacc > splitacc) && !outofmem;
+            const float beta = logf(startsplitacc / splitacc) / logf(adaptrange);
+            cursplitacc = fminf(cursplitacc, fmaxf(splitacc, splitacc * powf(avgsolcrit / (3.0f * endadaptsol), beta)));
+            if (solcrit <= endadaptsol) cursplitacc = splitacc;
+            if (splittesting) {
+                const double t0 = wall_ms();
+                cudaMemcpy(G.shptr.data(), sh[cur], ((size_t)npts + 1) * sizeof(int), cudaMemcpyDeviceToHost);
+                cudaMemcpy(G.rshptr.data(), rsh[rcur], ((size_t)npts + 2) * sizeof(int), cudaMemcpyDeviceToHost);
+                AdaptDev D = {gridptr_d, gridpos_d, total_ext_d, sh[cur], src[cur], nst};
+                ctx.osh_end = osh_end;
+                rc = G.split_grid(D, dosplit, outofmem, cursplitacc, splitcrit, d->nphi0max, nlm, adapt_interpolate_cb, &ctx, errmsg);
+                if (rc) break;
+                nsplit_calls++;
+                if (G.npts != npts) {
+                    npts = G.npts;
+                    total_s = G.shptr[npts]; total_r = G.rshptr[npts];
+                }
+                if (solcrit > startadaptsol) startsplitacc = splitcrit;
+                ms_split += wall_ms() - t0;
+            }
+            if (solcrit <= endadaptsol) splittesting = false;
+        }
+        a.npts = npts; rt.npts = npts;
+        nblk = cs_grid_blocks(npts);
+        const int pb = (npts + 255) / 256;
+        // RADIANCE_TRUNCATION -> new RSHPTR
+        rt.shptr = sh[cur]; rt.rshptr_old = rsh[rcur];
+        bool fixed = fixsh != 0;
+        for (int attempt = 0; attempt < 2; attempt++) {
+            if (!fixed) {
+                cudaMemcpyAsync(rt.first_zero, &npts, sizeof(int), cudaMemcpyHostToDevice, 0);
+                rt_first_zero_kernel<<<pb, 256>>>(rt);
+                rt_adaptive_kernel<<<pb, 256>>>(rt);
+            } else {
+                rt_fixed_kernel<<<pb, 256>>>(rt);
+            }
+            cudaMemsetAsync(nr + npts, 0, sizeof(int), 0);
+            cub::DeviceScan::ExclusiveSum(tmp, tmpb, nr, rsh[1 - rcur], npts + 1);
+            cudaMemcpy(&total_r, rsh[1 - rcur] + npts, sizeof(int), cudaMemcpyDeviceToHost);
+            if ((size_t)total_r <= maxir) break;
+            if (fixed) { set_msg(errmsg, "RADIANCE_TRUNCATION: Really out of memory for more radiance terms. Increase MAXIV."); rc = 2; break; }
+            fixed = true;
+        }
+        if (rc) break;
+        rcur = 1 - rcur;
+        cudaMemcpyAsync(rsh[rcur] + npts + 1, rsh[rcur] + npts, sizeof(int), cudaMemcpyDeviceToDevice, 0);
+        // the sweep structures of the current grid (SWEEPING_ORDER, BOUNDARY_PNTS, SURFACE_PARM_INTERP when NPTS changed)
+        if (npts != oldnpts) {
+            const double t0 = wall_ms();
+            int ntop = 0, nbot = 0;
+            if (G.boundary_points(d->nang, lamb, io->maxnbc, io->maxbcrad, d->zgrid[0], d->zgrid[d->nz - 1], io->bcptr, &ntop, &nbot)) {
+                set_msg(errmsg, "BOUNDARY_PNTS: MAXNBC exceeded"); rc = 1; break;
+            }
+            dd.npts = npts; dd.ncells = G.ncells; dd.gridptr = io->gridptr; dd.neighptr = io->neighptr; dd.treeptr = io->treeptr;
+            dd.cellflags = io->cellflags; dd.gridpos = io->gridpos; dd.total_ext = io->total_ext; dd.dirflux = io->dirflux;
+            dd.bcptr = io->bcptr; dd.maxnbc = io->maxnbc; dd.ntoppts = ntop; dd.nbotpts = nbot; dd.sfcgridrad = nullptr;
+            if (d->sfctype0 == 'V' && io->sfcparms) {
+                surface_parm_interp(nbot, io->bcptr + io->maxnbc, io->gridpos, d->srctype, d->units, d->wavelen, io->nxsfc, io->nysfc,
+                                    io->delxsfc, io->delysfc, d->nsfcpar, io->sfcparms, io->sfcgridparms);
+                dd.sfcgridparms = io->sfcgridparms;
+            } else if (io->sfcgridparms) dd.sfcgridparms = io->sfcgridparms;
+            else { sfcgp.assign((size_t)std::max(1, d->nsfcpar) * std::max(1, nbot), 0.0f); dd.sfcgridparms = sfcgp.data(); }
+            if (sv) at3d_solver_destroy(sv);
+            sv = nullptr;
+            rc = at3d_solver_create(&dd, wtmu, io->transmin, &sv, errmsg);
+            if (rc) break;
+            io->ntoppts = ntop; io->nbotpts = nbot;
+            if (oldnpts != 0) mix_ready = false;      // the mixed tables of the new points exist already (cs_mix_points), but keep it simple
+            mix_ready = true;
+            oldnpts = npts;
+            ms_split += wall_ms() - t0;
+        }
+        // PATH_INTEGRATION
+        cudaEventRecord(ev[1], 0);
+        cudaError_t e = sv_path_integration_device(sv, sh[cur], src[cur], rsh[rcur], rad);
+        cudaEventRecord(ev[2], 0);
+        if (e != cudaSuccess) { set_msg(errmsg, "CUDA error %s in PATH_INTEGRATION", cudaGetErrorString(e)); rc = 4; break; }
+        if (solcrit < endadaptsol || iter > io->iterfixsh) fixsh = 1;
+        // COMPUTE_SOURCE
+        a.first = 0; a.fixsh = fixsh;
+        a.rshptr = rsh[rcur]; a.radiance = rad; a.shptr_old = sh[cur]; a.oshptr_old = osh; a.source_old = src[cur];
+        const int old_total = total_s;
+        cap_new = fixsh ? (size_t)old_total : std::min((size_t)maxiv, (size_t)npts * nlm);
+        rc = cs_device_step(a, nblk, tmp, tmpb, sh[1 - cur], sums, maxiv, cap_new, src[1 - cur], &total_s, mix_ready, errmsg);
+        cudaEventRecord(ev[3], 0);
+        if (rc) break;
+        if (io->accelflag) { cudaMemcpyAsync(osh, sh[cur], ((size_t)npts + 1) * sizeof(int), cudaMemcpyDeviceToDevice, 0); osh_end = old_total; }
+        cur = 1 - cur;
+        double hs[4];
+        e = cudaMemcpy(hs, sums, sizeof(hs), cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) { set_msg(errmsg, "CUDA error %s in the solution iterations", cudaGetErrorString(e)); rc = 4; break; }
+        rc = sv_sweep_error(sv, errmsg);
+        if (rc) break;
+        float t1 = 0, t2 = 0;
+        cudaEventElapsedTime(&t1, ev[1], ev[2]); cudaEventElapsedTime(&t2, ev[2], ev[3]);
+        ms_path += t1; ms_src += t2;
+        deljdot = (float)hs[0]; deljold = (float)hs[1]; deljnew = (float)hs[2]; jnorm = (float)hs[3];
+        if (io->accelflag && acc == 0.0f && deljnew < deljold) {
+            const float r = sqrtf(deljnew / deljold);
+            const float theta = acosf(deljdot / sqrtf(deljold * deljnew));
+            acc = (1 - r * cosf(theta) + powf(r, 1 + 0.5f * 3.14159f / theta)) / (1 + r * r - 2 * r * cosf(theta)) - 1.0f;
+            acc = fminf(10.0f, fmaxf(0.0f, acc));
+        } else {
+            acc = 0.0f;
+        }
+        if (jnorm > 0.0f) solcrit = sqrtf(deljnew / jnorm);
+        else if (deljnew == 0.0f) solcrit = 0.0f;
+        if (acc > 0.0f) sv_accelerate_kernel<<<(int)(((size_t)npts * 32 + 255) / 256), 256>>>(npts, nst, acc, sh[cur], osh, src[cur], dels);
+        if (albmax < solacc) solcrit = solacc;
+        if (getenv("AT3D_SOLVER_VERBOSE"))
+            fprintf(stderr, "  %4d %8.3f %10.3E %8d %8.2f %6.3f\n", iter, log10f(fmaxf(solcrit, 1.0e-20f)), splitcrit, npts,
+                    (float)total_s / npts, (float)total_s / (npts * (float)nlm));
+    }
+    float ms_all = 0.0f;
+    cudaEventRecord(ev[3], 0);
+    cudaError_t e = cudaEventSynchronize(ev[3]);
+    if (e == cudaSuccess) cudaEventElapsedTime(&ms_all, ev[0], ev[3]);
+    for (auto &x : ev) cudaEventDestroy(x);
+    if (!rc && e != cudaSuccess) { set_msg(errmsg, "CUDA error %s in the solution iterations", cudaGetErrorString(e)); rc = 4; }
+    if (!rc && sv) {
+        e = cudaMemcpy(io->shptr, sh[cur], ((size_t)npts + 1) * sizeof(int), cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess) e = cudaMemcpy(io->rshptr, rsh[rcur], ((size_t)npts + 2) * sizeof(int), cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess) e = cudaMemcpy(io->source, src[cur], (size_t)nst * total_s * sizeof(float), cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess) e = cudaMemcpy(io->radiance, rad, (size_t)nst * total_r * sizeof(float), cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess) e = cudaMemcpy(io->fluxes, sv->a.fluxes, (size_t)2 * npts * sizeof(float), cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess) e = cudaMemcpy(io->bcrad, sv->a.bcrad, std::min(sv->nbc, (size_t)nst * io->maxbcrad) * sizeof(float), cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) { set_msg(errmsg, "CUDA error %s copying the solution back", cudaGetErrorString(e)); rc = 4; }
+    }
+    if (sv) at3d_solver_destroy(sv);
+    ctx.recs.release();
+    io->npts = npts; io->ncells = G.ncells; io->iters = iter; io->solcrit = solcrit; io->splitcrit = splitcrit; io->nsplit_calls = nsplit_calls;
+    if (ms_out) { ms_out[0] = ms_path; ms_out[1] = ms_src; ms_out[2] = ms_split; ms_out[3] = wall_ms() - t_begin; (void)ms_all; }
     return rc;
 }

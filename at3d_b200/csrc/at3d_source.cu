@@ -45,12 +45,13 @@ __device__ __forceinline__ void cs_mix_newmethod(const CsArgs &a, int i, float *
 #pragma unroll
     for (int u = 0; u < CS_SLOTS; u++) acc[u] = 0.0f;
     for (int ipa = 0; ipa < a.npart; ipa++) {
-        const int *iph = a.iphase + (size_t)a.nq * (i + (size_t)a.npts * ipa);
-        const float *pw = a.phaseinterpwt + (size_t)a.nq * (i + (size_t)a.npts * ipa);
-        const float e = a.extinct[i + (size_t)a.npts * ipa], al = a.albedo[i + (size_t)a.npts * ipa];
+        const size_t ld = a.ldp ? a.ldp : a.npts;
+        const int *iph = a.iphase + (size_t)a.nq * (i + ld * ipa);
+        const float *pw = a.phaseinterpwt + (size_t)a.nq * (i + ld * ipa);
+        const float e = a.extinct[i + ld * ipa], al = a.albedo[i + ld * ipa];
         const double scat = (double)(e * al);
         alb = alb + scat;
-        if (a.planck) total_planck = total_planck + e * a.planck[i + (size_t)a.npts * ipa];
+        if (a.planck) total_planck = total_planck + e * a.planck[i + ld * ipa];
         float l1[CS_SLOTS];
         if (!a.interp_new) {
             const float *lg = a.legen + (size_t)nlt * (iph[0] - 1);
@@ -176,6 +177,51 @@ __device__ __forceinline__ void cs_calc_j(const CsArgs &a, const float *legen, i
         if (thermal && j == 0) v1 = v1 + 3.544907703f * planck;
         s[0] = v1; s[1] = v2; s[NST - 1] = v3;
     }
+}
+
+// ---- new grid points of SPLIT_GRID (INTERPOLATE_POINT, shdomsub1.f:5109-5211) ----
+// warp = new point: RADIANCE(:, IR+J) = 0.5*(RAD1 + RAD2) over NR = max(NR1, NR2) terms, then the source function of the
+// point from that radiance with the point's mixed Legendre row (cs_mix_points), first NS = max(NS1, NS2) terms.
+template <int NST>
+__global__ void interp_points_kernel(CsArgs a, const NewPointRec *rec, int count, const int *rshptr, float *radiance, float *source)
+{
+    const int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (k >= count) return;
+    const NewPointRec r = rec[k];
+    const int ir1 = rshptr[r.ip1], nr1 = rshptr[r.ip1 + 1] - ir1, ir2 = rshptr[r.ip2], nr2 = rshptr[r.ip2 + 1] - ir2;
+    const int nlt = a.nstleg * (a.nleg + 1);
+    const float *legen = a.mix_legent + (size_t)nlt * r.ip;
+    const float2 ap = a.mix_ap[r.ip];
+    const float flux0 = a.dirflux[r.ip] * a.secmu0;
+    const int nmax = r.nr > r.ns ? r.nr : r.ns;
+    for (int j = lane; j < nmax; j += 32) {
+        float rad[NST], s[NST];
+#pragma unroll
+        for (int q = 0; q < NST; q++) {
+            const float r1 = j < nr1 ? radiance[q + (size_t)NST * (ir1 + j)] : 0.0f;
+            const float r2 = j < nr2 ? radiance[q + (size_t)NST * (ir2 + j)] : 0.0f;
+            rad[q] = 0.5f * (r1 + r2);
+        }
+        if (j < r.nr) {
+#pragma unroll
+            for (int q = 0; q < NST; q++) radiance[q + (size_t)NST * (r.ir + j)] = rad[q];
+        }
+        if (j < r.ns) {
+            cs_calc_j<NST>(a, legen, j, a.lofj[j], a.ylmsun[(size_t)a.nstleg * j], j < r.nr, rad, flux0, ap.y, ap.x, s);
+#pragma unroll
+            for (int q = 0; q < NST; q++) source[q + (size_t)NST * (r.is + j)] = s[q];
+        }
+    }
+}
+
+cudaError_t launch_interp_points(const CsArgs &a, const NewPointRec *rec_d, int count, const int *rshptr_d, float *radiance,
+                                 float *source, cudaStream_t s)
+{
+    if (count < 1) return cudaSuccess;
+    const int nb = (int)(((size_t)count * 32 + 127) / 128);
+    if (a.nstokes == 1) interp_points_kernel<1><<<nb, 128, 0, s>>>(a, rec_d, count, rshptr_d, radiance, source);
+    else interp_points_kernel<3><<<nb, 128, 0, s>>>(a, rec_d, count, rshptr_d, radiance, source);
+    return cudaGetLastError();
 }
 
 // A point is one warp; its SH index j runs over the lanes in batches of CS_BATCH x 32.  The loads of a batch
@@ -499,6 +545,27 @@ int cs_grid_blocks(int npts)
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
     const int want = (npts + CS_WARPS - 1) / CS_WARPS;
     return want < nsm * 8 ? want : nsm * 8;          // persistent: a multiple of the SM count
+}
+
+// the mixed Legendre rows of the points [first, first+count) (new grid points of SPLIT_GRID): cs_mix_kernel on shifted
+// base pointers; a.ldp stays the leading dimension of the species arrays
+cudaError_t cs_mix_points(CsArgs a, int first, int count, cudaStream_t st)
+{
+    if (count < 1) return cudaSuccess;
+    const size_t nlt = (size_t)a.nstleg * (a.nleg + 1);
+    const int slots = nlt <= 32 ? 1 : nlt <= 64 ? 2 : nlt <= 128 ? 4 : 8;
+    const size_t smem = (size_t)CS_WARPS * 2 * nlt * sizeof(float);
+    if (!a.ldp) a.ldp = a.npts;
+    a.npts = count;
+    a.total_ext += first; a.extinct += first; a.albedo += first; if (a.planck) a.planck += first;
+    a.iphase += (size_t)a.nq * first; a.phaseinterpwt += (size_t)a.nq * first;
+    a.mix_legent += nlt * first; a.mix_ap += first;
+    const int nmix = (count + CS_WARPS - 1) / CS_WARPS;
+    if (slots == 1) cs_mix_kernel<1><<<nmix, CS_WARPS * 32, smem, st>>>(a);
+    else if (slots == 2) cs_mix_kernel<2><<<nmix, CS_WARPS * 32, smem, st>>>(a);
+    else if (slots == 4) cs_mix_kernel<4><<<nmix, CS_WARPS * 32, smem, st>>>(a);
+    else cs_mix_kernel<8><<<nmix, CS_WARPS * 32, smem, st>>>(a);
+    return cudaGetLastError();
 }
 
 int cs_device_step(CsArgs &a, int nblk, void *scan_tmp, size_t tmpb, int *shptr_new, double *sums, int maxiv, size_t cap_new,

@@ -16,6 +16,7 @@ from . import _lib
 from . import backend as B
 from . import grid as G
 from ._lib import vp
+from .state import i32
 
 
 def radiance_truncation(st, shptr, radiance, rshptr, fixsh, shacc, highorderrad, maxir):
@@ -289,3 +290,130 @@ def solve_fixed_grid(state, wtmu, maxiter=100, solacc=1e-4, shacc=0.0, accelflag
     st.shptr = shptr
     st.source = np.asfortranarray(source[:, :max(tot, 1)])
     return st, it, float(solcrit), dict(path_integration_ms=t_path, compute_source_ms=t_src)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the adaptive solve (C `at3d_solve_adaptive`): RTE.solve of at3d/solver.py:279 with split_accuracy > 0
+# ---------------------------------------------------------------------------------------------------------------------
+class PropDesc(C.Structure):
+    """at3d_prop_desc of include/at3d_b200.h."""
+    _fields_ = [(n, i32) for n in ('npx', 'npy', 'npz', 'numphase', 'nlegp', 'maxnmicro', 'npart', 'nzckd', 'nstleg')] + \
+               [(n, C.c_float) for n in ('delx', 'dely', 'xstart', 'ystart')] + \
+               [(n, C.c_void_p) for n in ('zlevels', 'tempp', 'extinctp', 'albedop', 'legenp', 'iphasep', 'phasewtp',
+                                          'zckd', 'gasabs')]
+
+
+class AdaptIO(C.Structure):
+    """at3d_adapt_io of include/at3d_b200.h."""
+    _fields_ = [(n, i32) for n in ('maxig', 'maxic', 'maxiv', 'maxido', 'maxnbc', 'maxbcrad', 'nbpts', 'nbcells',
+                                   'maxiter', 'accelflag', 'highorderrad', 'iterfixsh', 'inradflag')] + \
+               [(n, C.c_float) for n in ('solacc', 'splitacc', 'shacc', 'transmin')] + \
+               [('nxsfc', i32), ('nysfc', i32), ('delxsfc', C.c_float), ('delysfc', C.c_float), ('sfcparms', C.c_void_p)] + \
+               [(n, C.c_void_p) for n in ('gridpos', 'gridptr', 'neighptr', 'treeptr', 'cellflags', 'temp', 'planck',
+                                          'extinct', 'albedo', 'total_ext', 'dirflux', 'fluxes', 'iphase', 'phaseinterpwt',
+                                          'shptr', 'rshptr', 'source', 'radiance', 'bcptr', 'bcrad', 'sfcgridparms',
+                                          'extdirp')] + \
+               [(n, i32) for n in ('npts', 'ncells', 'ntoppts', 'nbotpts', 'iters', 'nsplit_calls')] + \
+               [('solcrit', C.c_float), ('splitcrit', C.c_float)]
+
+
+def memory_sizes(nbpts, nbcells, nlm, nz, nmu, nphi0max, lambertian, adapt_grid_factor=5.0, num_sh_term_factor=1.0,
+                 cell_to_point_ratio=1.5):
+    """MAXIG, MAXIC, MAXIV, MAXIDO, MAXNBC, MAXBCRAD of RTE._setup_memory (at3d/solver.py:2286-2322, :1942-1944)."""
+    maxig = int(adapt_grid_factor * nbpts)
+    maxic = max(int(cell_to_point_ratio * maxig), nbcells)
+    maxiv = max(int(num_sh_term_factor * nlm * maxig), nbpts * 4)
+    maxnbc = int(maxig * 3 / nz)
+    maxbcrad = 2 * maxnbc if lambertian else int((2 + nmu * nphi0max / 2) * maxnbc)
+    return maxig, maxic, maxiv, maxig * nphi0max, maxnbc, maxbcrad
+
+
+def solve_adaptive(state, pg, wtmu, tempp=None, temp=None, splitacc=0.03, shacc=0.0, solacc=1e-4, maxiter=100, accelflag=True,
+                   highorderrad=False, iterfixsh=30, adapt_grid_factor=5.0, num_sh_term_factor=1.0, cell_to_point_ratio=1.5,
+                   inradflag=True, transmin=1.0, sfcparms=None, delxsfc=0.0, delysfc=0.0, zckd=None, gasabs=None, timing=False):
+    """INIT_SOLUTION + SOLUTION_ITERATIONS with adaptive cell splitting on the GPU (C `at3d_solve_adaptive`).
+
+    ``state``: ShdomState of the BASE grid with the optical properties on it (TRANSFER_PA_TO_GRID) and YLMSUN; ``pg``: the
+    PropertyGrid; array capacities follow RTE._setup_memory.  Returns (solved state on the split grid, iters, solcrit,
+    splitcrit) and the ms[4] timings when ``timing``.  ``sfcparms``: SFCPARMS[nsfcpar, nxsfc+1, nysfc+1] of a variable surface."""
+    st = state.copy().normalize()
+    ns, nbpts, nbcells, npart, nq = st.nstokes, st.npts, st.ncells, st.npart, 8 * st.maxnmicro
+    lamb = st.sfctype1 in ('L', ord('L'))
+    maxig, maxic, maxiv, maxido, maxnbc, maxbcrad = memory_sizes(nbpts, nbcells, st.nlm, st.nz, st.nmu, st.nphi0max, lamb,
+                                                                 adapt_grid_factor, num_sh_term_factor, cell_to_point_ratio)
+    if splitacc <= 0.0:
+        maxig, maxic = nbpts, nbcells
+        maxiv = max(int(num_sh_term_factor * st.nlm * maxig), nbpts * 4)
+        maxido, maxnbc = maxig * st.nphi0max, max(int(maxig * 3 / st.nz), st.ntoppts, st.nbotpts)
+        maxbcrad = 2 * maxnbc if lamb else int((2 + st.nmu * st.nphi0max / 2) * maxnbc)
+
+    def grow(a, shape, dtype):
+        out = np.zeros(shape, dtype, order='F')
+        if a is not None:
+            a = np.asarray(a)
+            out[tuple(slice(0, s) for s in a.shape)] = a
+        return out
+    arr = dict(
+        gridpos=grow(st.gridpos, (3, maxig), np.float32), gridptr=grow(st.gridptr, (8, maxic), np.int32),
+        neighptr=grow(st.neighptr, (6, maxic), np.int32), treeptr=grow(st.treeptr, (2, maxic), np.int32),
+        cellflags=grow(st.cellflags, (maxic,), np.int16), temp=grow(temp if temp is not None else st.temp, (maxig,), np.float32),
+        planck=grow(st.planck, (maxig, npart), np.float32), extinct=grow(st.extinct, (maxig, npart), np.float32),
+        albedo=grow(st.albedo, (maxig, npart), np.float32), total_ext=grow(st.total_ext, (maxig,), np.float32),
+        dirflux=np.zeros(maxig, np.float32), fluxes=np.zeros((2, maxig), np.float32, order='F'),
+        iphase=grow(st.iphase, (nq, maxig, npart), np.int32), phaseinterpwt=grow(st.phaseinterpwt, (nq, maxig, npart), np.float32),
+        shptr=np.zeros(maxig + 1, np.int32), rshptr=np.zeros(maxig + 2, np.int32),
+        source=np.zeros((ns, maxiv), np.float32, order='F'), radiance=np.zeros((ns, maxiv + maxig), np.float32, order='F'),
+        bcptr=np.zeros((maxnbc, 2), np.int32, order='F'), bcrad=np.zeros((ns, maxbcrad), np.float32, order='F'),
+        sfcgridparms=np.zeros((max(st.nsfcpar, 1), maxnbc), np.float32, order='F'), extdirp=np.zeros(pg.maxpg, np.float32))
+    arr['iphase'][arr['iphase'] == 0] = 1
+    if st.sfcgridparms is not None:
+        sg = np.asarray(st.sfcgridparms)
+        arr['sfcgridparms'][:sg.shape[0], :sg.shape[1]] = sg
+    keep = [np.ascontiguousarray(pg.zlevels, np.float32),
+            None if tempp is None else np.ascontiguousarray(tempp, np.float32),
+            None if zckd is None else np.ascontiguousarray(zckd, np.float32),
+            None if gasabs is None else np.ascontiguousarray(gasabs, np.float32),
+            None if sfcparms is None else np.asfortranarray(sfcparms, np.float32)]
+    p = PropDesc(pg.npx, pg.npy, pg.npz, pg.numphase, pg.nlegp, pg.maxnmicro, pg.npart, 0 if zckd is None else len(zckd),
+                 pg.nstleg, pg.delx, pg.dely, pg.xstart, pg.ystart, _lib.vp(keep[0]), _lib.vp(keep[1]), _lib.vp(pg.extinctp),
+                 _lib.vp(pg.albedop), _lib.vp(pg.legenp), _lib.vp(pg.iphasep), _lib.vp(pg.phasewtp), _lib.vp(keep[2]),
+                 _lib.vp(keep[3]))
+    io = AdaptIO()
+    io.maxig, io.maxic, io.maxiv, io.maxido, io.maxnbc, io.maxbcrad = maxig, maxic, maxiv, maxido, maxnbc, maxbcrad
+    io.nbpts, io.nbcells, io.maxiter, io.accelflag, io.highorderrad = nbpts, nbcells, maxiter, int(accelflag), int(highorderrad)
+    io.iterfixsh, io.inradflag, io.solacc, io.splitacc, io.shacc, io.transmin = iterfixsh, int(inradflag), solacc, splitacc, shacc, transmin
+    if sfcparms is not None:
+        io.nxsfc, io.nysfc, io.delxsfc, io.delysfc = keep[4].shape[1] - 1, keep[4].shape[2] - 1, delxsfc, delysfc
+        io.sfcparms = _lib.vp(keep[4])
+    for k, v in arr.items():
+        setattr(io, k, _lib.vp(v))
+    d = st.desc()
+    wtmu = np.ascontiguousarray(wtmu, np.float32)
+    ms = (C.c_double * 4)()
+    buf = _lib.errbuf()
+    _lib.check(_lib.lib().at3d_solve_adaptive(C.byref(d), C.byref(p), _lib.vp(wtmu), C.byref(io), ms, buf), buf)
+    npts, ncells = io.npts, io.ncells
+    st.npts, st.ncells, st.ntoppts, st.nbotpts, st.maxnbc = npts, ncells, io.ntoppts, io.nbotpts, maxnbc
+    st.gridpos = np.asfortranarray(arr['gridpos'][:, :npts])
+    for n in ('gridptr', 'neighptr', 'treeptr'):
+        setattr(st, n, np.asfortranarray(arr[n][:, :ncells]))
+    st.cellflags = arr['cellflags'][:ncells].copy()
+    for n in ('extinct', 'albedo', 'planck'):
+        setattr(st, n, np.asfortranarray(arr[n][:npts, :]))
+    for n in ('iphase', 'phaseinterpwt'):
+        setattr(st, n, np.asfortranarray(arr[n][:, :npts, :]))
+    st.total_ext = arr['total_ext'][:npts].copy()
+    st.dirflux = arr['dirflux'][:npts].copy()
+    st.temp = arr['temp'][:npts].copy()
+    st.fluxes = np.asfortranarray(arr['fluxes'][:, :npts])
+    st.shptr = arr['shptr'][:npts + 1].copy()
+    st.rshptr = arr['rshptr'][:npts + 2].copy()
+    st.source = np.asfortranarray(arr['source'][:, :max(int(st.shptr[npts]), 1)])
+    st.radiance = np.asfortranarray(arr['radiance'][:, :max(int(st.rshptr[npts]), 1)])
+    st.bcptr = arr['bcptr']
+    nbc = io.ntoppts + io.nbotpts * (1 if lamb else 1 + st.nang // 2)
+    st.bcrad = np.asfortranarray(arr['bcrad'][:, :max(nbc, 1)])
+    st.sfcgridparms = np.asfortranarray(arr['sfcgridparms'][:, :max(io.nbotpts, 1)])
+    st.extdirp = arr['extdirp']
+    res = (st, io.iters, io.solcrit, io.splitcrit)
+    return res + (list(ms),) if timing else res

@@ -290,6 +290,59 @@ int at3d_solver_solve(at3d_solver *sv, const at3d_state_desc *desc, int maxiter,
                       float *radiance, float *fluxes, float *bcrad, int32_t *iters, float *solcrit, double *ms, char *errmsg);
 int at3d_solver_destroy(at3d_solver *sv);
 
+/* ---- f3: the adaptive solve: INIT_SOLUTION + SOLUTION_ITERATIONS with SPLIT_GRID ----
+ * Replaces INIT_SOLUTION (src/polarized/shdomsub1.f:113-443: MAKE_DIRECT, INIT_RADIANCE + EDDRTF shdomsub2.f:614-1057,
+ * first COMPUTE_SOURCE, BOUNDARY_PNTS) and SOLUTION_ITERATIONS (:445-822) including SPLIT_GRID, DIVIDE_CELL,
+ * INTERPOLATE_POINT, GRID_SMOOTH_TEST (:4703-5902) -- RTE.solve of at3d/solver.py:279 with the default
+ * split_accuracy > 0.  The SH arrays stay in HBM over the whole solve; the cell tree is split on the host between
+ * iterations (see csrc/at3d_adapt.cu), its criterion evaluated on the GPU.
+ *
+ * at3d_prop_desc: the property grid (ShdomPropertyArrays, at3d/solver.py:25-104).
+ * at3d_adapt_io: the arrays SOLUTION_ITERATIONS has intent(in,out), with the capacities of RTE._setup_memory
+ * (at3d/solver.py:2286-2322); HOST pointers; point arrays [maxig] or [maxig,npart] (leading dimension maxig).  On entry
+ * they hold the base grid and the optical properties on it (TRANSFER_PA_TO_GRID); on return the split grid and the
+ * solution, with npts / ncells / ntoppts / nbotpts / iters / solcrit / splitcrit filled.
+ * desc: scalars and constant tables (LEGEN, YLMSUN, ordinates, SKYRAD, XGRID/YGRID/ZGRID, SFCTYPE ...); its grid and
+ * point arrays are ignored in favour of io's. */
+typedef struct {
+    int32_t npx, npy, npz, numphase, nlegp, maxnmicro, npart, nzckd, nstleg;
+    float delx, dely, xstart, ystart;
+    const float *zlevels;      /* [npz] */
+    const float *tempp;        /* [maxpg] or NULL */
+    const float *extinctp;     /* [maxpg,npart] */
+    const float *albedop;      /* [maxpg,npart] */
+    const float *legenp;       /* [nstleg,0:nlegp,numphase] */
+    const int32_t *iphasep;    /* [maxnmicro,maxpg,npart] */
+    const float *phasewtp;     /* [maxnmicro,maxpg,npart] */
+    const float *zckd, *gasabs;/* [nzckd] */
+} at3d_prop_desc;
+
+typedef struct {
+    int32_t maxig, maxic, maxiv, maxido, maxnbc, maxbcrad, nbpts, nbcells;
+    int32_t maxiter, accelflag, highorderrad, iterfixsh, inradflag;
+    float solacc, splitacc, shacc, transmin;
+    int32_t nxsfc, nysfc;              /* variable surfaces: SFCPARMS[nsfcpar, nxsfc+1, nysfc+1] */
+    float delxsfc, delysfc;
+    const float *sfcparms;
+    float *gridpos;                    /* [3,maxig] */
+    int32_t *gridptr, *neighptr, *treeptr;   /* [8|6|2, maxic] */
+    int16_t *cellflags;                /* [maxic] */
+    float *temp, *planck, *extinct, *albedo, *total_ext, *dirflux, *fluxes;   /* fluxes [2,maxig] */
+    int32_t *iphase;                   /* [8*maxnmicro, maxig, npart] */
+    float *phaseinterpwt;
+    int32_t *shptr, *rshptr;           /* [maxig+1], [maxig+2] */
+    float *source, *radiance;          /* [nstokes,maxiv], [nstokes,maxiv+maxig] */
+    int32_t *bcptr;                    /* [maxnbc,2] */
+    float *bcrad;                      /* [nstokes,maxbcrad] */
+    float *sfcgridparms;               /* [nsfcpar,maxnbc] (variable surfaces) */
+    float *extdirp;                    /* [maxpg] out */
+    int32_t npts, ncells, ntoppts, nbotpts, iters, nsplit_calls;
+    float solcrit, splitcrit;
+} at3d_adapt_io;
+
+int at3d_solve_adaptive(const at3d_state_desc *desc, const at3d_prop_desc *prop, const float *wtmu, at3d_adapt_io *io,
+                        double *ms /*[4]: PATH_INTEGRATION, COMPUTE_SOURCE, SPLIT_GRID + sweep set-up, whole loop*/, char *errmsg);
+
 #ifdef __cplusplus
 }
 #endif

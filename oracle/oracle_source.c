@@ -231,6 +231,11 @@ void oracle_point_source(const oracle_state *st, int ld, int i, float *sourcet)
     free(wk.lofj); free(wk.legent); free(wk.legent1); free(wk.sourcet); free(wk.sourcet1);
 }
 
+/* The four norms of the last oracle_compute_source call accumulated in double (same per-term REAL products, f64
+ * running sums): the rounding-free value of what the reference sums sequentially in REAL. */
+static double last_sums64[4];
+void oracle_compute_source_sums64(double *out) { int k; for (k = 0; k < 4; k++) out[k] = last_sums64[k]; }
+
 /* COMPUTE_SOURCE  shdomsub1.f:967-1611.  st->shptr/st->source are ignored; the in/out arrays
  * are the explicit arguments (SHPTR, SOURCE, OSHPTR, DELSOURCE are intent(in,out)). */
 int oracle_compute_source(const oracle_state *st, int fixsh, float shacc, int maxiv,
@@ -244,6 +249,7 @@ int oracle_compute_source(const oracle_state *st, int fixsh, float shacc, int ma
     float srcmin = shacc;
     float secmu0 = 1.0f / fabsf(st->solarmu);
     float deljdot = 0.0f, deljold = 0.0f, deljnew = 0.0f, jnorm = 0.0f;
+    double s64[4] = {0.0, 0.0, 0.0, 0.0};
     int i, j, k, l, m, is, iso, ns = 0, ierr = 0;
 #define SRC(k, j) source[((k) - 1) + (size_t)nstokes * ((j) - 1)]
 #define DSRC(k, j) delsource[((k) - 1) + (size_t)nstokes * ((j) - 1)]
@@ -276,6 +282,10 @@ int oracle_compute_source(const oracle_state *st, int fixsh, float shacc, int ma
                         deljold = deljold + DSRC(k, iso + j) * DSRC(k, iso + j);
                         deljnew = deljnew + d * d;
                         jnorm = jnorm + SRC(k, is + j) * SRC(k, is + j);
+                        s64[0] += (double)(d * DSRC(k, iso + j));
+                        s64[1] += (double)(DSRC(k, iso + j) * DSRC(k, iso + j));
+                        s64[2] += (double)(d * d);
+                        s64[3] += (double)(SRC(k, is + j) * SRC(k, is + j));
                     }
             } else {
                 is = shptr[i - 1];
@@ -285,10 +295,13 @@ int oracle_compute_source(const oracle_state *st, int fixsh, float shacc, int ma
                         float d = ST(w->sourcet, k, j) - SRC(k, is + j);
                         deljnew = deljnew + d * d;
                         jnorm = jnorm + SRC(k, is + j) * SRC(k, is + j);
+                        s64[2] += (double)(d * d);
+                        s64[3] += (double)(SRC(k, is + j) * SRC(k, is + j));
                     }
             }
         }
     }
+    for (k = 0; k < 4; k++) last_sums64[k] = s64[k];
     if (!first && accelflag) {
         for (i = 1; i <= npts; i++) {
             point_source(st, w, i, newmethod, secmu0, w->sourcet);

@@ -152,6 +152,15 @@ def compute_source(state, shptr, source, oshptr, delsource, fixsh=False, shacc=0
     return res + (ms,) if timing else res
 
 
+def compute_source_sums64():
+    """The four norms of the last compute_source call with f64 running sums (the REAL products of the reference,
+    summed without the sequential f32 rounding of shdomsub1.f:1229-1246)."""
+    out = (f64 * 4)()
+    lib().oracle_compute_source_sums64.restype = None
+    lib().oracle_compute_source_sums64(out)
+    return list(out)
+
+
 def prepare_deriv_interps(state, pg, grad):
     st = state.copy().normalize()
     d = st.fill(OracleState())

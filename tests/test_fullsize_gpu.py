@@ -133,7 +133,7 @@ def test_gradient_pixel_sample_matches_oracle(cfg2, cfg2_gradient, oracle):
 
 def test_compute_source_full_size_matches_oracle(cfg2, oracle):
     """COMPUTE_SOURCE on all 38.6 k points x NLM=256: SHPTR (adaptive truncation) bit-exact, SOURCE within 1e-5, the four
-    norms within 5e-3 (see below)."""
+    norms within 1e-4 of their f64-summed value (see below)."""
     from at3d_b200 import backend as B
     sc, rays, dev = cfg2
     st = sc.state
@@ -146,11 +146,15 @@ def test_compute_source_full_size_matches_oracle(cfg2, oracle):
     delsource[:, :tot] = 0.01 * st.source[:, :tot]
     a = B.compute_source(st, st.shptr.copy(), source.copy(order='F'), st.shptr.copy(), delsource.copy(order='F'), maxiv=maxiv, shacc=0.003)
     b = oracle.compute_source(st, st.shptr.copy(), source.copy(order='F'), st.shptr.copy(), delsource.copy(order='F'), maxiv=maxiv, shacc=0.003)
+    sums64 = oracle.compute_source_sums64()
     assert a[0] == b[0] == 0
     np.testing.assert_array_equal(a[1], b[1])
     n = int(a[1][npts])
     np.testing.assert_allclose(a[2][:, :n], b[2][:, :n], rtol=1e-5, atol=1e-6 * np.abs(b[2][:, :n]).max())
     # the reference accumulates the four norms sequentially in REAL over ~10 M terms and loses the
     # small ones (all four oracle values come out low by ~2e-3); the GPU sums per point in f32 and across points in f64
-    np.testing.assert_allclose(np.asarray(a[5], np.float64), np.asarray(b[5], np.float64), rtol=5e-3)
+    # -> the bar of 1e-4 is asserted against the oracle's f64-summed norms (the same REAL products, no sequential rounding);
+    # the reference's own REAL value is documented by the 5e-3 bound
+    np.testing.assert_allclose(np.asarray(a[5], np.float64), np.asarray(sums64), rtol=1e-4)
+    np.testing.assert_allclose(np.asarray(b[5], np.float64), np.asarray(sums64), rtol=5e-3)
     assert np.all(np.abs(np.asarray(a[5])) >= np.abs(np.asarray(b[5])) * (1 - 1e-6))

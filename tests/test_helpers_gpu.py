@@ -92,15 +92,26 @@ def test_make_direct_derivative_overflow_is_an_error(oracle):
 
 @pytest.mark.parametrize('kw', [dict(bc='periodic', nsplits=6), dict(bc='open', nsplits=5, rayleigh=True),
                                 dict(bc='open', nstokes=3, deltam=False), dict(bc='periodic', nstokes=3, rayleigh=True)])
-def test_transfer_pa_to_grid(kw):
-    """TRANSFER_PA_TO_GRID on the GPU (property interpolation to base and split grid points, phase-table pointer lists,
-    delta-M scaling) against the host restatement that builds every test scene and the SHDOM verification states."""
-    from at3d_b200 import backend as B, medium as M, synthetic as S
+def test_transfer_pa_to_grid(kw, oracle):
+    """TRANSFER_PA_TO_GRID on the GPU (property interpolation to base and split grid points, phase-table pointer lists in
+    SSORT's order, delta-M scaling) against the ORACLE's TRILIN_INTERP_PROP / PREPARE_PROP (oracle/oracle_prop.c, pinned
+    through the SHDOM rico solve): every output bit for bit."""
+    from at3d_b200 import backend as B, synthetic as S
     sc = S.make_scene(nx=7, ny=6, nz=9, seed=17, **kw)
     st, pg = sc.state, sc.pg
-    ref = M.transfer_pa_to_grid(pg, st.gridpos, st.npts, st.ml, bool(st.deltam))
+    ref = oracle.transfer_pa_to_grid(pg, st.gridpos, st.npts, st.ml, bool(st.deltam))
     out = B.transfer_pa_to_grid(pg, st.gridpos, st.npts, st.ml, bool(st.deltam))
-    np.testing.assert_array_equal(out['iphase'], ref['iphase'])
-    for k in ('extinct', 'albedo', 'total_ext', 'phaseinterpwt', 'legen'):
-        np.testing.assert_allclose(out[k], ref[k], rtol=2e-6, atol=1e-9, err_msg=k)
+    for k in ('iphase', 'extinct', 'albedo', 'total_ext', 'phaseinterpwt', 'legen'):
+        np.testing.assert_array_equal(out[k], ref[k], err_msg=k)
     assert out['nleg'] == ref['nleg'] and out['extmin'] == ref['extmin']
+
+
+def test_transfer_pa_to_grid_on_the_shdom_property_file(oracle):
+    """... and on the 31 k base points of the reference's RICO property file (18 tabulated Mie phase functions)."""
+    import shdom_rico as R
+    from at3d_b200 import backend as B
+    st, pg, wtmu, tempp = R.make_state(oracle)
+    ref = oracle.transfer_pa_to_grid(pg, st.gridpos, st.npts, st.ml, True)
+    out = B.transfer_pa_to_grid(pg, st.gridpos, st.npts, st.ml, True)
+    for k in ('iphase', 'extinct', 'albedo', 'total_ext', 'phaseinterpwt', 'legen'):
+        np.testing.assert_array_equal(out[k], ref[k], err_msg=k)

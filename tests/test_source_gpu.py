@@ -35,6 +35,7 @@ def test_compute_source_matches_oracle(case, mode, oracle):
     kw = dict(first=mode == 'first', accelflag=mode != 'noaccel', fixsh=mode == 'fixsh',
               shacc=3e-4 if mode == 'shacc' else 0.0, maxiv=maxiv)
     rc_r, shptr_r, src_r, oshptr_r, del_r, sums_r = oracle.compute_source(sc.state, shptr, source, oshptr, delsource, **kw)
+    sums64 = oracle.compute_source_sums64()
     rc_g, shptr_g, src_g, oshptr_g, del_g, sums_g = B.compute_source(sc.state, shptr, source, oshptr, delsource, **kw)
     assert rc_r == 0 and rc_g == 0
     np.testing.assert_array_equal(shptr_g, shptr_r)                 # SHPTR: bit-exact
@@ -47,6 +48,9 @@ def test_compute_source_matches_oracle(case, mode, oracle):
         np.testing.assert_allclose(del_g[:, :m], del_r[:, :m], rtol=1e-4, atol=1e-6 * scale)
     # the four sums are float32 sequential sums in the reference: rtol 1e-4
     np.testing.assert_allclose(sums_g, sums_r, rtol=1e-4, atol=1e-7 * max(abs(sums_r[3]), 1e-30))
+    # ... and 1e-5 against the same REAL products summed in f64 (no sequential rounding)
+    if not kw['first']:
+        np.testing.assert_allclose(sums_g, sums64, rtol=1e-5, atol=1e-7 * max(abs(sums64[3]), 1e-30))
 
 
 def test_compute_source_out_of_sh_memory(oracle):
