@@ -8,9 +8,11 @@ variable names: only ``ds[name]`` and, for datasets, ``.data`` are used, so the 
 
 What runs where: grid construction and property interpolation follow ``_setup_grid`` / ``_prepare_optical_properties``
 (:2036-2520) on the host; ``TRANSFER_PA_TO_GRID`` (property interpolation + delta-M scaling), ``MAKE_DIRECT``, ``YLMALL``, ``PRECOMPUTE_PHASE_CHECK``, the whole ``SOLUTION_ITERATIONS``
-loop (``at3d_solver_solve``) and ``RENDER`` run on the GPU through the C ABI.  Not covered (NotImplementedError with
-the reason): ``split_accuracy > 0`` (SPLIT_GRID), thermal sources and non-Lambertian surfaces in
-this facade (the C ABI has them; they need SURFACE_PARM_INTERP / PLANCK tables built by the caller).
+loop -- with the Eddington first guess (``INIT_RADIANCE``) and adaptive cell splitting (``SPLIT_GRID``) for 3-D grids:
+``at3d_solve_adaptive``; ``at3d_solver_solve`` for independent-pixel grids -- and ``RENDER`` run on the GPU through the
+C ABI.  Not covered (NotImplementedError with the reason): warm starts (``init_solution=False``), cell splitting on
+independent-pixel grids (``ip_flag=3``), thermal sources and non-Lambertian surfaces in this facade (the C ABI has
+them; they need SURFACE_PARM_INTERP / PLANCK tables built by the caller).
 """
 import numpy as np
 from . import backend as B
@@ -64,6 +66,9 @@ class RTE:
         self._tautol = float(_scalar(p, 'tautol', 0.2))
         self._transcut = float(_scalar(p, 'transcut', 5e-5))
         self._transmin = float(_scalar(p, 'transmin', 1.0))
+        self._adapt_grid_factor = float(_scalar(p, 'adapt_grid_factor', 5.0))
+        self._num_sh_term_factor = float(_scalar(p, 'num_sh_term_factor', 1.0))
+        self._cell_to_point_ratio = float(_scalar(p, 'cell_to_point_ratio', 1.5))
         self._xbc = str(_scalar(p, 'x_boundary_condition', 'periodic'))
         self._ybc = str(_scalar(p, 'y_boundary_condition', 'periodic'))
         if int(_scalar(p, 'angle_set', 2)) != 2:
@@ -89,7 +94,8 @@ class RTE:
         self._prepare_optical_properties()
         self._solved = None
         self._dev = None
-        self._iters, self._solcrit, self._timings = 0, 1.0, {}
+        self._unsplit = None
+        self._iters, self._solcrit, self._splitcrit, self._timings = 0, 1.0, 0.0, {}
 
     # -- _setup_grid (at3d/solver.py:2036-2168) --
     def _setup_grid(self, grid):
@@ -209,18 +215,52 @@ class RTE:
         return st
 
     def solve(self, maxiter, init_solution=True, setup_grid=True, verbose=False, solve=True):
-        """``RTE.solve`` (at3d/solver.py:279): SHDOM solution iterations on the GPU; fixed grid (``split_accuracy`` 0)."""
-        if self._splitacc > 0.0:
-            raise NotImplementedError('adaptive grid splitting (split_accuracy > 0: SPLIT_GRID) is not implemented; '
+        """``RTE.solve`` (at3d/solver.py:279): INIT_SOLUTION + SOLUTION_ITERATIONS on the GPU.  3-D grids (and 2-D ones with
+        ``ny = 1``) go through ``at3d_solve_adaptive``: Eddington first guess, adaptive cell splitting when
+        ``split_accuracy > 0`` (the base grid is re-created, as with ``setup_grid=True`` in the reference), array
+        capacities from ``adapt_grid_factor`` / ``num_sh_term_factor`` / ``cell_to_point_ratio``.  Independent-pixel
+        grids (``ip_flag=3``) take the fixed-grid column solver."""
+        if not init_solution:
+            raise NotImplementedError('solve(init_solution=False) (continuing from the previous SOURCE / RADIANCE) is not '
+                                      'implemented: every solve starts from INIT_RADIANCE')
+        if (self._ipflag & 3) == 3 and self._splitacc > 0.0:
+            raise NotImplementedError('cell splitting on independent-pixel grids (ip_flag=3) is not implemented; '
                                       'set split_accuracy=0.0')
+        if self._unsplit is not None:
+            (self._npts, self._ncells, self._gridpos, self._gridptr, self._neighptr, self._treeptr, self._cellflags,
+             self._t) = self._unsplit
         st = self._init_solution()
         if not solve:
             return
-        sol, self._iters, self._solcrit, self._timings = S.solve_fixed_grid(
-            st, self._wtmu, maxiter=maxiter, solacc=self._solacc, shacc=self._shacc, accelflag=self._accelflag,
-            highorderrad=self._highorderrad, iterfixsh=self._iterfixsh, transmin=self._transmin)
+        if (self._ipflag & 3) == 3:
+            sol, iters, self._solcrit, self._timings = S.solve_fixed_grid(
+                st, self._wtmu, maxiter=maxiter, solacc=self._solacc, shacc=self._shacc, accelflag=self._accelflag,
+                highorderrad=self._highorderrad, iterfixsh=self._iterfixsh, transmin=self._transmin)
+        else:
+            if self._unsplit is None:
+                self._unsplit = (self._npts, self._ncells, self._gridpos, self._gridptr, self._neighptr, self._treeptr,
+                                 self._cellflags, self._t)
+            sol, iters, self._solcrit, self._splitcrit, ms = S.solve_adaptive(
+                st, self._pg, self._wtmu, splitacc=self._splitacc, shacc=self._shacc, solacc=self._solacc, maxiter=maxiter,
+                accelflag=self._accelflag, highorderrad=self._highorderrad, iterfixsh=self._iterfixsh,
+                adapt_grid_factor=self._adapt_grid_factor, num_sh_term_factor=self._num_sh_term_factor,
+                cell_to_point_ratio=self._cell_to_point_ratio, transmin=self._transmin, timing=True)
+            self._timings = dict(path_integration_ms=ms[0], compute_source_ms=ms[1], split_ms=ms[2], total_ms=ms[3])
+            # the solved state carries the split grid and the optical properties on it
+            self._npts, self._ncells = sol.npts, sol.ncells
+            self._gridpos, self._gridptr, self._neighptr = sol.gridpos, sol.gridptr, sol.neighptr
+            self._treeptr, self._cellflags = sol.treeptr, sol.cellflags
+            self._t = dict(self._t, extinct=sol.extinct, albedo=sol.albedo, total_ext=sol.total_ext, iphase=sol.iphase,
+                           phaseinterpwt=sol.phaseinterpwt)
+            # SKYRAD-free Lambertian boundary radiances are rebuilt by the device state from FLUXES
+            ntop, nbot, bcptr = G.boundary_pnts(sol.npts, sol.gridpos, self._zgrid[0], self._zgrid[-1])
+            sol.bcptr, sol.maxnbc, sol.ntoppts, sol.nbotpts = bcptr, bcptr.shape[0], ntop, nbot
+            sol.bcrad = np.zeros((self._nstokes, ntop + nbot), np.float32, order='F')
+            sol.sfcgridparms = np.zeros((2, nbot), np.float32, order='F')
+            sol.normalize()
+        self._iters = iters
         if verbose:
-            print('  %d iterations, solution criterion %.3e' % (self._iters, self._solcrit))
+            print('  %d iterations, solution criterion %.3e, %d grid points' % (self._iters, self._solcrit, sol.npts))
         self._set_solution(sol)
 
     def _set_solution(self, sol):
@@ -255,25 +295,49 @@ class RTE:
         if (np.any(_v(d, 'xgrid') != self._xgrid[:self._nx1]) or np.any(_v(d, 'ygrid') != self._ygrid[:self._ny1])
                 or np.any(_v(d, 'zgrid') != self._zgrid)):
             raise ValueError('Incompatible base grid in the saved solution')
-        self._npts, self._ncells = int(_scalar(d, 'npts')), int(_scalar(d, 'ncells'))
-        self._gridpos = np.asfortranarray(_v(d, 'gridpos'), np.float32)[:, :self._npts]
-        self._gridptr = np.asfortranarray(_v(d, 'gridptr'), np.int32)[:, :self._ncells]
-        self._neighptr = np.asfortranarray(_v(d, 'neighptr'), np.int32)[:, :self._ncells]
-        self._treeptr = np.asfortranarray(_v(d, 'treeptr'), np.int32)[:, :self._ncells]
-        self._cellflags = np.ascontiguousarray(_v(d, 'cellflags'), np.int16)[:self._ncells]
+        # validate everything before touching the object (a rejected dataset must leave the RTE as it was)
+        npts, ncells = int(_scalar(d, 'npts')), int(_scalar(d, 'ncells'))
+        gridpos = np.asfortranarray(_v(d, 'gridpos'), np.float32)
+        gridptr = np.asfortranarray(_v(d, 'gridptr'), np.int32)
+        neighptr = np.asfortranarray(_v(d, 'neighptr'), np.int32)
+        treeptr = np.asfortranarray(_v(d, 'treeptr'), np.int32)
+        cellflags = np.ascontiguousarray(_v(d, 'cellflags'), np.int16)
+        if (gridpos.shape[0] != 3 or gridpos.shape[1] < npts or gridptr.shape[0] != 8 or neighptr.shape[0] != 6
+                or treeptr.shape[0] != 2 or min(gridptr.shape[1], neighptr.shape[1], treeptr.shape[1], cellflags.shape[0]) < ncells):
+            raise ValueError('grid arrays of the saved solution do not match npts / ncells')
+        if ncells and (gridptr[:, :ncells].min() < 1 or gridptr[:, :ncells].max() > npts):
+            raise ValueError('GRIDPTR of the saved solution points outside 1..npts')
+        sh = None
+        if load_radiance:
+            if int(_scalar(d, 'nstokes')) != self._nstokes:
+                raise ValueError('Incompatible nstokes in the saved solution')
+            if int(_scalar(d, 'ml')) != self._ml or int(_scalar(d, 'mm')) != self._mm:
+                raise NotImplementedError('a saved solution with another angular resolution (ml, mm) is not re-truncated here')
+            sh = dict(shptr=np.ascontiguousarray(_v(d, 'shptr'), np.int32), rshptr=np.ascontiguousarray(_v(d, 'rshptr'), np.int32),
+                      source=np.asfortranarray(_v(d, 'source'), np.float32), radiance=np.asfortranarray(_v(d, 'radiance'), np.float32),
+                      fluxes=np.asfortranarray(_v(d, 'fluxes'), np.float32))
+            if (sh['shptr'].size < npts + 1 or sh['rshptr'].size < npts + 1 or sh['source'].shape[0] != self._nstokes
+                    or sh['radiance'].shape[0] != self._nstokes or sh['source'].shape[1] < int(sh['shptr'][npts])
+                    or sh['radiance'].shape[1] < int(sh['rshptr'][npts]) or sh['fluxes'].shape != (2, sh['fluxes'].shape[1])
+                    or sh['fluxes'].shape[1] < npts):
+                raise ValueError('SH arrays of the saved solution do not match npts / SHPTR / RSHPTR')
+            if sh['rshptr'].size < npts + 2:
+                sh['rshptr'] = np.append(sh['rshptr'][:npts + 1], sh['rshptr'][npts]).astype(np.int32)
+        if self._unsplit is None:
+            self._unsplit = (self._npts, self._ncells, self._gridpos, self._gridptr, self._neighptr, self._treeptr,
+                             self._cellflags, self._t)
+        self._npts, self._ncells = npts, ncells
+        self._gridpos = np.asfortranarray(gridpos[:, :npts])
+        self._gridptr = np.asfortranarray(gridptr[:, :ncells])
+        self._neighptr = np.asfortranarray(neighptr[:, :ncells])
+        self._treeptr = np.asfortranarray(treeptr[:, :ncells])
+        self._cellflags = cellflags[:ncells].copy()
         self._t = B.transfer_pa_to_grid(self._pg, self._gridpos, self._npts, self._ml, self._deltam)
         st = self._init_solution()
         if not load_radiance:
             return
-        if int(_scalar(d, 'nstokes')) != self._nstokes:
-            raise ValueError('Incompatible nstokes in the saved solution')
-        if int(_scalar(d, 'ml')) != self._ml or int(_scalar(d, 'mm')) != self._mm:
-            raise NotImplementedError('a saved solution with another angular resolution (ml, mm) is not re-truncated here')
-        st.shptr = np.ascontiguousarray(_v(d, 'shptr'), np.int32)
-        st.rshptr = np.ascontiguousarray(_v(d, 'rshptr'), np.int32)
-        st.source = np.asfortranarray(_v(d, 'source'), np.float32)
-        st.radiance = np.asfortranarray(_v(d, 'radiance'), np.float32)
-        st.fluxes = np.asfortranarray(_v(d, 'fluxes'), np.float32)
+        st.shptr, st.rshptr = sh['shptr'][:npts + 1].copy(), sh['rshptr'][:npts + 2].copy()
+        st.source, st.radiance, st.fluxes = sh['source'], sh['radiance'], np.asfortranarray(sh['fluxes'][:, :npts])
         self._solcrit = self._solacc                       # the saved fields are taken as converged
         self._set_solution(st.normalize())
 

@@ -81,8 +81,8 @@ def test_rte_solve_and_integrate_to_sensor(bc, nstokes, two):
     dirflux_ref = O.make_direct(st0, rte._pg)[0]
     np.testing.assert_allclose(st0.dirflux, dirflux_ref, rtol=1e-5, atol=1e-7)
     assert st0.bcflag == (3 if bc == 'open' else 0) and st0.npart == (2 if two else 1)
-    # the solve and the rendering against the oracle on the same prepared state
-    ref, iters, solcrit = O.solve_fixed_grid(st0, rte._wtmu, solacc=1e-4, maxiter=60)
+    # the solve (Eddington first guess, no splitting) and the rendering against the oracle on the same prepared state
+    ref, iters, solcrit, _ = O.solve_adaptive(st0, rte._pg, rte._wtmu, splitacc=0.0, solacc=1e-4, maxiter=60)
     assert iters == rte.num_iterations
     np.testing.assert_array_equal(rte._solved.shptr, ref.shptr)
     np.testing.assert_allclose(rte._solved.fluxes, ref.fluxes, rtol=1e-4, atol=1e-7)
@@ -167,7 +167,7 @@ def test_rte_two_dimensional_domain():
     rte.solve(maxiter=60)
     st0 = rte._unsolved
     assert st0.ipflag == 2 and rte.check_solved()
-    ref, iters, solcrit = O.solve_fixed_grid(st0, rte._wtmu, solacc=1e-4, maxiter=60)
+    ref, iters, solcrit, _ = O.solve_adaptive(st0, rte._pg, rte._wtmu, splitacc=0.0, solacc=1e-4, maxiter=60)
     assert iters == rte.num_iterations
     np.testing.assert_allclose(rte._solved.fluxes, ref.fluxes, rtol=1e-4, atol=1e-7)
     n = 40
@@ -232,10 +232,50 @@ def test_rte_save_and_load_solution():
         r.close()
 
 
-def test_rte_refuses_adaptive_splitting():
+def test_rte_default_config_adaptive_solve():
+    """The reference's default numerical parameters (default_config.json: split_accuracy 0.03, open boundaries, adapt grid
+    factor 5 ...) through RTE.solve: the grid is split on the way exactly as the oracle's SPLIT_GRID does, and
+    integrate_to_sensor works on the split grid; a second solve starts again from the base grid."""
     from at3d_b200.rte import RTE
-    params, medium, source, surface = make_inputs(5, 5, 6, 'periodic', 1, False)
-    params['split_accuracy'] = 0.03
+    from at3d_b200.state import Rays
+    params, medium, source, surface = make_inputs(8, 7, 10, 'open', 1, True)
+    params.update(split_accuracy=0.03, adapt_grid_factor=5, num_sh_term_factor=1, cell_to_point_ratio=1.5)
     rte = RTE(params, medium, source, surface)
+    rte.solve(maxiter=60)
+    st0 = rte._unsolved
+    ref, iters, solcrit, splitcrit = O.solve_adaptive(st0, rte._pg, rte._wtmu, splitacc=0.03, solacc=1e-4, maxiter=60)
+    assert ref.npts > st0.npts and rte.check_solved()
+    assert (rte._solved.npts, rte._solved.ncells, rte.num_iterations) == (ref.npts, ref.ncells, iters)
+    np.testing.assert_array_equal(rte._solved.gridptr, ref.gridptr)
+    np.testing.assert_array_equal(rte._solved.shptr, ref.shptr)
+    sensor = make_sensor(0.05 * 7, 0.05 * 6)
+    sensor['stokes'] = np.array([True, False, False, False])
+    out = rte.integrate_to_sensor(sensor)
+    rays = Rays(sensor['ray_x'], sensor['ray_y'], sensor['ray_z'], sensor['ray_mu'], sensor['ray_phi'])
+    refrad = O.render(ref, rays)
+    np.testing.assert_allclose(out['I'], refrad[0], rtol=1e-4, atol=1e-6 * refrad[0].max())
+    ds = rte.save_solution()
+    assert ds['npts'] == ref.npts and ds['nbcells'] == st0.ncells
+    npts1 = rte._solved.npts
+    rte.solve(maxiter=60)
+    assert rte._solved.npts == npts1 and rte._unsolved.npts == st0.npts
     with pytest.raises(NotImplementedError):
-        rte.solve(maxiter=5)
+        rte.solve(maxiter=5, init_solution=False)
+    rte.close()
+
+
+def test_rte_load_solution_validates_before_mutating():
+    from at3d_b200.rte import RTE
+    params, medium, source, surface = make_inputs(6, 6, 7, 'periodic', 1, False)
+    a = RTE(params, medium, source, surface)
+    a.solve(maxiter=40)
+    ds = a.save_solution()
+    before = (a._npts, a._ncells, a._solved.npts)
+    bad = dict(ds, shptr=ds['shptr'][:-3])
+    with pytest.raises(ValueError):
+        a.load_solution(bad)
+    bad = dict(ds, nstokes=3)
+    with pytest.raises(ValueError):
+        a.load_solution(bad)
+    assert (a._npts, a._ncells, a._solved.npts) == before
+    a.close()

@@ -49,15 +49,6 @@ def test_sweep3d_transmin_below_one(transmin):
         assert np.abs(rad - base).max() > 0            # the parameter does change the result
 
 
-def test_sweep3d_more_than_512_ordinates():
-    """NMU=28 / NPHI=56: ~1200 ordinates, more than 9 bits of the level-sort key (the key's ordinate field must be
-    sorted in full, otherwise plan slots of ordinates ia and ia+512 interleave)."""
-    sc = S.make_scene(nx=5, ny=5, nz=6, nmu=28, nphi=56, nstokes=1, bc='periodic', nsplits=3, seed=31)
-    O.finalize_scene(sc)
-    assert sc.state.nang > 1024
-    compare_path_integration(sc.state)
-
-
 def test_sweep3d_independent_pixel_in_x():
     """IPFLAG=1: the 3-D routine with the cells' IPINX flags (rays never leave through x faces)."""
     sc = S.make_scene(nx=6, ny=7, nz=8, nstokes=1, bc='periodic', nsplits=0, seed=21, ipflag=1)
