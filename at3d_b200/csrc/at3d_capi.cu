@@ -113,7 +113,7 @@ extern "C" int at3d_state_destroy(at3d_state *st)
     st->hits.release(); st->viewsrc.release();
     if (st->packs_h) cudaFreeHost(st->packs_h);
     st->rays.release(); st->out.release(); st->trace.release(); st->misc.release();
-    st->slabs.release(); st->err.release(); st->recs.release();
+    st->slabs.release(); st->err.release(); st->recs.release(); st->pairs.release();
     delete st;
     return 0;
 }

@@ -76,7 +76,22 @@ struct DevState {
     // [2] sum of NS over evaluated points, [3] sum of NR (gradient), [4] sub-intervals, [5] rays marched,
     // [6] rays that ended on a general-BRDF surface
     unsigned long long *counts;
+    // source stream of the gradient's forward pass (thread-per-ray kernels): every corner evaluated while the adjoint
+    // arithmetic is still integrating leaves (SRCEXT8/EXT, single-scatter part * EXT), in evaluation order, in chunks of
+    // AT3D_SRC_CHUNK entries drawn from a pool; the last entry of a chunk links to the ray's next chunk.  nullptr: off.
+    // Chunk cursors: same-address atomics serialise in L2 (one cursor for all blocks cost 7.5 ms per 1.2 M chunks), so
+    // the pool is split into AT3D_SRC_REGIONS regions of srcpool_region chunks with a cursor each (block b draws from
+    // region b mod AT3D_SRC_REGIONS) and a shared tail behind them for blocks that exhaust their region.
+    float2 *srcpool;
+    unsigned srcpool_chunks;                 // all chunks
+    unsigned srcpool_region;                 // chunks per region
+    unsigned srcpool_nreg;                   // regions in use (<= AT3D_SRC_REGIONS): the SM count
+    unsigned *srcpool_top;                   // [0] shared-tail cursor, [1] overflow flag, [32 * (r + 1)] cursor of region r
+    long long *srcstart;                     // [nrays of the launch] first entry of the ray, -1: none
 };
+#define AT3D_SRC_CHUNK 64
+#define AT3D_SRC_REGIONS 256
+#define AT3D_SRC_TOP_WORDS (32 * (AT3D_SRC_REGIONS + 1))
 
 // Derivative tables of LEVISAPPROX_GRADIENT resident in HBM (reference layouts, see at3d_grad_desc).
 struct DevGrad {

@@ -36,6 +36,8 @@ struct __align__(16) VisitRec {
     int ip;                 // grid point (1-based)
     float srcfull[3];       // SRCEXT8 before the multiplication by the extinction
     double W, G;            // accumulated source-term / radiance-term weights
+    double B;               // adjoint-weighted SRCSINGSCAT of the visit: the point's BEAM_WEIGHT contribution
+    double pad;
 };
 
 // "unscaling" of a delta-M scaled tabulated Legendre entry (shdomsub4.f:1905-1925)
@@ -384,7 +386,7 @@ struct GCorner {
     int pt;
     float x, y, z, ext;
     float src[NST], ss[NST], srcfull[NST];
-    double W, G;            // weights accumulated since the point became a corner
+    double W, G, B;         // weights accumulated since the point became a corner
 };
 
 template <int NST>
@@ -397,6 +399,86 @@ __device__ __forceinline__ void write_visit(VisitRec *dst, const GCorner<NST> &K
     a.w = NST > 2 ? __float_as_int(K.srcfull[NST > 2 ? 2 : 0]) : 0;
     *(int4 *)dst = a;
     *((double2 *)dst + 1) = make_double2(K.W, K.G);
+    *((double2 *)dst + 2) = make_double2(K.B, 0.0);
+}
+
+// rows of GRADOUT a visit of grid point ip contributes to (+1: its BEAM_WEIGHT entry) = pair slots of its record
+__device__ __forceinline__ int visit_pairs(const DevGrad &G, int ip) { return (__ldg(&G.gptrec[ip - 1]).y & 0xFFFF) + 1; }
+
+#include "at3d_gwalk.cuh"
+#ifndef GW_BT
+#define GW_BT 256
+#endif
+#ifndef GW_MINB
+#define GW_MINB 1
+#endif
+
+// ------------------------------------------------------------------------------------------
+// Phase A for NSTOKES=1 with delta-M: the thread-per-ray walk of at3d_gwalk.cuh (sources from the forward pass's stream)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(GW_BT, GW_MINB)
+weights_kernel_t(DevState S, DevGrad G, int nrays, int ray0, const float *camx, const float *camy, const float *camz,
+                 const double *cammu, const double *camphi, const RayPack *packs, const int *raypix, const double *adjw,
+                 const double *ray_weights, const double *stokes_weights, const double *total,
+                 const long long *recoff /*[nrays+1]*/, long long rec_base, VisitRec *recs, int *nrec_out, int *npairs_out,
+                 int *trace_cells, int trace_cap, int *trace_n, int *trace_nsub, RayErr *err, int *ray_counter)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int bt = blockDim.x, lane = threadIdx.x & 31, tid = threadIdx.x;
+    GwShared M;
+    M.bt = bt;
+    {
+        unsigned char *q = smem_raw;
+        M.W = (double *)q + tid; q += (size_t)8 * 8 * bt;
+        M.Gr = (double *)q + tid; q += (size_t)8 * 8 * bt;
+        M.B = (double *)q + tid; q += (size_t)8 * 8 * bt;
+        M.sf = (float *)q + tid; q += (size_t)8 * 4 * bt;
+        M.ss = (float *)q + tid; q += (size_t)8 * 4 * bt;
+        M.bw = (float *)q + tid;
+    }
+    for (;;) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(ray_counter, 32);
+        base = __shfl_sync(FULLMASK, base, 0);
+        if (ray0 + base >= nrays) break;
+        const int iray = ray0 + base + lane;
+        int ntrace = 0, nsub = 0, npt = 0, marched = 0, nrec = 0, npairs = 0;
+        if (iray < nrays) {
+            const double mu2 = __ldg(&cammu[iray]), phi2 = __ldg(&camphi[iray]);
+            const RayPack pk = dev_get_pack(S, packs, iray, camx, camy, camz, mu2, phi2);
+            if (pk.status == 2) set_err(err, 2, iray);
+            else if (pk.status == 0) {
+                const int pix = __ldg(&raypix[iray]);
+                const double adj = __ldg(&adjw[pix]) * __ldg(&ray_weights[iray]) * __ldg(&stokes_weights[pix]);
+                RayDir rd;
+                dev_ray_dir(S, pk, rd); rd.phi2 = (float)phi2;
+                rd.hit = nullptr;
+                const float sky = (-mu2 > 0.0) ? dev_sky_radiance(S, (float)mu2, (float)phi2) : 0.0f;
+                const long long r0 = __ldg(&recoff[iray]), r1 = __ldg(&recoff[iray + 1]);
+                SrcReader sr;
+                const long long s0 = __ldg(&S.srcstart[iray]);
+                sr.pool = S.srcpool; sr.p = S.srcpool + (s0 < 0 ? 0 : s0); sr.left = AT3D_SRC_CHUNK - 1;
+                const int e = thread_march_weights(S, G, M, rd, mu2, pk.x0, pk.y0, pk.z0, sky, adj, __ldg(&total[iray]), sr,
+                                                   recs + (r0 - rec_base), (int)(r1 - r0),
+                                                   trace_cells ? trace_cells + (size_t)trace_cap * iray : nullptr, trace_cap,
+                                                   ntrace, nsub, npt, nrec, npairs);
+                if (e) { set_err(err, e, iray); nrec = 0; npairs = 0; }
+                else marched = 1;
+            }
+            nrec_out[iray] = nrec;
+            npairs_out[iray] = npairs;
+            if (trace_n) { trace_n[iray] = ntrace; trace_nsub[iray] = nsub; }
+        }
+        __syncwarp();
+        if (S.counts) {
+            const int c0 = __reduce_add_sync(FULLMASK, marched ? ntrace : 0), c1 = __reduce_add_sync(FULLMASK, marched ? npt : 0);
+            const int c4 = __reduce_add_sync(FULLMASK, marched ? nsub : 0), c5 = __reduce_add_sync(FULLMASK, marched);
+            if (lane == 0) {
+                atomicAdd(&S.counts[0], (unsigned long long)c0); atomicAdd(&S.counts[1], (unsigned long long)c1);
+                atomicAdd(&S.counts[4], (unsigned long long)c4); atomicAdd(&S.counts[5], (unsigned long long)c5);
+            }
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -406,8 +488,8 @@ template <int NST>
 __device__ int march_weights(const DevState &S, const DevGrad &G, const float *Ysh, const float *Vsh,
                              const RayDir &rd, double mu2, double x0, double y0, double z0, float sky,
                              const double (&adj)[NST], const double (&total)[NST], const Oct &o,
-                             VisitRec *rec, int cap, double *beam_weight,
-                             int *trace_cells, int trace_cap, int &ntrace, int &nsub, int &nrec)
+                             VisitRec *rec, int cap,
+                             int *trace_cells, int trace_cap, int &ntrace, int &nsub, int &nrec, int &npairs)
 {
     double xe = x0, ye = y0, ze = z0, transmit = 1.0;
     double radout[NST];
@@ -422,11 +504,13 @@ __device__ int march_weights(const DevState &S, const DevGrad &G, const float *Y
     int iface = 0, npassed = 1, jf = 0;
     bool done = false;
     int npt_eval = 0, nsh_eval = 0;
+    int bnd_pt = 0; double bnd_val = 0.0;            // surface point of lanes 0..3 (ray ends on the ground)
     GCorner<NST> K;
-    K.pt = 0; K.x = K.y = K.z = K.ext = 0.0f; K.W = 0.0; K.G = 0.0;
+    K.pt = 0; K.x = K.y = K.z = K.ext = 0.0f; K.W = 0.0; K.G = 0.0; K.B = 0.0;
 #pragma unroll
     for (int k = 0; k < NST; k++) { K.src[k] = 0.0f; K.ss[k] = 0.0f; K.srcfull[k] = 0.0f; }
     ntrace = 0; nsub = 0; nrec = 0;
+    int mypairs = 0;                                 // pair slots of the records this lane wrote
     int err = 0;
     bool any_cell = false;
     CellRec c;
@@ -442,17 +526,19 @@ __device__ int march_weights(const DevState &S, const DevGrad &G, const float *Y
             const bool hit = (jf != 0) && (cand == myp);
             // the old corner of this lane survives iff lane `from` (its only possible heir) hit it
             const bool heir_hit = __shfl_sync(o.m, (int)hit, from, 8) != 0;
-            const bool evict = any_cell && !heir_hit;
+            // (a visit in clear air contributes exactly nothing: no record)
+            const bool evict = any_cell && !heir_hit && (K.W != 0.0 || K.G != 0.0 || K.B != 0.0);
             const unsigned ev = oct_ballot(o, evict);
             if (evict) {
                 const int k = nrec + __popc(ev & ((1u << o.ol) - 1));
-                if (k < cap) write_visit<NST>(rec + k, K); else err = 5;
+                if (k < cap) { write_visit<NST>(rec + k, K); mypairs += visit_pairs(G, K.pt); } else err = 5;
             }
             nrec += __popc(ev);
             const int src_lane = hit ? from : o.ol;
             K.x = __shfl_sync(o.m, K.x, src_lane, 8); K.y = __shfl_sync(o.m, K.y, src_lane, 8);
             K.z = __shfl_sync(o.m, K.z, src_lane, 8); K.ext = __shfl_sync(o.m, K.ext, src_lane, 8);
             K.W = __shfl_sync(o.m, K.W, src_lane, 8); K.G = __shfl_sync(o.m, K.G, src_lane, 8);
+            K.B = __shfl_sync(o.m, K.B, src_lane, 8);
 #pragma unroll
             for (int k = 0; k < NST; k++) {
                 K.src[k] = __shfl_sync(o.m, K.src[k], src_lane, 8);
@@ -467,7 +553,7 @@ __device__ int march_weights(const DevState &S, const DevGrad &G, const float *Y
             for (int k = 0; k < NST; k++) b[k] = 0.0f;
             if (!hit) {
                 load_corner<NST>(S, myp, rd, K.x, K.y, K.z, K.ext, soff, sns, b);
-                K.W = 0.0; K.G = 0.0;
+                K.W = 0.0; K.G = 0.0; K.B = 0.0;
             }
             unsigned need = oct_ballot(o, !hit);
             npt_eval += __popc(need);
@@ -642,7 +728,7 @@ __device__ int march_weights(const DevState &S, const DevGrad &G, const float *Y
             double bsum = 0.0;
 #pragma unroll
             for (int k = 0; k < NST; k++) bsum += adj[k] * (double)bw[k];
-            if (bsum != 0.0) atomicAdd(&beam_weight[K.pt - 1], bsum);
+            K.B += bsum;
         }
         if (inextcell > 0) {
             if (jface == 1) xn = (double)snap;
@@ -662,8 +748,8 @@ __device__ int march_weights(const DevState &S, const DevGrad &G, const float *Y
                 int bp = boundpts[0]; double bi = boundinterp[0], dr = dirrad1[0];
 #pragma unroll
                 for (int n = 1; n < 4; n++) if (o.ol == n) { bp = boundpts[n]; bi = boundinterp[n]; dr = dirrad1[n]; }
-                const double val = adj[0] * transmit * bi * dr;
-                if (val != 0.0) atomicAdd(&beam_weight[bp - 1], val);
+                bnd_val = adj[0] * transmit * bi * dr;
+                if (bnd_val != 0.0) bnd_pt = bp;
             }
         } else {
             icell = inextcell; c = cn;
@@ -673,9 +759,34 @@ __device__ int march_weights(const DevState &S, const DevGrad &G, const float *Y
     }
     // the corners of the last cell
     if (any_cell && !err) {
-        const int k = nrec + o.ol;
-        if (k < cap) write_visit<NST>(rec + k, K); else err = 5;
-        nrec += 8;
+        const bool keep = K.W != 0.0 || K.G != 0.0 || K.B != 0.0;
+        const unsigned kb = oct_ballot(o, keep);
+        if (keep) {
+            const int k = nrec + __popc(kb & ((1u << o.ol) - 1));
+            if (k < cap) { write_visit<NST>(rec + k, K); mypairs += visit_pairs(G, K.pt); } else err = 5;
+        }
+        nrec += __popc(kb);
+    }
+    // the four surface points of a ray that ends on the ground carry the direct-beam part of the reflected radiance
+    // (FIND_BOUNDARY_RADIANCE_GRAD): four records with a beam weight only
+    const unsigned bm = oct_ballot(o, bnd_pt > 0);
+    if (any_cell && !err && bm) {
+        if (bnd_pt > 0) {
+            const int k = nrec + __popc(bm & ((1u << o.ol) - 1));
+            if (k < cap) {
+                GCorner<NST> Z;
+                Z.pt = bnd_pt; Z.W = 0.0; Z.G = 0.0; Z.B = bnd_val;
+#pragma unroll
+                for (int q = 0; q < NST; q++) Z.srcfull[q] = 0.0f;
+                write_visit<NST>(rec + k, Z); mypairs += visit_pairs(G, bnd_pt);
+            } else err = 5;
+        }
+        nrec += __popc(bm);
+    }
+    {
+        int t = mypairs;
+        t += __shfl_xor_sync(o.m, t, 1, 8); t += __shfl_xor_sync(o.m, t, 2, 8); t += __shfl_xor_sync(o.m, t, 4, 8);
+        npairs = t;
     }
     err = __reduce_max_sync(o.m, err);
     if (S.counts && o.ol == 0) {
@@ -738,7 +849,7 @@ weights_kernel(DevState S, DevGrad G, int nrays, const float *camx, const float 
                const int *raypix, const double *adjw /*[NST,npix]*/, const double *ray_weights,
                const double *stokes_weights, const double *total /*[NST,nrays]*/,
                const long long *recoff /*[nrays+1]*/, long long rec_base, VisitRec *recs, int *nrec_out,
-               double *beam_weight, int *trace_cells, int trace_cap, int *trace_n, int *trace_nsub, RayErr *err,
+               int *npairs_out, int *trace_cells, int trace_cap, int *trace_n, int *trace_nsub, RayErr *err,
                int *ray_counter, int ray0)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -755,7 +866,7 @@ weights_kernel(DevState S, DevGrad G, int nrays, const float *camx, const float 
         const int iray = ray0 + base + (lane >> 3);
         if (iray < nrays) {
             RayPack pk; RayDir rd; double mu2, phi2, adj[NST];
-            int ntrace = 0, nsub = 0, nrec = 0;
+            int ntrace = 0, nsub = 0, nrec = 0, npairs = 0;
             if (ray_setup<NST>(S, iray, camx, camy, camz, cammu, camphi, packs, raypix, adjw, ray_weights,
                                stokes_weights, Ysh, Vsh, o, err, pk, rd, mu2, phi2, adj)) {
                 double tot[NST];
@@ -764,14 +875,15 @@ weights_kernel(DevState S, DevGrad G, int nrays, const float *camx, const float 
                 const float sky = (-mu2 > 0.0) ? dev_sky_radiance(S, (float)mu2, (float)phi2) : 0.0f;
                 const long long r0 = __ldg(&recoff[iray]), r1 = __ldg(&recoff[iray + 1]);
                 const int e = march_weights<NST>(S, G, Ysh, Vsh, rd, mu2, pk.x0, pk.y0, pk.z0, sky, adj, tot, o,
-                                                 recs + (r0 - rec_base), (int)(r1 - r0), beam_weight,
+                                                 recs + (r0 - rec_base), (int)(r1 - r0),
                                                  trace_cells ? trace_cells + (size_t)trace_cap * iray : nullptr,
-                                                 trace_cap, ntrace, nsub, nrec);
+                                                 trace_cap, ntrace, nsub, nrec, npairs);
                 if (e && o.ol == 0) set_err(err, e, iray);
-                if (e) nrec = 0;
+                if (e) { nrec = 0; npairs = 0; }
             }
             if (o.ol == 0) {
                 nrec_out[iray] = nrec;
+                npairs_out[iray] = npairs;
                 if (trace_n) { trace_n[iray] = ntrace; trace_nsub[iray] = nsub; }
             }
         }
@@ -784,10 +896,19 @@ weights_kernel(DevState S, DevGrad G, int nrays, const float *camx, const float 
 // (shdomsub4.f:1786-2019 with the tables of grad_prep_kernel) and the scatter into GRADOUT
 // (shdomsub4.f:3751-3764, 4101-4109).  One octet per ray.
 // ------------------------------------------------------------------------------------------
-template <int NST>
+// destination of the contributions: PAIRS: (key, value) slots of the ray (sorted by key and summed per key afterwards:
+// no atomics, one owner per GRADOUT entry, deterministic); otherwise red.global.add.f64 (Jacobian path)
+struct PairOut {
+    unsigned *keys;         // slot -> entry of GRADOUT (< ngrad) or ngrad + grid point (BEAM_WEIGHT)
+    double *vals;
+    unsigned ngrad;
+};
+
+template <int NST, bool PAIRS>
 __device__ __forceinline__ void apply_record(const DevState &S, const DevGrad &G, const VisitRec &rc,
                                              const float *Ysh, const float *Vsh, const RayDir &rd,
                                              const double (&adj)[NST], const Oct &o, double *gradout,
+                                             double *beam_weight, const PairOut &po, long long &slot,
                                              int &nrh_eval)
 {
     const int nlmp = S.nlmp, ml = S.ml, nd = G.numder;
@@ -896,17 +1017,25 @@ __device__ __forceinline__ void apply_record(const DevState &S, const DevGrad &G
         for (int k = 0; k < NST; k++) v += adj[k] * (double)(c_src * sourcet[k]);
         if (o.ol == 0) {
             const double val = rc.W * v + (double)__int_as_float(h0.z) * rc.G;
-            if (val != 0.0) atomicAdd(&gradout[(size_t)(h0.w - 1) + (size_t)G.maxpg * idr], val);
+            const size_t dst = (size_t)(h0.w - 1) + (size_t)G.maxpg * idr;
+            if (PAIRS) { po.keys[slot + r] = (unsigned)dst; po.vals[slot + r] = val; }
+            else if (val != 0.0) atomicAdd(&gradout[dst], val);
         }
     }
+    if (o.ol == 0) {
+        if (PAIRS) { po.keys[slot + nrows] = po.ngrad + (unsigned)ipz; po.vals[slot + nrows] = rc.B; }
+        else if (rc.B != 0.0) atomicAdd(&beam_weight[ipz], rc.B);
+    }
+    slot += nrows + 1;
 }
 
-template <int NST>
+template <int NST, bool PAIRS>
 __global__ void __launch_bounds__(AT3D_RAY_THREADS)
 apply_kernel(DevState S, DevGrad G, int nrays, const float *camx, const float *camy,
              const float *camz, const double *cammu, const double *camphi, const RayPack *packs,
              const int *raypix, const double *adjw, const double *ray_weights, const double *stokes_weights,
              const long long *recoff, long long rec_base, const VisitRec *recs, const int *nrec_in, double *gradout,
+             double *beam_weight, PairOut po, const long long *pairoff /*[nrays - ray0 + 1], PAIRS only*/,
              RayErr *err, int *ray_counter, int ray0)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -928,13 +1057,16 @@ apply_kernel(DevState S, DevGrad G, int nrays, const float *camx, const float *c
                                            stokes_weights, Ysh, Vsh, o, err, pk, rd, mu2, phi2, adj)) {
                 const VisitRec *rp = recs + (__ldg(&recoff[iray]) - rec_base);
                 int nrh = 0;
+                long long slot = PAIRS ? __ldg(&pairoff[iray - ray0]) : 0;
                 for (int i = 0; i < nrec; i++) {
                     VisitRec rc;
-                    const int4 a = __ldg((const int4 *)(rp + i));
-                    const double2 b = __ldg((const double2 *)(rp + i) + 1);
+                    const int4 a = __ldg((const int4 *)rp);
+                    const double2 b = __ldg((const double2 *)rp + 1);
+                    const double2 c = __ldg((const double2 *)rp + 2);
                     rc.ip = a.x; rc.srcfull[0] = __int_as_float(a.y); rc.srcfull[1] = __int_as_float(a.z);
-                    rc.srcfull[2] = __int_as_float(a.w); rc.W = b.x; rc.G = b.y;
-                    apply_record<NST>(S, G, rc, Ysh, Vsh, rd, adj, o, gradout, nrh);
+                    rc.srcfull[2] = __int_as_float(a.w); rc.W = b.x; rc.G = b.y; rc.B = c.x;
+                    apply_record<NST, PAIRS>(S, G, rc, Ysh, Vsh, rd, adj, o, gradout, beam_weight, po, slot, nrh);
+                    rp++;
                 }
                 if (S.counts && o.ol == 0) atomicAdd(&S.counts[3], (unsigned long long)nrh);
             }
@@ -947,12 +1079,12 @@ apply_kernel(DevState S, DevGrad G, int nrays, const float *camx, const float *c
 // Phase 1 tail / Phase 2: ray -> pixel accumulation (shdomsub4.f:693-696), COMPUTE_ADJOINT_WEIGHTS
 // ------------------------------------------------------------------------------------------
 template <int NST>
-__global__ void pixel_kernel(int npix, const int *pixstart, const int *rays_per_pixel, const double *visrad,
+__global__ void pixel_kernel(int pix0, int npix, const int *pixstart, const int *rays_per_pixel, const double *visrad,
                              const double *ray_weights, const double *stokes_weights, const float *measurements,
                              const double *unc, int nunc, int costfunc_ll, float *stokesout, double *adjw,
                              double *costp, int *raypix)
 {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    const int p = pix0 + blockIdx.x * blockDim.x + threadIdx.x;      // pixels [pix0, npix)
     if (p >= npix) return;
     const int r0 = pixstart[p], n = rays_per_pixel[p];
     float so[NST];
@@ -1016,8 +1148,30 @@ __global__ void cost_reduce_kernel(int n, const double *costp, double *cost)
 }
 
 // Phase 4: COMPUTE_DIRECT_BEAM_DERIV_ADJOINT (shdomsub4.f:792-802,4117-4143): one warp per grid point
-// with a non-zero beam weight walks its zero-terminated DPTR/DPATH list.
-__global__ void beam_kernel(DevGrad G, int npts, const double *beam_weight, double *gradout)
+// with a non-zero beam weight walks its zero-terminated DPTR/DPATH list.  PAIRS: the contributions go to the
+// point's (key, value) slots (beam_count_kernel sized them) and are summed per GRADOUT entry by pair_sum_kernel.
+__global__ void beam_count_kernel(DevGrad G, int npts, const double *beam_weight, int *count)
+{
+    const int ip = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (ip >= npts) return;
+    int len = 0;
+    if (beam_weight[ip] != 0.0) {
+        const int *dptr = G.dptr + (size_t)G.longest_path_pts * ip;
+        for (int base = 0; base < G.longest_path_pts; base += 32) {
+            const int ii = base + lane;
+            const int ib = ii < G.longest_path_pts ? __ldg(&dptr[ii]) : 0;
+            const unsigned stop = __ballot_sync(FULLMASK, ib <= 0);
+            len += stop ? __ffs(stop) - 1 : 32;
+            if (stop) break;
+        }
+    }
+    if (lane == 0) count[ip] = len * G.numder;
+}
+
+template <bool PAIRS>
+__global__ void beam_kernel(DevGrad G, int npts, const double *beam_weight, double *gradout, const long long *pairoff,
+                            unsigned *keys, double *vals)
 {
     const int ip = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -1026,6 +1180,7 @@ __global__ void beam_kernel(DevGrad G, int npts, const double *beam_weight, doub
     if (bwt == 0.0) return;
     const float *dpath = G.dpath + (size_t)G.longest_path_pts * ip;
     const int *dptr = G.dptr + (size_t)G.longest_path_pts * ip;
+    const long long slot0 = PAIRS ? pairoff[ip] : 0;
     for (int base = 0; base < G.longest_path_pts; base += 32) {
         const int ii = base + lane;
         const int ib = ii < G.longest_path_pts ? __ldg(&dptr[ii]) : 0;
@@ -1037,10 +1192,46 @@ __global__ void beam_kernel(DevGrad G, int npts, const double *beam_weight, doub
             for (int idr = 0; idr < G.numder; idr++) {
                 const float dm = __ldg(&G.dextm[(ib - 1) + (size_t)G.maxpg * idr]);
                 const double val = dm * pb;
-                if (val != 0.0) atomicAdd(&gradout[(ib - 1) + (size_t)G.maxpg * idr], -val);
+                const size_t dst = (size_t)(ib - 1) + (size_t)G.maxpg * idr;
+                if (PAIRS) { keys[slot0 + (size_t)ii * G.numder + idr] = (unsigned)dst; vals[slot0 + (size_t)ii * G.numder + idr] = -val; }
+                else if (val != 0.0) atomicAdd(&gradout[dst], -val);
             }
         }
         if (stop) break;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Atomics-free accumulation of the (GRADOUT entry, value) pairs of the derivative pass: the pairs are sorted by entry
+// (cub radix sort, stable: equal keys keep their slot order, which is fixed by the ray order), pair_bounds_kernel finds
+// the run of every entry and pair_sum_kernel gives every entry to ONE warp, which adds the run in a fixed order
+// (lane-strided partial sums, then a fixed shuffle tree).  The result does not depend on scheduling: the gradient is
+// reproducible bit for bit.
+// ------------------------------------------------------------------------------------------
+__global__ void pair_bounds_kernel(long long n, const unsigned *keys, unsigned nkeys, long long *lo, long long *hi)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned k = keys[i];
+    if (k >= nkeys) return;
+    if (i == 0 || keys[i - 1] != k) lo[k] = i;
+    if (i == n - 1 || keys[i + 1] != k) hi[k] = i + 1;
+}
+
+__global__ void pair_sum_kernel(unsigned nkeys, unsigned ngrad, const long long *lo, const long long *hi, const double *vals,
+                                double *gradout, double *beam_weight)
+{
+    const unsigned k = (unsigned)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
+    if (k >= nkeys) return;
+    const long long a = lo[k], b = hi[k];
+    if (b <= a) return;
+    double acc = 0.0;
+    for (long long i = a + lane; i < b; i += 32) acc += vals[i];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(FULLMASK, acc, d);
+    if (lane == 0) {
+        if (k < ngrad) gradout[k] += acc; else beam_weight[k - ngrad] += acc;
     }
 }
 
@@ -1202,6 +1393,8 @@ static int stage_in(const T *src, size_t n, int host, void *dst, const T **out, 
 }
 
 struct IntToLL { __host__ __device__ long long operator()(int v) const { return (long long)v; } };
+// visit records of a ray: one per visit + up to four surface records (FIND_BOUNDARY_RADIANCE_GRAD's beam weights)
+struct VisitsToLL { __host__ __device__ long long operator()(int v) const { return (long long)v + 4; } };
 
 static size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
 
@@ -1220,6 +1413,59 @@ __global__ void jac_gather_kernel(int nst, int nd, int njac, int maxpg, int k, i
     if (i >= nd * njac) return;
     const int idr = i % nd, ji = i / nd;
     jac[k + nst * (idr + nd * ((size_t)ji + (size_t)njac * ipix))] = (float)gtmp[(size_t)(jacptr[ji] - 1) + (size_t)maxpg * idr];
+}
+
+// The pair buffers of the derivative pass: keys / values double-buffered for the radix sort, the run bounds per key
+// and the sort's scratch, carved out of one allocation.
+struct PairBufs {
+    unsigned *k0, *k1;
+    double *v0, *v1;
+    long long *lo, *hi;
+    void *tmp;
+    size_t tmpb;
+};
+
+static int pair_reserve(at3d_state *st, size_t npairs, unsigned nkeys, PairBufs &pb, char *errmsg)
+{
+    size_t tmpb = 0;
+    cub::DoubleBuffer<unsigned> dk((unsigned *)nullptr, (unsigned *)nullptr);
+    cub::DoubleBuffer<double> dv((double *)nullptr, (double *)nullptr);
+    cub::DeviceRadixSort::SortPairs(nullptr, tmpb, dk, dv, (long long)npairs, 0, 32, (cudaStream_t)0);
+    size_t o = 0;
+    const size_t o_k0 = o; o += al256(sizeof(unsigned) * npairs);
+    const size_t o_k1 = o; o += al256(sizeof(unsigned) * npairs);
+    const size_t o_v0 = o; o += al256(sizeof(double) * npairs);
+    const size_t o_v1 = o; o += al256(sizeof(double) * npairs);
+    const size_t o_lo = o; o += al256(sizeof(long long) * nkeys);
+    const size_t o_hi = o; o += al256(sizeof(long long) * nkeys);
+    const size_t o_tmp = o; o += al256(tmpb);
+    CUDA_TRY(st->pairs.reserve(o + 256));
+    unsigned char *b = (unsigned char *)st->pairs.p;
+    pb.k0 = (unsigned *)(b + o_k0); pb.k1 = (unsigned *)(b + o_k1);
+    pb.v0 = (double *)(b + o_v0); pb.v1 = (double *)(b + o_v1);
+    pb.lo = (long long *)(b + o_lo); pb.hi = (long long *)(b + o_hi);
+    pb.tmp = b + o_tmp; pb.tmpb = tmpb;
+    return 0;
+}
+
+// GRADOUT(key) += sum of the values with that key (keys >= ngrad: BEAM_WEIGHT(key - ngrad)), in a fixed order
+static int pair_accumulate(const PairBufs &pb, size_t npairs, unsigned nkeys, unsigned ngrad, double *grad_d, double *beam,
+                           cudaStream_t stream, char *errmsg)
+{
+    if (npairs == 0) return 0;
+    int bits = 1;
+    while (bits < 32 && (1ull << bits) < (unsigned long long)nkeys) bits++;
+    cub::DoubleBuffer<unsigned> dk(pb.k0, pb.k1);
+    cub::DoubleBuffer<double> dv(pb.v0, pb.v1);
+    size_t tmpb = pb.tmpb;
+    CUDA_TRY(cub::DeviceRadixSort::SortPairs(pb.tmp, tmpb, dk, dv, (long long)npairs, 0, bits, stream));
+    CUDA_TRY(cudaMemsetAsync(pb.lo, 0, sizeof(long long) * nkeys, stream));
+    CUDA_TRY(cudaMemsetAsync(pb.hi, 0, sizeof(long long) * nkeys, stream));
+    pair_bounds_kernel<<<(unsigned)((npairs + 255) / 256), 256, 0, stream>>>((long long)npairs, dk.Current(), nkeys, pb.lo, pb.hi);
+    pair_sum_kernel<<<(unsigned)(((size_t)nkeys * 32 + 255) / 256), 256, 0, stream>>>(nkeys, ngrad, pb.lo, pb.hi, dv.Current(),
+                                                                                     grad_d, beam);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
 }
 
 static int gradient_impl(at3d_state *st, const at3d_rays *rays, const at3d_grad_desc *g,
@@ -1265,7 +1511,7 @@ static int gradient_impl(at3d_state *st, const at3d_rays *rays, const at3d_grad_
     {
         size_t t2 = 0;
         cub::TransformInputIterator<long long, IntToLL, const int *> it((const int *)nullptr, IntToLL());
-        cub::DeviceScan::ExclusiveSum(nullptr, t2, it, (long long *)nullptr, (int)(n + 1), stream);
+        cub::DeviceScan::ExclusiveSum(nullptr, t2, it, (long long *)nullptr, (int)((n > (size_t)S.npts ? n : (size_t)S.npts) + 1), stream);
         if (t2 > cubtmp) cubtmp = t2;
     }
     o = 0;
@@ -1280,6 +1526,9 @@ static int gradient_impl(at3d_state *st, const at3d_rays *rays, const at3d_grad_
     const size_t w_npt = o; o += al256(sizeof(int) * (n + 1));
     const size_t w_recoff = o; o += al256(sizeof(long long) * (n + 1));
     const size_t w_nrec = o; o += al256(sizeof(int) * n);
+    const size_t w_npairs = o; o += al256(sizeof(int) * (n + 1));
+    const size_t w_pairoff = o; o += al256(sizeof(long long) * ((n > (size_t)S.npts ? n : (size_t)S.npts) + 2));
+    const size_t w_bcount = o; o += al256(sizeof(int) * ((size_t)S.npts + 1));
     const size_t w_grad = o; o += al256(sizeof(double) * ngrad);
     const size_t w_so = o; o += al256(sizeof(float) * nst * npix);
     const size_t w_cost = o; o += 256;
@@ -1290,6 +1539,11 @@ static int gradient_impl(at3d_state *st, const at3d_rays *rays, const at3d_grad_
     int *pixstart = (int *)(wb + w_pixstart), *raypix = (int *)(wb + w_raypix);
     int *npt = (int *)(wb + w_npt), *nrec = (int *)(wb + w_nrec);
     long long *recoff = (long long *)(wb + w_recoff);
+    int *npairs = (int *)(wb + w_npairs), *bcount = (int *)(wb + w_bcount);
+    long long *pairoff = (long long *)(wb + w_pairoff);
+    const size_t nkeys_sz = ngrad + (size_t)S.npts;
+    if (nkeys_sz >= 0xFFFFFFF0ull) { set_msg(errmsg, "GRADOUT has too many entries for 32-bit pair keys"); return 2; }
+    const unsigned nkeys = (unsigned)nkeys_sz;
     double *grad_d = host ? (double *)(wb + w_grad) : gradout;
     float *so_d = host ? (float *)(wb + w_so) : stokesout;
     double *cost_d = host ? (double *)(wb + w_cost) : cost;
@@ -1309,37 +1563,93 @@ static int gradient_impl(at3d_state *st, const at3d_rays *rays, const at3d_grad_
     CUDA_TRY(cudaMemsetAsync(so_d, 0, sizeof(float) * nst * npix, stream));
     CUDA_TRY(cudaMemsetAsync(cost_d, 0, sizeof(double), stream));
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-    if (kernel_ms) { for (int i = 0; i < 4; i++) cudaEventCreate(&ev[i]); cudaEventRecord(ev[0], stream); kernel_ms[4] = 0.0; }
+    if (kernel_ms) { for (int i = 0; i < 4; i++) cudaEventCreate(&ev[i]); cudaEventRecord(ev[0], stream); kernel_ms[4] = 0.0; kernel_ms[5] = 0.0; kernel_ms[6] = 0.0; kernel_ms[7] = 0.0; }
     if (n > 0 && npix > 0) {
         // ---- Phase 1: forward radiances (INTEGRATE_1RAY arithmetic for the pixel values; the
         //      ADJOINT_INTEGRATE_1RAY arithmetic for the totals the derivative pass needs) ----
         DevState Sf = S;          // the work counters describe the adjoint pass only
         Sf.counts = nullptr;
         CUDA_TRY(cudaMemsetAsync(st->counts_dev, 0, 8 * sizeof(unsigned long long), stream));
-        CUDA_TRY(cudaMemsetAsync(npt, 0, sizeof(int) * (n + 1), stream));
+        // NSTOKES=1 with delta-M: the forward pass leaves the corner sources in a stream and the derivative walk is the
+        // thread-per-ray one (at3d_gwalk.cuh); AT3D_B200_GRAD_PATH=legacy selects the octet walk, which also serves
+        // NSTOKES=3, no delta-M and the Jacobian
+        bool use_t = nst == 1 && S.deltam && njac == 0 && tray_block_threads(S) > 0;
+        if (const char *e = getenv("AT3D_B200_GRAD_PATH")) { if (!strcmp(e, "legacy")) use_t = false; }
+        long long *srcstart = nullptr;
+        unsigned *srctop = nullptr;
+        size_t src_chunks = 0;
         // orthographic views (runs of rays with one direction) read a per-view source evaluated once per grid point
         std::vector<size_t> seg_start, seg_len;
         std::vector<char> seg_view;
         view_segments(st, rays, seg_start, seg_len, seg_view);
-        for (size_t sgi = 0; sgi < seg_start.size(); sgi++) {
-            const size_t s0 = seg_start[sgi], sn = seg_len[sgi];
-            DevState Sg = Sf;
-            Sg.ray_base = (int)s0;
-            if (seg_view[sgi]) {
-                CUDA_TRY(st->viewsrc.reserve((size_t)S.npts * nst * sizeof(float)));
-                CUDA_TRY(launch_view_source(Sf, st->packs_h[s0], rays->cammu[s0], rays->camphi[s0], G.singlescatter,
-                                            (float *)st->viewsrc.p, stream));
-                Sg.viewsrc = (const float *)st->viewsrc.p;
+        for (int attempt = 0;; attempt++) {
+            bool at_limit = false;
+            if (use_t) {
+                // the stream pool is sized by the entries per ray the last call on this state saw
+                double src_gb = 16.0;
+                if (const char *e = getenv("AT3D_B200_SRC_GB")) { const double v = atof(e); if (v > 0.0) src_gb = v; }
+                const double est = st->gw_rec_per_ray > 0.0 ? st->gw_rec_per_ray : (double)(6 * (S.nx + S.ny + S.nz) + 64);
+                src_chunks = (size_t)(((double)n * (est * 1.5 + AT3D_SRC_CHUNK) + 4096.0) / AT3D_SRC_CHUNK);
+                if (src_chunks < 8 * AT3D_SRC_REGIONS) src_chunks = 8 * AT3D_SRC_REGIONS;
+                size_t lim = (size_t)(src_gb * 1073741824.0 / (sizeof(float2) * AT3D_SRC_CHUNK));
+                if (lim > 0x7FFFFFF0u) lim = 0x7FFFFFF0u;
+                if (src_chunks >= lim) { src_chunks = lim; at_limit = true; }
+                CUDA_TRY(st->slabs.reserve(src_chunks * AT3D_SRC_CHUNK * sizeof(float2)));
+                const size_t topb = sizeof(unsigned) * AT3D_SRC_TOP_WORDS;
+                CUDA_TRY(st->misc.reserve(topb + sizeof(long long) * (n + 1)));
+                srctop = (unsigned *)st->misc.p;
+                srcstart = (long long *)((unsigned char *)st->misc.p + topb);
+                CUDA_TRY(cudaMemsetAsync(srctop, 0, topb, stream));
+                Sf.srcpool = (float2 *)st->slabs.p; Sf.srcpool_chunks = (unsigned)src_chunks; Sf.srcpool_top = srctop;
+                int dev_ = 0, nsm_ = 148;
+                cudaGetDevice(&dev_);
+                cudaDeviceGetAttribute(&nsm_, cudaDevAttrMultiProcessorCount, dev_);
+                size_t nreg = (n + tray_block_threads(S) - 1) / tray_block_threads(S);     // blocks of the largest launch
+                if (nreg > (size_t)nsm_) nreg = (size_t)nsm_;
+                if (nreg > AT3D_SRC_REGIONS) nreg = AT3D_SRC_REGIONS;
+                Sf.srcpool_nreg = (unsigned)nreg;
+                Sf.srcpool_region = (unsigned)(src_chunks / 5 * 4 / nreg);
+            } else {
+                Sf.srcpool = nullptr;
             }
-            CUDA_TRY(launch_forward(Sg, (int)sn, camx ? camx + s0 : nullptr, camy ? camy + s0 : nullptr,
-                                    camz ? camz + s0 : nullptr, cammu + s0, camphi + s0, packs ? packs + s0 : nullptr,
-                                    nullptr, visrad + (size_t)nst * s0, total + (size_t)nst * s0, 3, 1,
-                                    G.singlescatter, 0, G.maxsub, nullptr, 0, nullptr, nullptr, (RayErr *)st->err.p,
-                                    st->ray_counter, npt + s0, stream));
+            CUDA_TRY(cudaMemsetAsync(npt, 0, sizeof(int) * (n + 1), stream));
+            for (size_t sgi = 0; sgi < seg_start.size(); sgi++) {
+                const size_t s0 = seg_start[sgi], sn = seg_len[sgi];
+                DevState Sg = Sf;
+                Sg.ray_base = (int)s0;
+                if (use_t) Sg.srcstart = srcstart + s0;
+                else if (seg_view[sgi]) {
+                    CUDA_TRY(st->viewsrc.reserve((size_t)S.npts * nst * sizeof(float)));
+                    CUDA_TRY(launch_view_source(Sf, st->packs_h[s0], rays->cammu[s0], rays->camphi[s0], G.singlescatter,
+                                                (float *)st->viewsrc.p, stream));
+                    Sg.viewsrc = (const float *)st->viewsrc.p;
+                }
+                CUDA_TRY(launch_forward(Sg, (int)sn, camx ? camx + s0 : nullptr, camy ? camy + s0 : nullptr,
+                                        camz ? camz + s0 : nullptr, cammu + s0, camphi + s0, packs ? packs + s0 : nullptr,
+                                        nullptr, visrad + (size_t)nst * s0, total + (size_t)nst * s0, 3, 1,
+                                        G.singlescatter, 0, G.maxsub, nullptr, 0, nullptr, nullptr, (RayErr *)st->err.p,
+                                        st->ray_counter, npt + s0, stream));
+            }
+            if (!use_t) break;
+            std::vector<unsigned> htop(AT3D_SRC_TOP_WORDS);
+            CUDA_TRY(cudaMemcpyAsync(htop.data(), srctop, sizeof(unsigned) * AT3D_SRC_TOP_WORDS, cudaMemcpyDeviceToHost, stream));
+            CUDA_TRY(cudaStreamSynchronize(stream));
+            double drawn = (double)htop[0];
+            for (int r = 0; r < AT3D_SRC_REGIONS; r++) {
+                const double d = (double)htop[32 * (r + 1)];
+                drawn += d < (double)Sf.srcpool_region ? d : (double)Sf.srcpool_region;
+            }
+            const double seen = drawn * AT3D_SRC_CHUNK / (double)n;
+            if (!htop[1]) { if (seen > st->gw_rec_per_ray) st->gw_rec_per_ray = seen; break; }
+            // the pool overflowed: walk again with a pool twice as large; at the memory limit (AT3D_B200_SRC_GB) the octet walk,
+            // which evaluates its sources itself, takes over (the radiances of this attempt are complete either way)
+            if (at_limit || attempt >= 6) { use_t = false; break; }
+            const double est = st->gw_rec_per_ray > 0.0 ? st->gw_rec_per_ray : (double)(6 * (S.nx + S.ny + S.nz) + 64);
+            st->gw_rec_per_ray = 2.0 * (seen > est ? seen : est);
         }
         // visit records of a ray are contiguous: offsets = exclusive scan (64-bit) of the per-ray visit counts
         {
-            cub::TransformInputIterator<long long, IntToLL, const int *> it(npt, IntToLL());
+            cub::TransformInputIterator<long long, VisitsToLL, const int *> it(npt, VisitsToLL());
             CUDA_TRY(cub::DeviceScan::ExclusiveSum(wb + w_cub, cubtmp, it, recoff, (int)(n + 1), stream));
         }
         if (kernel_ms) cudaEventRecord(ev[1], stream);
@@ -1347,10 +1657,10 @@ static int gradient_impl(at3d_state *st, const at3d_rays *rays, const at3d_grad_
         CUDA_TRY(cub::DeviceScan::ExclusiveSum(wb + w_cub, cubtmp, rpp, pixstart, (int)npix, stream));
         const int nb = (int)((npix + 127) / 128);
         if (nst == 1)
-            pixel_kernel<1><<<nb, 128, 0, stream>>>((int)npix, pixstart, rpp, visrad, rw, sw, meas, unc, nunc,
+            pixel_kernel<1><<<nb, 128, 0, stream>>>(0, (int)npix, pixstart, rpp, visrad, rw, sw, meas, unc, nunc,
                                                       g->costfunc_ll, so_d, adjw, costp, raypix);
         else
-            pixel_kernel<3><<<nb, 128, 0, stream>>>((int)npix, pixstart, rpp, visrad, rw, sw, meas, unc, nunc,
+            pixel_kernel<3><<<nb, 128, 0, stream>>>(0, (int)npix, pixstart, rpp, visrad, rw, sw, meas, unc, nunc,
                                                       g->costfunc_ll, so_d, adjw, costp, raypix);
         CUDA_TRY(cudaGetLastError());
         cost_reduce_kernel<<<1, 1024, 0, stream>>>((int)npix, costp, cost_d);
@@ -1364,20 +1674,31 @@ static int gradient_impl(at3d_state *st, const at3d_rays *rays, const at3d_grad_
         const long long *roff = st->recoff_h.data();
         double budget_gb = 8.0;
         if (const char *e = getenv("AT3D_B200_REC_GB")) { const double v = atof(e); if (v > 0.0) budget_gb = v; }
-        const long long budget = (long long)(budget_gb * 1073741824.0 / sizeof(VisitRec));
+        long long budget = (long long)(budget_gb * 1073741824.0 / sizeof(VisitRec));
+        {   // the pairs of a chunk are counted with 31 bits (at most 8*NUMDER+1 per record)
+            const long long lim = 0x7FFFFFFFll / (8ll * G.numder + 1);
+            if (budget > lim) budget = lim;
+        }
         const size_t smem = (size_t)AT3D_RAYS_PER_BLOCK * (S.ny_comp * S.nlmp + ((3 * (S.ml + 1) + 3) & ~3)) * sizeof(float);
         int dev = 0, nsm = 148, per_sm_w = 1, per_sm_a = 1;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
         const void *fnw = nst == 1 ? (const void *)weights_kernel<1> : (const void *)weights_kernel<3>;
-        const void *fna = nst == 1 ? (const void *)apply_kernel<1> : (const void *)apply_kernel<3>;
+        const void *fna = nst == 1 ? (const void *)apply_kernel<1, true> : (const void *)apply_kernel<3, true>;
         CUDA_TRY(cudaFuncSetAttribute(fnw, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CUDA_TRY(cudaFuncSetAttribute(fna, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_w, fnw, AT3D_RAY_THREADS, smem);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_a, fna, AT3D_RAY_THREADS, smem);
         if (per_sm_w < 1) per_sm_w = 1;
         if (per_sm_a < 1) per_sm_a = 1;
-        float ms_weights = 0.0f;
+        const int gw_bt = GW_BT;
+        const size_t smem_t = gw_smem_per_thread() * gw_bt;
+        int per_sm_t = 1;
+        CUDA_TRY(cudaFuncSetAttribute(weights_kernel_t, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_t, weights_kernel_t, gw_bt, smem_t);
+        if (per_sm_t < 1) per_sm_t = 1;
+        CUDA_TRY(cudaMemsetAsync(npairs, 0, sizeof(int) * (n + 1), stream));
+        float ms_weights = 0.0f, ms_accum = 0.0f;
         size_t r0 = 0;
         while (r0 < n) {
             size_t r1 = r0 + 1;
@@ -1388,46 +1709,80 @@ static int gradient_impl(at3d_state *st, const at3d_rays *rays, const at3d_grad_
             const long want = ((long)(r1 - r0) + AT3D_RAYS_PER_BLOCK - 1) / AT3D_RAYS_PER_BLOCK;
             const long capw = (long)nsm * per_sm_w, capa = (long)nsm * per_sm_a;
             const int nblkw = (int)(want < capw ? want : capw), nblka = (int)(want < capa ? want : capa);
-            cudaEvent_t c0 = nullptr, c1 = nullptr;
-            if (kernel_ms) { cudaEventCreate(&c0); cudaEventCreate(&c1); cudaEventRecord(c0, stream); }
+            cudaEvent_t c0 = nullptr, c1 = nullptr, c2 = nullptr, c3 = nullptr;
+            if (kernel_ms) { cudaEventCreate(&c0); cudaEventCreate(&c1); cudaEventCreate(&c2); cudaEventCreate(&c3); cudaEventRecord(c0, stream); }
             CUDA_TRY(cudaMemsetAsync(st->ray_counter, 0, sizeof(int), stream));
-            if (nst == 1)
+            if (use_t) {
+                DevState St = S;
+                St.srcpool = (float2 *)st->slabs.p; St.srcstart = srcstart;
+                const long wantt = ((long)(r1 - r0) + gw_bt - 1) / gw_bt, capt = (long)nsm * per_sm_t;
+                weights_kernel_t<<<(int)(wantt < capt ? wantt : capt), gw_bt, smem_t, stream>>>(St, G, (int)r1, (int)r0, camx, camy,
+                    camz, cammu, camphi, packs, raypix, adjw, rw, sw, total, recoff, roff[r0], recs, nrec, npairs, tc, tcap, tn, ts,
+                    (RayErr *)st->err.p, st->ray_counter);
+            } else if (nst == 1)
                 weights_kernel<1><<<nblkw, AT3D_RAY_THREADS, smem, stream>>>(S, G, (int)r1, camx, camy, camz, cammu, camphi,
-                    packs, raypix, adjw, rw, sw, total, recoff, roff[r0], recs, nrec, beam, tc, tcap, tn, ts,
+                    packs, raypix, adjw, rw, sw, total, recoff, roff[r0], recs, nrec, npairs, tc, tcap, tn, ts,
                     (RayErr *)st->err.p, st->ray_counter, (int)r0);
             else
                 weights_kernel<3><<<nblkw, AT3D_RAY_THREADS, smem, stream>>>(S, G, (int)r1, camx, camy, camz, cammu, camphi,
-                    packs, raypix, adjw, rw, sw, total, recoff, roff[r0], recs, nrec, beam, tc, tcap, tn, ts,
+                    packs, raypix, adjw, rw, sw, total, recoff, roff[r0], recs, nrec, npairs, tc, tcap, tn, ts,
                     (RayErr *)st->err.p, st->ray_counter, (int)r0);
             CUDA_TRY(cudaGetLastError());
             if (kernel_ms) cudaEventRecord(c1, stream);
+            // pair slots of the chunk's rays: exclusive scan of the per-ray counts (entry r1 is still zero), total to the host
+            long long npair_chunk = 0;
+            {
+                cub::TransformInputIterator<long long, IntToLL, const int *> it(npairs + r0, IntToLL());
+                CUDA_TRY(cub::DeviceScan::ExclusiveSum(wb + w_cub, cubtmp, it, pairoff, (int)(r1 - r0 + 1), stream));
+                CUDA_TRY(cudaMemcpyAsync(&npair_chunk, pairoff + (r1 - r0), sizeof(long long), cudaMemcpyDeviceToHost, stream));
+                CUDA_TRY(cudaStreamSynchronize(stream));
+            }
+            PairBufs pb;
+            if ((rc = pair_reserve(st, (size_t)npair_chunk + 1, nkeys, pb, errmsg))) return rc;
+            PairOut po; po.keys = pb.k0; po.vals = pb.v0; po.ngrad = (unsigned)ngrad;
             CUDA_TRY(cudaMemsetAsync(st->ray_counter, 0, sizeof(int), stream));
             if (nst == 1)
-                apply_kernel<1><<<nblka, AT3D_RAY_THREADS, smem, stream>>>(S, G, (int)r1, camx, camy, camz, cammu, camphi,
-                    packs, raypix, adjw, rw, sw, recoff, roff[r0], recs, nrec, grad_d, (RayErr *)st->err.p,
+                apply_kernel<1, true><<<nblka, AT3D_RAY_THREADS, smem, stream>>>(S, G, (int)r1, camx, camy, camz, cammu, camphi,
+                    packs, raypix, adjw, rw, sw, recoff, roff[r0], recs, nrec, grad_d, beam, po, pairoff, (RayErr *)st->err.p,
                     st->ray_counter, (int)r0);
             else
-                apply_kernel<3><<<nblka, AT3D_RAY_THREADS, smem, stream>>>(S, G, (int)r1, camx, camy, camz, cammu, camphi,
-                    packs, raypix, adjw, rw, sw, recoff, roff[r0], recs, nrec, grad_d, (RayErr *)st->err.p,
+                apply_kernel<3, true><<<nblka, AT3D_RAY_THREADS, smem, stream>>>(S, G, (int)r1, camx, camy, camz, cammu, camphi,
+                    packs, raypix, adjw, rw, sw, recoff, roff[r0], recs, nrec, grad_d, beam, po, pairoff, (RayErr *)st->err.p,
                     st->ray_counter, (int)r0);
             CUDA_TRY(cudaGetLastError());
+            if (kernel_ms) cudaEventRecord(c2, stream);
+            if ((rc = pair_accumulate(pb, (size_t)npair_chunk, nkeys, (unsigned)ngrad, grad_d, beam, stream, errmsg))) return rc;
             if (kernel_ms) {
                 float t = 0.0f;
-                cudaEventSynchronize(c1); cudaEventElapsedTime(&t, c0, c1); ms_weights += t;
-                cudaEventDestroy(c0); cudaEventDestroy(c1);
-            } else if (r1 < n) {
-                CUDA_TRY(cudaStreamSynchronize(stream));      // the record buffer is reused by the next chunk
+                cudaEventRecord(c3, stream);
+                cudaEventSynchronize(c3);
+                cudaEventElapsedTime(&t, c0, c1); ms_weights += t;
+                cudaEventElapsedTime(&t, c2, c3); ms_accum += t;
+                cudaEventDestroy(c0); cudaEventDestroy(c1); cudaEventDestroy(c2); cudaEventDestroy(c3);
             }
             r0 = r1;
         }
-        if (kernel_ms) kernel_ms[4] = ms_weights;
+        if (kernel_ms) { kernel_ms[4] = ms_weights; kernel_ms[5] = ms_accum; }
         CUDA_TRY(cudaGetLastError());
         if (kernel_ms) cudaEventRecord(ev[2], stream);
         // ---- Phase 4 ----
         if (G.exact_single_scatter) {
-            const int wpb = 8;
-            beam_kernel<<<(S.npts + wpb - 1) / wpb, wpb * 32, 0, stream>>>(G, S.npts, beam, grad_d);
+            const int wpb = 8, nbb = (S.npts + wpb - 1) / wpb;
+            long long nbp = 0;
+            beam_count_kernel<<<nbb, wpb * 32, 0, stream>>>(G, S.npts, beam, bcount);
+            CUDA_TRY(cudaMemsetAsync(bcount + S.npts, 0, sizeof(int), stream));
+            {
+                cub::TransformInputIterator<long long, IntToLL, const int *> it(bcount, IntToLL());
+                CUDA_TRY(cub::DeviceScan::ExclusiveSum(wb + w_cub, cubtmp, it, pairoff, S.npts + 1, stream));
+                CUDA_TRY(cudaMemcpyAsync(&nbp, pairoff + S.npts, sizeof(long long), cudaMemcpyDeviceToHost, stream));
+                CUDA_TRY(cudaStreamSynchronize(stream));
+            }
+            if (nbp > 0x7FFFFFF0ll) { set_msg(errmsg, "too many direct-beam derivative terms for one pass"); return 2; }
+            PairBufs pb;
+            if ((rc = pair_reserve(st, (size_t)nbp + 1, nkeys, pb, errmsg))) return rc;
+            beam_kernel<true><<<nbb, wpb * 32, 0, stream>>>(G, S.npts, beam, grad_d, pairoff, pb.k0, pb.v0);
             CUDA_TRY(cudaGetLastError());
+            if ((rc = pair_accumulate(pb, (size_t)nbp, nkeys, (unsigned)ngrad, grad_d, beam, stream, errmsg))) return rc;
         }
         // ---- Jacobian (MAKEJACOBIAN=.TRUE., shdomsub4.f:536-631): RAYGRAD_PIXEL(k,:,:) of a pixel is the
         //      derivative pass over that pixel's rays with the unit adjoint weight e_k (the pass is linear in
@@ -1455,6 +1810,8 @@ static int gradient_impl(at3d_state *st, const at3d_rays *rays, const at3d_grad_
             Sq.counts = nullptr;
             const size_t smem = (size_t)AT3D_RAYS_PER_BLOCK * (S.ny_comp * S.nlmp + ((3 * (S.ml + 1) + 3) & ~3)) * sizeof(float);
             const long long *roff = st->recoff_h.data();
+            CUDA_TRY(cudaFuncSetAttribute(nst == 1 ? (const void *)apply_kernel<1, false> : (const void *)apply_kernel<3, false>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             {   // one record buffer large enough for the rays of any single pixel
                 long long mx = 0; size_t q0 = 0;
                 for (size_t p = 0; p < npix; p++) { const size_t q1 = q0 + rpp_h[p]; if (roff[q1] - roff[q0] > mx) mx = roff[q1] - roff[q0]; q0 = q1; }
@@ -1473,24 +1830,24 @@ static int gradient_impl(at3d_state *st, const at3d_rays *rays, const at3d_grad_
                         CUDA_TRY(cudaMemsetAsync(st->ray_counter, 0, sizeof(int), stream));
                         if (nst == 1)
                             weights_kernel<1><<<nblk, AT3D_RAY_THREADS, smem, stream>>>(Sq, G, (int)r1, camx, camy, camz, cammu,
-                                camphi, packs, raypix, adj1, rw, sw, total, recoff, roff[r0], recs, nrec, beam1, nullptr, 0,
+                                camphi, packs, raypix, adj1, rw, sw, total, recoff, roff[r0], recs, nrec, npairs, nullptr, 0,
                                 nullptr, nullptr, (RayErr *)st->err.p, st->ray_counter, (int)r0);
                         else
                             weights_kernel<3><<<nblk, AT3D_RAY_THREADS, smem, stream>>>(Sq, G, (int)r1, camx, camy, camz, cammu,
-                                camphi, packs, raypix, adj1, rw, sw, total, recoff, roff[r0], recs, nrec, beam1, nullptr, 0,
+                                camphi, packs, raypix, adj1, rw, sw, total, recoff, roff[r0], recs, nrec, npairs, nullptr, 0,
                                 nullptr, nullptr, (RayErr *)st->err.p, st->ray_counter, (int)r0);
                         CUDA_TRY(cudaMemsetAsync(st->ray_counter, 0, sizeof(int), stream));
                         if (nst == 1)
-                            apply_kernel<1><<<nblk, AT3D_RAY_THREADS, smem, stream>>>(Sq, G, (int)r1, camx, camy, camz, cammu,
-                                camphi, packs, raypix, adj1, rw, sw, recoff, roff[r0], recs, nrec, gtmp, (RayErr *)st->err.p,
-                                st->ray_counter, (int)r0);
+                            apply_kernel<1, false><<<nblk, AT3D_RAY_THREADS, smem, stream>>>(Sq, G, (int)r1, camx, camy, camz, cammu,
+                                camphi, packs, raypix, adj1, rw, sw, recoff, roff[r0], recs, nrec, gtmp, beam1, PairOut(), nullptr,
+                                (RayErr *)st->err.p, st->ray_counter, (int)r0);
                         else
-                            apply_kernel<3><<<nblk, AT3D_RAY_THREADS, smem, stream>>>(Sq, G, (int)r1, camx, camy, camz, cammu,
-                                camphi, packs, raypix, adj1, rw, sw, recoff, roff[r0], recs, nrec, gtmp, (RayErr *)st->err.p,
-                                st->ray_counter, (int)r0);
+                            apply_kernel<3, false><<<nblk, AT3D_RAY_THREADS, smem, stream>>>(Sq, G, (int)r1, camx, camy, camz, cammu,
+                                camphi, packs, raypix, adj1, rw, sw, recoff, roff[r0], recs, nrec, gtmp, beam1, PairOut(), nullptr,
+                                (RayErr *)st->err.p, st->ray_counter, (int)r0);
                         if (G.exact_single_scatter) {
                             const int wpb = 8;
-                            beam_kernel<<<(S.npts + wpb - 1) / wpb, wpb * 32, 0, stream>>>(G, S.npts, beam1, gtmp);
+                            beam_kernel<false><<<(S.npts + wpb - 1) / wpb, wpb * 32, 0, stream>>>(G, S.npts, beam1, gtmp, nullptr, nullptr, nullptr);
                         }
                         jac_gather_kernel<<<(G.numder * njac + 127) / 128, 128, 0, stream>>>(nst, G.numder, njac, G.maxpg, k,
                                                                                            (int)p, jptr_d, gtmp, jac_d);

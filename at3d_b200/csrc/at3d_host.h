@@ -34,7 +34,7 @@ struct at3d_state {
     size_t bytes = 0;
     int device = 0;
     // reusable per-call buffers
-    DevBuf rays, out, trace, misc, slabs, err, pix, work, recs, hits, viewsrc;
+    DevBuf rays, out, trace, misc, slabs, err, pix, work, recs, hits, viewsrc, pairs;
     RayGeom geom;                   // host copy of the per-ray setup constants
     RayPack *packs_h = nullptr;     // pinned host staging of the per-ray packs (grows on demand)
     size_t packs_cap = 0;
@@ -46,6 +46,7 @@ struct at3d_state {
     int nbcrad = 0;
     std::mutex mu;                  // the per-call buffers above are shared: calls on one state are serialised (the
                                     // reference calls RENDER from several joblib threads on slices of the rays)
+    double gw_rec_per_ray = 0.0;    // visit records per ray seen by the single-walk derivative pass (sizes its pool)
     int view_min_rays = 256;        // shortest run of equal-direction rays that gets a pre-evaluated view source (0: off)
 };
 

@@ -250,6 +250,8 @@ forward_kernel_t(DevState S, int nrays, const float *camx, const float *camy, co
             const double mu2 = __ldg(&cammu[iray]), phi2 = __ldg(&camphi[iray]);
             const RayPack pk = dev_get_pack(S, packs, iray, camx, camy, camz, mu2, phi2);
             double radA = 0.0, radB = 0.0;
+            SrcWriter sw = -1;
+            if ((MODES & 2) && S.srcpool) S.srcstart[iray] = -1;
             if (pk.status == 2) set_err(err, 2, iray + S.ray_base);
             else if (pk.status == 0) {
                 RayDir rd;
@@ -261,7 +263,8 @@ forward_kernel_t(DevState S, int nrays, const float *camx, const float *camy, co
                                                           correctinterpolate != 0, singlescatter != 0, nosurface != 0,
                                                           maxsub, radA, radB,
                                                           trace_cells ? trace_cells + (size_t)trace_cap * iray : nullptr,
-                                                          trace_cap, ntrace, nsubA, nsubB, npt, nsh, nptB);
+                                                          trace_cap, ntrace, nsubA, nsubB, npt, nsh, nptB,
+                                                          sw, S.srcstart + iray, (MODES & 2) && S.srcpool != nullptr);
                 if (e) set_err(err, e, iray + S.ray_base);
                 else marched = 1;
             }

@@ -75,13 +75,46 @@ __device__ __forceinline__ float thread_singscat_sum(const DevState &S, int ip, 
 
 // SRCEXT of one grid point for the direction whose YLMDIR is in Y4 (column stride bt): COMPUTE_SOURCE_1CELL_UNPOL
 // (shdomsub2.f:3046-3192) with the TMS-corrected SH block of the point, times the extinction
+// Per-thread writer of the gradient's source stream (DevState::srcpool): the state is ONE register pair, the next entry
+// `cur` (-1: nothing written yet, SRC_OVF: the pool overflowed).  The common case is a store and an increment; drawing a
+// chunk (once per AT3D_SRC_CHUNK - 1 entries) is kept out of line, so that the march's register allocation is the one
+// of the kernel without a stream (inlined, the cursor code cost 58 % more executed instructions in the whole kernel).
+typedef long long SrcWriter;
+#define SRC_OVF (-1ll - AT3D_SRC_CHUNK)
+
+static __device__ __noinline__ long long src_draw_chunk(float2 *pool, unsigned *top, unsigned nreg, unsigned region, unsigned chunks,
+                                                 long long cur, long long *startslot)
+{
+    if (cur == SRC_OVF) return cur;
+    const unsigned reg = blockIdx.x % nreg;
+    unsigned c = atomicAdd(top + 32 * (reg + 1), 1u);
+    if (c < region) c += reg * region;
+    else c = nreg * region + atomicAdd(top, 1u);
+    if (c >= chunks) { atomicExch(top + 1, 1u); return SRC_OVF; }
+    const long long base = (long long)c * AT3D_SRC_CHUNK;
+    if (cur < 0) *startslot = base;
+    else __stcs(&pool[cur], make_float2(__int_as_float((int)c), 0.0f));     // link slot of the full chunk
+    return base;
+}
+
+__device__ __forceinline__ void src_emit(const DevState &S, SrcWriter &cur, long long *startslot, float srcfull, float ss)
+{
+    if ((cur & (AT3D_SRC_CHUNK - 1)) == AT3D_SRC_CHUNK - 1)
+        cur = src_draw_chunk(S.srcpool, S.srcpool_top, S.srcpool_nreg, S.srcpool_region, S.srcpool_chunks, cur, startslot);
+    if (cur >= 0) {
+        __stcs(&S.srcpool[cur], make_float2(srcfull, ss));   // streaming: the L1 left beside the YLMDIR table holds SH rows
+        cur++;
+    }
+}
+
 __device__ __forceinline__ float thread_point_source(const DevState &S, const float4 *Y4, int bt, const RayDir &rd,
-                                                     bool singlescatter, int ip, float ext, int &ns)
+                                                     bool singlescatter, int ip, float ext, int &ns,
+                                                     SrcWriter &sw, long long *startslot, bool stream)
 {
     const int4 ps = __ldg(&S.ptsrc[ip - 1]);
     ns = ps.y & 0xFFFF;
     float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
-    if (!singlescatter) {
+    if (!singlescatter || stream) {           // the gradient's source stream wants the SH part in any case
         const float4 *base = (const float4 *)(S.shsrc + ps.x);
         const int n4 = AT3D_SHPAD(ns) >> 2;                 // multiple of 8
 #pragma unroll 1
@@ -96,7 +129,17 @@ __device__ __forceinline__ float thread_point_source(const DevState &S, const fl
         }
     }
     const float b = thread_singscat_sum(S, ip, ps, rd);
+    if (stream) {
+        src_emit(S, sw, startslot, ((a0 + a1) + (a2 + a3)) + b, b * ext);
+        if (singlescatter) return b * ext;
+    }
     return (((a0 + a1) + (a2 + a3)) + b) * ext;
+}
+__device__ __forceinline__ float thread_point_source(const DevState &S, const float4 *Y4, int bt, const RayDir &rd,
+                                                     bool singlescatter, int ip, float ext, int &ns)
+{
+    SrcWriter none = SRC_OVF;
+    return thread_point_source(S, Y4, bt, rd, singlescatter, ip, ext, ns, none, nullptr, false);
 }
 
 // Corner refresh of one thread.  Points shared with the previous cell are found with the reference's
@@ -106,7 +149,8 @@ __device__ __forceinline__ float thread_point_source(const DevState &S, const fl
 // (shdomsub2.f:3046-3192) with the TMS-corrected SH block of the point.
 __device__ __forceinline__ void thread_refresh(const DevState &S, const CellRec &c, const float4 *Y4, int bt,
                                                const RayDir &rd, bool singlescatter, int jf /*0: first cell*/,
-                                               TCorners &K, int &npt_eval, int &nsh_eval)
+                                               TCorners &K, int &npt_eval, int &nsh_eval, SrcWriter &sw, long long *startslot,
+                                               bool stream)
 {
     TCorners N;
     unsigned need = 0;
@@ -137,7 +181,7 @@ __device__ __forceinline__ void thread_refresh(const DevState &S, const CellRec 
             npt_eval++; nsh_eval += __ldg(&S.ptsrc[ip - 1]).y & 0xFFFF;
         } else {
             int ns;
-            src = thread_point_source(S, Y4, bt, rd, singlescatter, ip, pr.w, ns);
+            src = thread_point_source(S, Y4, bt, rd, singlescatter, ip, pr.w, ns, sw, startslot, stream);
             npt_eval++; nsh_eval += ns;
         }
 #pragma unroll
@@ -148,12 +192,13 @@ __device__ __forceinline__ void thread_refresh(const DevState &S, const CellRec 
 
 // Forward integration of one ray by one thread (NSTOKES=1).  MODES as in march_forward (at3d_ray.cuh).
 template <int MODES>
-__device__ int thread_march_forward(const DevState &S, const float4 *Y4, int bt, const RayDir &rd, double mu2,
+__device__ __forceinline__ int thread_march_forward(const DevState &S, const float4 *Y4, int bt, const RayDir &rd, double mu2,
                                     double x0, double y0, double z0, float sky, bool correctinterpolate,
                                     bool singlescatter, bool nosurface, int maxsub,
                                     double &radA, double &radB,
                                     int *trace_cells, int trace_cap, int &ntrace, int &nsubA, int &nsubB,
-                                    int &npt_eval, int &nsh_eval, int &nptB)
+                                    int &npt_eval, int &nsh_eval, int &nptB, SrcWriter &sw, long long *startslot,
+                                                    bool stream)
 {
     double xe = x0, ye = y0, ze = z0, trA = 1.0, trB = 1.0;
     float ext1A = 0.0f, srcext1A = 0.0f, ext1B = 0.0f, srcext1B = 0.0f;
@@ -176,7 +221,8 @@ __device__ int thread_march_forward(const DevState &S, const float4 *Y4, int bt,
         if (trace_cells && ntrace < trace_cap) trace_cells[ntrace] = icell;
         ntrace++;
         const int ne0 = npt_eval;
-        thread_refresh(S, c, Y4, bt, rd, singlescatter, jf, K, npt_eval, nsh_eval);
+        thread_refresh(S, c, Y4, bt, rd, singlescatter, jf, K, npt_eval, nsh_eval, sw, startslot,
+                       (MODES & 2) && stream && !doneB);
         if ((MODES & 2) && !doneB) nptB += npt_eval - ne0;
         const float q1x = K.x[0], q1y = K.y[0], q1z = K.z[0];
         const float q8x = K.x[7], q8y = K.y[7], q8z = K.z[7];

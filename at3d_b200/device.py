@@ -186,7 +186,7 @@ class DeviceState:
             trace = dict(cells=np.zeros((trace_cap, n), np.int32, order='F'),
                          ncells=np.zeros(n, np.int32), nsub=np.zeros(n, np.int32))
             tr = TraceC(trace_cap, vp(trace['cells']), vp(trace['ncells']), vp(trace['nsub']))
-        ms = (C.c_double * 5)()
+        ms = (C.c_double * 8)()
         buf = _lib.errbuf()
         code = self._L.at3d_levisapprox_gradient(self._h, C.byref(r), C.byref(gd), vp(gradout), vp(cost),
                                                  vp(stokesout), C.byref(tr) if tr is not None else None,

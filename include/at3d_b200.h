@@ -177,7 +177,7 @@ int at3d_render(at3d_state *st, const at3d_rays *rays, float *stokes /*[nstokes,
 int at3d_levisapprox_gradient(at3d_state *st, const at3d_rays *rays, const at3d_grad_desc *g,
                               double *gradout, double *cost, float *stokesout,
                               const at3d_trace *trace /*optional*/, void *cuda_stream /*optional*/,
-                              double *kernel_ms /*optional [5]: forward, adjoint (weights+apply), beam, total, weights*/,
+                              double *kernel_ms /*optional [8]: forward, derivative pass (weights + apply + pair sums), beam, total, weights, pair sort + sums; [6..7] reserved*/,
                               char *errmsg);
 
 /* ---- a10: LEVISAPPROX_GRADIENT with MAKEJACOBIAN=.TRUE. (shdomsub4.f:536-631, GRAD_INTEGRATE_1RAY :811) ----
