@@ -283,7 +283,7 @@ extern "C" int at3d_state_create(const at3d_state_desc *d, at3d_state **out, cha
         if (!rc) {
             int4 *ptsrc = nullptr;
             rc = dalloc(st, (size_t)d->npts, &ptsrc, errmsg);
-            if (!rc && launch_build_ptsrc(d->npts, S.kmax, S.srcrec, sscount, ssent, ptsrc, 0) != cudaSuccess) { set_msg(errmsg, "ptsrc launch failed"); rc = 4; }
+            if (!rc && launch_build_ptsrc(d->npts, S.kmax, S.srcrec, sscount, ssent, d->ncells, S.cellrec, S.ptrec, ptsrc, 0) != cudaSuccess) { set_msg(errmsg, "ptsrc launch failed"); rc = 4; }
             cudaDeviceSynchronize();
             S.ptsrc = ptsrc;
         }

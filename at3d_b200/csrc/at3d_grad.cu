@@ -442,7 +442,7 @@ weights_kernel_t(DevState S, DevGrad G, int nrays, int ray0, const float *camx, 
         base = __shfl_sync(FULLMASK, base, 0);
         if (ray0 + base >= nrays) break;
         const int iray = ray0 + base + lane;
-        int ntrace = 0, nsub = 0, npt = 0, marched = 0, nrec = 0, npairs = 0;
+        int ntrace = 0, nsub = 0, npt = 0, nsh = 0, marched = 0, nrec = 0, npairs = 0;
         if (iray < nrays) {
             const double mu2 = __ldg(&cammu[iray]), phi2 = __ldg(&camphi[iray]);
             const RayPack pk = dev_get_pack(S, packs, iray, camx, camy, camz, mu2, phi2);
@@ -461,7 +461,7 @@ weights_kernel_t(DevState S, DevGrad G, int nrays, int ray0, const float *camx, 
                 const int e = thread_march_weights(S, G, M, rd, mu2, pk.x0, pk.y0, pk.z0, sky, adj, __ldg(&total[iray]), sr,
                                                    recs + (r0 - rec_base), (int)(r1 - r0),
                                                    trace_cells ? trace_cells + (size_t)trace_cap * iray : nullptr, trace_cap,
-                                                   ntrace, nsub, npt, nrec, npairs);
+                                                   ntrace, nsub, npt, nsh, nrec, npairs);
                 if (e) { set_err(err, e, iray); nrec = 0; npairs = 0; }
                 else marched = 1;
             }
@@ -473,8 +473,10 @@ weights_kernel_t(DevState S, DevGrad G, int nrays, int ray0, const float *camx, 
         if (S.counts) {
             const int c0 = __reduce_add_sync(FULLMASK, marched ? ntrace : 0), c1 = __reduce_add_sync(FULLMASK, marched ? npt : 0);
             const int c4 = __reduce_add_sync(FULLMASK, marched ? nsub : 0), c5 = __reduce_add_sync(FULLMASK, marched);
+            const int c2 = __reduce_add_sync(FULLMASK, marched ? nsh : 0);
             if (lane == 0) {
                 atomicAdd(&S.counts[0], (unsigned long long)c0); atomicAdd(&S.counts[1], (unsigned long long)c1);
+                atomicAdd(&S.counts[2], (unsigned long long)c2);
                 atomicAdd(&S.counts[4], (unsigned long long)c4); atomicAdd(&S.counts[5], (unsigned long long)c5);
             }
         }

@@ -59,7 +59,8 @@ __device__ __forceinline__ void gw_write(VisitRec *dst, int ip, float srcfull, d
 // follows it, a corner that is not inherited leaves its record and frees its slot; new corners read the stream.
 __device__ __forceinline__ int gw_refresh(const DevState &S, const DevGrad &G, const CellRec &c, const GwShared &M,
                                           bool singlescatter, int jf, bool first_cell, TCorners &K, unsigned &perm,
-                                          SrcReader &rd, VisitRec *rec, int cap, int &nrec, int &npairs, int &npt_eval)
+                                          SrcReader &rd, VisitRec *rec, int cap, int &nrec, int &npairs, int &npt_eval,
+                                          int &nsh_eval)
 {
     TCorners N;
     unsigned need = 0, used_old = 0, newperm = 0;
@@ -109,8 +110,10 @@ __device__ __forceinline__ int gw_refresh(const DevState &S, const DevGrad &G, c
         newperm |= s << (4 * n);
         const int ip = SEL8(K.pt, n);
         const float4 pr = __ldg(&S.ptrec[ip - 1]);
-        const float2 sv = src_next(rd);
-        npt_eval++;
+        // dark points (build_ptsrc_kernel) have no stream entry: their SRCEXT8 is exactly 0 and their record stays empty
+        const int psy = __ldg(&S.ptsrc[ip - 1].y);
+        const float2 sv = psy < 0 ? make_float2(0.0f, 0.0f) : src_next(rd);
+        npt_eval++; nsh_eval += psy & 0xFFFF;
         const float src = singlescatter ? sv.y : sv.x * pr.w;
         M.sf[s * bt] = sv.x; M.ss[s * bt] = sv.y;
         M.W[s * bt] = 0.0; M.Gr[s * bt] = 0.0; M.B[s * bt] = 0.0;
@@ -126,7 +129,7 @@ __device__ __forceinline__ int gw_refresh(const DevState &S, const DevGrad &G, c
 __device__ int thread_march_weights(const DevState &S, const DevGrad &G, const GwShared &M, const RayDir &rd, double mu2,
                                     double x0, double y0, double z0, float sky, double adj, double total,
                                     SrcReader &sr, VisitRec *rec, int cap, int *trace_cells, int trace_cap,
-                                    int &ntrace, int &nsub, int &npt_eval, int &nrec, int &npairs)
+                                    int &ntrace, int &nsub, int &npt_eval, int &nsh_eval, int &nrec, int &npairs)
 {
     double xe = x0, ye = y0, ze = z0, tr = 1.0, radout = 0.0;
     float ext1 = 0.0f, srcext1 = 0.0f;
@@ -140,7 +143,7 @@ __device__ int thread_march_weights(const DevState &S, const DevGrad &G, const G
     bool done = false, first_cell = true;
     unsigned perm = 0x76543210u;
     TCorners K;
-    npt_eval = 0; nrec = 0; npairs = 0; ntrace = 0; nsub = 0;
+    npt_eval = 0; nsh_eval = 0; nrec = 0; npairs = 0; ntrace = 0; nsub = 0;
 #pragma unroll
     for (int n = 0; n < 8; n++) { K.pt[n] = 0; K.x[n] = K.y[n] = K.z[n] = K.ext[n] = K.src[n] = 0.0f; }
     int boundpts[4] = {0, 0, 0, 0};
@@ -150,7 +153,7 @@ __device__ int thread_march_weights(const DevState &S, const DevGrad &G, const G
     while (!done && icell > 0) {
         if (trace_cells && ntrace < trace_cap) trace_cells[ntrace] = icell;
         ntrace++;
-        err = gw_refresh(S, G, c, M, singlescatter, jf, first_cell, K, perm, sr, rec, cap, nrec, npairs, npt_eval);
+        err = gw_refresh(S, G, c, M, singlescatter, jf, first_cell, K, perm, sr, rec, cap, nrec, npairs, npt_eval, nsh_eval);
         if (err) return err;
         first_cell = false;
         const float q1x = K.x[0], q1y = K.y[0], q1z = K.z[0];

@@ -61,7 +61,7 @@ cudaError_t launch_build_cellrec(int ncells, const int *gridptr, const int *neig
                                  const short *cellflags, int4 *cellrec, cudaStream_t s);
 cudaError_t launch_build_ptrec(int npts, const float *gridpos, const float *total_ext, float4 *ptrec, cudaStream_t s);
 cudaError_t launch_build_ptsrc(int npts, int kmax, const int2 *srcrec, const int *sscount, const int2 *ssent,
-                               int4 *ptsrc, cudaStream_t s);
+                               int ncells, const int4 *cellrec, const float4 *ptrec, int4 *ptsrc, cudaStream_t s);
 cudaError_t launch_lambertian_boundary(const DevState &S, const float *fluxes, float *bcrad, cudaStream_t s);
 void view_segments(const at3d_state *st, const at3d_rays *rays, std::vector<size_t> &seg_start,
                    std::vector<size_t> &seg_len, std::vector<char> &seg_view);

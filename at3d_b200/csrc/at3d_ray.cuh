@@ -110,7 +110,8 @@ __device__ __forceinline__ void load_corner(const DevState &S, int ip, const Ray
     const int4 ps = __ldg(&S.ptsrc[ip - 1]);
     x = pr.x; y = pr.y; z = pr.z; ext = pr.w;
     soff = ps.x; sns = ps.y & 0xFFFF;
-    const int cnt = ps.y >> 16;
+    int cnt = (ps.y >> 16) & 0x7FFF;
+    if (ps.y < 0) { sns = 0; cnt = 0; }       // dark point (build_ptsrc_kernel): SRCEXT8 is exactly 0
 #pragma unroll
     for (int k = 0; k < NST; k++) b[k] = 0.0f;
     if (cnt > 0) {

@@ -31,8 +31,29 @@ __global__ void build_ptrec_kernel(int npts, const float *gridpos, const float *
 
 // one 16-byte record per point with everything a new corner needs besides its coordinates:
 // SH block offset, NS, single-scatter count and the first single-scatter entry
+// Bit 31 of .y marks a DARK point: every end cell it is a corner of has zero extinction at all eight corners.  The
+// extinction-weighted source SRCEXT8 = SOURCE*EXT of such a point is exactly 0 and nothing can be absorbed or emitted in
+// its cells, so the ray kernels neither contract its SH block nor look up its phase functions (clear air around
+// cumulus fields: more than half of the corner visits of BASELINE configs[1]).
+__global__ void mark_lit_kernel(int ncells, const int4 *cellrec, const float4 *ptrec, int *lit)
+{
+    const int ic = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ic >= ncells) return;
+    const int4 *p = cellrec + 4 * (size_t)ic;
+    const int4 a = p[0], b = p[1], d = p[3];
+    if (d.z != 0) return;                                     // not an end cell (TREEPTR(2) > 0)
+    const int gp[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    float m = 0.0f;
+#pragma unroll
+    for (int n = 0; n < 8; n++) m = fmaxf(m, fabsf(ptrec[gp[n] - 1].w));
+    if (!(m == 0.0f)) {                                       // also lit if the extinction is not finite
+#pragma unroll
+        for (int n = 0; n < 8; n++) lit[gp[n] - 1] = 1;
+    }
+}
+
 __global__ void build_ptsrc_kernel(int npts, int kmax, const int2 *srcrec, const int *sscount, const int2 *ssent,
-                                   int4 *ptsrc)
+                                   const int *lit, int4 *ptsrc)
 {
     int ip = blockIdx.x * blockDim.x + threadIdx.x;
     if (ip >= npts) return;
@@ -40,7 +61,7 @@ __global__ void build_ptsrc_kernel(int npts, int kmax, const int2 *srcrec, const
     const int cnt = sscount[ip];
     int2 e = make_int2(1, 0);
     if (cnt > 0) e = ssent[(size_t)ip * kmax];
-    ptsrc[ip] = make_int4(r.x, r.y | (cnt << 16), e.x, e.y);
+    ptsrc[ip] = make_int4(r.x, r.y | (cnt << 16) | (lit[ip] ? 0 : (int)0x80000000), e.x, e.y);
 }
 
 // FIXED / VARIABLE_LAMBERTIAN_BOUNDARY (shdomsub1.f:2438-2529): bottom BCRAD
@@ -467,10 +488,18 @@ cudaError_t launch_build_ptrec(int npts, const float *gridpos, const float *tota
     return cudaGetLastError();
 }
 cudaError_t launch_build_ptsrc(int npts, int kmax, const int2 *srcrec, const int *sscount, const int2 *ssent,
-                               int4 *ptsrc, cudaStream_t s)
+                               int ncells, const int4 *cellrec, const float4 *ptrec, int4 *ptsrc, cudaStream_t s)
 {
-    build_ptsrc_kernel<<<(npts + 255) / 256, 256, 0, s>>>(npts, kmax, srcrec, sscount, ssent, ptsrc);
-    return cudaGetLastError();
+    int *lit = nullptr;
+    cudaError_t e = cudaMalloc(&lit, sizeof(int) * (size_t)npts);
+    if (e != cudaSuccess) return e;
+    cudaMemsetAsync(lit, 0, sizeof(int) * (size_t)npts, s);
+    mark_lit_kernel<<<(ncells + 255) / 256, 256, 0, s>>>(ncells, cellrec, ptrec, lit);
+    build_ptsrc_kernel<<<(npts + 255) / 256, 256, 0, s>>>(npts, kmax, srcrec, sscount, ssent, lit, ptsrc);
+    e = cudaGetLastError();
+    cudaStreamSynchronize(s);
+    cudaFree(lit);
+    return e;
 }
 cudaError_t launch_lambertian_boundary(const DevState &S, const float *fluxes, float *bcrad, cudaStream_t s)
 {

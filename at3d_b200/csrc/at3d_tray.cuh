@@ -58,7 +58,7 @@ struct TCorners {
 // exact single-scatter sum of one point from its record / list (shdomsub2.f:3172-3183)
 __device__ __forceinline__ float thread_singscat_sum(const DevState &S, int ip, const int4 ps, const RayDir &rd)
 {
-    const int cnt = ps.y >> 16;
+    const int cnt = (ps.y >> 16) & 0x7FFF;
     float b = 0.0f;
     if (cnt > 0) {
         float sv[1];
@@ -113,6 +113,7 @@ __device__ __forceinline__ float thread_point_source(const DevState &S, const fl
 {
     const int4 ps = __ldg(&S.ptsrc[ip - 1]);
     ns = ps.y & 0xFFFF;
+    if (ps.y < 0) return 0.0f;                // dark point (build_ptsrc_kernel): SRCEXT8 is exactly 0, no stream entry
     float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
     if (!singlescatter || stream) {           // the gradient's source stream wants the SH part in any case
         const float4 *base = (const float4 *)(S.shsrc + ps.x);

@@ -317,11 +317,12 @@ class ClockSampler:
         return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons)
 
 
-def measured_traffic(workload, kernel):
-    """DRAM bytes per launch of `kernel` from the committed ncu capture (profiles/traffic.json), or None."""
+def measured_traffic(workload):
+    """The ncu --set full capture of one gradient call of `workload` (profiles/traffic.json, written by
+    profiles/make_traffic.py from the .ncu-rep of the same round): DRAM bytes of the step, issue-slot utilisation and the
+    per-kernel shares, or None when the workload was not captured."""
     try:
-        d = json.load(open(os.path.join(ROOT, 'profiles', 'traffic.json')))
-        return int(d[workload][kernel]['bytes'])
+        return json.load(open(os.path.join(ROOT, 'profiles', 'traffic.json')))[workload]
     except Exception:
         return None
 
@@ -680,9 +681,24 @@ def main():
     devo.close()
     peak, peak_src = measured_peak()
     adj_ms = float(np.mean(kms[:, 1]))
+    step_kernel_ms = float(np.mean(kms[:, 3]))
+    # SURVEY 8(d) GRADIENT: the render bytes (SH blocks, point payload, cell topology of the walk) + radiance expansion,
+    # derivative tables and gradient scatter, for the work the derivative walk counted; over ALL kernels of the step (the
+    # SH sources are contracted once, in the forward pass, and handed to the derivative walk)
     abytes = algorithmic_bytes(st, gi, counts, gradient=True)
-    achieved = abytes / (adj_ms * 1e-3) / 1e9
+    achieved = abytes / (step_kernel_ms * 1e-3) / 1e9
     rbytes = algorithmic_bytes(st, gi, rcounts, gradient=False)
+    tr = measured_traffic(args.workload)
+    roof_extra = {}
+    if tr is not None:
+        roof_extra = dict(
+            dram_frac=tr['dram_bytes'] / (step_kernel_ms * 1e-3) / 1e9 / peak,
+            issue_active_pct=tr['issue_active_pct'], traffic_source=tr['source'],
+            per_kernel={k: dict(share=v['share'], dram_bytes=v['dram_bytes'], issue_active_pct=v['issue_active_pct'],
+                                warps_active_pct=v['warps_active_pct'], local_memory_instructions=v['local_memory_instructions'])
+                        for k, v in list(tr['kernels'].items())[:5]},
+            note='the state is L2-resident: frac is the SURVEY 8(d) algorithmic bytes over the HBM peak, dram_frac the DRAM '
+                 'bytes ncu counted for the same step over the same peak; the kernels are latency / issue bound')
 
     cpu = None
     orc = None
@@ -709,15 +725,16 @@ def main():
                         nlm=int(st.nlm), l2='flushed between steps (256 MiB memset)', hbm_state_bytes=dev.hbm_bytes),
             e2e=dict(value=world * nrays * args.steps / t_e2e, unit='rays/s', h2d_bytes_per_step=int(h2d),
                      d2h_bytes_per_step=int(d2h)),
-            gpu_launches=int(args.steps * (5 + (1 if gi.exact_single_scatter else 0))),
-            roofline=dict(kernel='weights_kernel+apply_kernel (derivative pass)', bound='hbm', achieved=achieved, peak=peak, unit='GB/s',
-                          frac=achieved / peak,
-                          traffic=measured_traffic(args.workload, 'weights_kernel+apply_kernel (derivative pass)'),
-                          peak_source=peak_src,
-                          algorithmic_bytes_per_launch=abytes, kernel_ms=adj_ms, counts=counts),
-            phases_ms=dict(forward=float(np.mean(kms[:, 0])), adjoint=adj_ms, weights=float(np.mean(kms[:, 4])),
-                           apply=adj_ms - float(np.mean(kms[:, 4])), beam=float(np.mean(kms[:, 2])),
-                           total=float(np.mean(kms[:, 3]))),
+            gpu_launches=int(args.steps * (7 + (4 if gi.exact_single_scatter else 0))),   # forward, pixel, cost, derivative walk, apply, pair bounds + sums (+ beam count, beam, bounds, sums); cub scans and sorts not counted
+            roofline=dict(kernel='gradient step: forward pass + derivative walk + apply + pair sort/sums + beam (all kernels of '
+                                 'at3d_levisapprox_gradient)', bound='hbm', achieved=achieved, peak=peak, unit='GB/s',
+                          frac=achieved / peak, traffic=(tr['dram_bytes'] if tr is not None else None),
+                          peak_source=peak_src, algorithmic_bytes_per_launch=abytes, kernel_ms=step_kernel_ms, counts=counts,
+                          **roof_extra),
+            phases_ms=dict(forward=float(np.mean(kms[:, 0])), derivative=adj_ms, weights=float(np.mean(kms[:, 4])),
+                           pair_sort_sums=float(np.mean(kms[:, 5])),
+                           apply=adj_ms - float(np.mean(kms[:, 4])) - float(np.mean(kms[:, 5])), beam=float(np.mean(kms[:, 2])),
+                           total=step_kernel_ms),
             render=dict(rays_per_s=nrays / (np.mean(rms) * 1e-3), kernel_ms=float(np.mean(rms)),
                         achieved_gbs=rbytes / (np.mean(rms) * 1e-3) / 1e9, frac=rbytes / (np.mean(rms) * 1e-3) / 1e9 / peak,
                         algorithmic_bytes=rbytes, counts=rcounts),

@@ -15,6 +15,11 @@ gi = gradsetup.make_gradient_inputs(sc, B, seed=0, numder=1)
 dev.attach_gradient(gi)
 rad = dev.render(rays)
 pix = gradsetup.make_pixels(sc.state.nstokes, rays.nrays, rad, seed=1)
+import torch
 for i in range(n):
+    if i == n - 1:
+        torch.cuda.synchronize(); torch.cuda.profiler.start()      # ncu --profile-from-start off: the last call only
     res = dev.gradient(rays, pix, timing=True)
+    if i == n - 1:
+        torch.cuda.synchronize(); torch.cuda.profiler.stop()
     print(json.dumps(dict(ms=res[-1])), flush=True)

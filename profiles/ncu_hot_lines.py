@@ -17,10 +17,10 @@ for r in rows:
 def num(x):
     try: return float(x)
     except Exception: return 0.0
-tot = sum(num(d['Instructions Executed']) for d in data)
-tots = sum(num(d['# Samples']) for d in data)
+tot = sum(num(d.get('Instructions Executed', 0)) for d in data)
+tots = sum(num(d.get('# Samples', 0)) for d in data)
 print('total warp instructions %.4g, stall samples %.4g' % (tot, tots))
-data.sort(key=lambda d: -num(d['# Samples']))
+data.sort(key=lambda d: -num(d.get('# Samples', 0)))
 for d in data[:topn]:
-    print('%5.1f%% inst %5.1f%% smp  %s:%s  %s' % (100 * num(d['Instructions Executed']) / tot,
-          100 * num(d['# Samples']) / tots, d['file'], d['Line No'], d['Source'].strip()[:110]))
+    print('%5.1f%% inst %5.1f%% smp  %s:%s  %s' % (100 * num(d.get('Instructions Executed', 0)) / tot,
+          100 * num(d.get('# Samples', 0)) / tots, d['file'], d['Line No'], d['Source'].strip()[:110]))
