@@ -24,6 +24,15 @@ class RaysC(C.Structure):
                 ('camz', C.c_void_p), ('cammu', C.c_void_p), ('camphi', C.c_void_p)]
 
 
+class CsDeviceDesc(C.Structure):
+    """at3d_cs_device_desc (include/at3d_b200.h): COMPUTE_SOURCE on device-resident arrays."""
+    _fields_ = [(k, i32) for k in ('npts', 'nstokes', 'nstleg', 'nlm', 'ml', 'mm', 'nleg', 'npart', 'maxnmicro', 'numphase',
+                                   'deltam', 'interp_new')] + \
+               [('srctype', C.c_char), ('phasemax', f32), ('solarmu', f32)] + \
+               [(k, C.c_void_p) for k in ('extinct', 'albedo', 'total_ext', 'legen', 'iphase', 'phaseinterpwt', 'dirflux',
+                                          'rshptr', 'radiance', 'ylmsun', 'planck')]
+
+
 class TraceC(C.Structure):
     _fields_ = [('max_per_ray', i32), ('cells', C.c_void_p), ('ncells', C.c_void_p), ('nsub', C.c_void_p)]
 
@@ -37,7 +46,7 @@ SYMBOLS = ['at3d_b200_version', 'at3d_device_count', 'at3d_set_device', 'at3d_st
            'at3d_levisapprox_gradient', 'at3d_levisapprox_gradient_jacobian', 'at3d_prepare_deriv_interps', 'at3d_make_direct_derivative',
            'at3d_average_subpixel_rays', 'at3d_update_costfunction', 'at3d_make_direct', 'at3d_state_get_counts',
            'at3d_sh_to_do', 'at3d_do_to_sh', 'at3d_path_integration_ip', 'at3d_solver_create',
-           'at3d_solver_path_integration', 'at3d_solver_solve', 'at3d_solver_destroy', 'at3d_sweeping_order', 'at3d_transfer_pa_to_grid', 'at3d_solve_adaptive']
+           'at3d_solver_path_integration', 'at3d_solver_solve', 'at3d_solver_destroy', 'at3d_sweeping_order', 'at3d_transfer_pa_to_grid', 'at3d_solve_adaptive', 'at3d_compute_source_device']
 
 
 class _Missing:
@@ -89,6 +98,8 @@ def lib():
     L.at3d_compute_source.argtypes = [P(StateDesc), i32, f32, i32, i32, i32, i32, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_void_p, P(f32), P(f32), P(f32), P(f32), P(f64),
                                       C.c_char_p]
+    L.at3d_compute_source_device.argtypes = [P(CsDeviceDesc), i32, f32, C.c_int64, i32, i32] + [C.c_void_p] * 7 + \
+        [C.c_int64, i32, C.c_void_p, P(i32), P(f64), C.c_char_p]
     L.at3d_ylmall.argtypes = [i32, f32, f32, i32, i32, i32, C.c_void_p, C.c_char_p]
     L.at3d_precompute_phase_check.argtypes = [i32, i32, i32, i32, i32, i32, i32, i32, C.c_void_p,
                                               C.c_void_p, i32, i32, i32, C.c_char_p]

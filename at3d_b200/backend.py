@@ -153,6 +153,69 @@ def compute_source(state, shptr, source, oshptr, delsource, fixsh=False, shacc=0
     return res + (ms.value,) if timing else res
 
 
+class DeviceSourceState:
+    """The arrays COMPUTE_SOURCE reads, resident on the GPU as torch tensors with the reference's (Fortran) layout: what a
+    GPU-resident solver holds between iterations (RTE._extinct, _albedo, _legen, _iphase, ... at3d/solver.py:1609-1760).
+    ``radiance`` / ``rshptr`` are the current SH radiance; SOURCE / SHPTR / DELSOURCE / OSHPTR are passed per call."""
+
+    FIELDS = ('extinct', 'albedo', 'total_ext', 'legen', 'iphase', 'phaseinterpwt', 'dirflux', 'rshptr', 'radiance',
+              'ylmsun', 'planck')
+
+    def __init__(self, state=None, device='cuda', **arrays):
+        import torch
+        self._t = {}
+        if state is not None:
+            st = state
+            self.meta = dict(npts=st.npts, nstokes=st.nstokes, nstleg=st.nstleg, nlm=st.nlm, ml=st.ml, mm=st.mm, nleg=st.nleg,
+                             npart=st.npart, maxnmicro=st.maxnmicro, numphase=st.numphase, deltam=int(st.deltam),
+                             interp_new=int(st.interp_new), srctype=st.srctype, phasemax=st.phasemax, solarmu=st.solarmu)
+            for k in self.FIELDS:
+                a = getattr(st, k, None)
+                if a is None:
+                    continue
+                # bytes in Fortran order: ravel(order='K') of the F-ordered host array
+                self._t[k] = torch.from_numpy(np.ascontiguousarray(np.asarray(a).ravel(order='F'))).to(device)
+        else:
+            self.meta = arrays.pop('meta')
+            self._t = dict(arrays)
+
+    def tensor(self, k):
+        return self._t.get(k)
+
+    def desc(self):
+        d = _lib.CsDeviceDesc()
+        for k, v in self.meta.items():
+            setattr(d, k, v.encode() if k == 'srctype' else v)
+        for k in self.FIELDS:
+            t = self._t.get(k)
+            setattr(d, k, t.data_ptr() if t is not None else None)
+        return d
+
+
+def compute_source_device(dstate, shptr_old, source_old, oshptr_old, delsource, shptr_new, source_new, fixsh=False,
+                          shacc=0.0, maxiv=None, first=False, accelflag=True, properties_changed=False, timing=False):
+    """COMPUTE_SOURCE (shdomsub1.f:967) on device-resident torch tensors (C: at3d_compute_source_device).  SOURCE and SHPTR
+    are double-buffered by the caller (``*_old`` in, ``*_new`` out); DELSOURCE is updated in place at the old SHPTR offsets.
+    Returns (ierr, total_new, [deljdot, deljold, deljnew, jnorm]) (+ kernel ms when ``timing``)."""
+    nst = dstate.meta['nstokes']
+    cap = source_new.numel() // nst
+    if maxiv is None:
+        maxiv = cap
+    norms = np.zeros(4, np.float32)
+    tot = C.c_int32(0)
+    ms = C.c_double(0.0)
+    buf = _lib.errbuf()
+    d = dstate.desc()
+    code = _lib.lib().at3d_compute_source_device(
+        C.byref(d), int(fixsh), shacc, int(maxiv), int(first), int(accelflag), vp(shptr_old), vp(source_old),
+        vp(oshptr_old), vp(delsource), vp(delsource), vp(shptr_new), vp(source_new), int(cap), int(properties_changed),
+        vp(norms), C.byref(tot), C.byref(ms), buf)
+    if code not in (0, 2):
+        _lib.check(code, buf)
+    res = (code, tot.value, [float(x) for x in norms])
+    return res + (ms.value,) if timing else res
+
+
 def _angles(state, wtmu):
     return (np.ascontiguousarray(state.nphi0, np.int32), np.ascontiguousarray(state.mu, np.float32),
             np.asfortranarray(state.phi, np.float32), np.ascontiguousarray(wtmu, np.float32))

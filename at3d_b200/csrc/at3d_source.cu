@@ -14,6 +14,7 @@
 #include <cstdarg>
 #include <vector>
 #include <cub/cub.cuh>
+#include <mutex>
 #include "at3d_host.h"
 
 static void set_msg(char *errmsg, const char *fmt, ...)
@@ -490,6 +491,131 @@ __global__ void __launch_bounds__(CS_WARPS * 32) cs_write_kernel(CsArgs a)
     }
 }
 
+// Kernel F (FIXSH): the truncation lengths stay (NS_new = NS_old), so the offsets of the new SOURCE are known and the
+// routine is ONE streaming pass: norms, DELSOURCE and SOURCE from a single evaluation of the temporary source -- RADIANCE
+// is read once instead of twice and nothing beyond NS_old is evaluated.  Same per-j arithmetic and the same per-lane
+// summation order as cs_norms_kernel + cs_write_kernel (identical SOURCE, DELSOURCE and norms).  source_new may alias
+// source_old and delsource_new delsource_old (every element is read and then written by the same thread).
+template <int NST, int SLOTS>
+__global__ void __launch_bounds__(CS_WARPS * 32, (NST == 1 ? AT3D_CS_MINB : 1)) cs_fused_kernel(CsArgs a)
+{
+    extern __shared__ float smem[];
+    constexpr int NB = CsBatch<NST>::N;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nlt = a.nstleg * (a.nleg + 1);
+    float *legent = smem + (size_t)warp * 2 * nlt;
+    __shared__ double red[CS_WARPS][4];
+    double sdot = 0.0, sold = 0.0, snew = 0.0, snorm = 0.0;
+    const bool donorm = !a.first, doacc = a.accelflag && !a.first;
+    CsLaneTab tab;
+    tab.init(a, lane);
+    const int stride = gridDim.x * CS_WARPS;
+    int i = blockIdx.x * CS_WARPS + warp;
+    int ir = 0, nr = 0, is = 0, ns = 0, iso = 0, nsc = 0;      // ns: NS_old; nsc: terms common with the old DELSOURCE
+    float dfl = 0.0f;
+    float r[NB][NST], so[NB][NST], ds[NB][NST];
+    auto load_ptrs = [&](int ip, int &ir_, int &nr_, int &is_, int &ns_, int &iso_, int &nsc_, float &dfl_) {
+        dfl_ = __ldg(&a.dirflux[ip]);
+        ir_ = a.rshptr[ip]; nr_ = a.rshptr[ip + 1] - ir_;
+        is_ = a.shptr_old[ip]; ns_ = a.shptr_old[ip + 1] - is_;
+        iso_ = 0; nsc_ = ns_;
+        if (doacc) {
+            iso_ = a.oshptr_old[ip];
+            const int nso = a.oshptr_old[ip + 1] - iso_;
+            if (nso < nsc_) nsc_ = nso;
+        }
+    };
+    auto load_batch = [&](int j0, int ir_, int nr_, int is_, int ns_, int iso_, int nsc_) {
+        const float *rad = a.radiance + (size_t)NST * ir_;
+        const float *sop = a.source_old + (size_t)NST * is_, *dsp = a.delsource_old + (size_t)NST * iso_;
+#pragma unroll
+        for (int u = 0; u < NB; u++) {
+            const int j = j0 + 32 * u + lane;
+#pragma unroll
+            for (int k = 0; k < NST; k++) {
+                r[u][k] = (j < nr_) ? __ldg(&rad[(size_t)NST * j + k]) : 0.0f;
+                so[u][k] = (donorm && j < ns_) ? __ldg(&sop[(size_t)NST * j + k]) : 0.0f;
+                ds[u][k] = (doacc && j < nsc_) ? __ldg(&dsp[(size_t)NST * j + k]) : 0.0f;
+            }
+        }
+    };
+    auto body = [&](int j, int l, float ysun, const float (&rr)[NST], const float (&soo)[NST], const float (&dss)[NST],
+                    float flux0, float planck, float albedo, float &pdot, float &pold, float &pnew, float &pnorm) {
+        float sv[NST];
+        cs_calc_j<NST>(a, legent, j, l, ysun, j < nr, rr, flux0, planck, albedo, sv);
+        if (donorm && j < nsc) {
+#pragma unroll
+            for (int k = 0; k < NST; k++) {
+                const float d = sv[k] - soo[k];
+                if (a.accelflag) {
+                    pdot = pdot + d * dss[k];
+                    pold = pold + dss[k] * dss[k];
+                }
+                pnew = pnew + d * d;
+                pnorm = pnorm + soo[k] * soo[k];
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < NST; k++) {
+            if (doacc) a.delsource_new[(size_t)NST * (is + j) + k] = sv[k] - soo[k];
+            a.source_new[(size_t)NST * (is + j) + k] = sv[k];
+        }
+    };
+    CsMixRow<SLOTS> mix;
+    if (i < a.npts) { load_ptrs(i, ir, nr, is, ns, iso, nsc, dfl); mix.load(a, i, lane, nlt); load_batch(0, ir, nr, is, ns, iso, nsc); }
+    for (; i < a.npts; i += stride) {
+        const int inext = i + stride;
+        int ir2 = 0, nr2 = 0, is2 = 0, ns2 = 0, iso2 = 0, nsc2 = 0;
+        float dfl2 = 0.0f;
+        if (inext < a.npts) load_ptrs(inext, ir2, nr2, is2, ns2, iso2, nsc2, dfl2);
+        if (nr > a.nlm) {
+            if (lane == 0) atomicCAS(a.bad, 0, i + 1);
+            ir = ir2; nr = nr2; is = is2; ns = ns2; iso = iso2; nsc = nsc2; dfl = dfl2;
+            if (inext < a.npts) { mix.load(a, inext, lane, nlt); load_batch(0, ir, nr, is, ns, iso, nsc); }
+            continue;
+        }
+        const float flux0 = dfl * a.secmu0;
+        mix.to_shared(legent, lane, nlt);
+        const float albedo = mix.ap.x, planck = mix.ap.y;
+        if (inext < a.npts) mix.load(a, inext, lane, nlt);
+        float pdot = 0.0f, pold = 0.0f, pnew = 0.0f, pnorm = 0.0f;
+#pragma unroll
+        for (int b = 0; b < CS_JSLOTS / NB; b++) {
+            const int j0 = 32 * NB * b;
+            if (j0 >= ns) break;
+            if (b > 0) load_batch(j0, ir, nr, is, ns, iso, nsc);
+#pragma unroll
+            for (int u = 0; u < NB; u++) {
+                const int j = j0 + 32 * u + lane;
+                if (j >= ns) continue;
+                body(j, tab.l[b * NB + u], tab.ys[b * NB + u], r[u], so[u], ds[u], flux0, planck, albedo, pdot, pold, pnew, pnorm);
+            }
+        }
+        for (int j0 = 32 * CS_JSLOTS; j0 < ns; j0 += 32 * NB) {            // NLM > 256: table loads
+            load_batch(j0, ir, nr, is, ns, iso, nsc);
+#pragma unroll
+            for (int u = 0; u < NB; u++) {
+                const int j = j0 + 32 * u + lane;
+                if (j >= ns) continue;
+                body(j, a.lofj[j], a.ylmsun[(size_t)a.nstleg * j], r[u], so[u], ds[u], flux0, planck, albedo, pdot, pold, pnew, pnorm);
+            }
+        }
+        sdot += (double)pdot; sold += (double)pold; snew += (double)pnew; snorm += (double)pnorm;
+        if (lane == 0) a.ns_new[i] = ns;
+        __syncwarp();
+        ir = ir2; nr = nr2; is = is2; ns = ns2; iso = iso2; nsc = nsc2; dfl = dfl2;
+        if (inext < a.npts) load_batch(0, ir, nr, is, ns, iso, nsc);
+    }
+    sdot = warp_sum_d(sdot); sold = warp_sum_d(sold); snew = warp_sum_d(snew); snorm = warp_sum_d(snorm);
+    if (lane == 0) { red[warp][0] = sdot; red[warp][1] = sold; red[warp][2] = snew; red[warp][3] = snorm; }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        double t = 0.0;
+        for (int w = 0; w < CS_WARPS; w++) t += red[w][threadIdx.x];
+        a.partials[(size_t)blockIdx.x * 4 + threadIdx.x] = t;
+    }
+}
+
 // deterministic final reduction of the per-block partial sums
 __global__ void cs_reduce_kernel(int nblocks, const double *partials, double *out)
 {
@@ -598,6 +724,22 @@ int cs_device_step(CsArgs &a, int nblk, void *scan_tmp, size_t tmpb, int *shptr_
         else if (slots == 2) cs_mix_kernel<2><<<nmix, CS_WARPS * 32, smem>>>(a);
         else if (slots == 4) cs_mix_kernel<4><<<nmix, CS_WARPS * 32, smem>>>(a);
         else cs_mix_kernel<8><<<nmix, CS_WARPS * 32, smem>>>(a);
+    }
+    if (a.fixsh && source_new) {
+        // FIXSH: one pass (cs_fused_kernel); SHPTR is unchanged
+        int total_new = 0, hbad = 0;
+        cudaMemcpy(&total_new, a.shptr_old + npts, sizeof(int), cudaMemcpyDeviceToHost);
+        if (total_new_out) *total_new_out = total_new;
+        if ((size_t)total_new > cap_new) { set_msg(errmsg, "COMPUTE_SOURCE: the new SOURCE buffer is too small for FIXSH"); return 2; }
+        a.source_new = source_new;
+        if (shptr_new != a.shptr_old)
+            cudaMemcpyAsync(shptr_new, a.shptr_old, sizeof(int) * ((size_t)npts + 1), cudaMemcpyDeviceToDevice, 0);
+        CS_LAUNCH(cs_fused_kernel)
+        cs_reduce_kernel<<<1, 1024>>>(nblk, a.partials, sums);
+        cudaMemcpy(&hbad, a.bad, sizeof(int), cudaMemcpyDeviceToHost);
+        a.shptr_new = shptr_new;
+        if (hbad) { set_msg(errmsg, "COMPUTE_SOURCE: NR>NLM 3 %d", hbad); return 1; }
+        return 0;
     }
     CS_LAUNCH(cs_norms_kernel)
     cs_reduce_kernel<<<1, 1024>>>(nblk, a.partials, sums);
@@ -731,5 +873,104 @@ extern "C" int at3d_compute_source(const at3d_state_desc *d, int fixsh, float sh
     }
     if (kernel_ms) *kernel_ms = ms;
     cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return rc;
+}
+
+
+// ---- a1 on device-resident arrays: every array pointer is a DEVICE pointer, nothing is staged or copied back except
+//      the four norms, the new SHPTR(NPTS+1) and the error flag (at3d_b200.h) ----
+namespace {
+struct CsWork {                      // scratch of at3d_compute_source_device, kept between calls (one per process)
+    std::mutex mu;
+    DevBuf ns_new, partials, bad, sums, mix_legent, mix_ap, scan, lofj;
+    int lofj_key[3] = {-1, -1, -1};
+    const void *mix_key[4] = {nullptr, nullptr, nullptr, nullptr};
+    int mix_npts = -1;
+};
+CsWork g_cswork;
+}
+
+extern "C" int at3d_compute_source_device(const at3d_cs_device_desc *d, int fixsh, float shacc, int64_t maxiv, int first,
+                                          int accelflag, const int32_t *shptr_old, const float *source_old,
+                                          const int32_t *oshptr_old, const float *delsource_old, float *delsource_new,
+                                          int32_t *shptr_new, float *source_new, int64_t source_new_capacity,
+                                          int properties_changed, float *norms /*host [4]*/, int32_t *total_new /*host*/,
+                                          double *kernel_ms, char *errmsg)
+{
+    if (errmsg) errmsg[0] = 0;
+    if (!d || !shptr_old || !source_old || !shptr_new || !source_new || !norms || !total_new) { set_msg(errmsg, "null argument"); return 1; }
+    if (accelflag && !first && (!oshptr_old || !delsource_old || !delsource_new)) { set_msg(errmsg, "the acceleration needs OSHPTR and DELSOURCE"); return 1; }
+    if (at3d_device_count() < 1) { set_msg(errmsg, "no CUDA device: at3d_b200 has no CPU fallback"); return 4; }
+    if (!(d->nstokes == 1 || d->nstokes == 3)) { set_msg(errmsg, "NSTOKES must be 1 or 3"); return 3; }
+    if (!d->rshptr || !d->radiance || !d->extinct || !d->albedo || !d->total_ext || !d->legen || !d->iphase ||
+        !d->phaseinterpwt || !d->dirflux || !d->ylmsun) { set_msg(errmsg, "a required device array is NULL"); return 1; }
+    std::lock_guard<std::mutex> lock(g_cswork.mu);
+    CsWork &W = g_cswork;
+    const size_t npts = d->npts;
+    const size_t nlt = (size_t)d->nstleg * (d->nleg + 1);
+    if (nlt > 256) { set_msg(errmsg, "COMPUTE_SOURCE: Legendre table longer than 256 entries"); return 3; }
+    CsArgs a;
+    memset(&a, 0, sizeof(a));
+    a.npts = d->npts; a.nstokes = d->nstokes; a.nstleg = d->nstleg; a.nlm = d->nlm; a.ml = d->ml; a.mm = d->mm; a.nleg = d->nleg;
+    a.npart = d->npart; a.nq = 8 * d->maxnmicro; a.srctype = d->srctype; a.deltam = d->deltam; a.interp_new = d->interp_new;
+    a.newmethod = 1; a.first = first; a.accelflag = accelflag; a.fixsh = fixsh;
+    a.phasemax = d->phasemax; a.secmu0 = 1.0f / fabsf(d->solarmu); a.srcmin = shacc;
+    a.extinct = d->extinct; a.albedo = d->albedo; a.total_ext = d->total_ext; a.legen = d->legen; a.iphase = d->iphase;
+    a.phaseinterpwt = d->phaseinterpwt; a.dirflux = d->dirflux; a.rshptr = d->rshptr; a.radiance = d->radiance;
+    a.ylmsun = d->ylmsun; a.planck = d->planck;
+    a.shptr_old = shptr_old; a.oshptr_old = oshptr_old ? oshptr_old : shptr_old; a.source_old = source_old;
+    a.delsource_old = delsource_old ? delsource_old : source_old; a.delsource_new = delsource_new;
+    const int nblk = cs_grid_blocks(d->npts);
+    const size_t tmpb = cs_scan_bytes(d->npts);
+    cudaError_t ce = cudaSuccess;
+    if (ce == cudaSuccess) ce = W.ns_new.reserve(sizeof(int) * (npts + 1));
+    if (ce == cudaSuccess) ce = W.partials.reserve(sizeof(double) * 4 * (size_t)nblk);
+    if (ce == cudaSuccess) ce = W.bad.reserve(256);
+    if (ce == cudaSuccess) ce = W.sums.reserve(256);
+    if (ce == cudaSuccess) ce = W.scan.reserve(tmpb + 256);
+    if (ce == cudaSuccess) ce = W.lofj.reserve(sizeof(int) * (size_t)d->nlm);
+    const bool mix_realloc = W.mix_legent.cap < sizeof(float) * npts * nlt || W.mix_ap.cap < sizeof(float2) * npts;
+    if (ce == cudaSuccess) ce = W.mix_legent.reserve(sizeof(float) * npts * nlt);
+    if (ce == cudaSuccess) ce = W.mix_ap.reserve(sizeof(float2) * npts);
+    if (ce != cudaSuccess) { set_msg(errmsg, "device allocation failure (%s)", cudaGetErrorString(ce)); return 4; }
+    if (W.lofj_key[0] != d->ml || W.lofj_key[1] != d->mm || W.lofj_key[2] != d->nlm) {
+        std::vector<int> lofj(d->nlm);
+        int j = 0;
+        for (int l = 0; l <= d->ml; l++) {
+            const int me = l < d->mm ? l : d->mm;
+            for (int m = -me; m <= me; m++) { if (j < d->nlm) lofj[j] = l; j++; }
+        }
+        if (j != d->nlm) { set_msg(errmsg, "NLM inconsistent with ML, MM"); return 1; }
+        cudaMemcpy(W.lofj.p, lofj.data(), sizeof(int) * lofj.size(), cudaMemcpyHostToDevice);
+        W.lofj_key[0] = d->ml; W.lofj_key[1] = d->mm; W.lofj_key[2] = d->nlm;
+    }
+    a.lofj = (const int *)W.lofj.p;
+    a.ns_new = (int *)W.ns_new.p; a.partials = (double *)W.partials.p; a.bad = (int *)W.bad.p;
+    a.mix_legent = (float *)W.mix_legent.p; a.mix_ap = (float2 *)W.mix_ap.p;
+    // the mixed Legendre rows depend on the optical properties only: they are kept between calls on the same arrays
+    // unless the caller says the properties changed
+    const bool mix_ready = !properties_changed && !mix_realloc && W.mix_npts == d->npts && W.mix_key[0] == d->extinct &&
+                           W.mix_key[1] == d->albedo && W.mix_key[2] == d->iphase && W.mix_key[3] == d->legen;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0, 0);
+    int tot = 0;
+    const int maxiv_i = maxiv > 0x7FFFFFFFll ? 0x7FFFFFFF : (int)maxiv;
+    int rc = cs_device_step(a, nblk, W.scan.p, tmpb, shptr_new, (double *)W.sums.p, maxiv_i, (size_t)source_new_capacity, source_new,
+                            &tot, mix_ready, errmsg);
+    float ms = 0.0f;
+    cudaEventRecord(e1, 0);
+    cudaError_t e = cudaEventSynchronize(e1);
+    if (e != cudaSuccess && !rc) { set_msg(errmsg, "CUDA error %s in at3d_compute_source_device", cudaGetErrorString(e)); rc = 4; }
+    else cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (!rc) {
+        W.mix_npts = d->npts; W.mix_key[0] = d->extinct; W.mix_key[1] = d->albedo; W.mix_key[2] = d->iphase; W.mix_key[3] = d->legen;
+        double hs[4];
+        cudaMemcpy(hs, W.sums.p, sizeof(hs), cudaMemcpyDeviceToHost);
+        for (int q = 0; q < 4; q++) norms[q] = (float)hs[q];
+        *total_new = tot;
+    } else W.mix_npts = -1;
+    if (kernel_ms) *kernel_ms = ms;
     return rc;
 }

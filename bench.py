@@ -109,6 +109,85 @@ def compute_source_leg(B, st, steps, warmup, oracle=None):
     return out
 
 
+def compute_source_cfg4_leg(B, steps, warmup, peak, nx=256, ny=256, nz=100):
+    """COMPUTE_SOURCE at the size of BASELINE.json configs[3] (256x256x100 = 6.55 M grid points, NLM=256, NSTOKES=1,
+    cloud + Rayleigh) on DEVICE-RESIDENT arrays through at3d_compute_source_device: synthetic fields generated on the GPU
+    (random SH with power-law decay, 35 % of the points truncated to a random shell, seed 0).  Two variants: the general
+    call (adaptive truncation: norms kernel, SHPTR scan, write kernel) and FIXSH (one fused pass).  ms per call = CUDA
+    events around the launches inside the call; bytes per SURVEY 8(d)."""
+    import torch
+    from at3d_b200 import grid as G
+    try:
+        g = torch.Generator(device='cuda'); g.manual_seed(0)
+        npts, nmu, nphi, npart, nq = nx * ny * nz, 16, 32, 2, 8
+        ml, mm, nlm = G.sh_sizes(nmu, nphi)
+        nleg, numphase = ml, 19
+        lj = torch.from_numpy(G.lofj(ml, mm).astype(np.int64)).cuda()
+
+        def sh_field(scale):
+            ltr = torch.where(torch.rand(npts, generator=g, device='cuda') < 0.35,
+                              torch.randint(0, ml + 1, (npts,), generator=g, device='cuda'), torch.full((npts,), ml, device='cuda'))
+            ns = torch.where(ltr <= mm, ltr * (ltr + 1) + ltr + 1, (2 * mm + 1) * ltr - mm * mm + mm + 1).to(torch.int32)
+            ptr = torch.zeros(npts + 1, dtype=torch.int32, device='cuda')
+            ptr[1:] = torch.cumsum(ns, 0).to(torch.int32)
+            tot = int(ptr[npts])
+            arr = torch.empty(tot, dtype=torch.float32, device='cuda')
+            chunk = 1 << 26
+            for a in range(0, tot, chunk):                       # bounded temporaries
+                b = min(tot, a + chunk)
+                arr[a:b] = scale * torch.randn(b - a, generator=g, device='cuda')
+            return ptr, arr, tot
+        rshptr, radiance, nr = sh_field(0.05)
+        shptr, source, ns_tot = sh_field(0.1)
+        delsource = 0.01 * source
+        ext = torch.zeros((npart, npts), dtype=torch.float32, device='cuda')      # Fortran [npts, npart]
+        ext[0] = 30.0 * torch.clamp(torch.rand(npts, generator=g, device='cuda') - 0.5, min=0.0)
+        ext[1] = 0.02
+        alb = torch.ones((npart, npts), dtype=torch.float32, device='cuda')
+        total_ext = ext.sum(0)
+        gs = np.linspace(0.80, 0.87, numphase - 1)
+        legen = np.zeros((numphase, nleg + 1), np.float32)                         # Fortran [1, nleg+1, numphase]
+        for k, gg in enumerate(gs):
+            legen[k] = gg ** np.arange(nleg + 1) * (1.0 - gg ** (nleg + 1))        # delta-M-like scaling, values only matter as floats
+        legen[-1, 0], legen[-1, 2] = 1.0, 0.5
+        iphase = torch.ones((npart, npts, nq), dtype=torch.int32, device='cuda')   # Fortran [nq, npts, npart]
+        iphase[0, :, 0] = torch.randint(1, numphase, (npts,), generator=g, device='cuda').to(torch.int32)
+        iphase[1, :, 0] = numphase
+        pwt = torch.zeros((npart, npts, nq), dtype=torch.float32, device='cuda')
+        pwt[:, :, 0] = 1.0
+        ylmsun = np.asfortranarray(B.ylmall(True, np.float32(-0.5), np.float32(0.3), ml, mm, 1, nlm).reshape(1, nlm))
+        meta = dict(npts=npts, nstokes=1, nstleg=1, nlm=nlm, ml=ml, mm=mm, nleg=nleg, npart=npart, maxnmicro=1,
+                    numphase=numphase, deltam=1, interp_new=1, srctype='S', phasemax=0.999, solarmu=-0.5)
+        dev = B.DeviceSourceState(meta=meta, extinct=ext, albedo=alb, total_ext=total_ext,
+                                  legen=torch.from_numpy(legen).cuda(), iphase=iphase, phaseinterpwt=pwt,
+                                  dirflux=torch.rand(npts, generator=g, device='cuda'), rshptr=rshptr, radiance=radiance,
+                                  ylmsun=torch.from_numpy(np.ascontiguousarray(ylmsun.ravel(order='F'))).cuda())
+        cap = npts * nlm                                              # adaptive truncation may grow every point to NLM
+        source_new = torch.empty(cap, dtype=torch.float32, device='cuda')
+        shptr_new = torch.empty_like(shptr)
+        out = dict(npts=npts, nlm=nlm, npart=npart, sum_nr=nr, sum_ns=ns_tot,
+                   hbm_bytes=int(sum(t.numel() * t.element_size() for t in (radiance, source, delsource, source_new, iphase, pwt, ext, alb))))
+        P = 28 + npart * (8 + 64 * 1)
+        for name, fixsh in (('adaptive_truncation', False), ('fixsh_fused', True)):
+            kms = []
+            tot_new = ns_tot
+            for i in range(warmup + steps):
+                dl = delsource.clone()
+                rc, tot_new, sums, ms = B.compute_source_device(dev, shptr, source, shptr, dl, shptr_new, source_new, fixsh=fixsh,
+                                                                shacc=0.0 if fixsh else 3e-3, maxiv=cap, timing=True)
+                if rc != 0:
+                    return dict(error='COMPUTE_SOURCE returned %d' % rc)
+                if i >= warmup:
+                    kms.append(ms)
+            b = 4 * (nr + ns_tot + tot_new + 2 * ns_tot) + npts * (P + 4 * npart + 8)
+            k = float(np.mean(kms))
+            out[name] = dict(kernel_ms=k, algorithmic_bytes=int(b), achieved_gbs=b / (k * 1e-3) / 1e9,
+                             frac=b / (k * 1e-3) / 1e9 / peak, sum_ns_new=int(tot_new))
+        return out
+    except Exception as e:                                            # e.g. not enough device memory on a shared GPU
+        return dict(skipped='%s: %s' % (type(e).__name__, e))
+
+
 def orthographic_leg(dev, sc, npix_side, steps, warmup):
     """RENDER of 9 orthographic views (all rays of a view share their direction): the library evaluates the source of
     every grid point once per view (view_source_kernel) instead of once per (ray, corner).  Host ray arrays through the
@@ -471,7 +550,8 @@ def render_only(args, dev, st, sc, rays, dr, l2flush, stream, barrier, world, ra
             render_ocean=dict(rays_per_s=world * nrays * args.steps / t_ocean, kernel_ms=ms_ocean,
                               surface_ms=ms_ocean - ms_lamb, surface_hits=c_ocean['surface_hits'],
                               brdf_evals=c_ocean['surface_hits'] * 4 * (st.nang // 2 + 1)),
-            compute_source=csrc, transforms=transform_leg(B, st, args.steps, args.warmup),
+            compute_source=csrc, compute_source_cfg4=compute_source_cfg4_leg(B, max(3, args.steps // 2), 2, peak),
+            transforms=transform_leg(B, st, args.steps, args.warmup),
             render_orthographic=orthographic_leg(dev, sc, int(round((nrays / 9) ** 0.5)), args.steps, args.warmup),
             clocks=cs.summary(), cpu_baseline=None, wall_s=wall)
         print(json.dumps(line))
@@ -738,7 +818,8 @@ def main():
             render=dict(rays_per_s=nrays / (np.mean(rms) * 1e-3), kernel_ms=float(np.mean(rms)),
                         achieved_gbs=rbytes / (np.mean(rms) * 1e-3) / 1e9, frac=rbytes / (np.mean(rms) * 1e-3) / 1e9 / peak,
                         algorithmic_bytes=rbytes, counts=rcounts),
-            compute_source=csrc, transforms=transform_leg(B, st, args.steps, args.warmup),
+            compute_source=csrc, compute_source_cfg4=compute_source_cfg4_leg(B, max(3, args.steps // 2), 2, peak),
+            transforms=transform_leg(B, st, args.steps, args.warmup),
             render_orthographic=orthographic_leg(dev, sc, cfg['pixels_per_view'] ** 0.5, args.steps, args.warmup),
             solver_iteration=solver_leg(max(1, args.steps // 2), 1, orc if args.workload == 'cfg2' else None),
             path_integration_3d=sweep3d_leg(st, args.steps, 1, orc if args.workload == 'cfg2' else None),

@@ -166,6 +166,36 @@ int at3d_compute_source(const at3d_state_desc *desc, int fixsh, float shacc, int
                         float *deljdot, float *deljold, float *deljnew, float *jnorm,
                         double *kernel_ms /*optional: device time of the kernels*/, char *errmsg);
 
+/* ---- a1 on device-resident arrays (what the solution iterations of a GPU-resident solver call every iteration,
+ *      shdomsub1.f:600-640): every array below is a DEVICE pointer with the reference's layout.  SOURCE / SHPTR are
+ *      double-buffered by the caller (source_new may alias source_old only with fixsh); DELSOURCE is rewritten at the
+ *      OLD SHPTR offsets and delsource_new may alias delsource_old.  Only the four norms (DELJDOT, DELJOLD, DELJNEW,
+ *      JNORM), the new SHPTR(NPTS+1) and the error flag come back to the host.  The mixed Legendre rows of the points
+ *      (NEWMETHOD, shdomsub1.f:1089-1141) are kept between calls on the same property arrays: pass properties_changed=1
+ *      after the optical properties were modified in place. ---- */
+typedef struct {
+    int32_t npts, nstokes, nstleg, nlm, ml, mm, nleg, npart, maxnmicro, numphase, deltam, interp_new;
+    char srctype;                 /* 'S', 'T' or 'B' */
+    float phasemax, solarmu;
+    const float *extinct, *albedo;            /* [npts, npart] */
+    const float *total_ext;                   /* [npts] */
+    const float *legen;                       /* [nstleg, nleg+1, numphase] */
+    const int32_t *iphase;                    /* [8*maxnmicro, npts, npart] */
+    const float *phaseinterpwt;               /* [8*maxnmicro, npts, npart] */
+    const float *dirflux;                     /* [npts] */
+    const int32_t *rshptr;                    /* [npts+1] */
+    const float *radiance;                    /* [nstokes, rshptr[npts]] */
+    const float *ylmsun;                      /* [nstleg, nlm] */
+    const float *planck;                      /* [npts, npart] or NULL */
+} at3d_cs_device_desc;
+
+int at3d_compute_source_device(const at3d_cs_device_desc *desc, int fixsh, float shacc, int64_t maxiv, int first,
+                               int accelflag, const int32_t *shptr_old, const float *source_old,
+                               const int32_t *oshptr_old, const float *delsource_old, float *delsource_new,
+                               int32_t *shptr_new, float *source_new, int64_t source_new_capacity /*entries per Stokes component*/,
+                               int properties_changed, float *norms /*host [4]*/, int32_t *total_new /*host*/,
+                               double *kernel_ms /*optional*/, char *errmsg);
+
 /* ---- a2/a3/a4/a5/a6: RENDER (shdomsub4.f:93) ---- */
 int at3d_render(at3d_state *st, const at3d_rays *rays, float *stokes /*[nstokes,nrays], rays->memspace*/,
                 int correctinterpolate, int singlescatter, int nosurface,

@@ -53,6 +53,37 @@ def test_compute_source_matches_oracle(case, mode, oracle):
         np.testing.assert_allclose(sums_g, sums64, rtol=1e-5, atol=1e-7 * max(abs(sums64[3]), 1e-30))
 
 
+@pytest.mark.parametrize('case', ['scalar_periodic_split', 'polarized_periodic_split', 'rayleigh_two_species'])
+@pytest.mark.parametrize('mode', ['accel', 'fixsh', 'first'])
+def test_compute_source_device_resident_matches_oracle(case, mode, oracle):
+    """at3d_compute_source_device: every array a device pointer (torch tensors), SOURCE / SHPTR double-buffered; twice in a
+    row on the same properties (the second call reuses the mixed Legendre rows)."""
+    import torch
+    from at3d_b200 import backend as B
+    sc, shptr, source, oshptr, delsource, maxiv = _state_for_source(case, oracle)
+    st = sc.state
+    kw = dict(first=mode == 'first', accelflag=True, fixsh=mode == 'fixsh', shacc=0.0, maxiv=maxiv)
+    rc_r, shptr_r, src_r, oshptr_r, del_r, sums_r = oracle.compute_source(st, shptr, source, oshptr, delsource, **kw)
+    dev = B.DeviceSourceState(st)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(np.asarray(a).ravel(order='F'))).cuda()
+    for rep in range(2):
+        d_shptr, d_src, d_oshptr, d_del = t(shptr), t(source), t(oshptr), t(delsource)
+        d_shptr_new = torch.zeros_like(d_shptr)
+        d_src_new = torch.zeros_like(d_src)
+        rc, total, sums = B.compute_source_device(dev, d_shptr, d_src, d_oshptr, d_del, d_shptr_new, d_src_new, **kw)
+        assert rc == 0 and total == shptr_r[st.npts]
+        np.testing.assert_array_equal(d_shptr_new.cpu().numpy(), shptr_r)
+        n = shptr_r[st.npts]
+        src_g = d_src_new.cpu().numpy().reshape(source.shape, order='F')
+        scale = np.abs(src_r[:, :n]).max()
+        np.testing.assert_allclose(src_g[:, :n], src_r[:, :n], rtol=1e-5, atol=1e-6 * scale)
+        if not kw['first']:
+            m = oshptr_r[st.npts]
+            del_g = d_del.cpu().numpy().reshape(delsource.shape, order='F')
+            np.testing.assert_allclose(del_g[:, :m], del_r[:, :m], rtol=1e-4, atol=1e-6 * scale)
+            np.testing.assert_allclose(sums, sums_r, rtol=1e-4, atol=1e-7 * max(abs(sums_r[3]), 1e-30))
+
+
 def test_compute_source_out_of_sh_memory(oracle):
     from at3d_b200 import backend as B
     sc, shptr, source, oshptr, delsource, maxiv = _state_for_source('scalar_periodic_split', oracle)
