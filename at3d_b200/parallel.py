@@ -68,11 +68,14 @@ def allreduce_gradient(gradient, cost, group=None):
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return gradient, cost
+    nccl = dist.get_backend(group) == 'nccl'
     def red(x):
         if isinstance(x, np.ndarray):
             t = torch.from_numpy(np.ascontiguousarray(x))
+            if nccl:                            # NCCL reduces device tensors only: stage through the rank's GPU
+                t = t.cuda()
             dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
-            x[...] = t.numpy().reshape(x.shape)
+            x[...] = t.cpu().numpy().reshape(x.shape)
             return x
         dist.all_reduce(x, op=dist.ReduceOp.SUM, group=group)
         return x

@@ -712,6 +712,54 @@ def main():
     kms = np.array(kms)            # [steps, 4] forward, adjoint(+pixel), beam, total
     value = world * nrays * args.steps / t_total
 
+    # ---- strong scaling (N > 1): the SAME ray set cut into N contiguous pixel-aligned ranges (the rule of
+    # at3d/parallel.py:114-174), one per rank on its replica of the state; the pixel values are gathered and the
+    # gradient and cost all-reduced over NCCL inside the timed region ----
+    strong = None
+    if world > 1:
+        from at3d_b200.parallel import shard_for_rank
+        r0, r1, p0, p1 = shard_for_rank(pix.rays_per_pixel, rank, world)
+        drk, dpk = Bag(), Bag()
+        for k in ('camx', 'camy', 'camz', 'cammu', 'camphi'):
+            setattr(drk, k, getattr(dr, k)[r0:r1])
+        dpk.measurements = dp.measurements[p0:p1]
+        dpk.uncertainties = dp.uncertainties[p0:p1]
+        dpk.rays_per_pixel = dp.rays_per_pixel[p0:p1]
+        dpk.ray_weights = dp.ray_weights[r0:r1]
+        dpk.stokes_weights = dp.stokes_weights[p0:p1]
+        gout_s = torch.zeros_like(gout)
+        cout_s = torch.zeros_like(cout)
+        sout_all = torch.zeros_like(sout)
+
+        def step_strong():
+            l2flush.zero_()
+            sout_all.zero_()
+            dev.gradient(drk, dpk, gradout=gout_s, stokesout=sout_all[p0:p1], cost=cout_s, stream=stream)
+            dist.all_reduce(gout_s)
+            dist.all_reduce(cout_s)
+            dist.all_reduce(sout_all)          # ranks own disjoint pixel ranges: the sum is the gather of the pixel values
+        for _ in range(args.warmup):
+            step_strong()
+        barrier()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        for i in range(args.steps):
+            evs[i][0].record()
+            step_strong()
+            evs[i][1].record()
+        barrier()
+        tt = torch.tensor([sum(a.elapsed_time(b) for a, b in evs) * 1e-3], dtype=torch.float64, device='cuda')
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_strong = float(tt.item())
+        # the sharded evaluation must reproduce the replica's: same pixel values, gradient equal to FP64 rounding
+        gerr = float((gout_s - gout / world).abs().max() / (gout / world).abs().max()) if world > 1 else 0.0
+        strong = dict(value=nrays * args.steps / t_strong, unit='rays/s', ms_per_step=1e3 * t_strong / args.steps,
+                      rays_per_rank=int(r1 - r0), scaling='strong',
+                      efficiency_vs_one_gpu_same_run=(t_total / args.steps) / (world * t_strong / args.steps),
+                      gradient_max_rel_diff_vs_replica=gerr,
+                      note='one_gpu time = this run\'s weak step (every rank marches the whole ray set); collectives: '
+                           'all-reduce of GRADOUT f64[%d], cost, and the gathered pixel values f32[%d]'
+                           % (gi.maxpg * gi.numder, npix * st.nstokes))
+
     # ---- e2e: host buffers (pinned) through the C-ABI call, copies inside the timed region ----
     def pinned(a):
         t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
@@ -828,6 +876,8 @@ def main():
                               surface_ms=float(np.mean(oms) - np.mean(rms)), surface_hits=ocounts['surface_hits'],
                               brdf_evals=ocounts['surface_hits'] * 4 * (st.nang // 2 + 1)),
             clocks=cs.summary(), cpu_baseline=cpu, wall_s=wall)
+        if strong is not None:
+            line['strong'] = strong
         print(json.dumps(line))
     dev.close()
     if world > 1:
