@@ -15,6 +15,7 @@
 #include <cstring>
 #include <cstdarg>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 #include "at3d_host.h"
 
@@ -448,6 +449,10 @@ struct TrPlan {
     TrArgs fwd, bwd;            // table pointers of the two directions (point arrays are filled per launch)
     size_t smem_fwd = 0, smem_bwd = 0;
     int nang = 0, nsm = 148;
+    // tensor-core SH_TO_DO (sh_to_do_tc_kernel): pre-split, pre-swizzled basis tiles; 0 chunks = not available
+    const unsigned char *tc_b = nullptr;
+    int tc_kch = 0, tc_n1 = 0, tc_n2 = 0;
+    size_t tc_smem = 0;
     ~TrPlan() { for (void *p : ptrs) cudaFree(p); }
     template <typename T> T *alloc(size_t n)
     {
@@ -464,6 +469,7 @@ struct TrPlan {
     }
 };
 
+static int tr_tc_build(TrPlan *P, char *errmsg);
 void tr_plan_destroy(TrPlan *p) { delete p; }
 int tr_plan_nang(const TrPlan *p) { return p->nang; }
 
@@ -550,13 +556,337 @@ int tr_plan_create(int nstokes, int nstleg, int ml, int mm, int nlm, int nmu, in
     cudaFuncSetAttribute(do_to_sh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->smem_bwd);
     P->nang = nang;
     if (cudaDeviceSynchronize() != cudaSuccess) { delete P; set_msg(errmsg, "CUDA error building the SH/DO tables"); return 4; }
+    {
+        const int rc = tr_tc_build(P, errmsg);
+        if (rc) { delete P; return rc; }
+    }
     *out = P;
     return 0;
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// SH_TO_DO on the 5th-generation tensor cores (NSTOKES=1): DOFIELD[128 points x NANG] = SH[128 x NLM] . Y[NLM x NANG] as
+// one tcgen05.mma chain per tile of 128 grid points, accumulators in tensor memory, 3xTF32 (north_star: "tensor cores
+// only if 3xTF32 ... meets tolerance"): every FP32 operand is split a = hi + lo with hi, lo in TF32 and the product is
+// hi.hi + lo.hi + hi.lo accumulated in FP32 (the dropped lo.lo term is 2^-22 relative), so the result has FP32 accuracy.
+//
+//  * The dense form needs 6x the multiply-adds of the factorised Legendre + Fourier form of the FP32 kernels (and 3x
+//    more for the split), but the tensor pipe has ~27x the FP32-FMA rate: measured numbers in DESIGN.md 3.6.
+//  * B = the basis Y(j, ordinate), built once per plan by running the FP32 kernel on the NLM unit vectors (so both
+//    variants use the same basis values), split into hi / lo, cut into K chunks of 32 (one 128-byte swizzle row) and
+//    two ordinate chunks (N <= 256 per MMA), stored in global memory ALREADY in the canonical K-major SWIZZLE_128B
+//    shared-memory layout: one elected thread streams a tile with cp.async.bulk (TMA) into place.
+//  * A = the ragged SH rows (adaptive truncation, CSR): 128 threads stage a [128 x 32] chunk, zero-filled beyond NS(point),
+//    split it and write hi / lo in the same swizzled layout (16-byte chunk c of row r at c ^ (r & 7)).
+//  * One thread issues the MMAs (M=128, N=N1 | N2, K=8 per instruction, 24 per K chunk); tcgen05.commit releases the
+//    A stage and each B half as soon as the MMAs reading them retire, so the TMA of the next chunk's first half runs
+//    under the MMAs of this chunk's second half.
+//  * Epilogue: each of the four staging warps owns 32 TMEM lanes (= 32 consecutive grid points), tcgen05.ld 16 columns
+//    at a time and writes DOFIELD(NPTS, 1, NANG) in 128-byte rows (points fastest).
+// ------------------------------------------------------------------------------------------------------------------
+#define TC_BM 128
+#define TC_BK 32
+#define TC_THREADS 192
+
+__device__ __forceinline__ unsigned tc_smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void tc_mbar_init(unsigned long long *b, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tc_smem_u32(b)), "r"(count));
+}
+__device__ __forceinline__ void tc_mbar_arrive(unsigned long long *b)
+{
+    asm volatile("{ .reg .b64 st; mbarrier.arrive.shared::cta.b64 st, [%0]; }" ::"r"(tc_smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void tc_mbar_expect_tx(unsigned long long *b, unsigned bytes)
+{
+    asm volatile("{ .reg .b64 st; mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1; }" ::"r"(tc_smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tc_mbar_wait(unsigned long long *b, unsigned parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "TC_WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra TC_DONE_%=;\n\t"
+        "bra TC_WAIT_%=;\n\t"
+        "TC_DONE_%=:\n\t}" ::"r"(tc_smem_u32(b)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tc_bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(tc_smem_u32(dst)), "l"(src), "r"(bytes), "r"(tc_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_commit(unsigned long long *bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tc_smem_u32(bar)) : "memory");
+}
+// K-major, SWIZZLE_128B operand descriptor (cute::UMMA::SmemDescriptor): start address >> 4, SBO = 1024 B (8 rows of
+// 128 B), version 1, layout type 2
+__device__ __forceinline__ unsigned long long tc_desc(unsigned smem_addr)
+{
+    return (unsigned long long)((smem_addr & 0x3FFFFu) >> 4) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ void tc_mma_tf32(unsigned tmem_d, unsigned long long adesc, unsigned long long bdesc, unsigned idesc,
+                                            unsigned accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ unsigned tc_tf32(float x)
+{
+    unsigned r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+
+struct TcArgs {
+    int npts, nang, nlm, kch, n1, n2;
+    const int *shptr;
+    const float *sh;
+    float *dofield;
+    const unsigned char *bpack;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1) sh_to_do_tc_kernel(TcArgs a, int ntiles)
+{
+    extern __shared__ __align__(1024) unsigned char tc_smem[];
+    // carve: A stages (hi | lo) x 2, B1 (hi | lo), B2 (hi | lo), barriers
+    unsigned char *base = (unsigned char *)(((size_t)tc_smem + 1023) & ~(size_t)1023);
+    unsigned char *A[2] = {base, base + 2 * TC_BM * 128};
+    unsigned char *B1 = base + 4 * TC_BM * 128;
+    unsigned char *B2 = B1 + 2 * (size_t)a.n1 * 128;
+    unsigned long long *bars = (unsigned long long *)(B2 + 2 * (size_t)a.n2 * 128);
+    unsigned long long *a_full = bars, *a_empty = bars + 2, *b_full = bars + 4, *b_empty = bars + 6;
+    unsigned long long *t_full = bars + 8, *t_empty = bars + 9;
+    unsigned *tmem_slot = (unsigned *)(bars + 10);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nq = a.n2 > 0 ? 2 : 1;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 2; i++) { tc_mbar_init(&a_full[i], 128); tc_mbar_init(&a_empty[i], 1); tc_mbar_init(&b_full[i], 1); tc_mbar_init(&b_empty[i], 1); }
+        tc_mbar_init(t_full, 1); tc_mbar_init(t_empty, 128);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 4) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(tc_smem_u32(tmem_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const unsigned tmem = *tmem_slot;
+    const size_t bstride = 2 * (size_t)(a.n1 + a.n2) * 128;           // bytes of one K chunk of bpack
+
+    if (warp < 4) {
+        // ===== A staging (128 threads), then the epilogue of the tile =====
+        const int t = threadIdx.x, c = t & 7, r0 = t >> 3;
+        unsigned g = 0;                                               // chunks staged so far (stage = g & 1)
+        unsigned tile_iter = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, tile_iter++) {
+            int off[8], ns[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const int p = tile * TC_BM + r0 + 16 * i;
+                if (p < a.npts) { off[i] = __ldg(&a.shptr[p]); ns[i] = __ldg(&a.shptr[p + 1]) - off[i]; }
+                else { off[i] = 0; ns[i] = 0; }
+            }
+            for (int kc = 0; kc < a.kch; kc++, g++) {
+                const unsigned st = g & 1;
+                tc_mbar_wait(&a_empty[st], ((g >> 1) & 1) ^ 1);
+                unsigned char *hi = A[st], *lo = A[st] + TC_BM * 128;
+                const int j0 = kc * TC_BK + c * 4;
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const int row = r0 + 16 * i;
+                    const float *src = a.sh + off[i] + j0;
+                    float v[4];
+#pragma unroll
+                    for (int e = 0; e < 4; e++) v[e] = (j0 + e < ns[i]) ? __ldg(src + e) : 0.0f;
+                    uint4 h, l;
+                    h.x = tc_tf32(v[0]); h.y = tc_tf32(v[1]); h.z = tc_tf32(v[2]); h.w = tc_tf32(v[3]);
+                    l.x = tc_tf32(v[0] - __uint_as_float(h.x)); l.y = tc_tf32(v[1] - __uint_as_float(h.y));
+                    l.z = tc_tf32(v[2] - __uint_as_float(h.z)); l.w = tc_tf32(v[3] - __uint_as_float(h.w));
+                    const unsigned o = (unsigned)((row >> 3) * 1024 + (row & 7) * 128 + ((c ^ (row & 7)) << 4));
+                    *(uint4 *)(hi + o) = h;
+                    *(uint4 *)(lo + o) = l;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> async proxy (MMA)
+                tc_mbar_arrive(&a_full[st]);
+            }
+            // epilogue: TMEM lanes 32*warp .. +31 are grid points tile*128 + 32*warp + lane
+            tc_mbar_wait(t_full, tile_iter & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int p = tile * TC_BM + 32 * warp + lane;
+            const int ncols = a.n1 + a.n2;
+            for (int c0 = 0; c0 < ncols; c0 += 16) {
+                unsigned v[16];
+                const unsigned taddr = tmem + ((unsigned)(32 * warp) << 16) + (unsigned)c0;
+                asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                             : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                               "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                             : "r"(taddr) : "memory");
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (p < a.npts) {
+#pragma unroll
+                    for (int e = 0; e < 16; e++)
+                        if (c0 + e < a.nang) a.dofield[(size_t)(c0 + e) * a.npts + p] = __uint_as_float(v[e]);
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            tc_mbar_arrive(t_empty);
+        }
+    } else if (warp == 4) {
+        // ===== MMA issuer: one thread =====
+        if (lane == 0) {
+            const unsigned idesc1 = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(a.n1 >> 3) << 17) | ((unsigned)(TC_BM >> 4) << 24);
+            const unsigned idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(a.n2 >> 3) << 17) | ((unsigned)(TC_BM >> 4) << 24);
+            unsigned g = 0, tile_iter = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, tile_iter++) {
+                tc_mbar_wait(t_empty, (tile_iter & 1) ^ 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                for (int kc = 0; kc < a.kch; kc++, g++) {
+                    const unsigned st = g & 1;
+                    tc_mbar_wait(&a_full[st], (g >> 1) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const unsigned ahi = tc_smem_u32(A[st]), alo = ahi + TC_BM * 128;
+                    for (int q = 0; q < nq; q++) {
+                        tc_mbar_wait(&b_full[q], g & 1);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const unsigned bhi = tc_smem_u32(q == 0 ? B1 : B2), blo = bhi + (unsigned)(q == 0 ? a.n1 : a.n2) * 128;
+                        const unsigned d = tmem + (unsigned)(q == 0 ? 0 : a.n1);
+                        const unsigned idesc = q == 0 ? idesc1 : idesc2;
+#pragma unroll
+                        for (int k = 0; k < TC_BK / 8; k++) {
+                            const unsigned ko = (unsigned)k * 32;                  // 8 TF32 = 32 bytes along K inside the swizzle row
+                            tc_mma_tf32(d, tc_desc(ahi + ko), tc_desc(bhi + ko), idesc, (kc | k) != 0);
+                            tc_mma_tf32(d, tc_desc(alo + ko), tc_desc(bhi + ko), idesc, 1u);
+                            tc_mma_tf32(d, tc_desc(ahi + ko), tc_desc(blo + ko), idesc, 1u);
+                        }
+                        tc_commit(&b_empty[q]);                                    // this half of B may be overwritten
+                    }
+                    tc_commit(&a_empty[st]);
+                }
+                tc_commit(t_full);
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===== B loader: one thread streams the pre-swizzled basis tiles with cp.async.bulk =====
+        if (lane == 0) {
+            unsigned g = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                for (int kc = 0; kc < a.kch; kc++, g++) {
+                    const unsigned char *src = a.bpack + (size_t)kc * bstride;
+                    for (int q = 0; q < nq; q++) {
+                        const unsigned bytes = 2u * (unsigned)(q == 0 ? a.n1 : a.n2) * 128u;
+                        tc_mbar_wait(&b_empty[q], (g & 1) ^ 1);
+                        tc_mbar_expect_tx(&b_full[q], bytes);
+                        tc_bulk_g2s(q == 0 ? B1 : B2, src + (q == 0 ? 0 : 2 * (size_t)a.n1 * 128), bytes, &b_full[q]);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 4) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+    }
+}
+
+// basis tiles of the tensor-core variant (once per plan): Y(j, ordinate) from the FP32 kernel applied to the unit
+// vectors, split into TF32 hi / lo and laid out as the kernel's shared-memory tiles
+static unsigned tc_host_tf32(float x)
+{
+    unsigned u;
+    memcpy(&u, &x, 4);
+    if ((u & 0x7F800000u) == 0x7F800000u) return u;
+    u += 0x1000u;                                  // cvt.rna: round to nearest, ties away from zero, 13 low bits dropped
+    return u & 0xFFFFE000u;
+}
+
+static int tr_tc_build(TrPlan *P, char *errmsg)
+{
+    const TrArgs &f = P->fwd;
+    if (f.nst != 1) return 0;
+    const int nlm = f.nlm, nang = P->nang;
+    const int ntot = (nang + 15) & ~15;
+    if (ntot > 512 || nlm > 512) return 0;
+    int n1 = ntot, n2 = 0;
+    if (ntot > 256) { n1 = ((ntot / 2) + 15) & ~15; n2 = ntot - n1; }
+    const int kch = (nlm + TC_BK - 1) / TC_BK;
+    const size_t smem = 1024 + 4 * TC_BM * 128 + 2 * (size_t)(n1 + n2) * 128 + 256;
+    if (smem > 227 * 1024) return 0;
+    // unit vectors through the FP32 kernel
+    std::vector<int> ptr(nlm + 1);
+    for (int i = 0; i <= nlm; i++) ptr[i] = i * nlm;
+    std::vector<float> eye((size_t)nlm * nlm, 0.0f);
+    for (int i = 0; i < nlm; i++) eye[(size_t)i * nlm + i] = 1.0f;
+    int *ptr_d = nullptr; float *eye_d = nullptr, *y_d = nullptr;
+    if (cudaMalloc(&ptr_d, sizeof(int) * (nlm + 1)) != cudaSuccess || cudaMalloc(&eye_d, sizeof(float) * eye.size()) != cudaSuccess ||
+        cudaMalloc(&y_d, sizeof(float) * (size_t)nlm * nang) != cudaSuccess) { set_msg(errmsg, "device allocation failure"); return 4; }
+    cudaMemcpy(ptr_d, ptr.data(), sizeof(int) * (nlm + 1), cudaMemcpyHostToDevice);
+    cudaMemcpy(eye_d, eye.data(), sizeof(float) * eye.size(), cudaMemcpyHostToDevice);
+    TrArgs a = f;
+    a.npts = nlm; a.shptr = ptr_d; a.sh = eye_d; a.dofield = y_d;
+    const int ntiles = (nlm + TR_TP - 1) / TR_TP;
+    sh_to_do_kernel_s1<<<ntiles < P->nsm ? ntiles : P->nsm, TR_THREADS, P->smem_fwd + (size_t)a.nlm * 33 * sizeof(float)>>>(a, ntiles);
+    std::vector<float> y((size_t)nlm * nang);                       // y[j + nlm*ia]
+    cudaError_t e = cudaMemcpy(y.data(), y_d, sizeof(float) * y.size(), cudaMemcpyDeviceToHost);
+    cudaFree(ptr_d); cudaFree(eye_d); cudaFree(y_d);
+    if (e != cudaSuccess) { set_msg(errmsg, "CUDA error building the tensor-core basis (%s)", cudaGetErrorString(e)); return 4; }
+    const size_t bstride = 2 * (size_t)(n1 + n2) * 128;
+    std::vector<unsigned char> pack(bstride * kch, 0);
+    for (int kc = 0; kc < kch; kc++)
+        for (int q = 0; q < (n2 ? 2 : 1); q++) {
+            const int nq_ = q == 0 ? n1 : n2, col0 = q == 0 ? 0 : n1;
+            unsigned char *hi = pack.data() + (size_t)kc * bstride + (q == 0 ? 0 : 2 * (size_t)n1 * 128), *lo = hi + (size_t)nq_ * 128;
+            for (int n = 0; n < nq_; n++)
+                for (int k = 0; k < TC_BK; k++) {
+                    const int j = kc * TC_BK + k, ia = col0 + n;
+                    const float v = (j < nlm && ia < nang) ? y[(size_t)j + (size_t)nlm * ia] : 0.0f;
+                    const unsigned h = tc_host_tf32(v);
+                    float hf; memcpy(&hf, &h, 4);
+                    const unsigned l = tc_host_tf32(v - hf);
+                    const size_t o = (size_t)(n >> 3) * 1024 + (size_t)(n & 7) * 128 + (size_t)(((k >> 2) ^ (n & 7)) << 4) + (size_t)(k & 3) * 4;
+                    memcpy(hi + o, &h, 4);
+                    memcpy(lo + o, &l, 4);
+                }
+        }
+    unsigned char *b_d = P->up(pack.data(), pack.size());
+    if (!b_d) { set_msg(errmsg, "device allocation failure"); return 4; }
+    if (cudaFuncSetAttribute(sh_to_do_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
+    P->tc_b = b_d; P->tc_kch = kch; P->tc_n1 = n1; P->tc_n2 = n2; P->tc_smem = smem;
+    return 0;
+}
+
+static int tr_variant()
+{
+    // 0: FP32 FMA kernels, 1: tensor cores (3xTF32) where available.  AT3D_B200_TRANSFORM=fp32|tc
+    const char *e = getenv("AT3D_B200_TRANSFORM");
+    if (e && !strcmp(e, "tc")) return 1;
+    return 0;
+}
+
+cudaError_t tr_sh_to_do_tc(const TrPlan *P, int npts, const int *shptr_d, const float *sh_d, float *do_d, cudaStream_t st)
+{
+    TcArgs a;
+    a.npts = npts; a.nang = P->nang; a.nlm = P->fwd.nlm; a.kch = P->tc_kch; a.n1 = P->tc_n1; a.n2 = P->tc_n2;
+    a.shptr = shptr_d; a.sh = sh_d; a.dofield = do_d; a.bpack = P->tc_b;
+    const int ntiles = (npts + TC_BM - 1) / TC_BM;
+    sh_to_do_tc_kernel<<<ntiles < P->nsm ? ntiles : P->nsm, TC_THREADS, P->tc_smem, st>>>(a, ntiles);
+    return cudaGetLastError();
+}
+int tr_plan_has_tc(const TrPlan *P) { return P->tc_kch > 0; }
+
 // device-resident launches: SH array (NSTOKES,*) at shptr offsets <-> DOFIELD(NPTS,NSTOKES,NANG)
 cudaError_t tr_sh_to_do(const TrPlan *P, int npts, const int *shptr_d, const float *sh_d, float *do_d, cudaStream_t st)
 {
+    if (P->tc_kch > 0 && tr_variant() == 1) return tr_sh_to_do_tc(P, npts, shptr_d, sh_d, do_d, st);
     TrArgs a = P->fwd;
     a.npts = npts; a.shptr = shptr_d; a.sh = sh_d; a.dofield = do_d;
     const int ntiles = (npts + TR_TP - 1) / TR_TP;

@@ -28,6 +28,23 @@ def test_sh_to_do_matches_oracle(case):
     np.testing.assert_allclose(out, ref, rtol=1e-4, atol=2e-6 * scale)
 
 
+@pytest.mark.parametrize('case', ['scalar_periodic_split', 'scalar_nmu16', 'scalar_open_split'])
+def test_sh_to_do_tensor_core_variant_matches_oracle(case, monkeypatch):
+    """The tcgen05 3xTF32 variant (AT3D_B200_TRANSFORM=tc, NSTOKES=1): same 1e-4 bar against the oracle, and within FP32
+    rounding of the FP32-FMA kernels (both use the same basis values)."""
+    from at3d_b200 import backend as B
+    st = scenes.make(case, O).state
+    w = wtmu_of(st)
+    ref = O.sh_to_do(st, w, st.shptr, st.source)
+    fp32 = B.sh_to_do(st, w, st.shptr, st.source)
+    monkeypatch.setenv('AT3D_B200_TRANSFORM', 'tc')
+    out = B.sh_to_do(st, w, st.shptr, st.source)
+    scale = np.abs(ref).max()
+    np.testing.assert_allclose(out, ref, rtol=1e-4, atol=2e-6 * scale)
+    np.testing.assert_allclose(out, fp32, rtol=2e-5, atol=2e-6 * scale)
+    assert np.abs(out).max() > 0
+
+
 @pytest.mark.parametrize('case', CASES)
 def test_do_to_sh_matches_oracle(case):
     from at3d_b200 import backend as B
