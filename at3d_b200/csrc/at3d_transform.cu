@@ -451,7 +451,7 @@ struct TrPlan {
     int nang = 0, nsm = 148;
     // tensor-core SH_TO_DO (sh_to_do_tc_kernel): pre-split, pre-swizzled basis tiles; 0 chunks = not available
     const unsigned char *tc_b = nullptr;
-    int tc_kch = 0, tc_n1 = 0, tc_n2 = 0;
+    int tc_kch = 0, tc_n1 = 0 /*ordinate chunks*/, tc_n2 = 0 /*ordinates of the last chunk*/;
     size_t tc_smem = 0;
     ~TrPlan() { for (void *p : ptrs) cudaFree(p); }
     template <typename T> T *alloc(size_t n)
@@ -643,30 +643,33 @@ __device__ __forceinline__ unsigned tc_tf32(float x)
     return r;
 }
 
+#define TC_BN 128                  // ordinates per MMA / basis tile
+#define TC_RING 4                  // basis tiles in flight
+#define TC_SLOT (2 * TC_BN * 128)  // bytes of a ring slot: hi | lo of [128 ordinates x 32 k]
+
 struct TcArgs {
-    int npts, nang, nlm, kch, n1, n2;
+    int npts, nang, nlm, kch, nq, nlast;     // nq ordinate chunks: nq-1 of TC_BN, the last of nlast (multiple of 16)
     const int *shptr;
     const float *sh;
     float *dofield;
-    const unsigned char *bpack;
+    const unsigned char *bpack;              // [kch][nq] tiles of TC_SLOT bytes
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1) sh_to_do_tc_kernel(TcArgs a, int ntiles)
 {
     extern __shared__ __align__(1024) unsigned char tc_smem[];
-    // carve: A stages (hi | lo) x 2, B1 (hi | lo), B2 (hi | lo), barriers
+    // carve: A stages (hi | lo) x 2, the ring of basis tiles, barriers
     unsigned char *base = (unsigned char *)(((size_t)tc_smem + 1023) & ~(size_t)1023);
-    unsigned char *A[2] = {base, base + 2 * TC_BM * 128};
-    unsigned char *B1 = base + 4 * TC_BM * 128;
-    unsigned char *B2 = B1 + 2 * (size_t)a.n1 * 128;
-    unsigned long long *bars = (unsigned long long *)(B2 + 2 * (size_t)a.n2 * 128);
-    unsigned long long *a_full = bars, *a_empty = bars + 2, *b_full = bars + 4, *b_empty = bars + 6;
-    unsigned long long *t_full = bars + 8, *t_empty = bars + 9;
-    unsigned *tmem_slot = (unsigned *)(bars + 10);
+    unsigned char *A0 = base, *A1 = base + 2 * TC_BM * 128;
+    unsigned char *Bring = base + 4 * TC_BM * 128;
+    unsigned long long *bars = (unsigned long long *)(Bring + (size_t)TC_RING * TC_SLOT);
+    unsigned long long *a_full = bars, *a_empty = bars + 2, *b_full = bars + 4, *b_empty = bars + 4 + TC_RING;
+    unsigned long long *t_full = bars + 4 + 2 * TC_RING, *t_empty = t_full + 1;
+    unsigned *tmem_slot = (unsigned *)(t_empty + 1);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nq = a.n2 > 0 ? 2 : 1;
     if (threadIdx.x == 0) {
-        for (int i = 0; i < 2; i++) { tc_mbar_init(&a_full[i], 128); tc_mbar_init(&a_empty[i], 1); tc_mbar_init(&b_full[i], 1); tc_mbar_init(&b_empty[i], 1); }
+        for (int i = 0; i < 2; i++) { tc_mbar_init(&a_full[i], 128); tc_mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < TC_RING; i++) { tc_mbar_init(&b_full[i], 1); tc_mbar_init(&b_empty[i], 1); }
         tc_mbar_init(t_full, 1); tc_mbar_init(t_empty, 128);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -678,7 +681,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sh_to_do_tc_kernel(TcArgs a, in
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const unsigned tmem = *tmem_slot;
-    const size_t bstride = 2 * (size_t)(a.n1 + a.n2) * 128;           // bytes of one K chunk of bpack
 
     if (warp < 4) {
         // ===== A staging (128 threads), then the epilogue of the tile =====
@@ -693,25 +695,36 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sh_to_do_tc_kernel(TcArgs a, in
                 if (p < a.npts) { off[i] = __ldg(&a.shptr[p]); ns[i] = __ldg(&a.shptr[p + 1]) - off[i]; }
                 else { off[i] = 0; ns[i] = 0; }
             }
-            for (int kc = 0; kc < a.kch; kc++, g++) {
-                const unsigned st = g & 1;
-                tc_mbar_wait(&a_empty[st], ((g >> 1) & 1) ^ 1);
-                unsigned char *hi = A[st], *lo = A[st] + TC_BM * 128;
+            // the values of chunk kc+1 are requested before chunk kc is written: their latency runs under the wait
+            float v[8][4];
+            auto fetch = [&](int kc) {
                 const int j0 = kc * TC_BK + c * 4;
 #pragma unroll
                 for (int i = 0; i < 8; i++) {
-                    const int row = r0 + 16 * i;
                     const float *src = a.sh + off[i] + j0;
-                    float v[4];
 #pragma unroll
-                    for (int e = 0; e < 4; e++) v[e] = (j0 + e < ns[i]) ? __ldg(src + e) : 0.0f;
-                    uint4 h, l;
-                    h.x = tc_tf32(v[0]); h.y = tc_tf32(v[1]); h.z = tc_tf32(v[2]); h.w = tc_tf32(v[3]);
-                    l.x = tc_tf32(v[0] - __uint_as_float(h.x)); l.y = tc_tf32(v[1] - __uint_as_float(h.y));
-                    l.z = tc_tf32(v[2] - __uint_as_float(h.z)); l.w = tc_tf32(v[3] - __uint_as_float(h.w));
+                    for (int e = 0; e < 4; e++) v[i][e] = (j0 + e < ns[i]) ? __ldg(src + e) : 0.0f;
+                }
+            };
+            fetch(0);
+            for (int kc = 0; kc < a.kch; kc++, g++) {
+                const unsigned st = g & 1;
+                uint4 h[8], l[8];
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    h[i].x = tc_tf32(v[i][0]); h[i].y = tc_tf32(v[i][1]); h[i].z = tc_tf32(v[i][2]); h[i].w = tc_tf32(v[i][3]);
+                    l[i].x = tc_tf32(v[i][0] - __uint_as_float(h[i].x)); l[i].y = tc_tf32(v[i][1] - __uint_as_float(h[i].y));
+                    l[i].z = tc_tf32(v[i][2] - __uint_as_float(h[i].z)); l[i].w = tc_tf32(v[i][3] - __uint_as_float(h[i].w));
+                }
+                if (kc + 1 < a.kch) fetch(kc + 1);
+                tc_mbar_wait(&a_empty[st], ((g >> 1) & 1) ^ 1);
+                unsigned char *hi = st ? A1 : A0, *lo = hi + TC_BM * 128;
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const int row = r0 + 16 * i;
                     const unsigned o = (unsigned)((row >> 3) * 1024 + (row & 7) * 128 + ((c ^ (row & 7)) << 4));
-                    *(uint4 *)(hi + o) = h;
-                    *(uint4 *)(lo + o) = l;
+                    *(uint4 *)(hi + o) = h[i];
+                    *(uint4 *)(lo + o) = l[i];
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> async proxy (MMA)
                 tc_mbar_arrive(&a_full[st]);
@@ -720,19 +733,33 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sh_to_do_tc_kernel(TcArgs a, in
             tc_mbar_wait(t_full, tile_iter & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const int p = tile * TC_BM + 32 * warp + lane;
-            const int ncols = a.n1 + a.n2;
-            for (int c0 = 0; c0 < ncols; c0 += 16) {
-                unsigned v[16];
+            const int ncols = (a.nq - 1) * TC_BN + a.nlast;
+            float *outp = a.dofield + (p < a.npts ? p : 0);
+            const size_t np_ = (size_t)a.npts;
+            for (int c0 = 0; c0 < ncols; c0 += 32) {
+                unsigned w[32];
                 const unsigned taddr = tmem + ((unsigned)(32 * warp) << 16) + (unsigned)c0;
+                // two x16 loads in flight, one wait (the last block of 16 columns may be the only one left)
                 asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-                             : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                               "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                             : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]),
+                               "=r"(w[8]), "=r"(w[9]), "=r"(w[10]), "=r"(w[11]), "=r"(w[12]), "=r"(w[13]), "=r"(w[14]), "=r"(w[15])
                              : "r"(taddr) : "memory");
+                const bool two = c0 + 16 < ncols;
+                if (two)
+                    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                                 : "=r"(w[16]), "=r"(w[17]), "=r"(w[18]), "=r"(w[19]), "=r"(w[20]), "=r"(w[21]), "=r"(w[22]), "=r"(w[23]),
+                                   "=r"(w[24]), "=r"(w[25]), "=r"(w[26]), "=r"(w[27]), "=r"(w[28]), "=r"(w[29]), "=r"(w[30]), "=r"(w[31])
+                                 : "r"(taddr + 16u) : "memory");
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 if (p < a.npts) {
+                    float *o = outp + (size_t)c0 * np_;
+                    if (c0 + 32 <= a.nang) {
 #pragma unroll
-                    for (int e = 0; e < 16; e++)
-                        if (c0 + e < a.nang) a.dofield[(size_t)(c0 + e) * a.npts + p] = __uint_as_float(v[e]);
+                        for (int e = 0; e < 32; e++) { __stcs(o, __uint_as_float(w[e])); o += np_; }
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 32; e++) { if (c0 + e < a.nang) __stcs(o, __uint_as_float(w[e])); o += np_; }
+                    }
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -741,9 +768,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sh_to_do_tc_kernel(TcArgs a, in
     } else if (warp == 4) {
         // ===== MMA issuer: one thread =====
         if (lane == 0) {
-            const unsigned idesc1 = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(a.n1 >> 3) << 17) | ((unsigned)(TC_BM >> 4) << 24);
-            const unsigned idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(a.n2 >> 3) << 17) | ((unsigned)(TC_BM >> 4) << 24);
-            unsigned g = 0, tile_iter = 0;
+            const unsigned idesc_full = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(TC_BN >> 3) << 17) | ((unsigned)(TC_BM >> 4) << 24);
+            const unsigned idesc_last = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(a.nlast >> 3) << 17) | ((unsigned)(TC_BM >> 4) << 24);
+            unsigned g = 0, tile_iter = 0, rb = 0;                     // rb: basis tiles consumed (ring slot = rb % TC_RING)
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, tile_iter++) {
                 tc_mbar_wait(t_empty, (tile_iter & 1) ^ 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -751,13 +778,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sh_to_do_tc_kernel(TcArgs a, in
                     const unsigned st = g & 1;
                     tc_mbar_wait(&a_full[st], (g >> 1) & 1);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const unsigned ahi = tc_smem_u32(A[st]), alo = ahi + TC_BM * 128;
-                    for (int q = 0; q < nq; q++) {
-                        tc_mbar_wait(&b_full[q], g & 1);
+                    const unsigned ahi = tc_smem_u32(st ? A1 : A0), alo = ahi + TC_BM * 128;
+                    for (int q = 0; q < a.nq; q++, rb++) {
+                        const unsigned slot = rb % TC_RING;
+                        tc_mbar_wait(&b_full[slot], (rb / TC_RING) & 1);
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                        const unsigned bhi = tc_smem_u32(q == 0 ? B1 : B2), blo = bhi + (unsigned)(q == 0 ? a.n1 : a.n2) * 128;
-                        const unsigned d = tmem + (unsigned)(q == 0 ? 0 : a.n1);
-                        const unsigned idesc = q == 0 ? idesc1 : idesc2;
+                        const unsigned bhi = tc_smem_u32(Bring + (size_t)slot * TC_SLOT), blo = bhi + TC_BN * 128;
+                        const unsigned d = tmem + (unsigned)(q * TC_BN);
+                        const unsigned idesc = q == a.nq - 1 ? idesc_last : idesc_full;
 #pragma unroll
                         for (int k = 0; k < TC_BK / 8; k++) {
                             const unsigned ko = (unsigned)k * 32;                  // 8 TF32 = 32 bytes along K inside the swizzle row
@@ -765,7 +793,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sh_to_do_tc_kernel(TcArgs a, in
                             tc_mma_tf32(d, tc_desc(alo + ko), tc_desc(bhi + ko), idesc, 1u);
                             tc_mma_tf32(d, tc_desc(ahi + ko), tc_desc(blo + ko), idesc, 1u);
                         }
-                        tc_commit(&b_empty[q]);                                    // this half of B may be overwritten
+                        tc_commit(&b_empty[slot]);                                 // this basis tile may be overwritten
                     }
                     tc_commit(&a_empty[st]);
                 }
@@ -774,17 +802,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sh_to_do_tc_kernel(TcArgs a, in
         }
         __syncwarp();
     } else {
-        // ===== B loader: one thread streams the pre-swizzled basis tiles with cp.async.bulk =====
+        // ===== basis loader: one thread streams the pre-swizzled tiles with cp.async.bulk, TC_RING tiles ahead =====
         if (lane == 0) {
-            unsigned g = 0;
+            unsigned rb = 0;
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-                for (int kc = 0; kc < a.kch; kc++, g++) {
-                    const unsigned char *src = a.bpack + (size_t)kc * bstride;
-                    for (int q = 0; q < nq; q++) {
-                        const unsigned bytes = 2u * (unsigned)(q == 0 ? a.n1 : a.n2) * 128u;
-                        tc_mbar_wait(&b_empty[q], (g & 1) ^ 1);
-                        tc_mbar_expect_tx(&b_full[q], bytes);
-                        tc_bulk_g2s(q == 0 ? B1 : B2, src + (q == 0 ? 0 : 2 * (size_t)a.n1 * 128), bytes, &b_full[q]);
+                for (int kc = 0; kc < a.kch; kc++) {
+                    for (int q = 0; q < a.nq; q++, rb++) {
+                        const unsigned slot = rb % TC_RING;
+                        tc_mbar_wait(&b_empty[slot], ((rb / TC_RING) & 1) ^ 1);
+                        tc_mbar_expect_tx(&b_full[slot], TC_SLOT);
+                        tc_bulk_g2s(Bring + (size_t)slot * TC_SLOT, a.bpack + ((size_t)kc * a.nq + q) * TC_SLOT, TC_SLOT, &b_full[slot]);
                     }
                 }
             }
@@ -816,10 +843,9 @@ static int tr_tc_build(TrPlan *P, char *errmsg)
     const int nlm = f.nlm, nang = P->nang;
     const int ntot = (nang + 15) & ~15;
     if (ntot > 512 || nlm > 512) return 0;
-    int n1 = ntot, n2 = 0;
-    if (ntot > 256) { n1 = ((ntot / 2) + 15) & ~15; n2 = ntot - n1; }
+    const int nq = (ntot + TC_BN - 1) / TC_BN, nlast = ntot - (nq - 1) * TC_BN;
     const int kch = (nlm + TC_BK - 1) / TC_BK;
-    const size_t smem = 1024 + 4 * TC_BM * 128 + 2 * (size_t)(n1 + n2) * 128 + 256;
+    const size_t smem = 1024 + 4 * TC_BM * 128 + (size_t)TC_RING * TC_SLOT + 256;
     if (smem > 227 * 1024) return 0;
     // unit vectors through the FP32 kernel
     std::vector<int> ptr(nlm + 1);
@@ -839,15 +865,13 @@ static int tr_tc_build(TrPlan *P, char *errmsg)
     cudaError_t e = cudaMemcpy(y.data(), y_d, sizeof(float) * y.size(), cudaMemcpyDeviceToHost);
     cudaFree(ptr_d); cudaFree(eye_d); cudaFree(y_d);
     if (e != cudaSuccess) { set_msg(errmsg, "CUDA error building the tensor-core basis (%s)", cudaGetErrorString(e)); return 4; }
-    const size_t bstride = 2 * (size_t)(n1 + n2) * 128;
-    std::vector<unsigned char> pack(bstride * kch, 0);
+    std::vector<unsigned char> pack((size_t)kch * nq * TC_SLOT, 0);
     for (int kc = 0; kc < kch; kc++)
-        for (int q = 0; q < (n2 ? 2 : 1); q++) {
-            const int nq_ = q == 0 ? n1 : n2, col0 = q == 0 ? 0 : n1;
-            unsigned char *hi = pack.data() + (size_t)kc * bstride + (q == 0 ? 0 : 2 * (size_t)n1 * 128), *lo = hi + (size_t)nq_ * 128;
-            for (int n = 0; n < nq_; n++)
+        for (int q = 0; q < nq; q++) {
+            unsigned char *hi = pack.data() + ((size_t)kc * nq + q) * TC_SLOT, *lo = hi + TC_BN * 128;
+            for (int n = 0; n < TC_BN; n++)
                 for (int k = 0; k < TC_BK; k++) {
-                    const int j = kc * TC_BK + k, ia = col0 + n;
+                    const int j = kc * TC_BK + k, ia = q * TC_BN + n;
                     const float v = (j < nlm && ia < nang) ? y[(size_t)j + (size_t)nlm * ia] : 0.0f;
                     const unsigned h = tc_host_tf32(v);
                     float hf; memcpy(&hf, &h, 4);
@@ -860,7 +884,7 @@ static int tr_tc_build(TrPlan *P, char *errmsg)
     unsigned char *b_d = P->up(pack.data(), pack.size());
     if (!b_d) { set_msg(errmsg, "device allocation failure"); return 4; }
     if (cudaFuncSetAttribute(sh_to_do_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
-    P->tc_b = b_d; P->tc_kch = kch; P->tc_n1 = n1; P->tc_n2 = n2; P->tc_smem = smem;
+    P->tc_b = b_d; P->tc_kch = kch; P->tc_n1 = nq; P->tc_n2 = nlast; P->tc_smem = smem;
     return 0;
 }
 
@@ -875,7 +899,7 @@ static int tr_variant()
 cudaError_t tr_sh_to_do_tc(const TrPlan *P, int npts, const int *shptr_d, const float *sh_d, float *do_d, cudaStream_t st)
 {
     TcArgs a;
-    a.npts = npts; a.nang = P->nang; a.nlm = P->fwd.nlm; a.kch = P->tc_kch; a.n1 = P->tc_n1; a.n2 = P->tc_n2;
+    a.npts = npts; a.nang = P->nang; a.nlm = P->fwd.nlm; a.kch = P->tc_kch; a.nq = P->tc_n1; a.nlast = P->tc_n2;
     a.shptr = shptr_d; a.sh = sh_d; a.dofield = do_d; a.bpack = P->tc_b;
     const int ntiles = (npts + TC_BM - 1) / TC_BM;
     sh_to_do_tc_kernel<<<ntiles < P->nsm ? ntiles : P->nsm, TC_THREADS, P->tc_smem, st>>>(a, ntiles);

@@ -308,6 +308,17 @@ def inversion_step_leg(sc, rays, gi, pix, DeviceState):
                 rays=int(rays.nrays), cost=float(cost[0]))
 
 
+def tensor_peak_tf32():
+    """Dense TF32 tensor peak in TFLOP/s: half of the measured dense bf16 figure of MEASURED_PEAKS.json (the TF32 path of
+    tcgen05 runs at half the bf16 rate: ncu's sm__ops_path_tensor_op_utchmma peaks, 4096 vs 8192 per cycle and SM), else
+    half of the 2250 nominal."""
+    try:
+        d = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+        return float(d.get('bf16_tflops', 2250.0)) / 2.0
+    except Exception:
+        return 1125.0
+
+
 def transform_leg(B, st, steps, warmup):
     """SH_TO_DO / DO_TO_SH on the workload's SOURCE / RADIANCE: kernel ms (CUDA events inside the
     C-ABI call), FP32 FMA rate against the CUDA-core peak and bytes against HBM."""
@@ -336,7 +347,31 @@ def transform_leg(B, st, steps, warmup):
     by2 = 4.0 * nst * (tot_r + npts * nang)
     fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12                         # TFLOP/s, CUDA-core FMA at the boost clock
     t1, t2 = float(np.mean(ms1)) * 1e-3, float(np.mean(ms2)) * 1e-3
-    return dict(sh_to_do_ms=1e3 * t1, do_to_sh_ms=1e3 * t2, nang=nang,
+    # the tensor-core variant of SH_TO_DO (NSTOKES=1): tcgen05.mma kind::tf32, 3xTF32 split, dense [NPTS x NLM].[NLM x NANG]
+    tc = None
+    if nst == 1:
+        old = os.environ.get('AT3D_B200_TRANSFORM')
+        os.environ['AT3D_B200_TRANSFORM'] = 'tc'
+        try:
+            ms3 = []
+            for i in range(warmup + steps):
+                do_tc, t = B.sh_to_do(st, wtmu, st.shptr, st.source, timing=True)
+                if i >= warmup:
+                    ms3.append(t)
+            t3 = float(np.mean(ms3)) * 1e-3
+            ntot = (nang + 15) // 16 * 16
+            tensor_flops = 3 * 2.0 * (-(-npts // 128) * 128) * (-(-st.nlm // 32) * 32) * ntot     # what the MMAs execute
+            tf32_peak = tensor_peak_tf32()
+            tc = dict(ms=1e3 * t3, speedup_vs_fp32=t1 / t3, tensor_tflops=tensor_flops / t3 / 1e12,
+                      tensor_pipe_frac=tensor_flops / t3 / 1e12 / tf32_peak, tf32_peak_tflops=tf32_peak,
+                      max_rel_diff_vs_fp32=float(np.abs(do_tc - do).max() / np.abs(do).max()),
+                      note='3xTF32: hi.hi + lo.hi + hi.lo, FP32 accumulation in TMEM; opt-in (AT3D_B200_TRANSFORM=tc)')
+        finally:
+            if old is None:
+                del os.environ['AT3D_B200_TRANSFORM']
+            else:
+                os.environ['AT3D_B200_TRANSFORM'] = old
+    return dict(sh_to_do_ms=1e3 * t1, do_to_sh_ms=1e3 * t2, nang=nang, sh_to_do_tensor_core=tc,
                 sh_to_do=dict(tflops=fl1 / t1 / 1e12, fma_pipe_frac=fl1 / t1 / 1e12 / fp32_peak, gbs=by1 / t1 / 1e9),
                 do_to_sh=dict(tflops=fl2 / t2 / 1e12, fma_pipe_frac=fl2 / t2 / 1e12 / fp32_peak, gbs=by2 / t2 / 1e9),
                 fp32_peak_tflops=fp32_peak)
