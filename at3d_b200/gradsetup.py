@@ -161,32 +161,26 @@ def make_gradient_inputs(scene, backend, seed=0, numder=2, exact_single_scatter=
     return gi.normalize()
 
 
-def extinction_gradient_inputs(state, pg, backend, species, extmin, scatmin, exact_single_scatter=True,
-                               costfunc='L2', maxsubgridints=0):
-    """Derivative tables for the unknowns "extinction of species k" (k in `species`, 0-based), the unknown of
-    BASELINE.json configs[1]: d(extinction)/d(unknown) = 1 on the property grid, albedo and phase function unchanged
-    (what at3d.solver.RTE.calculate_microphysical_partial_derivatives produces for variable 'extinction',
-    at3d/solver.py:1327-1517)."""
+def optical_gradient_inputs(state, pg, backend, partder, doexact, dext, dalb, diphasep, dphasewtp, dleg, dphasetab,
+                            extmin, scatmin, exact_single_scatter=True, costfunc='L2', maxsubgridints=0):
+    """The derivative tables LEVISAPPROX_GRADIENT takes (what at3d.solver.RTE.calculate_microphysical_partial_derivatives
+    leaves on the solver, at3d/solver.py:1327-1517) from the partial derivatives of the optical properties on the property
+    grid: `partder` [numder] species (1-based) of every unknown, `doexact` [numder] 1 where the phase derivative comes from
+    the DLEG table, `dext` / `dalb` [maxpg, numder], `diphasep` / `dphasewtp` [deriv_maxnmicro, maxpg, numder],
+    `dleg` [nstleg, nleg+1, dnumphase] and its `dphasetab` [nstphase, dnumphase, nscatangle].  Runs PREPARE_DERIV_INTERPS and
+    (exact single scatter) MAKE_DIRECT_DERIVATIVE on the GPU."""
     st = state
-    numder = len(species)
-    maxpg, mnm = pg.maxpg, pg.maxnmicro
-    partder = np.asarray([k + 1 for k in species], np.int32)
-    doexact = np.zeros(numder, np.int32)
-    dext = np.ones((maxpg, numder), np.float32, order='F')
-    dalb = np.zeros((maxpg, numder), np.float32, order='F')
-    diphasep = np.ones((mnm, maxpg, numder), np.int32, order='F')
-    dphasewtp = np.zeros((mnm, maxpg, numder), np.float32, order='F')
-    for i, k in enumerate(species):
-        diphasep[:, :, i] = pg.iphasep[:, :, k]
+    numder = int(np.asarray(partder).size)
+    maxpg = pg.maxpg
     gi = GradInputs(
-        npix=0, maxpg=maxpg, numder=numder, dnumphase=1, deriv_maxnmicro=mnm,
+        npix=0, maxpg=maxpg, numder=numder, dnumphase=int(dleg.shape[2]), deriv_maxnmicro=int(diphasep.shape[0]),
         longest_path_pts=1, nuncertainty=st.nstokes, maxsubgridints=maxsubgridints,
         exact_single_scatter=int(exact_single_scatter), singlescatter=0,
         costfunc_ll=1 if costfunc == 'LL' else 0, extmin=extmin, scatmin=scatmin,
-        partder=partder, doexact=doexact, dext=dext, dalb=dalb,
-        dleg=np.zeros((st.nstleg, st.nleg + 1, 1), np.float32, order='F'),
-        dphasetab=np.zeros((st.nstphase, 1, st.nscatangle), np.float32, order='F'),
-        diphasep=diphasep, dphasewtp=dphasewtp,
+        partder=np.asarray(partder, np.int32), doexact=np.asarray(doexact, np.int32),
+        dext=np.asfortranarray(dext, np.float32), dalb=np.asfortranarray(dalb, np.float32),
+        dleg=np.asfortranarray(dleg, np.float32), dphasetab=np.asfortranarray(dphasetab, np.float32),
+        diphasep=np.asfortranarray(diphasep, np.int32), dphasewtp=np.asfortranarray(dphasewtp, np.float32),
         iphasep=pg.iphasep, phasewtp=pg.phasewtp, extinctp=pg.extinctp, albedop=pg.albedop,
         dtemp=np.zeros((maxpg, numder), np.float32, order='F'))
     gi.normalize()
@@ -201,6 +195,37 @@ def extinction_gradient_inputs(state, pg, backend, species, extmin, scatmin, exa
         gi.dpath = np.zeros((1, st.npts), np.float32, order='F')
         gi.dptr = np.zeros((1, st.npts), np.int32, order='F')
     return gi.normalize()
+
+
+def extinction_gradient_inputs(state, pg, backend, species, extmin, scatmin, exact_single_scatter=True,
+                               costfunc='L2', maxsubgridints=0, variables=None):
+    """Derivative tables for the optical unknowns "extinction (or single-scattering albedo) of species k" (k in
+    `species`, 0-based; `variables` per unknown, default all 'extinction', the unknown of BASELINE.json configs[1]):
+    d(extinction)/d(unknown) = 1 on the property grid for 'extinction', d(ssalb)/d(unknown) = 1 for 'ssalb', phase function
+    unchanged (what at3d.solver.RTE.calculate_microphysical_partial_derivatives produces for the optical variables
+    'extinction' and 'ssalb', at3d/solver.py:1327-1517; at3d/medium.py OpticalDerivativeGenerator)."""
+    st = state
+    numder = len(species)
+    variables = list(variables) if variables is not None else ['extinction'] * numder
+    maxpg, mnm = pg.maxpg, pg.maxnmicro
+    dext = np.zeros((maxpg, numder), np.float32, order='F')
+    dalb = np.zeros((maxpg, numder), np.float32, order='F')
+    diphasep = np.ones((mnm, maxpg, numder), np.int32, order='F')
+    dphasewtp = np.zeros((mnm, maxpg, numder), np.float32, order='F')
+    for i, (k, var) in enumerate(zip(species, variables)):
+        if var == 'extinction':
+            dext[:, i] = 1.0
+        elif var == 'ssalb':
+            dalb[:, i] = 1.0
+        else:
+            raise NotImplementedError("optical unknown '%s' (supported: 'extinction', 'ssalb'; phase-function unknowns go "
+                                      "through RTE.calculate_microphysical_partial_derivatives)" % var)
+        diphasep[:, :, i] = pg.iphasep[:, :, k]
+    return optical_gradient_inputs(
+        st, pg, backend, [k + 1 for k in species], np.zeros(numder, np.int32), dext, dalb, diphasep, dphasewtp,
+        np.zeros((st.nstleg, st.nleg + 1, 1), np.float32, order='F'),
+        np.zeros((st.nstphase, 1, st.nscatangle), np.float32, order='F'), extmin, scatmin,
+        exact_single_scatter=exact_single_scatter, costfunc=costfunc, maxsubgridints=maxsubgridints)
 
 
 def with_pixels(gi, pix):

@@ -1,0 +1,163 @@
+"""``ObjectiveFunction`` / ``Optimizer`` / ``GridStateGenerator``: the host-side mirror of at3d/optimize.py and of the state
+<-> solver glue of at3d/medium.py (StateGenerator, :1649-1831) for the B200 hot path.
+
+``ObjectiveFunction.LevisApproxUncorrelatedL2`` and ``Optimizer.minimize`` take the arguments of the reference
+(at3d/optimize.py:20-144, 146-230) and drive ``scipy.optimize.minimize(jac=True)`` with the GPU cost + gradient.
+``GridStateGenerator`` is the identity-transform case of ``StateGenerator``: the state vector is the unknown optical
+property (extinction and / or ssalb) of the named scatterers on the property grid (optionally masked); calling it with a
+state rebuilds the solvers (as the reference does every evaluation, at3d/medium.py:1813-1831) and
+``project_gradient_to_state`` restricts the gridded gradient to the state's entries (:1751-1811).
+"""
+import time
+from collections import OrderedDict
+import numpy as np
+from . import containers
+from . import gradient as gradient_mod
+from .rte import RTE, _v
+
+
+class ObjectiveFunction:
+    def __init__(self, measurements, loss_fn, min_bounds=None, max_bounds=None):
+        self.measurements = measurements
+        self.loss_fn = loss_fn
+        self._bounds = list(zip(np.atleast_1d(min_bounds), np.atleast_1d(max_bounds)))
+        self._loss = None
+        self._total_obj_fn_time = 0.0
+        self._ncalls = 0
+
+    def __call__(self, state):
+        t = time.perf_counter()
+        loss, gradient = self.loss_fn(state, self.measurements)
+        self._total_obj_fn_time += time.perf_counter() - t
+        self._loss = loss
+        self._ncalls += 1
+        return loss, gradient
+
+    @classmethod
+    def LevisApproxUncorrelatedL2(cls, measurements, solvers, forward_sensors, unknown_scatterers, set_state_fn,
+                                  project_gradient_to_state, parallel_solve_kwargs=None, gradient_kwargs=None,
+                                  uncertainty_kwargs=None, min_bounds=None, max_bounds=None):
+        parallel_solve_kwargs = dict(parallel_solve_kwargs or {'n_jobs': 1, 'mpi_comm': None, 'verbose': True, 'maxiter': 100,
+                                                               'init_solution': True})
+        gradient_kwargs = dict(gradient_kwargs or {'cost_function': 'L2', 'exact_single_scatter': True})
+        uncertainty_kwargs = dict(uncertainty_kwargs or {'add_noise': False})
+        gradient_fun = gradient_mod.LevisApproxGradientUncorrelated(
+            measurements, solvers, forward_sensors, unknown_scatterers, parallel_solve_kwargs, gradient_kwargs, uncertainty_kwargs)
+
+        def loss_function(state, measurements):
+            set_state_fn(state)
+            loss, gradient, _ = gradient_fun()
+            return loss, project_gradient_to_state(state, gradient)
+        return cls(measurements, loss_function, min_bounds=min_bounds, max_bounds=max_bounds)
+
+    @property
+    def loss(self):
+        return self._loss
+
+    @property
+    def bounds(self):
+        return self._bounds
+
+
+class Optimizer:
+    """scipy.optimize.minimize around an ObjectiveFunction (at3d/optimize.py:146-260)."""
+
+    def __init__(self, objective_fn, prior_fn=None, callback_fn=None, method='L-BFGS-B', options=None):
+        self._method = method
+        self._options = dict(options or {'maxiter': 100, 'maxls': 30, 'gtol': 1e-16, 'ftol': 1e-8})
+        self._objective_fn = objective_fn
+        self._prior_fn = list(np.atleast_1d(prior_fn)) if prior_fn is not None else []
+        self._callback_fn = list(np.atleast_1d(callback_fn)) if callback_fn is not None else []
+        self._iteration = 0
+        self._state = None
+        self._loss_history = []
+
+    def callback(self, state):
+        self._iteration += 1
+        self._state = state
+        return [fn(optimizer=self) for fn in self._callback_fn]
+
+    def objective(self, state):
+        loss, gradient = self._objective_fn(state)
+        for prior in self._prior_fn:
+            p_loss, p_grad = prior(state)
+            loss += p_loss
+            gradient = gradient + p_grad
+        self._loss_history.append(float(loss))
+        return loss, np.asarray(gradient, np.float64)
+
+    def minimize(self, initial_state, iteration_step=0, **kwargs):
+        import scipy.optimize
+        self._iteration = iteration_step
+        args = dict(fun=self.objective, x0=np.asarray(initial_state, np.float64), method=self._method, jac=True,
+                    options=self._options, callback=self.callback)
+        args.update(kwargs)
+        if self._method not in ('CG', 'Newton-CG'):
+            b = self._objective_fn.bounds
+            if len(b) == 1 and b[0] == (None, None):
+                args['bounds'] = [(None, None)] * len(initial_state)
+            elif len(b) == len(initial_state):
+                args['bounds'] = b
+            elif len(b) == 1:
+                args['bounds'] = [b[0]] * len(initial_state)
+        return scipy.optimize.minimize(**args)
+
+    @property
+    def objective_fn(self):
+        return self._objective_fn
+
+    @property
+    def loss_history(self):
+        return self._loss_history
+
+
+class GridStateGenerator:
+    """state vector <-> solvers for optical unknowns on the property grid (identity transform of at3d.medium.StateGenerator).
+
+    `solvers`: the SolversDict to (re)fill; `unknown_scatterers`; `mediums`: key -> OrderedDict scatterer name -> scatterer
+    mapping (the fixed part; the unknown variables are overwritten from the state); `sources`, `surfaces`,
+    `numerical_parameters`: key -> mapping; `num_stokes`: key -> int; `mask`: optional boolean [x, y, z] of the grid points
+    in the state."""
+
+    def __init__(self, solvers, unknown_scatterers, mediums, sources, surfaces, numerical_parameters, num_stokes, mask=None):
+        self._solvers, self._unknown = solvers, unknown_scatterers
+        self._mediums, self._sources, self._surfaces = mediums, sources, surfaces
+        self._params, self._num_stokes = numerical_parameters, num_stokes
+        grid = next(iter(next(iter(mediums.values())).values()))
+        shape = np.asarray(_v(grid, 'extinction')).shape
+        self._mask = np.ones(shape, bool) if mask is None else np.asarray(mask, bool)
+        self._nper = int(self._mask.sum())
+        self._slots = [(name, v) for name, e in unknown_scatterers.items() for v in e.variables]
+
+    @property
+    def state_size(self):
+        return self._nper * len(self._slots)
+
+    def get_state(self, key=None):
+        """The state vector of the current mediums."""
+        key = next(iter(self._mediums)) if key is None else key
+        return np.concatenate([np.asarray(_v(self._mediums[key][n], v), np.float64)[self._mask] for n, v in self._slots])
+
+    def __call__(self, state):
+        """set_state_fn: rebuild every solver with the unknown variables taken from `state`."""
+        state = np.asarray(state, np.float64)
+        for key in list(self._mediums):
+            medium = OrderedDict()
+            for name, sc in self._mediums[key].items():
+                sc = dict(sc)
+                for i, (n, v) in enumerate(self._slots):
+                    if n == name:
+                        arr = np.array(_v(sc, v), np.float32)
+                        arr[self._mask] = state[i * self._nper:(i + 1) * self._nper]
+                        sc[v] = arr
+                medium[name] = sc
+            old = self._solvers.get(key)
+            if old is not None:
+                old.close()
+            self._mediums[key] = medium
+            self._solvers[key] = RTE(self._params[key], medium, self._sources[key], self._surfaces[key],
+                                     num_stokes=self._num_stokes[key])
+
+    def project_gradient_to_state(self, state, gradient_dataset):
+        g = np.asarray(gradient_dataset['gradient'])
+        return np.concatenate([g[..., i][self._mask] for i in range(len(self._slots))]).astype(np.float64)

@@ -383,6 +383,74 @@ class RTE:
         ws = np.asfortranarray(np.stack([_v(sensor, n) * w for n in ('I', 'Q', 'U')[:self._nstokes]]).astype(np.float32))
         return B.average_subpixel_rays(ws, pix, npix)            # pixel_index is 0-based, as in the reference
 
+    def calculate_microphysical_partial_derivatives(self, derivative_information):
+        """``RTE.calculate_microphysical_partial_derivatives`` (at3d/solver.py:1327-1517): the partial derivatives of the
+        optical properties with respect to the unknowns, for the gradient.
+
+        `derivative_information`: mapping scatterer name -> mapping variable name -> dataset / dict with the variables of
+        at3d.medium's derivative generators on the property grid: ``extinction``, ``ssalb`` [x, y, z], ``table_index``,
+        ``phase_weights`` [num_micro, x, y, z], ``legcoef`` [stokes_index, legendre_index, table_index] and
+        ``derivative_method`` ('table': table_index points into the scatterer's own phase tables; 'exact': into the
+        derivative tables ``legcoef`` of this unknown).  Leaves DEXT, DALB, DIPHASEP, DPHASEWTP, DLEG, DPHASETAB, the unknown
+        scatterer indices and the exact-derivative flags on the solver; PREPARE_DERIV_INTERPS runs with the solved grid in
+        `levis_approx_gradient`."""
+        maxpg = self._npx * self._npy * self._npz
+        names = list(self.medium.keys())
+        items = [(sname, vname, info) for sname, d in derivative_information.items() for vname, info in d.items()]
+        numder = len(items)
+        if numder < 1:
+            raise ValueError('no unknowns')
+        nmicro = [int(np.asarray(_v(i, 'table_index')).shape[0]) for _, _, i in items]
+        dmax = max(nmicro)
+        dext = np.zeros((maxpg, numder), np.float32, order='F')
+        dalb = np.zeros((maxpg, numder), np.float32, order='F')
+        diphase = np.zeros((dmax, maxpg, numder), np.int32, order='F')
+        dphasewt = np.zeros((dmax, maxpg, numder), np.float32, order='F')
+        partder, doexact, dleg_tables, variables = [], [], [], []
+        for k, (sname, vname, info) in enumerate(items):
+            if sname not in names:
+                raise KeyError("unknown scatterer '%s' is not in the medium" % sname)
+            method = str(_scalar(info, 'derivative_method', 'table'))
+            if method not in ('exact', 'table'):
+                raise ValueError('Bad `derivative_method`')
+            partder.append(names.index(sname) + 1)
+            doexact.append(1 if method == 'exact' else 0)
+            variables.append((sname, vname))
+            dext[:, k] = _v(info, 'extinction').reshape(-1)
+            dalb[:, k] = _v(info, 'ssalb').reshape(-1)
+            ti = _v(info, 'table_index').reshape(nmicro[k], -1)
+            dphasewt[:nmicro[k], :, k] = _v(info, 'phase_weights').reshape(nmicro[k], -1)
+            if method == 'exact':
+                # the phase pointers of this unknown point into the derivative table
+                offset = sum(t.shape[2] for t in dleg_tables)
+                dleg_tables.append(_v(info, 'legcoef').astype(np.float32))
+            else:
+                # ... or into the scatterer's own tables, offset by the tables of the scatterers before it
+                offset = sum(int(_v(self.medium[n], 'legcoef').shape[2]) for n in names[:names.index(sname)])
+            diphase[:nmicro[k], :, k] = ti + offset
+        diphase[diphase == 0] = 1
+        nlegp = self._pg.nlegp
+        if dleg_tables:
+            ml_ = max(t.shape[1] for t in dleg_tables)
+            cat = np.concatenate([np.pad(t, ((0, 0), (0, ml_ - t.shape[1]), (0, 0))) for t in dleg_tables], axis=2)
+            if nlegp + 1 > cat.shape[1]:
+                cat = np.pad(cat, ((0, 0), (0, nlegp + 1 - cat.shape[1]), (0, 0)))
+            cat = cat[:, :nlegp + 1]
+            cat[0, 0, :] = 0.0
+            scaling = (2.0 * np.arange(nlegp + 1) + 1.0)[None, :, None]
+            dleg_full = np.asfortranarray((cat[:self._nstleg] / scaling).astype(np.float32))
+            nscat = max(36, min(721, 2 * nlegp))
+            dphasetab = B.precompute_phase_check(dleg_full, nscat, self._nstokes, self._ml, self._deltam, negcheck=False, grad=True)
+            dleg = np.asfortranarray(dleg_full[:, :self._t['nleg'] + 1])
+        else:
+            dleg = np.zeros((self._nstleg, self._t['nleg'] + 1, 1), np.float32, order='F')
+            dphasetab = np.zeros((1 if self._nstokes == 1 else 2, 1, max(36, min(721, 2 * nlegp))), np.float32, order='F')
+        self._deriv = dict(partder=np.asarray(partder, np.int32), doexact=np.asarray(doexact, np.int32), dext=dext, dalb=dalb,
+                           diphasep=diphase, dphasewtp=dphasewt, dleg=dleg, dphasetab=dphasetab, variables=variables)
+        self._unknown_scatterer_indices = np.asarray(partder, np.int32)
+        self._num_derivatives = numder
+        return self._deriv
+
     def levis_approx_gradient(self, sensor, unknown_scatterers=None, exact_single_scatter=True, cost_function='L2'):
         """The Levis-approximation gradient of the cost function with respect to the extinction of the named scatterers
         (at3d/gradient.py:262-398 `levis_approximation_grad` -> `core.levisapprox_gradient`, MAKEJACOBIAN=.FALSE.).
@@ -395,9 +463,18 @@ class RTE:
         if self._solved is None:
             raise RuntimeError('solve() first')
         names = list(self.medium.keys())
-        species = [names.index(n) for n in (unknown_scatterers or names[:1])]
-        gi = gradsetup.extinction_gradient_inputs(self._solved, self._pg, B, species, self._t['extmin'], self._t['scatmin'],
-                                                  exact_single_scatter=exact_single_scatter, costfunc=cost_function)
+        if unknown_scatterers is None and getattr(self, '_deriv', None) is not None:
+            # the unknowns of calculate_microphysical_partial_derivatives
+            d = self._deriv
+            gi = gradsetup.optical_gradient_inputs(self._solved, self._pg, B, d['partder'], d['doexact'], d['dext'], d['dalb'],
+                                                   d['diphasep'], d['dphasewtp'], d['dleg'], d['dphasetab'], self._t['extmin'],
+                                                   self._t['scatmin'], exact_single_scatter=exact_single_scatter,
+                                                   costfunc=cost_function)
+            species = list(d['partder'])
+        else:
+            species = [names.index(n) for n in (unknown_scatterers or names[:1])]
+            gi = gradsetup.extinction_gradient_inputs(self._solved, self._pg, B, species, self._t['extmin'], self._t['scatmin'],
+                                                      exact_single_scatter=exact_single_scatter, costfunc=cost_function)
         self._dev.attach_gradient(gi)
         rays = Rays(_v(sensor, 'ray_x'), _v(sensor, 'ray_y'), _v(sensor, 'ray_z'), _v(sensor, 'ray_mu'), _v(sensor, 'ray_phi'))
         pix = gradsetup.PixelData(_v(sensor, 'measurement_data')[:self._nstokes], _v(sensor, 'uncertainties'),
