@@ -451,7 +451,7 @@ struct TrPlan {
     int nang = 0, nsm = 148;
     // tensor-core SH_TO_DO (sh_to_do_tc_kernel): pre-split, pre-swizzled basis tiles; 0 chunks = not available
     const unsigned char *tc_b = nullptr;
-    int tc_kch = 0, tc_n1 = 0 /*ordinate chunks*/, tc_n2 = 0 /*ordinates of the last chunk*/;
+    int tc_kch = 0, tc_n1 = 0, tc_n2 = 0 /*ordinates of the two halves*/, tc_ring = 0;
     size_t tc_smem = 0;
     ~TrPlan() { for (void *p : ptrs) cudaFree(p); }
     template <typename T> T *alloc(size_t n)
@@ -587,7 +587,8 @@ int tr_plan_create(int nstokes, int nstleg, int ml, int mm, int nlm, int nmu, in
 // ------------------------------------------------------------------------------------------------------------------
 #define TC_BM 128
 #define TC_BK 32
-#define TC_THREADS 192
+#define TC_PWARPS 8                // staging warps
+#define TC_THREADS ((TC_PWARPS + 2 + 4) * 32)
 
 __device__ __forceinline__ unsigned tc_smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void tc_mbar_init(unsigned long long *b, unsigned count)
@@ -643,37 +644,40 @@ __device__ __forceinline__ unsigned tc_tf32(float x)
     return r;
 }
 
-#define TC_BN 128                  // ordinates per MMA / basis tile
-#define TC_RING 4                  // basis tiles in flight
-#define TC_SLOT (2 * TC_BN * 128)  // bytes of a ring slot: hi | lo of [128 ordinates x 32 k]
-
+// Work item = (tile of 128 grid points, ordinate half): each half (<= 256 ordinates, one MMA wide) has its own accumulator
+// stage in tensor memory (2 x n0 <= 512 columns), so the epilogue of an item drains under the MMAs of the next one.  The
+// grid is even (one CTA per SM), so a CTA always works on the same half and streams only that half's basis tiles.
 struct TcArgs {
-    int npts, nang, nlm, kch, nq, nlast;     // nq ordinate chunks: nq-1 of TC_BN, the last of nlast (multiple of 16)
+    int npts, nang, nlm, kch, n0, n1, ring, nhalves;   // n0 >= n1 ordinates per half (multiples of 16), ring slots in shared memory
     const int *shptr;
     const float *sh;
     float *dofield;
-    const unsigned char *bpack;              // [kch][nq] tiles of TC_SLOT bytes
+    const unsigned char *bpack;                        // [half][kch] tiles of 2*n0*128 bytes (hi | lo)
 };
+#define TC_RING_MAX 4
 
-__global__ void __launch_bounds__(TC_THREADS, 1) sh_to_do_tc_kernel(TcArgs a, int ntiles)
+__global__ void __launch_bounds__(TC_THREADS, 1) sh_to_do_tc_kernel(TcArgs a, int nitems)
 {
     extern __shared__ __align__(1024) unsigned char tc_smem[];
     // carve: A stages (hi | lo) x 2, the ring of basis tiles, barriers
     unsigned char *base = (unsigned char *)(((size_t)tc_smem + 1023) & ~(size_t)1023);
     unsigned char *A0 = base, *A1 = base + 2 * TC_BM * 128;
     unsigned char *Bring = base + 4 * TC_BM * 128;
-    unsigned long long *bars = (unsigned long long *)(Bring + (size_t)TC_RING * TC_SLOT);
-    unsigned long long *a_full = bars, *a_empty = bars + 2, *b_full = bars + 4, *b_empty = bars + 4 + TC_RING;
-    unsigned long long *t_full = bars + 4 + 2 * TC_RING, *t_empty = t_full + 1;
-    unsigned *tmem_slot = (unsigned *)(t_empty + 1);
+    const unsigned slotb = 2u * (unsigned)a.n0 * 128u;
+    unsigned long long *bars = (unsigned long long *)(Bring + (size_t)a.ring * slotb);
+    unsigned long long *a_full = bars, *a_empty = bars + 2, *b_full = bars + 4, *b_empty = bars + 4 + TC_RING_MAX;
+    unsigned long long *t_full = bars + 4 + 2 * TC_RING_MAX, *t_empty = t_full + 2;
+    unsigned *tmem_slot = (unsigned *)(t_empty + 2);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
-        for (int i = 0; i < 2; i++) { tc_mbar_init(&a_full[i], 128); tc_mbar_init(&a_empty[i], 1); }
-        for (int i = 0; i < TC_RING; i++) { tc_mbar_init(&b_full[i], 1); tc_mbar_init(&b_empty[i], 1); }
-        tc_mbar_init(t_full, 1); tc_mbar_init(t_empty, 128);
+        for (int i = 0; i < 2; i++) {
+            tc_mbar_init(&a_full[i], TC_PWARPS * 32); tc_mbar_init(&a_empty[i], 1);
+            tc_mbar_init(&t_full[i], 1); tc_mbar_init(&t_empty[i], 128);
+        }
+        for (int i = 0; i < TC_RING_MAX; i++) { tc_mbar_init(&b_full[i], 1); tc_mbar_init(&b_empty[i], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 4) {
+    if (warp == TC_PWARPS) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(tc_smem_u32(tmem_slot)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -681,71 +685,137 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sh_to_do_tc_kernel(TcArgs a, in
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const unsigned tmem = *tmem_slot;
+    // item -> (tile, half): consecutive items are the two halves of a tile
+    const int nh = a.nhalves;
 
-    if (warp < 4) {
-        // ===== A staging (128 threads), then the epilogue of the tile =====
+    if (warp < TC_PWARPS) {
+        // ===== A staging (256 threads: 8 lanes x 16 bytes per row, 4 rows per thread and chunk) =====
         const int t = threadIdx.x, c = t & 7, r0 = t >> 3;
         unsigned g = 0;                                               // chunks staged so far (stage = g & 1)
-        unsigned tile_iter = 0;
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, tile_iter++) {
-            int off[8], ns[8];
+        for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+            const int tile = item / nh;
+            int off[4], ns[4];
 #pragma unroll
-            for (int i = 0; i < 8; i++) {
-                const int p = tile * TC_BM + r0 + 16 * i;
+            for (int i = 0; i < 4; i++) {
+                const int p = tile * TC_BM + r0 + 32 * i;
                 if (p < a.npts) { off[i] = __ldg(&a.shptr[p]); ns[i] = __ldg(&a.shptr[p + 1]) - off[i]; }
                 else { off[i] = 0; ns[i] = 0; }
             }
-            // the values of chunk kc+1 are requested before chunk kc is written: their latency runs under the wait
-            float v[8][4];
-            auto fetch = [&](int kc) {
+            // two chunks of values are in flight while a third is converted and written
+            float va[4][4], vb[4][4];
+            auto fetch = [&](float (&v)[4][4], int kc) {
                 const int j0 = kc * TC_BK + c * 4;
 #pragma unroll
-                for (int i = 0; i < 8; i++) {
+                for (int i = 0; i < 4; i++) {
                     const float *src = a.sh + off[i] + j0;
 #pragma unroll
                     for (int e = 0; e < 4; e++) v[i][e] = (j0 + e < ns[i]) ? __ldg(src + e) : 0.0f;
                 }
             };
-            fetch(0);
-            for (int kc = 0; kc < a.kch; kc++, g++) {
+            auto stage = [&](const float (&v)[4][4]) {
                 const unsigned st = g & 1;
-                uint4 h[8], l[8];
+                uint4 h[4], l[4];
 #pragma unroll
-                for (int i = 0; i < 8; i++) {
+                for (int i = 0; i < 4; i++) {
                     h[i].x = tc_tf32(v[i][0]); h[i].y = tc_tf32(v[i][1]); h[i].z = tc_tf32(v[i][2]); h[i].w = tc_tf32(v[i][3]);
                     l[i].x = tc_tf32(v[i][0] - __uint_as_float(h[i].x)); l[i].y = tc_tf32(v[i][1] - __uint_as_float(h[i].y));
                     l[i].z = tc_tf32(v[i][2] - __uint_as_float(h[i].z)); l[i].w = tc_tf32(v[i][3] - __uint_as_float(h[i].w));
                 }
-                if (kc + 1 < a.kch) fetch(kc + 1);
                 tc_mbar_wait(&a_empty[st], ((g >> 1) & 1) ^ 1);
                 unsigned char *hi = st ? A1 : A0, *lo = hi + TC_BM * 128;
 #pragma unroll
-                for (int i = 0; i < 8; i++) {
-                    const int row = r0 + 16 * i;
+                for (int i = 0; i < 4; i++) {
+                    const int row = r0 + 32 * i;
                     const unsigned o = (unsigned)((row >> 3) * 1024 + (row & 7) * 128 + ((c ^ (row & 7)) << 4));
                     *(uint4 *)(hi + o) = h[i];
                     *(uint4 *)(lo + o) = l[i];
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> async proxy (MMA)
                 tc_mbar_arrive(&a_full[st]);
+                g++;
+            };
+            fetch(va, 0);
+            if (a.kch > 1) fetch(vb, 1);
+            for (int kc = 0; kc < a.kch; kc += 2) {
+                stage(va);
+                if (kc + 2 < a.kch) fetch(va, kc + 2);
+                if (kc + 1 < a.kch) {
+                    stage(vb);
+                    if (kc + 3 < a.kch) fetch(vb, kc + 3);
+                }
             }
-            // epilogue: TMEM lanes 32*warp .. +31 are grid points tile*128 + 32*warp + lane
-            tc_mbar_wait(t_full, tile_iter & 1);
+        }
+    } else if (warp == TC_PWARPS) {
+        // ===== MMA issuer: one thread =====
+        if (lane == 0) {
+            unsigned g = 0, it = 0, rb = 0;                            // rb: basis tiles consumed (ring slot = rb % ring)
+            for (int item = blockIdx.x; item < nitems; item += gridDim.x, it++) {
+                const int half = item % nh;
+                const int n = half == 0 ? a.n0 : a.n1;
+                const unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(n >> 3) << 17) | ((unsigned)(TC_BM >> 4) << 24);
+                const unsigned ts = it & 1;                            // accumulator stage
+                tc_mbar_wait(&t_empty[ts], ((it >> 1) & 1) ^ 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const unsigned d = tmem + ts * (unsigned)a.n0;
+                for (int kc = 0; kc < a.kch; kc++, g++, rb++) {
+                    const unsigned st = g & 1;
+                    const unsigned slot = rb % (unsigned)a.ring;
+                    tc_mbar_wait(&a_full[st], (g >> 1) & 1);
+                    tc_mbar_wait(&b_full[slot], (rb / (unsigned)a.ring) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const unsigned ahi = tc_smem_u32(st ? A1 : A0), alo = ahi + TC_BM * 128;
+                    const unsigned bhi = tc_smem_u32(Bring + (size_t)slot * slotb), blo = bhi + (unsigned)a.n0 * 128u;
+#pragma unroll
+                    for (int k = 0; k < TC_BK / 8; k++) {
+                        const unsigned ko = (unsigned)k * 32;                      // 8 TF32 = 32 bytes along K inside the swizzle row
+                        tc_mma_tf32(d, tc_desc(ahi + ko), tc_desc(bhi + ko), idesc, (kc | k) != 0);
+                        tc_mma_tf32(d, tc_desc(alo + ko), tc_desc(bhi + ko), idesc, 1u);
+                        tc_mma_tf32(d, tc_desc(ahi + ko), tc_desc(blo + ko), idesc, 1u);
+                    }
+                    tc_commit(&b_empty[slot]);                                     // this basis tile may be overwritten
+                    tc_commit(&a_empty[st]);
+                }
+                tc_commit(&t_full[ts]);
+            }
+        }
+        __syncwarp();
+    } else if (warp == TC_PWARPS + 1) {
+        // ===== basis loader: one thread streams the pre-swizzled tiles with cp.async.bulk, `ring` tiles ahead =====
+        if (lane == 0) {
+            unsigned rb = 0;
+            for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+                const int half = item % nh;
+                for (int kc = 0; kc < a.kch; kc++, rb++) {
+                    const unsigned slot = rb % (unsigned)a.ring;
+                    tc_mbar_wait(&b_empty[slot], ((rb / (unsigned)a.ring) & 1) ^ 1);
+                    tc_mbar_expect_tx(&b_full[slot], slotb);
+                    tc_bulk_g2s(Bring + (size_t)slot * slotb, a.bpack + ((size_t)half * a.kch + kc) * slotb, slotb, &b_full[slot]);
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===== epilogue warps (the last four): TMEM lanes 32*(warp & 3) .. +31 are grid points tile*128 + 32*(warp & 3) + lane =====
+        const int q4 = warp & 3;
+        unsigned it = 0;
+        for (int item = blockIdx.x; item < nitems; item += gridDim.x, it++) {
+            const int tile = item / nh, half = item % nh;
+            const int ncols = half == 0 ? a.n0 : a.n1, col0 = half == 0 ? 0 : a.n0;
+            const unsigned ts = it & 1;
+            tc_mbar_wait(&t_full[ts], (it >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const int p = tile * TC_BM + 32 * warp + lane;
-            const int ncols = (a.nq - 1) * TC_BN + a.nlast;
-            float *outp = a.dofield + (p < a.npts ? p : 0);
+            const int p = tile * TC_BM + 32 * q4 + lane;
+            float *outp = a.dofield + (p < a.npts ? p : 0) + (size_t)col0 * (size_t)a.npts;
             const size_t np_ = (size_t)a.npts;
+            const int nvalid = min(a.nang - col0, ncols);                          // ordinates of this half that exist
             for (int c0 = 0; c0 < ncols; c0 += 32) {
                 unsigned w[32];
-                const unsigned taddr = tmem + ((unsigned)(32 * warp) << 16) + (unsigned)c0;
-                // two x16 loads in flight, one wait (the last block of 16 columns may be the only one left)
+                const unsigned taddr = tmem + ((unsigned)(32 * q4) << 16) + ts * (unsigned)a.n0 + (unsigned)c0;
                 asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
                              : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]),
                                "=r"(w[8]), "=r"(w[9]), "=r"(w[10]), "=r"(w[11]), "=r"(w[12]), "=r"(w[13]), "=r"(w[14]), "=r"(w[15])
                              : "r"(taddr) : "memory");
-                const bool two = c0 + 16 < ncols;
-                if (two)
+                if (c0 + 16 < ncols)
                     asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
                                  : "=r"(w[16]), "=r"(w[17]), "=r"(w[18]), "=r"(w[19]), "=r"(w[20]), "=r"(w[21]), "=r"(w[22]), "=r"(w[23]),
                                    "=r"(w[24]), "=r"(w[25]), "=r"(w[26]), "=r"(w[27]), "=r"(w[28]), "=r"(w[29]), "=r"(w[30]), "=r"(w[31])
@@ -753,74 +823,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sh_to_do_tc_kernel(TcArgs a, in
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 if (p < a.npts) {
                     float *o = outp + (size_t)c0 * np_;
-                    if (c0 + 32 <= a.nang) {
+                    if (c0 + 32 <= nvalid) {
 #pragma unroll
                         for (int e = 0; e < 32; e++) { __stcs(o, __uint_as_float(w[e])); o += np_; }
                     } else {
 #pragma unroll
-                        for (int e = 0; e < 32; e++) { if (c0 + e < a.nang) __stcs(o, __uint_as_float(w[e])); o += np_; }
+                        for (int e = 0; e < 32; e++) { if (c0 + e < nvalid) __stcs(o, __uint_as_float(w[e])); o += np_; }
                     }
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            tc_mbar_arrive(t_empty);
+            tc_mbar_arrive(&t_empty[ts]);
         }
-    } else if (warp == 4) {
-        // ===== MMA issuer: one thread =====
-        if (lane == 0) {
-            const unsigned idesc_full = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(TC_BN >> 3) << 17) | ((unsigned)(TC_BM >> 4) << 24);
-            const unsigned idesc_last = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(a.nlast >> 3) << 17) | ((unsigned)(TC_BM >> 4) << 24);
-            unsigned g = 0, tile_iter = 0, rb = 0;                     // rb: basis tiles consumed (ring slot = rb % TC_RING)
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, tile_iter++) {
-                tc_mbar_wait(t_empty, (tile_iter & 1) ^ 1);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                for (int kc = 0; kc < a.kch; kc++, g++) {
-                    const unsigned st = g & 1;
-                    tc_mbar_wait(&a_full[st], (g >> 1) & 1);
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const unsigned ahi = tc_smem_u32(st ? A1 : A0), alo = ahi + TC_BM * 128;
-                    for (int q = 0; q < a.nq; q++, rb++) {
-                        const unsigned slot = rb % TC_RING;
-                        tc_mbar_wait(&b_full[slot], (rb / TC_RING) & 1);
-                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                        const unsigned bhi = tc_smem_u32(Bring + (size_t)slot * TC_SLOT), blo = bhi + TC_BN * 128;
-                        const unsigned d = tmem + (unsigned)(q * TC_BN);
-                        const unsigned idesc = q == a.nq - 1 ? idesc_last : idesc_full;
-#pragma unroll
-                        for (int k = 0; k < TC_BK / 8; k++) {
-                            const unsigned ko = (unsigned)k * 32;                  // 8 TF32 = 32 bytes along K inside the swizzle row
-                            tc_mma_tf32(d, tc_desc(ahi + ko), tc_desc(bhi + ko), idesc, (kc | k) != 0);
-                            tc_mma_tf32(d, tc_desc(alo + ko), tc_desc(bhi + ko), idesc, 1u);
-                            tc_mma_tf32(d, tc_desc(ahi + ko), tc_desc(blo + ko), idesc, 1u);
-                        }
-                        tc_commit(&b_empty[slot]);                                 // this basis tile may be overwritten
-                    }
-                    tc_commit(&a_empty[st]);
-                }
-                tc_commit(t_full);
-            }
-        }
-        __syncwarp();
-    } else {
-        // ===== basis loader: one thread streams the pre-swizzled tiles with cp.async.bulk, TC_RING tiles ahead =====
-        if (lane == 0) {
-            unsigned rb = 0;
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-                for (int kc = 0; kc < a.kch; kc++) {
-                    for (int q = 0; q < a.nq; q++, rb++) {
-                        const unsigned slot = rb % TC_RING;
-                        tc_mbar_wait(&b_empty[slot], ((rb / TC_RING) & 1) ^ 1);
-                        tc_mbar_expect_tx(&b_full[slot], TC_SLOT);
-                        tc_bulk_g2s(Bring + (size_t)slot * TC_SLOT, a.bpack + ((size_t)kc * a.nq + q) * TC_SLOT, TC_SLOT, &b_full[slot]);
-                    }
-                }
-            }
-        }
-        __syncwarp();
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 4) {
+    if (warp == TC_PWARPS) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
     }
 }
@@ -843,10 +861,17 @@ static int tr_tc_build(TrPlan *P, char *errmsg)
     const int nlm = f.nlm, nang = P->nang;
     const int ntot = (nang + 15) & ~15;
     if (ntot > 512 || nlm > 512) return 0;
-    const int nq = (ntot + TC_BN - 1) / TC_BN, nlast = ntot - (nq - 1) * TC_BN;
+    // two ordinate halves (one accumulator stage each); a single half when everything fits 16 columns
+    int n0 = ntot, n1 = 0;
+    if (ntot > 16) { n0 = ((ntot / 2) + 15) & ~15; n1 = ntot - n0; }
+    if (n0 > 256) return 0;
+    const int nhalves = n1 > 0 ? 2 : 1;
     const int kch = (nlm + TC_BK - 1) / TC_BK;
-    const size_t smem = 1024 + 4 * TC_BM * 128 + (size_t)TC_RING * TC_SLOT + 256;
-    if (smem > 227 * 1024) return 0;
+    const size_t slotb = 2 * (size_t)n0 * 128;
+    int ring = (int)(((size_t)227 * 1024 - 1024 - 4 * TC_BM * 128 - 512) / slotb);
+    if (ring > TC_RING_MAX) ring = TC_RING_MAX;
+    if (ring < 2) return 0;
+    const size_t smem = 1024 + 4 * TC_BM * 128 + (size_t)ring * slotb + 512;
     // unit vectors through the FP32 kernel
     std::vector<int> ptr(nlm + 1);
     for (int i = 0; i <= nlm; i++) ptr[i] = i * nlm;
@@ -865,13 +890,14 @@ static int tr_tc_build(TrPlan *P, char *errmsg)
     cudaError_t e = cudaMemcpy(y.data(), y_d, sizeof(float) * y.size(), cudaMemcpyDeviceToHost);
     cudaFree(ptr_d); cudaFree(eye_d); cudaFree(y_d);
     if (e != cudaSuccess) { set_msg(errmsg, "CUDA error building the tensor-core basis (%s)", cudaGetErrorString(e)); return 4; }
-    std::vector<unsigned char> pack((size_t)kch * nq * TC_SLOT, 0);
-    for (int kc = 0; kc < kch; kc++)
-        for (int q = 0; q < nq; q++) {
-            unsigned char *hi = pack.data() + ((size_t)kc * nq + q) * TC_SLOT, *lo = hi + TC_BN * 128;
-            for (int n = 0; n < TC_BN; n++)
+    std::vector<unsigned char> pack((size_t)nhalves * kch * slotb, 0);
+    for (int half = 0; half < nhalves; half++)
+        for (int kc = 0; kc < kch; kc++) {
+            unsigned char *hi = pack.data() + ((size_t)half * kch + kc) * slotb, *lo = hi + (size_t)n0 * 128;
+            const int nn = half == 0 ? n0 : n1, col0 = half == 0 ? 0 : n0;
+            for (int n = 0; n < nn; n++)
                 for (int k = 0; k < TC_BK; k++) {
-                    const int j = kc * TC_BK + k, ia = q * TC_BN + n;
+                    const int j = kc * TC_BK + k, ia = col0 + n;
                     const float v = (j < nlm && ia < nang) ? y[(size_t)j + (size_t)nlm * ia] : 0.0f;
                     const unsigned h = tc_host_tf32(v);
                     float hf; memcpy(&hf, &h, 4);
@@ -884,7 +910,7 @@ static int tr_tc_build(TrPlan *P, char *errmsg)
     unsigned char *b_d = P->up(pack.data(), pack.size());
     if (!b_d) { set_msg(errmsg, "device allocation failure"); return 4; }
     if (cudaFuncSetAttribute(sh_to_do_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
-    P->tc_b = b_d; P->tc_kch = kch; P->tc_n1 = nq; P->tc_n2 = nlast; P->tc_smem = smem;
+    P->tc_b = b_d; P->tc_kch = kch; P->tc_n1 = n0; P->tc_n2 = n1; P->tc_ring = ring; P->tc_smem = smem;
     return 0;
 }
 
@@ -899,10 +925,14 @@ static int tr_variant()
 cudaError_t tr_sh_to_do_tc(const TrPlan *P, int npts, const int *shptr_d, const float *sh_d, float *do_d, cudaStream_t st)
 {
     TcArgs a;
-    a.npts = npts; a.nang = P->nang; a.nlm = P->fwd.nlm; a.kch = P->tc_kch; a.nq = P->tc_n1; a.nlast = P->tc_n2;
+    a.npts = npts; a.nang = P->nang; a.nlm = P->fwd.nlm; a.kch = P->tc_kch; a.n0 = P->tc_n1; a.n1 = P->tc_n2;
+    a.ring = P->tc_ring; a.nhalves = P->tc_n2 > 0 ? 2 : 1;
     a.shptr = shptr_d; a.sh = sh_d; a.dofield = do_d; a.bpack = P->tc_b;
-    const int ntiles = (npts + TC_BM - 1) / TC_BM;
-    sh_to_do_tc_kernel<<<ntiles < P->nsm ? ntiles : P->nsm, TC_THREADS, P->tc_smem, st>>>(a, ntiles);
+    const int nitems = ((npts + TC_BM - 1) / TC_BM) * a.nhalves;
+    int grid = nitems < P->nsm ? nitems : P->nsm;
+    if (a.nhalves == 2) grid &= ~1;              // an even grid: a CTA keeps its ordinate half (and its basis tiles in L2)
+    if (grid < 1) grid = 1;
+    sh_to_do_tc_kernel<<<grid, TC_THREADS, P->tc_smem, st>>>(a, nitems);
     return cudaGetLastError();
 }
 int tr_plan_has_tc(const TrPlan *P) { return P->tc_kch > 0; }
