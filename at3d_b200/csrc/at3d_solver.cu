@@ -432,6 +432,27 @@ __device__ __forceinline__ int face_corner(int kface, int n)
 #ifndef AT3D_SWEEP_MINB
 #define AT3D_SWEEP_MINB 3
 #endif
+// A waiting thread gives up after AT3D_SWEEP_WAIT_NS of WALL CLOCK (%globaltimer), not after a number of polls: under
+// time slicing, MPS, compute-sanitizer or a co-tenant kernel a legitimate wait can be long.  The waits rely on the
+// independent thread scheduling of sm_70+ (a lane may wait for another lane of its own warp at a level boundary).
+#ifndef AT3D_SWEEP_WAIT_NS
+#define AT3D_SWEEP_WAIT_NS 5000000000ull
+#endif
+__device__ __forceinline__ unsigned long long sweep_now()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+// true when the wait has to be abandoned: another thread reported an error, or the wall-clock budget is spent
+__device__ __forceinline__ bool sweep_give_up(int &spins, unsigned long long &t0, const int *err)
+{
+    if ((++spins & 255) != 0) return false;
+    if (*(volatile const int *)err) return true;
+    const unsigned long long now = sweep_now();
+    if (t0 == 0) { t0 = now; return false; }
+    return now - t0 > AT3D_SWEEP_WAIT_NS;
+}
 template <int NST, bool LEVEL>
 __global__ void __launch_bounds__(256, (NST == 1 ? AT3D_SWEEP_MINB : 2)) sweep3d_kernel(SwArgs a, int up)
 {
@@ -613,11 +634,12 @@ __global__ void __launch_bounds__(256, (NST == 1 ? AT3D_SWEEP_MINB : 2)) sweep3d
         int lv = 0;
         if (!fail) {
             int spins = 0;
+            unsigned long long t0 = 0;
             for (;;) {
                 const int l1 = *(volatile int *)&L[i1 - 1], l2 = *(volatile int *)&L[i2 - 1];
                 const int l3 = *(volatile int *)&L[i3 - 1], l4 = *(volatile int *)&L[i4 - 1];
                 if (l1 >= 0 && l2 >= 0 && l3 >= 0 && l4 >= 0) { lv = 1 + max(max(l1, l2), max(l3, l4)); break; }
-                if (++spins > (1 << 22) || ((spins & 255) == 0 && *(volatile int *)a.err)) { fail = 4; break; }
+                if (sweep_give_up(spins, t0, a.err)) { fail = 4; break; }
                 __nanosleep(AT3D_SWEEP_SLEEP);
             }
         }
@@ -631,10 +653,11 @@ __global__ void __launch_bounds__(256, (NST == 1 ? AT3D_SWEEP_MINB : 2)) sweep3d
         // wait for the four face radiances (bounded; polls go to L2)
         float g1, g2, g3, g4;
         int spins = 0;
+        unsigned long long t0 = 0;
         for (;;) {
             g1 = ld_vol(&R[i1 - 1]); g2 = ld_vol(&R[i2 - 1]); g3 = ld_vol(&R[i3 - 1]); g4 = ld_vol(&R[i4 - 1]);
             if (g1 >= -0.1f && g2 >= -0.1f && g3 >= -0.1f && g4 >= -0.1f) break;
-            if (++spins > (1 << 22) || ((spins & 255) == 0 && *(volatile int *)a.err)) { fail = 4; break; }
+            if (sweep_give_up(spins, t0, a.err)) { fail = 4; break; }
             __nanosleep(AT3D_SWEEP_SLEEP);
         }
         if (!fail) {
