@@ -89,7 +89,7 @@ struct DevState {
     unsigned *srcpool_top;                   // [0] shared-tail cursor, [1] overflow flag, [32 * (r + 1)] cursor of region r
     long long *srcstart;                     // [nrays of the launch] first entry of the ray, -1: none
 };
-#define AT3D_SRC_CHUNK 64
+#define AT3D_SRC_CHUNK 256
 #define AT3D_SRC_REGIONS 256
 #define AT3D_SRC_TOP_WORDS (32 * (AT3D_SRC_REGIONS + 1))
 
