@@ -452,6 +452,9 @@ struct TrPlan {
     // tensor-core SH_TO_DO (sh_to_do_tc_kernel): pre-split, pre-swizzled basis tiles; 0 chunks = not available
     const unsigned char *tc_b = nullptr;
     int tc_kch = 0, tc_n1 = 0, tc_n2 = 0 /*ordinates of the two halves*/, tc_ring = 0;
+    const unsigned char *tcb_b = nullptr;      // DO_TO_SH (do_to_sh_tc_kernel)
+    int tcb_kch = 0, tcb_nn = 0, tcb_ring = 0;
+    size_t tcb_smem = 0;
     size_t tc_smem = 0;
     ~TrPlan() { for (void *p : ptrs) cudaFree(p); }
     template <typename T> T *alloc(size_t n)
@@ -470,6 +473,7 @@ struct TrPlan {
 };
 
 static int tr_tc_build(TrPlan *P, char *errmsg);
+static int tr_tc_build_back(TrPlan *P, char *errmsg);
 void tr_plan_destroy(TrPlan *p) { delete p; }
 int tr_plan_nang(const TrPlan *p) { return p->nang; }
 
@@ -557,7 +561,8 @@ int tr_plan_create(int nstokes, int nstleg, int ml, int mm, int nlm, int nmu, in
     P->nang = nang;
     if (cudaDeviceSynchronize() != cudaSuccess) { delete P; set_msg(errmsg, "CUDA error building the SH/DO tables"); return 4; }
     {
-        const int rc = tr_tc_build(P, errmsg);
+        int rc = tr_tc_build(P, errmsg);
+        if (!rc) rc = tr_tc_build_back(P, errmsg);
         if (rc) { delete P; return rc; }
     }
     *out = P;
@@ -843,6 +848,191 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sh_to_do_tc_kernel(TcArgs a, in
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// DO_TO_SH on the tensor cores (NSTOKES=1): SH[128 points x NLM] = DOFIELD[128 x NANG] . W[NANG x NLM], the same
+// machinery as sh_to_do_tc_kernel with the roles of the two index sets exchanged.  K = ordinates in chunks of 32, N = all
+// NLM coefficients in one MMA (<= 256), two accumulator stages of NLM columns in tensor memory.  The A operand comes from
+// DOFIELD(NPTS,1,NANG) (points fastest): a staging thread owns one grid point (row) and 16 ordinates of the chunk, so
+// every global load of a warp is one 128-byte row, and writes 16-byte pieces of its row into the K-major SWIZZLE_128B
+// layout.  The epilogue writes each point's coefficients to its ragged RADIANCE row (j < NR(point)).
+// ------------------------------------------------------------------------------------------------------------------
+struct TcBackArgs {
+    int npts, nang, nlm, kch, nn, ring;        // nn: NLM rounded up to 16 (MMA N), kch: ordinate chunks of 32
+    const int *rshptr;
+    const float *dofield;
+    float *sh_out;
+    const unsigned char *bpack;                // [kch] tiles of 2*nn*128 bytes (hi | lo), rows = coefficient j, k = ordinate
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1) do_to_sh_tc_kernel(TcBackArgs a, int nitems)
+{
+    extern __shared__ __align__(1024) unsigned char tc_smem[];
+    unsigned char *base = (unsigned char *)(((size_t)tc_smem + 1023) & ~(size_t)1023);
+    unsigned char *A0 = base, *A1 = base + 2 * TC_BM * 128;
+    unsigned char *Bring = base + 4 * TC_BM * 128;
+    const unsigned slotb = 2u * (unsigned)a.nn * 128u;
+    unsigned long long *bars = (unsigned long long *)(Bring + (size_t)a.ring * slotb);
+    unsigned long long *a_full = bars, *a_empty = bars + 2, *b_full = bars + 4, *b_empty = bars + 4 + TC_RING_MAX;
+    unsigned long long *t_full = bars + 4 + 2 * TC_RING_MAX, *t_empty = t_full + 2;
+    unsigned *tmem_slot = (unsigned *)(t_empty + 2);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 2; i++) {
+            tc_mbar_init(&a_full[i], TC_PWARPS * 32); tc_mbar_init(&a_empty[i], 1);
+            tc_mbar_init(&t_full[i], 1); tc_mbar_init(&t_empty[i], 128);
+        }
+        for (int i = 0; i < TC_RING_MAX; i++) { tc_mbar_init(&b_full[i], 1); tc_mbar_init(&b_empty[i], 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == TC_PWARPS) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(tc_smem_u32(tmem_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const unsigned tmem = *tmem_slot;
+
+    if (warp < TC_PWARPS) {
+        // ===== A staging: thread = (row = t & 127, ordinates 16*(t >> 7) .. +15 of the chunk) =====
+        const int t = threadIdx.x, row = t & 127, kh = t >> 7;
+        unsigned g = 0;
+        for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+            const int p = item * TC_BM + row;
+            const bool pin = p < a.npts;
+            const float *col = a.dofield + (pin ? p : 0);
+            float va[16], vb[16];
+            auto fetch = [&](float (&v)[16], int kc) {
+#pragma unroll
+                for (int e = 0; e < 16; e++) {
+                    const int ia = kc * TC_BK + kh * 16 + e;
+                    v[e] = (pin && ia < a.nang) ? __ldg(col + (size_t)ia * a.npts) : 0.0f;
+                }
+            };
+            auto stage = [&](const float (&v)[16]) {
+                const unsigned st = g & 1;
+                uint4 h[4], l[4];
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    h[q].x = tc_tf32(v[4 * q]); h[q].y = tc_tf32(v[4 * q + 1]); h[q].z = tc_tf32(v[4 * q + 2]); h[q].w = tc_tf32(v[4 * q + 3]);
+                    l[q].x = tc_tf32(v[4 * q] - __uint_as_float(h[q].x)); l[q].y = tc_tf32(v[4 * q + 1] - __uint_as_float(h[q].y));
+                    l[q].z = tc_tf32(v[4 * q + 2] - __uint_as_float(h[q].z)); l[q].w = tc_tf32(v[4 * q + 3] - __uint_as_float(h[q].w));
+                }
+                tc_mbar_wait(&a_empty[st], ((g >> 1) & 1) ^ 1);
+                unsigned char *hi = st ? A1 : A0, *lo = hi + TC_BM * 128;
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const int c = kh * 4 + q;
+                    const unsigned o = (unsigned)((row >> 3) * 1024 + (row & 7) * 128 + ((c ^ (row & 7)) << 4));
+                    *(uint4 *)(hi + o) = h[q];
+                    *(uint4 *)(lo + o) = l[q];
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                tc_mbar_arrive(&a_full[st]);
+                g++;
+            };
+            fetch(va, 0);
+            if (a.kch > 1) fetch(vb, 1);
+            for (int kc = 0; kc < a.kch; kc += 2) {
+                stage(va);
+                if (kc + 2 < a.kch) fetch(va, kc + 2);
+                if (kc + 1 < a.kch) {
+                    stage(vb);
+                    if (kc + 3 < a.kch) fetch(vb, kc + 3);
+                }
+            }
+        }
+    } else if (warp == TC_PWARPS) {
+        if (lane == 0) {
+            const unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(a.nn >> 3) << 17) | ((unsigned)(TC_BM >> 4) << 24);
+            unsigned g = 0, it = 0, rb = 0;
+            for (int item = blockIdx.x; item < nitems; item += gridDim.x, it++) {
+                const unsigned ts = it & 1;
+                tc_mbar_wait(&t_empty[ts], ((it >> 1) & 1) ^ 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const unsigned d = tmem + ts * (unsigned)a.nn;
+                for (int kc = 0; kc < a.kch; kc++, g++, rb++) {
+                    const unsigned st = g & 1;
+                    const unsigned slot = rb % (unsigned)a.ring;
+                    tc_mbar_wait(&a_full[st], (g >> 1) & 1);
+                    tc_mbar_wait(&b_full[slot], (rb / (unsigned)a.ring) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const unsigned ahi = tc_smem_u32(st ? A1 : A0), alo = ahi + TC_BM * 128;
+                    const unsigned bhi = tc_smem_u32(Bring + (size_t)slot * slotb), blo = bhi + (unsigned)a.nn * 128u;
+#pragma unroll
+                    for (int k = 0; k < TC_BK / 8; k++) {
+                        const unsigned ko = (unsigned)k * 32;
+                        tc_mma_tf32(d, tc_desc(ahi + ko), tc_desc(bhi + ko), idesc, (kc | k) != 0);
+                        tc_mma_tf32(d, tc_desc(alo + ko), tc_desc(bhi + ko), idesc, 1u);
+                        tc_mma_tf32(d, tc_desc(ahi + ko), tc_desc(blo + ko), idesc, 1u);
+                    }
+                    tc_commit(&b_empty[slot]);
+                    tc_commit(&a_empty[st]);
+                }
+                tc_commit(&t_full[ts]);
+            }
+        }
+        __syncwarp();
+    } else if (warp == TC_PWARPS + 1) {
+        if (lane == 0) {
+            unsigned rb = 0;
+            for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+                for (int kc = 0; kc < a.kch; kc++, rb++) {
+                    const unsigned slot = rb % (unsigned)a.ring;
+                    tc_mbar_wait(&b_empty[slot], ((rb / (unsigned)a.ring) & 1) ^ 1);
+                    tc_mbar_expect_tx(&b_full[slot], slotb);
+                    tc_bulk_g2s(Bring + (size_t)slot * slotb, a.bpack + (size_t)kc * slotb, slotb, &b_full[slot]);
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===== epilogue: lane = grid point, its coefficients go to its ragged row =====
+        const int q4 = warp & 3;
+        unsigned it = 0;
+        for (int item = blockIdx.x; item < nitems; item += gridDim.x, it++) {
+            const unsigned ts = it & 1;
+            const int p = item * TC_BM + 32 * q4 + lane;
+            int off = 0, nr = 0;
+            if (p < a.npts) { off = __ldg(&a.rshptr[p]); nr = __ldg(&a.rshptr[p + 1]) - off; }
+            if (nr > a.nlm) nr = a.nlm;
+            float *outp = a.sh_out + off;
+            tc_mbar_wait(&t_full[ts], (it >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            for (int c0 = 0; c0 < a.nn; c0 += 32) {
+                unsigned w[32];
+                const unsigned taddr = tmem + ((unsigned)(32 * q4) << 16) + ts * (unsigned)a.nn + (unsigned)c0;
+                asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                             : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]),
+                               "=r"(w[8]), "=r"(w[9]), "=r"(w[10]), "=r"(w[11]), "=r"(w[12]), "=r"(w[13]), "=r"(w[14]), "=r"(w[15])
+                             : "r"(taddr) : "memory");
+                if (c0 + 16 < a.nn)
+                    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                                 : "=r"(w[16]), "=r"(w[17]), "=r"(w[18]), "=r"(w[19]), "=r"(w[20]), "=r"(w[21]), "=r"(w[22]), "=r"(w[23]),
+                                   "=r"(w[24]), "=r"(w[25]), "=r"(w[26]), "=r"(w[27]), "=r"(w[28]), "=r"(w[29]), "=r"(w[30]), "=r"(w[31])
+                                 : "r"(taddr + 16u) : "memory");
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                const int lim = min(nr, a.nn) - c0;
+                if (lim >= 32) {
+#pragma unroll
+                    for (int e = 0; e < 32; e++) outp[c0 + e] = __uint_as_float(w[e]);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 32; e++) if (e < lim) outp[c0 + e] = __uint_as_float(w[e]);
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            tc_mbar_arrive(&t_empty[ts]);
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == TC_PWARPS) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+    }
+}
+
 // basis tiles of the tensor-core variant (once per plan): Y(j, ordinate) from the FP32 kernel applied to the unit
 // vectors, split into TF32 hi / lo and laid out as the kernel's shared-memory tiles
 static unsigned tc_host_tf32(float x)
@@ -914,6 +1104,61 @@ static int tr_tc_build(TrPlan *P, char *errmsg)
     return 0;
 }
 
+// basis tiles of the tensor-core DO_TO_SH: W(ordinate, j) from the FP32 kernel applied to the NANG unit ordinate fields
+static int tr_tc_build_back(TrPlan *P, char *errmsg)
+{
+    const TrArgs &f = P->bwd;
+    if (f.nst != 1) return 0;
+    const int nlm = f.nlm, nang = P->nang;
+    const int nn = (nlm + 15) & ~15;
+    if (nn > 256) return 0;
+    const int kch = (nang + TC_BK - 1) / TC_BK;
+    const size_t slotb = 2 * (size_t)nn * 128;
+    int ring = (int)(((size_t)227 * 1024 - 1024 - 4 * TC_BM * 128 - 512) / slotb);
+    if (ring > TC_RING_MAX) ring = TC_RING_MAX;
+    if (ring < 2) return 0;
+    const size_t smem = 1024 + 4 * TC_BM * 128 + (size_t)ring * slotb + 512;
+    // unit ordinate fields: point p has DOFIELD(p, 1, ia) = (ia == p), full-length rows
+    std::vector<int> ptr(nang + 1);
+    for (int i = 0; i <= nang; i++) ptr[i] = i * nlm;
+    std::vector<float> eye((size_t)nang * nang, 0.0f);
+    for (int i = 0; i < nang; i++) eye[(size_t)i * nang + i] = 1.0f;
+    int *ptr_d = nullptr; float *eye_d = nullptr, *w_d = nullptr;
+    if (cudaMalloc(&ptr_d, sizeof(int) * (nang + 1)) != cudaSuccess || cudaMalloc(&eye_d, sizeof(float) * eye.size()) != cudaSuccess ||
+        cudaMalloc(&w_d, sizeof(float) * (size_t)nlm * nang) != cudaSuccess) { set_msg(errmsg, "device allocation failure"); return 4; }
+    cudaMemcpy(ptr_d, ptr.data(), sizeof(int) * (nang + 1), cudaMemcpyHostToDevice);
+    cudaMemcpy(eye_d, eye.data(), sizeof(float) * eye.size(), cudaMemcpyHostToDevice);
+    cudaMemset(w_d, 0, sizeof(float) * (size_t)nlm * nang);
+    TrArgs a = f;
+    a.npts = nang; a.shptr = ptr_d; a.sh_out = w_d; a.dofield = eye_d;
+    const int ntiles = (nang + TR_TP - 1) / TR_TP;
+    do_to_sh_kernel<<<ntiles < P->nsm ? ntiles : P->nsm, TR_THREADS, P->smem_bwd>>>(a, ntiles);
+    std::vector<float> w((size_t)nlm * nang);                       // w[j + nlm*ia]
+    cudaError_t e = cudaMemcpy(w.data(), w_d, sizeof(float) * w.size(), cudaMemcpyDeviceToHost);
+    cudaFree(ptr_d); cudaFree(eye_d); cudaFree(w_d);
+    if (e != cudaSuccess) { set_msg(errmsg, "CUDA error building the tensor-core basis (%s)", cudaGetErrorString(e)); return 4; }
+    std::vector<unsigned char> pack((size_t)kch * slotb, 0);
+    for (int kc = 0; kc < kch; kc++) {
+        unsigned char *hi = pack.data() + (size_t)kc * slotb, *lo = hi + (size_t)nn * 128;
+        for (int n = 0; n < nlm; n++)
+            for (int k = 0; k < TC_BK; k++) {
+                const int ia = kc * TC_BK + k;
+                const float v = ia < nang ? w[(size_t)n + (size_t)nlm * ia] : 0.0f;
+                const unsigned h = tc_host_tf32(v);
+                float hf; memcpy(&hf, &h, 4);
+                const unsigned l = tc_host_tf32(v - hf);
+                const size_t o = (size_t)(n >> 3) * 1024 + (size_t)(n & 7) * 128 + (size_t)(((k >> 2) ^ (n & 7)) << 4) + (size_t)(k & 3) * 4;
+                memcpy(hi + o, &h, 4);
+                memcpy(lo + o, &l, 4);
+            }
+    }
+    unsigned char *b_d = P->up(pack.data(), pack.size());
+    if (!b_d) { set_msg(errmsg, "device allocation failure"); return 4; }
+    if (cudaFuncSetAttribute(do_to_sh_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
+    P->tcb_b = b_d; P->tcb_kch = kch; P->tcb_nn = nn; P->tcb_ring = ring; P->tcb_smem = smem;
+    return 0;
+}
+
 static int tr_variant()
 {
     // 0: FP32 FMA kernels, 1: tensor cores (3xTF32) where available.  AT3D_B200_TRANSFORM=fp32|tc
@@ -953,6 +1198,14 @@ cudaError_t tr_sh_to_do(const TrPlan *P, int npts, const int *shptr_d, const flo
 
 cudaError_t tr_do_to_sh(const TrPlan *P, int npts, const int *rshptr_d, const float *do_d, float *sh_d, cudaStream_t st)
 {
+    if (P->tcb_kch > 0 && tr_variant() == 1) {
+        TcBackArgs b;
+        b.npts = npts; b.nang = P->nang; b.nlm = P->bwd.nlm; b.kch = P->tcb_kch; b.nn = P->tcb_nn; b.ring = P->tcb_ring;
+        b.rshptr = rshptr_d; b.dofield = do_d; b.sh_out = sh_d; b.bpack = P->tcb_b;
+        const int nitems = (npts + TC_BM - 1) / TC_BM;
+        do_to_sh_tc_kernel<<<nitems < P->nsm ? nitems : P->nsm, TC_THREADS, P->tcb_smem, st>>>(b, nitems);
+        return cudaGetLastError();
+    }
     TrArgs a = P->bwd;
     a.npts = npts; a.shptr = rshptr_d; a.sh_out = sh_d; a.dofield = (float *)do_d;
     const int ntiles = (npts + TR_TP - 1) / TR_TP;

@@ -359,11 +359,20 @@ def transform_leg(B, st, steps, warmup):
                 if i >= warmup:
                     ms3.append(t)
             t3 = float(np.mean(ms3)) * 1e-3
+            ms4 = []
+            for i in range(warmup + steps):
+                sh_tc, t = B.do_to_sh(st, wtmu, st.rshptr, do, timing=True)
+                if i >= warmup:
+                    ms4.append(t)
+            t4 = float(np.mean(ms4)) * 1e-3
             ntot = (nang + 15) // 16 * 16
             tensor_flops = 3 * 2.0 * (-(-npts // 128) * 128) * (-(-st.nlm // 32) * 32) * ntot     # what the MMAs execute
             tf32_peak = tensor_peak_tf32()
+            back_flops = 3 * 2.0 * (-(-npts // 128) * 128) * (-(-nang // 32) * 32) * (-(-st.nlm // 16) * 16)
             tc = dict(ms=1e3 * t3, speedup_vs_fp32=t1 / t3, tensor_tflops=tensor_flops / t3 / 1e12,
                       tensor_pipe_frac=tensor_flops / t3 / 1e12 / tf32_peak, tf32_peak_tflops=tf32_peak,
+                      do_to_sh=dict(ms=1e3 * t4, speedup_vs_fp32=t2 / t4, tensor_tflops=back_flops / t4 / 1e12,
+                                    tensor_pipe_frac=back_flops / t4 / 1e12 / tf32_peak),
                       max_rel_diff_vs_fp32=float(np.abs(do_tc - do).max() / np.abs(do).max()),
                       note='3xTF32: hi.hi + lo.hi + hi.lo, FP32 accumulation in TMEM; opt-in (AT3D_B200_TRANSFORM=tc)')
         finally:

@@ -21,6 +21,16 @@ for v in ('fp32', 'tc'):
         if i >= 2: ms.append(t)
     res[v] = float(np.mean(ms)); outs[v] = do
 nang = int(st.nphi0.sum())
+resb, outb = {}, {}
+for v in ('fp32', 'tc'):
+    os.environ['AT3D_B200_TRANSFORM'] = v
+    ms = []
+    for i in range(6):
+        sh, t = B.do_to_sh(st, wtmu, st.rshptr, outs['fp32'], timing=True)
+        if i >= 2: ms.append(t)
+    resb[v] = float(np.mean(ms)); outb[v] = sh
+errb = float(np.abs(outb['tc'] - outb['fp32']).max() / np.abs(outb['fp32']).max())
+print(json.dumps(dict(do_to_sh_ms=resb, max_rel_diff=errb)))
 err = float(np.abs(outs['tc'] - outs['fp32']).max() / np.abs(outs['fp32']).max())
 dense = 2.0 * st.npts * st.nlm * nang
 print(json.dumps(dict(npts=int(st.npts), nang=nang, ms=res, max_rel_diff=err,

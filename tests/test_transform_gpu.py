@@ -45,6 +45,27 @@ def test_sh_to_do_tensor_core_variant_matches_oracle(case, monkeypatch):
     assert np.abs(out).max() > 0
 
 
+@pytest.mark.parametrize('case', ['scalar_periodic_split', 'scalar_nmu16', 'scalar_open_split'])
+def test_do_to_sh_tensor_core_variant_matches_oracle(case, monkeypatch):
+    """DO_TO_SH through tcgen05 (3xTF32): the 1e-4 bar against the oracle, FP32 rounding against the FP32-FMA kernel, and
+    nothing written beyond a point's RADIANCE length."""
+    from at3d_b200 import backend as B
+    st = scenes.make(case, O).state
+    w = wtmu_of(st)
+    rng = np.random.default_rng(5)
+    do = O.sh_to_do(st, w, st.rshptr[:st.npts + 1], st.radiance)
+    do = do + 0.01 * np.abs(do).max() * rng.standard_normal(do.shape).astype(np.float32)
+    ref = O.do_to_sh(st, w, st.rshptr, do)
+    fp32 = B.do_to_sh(st, w, st.rshptr, do)
+    monkeypatch.setenv('AT3D_B200_TRANSFORM', 'tc')
+    out = B.do_to_sh(st, w, st.rshptr, do)
+    n = int(st.rshptr[st.npts])
+    scale = np.abs(ref[:, :n]).max()
+    np.testing.assert_allclose(out[:, :n], ref[:, :n], rtol=1e-4, atol=2e-6 * scale)
+    np.testing.assert_allclose(out[:, :n], fp32[:, :n], rtol=2e-5, atol=2e-6 * scale)
+    np.testing.assert_array_equal(out[:, n:], fp32[:, n:])
+
+
 @pytest.mark.parametrize('case', CASES)
 def test_do_to_sh_matches_oracle(case):
     from at3d_b200 import backend as B
