@@ -118,6 +118,30 @@ __device__ __forceinline__ float thread_point_source(const DevState &S, const fl
     if (!singlescatter || stream) {           // the gradient's source stream wants the SH part in any case
         const float4 *base = (const float4 *)(S.shsrc + ps.x);
         const int n4 = AT3D_SHPAD(ns) >> 2;                 // multiple of 8
+#ifndef AT3D_SH_UNROLL4
+        // eight 16-byte loads of the row in flight per iteration (n4 is a multiple of 8); same summation order as below
+#pragma unroll 1
+        for (int j = 0; j < n4; j += 8) {
+            const float4 s0 = __ldg(base + j), s1 = __ldg(base + j + 1), s2 = __ldg(base + j + 2), s3 = __ldg(base + j + 3);
+            const float4 s4 = __ldg(base + j + 4), s5 = __ldg(base + j + 5), s6 = __ldg(base + j + 6), s7 = __ldg(base + j + 7);
+            {
+                const float4 y0 = Y4[(size_t)j * bt], y1 = Y4[(size_t)(j + 1) * bt];
+                const float4 y2 = Y4[(size_t)(j + 2) * bt], y3 = Y4[(size_t)(j + 3) * bt];
+                a0 = fmaf(s0.x, y0.x, a0); a1 = fmaf(s0.y, y0.y, a1); a2 = fmaf(s0.z, y0.z, a2); a3 = fmaf(s0.w, y0.w, a3);
+                a0 = fmaf(s1.x, y1.x, a0); a1 = fmaf(s1.y, y1.y, a1); a2 = fmaf(s1.z, y1.z, a2); a3 = fmaf(s1.w, y1.w, a3);
+                a0 = fmaf(s2.x, y2.x, a0); a1 = fmaf(s2.y, y2.y, a1); a2 = fmaf(s2.z, y2.z, a2); a3 = fmaf(s2.w, y2.w, a3);
+                a0 = fmaf(s3.x, y3.x, a0); a1 = fmaf(s3.y, y3.y, a1); a2 = fmaf(s3.z, y3.z, a2); a3 = fmaf(s3.w, y3.w, a3);
+            }
+            {
+                const float4 y0 = Y4[(size_t)(j + 4) * bt], y1 = Y4[(size_t)(j + 5) * bt];
+                const float4 y2 = Y4[(size_t)(j + 6) * bt], y3 = Y4[(size_t)(j + 7) * bt];
+                a0 = fmaf(s4.x, y0.x, a0); a1 = fmaf(s4.y, y0.y, a1); a2 = fmaf(s4.z, y0.z, a2); a3 = fmaf(s4.w, y0.w, a3);
+                a0 = fmaf(s5.x, y1.x, a0); a1 = fmaf(s5.y, y1.y, a1); a2 = fmaf(s5.z, y1.z, a2); a3 = fmaf(s5.w, y1.w, a3);
+                a0 = fmaf(s6.x, y2.x, a0); a1 = fmaf(s6.y, y2.y, a1); a2 = fmaf(s6.z, y2.z, a2); a3 = fmaf(s6.w, y2.w, a3);
+                a0 = fmaf(s7.x, y3.x, a0); a1 = fmaf(s7.y, y3.y, a1); a2 = fmaf(s7.z, y3.z, a2); a3 = fmaf(s7.w, y3.w, a3);
+            }
+        }
+#else
 #pragma unroll 1
         for (int j = 0; j < n4; j += 4) {
             const float4 s0 = __ldg(base + j), s1 = __ldg(base + j + 1), s2 = __ldg(base + j + 2), s3 = __ldg(base + j + 3);
@@ -128,6 +152,7 @@ __device__ __forceinline__ float thread_point_source(const DevState &S, const fl
             a0 = fmaf(s2.x, y2.x, a0); a1 = fmaf(s2.y, y2.y, a1); a2 = fmaf(s2.z, y2.z, a2); a3 = fmaf(s2.w, y2.w, a3);
             a0 = fmaf(s3.x, y3.x, a0); a1 = fmaf(s3.y, y3.y, a1); a2 = fmaf(s3.z, y3.z, a2); a3 = fmaf(s3.w, y3.w, a3);
         }
+#endif
     }
     const float b = thread_singscat_sum(S, ip, ps, rd);
     if (stream) {
