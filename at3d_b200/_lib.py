@@ -21,7 +21,7 @@ class At3dError(RuntimeError):
 
 class RaysC(C.Structure):
     _fields_ = [('nrays', i32), ('memspace', i32), ('camx', C.c_void_p), ('camy', C.c_void_p),
-                ('camz', C.c_void_p), ('cammu', C.c_void_p), ('camphi', C.c_void_p)]
+                ('camz', C.c_void_p), ('cammu', C.c_void_p), ('camphi', C.c_void_p), ('packs', C.c_void_p)]
 
 
 class CsDeviceDesc(C.Structure):
@@ -46,7 +46,7 @@ SYMBOLS = ['at3d_b200_version', 'at3d_device_count', 'at3d_set_device', 'at3d_st
            'at3d_levisapprox_gradient', 'at3d_levisapprox_gradient_jacobian', 'at3d_prepare_deriv_interps', 'at3d_make_direct_derivative',
            'at3d_average_subpixel_rays', 'at3d_update_costfunction', 'at3d_make_direct', 'at3d_state_get_counts',
            'at3d_sh_to_do', 'at3d_do_to_sh', 'at3d_path_integration_ip', 'at3d_solver_create',
-           'at3d_solver_path_integration', 'at3d_solver_solve', 'at3d_solver_destroy', 'at3d_sweeping_order', 'at3d_transfer_pa_to_grid', 'at3d_solve_adaptive', 'at3d_compute_source_device']
+           'at3d_solver_path_integration', 'at3d_solver_solve', 'at3d_solver_destroy', 'at3d_sweeping_order', 'at3d_transfer_pa_to_grid', 'at3d_solve_adaptive', 'at3d_compute_source_device', 'at3d_ray_pack_bytes', 'at3d_make_ray_packs']
 
 
 class _Missing:
@@ -100,6 +100,8 @@ def lib():
                                       C.c_char_p]
     L.at3d_compute_source_device.argtypes = [P(CsDeviceDesc), i32, f32, C.c_int64, i32, i32] + [C.c_void_p] * 7 + \
         [C.c_int64, i32, C.c_void_p, P(i32), P(f64), C.c_char_p]
+    L.at3d_ray_pack_bytes.restype = C.c_int64
+    L.at3d_make_ray_packs.argtypes = [C.c_void_p, P(RaysC), C.c_void_p, C.c_char_p]
     L.at3d_ylmall.argtypes = [i32, f32, f32, i32, i32, i32, C.c_void_p, C.c_char_p]
     L.at3d_precompute_phase_check.argtypes = [i32, i32, i32, i32, i32, i32, i32, i32, C.c_void_p,
                                               C.c_void_p, i32, i32, i32, C.c_char_p]

@@ -349,6 +349,7 @@ int stage_rays(at3d_state *st, const at3d_rays *rays, cudaStream_t stream, const
     *packs = nullptr;
     if (rays->memspace == AT3D_MEM_DEVICE) {
         *camx = rays->camx; *camy = rays->camy; *camz = rays->camz; *cammu = rays->cammu; *camphi = rays->camphi;
+        *packs = (const RayPack *)rays->packs;              // host-libm setup records of at3d_make_ray_packs, or NULL
         return 0;
     }
     const size_t nb = n * (sizeof(RayPack) + 2 * sizeof(double)) + 64;
@@ -381,6 +382,24 @@ int stage_rays(at3d_state *st, const at3d_rays *rays, cudaStream_t stream, const
     // before this call returns (every entry point synchronises the stream before returning results), and it is only
     // rewritten by the next call on this state
     *camx = nullptr; *camy = nullptr; *camz = nullptr; *cammu = dmu; *camphi = dphi; *packs = dpk;
+    return 0;
+}
+
+extern "C" int64_t at3d_ray_pack_bytes(void) { return (int64_t)sizeof(RayPack); }
+
+extern "C" int at3d_make_ray_packs(at3d_state *st, const at3d_rays *rays, void *packs_out, char *errmsg)
+{
+    if (errmsg) errmsg[0] = 0;
+    if (!st || !rays || !packs_out) { set_msg(errmsg, "null argument"); return 1; }
+    if (rays->memspace != AT3D_MEM_HOST) { set_msg(errmsg, "at3d_make_ray_packs takes host ray arrays"); return 1; }
+    const long long n = rays->nrays;
+    const RayGeom g = st->geom;
+    RayPack *hp = (RayPack *)packs_out;
+    const float *hx = rays->camx, *hy = rays->camy, *hz = rays->camz;
+    const double *hmu = rays->cammu, *hphi = rays->camphi;
+#pragma omp parallel for schedule(static) if (n > 4096)
+    for (long long i = 0; i < n; i++)
+        make_ray_pack(g, (double)hx[i], (double)hy[i], (double)hz[i], hmu[i], hphi[i], hp[i]);
     return 0;
 }
 

@@ -61,13 +61,27 @@ class DeviceState:
         return out
 
     # ------------------------------------------------------------------
-    def _rays_struct(self, camx, camy, camz, cammu, camphi):
+    def _rays_struct(self, camx, camy, camz, cammu, camphi, packs=None):
         dev = _is_torch(camx)
         r = RaysC()
         r.nrays = int(camx.shape[0])
         r.memspace = 1 if dev else 0
         r.camx, r.camy, r.camz, r.cammu, r.camphi = vp(camx), vp(camy), vp(camz), vp(cammu), vp(camphi)
+        r.packs = vp(packs) if (dev and packs is not None) else None
         return r, dev
+
+    def make_ray_packs(self, rays, device='cuda'):
+        """Per-ray setup records of HOST rays (at3d_make_ray_packs: host libm, bit-exact walk) as a CUDA uint8 tensor, to
+        be attached as ``.packs`` to device-resident rays of the same geometry."""
+        import torch
+        r, dev = self._rays_struct(rays.camx, rays.camy, rays.camz, rays.cammu, rays.camphi)
+        if dev:
+            raise ValueError('make_ray_packs takes host (numpy) rays')
+        nb = int(self._L.at3d_ray_pack_bytes())
+        out = np.zeros(r.nrays * nb, np.uint8)
+        buf = _lib.errbuf()
+        _lib.check(self._L.at3d_make_ray_packs(self._h, C.byref(r), vp(out), buf), buf)
+        return torch.from_numpy(out).to(device)
 
     def render(self, rays, correctinterpolate=True, singlescatter=False, nosurface=False,
                trace_cap=0, out=None, stream=None, timing=False):
@@ -75,7 +89,7 @@ class DeviceState:
         camx, camy, camz (float32) and cammu, camphi (float64) numpy arrays / torch CUDA tensors.
         Returns stokes [nstokes, nrays] (numpy F-order, or the torch tensor ``out``), plus the
         trace dict when ``trace_cap`` > 0 and the kernel milliseconds when ``timing``."""
-        r, dev = self._rays_struct(rays.camx, rays.camy, rays.camz, rays.cammu, rays.camphi)
+        r, dev = self._rays_struct(rays.camx, rays.camy, rays.camz, rays.cammu, rays.camphi, getattr(rays, 'packs', None))
         n = r.nrays
         if out is None:
             if dev:
@@ -120,7 +134,7 @@ class DeviceState:
         if self._grad is None:
             raise RuntimeError('attach_gradient() first')
         g = self._grad
-        r, dev = self._rays_struct(rays.camx, rays.camy, rays.camz, rays.cammu, rays.camphi)
+        r, dev = self._rays_struct(rays.camx, rays.camy, rays.camz, rays.cammu, rays.camphi, getattr(rays, 'packs', None))
         if dev:
             raise NotImplementedError('gradient_jacobian takes host (numpy) arrays')
         gd = g.desc()
@@ -152,7 +166,7 @@ class DeviceState:
         if self._grad is None:
             raise RuntimeError('attach_gradient() first')
         g = self._grad
-        r, dev = self._rays_struct(rays.camx, rays.camy, rays.camz, rays.cammu, rays.camphi)
+        r, dev = self._rays_struct(rays.camx, rays.camy, rays.camz, rays.cammu, rays.camphi, getattr(rays, 'packs', None))
         gd = g.desc()
         npix = int(pix.rays_per_pixel.shape[0])
         gd.npix = npix

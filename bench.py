@@ -689,6 +689,9 @@ def main():
     dr, dp = Bag(), Bag()
     for k in ('camx', 'camy', 'camz', 'cammu', 'camphi'):
         setattr(dr, k, torch.from_numpy(getattr(rays, k)).cuda())
+    # the per-ray setup records evaluated with the host libm (the reference's own), resident in HBM with the rays: the
+    # device-timed `value` walks exactly the cells of the host-buffer (`e2e`) path
+    dr.packs = dev.make_ray_packs(rays)
     l2flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device='cuda')   # > 126 MB L2
 
     def barrier():
@@ -894,7 +897,8 @@ def main():
             warmup=args.warmup, ms_per_step=1e3 * t_total / args.steps, higher_is_better=True, scaling='weak',
             vs_baseline=None, dtype='f32 optics / f64 geometry+accumulators', data='synthetic',
             config=dict(workload=workload_text(args.workload, st), rays=int(nrays), npts=int(st.npts), ncells=int(st.ncells),
-                        nlm=int(st.nlm), l2='flushed between steps (256 MiB memset)', hbm_state_bytes=dev.hbm_bytes),
+                        nlm=int(st.nlm), l2='flushed between steps (256 MiB memset)', hbm_state_bytes=dev.hbm_bytes,
+                        ray_setup='host-libm setup records resident in HBM (at3d_make_ray_packs): bit-exact walk in `value` and `e2e`'),
             e2e=dict(value=world * nrays * args.steps / t_e2e, unit='rays/s', h2d_bytes_per_step=int(h2d),
                      d2h_bytes_per_step=int(d2h)),
             gpu_launches=int(args.steps * (7 + (4 if gi.exact_single_scatter else 0))),   # forward, pixel, cost, derivative walk, apply, pair bounds + sums (+ beam count, beam, bounds, sums); cub scans and sorts not counted

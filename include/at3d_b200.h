@@ -88,7 +88,12 @@ typedef struct at3d_rays {
     int32_t memspace;           /* AT3D_MEM_HOST | AT3D_MEM_DEVICE */
     const float *camx, *camy, *camz;
     const double *cammu, *camphi;
+    const void *packs;          /* optional, AT3D_MEM_DEVICE only: device array of nrays per-ray setup records written by
+                                   at3d_make_ray_packs (evaluated with the HOST libm, the reference's own, so that the walk
+                                   of device-resident rays is bit-exact too); NULL: the kernels evaluate the setup themselves
+                                   with the CUDA math library (values agree, cell sequences may differ in rare ties) */
 } at3d_rays;
+
 
 /* The extra inputs of LEVISAPPROX_GRADIENT (shdomsub4.f:299-317); HOST pointers except the
  * per-ray / per-pixel arrays, which follow rays->memspace. */
@@ -195,6 +200,12 @@ int at3d_compute_source_device(const at3d_cs_device_desc *desc, int fixsh, float
                                int32_t *shptr_new, float *source_new, int64_t source_new_capacity /*entries per Stokes component*/,
                                int properties_changed, float *norms /*host [4]*/, int32_t *total_new /*host*/,
                                double *kernel_ms /*optional*/, char *errmsg);
+
+/* per-ray setup records of host rays (direction cosines, clipped entry point, scattering-angle interpolation; what RENDER
+ * computes at the top of its ray loop, shdomsub4.f:213-236): packs_out is a HOST array of nrays * at3d_ray_pack_bytes()
+ * bytes that the caller uploads next to its device-resident ray arrays (at3d_rays.packs). */
+int64_t at3d_ray_pack_bytes(void);
+int at3d_make_ray_packs(at3d_state *st, const at3d_rays *rays_host, void *packs_out, char *errmsg);
 
 /* ---- a2/a3/a4/a5/a6: RENDER (shdomsub4.f:93) ---- */
 int at3d_render(at3d_state *st, const at3d_rays *rays, float *stokes /*[nstokes,nrays], rays->memspace*/,

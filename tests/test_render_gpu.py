@@ -67,6 +67,10 @@ def test_render_device_pointers_match_host_path(oracle):
         setattr(r, k, torch.from_numpy(getattr(rays, k)).cuda())
     out = dev.render(r)
     np.testing.assert_array_equal(out.cpu().numpy().T, host)
+    # with the host-libm setup records attached (at3d_make_ray_packs) the device-resident rays take exactly the host path
+    r.packs = dev.make_ray_packs(rays)
+    out2 = dev.render(r)
+    np.testing.assert_array_equal(out2.cpu().numpy().T, host)
     dev.close()
 
 
