@@ -325,6 +325,7 @@ const char *ray_err_text(int code)
     case 2: return "RENDER: Level below domain";
     case 3: return "FIND_BOUNDARY_RADIANCE: Not at boundary";
     case 4: return "ADJOINT_INTEGRATE_1RAY: The maximum number of subgrid intervals for calculation of the radiance along the ray path has been exceeded.";
+    case 5: return "DIRECT_BEAM_AND_PATHS_PROP: the walk toward the sun left the property grid";
     default: return "unknown ray error";
     }
 }

@@ -94,6 +94,8 @@ struct DevState {
 #define AT3D_SRC_TOP_WORDS (32 * (AT3D_SRC_REGIONS + 1))
 
 // Derivative tables of LEVISAPPROX_GRADIENT resident in HBM (reference layouts, see at3d_grad_desc).
+#include "at3d_beam.cuh"
+
 struct DevGrad {
     int maxpg, numder, dnumphase, deriv_maxnmicro, pmaxnmicro, longest_path_pts;
     int exact_single_scatter, singlescatter, maxsub;
@@ -112,6 +114,9 @@ struct DevGrad {
     const float *extinctp, *albedop;        // [maxpg,npart]
     const float *dpath;                     // [longest_path_pts,npts]
     const int *dptr;
+    int stream_beam;                        // 1: no dense lists, the beam walks run inside the gradient call
+    BeamGeom bg;                            // property-grid beam constants (stream_beam)
+    const float *bzl;                       // [bg.npz] property-grid levels (stream_beam)
     // ray-independent tables built once per attach by the grad_prep kernels (at3d_grad.cu).  A grid point
     // owns NNZ*NUMDER "rows" (unknown-major, then its property corners with a non-zero weight).
     int ncomp, ntup;                        // Legendre components that reach I,Q,U (1|4); padded table length
@@ -469,16 +474,19 @@ struct __align__(16) RayPack {
 __host__ __device__ inline void make_ray_pack(const RayGeom &g, double x0, double y0, double z0,
                                               double mu2, double phi2, RayPack &p)
 {
-    const double pi = acos(-1.0);
+    const double pi = 3.14159265358979323846;      // = ACOS(-1.0D0), correctly rounded
     p.status = 0; p.pad = 0;
+    // SQRT(1-MU2**2), COS(PHI2-PI), SIN(PHI2-PI) appear three / two / two times in the reference with the same operands
+    // (MURAY = -MU2, PHIRAY = PHI2-PI): evaluated once here, bit for bit the same values
+    const double sinth = sqrt(1.0 - mu2 * mu2), cphi = cos(phi2 - pi), sphi = sin(phi2 - pi);
     {
-        const double muray = -mu2, phiray = phi2 - pi;
+        const double muray = -mu2;
         if (z0 > g.ztop) {
             if (muray >= 0.0) p.status = 1;
             else {
                 const double r = (g.ztop - z0) / muray;
-                x0 = x0 + r * sqrt(1 - muray * muray) * cos(phiray);
-                y0 = y0 + r * sqrt(1 - muray * muray) * sin(phiray);
+                x0 = x0 + r * sinth * cphi;
+                y0 = y0 + r * sinth * sphi;
                 z0 = g.ztop;
             }
         } else if (z0 < g.zbot) {
@@ -514,8 +522,8 @@ __host__ __device__ inline void make_ray_pack(const RayGeom &g, double x0, doubl
             p.cos22 = 1.0 - 2.0 * (sin2 * sin2);
         }
     }
-    p.cx = sqrt(1.0 - mu2 * mu2) * cos(phi2 - pi);
-    p.cy = sqrt(1.0 - mu2 * mu2) * sin(phi2 - pi);
+    p.cx = sinth * cphi;
+    p.cy = sinth * sphi;
     p.cz = -mu2;
     if (!(fabs(p.cx) > 1.0e-6f)) p.cx = 0.0;
     if (!(fabs(p.cy) > 1.0e-6f)) p.cy = 0.0;

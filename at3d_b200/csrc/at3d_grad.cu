@@ -24,6 +24,8 @@
 #include <cstdio>
 #include <cstring>
 #include <cstdarg>
+#include <cstdlib>
+#include <algorithm>
 #include <vector>
 #include <cub/cub.cuh>
 #include "at3d_host.h"
@@ -1203,6 +1205,61 @@ __global__ void beam_kernel(DevGrad G, int npts, const double *beam_weight, doub
     }
 }
 
+// Streaming variant of phase 4 (DevGrad::stream_beam): no DPATH/DPTR lists in memory.  A thread per grid point with a
+// non-zero beam weight repeats the walk of DIRECT_BEAM_AND_PATHS_PROP (shdomsub5.f:1646-2003; beam_walk<true>) and hands
+// every (property point, path integral) entry straight to the accumulation, entry by entry in the order the dense list
+// would hold them: the values and their summation order are those of beam_kernel, so the gradient is the same bit for bit.
+__global__ void beam_stream_count_kernel(DevGrad G, int npts, const float4 *ptrec, const double *beam_weight, int *count, RayErr *err)
+{
+    const int ip = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ip >= npts) return;
+    int n = 0;
+    if (beam_weight[ip] != 0.0) {
+        BeamCountSink sink{0};
+        double path; int npp;
+        const float4 pt = __ldg(&ptrec[ip]);
+        const int e = beam_walk<true>(G.bg, G.bzl, pt.x, pt.y, pt.z, nullptr, path, npp, sink);
+        if (e) { if (atomicCAS(&err->code, 0, 5) == 0) err->ray = ip + 1; }
+        n = sink.n;
+    }
+    count[ip] = n * G.numder;
+}
+
+template <bool PAIRS>
+struct BeamGradSink {
+    const DevGrad &G; double bwt; long long slot; unsigned *keys; double *vals; double *gradout;
+    __device__ bool put(const int *p, const float *v)
+    {
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+            const int ib = p[c];
+            const double pb = (double)v[c] * bwt;
+            for (int idr = 0; idr < G.numder; idr++) {
+                const size_t dst = (size_t)(ib - 1) + (size_t)G.maxpg * idr;
+                const float dm = __ldg(&G.dextm[dst]);
+                const double val = dm * pb;
+                if (PAIRS) { keys[slot] = (unsigned)dst; vals[slot] = -val; slot++; }
+                else if (val != 0.0) atomicAdd(&gradout[dst], -val);
+            }
+        }
+        return true;
+    }
+};
+
+template <bool PAIRS>
+__global__ void beam_stream_kernel(DevGrad G, int p0, int p1, const float4 *ptrec, const double *beam_weight, double *gradout,
+                                   const long long *pairoff, unsigned *keys, double *vals)
+{
+    const int ip = p0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (ip >= p1) return;
+    const double bwt = beam_weight[ip];
+    if (bwt == 0.0) return;
+    BeamGradSink<PAIRS> sink{G, bwt, PAIRS ? pairoff[ip] - pairoff[p0] : 0, keys, vals, gradout};
+    double path; int npp;
+    const float4 pt = __ldg(&ptrec[ip]);
+    beam_walk<true>(G.bg, G.bzl, pt.x, pt.y, pt.z, nullptr, path, npp, sink);
+}
+
 // ------------------------------------------------------------------------------------------
 // Atomics-free accumulation of the (GRADOUT entry, value) pairs of the derivative pass: the pairs are sorted by entry
 // (cub radix sort, stable: equal keys keep their slot order, which is fixed by the ray order), pair_bounds_kernel finds
@@ -1319,16 +1376,35 @@ extern "C" int at3d_state_attach_gradient(at3d_state *st, const at3d_grad_desc *
     GUP(diphasep, (size_t)g->deriv_maxnmicro * mp * nd); GUP(dphasewtp, (size_t)g->deriv_maxnmicro * mp * nd);
     GUP(iphasep, (size_t)S.maxnmicro * mp * S.npart); GUP(phasewtp, (size_t)S.maxnmicro * mp * S.npart);
     GUP(extinctp, mp * S.npart); GUP(albedop, mp * S.npart);
-    if (g->exact_single_scatter) { GUP(dpath, (size_t)g->longest_path_pts * np); GUP(dptr, (size_t)g->longest_path_pts * np); }
+    const bool stream_beam = g->exact_single_scatter && !g->dpath && !g->dptr;
+    if (g->exact_single_scatter && !stream_beam) { GUP(dpath, (size_t)g->longest_path_pts * np); GUP(dptr, (size_t)g->longest_path_pts * np); }
 #undef GUP
     if (rc) return rc;
+    if (stream_beam) {
+        if (!g->beam_d || !g->beam_i || !g->beam_zlevels || g->beam_npx < 1 || g->beam_npy < 1 || g->beam_npz < 2 ||
+            (size_t)g->beam_npx * g->beam_npy * g->beam_npz != mp) {
+            set_msg(errmsg, "streaming direct-beam derivative: beam_d / beam_i / beam_zlevels and the property-grid size are required");
+            return 1;
+        }
+        BeamGeom &b = G.bg;
+        b.bcflag = S.bcflag; b.npx = g->beam_npx; b.npy = g->beam_npy; b.npz = g->beam_npz;
+        b.xstart = g->beam_xstart; b.ystart = g->beam_ystart;
+        b.cx = g->beam_d[0]; b.cy = g->beam_d[1]; b.cz = g->beam_d[2];
+        b.cxinv = g->beam_d[3]; b.cyinv = g->beam_d[4]; b.czinv = g->beam_d[5];
+        b.epss = g->beam_d[6]; b.epsz = g->beam_d[7]; b.xdomain = g->beam_d[8]; b.ydomain = g->beam_d[9];
+        b.delxd = g->beam_d[11]; b.delyd = g->beam_d[12];
+        b.ipdirect = g->beam_i[0]; b.di = g->beam_i[1]; b.dj = g->beam_i[2]; b.dk = g->beam_i[3];
+        rc = gupload(st, own, g->beam_zlevels, (size_t)g->beam_npz, &G.bzl, errmsg);
+        if (rc) return rc;
+        G.stream_beam = 1;
+    }
     if (!G.partder || !G.doexact || !G.dext || !G.dalb || !G.dextm || !G.dalbm || !G.dfj || !G.optinterpwt ||
         !G.interpptr || !G.iphasep || !G.phasewtp || !G.extinctp || !G.albedop || !G.diphasep || !G.dphasewtp ||
         !G.dleg || !G.dphasetab) {
         set_msg(errmsg, "at3d_state_attach_gradient: a required derivative array is NULL");
         return 1;
     }
-    if (g->exact_single_scatter && (!G.dpath || !G.dptr)) { set_msg(errmsg, "EXACT_SINGLE_SCATTER needs DPATH/DPTR"); return 1; }
+    if (g->exact_single_scatter && !G.stream_beam && (!G.dpath || !G.dptr)) { set_msg(errmsg, "EXACT_SINGLE_SCATTER needs DPATH and DPTR (or neither: streaming)"); return 1; }
     // ray-independent tables of COMPUTE_SOURCE_GRAD_1CELL (grad_prep_kernel)
     {
         const bool deltam = S.deltam != 0;
@@ -1768,7 +1844,38 @@ static int gradient_impl(at3d_state *st, const at3d_rays *rays, const at3d_grad_
         CUDA_TRY(cudaGetLastError());
         if (kernel_ms) cudaEventRecord(ev[2], stream);
         // ---- Phase 4 ----
-        if (G.exact_single_scatter) {
+        if (G.exact_single_scatter && G.stream_beam) {
+            // streaming: count the entries of every walk, then passes over point ranges that fit the pair buffers
+            const int nbt = (S.npts + 127) / 128;
+            beam_stream_count_kernel<<<nbt, 128, 0, stream>>>(G, S.npts, S.ptrec, beam, bcount, (RayErr *)st->err.p);
+            CUDA_TRY(cudaMemsetAsync(bcount + S.npts, 0, sizeof(int), stream));
+            cub::TransformInputIterator<long long, IntToLL, const int *> it(bcount, IntToLL());
+            CUDA_TRY(cub::DeviceScan::ExclusiveSum(wb + w_cub, cubtmp, it, pairoff, S.npts + 1, stream));
+            std::vector<long long> off_h((size_t)S.npts + 1);
+            CUDA_TRY(cudaMemcpyAsync(off_h.data(), pairoff, sizeof(long long) * ((size_t)S.npts + 1), cudaMemcpyDeviceToHost, stream));
+            CUDA_TRY(cudaStreamSynchronize(stream));
+            if ((rc = check_ray_err(st, stream, errmsg))) return rc;
+            long long cap = 1ll << 29;                                     // pairs per pass: 12 B each, twice (sort buffers)
+            if (const char *e = getenv("AT3D_B200_BEAM_PAIRS")) { const long long v = atoll(e); if (v > 0) cap = v; }
+            int p0 = 0;
+            while (p0 < S.npts) {
+                if (off_h[S.npts] == off_h[p0]) break;                        // nothing left
+                int p1 = (int)(std::upper_bound(off_h.begin() + p0, off_h.end(), off_h[p0] + cap) - off_h.begin()) - 1;
+                if (p1 <= p0) p1 = p0 + 1;                                    // one point's walk always fits (< 2^31 entries)
+                if (p1 > S.npts) p1 = S.npts;
+                const long long nbp = off_h[p1] - off_h[p0];
+                if (nbp > 0) {
+                    if (nbp > 0x7FFFFFF0ll) { set_msg(errmsg, "too many direct-beam derivative terms for one grid point"); return 2; }
+                    PairBufs pb;
+                    if ((rc = pair_reserve(st, (size_t)nbp + 1, nkeys, pb, errmsg))) return rc;
+                    beam_stream_kernel<true><<<(p1 - p0 + 127) / 128, 128, 0, stream>>>(G, p0, p1, S.ptrec, beam, grad_d,
+                                                                                         pairoff, pb.k0, pb.v0);
+                    CUDA_TRY(cudaGetLastError());
+                    if ((rc = pair_accumulate(pb, (size_t)nbp, nkeys, (unsigned)ngrad, grad_d, beam, stream, errmsg))) return rc;
+                }
+                p0 = p1;
+            }
+        } else if (G.exact_single_scatter) {
             const int wpb = 8, nbb = (S.npts + wpb - 1) / wpb;
             long long nbp = 0;
             beam_count_kernel<<<nbb, wpb * 32, 0, stream>>>(G, S.npts, beam, bcount);
@@ -1847,7 +1954,10 @@ static int gradient_impl(at3d_state *st, const at3d_rays *rays, const at3d_grad_
                             apply_kernel<3, false><<<nblk, AT3D_RAY_THREADS, smem, stream>>>(Sq, G, (int)r1, camx, camy, camz, cammu,
                                 camphi, packs, raypix, adj1, rw, sw, recoff, roff[r0], recs, nrec, gtmp, beam1, PairOut(), nullptr,
                                 (RayErr *)st->err.p, st->ray_counter, (int)r0);
-                        if (G.exact_single_scatter) {
+                        if (G.exact_single_scatter && G.stream_beam) {
+                            beam_stream_kernel<false><<<(S.npts + 127) / 128, 128, 0, stream>>>(G, 0, S.npts, S.ptrec, beam1,
+                                                                                                 gtmp, nullptr, nullptr, nullptr);
+                        } else if (G.exact_single_scatter) {
                             const int wpb = 8;
                             beam_kernel<false><<<(S.npts + wpb - 1) / wpb, wpb * 32, 0, stream>>>(G, S.npts, beam1, gtmp, nullptr, nullptr, nullptr);
                         }

@@ -74,7 +74,7 @@ def make_pixels(nstokes, nrays, radiances, seed=0, rays_per_pixel=1, noise=0.05,
 
 
 def make_gradient_inputs(scene, backend, seed=0, numder=2, exact_single_scatter=True, singlescatter=False,
-                         costfunc='L2', exact_phase_derivative=False, maxsubgridints=0):
+                         costfunc='L2', exact_phase_derivative=False, maxsubgridints=0, stream_beam=False):
     """Derivative tables for ``numder`` unknowns of the scene.
 
     Unknown 1 is the extinction of species 1 (dext=1 where there is cloud); unknown 2 varies extinction,
@@ -148,21 +148,55 @@ def make_gradient_inputs(scene, backend, seed=0, numder=2, exact_single_scatter=
     gi.normalize()
     optw, iptr, dalbm, dextm, dfj = backend.prepare_deriv_interps(st, pg, gi)
     gi.optinterpwt, gi.interpptr, gi.dalbm, gi.dextm, gi.dfj = optw, iptr, dalbm, dextm, dfj
-    # direct-beam path lists (MAKE_DIRECT -> MAKE_DIRECT_DERIVATIVE)
-    if exact_single_scatter:
-        _, _, c = backend.make_direct(st, pg)
-        dpath, dptr = backend.make_direct_derivative(st, pg, c)
-        gi.longest_path_pts = int(dpath.shape[0])
-        gi.dpath, gi.dptr = dpath, dptr
-    else:
-        gi.longest_path_pts = 1
-        gi.dpath = np.zeros((1, st.npts), np.float32, order='F')
-        gi.dptr = np.zeros((1, st.npts), np.int32, order='F')
+    _beam_lists(gi, st, pg, backend, exact_single_scatter, stream_beam)
     return gi.normalize()
 
 
+_BEAM_NAMES = ['cx', 'cy', 'cz', 'cxinv', 'cyinv', 'czinv', 'epss', 'epsz', 'xdomain', 'ydomain', 'uniformzlev', 'delxd', 'delyd']
+STREAM_BEAM_BYTES = 4 << 30     # dense DPATH/DPTR lists larger than this are not built: the beam walks stream instead
+
+
+def _beam_lists(gi, st, pg, backend, exact_single_scatter, stream_beam):
+    """Direct-beam derivative inputs: the dense lists of MAKE_DIRECT -> MAKE_DIRECT_DERIVATIVE (shdomsub5.f:1553), or --
+    `stream_beam` True, or None and the lists would exceed STREAM_BEAM_BYTES -- only the beam constants, so that the
+    gradient call walks the paths itself (at3d_grad_desc.beam_*; CUDA backend only, the oracle takes the lists)."""
+    gi.longest_path_pts = 1
+    if not exact_single_scatter:
+        gi.dpath = np.zeros((1, st.npts), np.float32, order='F')
+        gi.dptr = np.zeros((1, st.npts), np.int32, order='F')
+        return
+    _, _, c = backend.make_direct(st, pg)
+    if stream_beam is None:
+        stream_beam = 8 * int(c['longest_path_pts']) * int(st.npts) > STREAM_BEAM_BYTES and getattr(backend, '__name__', '').startswith('at3d_b200')
+    if stream_beam:
+        _set_streaming(gi, pg, c)
+        return
+    dpath, dptr = backend.make_direct_derivative(st, pg, c)
+    gi.longest_path_pts = int(dpath.shape[0])
+    gi.dpath, gi.dptr = dpath, dptr
+
+
+def _set_streaming(gi, pg, c):
+    gi.longest_path_pts = int(c['longest_path_pts'])
+    gi.dpath = gi.dptr = None
+    gi.beam_npx, gi.beam_npy, gi.beam_npz = int(pg.npx), int(pg.npy), int(pg.npz)
+    gi.beam_xstart, gi.beam_ystart = float(pg.xstart), float(pg.ystart)
+    gi.beam_zlevels = np.ascontiguousarray(pg.zlevels, np.float32)
+    gi.beam_d = np.array([c[k] for k in _BEAM_NAMES], np.float64)
+    gi.beam_i = np.array([c['ipdirect'], c['di'], c['dj'], c['dk'], c['longest_path_pts']], np.int32)
+
+
+def with_streaming_beam(gi, state, pg, backend):
+    """Copy of ``gi`` without the dense DPATH/DPTR lists: the gradient call walks the direct-beam paths itself
+    (at3d_grad_desc.beam_*; same terms in the same order)."""
+    out = gi.copy()
+    _, _, c = backend.make_direct(state, pg)
+    _set_streaming(out, pg, c)
+    return out
+
+
 def optical_gradient_inputs(state, pg, backend, partder, doexact, dext, dalb, diphasep, dphasewtp, dleg, dphasetab,
-                            extmin, scatmin, exact_single_scatter=True, costfunc='L2', maxsubgridints=0):
+                            extmin, scatmin, exact_single_scatter=True, costfunc='L2', maxsubgridints=0, stream_beam=None):
     """The derivative tables LEVISAPPROX_GRADIENT takes (what at3d.solver.RTE.calculate_microphysical_partial_derivatives
     leaves on the solver, at3d/solver.py:1327-1517) from the partial derivatives of the optical properties on the property
     grid: `partder` [numder] species (1-based) of every unknown, `doexact` [numder] 1 where the phase derivative comes from
@@ -186,19 +220,12 @@ def optical_gradient_inputs(state, pg, backend, partder, doexact, dext, dalb, di
     gi.normalize()
     optw, iptr, dalbm, dextm, dfj = backend.prepare_deriv_interps(st, pg, gi)
     gi.optinterpwt, gi.interpptr, gi.dalbm, gi.dextm, gi.dfj = optw, iptr, dalbm, dextm, dfj
-    if exact_single_scatter:
-        _, _, c = backend.make_direct(st, pg)
-        dpath, dptr = backend.make_direct_derivative(st, pg, c)
-        gi.longest_path_pts = int(dpath.shape[0])
-        gi.dpath, gi.dptr = dpath, dptr
-    else:
-        gi.dpath = np.zeros((1, st.npts), np.float32, order='F')
-        gi.dptr = np.zeros((1, st.npts), np.int32, order='F')
+    _beam_lists(gi, st, pg, backend, exact_single_scatter, stream_beam)
     return gi.normalize()
 
 
 def extinction_gradient_inputs(state, pg, backend, species, extmin, scatmin, exact_single_scatter=True,
-                               costfunc='L2', maxsubgridints=0, variables=None):
+                               costfunc='L2', maxsubgridints=0, variables=None, stream_beam=None):
     """Derivative tables for the optical unknowns "extinction (or single-scattering albedo) of species k" (k in
     `species`, 0-based; `variables` per unknown, default all 'extinction', the unknown of BASELINE.json configs[1]):
     d(extinction)/d(unknown) = 1 on the property grid for 'extinction', d(ssalb)/d(unknown) = 1 for 'ssalb', phase function
@@ -225,7 +252,7 @@ def extinction_gradient_inputs(state, pg, backend, species, extmin, scatmin, exa
         st, pg, backend, [k + 1 for k in species], np.zeros(numder, np.int32), dext, dalb, diphasep, dphasewtp,
         np.zeros((st.nstleg, st.nleg + 1, 1), np.float32, order='F'),
         np.zeros((st.nstphase, 1, st.nscatangle), np.float32, order='F'), extmin, scatmin,
-        exact_single_scatter=exact_single_scatter, costfunc=costfunc, maxsubgridints=maxsubgridints)
+        exact_single_scatter=exact_single_scatter, costfunc=costfunc, maxsubgridints=maxsubgridints, stream_beam=stream_beam)
 
 
 def with_pixels(gi, pix):

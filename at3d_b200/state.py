@@ -66,6 +66,9 @@ GRAD_FIELDS = [
     ('extinctp', P(f32), np.float32), ('albedop', P(f32), np.float32),
     ('dtemp', P(f32), np.float32),
     ('dpath', P(f32), np.float32), ('dptr', P(i32), np.int32),
+    ('beam_npx', i32, None), ('beam_npy', i32, None), ('beam_npz', i32, None),
+    ('beam_xstart', f32, None), ('beam_ystart', f32, None),
+    ('beam_zlevels', P(f32), np.float32), ('beam_d', P(f64), np.float64), ('beam_i', P(i32), np.int32),
 ]
 
 

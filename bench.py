@@ -611,12 +611,15 @@ def main():
     ap.add_argument('--pixels', type=int, default=0, help='pixels per view side (default: per workload)')
     ap.add_argument('--cpu-seconds', type=float, default=12.0)
     ap.add_argument('--no-cpu', action='store_true')
-    ap.add_argument('--render-only', action='store_true',
-                    help='RENDER only (forced for cfg4: DPATH/DPTR of the direct-beam derivative need '
-                         'LONGEST_PATH_PTS x NPTS x 8 B = ~125 GB at 256x256x100, in the reference as well)')
+    ap.add_argument('--render-only', action='store_true', help='RENDER only')
+    ap.add_argument('--stream-beam', action='store_true',
+                    help='streaming direct-beam derivative: no dense DPATH/DPTR lists (forced for cfg4, where they would '
+                         'need LONGEST_PATH_PTS x NPTS x 8 B = ~125 GB at 256x256x100, in the reference as well)')
+    ap.add_argument('--lean', action='store_true', help='gradient step only: skip the side legs (forced for cfg4)')
     args = ap.parse_args()
     if args.workload == 'cfg4':
-        args.render_only = True
+        args.stream_beam = True
+        args.lean = True
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
     local = int(os.environ.get('LOCAL_RANK', 0))
@@ -707,7 +710,7 @@ def main():
             dist.destroy_process_group()
         return
 
-    gi = gradsetup.make_gradient_inputs(sc, B, seed=0, numder=1)
+    gi = gradsetup.make_gradient_inputs(sc, B, seed=0, numder=1, stream_beam=args.stream_beam)
     dev.attach_gradient(gi)
     rad = dev.render(rays)
     pix = gradsetup.make_pixels(st.nstokes, rays.nrays, rad, seed=1)
@@ -845,15 +848,16 @@ def main():
     # ---- RENDER over an ocean surface (BASELINE.json configs[3]: ocean BRDF): every ray that reaches the surface
     # costs 4 x (NANG/2 + 1) evaluations of ocean_brdf_sw in surface_kernel ----
     from at3d_b200 import synthetic as S
-    devo = DeviceState(S.with_brdf_surface(st, 'O' if st.nstokes == 1 else 'W', seed=2, wavelen=0.66))
-    oms = []
-    for i in range(args.warmup + args.steps):
-        l2flush.zero_()
-        o = devo.render(dr, out=rsout, stream=stream, timing=True)
-        if i >= args.warmup:
-            oms.append(o[-1])
-    ocounts = devo.counts()
-    devo.close()
+    oms, ocounts = [], None
+    if not args.lean:
+        devo = DeviceState(S.with_brdf_surface(st, 'O' if st.nstokes == 1 else 'W', seed=2, wavelen=0.66))
+        for i in range(args.warmup + args.steps):
+            l2flush.zero_()
+            o = devo.render(dr, out=rsout, stream=stream, timing=True)
+            if i >= args.warmup:
+                oms.append(o[-1])
+        ocounts = devo.counts()
+        devo.close()
     peak, peak_src = measured_peak()
     adj_ms = float(np.mean(kms[:, 1]))
     step_kernel_ms = float(np.mean(kms[:, 3]))
@@ -878,10 +882,20 @@ def main():
     cpu = None
     orc = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        rate, sample, _ = cpu_reference_rate(sc, rays, gi, pix, args.cpu_seconds, ncores)
-        cpu = dict(value=rate, unit='rays/s', cores=ncores, kind='port', sample=sample)
+        gi_cpu = gi
+        if gi.dpath is None and gi.exact_single_scatter:
+            # the oracle reads the dense DPATH/DPTR lists, as the reference does: built for it when they fit
+            gi_cpu = (gradsetup.make_gradient_inputs(sc, B, seed=0, numder=1)
+                      if 8 * gi.longest_path_pts * st.npts < gradsetup.STREAM_BEAM_BYTES else None)
+        if gi_cpu is not None:
+            rate, sample, _ = cpu_reference_rate(sc, rays, gi_cpu, pix, args.cpu_seconds, ncores)
+            cpu = dict(value=rate, unit='rays/s', cores=ncores, kind='port', sample=sample)
+        else:
+            cpu = dict(value=None, unit='rays/s', cores=ncores, kind='port',
+                       sample='not run: the reference algorithm needs DPATH/DPTR[%d, %d] (%.0f GB) for this gradient'
+                              % (gi.longest_path_pts, st.npts, 8e-9 * gi.longest_path_pts * st.npts))
         import oracle_lib as orc
-    csrc = compute_source_leg(B, st, args.steps, args.warmup, orc)
+    csrc = compute_source_leg(B, st, args.steps, args.warmup, orc if not args.lean else None)
     if 'kernel_ms' in csrc:
         csrc['frac'] = csrc['achieved_gbs'] / peak
         if cpu is not None and 'cpu_ms' in csrc:
@@ -914,16 +928,19 @@ def main():
             render=dict(rays_per_s=nrays / (np.mean(rms) * 1e-3), kernel_ms=float(np.mean(rms)),
                         achieved_gbs=rbytes / (np.mean(rms) * 1e-3) / 1e9, frac=rbytes / (np.mean(rms) * 1e-3) / 1e9 / peak,
                         algorithmic_bytes=rbytes, counts=rcounts),
-            compute_source=csrc, compute_source_cfg4=compute_source_cfg4_leg(B, max(3, args.steps // 2), 2, peak),
-            transforms=transform_leg(B, st, args.steps, args.warmup),
-            render_orthographic=orthographic_leg(dev, sc, cfg['pixels_per_view'] ** 0.5, args.steps, args.warmup),
-            solver_iteration=solver_leg(max(1, args.steps // 2), 1, orc if args.workload == 'cfg2' else None),
-            path_integration_3d=sweep3d_leg(st, args.steps, 1, orc if args.workload == 'cfg2' else None),
-            inversion_step=inversion_step_leg(sc, rays, gi, pix, DeviceState),
-            render_ocean=dict(rays_per_s=nrays / (np.mean(oms) * 1e-3), kernel_ms=float(np.mean(oms)),
-                              surface_ms=float(np.mean(oms) - np.mean(rms)), surface_hits=ocounts['surface_hits'],
-                              brdf_evals=ocounts['surface_hits'] * 4 * (st.nang // 2 + 1)),
+            compute_source=csrc, beam_derivative='streaming (no DPATH/DPTR lists)' if gi.dpath is None else 'dense DPATH/DPTR lists',
             clocks=cs.summary(), cpu_baseline=cpu, wall_s=wall)
+        if not args.lean:
+            line.update(
+                compute_source_cfg4=compute_source_cfg4_leg(B, max(3, args.steps // 2), 2, peak),
+                transforms=transform_leg(B, st, args.steps, args.warmup),
+                render_orthographic=orthographic_leg(dev, sc, cfg['pixels_per_view'] ** 0.5, args.steps, args.warmup),
+                solver_iteration=solver_leg(max(1, args.steps // 2), 1, orc if args.workload == 'cfg2' else None),
+                path_integration_3d=sweep3d_leg(st, args.steps, 1, orc if args.workload == 'cfg2' else None),
+                inversion_step=inversion_step_leg(sc, rays, gi, pix, DeviceState),
+                render_ocean=dict(rays_per_s=nrays / (np.mean(oms) * 1e-3), kernel_ms=float(np.mean(oms)),
+                                  surface_ms=float(np.mean(oms) - np.mean(rms)), surface_hits=ocounts['surface_hits'],
+                                  brdf_evals=ocounts['surface_hits'] * 4 * (st.nang // 2 + 1)))
         if strong is not None:
             line['strong'] = strong
         print(json.dumps(line))

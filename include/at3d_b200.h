@@ -122,8 +122,18 @@ typedef struct at3d_grad_desc {
     const float *phasewtp;          /* [maxnmicro,maxpg,npart] */
     const float *extinctp, *albedop;/* [maxpg,npart] */
     const float *dtemp;             /* unused (thermal) */
-    const float *dpath;             /* [longest_path_pts,npts] */
+    const float *dpath;             /* [longest_path_pts,npts]; NULL (with dptr) selects the streaming direct-beam term */
     const int32_t *dptr;            /* [longest_path_pts,npts] */
+    /* Streaming direct-beam derivative (exact_single_scatter with dpath == dptr == NULL): instead of reading the dense
+     * lists of MAKE_DIRECT_DERIVATIVE (shdomsub5.f:1553-2004; LONGEST_PATH_PTS x NPTS entries, ~125 GB at 6.5 M points),
+     * the gradient call walks from every grid point with a non-zero beam weight toward the sun through the property grid
+     * and accumulates the same terms in the same order (COMPUTE_DIRECT_BEAM_DERIV_ADJOINT, shdomsub4.f:4117-4143).
+     * beam_d / beam_i are the constants at3d_make_direct returned (out_d[13], out_i[5]). */
+    int32_t beam_npx, beam_npy, beam_npz;
+    float beam_xstart, beam_ystart;
+    const float *beam_zlevels;      /* [beam_npz] property-grid levels */
+    const double *beam_d;           /* [13] */
+    const int32_t *beam_i;          /* [5]  */
 } at3d_grad_desc;
 
 /* Optional per-ray trace of the visited cells (parity tests of the bit-exact indexing). */

@@ -154,6 +154,38 @@ def test_chunked_derivative_pass_matches_single_chunk(oracle, monkeypatch):
     np.testing.assert_allclose(g2, g1, rtol=1e-10, atol=1e-12 * np.max(np.abs(g1)))
 
 
+@pytest.mark.parametrize('case,gkw', [('scalar_periodic_split', dict(numder=2)),
+                                      ('scalar_open_split', dict(numder=3, exact_phase_derivative=True)),
+                                      ('polarized_periodic_split', dict(numder=2)),
+                                      ('rayleigh_two_species', dict(numder=3, exact_phase_derivative=True))])
+def test_streaming_beam_derivative_equals_dense_lists(case, gkw, oracle, monkeypatch):
+    """The streaming direct-beam derivative (no DPATH/DPTR in memory: the gradient call walks toward the sun itself) adds
+    the terms of COMPUTE_DIRECT_BEAM_DERIV_ADJOINT (shdomsub4.f:4117-4143) in the order of the dense lists: the gradient
+    is the same bit for bit, and equal to rounding when the walks run in several passes over point ranges."""
+    from at3d_b200.device import DeviceState
+    from at3d_b200 import gradsetup, backend as B
+    sc = scenes.make(case, oracle)
+    rays = scenes.ray_set(sc, n_persp=6, res=0.04)
+    gi = gradsetup.make_gradient_inputs(sc, oracle, seed=11, **gkw)
+    rad = oracle.render(sc.state, rays)
+    pix = gradsetup.make_pixels(sc.state.nstokes, rays.nrays, rad, seed=5)
+    dev = DeviceState(sc.state)
+    dev.attach_gradient(gi)
+    g1, c1, s1 = dev.gradient(rays, pix)
+    gs = gradsetup.with_streaming_beam(gi, sc.state, sc.pg, B)
+    assert gs.dpath is None and gs.dptr is None
+    dev.attach_gradient(gs)
+    g2, c2, s2 = dev.gradient(rays, pix)
+    monkeypatch.setenv('AT3D_B200_BEAM_PAIRS', '5000')
+    g3, c3, s3 = dev.gradient(rays, pix)
+    dev.close()
+    assert np.max(np.abs(g1)) > 0
+    np.testing.assert_array_equal(g2, g1)
+    np.testing.assert_array_equal(s2, s1)
+    assert float(c2[0]) == float(c1[0])
+    np.testing.assert_allclose(g3, g1, rtol=1e-10, atol=1e-12 * np.max(np.abs(g1)))
+
+
 @pytest.mark.parametrize('case,gkw', [('scalar_open_split', dict(numder=2)), ('polarized_periodic_split', dict(numder=2)),
                                       ('rayleigh_two_species', dict(numder=2))])
 def test_jacobian_path_matches_oracle_single_sweep(case, gkw, oracle):
@@ -182,6 +214,26 @@ def test_jacobian_path_matches_oracle_single_sweep(case, gkw, oracle):
         for idr in range(jref.shape[1]):
             scale = np.max(np.abs(jref[k, idr]))
             np.testing.assert_allclose(jac[k, idr], jref[k, idr], rtol=RTOL, atol=RTOL * scale)
+
+
+def test_streaming_beam_derivative_on_the_jacobian_path(oracle):
+    from at3d_b200.device import DeviceState
+    from at3d_b200 import gradsetup, backend as B
+    sc = scenes.make('scalar_open_split', oracle)
+    rays = scenes.ray_set(sc, n_persp=4, res=0.06)
+    gi = gradsetup.make_gradient_inputs(sc, oracle, seed=11, numder=2)
+    rad = oracle.render(sc.state, rays)
+    pix = gradsetup.make_pixels(sc.state.nstokes, rays.nrays, rad, seed=5)
+    dev = DeviceState(sc.state)
+    dev.attach_gradient(gi)
+    jp = (np.argsort(-np.abs(dev.gradient(rays, pix)[0][:, 0]))[:6] + 1).astype(np.int32)
+    g1, c1, s1, j1 = dev.gradient_jacobian(rays, pix, jp)
+    dev.attach_gradient(gradsetup.with_streaming_beam(gi, sc.state, sc.pg, B))
+    g2, c2, s2, j2 = dev.gradient_jacobian(rays, pix, jp)
+    dev.close()
+    np.testing.assert_array_equal(g2, g1)
+    assert np.max(np.abs(j1)) > 0
+    np.testing.assert_allclose(j2, j1, rtol=1e-5, atol=1e-7 * np.max(np.abs(j1)))
 
 
 @pytest.mark.parametrize('case', ['scalar_periodic_split', 'polarized_periodic_split'])
