@@ -173,6 +173,7 @@ extern "C" int at3d_state_create(const at3d_state_desc *d, at3d_state **out, cha
     UP(iphase, (size_t)S.nq * d->npts * d->npart); UP(phaseinterpwt, (size_t)S.nq * d->npts * d->npart);
     UP(ylmsun, (size_t)d->nstleg * d->nlm);
     UP(sfcgridparms, (size_t)d->nsfcpar * d->nbotpts);
+    if (d->srctype != 'S' && d->temp) UP(temp, d->npts);        // thermal component of the gradient (shdomsub4.f:1792-1799)
 #undef UP
     if (rc) { at3d_state_destroy(st); return rc; }
     // LOFJ (shdomsub1.f:1057-1065)

@@ -68,6 +68,7 @@ struct DevState {
     const float *up_mu, *up_phi;             // [nang/2] upward ordinates (surface-emission interpolation)
     const int *up_src;                       // [nang/2] row of SFCGRIDRAD each upward ordinate reads, or -1
     const float *sfcgridrad;                 // [nang/2+1, nbotpts] or null when identically zero
+    const float *temp;                       // [npts] grid-point temperatures (thermal sources with a gradient), or null
     void *surfhits;                          // SurfHit[nrays] of the current RENDER call (non-Lambertian only)
     int ray_base;                            // index of the launch's first ray in the caller's ray arrays (error reports)
     const float *viewsrc;                    // [npts] SRCEXT of every grid point for the direction shared by all rays of the
@@ -114,6 +115,7 @@ struct DevGrad {
     const float *extinctp, *albedop;        // [maxpg,npart]
     const float *dpath;                     // [longest_path_pts,npts]
     const int *dptr;
+    const float *dtemp;                     // [maxpg,numder] (thermal sources) or null
     int stream_beam;                        // 1: no dense lists, the beam walks run inside the gradient call
     BeamGeom bg;                            // property-grid beam constants (stream_beam)
     const float *bzl;                       // [bg.npz] property-grid levels (stream_beam)

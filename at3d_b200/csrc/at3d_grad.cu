@@ -76,8 +76,23 @@ __global__ void grad_prep_kernel(DevState S, DevGrad G, int4 *rowrec, int4 *spre
     float *legent = prep_smem + (size_t)warp * (nlt + ntup);
     float *dl = legent + nlt;                     // compact DLEGT (or SOURCET table) of the current row
     const bool deltam = S.deltam != 0, interp_new = S.interp_new != 0;
-    const float secmu0 = (float)(1.0 / fabs((double)S.solarmu));
-    const float dirflux = __ldg(&S.dirflux[ipz]);
+    // every solar term carries DIRFLUX*SECMU0 (shdomsub4.f:1996-2007, 2899-2911): none for SRCTYPE='T'
+    const bool solar = S.srctype != 'T', thermal = S.srctype != 'S';
+    const float secmu0 = solar ? (float)(1.0 / fabs((double)S.solarmu)) : 0.0f;
+    const float dirflux = solar ? __ldg(&S.dirflux[ipz]) : 0.0f;
+    // PLANCK / DPLANCK of the grid point (shdomsub4.f:1792-1799; PLANCK_DERIVATIVE :3171-3221, UNITS 'T' | 'R')
+    float planck = 0.0f, dplanck = 0.0f;
+    if (thermal) {
+        const float tk = __ldg(&S.temp[ipz]);
+        planck = dev_planck(tk, S.units, S.wavelen);
+        if (S.units == 'T') dplanck = 1.0f;
+        else if (tk > 0.0f) {
+            const float e = expf(1.4388e4f / (S.wavelen * tk));
+            const float w3 = S.wavelen * S.wavelen * S.wavelen;
+            dplanck = (1.1911e8f * 1.4388e4f) / (w3 * w3) * e / (tk * tk * ((e - 1) * (e - 1)));
+        }
+        if (planck < 1e-7f) dplanck = 0.0f;
+    }
     const int nb_l = lane & 7;
     const int ib_l = __ldg(&G.interpptr[nb_l + 8 * (size_t)ipz]);
     const float xi_l = __ldg(&G.optinterpwt[nb_l + 8 * (size_t)ipz]);
@@ -217,7 +232,7 @@ __global__ void grad_prep_kernel(DevState S, DevGrad G, int4 *rowrec, int4 *spre
             int4 *sp = sprec + ((size_t)ipz * nd + idr) * G.sp_stride;
             int2 *list = (int2 *)(sp + 1);
             int cnt = 0;
-            if (deltam) {
+            if (deltam && solar) {
                 const float sdiv = (scatterj > G.scatmin) ? scatterj : (float)G.scatmin;
                 for (int n = 0; n < 8; n++) {
                     const int ibn = __ldg(&G.interpptr[n + 8 * (size_t)ipz]);
@@ -324,9 +339,16 @@ __global__ void grad_prep_kernel(DevState S, DevGrad G, int4 *rowrec, int4 *spre
                         }
                     }
                 }
+                // thermal component of GRAD8(1,...) (shdomsub4.f:2009-2016): the same for every ray
+                float therm = 0.0f;
+                if (thermal) {
+                    const float dtemp_v = G.dtemp ? __ldg(&G.dtemp[(ib - 1) + (size_t)G.maxpg * idr]) : 0.0f;
+                    therm = xi * (__ldg(&S.extinct[ipz + (size_t)S.npts * (ipa - 1)]) * (1.0f - alb_ip) * dplanck * dtemp_v
+                                  - planck * dalbm_v + planck * (1.0f - alb_ip) * dextm_v);
+                }
                 rw[0] = make_int4(__float_as_int(xi * (alb_ip * dextm_v + dalbm_v)), __float_as_int(cj),
                                   __float_as_int(dextm_v * xi), ib);
-                rw[1] = make_int4(nb | (cnt << 8), 0, 0, 0);
+                rw[1] = make_int4(nb | (cnt << 8), __float_as_int(therm), 0, 0);
             }
             rank++;
         }
@@ -343,7 +365,7 @@ __device__ __forceinline__ void nodeltam_singscat(const DevState &S, int ip, int
     const int nlt = nstleg * (S.nleg + 1);
     const bool interp_new = S.interp_new != 0;
     const float dirflux = __ldg(&S.dirflux[ipz]);
-    const float secmu0 = (float)(1.0 / fabs((double)S.solarmu));
+    const float secmu0 = S.srctype != 'T' ? (float)(1.0 / fabs((double)S.solarmu)) : 0.0f;
     float t[NST];
 #pragma unroll
     for (int k = 0; k < NST; k++) t[k] = 0.0f;
@@ -923,7 +945,7 @@ __device__ __forceinline__ void apply_record(const DevState &S, const DevGrad &G
     const float *dshp = G.dsh + (size_t)(unsigned)gp.z * 32;
     nrh_eval += gp.w >> 8;
     float dirflux = 0.0f, secmu0 = 0.0f;
-    if (!deltam || S.npart > 1) {
+    if ((!deltam || S.npart > 1) && S.srctype != 'T') {
         dirflux = __ldg(&S.dirflux[ipz]);
         secmu0 = (float)(1.0 / fabs((double)S.solarmu));
     }
@@ -1019,6 +1041,7 @@ __device__ __forceinline__ void apply_record(const DevState &S, const DevGrad &G
         v = oct_sum_d(o.m, v);
 #pragma unroll
         for (int k = 0; k < NST; k++) v += adj[k] * (double)(c_src * sourcet[k]);
+        v += adj[0] * (double)__int_as_float(h1.y);             // thermal component (0 for solar sources)
         if (o.ol == 0) {
             const double val = rc.W * v + (double)__int_as_float(h0.z) * rc.G;
             const size_t dst = (size_t)(h0.w - 1) + (size_t)G.maxpg * idr;
@@ -1344,7 +1367,14 @@ extern "C" int at3d_state_attach_gradient(at3d_state *st, const at3d_grad_desc *
     std::lock_guard<std::mutex> lock(st->mu);
     if (!st->S.radrec) { set_msg(errmsg, "the state was created without RADIANCE/RSHPTR: the gradient needs them"); return 1; }
     if (g->numder < 1) { set_msg(errmsg, "NUMDER must be >= 1"); return 1; }
-    if (st->S.srctype != 'S') { set_msg(errmsg, "the gradient is implemented for SRCTYPE='S' (solar) only"); return 3; }
+    const bool solar = st->S.srctype != 'T', thermal = st->S.srctype != 'S';
+    if (thermal) {
+        if (st->S.units == 'B') { set_msg(errmsg, "thermal gradient: band-integrated Planck units (UNITS='B') are not implemented"); return 3; }
+        if (!st->S.temp) { set_msg(errmsg, "thermal gradient: the state was created without TEMP"); return 1; }
+        // surface emission enters FIND_BOUNDARY_RADIANCE_GRAD through SFCGRIDRAD (shdomsub4.f:2274-2290): zero for the
+        // Lambertian surfaces the gradient supports
+        if (st->S.sfcgridrad) { set_msg(errmsg, "thermal gradient: SFCGRIDRAD must be zero"); return 3; }
+    }
     // the reference itself stops here: SURFACE_BRDF_GRAD has no linearisation for W/D/O/R surfaces (surface.f:395-399)
     if (st->S.sfctype1 != 'L') { set_msg(errmsg, "the gradient needs a Lambertian surface (SFCTYPE 'FL','VL')"); return 3; }
     if (g->deriv_maxnmicro > st->S.maxnmicro) { set_msg(errmsg, "DERIV_MAXNMICRO > MAXNMICRO is not supported"); return 3; }
@@ -1358,7 +1388,8 @@ extern "C" int at3d_state_attach_gradient(at3d_state *st, const at3d_grad_desc *
     G.maxpg = g->maxpg; G.numder = g->numder; G.dnumphase = g->dnumphase;
     G.deriv_maxnmicro = g->deriv_maxnmicro; G.pmaxnmicro = S.maxnmicro;
     G.longest_path_pts = g->longest_path_pts;
-    G.exact_single_scatter = g->exact_single_scatter; G.singlescatter = g->singlescatter;
+    // the direct-beam derivative exists for solar sources only (shdomsub4.f:793-794)
+    G.exact_single_scatter = g->exact_single_scatter && solar; G.singlescatter = g->singlescatter;
     const int mx = S.nx > S.ny ? (S.nx > S.nz ? S.nx : S.nz) : (S.ny > S.nz ? S.ny : S.nz);
     G.maxsub = g->maxsubgridints > 50 * mx ? g->maxsubgridints : 50 * mx;
     G.scatmin = g->scatmin;
@@ -1376,8 +1407,9 @@ extern "C" int at3d_state_attach_gradient(at3d_state *st, const at3d_grad_desc *
     GUP(diphasep, (size_t)g->deriv_maxnmicro * mp * nd); GUP(dphasewtp, (size_t)g->deriv_maxnmicro * mp * nd);
     GUP(iphasep, (size_t)S.maxnmicro * mp * S.npart); GUP(phasewtp, (size_t)S.maxnmicro * mp * S.npart);
     GUP(extinctp, mp * S.npart); GUP(albedop, mp * S.npart);
-    const bool stream_beam = g->exact_single_scatter && !g->dpath && !g->dptr;
-    if (g->exact_single_scatter && !stream_beam) { GUP(dpath, (size_t)g->longest_path_pts * np); GUP(dptr, (size_t)g->longest_path_pts * np); }
+    const bool stream_beam = G.exact_single_scatter && !g->dpath && !g->dptr;
+    if (thermal && g->dtemp) GUP(dtemp, mp * nd);
+    if (G.exact_single_scatter && !stream_beam) { GUP(dpath, (size_t)g->longest_path_pts * np); GUP(dptr, (size_t)g->longest_path_pts * np); }
 #undef GUP
     if (rc) return rc;
     if (stream_beam) {
@@ -1404,7 +1436,7 @@ extern "C" int at3d_state_attach_gradient(at3d_state *st, const at3d_grad_desc *
         set_msg(errmsg, "at3d_state_attach_gradient: a required derivative array is NULL");
         return 1;
     }
-    if (g->exact_single_scatter && !G.stream_beam && (!G.dpath || !G.dptr)) { set_msg(errmsg, "EXACT_SINGLE_SCATTER needs DPATH and DPTR (or neither: streaming)"); return 1; }
+    if (G.exact_single_scatter && !G.stream_beam && (!G.dpath || !G.dptr)) { set_msg(errmsg, "EXACT_SINGLE_SCATTER needs DPATH and DPTR (or neither: streaming)"); return 1; }
     // ray-independent tables of COMPUTE_SOURCE_GRAD_1CELL (grad_prep_kernel)
     {
         const bool deltam = S.deltam != 0;
@@ -1664,7 +1696,15 @@ static int gradient_impl(at3d_state *st, const at3d_rays *rays, const at3d_grad_
             bool at_limit = false;
             if (use_t) {
                 // the stream pool is sized by the entries per ray the last call on this state saw
+                // (limit: AT3D_B200_SRC_GB, default 45 % of the memory this pool could get, between 4 and 64 GB)
                 double src_gb = 16.0;
+                {
+                    size_t fr = 0, tot = 0;
+                    if (cudaMemGetInfo(&fr, &tot) == cudaSuccess) {
+                        src_gb = 0.45 * (double)(fr + st->slabs.cap) / 1073741824.0;
+                        src_gb = src_gb < 4.0 ? 4.0 : (src_gb > 64.0 ? 64.0 : src_gb);
+                    }
+                }
                 if (const char *e = getenv("AT3D_B200_SRC_GB")) { const double v = atof(e); if (v > 0.0) src_gb = v; }
                 const double est = st->gw_rec_per_ray > 0.0 ? st->gw_rec_per_ray : (double)(6 * (S.nx + S.ny + S.nz) + 64);
                 src_chunks = (size_t)(((double)n * (est * 1.5 + AT3D_SRC_CHUNK) + 4096.0) / AT3D_SRC_CHUNK);

@@ -10,9 +10,12 @@ What runs where: grid construction and property interpolation follow ``_setup_gr
 (:2036-2520) on the host; ``TRANSFER_PA_TO_GRID`` (property interpolation + delta-M scaling), ``MAKE_DIRECT``, ``YLMALL``, ``PRECOMPUTE_PHASE_CHECK``, the whole ``SOLUTION_ITERATIONS``
 loop -- with the Eddington first guess (``INIT_RADIANCE``) and adaptive cell splitting (``SPLIT_GRID``) for 3-D grids:
 ``at3d_solve_adaptive``; ``at3d_solver_solve`` for independent-pixel grids -- and ``RENDER`` run on the GPU through the
-C ABI.  Not covered (NotImplementedError with the reason): warm starts (``init_solution=False``), cell splitting on
-independent-pixel grids (``ip_flag=3``), thermal sources and non-Lambertian surfaces in this facade (the C ABI has
-them; they need SURFACE_PARM_INTERP / PLANCK tables built by the caller).
+C ABI.  Thermal and combined sources (``srctype`` 'T' / 'B' with an ``atmosphere`` temperature field, optionally a
+horizontally uniform ``gas_absorption`` profile) and the variable surfaces of at3d/surface.py ('VL' Lambertian, 'VW'
+wave-Fresnel, 'VD' Diner, 'VO' ocean, 'VR' RPV: ``sfcparms`` as PREP_SURFACE lays them out) go through the adaptive
+solver, which runs PLANCK / SURFACE_PARM_INTERP itself.  Not covered (NotImplementedError with the reason): warm starts
+(``init_solution=False``), cell splitting, thermal sources and variable surfaces on independent-pixel grids
+(``ip_flag=3``), the Ross-Li surface ('VM'), band-integrated Planck units.
 """
 import numpy as np
 from . import backend as B
@@ -44,8 +47,6 @@ class RTE:
     def __init__(self, numerical_params, medium, source, surface, num_stokes=1, name=None, atmosphere=None):
         if num_stokes not in (1, 3):
             raise NotImplementedError('num_stokes must be 1 or 3 (NSTOKES=4 is not on the path)')
-        if atmosphere is not None:
-            raise NotImplementedError('`atmosphere` (temperature / gas absorption) is only needed by thermal sources')
         self._name = name
         self._nstokes = num_stokes
         self._nstleg = 1 if num_stokes == 1 else 6
@@ -76,21 +77,63 @@ class RTE:
         # ---- source (at3d/solver.py:1847-1888) ----
         self.wavelength = float(_scalar(source, 'wavelength'))
         self._srctype = str(_scalar(source, 'srctype', 'S'))
-        if self._srctype != 'S':
-            raise NotImplementedError("only solar sources (srctype 'S') in this facade")
+        if self._srctype not in ('S', 'T', 'B'):
+            raise ValueError("Invalid source type '%s'" % self._srctype)
+        self._units = str(_scalar(source, 'units', 'R'))
+        if self._units not in ('R', 'T'):
+            raise ValueError("Invalid units '%s' ('R' radiance or 'T' brightness temperature)" % self._units)
         self._solarflux = float(_scalar(source, 'solarflux'))
         self._solarmu = float(_scalar(source, 'solarmu'))
         self._solaraz = float(_scalar(source, 'solaraz'))
-        self._skyrad = float(_scalar(source, 'skyrad', 0.0))
+        self._skyrad = float(_scalar(source, 'skyrad', 0.0))      # a brightness temperature for thermal sources
         if not (-1.0 <= self._solarmu < 0.0):
             raise ValueError('solarmu must be in the range -1.0 <= solarmu < 0.0 (direction of propagation)')
         # ---- surface (:1890-1958) ----
         self._sfctype = str(_scalar(surface, 'sfctype', 'FL'))
-        if self._sfctype != 'FL':
-            raise NotImplementedError("only the fixed Lambertian surface ('FL') in this facade")
+        if self._sfctype not in ('FL', 'VL', 'VW', 'VD', 'VO', 'VR'):
+            raise NotImplementedError("surface type '%s' (supported: FL, VL, VW, VD, VO, VR)" % self._sfctype)
+        if self._sfctype[1] in ('R', 'O') and num_stokes > 1:
+            raise ValueError("surface brdf '%s' is only supported for unpolarized radiative transfer (num_stokes=1)" % self._sfctype)
         self._gndalbedo = float(_scalar(surface, 'gndalbedo'))
         self._gndtemp = float(_scalar(surface, 'gndtemp', 298.15))
+        self._sfcparms = None
+        self._nsfcpar, self._delxsfc, self._delysfc = 2, 0.0, 0.0
+        if self._sfctype[0] == 'V':
+            # SFCPARMS as PREP_SURFACE leaves them (at3d/surface.py:565-660): [nsfcpar, nxsfc+1, nysfc+1], flattened
+            self._nsfcpar = int(_scalar(surface, 'nsfcpar'))
+            nxs, nys = int(_scalar(surface, 'nxsfc')), int(_scalar(surface, 'nysfc'))
+            self._delxsfc, self._delysfc = float(_scalar(surface, 'delxsfc')), float(_scalar(surface, 'delysfc'))
+            sp = np.asarray(_v(surface, 'sfcparms'), np.float32)
+            if sp.size != self._nsfcpar * (nxs + 1) * (nys + 1):
+                raise ValueError('`sfcparms` must hold nsfcpar x (nxsfc+1) x (nysfc+1) values')
+            self._sfcparms = np.asfortranarray(sp.reshape((self._nsfcpar, nxs + 1, nys + 1), order='F'))
         self._setup_grid(next(iter(self.medium.values())))
+        # ---- atmosphere (:1762-1845): temperature for thermal sources, horizontally uniform gas absorption ----
+        self._tempp, self._zckd, self._gasabs = None, None, None
+        if atmosphere is not None:
+            try:
+                tfield = _v(atmosphere, 'temperature')
+            except KeyError:
+                tfield = None
+            if tfield is not None:
+                if tfield.shape != (self._npx, self._npy, self._npz):
+                    raise ValueError('`atmosphere` does not have a consistent grid with the medium')
+                self._tempp = np.ascontiguousarray(tfield, np.float32).reshape(-1)
+            try:
+                gas = _v(atmosphere, 'gas_absorption')
+            except KeyError:
+                gas = None
+            if gas is not None:
+                if not np.all(gas[0, 0] == gas):
+                    raise NotImplementedError('horizontally varying `gas_absorption` (an extra absorbing species in the '
+                                              'reference) is not implemented')
+                self._zckd, self._gasabs = self._zlevels.copy(), np.ascontiguousarray(gas[0, 0], np.float32)
+        if self._srctype != 'S' and self._tempp is None:
+            raise KeyError("'temperature' was not specified in `atmosphere` despite using thermal source.")
+        special = self._srctype != 'S' or self._sfctype != 'FL' or self._gasabs is not None
+        if special and (self._ipflag & 3) == 3:
+            raise NotImplementedError('thermal sources, variable surfaces and gas absorption on independent-pixel grids '
+                                      '(ip_flag=3) are not implemented in this facade')
         self._prepare_optical_properties()
         self._solved = None
         self._dev = None
@@ -190,9 +233,9 @@ class RTE:
             nstokes=nst, nstleg=self._nstleg, nx=self._nx, ny=self._ny, nz=self._nz, npts=npts, ncells=self._ncells,
             ml=self._ml, mm=self._mm, nlm=self._nlm, nleg=t['nleg'], numphase=self._pg.numphase, npart=self._pg.npart,
             maxnmicro=self._pg.maxnmicro, bcflag=self._bcflag, ipflag=self._ipflag, nmu=self._nmu, nphi0max=self._nphi,
-            nang=nang, maxnbc=bcptr.shape[0], ntoppts=ntop, nbotpts=nbot, nsfcpar=2, nscatangle=self._nscatangle,
-            nstphase=1 if nst == 1 else 2, deltam=int(self._deltam), srctype='S', units='R', sfctype0='F', sfctype1='L',
-            interp_new=1, solarmu=self._solarmu, solaraz=self._solaraz, solarflux=self._solarflux,
+            nang=nang, maxnbc=bcptr.shape[0], ntoppts=ntop, nbotpts=nbot, nsfcpar=self._nsfcpar, nscatangle=self._nscatangle,
+            nstphase=1 if nst == 1 else 2, deltam=int(self._deltam), srctype=self._srctype, units=self._units,
+            sfctype0=self._sfctype[0], sfctype1=self._sfctype[1], interp_new=1, solarmu=self._solarmu, solaraz=self._solaraz, solarflux=self._solarflux,
             wavelen=self.wavelength, gndtemp=self._gndtemp, gndalbedo=self._gndalbedo, phasemax=0.999, waveno0=0.0,
             waveno1=0.0, tautol=self._tautol, transcut=self._transcut,
             gridptr=self._gridptr, neighptr=self._neighptr, treeptr=self._treeptr, cellflags=self._cellflags,
@@ -205,7 +248,7 @@ class RTE:
             radiance=np.zeros((nst, 1), np.float32, order='F'), ylmsun=None, phasetab=None,
             planck=np.zeros((npts, self._pg.npart), np.float32, order='F'), temp=None, nphi0=nphi0, mu=mu, phi=phi,
             wtdo=wtdo, skyrad=skyrad, bcptr=bcptr, bcrad=lamb_bc,
-            sfcgridparms=np.zeros((2, nbot), np.float32, order='F'), sfcgridrad=None).normalize()
+            sfcgridparms=np.zeros((self._nsfcpar, nbot), np.float32, order='F'), sfcgridrad=None).normalize()
         st.dirflux, self._extdirp, self._beam = B.make_direct(st, self._pg)
         st.ylmsun = B.ylmall(True, np.float32(st.solarmu), np.float32(st.solaraz), st.ml, st.mm, st.nstleg, st.nlm)
         st.phasetab = B.precompute_phase_check(self._pg.legenp, st.nscatangle, st.nstokes, st.ml, bool(st.deltam))
@@ -244,7 +287,9 @@ class RTE:
                 st, self._pg, self._wtmu, splitacc=self._splitacc, shacc=self._shacc, solacc=self._solacc, maxiter=maxiter,
                 accelflag=self._accelflag, highorderrad=self._highorderrad, iterfixsh=self._iterfixsh,
                 adapt_grid_factor=self._adapt_grid_factor, num_sh_term_factor=self._num_sh_term_factor,
-                cell_to_point_ratio=self._cell_to_point_ratio, transmin=self._transmin, timing=True)
+                cell_to_point_ratio=self._cell_to_point_ratio, transmin=self._transmin, tempp=self._tempp,
+                sfcparms=self._sfcparms, delxsfc=self._delxsfc, delysfc=self._delysfc, zckd=self._zckd, gasabs=self._gasabs,
+                timing=True)
             self._timings = dict(path_integration_ms=ms[0], compute_source_ms=ms[1], split_ms=ms[2], total_ms=ms[3])
             # the solved state carries the split grid and the optical properties on it
             self._npts, self._ncells = sol.npts, sol.ncells
@@ -252,11 +297,14 @@ class RTE:
             self._treeptr, self._cellflags = sol.treeptr, sol.cellflags
             self._t = dict(self._t, extinct=sol.extinct, albedo=sol.albedo, total_ext=sol.total_ext, iphase=sol.iphase,
                            phaseinterpwt=sol.phaseinterpwt)
-            # SKYRAD-free Lambertian boundary radiances are rebuilt by the device state from FLUXES
-            ntop, nbot, bcptr = G.boundary_pnts(sol.npts, sol.gridpos, self._zgrid[0], self._zgrid[-1])
-            sol.bcptr, sol.maxnbc, sol.ntoppts, sol.nbotpts = bcptr, bcptr.shape[0], ntop, nbot
-            sol.bcrad = np.zeros((self._nstokes, ntop + nbot), np.float32, order='F')
-            sol.sfcgridparms = np.zeros((2, nbot), np.float32, order='F')
+            if self._sfctype == 'FL':
+                # SKYRAD-free Lambertian boundary radiances are rebuilt by the device state from FLUXES
+                ntop, nbot, bcptr = G.boundary_pnts(sol.npts, sol.gridpos, self._zgrid[0], self._zgrid[-1])
+                sol.bcptr, sol.maxnbc, sol.ntoppts, sol.nbotpts = bcptr, bcptr.shape[0], ntop, nbot
+                sol.bcrad = np.zeros((self._nstokes, ntop + nbot), np.float32, order='F')
+                sol.sfcgridparms = np.zeros((2, nbot), np.float32, order='F')
+            # variable surfaces keep the solver's boundary lists: SFCGRIDPARMS (SURFACE_PARM_INTERP) and, for the general
+            # BRDFs, the downwelling radiances stored per ordinate in BCRAD, which RENDER integrates
             sol.normalize()
         self._iters = iters
         if verbose:
@@ -290,6 +338,9 @@ class RTE:
         re-evaluated on the loaded grid points, after which `integrate_to_sensor` and `levis_approx_gradient` work without
         a solve."""
         d = input_dataset
+        if self._srctype != 'S' or self._sfctype != 'FL' or self._gasabs is not None:
+            raise NotImplementedError('load_solution with thermal sources, variable surfaces or gas absorption (TEMP / PLANCK / '
+                                      'SFCGRIDPARMS on the loaded grid points) is not implemented: solve() instead')
         if int(_scalar(d, 'nx')) != self._nx or int(_scalar(d, 'ny')) != self._ny or int(_scalar(d, 'nz')) != self._nz:
             raise ValueError('Incompatible grid sizes in the saved solution')
         if (np.any(_v(d, 'xgrid') != self._xgrid[:self._nx1]) or np.any(_v(d, 'ygrid') != self._ygrid[:self._ny1])

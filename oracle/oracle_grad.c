@@ -13,8 +13,13 @@
  *   UPDATE_COSTFUNCTION             shdomsub4.f:13-91
  *   GET_INTERP_KERNEL               /root/reference/src/shdomsub5.f:1497-1536
  *   average_subpixel_rays           /root/reference/src/util.f90:484-518
- * Solar source only (SRCTYPE='S'); the thermal terms (shdomsub4.f:1793-1799,2010-2016) are
- * out of scope.
+ * Solar, thermal and combined sources (SRCTYPE 'S','T','B'; UNITS 'R' or 'T'): the thermal terms are
+ *   PLANCK_DERIVATIVE               shdomsub4.f:3171-3221
+ *   PLANCK / DPLANCK per grid point shdomsub4.f:1792-1799, GRAD8 thermal component :2009-2016
+ *   surface emission (RADEMIS) in FIND_BOUNDARY_RADIANCE_GRAD :2274-2290
+ * With SRCTYPE='T' and delta-M the reference reads SINGSCAT without allocating it (shdomsub4.f:3413-3423 vs
+ * :1811-1824); the values only enter terms that are multiplied out for thermal sources, so here they are simply
+ * evaluated.
  */
 #include <math.h>
 #include <stdio.h>
@@ -117,6 +122,18 @@ static void compute_source_direction(const oracle_state *st, const grad_work *gw
 #undef LEG
 }
 
+/* PLANCK_DERIVATIVE  shdomsub4.f:3171-3221 (UNITS 'T' and 'R'; the band integration of UNITS='B' is not restated) */
+static float planck_derivative(float temp, int units, float wavelen)
+{
+    if (units == 'T') return 1.0f;
+    if (temp > 0.0f) {
+        const float e = expf(1.4388e4f / (wavelen * temp));
+        const float w3 = wavelen * wavelen * wavelen;
+        return (1.1911e8f * 1.4388e4f) / (w3 * w3) * e / (temp * temp * ((e - 1) * (e - 1)));
+    }
+    return 0.0f;
+}
+
 /* COMPUTE_SOURCE_GRAD_1CELL  shdomsub4.f:1546-2042 */
 static void compute_source_grad_1cell(const oracle_state *st, const oracle_grad_in *g, grad_work *gw,
                                       int icell, const float *ylmdir, const float *singscat,
@@ -130,7 +147,9 @@ static void compute_source_grad_1cell(const oracle_state *st, const oracle_grad_
     const int nq = 8 * st->maxnmicro, maxnmicro = st->maxnmicro;
     const int nlt = nstleg * (nleg + 1), numder = g->numder;
     const int solar = (st->srctype == 'S' || st->srctype == 'B');
+    const int thermal = (st->srctype == 'T' || st->srctype == 'B');
     float secmu0 = (float)(1.0 / fabs((double)st->solarmu));
+    float planck = 0.0f, dplanck = 0.0f;
     int n, k, j, l, m, q, ipa, t, idr, nb;
 #define SRC8(kk, nn) srcext8[((kk) - 1) + nstokes * ((nn) - 1)]
 #define OSRC8(kk, nn) osrcext8[((kk) - 1) + nstokes * ((nn) - 1)]
@@ -261,6 +280,12 @@ static void compute_source_grad_1cell(const oracle_state *st, const oracle_grad_
             }
 
             /* ---------------- gradient part (shdomsub4.f:1786-2019) ---------------- */
+            if (thermal) {          /* shdomsub4.f:1792-1799 */
+                const float wn[2] = {st->waveno0, st->waveno1};
+                dplanck = planck_derivative(st->temp[ip - 1], st->units, st->wavelen);
+                planck = oracle_planck_function(st->temp[ip - 1], st->units, wn, st->wavelen);
+                if (planck < 1e-7f) dplanck = 0.0f;
+            }
             last_ipa = -1;
             for (idr = 1; idr <= numder; idr++) {
                 ipa = g->partder[idr - 1];
@@ -438,6 +463,13 @@ static void compute_source_grad_1cell(const oracle_state *st, const oracle_grad_
                                   + dalb_v * (singscatp[k - 1] - singscatj[k - 1]) * EXTP(ib)
                                   + dext_v * (singscatp[k - 1] - singscatj[k - 1]) * ALBP(ib));
                     }
+                    if (thermal) {      /* shdomsub4.f:2009-2016 */
+                        const float dtemp_v = g->dtemp ? g->dtemp[(ib - 1) + (size_t)maxpg * (idr - 1)] : 0.0f;
+                        G8(gw->grad8, 1, nb, n, idr) = G8(gw->grad8, 1, nb, n, idr)
+                            + xi * (st->extinct[(ip - 1) + (size_t)npts * (ipa - 1)] * (1.0f - alb_ip) * dplanck * dtemp_v
+                                    - planck * dalbm_v
+                                    + planck * (1.0f - alb_ip) * dextm_v);
+                    }
                 }
             }
             for (k = 1; k <= nstokes; k++) SS8(k, n) = SS8(k, n) * ext;
@@ -495,9 +527,16 @@ static int find_boundary_radiance_grad(const oracle_state *st, const float *bcra
                 else if (st->sfctype0 == 'F')
                     dirrad[nstokes * j] = opi * st->gndalbedo * st->dirflux[ip - 1];
             }
-            /* RADEMIS (COMPUTE_TOP_RADIANCES_GRAD flag 2) is identically 0 for SRCTYPE='S' */
+            /* RADEMIS (COMPUTE_TOP_RADIANCES_GRAD flag 2 on SFCGRIDRAD, shdomsub4.f:2274-2290): SFCGRIDRAD is zero on
+             * this path (checked by the caller), so the interpolated value is 0 and RADEMIS = 0 ('S','B') or
+             * PLANCK_FUNCTION(0) ('T') */
+            for (k = 0; k < nstokes; k++) rad[j][k] = 0.0f;
+            if (st->srctype == 'T') {
+                const float wn[2] = {st->waveno0, st->waveno1};
+                rad[j][0] = oracle_planck_function(0.0f, st->units, wn, st->wavelen);
+            }
             for (k = 0; k < nstokes; k++)
-                rad[j][k] = 0.0f + bcrad[k + nstokes * (st->ntoppts + ibc - 1)];
+                rad[j][k] = rad[j][k] + bcrad[k + nstokes * (st->ntoppts + ibc - 1)];
         }
     }
     if (x[1] - x[0] > 0.0f) u = (xb - x[0]) / (x[1] - x[0]); else u = 0.0;
@@ -1063,8 +1102,15 @@ int oracle_levisapprox_gradient(const oracle_state *st, const oracle_rays *rays,
         return 3;
     }
     if (st->srctype != 'S') {
-        if (errmsg) snprintf(errmsg, 600, "oracle: only SRCTYPE='S' is restated");
-        return 3;
+        int i_;
+        if (st->units == 'B') { if (errmsg) snprintf(errmsg, 600, "oracle: UNITS='B' is not restated"); return 3; }
+        if (!st->temp) { if (errmsg) snprintf(errmsg, 600, "oracle: thermal gradient needs TEMP"); return 1; }
+        if (st->sfcgridrad)
+            for (i_ = 0; i_ < (st->nang / 2 + 1) * st->nbotpts; i_++)
+                if (st->sfcgridrad[i_] != 0.0f) {
+                    if (errmsg) snprintf(errmsg, 600, "oracle: gradient with SFCGRIDRAD != 0 is not restated");
+                    return 3;
+                }
     }
     if (nthreads < 1) nthreads = 1;
     oracle_lambertian_boundary(st, st->bcrad);
@@ -1250,8 +1296,15 @@ int oracle_levisapprox_jacobian(const oracle_state *st, const oracle_rays *rays,
         return 3;
     }
     if (st->srctype != 'S') {
-        if (errmsg) snprintf(errmsg, 600, "oracle: only SRCTYPE='S' is restated");
-        return 3;
+        int i_;
+        if (st->units == 'B') { if (errmsg) snprintf(errmsg, 600, "oracle: UNITS='B' is not restated"); return 3; }
+        if (!st->temp) { if (errmsg) snprintf(errmsg, 600, "oracle: thermal gradient needs TEMP"); return 1; }
+        if (st->sfcgridrad)
+            for (i_ = 0; i_ < (st->nang / 2 + 1) * st->nbotpts; i_++)
+                if (st->sfcgridrad[i_] != 0.0f) {
+                    if (errmsg) snprintf(errmsg, 600, "oracle: gradient with SFCGRIDRAD != 0 is not restated");
+                    return 3;
+                }
     }
     oracle_lambertian_boundary(st, st->bcrad);
     raygrad = (double *)calloc(nrg, sizeof(double));

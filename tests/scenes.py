@@ -35,7 +35,7 @@ SCENE_CASES = {
 }
 
 
-def make(case, oracle):
-    sc = S.make_scene(**SCENE_CASES[case])
+def make(case, oracle, **overrides):
+    sc = S.make_scene(**dict(SCENE_CASES[case], **overrides))
     oracle.finalize_scene(sc)
     return sc

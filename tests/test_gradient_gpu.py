@@ -13,13 +13,17 @@ pytestmark = pytest.mark.gpu
 RTOL = 1e-4
 
 
-def run_case(oracle, case, gkw, rays_per_pixel=1, trace=True, bright_only=False):
+def run_case(oracle, case, gkw, rays_per_pixel=1, trace=True, bright_only=False, mutate=None, mutate_grad=None, **scene_kw):
     from at3d_b200.device import DeviceState
     from at3d_b200 import gradsetup
     from at3d_b200.state import Rays
-    sc = scenes.make(case, oracle)
+    sc = scenes.make(case, oracle, **scene_kw)
+    if mutate is not None:
+        mutate(sc)
     rays = scenes.ray_set(sc, n_persp=7, res=0.035)
     gi = gradsetup.make_gradient_inputs(sc, oracle, seed=11, **gkw)
+    if mutate_grad is not None:
+        mutate_grad(sc, gi)
     rad = oracle.render(sc.state, rays)
     if bright_only:
         # the log cost function (COSTFUNC='LL') needs I > 0 and a non-zero polarized signal
@@ -152,6 +156,51 @@ def test_chunked_derivative_pass_matches_single_chunk(oracle, monkeypatch):
     assert float(c1[0]) == float(c2[0])
     np.testing.assert_array_equal(s1, s2)
     np.testing.assert_allclose(g2, g1, rtol=1e-10, atol=1e-12 * np.max(np.abs(g1)))
+
+
+THERMAL_CASES = [
+    ('scalar_periodic_split', 'T', 'R', dict(numder=2)),
+    ('scalar_open_split', 'B', 'R', dict(numder=3, exact_phase_derivative=True)),
+    ('scalar_no_deltam', 'T', 'R', dict(numder=2)),
+    ('scalar_no_deltam', 'B', 'R', dict(numder=2)),
+    ('polarized_periodic_split', 'T', 'R', dict(numder=2)),
+    ('rayleigh_two_species', 'B', 'R', dict(numder=3, exact_phase_derivative=True)),
+    ('scalar_nmu16', 'T', 'T', dict(numder=2)),
+]
+
+
+@pytest.mark.parametrize('case,srctype,units,gkw', THERMAL_CASES, ids=['%s-%s%s' % c[:3] for c in THERMAL_CASES])
+def test_thermal_source_gradient_matches_oracle(case, srctype, units, gkw, oracle):
+    """SRCTYPE 'T' (thermal) and 'B' (solar + thermal): PLANCK / PLANCK_DERIVATIVE per grid point and the thermal
+    component of COMPUTE_SOURCE_GRAD_1CELL (shdomsub4.f:1792-1799, 2009-2016, 3171-3221) with a non-zero DTEMP, the
+    Planck sky and the warm Lambertian surface, against the oracle (itself pinned by finite differences,
+    tests/test_oracle_golden.py)."""
+    def mutate(sc):
+        st = sc.state
+        st.srctype, st.units, st.wavelen, st.gndtemp = srctype, units, 10.5, 291.0
+        if srctype == 'T':
+            st.skyrad = np.asfortranarray(2.7 + 200.0 * (st.skyrad / max(float(st.skyrad.max()), 1e-30)))   # sky temperatures [K]
+            st.dirflux = np.zeros_like(st.dirflux)
+        gp = st.gridpos
+        st.temp = (286.0 - 30.0 * gp[2] + 5.0 * np.sin(11.0 * gp[0]) * np.cos(8.0 * gp[1])).astype(np.float32)
+
+    def mutate_grad(sc, gi):
+        gi.dtemp = np.asfortranarray(np.random.default_rng(2).uniform(-1.0, 1.0, gi.dext.shape).astype(np.float32))
+    sc, ref, out = run_case(oracle, case, gkw, mutate=mutate, mutate_grad=mutate_grad, ssalb=0.85)   # absorbing: emits
+    check(ref, out)
+
+
+def test_thermal_gradient_needs_temp(oracle):
+    from at3d_b200.device import DeviceState
+    from at3d_b200 import gradsetup
+    sc = scenes.make('scalar_periodic_split', oracle)
+    gi = gradsetup.make_gradient_inputs(sc, oracle, seed=11, numder=1)
+    sc.state.srctype, sc.state.units, sc.state.wavelen, sc.state.temp = 'T', 'R', 10.5, None
+    dev = DeviceState(sc.state)
+    with pytest.raises(Exception) as e:
+        dev.attach_gradient(gi)
+    assert 'TEMP' in str(e.value)
+    dev.close()
 
 
 @pytest.mark.parametrize('case,gkw', [('scalar_periodic_split', dict(numder=2)),

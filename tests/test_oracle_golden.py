@@ -209,6 +209,87 @@ def test_gradient_is_the_exact_derivative_for_an_absorbing_medium(oracle):
             assert abs(g_rad[ib, 0] - fd['ext']) <= 0.02 * abs(fd['ext']) + 2e-3 * scale, (bc, ib, g_rad[ib, 0], fd)
 
 
+def _planck(temp, wavelen):
+    """PLANCK_FUNCTION, UNITS='R' (shdomsub2.f:4756-4790)."""
+    t = np.asarray(temp, np.float64)
+    return 1.1911e8 / wavelen ** 5 / (np.exp(1.4388e4 / (wavelen * t)) - 1.0)
+
+
+def _set_emitting_fields(sc, temp, wavelen=10.5):
+    """Non-scattering medium with a thermal source: one SH term per point, SOURCE(1) = sqrt(4 pi) * (1 - albedo) * B(T)
+    (CALC_SOURCE_PNT, shdomsub1.f:890-898, with a single species), no solar beam, warm Lambertian surface."""
+    st = sc.state
+    t = M.transfer_pa_to_grid(sc.pg, st.gridpos, st.npts, st.ml, bool(st.deltam))
+    st.extinct, st.albedo, st.total_ext = t['extinct'], t['albedo'], t['total_ext']
+    st.srctype, st.units, st.wavelen, st.gndtemp = 'T', 'R', wavelen, 296.0
+    st.temp = np.asarray(temp, np.float32)
+    st.dirflux = np.zeros(st.npts, np.float32)
+    st.shptr = np.arange(st.npts + 1, dtype=np.int32)
+    st.source = np.asfortranarray((np.sqrt(4 * np.pi) * _planck(st.temp, wavelen))[None, :].astype(np.float32))
+    st.rshptr = np.concatenate([np.arange(st.npts + 1), [st.npts]]).astype(np.int32)
+    st.radiance = np.zeros((1, st.npts), np.float32, order='F')
+    st.planck = np.asfortranarray(_planck(st.temp, wavelen)[:, None].astype(np.float32))
+    st.fluxes = np.zeros_like(st.fluxes)
+    st.skyrad = np.full_like(st.skyrad, 2.7)
+    return st
+
+
+def test_thermal_gradient_is_the_exact_derivative_for_an_emitting_absorbing_medium(oracle):
+    """Thermal source, ssalb=0 (the set-up of the reference's thermal Jacobian tests, tests/test_derivatives.py:334-520,
+    "noscat"): the radiance is the emission integral, the Levis approximation neglects nothing, and the gradient --
+    radiance term plus the thermal component of COMPUTE_SOURCE_GRAD_1CELL (shdomsub4.f:2009-2016, PLANCK_DERIVATIVE
+    :3171) -- must equal finite differences of the oracle's own RENDER + cost, for an extinction unknown and for a
+    temperature unknown (DTEMP)."""
+    from at3d_b200 import gradsetup
+    for bc in ('open', 'periodic'):
+        sc = _absorbing_scene(oracle, ext=5.0, seed=4, cloud='slab', bc=bc)
+        rng = np.random.default_rng(3)
+        sc.pg.extinctp[:, 0] *= rng.uniform(0.4, 1.6, sc.pg.maxpg).astype(np.float32)
+        gp = sc.state.gridpos
+        temp = 285.0 - 40.0 * gp[2] + 6.0 * np.sin(9.0 * gp[0]) * np.cos(7.0 * gp[1])
+        st = _set_emitting_fields(sc, temp)
+        m = sc.meta
+        cx, cy = 0.5 * m['xmax'], 0.5 * m['ymax']
+        rays = S.concat_rays([S.orthographic_rays(sc, 0.0, 0.0, 0.03)[0],
+                              S.perspective_rays((cx + 0.5, cy - 0.3, 2.0), (cx, cy, 0.1), 9.0, 9, 9)[0]])
+        gi = gradsetup.make_gradient_inputs(sc, oracle, seed=0, numder=2, exact_single_scatter=False)
+        gi.dext[:, 0] = 1.0; gi.dalb[:] = 0.0; gi.dphasewtp[:] = 0.0       # unknown 1 = extinction everywhere
+        gi.dext[:, 1] = 0.0                                                 # unknown 2 = temperature everywhere
+        gi.partder[:] = 1
+        gi.doexact[:] = 0
+        gi.dtemp = np.zeros((sc.pg.maxpg, 2), np.float32, order='F')
+        gi.dtemp[:, 1] = 1.0
+        gi.optinterpwt, gi.interpptr, gi.dalbm, gi.dextm, gi.dfj = oracle.prepare_deriv_interps(st, sc.pg, gi)
+        rad0 = oracle.render(st, rays)
+        assert rad0.min() > 1.0                                              # W m-2 sr-1 um-1 at 10.5 um
+        pix = gradsetup.make_pixels(1, rays.nrays, rad0, seed=2, noise=0.2)
+
+        def cost_of(state):
+            r = oracle.render(state, rays)[0].astype(np.float64)
+            return 0.5 * np.sum(pix.uncertainties[0, 0] * (r - pix.measurements[0].astype(np.float64)) ** 2)
+        g, c, _ = oracle.levisapprox_gradient(st, rays, gradsetup.with_pixels(gi, pix))
+        assert abs(c - cost_of(st)) <= 1e-5 * abs(c)
+        base = sc.pg.extinctp.copy()
+        for idr, h in ((0, 0.02), (1, 0.05)):
+            scale = np.abs(g[:, idr]).max()
+            assert scale > 0
+            for ib in np.argsort(-np.abs(g[:, idr]))[:5]:
+                cs = []
+                for sgn in (+1, -1):
+                    sc.pg.extinctp = base.copy()
+                    tp = temp.copy()
+                    if idr == 0:
+                        sc.pg.extinctp[ib, 0] += sgn * h
+                    else:       # the grid-point temperatures follow the property-grid value through the trilinear weights
+                        for nb in range(8):
+                            sel = gi.interpptr[nb] == ib + 1
+                            tp[sel] += sgn * h * gi.optinterpwt[nb][sel]
+                    cs.append(cost_of(_set_emitting_fields(sc, tp)))
+                fd = (cs[0] - cs[1]) / (2 * h)
+                assert abs(g[ib, idr] - fd) <= 0.01 * abs(fd) + 2e-3 * scale, (bc, idr, ib, g[ib, idr], fd)
+        sc.pg.extinctp = base.copy()
+
+
 # ------------------------------------------------------------------------------------------
 # Single sweep vs double sweep.  The reference checks its adjoint ("double sweep",
 # ADJOINT_INTEGRATE_1RAY) gradient against its original single-sweep path (GRAD_INTEGRATE_1RAY +

@@ -279,3 +279,105 @@ def test_rte_load_solution_validates_before_mutating():
         a.load_solution(bad)
     assert (a._npts, a._ncells, a._solved.npts) == before
     a.close()
+
+
+def test_rte_thermal_source_solve_render_and_gradient():
+    """A thermal source through the facade (at3d.source.thermal + `atmosphere` temperature, at3d/solver.py:1762-1845):
+    PLANCK on the grid, the thermal solve, RENDER and the Levis gradient with its thermal component -- each against the
+    oracle on the same prepared state."""
+    from at3d_b200.rte import RTE
+    from at3d_b200.state import Rays
+    from at3d_b200 import gradsetup
+    params, medium, source, surface = make_inputs(7, 6, 9, 'periodic', 1, False)
+    medium['cloud']['ssalb'] = np.full_like(medium['cloud']['extinction'], 0.7)
+    source = dict(wavelength=10.5, srctype='T', solarflux=0.0, solarmu=-0.5, solaraz=0.0, skyrad=2.7, units='R')
+    surface = dict(sfctype='FL', gndalbedo=0.03, gndtemp=296.0)
+    c = medium['cloud']
+    X, Y, Z = np.meshgrid(c['x'], c['y'], c['z'], indexing='ij')
+    atmosphere = dict(x=c['x'], y=c['y'], z=c['z'], temperature=(292.0 - 30.0 * Z + 3.0 * np.sin(20.0 * X) * np.cos(15.0 * Y)).astype(np.float32))
+    with pytest.raises(KeyError):
+        RTE(params, medium, source, surface)                          # thermal source without a temperature field
+    rte = RTE(params, medium, source, surface, atmosphere=atmosphere)
+    rte.solve(maxiter=60)
+    st0 = rte._unsolved
+    assert st0.srctype in ('T', ord('T')) and rte.check_solved()
+    ref, iters, solcrit, _ = O.solve_adaptive(st0, rte._pg, rte._wtmu, tempp=rte._tempp, splitacc=0.0, solacc=1e-4, maxiter=60)
+    assert iters == rte.num_iterations
+    np.testing.assert_allclose(rte._solved.temp, ref.temp, rtol=1e-6)
+    np.testing.assert_allclose(rte._solved.planck, ref.planck, rtol=1e-5)
+    np.testing.assert_allclose(rte._solved.fluxes, ref.fluxes, rtol=1e-4, atol=1e-6 * ref.fluxes.max())
+    sensor = make_sensor(0.05 * 7, 0.05 * 6)
+    sensor['stokes'] = np.array([True, False, False, False])
+    out = rte.integrate_to_sensor(dict(sensor))
+    rays = Rays(sensor['ray_x'], sensor['ray_y'], sensor['ray_z'], sensor['ray_mu'], sensor['ray_phi'])
+    refrad = O.render(ref, rays)
+    assert refrad[0].min() > 1.0                                       # W m-2 sr-1 um-1 near 10 um
+    np.testing.assert_allclose(out['I'], refrad[0], rtol=1e-4)
+    obs = rte.average_subpixel_rays(out)
+    npix = obs.shape[1]
+    merged = dict(sensor, rays_per_pixel=np.full(npix, 4, np.int32), stokes_weights=np.ones((1, npix)),
+                  measurement_data=(obs * 1.03).astype(np.float32), uncertainties=np.full((1, 1, npix), 1.0 / (0.02 * obs.max()) ** 2))
+    loss, grad, images = rte.levis_approx_gradient(merged, ['cloud'])
+    gi = gradsetup.extinction_gradient_inputs(rte._solved, rte._pg, O, [0], rte._t['extmin'], rte._t['scatmin'])
+    pix = gradsetup.PixelData(merged['measurement_data'], merged['uncertainties'], merged['rays_per_pixel'],
+                              merged['ray_weight'], merged['stokes_weights'])
+    gref, cref, soref = O.levisapprox_gradient(rte._solved, rays, gradsetup.with_pixels(gi, pix))[:3]
+    assert abs(loss - cref) <= 1e-4 * abs(cref) and loss > 0
+    np.testing.assert_allclose(grad.reshape(-1), gref[:, 0], rtol=1e-4, atol=1e-4 * np.abs(gref).max())
+    rte.close()
+
+
+def test_rte_variable_lambertian_surface_equals_the_fixed_one():
+    """'VL' with uniform parameters is the 'FL' surface: SURFACE_PARM_INTERP + VARIABLE_LAMBERTIAN_BOUNDARY through the
+    facade must reproduce the fixed-Lambertian solve and radiances."""
+    from at3d_b200.rte import RTE
+    params, medium, source, surface = make_inputs(8, 7, 9, 'periodic', 1, False)
+    surface['gndalbedo'] = 0.3
+    fl = RTE(params, medium, source, surface)
+    fl.solve(maxiter=60)
+    nxs, nys = 3, 2
+    sp = np.zeros((2, nxs + 1, nys + 1), np.float32, order='F')
+    sp[0], sp[1] = 298.15, 0.3
+    vsurf = dict(sfctype='VL', gndalbedo=0.3, gndtemp=298.15, nsfcpar=2, nxsfc=nxs, nysfc=nys, delxsfc=0.05 * 8 / nxs,
+                 delysfc=0.05 * 7 / nys, sfcparms=sp.ravel(order='F'))
+    vl = RTE(params, medium, source, vsurf)
+    vl.solve(maxiter=60)
+    assert vl.num_iterations == fl.num_iterations
+    np.testing.assert_allclose(vl._solved.fluxes, fl._solved.fluxes, rtol=1e-5, atol=1e-7)
+    sensor = make_sensor(0.05 * 8, 0.05 * 7)
+    sensor['stokes'] = np.array([True, False, False, False])
+    a, b = fl.integrate_to_sensor(dict(sensor))['I'], vl.integrate_to_sensor(dict(sensor))['I']
+    np.testing.assert_allclose(b, a, rtol=1e-5, atol=1e-7)
+    fl.close(); vl.close()
+
+
+def test_rte_ocean_surface_matches_the_oracle():
+    """'VO' (ocean_unpolarized) through the facade: the solve with the stored downwelling radiances per ordinate and the
+    BRDF integration in RENDER against the oracle on the same prepared state (SFCGRIDPARMS interpolated on the host)."""
+    from at3d_b200.rte import RTE
+    from at3d_b200.state import Rays
+    import shdom_verification as V
+    params, medium, source, surface = make_inputs(7, 6, 9, 'periodic', 1, False)
+    nxs, nys = 2, 2
+    sp = np.zeros((3, nxs + 1, nys + 1), np.float32, order='F')
+    sp[0] = 290.0
+    sp[1] = 4.0 + 3.0 * np.arange(nxs + 1)[:, None] + 1.0 * np.arange(nys + 1)[None, :]      # wind speed [m/s]
+    sp[2] = 0.1 + 0.05 * np.arange(nys + 1)[None, :]                                         # pigment
+    dxs, dys = 0.05 * 7 / nxs, 0.05 * 6 / nys
+    vsurf = dict(sfctype='VO', gndalbedo=0.0, gndtemp=290.0, nsfcpar=3, nxsfc=nxs, nysfc=nys, delxsfc=dxs, delysfc=dys,
+                 sfcparms=sp.ravel(order='F'))
+    rte = RTE(params, medium, source, vsurf)
+    rte.solve(maxiter=60)
+    st0 = rte._unsolved.copy()
+    st0.sfcgridparms = np.asfortranarray(V.surface_parm_interp(st0.bcptr[:, 1], st0.nbotpts, st0.gridpos, sp, dxs, dys))
+    np.testing.assert_allclose(rte._solved.sfcgridparms[:, :st0.nbotpts], st0.sfcgridparms, rtol=1e-6, atol=1e-7)
+    ref, iters, solcrit, _ = O.solve_adaptive(st0, rte._pg, rte._wtmu, splitacc=0.0, solacc=1e-4, maxiter=60)
+    assert iters == rte.num_iterations
+    np.testing.assert_allclose(rte._solved.fluxes, ref.fluxes, rtol=1e-4, atol=1e-7)
+    sensor = make_sensor(0.05 * 7, 0.05 * 6)
+    sensor['stokes'] = np.array([True, False, False, False])
+    out = rte.integrate_to_sensor(dict(sensor))
+    rays = Rays(sensor['ray_x'], sensor['ray_y'], sensor['ray_z'], sensor['ray_mu'], sensor['ray_phi'])
+    refrad = O.render(ref, rays)
+    np.testing.assert_allclose(out['I'], refrad[0], rtol=1e-4, atol=1e-6 * refrad[0].max())
+    rte.close()
