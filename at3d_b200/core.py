@@ -76,6 +76,8 @@ def _state_from_kwargs(kw, with_radiance):
         wtdo=np.asarray(kw['wtdo']).reshape(int(kw['nmu']), -1), skyrad=_skyrad(kw), bcptr=kw['bcptr'],
         bcrad=np.asarray(kw['bcrad'])[:, :_nbcrad(kw)].copy(order='F'),
         sfcgridparms=kw['sfcgridparms'], sfcgridrad=_sfcgridrad(kw))
+    if kw.get('temp') is not None and _ch(kw['srctype']) != 'S':
+        st.temp = np.asarray(kw['temp'], np.float32)[:npts]       # TEMP of LEVISAPPROX_GRADIENT (thermal component)
     if with_radiance:
         rshptr = np.asarray(kw['rshptr'], np.int32)[:npts + 2]
         st.rshptr = rshptr
@@ -177,7 +179,8 @@ def _grad_from_kwargs(kw, st):
         partder=kw['partder'], doexact=kw['doexact'], dext=kw['dext'], dalb=kw['dalb'], dextm=kw['dextm'],
         dalbm=kw['dalbm'], dfj=kw['dfj'], optinterpwt=kw['optinterpwt'], interpptr=kw['interpptr'], dleg=kw['dleg'],
         dphasetab=kw['dphasetab'], diphasep=kw['diphasep'], dphasewtp=kw['dphasewtp'], iphasep=kw['iphasep'],
-        phasewtp=kw['phasewtp'], extinctp=kw['extinctp'], albedop=kw['albedop'], dpath=kw['dpath'], dptr=kw['dptr']).normalize()
+        phasewtp=kw['phasewtp'], extinctp=kw['extinctp'], albedop=kw['albedop'], dpath=kw['dpath'], dptr=kw['dptr'],
+        dtemp=kw.get('dtemp')).normalize()
 
 
 def levisapprox_gradient(**kw):

@@ -873,6 +873,9 @@ struct at3d_solver {
     int *shptr_d = nullptr, *rshptr_d = nullptr;
     int blocks_resident = 0;
     bool ip = false;            // IPFLAG=3: independent columns (BACK_INT_GRID1D), no sweep order, DOFIELD in place
+    const float *gpos_d = nullptr;      // GRIDPOS and the point records of the sweep (3-D / 2-D grids), rebuilt by update_medium
+    float4 *ptrec_d = nullptr;
+    double transmin = 1.0;
 };
 
 extern "C" int at3d_solver_destroy(at3d_solver *sv)
@@ -1076,6 +1079,7 @@ extern "C" int at3d_solver_create(const at3d_state_desc *d, const float *wtmu, f
                  launch_build_ptrec(npts, gpos, a.total_ext, ptrec, 0) == cudaSuccess && cudaDeviceSynchronize() == cudaSuccess;
     if (!ok) { at3d_solver_destroy(sv); set_msg(errmsg, "device allocation failure"); return 4; }
     lap("uploads, records, tables");
+    sv->gpos_d = gpos; sv->ptrec_d = ptrec; sv->transmin = (double)transmin;
     memset(&w.S, 0, sizeof(w.S));
     w.S.npts = npts; w.S.ncells = d->ncells; w.S.cellrec = cellrec; w.S.ptrec = ptrec;
     int dev = 0, nsm = 148, per_sm = 1;
@@ -1201,6 +1205,39 @@ static int sv_sweep_error(at3d_solver *sv, char *errmsg)
         set_msg(errmsg, "%s", what[err < 6 ? err : 0]);
         return 1;
     }
+    return 0;
+}
+
+// A new medium on the same grid (an optimisation step, at3d/medium.py:1813-1831 rebuilds the solver instead): the
+// extinction, the direct beam and the surface parameters the object keeps are replaced; the topology records, SWEEPING_ORDER,
+// the dependency levels and the sorted sweep plan stay -- with TRANSMIN >= 1 (the at3d default) the walks of BACK_INT_GRID
+// end at the first valid face whatever the extinction, so the plan depends on the grid only.
+extern "C" int at3d_solver_update_medium(at3d_solver *sv, const at3d_state_desc *d, char *errmsg)
+{
+    if (errmsg) errmsg[0] = 0;
+    if (!sv || !d || !d->total_ext || !d->dirflux) { set_msg(errmsg, "null argument"); return 1; }
+    PiArgs &a = sv->a;
+    if (d->npts != sv->npts || d->nstokes != sv->nst || d->ntoppts != a.ntop || d->nbotpts != a.nbot || d->nsfcpar != a.nsfcpar) {
+        set_msg(errmsg, "at3d_solver_update_medium: the state does not have the solver's grid");
+        return 1;
+    }
+    if (!sv->ip && sv->transmin < 1.0) {
+        set_msg(errmsg, "at3d_solver_update_medium: with TRANSMIN < 1 the sweep plan depends on the extinction; create a new solver");
+        return 3;
+    }
+    const size_t npts = (size_t)sv->npts;
+    cudaError_t e = cudaMemcpy((void *)a.total_ext, d->total_ext, npts * sizeof(float), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy((void *)a.dirflux, d->dirflux, npts * sizeof(float), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && d->sfcgridparms && a.sfcgridparms)
+        e = cudaMemcpy((void *)a.sfcgridparms, d->sfcgridparms, (size_t)d->nsfcpar * a.nbot * sizeof(float), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && d->skyrad && a.skyrad)
+        e = cudaMemcpy((void *)a.skyrad, d->skyrad, (size_t)sv->nst * (d->nmu / 2) * d->nphi0max * sizeof(float), cudaMemcpyHostToDevice);
+    a.gndalbedo = d->gndalbedo; a.gndtemp = d->gndtemp;
+    if (e == cudaSuccess && sv->ptrec_d) {
+        e = launch_build_ptrec((int)npts, sv->gpos_d, a.total_ext, sv->ptrec_d, 0);
+        if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    }
+    if (e != cudaSuccess) { set_msg(errmsg, "CUDA error %s in at3d_solver_update_medium", cudaGetErrorString(e)); return 4; }
     return 0;
 }
 

@@ -140,6 +140,17 @@ class SweepSolver:
         buf = _lib.errbuf()
         _lib.check(_lib.lib().at3d_solver_create(C.byref(self._keep), vp(wt), float(transmin), C.byref(self.h), buf), buf)
 
+    def update_medium(self, st):
+        """A new medium on the same grid (`at3d_solver_update_medium`): the sweep order, dependency levels and the sorted
+        sweep plan of the object are kept; only extinction, direct beam and surface parameters are replaced.  `st` is a
+        ShdomState of the solver's grid; the next `solve` reads its optical properties."""
+        if st.npts != self.st.npts or st.ncells != self.st.ncells:
+            raise ValueError('update_medium: the state is on another grid')
+        keep = st.desc()
+        buf = _lib.errbuf()
+        _lib.check(_lib.lib().at3d_solver_update_medium(self.h, C.byref(keep), buf), buf)
+        self.st, self._keep = st, keep
+
     def path_integration(self, shptr, source, rshptr, timing=False):
         st = self.st
         lamb = st.sfctype1 in ('L', ord('L'))

@@ -327,6 +327,11 @@ typedef struct at3d_solver at3d_solver;
  * cell<<3 | corner-1; no device needed. */
 int at3d_sweeping_order(const at3d_state_desc *desc, int32_t *sweepord, char *errmsg);
 int at3d_solver_create(const at3d_state_desc *desc, const float *wtmu, float transmin, at3d_solver **out, char *errmsg);
+/* A new medium on the solver's grid (what an optimisation step changes; the reference rebuilds its solver objects,
+ * at3d/medium.py:1813-1831): TOTAL_EXT, DIRFLUX, SFCGRIDPARMS, SKYRAD, GNDALBEDO / GNDTEMP of `desc` replace the ones the
+ * object holds; topology, sweep order and the sorted sweep plan are kept (TRANSMIN >= 1 only: code 3 otherwise).  The
+ * other optical arrays are read from the desc passed to at3d_solver_solve. */
+int at3d_solver_update_medium(at3d_solver *sv, const at3d_state_desc *desc, char *errmsg);
 int at3d_solver_path_integration(at3d_solver *sv, const int32_t *shptr, const float *source, const int32_t *rshptr,
                                  float *radiance, float *fluxes, float *bcrad, double *kernel_ms, char *errmsg);
 /* SOLUTION_ITERATIONS on a fixed grid (src/polarized/shdomsub1.f:445-822 without SPLIT_GRID; at3d/solver.py:279

@@ -118,6 +118,44 @@ def test_fixed_grid_solve_3d(case):
         np.testing.assert_allclose(out[k], refout[k], rtol=1e-4, atol=1e-6)
 
 
+@pytest.mark.parametrize('case', ['scalar_periodic_split', 'polarized_open', 'rayleigh_two_species'])
+def test_solver_update_medium_equals_a_fresh_solver(case):
+    """at3d_solver_update_medium: a live solver object (sweep order, dependency levels, sorted plan kept) given another
+    medium on its grid must solve exactly like a solver created for that medium."""
+    sc = scenes.make(case, O)
+    st = sc.state
+    w = wtmu_of(st)
+    st2 = st.copy()
+    st2.extinct = np.asfortranarray(st.extinct * np.float32(1.7))
+    st2.total_ext = st2.extinct.sum(axis=1).astype(np.float32)
+    st2.albedo = np.asfortranarray(st.albedo * np.float32(0.93))
+    st2.dirflux = (st.dirflux ** np.float32(1.7)).astype(np.float32)
+    st2.gndalbedo = 0.5 * st.gndalbedo + 0.2
+    st2.normalize()
+    sv = solver.SweepSolver(st, w)
+    a, ia, _, _ = sv.solve(solacc=1e-4, maxiter=50)
+    sv.update_medium(st2)
+    b, ib, cb, _ = sv.solve(solacc=1e-4, maxiter=50)
+    sv.close()
+    fresh = solver.SweepSolver(st2, w)
+    c, ic, cc, _ = fresh.solve(solacc=1e-4, maxiter=50)
+    fresh.close()
+    assert ib == ic and cb == cc
+    np.testing.assert_array_equal(b.shptr, c.shptr)
+    np.testing.assert_array_equal(b.source, c.source)
+    np.testing.assert_array_equal(b.radiance, c.radiance)
+    np.testing.assert_array_equal(b.fluxes, c.fluxes)
+    np.testing.assert_array_equal(b.bcrad, c.bcrad)
+    assert np.abs(a.fluxes - b.fluxes).max() > 1e-3 * np.abs(a.fluxes).max()        # it is another solution
+    with pytest.raises(Exception) as e:
+        sv = solver.SweepSolver(st, w, 0.5)
+        try:
+            sv.update_medium(st2)
+        finally:
+            sv.close()
+    assert 'TRANSMIN' in str(e.value)
+
+
 @pytest.mark.parametrize('case,kw', [('scalar_open_split', dict()), ('polarized_periodic_split', dict(shacc=0.003)),
                                      ('rayleigh_two_species', dict(accelflag=False)),
                                      ('scalar_nmu16', dict(highorderrad=True, iterfixsh=3))])
