@@ -19,7 +19,9 @@
  *   surface emission (RADEMIS) in FIND_BOUNDARY_RADIANCE_GRAD :2274-2290
  * With SRCTYPE='T' and delta-M the reference reads SINGSCAT without allocating it (shdomsub4.f:3413-3423 vs
  * :1811-1824); the values only enter terms that are multiplied out for thermal sources, so here they are simply
- * evaluated.
+ * evaluated.  Likewise LEGENT / F for NPART=1 are only set inside the solar block of COMPUTE_SOURCE_GRAD_1CELL
+ * (:1693-1722) but read by the gradient part (:1835-1840, :1963-1985): undefined for SRCTYPE='T' in the reference,
+ * evaluated as for 'S' / 'B' here (see compute_source_grad_1cell).
  */
 #include <math.h>
 #include <stdio.h>
@@ -122,6 +124,37 @@ static void compute_source_direction(const oracle_state *st, const grad_work *gw
 #undef LEG
 }
 
+/* LEGENT of one species at a grid point: the PHASEINTERPWT mix of the tabulated Legendre series and, with delta-M,
+ * F = LEGENT(1,ML+1) and the division by 1-F  (shdomsub4.f:1700-1722) */
+static void mix_legent(const oracle_state *st, grad_work *gw, const int *iph, const float *pw, float *legent)
+{
+    const int nstleg = st->nstleg, ml = st->ml, nlt = nstleg * (st->nleg + 1), nq = 8 * st->maxnmicro;
+    int t, q, l, k;
+    if (!st->interp_new) {
+        const float *lg = &st->legen[(size_t)nlt * (iph[0] - 1)];
+        for (t = 0; t < nlt; t++) legent[t] = lg[t];
+    } else {
+        if (pw[0] >= st->phasemax) {
+            const float *lg = &st->legen[(size_t)nlt * (iph[0] - 1)];
+            for (t = 0; t < nlt; t++) legent[t] = lg[t];
+        } else {
+            for (t = 0; t < nlt; t++) legent[t] = 0.0f;
+            for (q = 0; q < nq; q++) {
+                const float *lg;
+                if (pw[q] <= 1e-5f) continue;
+                lg = &st->legen[(size_t)nlt * (iph[q] - 1)];
+                for (t = 0; t < nlt; t++) legent[t] = legent[t] + lg[t] * pw[q];
+            }
+        }
+    }
+    if (st->deltam) {
+        gw->f = LT(legent, 1, ml + 1);
+        for (l = 0; l <= ml; l++)
+            for (k = 1; k <= nstleg; k++)
+                LT(legent, k, l) = LT(legent, k, l) / (1 - gw->f);
+    }
+}
+
 /* PLANCK_DERIVATIVE  shdomsub4.f:3171-3221 (UNITS 'T' and 'R'; the band integration of UNITS='B' is not restated) */
 static float planck_derivative(float temp, int units, float wavelen)
 {
@@ -212,29 +245,7 @@ static void compute_source_grad_1cell(const oracle_state *st, const oracle_grad_
                     if (ext == 0.0f) w = 1.0f;
                     else w = st->extinct[(ip - 1) + (size_t)npts * (ipa - 1)] / ext;
                     if (w == 0.0f) continue;
-                    if (!st->interp_new) {
-                        const float *lg = &st->legen[(size_t)nlt * (iph[0] - 1)];
-                        for (t = 0; t < nlt; t++) legent[t] = lg[t];
-                    } else {
-                        if (pw[0] >= st->phasemax) {
-                            const float *lg = &st->legen[(size_t)nlt * (iph[0] - 1)];
-                            for (t = 0; t < nlt; t++) legent[t] = lg[t];
-                        } else {
-                            for (t = 0; t < nlt; t++) legent[t] = 0.0f;
-                            for (q = 0; q < nq; q++) {
-                                const float *lg;
-                                if (pw[q] <= 1e-5f) continue;
-                                lg = &st->legen[(size_t)nlt * (iph[q] - 1)];
-                                for (t = 0; t < nlt; t++) legent[t] = legent[t] + lg[t] * pw[q];
-                            }
-                        }
-                    }
-                    if (st->deltam) {
-                        gw->f = LT(legent, 1, ml + 1);
-                        for (l = 0; l <= ml; l++)
-                            for (k = 1; k <= nstleg; k++)
-                                LT(legent, k, l) = LT(legent, k, l) / (1 - gw->f);
-                    }
+                    mix_legent(st, gw, iph, pw, legent);
                     da = st->albedo[(ip - 1) + (size_t)npts * (ipa - 1)] * st->dirflux[ip - 1] * secmu0 * w;
                     j = 1;
                     for (k = 0; k < 4; k++) truncsingscat[k] = 0.0f;
@@ -277,6 +288,11 @@ static void compute_source_grad_1cell(const oracle_state *st, const oracle_grad_
                 }
                 if (st->deltam)
                     for (k = 1; k <= nstokes; k++) SRC8(k, n) = SRC8(k, n) + SS8(k, n);
+            } else if (npart == 1) {
+                /* The reference sets LEGENT (and F) inside the solar block above only (shdomsub4.f:1693-1722) and then
+                 * uses it for NPART=1 in the gradient part (:1835-1840, :1963-1985): with SRCTYPE='T' it is read
+                 * undefined.  The defined value -- the same mix at this grid point -- is used here and on the GPU. */
+                mix_legent(st, gw, &st->iphase[(size_t)nq * (ip - 1)], &st->phaseinterpwt[(size_t)nq * (ip - 1)], legent);
             }
 
             /* ---------------- gradient part (shdomsub4.f:1786-2019) ---------------- */
