@@ -46,7 +46,7 @@ SYMBOLS = ['at3d_b200_version', 'at3d_device_count', 'at3d_set_device', 'at3d_st
            'at3d_levisapprox_gradient', 'at3d_levisapprox_gradient_jacobian', 'at3d_prepare_deriv_interps', 'at3d_make_direct_derivative',
            'at3d_average_subpixel_rays', 'at3d_update_costfunction', 'at3d_make_direct', 'at3d_state_get_counts',
            'at3d_sh_to_do', 'at3d_do_to_sh', 'at3d_path_integration_ip', 'at3d_solver_create',
-           'at3d_solver_path_integration', 'at3d_solver_solve', 'at3d_solver_update_medium', 'at3d_solver_destroy', 'at3d_sweeping_order', 'at3d_transfer_pa_to_grid', 'at3d_solve_adaptive', 'at3d_compute_source_device', 'at3d_ray_pack_bytes', 'at3d_make_ray_packs']
+           'at3d_solver_path_integration', 'at3d_solver_solve', 'at3d_solver_update_medium', 'at3d_solver_destroy', 'at3d_sweeping_order', 'at3d_transfer_pa_to_grid', 'at3d_solve_adaptive', 'at3d_compute_source_device', 'at3d_ray_pack_bytes', 'at3d_make_ray_packs', 'at3d_trim_memory', 'at3d_set_memory_reuse']
 
 
 class _Missing:

@@ -17,6 +17,31 @@ def _call(fn, *args):
     _lib.check(fn(*args, buf), buf)
 
 
+def memory_reuse(on=True):
+    """Switch the library's memory reuse (`at3d_set_memory_reuse`): freed device memory is kept for the next state / solver
+    object instead of going back to the system.  For loops that build states per step (inversions).  Returns the previous
+    setting; `trim_memory()` releases what is kept."""
+    return bool(_lib.lib().at3d_set_memory_reuse(int(bool(on))))
+
+
+def trim_memory():
+    _lib.lib().at3d_trim_memory()
+
+
+class reusing_memory:
+    """Context manager: memory reuse on inside the block, previous setting (and a trim) afterwards."""
+
+    def __enter__(self):
+        self._was = memory_reuse(True)
+        return self
+
+    def __exit__(self, *exc):
+        memory_reuse(self._was)
+        if not self._was:
+            trim_memory()
+        return False
+
+
 def ylmall(transpose, mu, phi, ml, mm, nstleg, nlm):
     """YLMALL (shdomsub2.f:4244): YR[nstleg,nlm]."""
     yr = np.zeros((nstleg, nlm), np.float32, order='F')

@@ -17,6 +17,7 @@
 // reference's libm so that the decisions ADAPTCRIT > CURSPLITACC agree bit for bit given the same SOURCE.  All new
 // points of a batch have parents that existed before the batch, so their properties (TRILIN_INTERP_PROP, direct beam),
 // radiance and source are evaluated together by kernels after the host pass.
+#include "at3d_mem.h"
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -623,8 +624,8 @@ int adapt_init_radiance(const at3d_state_desc *d, int ld, int ncol, const float 
     const size_t per = (size_t)4 * (2 * (size_t)(d->nz - 1) + 3);
     double *scratch = nullptr;
     int *bad = nullptr;
-    if (cudaMalloc(&scratch, (size_t)blocks * threads * per * sizeof(double)) != cudaSuccess || cudaMalloc(&bad, sizeof(int)) != cudaSuccess) {
-        if (scratch) cudaFree(scratch);
+    if (at3d_malloc(&scratch, (size_t)blocks * threads * per * sizeof(double)) != cudaSuccess || at3d_malloc(&bad, sizeof(int)) != cudaSuccess) {
+        if (scratch) at3d_free(scratch);
         if (errmsg) snprintf(errmsg, 600, "INIT_RADIANCE: device allocation failure"); return 4;
     }
     cudaMemset(bad, 0, sizeof(int));
@@ -632,7 +633,7 @@ int adapt_init_radiance(const at3d_state_desc *d, int ld, int ncol, const float 
     eddington_kernel<<<blocks, threads>>>(a);
     int hbad = 0;
     cudaError_t e = cudaMemcpy(&hbad, bad, sizeof(int), cudaMemcpyDeviceToHost);
-    cudaFree(scratch); cudaFree(bad);
+    at3d_free(scratch); at3d_free(bad);
     if (e != cudaSuccess) { if (errmsg) snprintf(errmsg, 600, "CUDA error %s in INIT_RADIANCE", cudaGetErrorString(e)); return 4; }
     if (hbad) { if (errmsg) snprintf(errmsg, 600, "EDDRTF: singular matrix in TRIDIAG or TAU<0"); return 1; }
     return 0;

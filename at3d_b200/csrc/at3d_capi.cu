@@ -1,9 +1,13 @@
 // at3d_capi.cu -- C-ABI of libat3d_b200.so (include/at3d_b200.h): state residency and RENDER.
+#include "at3d_mem.h"
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <cstdarg>
 #include <cmath>
+#include <mutex>
+#include <vector>
+#include <unordered_set>
 #include "at3d_host.h"
 #include "at3d_ray.cuh"
 
@@ -28,6 +32,196 @@ static void set_msg(char *errmsg, const char *fmt, ...)
 
 extern "C" const char *at3d_b200_version(void) { return "at3d_b200 0.1 (sm_100a)"; }
 
+// ---- device memory (at3d_mem.h).  Default: cudaMalloc / cudaFree.  With memory reuse switched on
+// (at3d_set_memory_reuse(1), or AT3D_B200_POOL_GB > 0 in the environment) the state arrays, derivative tables, solver
+// objects and per-call arenas come from the driver's stream-ordered pool with a release threshold, and the large
+// streaming buffers (DevBuf) are parked in a process-wide cache between owners. ----
+static bool g_pool_ready[64];
+static std::mutex g_pool_mu;
+static std::unordered_set<void *> g_pooled;          // pointers that came from cudaMallocAsync
+static double g_pool_gb = -1.0;                      // < 0: not initialised yet
+
+static double pool_gb()
+{
+    if (g_pool_gb < 0.0) {
+        double gb = 0.0;
+        if (const char *e = getenv("AT3D_B200_POOL_GB")) gb = atof(e);
+        g_pool_gb = gb > 0.0 ? gb : 0.0;
+    }
+    return g_pool_gb;
+}
+
+extern "C" int at3d_set_memory_reuse(int on)
+{
+    std::lock_guard<std::mutex> lock(g_pool_mu);
+    const int was = pool_gb() > 0.0 ? 1 : 0;
+    if (on) { if (g_pool_gb <= 0.0) g_pool_gb = 64.0; }
+    else g_pool_gb = 0.0;
+    for (int i = 0; i < 64; i++) g_pool_ready[i] = false;      // thresholds are set again on the next allocation
+    return was;
+}
+
+static bool pool_setup(int dev)
+{
+    std::lock_guard<std::mutex> lock(g_pool_mu);
+    const double gb = pool_gb();
+    if (gb <= 0.0 || dev < 0 || dev >= 64) return false;
+    if (g_pool_ready[dev]) return true;
+    int supported = 0;
+    cudaDeviceGetAttribute(&supported, cudaDevAttrMemoryPoolsSupported, dev);
+    if (!supported) return false;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) != cudaSuccess) { cudaGetLastError(); return false; }
+    unsigned long long thr = (unsigned long long)(gb * 1073741824.0);
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    g_pool_ready[dev] = true;
+    return true;
+}
+
+cudaError_t at3d_pool_alloc(void **p, size_t bytes)
+{
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!pool_setup(dev)) return cudaMalloc(p, bytes ? bytes : 1);
+    cudaError_t e = cudaMallocAsync(p, bytes ? bytes : 1, (cudaStream_t)0);
+    if (e == cudaErrorMemoryAllocation) {
+        // what the pool keeps may be what is missing: give it back and try once more
+        cudaGetLastError();
+        cudaDeviceSynchronize();
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+        e = cudaMallocAsync(p, bytes ? bytes : 1, (cudaStream_t)0);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)0);      // valid on every stream from here on
+    if (e == cudaSuccess) { std::lock_guard<std::mutex> lock(g_pool_mu); g_pooled.insert(*p); }
+    return e;
+}
+
+cudaError_t at3d_pool_free(void *p)
+{
+    if (!p) return cudaSuccess;
+    bool pooled;
+    { std::lock_guard<std::mutex> lock(g_pool_mu); pooled = g_pooled.erase(p) > 0; }
+    if (!pooled) return cudaFree(p);
+    cudaError_t e = cudaDeviceSynchronize();                               // cudaFree semantics: nothing uses p any more
+    if (e != cudaSuccess) return e;
+    return cudaFreeAsync(p, (cudaStream_t)0);
+}
+
+// ---- the cache of large buffers (DevBuf): cudaMalloc blocks parked between owners ----
+struct BigBlock { void *p; size_t cap; int dev; };
+static std::vector<BigBlock> g_big;
+static size_t g_big_bytes = 0;
+
+static size_t big_limit()
+{
+    const double gb = pool_gb();
+    return gb > 0.0 ? (size_t)(gb * 1073741824.0) : 0;
+}
+
+cudaError_t at3d_big_take(void **p, size_t bytes, size_t *cap)
+{
+    *p = nullptr; *cap = 0;
+    if (bytes == 0) bytes = 1;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    {
+        std::lock_guard<std::mutex> lock(g_pool_mu);
+        int best = -1;
+        for (int i = 0; i < (int)g_big.size(); i++)
+            if (g_big[i].dev == dev && g_big[i].cap >= bytes && (best < 0 || g_big[i].cap < g_big[best].cap)) best = i;
+        // a parked block serves requests down to a quarter of its size (a 16 GB block is not spent on 1 MB)
+        if (best >= 0 && g_big[best].cap / 4 <= bytes + (1 << 20)) {
+            *p = g_big[best].p; *cap = g_big[best].cap;
+            g_big_bytes -= g_big[best].cap;
+            g_big.erase(g_big.begin() + best);
+            return cudaSuccess;
+        }
+    }
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e == cudaErrorMemoryAllocation) {
+        // what is parked (here and in the driver's pool) may be what is missing
+        cudaGetLastError();
+        at3d_trim_memory();
+        e = cudaMalloc(p, bytes);
+    }
+    if (e == cudaSuccess) *cap = bytes;
+    return e;
+}
+
+void at3d_big_park(void *p, size_t cap)
+{
+    if (!p) return;
+    cudaDeviceSynchronize();                          // cudaFree semantics: nothing in flight uses the block any more
+    std::vector<void *> drop;
+    cudaPointerAttributes attr;
+    int dev = 0;
+    if (cudaPointerGetAttributes(&attr, p) == cudaSuccess) dev = attr.device; else cudaGetLastError();
+    {
+        std::lock_guard<std::mutex> lock(g_pool_mu);
+        const size_t limit = big_limit();
+        if (cap > limit) drop.push_back(p);
+        else {
+            g_big.push_back({p, cap, dev});
+            g_big_bytes += cap;
+            while (g_big_bytes > limit && !g_big.empty()) {       // oldest first
+                drop.push_back(g_big.front().p);
+                g_big_bytes -= g_big.front().cap;
+                g_big.erase(g_big.begin());
+            }
+        }
+    }
+    for (void *q : drop) cudaFree(q);
+}
+
+// one parked pinned staging buffer (the per-ray setup records of host rays, 128 B per ray): a state that is destroyed
+// leaves it for the next one instead of cudaFreeHost / cudaMallocHost (~15 ms for the 46 MB of BASELINE configs[1])
+static void *g_pinned_p = nullptr;
+static size_t g_pinned_bytes = 0;
+
+static void pinned_park(void *p, size_t bytes)
+{
+    if (!p) return;
+    void *drop = p;
+    {
+        std::lock_guard<std::mutex> lock(g_pool_mu);
+        if (bytes > g_pinned_bytes) { drop = g_pinned_p; g_pinned_p = p; g_pinned_bytes = bytes; }
+    }
+    if (drop) cudaFreeHost(drop);
+}
+
+static cudaError_t pinned_take(void **p, size_t bytes, size_t *got)
+{
+    {
+        std::lock_guard<std::mutex> lock(g_pool_mu);
+        if (g_pinned_p && g_pinned_bytes >= bytes) {
+            *p = g_pinned_p; *got = g_pinned_bytes;
+            g_pinned_p = nullptr; g_pinned_bytes = 0;
+            return cudaSuccess;
+        }
+    }
+    *got = bytes;
+    return cudaMallocHost(p, bytes);
+}
+
+extern "C" int at3d_trim_memory(void)
+{
+    {
+        void *drop = nullptr;
+        { std::lock_guard<std::mutex> lock(g_pool_mu); drop = g_pinned_p; g_pinned_p = nullptr; g_pinned_bytes = 0; }
+        if (drop) cudaFreeHost(drop);
+        std::vector<BigBlock> big;
+        { std::lock_guard<std::mutex> lock(g_pool_mu); big.swap(g_big); g_big_bytes = 0; }
+        for (auto &b : big) cudaFree(b.p);
+    }
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaMemPool_t pool;
+    if (cudaDeviceSynchronize() != cudaSuccess) return 4;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return cudaMemPoolTrimTo(pool, 0) == cudaSuccess ? 0 : 4;
+}
+
 extern "C" int at3d_device_count(void)
 {
     int n = 0;
@@ -46,7 +240,7 @@ static int upload(at3d_state *st, const T *host, size_t n, const T **dev, char *
     *dev = nullptr;
     if (!host || n == 0) return 0;
     void *p = nullptr;
-    CUDA_TRY(cudaMalloc(&p, n * sizeof(T)));
+    CUDA_TRY(at3d_malloc(&p, n * sizeof(T)));
     st->owned.push_back(p);
     st->bytes += n * sizeof(T);
     CUDA_TRY(cudaMemcpy(p, host, n * sizeof(T), cudaMemcpyHostToDevice));
@@ -59,7 +253,7 @@ static int dalloc(at3d_state *st, size_t n, T **dev, char *errmsg)
 {
     void *p = nullptr;
     if (n == 0) n = 1;
-    CUDA_TRY(cudaMalloc(&p, n * sizeof(T)));
+    CUDA_TRY(at3d_malloc(&p, n * sizeof(T)));
     st->owned.push_back(p);
     st->bytes += n * sizeof(T);
     *dev = (T *)p;
@@ -93,13 +287,13 @@ static int prep_sh_array(at3d_state *st, int tms, const int32_t *shptr_h, const 
     // staging copies of the reference-layout arrays (freed after the re-layout)
     int *shptr_d = nullptr; float *in_d = nullptr;
     size_t nin = (size_t)S.nstokes * (size_t)shptr_h[S.npts];
-    CUDA_TRY(cudaMalloc((void **)&shptr_d, (S.npts + 1) * sizeof(int)));
-    CUDA_TRY(cudaMalloc((void **)&in_d, (nin + 1) * sizeof(float)));
+    CUDA_TRY(at3d_malloc((void **)&shptr_d, (S.npts + 1) * sizeof(int)));
+    CUDA_TRY(at3d_malloc((void **)&in_d, (nin + 1) * sizeof(float)));
     CUDA_TRY(cudaMemcpy(shptr_d, shptr_h, (S.npts + 1) * sizeof(int), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(in_d, sh_h, nin * sizeof(float), cudaMemcpyHostToDevice));
     CUDA_TRY(launch_prep_sh(S, tms, shptr_d, in_d, rec_d, out_d, sscount, ssent, 0));
     CUDA_TRY(cudaDeviceSynchronize());
-    cudaFree(shptr_d); cudaFree(in_d);
+    at3d_free(shptr_d); at3d_free(in_d);
     *rec_out = rec_d; *sh_out = out_d;
     return 0;
 }
@@ -107,11 +301,12 @@ static int prep_sh_array(at3d_state *st, int tms, const int32_t *shptr_h, const 
 extern "C" int at3d_state_destroy(at3d_state *st)
 {
     if (!st) return 0;
-    for (void *p : st->owned) cudaFree(p);
-    for (void *p : st->grad_owned) cudaFree(p);
+    for (void *p : st->owned) at3d_free(p);
+    for (void *p : st->grad_owned) at3d_free(p);
     st->pix.release(); st->work.release();
     st->hits.release(); st->viewsrc.release();
-    if (st->packs_h) cudaFreeHost(st->packs_h);
+    pinned_park(st->packs_h, st->packs_cap * sizeof(RayPack));
+    st->packs_h = nullptr; st->packs_cap = 0;
     st->rays.release(); st->out.release(); st->trace.release(); st->misc.release();
     st->slabs.release(); st->err.release(); st->recs.release(); st->pairs.release();
     delete st;
@@ -245,7 +440,7 @@ extern "C" int at3d_state_create(const at3d_state_desc *d, at3d_state **out, cha
         if (!rc && launch_build_cellrec(d->ncells, gp, np, tp, cf, cellrec, 0) != cudaSuccess) { set_msg(errmsg, "cellrec launch failed"); rc = 4; }
         if (!rc && launch_build_ptrec(d->npts, gpos, text, ptrec, 0) != cudaSuccess) { set_msg(errmsg, "ptrec launch failed"); rc = 4; }
         cudaDeviceSynchronize();
-        for (void *p : tmp.owned) cudaFree(p);
+        for (void *p : tmp.owned) at3d_free(p);
         tmp.owned.clear();
         if (rc) { at3d_state_destroy(st); return rc; }
         S.cellrec = cellrec; S.ptrec = ptrec;
@@ -262,7 +457,7 @@ extern "C" int at3d_state_create(const at3d_state_desc *d, at3d_state **out, cha
         S.bcrad = bc; st->bcrad_dev = bc;
         if (!rc && launch_lambertian_boundary(S, fl, bc, 0) != cudaSuccess) { set_msg(errmsg, "boundary launch failed"); rc = 4; }
         cudaDeviceSynchronize();
-        for (void *p : tmp.owned) cudaFree(p);
+        for (void *p : tmp.owned) at3d_free(p);
         tmp.owned.clear();
         if (!rc && d->bcrad) cudaMemcpy(d->bcrad, bc, st->nbcrad * sizeof(float), cudaMemcpyDeviceToHost);
         if (rc) { at3d_state_destroy(st); return rc; }
@@ -360,10 +555,11 @@ int stage_rays(at3d_state *st, const at3d_rays *rays, cudaStream_t stream, const
     double *dmu = (double *)(dpk + n), *dphi = dmu + n;
     if (n > st->packs_cap) {
         // pinned, so that the copy below is a true asynchronous DMA
-        if (st->packs_h) cudaFreeHost(st->packs_h);
+        pinned_park(st->packs_h, st->packs_cap * sizeof(RayPack));
         st->packs_h = nullptr; st->packs_cap = 0;
-        CUDA_TRY(cudaMallocHost((void **)&st->packs_h, n * sizeof(RayPack)));
-        st->packs_cap = n;
+        size_t got = 0;
+        CUDA_TRY(pinned_take((void **)&st->packs_h, n * sizeof(RayPack), &got));
+        st->packs_cap = got / sizeof(RayPack);
     }
     RayPack *hp = st->packs_h;
     const RayGeom g = st->geom;

@@ -21,6 +21,7 @@
 //    by grad_prep_kernel; DLEGT is folded with the radiance into SH rows XI*DLEGT(l_j)*RADIANCE(.,j),
 //    so the reference's 8*NUMDER COMPUTE_SOURCE_DIRECTION calls per new point become one SH dot
 //    product per non-zero property corner.
+#include "at3d_mem.h"
 #include <cstdio>
 #include <cstring>
 #include <cstdarg>
@@ -1350,7 +1351,7 @@ static int gupload(at3d_state *st, std::vector<void *> &owned, const T *host, si
     *dev = nullptr;
     if (!host || n == 0) return 0;
     void *p = nullptr;
-    CUDA_TRY(cudaMalloc(&p, n * sizeof(T)));
+    CUDA_TRY(at3d_malloc(&p, n * sizeof(T)));
     owned.push_back(p);
     st->bytes += n * sizeof(T);
     CUDA_TRY(cudaMemcpy(p, host, n * sizeof(T), cudaMemcpyHostToDevice));
@@ -1379,7 +1380,7 @@ extern "C" int at3d_state_attach_gradient(at3d_state *st, const at3d_grad_desc *
     if (st->S.sfctype1 != 'L') { set_msg(errmsg, "the gradient needs a Lambertian surface (SFCTYPE 'FL','VL')"); return 3; }
     if (g->deriv_maxnmicro > st->S.maxnmicro) { set_msg(errmsg, "DERIV_MAXNMICRO > MAXNMICRO is not supported"); return 3; }
     // drop a previous attachment
-    for (void *p : st->grad_owned) cudaFree(p);
+    for (void *p : st->grad_owned) at3d_free(p);
     st->grad_owned.clear();
     st->grad_attached = 0;
     DevGrad &G = st->G;
@@ -1468,17 +1469,17 @@ extern "C" int at3d_state_attach_gradient(at3d_state *st, const at3d_grad_desc *
         int4 *rowrec = nullptr, *sprec = nullptr; float *dsh = nullptr, *dlegt = nullptr, *legs = nullptr;
         void *p = nullptr;
         size_t nb_ = (nrows_tot + 1) * G.prow_stride * sizeof(int4);
-        CUDA_TRY(cudaMalloc(&p, nb_)); own.push_back(p); rowrec = (int4 *)p; st->bytes += nb_;
+        CUDA_TRY(at3d_malloc(&p, nb_)); own.push_back(p); rowrec = (int4 *)p; st->bytes += nb_;
         nb_ = np * nd * G.sp_stride * sizeof(int4);
-        CUDA_TRY(cudaMalloc(&p, nb_)); own.push_back(p); sprec = (int4 *)p; st->bytes += nb_;
+        CUDA_TRY(at3d_malloc(&p, nb_)); own.push_back(p); sprec = (int4 *)p; st->bytes += nb_;
         nb_ = (units + 1) * 32 * sizeof(float);
-        CUDA_TRY(cudaMalloc(&p, nb_)); own.push_back(p); dsh = (float *)p; st->bytes += nb_;
+        CUDA_TRY(at3d_malloc(&p, nb_)); own.push_back(p); dsh = (float *)p; st->bytes += nb_;
         if (!deltam) {
             nb_ = (nrows_tot + 1) * G.ntup * sizeof(float);
-            CUDA_TRY(cudaMalloc(&p, nb_)); own.push_back(p); dlegt = (float *)p; st->bytes += nb_;
+            CUDA_TRY(at3d_malloc(&p, nb_)); own.push_back(p); dlegt = (float *)p; st->bytes += nb_;
             if (S.npart > 1) {
                 nb_ = np * nd * G.ntup * sizeof(float);
-                CUDA_TRY(cudaMalloc(&p, nb_)); own.push_back(p); legs = (float *)p; st->bytes += nb_;
+                CUDA_TRY(at3d_malloc(&p, nb_)); own.push_back(p); legs = (float *)p; st->bytes += nb_;
             }
         }
         const int wpb = 4;

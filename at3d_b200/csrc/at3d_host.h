@@ -1,5 +1,6 @@
 // at3d_host.h -- host-side declarations shared by the .cu translation units.
 #pragma once
+#include "at3d_mem.h"
 #include <cuda_runtime.h>
 #include <vector>
 #include <mutex>
@@ -9,20 +10,23 @@
 
 struct RayErr;
 
-// device buffer that grows on demand and is reused between calls
+// device buffer that grows on demand and is reused between calls.  These are the large streaming buffers (source stream,
+// visit records, pairs, ray staging): plain cudaMalloc blocks (contiguous, large pages), parked in a process-wide cache
+// when their owner goes away and taken from it by the next owner (at3d_capi.cu).
+cudaError_t at3d_big_take(void **p, size_t bytes, size_t *cap);
+void at3d_big_park(void *p, size_t cap);
+
 struct DevBuf {
     void *p = nullptr;
     size_t cap = 0;
     cudaError_t reserve(size_t bytes)
     {
         if (bytes <= cap) return cudaSuccess;
-        if (p) cudaFree(p);
+        if (p) at3d_big_park(p, cap);
         p = nullptr; cap = 0;
-        cudaError_t e = cudaMalloc(&p, bytes);
-        if (e == cudaSuccess) cap = bytes;
-        return e;
+        return at3d_big_take(&p, bytes, &cap);
     }
-    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    void release() { if (p) at3d_big_park(p, cap); p = nullptr; cap = 0; }
 };
 
 struct at3d_state {

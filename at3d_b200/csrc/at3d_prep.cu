@@ -4,6 +4,7 @@
 //   at3d_make_direct_derivative  MAKE_DIRECT_DERIVATIVE / DIRECT_BEAM_AND_PATHS_PROP (src/shdomsub5.f:1553-2004)
 // These run once per cost-function evaluation (StateGenerator rebuilds the solvers, medium.py:1813-1831).
 // All three are embarrassingly parallel over grid points / property points: one thread each.
+#include "at3d_mem.h"
 #include <cstdio>
 #include <cstring>
 #include <cstdarg>
@@ -23,11 +24,11 @@ static void set_msg(char *errmsg, const char *fmt, ...)
 namespace {
 struct Arena {      // device allocations of one call
     std::vector<void *> p;
-    ~Arena() { for (void *q : p) cudaFree(q); }
+    ~Arena() { for (void *q : p) at3d_free(q); }
     template <typename T> T *alloc(size_t n)
     {
         void *q = nullptr;
-        if (cudaMalloc(&q, (n ? n : 1) * sizeof(T)) != cudaSuccess) return nullptr;
+        if (at3d_malloc(&q, (n ? n : 1) * sizeof(T)) != cudaSuccess) return nullptr;
         p.push_back(q);
         return (T *)q;
     }

@@ -1,6 +1,7 @@
 // at3d_render.cu -- state preparation kernels and the RENDER kernel (sm_100a).
 // Replaces RENDER / INTEGRATE_1RAY / COMPUTE_SOURCE_1CELL[_UNPOL] / FIND_BOUNDARY_RADIANCE
 // (src/polarized/shdomsub4.f:93-286, shdomsub2.f:2311-3192 of the AT3D reference).
+#include "at3d_mem.h"
 #include <cstring>
 #include "at3d_tray.cuh"
 #include "at3d_host.h"
@@ -491,14 +492,14 @@ cudaError_t launch_build_ptsrc(int npts, int kmax, const int2 *srcrec, const int
                                int ncells, const int4 *cellrec, const float4 *ptrec, int4 *ptsrc, cudaStream_t s)
 {
     int *lit = nullptr;
-    cudaError_t e = cudaMalloc(&lit, sizeof(int) * (size_t)npts);
+    cudaError_t e = at3d_malloc(&lit, sizeof(int) * (size_t)npts);
     if (e != cudaSuccess) return e;
     cudaMemsetAsync(lit, 0, sizeof(int) * (size_t)npts, s);
     mark_lit_kernel<<<(ncells + 255) / 256, 256, 0, s>>>(ncells, cellrec, ptrec, lit);
     build_ptsrc_kernel<<<(npts + 255) / 256, 256, 0, s>>>(npts, kmax, srcrec, sscount, ssent, lit, ptsrc);
     e = cudaGetLastError();
     cudaStreamSynchronize(s);
-    cudaFree(lit);
+    at3d_free(lit);
     return e;
 }
 cudaError_t launch_lambertian_boundary(const DevState &S, const float *fluxes, float *bcrad, cudaStream_t s)

@@ -10,6 +10,7 @@
 // the arithmetic of BACK_INT_GRID1D (DOUBLE PRECISION), carrying the previous level's extinction and source in
 // registers.  The reference's loop over ordinates only carries a dependence through the surface, so all downward
 // ordinates run in one launch, then the surface, then all upward ordinates.
+#include "at3d_mem.h"
 #include <cstdio>
 #include <cstring>
 #include <cstdarg>
@@ -257,11 +258,11 @@ __global__ void pi_brdf_kernel(PiArgs a)
 namespace {
 struct Arena {
     std::vector<void *> ptrs;
-    ~Arena() { for (void *p : ptrs) cudaFree(p); }
+    ~Arena() { for (void *p : ptrs) at3d_free(p); }
     template <typename T> T *alloc(size_t n)
     {
         void *p = nullptr;
-        if (cudaMalloc(&p, (n ? n : 1) * sizeof(T)) != cudaSuccess) return nullptr;
+        if (at3d_malloc(&p, (n ? n : 1) * sizeof(T)) != cudaSuccess) return nullptr;
         ptrs.push_back(p);
         return (T *)p;
     }

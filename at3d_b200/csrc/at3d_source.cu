@@ -9,6 +9,7 @@
 // writes DELSOURCE and the re-packed SOURCE.  One warp per grid point, lanes over the SH index j
 // (coalesced on the CSR arrays); the mixed Legendre table of the point lives in shared memory.
 // HBM-bound: 4*NSTOKES*(2*NR + NS_old [+2*NS accel] + NS_new) bytes per point.
+#include "at3d_mem.h"
 #include <cstdio>
 #include <cstring>
 #include <cstdarg>
@@ -635,11 +636,11 @@ __global__ void cs_reduce_kernel(int nblocks, const double *partials, double *ou
 namespace {
 struct Arena {
     std::vector<void *> p;
-    ~Arena() { for (void *q : p) cudaFree(q); }
+    ~Arena() { for (void *q : p) at3d_free(q); }
     template <typename T> T *alloc(size_t n)
     {
         void *q = nullptr;
-        if (cudaMalloc(&q, (n ? n : 1) * sizeof(T)) != cudaSuccess) return nullptr;
+        if (at3d_malloc(&q, (n ? n : 1) * sizeof(T)) != cudaSuccess) return nullptr;
         p.push_back(q);
         return (T *)q;
     }

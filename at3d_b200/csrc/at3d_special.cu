@@ -2,6 +2,7 @@
 //   at3d_ylmall                  replaces YLMALL / YLMALL_UNPOL (src/polarized/shdomsub2.f:4244-4539)
 //   at3d_precompute_phase_check  replaces PRECOMPUTE_PHASE_CHECK[_GRAD] (shdomsub4.f:2388-2585)
 // Both produce the reference's own array layouts (Fortran order) in HOST memory.
+#include "at3d_mem.h"
 #include <cstdio>
 #include <cstring>
 #include <vector>
@@ -131,11 +132,11 @@ extern "C" int at3d_ylmall(int transpose, float mu, float phi, int ml, int mm, i
     for (int l = 0; l <= ml; l++) nlm += 2 * (l < mm ? l : mm) + 1;
     float *d = nullptr;
     const size_t nb = (size_t)nstleg * nlm * sizeof(float);
-    if (cudaMalloc((void **)&d, nb) != cudaSuccess) { set_msg2(errmsg, "at3d_ylmall: cudaMalloc failed"); return 4; }
+    if (at3d_malloc((void **)&d, nb) != cudaSuccess) { set_msg2(errmsg, "at3d_ylmall: cudaMalloc failed"); return 4; }
     cudaMemset(d, 0, nb);
     ylmall_kernel<<<(mm + 32) / 32, 32>>>(transpose, mu, phi, ml, mm, nstleg, d);
     cudaError_t e = cudaMemcpy(yr, d, nb, cudaMemcpyDeviceToHost);
-    cudaFree(d);
+    at3d_free(d);
     if (e != cudaSuccess) { set_msg2(errmsg, cudaGetErrorString(e)); return 4; }
     return 0;
 }
@@ -208,8 +209,8 @@ extern "C" int at3d_precompute_phase_check(int nscatangle, int numphase, int nst
     float *dl = nullptr, *dt = nullptr; int *bad = nullptr;
     const size_t nl = (size_t)nstleg * (nleg + 1) * numphase, nt = (size_t)nstphase * numphase * nscatangle;
     int rc = 0;
-    if (cudaMalloc((void **)&dl, nl * sizeof(float)) != cudaSuccess || cudaMalloc((void **)&dt, nt * sizeof(float)) != cudaSuccess ||
-        cudaMalloc((void **)&bad, sizeof(int)) != cudaSuccess) { set_msg2(errmsg, "cudaMalloc failed"); rc = 4; }
+    if (at3d_malloc((void **)&dl, nl * sizeof(float)) != cudaSuccess || at3d_malloc((void **)&dt, nt * sizeof(float)) != cudaSuccess ||
+        at3d_malloc((void **)&bad, sizeof(int)) != cudaSuccess) { set_msg2(errmsg, "cudaMalloc failed"); rc = 4; }
     if (!rc) {
         cudaMemcpy(dl, legen, nl * sizeof(float), cudaMemcpyHostToDevice);
         cudaMemset(dt, 0, nt * sizeof(float));
@@ -225,7 +226,7 @@ extern "C" int at3d_precompute_phase_check(int nscatangle, int numphase, int nst
             rc = 1;
         } else if (cudaMemcpy(phasetab, dt, nt * sizeof(float), cudaMemcpyDeviceToHost) != cudaSuccess) { set_msg2(errmsg, "copy back failed"); rc = 4; }
     }
-    cudaFree(dl); cudaFree(dt); cudaFree(bad);
+    at3d_free(dl); at3d_free(dt); at3d_free(bad);
     return rc;
 }
 
@@ -270,16 +271,16 @@ extern "C" int at3d_average_subpixel_rays(int npixels, int nrays, int nstokes, c
     if (at3d_device_count() < 1) { set_msg2(errmsg, "no CUDA device: at3d_b200 has no CPU fallback"); return 4; }
     float *w = nullptr, *o = nullptr; int *pi = nullptr;
     int rc = 0;
-    if (cudaMalloc((void **)&w, (size_t)nstokes * nrays * sizeof(float)) != cudaSuccess ||
-        cudaMalloc((void **)&o, (size_t)nstokes * npixels * sizeof(float)) != cudaSuccess ||
-        cudaMalloc((void **)&pi, (size_t)nrays * sizeof(int)) != cudaSuccess) { set_msg2(errmsg, "cudaMalloc failed"); rc = 4; }
+    if (at3d_malloc((void **)&w, (size_t)nstokes * nrays * sizeof(float)) != cudaSuccess ||
+        at3d_malloc((void **)&o, (size_t)nstokes * npixels * sizeof(float)) != cudaSuccess ||
+        at3d_malloc((void **)&pi, (size_t)nrays * sizeof(int)) != cudaSuccess) { set_msg2(errmsg, "cudaMalloc failed"); rc = 4; }
     if (!rc) {
         cudaMemcpy(w, weighted_stokes, (size_t)nstokes * nrays * sizeof(float), cudaMemcpyHostToDevice);
         cudaMemcpy(pi, pixel_index, (size_t)nrays * sizeof(int), cudaMemcpyHostToDevice);
         average_subpixel_kernel<<<(npixels + 127) / 128, 128>>>(npixels, nrays, nstokes, w, pi, o);
         if (cudaMemcpy(observables, o, (size_t)nstokes * npixels * sizeof(float), cudaMemcpyDeviceToHost) != cudaSuccess) { set_msg2(errmsg, "CUDA error in average_subpixel_kernel"); rc = 4; }
     }
-    cudaFree(w); cudaFree(o); cudaFree(pi);
+    at3d_free(w); at3d_free(o); at3d_free(pi);
     return rc;
 }
 
@@ -337,13 +338,13 @@ extern "C" int at3d_update_costfunction(const double *stokesout, const double *r
     const size_t n = (size_t)maxpg * numder;
     double *rg = nullptr, *go = nullptr;
     int rc = 0;
-    if (cudaMalloc((void **)&rg, n * nstokes * sizeof(double)) != cudaSuccess || cudaMalloc((void **)&go, n * sizeof(double)) != cudaSuccess) { set_msg2(errmsg, "cudaMalloc failed"); rc = 4; }
+    if (at3d_malloc((void **)&rg, n * nstokes * sizeof(double)) != cudaSuccess || at3d_malloc((void **)&go, n * sizeof(double)) != cudaSuccess) { set_msg2(errmsg, "cudaMalloc failed"); rc = 4; }
     if (!rc) {
         cudaMemcpy(rg, raygrad_pixel, n * nstokes * sizeof(double), cudaMemcpyHostToDevice);
         cudaMemcpy(go, gradout, n * sizeof(double), cudaMemcpyHostToDevice);
         update_cost_kernel<<<(unsigned)((n + 255) / 256), 256>>>(n, nstokes, rg, go, w[0], w[1], w[2], w[3]);
         if (cudaMemcpy(gradout, go, n * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess) { set_msg2(errmsg, "CUDA error in update_cost_kernel"); rc = 4; }
     }
-    cudaFree(rg); cudaFree(go);
+    at3d_free(rg); at3d_free(go);
     return rc;
 }

@@ -11,6 +11,7 @@
 // FP32 FMA with both stages fused through shared memory, so HBM sees each SH block and each ordinate value once.
 // A block owns a tile of 32 grid points; lane = point, so every shared-memory access is conflict free (points are
 // the fastest index) and the discrete-ordinate field DOFIELD(NPTS, NSTOKES, NANG) is written/read in 128-byte rows.
+#include "at3d_mem.h"
 #include <cstdio>
 #include <cstring>
 #include <cstdarg>
@@ -456,11 +457,11 @@ struct TrPlan {
     int tcb_kch = 0, tcb_nn = 0, tcb_ring = 0;
     size_t tcb_smem = 0;
     size_t tc_smem = 0;
-    ~TrPlan() { for (void *p : ptrs) cudaFree(p); }
+    ~TrPlan() { for (void *p : ptrs) at3d_free(p); }
     template <typename T> T *alloc(size_t n)
     {
         void *p = nullptr;
-        if (cudaMalloc(&p, (n ? n : 1) * sizeof(T)) != cudaSuccess) return nullptr;
+        if (at3d_malloc(&p, (n ? n : 1) * sizeof(T)) != cudaSuccess) return nullptr;
         ptrs.push_back(p);
         return (T *)p;
     }
@@ -1068,8 +1069,8 @@ static int tr_tc_build(TrPlan *P, char *errmsg)
     std::vector<float> eye((size_t)nlm * nlm, 0.0f);
     for (int i = 0; i < nlm; i++) eye[(size_t)i * nlm + i] = 1.0f;
     int *ptr_d = nullptr; float *eye_d = nullptr, *y_d = nullptr;
-    if (cudaMalloc(&ptr_d, sizeof(int) * (nlm + 1)) != cudaSuccess || cudaMalloc(&eye_d, sizeof(float) * eye.size()) != cudaSuccess ||
-        cudaMalloc(&y_d, sizeof(float) * (size_t)nlm * nang) != cudaSuccess) { set_msg(errmsg, "device allocation failure"); return 4; }
+    if (at3d_malloc(&ptr_d, sizeof(int) * (nlm + 1)) != cudaSuccess || at3d_malloc(&eye_d, sizeof(float) * eye.size()) != cudaSuccess ||
+        at3d_malloc(&y_d, sizeof(float) * (size_t)nlm * nang) != cudaSuccess) { set_msg(errmsg, "device allocation failure"); return 4; }
     cudaMemcpy(ptr_d, ptr.data(), sizeof(int) * (nlm + 1), cudaMemcpyHostToDevice);
     cudaMemcpy(eye_d, eye.data(), sizeof(float) * eye.size(), cudaMemcpyHostToDevice);
     TrArgs a = f;
@@ -1078,7 +1079,7 @@ static int tr_tc_build(TrPlan *P, char *errmsg)
     sh_to_do_kernel_s1<<<ntiles < P->nsm ? ntiles : P->nsm, TR_THREADS, P->smem_fwd + (size_t)a.nlm * 33 * sizeof(float)>>>(a, ntiles);
     std::vector<float> y((size_t)nlm * nang);                       // y[j + nlm*ia]
     cudaError_t e = cudaMemcpy(y.data(), y_d, sizeof(float) * y.size(), cudaMemcpyDeviceToHost);
-    cudaFree(ptr_d); cudaFree(eye_d); cudaFree(y_d);
+    at3d_free(ptr_d); at3d_free(eye_d); at3d_free(y_d);
     if (e != cudaSuccess) { set_msg(errmsg, "CUDA error building the tensor-core basis (%s)", cudaGetErrorString(e)); return 4; }
     std::vector<unsigned char> pack((size_t)nhalves * kch * slotb, 0);
     for (int half = 0; half < nhalves; half++)
@@ -1124,8 +1125,8 @@ static int tr_tc_build_back(TrPlan *P, char *errmsg)
     std::vector<float> eye((size_t)nang * nang, 0.0f);
     for (int i = 0; i < nang; i++) eye[(size_t)i * nang + i] = 1.0f;
     int *ptr_d = nullptr; float *eye_d = nullptr, *w_d = nullptr;
-    if (cudaMalloc(&ptr_d, sizeof(int) * (nang + 1)) != cudaSuccess || cudaMalloc(&eye_d, sizeof(float) * eye.size()) != cudaSuccess ||
-        cudaMalloc(&w_d, sizeof(float) * (size_t)nlm * nang) != cudaSuccess) { set_msg(errmsg, "device allocation failure"); return 4; }
+    if (at3d_malloc(&ptr_d, sizeof(int) * (nang + 1)) != cudaSuccess || at3d_malloc(&eye_d, sizeof(float) * eye.size()) != cudaSuccess ||
+        at3d_malloc(&w_d, sizeof(float) * (size_t)nlm * nang) != cudaSuccess) { set_msg(errmsg, "device allocation failure"); return 4; }
     cudaMemcpy(ptr_d, ptr.data(), sizeof(int) * (nang + 1), cudaMemcpyHostToDevice);
     cudaMemcpy(eye_d, eye.data(), sizeof(float) * eye.size(), cudaMemcpyHostToDevice);
     cudaMemset(w_d, 0, sizeof(float) * (size_t)nlm * nang);
@@ -1135,7 +1136,7 @@ static int tr_tc_build_back(TrPlan *P, char *errmsg)
     do_to_sh_kernel<<<ntiles < P->nsm ? ntiles : P->nsm, TR_THREADS, P->smem_bwd>>>(a, ntiles);
     std::vector<float> w((size_t)nlm * nang);                       // w[j + nlm*ia]
     cudaError_t e = cudaMemcpy(w.data(), w_d, sizeof(float) * w.size(), cudaMemcpyDeviceToHost);
-    cudaFree(ptr_d); cudaFree(eye_d); cudaFree(w_d);
+    at3d_free(ptr_d); at3d_free(eye_d); at3d_free(w_d);
     if (e != cudaSuccess) { set_msg(errmsg, "CUDA error building the tensor-core basis (%s)", cudaGetErrorString(e)); return 4; }
     std::vector<unsigned char> pack((size_t)kch * slotb, 0);
     for (int kc = 0; kc < kch; kc++) {

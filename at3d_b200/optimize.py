@@ -100,7 +100,11 @@ class Optimizer:
                 args['bounds'] = b
             elif len(b) == 1:
                 args['bounds'] = [b[0]] * len(initial_state)
-        return scipy.optimize.minimize(**args)
+        # every evaluation builds new solvers and render states (like the reference): the freed device memory of one
+        # evaluation is kept for the next one while the loop runs
+        from . import backend
+        with backend.reusing_memory():
+            return scipy.optimize.minimize(**args)
 
     @property
     def objective_fn(self):

@@ -176,9 +176,9 @@ class SweepSolver:
         lamb = st.sfctype1 in ('L', ord('L'))
         nbc = st.ntoppts + st.nbotpts * (1 if lamb else 1 + st.nang // 2)
         shptr = np.zeros(npts + 1, np.int32)
-        source = np.zeros((ns, maxiv), np.float32, order='F')
+        source = np.empty((ns, maxiv), np.float32, order='F')              # only [:, :shptr[npts]] is written and kept
         rshptr = np.zeros(npts + 2, np.int32)
-        radiance = np.zeros((ns, maxiv + npts), np.float32, order='F')
+        radiance = np.empty((ns, maxiv + npts), np.float32, order='F')
         fluxes = np.zeros((2, npts), np.float32, order='F')
         bcrad = np.zeros((ns, nbc), np.float32, order='F')
         iters, solcrit = C.c_int32(0), C.c_float(0.0)

@@ -292,7 +292,8 @@ def inversion_step_leg(sc, rays, gi, pix, DeviceState):
     the derivative tables, and the radiance + gradient pass with host buffers; wall-clock ms of each part.  `warm` is the
     next evaluation of the loop: a slightly different medium on the same grid given to the LIVE solver object
     (at3d_solver_update_medium: sweep order, dependency levels and sorted plan kept), solved, uploaded, differentiated."""
-    from at3d_b200 import solver
+    from at3d_b200 import solver, backend
+    was = backend.memory_reuse(True)      # what Optimizer.minimize does: freed device memory stays with the library
     st = sc.state
     delphi = np.float32(2.0 * np.pi) / st.nphi0.astype(np.float32)
     wtmu = (st.wtdo[:, 0] / delphi).astype(np.float32)
@@ -329,7 +330,11 @@ def inversion_step_leg(sc, rays, gi, pix, DeviceState):
     sv.close()
     out['warm'] = dict(update_medium_ms=1e3 * (w1 - w0), solve_ms=1e3 * (w2 - w1), solve_loop_ms=tm2.get('loop_ms'),
                        solve_iterations=iters2, state_upload_ms=1e3 * (w3 - w2), gradient_ms=1e3 * (w4 - w3),
-                       total_ms=1e3 * (w4 - w0), cost=float(cost2[0]))
+                       total_ms=1e3 * (w4 - w0), cost=float(cost2[0]),
+                       note='live solver object (at3d_solver_update_medium) + memory reuse (at3d_set_memory_reuse)')
+    backend.memory_reuse(was)
+    if not was:
+        backend.trim_memory()
     return out
 
 

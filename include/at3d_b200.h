@@ -150,6 +150,14 @@ typedef struct at3d_state at3d_state;   /* opaque: the state resident in HBM */
 const char *at3d_b200_version(void);
 int at3d_device_count(void);
 int at3d_set_device(int device);
+/* Memory reuse for loops that build and drop states (an inversion evaluates a new medium per step; the reference rebuilds
+ * its solvers, at3d/medium.py:1813-1831).  Off (default): cudaMalloc / cudaFree.  On: state arrays, derivative tables,
+ * solver objects and per-call arenas come from the CUDA driver's stream-ordered pool, which keeps up to AT3D_B200_POOL_GB
+ * (default 64) of freed memory reserved, and the large streaming buffers are parked between owners; a destroyed state
+ * hands its memory to the next one.  Returns the previous setting.  AT3D_B200_POOL_GB > 0 in the environment switches it
+ * on from the start.  at3d_trim_memory returns everything that is kept to the system. */
+int at3d_set_memory_reuse(int on);
+int at3d_trim_memory(void);
 
 /* ---- state residency (replaces the per-call array marshalling of f2py) ---- */
 int at3d_state_create(const at3d_state_desc *desc, at3d_state **out, char *errmsg);

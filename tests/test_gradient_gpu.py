@@ -304,3 +304,36 @@ def test_gradient_with_orthographic_views(case, oracle):
     out = dev.gradient(rays, pix, trace_cap=128)
     dev.close()
     check(ref, out)
+
+
+def test_memory_reuse_between_states_changes_nothing(oracle):
+    """at3d_set_memory_reuse: states built and dropped in a loop take their memory from what the previous one left (driver
+    pool + parked buffers); radiances and gradient are those of plain allocation, bit for bit."""
+    from at3d_b200.device import DeviceState
+    from at3d_b200 import gradsetup, backend as B
+    sc = scenes.make('scalar_periodic_split', oracle)
+    rays = scenes.ray_set(sc, n_persp=6, res=0.04)
+    gi = gradsetup.make_gradient_inputs(sc, oracle, seed=11, numder=2)
+    pix = gradsetup.make_pixels(sc.state.nstokes, rays.nrays, oracle.render(sc.state, rays), seed=5)
+
+    def evaluate():
+        dev = DeviceState(sc.state)
+        r = dev.render(rays)
+        dev.attach_gradient(gi)
+        g, c, s = dev.gradient(rays, pix)
+        dev.close()
+        return r, g, float(c[0]), s
+    r0, g0, c0, s0 = evaluate()
+    assert B.memory_reuse(True) is False
+    try:
+        for _ in range(3):
+            r, g, c, s = evaluate()
+            np.testing.assert_array_equal(r, r0)
+            np.testing.assert_array_equal(g, g0)
+            np.testing.assert_array_equal(s, s0)
+            assert c == c0
+    finally:
+        assert B.memory_reuse(False) is True
+        B.trim_memory()
+    r, g, c, s = evaluate()
+    np.testing.assert_array_equal(g, g0)
