@@ -46,7 +46,7 @@ SYMBOLS = ['at3d_b200_version', 'at3d_device_count', 'at3d_set_device', 'at3d_st
            'at3d_levisapprox_gradient', 'at3d_levisapprox_gradient_jacobian', 'at3d_prepare_deriv_interps', 'at3d_make_direct_derivative',
            'at3d_average_subpixel_rays', 'at3d_update_costfunction', 'at3d_make_direct', 'at3d_state_get_counts',
            'at3d_sh_to_do', 'at3d_do_to_sh', 'at3d_path_integration_ip', 'at3d_solver_create',
-           'at3d_solver_path_integration', 'at3d_solver_solve', 'at3d_solver_update_medium', 'at3d_solver_destroy', 'at3d_sweeping_order', 'at3d_transfer_pa_to_grid', 'at3d_solve_adaptive', 'at3d_compute_source_device', 'at3d_ray_pack_bytes', 'at3d_make_ray_packs', 'at3d_trim_memory', 'at3d_set_memory_reuse']
+           'at3d_solver_path_integration', 'at3d_solver_solve', 'at3d_solver_solve_from', 'at3d_solver_update_medium', 'at3d_solver_destroy', 'at3d_sweeping_order', 'at3d_transfer_pa_to_grid', 'at3d_solve_adaptive', 'at3d_compute_source_device', 'at3d_ray_pack_bytes', 'at3d_make_ray_packs', 'at3d_trim_memory', 'at3d_set_memory_reuse']
 
 
 class _Missing:
@@ -120,6 +120,8 @@ def lib():
     L.at3d_solver_create.argtypes = [P(StateDesc), C.c_void_p, f32, P(C.c_void_p), C.c_char_p]
     L.at3d_solver_path_integration.argtypes = [C.c_void_p] * 7 + [P(C.c_double), C.c_char_p]
     L.at3d_solver_solve.argtypes = [C.c_void_p, P(StateDesc), i32, f32, f32, i32, i32, i32, i32] + [C.c_void_p] * 6 + \
+        [P(i32), P(f32), C.c_void_p, C.c_char_p]
+    L.at3d_solver_solve_from.argtypes = [C.c_void_p, P(StateDesc), i32, f32, f32, i32, i32, i32, i32, i32] + [C.c_void_p] * 6 + \
         [P(i32), P(f32), C.c_void_p, C.c_char_p]
     L.at3d_solver_update_medium.argtypes = [C.c_void_p, P(StateDesc), C.c_char_p]
     L.at3d_solver_destroy.argtypes = [C.c_void_p]

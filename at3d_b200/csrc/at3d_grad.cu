@@ -1057,8 +1057,11 @@ __device__ __forceinline__ void apply_record(const DevState &S, const DevGrad &G
     slot += nrows + 1;
 }
 
+#ifndef AT3D_MINB_APPLY
+#define AT3D_MINB_APPLY 6
+#endif
 template <int NST, bool PAIRS>
-__global__ void __launch_bounds__(AT3D_RAY_THREADS)
+__global__ void __launch_bounds__(AT3D_RAY_THREADS, (NST == 1 ? AT3D_MINB_APPLY : 1))
 apply_kernel(DevState S, DevGrad G, int nrays, const float *camx, const float *camy,
              const float *camz, const double *cammu, const double *camphi, const RayPack *packs,
              const int *raypix, const double *adjw, const double *ray_weights, const double *stokes_weights,

@@ -1397,6 +1397,18 @@ extern "C" int at3d_solver_solve(at3d_solver *sv, const at3d_state_desc *d, int 
                                  float *radiance, float *fluxes, float *bcrad, int32_t *iters_out, float *solcrit_out,
                                  double *ms_out /*[3]: PATH_INTEGRATION, COMPUTE_SOURCE, whole loop*/, char *errmsg)
 {
+    return at3d_solver_solve_from(sv, d, maxiter, solacc, shacc, accelflag, highorderrad, iterfixsh, maxiv, 0, shptr, source,
+                                  rshptr, radiance, fluxes, bcrad, iters_out, solcrit_out, ms_out, errmsg);
+}
+
+// restore != 0: the iterations continue from the SHPTR / SOURCE / RSHPTR / RADIANCE passed in -- the solution of a nearby
+// medium on the same grid, what RTE.load_solution + INIT_SOLUTION with INRADFLAG=.FALSE. set up (at3d/solver.py:2654-2666,
+// shdomsub1.f:356-391): no first guess, no first COMPUTE_SOURCE, OSHPTR = SHPTR, DELSOURCE = 0, ITER = 0.
+extern "C" int at3d_solver_solve_from(at3d_solver *sv, const at3d_state_desc *d, int maxiter, float solacc, float shacc,
+                                      int accelflag, int highorderrad, int iterfixsh, int maxiv, int restore, int32_t *shptr,
+                                      float *source, int32_t *rshptr, float *radiance, float *fluxes, float *bcrad,
+                                      int32_t *iters_out, float *solcrit_out, double *ms_out, char *errmsg)
+{
     if (errmsg) errmsg[0] = 0;
     if (!sv || !d || !shptr || !source || !rshptr || !radiance || !fluxes || !bcrad) { set_msg(errmsg, "null argument"); return 1; }
     if (d->npts != sv->npts || d->nstokes != sv->nst) { set_msg(errmsg, "at3d_solver_solve: desc does not match the solver object"); return 1; }
@@ -1465,20 +1477,39 @@ extern "C" int at3d_solver_solve(at3d_solver *sv, const at3d_state_desc *d, int 
     cudaEvent_t ev[4];
     for (auto &x : ev) cudaEventCreate(&x);
     cudaEventRecord(ev[0], 0);
-    // first guess: zero radiance with 4 terms per point, SOURCE from COMPUTE_SOURCE(FIRST=.TRUE.)
     int cur = 0, rcur = 0, rc = 0, total_s = 0, iter = 0, fixsh = 0;
-    sv_iota_kernel<<<(npts + 2 + 255) / 256, 256>>>(npts + 1, 4, rsh[rcur]);
-    cudaMemcpyAsync(rsh[rcur] + npts + 1, rsh[rcur] + npts, sizeof(int), cudaMemcpyDeviceToDevice, 0);
-    cudaMemsetAsync(rad, 0, (size_t)nst * 4 * npts * sizeof(float), 0);
-    cudaMemsetAsync(sh[cur], 0, ((size_t)npts + 1) * sizeof(int), 0);
-    cudaMemsetAsync(osh, 0, ((size_t)npts + 1) * sizeof(int), 0);
     int total_r = 4 * npts;
-    a.first = 1; a.fixsh = 0;
-    a.rshptr = rsh[rcur]; a.radiance = rad; a.shptr_old = sh[cur]; a.oshptr_old = osh; a.source_old = src[cur];
-    a.delsource_old = dels; a.delsource_new = dels;
     size_t cap_new = (size_t)maxiv < (size_t)npts * d->nlm ? (size_t)maxiv : (size_t)npts * d->nlm;
-    rc = cs_device_step(a, nblk, tmp, tmpb, sh[1 - cur], sums, maxiv, cap_new, src[1 - cur], &total_s, false, errmsg);
-    cur = 1 - cur;
+    a.delsource_old = dels; a.delsource_new = dels;
+    if (restore) {
+        // the caller's solution becomes the current one
+        total_s = shptr[npts]; total_r = rshptr[npts];
+        if (total_s < 0 || total_r < 0 || total_s > maxiv || (size_t)total_r > maxir) {
+            set_msg(errmsg, "at3d_solver_solve_from: the restored solution does not fit MAXIV"); rc = 2;
+        } else {
+            cudaMemcpyAsync(sh[cur], shptr, ((size_t)npts + 1) * sizeof(int), cudaMemcpyHostToDevice, 0);
+            cudaMemcpyAsync(rsh[rcur], rshptr, ((size_t)npts + 1) * sizeof(int), cudaMemcpyHostToDevice, 0);
+            cudaMemcpyAsync(rsh[rcur] + npts + 1, rsh[rcur] + npts, sizeof(int), cudaMemcpyDeviceToDevice, 0);
+            cudaMemcpyAsync(src[cur], source, (size_t)nst * total_s * sizeof(float), cudaMemcpyHostToDevice, 0);
+            cudaMemcpyAsync(rad, radiance, (size_t)nst * total_r * sizeof(float), cudaMemcpyHostToDevice, 0);
+            cudaMemsetAsync(osh, 0, ((size_t)npts + 1) * sizeof(int), 0);
+            // the mixed Legendre rows of the optical properties, which the first COMPUTE_SOURCE builds on a cold start
+            a.first = 0; a.fixsh = 0;
+            a.rshptr = rsh[rcur]; a.radiance = rad; a.shptr_old = sh[cur]; a.oshptr_old = osh; a.source_old = src[cur];
+            if (cs_mix_points(a, 0, npts, 0) != cudaSuccess) { set_msg(errmsg, "CUDA error in cs_mix_points"); rc = 4; }
+        }
+    } else {
+        // first guess: zero radiance with 4 terms per point, SOURCE from COMPUTE_SOURCE(FIRST=.TRUE.)
+        sv_iota_kernel<<<(npts + 2 + 255) / 256, 256>>>(npts + 1, 4, rsh[rcur]);
+        cudaMemcpyAsync(rsh[rcur] + npts + 1, rsh[rcur] + npts, sizeof(int), cudaMemcpyDeviceToDevice, 0);
+        cudaMemsetAsync(rad, 0, (size_t)nst * 4 * npts * sizeof(float), 0);
+        cudaMemsetAsync(sh[cur], 0, ((size_t)npts + 1) * sizeof(int), 0);
+        cudaMemsetAsync(osh, 0, ((size_t)npts + 1) * sizeof(int), 0);
+        a.first = 1; a.fixsh = 0;
+        a.rshptr = rsh[rcur]; a.radiance = rad; a.shptr_old = sh[cur]; a.oshptr_old = osh; a.source_old = src[cur];
+        rc = cs_device_step(a, nblk, tmp, tmpb, sh[1 - cur], sums, maxiv, cap_new, src[1 - cur], &total_s, false, errmsg);
+        cur = 1 - cur;
+    }
     if (!rc && accelflag) {
         cudaMemcpyAsync(osh, sh[cur], ((size_t)npts + 1) * sizeof(int), cudaMemcpyDeviceToDevice, 0);
         cudaMemsetAsync(dels, 0, (size_t)nst * total_s * sizeof(float), 0);

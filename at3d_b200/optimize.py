@@ -123,8 +123,10 @@ class GridStateGenerator:
     `numerical_parameters`: key -> mapping; `num_stokes`: key -> int; `mask`: optional boolean [x, y, z] of the grid points
     in the state."""
 
-    def __init__(self, solvers, unknown_scatterers, mediums, sources, surfaces, numerical_parameters, num_stokes, mask=None):
+    def __init__(self, solvers, unknown_scatterers, mediums, sources, surfaces, numerical_parameters, num_stokes, mask=None,
+                 warm_start=True):
         self._solvers, self._unknown = solvers, unknown_scatterers
+        self._warm_start = bool(warm_start)
         self._mediums, self._sources, self._surfaces = mediums, sources, surfaces
         self._params, self._num_stokes = numerical_parameters, num_stokes
         grid = next(iter(next(iter(mediums.values())).values()))
@@ -156,11 +158,19 @@ class GridStateGenerator:
                         sc[v] = arr
                 medium[name] = sc
             old = self._solvers.get(key)
+            previous = None
             if old is not None:
+                # the old solution is the first guess of the new solve (at3d/medium.py:1829-1830), where the facade can
+                # continue from it: fixed grids
+                if self._warm_start and getattr(old, '_solved', None) is not None and old._splitacc == 0.0 \
+                        and old._srctype == 'S' and old._sfctype == 'FL':
+                    previous = old.save_solution()
                 old.close()
             self._mediums[key] = medium
             self._solvers[key] = RTE(self._params[key], medium, self._sources[key], self._surfaces[key],
                                      num_stokes=self._num_stokes[key])
+            if previous is not None:
+                self._solvers[key].load_solution(previous)
 
     def project_gradient_to_state(self, state, gradient_dataset):
         g = np.asarray(gradient_dataset['gradient'])

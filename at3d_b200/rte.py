@@ -10,11 +10,12 @@ What runs where: grid construction and property interpolation follow ``_setup_gr
 (:2036-2520) on the host; ``TRANSFER_PA_TO_GRID`` (property interpolation + delta-M scaling), ``MAKE_DIRECT``, ``YLMALL``, ``PRECOMPUTE_PHASE_CHECK``, the whole ``SOLUTION_ITERATIONS``
 loop -- with the Eddington first guess (``INIT_RADIANCE``) and adaptive cell splitting (``SPLIT_GRID``) for 3-D grids:
 ``at3d_solve_adaptive``; ``at3d_solver_solve`` for independent-pixel grids -- and ``RENDER`` run on the GPU through the
-C ABI.  Thermal and combined sources (``srctype`` 'T' / 'B' with an ``atmosphere`` temperature field, optionally a
+C ABI.  `solve` after `load_solution` (or with ``init_solution=False``) continues the iterations from the loaded / previous
+SOURCE and RADIANCE on that grid (``at3d_solver_solve_from``; fixed grids, ``split_accuracy=0``).  Thermal and combined sources (``srctype`` 'T' / 'B' with an ``atmosphere`` temperature field, optionally a
 horizontally uniform ``gas_absorption`` profile) and the variable surfaces of at3d/surface.py ('VL' Lambertian, 'VW'
 wave-Fresnel, 'VD' Diner, 'VO' ocean, 'VR' RPV: ``sfcparms`` as PREP_SURFACE lays them out) go through the adaptive
-solver, which runs PLANCK / SURFACE_PARM_INTERP itself.  Not covered (NotImplementedError with the reason): warm starts
-(``init_solution=False``), cell splitting, thermal sources and variable surfaces on independent-pixel grids
+solver, which runs PLANCK / SURFACE_PARM_INTERP itself.  Not covered (NotImplementedError with the reason): continuing a
+loaded solution with cell splitting, cell splitting, thermal sources and variable surfaces on independent-pixel grids
 (``ip_flag=3``), the Ross-Li surface ('VM'), band-integrated Planck units.
 """
 import numpy as np
@@ -138,6 +139,7 @@ class RTE:
         self._solved = None
         self._dev = None
         self._unsplit = None
+        self._restore = None
         self._iters, self._solcrit, self._splitcrit, self._timings = 0, 1.0, 0.0, {}
 
     # -- _setup_grid (at3d/solver.py:2036-2168) --
@@ -263,12 +265,35 @@ class RTE:
         ``split_accuracy > 0`` (the base grid is re-created, as with ``setup_grid=True`` in the reference), array
         capacities from ``adapt_grid_factor`` / ``num_sh_term_factor`` / ``cell_to_point_ratio``.  Independent-pixel
         grids (``ip_flag=3``) take the fixed-grid column solver."""
-        if not init_solution:
-            raise NotImplementedError('solve(init_solution=False) (continuing from the previous SOURCE / RADIANCE) is not '
-                                      'implemented: every solve starts from INIT_RADIANCE')
+        if not init_solution and self._solved is not None and self._restore is None:
+            # continue the iterations from the object's own SOURCE / RADIANCE (e.g. with a larger maxiter); without a
+            # previous solution the flag is overridden and a solution is initialised, as in the reference (:316-322)
+            self._restore = self._solved
         if (self._ipflag & 3) == 3 and self._splitacc > 0.0:
             raise NotImplementedError('cell splitting on independent-pixel grids (ip_flag=3) is not implemented; '
                                       'set split_accuracy=0.0')
+        if self._restore is not None:
+            # a loaded solution (load_solution: another medium's SOURCE / RADIANCE on this grid) is the starting point of
+            # the iterations -- INIT_SOLUTION with INRADFLAG=.FALSE. (at3d/solver.py:2654-2666) -- on the loaded grid
+            if self._splitacc > 0.0:
+                raise NotImplementedError('continuing a loaded solution with cell splitting (split_accuracy > 0) is not '
+                                          'implemented: set split_accuracy=0.0 or start from INIT_RADIANCE')
+            if not solve:
+                return
+            st0, self._restore = self._restore, None
+            sv = S.SweepSolver(st0, self._wtmu, self._transmin)
+            try:
+                sol, iters, self._solcrit, tm = sv.solve(maxiter=maxiter, solacc=self._solacc, shacc=self._shacc,
+                                                        accelflag=self._accelflag, highorderrad=self._highorderrad,
+                                                        iterfixsh=self._iterfixsh, initial=st0)
+            finally:
+                sv.close()
+            self._timings = tm
+            self._iters = iters
+            if verbose:
+                print('  %d iterations from the loaded solution, solution criterion %.3e' % (iters, self._solcrit))
+            self._set_solution(sol)
+            return
         if self._unsplit is not None:
             (self._npts, self._ncells, self._gridpos, self._gridptr, self._neighptr, self._treeptr, self._cellflags,
              self._t) = self._unsplit
@@ -389,11 +414,13 @@ class RTE:
             return
         st.shptr, st.rshptr = sh['shptr'][:npts + 1].copy(), sh['rshptr'][:npts + 2].copy()
         st.source, st.radiance, st.fluxes = sh['source'], sh['radiance'], np.asfortranarray(sh['fluxes'][:, :npts])
-        self._solcrit = self._solacc                       # the saved fields are taken as converged
+        self._solcrit = self._solacc                       # the saved fields are taken as converged ...
         self._set_solution(st.normalize())
+        self._restore = self._solved                       # ... until solve() continues the iterations from them
 
     def check_solved(self, verbose=True):
-        return self._solved is not None and self._solcrit <= self._solacc
+        # a loaded solution is a starting point, not this medium's solution: solve() continues from it
+        return self._solved is not None and self._solcrit <= self._solacc and self._restore is None
 
     @property
     def num_iterations(self):

@@ -166,9 +166,12 @@ class SweepSolver:
                                                            vp(bcrad), C.byref(ms), buf), buf)
         return (rad, fluxes, bcrad, ms.value) if timing else (rad, fluxes, bcrad)
 
-    def solve(self, maxiter=100, solacc=1e-4, shacc=0.0, accelflag=True, highorderrad=False, iterfixsh=30, maxiv=None):
+    def solve(self, maxiter=100, solacc=1e-4, shacc=0.0, accelflag=True, highorderrad=False, iterfixsh=30, maxiv=None,
+              initial=None):
         """The whole fixed-grid solve on the device (at3d_solver_solve).  Returns (solved copy of the state, iterations,
-        solcrit, timings)."""
+        solcrit, timings).  `initial`: a solved state on the same grid (e.g. the previous step of an optimisation): the
+        iterations continue from its SHPTR / SOURCE / RSHPTR / RADIANCE instead of the first guess
+        (at3d_solver_solve_from; the reference's load_solution + INRADFLAG=.FALSE.)."""
         st = self.st.copy().normalize()
         npts, ns = st.npts, st.nstokes
         if maxiv is None:
@@ -184,9 +187,20 @@ class SweepSolver:
         iters, solcrit = C.c_int32(0), C.c_float(0.0)
         ms = np.zeros(3, np.float64)
         buf = _lib.errbuf()
-        rc = _lib.lib().at3d_solver_solve(self.h, C.byref(self._keep), int(maxiter), float(solacc), float(shacc), int(accelflag),
-                                          int(highorderrad), int(iterfixsh), int(maxiv), vp(shptr), vp(source), vp(rshptr),
-                                          vp(radiance), vp(fluxes), vp(bcrad), C.byref(iters), C.byref(solcrit), vp(ms), buf)
+        if initial is not None:
+            if initial.npts != npts or initial.nstokes != ns:
+                raise ValueError('solve(initial=...): the initial solution is on another grid')
+            ts, tr = int(initial.shptr[npts]), int(initial.rshptr[npts])
+            if ts > maxiv or tr > maxiv + npts:
+                raise MemoryError('solve(initial=...): the initial solution does not fit maxiv')
+            shptr[:] = np.asarray(initial.shptr)[:npts + 1]
+            rshptr[:npts + 1] = np.asarray(initial.rshptr)[:npts + 1]
+            source[:, :ts] = np.asarray(initial.source)[:, :ts]
+            radiance[:, :tr] = np.asarray(initial.radiance)[:, :tr]
+        rc = _lib.lib().at3d_solver_solve_from(self.h, C.byref(self._keep), int(maxiter), float(solacc), float(shacc),
+                                               int(accelflag), int(highorderrad), int(iterfixsh), int(maxiv),
+                                               int(initial is not None), vp(shptr), vp(source), vp(rshptr), vp(radiance),
+                                               vp(fluxes), vp(bcrad), C.byref(iters), C.byref(solcrit), vp(ms), buf)
         if rc == 2:
             raise MemoryError(buf.value.decode(errors='replace'))
         _lib.check(rc, buf)

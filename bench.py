@@ -319,7 +319,7 @@ def inversion_step_leg(sc, rays, gi, pix, DeviceState):
     w0 = time.perf_counter()
     sv.update_medium(st2)
     w1 = time.perf_counter()
-    sol2, iters2, solcrit2, tm2 = sv.solve(solacc=1e-4, maxiter=60)
+    sol2, iters2, solcrit2, tm2 = sv.solve(solacc=1e-4, maxiter=60, initial=sol)   # continued from the previous solution
     w2 = time.perf_counter()
     dev = DeviceState(sol2)
     dev.attach_gradient(gi)
@@ -331,7 +331,7 @@ def inversion_step_leg(sc, rays, gi, pix, DeviceState):
     out['warm'] = dict(update_medium_ms=1e3 * (w1 - w0), solve_ms=1e3 * (w2 - w1), solve_loop_ms=tm2.get('loop_ms'),
                        solve_iterations=iters2, state_upload_ms=1e3 * (w3 - w2), gradient_ms=1e3 * (w4 - w3),
                        total_ms=1e3 * (w4 - w0), cost=float(cost2[0]),
-                       note='live solver object (at3d_solver_update_medium) + memory reuse (at3d_set_memory_reuse)')
+                       note='live solver object (at3d_solver_update_medium), iterations continued from the previous solution (at3d_solver_solve_from), memory reuse (at3d_set_memory_reuse)')
     backend.memory_reuse(was)
     if not was:
         backend.trim_memory()

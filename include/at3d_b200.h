@@ -352,6 +352,14 @@ int at3d_solver_path_integration(at3d_solver *sv, const int32_t *shptr, const fl
 int at3d_solver_solve(at3d_solver *sv, const at3d_state_desc *desc, int maxiter, float solacc, float shacc, int accelflag,
                       int highorderrad, int iterfixsh, int maxiv, int32_t *shptr, float *source, int32_t *rshptr,
                       float *radiance, float *fluxes, float *bcrad, int32_t *iters, float *solcrit, double *ms, char *errmsg);
+/* The same loop continued from a solution (restore != 0): shptr / source / rshptr / radiance hold, on entry, the solution of a
+ * nearby medium on the same grid -- what RTE.load_solution + INIT_SOLUTION with INRADFLAG=.FALSE. set up in the reference
+ * (at3d/solver.py:2654-2666, shdomsub1.f:356-391: no first guess, OSHPTR = SHPTR, DELSOURCE = 0) and what an optimisation
+ * loop does between its steps.  restore = 0 is at3d_solver_solve. */
+int at3d_solver_solve_from(at3d_solver *sv, const at3d_state_desc *desc, int maxiter, float solacc, float shacc, int accelflag,
+                           int highorderrad, int iterfixsh, int maxiv, int restore, int32_t *shptr, float *source,
+                           int32_t *rshptr, float *radiance, float *fluxes, float *bcrad, int32_t *iters, float *solcrit,
+                           double *ms, char *errmsg);
 int at3d_solver_destroy(at3d_solver *sv);
 
 /* ---- f3: the adaptive solve: INIT_SOLUTION + SOLUTION_ITERATIONS with SPLIT_GRID ----

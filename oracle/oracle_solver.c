@@ -920,6 +920,19 @@ int oracle_solve_fixed_grid(const oracle_state *st_in, const float *wtmu, int ma
                             int *shptr, float *source, int *rshptr, float *radiance, float *fluxes, float *bcrad,
                             int *iters_out, float *solcrit_out, char *errmsg)
 {
+    return oracle_solve_fixed_grid_from(st_in, wtmu, maxiter, solacc, shacc, accelflag, highorderrad, iterfixsh, maxiv, 0,
+                                        shptr, source, rshptr, radiance, fluxes, bcrad, iters_out, solcrit_out, errmsg);
+}
+
+/* restore != 0: the solution iterations continue from the SHPTR / SOURCE / RSHPTR / RADIANCE passed in (a solution of a
+ * nearby medium on the same grid) instead of the first guess -- INIT_SOLUTION with INRADFLAG=.FALSE. after
+ * RTE.load_solution (at3d/solver.py:2654-2666, shdomsub1.f:356-391): no INIT_RADIANCE, no first COMPUTE_SOURCE,
+ * OSHPTR = SHPTR and DELSOURCE = 0, then SOLUTION_ITERATIONS from ITER = 0. */
+int oracle_solve_fixed_grid_from(const oracle_state *st_in, const float *wtmu, int maxiter, float solacc, float shacc,
+                                 int accelflag, int highorderrad, int iterfixsh, int maxiv, int restore,
+                                 int *shptr, float *source, int *rshptr, float *radiance, float *fluxes, float *bcrad,
+                                 int *iters_out, float *solcrit_out, char *errmsg)
+{
     oracle_state st = *st_in;
     const int npts = st.npts, ns = st.nstokes, maxir = maxiv + npts;
     shdo_coef *c = make_sh_do_coef(&st, wtmu);
@@ -939,15 +952,20 @@ int oracle_solve_fixed_grid(const oracle_state *st_in, const float *wtmu, int ma
     for (i = 0; i < npts * st.npart; i++) if (st.albedo[i] > albmax) albmax = st.albedo[i];
     ierr = sweeping_order(&st, sweepord);
     if (ierr) { if (errmsg) snprintf(errmsg, 600, "SWEEPING_ORDER: not every grid point was reached"); goto done; }
-    /* first guess (see header): zero radiance, 4 terms per point; source from COMPUTE_SOURCE(FIRST=.TRUE.) */
-    for (i = 0; i <= npts; i++) rshptr[i] = 4 * i;
-    rshptr[npts + 1] = rshptr[npts];
-    memset(radiance, 0, sizeof(float) * (size_t)ns * rshptr[npts]);
     st.rshptr = rshptr; st.radiance = radiance; st.shptr = shptr; st.source = source;
     st.fluxes = fluxes; st.bcrad = bcrad;
-    ierr = oracle_compute_source(&st, 0, shacc, maxiv, 1, accelflag, 1, shptr, source, oshptr, delsource,
-                                 &deljdot, &deljold, &deljnew, &jnorm, errmsg);
-    if (ierr) goto done;
+    if (!restore) {
+        /* first guess (see header): zero radiance, 4 terms per point; source from COMPUTE_SOURCE(FIRST=.TRUE.) */
+        for (i = 0; i <= npts; i++) rshptr[i] = 4 * i;
+        rshptr[npts + 1] = rshptr[npts];
+        memset(radiance, 0, sizeof(float) * (size_t)ns * rshptr[npts]);
+        ierr = oracle_compute_source(&st, 0, shacc, maxiv, 1, accelflag, 1, shptr, source, oshptr, delsource,
+                                     &deljdot, &deljold, &deljnew, &jnorm, errmsg);
+        if (ierr) goto done;
+    } else {
+        rshptr[npts + 1] = rshptr[npts];
+        if (shptr[npts] > maxiv || rshptr[npts] > maxir) { ierr = 2; if (errmsg) snprintf(errmsg, 600, "restored solution larger than MAXIV"); goto done; }
+    }
     if (accelflag) {
         memcpy(oshptr, shptr, sizeof(int) * (npts + 1));
         memset(delsource, 0, sizeof(float) * (size_t)ns * oshptr[npts]);

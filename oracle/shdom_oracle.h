@@ -187,6 +187,11 @@ int  oracle_solve_fixed_grid(const oracle_state *st, const float *wtmu, int maxi
                              int accelflag, int highorderrad, int iterfixsh, int maxiv,
                              int *shptr, float *source, int *rshptr, float *radiance, float *fluxes, float *bcrad,
                              int *iters_out, float *solcrit_out, char *errmsg);
+/* restore != 0: continue from the SHPTR / SOURCE / RSHPTR / RADIANCE passed in (INIT_SOLUTION with INRADFLAG=.FALSE.) */
+int  oracle_solve_fixed_grid_from(const oracle_state *st, const float *wtmu, int maxiter, float solacc, float shacc,
+                                  int accelflag, int highorderrad, int iterfixsh, int maxiv, int restore,
+                                  int *shptr, float *source, int *rshptr, float *radiance, float *fluxes, float *bcrad,
+                                  int *iters_out, float *solcrit_out, char *errmsg);
 int  oracle_sweeping_order(const oracle_state *st, int *sweepord /*[npts,8]*/);
 void oracle_set_transmin(float transmin);   /* TRANSMIN of the 3-D sweeps (default 1.0) */
 int  oracle_path_integration_once(const oracle_state *st, const float *wtmu, const int *shptr, const float *source,

@@ -20,8 +20,9 @@ B.memory_reuse(len(sys.argv) < 2 or sys.argv[1] != 'plain')
 sv = solver.SweepSolver(st.copy().normalize(), wtmu)
 def T():
     torch.cuda.synchronize(); return time.perf_counter()
+sol = None
 for rep in range(3):
-    t0 = T(); sol, iters, solcrit, tm = sv.solve(solacc=1e-4, maxiter=60)
+    t0 = T(); sol, iters, solcrit, tm = sv.solve(solacc=1e-4, maxiter=60, initial=(sol if rep and 'warm' in sys.argv else None))
     t1 = T(); dev = DeviceState(sol)
     t2 = T(); dev.attach_gradient(gi)
     t3 = T(); dev.gradient(rays, pix)
@@ -29,6 +30,6 @@ for rep in range(3):
     t5 = T(); dev.gradient(rays, pix)
     t6 = T(); dev.close()
     t7 = T()
-    print('rep %d: solve %.1f (loop %.1f)  state_create %.1f  attach %.1f  grad#1 %.1f  grad#2 %.1f  grad#3 %.1f  close %.1f ms'
-          % (rep, 1e3*(t1-t0), tm['loop_ms'], 1e3*(t2-t1), 1e3*(t3-t2), 1e3*(t4-t3), 1e3*(t5-t4), 1e3*(t6-t5), 1e3*(t7-t6)))
+    print('rep %d: iters %d solve %.1f (loop %.1f)  state_create %.1f  attach %.1f  grad#1 %.1f  grad#2 %.1f  grad#3 %.1f  close %.1f ms'
+          % (rep, iters, 1e3*(t1-t0), tm['loop_ms'], 1e3*(t2-t1), 1e3*(t3-t2), 1e3*(t4-t3), 1e3*(t5-t4), 1e3*(t6-t5), 1e3*(t7-t6)))
 sv.close()

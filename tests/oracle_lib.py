@@ -282,9 +282,11 @@ def average_subpixel_rays(weighted_stokes, pixel_index, npixels):
 
 
 def solve_fixed_grid(state, wtmu, maxiter=100, solacc=1e-5, shacc=0.0, accelflag=True, highorderrad=False,
-                     iterfixsh=30, maxiv=None):
+                     iterfixsh=30, maxiv=None, initial=None):
     """Fixed-grid SHDOM solution iterations (oracle/oracle_solver.c).  Fills and returns a copy of `state`
-    with shptr/source/rshptr/radiance/fluxes/bcrad of the converged solution, plus (iters, solcrit)."""
+    with shptr/source/rshptr/radiance/fluxes/bcrad of the converged solution, plus (iters, solcrit).  `initial`: a solved
+    state on the same grid whose SHPTR / SOURCE / RSHPTR / RADIANCE the iterations continue from (INIT_SOLUTION with
+    INRADFLAG=.FALSE. after RTE.load_solution)."""
     st = state.copy().normalize()
     npts, ns = st.npts, st.nstokes
     if maxiv is None:
@@ -295,17 +297,23 @@ def solve_fixed_grid(state, wtmu, maxiter=100, solacc=1e-5, shacc=0.0, accelflag
     st.source = np.zeros((ns, maxiv), np.float32, order='F')
     st.rshptr = np.zeros(npts + 2, np.int32)
     st.radiance = np.zeros((ns, maxiv + npts), np.float32, order='F')
+    if initial is not None:
+        ts, tr = int(initial.shptr[npts]), int(initial.rshptr[npts])
+        st.shptr[:] = initial.shptr[:npts + 1]
+        st.rshptr[:npts + 1] = initial.rshptr[:npts + 1]
+        st.source[:, :ts] = initial.source[:, :ts]
+        st.radiance[:, :tr] = initial.radiance[:, :tr]
     st.fluxes = np.zeros((2, npts), np.float32, order='F')
     st.bcrad = np.zeros((ns, nbc), np.float32, order='F')
     d = st.fill(OracleState())
     wtmu = np.ascontiguousarray(wtmu, np.float32)
     iters, solcrit = i32(0), f32(0)
     buf = C.create_string_buffer(600)
-    fn = lib().oracle_solve_fixed_grid
-    fn.argtypes = [P(OracleState), C.c_void_p, i32, f32, f32, i32, i32, i32, i32, C.c_void_p, C.c_void_p,
+    fn = lib().oracle_solve_fixed_grid_from
+    fn.argtypes = [P(OracleState), C.c_void_p, i32, f32, f32, i32, i32, i32, i32, i32, C.c_void_p, C.c_void_p,
                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, P(i32), P(f32), C.c_char_p]
     _check(fn(C.byref(d), _vp(wtmu), maxiter, solacc, shacc, int(accelflag), int(highorderrad), iterfixsh, maxiv,
-              _vp(st.shptr), _vp(st.source), _vp(st.rshptr), _vp(st.radiance), _vp(st.fluxes), _vp(st.bcrad),
+              int(initial is not None), _vp(st.shptr), _vp(st.source), _vp(st.rshptr), _vp(st.radiance), _vp(st.fluxes), _vp(st.bcrad),
               C.byref(iters), C.byref(solcrit), buf), buf)
     tot = int(st.shptr[npts])
     st.source = np.asfortranarray(st.source[:, :max(tot, 1)])

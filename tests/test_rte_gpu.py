@@ -381,3 +381,35 @@ def test_rte_ocean_surface_matches_the_oracle():
     refrad = O.render(ref, rays)
     np.testing.assert_allclose(out['I'], refrad[0], rtol=1e-4, atol=1e-6 * refrad[0].max())
     rte.close()
+
+
+def test_rte_solve_continues_from_a_loaded_solution():
+    """The warm start of an optimisation step (at3d/medium.py:1829-1830: the new solver loads the old solution, then
+    solves): `load_solution` + `solve` continues SOLUTION_ITERATIONS from the loaded SOURCE / RADIANCE on this grid --
+    fewer iterations than from INIT_RADIANCE, the same solution within the solution accuracy, and the same iterations as the
+    oracle continued from the same fields."""
+    from at3d_b200.rte import RTE
+    params, medium, source, surface = make_inputs(8, 7, 9, 'periodic', 1, False)
+    params['solution_accuracy'] = 1e-5
+    a = RTE(params, medium, source, surface)
+    a.solve(maxiter=100)
+    ds = a.save_solution()
+    med2 = {'cloud': dict(medium['cloud'], extinction=(medium['cloud']['extinction'] * 1.04).astype(np.float32))}
+    cold = RTE(params, med2, source, surface)
+    cold.solve(maxiter=100)
+    warm = RTE(params, med2, source, surface)
+    warm.load_solution(ds)
+    assert not warm.check_solved()                       # a starting point, not this medium's solution
+    st0 = warm._restore
+    warm.solve(maxiter=100)
+    assert warm.check_solved() and warm.num_iterations < cold.num_iterations
+    ref, iters, solcrit = O.solve_fixed_grid(st0, warm._wtmu, solacc=1e-5, maxiter=100, initial=st0)
+    assert iters == warm.num_iterations
+    np.testing.assert_array_equal(warm._solved.shptr, ref.shptr)
+    np.testing.assert_allclose(warm._solved.fluxes, ref.fluxes, rtol=1e-4, atol=1e-7)
+    np.testing.assert_allclose(warm._solved.fluxes, cold._solved.fluxes, rtol=2e-3, atol=1e-4 * cold._solved.fluxes.max())
+    # init_solution=False on a solved object: nothing left to do, one iteration confirms it
+    warm.solve(maxiter=100, init_solution=False)
+    assert warm.num_iterations <= 2 and warm.check_solved()
+    for r in (a, cold, warm):
+        r.close()

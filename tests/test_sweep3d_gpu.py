@@ -156,6 +156,37 @@ def test_solver_update_medium_equals_a_fresh_solver(case):
     assert 'TRANSMIN' in str(e.value)
 
 
+@pytest.mark.parametrize('case,kw', [('scalar_periodic_split', dict()), ('polarized_open', dict(shacc=0.002)),
+                                     ('rayleigh_two_species', dict(accelflag=False))])
+def test_solve_continued_from_the_previous_solution(case, kw):
+    """at3d_solver_solve_from: the iterations continue from the solution of a nearby medium on the same grid (the
+    reference's load_solution + INIT_SOLUTION with INRADFLAG=.FALSE., what an optimisation step does) -- same iterations,
+    truncation and fields as the oracle continued from the same solution, and fewer iterations than from the first guess."""
+    sc = scenes.make(case, O)
+    st = sc.state
+    w = wtmu_of(st)
+    sv = solver.SweepSolver(st, w)
+    prev, it0, _, _ = sv.solve(solacc=1e-4, maxiter=60, **kw)
+    st2 = st.copy()
+    st2.extinct = np.asfortranarray(st.extinct * np.float32(1.05))
+    st2.total_ext = st2.extinct.sum(axis=1).astype(np.float32)
+    st2.normalize()
+    sv.update_medium(st2)
+    warm, it_w, sc_w, _ = sv.solve(solacc=1e-4, maxiter=60, initial=prev, **kw)
+    cold, it_c, _, _ = sv.solve(solacc=1e-4, maxiter=60, **kw)
+    sv.close()
+    ref, it_r, sc_r = O.solve_fixed_grid(st2, w, solacc=1e-4, maxiter=60, initial=prev, **kw)
+    assert it_w == it_r and it_w < it_c and sc_w <= 1e-4
+    np.testing.assert_array_equal(warm.shptr, ref.shptr)
+    np.testing.assert_array_equal(warm.rshptr, ref.rshptr)
+    scale = np.abs(ref.radiance).max()
+    np.testing.assert_allclose(warm.radiance, ref.radiance, rtol=1e-4, atol=5e-6 * scale)
+    np.testing.assert_allclose(warm.source, ref.source, rtol=1e-4, atol=5e-6 * np.abs(ref.source).max())
+    np.testing.assert_allclose(warm.fluxes, ref.fluxes, rtol=1e-4, atol=1e-7)
+    # both routes end at the same solution within the solution accuracy
+    np.testing.assert_allclose(warm.fluxes, cold.fluxes, rtol=5e-3, atol=1e-4 * np.abs(cold.fluxes).max())
+
+
 @pytest.mark.parametrize('case,kw', [('scalar_open_split', dict()), ('polarized_periodic_split', dict(shacc=0.003)),
                                      ('rayleigh_two_species', dict(accelflag=False)),
                                      ('scalar_nmu16', dict(highorderrad=True, iterfixsh=3))])
