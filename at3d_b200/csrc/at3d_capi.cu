@@ -307,6 +307,7 @@ extern "C" int at3d_state_destroy(at3d_state *st)
     st->hits.release(); st->viewsrc.release();
     pinned_park(st->packs_h, st->packs_cap * sizeof(RayPack));
     st->packs_h = nullptr; st->packs_cap = 0;
+    if (st->hpin) cudaFreeHost(st->hpin);
     st->rays.release(); st->out.release(); st->trace.release(); st->misc.release();
     st->slabs.release(); st->err.release(); st->recs.release(); st->pairs.release();
     delete st;

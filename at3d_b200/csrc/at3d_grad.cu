@@ -1696,6 +1696,7 @@ static int gradient_impl(at3d_state *st, const at3d_rays *rays, const at3d_grad_
         std::vector<size_t> seg_start, seg_len;
         std::vector<char> seg_view;
         view_segments(st, rays, seg_start, seg_len, seg_view);
+        long long nrec_total = 0;
         for (int attempt = 0;; attempt++) {
             bool at_limit = false;
             if (use_t) {
@@ -1752,16 +1753,47 @@ static int gradient_impl(at3d_state *st, const at3d_rays *rays, const at3d_grad_
                                         G.singlescatter, 0, G.maxsub, nullptr, 0, nullptr, nullptr, (RayErr *)st->err.p,
                                         st->ray_counter, npt + s0, stream));
             }
-            if (!use_t) break;
-            std::vector<unsigned> htop(AT3D_SRC_TOP_WORDS);
-            CUDA_TRY(cudaMemcpyAsync(htop.data(), srctop, sizeof(unsigned) * AT3D_SRC_TOP_WORDS, cudaMemcpyDeviceToHost, stream));
+            // The rest of phase 1 and phase 2 are queued behind the forward pass without waiting for it: the pool's overflow
+            // flag and the total number of visit records come back together, in ONE host round trip per step (pinned
+            // buffer, so the copies are asynchronous); an overflow -- rare -- repeats the attempt with a larger pool.
+            if (!st->hpin) CUDA_TRY(cudaMallocHost(&st->hpin, sizeof(unsigned) * AT3D_SRC_TOP_WORDS + 64));
+            unsigned *htop = (unsigned *)st->hpin;
+            long long *htot = (long long *)((unsigned char *)st->hpin + sizeof(unsigned) * AT3D_SRC_TOP_WORDS);
+            if (use_t) CUDA_TRY(cudaMemcpyAsync(htop, srctop, sizeof(unsigned) * AT3D_SRC_TOP_WORDS, cudaMemcpyDeviceToHost, stream));
+            // visit records of a ray are contiguous: offsets = exclusive scan (64-bit) of the per-ray visit counts
+            {
+                cub::TransformInputIterator<long long, VisitsToLL, const int *> it(npt, VisitsToLL());
+                CUDA_TRY(cub::DeviceScan::ExclusiveSum(wb + w_cub, cubtmp, it, recoff, (int)(n + 1), stream));
+            }
+            if (kernel_ms) cudaEventRecord(ev[1], stream);
+            // ---- Phase 2 ----
+            CUDA_TRY(cub::DeviceScan::ExclusiveSum(wb + w_cub, cubtmp, rpp, pixstart, (int)npix, stream));
+            const int nb = (int)((npix + 127) / 128);
+            if (nst == 1)
+                pixel_kernel<1><<<nb, 128, 0, stream>>>(0, (int)npix, pixstart, rpp, visrad, rw, sw, meas, unc, nunc,
+                                                          g->costfunc_ll, so_d, adjw, costp, raypix);
+            else
+                pixel_kernel<3><<<nb, 128, 0, stream>>>(0, (int)npix, pixstart, rpp, visrad, rw, sw, meas, unc, nunc,
+                                                          g->costfunc_ll, so_d, adjw, costp, raypix);
+            CUDA_TRY(cudaGetLastError());
+            cost_reduce_kernel<<<1, 1024, 0, stream>>>((int)npix, costp, cost_d);
+            CUDA_TRY(cudaGetLastError());
+            CUDA_TRY(cudaMemcpyAsync(htot, recoff + n, sizeof(long long), cudaMemcpyDeviceToHost, stream));
             CUDA_TRY(cudaStreamSynchronize(stream));
+            nrec_total = *htot;
+            if (!use_t) break;
             double drawn = (double)htop[0];
             for (int r = 0; r < AT3D_SRC_REGIONS; r++) {
                 const double d = (double)htop[32 * (r + 1)];
                 drawn += d < (double)Sf.srcpool_region ? d : (double)Sf.srcpool_region;
             }
             const double seen = drawn * AT3D_SRC_CHUNK / (double)n;
+            if (getenv("AT3D_B200_DEBUG_POOL")) {
+                int full = 0;
+                for (int r = 0; r < AT3D_SRC_REGIONS; r++) if ((double)htop[32 * (r + 1)] >= (double)Sf.srcpool_region) full++;
+                fprintf(stderr, "[pool] attempt %d chunks %zu region %u nreg %u tail_drawn %u overflow %u full_regions %d seen/ray %.1f est %.1f\n",
+                        attempt, src_chunks, Sf.srcpool_region, Sf.srcpool_nreg, htop[0], htop[1], full, seen, st->gw_rec_per_ray);
+            }
             if (!htop[1]) { if (seen > st->gw_rec_per_ray) st->gw_rec_per_ray = seen; break; }
             // the pool overflowed: walk again with a pool twice as large; at the memory limit (AT3D_B200_SRC_GB) the octet walk,
             // which evaluates its sources itself, takes over (the radiances of this attempt are complete either way)
@@ -1769,31 +1801,10 @@ static int gradient_impl(at3d_state *st, const at3d_rays *rays, const at3d_grad_
             const double est = st->gw_rec_per_ray > 0.0 ? st->gw_rec_per_ray : (double)(6 * (S.nx + S.ny + S.nz) + 64);
             st->gw_rec_per_ray = 2.0 * (seen > est ? seen : est);
         }
-        // visit records of a ray are contiguous: offsets = exclusive scan (64-bit) of the per-ray visit counts
-        {
-            cub::TransformInputIterator<long long, VisitsToLL, const int *> it(npt, VisitsToLL());
-            CUDA_TRY(cub::DeviceScan::ExclusiveSum(wb + w_cub, cubtmp, it, recoff, (int)(n + 1), stream));
-        }
-        if (kernel_ms) cudaEventRecord(ev[1], stream);
-        // ---- Phase 2 ----
-        CUDA_TRY(cub::DeviceScan::ExclusiveSum(wb + w_cub, cubtmp, rpp, pixstart, (int)npix, stream));
-        const int nb = (int)((npix + 127) / 128);
-        if (nst == 1)
-            pixel_kernel<1><<<nb, 128, 0, stream>>>(0, (int)npix, pixstart, rpp, visrad, rw, sw, meas, unc, nunc,
-                                                      g->costfunc_ll, so_d, adjw, costp, raypix);
-        else
-            pixel_kernel<3><<<nb, 128, 0, stream>>>(0, (int)npix, pixstart, rpp, visrad, rw, sw, meas, unc, nunc,
-                                                      g->costfunc_ll, so_d, adjw, costp, raypix);
-        CUDA_TRY(cudaGetLastError());
-        cost_reduce_kernel<<<1, 1024, 0, stream>>>((int)npix, costp, cost_d);
-        CUDA_TRY(cudaGetLastError());
         // ---- Phase 3 ----
         // The records of all rays may not fit (cfg4: ~80 GB): the derivative pass runs over chunks of rays whose
-        // records fit the budget (AT3D_B200_REC_GB, default 8 GB); chunk boundaries from the offsets on the host.
-        st->recoff_h.resize(n + 1);
-        CUDA_TRY(cudaMemcpyAsync(st->recoff_h.data(), recoff, sizeof(long long) * (n + 1), cudaMemcpyDeviceToHost, stream));
-        CUDA_TRY(cudaStreamSynchronize(stream));
-        const long long *roff = st->recoff_h.data();
+        // records fit the budget (AT3D_B200_REC_GB, default 8 GB); chunk boundaries from the offsets on the host, which are
+        // only read back when there is more than one chunk (or for the per-pixel passes of the Jacobian).
         double budget_gb = 8.0;
         if (const char *e = getenv("AT3D_B200_REC_GB")) { const double v = atof(e); if (v > 0.0) budget_gb = v; }
         long long budget = (long long)(budget_gb * 1073741824.0 / sizeof(VisitRec));
@@ -1801,6 +1812,15 @@ static int gradient_impl(at3d_state *st, const at3d_rays *rays, const at3d_grad_
             const long long lim = 0x7FFFFFFFll / (8ll * G.numder + 1);
             if (budget > lim) budget = lim;
         }
+        const bool one_chunk = nrec_total <= budget && !(njac > 0 && jacobian);
+        st->recoff_h.resize(n + 1);
+        if (one_chunk) {
+            st->recoff_h[0] = 0; st->recoff_h[n] = nrec_total;          // the only entries the single-chunk pass reads
+        } else {
+            CUDA_TRY(cudaMemcpyAsync(st->recoff_h.data(), recoff, sizeof(long long) * (n + 1), cudaMemcpyDeviceToHost, stream));
+            CUDA_TRY(cudaStreamSynchronize(stream));
+        }
+        const long long *roff = st->recoff_h.data();
         const size_t smem = (size_t)AT3D_RAYS_PER_BLOCK * (S.ny_comp * S.nlmp + ((3 * (S.ml + 1) + 3) & ~3)) * sizeof(float);
         int dev = 0, nsm = 148, per_sm_w = 1, per_sm_a = 1;
         cudaGetDevice(&dev);
@@ -1824,7 +1844,8 @@ static int gradient_impl(at3d_state *st, const at3d_rays *rays, const at3d_grad_
         size_t r0 = 0;
         while (r0 < n) {
             size_t r1 = r0 + 1;
-            while (r1 < n && roff[r1 + 1] - roff[r0] <= budget) r1++;
+            if (one_chunk) r1 = n;
+            else while (r1 < n && roff[r1 + 1] - roff[r0] <= budget) r1++;
             const long long nrec_chunk = roff[r1] - roff[r0];
             CUDA_TRY(st->recs.reserve(((size_t)nrec_chunk + 8) * sizeof(VisitRec)));
             VisitRec *recs = (VisitRec *)st->recs.p;

@@ -437,28 +437,42 @@ class ClockSampler:
          'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
 
     def __init__(self, index):
-        self.index, self.samples, self._stop, self._t = index, [], threading.Event(), None
+        self.index, self.samples, self._p, self._t = index, [], None, None
 
     def _run(self):
-        while not self._stop.is_set():
-            try:
-                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
-                                      '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5).stdout
-                f = [x.strip() for x in out.strip().split(',')]
-                if len(f) >= 6:
-                    self.samples.append(f)
-            except Exception:
-                pass
-            self._stop.wait(0.2)
+        for line in self._p.stdout:
+            f = [x.strip() for x in line.strip().split(',')]
+            if len(f) >= 6:
+                self.samples.append(f)
 
     def __enter__(self):
-        self._t = threading.Thread(target=self._run, daemon=True)
-        self._t.start()
+        # ONE nvidia-smi process looping every 200 ms (the recipe's clocks line): started before the timed region -- its
+        # start-up (driver / NVML initialisation) is over when the first sample arrives -- and stopped after it.  Spawning
+        # a new nvidia-smi per sample stalls CUDA calls of the timed process on some boxes (tens of ms per spawn).
+        try:
+            self._p = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                        '--format=csv,noheader,nounits', '-lms', '200'], stdout=subprocess.PIPE,
+                                       stderr=subprocess.DEVNULL, text=True)
+            first = self._p.stdout.readline()
+            f = [x.strip() for x in first.strip().split(',')]
+            if len(f) >= 6:
+                self.samples.append(f)
+            self._t = threading.Thread(target=self._run, daemon=True)
+            self._t.start()
+        except Exception:
+            self._p = None
         return self
 
     def __exit__(self, *a):
-        self._stop.set()
-        self._t.join(timeout=6)
+        if self._p is not None:
+            time.sleep(0.25)                      # one more sample under load
+            self._p.terminate()                   # the exact process started above
+            try:
+                self._p.wait(timeout=5)
+            except Exception:
+                self._p.kill()
+            if self._t is not None:
+                self._t.join(timeout=5)
 
     def summary(self):
         if not self.samples:

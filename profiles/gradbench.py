@@ -33,5 +33,7 @@ ms = []
 for i in range(n + 2):
     out = dev.gradient(dr, dp, gradout=gout, stokesout=sout, cost=cout, stream=stream, timing=True)
     if i >= 2: ms.append(out[-1])
+if os.environ.get('GRADBENCH_EACH'):
+    print('forward per call:', ' '.join('%.1f' % x[0] for x in ms), flush=True)
 m = np.mean(np.array(ms), axis=0)
 print(os.environ.get('AT3D_B200_LIB', 'default').split('/')[-1], 'forward %.2f deriv %.2f (weights %.2f pairs %.2f) beam %.2f total %.2f' % (m[0], m[1], m[4], m[5], m[2], m[3]), flush=True)
