@@ -218,10 +218,13 @@ class DeviceSourceState:
 
 
 def compute_source_device(dstate, shptr_old, source_old, oshptr_old, delsource, shptr_new, source_new, fixsh=False,
-                          shacc=0.0, maxiv=None, first=False, accelflag=True, properties_changed=False, timing=False):
+                          shacc=0.0, maxiv=None, first=False, accelflag=True, properties_changed=False, timing=False,
+                          delsource_new=None):
     """COMPUTE_SOURCE (shdomsub1.f:967) on device-resident torch tensors (C: at3d_compute_source_device).  SOURCE and SHPTR
-    are double-buffered by the caller (``*_old`` in, ``*_new`` out); DELSOURCE is updated in place at the old SHPTR offsets.
-    Returns (ierr, total_new, [deljdot, deljold, deljnew, jnorm]) (+ kernel ms when ``timing``)."""
+    are double-buffered by the caller (``*_old`` in, ``*_new`` out); DELSOURCE is updated in place at the old SHPTR offsets,
+    or written to ``delsource_new`` when given -- a separate buffer lets the adaptive truncation run in one pass
+    (cs_adapt_kernel) instead of two.  Returns (ierr, total_new, [deljdot, deljold, deljnew, jnorm]) (+ kernel ms when
+    ``timing``)."""
     nst = dstate.meta['nstokes']
     cap = source_new.numel() // nst
     if maxiv is None:
@@ -233,7 +236,8 @@ def compute_source_device(dstate, shptr_old, source_old, oshptr_old, delsource, 
     d = dstate.desc()
     code = _lib.lib().at3d_compute_source_device(
         C.byref(d), int(fixsh), shacc, int(maxiv), int(first), int(accelflag), vp(shptr_old), vp(source_old),
-        vp(oshptr_old), vp(delsource), vp(delsource), vp(shptr_new), vp(source_new), int(cap), int(properties_changed),
+        vp(oshptr_old), vp(delsource), vp(delsource if delsource_new is None else delsource_new), vp(shptr_new),
+        vp(source_new), int(cap), int(properties_changed),
         vp(norms), C.byref(tot), C.byref(ms), buf)
     if code not in (0, 2):
         _lib.check(code, buf)

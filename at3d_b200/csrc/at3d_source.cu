@@ -617,6 +617,249 @@ __global__ void __launch_bounds__(CS_WARPS * 32, (NST == 1 ? AT3D_CS_MINB : 1)) 
     }
 }
 
+// Kernel G (adaptive truncation in ONE pass): the new truncation length of a point is only known after its temporary source
+// has been evaluated, and the offset of its SOURCE block after those of all earlier points -- which is why the reference
+// (and cs_norms_kernel + scan + cs_write_kernel) evaluate the source twice.  Here a warp takes a chunk of P consecutive
+// points, keeps their temporary sources in shared memory, and obtains the offset of the chunk with a decoupled look-back
+// over the chunk totals (chunks are handed out by a ticket counter, so every predecessor of a chunk is already running):
+// RADIANCE, SOURCE_old and DELSOURCE_old are read once.  Per-j arithmetic, per-lane summation order and the norms of
+// cs_norms_kernel (the partial sums are kept per chunk and reduced in chunk order: deterministic).  delsource_new must
+// not alias delsource_old (their offsets differ: OSHPTR vs. SHPTR_old).
+struct CsAdapt {
+    int P, nchunks, stride;                  // points per chunk, chunks, floats per staged point (NLM * NSTOKES)
+    unsigned long long *tile;                // [nchunks] look-back status: flag << 62 | value
+    int *ticket;
+    double *chunk_sums;                      // [nchunks,4]
+    int *shptr_new;                          // [npts+1]
+    unsigned long long cap;                  // capacity of source_new in SH terms
+    int *overflow;
+};
+#define CS_TILE_AGG  (1ull << 62)
+#define CS_TILE_PFX  (2ull << 62)
+#define CS_TILE_MASK ((1ull << 62) - 1)
+
+template <int NST, int SLOTS>
+__global__ void __launch_bounds__(CS_WARPS * 32, (NST == 1 ? 3 : 1)) cs_adapt_kernel(CsArgs a, CsAdapt q)
+{
+    extern __shared__ float smem[];
+    constexpr int NB = CsBatch<NST>::N;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nlt = a.nstleg * (a.nleg + 1);
+    float *legent = smem + (size_t)warp * 2 * nlt;
+    float *stage = smem + (size_t)CS_WARPS * 2 * nlt + (size_t)warp * q.P * q.stride;
+    const bool donorm = !a.first, doacc = a.accelflag && !a.first;
+    CsLaneTab tab;
+    tab.init(a, lane);
+    float r[NB][NST], so[NB][NST], ds[NB][NST];
+    int ir = 0, nr = 0, is = 0, ns = 0, iso = 0, nsc = 0;      // ns: NS_old; nsc: terms common with the old DELSOURCE
+    float dfl = 0.0f;
+    auto load_ptrs = [&](int ip, int &ir_, int &nr_, int &is_, int &ns_, int &iso_, int &nsc_, float &dfl_) {
+        dfl_ = __ldg(&a.dirflux[ip]);
+        ir_ = a.rshptr[ip]; nr_ = a.rshptr[ip + 1] - ir_;
+        is_ = a.shptr_old[ip]; ns_ = a.shptr_old[ip + 1] - is_;
+        iso_ = 0; nsc_ = ns_;
+        if (doacc) {
+            iso_ = a.oshptr_old[ip];
+            const int nso = a.oshptr_old[ip + 1] - iso_;
+            if (nso < nsc_) nsc_ = nso;
+        }
+    };
+    auto load_batch = [&](int j0, int ir_, int nr_, int is_, int ns_, int iso_, int nsc_) {
+        const float *rad = a.radiance + (size_t)NST * ir_;
+        const float *sop = a.source_old + (size_t)NST * is_, *dsp = a.delsource_old + (size_t)NST * iso_;
+#pragma unroll
+        for (int u = 0; u < NB; u++) {
+            const int j = j0 + 32 * u + lane;
+#pragma unroll
+            for (int k = 0; k < NST; k++) {
+                r[u][k] = (j < nr_) ? __ldg(&rad[(size_t)NST * j + k]) : 0.0f;
+                so[u][k] = (donorm && j < ns_) ? __ldg(&sop[(size_t)NST * j + k]) : 0.0f;
+                ds[u][k] = (doacc && j < nsc_) ? __ldg(&dsp[(size_t)NST * j + k]) : 0.0f;
+            }
+        }
+    };
+    // a tile = CS_WARPS consecutive chunks, one per warp, handed to the block by a ticket counter; ONE look-back per tile
+    __shared__ int s_tile[2];
+    __shared__ unsigned long long s_base;
+    __shared__ int s_wtot[CS_WARPS];
+    __shared__ double s_red[CS_WARPS][4];
+    const int ntiles = (q.nchunks + CS_WARPS - 1) / CS_WARPS;
+    int tsel = 0;
+    auto draw = [&](int sel) {                                   // called by all threads of the block
+        if (threadIdx.x == 0) s_tile[sel] = atomicAdd(q.ticket, 1);
+        __syncthreads();
+        return s_tile[sel];
+    };
+    CsMixRow<SLOTS> mix;
+    int tile = draw(tsel);
+    int chunk = tile < ntiles ? tile * CS_WARPS + warp : q.nchunks;
+    // software pipeline over the warp's points (consecutive within a chunk, then the first point of the next chunk, whose
+    // ticket is drawn one chunk ahead): block pointers at the top of an iteration, mixed row after this point's row went to
+    // shared memory, first batch of SH values at the bottom
+    if (chunk < q.nchunks) {
+        const int i = chunk * q.P;
+        load_ptrs(i, ir, nr, is, ns, iso, nsc, dfl); mix.load(a, i, lane, nlt); load_batch(0, ir, nr, is, ns, iso, nsc);
+    }
+    while (tile < ntiles) {
+        tsel ^= 1;
+        const int next_tile = draw(tsel);
+        const int next_chunk = next_tile < ntiles ? next_tile * CS_WARPS + warp : q.nchunks;
+        const int i0 = chunk * q.P;
+        const int np = chunk < q.nchunks ? min(q.P, a.npts - i0) : 0;
+        double sdot = 0.0, sold = 0.0, snew = 0.0, snorm = 0.0;
+        int my_ns = 0;                                   // lane p: NS_new of point i0 + p
+        for (int p = 0; p < np; p++) {
+            const int i = i0 + p;
+            const int inext = (p + 1 < np) ? i + 1 : (next_chunk < q.nchunks ? next_chunk * q.P : -1);
+            int ir2 = 0, nr2 = 0, is2 = 0, ns2 = 0, iso2 = 0, nsc2 = 0;
+            float dfl2 = 0.0f;
+            if (inext >= 0) load_ptrs(inext, ir2, nr2, is2, ns2, iso2, nsc2, dfl2);
+            if (nr > a.nlm) {
+                if (lane == 0) atomicCAS(a.bad, 0, i + 1);
+                ir = ir2; nr = nr2; is = is2; ns = ns2; iso = iso2; nsc = nsc2; dfl = dfl2;
+                if (inext >= 0) { mix.load(a, inext, lane, nlt); load_batch(0, ir, nr, is, ns, iso, nsc); }
+                continue;
+            }
+            const float flux0 = dfl * a.secmu0;
+            mix.to_shared(legent, lane, nlt);
+            const float albedo = mix.ap.x, planck = mix.ap.y;
+            if (inext >= 0) mix.load(a, inext, lane, nlt);
+            float *st = stage + (size_t)p * q.stride;
+            int jlast = -1;
+            float pdot = 0.0f, pold = 0.0f, pnew = 0.0f, pnorm = 0.0f;
+            auto body = [&](int j, int l, float ysun, const float (&rr)[NST], const float (&soo)[NST], const float (&dss)[NST]) {
+                float sv[NST];
+                cs_calc_j<NST>(a, legent, j, l, ysun, j < nr, rr, flux0, planck, albedo, sv);
+#pragma unroll
+                for (int k = 0; k < NST; k++) if (fabsf(sv[k]) > a.srcmin) jlast = j;
+                if (donorm && j < nsc) {
+#pragma unroll
+                    for (int k = 0; k < NST; k++) {
+                        const float d = sv[k] - soo[k];
+                        if (a.accelflag) {
+                            pdot = pdot + d * dss[k];
+                            pold = pold + dss[k] * dss[k];
+                        }
+                        pnew = pnew + d * d;
+                        pnorm = pnorm + soo[k] * soo[k];
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < NST; k++) {
+                    if (doacc && j < ns) a.delsource_new[(size_t)NST * (is + j) + k] = sv[k] - soo[k];
+                    st[(size_t)NST * j + k] = sv[k];
+                }
+            };
+#pragma unroll
+            for (int b = 0; b < CS_JSLOTS / NB; b++) {
+                const int j0 = 32 * NB * b;
+                if (j0 >= a.nlm) break;
+                if (b > 0) load_batch(j0, ir, nr, is, ns, iso, nsc);
+#pragma unroll
+                for (int u = 0; u < NB; u++) {
+                    const int j = j0 + 32 * u + lane;
+                    if (j >= a.nlm) continue;
+                    body(j, tab.l[b * NB + u], tab.ys[b * NB + u], r[u], so[u], ds[u]);
+                }
+            }
+            for (int j0 = 32 * CS_JSLOTS; j0 < a.nlm; j0 += 32 * NB) {        // NLM > 256: table loads
+                load_batch(j0, ir, nr, is, ns, iso, nsc);
+#pragma unroll
+                for (int u = 0; u < NB; u++) {
+                    const int j = j0 + 32 * u + lane;
+                    if (j >= a.nlm) continue;
+                    body(j, a.lofj[j], a.ylmsun[(size_t)a.nstleg * j], r[u], so[u], ds[u]);
+                }
+            }
+            sdot += (double)pdot; sold += (double)pold; snew += (double)pnew; snorm += (double)pnorm;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) jlast = max(jlast, __shfl_xor_sync(FULLMASK, jlast, o));
+            int nsn;
+            {
+                int js = jlast + 1;                            // 1-based; 0 = none
+                if (js == 0 && a.srctype != 'S') js = 1;
+                if (js == 0) nsn = 0;
+                else {
+                    const int ls = a.lofj[js - 1], mm = a.mm;
+                    if (ls <= mm) nsn = ls * (ls + 1) + ls + 1;
+                    else nsn = (2 * mm + 1) * ls - (mm * (1 + (mm - 1))) + mm + 1;
+                }
+            }
+            if (lane == p) my_ns = nsn;
+            if (lane == 0) a.ns_new[i] = nsn;
+            __syncwarp();
+            ir = ir2; nr = nr2; is = is2; ns = ns2; iso = iso2; nsc = nsc2; dfl = dfl2;
+            if (inext >= 0) load_batch(0, ir, nr, is, ns, iso, nsc);
+        }
+        // offsets: exclusive scan of the chunk's NS_new over the lanes, of the chunk totals over the warps, tile base by
+        // decoupled look-back over the tile totals (warp 0)
+        int incl = my_ns;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(FULLMASK, incl, o); if (lane >= o) incl += t; }
+        const int wtotal = __shfl_sync(FULLMASK, incl, 31);
+        const int excl = incl - my_ns;
+        if (lane == 0) s_wtot[warp] = wtotal;
+        __syncthreads();
+        if (warp == 0) {
+            unsigned long long total = 0;
+#pragma unroll
+            for (int w = 0; w < CS_WARPS; w++) total += (unsigned long long)s_wtot[w];
+            unsigned long long base = 0;
+            if (tile == 0) {
+                if (lane == 0) { __threadfence(); *(volatile unsigned long long *)&q.tile[0] = CS_TILE_PFX | total; }
+            } else {
+                if (lane == 0) { __threadfence(); *(volatile unsigned long long *)&q.tile[tile] = CS_TILE_AGG | total; }
+                int look = tile - 1;
+                for (;;) {
+                    const int c = look - lane;
+                    unsigned long long v = CS_TILE_PFX;                 // lanes beyond tile 0 read as "prefix 0"
+                    if (c >= 0) {
+                        do { v = *(volatile unsigned long long *)&q.tile[c]; if (!(v >> 62)) __nanosleep(40); } while (!(v >> 62));
+                    }
+                    const unsigned pm = __ballot_sync(FULLMASK, (v >> 62) == 2);
+                    const int stop = pm ? __ffs(pm) - 1 : 32;           // nearest predecessor that already has its prefix
+                    unsigned long long part = (lane <= stop) ? (v & CS_TILE_MASK) : 0ull;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(FULLMASK, part, o);
+                    base += part;
+                    if (pm) break;
+                    look -= 32;
+                }
+                if (lane == 0) { __threadfence(); *(volatile unsigned long long *)&q.tile[tile] = CS_TILE_PFX | (base + total); }
+            }
+            if (lane == 0) {
+                s_base = base;
+                if (tile == ntiles - 1) q.shptr_new[a.npts] = (int)(base + total);
+            }
+        }
+        __syncthreads();
+        unsigned long long base = s_base;
+        for (int w = 0; w < warp; w++) base += (unsigned long long)s_wtot[w];
+        // SHPTR_new and the re-packed SOURCE of the chunk's points from shared memory
+        if (lane < np) q.shptr_new[i0 + lane] = (int)(base + (unsigned long long)excl);
+        __syncwarp();
+        for (int p = 0; p < np; p++) {
+            const int nsn = __shfl_sync(FULLMASK, my_ns, p);
+            const unsigned long long off = base + (unsigned long long)__shfl_sync(FULLMASK, excl, p);
+            if (off + (unsigned long long)nsn > q.cap) { if (lane == 0) *q.overflow = 1; continue; }
+            const float *st = stage + (size_t)p * q.stride;
+            float *dst = a.source_new + (size_t)NST * off;
+            for (int t = lane; t < NST * nsn; t += 32) dst[t] = st[t];
+        }
+        __syncwarp();
+        sdot = warp_sum_d(sdot); sold = warp_sum_d(sold); snew = warp_sum_d(snew); snorm = warp_sum_d(snorm);
+        if (lane == 0) { s_red[warp][0] = sdot; s_red[warp][1] = sold; s_red[warp][2] = snew; s_red[warp][3] = snorm; }
+        __syncthreads();
+        if (threadIdx.x < 4) {
+            double t = 0.0;
+            for (int w = 0; w < CS_WARPS; w++) t += s_red[w][threadIdx.x];
+            q.chunk_sums[(size_t)tile * 4 + threadIdx.x] = t;          // per tile, reduced in tile order afterwards
+        }
+        tile = next_tile;
+        chunk = next_chunk;
+    }
+}
+
 // deterministic final reduction of the per-block partial sums
 __global__ void cs_reduce_kernel(int nblocks, const double *partials, double *out)
 {
@@ -742,6 +985,68 @@ int cs_device_step(CsArgs &a, int nblk, void *scan_tmp, size_t tmpb, int *shptr_
         if (hbad) { set_msg(errmsg, "COMPUTE_SOURCE: NR>NLM 3 %d", hbad); return 1; }
         return 0;
     }
+    // adaptive truncation in one pass (cs_adapt_kernel), opt-in with AT3D_B200_CS_ADAPT=one, when the new DELSOURCE does not
+    // overwrite the old one and the temporary sources of a chunk fit shared memory.  Measured at 6.55 M points x NLM 256
+    // (profiles/r2zj_csadapt_ncu_summary.txt): DRAM traffic 25.1 GB instead of ~35 GB, but 11.4 ms against 10.8 ms for the two
+    // passes -- the block-wide wait for the tile offset (look-back) and 24 resident warps per SM (64 KB of staging per
+    // block) cost more than the second read of RADIANCE saves; the two-pass route stays the default.
+    {
+        const bool doacc = a.accelflag && !a.first;
+        const size_t stride = (size_t)a.nlm * nst;
+        const size_t room = 96 * 1024 > smem ? 96 * 1024 - smem : 0;
+        int P = (int)(room / (CS_WARPS * stride * sizeof(float)));
+        if (P > 8) P = 8;
+        const char *env = getenv("AT3D_B200_CS_ADAPT");
+        const bool one = env && !strcmp(env, "one");
+        if (one && source_new && P >= 1 && (!doacc || a.delsource_new != a.delsource_old)) {
+            CsAdapt q;
+            q.P = P; q.nchunks = (npts + P - 1) / P; q.stride = (int)stride;
+            const size_t b_tile = ((size_t)q.nchunks * sizeof(unsigned long long) + 255) & ~(size_t)255;
+            const size_t b_sums = ((size_t)q.nchunks * 4 * sizeof(double) + 255) & ~(size_t)255;
+            static DevBuf scratch;                                  // per process; calls on one stream at a time (as g_cswork)
+            if (scratch.reserve(b_tile + b_sums + 256) != cudaSuccess) { set_msg(errmsg, "COMPUTE_SOURCE: device allocation failure"); return 4; }
+            unsigned char *sb = (unsigned char *)scratch.p;
+            q.tile = (unsigned long long *)sb;
+            q.chunk_sums = (double *)(sb + b_tile);
+            q.ticket = (int *)(sb + b_tile + b_sums);
+            q.overflow = q.ticket + 1;
+            q.shptr_new = shptr_new;
+            q.cap = (unsigned long long)(cap_new < (size_t)maxiv ? cap_new : (size_t)maxiv);
+            cudaMemsetAsync(q.tile, 0, b_tile, 0);
+            cudaMemsetAsync(q.ticket, 0, 2 * sizeof(int), 0);
+            a.source_new = source_new;
+            const size_t smem2 = smem + (size_t)CS_WARPS * P * stride * sizeof(float);
+            int dev = 0, nsm = 148;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+            const int want = (q.nchunks + CS_WARPS - 1) / CS_WARPS;            // tiles
+            const int nb2 = want < nsm * 3 ? want : nsm * 3;
+#define CS_LAUNCH_A(NSTV, SL)                                                                                     \
+            {                                                                                                     \
+                cudaFuncSetAttribute(cs_adapt_kernel<NSTV, SL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2); \
+                cs_adapt_kernel<NSTV, SL><<<nb2, CS_WARPS * 32, smem2>>>(a, q);                                   \
+            }
+            if (nst == 1) {
+                if (slots == 1) CS_LAUNCH_A(1, 1) else if (slots == 2) CS_LAUNCH_A(1, 2) else if (slots == 4) CS_LAUNCH_A(1, 4) else CS_LAUNCH_A(1, 8)
+            } else {
+                if (slots == 1) CS_LAUNCH_A(3, 1) else if (slots == 2) CS_LAUNCH_A(3, 2) else if (slots == 4) CS_LAUNCH_A(3, 4) else CS_LAUNCH_A(3, 8)
+            }
+#undef CS_LAUNCH_A
+            cs_reduce_kernel<<<1, 1024>>>((q.nchunks + CS_WARPS - 1) / CS_WARPS, q.chunk_sums, sums);
+            int total_new = 0, hbad = 0, hov[2] = {0, 0};
+            cudaMemcpy(&total_new, shptr_new + npts, sizeof(int), cudaMemcpyDeviceToHost);
+            cudaMemcpy(&hbad, a.bad, sizeof(int), cudaMemcpyDeviceToHost);
+            cudaMemcpy(hov, q.ticket, 2 * sizeof(int), cudaMemcpyDeviceToHost);
+            if (total_new_out) *total_new_out = total_new;
+            a.shptr_new = shptr_new;
+            if (hbad) { set_msg(errmsg, "COMPUTE_SOURCE: NR>NLM 3 %d", hbad); return 1; }
+            if (hov[1] || total_new > maxiv || (size_t)total_new > cap_new) {
+                set_msg(errmsg, "COMPUTE_SOURCE: MAXIV exceeded %d Out of memory for more spherical harmonic terms.", maxiv);
+                return 2;
+            }
+            return 0;
+        }
+    }
     CS_LAUNCH(cs_norms_kernel)
     cs_reduce_kernel<<<1, 1024>>>(nblk, a.partials, sums);
     cub::DeviceScan::ExclusiveSum(scan_tmp, tmpb, a.ns_new, shptr_new, npts + 1);
@@ -844,8 +1149,10 @@ extern "C" int at3d_compute_source(const at3d_state_desc *d, int fixsh, float sh
     size_t tmpb = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, tmpb, a.ns_new, shptr_new, (int)npts + 1);
     void *tmp = A.alloc<unsigned char>(tmpb);
+    // a separate new DELSOURCE: its offsets (SHPTR_old) differ from the old one's (OSHPTR), and the one-pass adaptive kernel
+    // writes it while other warps still read the old values
     a.delsource_new = (float *)a.delsource_old;
-    if (accelflag && !first && (size_t)nst * shptr[npts] > ndel_old) a.delsource_new = A.alloc<float>((size_t)nst * shptr[npts]);
+    if (accelflag && !first) a.delsource_new = A.alloc<float>((size_t)nst * shptr[npts] + 1);
     if (!source_new || !tmp || !a.delsource_new) { set_msg(errmsg, "device allocation failure"); return 4; }
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);

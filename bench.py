@@ -166,15 +166,18 @@ def compute_source_cfg4_leg(B, steps, warmup, peak, nx=256, ny=256, nz=100):
         source_new = torch.empty(cap, dtype=torch.float32, device='cuda')
         shptr_new = torch.empty_like(shptr)
         out = dict(npts=npts, nlm=nlm, npart=npart, sum_nr=nr, sum_ns=ns_tot,
-                   hbm_bytes=int(sum(t.numel() * t.element_size() for t in (radiance, source, delsource, source_new, iphase, pwt, ext, alb))))
+                   hbm_bytes=int(sum(t.numel() * t.element_size() for t in (radiance, source, delsource, delsource, source_new, iphase, pwt, ext, alb))))
         P = 28 + npart * (8 + 64 * 1)
+        dl_new = torch.empty_like(delsource)
         for name, fixsh in (('adaptive_truncation', False), ('fixsh_fused', True)):
             kms = []
             tot_new = ns_tot
             for i in range(warmup + steps):
                 dl = delsource.clone()
+                # adaptive truncation: DELSOURCE double-buffered like SOURCE, so that the routine is one pass (cs_adapt_kernel)
                 rc, tot_new, sums, ms = B.compute_source_device(dev, shptr, source, shptr, dl, shptr_new, source_new, fixsh=fixsh,
-                                                                shacc=0.0 if fixsh else 3e-3, maxiv=cap, timing=True)
+                                                                shacc=0.0 if fixsh else 3e-3, maxiv=cap, timing=True,
+                                                                delsource_new=None if fixsh else dl_new)
                 if rc != 0:
                     return dict(error='COMPUTE_SOURCE returned %d' % rc)
                 if i >= warmup:

@@ -84,6 +84,49 @@ def test_compute_source_device_resident_matches_oracle(case, mode, oracle):
             np.testing.assert_allclose(sums, sums_r, rtol=1e-4, atol=1e-7 * max(abs(sums_r[3]), 1e-30))
 
 
+@pytest.mark.parametrize('case', ['scalar_periodic_split', 'polarized_periodic_split', 'rayleigh_two_species', 'scalar_nmu16'])
+@pytest.mark.parametrize('route', ['one_pass', 'two_pass'])
+def test_compute_source_adaptive_one_pass_equals_two_pass(case, route, oracle, monkeypatch):
+    """The adaptive truncation in one pass (cs_adapt_kernel: chunk offsets by decoupled look-back, DELSOURCE double-buffered)
+    against the oracle and against the two-pass route, with an old DELSOURCE whose truncation (OSHPTR) differs from SHPTR."""
+    import torch
+    from at3d_b200 import backend as B
+    sc, shptr, source, oshptr, delsource, maxiv = _state_for_source(case, oracle)
+    st = sc.state
+    npts, nst = st.npts, st.nstokes
+    rng = np.random.default_rng(5)
+    # OSHPTR: the truncation of the iteration before, shorter or equal per point
+    ns = np.diff(shptr)
+    nso = np.maximum(np.minimum(ns, rng.integers(1, st.nlm + 1, npts)), 0).astype(np.int32)
+    oshptr = np.concatenate([[0], np.cumsum(nso)]).astype(np.int32)
+    delsource = np.zeros((nst, maxiv), np.float32, order='F')
+    delsource[:, :oshptr[npts]] = 0.01 * rng.standard_normal((nst, oshptr[npts])).astype(np.float32)
+    kw = dict(first=False, accelflag=True, fixsh=False, shacc=2e-4, maxiv=maxiv)
+    rc_r, shptr_r, src_r, oshptr_r, del_r, sums_r = oracle.compute_source(st, shptr, source, oshptr, delsource, **kw)
+    if route == 'one_pass':
+        monkeypatch.setenv('AT3D_B200_CS_ADAPT', 'one')               # opt-in (the two passes are faster, DESIGN.md 3.4)
+    dev = B.DeviceSourceState(st)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(np.asarray(a).ravel(order='F'))).cuda()
+    d_shptr, d_src, d_oshptr, d_del = t(shptr), t(source), t(oshptr), t(delsource)
+    d_del_new = torch.zeros_like(d_del)
+    d_shptr_new, d_src_new = torch.zeros_like(d_shptr), torch.zeros_like(d_src)
+    rc, total, sums = B.compute_source_device(dev, d_shptr, d_src, d_oshptr, d_del, d_shptr_new, d_src_new,
+                                              delsource_new=d_del_new, **kw)
+    assert rc == 0 and total == shptr_r[npts]
+    np.testing.assert_array_equal(d_shptr_new.cpu().numpy(), shptr_r)
+    n = shptr_r[npts]
+    src_g = d_src_new.cpu().numpy().reshape(source.shape, order='F')
+    scale = np.abs(src_r[:, :n]).max()
+    np.testing.assert_allclose(src_g[:, :n], src_r[:, :n], rtol=1e-5, atol=1e-6 * scale)
+    m = oshptr_r[npts]                                               # the new OSHPTR is the old SHPTR
+    assert m == shptr[npts]
+    del_g = d_del_new.cpu().numpy().reshape(delsource.shape, order='F')
+    np.testing.assert_allclose(del_g[:, :m], del_r[:, :m], rtol=1e-4, atol=1e-6 * scale)
+    np.testing.assert_allclose(sums, sums_r, rtol=1e-4, atol=1e-7 * max(abs(sums_r[3]), 1e-30))
+    # the old DELSOURCE is untouched
+    np.testing.assert_array_equal(d_del.cpu().numpy(), np.asarray(delsource).ravel(order='F'))
+
+
 def test_compute_source_out_of_sh_memory(oracle):
     from at3d_b200 import backend as B
     sc, shptr, source, oshptr, delsource, maxiv = _state_for_source('scalar_periodic_split', oracle)
