@@ -86,18 +86,23 @@ __device__ __forceinline__ int gw_refresh(const DevState &S, const DevGrad &G, c
     unsigned freeslots = 0;
     if (first_cell) freeslots = 0xFFu;
     else {
-#pragma unroll
-        for (int k = 0; k < 8; k++) {
-            if (!((used_old >> k) & 1u)) {
-                const unsigned s = GW_SLOT(perm, k);
-                freeslots |= 1u << s;
-                const double w_ = M.W[s * bt], g_ = M.Gr[s * bt], b_ = M.B[s * bt];
-                if (w_ != 0.0 || g_ != 0.0 || b_ != 0.0) {         // a visit in clear air contributes exactly nothing
-                    if (nrec < cap) gw_write(rec + nrec, K.pt[k], M.sf[s * bt], w_, g_, b_);
-                    else err = 5;
-                    nrec++;
-                    npairs += visit_pairs(G, K.pt[k]);
-                }
+        // (rolled: one copy of the record write instead of eight keeps the loop body of the march in the instruction cache)
+        unsigned leave = ~used_old & 0xFFu;
+#ifndef GW_UNROLL_EVICT
+#pragma unroll 1
+#endif
+        while (leave) {
+            const int k = __ffs(leave) - 1;
+            leave &= leave - 1;
+            const unsigned s = GW_SLOT(perm, k);
+            freeslots |= 1u << s;
+            const double w_ = M.W[s * bt], g_ = M.Gr[s * bt], b_ = M.B[s * bt];
+            if (w_ != 0.0 || g_ != 0.0 || b_ != 0.0) {         // a visit in clear air contributes exactly nothing
+                const int ptk = SEL8(K.pt, k);
+                if (nrec < cap) gw_write(rec + nrec, ptk, M.sf[s * bt], w_, g_, b_);
+                else err = 5;
+                nrec++;
+                npairs += visit_pairs(G, ptk);
             }
         }
     }
@@ -267,7 +272,7 @@ __device__ int thread_march_weights(const DevState &S, const DevGrad &G, const G
             for (int n = 0; n < 8; n++) f1[n] = fc[n];
         }
         if (exact_ss) {
-#pragma unroll
+#pragma unroll 1
             for (int n = 0; n < 8; n++) {
                 const unsigned sl = GW_SLOT(perm, n);
                 M.B[sl * bt] += adj * (double)M.bw[n * bt];
@@ -296,24 +301,27 @@ __device__ int thread_march_weights(const DevState &S, const DevGrad &G, const G
     }
     if (!first_cell) {
         // the corners of the last cell, then the surface points (FIND_BOUNDARY_RADIANCE_GRAD's beam weights)
-#pragma unroll
+#pragma unroll 1
         for (int k = 0; k < 8; k++) {
             const unsigned sl = GW_SLOT(perm, k);
             const double w_ = M.W[sl * bt], g_ = M.Gr[sl * bt], b_ = M.B[sl * bt];
             if (w_ != 0.0 || g_ != 0.0 || b_ != 0.0) {
-                if (nrec < cap) gw_write(rec + nrec, K.pt[k], M.sf[sl * bt], w_, g_, b_);
+                const int ptk = SEL8(K.pt, k);
+                if (nrec < cap) gw_write(rec + nrec, ptk, M.sf[sl * bt], w_, g_, b_);
                 else err = 5;
                 nrec++;
-                npairs += visit_pairs(G, K.pt[k]);
+                npairs += visit_pairs(G, ptk);
             }
         }
-#pragma unroll
+#pragma unroll 1
         for (int j = 0; j < 4; j++) {
-            if (bval[j] != 0.0) {
-                if (nrec < cap) gw_write(rec + nrec, boundpts[j], 0.0f, 0.0, 0.0, bval[j]);
+            const double bv = j == 0 ? bval[0] : j == 1 ? bval[1] : j == 2 ? bval[2] : bval[3];
+            const int bp = j == 0 ? boundpts[0] : j == 1 ? boundpts[1] : j == 2 ? boundpts[2] : boundpts[3];
+            if (bv != 0.0) {
+                if (nrec < cap) gw_write(rec + nrec, bp, 0.0f, 0.0, 0.0, bv);
                 else err = 5;
                 nrec++;
-                npairs += visit_pairs(G, boundpts[j]);
+                npairs += visit_pairs(G, bp);
             }
         }
     }
