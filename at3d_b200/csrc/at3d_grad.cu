@@ -459,7 +459,9 @@ weights_kernel_t(DevState S, DevGrad G, int nrays, int ray0, const float *camx, 
         M.B = (double *)q + tid; q += (size_t)8 * 8 * bt;
         M.sf = (float *)q + tid; q += (size_t)8 * 4 * bt;
         M.ss = (float *)q + tid; q += (size_t)8 * 4 * bt;
-        M.bw = (float *)q + tid;
+        M.bw = (float *)q + tid; q += (size_t)8 * 4 * bt;
+        M.fa = (double *)q + tid; q += (size_t)8 * 8 * bt;
+        M.fb = (double *)q + tid;
     }
     for (;;) {
         int base = 0;

@@ -19,13 +19,18 @@
 #include "at3d_tray.cuh"
 
 // per-thread view of the block's shared memory: element (slot s) of this thread at ptr[s * bt]
+#ifndef GW_FC_UNROLL
+#define GW_FC_UNROLL 8          // corners per iteration of the sub-interval update (8: fully unrolled, weights in registers)
+#endif
+constexpr int kGwFcUnroll = GW_FC_UNROLL;
 struct GwShared {
     double *W, *Gr, *B;
     float *sf, *ss, *bw;           // SRCEXT8/EXT, single-scatter part times EXT, SRCSINGSCAT of the current cell
+    double *fa, *fb;               // interpolation weights of the two ends of a sub-interval (GW_FC_UNROLL < 8)
     int bt;
 };
 
-__host__ __device__ inline size_t gw_smem_per_thread() { return 8 * (3 * 8 + 3 * 4); }
+__host__ __device__ inline size_t gw_smem_per_thread() { return 8 * (3 * 8 + 3 * 4) + (GW_FC_UNROLL < 8 ? 2 * 8 * 8 : 0); }
 
 // sequential reader of a ray's source stream
 struct SrcReader {
@@ -66,22 +71,27 @@ __device__ __forceinline__ int gw_refresh(const DevState &S, const DevGrad &G, c
     unsigned need = 0, used_old = 0, newperm = 0;
     const int bt = M.bt;
     int err = 0;
-#pragma unroll
-    for (int n = 0; n < 8; n++) {
-        const int ip = c.gp[n];
-        const int k1 = n ^ 1, k2 = n ^ 2, k4 = n ^ 4;
-        const int cp = jf == 1 ? K.pt[k1] : jf == 2 ? K.pt[k2] : K.pt[k4];
-        N.x[n] = jf == 1 ? K.x[k1] : jf == 2 ? K.x[k2] : K.x[k4];
-        N.y[n] = jf == 1 ? K.y[k1] : jf == 2 ? K.y[k2] : K.y[k4];
-        N.z[n] = jf == 1 ? K.z[k1] : jf == 2 ? K.z[k2] : K.z[k4];
-        N.ext[n] = jf == 1 ? K.ext[k1] : jf == 2 ? K.ext[k2] : K.ext[k4];
-        N.src[n] = jf == 1 ? K.src[k1] : jf == 2 ? K.src[k2] : K.src[k4];
-        N.pt[n] = ip;
-        const unsigned os = jf == 1 ? GW_SLOT(perm, k1) : jf == 2 ? GW_SLOT(perm, k2) : GW_SLOT(perm, k4);
-        const unsigned kb = jf == 1 ? (1u << k1) : jf == 2 ? (1u << k2) : (1u << k4);
-        if (jf != 0 && cp == ip) { used_old |= kb; newperm |= os << (4 * n); }
-        else need |= 1u << n;
+    // one copy of the inheritance per entry face (the face fixes which old corner n ^ 1 | 2 | 4 a new corner can inherit
+    // from): three times the code, a third of the instructions executed per cell
+#define GW_INHERIT(MASK)                                                                            \
+    _Pragma("unroll")                                                                               \
+    for (int n = 0; n < 8; n++) {                                                                   \
+        const int ip = c.gp[n];                                                                     \
+        const int k = n ^ (MASK);                                                                   \
+        N.x[n] = K.x[k]; N.y[n] = K.y[k]; N.z[n] = K.z[k]; N.ext[n] = K.ext[k]; N.src[n] = K.src[k]; \
+        N.pt[n] = ip;                                                                               \
+        if (K.pt[k] == ip) { used_old |= 1u << k; newperm |= GW_SLOT(perm, k) << (4 * n); }         \
+        else need |= 1u << n;                                                                       \
     }
+    if (jf == 1) { GW_INHERIT(1) }
+    else if (jf == 2) { GW_INHERIT(2) }
+    else if (jf == 3) { GW_INHERIT(4) }
+    else {
+#pragma unroll
+        for (int n = 0; n < 8; n++) { N.x[n] = N.y[n] = N.z[n] = N.ext[n] = N.src[n] = 0.0f; N.pt[n] = c.gp[n]; }
+        need = 0xFFu;
+    }
+#undef GW_INHERIT
     // old corners without an heir leave their record
     unsigned freeslots = 0;
     if (first_cell) freeslots = 0xFFu;
@@ -174,6 +184,13 @@ __device__ int thread_march_weights(const DevState &S, const DevGrad &G, const G
         interp_kernel(u, v, w, f1);
         srcext1 = fmaxf(0.0f, (float)fcsum(f1, K.src));
         ext1d = fcsum(f1, K.ext);
+#if GW_FC_UNROLL < 8
+        // the weights of the two ends of a sub-interval live in shared memory, so that the corner update below is a short
+        // loop instead of eight copies (the loop body of the march has to come out of the instruction cache every cell)
+        double *fprev = M.fa, *fcur = M.fb;
+#pragma unroll
+        for (int n = 0; n < 8; n++) fprev[n * bt] = f1[n];
+#endif
         ext1 = (float)ext1d;
         const bool ipinx = DBTEST(c.flags, 0) &&
             !(DBTEST(S.bcflag, 0) && ((rd.cx > 0 && xe < rd.xm) || (rd.cx < 0 && xe > rd.xm)));
@@ -244,10 +261,20 @@ __device__ int thread_march_weights(const DevState &S, const DevGrad &G, const G
                 const double aext = 0.5f * (ext0d + ext1d);
                 const double raext = aext != 0.0 ? 1.0 / aext : 0.0;
                 const double cg = 0.08333333333f * dels * (1.0f - 0.05f * (ext1d - ext0d) * dels);
+#if GW_FC_UNROLL < 8
 #pragma unroll
+                for (int n = 0; n < 8; n++) fcur[n * bt] = fc[n];
+#pragma unroll kGwFcUnroll
+#else
+#pragma unroll
+#endif
                 for (int n = 0; n < 8; n++) {
                     const unsigned sl = GW_SLOT(perm, n);
+#if GW_FC_UNROLL < 8
+                    const double f0n = fcur[n * bt], f1n = fprev[n * bt];
+#else
                     const double f0n = fc[n], f1n = f1[n];
+#endif
                     M.W[sl * bt] += wgt * ((0.5f * (f0n + f1n) + 0.08333333333f * (ext0 * f1n - ext1 * f0n) * corr) * rext);
                     if (exact_ss) {
                         const float ssn = M.ss[sl * bt];
@@ -268,8 +295,16 @@ __device__ int thread_march_weights(const DevState &S, const DevGrad &G, const G
             }
             ext1 = ext0; ext1d = ext0d;
             srcext1 = srcext0;
+#if GW_FC_UNROLL < 8
+            if (ext != 0.0) { double *t_ = fprev; fprev = fcur; fcur = t_; }
+            else {
+#pragma unroll
+                for (int n = 0; n < 8; n++) fprev[n * bt] = fc[n];
+            }
+#else
 #pragma unroll
             for (int n = 0; n < 8; n++) f1[n] = fc[n];
+#endif
         }
         if (exact_ss) {
 #pragma unroll 1

@@ -180,20 +180,25 @@ __device__ __forceinline__ void thread_refresh(const DevState &S, const CellRec 
 {
     TCorners N;
     unsigned need = 0;
-#pragma unroll
-    for (int n = 0; n < 8; n++) {
-        const int ip = c.gp[n];
-        // candidate: old corner n^1, n^2 or n^4
-        const int k1 = n ^ 1, k2 = n ^ 2, k4 = n ^ 4;
-        const int cp = jf == 1 ? K.pt[k1] : jf == 2 ? K.pt[k2] : K.pt[k4];
-        N.x[n] = jf == 1 ? K.x[k1] : jf == 2 ? K.x[k2] : K.x[k4];
-        N.y[n] = jf == 1 ? K.y[k1] : jf == 2 ? K.y[k2] : K.y[k4];
-        N.z[n] = jf == 1 ? K.z[k1] : jf == 2 ? K.z[k2] : K.z[k4];
-        N.ext[n] = jf == 1 ? K.ext[k1] : jf == 2 ? K.ext[k2] : K.ext[k4];
-        N.src[n] = jf == 1 ? K.src[k1] : jf == 2 ? K.src[k2] : K.src[k4];
-        N.pt[n] = ip;
-        if (jf == 0 || cp != ip) need |= 1u << n;
+    // one copy of the inheritance per entry face (candidate: old corner n^1, n^2 or n^4): a third of the instructions per cell
+#define T_INHERIT(MASK)                                                                             \
+    _Pragma("unroll")                                                                               \
+    for (int n = 0; n < 8; n++) {                                                                   \
+        const int ip = c.gp[n];                                                                     \
+        const int k = n ^ (MASK);                                                                   \
+        N.x[n] = K.x[k]; N.y[n] = K.y[k]; N.z[n] = K.z[k]; N.ext[n] = K.ext[k]; N.src[n] = K.src[k]; \
+        N.pt[n] = ip;                                                                               \
+        if (K.pt[k] != ip) need |= 1u << n;                                                         \
     }
+    if (jf == 1) { T_INHERIT(1) }
+    else if (jf == 2) { T_INHERIT(2) }
+    else if (jf == 3) { T_INHERIT(4) }
+    else {
+#pragma unroll
+        for (int n = 0; n < 8; n++) { N.x[n] = N.y[n] = N.z[n] = N.ext[n] = N.src[n] = 0.0f; N.pt[n] = c.gp[n]; }
+        need = 0xFFu;
+    }
+#undef T_INHERIT
     K = N;
     while (need) {
         const int n = __ffs(need) - 1;
