@@ -390,6 +390,9 @@ cudaError_t launch_view_source(const DevState &S, const RayPack &pk, double mu2,
 }
 
 // threads per block of the thread-per-ray kernels: as many YLMDIR columns (4*NLMP bytes) as fit
+#ifndef AT3D_TRAY_SMEM_KB
+#define AT3D_TRAY_SMEM_KB 220
+#endif
 int tray_block_threads(const DevState &S)
 {
 #ifdef AT3D_FORCE_OCTET
@@ -397,7 +400,7 @@ int tray_block_threads(const DevState &S)
 #endif
     if (S.nstokes != 1) return 0;
     const size_t per = (size_t)S.nlmp * sizeof(float);
-    int bt = (int)((220 * 1024) / per) & ~31;
+    int bt = (int)((AT3D_TRAY_SMEM_KB * 1024) / per) & ~31;
     if (bt > 256) bt = 256;
     return bt >= 64 ? bt : 0;
 }
