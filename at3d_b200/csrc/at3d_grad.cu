@@ -27,6 +27,7 @@
 #include <cstdarg>
 #include <cstdlib>
 #include <algorithm>
+#include <chrono>
 #include <vector>
 #include <cub/cub.cuh>
 #include "at3d_host.h"
@@ -1371,6 +1372,9 @@ extern "C" int at3d_state_attach_gradient(at3d_state *st, const at3d_grad_desc *
     if (errmsg) errmsg[0] = 0;
     if (!st || !g) { set_msg(errmsg, "null argument"); return 1; }
     std::lock_guard<std::mutex> lock(st->mu);
+    const bool attach_timing = getenv("AT3D_B200_ATTACH_TIMING") != nullptr;
+    auto tnow = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_attach0 = tnow();
     if (!st->S.radrec) { set_msg(errmsg, "the state was created without RADIANCE/RSHPTR: the gradient needs them"); return 1; }
     if (g->numder < 1) { set_msg(errmsg, "NUMDER must be >= 1"); return 1; }
     const bool solar = st->S.srctype != 'T', thermal = st->S.srctype != 'S';
@@ -1443,6 +1447,7 @@ extern "C" int at3d_state_attach_gradient(at3d_state *st, const at3d_grad_desc *
         return 1;
     }
     if (G.exact_single_scatter && !G.stream_beam && (!G.dpath || !G.dptr)) { set_msg(errmsg, "EXACT_SINGLE_SCATTER needs DPATH and DPTR (or neither: streaming)"); return 1; }
+    const double t_attach1 = tnow();
     // ray-independent tables of COMPUTE_SOURCE_GRAD_1CELL (grad_prep_kernel)
     {
         const bool deltam = S.deltam != 0;
@@ -1490,10 +1495,14 @@ extern "C" int at3d_state_attach_gradient(at3d_state *st, const at3d_grad_desc *
         const int wpb = 4;
         const size_t smem = (size_t)wpb * (nlt + G.ntup) * sizeof(float);
         if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(grad_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const double t_attach2 = tnow();
         grad_prep_kernel<<<(S.npts + wpb - 1) / wpb, wpb * 32, smem>>>(S, G, rowrec, sprec, dsh, dlegt, legs);
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaDeviceSynchronize());
         G.rowrec = rowrec; G.sprec = sprec; G.dsh = dsh; G.dlegt = dlegt; G.legs = legs;
+        if (attach_timing)
+            fprintf(stderr, "[attach] uploads %.2f ms, row tables (host prefix sums, allocations) %.2f ms, grad_prep_kernel %.2f ms\n",
+                    t_attach1 - t_attach0, t_attach2 - t_attach1, tnow() - t_attach2);
     }
     st->grad_attached = 1;
     return 0;

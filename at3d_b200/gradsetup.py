@@ -158,8 +158,9 @@ STREAM_BEAM_BYTES = 4 << 30     # dense DPATH/DPTR lists larger than this are no
 
 def _beam_lists(gi, st, pg, backend, exact_single_scatter, stream_beam):
     """Direct-beam derivative inputs: the dense lists of MAKE_DIRECT -> MAKE_DIRECT_DERIVATIVE (shdomsub5.f:1553), or --
-    `stream_beam` True, or None and the lists would exceed STREAM_BEAM_BYTES -- only the beam constants, so that the
-    gradient call walks the paths itself (at3d_grad_desc.beam_*; CUDA backend only, the oracle takes the lists)."""
+    `stream_beam` True, or None with the CUDA backend -- only the beam constants, so that the gradient call walks the paths
+    itself (at3d_grad_desc.beam_*; the oracle takes the lists).  STREAM_BEAM_BYTES: the size above which bench.py does not
+    build the lists for its CPU arm."""
     gi.longest_path_pts = 1
     if not exact_single_scatter:
         gi.dpath = np.zeros((1, st.npts), np.float32, order='F')
@@ -167,7 +168,9 @@ def _beam_lists(gi, st, pg, backend, exact_single_scatter, stream_beam):
         return
     _, _, c = backend.make_direct(st, pg)
     if stream_beam is None:
-        stream_beam = 8 * int(c['longest_path_pts']) * int(st.npts) > STREAM_BEAM_BYTES and getattr(backend, '__name__', '').startswith('at3d_b200')
+        # the CUDA backend walks the paths inside the gradient call: no LONGEST_PATH_PTS x NPTS lists to build, read back and
+        # upload again per cost-function evaluation (185 MB and ~40 ms at BASELINE configs[1] for +0.2 ms per gradient call)
+        stream_beam = getattr(backend, '__name__', '').startswith('at3d_b200')
     if stream_beam:
         _set_streaming(gi, pg, c)
         return

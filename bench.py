@@ -295,8 +295,12 @@ def inversion_step_leg(sc, rays, gi, pix, DeviceState):
     the derivative tables, and the radiance + gradient pass with host buffers; wall-clock ms of each part.  `warm` is the
     next evaluation of the loop: a slightly different medium on the same grid given to the LIVE solver object
     (at3d_solver_update_medium: sweep order, dependency levels and sorted plan kept), solved, uploaded, differentiated."""
-    from at3d_b200 import solver, backend
+    from at3d_b200 import solver, backend, gradsetup
     was = backend.memory_reuse(True)      # what Optimizer.minimize does: freed device memory stays with the library
+    # what RTE.levis_approx_gradient attaches: no dense DPATH/DPTR lists (185 MB to upload per evaluation here), the beam
+    # walks run inside the gradient call
+    if gi.dpath is not None and gi.exact_single_scatter:
+        gi = gradsetup.with_streaming_beam(gi, sc.state, sc.pg, backend)
     st = sc.state
     delphi = np.float32(2.0 * np.pi) / st.nphi0.astype(np.float32)
     wtmu = (st.wtdo[:, 0] / delphi).astype(np.float32)
