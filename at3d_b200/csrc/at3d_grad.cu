@@ -1713,14 +1713,15 @@ static int gradient_impl(at3d_state *st, const at3d_rays *rays, const at3d_grad_
             if (use_t) {
                 // the stream pool is sized by the entries per ray the last call on this state saw
                 // (limit: AT3D_B200_SRC_GB, default 45 % of the memory this pool could get, between 4 and 64 GB)
-                double src_gb = 16.0;
-                {
+                if (st->src_gb_limit <= 0.0) {              // once per state: cudaMemGetInfo is not a call for every step
                     size_t fr = 0, tot = 0;
+                    st->src_gb_limit = 16.0;
                     if (cudaMemGetInfo(&fr, &tot) == cudaSuccess) {
-                        src_gb = 0.45 * (double)(fr + st->slabs.cap) / 1073741824.0;
-                        src_gb = src_gb < 4.0 ? 4.0 : (src_gb > 64.0 ? 64.0 : src_gb);
+                        const double v = 0.45 * (double)(fr + st->slabs.cap) / 1073741824.0;
+                        st->src_gb_limit = v < 4.0 ? 4.0 : (v > 64.0 ? 64.0 : v);
                     }
                 }
+                double src_gb = st->src_gb_limit;
                 if (const char *e = getenv("AT3D_B200_SRC_GB")) { const double v = atof(e); if (v > 0.0) src_gb = v; }
                 const double est = st->gw_rec_per_ray > 0.0 ? st->gw_rec_per_ray : (double)(6 * (S.nx + S.ny + S.nz) + 64);
                 src_chunks = (size_t)(((double)n * (est * 1.5 + AT3D_SRC_CHUNK) + 4096.0) / AT3D_SRC_CHUNK);

@@ -46,6 +46,7 @@ struct at3d_state {
     unsigned long long *counts_dev = nullptr;
     std::vector<long long> recoff_h; // per-ray visit-record offsets of the last gradient call (host copy)
     void *hpin = nullptr;            // small pinned buffer for the asynchronous read-backs of the gradient call
+    double src_gb_limit = 0.0;       // size limit of the source-stream pool (from the free memory, once per state)
     std::vector<int> nr_h;          // radiance SH length per point (host copy, for the gradient tables)
     int *ray_counter = nullptr;     // work counter of the persistent ray kernels
     int nbcrad = 0;
