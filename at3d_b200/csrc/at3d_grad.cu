@@ -1834,23 +1834,13 @@ static int gradient_impl(at3d_state *st, const at3d_rays *rays, const at3d_grad_
         }
         const long long *roff = st->recoff_h.data();
         const size_t smem = (size_t)AT3D_RAYS_PER_BLOCK * (S.ny_comp * S.nlmp + ((3 * (S.ml + 1) + 3) & ~3)) * sizeof(float);
-        int dev = 0, nsm = 148, per_sm_w = 1, per_sm_a = 1;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
-        const void *fnw = nst == 1 ? (const void *)weights_kernel<1> : (const void *)weights_kernel<3>;
-        const void *fna = nst == 1 ? (const void *)apply_kernel<1, true> : (const void *)apply_kernel<3, true>;
-        CUDA_TRY(cudaFuncSetAttribute(fnw, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CUDA_TRY(cudaFuncSetAttribute(fna, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_w, fnw, AT3D_RAY_THREADS, smem);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_a, fna, AT3D_RAY_THREADS, smem);
-        if (per_sm_w < 1) per_sm_w = 1;
-        if (per_sm_a < 1) per_sm_a = 1;
+        static thread_local KernelFit fit_w, fit_a, fit_t;
+        if (nst == 1) { kernel_fit(fit_w, weights_kernel<1>, AT3D_RAY_THREADS, smem); kernel_fit(fit_a, apply_kernel<1, true>, AT3D_RAY_THREADS, smem); }
+        else { kernel_fit(fit_w, weights_kernel<3>, AT3D_RAY_THREADS, smem); kernel_fit(fit_a, apply_kernel<3, true>, AT3D_RAY_THREADS, smem); }
         const int gw_bt = GW_BT;
         const size_t smem_t = gw_smem_per_thread() * gw_bt;
-        int per_sm_t = 1;
-        CUDA_TRY(cudaFuncSetAttribute(weights_kernel_t, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_t, weights_kernel_t, gw_bt, smem_t);
-        if (per_sm_t < 1) per_sm_t = 1;
+        kernel_fit(fit_t, weights_kernel_t, gw_bt, smem_t);
+        const int nsm = fit_t.nsm, per_sm_w = fit_w.per_sm, per_sm_a = fit_a.per_sm, per_sm_t = fit_t.per_sm;
         CUDA_TRY(cudaMemsetAsync(npairs, 0, sizeof(int) * (n + 1), stream));
         float ms_weights = 0.0f, ms_accum = 0.0f;
         size_t r0 = 0;

@@ -10,6 +10,28 @@
 
 struct RayErr;
 
+// cudaFuncSetAttribute + occupancy query of a kernel for (device, block size, dynamic shared memory): asked once and
+// remembered at the call site -- driver queries are not free on a box where several processes (or nvidia-smi) talk to the
+// driver at the same time, and these sit between the launches of every step
+struct KernelFit {
+    const void *fn = nullptr;
+    int dev = -1, threads = 0;
+    size_t smem = 0;
+    int per_sm = 1, nsm = 148;
+};
+template <class K>
+inline void kernel_fit(KernelFit &c, K kernel, int threads, size_t smem)
+{
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (c.fn == (const void *)kernel && c.dev == dev && c.threads == threads && c.smem == smem) return;
+    cudaDeviceGetAttribute(&c.nsm, cudaDevAttrMultiProcessorCount, dev);
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c.per_sm, kernel, threads, smem);
+    if (c.per_sm < 1) c.per_sm = 1;
+    c.fn = (const void *)kernel; c.dev = dev; c.threads = threads; c.smem = smem;
+}
+
 // device buffer that grows on demand and is reused between calls.  These are the large streaming buffers (source stream,
 // visit records, pairs, ray staging): plain cudaMalloc blocks (contiguous, large pages), parked in a process-wide cache
 // when their owner goes away and taken from it by the next owner (at3d_capi.cu).

@@ -414,14 +414,9 @@ size_t render_smem_bytes(const DevState &S)
 template <typename K>
 static int persistent_blocks(K kernel, int nrays, size_t smem)
 {
-    int dev = 0, nsm = 148, per_sm = 1;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
-    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, AT3D_RAY_THREADS, smem);
-    if (per_sm < 1) per_sm = 1;
-    const long want = ((long)nrays + AT3D_RAYS_PER_BLOCK - 1) / AT3D_RAYS_PER_BLOCK;
-    const long cap = (long)nsm * per_sm;
+    static thread_local KernelFit fit;                  // one per kernel instantiation
+    kernel_fit(fit, kernel, AT3D_RAY_THREADS, smem);
+    const long want = ((long)nrays + AT3D_RAYS_PER_BLOCK - 1) / AT3D_RAYS_PER_BLOCK, cap = (long)fit.nsm * fit.per_sm;
     return (int)(want < cap ? want : cap);
 }
 
@@ -440,15 +435,11 @@ cudaError_t launch_forward(const DevState &S, int nrays, const float *camx, cons
     const int bt = tray_block_threads(S);
     if (bt > 0) {
         const size_t smem_t = (size_t)bt * S.nlmp * sizeof(float);
-        int dev = 0, nsm = 148, per_sm = 1;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
 #define LAUNCHT(MODES, OUTA, outa)                                                                 \
         {                                                                                          \
-            cudaFuncSetAttribute(forward_kernel_t<MODES, OUTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t); \
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, forward_kernel_t<MODES, OUTA>, bt, smem_t);    \
-            if (per_sm < 1) per_sm = 1;                                                            \
-            const long want = ((long)nrays + bt - 1) / bt, cap = (long)nsm * per_sm;               \
+            static thread_local KernelFit fit;                                                     \
+            kernel_fit(fit, forward_kernel_t<MODES, OUTA>, bt, smem_t);                            \
+            const long want = ((long)nrays + bt - 1) / bt, cap = (long)fit.nsm * fit.per_sm;       \
             forward_kernel_t<MODES, OUTA><<<(int)(want < cap ? want : cap), bt, smem_t, stream>>>(S, nrays, camx, camy, \
                 camz, cammu, camphi, packs, outa, out_tot, correctinterpolate, singlescatter, nosurface, maxsub,  \
                 trace_cells, trace_cap, trace_n, trace_nsub, err, ray_counter, npt_out);           \
