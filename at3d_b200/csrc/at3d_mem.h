@@ -7,8 +7,8 @@
 //   at3d_malloc : the pointer is valid on every stream when the call returns (pooled: the allocation is completed on the
 //                 legacy default stream and that stream is synchronised).
 //   at3d_free   : cudaFree semantics -- the device is idle when the memory goes back to the pool.
-// Off by default because the thread-per-ray forward pass was measured 0-20 % slower (run to run) on recycled memory than on
-// fresh cudaMalloc blocks (DESIGN.md "Allocation"); loops that build states per step gain far more than that.
+// Off by default only because the library would keep freed memory away from the other allocators of the process (torch's);
+// the kernels run at the same speed on recycled and on fresh memory.
 #pragma once
 #include <cuda_runtime.h>
 
