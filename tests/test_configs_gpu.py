@@ -270,3 +270,30 @@ def test_cfg4s_chunked_derivative_pass_equals_the_single_pass(cfg4s, cfg4s_gradi
     assert float(costc[0]) == float(cost[0])
     np.testing.assert_allclose(gc, g, rtol=1e-9, atol=1e-12 * np.abs(g).max())
     assert np.count_nonzero(g) > 100000 and np.all(np.isfinite(g))
+
+
+def test_cfg4s_streaming_beam_derivative_equals_the_dense_lists(cfg4s, cfg4s_gradient):
+    """All 590 k rays over 1.05 M grid points: the gradient with the direct-beam walks done inside the call (no DPATH / DPTR
+    lists: what the cfg4 gradient needs, where they would take 125 GB) equals the one from the dense lists to the rounding of
+    its FP64 sums, also with many more passes over point ranges.  Runs last: it re-attaches the derivative tables."""
+    from at3d_b200 import backend as B, gradsetup
+    sc, rays, dev = cfg4s
+    gi, pix = cfg4s_gradient
+    g, cost, so = dev.gradient(rays, pix)
+    dev.attach_gradient(gradsetup.with_streaming_beam(gi, sc.state, sc.pg, B))
+    gs, costs, sos = dev.gradient(rays, pix)
+    # ~1e9 terms here: the streaming walks run in passes of 2^29 pairs, each pass summed on its own and added to GRADOUT, so
+    # the sums agree to rounding (bit for bit in a single pass: tests/test_gradient_gpu.py)
+    np.testing.assert_allclose(gs, g, rtol=1e-9, atol=1e-12 * np.abs(g).max())
+    np.testing.assert_array_equal(sos, so)
+    old = os.environ.get('AT3D_B200_BEAM_PAIRS')
+    os.environ['AT3D_B200_BEAM_PAIRS'] = str(1 << 24)
+    try:
+        gp, costp, sop = dev.gradient(rays, pix)
+    finally:
+        if old is None:
+            del os.environ['AT3D_B200_BEAM_PAIRS']
+        else:
+            os.environ['AT3D_B200_BEAM_PAIRS'] = old
+    np.testing.assert_allclose(gp, g, rtol=1e-9, atol=1e-12 * np.abs(g).max())
+    dev.attach_gradient(gi)
