@@ -53,7 +53,7 @@ class RTE:
         self._nstleg = 1 if num_stokes == 1 else 6
         self.numerical_params = numerical_params
         self.medium = dict(medium) if isinstance(medium, dict) else {'medium': medium}
-        self.source, self.surface = source, surface
+        self.source, self.surface, self.atmosphere = source, surface, atmosphere
         p = numerical_params
         self._nmu = max(2, 2 * int((int(_scalar(p, 'num_mu_bins')) + 1) / 2))
         self._nphi = max(1, int(_scalar(p, 'num_phi_bins')))
@@ -150,6 +150,8 @@ class RTE:
         self._npx, self._npy, self._npz = x.size, y.size, z.size
         self._delx, self._dely = np.float32(_scalar(grid, 'delx')), np.float32(_scalar(grid, 'dely'))
         self._zlevels = z.astype(np.float32)
+        # the reference's `_grid` dataset (at3d/solver.py:2055-2060): what save_forward_model stores as the solver's grid
+        self._grid = {'x': x, 'y': y, 'z': z, 'delx': _v(grid, 'delx'), 'dely': _v(grid, 'dely')}
         self._nx, self._ny, self._nz = max(1, self._npx), max(1, self._npy), max(2, self._npz)
         if self._nx == 1:
             self._ipflag |= 1
