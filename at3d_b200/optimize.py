@@ -3,16 +3,18 @@
 
 ``ObjectiveFunction.LevisApproxUncorrelatedL2`` and ``Optimizer.minimize`` take the arguments of the reference
 (at3d/optimize.py:20-144, 146-230) and drive ``scipy.optimize.minimize(jac=True)`` with the GPU cost + gradient.
-``GridStateGenerator`` is the identity-transform case of ``StateGenerator``: the state vector is the unknown optical
-property (extinction and / or ssalb) of the named scatterers on the property grid (optionally masked); calling it with a
-state rebuilds the solvers (as the reference does every evaluation, at3d/medium.py:1813-1831) and
-``project_gradient_to_state`` restricts the gridded gradient to the state's entries (:1751-1811).
+``GridStateGenerator`` is ``StateGenerator`` for optical unknowns: the state vector holds the unknown optical property
+(extinction and / or ssalb) of the named scatterers, each through its own coordinate transform and state <-> grid map
+(at3d_b200/transforms.py; default: no transform, the masked grid points); calling it with a state rebuilds the solvers
+(as the reference does every evaluation, at3d/medium.py:1813-1831), ``project_gradient_to_state`` takes the gridded
+gradient back to the state (:1860-1890) and ``transform_bounds`` the physical bounds (:1892-1925).
 """
 import time
 from collections import OrderedDict
 import numpy as np
 from . import containers
 from . import gradient as gradient_mod
+from . import transforms as TR
 from .rte import RTE, _v
 
 
@@ -116,15 +118,19 @@ class Optimizer:
 
 
 class GridStateGenerator:
-    """state vector <-> solvers for optical unknowns on the property grid (identity transform of at3d.medium.StateGenerator).
+    """state vector <-> solvers for optical unknowns on the property grid (at3d.medium.StateGenerator, at3d/medium.py:1649-1925).
 
     `solvers`: the SolversDict to (re)fill; `unknown_scatterers`; `mediums`: key -> OrderedDict scatterer name -> scatterer
     mapping (the fixed part; the unknown variables are overwritten from the state); `sources`, `surfaces`,
     `numerical_parameters`: key -> mapping; `num_stokes`: key -> int; `mask`: optional boolean [x, y, z] of the grid points
-    in the state."""
+    in the state; `transforms`: optional mapping ``(scatterer name, variable name) -> (coordinate_transform,
+    state_to_grid)`` with the objects of at3d_b200/transforms.py (the reference's ``UnknownScatterer.add_variable``,
+    :1502-1537; None = no coordinate transform / the mask map).  The state vector is the concatenation of the variables'
+    parts, each as long as its state_to_grid map says (``StateRepresentation``, :1596-1647).  Grid points a map leaves
+    out (outside its mask) keep the value of the fixed medium."""
 
     def __init__(self, solvers, unknown_scatterers, mediums, sources, surfaces, numerical_parameters, num_stokes, mask=None,
-                 warm_start=True):
+                 warm_start=True, transforms=None):
         self._solvers, self._unknown = solvers, unknown_scatterers
         self._warm_start = bool(warm_start)
         self._mediums, self._sources, self._surfaces = mediums, sources, surfaces
@@ -132,29 +138,48 @@ class GridStateGenerator:
         grid = next(iter(next(iter(mediums.values())).values()))
         shape = np.asarray(_v(grid, 'extinction')).shape
         self._mask = np.ones(shape, bool) if mask is None else np.asarray(mask, bool)
-        self._nper = int(self._mask.sum())
         self._slots = [(name, v) for name, e in unknown_scatterers.items() for v in e.variables]
+        transforms = {} if transforms is None else dict(transforms)
+        unknown = set(transforms) - set(self._slots)
+        if unknown:
+            raise KeyError('`transforms` names variables that are not unknowns: {}'.format(sorted(unknown)))
+        self._transforms = []
+        for slot in self._slots:
+            coordinate, to_grid = transforms.get(slot, (None, None))
+            coordinate = TR.CoordinateTransform() if coordinate is None else coordinate
+            to_grid = TR.StateToGridMask(mask=self._mask) if to_grid is None else to_grid
+            if tuple(to_grid._grid_shape) != tuple(shape):
+                raise ValueError("the state_to_grid map of {} is for grid shape {}, the medium has {}".format(
+                    slot, tuple(to_grid._grid_shape), tuple(shape)))
+            self._transforms.append((coordinate, to_grid))
+        ends = np.cumsum([t[1].state_size for t in self._transforms])
+        self._bounds = list(zip(np.concatenate(([0], ends[:-1])).tolist(), ends.tolist()))
 
     @property
     def state_size(self):
-        return self._nper * len(self._slots)
+        return self._bounds[-1][1] if self._bounds else 0
 
     def get_state(self, key=None):
-        """The state vector of the current mediums."""
+        """The state vector of the current mediums (:1834-1858)."""
         key = next(iter(self._mediums)) if key is None else key
-        return np.concatenate([np.asarray(_v(self._mediums[key][n], v), np.float64)[self._mask] for n, v in self._slots])
+        return np.concatenate([np.asarray(ct.inverse_transform(s2g.inverse_transform(
+            np.asarray(_v(self._mediums[key][n], v), np.float64))), np.float64).reshape(-1)
+            for (n, v), (ct, s2g) in zip(self._slots, self._transforms)])
 
     def __call__(self, state):
-        """set_state_fn: rebuild every solver with the unknown variables taken from `state`."""
+        """set_state_fn: rebuild every solver with the unknown variables taken from `state` (:1787-1832)."""
         state = np.asarray(state, np.float64)
+        if state.shape != (self.state_size,):
+            raise ValueError('state must have {} entries'.format(self.state_size))
         for key in list(self._mediums):
             medium = OrderedDict()
             for name, sc in self._mediums[key].items():
                 sc = dict(sc)
-                for i, (n, v) in enumerate(self._slots):
+                for (n, v), (ct, s2g), (a, b) in zip(self._slots, self._transforms, self._bounds):
                     if n == name:
                         arr = np.array(_v(sc, v), np.float32)
-                        arr[self._mask] = state[i * self._nper:(i + 1) * self._nper]
+                        gridded = s2g(ct(state[a:b]))                    # UnknownScatterer.get_grid_data (:1539-1559)
+                        arr[s2g._where] = gridded[s2g._where]
                         sc[v] = arr
                 medium[name] = sc
             old = self._solvers.get(key)
@@ -173,5 +198,20 @@ class GridStateGenerator:
                 self._solvers[key].load_solution(previous)
 
     def project_gradient_to_state(self, state, gradient_dataset):
+        """Gridded gradient -> state gradient: state_to_grid, then the chain rule of the coordinate transform on that
+        variable's part of the state (:1860-1890)."""
         g = np.asarray(gradient_dataset['gradient'])
-        return np.concatenate([g[..., i][self._mask] for i in range(len(self._slots))]).astype(np.float64)
+        state = np.asarray(state, np.float64)
+        return np.concatenate([np.asarray(ct.gradient_transform(state[a:b], s2g.gradient_transform(g[..., i])),
+                                          np.float64).reshape(-1)
+                               for i, ((ct, s2g), (a, b)) in enumerate(zip(self._transforms, self._bounds))])
+
+    def transform_bounds(self, bounds):
+        """``(lower, upper)`` of the state vector from physical bounds (:1892-1925).  `bounds`: mapping ``(scatterer name,
+        variable name) -> (lower, upper)``, scalars or gridded arrays; swapped where a transform reverses the order."""
+        lower, upper = np.zeros(self.state_size), np.zeros(self.state_size)
+        shape = self._mask.shape
+        for slot, (ct, s2g), (a, b) in zip(self._slots, self._transforms, self._bounds):
+            for value, out in zip(bounds[slot], (lower, upper)):
+                out[a:b] = ct.inverse_transform(s2g.inverse_bounds_transform(np.broadcast_to(np.asarray(value, float), shape)))
+        return np.minimum(lower, upper), np.maximum(lower, upper)
