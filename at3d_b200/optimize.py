@@ -66,7 +66,7 @@ class Optimizer:
 
     def __init__(self, objective_fn, prior_fn=None, callback_fn=None, method='L-BFGS-B', options=None):
         self._method = method
-        self._options = dict(options or {'maxiter': 100, 'maxls': 30, 'gtol': 1e-16, 'ftol': 1e-8})
+        self._options = dict(options or {'maxiter': 100, 'maxls': 10, 'gtol': 1e-16, 'ftol': 1e-8})      # the reference's, less 'disp'
         self._objective_fn = objective_fn
         self._prior_fn = list(np.atleast_1d(prior_fn)) if prior_fn is not None else []
         self._callback_fn = list(np.atleast_1d(callback_fn)) if callback_fn is not None else []
@@ -76,13 +76,13 @@ class Optimizer:
 
     def callback(self, state):
         self._iteration += 1
-        self._state = state
         return [fn(optimizer=self) for fn in self._callback_fn]
 
     def objective(self, state):
+        self._state = state
         loss, gradient = self._objective_fn(state)
         for prior in self._prior_fn:
-            p_loss, p_grad = prior(state)
+            p_loss, p_grad = prior(state, self._iteration)          # at3d/optimize.py:196
             loss += p_loss
             gradient = gradient + p_grad
         self._loss_history.append(float(loss))
@@ -115,6 +115,42 @@ class Optimizer:
     @property
     def loss_history(self):
         return self._loss_history
+
+    @property
+    def iteration(self):
+        return self._iteration
+
+    @property
+    def method(self):
+        return self._method
+
+    @property
+    def options(self):
+        return self._options
+
+    @property
+    def state(self):
+        """The state of the latest objective evaluation (what callbacks read through ``optimizer``)."""
+        return self._state
+
+
+class CallbackFn:
+    """Calls ``callback_fn(optimizer=...)`` at most every `ckpt_period` seconds and collects the values of the dictionary
+    it returns, by name, in ``output`` (at3d/callback.py:32-75)."""
+
+    def __init__(self, callback_fn, ckpt_period=-1):
+        self._ckpt_period = ckpt_period
+        self._ckpt_time = time.time()
+        self._callback_fn = callback_fn
+        self.output = {}
+
+    def __call__(self, optimizer=None):
+        now = time.time()
+        if now - self._ckpt_time > self._ckpt_period:
+            self._ckpt_time = now
+            out = self._callback_fn(optimizer=optimizer)
+            for name, value in (out or {}).items():
+                self.output.setdefault(name, []).append(value)
 
 
 class GridStateGenerator:
