@@ -1,0 +1,90 @@
+"""at3d_b200/sensor.py and at3d_b200/transforms.py against outputs of the reference's own modules
+(tests/golden/make_host_goldens.py ran at3d/sensor.py and at3d/transforms.py unmodified): bit for bit."""
+import os
+import warnings
+import numpy as np
+import pytest
+from at3d_b200 import sensor as SN
+from at3d_b200 import transforms as TR
+
+GOLD = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'host_goldens.npz'))
+BOX = {'x': np.linspace(0.0, 0.64, 33), 'y': np.linspace(0.0, 0.72, 37), 'z': np.linspace(0.0, 1.04, 27)}
+
+SENSORS = {
+    'ortho': lambda: SN.orthographic_projection(0.672, BOX, 0.08, 0.09, 37.0, 25.0, stokes=['I', 'Q']),
+    'ortho_gauss': lambda: SN.orthographic_projection(0.672, BOX, 0.16, 0.12, 200.0, 40.0, altitude=1.5, stokes='I',
+                                                      sub_pixel_ray_args={'method': SN.gaussian, 'degree': (2, 3)}),
+    'ortho_uniform': lambda: SN.orthographic_projection(1.65, BOX, 0.2, 0.2, 0.0, 0.0,
+                                                        sub_pixel_ray_args={'method': SN.uniform, 'nrays': 2}),
+    'persp': lambda: SN.perspective_projection(0.672, 17.0, 7, 5, [0.3, -0.2, 5.0], [0.32, 0.36, 0.5], [0, 1, 0],
+                                               stokes=['I', 'Q', 'U']),
+    'persp_stoch': lambda: SN.perspective_projection(0.672, 30.0, 4, 6, [2.0, 1.5, 3.0], [0.3, 0.3, 0.4], [0, 0, 1], stokes='I',
+                                                     sub_pixel_ray_args={'method': SN.stochastic, 'nrays': (3, 2), 'seed': 11}),
+    'domaintop': lambda: SN.domaintop_projection(0.672, BOX, 0.1, 0.15, 75.0, 35.0, x_offset=0.01, y_offset=-0.02),
+}
+
+
+@pytest.mark.parametrize('case', sorted(SENSORS))
+def test_sensor_matches_the_reference(case):
+    got = SENSORS[case]()
+    names = [k.split('/', 1)[1] for k in GOLD.files if k.startswith(case + '/')]
+    assert set(names) == set(got) and len(names) >= 14
+    for name in names:
+        ref, mine = GOLD[case + '/' + name], np.asarray(got[name])
+        assert mine.shape == ref.shape, name
+        assert mine.dtype.kind == ref.dtype.kind, name
+        np.testing.assert_array_equal(mine, ref, err_msg=name)
+    # what the ray lists must satisfy whatever the projection
+    w = np.bincount(got['pixel_index'], weights=got['ray_weight'])
+    np.testing.assert_allclose(w, 1.0, rtol=1e-12)
+    assert got['stokes'].dtype == bool and got['stokes'].shape == (4,)
+
+
+def test_sensor_argument_checks():
+    with pytest.raises(ValueError, match='1-D'):
+        SN.make_sensor_dataset(np.zeros((2, 2)), np.zeros(4), np.zeros(4), np.ones(4), np.zeros(4), 'I', 0.6)
+    with pytest.raises(ValueError, match='same size'):
+        SN.make_sensor_dataset(np.zeros(3), np.zeros(4), np.zeros(4), np.ones(4), np.zeros(4), 'I', 0.6)
+    with pytest.raises(ValueError, match='altitudes'):
+        SN.make_sensor_dataset(np.zeros(2), np.zeros(2), -np.ones(2), np.ones(2), np.zeros(2), 'I', 0.6)
+    with pytest.raises(ValueError, match='0.0 are not allowed'):
+        SN.make_sensor_dataset(np.zeros(2), np.zeros(2), np.ones(2), np.zeros(2), np.zeros(2), 'I', 0.6)
+    with pytest.raises(ValueError, match='Stokes'):
+        SN.make_sensor_dataset(np.zeros(2), np.zeros(2), np.ones(2), np.ones(2), np.zeros(2), 'X', 0.6)
+    with pytest.raises(KeyError, match='Invalid kwarg'):
+        SN.orthographic_projection(0.6, BOX, 0.2, 0.2, 0.0, 0.0, sub_pixel_ray_args={'method': SN.gaussian, 'nrays': 2})
+    with pytest.raises(TypeError, match='callable'):
+        SN.orthographic_projection(0.6, BOX, 0.2, 0.2, 0.0, 0.0, sub_pixel_ray_args={'method': 'gaussian'})
+    s = SN.make_sensor_dataset(np.zeros(2), np.zeros(2), np.ones(2), np.ones(2), np.zeros(2), ['I', 'U'], 0.6,
+                               fill_ray_variables=True)
+    assert list(s['stokes']) == [True, False, True, False] and s['use_subpixel_rays'] is False
+    np.testing.assert_array_equal(s['pixel_index'], [0, 1])
+
+
+COORD = {'null': TR.CoordinateTransform(), 'log': TR.CoordinateTransformLog(), 'scaling': TR.CoordinateTransformScaling(2.0, 0.25),
+         'exp': TR.CoordinateTransformExp(10.0), 'hyperbol': TR.CoordinateTransformHyperBol(0.05)}
+
+
+@pytest.mark.parametrize('name', sorted(COORD))
+def test_coordinate_transform_matches_the_reference(name):
+    tr, phys, grad = COORD[name], GOLD['tr/phys'], GOLD['tr/grad']
+    a = tr.inverse_transform(phys)
+    np.testing.assert_array_equal(a, GOLD['tr/%s/abstract' % name])
+    np.testing.assert_array_equal(tr(a), GOLD['tr/%s/physical' % name])
+    np.testing.assert_array_equal(tr.gradient_transform(a, grad), GOLD['tr/%s/gradient' % name])
+
+
+@pytest.mark.parametrize('name,cls', [('mask', TR.StateToGridMask), ('2d', TR.StateToGrid2D),
+                                      ('uniform', TR.StateToGridUniform), ('profile', TR.StateToGridProfile)])
+def test_state_to_grid_matches_the_reference(name, cls):
+    mask, data = GOLD['s2g/mask'], GOLD['s2g/data']
+    s2g = cls(mask=mask)
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore', RuntimeWarning)              # empty levels / columns: NaN, as the reference
+        state = s2g.inverse_transform(data)
+        np.testing.assert_array_equal(state, GOLD['s2g/%s/state' % name])
+        np.testing.assert_array_equal(s2g.gradient_transform(data), GOLD['s2g/%s/gradient' % name])
+        np.testing.assert_array_equal(s2g.inverse_bounds_transform(np.full(mask.shape, 3.0)), GOLD['s2g/%s/bounds' % name])
+    assert state.shape == (s2g.state_size,)
+    if name != 'profile':
+        np.testing.assert_array_equal(s2g(state), GOLD['s2g/%s/gridded' % name])

@@ -413,3 +413,44 @@ def test_rte_solve_continues_from_a_loaded_solution():
     assert warm.num_iterations <= 2 and warm.check_solved()
     for r in (a, cold, warm):
         r.close()
+
+
+def test_rte_from_the_factory_datasets():
+    """`configuration.get_config`, `source.solar`, `surface.lambertian` / `surface.ocean_unpolarized` and the `sensor`
+    projections give the datasets the reference's scripts pass to RTE: same result as the hand-written mappings."""
+    from at3d_b200 import configuration, source as SRC, surface as SFC, sensor as SNS
+    from at3d_b200.rte import RTE
+    params, medium, source, surface = make_inputs(8, 7, 9, 'open', 1, False)
+    cfg = configuration.get_config()
+    assert cfg['split_accuracy'] == 0.03 and cfg['num_mu_bins'] == 16 and cfg['x_boundary_condition'] == 'open'
+    for k, v in params.items():
+        cfg[k] = v
+    a = RTE(params, medium, source, surface)
+    b = RTE(cfg, medium, SRC.solar(0.672, 0.5, np.rad2deg(0.2)), SFC.lambertian(0.05))
+    a.solve(maxiter=60); b.solve(maxiter=60)
+    assert a.num_iterations == b.num_iterations
+    grid = medium['cloud']
+    cams = [SNS.orthographic_projection(0.672, grid, 0.04, 0.04, 20.0, 30.0, altitude=0.5,
+                                        sub_pixel_ray_args={'method': SNS.gaussian, 'degree': 2}),
+            SNS.perspective_projection(0.672, 12.0, 12, 10, [0.2, 0.15, 2.5], [0.2, 0.17, 0.25], [0, 1, 0])]
+    for cam in cams:
+        ia = a.integrate_to_sensor(cam.copy())['I']
+        ib = b.integrate_to_sensor(cam.copy())['I']
+        np.testing.assert_allclose(ib, ia, rtol=2e-6, atol=1e-8)         # solaraz went through degrees and back
+        assert ia.shape == cam['ray_mu'].shape and ia.max() > 0.01
+        pix = b.average_subpixel_rays(b.integrate_to_sensor(cam))
+        assert pix.shape == (1, int(np.prod(cam['image_shape'])))
+    a.close(); b.close()
+    # the ocean factory lays SFCPARMS out as the facade test above does by hand
+    nxs, nys = 2, 2
+    wind = 4.0 + 3.0 * np.arange(nxs)[:, None] + 1.0 * np.arange(nys)[None, :]
+    pig = 0.1 + 0.05 * np.arange(nys)[None, :] + 0.0 * wind
+    ds = SFC.ocean_unpolarized(wind, pig, ground_temperature=290.0, delx=0.2, dely=0.15)
+    sp = np.asarray(ds['sfcparms']).reshape((3, nxs + 1, nys + 1), order='F')
+    np.testing.assert_array_equal(sp[1, :nxs, :nys], wind.astype(np.float32))
+    np.testing.assert_array_equal(sp[:, nxs, :], sp[:, 0, :]); np.testing.assert_array_equal(sp[:, :, nys], sp[:, :, 0])
+    params, medium, source, _ = make_inputs(7, 6, 9, 'periodic', 1, False)
+    rte = RTE(params, medium, source, ds)
+    rte.solve(maxiter=60)
+    assert rte.check_solved(verbose=False) and ds['sfctype'] == 'VO' and float(ds['gndtemp']) == 290.0
+    rte.close()
