@@ -4,6 +4,8 @@ on the GPU box, the .npz travels):
 
     at3d/sensor.py      orthographic_projection, perspective_projection, domaintop_projection (+ sub-pixel rays)
     at3d/transforms.py  coordinate transforms and state-to-grid maps
+    at3d/parallel.py    subdivide_raytrace_jobs (pixel-aligned ray ranges per worker)
+    at3d/uncertainties.py  inverse error covariances and noise draws of the radiometric models
 
 xarray is absent from the image, so the sensor module is loaded with a minimal stand-in for the few xarray calls it makes
 (Dataset(data_vars, coords), ds[name] = (dims, data) | DataArray, ds.name.data, ds.attrs) -- the arithmetic is the
@@ -24,14 +26,21 @@ class _Var:
         self.data = np.asarray(data)
 
     def __setitem__(self, key, value):
-        self.data[key] = value
+        self.data[key] = value.data if isinstance(value, _Var) else value
 
     def __getitem__(self, key):
-        return self.data[key]
+        return _Var(self.data[key])
+
+    def __str__(self):
+        return str(self.data)
 
     def __iadd__(self, other):
         self.data = self.data + other
         return self
+
+    @property
+    def size(self):
+        return self.data.size
 
 
 class _Dataset:
@@ -142,6 +151,53 @@ def main():
         out['s2g/%s/bounds' % name] = s2g.inverse_bounds_transform(np.full(mask.shape, 3.0))
         if name != 'profile':               # the reference's StateToGridProfile.__call__ raises for nz > ny (see transforms.py)
             out['s2g/%s/gridded' % name] = s2g(state)
+    # ---- subdivide_raytrace_jobs: merged sensors with 1..4 rays per pixel ----
+    parallel = _load('parallel', {})
+
+    class _Merged:
+        def __init__(self, rays_per_pixel):
+            self.rays_per_pixel = _Var(rays_per_pixel)
+            pixel_index = np.repeat(np.arange(rays_per_pixel.size), rays_per_pixel)
+            self.sizes = {'nrays': pixel_index.size}
+            self.nrays = _Var(np.arange(pixel_index.size))
+            self.npixels = _Var(np.arange(rays_per_pixel.size))
+            self.pixel_index = types.SimpleNamespace(diff=lambda dim: _Var(np.diff(pixel_index)))
+
+    for case, (sizes, n_jobs, job_factor) in enumerate((((37,), 4, 1), ((50, 13, 29), 8, 1), ((20, 21), 3, 2), ((9,), 4, 1))):
+        sensors = {}
+        for i, npix in enumerate(sizes):
+            rpp = rng.integers(1, 5, npix)
+            sensors[0.4 + 0.1 * i] = _Merged(rpp)
+            out['jobs/%d/rpp%d' % (case, i)] = rpp
+        keys, rays, pixels = parallel.subdivide_raytrace_jobs(sensors, n_jobs, job_factor)
+        out['jobs/%d/args' % case] = np.array([n_jobs, job_factor])
+        out['jobs/%d/keys' % case] = np.array(keys)
+        out['jobs/%d/rays' % case] = np.array(rays, np.int64)
+        out['jobs/%d/pixels' % case] = np.array(pixels, np.int64)
+    # ---- uncertainty models ----
+    at3d.checks.check_sensor = lambda sensor: None
+    unc = _load('uncertainties', {'at3d': at3d, 'at3d.checks': at3d.checks})
+    radiance = rng.uniform(0.0005, 0.45, 60)
+    out['unc/I'] = radiance
+
+    def pixel_sensor():
+        return _Dataset({'I': radiance.copy(), 'npixels': np.arange(radiance.size), 'stokes': np.array([True, False, False, False]),
+                         'stokes_index': np.array(['I', 'Q', 'U', 'V'])})
+
+    models = {'null': lambda: unc.NullUncertainty('L2', 2.5),
+              'radiometric': lambda: unc.RadiometricUncertainty('L2', lambda r: 200.0 * np.sqrt(r / 0.1), 1e-4, 0.03, 0.01, seed=5),
+              'radiometric_ll': lambda: unc.RadiometricUncertainty('LL', lambda r: 150.0 + 0.0 * r, 2e-4, 0.02, 0.0, seed=9),
+              'tandem': lambda: unc.TandemStereoCamera('L2')}
+    for name, make in models.items():
+        np.random.seed(123)
+        model = make()
+        s = pixel_sensor()
+        model.calculate_uncertainties(s)
+        out['unc/%s/uncertainties' % name] = s['uncertainties'].data
+        if name != 'null':
+            np.random.seed(77)
+            model.add_noise(s)
+            out['unc/%s/noisy' % name] = s['I'].data
     with open(os.path.join(HERE, 'host_goldens.npz'), 'wb') as fh:
         np.savez_compressed(fh, **out)
     print(len(out), 'arrays ->', os.path.join(HERE, 'host_goldens.npz'))

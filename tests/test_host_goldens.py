@@ -88,3 +88,57 @@ def test_state_to_grid_matches_the_reference(name, cls):
     assert state.shape == (s2g.state_size,)
     if name != 'profile':
         np.testing.assert_array_equal(s2g(state), GOLD['s2g/%s/gridded' % name])
+
+
+@pytest.mark.parametrize('case', range(4))
+def test_subdivide_raytrace_jobs_matches_the_reference(case):
+    from collections import OrderedDict
+    from at3d_b200.parallel import subdivide_raytrace_jobs
+    sensors = OrderedDict()
+    i = 0
+    while 'jobs/%d/rpp%d' % (case, i) in GOLD.files:
+        sensors[0.4 + 0.1 * i] = {'rays_per_pixel': GOLD['jobs/%d/rpp%d' % (case, i)]}
+        i += 1
+    n_jobs, job_factor = GOLD['jobs/%d/args' % case]
+    keys, rays, pixels = subdivide_raytrace_jobs(sensors, int(n_jobs), int(job_factor))
+    np.testing.assert_array_equal(np.array(keys), GOLD['jobs/%d/keys' % case])
+    np.testing.assert_array_equal(np.array(rays, np.int64), GOLD['jobs/%d/rays' % case])
+    np.testing.assert_array_equal(np.array(pixels, np.int64), GOLD['jobs/%d/pixels' % case])
+
+
+UNC = {'null': lambda U: U.NullUncertainty('L2', 2.5),
+       'radiometric': lambda U: U.RadiometricUncertainty('L2', lambda r: 200.0 * np.sqrt(r / 0.1), 1e-4, 0.03, 0.01, seed=5),
+       'radiometric_ll': lambda U: U.RadiometricUncertainty('LL', lambda r: 150.0 + 0.0 * r, 2e-4, 0.02, 0.0, seed=9),
+       'tandem': lambda U: U.TandemStereoCamera('L2')}
+
+
+@pytest.mark.parametrize('name', sorted(UNC))
+def test_uncertainty_model_matches_the_reference(name):
+    from at3d_b200 import uncertainties as U
+    radiance = GOLD['unc/I']
+    np.random.seed(123)
+    model = UNC[name](U)
+    sensor = {'I': radiance.copy(), 'npixels': np.arange(radiance.size), 'stokes': np.array([True, False, False, False])}
+    model.calculate_uncertainties(sensor)
+    ref = GOLD['unc/%s/uncertainties' % name]
+    assert sensor['uncertainties'].shape == ref.shape == (model.num_uncertainty, model.num_uncertainty, radiance.size)
+    np.testing.assert_array_equal(sensor['uncertainties'], ref)
+    if name == 'null':
+        with pytest.raises(ValueError, match='cannot be used to generate measurement noise'):
+            model.add_noise(sensor)
+        return
+    np.random.seed(77)
+    model.add_noise(sensor)
+    np.testing.assert_array_equal(sensor['I'], GOLD['unc/%s/noisy' % name])
+    assert np.any(sensor['I'] != radiance)
+
+
+def test_uncertainty_argument_checks():
+    from at3d_b200 import uncertainties as U
+    with pytest.raises(NotImplementedError):
+        U.NullUncertainty('L1')
+    m = U.NullUncertainty('LL')
+    assert m.num_uncertainty == 2 and m.cost_function == 'LL' and m.valid_cost_functions == ('L2', 'LL')
+    model = U.RadiometricUncertainty('L2', lambda r: 100.0 + 0 * r, 1e-4)
+    with pytest.raises(KeyError, match="Stokes component 'Q'"):
+        model.add_noise({'I': np.ones(3), 'stokes': np.array([True, True, False, False])})

@@ -71,6 +71,27 @@ def test_reference_style_inversion_script():
                                               dict(cost_function='L2', exact_single_scatter=True), dict(add_noise=False))
     loss, gds, jac = grad_fn()
     assert jac is None and gds['gradient'].shape == (7, 6, 9, 2)
+    # an uncertainty model of at3d_b200/uncertainties.py attached to the instrument fills `uncertainties` itself:
+    # NullUncertainty(scaling 2) doubles the unweighted cost and gradient
+    import copy
+    from at3d_b200 import uncertainties as UNC
+    plain = copy.deepcopy(measurements)
+    for sensor in plain['cam']['sensor_list']:
+        del sensor['uncertainties']
+    scaled = copy.deepcopy(plain)
+    scaled.add_uncertainty_model('cam', UNC.NullUncertainty('L2', 2.0))
+    with pytest.raises(ValueError, match='inconsistent'):
+        LevisApproxGradientUncorrelated(scaled, solvers, forward, unknowns, dict(verbose=False, maxiter=100, init_solution=True),
+                                        dict(cost_function='LL', exact_single_scatter=True), dict(add_noise=False))
+    pair = []
+    for meas in (plain, scaled):
+        fn = LevisApproxGradientUncorrelated(meas, solvers, meas.make_forward_sensors(), unknowns,
+                                             dict(verbose=False, maxiter=100, init_solution=True),
+                                             dict(cost_function='L2', exact_single_scatter=True), dict(add_noise=False))
+        pair.append(fn()[:2])
+    assert scaled['cam']['sensor_list'][0]['uncertainties'].shape == (4, 4, 144)
+    assert pair[1][0] == pytest.approx(2.0 * pair[0][0], rel=1e-12)
+    np.testing.assert_allclose(pair[1][1]['gradient'], 2.0 * pair[0][1]['gradient'], rtol=1e-12)
     assert gds['derivative_index'] == [('cloud', 'extinction'), ('cloud', 'ssalb')]
     # the oracle on the same solved states and derivative tables
     rte_sensors, _ = forward.sort_sensors(solvers, measurements)
