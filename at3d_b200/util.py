@@ -15,17 +15,20 @@ solver keys back to floats, :533-535, :586-587, :611).  The solution itself is n
 
 Container: the reference writes netCDF-4 groups through xarray; neither netCDF4 / HDF5 nor xarray exist in this image, so
 the tree is stored as one NumPy ``.npz`` archive whose member names are the group paths above (``numpy.load`` lists them;
-a file written by the reference is NOT readable here and vice versa).  Datasets come back as plain mappings
-``name -> array``, which is what ``RTE`` and ``SensorsDict`` of this package take.
+a file written by the reference is NOT readable here and vice versa; dataset attributes are the members ``@name`` of
+their group).  Datasets come back as plain mappings ``name -> array`` with ``attrs`` (at3d_b200/_dataset.py), which is
+what ``RTE`` and ``SensorsDict`` of this package take.
 """
 import os
 import warnings
 from collections import OrderedDict
 import numpy as np
+from ._dataset import Dataset
 from .containers import SensorsDict, SolversDict
 from .rte import RTE
 
 _SEP = '/'
+_ATTR = '@'
 
 
 def _variables(ds):
@@ -45,9 +48,14 @@ def _variables(ds):
 
 def _put(tree, group, ds):
     for name, a in _variables(ds):
-        if _SEP in name:
-            raise ValueError("variable name '%s' contains '%s'" % (name, _SEP))
+        if _SEP in name or name.startswith(_ATTR):
+            raise ValueError("variable name '%s' contains '%s' or starts with '%s'" % (name, _SEP, _ATTR))
         tree[group + _SEP + name] = a
+    # dataset attributes (projection, resolution, sub-pixel ray arguments ...) travel as '@name' members
+    for name, value in dict(getattr(ds, 'attrs', None) or {}).items():
+        a = np.asarray(value)
+        if a.dtype != object and _SEP not in str(name):
+            tree[group + _SEP + _ATTR + str(name)] = a
 
 
 def _read(file_name):
@@ -80,10 +88,14 @@ def _groups(tree, prefix):
 
 def _dataset(tree, group):
     n = len(group) + 1
-    ds = OrderedDict()
+    ds = Dataset()
     for k, a in tree.items():
         if k.startswith(group + _SEP) and _SEP not in k[n:]:
-            ds[k[n:]] = a[()] if a.ndim == 0 else a
+            value = a[()] if a.ndim == 0 else a
+            if k[n:].startswith(_ATTR):
+                ds.attrs[k[n + len(_ATTR):]] = value.item() if isinstance(value, np.generic) else value
+            else:
+                ds[k[n:]] = value
     return ds
 
 

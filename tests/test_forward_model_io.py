@@ -58,6 +58,26 @@ def test_tree_types_and_grid_round_trip(tmp_path):
     assert float(grid['delx']) == cloud['delx']
 
 
+def test_sensor_attributes_survive(tmp_path):
+    from at3d_b200 import sensor as SN
+    sensors = SensorsDict()
+    box = {'x': np.linspace(0, 0.4, 9), 'y': np.linspace(0, 0.3, 7), 'z': np.linspace(0, 0.5, 6)}
+    sensors.add_sensor('MISR', SN.orthographic_projection(0.672, box, 0.05, 0.05, 30.0, 40.0,
+                                                          sub_pixel_ray_args={'method': SN.gaussian, 'degree': (2, 3)}))
+    sensors.add_sensor('MISR', SN.perspective_projection(0.672, 20.0, 5, 4, [0.2, 0.1, 3.0], [0.2, 0.15, 0.2], [0, 1, 0]))
+    name = U.save_forward_model(str(tmp_path / 'm.nc'), sensors, _stub_solvers())
+    back = U.load_sensors(name)
+    for a, b in zip(sensors['MISR']['sensor_list'], back['MISR']['sensor_list']):
+        assert set(a) == set(b) and set(a.attrs) == set(b.attrs)
+        for k in a:
+            np.testing.assert_array_equal(np.asarray(a[k]), np.asarray(b[k]))
+        for k in a.attrs:
+            np.testing.assert_array_equal(np.asarray(a.attrs[k]), np.asarray(b.attrs[k]))
+    first = back['MISR']['sensor_list'][0]
+    assert first.attrs['projection'] == 'Orthographic' and first.attrs['sub_pixel_ray_args_method'] == 'gaussian'
+    assert list(first.attrs['sub_pixel_ray_args_degree']) == [2, 3] and first['use_subpixel_rays'] is True
+
+
 def test_existing_file_gets_a_numbered_name(tmp_path):
     name = str(tmp_path / 'model.nc')
     sensors, solvers = _sensors(), _stub_solvers()
