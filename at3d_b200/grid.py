@@ -11,9 +11,28 @@ checkout):
 * ``sh_sizes``, ``lofj``   -- ML/MM/NLM bookkeeping, at3d/solver.py:2188-2191,
                               shdomsub1.f:1057-1065
 
+* ``make_grid``            -- at3d/grid.py:36-97, the property-grid dataset (``x, y, z, delx, dely``) every
+                              scatterer and sensor bounding box is defined on
+
 All arrays use the reference layout: Fortran order, 1-based index contents.
 """
 import numpy as np
+from ._dataset import Dataset
+
+
+def make_grid(delx, npx, dely, npy, z, nx=None, ny=None, nz=None):
+    """Regular horizontal grid starting at 0 with spacings `delx`, `dely` and the (irregular) vertical levels `z`; `nx`,
+    `ny`, `nz` optionally ask for a different base-grid resolution of the solver (at3d/grid.py:36-97)."""
+    z = np.asarray(z)
+    if (z.ndim != 1) or (z.size < 2) or (not np.all(np.sort(z) == z)) or (not np.all(z >= 0.0)) or \
+            (np.unique(z).size != z.size):
+        raise ValueError('z must be >= 0, strictly increasing, 1-D and contain at least 2 points.')
+    grid = Dataset(x=np.linspace(0.0, delx * (npx - 1), npx), y=np.linspace(0.0, dely * (npy - 1), npy), z=z,
+                   delx=delx, dely=dely)
+    for name, value in (('nx', nx), ('ny', ny), ('nz', nz)):
+        if value is not None:
+            grid[name] = value
+    return grid
 
 OPPFACE = (2, 1, 4, 3, 6, 5)
 GRIDFACE = ((1, 3, 5, 7), (2, 4, 6, 8), (1, 2, 5, 6), (3, 4, 7, 8), (1, 2, 3, 4), (5, 6, 7, 8))

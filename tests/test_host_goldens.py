@@ -142,3 +142,13 @@ def test_uncertainty_argument_checks():
     model = U.RadiometricUncertainty('L2', lambda r: 100.0 + 0 * r, 1e-4)
     with pytest.raises(KeyError, match="Stokes component 'Q'"):
         model.add_noise({'I': np.ones(3), 'stokes': np.array([True, True, False, False])})
+
+
+def test_make_grid():
+    from at3d_b200.grid import make_grid
+    g = make_grid(0.02, 5, 0.03, 4, [0.0, 0.1, 0.4], nz=7)
+    np.testing.assert_array_equal(g['x'], np.linspace(0.0, 0.08, 5)); np.testing.assert_array_equal(g['y'], np.linspace(0.0, 0.09, 4))
+    assert g['delx'] == 0.02 and g['dely'] == 0.03 and g['nz'] == 7 and 'nx' not in g
+    for bad in ([0.1], [0.0, 0.2, 0.2], [0.3, 0.1], [-0.1, 0.2], [[0.0, 1.0]]):
+        with pytest.raises(ValueError, match='strictly increasing'):
+            make_grid(0.02, 5, 0.03, 4, bad)
