@@ -77,56 +77,54 @@ class RadiometricUncertainty(Uncertainty):
     def __init__(self, cost_function, snr_func, sigma_floor, absolute_calibration_uncertainty=0.0,
                  camera_to_camera_calibration_uncertainty=0.0, seed=None):
         super().__init__(cost_function)
-        self._minimum_noise = sigma_floor
-        self._snr_func = snr_func
-        self._camera_to_camera_calibration_uncertainty = camera_to_camera_calibration_uncertainty
-        self._absolute_calibration_uncertainty = absolute_calibration_uncertainty
+        self._snr_func, self._floor = snr_func, sigma_floor
+        self._camera_sigma, self._absolute_sigma = camera_to_camera_calibration_uncertainty, absolute_calibration_uncertainty
         if seed is not None:
             np.random.seed(seed)
-        # one draw per instrument, shared by all of its images
-        self._absolute_calibration_perturbation = np.random.normal(loc=0.0, scale=absolute_calibration_uncertainty)
+        # one draw per instrument, shared by all of its images (and drawn even when the uncertainty is zero, so that
+        # the global random stream advances as it does in the reference)
+        self._absolute_bias = np.random.normal(loc=0.0, scale=absolute_calibration_uncertainty)
 
     def noise_curve(self, reflectance):
         return self._snr_func(np.atleast_1d(reflectance))
 
     def _noise_variance(self, radiance):
+        """(radiance / SNR)^2, not below the floor; the floor where the curve gives no signal."""
         snr = self.noise_curve(radiance)
-        noise_levels = np.maximum(radiance / snr, self._minimum_noise)
-        noise_levels[np.where(snr == 0.0)] = self._minimum_noise
-        return noise_levels ** 2
+        sigma = np.maximum(radiance / snr, self._floor)
+        sigma[np.where(snr == 0.0)] = self._floor
+        return sigma ** 2
 
     def _process_noise(self, sensor, seed=None, camera_cal=True, noise=True, absolute_cal=True):
+        """Perturbed Stokes vector [4, npixels]: only I is perturbed (:208-243)."""
         radiance = _get(sensor, 'I')
         if seed is not None:
             np.random.seed(seed)
         if noise:
-            # Poisson counts with the mean and variance of the signal (:222-229)
-            signal_var = self._noise_variance(radiance)
-            samples = np.random.poisson((radiance ** 2) / signal_var)
-            radiance = np.sqrt(samples * signal_var)
+            # Poisson counts with the mean and the variance of the signal, scaled back to radiance
+            variance = self._noise_variance(radiance)
+            counts = np.random.poisson((radiance ** 2) / variance)
+            radiance = np.sqrt(counts * variance)
         else:
             radiance = np.array(radiance)
         if camera_cal:
-            radiance *= np.random.normal(loc=1.0, scale=self._camera_to_camera_calibration_uncertainty)
+            radiance *= np.random.normal(loc=1.0, scale=self._camera_sigma)
         if absolute_cal:
-            radiance *= (1.0 + self._absolute_calibration_perturbation)
-        big_noise = np.zeros((4, radiance.size))
-        big_noise[0] = radiance
-        return big_noise
+            radiance *= (1.0 + self._absolute_bias)
+        perturbed = np.zeros((4, radiance.size))
+        perturbed[0] = radiance
+        return perturbed
 
     def _process_uncertainties(self, sensor, camera_cal=True, noise=True, absolute_cal=True):
+        """Inverse variance of I in entry [0, 0], ones elsewhere (:245-282)."""
         radiance = _get(sensor, 'I')
-        errors = []
-        if noise:
-            errors.append(self._noise_variance(radiance))
-        if camera_cal:
-            errors.append((self._camera_to_camera_calibration_uncertainty * radiance) ** 2)
-        if absolute_cal:
-            errors.append((self._absolute_calibration_perturbation * radiance) ** 2)
-        uncertainties = 1.0 / sum(errors) if errors else np.ones(radiance.shape)
-        big_uncertainties = np.ones((self._num_uncertainty, self._num_uncertainty, uncertainties.size))
-        big_uncertainties[0, 0] = uncertainties
-        return big_uncertainties
+        terms = ([self._noise_variance(radiance)] if noise else []) \
+            + ([(self._camera_sigma * radiance) ** 2] if camera_cal else []) \
+            + ([(self._absolute_bias * radiance) ** 2] if absolute_cal else [])
+        inverse_variance = 1.0 / sum(terms) if terms else np.ones(radiance.shape)
+        out = np.ones((self._num_uncertainty, self._num_uncertainty, inverse_variance.size))
+        out[0, 0] = inverse_variance
+        return out
 
 
 class TabulatedRadiometricUncertainty(RadiometricUncertainty):
@@ -135,24 +133,26 @@ class TabulatedRadiometricUncertainty(RadiometricUncertainty):
 
     def __init__(self, cost_function, reflectance_values, SNR_values, absolute_calibration_uncertainty=0.0,
                  camera_to_camera_calibration_uncertainty=0.0, seed=None):
-        import scipy.interpolate as si
-        import scipy.optimize as so
-        noise = reflectance_values / SNR_values
-        noise_spline = si.CubicSpline(reflectance_values, SNR_values, extrapolate=True)
+        from scipy.interpolate import CubicSpline
+        from scipy.optimize import curve_fit
+        self._table = np.asarray(reflectance_values)
+        self._spline = CubicSpline(reflectance_values, SNR_values, extrapolate=True)
+        self._fit, _ = curve_fit(self._sqrt_law, reflectance_values, SNR_values, p0=[1e-5, 10])
+        self._noise_at_table_start = (reflectance_values / SNR_values)[0]
+        super().__init__(cost_function, self._tabulated_snr, self._noise_at_table_start)
 
-        def func(x, a, b):
-            return a + b * np.sqrt(x)
-        popt, _ = so.curve_fit(func, reflectance_values, SNR_values, p0=[1e-5, 10])
+    @staticmethod
+    def _sqrt_law(x, a, b):
+        return a + b * np.sqrt(x)
 
-        def snr_func(x):
-            reflectance = np.atleast_1d(x)
-            snr_out = noise_spline(reflectance)
-            above = np.where(reflectance > reflectance_values.max())
-            snr_out[above] = func(reflectance[above], *popt)
-            below = np.where(reflectance < reflectance_values.min())
-            snr_out[below] = reflectance[below] / noise[0]
-            return snr_out
-        super().__init__(cost_function, snr_func, noise[0])
+    def _tabulated_snr(self, x):
+        reflectance = np.atleast_1d(x)
+        snr = self._spline(reflectance)
+        above = np.where(reflectance > self._table.max())
+        snr[above] = self._sqrt_law(reflectance[above], *self._fit)
+        below = np.where(reflectance < self._table.min())
+        snr[below] = reflectance[below] / self._noise_at_table_start
+        return snr
 
 
 class ResearchScanningPolarimeter(RadiometricUncertainty):
