@@ -184,11 +184,17 @@ class GridStateGenerator:
             coordinate, to_grid = transforms.get(slot, (None, None))
             coordinate = TR.CoordinateTransform() if coordinate is None else coordinate
             to_grid = TR.StateToGridMask(mask=self._mask) if to_grid is None else to_grid
-            if tuple(to_grid._grid_shape) != tuple(shape):
+            map_shape = getattr(to_grid, '_grid_shape', shape)          # user-defined maps need not carry one
+            if tuple(map_shape) != tuple(shape):
                 raise ValueError("the state_to_grid map of {} is for grid shape {}, the medium has {}".format(
-                    slot, tuple(to_grid._grid_shape), tuple(shape)))
+                    slot, tuple(map_shape), tuple(shape)))
             self._transforms.append((coordinate, to_grid))
-        ends = np.cumsum([t[1].state_size for t in self._transforms])
+        sizes = [getattr(t[1], 'state_size', None) for t in self._transforms]
+        for i, (slot, size) in enumerate(zip(self._slots, sizes)):
+            if size is None:                 # a map without the property: the length of what it makes of the medium
+                sizes[i] = int(np.size(self._transforms[i][1].inverse_transform(
+                    np.asarray(_v(next(iter(mediums.values()))[slot[0]], slot[1]), np.float64))))
+        ends = np.cumsum(sizes)
         self._bounds = list(zip(np.concatenate(([0], ends[:-1])).tolist(), ends.tolist()))
 
     @property
@@ -215,7 +221,9 @@ class GridStateGenerator:
                     if n == name:
                         arr = np.array(_v(sc, v), np.float32)
                         gridded = s2g(ct(state[a:b]))                    # UnknownScatterer.get_grid_data (:1539-1559)
-                        arr[s2g._where] = gridded[s2g._where]
+                        where = getattr(s2g, '_where', None)                 # a user-defined map: its finite entries
+                        where = np.isfinite(gridded) if where is None else where
+                        arr[where] = gridded[where]
                         sc[v] = arr
                 medium[name] = sc
             old = self._solvers.get(key)

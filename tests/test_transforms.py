@@ -170,3 +170,32 @@ def test_generator_builds_the_solvers_from_a_transformed_state():
     for s in (solvers, solvers2):
         for r in s.values():
             r.close()
+
+
+def test_generator_accepts_a_user_defined_map():
+    """A state_to_grid object with only the reference's four methods (no sizes, no mask attribute): one unknown per x-row."""
+    class Rows:
+        def __init__(self, mask):
+            self.mask = mask
+
+        def __call__(self, state):
+            return np.where(self.mask, np.asarray(state)[:, None, None], np.nan)
+
+        def inverse_transform(self, gridded):
+            return np.nanmean(np.where(self.mask, gridded, np.nan), axis=(1, 2))
+
+        def gradient_transform(self, gridded_gradient):
+            return np.nansum(np.where(self.mask, gridded_gradient, np.nan), axis=(1, 2))
+
+        def inverse_bounds_transform(self, gridded_bounds):
+            return self.inverse_transform(gridded_bounds)
+
+    _, _, medium, mask = _generator()
+    mask = mask.copy(); mask[:, 0, 0] = True                      # every row has a point
+    gen, _, _, _ = _generator({('cloud', 'extinction'): (TR.CoordinateTransformLog(), Rows(mask))}, ('extinction',))
+    assert gen.state_size == mask.shape[0]
+    x = gen.get_state()
+    assert x.shape == (mask.shape[0],) and np.all(np.isfinite(x))
+    g = RNG.normal(size=mask.shape + (1,))
+    np.testing.assert_allclose(gen.project_gradient_to_state(x, {'gradient': g}),
+                               np.where(mask, g[..., 0], 0.0).sum(axis=(1, 2)) * np.exp(x), rtol=1e-13)
