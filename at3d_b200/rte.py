@@ -18,6 +18,7 @@ solver, which runs PLANCK / SURFACE_PARM_INTERP itself.  Not covered (NotImpleme
 loaded solution with cell splitting, cell splitting, thermal sources and variable surfaces on independent-pixel grids
 (``ip_flag=3``), the Ross-Li surface ('VM'), band-integrated Planck units.
 """
+import warnings
 import numpy as np
 from . import backend as B
 from . import grid as G
@@ -267,9 +268,17 @@ class RTE:
         ``split_accuracy > 0`` (the base grid is re-created, as with ``setup_grid=True`` in the reference), array
         capacities from ``adapt_grid_factor`` / ``num_sh_term_factor`` / ``cell_to_point_ratio``.  Independent-pixel
         grids (``ip_flag=3``) take the fixed-grid column solver."""
+        done_before = 0
         if not init_solution and self._solved is not None and self._restore is None:
             # continue the iterations from the object's own SOURCE / RADIANCE (e.g. with a larger maxiter); without a
-            # previous solution the flag is overridden and a solution is initialised, as in the reference (:316-322)
+            # previous solution the flag is overridden and a solution is initialised, as in the reference (:316-322).
+            # The iteration count carries on and `maxiter` caps the total (ITER is passed in and out, :447-475).
+            done_before = self._iters
+            if maxiter <= done_before:
+                if not self.check_solved(verbose=False):
+                    warnings.warn("The solver is not converged to the specified accuracy but maxiter "
+                                  "has already been exceeded. Please increase `maxiter`.")
+                return
             self._restore = self._solved
         if (self._ipflag & 3) == 3 and self._splitacc > 0.0:
             raise NotImplementedError('cell splitting on independent-pixel grids (ip_flag=3) is not implemented; '
@@ -285,15 +294,16 @@ class RTE:
             st0, self._restore = self._restore, None
             sv = S.SweepSolver(st0, self._wtmu, self._transmin)
             try:
-                sol, iters, self._solcrit, tm = sv.solve(maxiter=maxiter, solacc=self._solacc, shacc=self._shacc,
+                sol, iters, self._solcrit, tm = sv.solve(maxiter=maxiter - done_before, solacc=self._solacc, shacc=self._shacc,
                                                         accelflag=self._accelflag, highorderrad=self._highorderrad,
                                                         iterfixsh=self._iterfixsh, initial=st0)
             finally:
                 sv.close()
             self._timings = tm
-            self._iters = iters
+            self._iters = done_before + iters            # a loaded solution starts the count at zero (_init_solution, :2629)
             if verbose:
-                print('  %d iterations from the loaded solution, solution criterion %.3e' % (iters, self._solcrit))
+                print('  %d iterations from the %s solution, solution criterion %.3e'
+                      % (iters, 'previous' if done_before else 'loaded', self._solcrit))
             self._set_solution(sol)
             return
         if self._unsplit is not None:
@@ -431,6 +441,18 @@ class RTE:
     @property
     def solution_accuracy(self):
         return self._solacc
+
+    def set_solution_accuracy(self, val):
+        """``RTE.set_solution_accuracy`` (at3d/solver.py:270-277): a new tolerance for the next ``solve``."""
+        self._solacc = float(val)
+        self.numerical_params['solution_accuracy'] = val
+
+    @property
+    def adaptive_fluxes(self):
+        """Hemispheric fluxes at all grid points of the (adaptive) grid, [2 (down, up), npts] (at3d/solver.py:1141-1146)."""
+        if self._solved is None:
+            raise RuntimeError('solve() first')
+        return self._solved.fluxes[:, :self._solved.npts]
 
     def integrate_to_sensor(self, sensor, single_scatter=False, nosurface=False):
         """``RTE.integrate_to_sensor`` (at3d/solver.py:633): RENDER of the sensor's rays; adds per-ray ``I`` (``Q``,

@@ -259,8 +259,11 @@ def test_rte_default_config_adaptive_solve():
     npts1 = rte._solved.npts
     rte.solve(maxiter=60)
     assert rte._solved.npts == npts1 and rte._unsolved.npts == st0.npts
+    done = rte.num_iterations
+    rte.solve(maxiter=5, init_solution=False)            # `maxiter` is a cap on the total: already used up, nothing runs
+    assert rte.num_iterations == done and rte.check_solved(verbose=False)
     with pytest.raises(NotImplementedError):
-        rte.solve(maxiter=5, init_solution=False)
+        rte.solve(maxiter=200, init_solution=False)      # continuing with cell splitting
     rte.close()
 
 
@@ -409,8 +412,12 @@ def test_rte_solve_continues_from_a_loaded_solution():
     np.testing.assert_allclose(warm._solved.fluxes, ref.fluxes, rtol=1e-4, atol=1e-7)
     np.testing.assert_allclose(warm._solved.fluxes, cold._solved.fluxes, rtol=2e-3, atol=1e-4 * cold._solved.fluxes.max())
     # init_solution=False on a solved object: nothing left to do, one iteration confirms it
+    before = warm.num_iterations
     warm.solve(maxiter=100, init_solution=False)
-    assert warm.num_iterations <= 2 and warm.check_solved()
+    assert before < warm.num_iterations <= before + 2 and warm.check_solved()       # the count carries on
+    # `maxiter` caps the total: nothing runs when it is already used up
+    warm.solve(maxiter=before, init_solution=False)
+    assert warm.num_iterations <= before + 2 and warm.check_solved()
     for r in (a, cold, warm):
         r.close()
 
@@ -440,6 +447,13 @@ def test_rte_from_the_factory_datasets():
         assert ia.shape == cam['ray_mu'].shape and ia.max() > 0.01
         pix = b.average_subpixel_rays(b.integrate_to_sensor(cam))
         assert pix.shape == (1, int(np.prod(cam['image_shape'])))
+    assert a.adaptive_fluxes.shape == (2, a._solved.npts) and np.all(a.adaptive_fluxes >= 0)
+    np.testing.assert_array_equal(a.fluxes.reshape(2, -1), a.adaptive_fluxes[:, :a.fluxes[0].size])
+    # a tighter tolerance, continuing from the solution at hand
+    first = a.num_iterations
+    a.set_solution_accuracy(1e-6)
+    a.solve(maxiter=60, init_solution=False)
+    assert a.solution_accuracy == 1e-6 and a.check_solved(verbose=False) and a.num_iterations > first
     a.close(); b.close()
     # the ocean factory lays SFCPARMS out as the facade test above does by hand
     nxs, nys = 2, 2
