@@ -247,6 +247,18 @@ class SolversDict(OrderedDict):
 
     parallel_solve = solve
 
+    def calculate_direct_beam_derivative(self):
+        """at3d/containers.py:769-776."""
+        for solver in self.values():
+            solver.calculate_direct_beam_derivative()
+
+    def calculate_microphysical_partial_derivatives(self, unknown_scatterers):
+        """Derivative tables of every solver for the unknowns (at3d/containers.py:778-800)."""
+        if not isinstance(unknown_scatterers, UnknownScatterers):
+            raise TypeError("`unknown_scatterers` should be of type '{}' not '{}'".format(UnknownScatterers, type(unknown_scatterers)))
+        for solver in self.values():
+            solver.calculate_microphysical_partial_derivatives(unknown_scatterers.derivative_information(solver))
+
     @property
     def npixels(self):
         return None

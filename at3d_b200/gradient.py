@@ -57,8 +57,8 @@ class LevisApproxGradient:
         rank, world = int(kw.pop('rank', 0)), int(kw.pop('world', 1))
         kw.pop('n_jobs', None); kw.pop('mpi_comm', None)
         self.solvers.solve(rank=rank, world=world, **kw)
-        for solver in self.solvers.values():
-            solver.calculate_microphysical_partial_derivatives(self.unknown_scatterers.derivative_information(solver))
+        self.solvers.calculate_microphysical_partial_derivatives(self.unknown_scatterers)      # at3d/gradient.py:140-141
+        self.solvers.calculate_direct_beam_derivative()
         rte_sensors, sensor_mapping = self.forward_sensors.sort_sensors(self.solvers, self.measurements)
         self._rte_sensors, self._sensor_mapping = rte_sensors, sensor_mapping
         losses, gradients, outs, keys = [], [], [], []

@@ -586,6 +586,13 @@ class RTE:
         grad = g.reshape(self._npx, self._npy, self._npz, len(species))
         return float(cost[0]), grad, images
 
+    def calculate_direct_beam_derivative(self):
+        """``RTE.calculate_direct_beam_derivative`` (at3d/solver.py:1266-1325) builds the dense DPATH / DPTR lists of
+        MAKE_DIRECT_DERIVATIVE.  Here the gradient call walks the sun paths itself (the streaming direct-beam derivative of
+        at3d_levisapprox_gradient), so there is nothing to precompute: kept so that scripts which call it
+        (at3d/gradient.py:141) run unchanged."""
+        return None
+
     @property
     def fluxes(self):
         """Hemispheric fluxes on the base grid, [2 (down, up), nx1, ny1, nz] (at3d/solver.py:1148)."""

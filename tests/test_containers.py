@@ -52,3 +52,29 @@ def test_unknown_scatterers_optical_unknowns():
         assert False
     except NotImplementedError:
         pass
+
+
+def test_solvers_dict_derivative_entry_points():
+    from at3d_b200.containers import SolversDict, UnknownScatterers
+    calls = []
+
+    class Stub:
+        medium = {'cloud': dict(extinction=np.ones((2, 2, 2), np.float32), table_index=np.ones((1, 2, 2, 2), np.int32),
+                                phase_weights=np.ones((1, 2, 2, 2), np.float32), legcoef=np.ones((6, 3, 1), np.float32))}
+
+        def calculate_direct_beam_derivative(self):
+            calls.append('beam')
+
+        def calculate_microphysical_partial_derivatives(self, info):
+            calls.append(sorted(info['cloud']))
+
+    solvers = SolversDict()
+    solvers[0.66], solvers[0.86] = Stub(), Stub()
+    unknown = UnknownScatterers()
+    unknown.add_unknowns('cloud', ['extinction', 'ssalb'])
+    solvers.calculate_microphysical_partial_derivatives(unknown)
+    solvers.calculate_direct_beam_derivative()
+    assert calls == [['extinction', 'ssalb']] * 2 + ['beam'] * 2
+    import pytest
+    with pytest.raises(TypeError):
+        solvers.calculate_microphysical_partial_derivatives({'cloud': ['extinction']})
