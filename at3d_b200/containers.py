@@ -69,6 +69,24 @@ class SensorsDict(OrderedDict):
                                                uncertainty_model=inst['uncertainty_model'])
         return forward_sensors
 
+    def get_images(self, instrument):
+        """Every image of `instrument` as 2-D arrays (:389-411)."""
+        return [self.get_image(instrument, index) for index in range(len(self[instrument]['sensor_list']))]
+
+    def get_image(self, instrument, sensor_index):
+        """Pixel positions, directions and the observed Stokes components of one sensor on its image plane
+        (``image_shape``, first image dimension fastest) (:414-459)."""
+        sensor = self[instrument]['sensor_list'][sensor_index]
+        if 'image_shape' not in sensor:
+            raise ValueError("Sensor dataset does not have an 'image_shape' variable. A 2D image cannot be formed.")
+        shape = tuple(int(n) for n in _v(sensor, 'image_shape'))
+        image = OrderedDict((name, np.asarray(_v(sensor, 'cam_' + name)).reshape(shape, order='F'))
+                            for name in ('x', 'y', 'mu', 'phi'))
+        for name, observed in zip(STOKES_NAMES, np.asarray(_v(sensor, 'stokes'), bool)):
+            if observed:
+                image[name] = np.asarray(_v(sensor, name)).reshape(shape, order='F')
+        return image
+
     def get_unique_solvers(self):
         return np.unique([_wavelength(s) for inst in self.values() for s in inst['sensor_list']])
 

@@ -78,3 +78,20 @@ def test_solvers_dict_derivative_entry_points():
     import pytest
     with pytest.raises(TypeError):
         solvers.calculate_microphysical_partial_derivatives({'cloud': ['extinction']})
+
+
+def test_get_image_reshapes_to_the_image_plane():
+    import pytest
+    from at3d_b200 import sensor as SN
+    from at3d_b200.containers import SensorsDict
+    sensors = SensorsDict()
+    cam = SN.perspective_projection(0.66, 20.0, 5, 3, [0.2, 0.1, 3.0], [0.2, 0.15, 0.2], [0, 1, 0], stokes=['I', 'Q'])
+    cam['I'], cam['Q'] = np.arange(15.0), -np.arange(15.0)
+    sensors.add_sensor('cam', cam)
+    img = sensors.get_images('cam')[0]
+    assert set(img) == {'x', 'y', 'mu', 'phi', 'I', 'Q'} and img['I'].shape == (5, 3)
+    np.testing.assert_array_equal(img['I'][:, 0], np.arange(5.0))           # x fastest within the image
+    np.testing.assert_array_equal(img['mu'], cam['cam_mu'].reshape((5, 3), order='F'))
+    del cam['image_shape']
+    with pytest.raises(ValueError, match='image_shape'):
+        sensors.get_image('cam', 0)
