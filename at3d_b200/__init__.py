@@ -5,3 +5,16 @@ The compute path lives in ``lib/libat3d_b200.so`` (hand-written CUDA behind the 
 Python interface for the path (``at3d.core`` keyword API, ``solver.RTE`` state, sensors).
 """
 __version__ = '0.1.0'
+
+_SUBMODULES = ('backend', 'callback', 'configuration', 'containers', 'core', 'device', 'gradient', 'gradsetup', 'grid',
+               'medium', 'optimize', 'parallel', 'rte', 'sensor', 'solver', 'source', 'state', 'surface', 'synthetic',
+               'transforms', 'uncertainties', 'util')
+
+
+def __getattr__(name):
+    """``import at3d_b200 as at3d; at3d.sensor.perspective_projection(...)``: submodules load on first use (the
+    reference's ``at3d/__init__.py`` imports them all; here importing the package does not load the CUDA library)."""
+    if name in _SUBMODULES:
+        import importlib
+        return importlib.import_module('.' + name, __name__)
+    raise AttributeError("module '{}' has no attribute '{}'".format(__name__, name))

@@ -442,3 +442,11 @@ def solve_adaptive(state, pg, wtmu, tempp=None, temp=None, splitacc=0.03, shacc=
     st.extdirp = arr['extdirp']
     res = (st, io.iters, io.solcrit, io.splitcrit)
     return res + (list(ms),) if timing else res
+
+
+def __getattr__(name):
+    # the reference keeps its RTE class in at3d/solver.py: ``at3d.solver.RTE`` resolves here too (at3d_b200/rte.py)
+    if name == 'RTE':
+        from .rte import RTE
+        return RTE
+    raise AttributeError("module '{}' has no attribute '{}'".format(__name__, name))

@@ -69,3 +69,12 @@ def test_surfaces():
         surface.ocean_unpolarized(np.ones((2, 2)), np.ones((2, 2)))
     with pytest.raises(ValueError, match='Illegal surface albedo'):
         surface.prep_surface('VL', np.stack([np.full((2, 2), 290.0), np.full((2, 2), 1.5)]))
+
+
+def test_package_namespace_resolves_the_reference_module_names():
+    import at3d_b200 as at3d
+    assert at3d.solver.RTE is at3d.rte.RTE and at3d.callback.CallbackFn is at3d.optimize.CallbackFn
+    assert callable(at3d.sensor.perspective_projection) and callable(at3d.util.save_forward_model)
+    assert at3d.containers.SensorsDict.__name__ == 'SensorsDict' and callable(at3d.grid.make_grid)
+    with pytest.raises(AttributeError):
+        at3d.visualization
